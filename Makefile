@@ -1,0 +1,45 @@
+# Top-level build: the CUDA hot-path library, the host-side drop-in library and
+# CLI, and (test infrastructure) the oracle.  `python -c "import __graft_entry__ as g; g.build()"`
+# runs exactly this.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+PKG       := pbrt_v2_b200
+HOSTDIR   := $(PKG)/csrc/host
+DEVDIR    := $(PKG)/csrc/device
+# -fmad=false: the reference is compiled for x86-64 without FMA; contraction would
+# change hit/miss decisions and with them the RNG stream.
+NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+             -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
+             -Xcompiler -fPIC -Xptxas -v
+# host code must not contract to FMA either (no -march=native)
+HOSTFLAGS := -O2 -std=c++17 -ffp-contract=off -fPIC -Wall -Wno-unused-function
+
+HOSTSRC   := transform parser shapes bvh measured renderer render_call capi
+HOSTOBJ   := $(patsubst %,build/host/%.o,$(HOSTSRC))
+DEVSRC    := $(wildcard $(DEVDIR)/*.cu)
+DEVHDR    := $(wildcard $(DEVDIR)/*.cuh) include/pbrtgpu.h
+
+all: $(PKG)/libpbrtgpu.so $(PKG)/libpbrthost.so $(PKG)/pbrt_b200 oracle
+
+$(PKG)/libpbrtgpu.so: $(DEVSRC) $(DEVHDR)
+	$(NVCC) $(NVFLAGS) -shared $(DEVSRC) -o $@ 2> build/ptxas.log || (cat build/ptxas.log; false)
+	@grep -E "registers|spill|error" build/ptxas.log | sort | uniq -c | sort -rn | head -20 || true
+
+build/host/%.o: $(HOSTDIR)/%.cpp $(HOSTDIR)/scene.h $(HOSTDIR)/geom.h include/pbrtgpu.h
+	@mkdir -p build/host
+	$(CXX) $(HOSTFLAGS) -c $< -o $@
+
+$(PKG)/libpbrthost.so: $(HOSTOBJ) $(PKG)/libpbrtgpu.so
+	$(CXX) -shared $(HOSTOBJ) -o $@ -L$(PKG) -lpbrtgpu -Wl,-rpath,'$$ORIGIN' -lpthread
+
+$(PKG)/pbrt_b200: build/host/main.o $(PKG)/libpbrthost.so
+	$(CXX) build/host/main.o -o $@ -L$(PKG) -lpbrthost -lpbrtgpu -Wl,-rpath,'$$ORIGIN' -lpthread
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf build $(PKG)/*.so $(PKG)/pbrt_b200
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

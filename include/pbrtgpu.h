@@ -1,0 +1,244 @@
+/*
+ * pbrtgpu.h -- C ABI of the B200 path-tracing hot path (libpbrtgpu.so).
+ *
+ * This is the drop-in boundary for pbrt-v2's per-pixel-sample path-tracing loop
+ *   SamplerRenderer::Render      /root/reference/src/renderers/samplerrenderer.cpp:188-222
+ *   SamplerRendererTask::Run     renderers/samplerrenderer.cpp:60-164
+ *   PathIntegrator::Li           integrators/path.cpp:52-123
+ *   BVHAccel::Intersect/P        accelerators/bvh.cpp:403-503
+ *   ImageFilm::AddSample         film/image.cpp:77-137
+ * pbrt-v2 has no FFI of its own (no DSO plugins, README.txt:55-61); its
+ * "plugin surface" is the abstract classes Renderer (core/renderer.h:43-54),
+ * SurfaceIntegrator (core/integrator.h:51-70) and Aggregate
+ * (core/primitive.h:126-134).  The only batch-granular virtual on the path is
+ * Renderer::Render(const Scene*), so that is where the host<->device boundary
+ * sits: a host-side Renderer subclass flattens the scene objects into the POD
+ * arrays below and makes ONE pbrtgpu_render() call (see INTEGRATION.md for the
+ * reference-side binding).
+ *
+ * Conventions: plain pointers and sizes, caller owns every host buffer, the
+ * library owns all device memory, every entry point returns 0 on success or a
+ * PBRTGPU_E* code (never aborts; pbrtgpu_last_error() gives text), calls on
+ * one scene handle must be serialised by the caller.  Matrices are row-major
+ * m[4*row+col] exactly like Matrix4x4::m[row][col] (core/transform.h).
+ */
+#ifndef PBRTGPU_H
+#define PBRTGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBRTGPU_OK            0
+#define PBRTGPU_EINVAL        1   /* malformed descriptor / argument          */
+#define PBRTGPU_EUNSUPPORTED  2   /* scene feature outside the hot-path scope */
+#define PBRTGPU_ECUDA         3   /* CUDA runtime failure (text in last_error)*/
+#define PBRTGPU_ENODEVICE     4   /* no CUDA device: there is NO CPU fallback */
+
+/* ---- transforms: Transform{m, mInv}, core/transform.h:86-178 --------------- */
+typedef struct PbrtGpuXform {
+    float m[16];
+    float mInv[16];
+} PbrtGpuXform;
+
+/* ---- LinearBVHNode, accelerators/bvh.cpp:113-123 (same 32-byte layout) ----- */
+typedef struct PbrtGpuBVHNode {
+    float    bmin[3];
+    float    bmax[3];
+    uint32_t offset;       /* leaf: primitivesOffset; interior: secondChildOffset */
+    uint8_t  nPrimitives;  /* 0 -> interior node */
+    uint8_t  axis;
+    uint8_t  pad[2];
+} PbrtGpuBVHNode;
+
+/* ---- primitives, in BVHAccel::primitives (leaf) order ---------------------- */
+enum { PBRTGPU_PRIM_TRIANGLE = 0, PBRTGPU_PRIM_SPHERE = 1, PBRTGPU_PRIM_DISK = 2 };
+
+/* GeometricPrimitive{shape, material, areaLight}, core/primitive.cpp:149-190 */
+typedef struct PbrtGpuPrimitive {
+    uint32_t type;       /* PBRTGPU_PRIM_*                                      */
+    uint32_t index;      /* TRIANGLE: into triangles[]; else into quadrics[]    */
+    int32_t  material;   /* into materials[]                                    */
+    int32_t  areaLight;  /* into lights[] or -1 (GetAreaLight()==NULL)          */
+} PbrtGpuPrimitive;
+
+/* Triangle{mesh, v}, shapes/trianglemesh.h:70-109 */
+typedef struct PbrtGpuTriangle {
+    uint32_t v[3];       /* indices into P/N/uv (mesh base already added)       */
+    uint32_t mesh;       /* into meshes[]                                       */
+} PbrtGpuTriangle;
+
+#define PBRTGPU_MESH_HAS_N            1u
+#define PBRTGPU_MESH_HAS_UV           2u
+#define PBRTGPU_SHAPE_REVERSE_ORIENT  4u   /* Shape::ReverseOrientation         */
+#define PBRTGPU_SHAPE_SWAPS_HANDED    8u   /* Shape::TransformSwapsHandedness   */
+
+/* TriangleMesh, shapes/trianglemesh.cpp:42-71: P is world space, N/uv as given */
+typedef struct PbrtGpuMesh {
+    uint32_t flags;
+    uint32_t xform;        /* ObjectToWorld, into xforms[] (normals: :322-324)  */
+    uint32_t firstVertex;
+    uint32_t nVertices;
+} PbrtGpuMesh;
+
+/* Sphere (shapes/sphere.cpp:39-49) / Disk (shapes/disk.cpp:39-46) */
+typedef struct PbrtGpuQuadric {
+    uint32_t type;         /* PBRTGPU_PRIM_SPHERE | PBRTGPU_PRIM_DISK           */
+    uint32_t flags;        /* PBRTGPU_SHAPE_*                                   */
+    uint32_t xform;        /* ObjectToWorld (WorldToObject = its inverse)       */
+    float radius;
+    float zmin, zmax, thetaMin, thetaMax;   /* sphere */
+    float phiMax;
+    float height, innerRadius;               /* disk   */
+    float area;            /* Shape::Area() evaluated on the host               */
+} PbrtGpuQuadric;
+
+/* ---- materials (constant textures only), materials/{matte,plastic,measured} - */
+enum { PBRTGPU_MAT_MATTE = 0, PBRTGPU_MAT_PLASTIC = 1, PBRTGPU_MAT_MEASURED = 2 };
+typedef struct PbrtGpuMaterial {
+    uint32_t type;
+    float Kd[3];
+    float sigma;        /* matte: Oren-Nayar sigma; only 0 is in scope          */
+    float Ks[3];
+    float roughness;
+    int32_t measured;   /* into measured[] (IrregIsotropicBRDF) or -1           */
+} PbrtGpuMaterial;
+
+/* KdTree<IrregIsotropicBRDFSample>, core/kdtree.h:44-60, reflection.h:44-50 */
+typedef struct PbrtGpuKdNode {
+    float    splitPos;
+    uint32_t bits;      /* splitAxis:2 | hasLeftChild:1 (bit 2) | rightChild:29 (bits 3..31) */
+} PbrtGpuKdNode;
+typedef struct PbrtGpuBrdfSample {
+    float p[3];
+    float v[3];
+} PbrtGpuBrdfSample;
+typedef struct PbrtGpuMeasured {
+    uint32_t firstNode;   /* into kdNodes[] / kdData[]                          */
+    uint32_t nNodes;
+} PbrtGpuMeasured;
+
+/* ---- lights, lights/{point,diffuse}.cpp, core/light.cpp:114-171 ------------ */
+enum { PBRTGPU_LIGHT_POINT = 0, PBRTGPU_LIGHT_DIFFUSE_AREA = 1 };
+typedef struct PbrtGpuLight {
+    uint32_t type;
+    float    L[3];        /* POINT: Intensity; AREA: Lemit                      */
+    float    pos[3];      /* POINT: lightPos (world)                            */
+    uint32_t firstShape;  /* AREA: ShapeSet::shapes, into lightShapes[]         */
+    uint32_t nShapes;     /* in scope: exactly 1 (sphere or disk)               */
+    float    sumArea;     /* ShapeSet::sumArea                                  */
+} PbrtGpuLight;
+typedef struct PbrtGpuLightShape {
+    uint32_t type;        /* PBRTGPU_PRIM_SPHERE | PBRTGPU_PRIM_DISK            */
+    uint32_t index;       /* into quadrics[]                                    */
+    float    area;        /* ShapeSet::areas[i]                                 */
+} PbrtGpuLightShape;
+
+/* ---- the flattened Scene --------------------------------------------------- */
+typedef struct PbrtGpuSceneDesc {
+    uint32_t nNodes;        const PbrtGpuBVHNode    *nodes;
+    uint32_t nPrimitives;   const PbrtGpuPrimitive  *primitives;
+    uint32_t nTriangles;    const PbrtGpuTriangle   *triangles;
+    uint32_t nMeshes;       const PbrtGpuMesh       *meshes;
+    uint32_t nVertices;     const float *P;   /* 3*nVertices                    */
+                            const float *N;   /* 3*nVertices or NULL            */
+                            const float *uv;  /* 2*nVertices or NULL            */
+    uint32_t nQuadrics;     const PbrtGpuQuadric    *quadrics;
+    uint32_t nXforms;       const PbrtGpuXform      *xforms;
+    uint32_t nMaterials;    const PbrtGpuMaterial   *materials;
+    uint32_t nMeasured;     const PbrtGpuMeasured   *measured;
+    uint32_t nKdNodes;      const PbrtGpuKdNode     *kdNodes;
+                            const PbrtGpuBrdfSample *kdData;
+    uint32_t nLights;       const PbrtGpuLight      *lights;
+    uint32_t nLightShapes;  const PbrtGpuLightShape *lightShapes;
+} PbrtGpuSceneDesc;
+
+/* ---- one Render() call ----------------------------------------------------- */
+typedef struct PbrtGpuRenderDesc {
+    /* PerspectiveCamera (cameras/perspective.cpp:41-49, core/camera.cpp:83-102) */
+    float rasterToCamera[16];   /* RasterToCamera.m                             */
+    float cameraToWorld[16];    /* CameraToWorld start transform .m (static)    */
+    float lensRadius, focalDistance;
+    float shutterOpen, shutterClose;
+    /* ImageFilm (film/image.cpp:40-51) */
+    int32_t xResolution, yResolution;
+    float   cropWindow[4];
+    float   filterXWidth, filterYWidth;   /* box filter only (filters/box.cpp)  */
+    /* LDSampler (samplers/lowdiscrepancy.cpp:40-51): power of two              */
+    int32_t samplesPerPixel;
+    /* PathIntegrator (integrators/path.cpp:125-128)                            */
+    int32_t maxDepth;
+    /* SamplerRenderer::Render task decomposition (samplerrenderer.cpp:203-205):
+     * nTasks is a reference INPUT (it fixes which RNG stream feeds which
+     * pixel); tasks [taskBegin, taskEnd) are rendered by this call, which is
+     * how an image is sharded across GPUs.                                      */
+    int32_t nTasks;
+    int32_t taskBegin, taskEnd;
+} PbrtGpuRenderDesc;
+
+/* ImageFilm::Pixel {Lxyz[3], weightSum} (film/image.h:69-78), row-major over
+ * the film's pixel extent (xPixelCount x yPixelCount, image.cpp:48-51).        */
+typedef struct PbrtGpuPixel {
+    float Lxyz[3];
+    float weightSum;
+} PbrtGpuPixel;
+
+typedef struct PbrtGpuStats {
+    double   renderMs;        /* CUDA-event time of the device work             */
+    double   tableMs;         /* ... of which LD table generation               */
+    double   traceMs;         /* ... of which the path kernel                   */
+    uint64_t cameraSamples;
+    uint64_t closestRays, shadowRays;
+    uint64_t nodesVisited;    /* BVH nodes whose bounds were tested             */
+    uint64_t primTests;
+    uint64_t kernelLaunches;
+} PbrtGpuStats;
+
+typedef struct PbrtGpuRay { float o[3], d[3], mint, maxt; } PbrtGpuRay;
+typedef struct PbrtGpuHit {
+    int32_t  hit;             /* 0/1                                            */
+    uint32_t primitive;       /* index into primitives[]                        */
+    float    t;               /* ray.maxt after BVHAccel::Intersect             */
+    float    b1, b2;          /* triangle barycentrics (0 for quadrics)         */
+    float    p[3], n[3];      /* dg.p, dg.nn                                    */
+} PbrtGpuHit;
+
+typedef struct PbrtGpuScene PbrtGpuScene;
+
+int  pbrtgpu_device_count(void);
+int  pbrtgpu_set_device(int ordinal);
+const char *pbrtgpu_last_error(void);
+
+/* replaces: Scene / BVHAccel / GeometricPrimitive object graph (core/scene.h) */
+int  pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out);
+void pbrtgpu_scene_destroy(PbrtGpuScene *scene);
+
+/* replaces: SamplerRenderer::Render (samplerrenderer.cpp:188-222) minus the
+ * final WriteImage().  `pixels` is HOST memory (xPixelCount*yPixelCount);
+ * pixels of tasks outside [taskBegin,taskEnd) are left zero.                   */
+int  pbrtgpu_render(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd,
+                    PbrtGpuPixel *pixels, PbrtGpuStats *stats);
+/* same, but `d_pixels` is DEVICE memory on the current device (e.g. a torch
+ * tensor about to be NCCL-gathered) and `stream` a cudaStream_t (NULL = default);
+ * asynchronous unless stats != NULL.                                            */
+int  pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd,
+                           void *d_pixels, void *stream, PbrtGpuStats *stats);
+
+/* replaces: BVHAccel::Intersect (bvh.cpp:403-454) over a ray batch             */
+int  pbrtgpu_intersect(PbrtGpuScene *scene, const PbrtGpuRay *rays, int n,
+                       PbrtGpuHit *hits);
+/* replaces: BVHAccel::IntersectP (bvh.cpp:457-503) over a ray batch            */
+int  pbrtgpu_intersect_p(PbrtGpuScene *scene, const PbrtGpuRay *rays, int n,
+                         uint8_t *occluded);
+/* replaces: LDSampler::GetMoreSamples / LDPixelSample (montecarlo.cpp:200-252)
+ * for the FIRST pixel of task `taskNum` (test hook).  out = spp rows of 37
+ * floats: imageX,imageY,lensU,lensV,time, 14 1-D values, 9 2-D pairs (in
+ * Sample::oneD / twoD order).                                                  */
+int  pbrtgpu_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBRTGPU_H */

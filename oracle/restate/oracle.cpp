@@ -1,0 +1,1261 @@
+// oracle.cpp -- TEST INFRASTRUCTURE: CPU restatement of pbrt-v2's path-tracing
+// hot path over the flattened scene (include/pbrtgpu.h PODs).
+//
+// This file is the CHECKER for the CUDA path.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline leg may load it; the product (libpbrtgpu.so,
+// libpbrthost.so, pbrt_v2_b200/*.py) never does.  It is pinned against the
+// UNMODIFIED reference binary (oracle/_ref/bin/pbrt, built by oracle/Makefile):
+// tests/test_oracle_vs_reference.py requires bit-identical PFM output at equal
+// nTasks on the bunny and killeroo config scenes.
+//
+// Structure follows the reference function by function (file:line cited at each);
+// it is scalar, recursive where the reference is, and uses the host libm.
+// Build: g++ -O2 -ffp-contract=off (no -march=native: no FMA).
+#include "oracle_math.h"
+#include "../../include/pbrtgpu.h"
+
+#include <atomic>
+#include <cstdio>
+#include <thread>
+#include <vector>
+
+using namespace orc;
+
+namespace {
+
+// =============================================================== RNG (MT19937)
+// core/rng.h:44-59, core/rng.cpp:43-107
+struct RNG {
+    static const int N = 624;
+    uint32_t mt[N];
+    int mti;
+    uint64_t draws;
+    explicit RNG(uint32_t seed) { Seed(seed); draws = 0; }
+    void Seed(uint32_t seed) {
+        mt[0] = seed;
+        for (mti = 1; mti < N; mti++)
+            mt[mti] = 1812433253u * (mt[mti - 1] ^ (mt[mti - 1] >> 30)) + (uint32_t)mti;
+    }
+    uint32_t RandomUInt() {
+        const int M = 397;
+        if (mti >= N) {
+            int kk;
+            uint32_t y;
+            for (kk = 0; kk < N - M; kk++) {
+                y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + M] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            for (; kk < N - 1; kk++) {
+                y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            y = (mt[N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            mti = 0;
+        }
+        uint32_t y = mt[mti++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        ++draws;
+        return y;
+    }
+    float RandomFloat() { return (RandomUInt() & 0xffffff) / float(1 << 24); }
+};
+
+// ========================================================= low-discrepancy tables
+// core/montecarlo.h:274-327
+inline float VanDerCorput(uint32_t n, uint32_t scramble) {
+    n = (n << 16) | (n >> 16);
+    n = ((n & 0x00ff00ff) << 8) | ((n & 0xff00ff00) >> 8);
+    n = ((n & 0x0f0f0f0f) << 4) | ((n & 0xf0f0f0f0) >> 4);
+    n = ((n & 0x33333333) << 2) | ((n & 0xcccccccc) >> 2);
+    n = ((n & 0x55555555) << 1) | ((n & 0xaaaaaaaa) >> 1);
+    n ^= scramble;
+    return std::min(((n >> 8) & 0xffffff) / float(1 << 24), OneMinusEpsilon);
+}
+inline float Sobol2(uint32_t n, uint32_t scramble) {
+    for (uint32_t v = 1u << 31; n != 0; n >>= 1, v ^= v >> 1)
+        if (n & 0x1) scramble ^= v;
+    return std::min(((scramble >> 8) & 0xffffff) / float(1 << 24), OneMinusEpsilon);
+}
+void Shuffle(float *samp, uint32_t count, uint32_t dims, RNG &rng) {   // montecarlo.h:174-181
+    for (uint32_t i = 0; i < count; ++i) {
+        uint32_t other = i + (rng.RandomUInt() % (count - i));
+        for (uint32_t j = 0; j < dims; ++j) std::swap(samp[dims * i + j], samp[dims * other + j]);
+    }
+}
+void LDShuffleScrambled1D(int nSamples, int nPixel, float *samples, RNG &rng) {
+    uint32_t scramble = rng.RandomUInt();
+    for (int i = 0; i < nSamples * nPixel; ++i) samples[i] = VanDerCorput(i, scramble);
+    for (int i = 0; i < nPixel; ++i) Shuffle(samples + i * nSamples, nSamples, 1, rng);
+    Shuffle(samples, nPixel, nSamples, rng);
+}
+void LDShuffleScrambled2D(int nSamples, int nPixel, float *samples, RNG &rng) {
+    uint32_t s0 = rng.RandomUInt();
+    uint32_t s1 = rng.RandomUInt();
+    for (int i = 0; i < nSamples * nPixel; ++i) {
+        samples[2 * i] = VanDerCorput(i, s0);
+        samples[2 * i + 1] = Sobol2(i, s1);
+    }
+    for (int i = 0; i < nPixel; ++i) Shuffle(samples + 2 * i * nSamples, nSamples, 2, rng);
+    Shuffle(samples, nPixel, 2 * nSamples, rng);
+}
+
+// struct Sample for PathIntegrator + EmissionIntegrator requests:
+//   1-D (core/sampler.h Add1D order; path.cpp:43-48, light.cpp:64-68,
+//   reflection.cpp:502-506, emission.cpp:41-42):
+//      per depth d<3: [4d+0] light.component [4d+1] lightNum [4d+2] bsdf.component [4d+3] path.component
+//      [12] emission tau  [13] emission scatter
+//   2-D: per depth d<3: [3d+0] light.pos [3d+1] bsdf.dir [3d+2] path.dir
+enum { N1D = 14, N2D = 9, SAMPLE_FLOATS = 5 + N1D + 2 * N2D };
+struct Sample {
+    float imageX, imageY, lensU, lensV, time;
+    float oneD[N1D];
+    float twoD[N2D][2];
+};
+
+// LDPixelSample, core/montecarlo.cpp:200-252 (all n1D[i] == n2D[i] == 1 here)
+void LDPixelSample(int xPos, int yPos, float shutterOpen, float shutterClose, int nPixelSamples,
+                   Sample *samples, float *buf, RNG &rng) {
+    float *imageSamples = buf; buf += 2 * nPixelSamples;
+    float *lensSamples = buf;  buf += 2 * nPixelSamples;
+    float *timeSamples = buf;  buf += nPixelSamples;
+    float *oneDSamples[N1D], *twoDSamples[N2D];
+    for (int i = 0; i < N1D; ++i) { oneDSamples[i] = buf; buf += nPixelSamples; }
+    for (int i = 0; i < N2D; ++i) { twoDSamples[i] = buf; buf += 2 * nPixelSamples; }
+    LDShuffleScrambled2D(1, nPixelSamples, imageSamples, rng);
+    LDShuffleScrambled2D(1, nPixelSamples, lensSamples, rng);
+    LDShuffleScrambled1D(1, nPixelSamples, timeSamples, rng);
+    for (int i = 0; i < N1D; ++i) LDShuffleScrambled1D(1, nPixelSamples, oneDSamples[i], rng);
+    for (int i = 0; i < N2D; ++i) LDShuffleScrambled2D(1, nPixelSamples, twoDSamples[i], rng);
+    for (int i = 0; i < nPixelSamples; ++i) {
+        samples[i].imageX = xPos + imageSamples[2 * i];
+        samples[i].imageY = yPos + imageSamples[2 * i + 1];
+        samples[i].time = Lerp(timeSamples[i], shutterOpen, shutterClose);
+        samples[i].lensU = lensSamples[2 * i];
+        samples[i].lensV = lensSamples[2 * i + 1];
+        for (int j = 0; j < N1D; ++j) samples[i].oneD[j] = oneDSamples[j][i];
+        for (int j = 0; j < N2D; ++j) {
+            samples[i].twoD[j][0] = twoDSamples[j][2 * i];
+            samples[i].twoD[j][1] = twoDSamples[j][2 * i + 1];
+        }
+    }
+}
+
+// ================================================================== geometry
+struct Ray {
+    Vec o, d;
+    mutable float mint, maxt;
+    float time;
+    Ray() : mint(0.f), maxt(INF_F), time(0.f) {}
+    Ray(const Vec &oo, const Vec &dd, float start, float end = INF_F, float t = 0.f)
+        : o(oo), d(dd), mint(start), maxt(end), time(t) {}
+    Vec operator()(float t) const { return o + d * t; }   // geometry.h:333
+};
+
+struct DiffGeom {   // core/diffgeom.h:44-65 (screen-space differentials omitted: they
+    Vec p, nn, dpdu, dpdv;   // only feed textures, constant in scope)
+    float u, v;
+};
+// DifferentialGeometry ctor, core/diffgeom.cpp:40-55
+inline void InitDG(DiffGeom *dg, const Vec &P, const Vec &DPDU, const Vec &DPDV, float uu, float vv,
+                   uint32_t shapeFlags) {
+    dg->p = P; dg->dpdu = DPDU; dg->dpdv = DPDV;
+    dg->nn = Normalize(Cross(DPDU, DPDV));
+    dg->u = uu; dg->v = vv;
+    bool ro = (shapeFlags & PBRTGPU_SHAPE_REVERSE_ORIENT) != 0, sh = (shapeFlags & PBRTGPU_SHAPE_SWAPS_HANDED) != 0;
+    if (ro ^ sh) dg->nn = dg->nn * -1.f;
+}
+
+struct Counters {
+    uint64_t closestRays = 0, shadowRays = 0, nodesVisited = 0, primTests = 0, shadedN = 0, rngDraws = 0;
+    uint64_t closestNodes = 0, closestPrims = 0;
+};
+
+struct Intersection {   // core/intersection.h:45-62
+    DiffGeom dg;
+    uint32_t prim;
+    float rayEpsilon;
+};
+
+struct SceneView {
+    const PbrtGpuSceneDesc *d;
+
+    void TriVerts(const PbrtGpuTriangle &t, Vec *p1, Vec *p2, Vec *p3) const {
+        *p1 = Vec(d->P + 3 * t.v[0]); *p2 = Vec(d->P + 3 * t.v[1]); *p3 = Vec(d->P + 3 * t.v[2]);
+    }
+    void GetUVs(const PbrtGpuTriangle &t, float uv[3][2]) const {   // trianglemesh.h:86-101
+        if (d->meshes[t.mesh].flags & PBRTGPU_MESH_HAS_UV) {
+            for (int i = 0; i < 3; ++i) { uv[i][0] = d->uv[2 * t.v[i]]; uv[i][1] = d->uv[2 * t.v[i] + 1]; }
+        } else {
+            uv[0][0] = 0.; uv[0][1] = 0.; uv[1][0] = 1.; uv[1][1] = 0.; uv[2][0] = 1.; uv[2][1] = 1.;
+        }
+    }
+
+    // Triangle::Intersect, shapes/trianglemesh.cpp:127-208
+    bool TriIntersect(const PbrtGpuTriangle &tri, const Ray &ray, float *tHit, float *rayEpsilon, DiffGeom *dg,
+                      float *ob1 = nullptr, float *ob2 = nullptr) const {
+        Vec p1, p2, p3;
+        TriVerts(tri, &p1, &p2, &p3);
+        Vec e1 = p2 - p1;
+        Vec e2 = p3 - p1;
+        Vec s1 = Cross(ray.d, e2);
+        float divisor = Dot(s1, e1);
+        if (divisor == 0.) return false;
+        float invDivisor = 1.f / divisor;
+        Vec s = ray.o - p1;
+        float b1 = Dot(s, s1) * invDivisor;
+        if (b1 < 0. || b1 > 1.) return false;
+        Vec s2 = Cross(s, e1);
+        float b2 = Dot(ray.d, s2) * invDivisor;
+        if (b2 < 0. || b1 + b2 > 1.) return false;
+        float t = Dot(e2, s2) * invDivisor;
+        if (t < ray.mint || t > ray.maxt) return false;
+        if (dg) {
+            Vec dpdu, dpdv;
+            float uvs[3][2];
+            GetUVs(tri, uvs);
+            float du1 = uvs[0][0] - uvs[2][0];
+            float du2 = uvs[1][0] - uvs[2][0];
+            float dv1 = uvs[0][1] - uvs[2][1];
+            float dv2 = uvs[1][1] - uvs[2][1];
+            Vec dp1 = p1 - p3, dp2 = p2 - p3;
+            float determinant = du1 * dv2 - dv1 * du2;
+            if (determinant == 0.f) {
+                CoordinateSystem(Normalize(Cross(e2, e1)), &dpdu, &dpdv);
+            } else {
+                float invdet = 1.f / determinant;
+                dpdu = (dv2 * dp1 - dv1 * dp2) * invdet;
+                dpdv = (-du2 * dp1 + du1 * dp2) * invdet;
+            }
+            float b0 = 1 - b1 - b2;
+            float tu = b0 * uvs[0][0] + b1 * uvs[1][0] + b2 * uvs[2][0];
+            float tv = b0 * uvs[0][1] + b1 * uvs[1][1] + b2 * uvs[2][1];
+            InitDG(dg, ray(t), dpdu, dpdv, tu, tv, d->meshes[tri.mesh].flags);
+        }
+        *tHit = t;
+        if (rayEpsilon) *rayEpsilon = 1e-3f * *tHit;
+        if (ob1) { *ob1 = b1; *ob2 = b2; }
+        return true;
+    }
+
+    // Sphere::Intersect / IntersectP, shapes/sphere.cpp:58-209
+    bool SphereIntersect(const PbrtGpuQuadric &q, const Ray &r, float *tHit, float *rayEpsilon, DiffGeom *dg) const {
+        const PbrtGpuXform &x = d->xforms[q.xform];
+        Ray ray;
+        ray.o = XfPoint(x.mInv, r.o); ray.d = XfVector(x.mInv, r.d);
+        ray.mint = r.mint; ray.maxt = r.maxt;
+        const float radius = q.radius, zmin = q.zmin, zmax = q.zmax, phiMax = q.phiMax;
+        float A = ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z;
+        float B = 2 * (ray.d.x * ray.o.x + ray.d.y * ray.o.y + ray.d.z * ray.o.z);
+        float C = ray.o.x * ray.o.x + ray.o.y * ray.o.y + ray.o.z * ray.o.z - radius * radius;
+        float t0, t1;
+        if (!Quadratic(A, B, C, &t0, &t1)) return false;
+        if (t0 > ray.maxt || t1 < ray.mint) return false;
+        float thit = t0;
+        if (t0 < ray.mint) {
+            thit = t1;
+            if (thit > ray.maxt) return false;
+        }
+        Vec phit = ray(thit);
+        if (phit.x == 0.f && phit.y == 0.f) phit.x = 1e-5f * radius;
+        float phi = atan2f(phit.y, phit.x);
+        if (phi < 0.) phi += 2.f * PI_F;
+        if ((zmin > -radius && phit.z < zmin) || (zmax < radius && phit.z > zmax) || phi > phiMax) {
+            if (thit == t1) return false;
+            if (t1 > ray.maxt) return false;
+            thit = t1;
+            phit = ray(thit);
+            if (phit.x == 0.f && phit.y == 0.f) phit.x = 1e-5f * radius;
+            phi = atan2f(phit.y, phit.x);
+            if (phi < 0.) phi += 2.f * PI_F;
+            if ((zmin > -radius && phit.z < zmin) || (zmax < radius && phit.z > zmax) || phi > phiMax) return false;
+        }
+        if (dg) {
+            float u = phi / phiMax;
+            float theta = acosf(Clampf(phit.z / radius, -1.f, 1.f));
+            float v = (theta - q.thetaMin) / (q.thetaMax - q.thetaMin);
+            float zradius = sqrtf(phit.x * phit.x + phit.y * phit.y);
+            float invzradius = 1.f / zradius;
+            float cosphi = phit.x * invzradius;
+            float sinphi = phit.y * invzradius;
+            Vec dpdu(-phiMax * phit.y, phiMax * phit.x, 0);
+            Vec dpdv = (q.thetaMax - q.thetaMin) * Vec(phit.z * cosphi, phit.z * sinphi, -radius * sinf(theta));
+            // dndu/dndv (sphere.cpp:116-136) only feed bump/texture code: omitted
+            InitDG(dg, XfPoint(x.m, phit), XfVector(x.m, dpdu), XfVector(x.m, dpdv), u, v, q.flags);
+        }
+        *tHit = thit;
+        if (rayEpsilon) *rayEpsilon = 5e-4f * *tHit;
+        return true;
+    }
+
+    // Disk::Intersect / IntersectP, shapes/disk.cpp:56-130
+    bool DiskIntersect(const PbrtGpuQuadric &q, const Ray &r, float *tHit, float *rayEpsilon, DiffGeom *dg) const {
+        const PbrtGpuXform &x = d->xforms[q.xform];
+        Ray ray;
+        ray.o = XfPoint(x.mInv, r.o); ray.d = XfVector(x.mInv, r.d);
+        ray.mint = r.mint; ray.maxt = r.maxt;
+        if (fabsf(ray.d.z) < 1e-7) return false;
+        float thit = (q.height - ray.o.z) / ray.d.z;
+        if (thit < ray.mint || thit > ray.maxt) return false;
+        Vec phit = ray(thit);
+        float dist2 = phit.x * phit.x + phit.y * phit.y;
+        if (dist2 > q.radius * q.radius || dist2 < q.innerRadius * q.innerRadius) return false;
+        float phi = atan2f(phit.y, phit.x);
+        if (phi < 0) phi += 2. * PI_F;   // NB double arithmetic (disk.cpp:77)
+        if (phi > q.phiMax) return false;
+        if (dg) {
+            float u = phi / q.phiMax;
+            float R = sqrtf(dist2);
+            float oneMinusV = ((R - q.innerRadius) / (q.radius - q.innerRadius));
+            float v = 1.f - oneMinusV;
+            Vec dpdu(-q.phiMax * phit.y, q.phiMax * phit.x, 0.);
+            Vec dpdv(phit.x, phit.y, 0.);
+            dpdv = dpdv * ((q.radius - q.innerRadius) / R);
+            InitDG(dg, XfPoint(x.m, phit), XfVector(x.m, dpdu), XfVector(x.m, dpdv), u, v, q.flags);
+        }
+        *tHit = thit;
+        if (rayEpsilon) *rayEpsilon = 5e-4f * *tHit;
+        return true;
+    }
+
+    bool QuadricIntersect(const PbrtGpuQuadric &q, const Ray &r, float *tHit, float *rayEps, DiffGeom *dg) const {
+        return q.type == PBRTGPU_PRIM_SPHERE ? SphereIntersect(q, r, tHit, rayEps, dg) : DiskIntersect(q, r, tHit, rayEps, dg);
+    }
+
+    // GeometricPrimitive::Intersect, core/primitive.cpp:163-177
+    bool PrimIntersect(uint32_t pi, const Ray &r, Intersection *isect, float *b1 = nullptr, float *b2 = nullptr) const {
+        const PbrtGpuPrimitive &p = d->primitives[pi];
+        float thit, rayEpsilon;
+        bool hit;
+        if (p.type == PBRTGPU_PRIM_TRIANGLE) hit = TriIntersect(d->triangles[p.index], r, &thit, &rayEpsilon, &isect->dg, b1, b2);
+        else {
+            hit = QuadricIntersect(d->quadrics[p.index], r, &thit, &rayEpsilon, &isect->dg);
+            if (hit && b1) { *b1 = 0.f; *b2 = 0.f; }
+        }
+        if (!hit) return false;
+        isect->prim = pi;
+        isect->rayEpsilon = rayEpsilon;
+        r.maxt = thit;
+        return true;
+    }
+    bool PrimIntersectP(uint32_t pi, const Ray &r) const {
+        const PbrtGpuPrimitive &p = d->primitives[pi];
+        float thit;
+        if (p.type == PBRTGPU_PRIM_TRIANGLE) return TriIntersect(d->triangles[p.index], r, &thit, nullptr, nullptr);
+        return QuadricIntersect(d->quadrics[p.index], r, &thit, nullptr, nullptr);
+    }
+
+    // ::IntersectP(BBox, Ray, invDir, dirIsNeg), accelerators/bvh.cpp:126-148
+    static inline bool BoxTest(const PbrtGpuBVHNode &n, const Ray &ray, const Vec &invDir, const uint32_t dirIsNeg[3]) {
+        const float *b0 = n.bmin, *b1 = n.bmax;
+        float tmin = ((dirIsNeg[0] ? b1 : b0)[0] - ray.o.x) * invDir.x;
+        float tmax = ((dirIsNeg[0] ? b0 : b1)[0] - ray.o.x) * invDir.x;
+        float tymin = ((dirIsNeg[1] ? b1 : b0)[1] - ray.o.y) * invDir.y;
+        float tymax = ((dirIsNeg[1] ? b0 : b1)[1] - ray.o.y) * invDir.y;
+        if ((tmin > tymax) || (tymin > tmax)) return false;
+        if (tymin > tmin) tmin = tymin;
+        if (tymax < tmax) tmax = tymax;
+        float tzmin = ((dirIsNeg[2] ? b1 : b0)[2] - ray.o.z) * invDir.z;
+        float tzmax = ((dirIsNeg[2] ? b0 : b1)[2] - ray.o.z) * invDir.z;
+        if ((tmin > tzmax) || (tzmin > tmax)) return false;
+        if (tzmin > tmin) tmin = tzmin;
+        if (tzmax < tmax) tmax = tzmax;
+        return (tmin < ray.maxt) && (tmax > ray.mint);
+    }
+
+    // BVHAccel::Intersect, accelerators/bvh.cpp:403-454
+    bool Intersect(const Ray &ray, Intersection *isect, Counters *cnt, float *b1 = nullptr, float *b2 = nullptr) const {
+        if (cnt) cnt->closestRays++;
+        bool hit = false;
+        Vec invDir(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+        uint32_t dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
+        uint32_t todoOffset = 0, nodeNum = 0;
+        uint32_t todo[64];
+        while (true) {
+            const PbrtGpuBVHNode *node = &d->nodes[nodeNum];
+            if (cnt) { cnt->nodesVisited++; cnt->closestNodes++; }
+            if (BoxTest(*node, ray, invDir, dirIsNeg)) {
+                if (node->nPrimitives > 0) {
+                    for (uint32_t i = 0; i < node->nPrimitives; ++i) {
+                        if (cnt) { cnt->primTests++; cnt->closestPrims++; }
+                        if (PrimIntersect(node->offset + i, ray, isect, b1, b2)) hit = true;
+                    }
+                    if (todoOffset == 0) break;
+                    nodeNum = todo[--todoOffset];
+                } else {
+                    if (dirIsNeg[node->axis]) {
+                        todo[todoOffset++] = nodeNum + 1;
+                        nodeNum = node->offset;
+                    } else {
+                        todo[todoOffset++] = node->offset;
+                        nodeNum = nodeNum + 1;
+                    }
+                }
+            } else {
+                if (todoOffset == 0) break;
+                nodeNum = todo[--todoOffset];
+            }
+        }
+        return hit;
+    }
+    // BVHAccel::IntersectP, accelerators/bvh.cpp:457-503
+    bool IntersectP(const Ray &ray, Counters *cnt) const {
+        if (cnt) cnt->shadowRays++;
+        Vec invDir(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+        uint32_t dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
+        uint32_t todo[64];
+        uint32_t todoOffset = 0, nodeNum = 0;
+        while (true) {
+            const PbrtGpuBVHNode *node = &d->nodes[nodeNum];
+            if (cnt) cnt->nodesVisited++;
+            if (BoxTest(*node, ray, invDir, dirIsNeg)) {
+                if (node->nPrimitives > 0) {
+                    for (uint32_t i = 0; i < node->nPrimitives; ++i) {
+                        if (cnt) cnt->primTests++;
+                        if (PrimIntersectP(node->offset + i, ray)) return true;
+                    }
+                    if (todoOffset == 0) break;
+                    nodeNum = todo[--todoOffset];
+                } else {
+                    if (dirIsNeg[node->axis]) {
+                        todo[todoOffset++] = nodeNum + 1;
+                        nodeNum = node->offset;
+                    } else {
+                        todo[todoOffset++] = node->offset;
+                        nodeNum = nodeNum + 1;
+                    }
+                }
+            } else {
+                if (todoOffset == 0) break;
+                nodeNum = todo[--todoOffset];
+            }
+        }
+        return false;
+    }
+};
+
+// ====================================================================== BSDF
+// core/reflection.h / reflection.cpp
+enum {
+    BSDF_REFLECTION = 1 << 0, BSDF_TRANSMISSION = 1 << 1, BSDF_DIFFUSE = 1 << 2, BSDF_GLOSSY = 1 << 3,
+    BSDF_SPECULAR = 1 << 4,
+    BSDF_ALL_TYPES = BSDF_DIFFUSE | BSDF_GLOSSY | BSDF_SPECULAR,
+    BSDF_ALL_REFLECTION = BSDF_REFLECTION | BSDF_ALL_TYPES,
+    BSDF_ALL_TRANSMISSION = BSDF_TRANSMISSION | BSDF_ALL_TYPES,
+    BSDF_ALL = BSDF_ALL_REFLECTION | BSDF_ALL_TRANSMISSION
+};
+inline float CosTheta(const Vec &w) { return w.z; }
+inline float AbsCosTheta(const Vec &w) { return fabsf(w.z); }
+inline float SinTheta2(const Vec &w) { return std::max(0.f, 1.f - CosTheta(w) * CosTheta(w)); }
+inline float SinTheta(const Vec &w) { return sqrtf(SinTheta2(w)); }
+inline bool SameHemisphere(const Vec &w, const Vec &wp) { return w.z * wp.z > 0.f; }
+inline float SphericalPhi(const Vec &v) {   // geometry.h:644-647
+    float p = atan2f(v.y, v.x);
+    return (p < 0.f) ? p + 2.f * PI_F : p;
+}
+inline Vec SphericalDirection(float sintheta, float costheta, float phi) {
+    return Vec(sintheta * cosf(phi), sintheta * sinf(phi), costheta);
+}
+
+void ConcentricSampleDisk(float u1, float u2, float *dx, float *dy) {   // core/montecarlo.cpp:306-348
+    float r, theta;
+    float sx = 2 * u1 - 1;
+    float sy = 2 * u2 - 1;
+    if (sx == 0.0 && sy == 0.0) { *dx = 0.0; *dy = 0.0; return; }
+    if (sx >= -sy) {
+        if (sx > sy) {
+            r = sx;
+            if (sy > 0.0) theta = sy / r;
+            else theta = 8.0f + sy / r;
+        } else {
+            r = sy;
+            theta = 2.0f - sx / r;
+        }
+    } else {
+        if (sx <= sy) {
+            r = -sx;
+            theta = 4.0f - sy / r;
+        } else {
+            r = -sy;
+            theta = 6.0f + sx / r;
+        }
+    }
+    theta *= PI_F / 4.f;
+    *dx = r * cosf(theta);
+    *dy = r * sinf(theta);
+}
+inline Vec CosineSampleHemisphere(float u1, float u2) {   // montecarlo.h:128-133
+    Vec ret;
+    ConcentricSampleDisk(u1, u2, &ret.x, &ret.y);
+    ret.z = sqrtf(std::max(0.f, 1.f - ret.x * ret.x - ret.y * ret.y));
+    return ret;
+}
+inline Vec UniformSampleSphere(float u1, float u2) {   // montecarlo.cpp:283-290
+    float z = 1.f - 2.f * u1;
+    float r = sqrtf(std::max(0.f, 1.f - z * z));
+    float phi = 2.f * PI_F * u2;
+    return Vec(r * cosf(phi), r * sinf(phi), z);
+}
+inline float UniformConePdf(float cosThetaMax) { return 1.f / (2.f * PI_F * (1.f - cosThetaMax)); }
+inline Vec UniformSampleCone(float u1, float u2, float costhetamax, const Vec &x, const Vec &y, const Vec &z) {
+    // montecarlo.cpp:423-430
+    float costheta = Lerp(u1, costhetamax, 1.f);
+    float sintheta = sqrtf(1.f - costheta * costheta);
+    float phi = u2 * 2.f * PI_F;
+    return cosf(phi) * sintheta * x + sinf(phi) * sintheta * y + costheta * z;
+}
+inline float PowerHeuristic(int nf, float fPdf, int ng, float gPdf) {   // montecarlo.h:266-269
+    float f = nf * fPdf, g = ng * gPdf;
+    return (f * f) / (f * f + g * g);
+}
+
+enum BxDFKind { BX_LAMBERTIAN, BX_MICROFACET_BLINN, BX_IRREG_ISO };
+struct BxDF {
+    BxDFKind kind;
+    int type;         // BxDFType flags
+    Spec R;
+    float exponent;   // Blinn
+    int measured;     // IrregIsotropicBRDF kd-tree
+};
+
+struct BSDFSample { float uDir[2], uComponent; };
+struct LightSample { float uPos[2], uComponent; };
+
+struct KdLookup {   // IrregIsoProc, reflection.cpp:40-55
+    Spec v;
+    float sumWeights = 0.f;
+    int nFound = 0;
+};
+
+struct BSDF {
+    const SceneView *sv;
+    Vec p;               // dgShading.p
+    Vec nn, ng, sn, tn;  // shading normal, geometric normal, tangents
+    int nBxDFs;
+    BxDF bxdfs[2];
+
+    Vec WorldToLocal(const Vec &v) const { return Vec(Dot(v, sn), Dot(v, tn), Dot(v, nn)); }
+    Vec LocalToWorld(const Vec &v) const {
+        return Vec(sn.x * v.x + tn.x * v.y + nn.x * v.z, sn.y * v.x + tn.y * v.y + nn.y * v.z,
+                   sn.z * v.x + tn.z * v.y + nn.z * v.z);
+    }
+    static bool Matches(const BxDF &b, int flags) { return (b.type & flags) == b.type; }
+    int NumComponents(int flags) const {
+        int n = 0;
+        for (int i = 0; i < nBxDFs; ++i) if (Matches(bxdfs[i], flags)) ++n;
+        return n;
+    }
+
+    // KdTree::privateLookup, core/kdtree.h:157-183 (recursive, children before node)
+    void KdLookupRec(const PbrtGpuMeasured &m, uint32_t nodeNum, const Vec &p, KdLookup &proc, float &maxDistSquared) const {
+        const PbrtGpuKdNode &node = sv->d->kdNodes[m.firstNode + nodeNum];
+        int axis = node.bits & 3u;
+        uint32_t hasLeft = (node.bits >> 2) & 1u, rightChild = node.bits >> 3;
+        if (axis != 3) {
+            float dist2 = (p[axis] - node.splitPos) * (p[axis] - node.splitPos);
+            if (p[axis] <= node.splitPos) {
+                if (hasLeft) KdLookupRec(m, nodeNum + 1, p, proc, maxDistSquared);
+                if (dist2 < maxDistSquared && rightChild < m.nNodes) KdLookupRec(m, rightChild, p, proc, maxDistSquared);
+            } else {
+                if (rightChild < m.nNodes) KdLookupRec(m, rightChild, p, proc, maxDistSquared);
+                if (dist2 < maxDistSquared && hasLeft) KdLookupRec(m, nodeNum + 1, p, proc, maxDistSquared);
+            }
+        }
+        const PbrtGpuBrdfSample &s = sv->d->kdData[m.firstNode + nodeNum];
+        float dist2 = DistanceSquared(Vec(s.p), p);
+        if (dist2 < maxDistSquared) {   // IrregIsoProc::operator()
+            float weight = expf(-100.f * dist2);
+            proc.v += weight * Spec(s.v);
+            proc.sumWeights += weight;
+            ++proc.nFound;
+        }
+    }
+
+    // ---- individual BxDFs ----
+    static Spec FrDiel(float cosi, float cost, const Spec &etai, const Spec &etat) {   // reflection.cpp:60-67
+        Spec Rparl = ((etat * cosi) - (etai * cost)) / ((etat * cosi) + (etai * cost));
+        Spec Rperp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
+        return (Rparl * Rparl + Rperp * Rperp) / 2.f;
+    }
+    static Spec FresnelDielectricEvaluate(float cosi, float eta_i, float eta_t) {   // reflection.cpp:115-135
+        cosi = Clampf(cosi, -1.f, 1.f);
+        bool entering = cosi > 0.;
+        float ei = eta_i, et = eta_t;
+        if (!entering) std::swap(ei, et);
+        float sint = ei / et * sqrtf(std::max(0.f, 1.f - cosi * cosi));
+        if (sint >= 1.) return Spec(1.);
+        float cost = sqrtf(std::max(0.f, 1.f - sint * sint));
+        return FrDiel(fabsf(cosi), cost, Spec(ei), Spec(et));
+    }
+    static float BlinnD(float exponent, const Vec &wh) {   // reflection.h:427-430
+        float costhetah = AbsCosTheta(wh);
+        return (exponent + 2) * INV_TWOPI_F * powf(costhetah, exponent);
+    }
+    static float MicrofacetG(const Vec &wo, const Vec &wi, const Vec &wh) {   // reflection.h:403-410
+        float NdotWh = AbsCosTheta(wh);
+        float NdotWo = AbsCosTheta(wo);
+        float NdotWi = AbsCosTheta(wi);
+        float WOdotWh = AbsDot(wo, wh);
+        return std::min(1.f, std::min((2.f * NdotWh * NdotWo / WOdotWh), (2.f * NdotWh * NdotWi / WOdotWh)));
+    }
+    static Vec BRDFRemap(const Vec &wo, const Vec &wi) {   // reflection.cpp:247-256
+        float cosi = CosTheta(wi), coso = CosTheta(wo);
+        float sini = SinTheta(wi), sino = SinTheta(wo);
+        float phii = SphericalPhi(wi), phio = SphericalPhi(wo);
+        float dphi = phii - phio;
+        if (dphi < 0.) dphi += 2.f * PI_F;
+        if (dphi > 2.f * PI_F) dphi -= 2.f * PI_F;
+        if (dphi > PI_F) dphi = 2.f * PI_F - dphi;
+        return Vec(sini * sino, dphi / PI_F, cosi * coso);
+    }
+
+    Spec BxF(const BxDF &b, const Vec &wo, const Vec &wi) const {
+        switch (b.kind) {
+        case BX_LAMBERTIAN: return b.R * INV_PI_F;   // reflection.cpp:173-175
+        case BX_MICROFACET_BLINN: {                  // Microfacet::f, reflection.cpp:211-222
+            float cosThetaO = AbsCosTheta(wo);
+            float cosThetaI = AbsCosTheta(wi);
+            if (cosThetaI == 0.f || cosThetaO == 0.f) return Spec(0.f);
+            Vec wh = wi + wo;
+            if (wh.x == 0. && wh.y == 0. && wh.z == 0.) return Spec(0.f);
+            wh = Normalize(wh);
+            float cosThetaH = Dot(wi, wh);
+            Spec F = FresnelDielectricEvaluate(cosThetaH, 1.5f, 1.f);
+            return b.R * BlinnD(b.exponent, wh) * MicrofacetG(wo, wi, wh) * F / (4.f * cosThetaI * cosThetaO);
+        }
+        case BX_IRREG_ISO: {                         // IrregIsotropicBRDF::f, reflection.cpp:259-272
+            Vec m = BRDFRemap(wo, wi);
+            float lastMaxDist2 = .001f;
+            const PbrtGpuMeasured &md = sv->d->measured[b.measured];
+            while (true) {
+                KdLookup proc;
+                float maxDist2 = lastMaxDist2;
+                KdLookupRec(md, 0, m, proc, maxDist2);
+                if (proc.nFound > 2 || lastMaxDist2 > 1.5f) return proc.v.Clamp() / proc.sumWeights;
+                lastMaxDist2 *= 2.f;
+            }
+        }
+        }
+        return Spec(0.f);
+    }
+    float BxPdf(const BxDF &b, const Vec &wo, const Vec &wi) const {
+        if (b.kind == BX_MICROFACET_BLINN) {   // Microfacet::Pdf + Blinn::Pdf, reflection.cpp:340-343,365-374
+            if (!SameHemisphere(wo, wi)) return 0.f;
+            Vec wh = Normalize(wo + wi);
+            float costheta = AbsCosTheta(wh);
+            float blinn_pdf = ((b.exponent + 1.f) * powf(costheta, b.exponent)) / (2.f * PI_F * 4.f * Dot(wo, wh));
+            if (Dot(wo, wh) <= 0.f) blinn_pdf = 0.f;
+            return blinn_pdf;
+        }
+        // BxDF::Pdf, reflection.cpp:321-323
+        return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * INV_PI_F : 0.f;
+    }
+    Spec BxSample_f(const BxDF &b, const Vec &wo, Vec *wi, float u1, float u2, float *pdf) const {
+        if (b.kind == BX_MICROFACET_BLINN) {   // Microfacet::Sample_f + Blinn::Sample_f, reflection.cpp:332-363
+            float costheta = powf(u1, 1.f / (b.exponent + 1));
+            float sintheta = sqrtf(std::max(0.f, 1.f - costheta * costheta));
+            float phi = u2 * 2.f * PI_F;
+            Vec wh = SphericalDirection(sintheta, costheta, phi);
+            if (!SameHemisphere(wo, wh)) wh = -wh;
+            *wi = -wo + 2.f * Dot(wo, wh) * wh;
+            float blinn_pdf = ((b.exponent + 1.f) * powf(costheta, b.exponent)) / (2.f * PI_F * 4.f * Dot(wo, wh));
+            if (Dot(wo, wh) <= 0.f) blinn_pdf = 0.f;
+            *pdf = blinn_pdf;
+            if (!SameHemisphere(wo, *wi)) return Spec(0.f);
+            return BxF(b, wo, *wi);
+        }
+        // BxDF::Sample_f (cosine hemisphere), reflection.cpp:311-318
+        *wi = CosineSampleHemisphere(u1, u2);
+        if (wo.z < 0.) wi->z *= -1.f;
+        *pdf = BxPdf(b, wo, *wi);
+        return BxF(b, wo, *wi);
+    }
+
+    // BSDF::f, reflection.cpp:612-626
+    Spec f(const Vec &woW, const Vec &wiW, int flags) const {
+        Vec wi = WorldToLocal(wiW), wo = WorldToLocal(woW);
+        if (Dot(wiW, ng) * Dot(woW, ng) > 0) flags &= ~BSDF_TRANSMISSION;
+        else flags &= ~BSDF_REFLECTION;
+        Spec f(0.);
+        for (int i = 0; i < nBxDFs; ++i)
+            if (Matches(bxdfs[i], flags)) f += BxF(bxdfs[i], wo, wi);
+        return f;
+    }
+    // BSDF::Pdf, reflection.cpp:583-598
+    float Pdf(const Vec &woW, const Vec &wiW, int flags) const {
+        if (nBxDFs == 0.) return 0.;
+        Vec wo = WorldToLocal(woW), wi = WorldToLocal(wiW);
+        float pdf = 0.f;
+        int matchingComps = 0;
+        for (int i = 0; i < nBxDFs; ++i)
+            if (Matches(bxdfs[i], flags)) {
+                ++matchingComps;
+                pdf += BxPdf(bxdfs[i], wo, wi);
+            }
+        return matchingComps > 0 ? pdf / matchingComps : 0.f;
+    }
+    // BSDF::Sample_f, reflection.cpp:522-580
+    Spec Sample_f(const Vec &woW, Vec *wiW, const BSDFSample &bsdfSample, float *pdf, int flags, int *sampledType) const {
+        int matchingComps = NumComponents(flags);
+        if (matchingComps == 0) {
+            *pdf = 0.f;
+            if (sampledType) *sampledType = 0;
+            return Spec(0.f);
+        }
+        int which = std::min(Floor2Int(bsdfSample.uComponent * matchingComps), matchingComps - 1);
+        const BxDF *bxdf = nullptr;
+        int count = which;
+        for (int i = 0; i < nBxDFs; ++i)
+            if (Matches(bxdfs[i], flags) && count-- == 0) { bxdf = &bxdfs[i]; break; }
+        Vec wo = WorldToLocal(woW);
+        Vec wi;
+        *pdf = 0.f;
+        Spec f = BxSample_f(*bxdf, wo, &wi, bsdfSample.uDir[0], bsdfSample.uDir[1], pdf);
+        if (*pdf == 0.f) {
+            if (sampledType) *sampledType = 0;
+            return Spec(0.f);
+        }
+        if (sampledType) *sampledType = bxdf->type;
+        *wiW = LocalToWorld(wi);
+        if (!(bxdf->type & BSDF_SPECULAR) && matchingComps > 1)
+            for (int i = 0; i < nBxDFs; ++i)
+                if (&bxdfs[i] != bxdf && Matches(bxdfs[i], flags)) *pdf += BxPdf(bxdfs[i], wo, wi);
+        if (matchingComps > 1) *pdf /= matchingComps;
+        if (!(bxdf->type & BSDF_SPECULAR)) {
+            f = Spec(0.);
+            if (Dot(*wiW, ng) * Dot(woW, ng) > 0) flags &= ~BSDF_TRANSMISSION;
+            else flags &= ~BSDF_REFLECTION;
+            for (int i = 0; i < nBxDFs; ++i)
+                if (Matches(bxdfs[i], flags)) f += BxF(bxdfs[i], wo, wi);
+        }
+        return f;
+    }
+};
+
+// ================================================================ the renderer
+struct Renderer {
+    SceneView sv;
+    const PbrtGpuRenderDesc *rd;
+    int xPixelStart, yPixelStart, xPixelCount, yPixelCount;   // film extent, image.cpp:48-51
+    int sxStart, sxEnd, syStart, syEnd;                       // sampler extent, image.cpp:157-166
+    PbrtGpuPixel *pixels;
+
+    void Init(const PbrtGpuSceneDesc *d, const PbrtGpuRenderDesc *r, PbrtGpuPixel *out) {
+        sv.d = d; rd = r; pixels = out;
+        xPixelStart = Ceil2Int(rd->xResolution * rd->cropWindow[0]);
+        xPixelCount = std::max(1, Ceil2Int(rd->xResolution * rd->cropWindow[1]) - xPixelStart);
+        yPixelStart = Ceil2Int(rd->yResolution * rd->cropWindow[2]);
+        yPixelCount = std::max(1, Ceil2Int(rd->yResolution * rd->cropWindow[3]) - yPixelStart);
+        sxStart = Floor2Int(xPixelStart + 0.5f - rd->filterXWidth);
+        sxEnd = Ceil2Int(xPixelStart - 0.5f + xPixelCount + rd->filterXWidth);
+        syStart = Floor2Int(yPixelStart + 0.5f - rd->filterYWidth);
+        syEnd = Ceil2Int(yPixelStart - 0.5f + yPixelCount + rd->filterYWidth);
+    }
+
+    // Sampler::ComputeSubWindow, core/sampler.cpp:55-74
+    void ComputeSubWindow(int num, int count, int *x0, int *x1, int *y0, int *y1) const {
+        int dx = sxEnd - sxStart, dy = syEnd - syStart;
+        int nx = count, ny = 1;
+        while ((nx & 0x1) == 0 && 2 * dx * ny < dy * nx) { nx >>= 1; ny <<= 1; }
+        int xo = num % nx, yo = num / nx;
+        float tx0 = float(xo) / float(nx), tx1 = float(xo + 1) / float(nx);
+        float ty0 = float(yo) / float(ny), ty1 = float(yo + 1) / float(ny);
+        *x0 = Floor2Int(Lerp(tx0, sxStart, sxEnd));
+        *x1 = Floor2Int(Lerp(tx1, sxStart, sxEnd));
+        *y0 = Floor2Int(Lerp(ty0, syStart, syEnd));
+        *y1 = Floor2Int(Lerp(ty1, syStart, syEnd));
+    }
+
+    // PerspectiveCamera::GenerateRayDifferential, cameras/perspective.cpp:81-138 (main ray only:
+    // the auxiliary rx/ry rays feed texture filtering, which no in-scope material uses)
+    void GenerateRay(const Sample &sample, Ray *ray) const {
+        Vec Pras(sample.imageX, sample.imageY, 0);
+        Vec Pcamera = XfPoint(rd->rasterToCamera, Pras);
+        Vec dir = Normalize(Vec(Pcamera.x, Pcamera.y, Pcamera.z));
+        *ray = Ray(Vec(0, 0, 0), dir, 0.f, INF_F);
+        if (rd->lensRadius > 0.) {
+            float lensU, lensV;
+            ConcentricSampleDisk(sample.lensU, sample.lensV, &lensU, &lensV);
+            lensU *= rd->lensRadius;
+            lensV *= rd->lensRadius;
+            float ft = rd->focalDistance / ray->d.z;
+            Vec Pfocus = (*ray)(ft);
+            ray->o = Vec(lensU, lensV, 0.f);
+            ray->d = Normalize(Pfocus - ray->o);
+        }
+        ray->time = sample.time;
+        ray->o = XfPoint(rd->cameraToWorld, ray->o);   // CameraToWorld(*ray, ray), transform.h:253-262
+        ray->d = XfVector(rd->cameraToWorld, ray->d);
+    }
+
+    // Triangle::GetShadingGeometry, shapes/trianglemesh.cpp:293-368; Shape::GetShadingGeometry shape.h:58-62
+    void ShadingGeometry(const Intersection &isect, DiffGeom *dgs, Counters *cnt) const {
+        const PbrtGpuPrimitive &p = sv.d->primitives[isect.prim];
+        *dgs = isect.dg;
+        if (p.type != PBRTGPU_PRIM_TRIANGLE) return;
+        const PbrtGpuTriangle &tri = sv.d->triangles[p.index];
+        const PbrtGpuMesh &mesh = sv.d->meshes[tri.mesh];
+        if (!(mesh.flags & PBRTGPU_MESH_HAS_N)) return;
+        if (cnt) cnt->shadedN++;
+        const DiffGeom &dg = isect.dg;
+        float b[3];
+        float uv[3][2];
+        sv.GetUVs(tri, uv);
+        float A[2][2] = {{uv[1][0] - uv[0][0], uv[2][0] - uv[0][0]}, {uv[1][1] - uv[0][1], uv[2][1] - uv[0][1]}};
+        float C[2] = {dg.u - uv[0][0], dg.v - uv[0][1]};
+        {   // SolveLinearSystem2x2, core/transform.cpp:40-50
+            float det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+            bool ok = !(fabsf(det) < 1e-10f);
+            if (ok) {
+                b[1] = (A[1][1] * C[0] - A[0][1] * C[1]) / det;
+                b[2] = (A[0][0] * C[1] - A[1][0] * C[0]) / det;
+                if (std::isnan(b[1]) || std::isnan(b[2])) ok = false;
+            }
+            if (!ok) b[0] = b[1] = b[2] = 1.f / 3.f;
+            else b[0] = 1.f - b[1] - b[2];
+        }
+        const PbrtGpuXform &o2w = sv.d->xforms[mesh.xform];
+        Vec n0(sv.d->N + 3 * tri.v[0]), n1(sv.d->N + 3 * tri.v[1]), n2(sv.d->N + 3 * tri.v[2]);
+        Vec ns = Normalize(XfNormal(o2w.mInv, b[0] * n0 + b[1] * n1 + b[2] * n2));
+        Vec ss = Normalize(dg.dpdu);
+        Vec ts = Cross(ss, ns);
+        if (LengthSquared(ts) > 0.f) {
+            ts = Normalize(ts);
+            ss = Cross(ts, ns);
+        } else
+            CoordinateSystem(ns, &ss, &ts);
+        // dndu/dndv are texture-only: omitted.  DifferentialGeometry ctor recomputes nn from (ss, ts).
+        InitDG(dgs, dg.p, ss, ts, dg.u, dg.v, mesh.flags);
+    }
+
+    // Material::GetBSDF: matte.cpp:42-63, plastic.cpp:42-66, measured.cpp:194-210; BSDF ctor reflection.cpp:601-609
+    void GetBSDF(const Intersection &isect, BSDF *bsdf, Counters *cnt) const {
+        DiffGeom dgs;
+        ShadingGeometry(isect, &dgs, cnt);
+        bsdf->sv = &sv;
+        bsdf->p = dgs.p;
+        bsdf->ng = isect.dg.nn;
+        bsdf->nn = dgs.nn;
+        bsdf->sn = Normalize(dgs.dpdu);
+        bsdf->tn = Cross(bsdf->nn, bsdf->sn);
+        bsdf->nBxDFs = 0;
+        const PbrtGpuMaterial &m = sv.d->materials[sv.d->primitives[isect.prim].material];
+        if (m.type == PBRTGPU_MAT_MATTE) {
+            Spec r = Spec(m.Kd).Clamp();
+            if (!r.IsBlack()) bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_LAMBERTIAN, BSDF_REFLECTION | BSDF_DIFFUSE, r, 0.f, -1};
+        } else if (m.type == PBRTGPU_MAT_PLASTIC) {
+            Spec kd = Spec(m.Kd).Clamp();
+            if (!kd.IsBlack()) bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_LAMBERTIAN, BSDF_REFLECTION | BSDF_DIFFUSE, kd, 0.f, -1};
+            Spec ks = Spec(m.Ks).Clamp();
+            if (!ks.IsBlack()) {
+                float e = 1.f / m.roughness;
+                if (e > 10000.f || std::isnan(e)) e = 10000.f;   // Blinn ctor, reflection.h:424-425
+                bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_MICROFACET_BLINN, BSDF_REFLECTION | BSDF_GLOSSY, ks, e, -1};
+            }
+        } else {
+            bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_IRREG_ISO, BSDF_REFLECTION | BSDF_GLOSSY, Spec(0.f), 0.f, m.measured};
+        }
+    }
+
+    // Intersection::Le, core/intersection.cpp:61-64 + DiffuseAreaLight::L, lights/diffuse.h:51-53
+    Spec Le(const Intersection &isect, const Vec &w) const {
+        int al = sv.d->primitives[isect.prim].areaLight;
+        if (al < 0) return Spec(0.);
+        return Dot(isect.dg.nn, w) > 0.f ? Spec(sv.d->lights[al].L) : Spec(0.f);
+    }
+
+    // ---- shape sampling for area lights ----
+    // Shape::Pdf(p, wi), core/shape.cpp:86-99
+    float ShapePdf(const PbrtGpuQuadric &q, const Vec &p, const Vec &wi) const {
+        DiffGeom dgLight;
+        Ray ray(p, wi, 1e-3f);
+        float thit, rayEpsilon;
+        if (!sv.QuadricIntersect(q, ray, &thit, &rayEpsilon, &dgLight)) return 0.;
+        float pdf = DistanceSquared(p, ray(thit)) / (AbsDot(dgLight.nn, -wi) * q.area);
+        if (std::isinf(pdf)) pdf = 0.f;
+        return pdf;
+    }
+    // Sphere::Sample(u1,u2), sphere.cpp:226-231
+    Vec SphereSampleUniform(const PbrtGpuQuadric &q, float u1, float u2, Vec *ns) const {
+        const PbrtGpuXform &x = sv.d->xforms[q.xform];
+        Vec p = Vec(0, 0, 0) + q.radius * UniformSampleSphere(u1, u2);
+        *ns = Normalize(XfNormal(x.mInv, Vec(p.x, p.y, p.z)));
+        if (q.flags & PBRTGPU_SHAPE_REVERSE_ORIENT) *ns = *ns * -1.f;
+        return XfPoint(x.m, p);
+    }
+    // Sphere::Sample(p,u1,u2), sphere.cpp:236-261
+    Vec SphereSample(const PbrtGpuQuadric &q, const Vec &p, float u1, float u2, Vec *ns) const {
+        const PbrtGpuXform &x = sv.d->xforms[q.xform];
+        Vec Pcenter = XfPoint(x.m, Vec(0, 0, 0));
+        Vec wc = Normalize(Pcenter - p);
+        Vec wcX, wcY;
+        CoordinateSystem(wc, &wcX, &wcY);
+        if (DistanceSquared(p, Pcenter) - q.radius * q.radius < 1e-4f) return SphereSampleUniform(q, u1, u2, ns);
+        float sinThetaMax2 = q.radius * q.radius / DistanceSquared(p, Pcenter);
+        float cosThetaMax = sqrtf(std::max(0.f, 1.f - sinThetaMax2));
+        DiffGeom dgSphere;
+        float thit, rayEpsilon;
+        Vec ps;
+        Ray r(p, UniformSampleCone(u1, u2, cosThetaMax, wcX, wcY, wc), 1e-3f);
+        if (!sv.SphereIntersect(q, r, &thit, &rayEpsilon, &dgSphere)) thit = Dot(Pcenter - p, Normalize(r.d));
+        ps = r(thit);
+        *ns = Normalize(ps - Pcenter);
+        if (q.flags & PBRTGPU_SHAPE_REVERSE_ORIENT) *ns = *ns * -1.f;
+        return ps;
+    }
+    // Sphere::Pdf(p,wi), sphere.cpp:264-274
+    float SpherePdf(const PbrtGpuQuadric &q, const Vec &p, const Vec &wi) const {
+        const PbrtGpuXform &x = sv.d->xforms[q.xform];
+        Vec Pcenter = XfPoint(x.m, Vec(0, 0, 0));
+        if (DistanceSquared(p, Pcenter) - q.radius * q.radius < 1e-4f) return ShapePdf(q, p, wi);
+        float sinThetaMax2 = q.radius * q.radius / DistanceSquared(p, Pcenter);
+        float cosThetaMax = sqrtf(std::max(0.f, 1.f - sinThetaMax2));
+        return UniformConePdf(cosThetaMax);
+    }
+    // Disk::Sample, disk.cpp:148-156 (Shape::Sample(p,...) forwards to it, shape.h:77-80)
+    Vec DiskSample(const PbrtGpuQuadric &q, float u1, float u2, Vec *Ns) const {
+        const PbrtGpuXform &x = sv.d->xforms[q.xform];
+        Vec p;
+        ConcentricSampleDisk(u1, u2, &p.x, &p.y);
+        p.x *= q.radius;
+        p.y *= q.radius;
+        p.z = q.height;
+        *Ns = Normalize(XfNormal(x.mInv, Vec(0, 0, 1)));
+        if (q.flags & PBRTGPU_SHAPE_REVERSE_ORIENT) *Ns = *Ns * -1.f;
+        return XfPoint(x.m, p);
+    }
+
+    // ShapeSet::Pdf(p, wi), core/light.cpp:157-162 (one shape)
+    float LightPdf(const PbrtGpuLight &l, const Vec &p, const Vec &wi) const {
+        if (l.type == PBRTGPU_LIGHT_POINT) return 0.;
+        float pdf = 0.f;
+        for (uint32_t i = 0; i < l.nShapes; ++i) {
+            const PbrtGpuLightShape &ls = sv.d->lightShapes[l.firstShape + i];
+            const PbrtGpuQuadric &q = sv.d->quadrics[ls.index];
+            pdf += ls.area * (q.type == PBRTGPU_PRIM_SPHERE ? SpherePdf(q, p, wi) : ShapePdf(q, p, wi));
+        }
+        return pdf / l.sumArea;
+    }
+
+    // Light::Sample_L: PointLight point.cpp:50-57; DiffuseAreaLight diffuse.cpp:69-81; VisibilityTester light.h:87-92
+    Spec Sample_L(const PbrtGpuLight &l, const Vec &p, float pEpsilon, const LightSample &ls, float time, Vec *wi,
+                  float *pdf, Ray *vis) const {
+        if (l.type == PBRTGPU_LIGHT_POINT) {
+            Vec lightPos(l.pos);
+            *wi = Normalize(lightPos - p);
+            *pdf = 1.f;
+            float dist = Distance(p, lightPos);
+            *vis = Ray(p, (lightPos - p) / dist, pEpsilon, dist * (1.f - 0.f), time);
+            return Spec(l.L) / DistanceSquared(lightPos, p);
+        }
+        Vec ns;
+        // ShapeSet::Sample(p, ls, Ns), light.cpp:142-146: SampleDiscrete over one shape is always 0
+        const PbrtGpuLightShape &lsh = sv.d->lightShapes[l.firstShape];
+        const PbrtGpuQuadric &q = sv.d->quadrics[lsh.index];
+        Vec ps = q.type == PBRTGPU_PRIM_SPHERE ? SphereSample(q, p, ls.uPos[0], ls.uPos[1], &ns)
+                                               : DiskSample(q, ls.uPos[0], ls.uPos[1], &ns);
+        *wi = Normalize(ps - p);
+        *pdf = LightPdf(l, p, *wi);
+        float dist = Distance(p, ps);
+        *vis = Ray(p, (ps - p) / dist, pEpsilon, dist * (1.f - 1e-3f), time);
+        return Dot(ns, -*wi) > 0.f ? Spec(l.L) : Spec(0.f);
+    }
+
+    // EstimateDirect, core/integrator.cpp:117-174
+    Spec EstimateDirect(int lightIdx, const Vec &p, const Vec &n, const Vec &wo, float rayEpsilon, float time,
+                        const BSDF &bsdf, const LightSample &lightSample, const BSDFSample &bsdfSample, int flags,
+                        Counters *cnt) const {
+        const PbrtGpuLight &light = sv.d->lights[lightIdx];
+        Spec Ld(0.);
+        Vec wi;
+        float lightPdf, bsdfPdf;
+        Ray visibility;
+        Spec Li = Sample_L(light, p, rayEpsilon, lightSample, time, &wi, &lightPdf, &visibility);
+        if (lightPdf > 0. && !Li.IsBlack()) {
+            Spec f = bsdf.f(wo, wi, flags);
+            if (!f.IsBlack() && !sv.IntersectP(visibility, cnt)) {
+                if (light.type == PBRTGPU_LIGHT_POINT)
+                    Ld += f * Li * (AbsDot(wi, n) / lightPdf);
+                else {
+                    bsdfPdf = bsdf.Pdf(wo, wi, flags);
+                    float weight = PowerHeuristic(1, lightPdf, 1, bsdfPdf);
+                    Ld += f * Li * (AbsDot(wi, n) * weight / lightPdf);
+                }
+            }
+        }
+        if (light.type != PBRTGPU_LIGHT_POINT) {
+            int sampledType;
+            Spec f = bsdf.Sample_f(wo, &wi, bsdfSample, &bsdfPdf, flags, &sampledType);
+            if (!f.IsBlack() && bsdfPdf > 0.) {
+                float weight = 1.f;
+                if (!(sampledType & BSDF_SPECULAR)) {
+                    lightPdf = LightPdf(light, p, wi);
+                    if (lightPdf == 0.) return Ld;
+                    weight = PowerHeuristic(1, bsdfPdf, 1, lightPdf);
+                }
+                Intersection lightIsect;
+                Spec Li(0.f);
+                Ray ray(p, wi, rayEpsilon, INF_F, time);
+                if (sv.Intersect(ray, &lightIsect, cnt)) {
+                    if (sv.d->primitives[lightIsect.prim].areaLight == lightIdx) Li = Le(lightIsect, -wi);
+                }   // else light->Le(ray) == 0 for area lights
+                if (!Li.IsBlack()) Ld += f * Li * AbsDot(wi, n) * weight / bsdfPdf;
+            }
+        }
+        return Ld;
+    }
+
+    // UniformSampleOneLight, core/integrator.cpp:82-114
+    Spec UniformSampleOneLight(const Vec &p, const Vec &n, const Vec &wo, float rayEpsilon, float time, const BSDF &bsdf,
+                               const Sample *sample, RNG &rng, int depthSlot, Counters *cnt) const {
+        int nLights = int(sv.d->nLights);
+        if (nLights == 0) return Spec(0.);
+        int lightNum;
+        if (depthSlot >= 0) lightNum = Floor2Int(sample->oneD[4 * depthSlot + 1] * nLights);
+        else lightNum = Floor2Int(rng.RandomFloat() * nLights);
+        lightNum = std::min(lightNum, nLights - 1);
+        LightSample lightSample;
+        BSDFSample bsdfSample;
+        if (depthSlot >= 0) {
+            lightSample.uPos[0] = sample->twoD[3 * depthSlot + 0][0];
+            lightSample.uPos[1] = sample->twoD[3 * depthSlot + 0][1];
+            lightSample.uComponent = sample->oneD[4 * depthSlot + 0];
+            bsdfSample.uDir[0] = sample->twoD[3 * depthSlot + 1][0];
+            bsdfSample.uDir[1] = sample->twoD[3 * depthSlot + 1][1];
+            bsdfSample.uComponent = sample->oneD[4 * depthSlot + 2];
+        } else {
+            lightSample.uPos[0] = rng.RandomFloat();   // LightSample(RNG&), light.h:117-121
+            lightSample.uPos[1] = rng.RandomFloat();
+            lightSample.uComponent = rng.RandomFloat();
+            bsdfSample.uDir[0] = rng.RandomFloat();    // BSDFSample(RNG&), reflection.h:135-139
+            bsdfSample.uDir[1] = rng.RandomFloat();
+            bsdfSample.uComponent = rng.RandomFloat();
+        }
+        return (float)nLights * EstimateDirect(lightNum, p, n, wo, rayEpsilon, time, bsdf, lightSample, bsdfSample,
+                                               BSDF_ALL & ~BSDF_SPECULAR, cnt);
+    }
+
+    // PathIntegrator::Li, integrators/path.cpp:52-123
+    Spec PathLi(const Ray &r, const Intersection &isect, const Sample *sample, RNG &rng, Counters *cnt) const {
+        const int SAMPLE_DEPTH = 3;
+        Spec pathThroughput(1.), L(0.);
+        Ray ray(r);
+        bool specularBounce = false;
+        Intersection localIsect;
+        const Intersection *isectp = &isect;
+        for (int bounces = 0;; ++bounces) {
+            if (bounces == 0 || specularBounce) L += pathThroughput * Le(*isectp, -ray.d);
+            BSDF bsdf;
+            GetBSDF(*isectp, &bsdf, cnt);
+            const Vec &p = bsdf.p;
+            const Vec &n = bsdf.nn;
+            Vec wo = -ray.d;
+            if (bounces < SAMPLE_DEPTH)
+                L += pathThroughput * UniformSampleOneLight(p, n, wo, isectp->rayEpsilon, ray.time, bsdf, sample, rng, bounces, cnt);
+            else
+                L += pathThroughput * UniformSampleOneLight(p, n, wo, isectp->rayEpsilon, ray.time, bsdf, sample, rng, -1, cnt);
+            BSDFSample outgoingBSDFSample;
+            if (bounces < SAMPLE_DEPTH) {
+                outgoingBSDFSample.uDir[0] = sample->twoD[3 * bounces + 2][0];
+                outgoingBSDFSample.uDir[1] = sample->twoD[3 * bounces + 2][1];
+                outgoingBSDFSample.uComponent = sample->oneD[4 * bounces + 3];
+            } else {
+                outgoingBSDFSample.uDir[0] = rng.RandomFloat();
+                outgoingBSDFSample.uDir[1] = rng.RandomFloat();
+                outgoingBSDFSample.uComponent = rng.RandomFloat();
+            }
+            Vec wi;
+            float pdf;
+            int flags;
+            Spec f = bsdf.Sample_f(wo, &wi, outgoingBSDFSample, &pdf, BSDF_ALL, &flags);
+            if (f.IsBlack() || pdf == 0.) break;
+            specularBounce = (flags & BSDF_SPECULAR) != 0;
+            pathThroughput *= f * AbsDot(wi, n) / pdf;
+            ray = Ray(p, wi, isectp->rayEpsilon, INF_F, ray.time);
+            if (bounces > 3) {
+                float continueProbability = std::min(.5f, pathThroughput.y());
+                if (rng.RandomFloat() > continueProbability) break;
+                pathThroughput /= continueProbability;
+            }
+            if (bounces == rd->maxDepth) break;
+            if (!sv.Intersect(ray, &localIsect, cnt)) break;   // (specularBounce: lights' Le(ray) == 0)
+            isectp = &localIsect;
+        }
+        return L;
+    }
+
+    // ImageFilm::AddSample, film/image.cpp:77-137 (box filter: every table weight is 1)
+    void AddSample(const Sample &sample, const Spec &L) const {
+        float dimageX = sample.imageX - 0.5f;
+        float dimageY = sample.imageY - 0.5f;
+        int x0 = Ceil2Int(dimageX - rd->filterXWidth);
+        int x1 = Floor2Int(dimageX + rd->filterXWidth);
+        int y0 = Ceil2Int(dimageY - rd->filterYWidth);
+        int y1 = Floor2Int(dimageY + rd->filterYWidth);
+        x0 = std::max(x0, xPixelStart);
+        x1 = std::min(x1, xPixelStart + xPixelCount - 1);
+        y0 = std::max(y0, yPixelStart);
+        y1 = std::min(y1, yPixelStart + yPixelCount - 1);
+        if ((x1 - x0) < 0 || (y1 - y0) < 0) return;
+        float xyz[3];
+        xyz[0] = 0.412453f * L.c[0] + 0.357580f * L.c[1] + 0.180423f * L.c[2];
+        xyz[1] = 0.212671f * L.c[0] + 0.715160f * L.c[1] + 0.072169f * L.c[2];
+        xyz[2] = 0.019334f * L.c[0] + 0.119193f * L.c[1] + 0.950227f * L.c[2];
+        const float filterWt = 1.f;
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) {
+                PbrtGpuPixel &pixel = pixels[(size_t)(y - yPixelStart) * xPixelCount + (x - xPixelStart)];
+                pixel.Lxyz[0] += filterWt * xyz[0];   // non-atomic, like the reference (image.cpp:122-127)
+                pixel.Lxyz[1] += filterWt * xyz[1];
+                pixel.Lxyz[2] += filterWt * xyz[2];
+                pixel.weightSum += filterWt;
+            }
+    }
+
+    // SamplerRendererTask::Run, renderers/samplerrenderer.cpp:60-164
+    void RunTask(int taskNum, Counters *cnt) const {
+        int x0, x1, y0, y1;
+        ComputeSubWindow(taskNum, rd->nTasks, &x0, &x1, &y0, &y1);
+        if (x0 == x1 || y0 == y1) return;   // GetSubSampler returns NULL, lowdiscrepancy.cpp:62
+        RNG rng((uint32_t)taskNum);
+        const int spp = rd->samplesPerPixel;
+        std::vector<Sample> samples(spp);
+        std::vector<float> buf((size_t)SAMPLE_FLOATS * spp);
+        std::vector<Spec> Ls(spp);
+        for (int yPos = y0; yPos < y1; ++yPos)
+            for (int xPos = x0; xPos < x1; ++xPos) {
+                LDPixelSample(xPos, yPos, rd->shutterOpen, rd->shutterClose, spp, samples.data(), buf.data(), rng);
+                for (int i = 0; i < spp; ++i) {
+                    Ray ray;
+                    GenerateRay(samples[i], &ray);
+                    // SamplerRenderer::Li, samplerrenderer.cpp:225-247 (volume integrator: T=1, Lvi=0)
+                    Intersection isect;
+                    Spec Li(0.f);
+                    if (sv.Intersect(ray, &isect, cnt)) Li = PathLi(ray, isect, &samples[i], rng, cnt);
+                    Ls[i] = 1.f * (Spec(1.f) * Li + Spec(0.f));
+                    if (Ls[i].HasNaNs()) Ls[i] = Spec(0.f);
+                    else if (Ls[i].y() < -1e-5) Ls[i] = Spec(0.f);
+                    else if (std::isinf(Ls[i].y())) Ls[i] = Spec(0.f);
+                }
+                for (int i = 0; i < spp; ++i) AddSample(samples[i], Ls[i]);
+            }
+        if (cnt) cnt->rngDraws += rng.draws;
+    }
+};
+
+}  // namespace
+
+// ================================================================== C exports
+extern "C" {
+
+struct OracleCounters {
+    uint64_t cameraSamples, closestRays, shadowRays, nodesVisited, primTests, shadedHitsWithNormals, rngDraws;
+};
+
+// Render tasks [taskBegin, taskEnd) with `nThreads` host threads (tasks are
+// independent units: own RNG stream, own pixels -- samplerrenderer.cpp:72-73).
+int oracle_render(const PbrtGpuSceneDesc *scene, const PbrtGpuRenderDesc *rd, PbrtGpuPixel *pixels, int nThreads,
+                  OracleCounters *counters) {
+    Renderer R;
+    R.Init(scene, rd, pixels);
+    memset(pixels, 0, sizeof(PbrtGpuPixel) * (size_t)R.xPixelCount * R.yPixelCount);
+    if (nThreads < 1) nThreads = 1;
+    std::atomic<int> next(rd->taskBegin);
+    std::vector<Counters> cnts(nThreads);
+    std::vector<std::thread> threads;
+    for (int t = 0; t < nThreads; ++t)
+        threads.emplace_back([&, t]() {
+            for (;;) {
+                // same enqueue order as the reference: nTasks-1-i (samplerrenderer.cpp:212)
+                int i = next.fetch_add(1);
+                if (i >= rd->taskEnd) break;
+                R.RunTask(rd->taskBegin + (rd->taskEnd - 1 - i), &cnts[t]);
+            }
+        });
+    for (auto &th : threads) th.join();
+    if (counters) {
+        memset(counters, 0, sizeof(*counters));
+        for (const Counters &c : cnts) {
+            counters->closestRays += c.closestRays; counters->shadowRays += c.shadowRays;
+            counters->nodesVisited += c.nodesVisited; counters->primTests += c.primTests;
+            counters->shadedHitsWithNormals += c.shadedN; counters->rngDraws += c.rngDraws;
+        }
+        // camera samples = pixels of the rendered tasks x spp
+        uint64_t px = 0;
+        for (int t = rd->taskBegin; t < rd->taskEnd; ++t) {
+            int x0, x1, y0, y1;
+            R.ComputeSubWindow(t, rd->nTasks, &x0, &x1, &y0, &y1);
+            px += (uint64_t)std::max(0, x1 - x0) * std::max(0, y1 - y0);
+        }
+        counters->cameraSamples = px * rd->samplesPerPixel;
+    }
+    return 0;
+}
+
+int oracle_intersect(const PbrtGpuSceneDesc *scene, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits) {
+    SceneView sv{scene};
+    for (int i = 0; i < n; ++i) {
+        Ray r(Vec(rays[i].o), Vec(rays[i].d), rays[i].mint, rays[i].maxt);
+        Intersection isect;
+        float b1 = 0, b2 = 0;
+        memset(&hits[i], 0, sizeof(PbrtGpuHit));
+        if (sv.Intersect(r, &isect, nullptr, &b1, &b2)) {
+            hits[i].hit = 1;
+            hits[i].primitive = isect.prim;
+            hits[i].t = r.maxt;
+            hits[i].b1 = b1; hits[i].b2 = b2;
+            hits[i].p[0] = isect.dg.p.x; hits[i].p[1] = isect.dg.p.y; hits[i].p[2] = isect.dg.p.z;
+            hits[i].n[0] = isect.dg.nn.x; hits[i].n[1] = isect.dg.nn.y; hits[i].n[2] = isect.dg.nn.z;
+        } else {
+            hits[i].t = r.maxt;
+        }
+    }
+    return 0;
+}
+
+int oracle_intersect_p(const PbrtGpuSceneDesc *scene, const PbrtGpuRay *rays, int n, uint8_t *occluded) {
+    SceneView sv{scene};
+    for (int i = 0; i < n; ++i) {
+        Ray r(Vec(rays[i].o), Vec(rays[i].d), rays[i].mint, rays[i].maxt);
+        occluded[i] = sv.IntersectP(r, nullptr) ? 1 : 0;
+    }
+    return 0;
+}
+
+// spp rows of 37 floats for the first pixel of task `taskNum`
+int oracle_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
+    Renderer R;
+    PbrtGpuSceneDesc dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    R.Init(&dummy, rd, nullptr);
+    int x0, x1, y0, y1;
+    R.ComputeSubWindow(taskNum, rd->nTasks, &x0, &x1, &y0, &y1);
+    if (x0 == x1 || y0 == y1) return 1;
+    RNG rng((uint32_t)taskNum);
+    const int spp = rd->samplesPerPixel;
+    std::vector<Sample> samples(spp);
+    std::vector<float> buf((size_t)SAMPLE_FLOATS * spp);
+    LDPixelSample(x0, y0, rd->shutterOpen, rd->shutterClose, spp, samples.data(), buf.data(), rng);
+    for (int i = 0; i < spp; ++i) {
+        float *o = out + (size_t)SAMPLE_FLOATS * i;
+        o[0] = samples[i].imageX; o[1] = samples[i].imageY; o[2] = samples[i].lensU; o[3] = samples[i].lensV;
+        o[4] = samples[i].time;
+        for (int j = 0; j < N1D; ++j) o[5 + j] = samples[i].oneD[j];
+        for (int j = 0; j < N2D; ++j) { o[5 + N1D + 2 * j] = samples[i].twoD[j][0]; o[5 + N1D + 2 * j + 1] = samples[i].twoD[j][1]; }
+    }
+    return 0;
+}
+
+int oracle_task_window(const PbrtGpuRenderDesc *rd, int taskNum, int *win) {
+    Renderer R;
+    PbrtGpuSceneDesc dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    R.Init(&dummy, rd, nullptr);
+    R.ComputeSubWindow(taskNum, rd->nTasks, &win[0], &win[1], &win[2], &win[3]);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+"""pbrt_v2_b200 -- Python bindings (ctypes) for the B200 path-tracing hot path.
+
+Two in-tree shared libraries make up the product:
+
+* ``libpbrtgpu.so``  -- hand-written sm_100a CUDA kernels behind the C ABI of
+  ``include/pbrtgpu.h`` (scene upload, render, ray-batch intersect, LD samples).
+* ``libpbrthost.so`` -- the C++ host side that mirrors pbrt-v2's
+  Renderer / SurfaceIntegrator / Aggregate surface: scene-file front end,
+  ``GpuBVHAccel`` build, flattening, ``GpuSamplerRenderer::Render``.
+
+There is NO CPU fallback: if the libraries are missing or no CUDA device is
+present the calls raise.  (The CPU restatement under ``oracle/`` is test
+infrastructure and is never imported from here.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(_HERE)
+
+
+class PbrtGpuError(RuntimeError):
+    pass
+
+
+# ---- POD mirrors of include/pbrtgpu.h ---------------------------------------
+class RenderDesc(C.Structure):
+    _fields_ = [
+        ("rasterToCamera", C.c_float * 16),
+        ("cameraToWorld", C.c_float * 16),
+        ("lensRadius", C.c_float), ("focalDistance", C.c_float),
+        ("shutterOpen", C.c_float), ("shutterClose", C.c_float),
+        ("xResolution", C.c_int32), ("yResolution", C.c_int32),
+        ("cropWindow", C.c_float * 4),
+        ("filterXWidth", C.c_float), ("filterYWidth", C.c_float),
+        ("samplesPerPixel", C.c_int32),
+        ("maxDepth", C.c_int32),
+        ("nTasks", C.c_int32),
+        ("taskBegin", C.c_int32), ("taskEnd", C.c_int32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("renderMs", C.c_double), ("tableMs", C.c_double), ("traceMs", C.c_double),
+        ("cameraSamples", C.c_uint64),
+        ("closestRays", C.c_uint64), ("shadowRays", C.c_uint64),
+        ("nodesVisited", C.c_uint64), ("primTests", C.c_uint64),
+        ("kernelLaunches", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+PIXEL_DTYPE = np.dtype([("Lxyz", np.float32, 3), ("weightSum", np.float32)])
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("mint", np.float32), ("maxt", np.float32)])
+HIT_DTYPE = np.dtype([("hit", np.int32), ("primitive", np.uint32), ("t", np.float32),
+                      ("b1", np.float32), ("b2", np.float32), ("p", np.float32, 3), ("n", np.float32, 3)])
+SAMPLE_FLOATS = 37
+
+_gpu = None
+_host = None
+
+
+def _load(name):
+    path = os.path.join(_HERE, name)
+    if not os.path.exists(path):
+        raise PbrtGpuError(
+            "%s is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make` in the repo root); there is no CPU fallback" % path)
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+def gpu_lib():
+    """libpbrtgpu.so (the CUDA hot path)."""
+    global _gpu
+    if _gpu is None:
+        lib = _load("libpbrtgpu.so")
+        lib.pbrtgpu_last_error.restype = C.c_char_p
+        lib.pbrtgpu_scene_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.pbrtgpu_scene_destroy.argtypes = [C.c_void_p]
+        lib.pbrtgpu_scene_destroy.restype = None
+        lib.pbrtgpu_render.argtypes = [C.c_void_p, C.POINTER(RenderDesc), C.c_void_p, C.POINTER(Stats)]
+        lib.pbrtgpu_render_device.argtypes = [C.c_void_p, C.POINTER(RenderDesc), C.c_void_p, C.c_void_p,
+                                              C.POINTER(Stats)]
+        lib.pbrtgpu_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.pbrtgpu_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.pbrtgpu_ld_samples.argtypes = [C.POINTER(RenderDesc), C.c_int, C.c_void_p]
+        lib.pbrtgpu_set_device.argtypes = [C.c_int]
+        _gpu = lib
+    return _gpu
+
+
+def host_lib():
+    """libpbrthost.so (scene front end + GpuBVHAccel + flattening)."""
+    global _host
+    if _host is None:
+        gpu_lib()
+        lib = _load("libpbrthost.so")
+        lib.pbrthost_load.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        lib.pbrthost_load.restype = C.c_void_p
+        lib.pbrthost_free.argtypes = [C.c_void_p]
+        lib.pbrthost_free.restype = None
+        lib.pbrthost_scene_desc.argtypes = [C.c_void_p]
+        lib.pbrthost_scene_desc.restype = C.c_void_p
+        lib.pbrthost_render_desc.argtypes = [C.c_void_p, C.POINTER(RenderDesc)]
+        lib.pbrthost_render_desc.restype = None
+        lib.pbrthost_film_extent.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        lib.pbrthost_film_extent.restype = None
+        lib.pbrthost_pixels_to_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pbrthost_write_image.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+        lib.pbrthost_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Stats)]
+        _host = lib
+    return _host
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise PbrtGpuError("%s failed (code %d): %s" % (what, rc, gpu_lib().pbrtgpu_last_error().decode()))
+
+
+class HostScene(object):
+    """A parsed + flattened scene (host memory only; no GPU needed)."""
+
+    def __init__(self, filename, ncores=0):
+        lib = host_lib()
+        err = C.create_string_buffer(1024)
+        self._h = lib.pbrthost_load(os.fsencode(filename), int(ncores), err, len(err))
+        if not self._h:
+            raise PbrtGpuError("cannot load %s: %s" % (filename, err.value.decode()))
+        self.filename = filename
+
+    def close(self):
+        if getattr(self, "_h", None):
+            host_lib().pbrthost_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def desc_ptr(self):
+        """const PbrtGpuSceneDesc* (valid while this object lives)."""
+        return host_lib().pbrthost_scene_desc(self._h)
+
+    def render_desc(self):
+        rd = RenderDesc()
+        host_lib().pbrthost_render_desc(self._h, C.byref(rd))
+        return rd
+
+    def film_extent(self):
+        v = [C.c_int() for _ in range(4)]
+        host_lib().pbrthost_film_extent(self._h, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)   # xStart, yStart, xCount, yCount
+
+    def new_pixels(self):
+        _, _, xc, yc = self.film_extent()
+        return np.zeros((yc, xc), dtype=PIXEL_DTYPE)
+
+    def pixels_to_rgb(self, pixels):
+        """ImageFilm::WriteImage's conversion (film/image.cpp:178-205) -> (H, W, 3) float32."""
+        _, _, xc, yc = self.film_extent()
+        pixels = np.ascontiguousarray(pixels)
+        rgb = np.zeros((yc, xc, 3), dtype=np.float32)
+        host_lib().pbrthost_pixels_to_rgb(self._h, pixels.ctypes.data, rgb.ctypes.data)
+        return rgb
+
+    def write_image(self, pixels, filename):
+        pixels = np.ascontiguousarray(pixels)
+        rc = host_lib().pbrthost_write_image(self._h, pixels.ctypes.data, os.fsencode(filename))
+        if rc:
+            raise PbrtGpuError("cannot write %s" % filename)
+
+    def render(self, write_image=False):
+        """Renderer::Render(scene) through the C++ host class (scene upload + render + D2H)."""
+        px = self.new_pixels()
+        st = Stats()
+        rc = host_lib().pbrthost_render(self._h, int(write_image), px.ctypes.data, C.byref(st))
+        if rc:
+            raise PbrtGpuError("GpuSamplerRenderer::Render failed: %s" % gpu_lib().pbrtgpu_last_error().decode())
+        return px, st
+
+
+class GpuScene(object):
+    """Device-resident scene (pbrtgpu_scene_create)."""
+
+    def __init__(self, host_scene):
+        self.host = host_scene
+        h = C.c_void_p()
+        _check(gpu_lib().pbrtgpu_scene_create(host_scene.desc_ptr, C.byref(h)), "pbrtgpu_scene_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            gpu_lib().pbrtgpu_scene_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def render(self, rd=None, out=None):
+        """pbrtgpu_render into HOST pixels; returns (pixels, Stats)."""
+        rd = rd or self.host.render_desc()
+        px = out if out is not None else self.host.new_pixels()
+        st = Stats()
+        _check(gpu_lib().pbrtgpu_render(self._h, C.byref(rd), px.ctypes.data, C.byref(st)), "pbrtgpu_render")
+        return px, st
+
+    def render_device(self, rd, device_ptr, stream=None, want_stats=False):
+        """pbrtgpu_render_device into DEVICE memory (e.g. a torch tensor's data_ptr())."""
+        st = Stats() if want_stats else None
+        _check(gpu_lib().pbrtgpu_render_device(self._h, C.byref(rd), C.c_void_p(device_ptr),
+                                               C.c_void_p(stream or 0),
+                                               C.byref(st) if st is not None else None), "pbrtgpu_render_device")
+        return st
+
+    def intersect(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        _check(gpu_lib().pbrtgpu_intersect(self._h, rays.ctypes.data, len(rays), hits.ctypes.data), "pbrtgpu_intersect")
+        return hits
+
+    def intersect_p(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        occ = np.zeros(len(rays), dtype=np.uint8)
+        _check(gpu_lib().pbrtgpu_intersect_p(self._h, rays.ctypes.data, len(rays), occ.ctypes.data), "pbrtgpu_intersect_p")
+        return occ
+
+
+def ld_samples(rd, task_num):
+    """LDPixelSample for the first pixel of `task_num` on the GPU -> (spp, 37) float32."""
+    out = np.zeros((rd.samplesPerPixel, SAMPLE_FLOATS), dtype=np.float32)
+    _check(gpu_lib().pbrtgpu_ld_samples(C.byref(rd), int(task_num), out.ctypes.data), "pbrtgpu_ld_samples")
+    return out
+
+
+def device_count():
+    return gpu_lib().pbrtgpu_device_count()

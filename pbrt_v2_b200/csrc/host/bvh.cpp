@@ -1,0 +1,220 @@
+// bvh.cpp -- GpuBVHAccel: host-side construction of the bounding volume
+// hierarchy the CUDA traversal kernels walk.
+//
+// The GPU reproduces BVHAccel::Intersect's traversal ORDER (near child first by
+// split axis, accelerators/bvh.cpp:403-454), so hit/miss ties and `t` ties
+// resolve as in the reference only if the tree itself is the same tree.  The
+// build therefore makes the same decisions as BVHAccel::recursiveBuild
+// (accelerators/bvh.cpp:210-380): same refinement order, same centroid/bucket
+// float arithmetic, same std::partition / std::nth_element calls from the same
+// libstdc++, same depth-first flattening (bvh.cpp:383-399).  The code is an
+// array-based rewrite (no BVHBuildNode tree: nodes are emitted directly in
+// depth-first order and the second-child offset is patched afterwards).
+#include "scene.h"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace pb {
+
+namespace {
+
+struct PrimInfo {   // BVHPrimitiveInfo, bvh.cpp:40-49
+    int primitiveNumber;
+    V3 centroid;
+    BBox bounds;
+};
+
+struct Builder {
+    const std::vector<RefinedPrim> &prims;
+    std::vector<PrimInfo> &info;
+    std::vector<RefinedPrim> &ordered;
+    std::vector<PbrtGpuBVHNode> &nodes;
+    uint32_t maxPrimsInNode;
+    int splitMethod;
+
+    static void SetBounds(PbrtGpuBVHNode &n, const BBox &b) {
+        n.bmin[0] = b.pMin.x; n.bmin[1] = b.pMin.y; n.bmin[2] = b.pMin.z;
+        n.bmax[0] = b.pMax.x; n.bmax[1] = b.pMax.y; n.bmax[2] = b.pMax.z;
+    }
+    static BBox GetBounds(const PbrtGpuBVHNode &n) {
+        BBox b;
+        b.pMin = V3(n.bmin[0], n.bmin[1], n.bmin[2]);
+        b.pMax = V3(n.bmax[0], n.bmax[1], n.bmax[2]);
+        return b;
+    }
+    uint32_t MakeLeaf(uint32_t nodeIdx, uint32_t start, uint32_t end, const BBox &bbox) {
+        uint32_t first = (uint32_t)ordered.size();
+        for (uint32_t i = start; i < end; ++i) ordered.push_back(prims[info[i].primitiveNumber]);
+        PbrtGpuBVHNode &n = nodes[nodeIdx];
+        SetBounds(n, bbox);
+        n.offset = first;
+        n.nPrimitives = (uint8_t)(end - start);
+        n.axis = 0;
+        return nodeIdx;
+    }
+    // interior node: children are built left then right so that the left child
+    // is nodeIdx+1 (what flattenBVHTree produces); the node's bounds are the
+    // union of the CHILDREN's bounds (BVHBuildNode::InitInterior, bvh.cpp:60-66)
+    uint32_t MakeInterior(uint32_t nodeIdx, int dim, uint32_t start, uint32_t mid, uint32_t end) {
+        uint32_t c0 = Build(start, mid);
+        uint32_t c1 = Build(mid, end);
+        PbrtGpuBVHNode &n = nodes[nodeIdx];
+        SetBounds(n, Union(GetBounds(nodes[c0]), GetBounds(nodes[c1])));
+        n.offset = c1;
+        n.nPrimitives = 0;
+        n.axis = (uint8_t)dim;
+        (void)c0;
+        return nodeIdx;
+    }
+
+    uint32_t Build(uint32_t start, uint32_t end) {   // recursiveBuild, bvh.cpp:210-380
+        uint32_t nodeIdx = (uint32_t)nodes.size();
+        nodes.push_back(PbrtGpuBVHNode());
+        memset(&nodes[nodeIdx], 0, sizeof(PbrtGpuBVHNode));
+        BBox bbox;
+        for (uint32_t i = start; i < end; ++i) bbox = Union(bbox, info[i].bounds);
+        uint32_t nPrimitives = end - start;
+        if (nPrimitives == 1) return MakeLeaf(nodeIdx, start, end, bbox);
+
+        BBox centroidBounds;
+        for (uint32_t i = start; i < end; ++i) centroidBounds = Union(centroidBounds, info[i].centroid);
+        int dim = centroidBounds.MaximumExtent();
+        uint32_t mid = (start + end) / 2;
+        if (centroidBounds.pMax[dim] == centroidBounds.pMin[dim]) {   // bvh.cpp:239-261
+            if (nPrimitives <= maxPrimsInNode) return MakeLeaf(nodeIdx, start, end, bbox);
+            return MakeInterior(nodeIdx, dim, start, mid, end);
+        }
+        PrimInfo *base = info.data();
+        auto equalCounts = [&]() {   // bvh.cpp:280-286
+            mid = (start + end) / 2;
+            std::nth_element(base + start, base + mid, base + end,
+                             [dim](const PrimInfo &a, const PrimInfo &b) { return a.centroid[dim] < b.centroid[dim]; });
+        };
+        if (splitMethod == 0) {   // SPLIT_MIDDLE, bvh.cpp:265-279 (falls through to equal counts)
+            float pmid = .5f * (centroidBounds.pMin[dim] + centroidBounds.pMax[dim]);
+            PrimInfo *midPtr = std::partition(base + start, base + end,
+                                              [dim, pmid](const PrimInfo &a) { return a.centroid[dim] < pmid; });
+            mid = (uint32_t)(midPtr - base);
+            if (mid == start || mid == end) equalCounts();
+        } else if (splitMethod == 1) {
+            equalCounts();
+        } else if (nPrimitives <= 4) {   // SPLIT_SAH small case, bvh.cpp:289-294
+            equalCounts();
+        } else {   // SPLIT_SAH, bvh.cpp:295-361
+            const int nBuckets = 12;
+            int count[nBuckets];
+            BBox bounds[nBuckets];
+            for (int i = 0; i < nBuckets; ++i) count[i] = 0;
+            const float cmin = centroidBounds.pMin[dim], cmax = centroidBounds.pMax[dim];
+            for (uint32_t i = start; i < end; ++i) {
+                int b = nBuckets * ((info[i].centroid[dim] - cmin) / (cmax - cmin));
+                if (b == nBuckets) b = nBuckets - 1;
+                count[b]++;
+                bounds[b] = Union(bounds[b], info[i].bounds);
+            }
+            float cost[nBuckets - 1];
+            for (int i = 0; i < nBuckets - 1; ++i) {
+                BBox b0, b1;
+                int count0 = 0, count1 = 0;
+                for (int j = 0; j <= i; ++j) { b0 = Union(b0, bounds[j]); count0 += count[j]; }
+                for (int j = i + 1; j < nBuckets; ++j) { b1 = Union(b1, bounds[j]); count1 += count[j]; }
+                // NB: an empty side gives 0 * inf = NaN exactly as in the reference
+                cost[i] = .125f + (count0 * b0.SurfaceArea() + count1 * b1.SurfaceArea()) / bbox.SurfaceArea();
+            }
+            float minCost = cost[0];
+            uint32_t minCostSplit = 0;
+            for (int i = 1; i < nBuckets - 1; ++i)
+                if (cost[i] < minCost) { minCost = cost[i]; minCostSplit = i; }
+            if (nPrimitives > maxPrimsInNode || minCost < nPrimitives) {
+                PrimInfo *pmid = std::partition(base + start, base + end, [=](const PrimInfo &p) {
+                    int b = nBuckets * ((p.centroid[dim] - cmin) / (cmax - cmin));
+                    if (b == nBuckets) b = nBuckets - 1;
+                    return b <= (int)minCostSplit;
+                });
+                mid = (uint32_t)(pmid - base);
+            } else {
+                return MakeLeaf(nodeIdx, start, end, bbox);
+            }
+        }
+        return MakeInterior(nodeIdx, dim, start, mid, end);
+    }
+};
+
+// Primitive::FullyRefine (core/primitive.cpp:57-69) uses a LIFO todo list, so a
+// mesh's triangles reach the accelerator in REVERSE index order; that order is
+// the input order of the build and must be kept.
+void FullyRefine(const GeometricPrimitive &gp, std::vector<RefinedPrim> *out,
+                 std::vector<std::shared_ptr<Shape>> *owned) {
+    const Shape *s = gp.shape.get();
+    auto emitMesh = [&](const TriangleMesh *m) {
+        for (int i = m->ntris - 1; i >= 0; --i) {
+            RefinedPrim r;
+            r.type = PBRTGPU_PRIM_TRIANGLE;
+            r.shape = m;
+            r.tri = i;
+            r.material = gp.material;
+            r.areaLight = gp.areaLight;
+            out->push_back(r);
+        }
+    };
+    switch (s->kind) {
+    case Shape::TRIANGLE_MESH: emitMesh(static_cast<const TriangleMesh *>(s)); break;
+    case Shape::LOOP_SUBDIV: {
+        std::shared_ptr<Shape> mesh(static_cast<const LoopSubdiv *>(s)->Refine());
+        owned->push_back(mesh);
+        emitMesh(static_cast<const TriangleMesh *>(mesh.get()));
+        break;
+    }
+    case Shape::SPHERE:
+    case Shape::DISK: {
+        RefinedPrim r;
+        r.type = s->kind == Shape::SPHERE ? PBRTGPU_PRIM_SPHERE : PBRTGPU_PRIM_DISK;
+        r.shape = s;
+        r.tri = 0;
+        r.material = gp.material;
+        r.areaLight = gp.areaLight;
+        out->push_back(r);
+        break;
+    }
+    }
+}
+
+}  // namespace
+
+GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, const std::string &sm) {
+    // BVHAccel::BVHAccel, bvh.cpp:153-202
+    maxPrimsInNode = std::min(255u, mp);
+    std::vector<RefinedPrim> refined;
+    for (const GeometricPrimitive &gp : p) FullyRefine(gp, &refined, &owned);
+    if (sm == "sah") splitMethod = 2;
+    else if (sm == "middle") splitMethod = 0;
+    else if (sm == "equal") splitMethod = 1;
+    else {
+        fprintf(stderr, "Warning: BVH split method \"%s\" unknown.  Using \"sah\".\n", sm.c_str());
+        splitMethod = 2;
+    }
+    if (refined.empty()) return;
+    std::vector<PrimInfo> info;
+    info.reserve(refined.size());
+    for (size_t i = 0; i < refined.size(); ++i) {
+        PrimInfo pi;
+        pi.primitiveNumber = (int)i;
+        pi.bounds = refined[i].WorldBound();
+        pi.centroid = .5f * pi.bounds.pMin + .5f * pi.bounds.pMax;   // bvh.cpp:44-46
+        info.push_back(pi);
+    }
+    primitives.reserve(refined.size());
+    nodes.reserve(2 * refined.size());
+    Builder b{refined, info, primitives, nodes, maxPrimsInNode, splitMethod};
+    b.Build(0, (uint32_t)refined.size());
+}
+
+GpuBVHAccel *CreateGpuBVHAccelerator(const std::vector<GeometricPrimitive> &prims, const ParamSet &ps) {
+    // CreateBVHAccelerator, bvh.cpp:506-511
+    std::string splitMethod = ps.FindOneString("splitmethod", "sah");
+    uint32_t maxPrimsInNode = ps.FindOneInt("maxnodeprims", 4);
+    return new GpuBVHAccel(prims, maxPrimsInNode, splitMethod);
+}
+
+}  // namespace pb

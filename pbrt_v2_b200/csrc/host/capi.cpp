@@ -1,0 +1,70 @@
+// capi.cpp -- C entry points of libpbrthost.so, the host-side half of the
+// drop-in (scene front end + BVH build + flattening).  Used by the Python
+// tests/bench (ctypes) and by the `pbrt_b200` command line.  No compute happens
+// here: rendering goes through include/pbrtgpu.h.
+#include "scene.h"
+
+#include <cstdio>
+#include <cstring>
+
+using namespace pb;
+
+extern "C" {
+
+struct PbrtHostScene {
+    LoadedScene ls;
+};
+
+PbrtHostScene *pbrthost_load(const char *filename, int ncores, char *err, int errlen) {
+    PbrtHostScene *h = new PbrtHostScene;
+    Options opt;
+    opt.nCores = ncores;
+    if (!LoadSceneFile(filename, opt, &h->ls)) {
+        if (err && errlen > 0) snprintf(err, errlen, "%s", h->ls.error.c_str());
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+void pbrthost_free(PbrtHostScene *h) { delete h; }
+
+const PbrtGpuSceneDesc *pbrthost_scene_desc(PbrtHostScene *h) { return &h->ls.scene->desc; }
+
+void pbrthost_render_desc(PbrtHostScene *h, PbrtGpuRenderDesc *rd) { h->ls.renderer->FillRenderDesc(rd); }
+
+void pbrthost_film_extent(PbrtHostScene *h, int *xStart, int *yStart, int *xCount, int *yCount) {
+    const ImageFilm *f = h->ls.renderer->film.get();
+    *xStart = f->xPixelStart; *yStart = f->yPixelStart; *xCount = f->xPixelCount; *yCount = f->yPixelCount;
+}
+
+// ImageFilm::WriteImage's XYZ->RGB / weight normalisation (film/image.cpp:178-205)
+int pbrthost_pixels_to_rgb(PbrtHostScene *h, const PbrtGpuPixel *pixels, float *rgb) {
+    ImageFilm *f = h->ls.renderer->film.get();
+    size_t n = (size_t)f->xPixelCount * f->yPixelCount;
+    memcpy(f->pixels.data(), pixels, n * sizeof(PbrtGpuPixel));
+    std::vector<float> out;
+    f->ToRGB(&out);
+    memcpy(rgb, out.data(), out.size() * sizeof(float));
+    return 0;
+}
+
+int pbrthost_write_image(PbrtHostScene *h, const PbrtGpuPixel *pixels, const char *filename) {
+    ImageFilm *f = h->ls.renderer->film.get();
+    size_t n = (size_t)f->xPixelCount * f->yPixelCount;
+    memcpy(f->pixels.data(), pixels, n * sizeof(PbrtGpuPixel));
+    if (filename && filename[0]) f->filename = filename;
+    return f->WriteImage() ? 0 : 1;
+}
+
+// full Renderer::Render(scene) (GPU required)
+int pbrthost_render(PbrtHostScene *h, int writeImage, PbrtGpuPixel *pixelsOut, PbrtGpuStats *stats) {
+    GpuSamplerRenderer *r = h->ls.renderer.get();
+    r->writeImage = writeImage != 0;
+    if (!r->Render(h->ls.scene.get())) return 1;
+    if (pixelsOut) memcpy(pixelsOut, r->film->pixels.data(), r->film->pixels.size() * sizeof(PbrtGpuPixel));
+    if (stats) *stats = r->lastStats;
+    return 0;
+}
+
+}  // extern "C"

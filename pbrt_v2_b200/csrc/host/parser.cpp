@@ -1,0 +1,639 @@
+// parser.cpp -- scene-description front end for the hot path's host side.
+//
+// pbrt-v2's own front end (core/pbrtlex.ll, pbrtparse.yy, api.cpp: ~8.7k lines)
+// is out of scope; this is a small from-scratch reader for the directive subset
+// the BASELINE.json config scenes use, with the same semantics where they affect
+// the numbers that reach the GPU:
+//   * numbers are (float)atof(token)                    core/pbrtlex.ll:165-168
+//   * CTM handling, named coordinate systems, attribute stacks   core/api.cpp:700-905
+//   * TransformCache: shapes share Transform objects    core/api.cpp:117-150
+//   * Shape / Material / AreaLightSource / LightSource  core/api.cpp:956-1059
+//   * light order = declaration order                   core/api.cpp:961-967,1055-1058
+//   * MakeCamera / MakeSampler / MakeRenderer defaults  core/api.cpp:196-209,1210-1281
+// Unsupported directives are reported as errors (never silently ignored).
+#include "scene.h"
+
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <set>
+#include <sstream>
+
+namespace pb {
+
+// ----------------------------------------------------------------- ParamSet --
+float ParamSet::FindOneFloat(const std::string &n, float d) const {
+    auto it = floats.find(n);
+    return (it != floats.end() && it->second.size() == 1) ? it->second[0] : d;
+}
+int ParamSet::FindOneInt(const std::string &n, int d) const {
+    auto it = ints.find(n);
+    return (it != ints.end() && it->second.size() == 1) ? it->second[0] : d;
+}
+bool ParamSet::FindOneBool(const std::string &n, bool d) const {
+    auto it = bools.find(n);
+    return (it != bools.end() && it->second.size() == 1) ? it->second[0] : d;
+}
+V3 ParamSet::FindOnePoint(const std::string &n, const V3 &d) const {
+    auto it = points.find(n);
+    return (it != points.end() && it->second.size() == 1) ? it->second[0] : d;
+}
+V3 ParamSet::FindOneSpectrum(const std::string &n, const V3 &d) const {
+    auto it = spectra.find(n);
+    return (it != spectra.end() && it->second.size() == 1) ? it->second[0] : d;
+}
+std::string ParamSet::FindOneString(const std::string &n, const std::string &d) const {
+    auto it = strings.find(n);
+    return (it != strings.end() && it->second.size() == 1) ? it->second[0] : d;
+}
+const std::vector<float> *ParamSet::FindFloat(const std::string &n) const {
+    auto it = floats.find(n);
+    return it == floats.end() ? nullptr : &it->second;
+}
+const std::vector<int> *ParamSet::FindInt(const std::string &n) const {
+    auto it = ints.find(n);
+    return it == ints.end() ? nullptr : &it->second;
+}
+const std::vector<V3> *ParamSet::FindPoint(const std::string &n) const {
+    auto it = points.find(n);
+    return it == points.end() ? nullptr : &it->second;
+}
+const std::vector<V3> *ParamSet::FindNormal(const std::string &n) const {
+    auto it = normals.find(n);
+    return it == normals.end() ? nullptr : &it->second;
+}
+
+// ---------------------------------------------------------------- tokenizer --
+namespace {
+
+struct Token {
+    enum Type { END, IDENT, STRING, NUMBER, LBRACK, RBRACK } type;
+    std::string text;
+    float num;
+};
+
+struct Lexer {
+    std::string buf;
+    size_t pos = 0;
+    std::string file;
+    int line = 1;
+    bool Load(const std::string &fn) {
+        std::ifstream f(fn, std::ios::binary);
+        if (!f) return false;
+        std::stringstream ss;
+        ss << f.rdbuf();
+        buf = ss.str();
+        file = fn;
+        return true;
+    }
+    Token Next() {
+        Token t;
+        t.num = 0;
+        for (;;) {
+            while (pos < buf.size() && isspace((unsigned char)buf[pos])) {
+                if (buf[pos] == '\n') ++line;
+                ++pos;
+            }
+            if (pos < buf.size() && buf[pos] == '#') {
+                while (pos < buf.size() && buf[pos] != '\n') ++pos;
+                continue;
+            }
+            break;
+        }
+        if (pos >= buf.size()) { t.type = Token::END; return t; }
+        char c = buf[pos];
+        if (c == '[') { ++pos; t.type = Token::LBRACK; return t; }
+        if (c == ']') { ++pos; t.type = Token::RBRACK; return t; }
+        if (c == '"') {
+            size_t e = buf.find('"', pos + 1);
+            if (e == std::string::npos) e = buf.size();
+            t.type = Token::STRING;
+            t.text = buf.substr(pos + 1, e - pos - 1);
+            pos = e + 1;
+            return t;
+        }
+        if (isalpha((unsigned char)c) || c == '_') {
+            size_t s = pos;
+            while (pos < buf.size() && (isalnum((unsigned char)buf[pos]) || buf[pos] == '_')) ++pos;
+            t.type = Token::IDENT;
+            t.text = buf.substr(s, pos - s);
+            return t;
+        }
+        // NUMBER [-+]?([0-9]+|(([0-9]+\.[0-9]*)|(\.[0-9]+)))([eE][-+]?[0-9]+)?   pbrtlex.ll:114
+        size_t s = pos;
+        if (buf[pos] == '-' || buf[pos] == '+') ++pos;
+        while (pos < buf.size() && (isdigit((unsigned char)buf[pos]) || buf[pos] == '.')) ++pos;
+        if (pos < buf.size() && (buf[pos] == 'e' || buf[pos] == 'E')) {
+            size_t save = pos;
+            ++pos;
+            if (pos < buf.size() && (buf[pos] == '-' || buf[pos] == '+')) ++pos;
+            if (pos < buf.size() && isdigit((unsigned char)buf[pos])) {
+                while (pos < buf.size() && isdigit((unsigned char)buf[pos])) ++pos;
+            } else {
+                pos = save;
+            }
+        }
+        if (pos == s) {   // unknown character
+            t.type = Token::IDENT;
+            t.text = std::string(1, buf[pos++]);
+            return t;
+        }
+        t.type = Token::NUMBER;
+        t.text = buf.substr(s, pos - s);
+        t.num = (float)atof(t.text.c_str());
+        return t;
+    }
+};
+
+// TransformCache (core/api.cpp:117-150): one Transform object per distinct CTM
+struct TransformCache {
+    std::map<Transform, std::pair<Transform *, Transform *>> cache;
+    std::vector<std::unique_ptr<Transform>> store;
+    void Lookup(const Transform &t, const Transform **tCached, const Transform **tInv) {
+        auto it = cache.find(t);
+        if (it == cache.end()) {
+            store.emplace_back(new Transform(t));
+            Transform *tr = store.back().get();
+            store.emplace_back(new Transform(Inverse(t)));
+            Transform *ti = store.back().get();
+            it = cache.insert(std::make_pair(t, std::make_pair(tr, ti))).first;
+        }
+        if (tCached) *tCached = it->second.first;
+        if (tInv) *tInv = it->second.second;
+    }
+};
+
+struct TransformSet {   // core/api.cpp:77-103 (MAX_TRANSFORMS == 2)
+    Transform t[2];
+    bool IsAnimated() const { return t[0] != t[1]; }
+};
+TransformSet InverseSet(const TransformSet &ts) {
+    TransformSet r;
+    r.t[0] = Inverse(ts.t[0]);
+    r.t[1] = Inverse(ts.t[1]);
+    return r;
+}
+
+struct GraphicsState {   // core/api.cpp:213-232
+    std::string material = "matte";
+    ParamSet materialParams;
+    std::string areaLight;
+    ParamSet areaLightParams;
+    bool reverseOrientation = false;
+};
+
+struct Api {
+    // render options (core/api.cpp:153-209)
+    float transformStartTime = 0.f, transformEndTime = 1.f;
+    std::string FilterName = "box", FilmName = "image", SamplerName = "lowdiscrepancy",
+                AcceleratorName = "bvh", RendererName = "sampler", SurfIntegratorName = "directlighting",
+                VolIntegratorName = "emission", CameraName = "perspective";
+    ParamSet FilterParams, FilmParams, SamplerParams, AcceleratorParams, RendererParams,
+        SurfIntegratorParams, VolIntegratorParams, CameraParams;
+    TransformSet CameraToWorld;
+    // state
+    TransformSet curTransform;
+    int activeBits = 3;
+    std::map<std::string, TransformSet> namedCoordinateSystems;
+    GraphicsState graphicsState;
+    std::vector<GraphicsState> pushedGraphicsStates;
+    std::vector<TransformSet> pushedTransforms;
+    std::vector<int> pushedActiveBits;
+    bool inWorld = false, worldEnded = false;
+    // scene under construction
+    std::unique_ptr<Scene> scene;
+    std::vector<GeometricPrimitive> primitives;
+    std::vector<std::unique_ptr<Transform>> lightXforms;
+    static TransformCache &Cache() { static TransformCache c; return c; }
+    std::string baseDir;
+    std::string error;
+    Options opt;
+
+    bool Fail(const std::string &msg) {
+        if (error.empty()) error = msg;
+        return false;
+    }
+    template <typename F> void ForActive(F f) {
+        for (int i = 0; i < 2; ++i)
+            if (activeBits & (1 << i)) f(curTransform.t[i]);
+    }
+    int MakeMaterial(const ParamSet &geomParams);
+    bool DoShape(const std::string &name, const ParamSet &params);
+    bool DoLight(const std::string &name, const ParamSet &params);
+    bool Finish(LoadedScene *out);
+};
+
+std::string ResolvePath(const std::string &baseDir, const std::string &fn) {   // core/fileutil.cpp
+    if (fn.empty() || fn[0] == '/' || baseDir.empty()) return fn;
+    return baseDir + "/" + fn;
+}
+
+// TextureParams lookup order: shape parameters first, then material parameters
+// (core/paramset.cpp:600-640)
+V3 TexSpectrum(const ParamSet &geom, const ParamSet &mat, const std::string &n, const V3 &def) {
+    return geom.FindOneSpectrum(n, mat.FindOneSpectrum(n, def));
+}
+float TexFloat(const ParamSet &geom, const ParamSet &mat, const std::string &n, float def) {
+    return geom.FindOneFloat(n, mat.FindOneFloat(n, def));
+}
+
+int Api::MakeMaterial(const ParamSet &geomParams) {   // core/api.cpp:1062-1077, 317-372
+    const ParamSet &mp = graphicsState.materialParams;
+    Material m;
+    memset(&m.desc, 0, sizeof(m.desc));
+    m.desc.measured = -1;
+    std::string name = graphicsState.material;
+    for (const auto &kv : mp.textures) { (void)kv; Fail("texture-valued material parameters are outside the hot-path scope"); return -1; }
+    for (const auto &kv : geomParams.textures) { (void)kv; Fail("texture-valued shape parameters are outside the hot-path scope"); return -1; }
+    if (geomParams.floats.count("bumpmap") || mp.floats.count("bumpmap")) { Fail("bump maps are out of scope"); return -1; }
+    if (name == "matte") {   // materials/matte.cpp:66-72
+        m.desc.type = PBRTGPU_MAT_MATTE;
+        V3 kd = TexSpectrum(geomParams, mp, "Kd", V3(0.5f, 0.5f, 0.5f));
+        m.desc.Kd[0] = kd.x; m.desc.Kd[1] = kd.y; m.desc.Kd[2] = kd.z;
+        m.desc.sigma = TexFloat(geomParams, mp, "sigma", 0.f);
+        if (Clampf(m.desc.sigma, 0.f, 90.f) != 0.f) { Fail("matte sigma != 0 (Oren-Nayar) is outside the hot-path scope"); return -1; }
+    } else if (name == "plastic") {   // materials/plastic.cpp:69-76
+        m.desc.type = PBRTGPU_MAT_PLASTIC;
+        V3 kd = TexSpectrum(geomParams, mp, "Kd", V3(0.25f, 0.25f, 0.25f));
+        V3 ks = TexSpectrum(geomParams, mp, "Ks", V3(0.25f, 0.25f, 0.25f));
+        m.desc.Kd[0] = kd.x; m.desc.Kd[1] = kd.y; m.desc.Kd[2] = kd.z;
+        m.desc.Ks[0] = ks.x; m.desc.Ks[1] = ks.y; m.desc.Ks[2] = ks.z;
+        m.desc.roughness = TexFloat(geomParams, mp, "roughness", .1f);
+    } else if (name == "measured") {   // materials/measured.cpp:213-217
+        m.desc.type = PBRTGPU_MAT_MEASURED;
+        std::string fn = geomParams.FindOneString("filename", mp.FindOneString("filename", ""));
+        fn = ResolvePath(baseDir, fn);
+        size_t dot = fn.rfind('.');
+        std::string suffix = dot == std::string::npos ? "" : fn.substr(dot);
+        if (suffix != ".brdf" && suffix != ".BRDF") { Fail("measured material: only .brdf (irregular isotropic) data is in scope: " + fn); return -1; }
+        int idx = -1;
+        for (size_t i = 0; i < scene->measuredNames.size(); ++i)
+            if (scene->measuredNames[i] == fn) idx = (int)i;
+        if (idx < 0) {   // loadedThetaPhi cache, measured.cpp:96-99
+            MeasuredData md;
+            std::string err;
+            if (!LoadIrregIsotropicBRDF(fn, &md, &err)) { Fail(err); return -1; }
+            scene->measured.push_back(std::move(md));
+            scene->measuredNames.push_back(fn);
+            idx = (int)scene->measured.size() - 1;
+        }
+        m.desc.measured = idx;
+    } else {
+        Fail("material \"" + name + "\" is outside the hot-path scope (matte, plastic, measured)");
+        return -1;
+    }
+    // identical descriptors share one slot
+    for (size_t i = 0; i < scene->materials.size(); ++i)
+        if (memcmp(&scene->materials[i].desc, &m.desc, sizeof(m.desc)) == 0) return (int)i;
+    scene->materials.push_back(m);
+    return (int)scene->materials.size() - 1;
+}
+
+bool Api::DoShape(const std::string &name, const ParamSet &params) {   // core/api.cpp:990-1059
+    if (curTransform.IsAnimated())
+        return Fail("animated shapes (TransformedPrimitive, config C4) are not implemented in this round");
+    const Transform *o2w, *w2o;
+    Cache().Lookup(curTransform.t[0], &o2w, &w2o);
+    bool ro = graphicsState.reverseOrientation;
+    std::shared_ptr<Shape> shape;
+    if (name == "trianglemesh") {
+        shape.reset(CreateTriangleMeshShape(o2w, w2o, ro, params));
+    } else if (name == "sphere") {   // shapes/sphere.cpp:216-224
+        float radius = params.FindOneFloat("radius", 1.f);
+        float zmin = params.FindOneFloat("zmin", -radius);
+        float zmax = params.FindOneFloat("zmax", radius);
+        float phimax = params.FindOneFloat("phimax", 360.f);
+        shape.reset(new Sphere(o2w, w2o, ro, radius, zmin, zmax, phimax));
+    } else if (name == "disk") {   // shapes/disk.cpp:139-146
+        float height = params.FindOneFloat("height", 0.);
+        float radius = params.FindOneFloat("radius", 1);
+        float inner = params.FindOneFloat("innerradius", 0);
+        float phimax = params.FindOneFloat("phimax", 360);
+        shape.reset(new Disk(o2w, w2o, ro, height, radius, inner, phimax));
+    } else if (name == "loopsubdiv") {   // shapes/loopsubdiv.cpp:492-505
+        int nlevels = params.FindOneInt("nlevels", 3);
+        const std::vector<int> *vi = params.FindInt("indices");
+        const std::vector<V3> *P = params.FindPoint("P");
+        if (vi && P)
+            shape.reset(new LoopSubdiv(o2w, w2o, ro, (int)vi->size() / 3, (int)P->size(), vi->data(),
+                                       P->data(), nlevels));
+    } else {
+        return Fail("shape \"" + name + "\" is outside the hot-path scope");
+    }
+    if (!shape) return true;   // MakeShape returned NULL: ignored like api.cpp:1001
+    int mtl = MakeMaterial(params);
+    if (mtl < 0) return false;
+    int area = -1;
+    if (!graphicsState.areaLight.empty()) {   // api.cpp:1005-1008, lights/diffuse.cpp:58-66
+        if (graphicsState.areaLight != "area" && graphicsState.areaLight != "diffuse")
+            return Fail("area light \"" + graphicsState.areaLight + "\" unknown");
+        if (shape->kind != Shape::SPHERE && shape->kind != Shape::DISK)
+            return Fail("area lights on shapes other than sphere/disk are outside the hot-path scope");
+        const ParamSet &ap = graphicsState.areaLightParams;
+        V3 L = ap.FindOneSpectrum("L", V3(1, 1, 1));
+        V3 sc = ap.FindOneSpectrum("scale", V3(1, 1, 1));
+        Light lt;
+        lt.desc.type = PBRTGPU_LIGHT_DIFFUSE_AREA;
+        lt.desc.L[0] = L.x * sc.x; lt.desc.L[1] = L.y * sc.y; lt.desc.L[2] = L.z * sc.z;
+        lt.shape = shape.get();
+        scene->lights.push_back(lt);
+        area = (int)scene->lights.size() - 1;
+    }
+    GeometricPrimitive gp;
+    gp.shape = shape;
+    gp.material = mtl;
+    gp.areaLight = area;
+    primitives.push_back(gp);
+    return true;
+}
+
+bool Api::DoLight(const std::string &name, const ParamSet &params) {   // core/api.cpp:956-967
+    if (name != "point") return Fail("light \"" + name + "\" is outside the hot-path scope (point, area)");
+    // lights/point.cpp:68-75 and :41-46
+    V3 I = params.FindOneSpectrum("I", V3(1, 1, 1));
+    V3 sc = params.FindOneSpectrum("scale", V3(1, 1, 1));
+    V3 P = params.FindOnePoint("from", V3(0, 0, 0));
+    Transform l2w = Translate(V3(P.x, P.y, P.z)) * curTransform.t[0];
+    Light lt;
+    lt.desc.type = PBRTGPU_LIGHT_POINT;
+    lt.desc.L[0] = I.x * sc.x; lt.desc.L[1] = I.y * sc.y; lt.desc.L[2] = I.z * sc.z;
+    V3 pos = l2w.Pt(V3(0, 0, 0));
+    lt.desc.pos[0] = pos.x; lt.desc.pos[1] = pos.y; lt.desc.pos[2] = pos.z;
+    scene->lights.push_back(lt);
+    return true;
+}
+
+bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
+    // --- film + filter + camera (api.cpp:1272-1281, film/image.cpp:220-258) ---
+    if (FilterName != "box") return Fail("pixel filter \"" + FilterName + "\" is out of scope (box only)");
+    float fxw = FilterParams.FindOneFloat("xwidth", 0.5f), fyw = FilterParams.FindOneFloat("ywidth", 0.5f);
+    if (fxw > 0.5f || fyw > 0.5f) return Fail("box filter wider than 0.5 needs cross-task splats: out of scope");
+    if (FilmName != "image") return Fail("film \"" + FilmName + "\" unknown");
+    std::string filename = FilmParams.FindOneString("filename", "");
+    if (!opt.imageFile.empty() && filename.empty()) filename = opt.imageFile;
+    if (filename.empty()) filename = "pbrt.pfm";
+    int xres = FilmParams.FindOneInt("xresolution", 640);
+    int yres = FilmParams.FindOneInt("yresolution", 480);
+    float crop[4] = {0, 1, 0, 1};
+    const std::vector<float> *cr = FilmParams.FindFloat("cropwindow");
+    if (cr && cr->size() == 4) {
+        crop[0] = Clampf(std::min((*cr)[0], (*cr)[1]), 0., 1.);
+        crop[1] = Clampf(std::max((*cr)[0], (*cr)[1]), 0., 1.);
+        crop[2] = Clampf(std::min((*cr)[2], (*cr)[3]), 0., 1.);
+        crop[3] = Clampf(std::max((*cr)[2], (*cr)[3]), 0., 1.);
+    }
+    std::unique_ptr<GpuSamplerRenderer> r(new GpuSamplerRenderer);
+    r->nCores = opt.nCores;
+    r->film.reset(new ImageFilm(xres, yres, fxw, fyw, crop, filename));
+    if (CameraName != "perspective") return Fail("camera \"" + CameraName + "\" is out of scope (perspective)");
+    if (CameraToWorld.IsAnimated()) return Fail("animated cameras are out of scope");
+    {   // cameras/perspective.cpp:141-180
+        float shutteropen = CameraParams.FindOneFloat("shutteropen", 0.f);
+        float shutterclose = CameraParams.FindOneFloat("shutterclose", 1.f);
+        if (shutterclose < shutteropen) std::swap(shutterclose, shutteropen);
+        float lensradius = CameraParams.FindOneFloat("lensradius", 0.f);
+        float focaldistance = CameraParams.FindOneFloat("focaldistance", 1e30f);
+        float frame = CameraParams.FindOneFloat("frameaspectratio", float(xres) / float(yres));
+        float screen[4];
+        if (frame > 1.f) { screen[0] = -frame; screen[1] = frame; screen[2] = -1.f; screen[3] = 1.f; }
+        else { screen[0] = -1.f; screen[1] = 1.f; screen[2] = -1.f / frame; screen[3] = 1.f / frame; }
+        const std::vector<float> *sw = CameraParams.FindFloat("screenwindow");
+        if (sw && sw->size() == 4) for (int i = 0; i < 4; ++i) screen[i] = (*sw)[i];
+        float fov = CameraParams.FindOneFloat("fov", 90.);
+        float halffov = CameraParams.FindOneFloat("halffov", -1.f);
+        if (halffov > 0.f) fov = 2.f * halffov;
+        r->camera.reset(new PerspectiveCamera(CameraToWorld.t[0], screen, shutteropen, shutterclose,
+                                              lensradius, focaldistance, fov, r->film.get()));
+    }
+    // --- sampler (samplers/lowdiscrepancy.cpp:40-51,82-92) ---
+    if (SamplerName != "lowdiscrepancy") return Fail("sampler \"" + SamplerName + "\" is out of scope (lowdiscrepancy)");
+    {
+        int nsamp = SamplerParams.FindOneInt("pixelsamples", 4);
+        uint32_t v = (uint32_t)nsamp;   // RoundUpPow2, core/pbrt.h:271-277
+        v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; v++;
+        r->sampler.samplesPerPixel = (int)v;
+        r->film->GetSampleExtent(&r->sampler.xPixelStart, &r->sampler.xPixelEnd, &r->sampler.yPixelStart,
+                                 &r->sampler.yPixelEnd);
+    }
+    // --- integrators (api.cpp:533-563) ---
+    if (SurfIntegratorName != "path" && SurfIntegratorName != "gpupath")
+        return Fail("surface integrator \"" + SurfIntegratorName + "\" is not on the hot path (use \"path\")");
+    r->surfaceIntegrator.reset(new GpuPathIntegrator(SurfIntegratorParams.FindOneInt("maxdepth", 5)));
+    if (VolIntegratorName != "emission") return Fail("volume integrator \"" + VolIntegratorName + "\" is out of scope");
+    if (RendererName != "sampler" && RendererName != "gpusampler")
+        return Fail("renderer \"" + RendererName + "\" is out of scope (sampler)");
+    // --- accelerator (api.cpp:580-594, 1186-1207) ---
+    if (AcceleratorName != "bvh" && AcceleratorName != "gpubvh")
+        return Fail("accelerator \"" + AcceleratorName + "\" is out of scope (bvh)");
+    scene->aggregate.reset(CreateGpuBVHAccelerator(primitives, AcceleratorParams));
+    std::string err;
+    if (!scene->Flatten(&err)) return Fail(err);
+    out->scene = std::move(scene);
+    out->renderer = std::move(r);
+    return true;
+}
+
+bool ParseParams(Lexer &lx, Token &tok, ParamSet *ps, std::string *err) {
+    // after the directive's fixed arguments: ("type name" value | [values])*
+    while (tok.type == Token::STRING) {
+        std::istringstream decl(tok.text);
+        std::string type, name;
+        decl >> type >> name;
+        if (name.empty()) { *err = "malformed parameter declaration \"" + tok.text + "\""; return false; }
+        std::vector<float> nums;
+        std::vector<std::string> strs;
+        tok = lx.Next();
+        auto take = [&](const Token &t) -> bool {
+            if (t.type == Token::NUMBER) { nums.push_back(t.num); return true; }
+            if (t.type == Token::STRING) { strs.push_back(t.text); return true; }
+            return false;
+        };
+        if (tok.type == Token::LBRACK) {
+            tok = lx.Next();
+            while (tok.type != Token::RBRACK) {
+                if (!take(tok)) { *err = "bad token in parameter array for \"" + name + "\""; return false; }
+                tok = lx.Next();
+            }
+            tok = lx.Next();
+        } else {
+            if (!take(tok)) { *err = "missing value for parameter \"" + name + "\""; return false; }
+            tok = lx.Next();
+        }
+        auto triples = [&](std::vector<V3> &dst) {
+            for (size_t i = 0; i + 2 < nums.size(); i += 3) dst.push_back(V3(nums[i], nums[i + 1], nums[i + 2]));
+        };
+        if (type == "float") ps->floats[name] = nums;
+        else if (type == "integer") {   // core/pbrtparse.yy: int(value)
+            std::vector<int> v;
+            for (float f : nums) v.push_back((int)f);
+            ps->ints[name] = v;
+        } else if (type == "bool") {
+            std::vector<bool> v;
+            for (const auto &s : strs) v.push_back(s == "true");
+            ps->bools[name] = v;
+        } else if (type == "point") triples(ps->points[name]);
+        else if (type == "vector") triples(ps->vectors[name]);
+        else if (type == "normal") triples(ps->normals[name]);
+        else if (type == "color" || type == "rgb") triples(ps->spectra[name]);   // RGBSpectrum::FromRGB
+        else if (type == "string") ps->strings[name] = strs;
+        else if (type == "texture") ps->textures[name] = strs.empty() ? "" : strs[0];
+        else { *err = "parameter type \"" + type + "\" is not supported by this front end"; return false; }
+    }
+    return true;
+}
+
+bool ParseStream(Api &api, const std::string &filename, int depth) {
+    Lexer lx;
+    if (!lx.Load(filename)) return api.Fail("unable to open scene file \"" + filename + "\"");
+    if (depth > 32) return api.Fail("Include nesting too deep");
+    Token tok = lx.Next();
+    auto nums = [&](int n, float *out) -> bool {
+        for (int i = 0; i < n; ++i) {
+            if (tok.type != Token::NUMBER) return false;
+            out[i] = tok.num;
+            tok = lx.Next();
+        }
+        return true;
+    };
+    while (tok.type != Token::END) {
+        if (tok.type != Token::IDENT) return api.Fail(filename + ": expected directive near line " + std::to_string(lx.line));
+        std::string d = tok.text;
+        tok = lx.Next();
+        float v[16];
+        std::string perr;
+        auto named = [&](std::string *name, ParamSet *ps) -> bool {
+            if (tok.type != Token::STRING) return api.Fail(d + ": expected a quoted name");
+            *name = tok.text;
+            tok = lx.Next();
+            if (!ParseParams(lx, tok, ps, &perr)) return api.Fail(d + ": " + perr);
+            return true;
+        };
+        if (d == "Identity") api.ForActive([&](Transform &t) { t = Transform(); });
+        else if (d == "Translate") {
+            if (!nums(3, v)) return api.Fail("Translate: expected 3 numbers");
+            api.ForActive([&](Transform &t) { t = t * Translate(V3(v[0], v[1], v[2])); });
+        } else if (d == "Scale") {
+            if (!nums(3, v)) return api.Fail("Scale: expected 3 numbers");
+            api.ForActive([&](Transform &t) { t = t * Scale(v[0], v[1], v[2]); });
+        } else if (d == "Rotate") {
+            if (!nums(4, v)) return api.Fail("Rotate: expected 4 numbers");
+            api.ForActive([&](Transform &t) { t = t * Rotate(v[0], V3(v[1], v[2], v[3])); });
+        } else if (d == "LookAt") {
+            if (!nums(9, v)) return api.Fail("LookAt: expected 9 numbers");
+            api.ForActive([&](Transform &t) { t = t * LookAt(V3(v[0], v[1], v[2]), V3(v[3], v[4], v[5]), V3(v[6], v[7], v[8]), nullptr); });
+        } else if (d == "Transform" || d == "ConcatTransform") {
+            if (tok.type != Token::LBRACK) return api.Fail(d + ": expected [");
+            tok = lx.Next();
+            if (!nums(16, v)) return api.Fail(d + ": expected 16 numbers");
+            if (tok.type != Token::RBRACK) return api.Fail(d + ": expected ]");
+            tok = lx.Next();
+            Matrix4x4 m(v[0], v[4], v[8], v[12], v[1], v[5], v[9], v[13], v[2], v[6], v[10], v[14], v[3], v[7], v[11], v[15]);
+            if (d == "Transform") api.ForActive([&](Transform &t) { t = Transform(m); });
+            else api.ForActive([&](Transform &t) { t = t * Transform(m); });
+        } else if (d == "CoordinateSystem") {
+            if (tok.type != Token::STRING) return api.Fail("CoordinateSystem: expected name");
+            api.namedCoordinateSystems[tok.text] = api.curTransform;
+            tok = lx.Next();
+        } else if (d == "CoordSysTransform") {
+            if (tok.type != Token::STRING) return api.Fail("CoordSysTransform: expected name");
+            auto it = api.namedCoordinateSystems.find(tok.text);
+            if (it != api.namedCoordinateSystems.end()) api.curTransform = it->second;
+            tok = lx.Next();
+        } else if (d == "ActiveTransform") {
+            if (tok.type != Token::IDENT) return api.Fail("ActiveTransform: expected All/StartTime/EndTime");
+            if (tok.text == "All") api.activeBits = 3;
+            else if (tok.text == "StartTime") api.activeBits = 1;
+            else if (tok.text == "EndTime") api.activeBits = 2;
+            else return api.Fail("ActiveTransform: bad argument");
+            tok = lx.Next();
+        } else if (d == "TransformTimes") {
+            if (!nums(2, v)) return api.Fail("TransformTimes: expected 2 numbers");
+            api.transformStartTime = v[0];
+            api.transformEndTime = v[1];
+        } else if (d == "Camera") {
+            if (!named(&api.CameraName, &api.CameraParams)) return false;
+            api.CameraToWorld = InverseSet(api.curTransform);
+            api.namedCoordinateSystems["camera"] = api.CameraToWorld;
+        } else if (d == "Film") { api.FilmParams = ParamSet(); if (!named(&api.FilmName, &api.FilmParams)) return false; }
+        else if (d == "Sampler") { api.SamplerParams = ParamSet(); if (!named(&api.SamplerName, &api.SamplerParams)) return false; }
+        else if (d == "PixelFilter") { api.FilterParams = ParamSet(); if (!named(&api.FilterName, &api.FilterParams)) return false; }
+        else if (d == "Accelerator") { api.AcceleratorParams = ParamSet(); if (!named(&api.AcceleratorName, &api.AcceleratorParams)) return false; }
+        else if (d == "SurfaceIntegrator") { api.SurfIntegratorParams = ParamSet(); if (!named(&api.SurfIntegratorName, &api.SurfIntegratorParams)) return false; }
+        else if (d == "VolumeIntegrator") { api.VolIntegratorParams = ParamSet(); if (!named(&api.VolIntegratorName, &api.VolIntegratorParams)) return false; }
+        else if (d == "Renderer") { api.RendererParams = ParamSet(); if (!named(&api.RendererName, &api.RendererParams)) return false; }
+        else if (d == "WorldBegin") {
+            api.inWorld = true;
+            api.curTransform = TransformSet();
+            api.activeBits = 3;
+            api.namedCoordinateSystems["world"] = api.curTransform;
+        } else if (d == "AttributeBegin") {
+            api.pushedGraphicsStates.push_back(api.graphicsState);
+            api.pushedTransforms.push_back(api.curTransform);
+            api.pushedActiveBits.push_back(api.activeBits);
+        } else if (d == "AttributeEnd") {
+            if (api.pushedGraphicsStates.empty()) return api.Fail("unmatched AttributeEnd");
+            api.graphicsState = api.pushedGraphicsStates.back(); api.pushedGraphicsStates.pop_back();
+            api.curTransform = api.pushedTransforms.back(); api.pushedTransforms.pop_back();
+            api.activeBits = api.pushedActiveBits.back(); api.pushedActiveBits.pop_back();
+        } else if (d == "TransformBegin") {
+            api.pushedTransforms.push_back(api.curTransform);
+            api.pushedActiveBits.push_back(api.activeBits);
+        } else if (d == "TransformEnd") {
+            if (api.pushedTransforms.empty()) return api.Fail("unmatched TransformEnd");
+            api.curTransform = api.pushedTransforms.back(); api.pushedTransforms.pop_back();
+            api.activeBits = api.pushedActiveBits.back(); api.pushedActiveBits.pop_back();
+        } else if (d == "ReverseOrientation") {
+            api.graphicsState.reverseOrientation = !api.graphicsState.reverseOrientation;
+        } else if (d == "Material") {
+            std::string n; ParamSet ps;
+            if (!named(&n, &ps)) return false;
+            api.graphicsState.material = n;
+            api.graphicsState.materialParams = ps;
+        } else if (d == "AreaLightSource") {
+            std::string n; ParamSet ps;
+            if (!named(&n, &ps)) return false;
+            api.graphicsState.areaLight = n;
+            api.graphicsState.areaLightParams = ps;
+        } else if (d == "LightSource") {
+            std::string n; ParamSet ps;
+            if (!named(&n, &ps)) return false;
+            if (!api.DoLight(n, ps)) return false;
+        } else if (d == "Shape") {
+            std::string n; ParamSet ps;
+            if (!named(&n, &ps)) return false;
+            if (!api.DoShape(n, ps)) return false;
+        } else if (d == "Include") {
+            if (tok.type != Token::STRING) return api.Fail("Include: expected filename");
+            std::string fn = ResolvePath(api.baseDir, tok.text);
+            tok = lx.Next();
+            if (!ParseStream(api, fn, depth + 1)) return false;
+        } else if (d == "WorldEnd") {
+            api.worldEnded = true;
+            return true;
+        } else {
+            return api.Fail("directive \"" + d + "\" is outside the hot-path scope of this front end (" + filename + ":" + std::to_string(lx.line) + ")");
+        }
+        if (api.worldEnded) return true;
+    }
+    return true;
+}
+
+}  // namespace
+
+bool LoadSceneFile(const std::string &filename, const Options &opt, LoadedScene *out) {
+    Api api;
+    api.opt = opt;
+    api.scene.reset(new Scene);
+    size_t slash = filename.rfind('/');
+    api.baseDir = slash == std::string::npos ? "" : filename.substr(0, slash);
+    if (!ParseStream(api, filename, 0) || !api.error.empty()) {
+        out->error = api.error;
+        return false;
+    }
+    if (!api.worldEnded) { out->error = "scene file has no WorldEnd"; return false; }
+    if (!api.Finish(out)) { out->error = api.error; return false; }
+    return true;
+}
+
+}  // namespace pb

@@ -1,0 +1,258 @@
+// renderer.cpp -- host side of the drop-in Renderer: camera/film set-up,
+// scene flattening into the PbrtGpuSceneDesc POD arrays, the single
+// pbrtgpu_render() call, and ImageFilm::WriteImage (PFM).
+#include "scene.h"
+
+#include <cstdio>
+#include <map>
+#include <thread>
+
+namespace pb {
+
+// ---------------------------------------------------------------- ImageFilm --
+ImageFilm::ImageFilm(int xres, int yres, float fxw, float fyw, const float crop[4], const std::string &fn)
+    : xResolution(xres), yResolution(yres), filterXWidth(fxw), filterYWidth(fyw), filename(fn) {
+    // film/image.cpp:40-51
+    memcpy(cropWindow, crop, 4 * sizeof(float));
+    xPixelStart = (int)ceilf(xResolution * cropWindow[0]);
+    xPixelCount = std::max(1, (int)ceilf(xResolution * cropWindow[1]) - xPixelStart);
+    yPixelStart = (int)ceilf(yResolution * cropWindow[2]);
+    yPixelCount = std::max(1, (int)ceilf(yResolution * cropWindow[3]) - yPixelStart);
+    pixels.assign((size_t)xPixelCount * yPixelCount, PbrtGpuPixel{{0, 0, 0}, 0});
+}
+
+void ImageFilm::GetSampleExtent(int *xstart, int *xend, int *ystart, int *yend) const {
+    // film/image.cpp:157-166
+    *xstart = (int)floorf(xPixelStart + 0.5f - filterXWidth);
+    *xend = (int)ceilf(xPixelStart - 0.5f + xPixelCount + filterXWidth);
+    *ystart = (int)floorf(yPixelStart + 0.5f - filterYWidth);
+    *yend = (int)ceilf(yPixelStart - 0.5f + yPixelCount + filterYWidth);
+}
+
+void ImageFilm::ToRGB(std::vector<float> *rgbOut) const {   // film/image.cpp:178-205
+    size_t nPix = (size_t)xPixelCount * yPixelCount;
+    rgbOut->assign(3 * nPix, 0.f);
+    float *rgb = rgbOut->data();
+    for (size_t o = 0; o < nPix; ++o) {
+        const float *xyz = pixels[o].Lxyz;
+        rgb[3 * o] = 3.240479f * xyz[0] - 1.537150f * xyz[1] - 0.498535f * xyz[2];
+        rgb[3 * o + 1] = -0.969256f * xyz[0] + 1.875991f * xyz[1] + 0.041556f * xyz[2];
+        rgb[3 * o + 2] = 0.055648f * xyz[0] - 0.204043f * xyz[1] + 1.057311f * xyz[2];
+        float weightSum = pixels[o].weightSum;
+        if (weightSum != 0.f) {
+            float invWt = 1.f / weightSum;
+            rgb[3 * o] = std::max(0.f, rgb[3 * o] * invWt);
+            rgb[3 * o + 1] = std::max(0.f, rgb[3 * o + 1] * invWt);
+            rgb[3 * o + 2] = std::max(0.f, rgb[3 * o + 2] * invWt);
+        }
+        // splatXYZ is always zero on this path (only MetropolisRenderer splats)
+    }
+}
+
+bool ImageFilm::WriteImage() const {
+    // PFM, bottom-to-top rows, little-endian (negative scale): core/imageio.cpp:419-455
+    std::vector<float> rgb;
+    ToRGB(&rgb);
+    FILE *fp = fopen(filename.c_str(), "wb");
+    if (!fp) { fprintf(stderr, "Error: unable to open output file \"%s\"\n", filename.c_str()); return false; }
+    fprintf(fp, "PF\n%d %d\n-1.000000\n", xPixelCount, yPixelCount);
+    for (int y = yPixelCount - 1; y >= 0; --y)
+        fwrite(&rgb[(size_t)3 * y * xPixelCount], sizeof(float), (size_t)3 * xPixelCount, fp);
+    fclose(fp);
+    return true;
+}
+
+// -------------------------------------------------------- PerspectiveCamera --
+PerspectiveCamera::PerspectiveCamera(const Transform &cam2world, const float screenWindow[4], float sopen,
+                                     float sclose, float lensr, float focald, float fov, ImageFilm *f)
+    : CameraToWorld(cam2world), shutterOpen(sopen), shutterClose(sclose), lensRadius(lensr),
+      focalDistance(focald), film(f) {
+    // ProjectiveCamera ctor, core/camera.cpp:83-102; Perspective(fov, 1e-2, 1000), perspective.cpp:44
+    Transform CameraToScreen = Perspective(fov, 1e-2f, 1000.f);
+    Transform ScreenToRaster = Scale(float(film->xResolution), float(film->yResolution), 1.f) *
+                               Scale(1.f / (screenWindow[1] - screenWindow[0]),
+                                     1.f / (screenWindow[2] - screenWindow[3]), 1.f) *
+                               Translate(V3(-screenWindow[0], -screenWindow[3], 0.f));
+    Transform RasterToScreen = Inverse(ScreenToRaster);
+    RasterToCamera = Inverse(CameraToScreen) * RasterToScreen;
+}
+
+// ------------------------------------------------------------------ Flatten --
+bool Scene::Flatten(std::string *err) {
+    const GpuBVHAccel &bvh = *aggregate;
+    std::map<const Transform *, uint32_t> xformIndex;
+    auto xformOf = [&](const Transform *t) -> uint32_t {
+        auto it = xformIndex.find(t);
+        if (it != xformIndex.end()) return it->second;
+        PbrtGpuXform x;
+        memcpy(x.m, t->m.m, sizeof(x.m));
+        memcpy(x.mInv, t->mInv.m, sizeof(x.mInv));
+        fXforms.push_back(x);
+        xformIndex[t] = (uint32_t)fXforms.size() - 1;
+        return (uint32_t)fXforms.size() - 1;
+    };
+    auto shapeFlags = [](const Shape *s) -> uint32_t {
+        return (s->ReverseOrientation ? PBRTGPU_SHAPE_REVERSE_ORIENT : 0u) |
+               (s->TransformSwapsHandedness ? PBRTGPU_SHAPE_SWAPS_HANDED : 0u);
+    };
+    std::map<const Shape *, uint32_t> meshIndex, quadricIndex;
+    std::map<std::pair<const Shape *, int>, uint32_t> triIndex;
+    hasN = hasUV = false;
+    // first pass: which optional vertex streams exist at all
+    for (const RefinedPrim &rp : bvh.primitives)
+        if (rp.type == PBRTGPU_PRIM_TRIANGLE) {
+            const TriangleMesh *m = static_cast<const TriangleMesh *>(rp.shape);
+            if (!m->n.empty()) hasN = true;
+            if (!m->uvs.empty()) hasUV = true;
+        }
+    auto meshOf = [&](const TriangleMesh *m) -> uint32_t {
+        auto it = meshIndex.find(m);
+        if (it != meshIndex.end()) return it->second;
+        PbrtGpuMesh gm;
+        gm.flags = shapeFlags(m) | (m->n.empty() ? 0u : PBRTGPU_MESH_HAS_N) | (m->uvs.empty() ? 0u : PBRTGPU_MESH_HAS_UV);
+        gm.xform = xformOf(m->ObjectToWorld);
+        gm.firstVertex = (uint32_t)(fP.size() / 3);
+        gm.nVertices = (uint32_t)m->nverts;
+        for (int i = 0; i < m->nverts; ++i) {
+            fP.push_back(m->p[i].x); fP.push_back(m->p[i].y); fP.push_back(m->p[i].z);
+            if (hasN) {
+                V3 nn = m->n.empty() ? V3(0, 0, 0) : m->n[i];
+                fN.push_back(nn.x); fN.push_back(nn.y); fN.push_back(nn.z);
+            }
+            if (hasUV) {
+                fUV.push_back(m->uvs.empty() ? 0.f : m->uvs[2 * i]);
+                fUV.push_back(m->uvs.empty() ? 0.f : m->uvs[2 * i + 1]);
+            }
+        }
+        fMeshes.push_back(gm);
+        meshIndex[m] = (uint32_t)fMeshes.size() - 1;
+        return (uint32_t)fMeshes.size() - 1;
+    };
+    auto quadricOf = [&](const Shape *s) -> uint32_t {
+        auto it = quadricIndex.find(s);
+        if (it != quadricIndex.end()) return it->second;
+        PbrtGpuQuadric q;
+        memset(&q, 0, sizeof(q));
+        q.flags = shapeFlags(s);
+        q.xform = xformOf(s->ObjectToWorld);
+        if (s->kind == Shape::SPHERE) {
+            const Sphere *sp = static_cast<const Sphere *>(s);
+            q.type = PBRTGPU_PRIM_SPHERE;
+            q.radius = sp->radius; q.zmin = sp->zmin; q.zmax = sp->zmax;
+            q.thetaMin = sp->thetaMin; q.thetaMax = sp->thetaMax; q.phiMax = sp->phiMax;
+        } else {
+            const Disk *d = static_cast<const Disk *>(s);
+            q.type = PBRTGPU_PRIM_DISK;
+            q.radius = d->radius; q.height = d->height; q.innerRadius = d->innerRadius; q.phiMax = d->phiMax;
+        }
+        q.area = s->Area();
+        fQuadrics.push_back(q);
+        quadricIndex[s] = (uint32_t)fQuadrics.size() - 1;
+        return (uint32_t)fQuadrics.size() - 1;
+    };
+
+    fPrims.reserve(bvh.primitives.size());
+    for (const RefinedPrim &rp : bvh.primitives) {
+        PbrtGpuPrimitive gp;
+        gp.type = rp.type;
+        gp.material = rp.material;
+        gp.areaLight = rp.areaLight;
+        if (rp.type == PBRTGPU_PRIM_TRIANGLE) {
+            const TriangleMesh *m = static_cast<const TriangleMesh *>(rp.shape);
+            uint32_t mi = meshOf(m);
+            PbrtGpuTriangle t;
+            uint32_t base = fMeshes[mi].firstVertex;
+            t.v[0] = base + (uint32_t)m->vertexIndex[3 * rp.tri];
+            t.v[1] = base + (uint32_t)m->vertexIndex[3 * rp.tri + 1];
+            t.v[2] = base + (uint32_t)m->vertexIndex[3 * rp.tri + 2];
+            t.mesh = mi;
+            fTris.push_back(t);
+            gp.index = (uint32_t)fTris.size() - 1;
+        } else {
+            gp.index = quadricOf(rp.shape);
+        }
+        fPrims.push_back(gp);
+    }
+    for (const Material &m : materials) fMaterials.push_back(m.desc);
+    for (const MeasuredData &md : measured) {
+        PbrtGpuMeasured gm;
+        gm.firstNode = (uint32_t)fKdNodes.size();
+        gm.nNodes = (uint32_t)md.nodes.size();
+        fKdNodes.insert(fKdNodes.end(), md.nodes.begin(), md.nodes.end());
+        fKdData.insert(fKdData.end(), md.data.begin(), md.data.end());
+        fMeasured.push_back(gm);
+    }
+    for (const Light &l : lights) {
+        PbrtGpuLight gl = l.desc;
+        if (gl.type == PBRTGPU_LIGHT_DIFFUSE_AREA) {
+            // ShapeSet (core/light.cpp:114-139) over one intersectable shape
+            PbrtGpuLightShape ls;
+            ls.type = l.shape->kind == Shape::SPHERE ? PBRTGPU_PRIM_SPHERE : PBRTGPU_PRIM_DISK;
+            ls.index = quadricOf(l.shape);
+            ls.area = l.shape->Area();
+            gl.firstShape = (uint32_t)fLightShapes.size();
+            gl.nShapes = 1;
+            float sumArea = 0.f;
+            sumArea += ls.area;
+            gl.sumArea = sumArea;
+            fLightShapes.push_back(ls);
+        }
+        fLights.push_back(gl);
+    }
+    if (bvh.nodes.empty()) { *err = "scene has no primitives"; return false; }
+
+    memset(&desc, 0, sizeof(desc));
+    desc.nNodes = (uint32_t)bvh.nodes.size();         desc.nodes = bvh.nodes.data();
+    desc.nPrimitives = (uint32_t)fPrims.size();       desc.primitives = fPrims.data();
+    desc.nTriangles = (uint32_t)fTris.size();         desc.triangles = fTris.data();
+    desc.nMeshes = (uint32_t)fMeshes.size();          desc.meshes = fMeshes.data();
+    desc.nVertices = (uint32_t)(fP.size() / 3);       desc.P = fP.data();
+    desc.N = hasN ? fN.data() : nullptr;
+    desc.uv = hasUV ? fUV.data() : nullptr;
+    desc.nQuadrics = (uint32_t)fQuadrics.size();      desc.quadrics = fQuadrics.data();
+    desc.nXforms = (uint32_t)fXforms.size();          desc.xforms = fXforms.data();
+    desc.nMaterials = (uint32_t)fMaterials.size();    desc.materials = fMaterials.data();
+    desc.nMeasured = (uint32_t)fMeasured.size();      desc.measured = fMeasured.data();
+    desc.nKdNodes = (uint32_t)fKdNodes.size();        desc.kdNodes = fKdNodes.data();
+    desc.kdData = fKdData.data();
+    desc.nLights = (uint32_t)fLights.size();          desc.lights = fLights.data();
+    desc.nLightShapes = (uint32_t)fLightShapes.size(); desc.lightShapes = fLightShapes.data();
+    return true;
+}
+
+// ------------------------------------------------------- GpuSamplerRenderer --
+static int NumSystemCores(int nCores) {   // core/parallel.cpp:878-886
+    if (nCores > 0) return nCores;
+    unsigned n = std::thread::hardware_concurrency();
+    return n ? (int)n : 1;
+}
+
+int GpuSamplerRenderer::TaskCount() const {   // samplerrenderer.cpp:203-205
+    int nPixels = film->xResolution * film->yResolution;
+    int nTasks = std::max(32 * NumSystemCores(nCores), nPixels / (16 * 16));
+    uint32_t v = (uint32_t)nTasks;
+    v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; v++;
+    return (int)v;
+}
+
+void GpuSamplerRenderer::FillRenderDesc(PbrtGpuRenderDesc *rd) const {
+    memset(rd, 0, sizeof(*rd));
+    memcpy(rd->rasterToCamera, camera->RasterToCamera.m.m, sizeof(rd->rasterToCamera));
+    memcpy(rd->cameraToWorld, camera->CameraToWorld.m.m, sizeof(rd->cameraToWorld));
+    rd->lensRadius = camera->lensRadius;
+    rd->focalDistance = camera->focalDistance;
+    rd->shutterOpen = camera->shutterOpen;
+    rd->shutterClose = camera->shutterClose;
+    rd->xResolution = film->xResolution;
+    rd->yResolution = film->yResolution;
+    memcpy(rd->cropWindow, film->cropWindow, sizeof(rd->cropWindow));
+    rd->filterXWidth = film->filterXWidth;
+    rd->filterYWidth = film->filterYWidth;
+    rd->samplesPerPixel = sampler.samplesPerPixel;
+    rd->maxDepth = surfaceIntegrator->maxDepth;
+    rd->nTasks = TaskCount();
+    rd->taskBegin = 0;
+    rd->taskEnd = rd->nTasks;
+}
+
+}  // namespace pb

@@ -1,0 +1,94 @@
+"""Scene fixtures for the BASELINE.json configs.
+
+The reference's example scenes (scenes/killeroo-simple.pbrt, scenes/bunny.pbrt,
+geometry/*.pbrt, brdfs/mystique.brdf) are INPUT DATA, not source code.  They are
+not committed: `stage()` copies them from the read-only reference checkout into
+`scenes/_staged/` (git-ignored, but shipped to the GPU box by gpurun together
+with the built .so files) and `variant()` derives the per-config scene files
+SURVEY.md section 8(d) specifies (resolution, pixelsamples, SurfaceIntegrator
+"path", .pfm output, optional crop window).
+"""
+import os
+import re
+import shutil
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED = os.path.join(REPO, "scenes", "_staged")
+REFERENCE = os.environ.get("PBRT_REFERENCE", "/root/reference")
+
+_FILES = [
+    "killeroo-simple.pbrt",
+    "bunny.pbrt",
+    "anim-killeroos-moving.pbrt",
+    "geometry/killeroo.pbrt",
+    "geometry/bunny.pbrt",
+    "brdfs/mystique.brdf",
+]
+
+
+def stage(reference_root=REFERENCE):
+    """Copy the fixture scenes out of the reference checkout (no-op if absent)."""
+    src_root = os.path.join(reference_root, "scenes")
+    if not os.path.isdir(src_root):
+        return False
+    for rel in _FILES:
+        dst = os.path.join(STAGED, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if not os.path.exists(dst):
+            shutil.copyfile(os.path.join(src_root, rel), dst)
+            os.chmod(dst, 0o644)
+    return True
+
+
+def have_staged():
+    return all(os.path.exists(os.path.join(STAGED, f)) for f in _FILES)
+
+
+def _film(xres, yres, filename, crop):
+    s = ('Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\n'
+         '    "string filename" "%s"\n' % (xres, yres, filename))
+    if crop is not None:
+        s += '    "float cropwindow" [%r %r %r %r]\n' % tuple(float(c) for c in crop)
+    return s
+
+
+def variant(base, out_path, xres, yres, spp, integrator="path", maxdepth=None,
+            crop=None, filename=None, nlevels=None):
+    """Write a config variant of staged scene `base` ('killeroo-simple' | 'bunny').
+
+    The variant lives next to the staged base so that relative Include /
+    filename paths (geometry/..., brdfs/...) keep resolving.  Returns out_path.
+    """
+    src = os.path.join(STAGED, base + ".pbrt")
+    text = open(src).read()
+    if filename is None:
+        filename = os.path.splitext(os.path.basename(out_path))[0] + ".pfm"
+    integ = 'SurfaceIntegrator "%s"' % integrator
+    if maxdepth is not None:
+        integ += ' "integer maxdepth" [%d]' % maxdepth
+    sampler = 'Sampler "lowdiscrepancy" "integer pixelsamples" [%d]' % spp
+    # drop the Film / Sampler / SurfaceIntegrator directives (incl. their
+    # continuation lines) and re-emit ours in front of WorldBegin
+    lines = text.split("\n")
+    out, skipping = [], False
+    for ln in lines:
+        st = ln.strip()
+        if re.match(r'^(Film|Sampler|SurfaceIntegrator)\b', st):
+            skipping = True
+            continue
+        if skipping and (st.startswith('"') or st == ""):
+            continue
+        skipping = False
+        if st.startswith("WorldBegin"):
+            out.append(_film(xres, yres, filename, crop))
+            out.append(sampler)
+            out.append(integ)
+        out.append(ln)
+    text = "\n".join(out)
+    if nlevels is not None:
+        raise NotImplementedError("nlevels override needs a geometry copy")
+    assert os.path.dirname(os.path.abspath(out_path)) == STAGED, \
+        "variants must live in scenes/_staged so relative includes resolve"
+    with open(out_path, "w") as f:
+        f.write(text)
+    return out_path
