@@ -1,0 +1,313 @@
+// dscene.cuh -- device-resident scene layout and the ray/primitive kernels'
+// building blocks: BVHAccel::Intersect / IntersectP traversal and the
+// Triangle / Sphere / Disk intersection tests.
+//
+// HBM layout (all read-only, loaded through the non-coherent path):
+//   nodes   2 x float4 per node  = the reference's 32-byte LinearBVHNode
+//           (accelerators/bvh.cpp:113-123): {bmin.xyz, bmax.x} {bmax.yz, offset, nPrims|axis<<8}
+//           -> two 128-bit loads per node visit.
+//   prims   3 x float4 per primitive in BVH leaf order = 48 bytes, the same
+//           "12 B indices + 36 B positions" the reference touches per triangle
+//           test (trianglemesh.cpp:133-135) but pre-gathered, so a leaf test is
+//           three coalescable 128-bit loads instead of index -> vertex chasing:
+//           {p1.xyz, type} {p2.xyz, index} {p3.xyz, material | (areaLight+1)<<16}
+//   everything else (normals, uvs, quadrics, materials, kd-tree, lights) is
+//   touched only when a hit is shaded and stays in the PbrtGpu* POD form.
+#pragma once
+#include "dmath.cuh"
+#include "../../../include/pbrtgpu.h"
+
+namespace dev {
+
+struct DScene {
+    const float4 *nodes;
+    const float4 *prims;
+    const uint4 *tris;
+    const PbrtGpuMesh *meshes;
+    const float *N;
+    const float *uv;
+    const PbrtGpuQuadric *quadrics;
+    const PbrtGpuXform *xforms;
+    const PbrtGpuMaterial *materials;
+    const PbrtGpuMeasured *measured;
+    const PbrtGpuKdNode *kdNodes;
+    const PbrtGpuBrdfSample *kdData;
+    const PbrtGpuLight *lights;
+    const PbrtGpuLightShape *lightShapes;
+    uint32_t nNodes, nPrims, nLights;
+};
+
+struct Ray {
+    V3 o, d;
+    float mint, maxt;
+};
+DEV V3 RayAt(const Ray &r, float t) { return r.o + r.d * t; }   // geometry.h:333
+
+struct DiffGeom {   // core/diffgeom.h (texture differentials omitted)
+    V3 p, nn, dpdu, dpdv;
+    float u, v;
+};
+// DifferentialGeometry ctor, core/diffgeom.cpp:40-55
+DEV void InitDG(DiffGeom *dg, const V3 &P, const V3 &DPDU, const V3 &DPDV, float uu, float vv, uint32_t shapeFlags) {
+    dg->p = P; dg->dpdu = DPDU; dg->dpdv = DPDV;
+    dg->nn = Normalize(Cross(DPDU, DPDV));
+    dg->u = uu; dg->v = vv;
+    bool ro = (shapeFlags & PBRTGPU_SHAPE_REVERSE_ORIENT) != 0, sh = (shapeFlags & PBRTGPU_SHAPE_SWAPS_HANDED) != 0;
+    if (ro != sh) dg->nn = dg->nn * -1.f;
+}
+
+struct Hit {
+    int prim;        // index into prims / -1
+    float t;         // == ray.maxt after traversal
+    float b1, b2;    // triangle barycentrics
+    float maxtIn;    // ray.maxt at the moment the winning primitive was tested (quadric dg replay)
+};
+
+// ---- Triangle::Intersect core, shapes/trianglemesh.cpp:127-165 / :211-243 ------
+DEV bool TriTest(const V3 &p1, const V3 &p2, const V3 &p3, const Ray &ray, float *tOut, float *b1Out, float *b2Out) {
+    V3 e1 = p2 - p1;
+    V3 e2 = p3 - p1;
+    V3 s1 = Cross(ray.d, e2);
+    float divisor = Dot(s1, e1);
+    if (divisor == 0.f) return false;
+    float invDivisor = 1.f / divisor;
+    V3 s = ray.o - p1;
+    float b1 = Dot(s, s1) * invDivisor;
+    if (b1 < 0.f || b1 > 1.f) return false;
+    V3 s2 = Cross(s, e1);
+    float b2 = Dot(ray.d, s2) * invDivisor;
+    if (b2 < 0.f || b1 + b2 > 1.f) return false;
+    float t = Dot(e2, s2) * invDivisor;
+    if (t < ray.mint || t > ray.maxt) return false;
+    *tOut = t; *b1Out = b1; *b2Out = b2;
+    return true;
+}
+
+DEV void GetUVs(const DScene &sc, const uint4 &tri, bool hasUV, float uv[3][2]) {   // trianglemesh.h:86-101
+    if (hasUV) {
+        uv[0][0] = __ldg(sc.uv + 2 * tri.x); uv[0][1] = __ldg(sc.uv + 2 * tri.x + 1);
+        uv[1][0] = __ldg(sc.uv + 2 * tri.y); uv[1][1] = __ldg(sc.uv + 2 * tri.y + 1);
+        uv[2][0] = __ldg(sc.uv + 2 * tri.z); uv[2][1] = __ldg(sc.uv + 2 * tri.z + 1);
+    } else {
+        uv[0][0] = 0.f; uv[0][1] = 0.f; uv[1][0] = 1.f; uv[1][1] = 0.f; uv[2][0] = 1.f; uv[2][1] = 1.f;
+    }
+}
+
+// the rest of Triangle::Intersect (dpdu/dpdv, (u,v), DifferentialGeometry), trianglemesh.cpp:167-205
+DEV void TriDG(const DScene &sc, const uint4 &tri, const V3 &p1, const V3 &p2, const V3 &p3, const Ray &ray, float t,
+               float b1, float b2, DiffGeom *dg) {
+    const uint32_t mflags = sc.meshes[tri.w].flags;
+    V3 e1 = p2 - p1, e2 = p3 - p1;
+    V3 dpdu, dpdv;
+    float uvs[3][2];
+    GetUVs(sc, tri, (mflags & PBRTGPU_MESH_HAS_UV) != 0, uvs);
+    float du1 = uvs[0][0] - uvs[2][0];
+    float du2 = uvs[1][0] - uvs[2][0];
+    float dv1 = uvs[0][1] - uvs[2][1];
+    float dv2 = uvs[1][1] - uvs[2][1];
+    V3 dp1 = p1 - p3, dp2 = p2 - p3;
+    float determinant = du1 * dv2 - dv1 * du2;
+    if (determinant == 0.f) {
+        CoordinateSystem(Normalize(Cross(e2, e1)), &dpdu, &dpdv);
+    } else {
+        float invdet = 1.f / determinant;
+        dpdu = (dv2 * dp1 - dv1 * dp2) * invdet;
+        dpdv = (-du2 * dp1 + du1 * dp2) * invdet;
+    }
+    float b0 = 1 - b1 - b2;
+    float tu = b0 * uvs[0][0] + b1 * uvs[1][0] + b2 * uvs[2][0];
+    float tv = b0 * uvs[0][1] + b1 * uvs[1][1] + b2 * uvs[2][1];
+    InitDG(dg, RayAt(ray, t), dpdu, dpdv, tu, tv, mflags);
+}
+
+// ---- Sphere::Intersect / IntersectP, shapes/sphere.cpp:58-209 -------------------
+DEV bool SphereIntersect(const DScene &sc, const PbrtGpuQuadric &q, const Ray &r, float *tHit, DiffGeom *dg) {
+    const PbrtGpuXform &x = sc.xforms[q.xform];
+    Ray ray;
+    ray.o = XfPoint(x.mInv, r.o); ray.d = XfVector(x.mInv, r.d);
+    ray.mint = r.mint; ray.maxt = r.maxt;
+    const float radius = q.radius, zmin = q.zmin, zmax = q.zmax, phiMax = q.phiMax;
+    float A = ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z;
+    float B = 2 * (ray.d.x * ray.o.x + ray.d.y * ray.o.y + ray.d.z * ray.o.z);
+    float C = ray.o.x * ray.o.x + ray.o.y * ray.o.y + ray.o.z * ray.o.z - radius * radius;
+    float t0, t1;
+    if (!Quadratic(A, B, C, &t0, &t1)) return false;
+    if (t0 > ray.maxt || t1 < ray.mint) return false;
+    float thit = t0;
+    if (t0 < ray.mint) {
+        thit = t1;
+        if (thit > ray.maxt) return false;
+    }
+    V3 phit = RayAt(ray, thit);
+    if (phit.x == 0.f && phit.y == 0.f) phit.x = 1e-5f * radius;
+    float phi = ref_atan2f(phit.y, phit.x);
+    if (phi < 0.f) phi += 2.f * PI_F;
+    if ((zmin > -radius && phit.z < zmin) || (zmax < radius && phit.z > zmax) || phi > phiMax) {
+        if (thit == t1) return false;
+        if (t1 > ray.maxt) return false;
+        thit = t1;
+        phit = RayAt(ray, thit);
+        if (phit.x == 0.f && phit.y == 0.f) phit.x = 1e-5f * radius;
+        phi = ref_atan2f(phit.y, phit.x);
+        if (phi < 0.f) phi += 2.f * PI_F;
+        if ((zmin > -radius && phit.z < zmin) || (zmax < radius && phit.z > zmax) || phi > phiMax) return false;
+    }
+    if (dg) {
+        float u = phi / phiMax;
+        float theta = ref_acosf(Clampf(phit.z / radius, -1.f, 1.f));
+        float v = (theta - q.thetaMin) / (q.thetaMax - q.thetaMin);
+        float zradius = sqrtf(phit.x * phit.x + phit.y * phit.y);
+        float invzradius = 1.f / zradius;
+        float cosphi = phit.x * invzradius;
+        float sinphi = phit.y * invzradius;
+        V3 dpdu(-phiMax * phit.y, phiMax * phit.x, 0);
+        V3 dpdv = (q.thetaMax - q.thetaMin) * V3(phit.z * cosphi, phit.z * sinphi, -radius * ref_sinf(theta));
+        InitDG(dg, XfPoint(x.m, phit), XfVector(x.m, dpdu), XfVector(x.m, dpdv), u, v, q.flags);
+    }
+    *tHit = thit;
+    return true;
+}
+
+// ---- Disk::Intersect / IntersectP, shapes/disk.cpp:56-130 -----------------------
+DEV bool DiskIntersect(const DScene &sc, const PbrtGpuQuadric &q, const Ray &r, float *tHit, DiffGeom *dg) {
+    const PbrtGpuXform &x = sc.xforms[q.xform];
+    Ray ray;
+    ray.o = XfPoint(x.mInv, r.o); ray.d = XfVector(x.mInv, r.d);
+    ray.mint = r.mint; ray.maxt = r.maxt;
+    if ((double)fabsf(ray.d.z) < 1e-7) return false;   // double compare, disk.cpp:62
+    float thit = (q.height - ray.o.z) / ray.d.z;
+    if (thit < ray.mint || thit > ray.maxt) return false;
+    V3 phit = RayAt(ray, thit);
+    float dist2 = phit.x * phit.x + phit.y * phit.y;
+    if (dist2 > q.radius * q.radius || dist2 < q.innerRadius * q.innerRadius) return false;
+    float phi = ref_atan2f(phit.y, phit.x);
+    if (phi < 0) phi = (float)((double)phi + 2. * (double)PI_F);   // double arithmetic, disk.cpp:77
+    if (phi > q.phiMax) return false;
+    if (dg) {
+        float u = phi / q.phiMax;
+        float R = sqrtf(dist2);
+        float oneMinusV = ((R - q.innerRadius) / (q.radius - q.innerRadius));
+        float v = 1.f - oneMinusV;
+        V3 dpdu(-q.phiMax * phit.y, q.phiMax * phit.x, 0.f);
+        V3 dpdv(phit.x, phit.y, 0.f);
+        dpdv = dpdv * ((q.radius - q.innerRadius) / R);
+        InitDG(dg, XfPoint(x.m, phit), XfVector(x.m, dpdu), XfVector(x.m, dpdv), u, v, q.flags);
+    }
+    *tHit = thit;
+    return true;
+}
+
+DEV bool QuadricIntersect(const DScene &sc, const PbrtGpuQuadric &q, const Ray &r, float *tHit, DiffGeom *dg) {
+    return q.type == PBRTGPU_PRIM_SPHERE ? SphereIntersect(sc, q, r, tHit, dg) : DiskIntersect(sc, q, r, tHit, dg);
+}
+
+// ---- BVH traversal ---------------------------------------------------------------
+// One loop serves BVHAccel::Intersect (bvh.cpp:403-454) and IntersectP
+// (:457-503): same node order (near child first by dirIsNeg[axis]), same strict
+// slab comparisons (:126-148), same in-place shrinking of ray.maxt; `anyHit`
+// only adds the early return.  Statistics are optional (null pointers = off).
+struct TraceStats {
+    unsigned long long nodes, prims;
+};
+
+DEV bool BoxTest(const float4 &n0, const float4 &n1, const Ray &ray, const V3 &invDir, const bool neg[3]) {
+    // n0 = {bmin.x, bmin.y, bmin.z, bmax.x}, n1 = {bmax.y, bmax.z, offset, meta}
+    float tmin = ((neg[0] ? n0.w : n0.x) - ray.o.x) * invDir.x;
+    float tmax = ((neg[0] ? n0.x : n0.w) - ray.o.x) * invDir.x;
+    float tymin = ((neg[1] ? n1.x : n0.y) - ray.o.y) * invDir.y;
+    float tymax = ((neg[1] ? n0.y : n1.x) - ray.o.y) * invDir.y;
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = ((neg[2] ? n1.y : n0.z) - ray.o.z) * invDir.z;
+    float tzmax = ((neg[2] ? n0.z : n1.y) - ray.o.z) * invDir.z;
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) tmax = tzmax;
+    return (tmin < ray.maxt) && (tmax > ray.mint);
+}
+
+template <bool STATS>
+DEV bool Traverse(const DScene &sc, Ray &ray, bool anyHit, Hit *hit, TraceStats *st) {
+    hit->prim = -1;
+    V3 invDir(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+    bool neg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
+    uint32_t todo[64];
+    uint32_t todoOffset = 0, nodeNum = 0;
+    bool found = false;
+    while (true) {
+        const float4 n0 = __ldg(sc.nodes + 2 * nodeNum);
+        const float4 n1 = __ldg(sc.nodes + 2 * nodeNum + 1);
+        if (STATS) st->nodes++;
+        if (BoxTest(n0, n1, ray, invDir, neg)) {
+            const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
+            const uint32_t nPrims = meta & 0xffu;
+            if (nPrims > 0) {
+                for (uint32_t i = 0; i < nPrims; ++i) {
+                    const uint32_t pi = offset + i;
+                    const float4 r0 = __ldg(sc.prims + 3 * pi);
+                    const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
+                    const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
+                    if (STATS) st->prims++;
+                    const uint32_t type = __float_as_uint(r0.w);
+                    float t, b1 = 0.f, b2 = 0.f;
+                    bool h;
+                    if (type == PBRTGPU_PRIM_TRIANGLE)
+                        h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), ray, &t, &b1, &b2);
+                    else
+                        h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], ray, &t, nullptr);
+                    if (h) {
+                        if (anyHit) { hit->prim = (int)pi; return true; }
+                        hit->prim = (int)pi; hit->b1 = b1; hit->b2 = b2; hit->maxtIn = ray.maxt;
+                        ray.maxt = t;   // GeometricPrimitive::Intersect, primitive.cpp:175
+                        found = true;
+                    }
+                }
+                if (todoOffset == 0) break;
+                nodeNum = todo[--todoOffset];
+            } else {
+                const uint32_t axis = (meta >> 8) & 0xffu;
+                if (neg[axis]) {
+                    todo[todoOffset++] = nodeNum + 1;
+                    nodeNum = offset;
+                } else {
+                    todo[todoOffset++] = offset;
+                    nodeNum = nodeNum + 1;
+                }
+            }
+        } else {
+            if (todoOffset == 0) break;
+            nodeNum = todo[--todoOffset];
+        }
+    }
+    hit->t = ray.maxt;
+    return found;
+}
+
+// Re-derive the winning primitive's DifferentialGeometry (what Shape::Intersect
+// filled in at the moment the hit was accepted) and its rayEpsilon.
+DEV void HitGeometry(const DScene &sc, const Ray &rayIn, const Hit &hit, DiffGeom *dg, float *rayEpsilon,
+                     int *material, int *areaLight, uint4 *triOut, uint32_t *primType) {
+    const float4 r0 = __ldg(sc.prims + 3 * hit.prim);
+    const float4 r1 = __ldg(sc.prims + 3 * hit.prim + 1);
+    const float4 r2 = __ldg(sc.prims + 3 * hit.prim + 2);
+    const uint32_t type = __float_as_uint(r0.w), index = __float_as_uint(r1.w), ml = __float_as_uint(r2.w);
+    *material = (int)(ml & 0xffffu);
+    *areaLight = (int)(ml >> 16) - 1;
+    *primType = type;
+    if (type == PBRTGPU_PRIM_TRIANGLE) {
+        const uint4 tri = __ldg(sc.tris + index);
+        *triOut = tri;
+        TriDG(sc, tri, V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), rayIn, hit.t, hit.b1, hit.b2, dg);
+        *rayEpsilon = 1e-3f * hit.t;   // trianglemesh.cpp:206
+    } else {
+        Ray r = rayIn;
+        r.maxt = hit.maxtIn;
+        float t;
+        QuadricIntersect(sc, sc.quadrics[index], r, &t, dg);
+        *rayEpsilon = 5e-4f * t;       // sphere.cpp:143, disk.cpp:100
+        *triOut = make_uint4(0, 0, 0, 0);
+    }
+}
+
+}  // namespace dev

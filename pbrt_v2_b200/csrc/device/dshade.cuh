@@ -1,0 +1,485 @@
+// dshade.cuh -- device-side BSDF / light / sampling routines of the path
+// integrator.  Branch-flattened restatements of the reference's virtual-call
+// hierarchy: a BSDF here is {shading frame, material id}; its (at most two)
+// BxDFs are implied by the material type instead of being arena-allocated
+// objects (materials/{matte,plastic,measured}.cpp, core/reflection.{h,cpp}).
+#pragma once
+#include "dscene.cuh"
+
+namespace dev {
+
+enum {
+    BSDF_REFLECTION = 1 << 0, BSDF_TRANSMISSION = 1 << 1, BSDF_DIFFUSE = 1 << 2, BSDF_GLOSSY = 1 << 3,
+    BSDF_SPECULAR = 1 << 4,
+    BSDF_ALL_TYPES = BSDF_DIFFUSE | BSDF_GLOSSY | BSDF_SPECULAR,
+    BSDF_ALL_REFLECTION = BSDF_REFLECTION | BSDF_ALL_TYPES,
+    BSDF_ALL_TRANSMISSION = BSDF_TRANSMISSION | BSDF_ALL_TYPES,
+    BSDF_ALL = BSDF_ALL_REFLECTION | BSDF_ALL_TRANSMISSION
+};
+enum { BX_LAMBERTIAN = 0, BX_MICROFACET_BLINN = 1, BX_IRREG_ISO = 2 };
+
+DEV float CosTheta(const V3 &w) { return w.z; }
+DEV float AbsCosTheta(const V3 &w) { return fabsf(w.z); }
+DEV float SinTheta2(const V3 &w) { return maxf(0.f, 1.f - CosTheta(w) * CosTheta(w)); }
+DEV float SinTheta(const V3 &w) { return sqrtf(SinTheta2(w)); }
+DEV bool SameHemisphere(const V3 &w, const V3 &wp) { return w.z * wp.z > 0.f; }
+DEV float SphericalPhi(const V3 &v) {   // geometry.h:644-647
+    float p = ref_atan2f(v.y, v.x);
+    return (p < 0.f) ? p + 2.f * PI_F : p;
+}
+DEV V3 SphericalDirection(float sintheta, float costheta, float phi) {
+    return V3(sintheta * ref_cosf(phi), sintheta * ref_sinf(phi), costheta);
+}
+
+DEV void ConcentricSampleDisk(float u1, float u2, float *dx, float *dy) {   // core/montecarlo.cpp:306-348
+    float r, theta;
+    float sx = 2 * u1 - 1;
+    float sy = 2 * u2 - 1;
+    if (sx == 0.f && sy == 0.f) { *dx = 0.f; *dy = 0.f; return; }
+    if (sx >= -sy) {
+        if (sx > sy) {
+            r = sx;
+            if (sy > 0.f) theta = sy / r;
+            else theta = 8.0f + sy / r;
+        } else {
+            r = sy;
+            theta = 2.0f - sx / r;
+        }
+    } else {
+        if (sx <= sy) {
+            r = -sx;
+            theta = 4.0f - sy / r;
+        } else {
+            r = -sy;
+            theta = 6.0f + sx / r;
+        }
+    }
+    theta *= PI_F / 4.f;
+    *dx = r * ref_cosf(theta);
+    *dy = r * ref_sinf(theta);
+}
+DEV V3 CosineSampleHemisphere(float u1, float u2) {   // montecarlo.h:128-133
+    V3 ret;
+    ConcentricSampleDisk(u1, u2, &ret.x, &ret.y);
+    ret.z = sqrtf(maxf(0.f, 1.f - ret.x * ret.x - ret.y * ret.y));
+    return ret;
+}
+DEV V3 UniformSampleSphere(float u1, float u2) {   // montecarlo.cpp:283-290
+    float z = 1.f - 2.f * u1;
+    float r = sqrtf(maxf(0.f, 1.f - z * z));
+    float phi = 2.f * PI_F * u2;
+    return V3(r * ref_cosf(phi), r * ref_sinf(phi), z);
+}
+DEV float UniformConePdf(float cosThetaMax) { return 1.f / (2.f * PI_F * (1.f - cosThetaMax)); }
+DEV V3 UniformSampleCone(float u1, float u2, float costhetamax, const V3 &x, const V3 &y, const V3 &z) {
+    float costheta = Lerp(u1, costhetamax, 1.f);   // montecarlo.cpp:423-430
+    float sintheta = sqrtf(1.f - costheta * costheta);
+    float phi = u2 * 2.f * PI_F;
+    return ref_cosf(phi) * sintheta * x + ref_sinf(phi) * sintheta * y + costheta * z;
+}
+DEV float PowerHeuristic(int nf, float fPdf, int ng, float gPdf) {   // montecarlo.h:266-269
+    float f = nf * fPdf, g = ng * gPdf;
+    return (f * f) / (f * f + g * g);
+}
+
+// ---- the shaded hit: Intersection + BSDF ------------------------------------------
+struct ShadeCtx {
+    V3 p;            // bsdf->dgShading.p
+    V3 nn, ng;       // shading / geometric normal
+    V3 sn, tn;       // shading tangents
+    V3 ngLe;         // isect.dg.nn (for Intersection::Le) == ng
+    int material;
+    int areaLight;
+    float rayEpsilon;
+};
+
+DEV V3 WorldToLocal(const ShadeCtx &c, const V3 &v) { return V3(Dot(v, c.sn), Dot(v, c.tn), Dot(v, c.nn)); }
+DEV V3 LocalToWorld(const ShadeCtx &c, const V3 &v) {
+    return V3(c.sn.x * v.x + c.tn.x * v.y + c.nn.x * v.z, c.sn.y * v.x + c.tn.y * v.y + c.nn.y * v.z,
+              c.sn.z * v.x + c.tn.z * v.y + c.nn.z * v.z);
+}
+
+// Intersection::GetBSDF -> GeometricPrimitive::GetBSDF -> Triangle::GetShadingGeometry
+// (shapes/trianglemesh.cpp:293-368) -> Material::GetBSDF -> BSDF ctor (reflection.cpp:601-609)
+DEV void BuildShadeCtx(const DScene &sc, const Ray &rayIn, const Hit &hit, ShadeCtx *c, unsigned long long *shadedN) {
+    DiffGeom dg;
+    uint4 tri;
+    uint32_t ptype;
+    HitGeometry(sc, rayIn, hit, &dg, &c->rayEpsilon, &c->material, &c->areaLight, &tri, &ptype);
+    c->ng = dg.nn;
+    DiffGeom dgs = dg;
+    if (ptype == PBRTGPU_PRIM_TRIANGLE) {
+        const PbrtGpuMesh mesh = sc.meshes[tri.w];
+        if (mesh.flags & PBRTGPU_MESH_HAS_N) {
+            if (shadedN) (*shadedN)++;
+            float b[3];
+            float uv[3][2];
+            GetUVs(sc, tri, (mesh.flags & PBRTGPU_MESH_HAS_UV) != 0, uv);
+            float A00 = uv[1][0] - uv[0][0], A01 = uv[2][0] - uv[0][0];
+            float A10 = uv[1][1] - uv[0][1], A11 = uv[2][1] - uv[0][1];
+            float C0 = dg.u - uv[0][0], C1 = dg.v - uv[0][1];
+            {   // SolveLinearSystem2x2, core/transform.cpp:40-50
+                float det = A00 * A11 - A01 * A10;
+                bool ok = !(fabsf(det) < 1e-10f);
+                if (ok) {
+                    b[1] = (A11 * C0 - A01 * C1) / det;
+                    b[2] = (A00 * C1 - A10 * C0) / det;
+                    if (isnan(b[1]) || isnan(b[2])) ok = false;
+                }
+                if (!ok) b[0] = b[1] = b[2] = 1.f / 3.f;
+                else b[0] = 1.f - b[1] - b[2];
+            }
+            const float *mInv = sc.xforms[mesh.xform].mInv;
+            V3 n0(__ldg(sc.N + 3 * tri.x), __ldg(sc.N + 3 * tri.x + 1), __ldg(sc.N + 3 * tri.x + 2));
+            V3 n1(__ldg(sc.N + 3 * tri.y), __ldg(sc.N + 3 * tri.y + 1), __ldg(sc.N + 3 * tri.y + 2));
+            V3 n2(__ldg(sc.N + 3 * tri.z), __ldg(sc.N + 3 * tri.z + 1), __ldg(sc.N + 3 * tri.z + 2));
+            V3 ns = Normalize(XfNormal(mInv, b[0] * n0 + b[1] * n1 + b[2] * n2));
+            V3 ss = Normalize(dg.dpdu);
+            V3 ts = Cross(ss, ns);
+            if (LengthSquared(ts) > 0.f) {
+                ts = Normalize(ts);
+                ss = Cross(ts, ns);
+            } else
+                CoordinateSystem(ns, &ss, &ts);
+            InitDG(&dgs, dg.p, ss, ts, dg.u, dg.v, mesh.flags);
+        }
+    }
+    c->p = dgs.p;
+    c->nn = dgs.nn;
+    c->sn = Normalize(dgs.dpdu);
+    c->tn = Cross(c->nn, c->sn);
+}
+
+// Intersection::Le + DiffuseAreaLight::L, core/intersection.cpp:61-64, lights/diffuse.h:51-53
+DEV Spec HitLe(const DScene &sc, int areaLight, const V3 &ngeom, const V3 &w) {
+    if (areaLight < 0) return Spec(0.f);
+    const PbrtGpuLight &l = sc.lights[areaLight];
+    return Dot(ngeom, w) > 0.f ? Spec(l.L[0], l.L[1], l.L[2]) : Spec(0.f);
+}
+
+// ---- BxDFs ----------------------------------------------------------------------
+struct BxSet {   // the BSDF's component list, implied by the material
+    int n;
+    int kind[2];
+    int type[2];
+    Spec R[2];
+    float exponent;
+    int measured;
+};
+DEV void MaterialBxDFs(const DScene &sc, int material, BxSet *s) {
+    const PbrtGpuMaterial &m = sc.materials[material];
+    s->n = 0;
+    s->exponent = 0.f;
+    s->measured = -1;
+    if (m.type == PBRTGPU_MAT_MATTE) {          // matte.cpp:42-63 (sigma == 0)
+        Spec r = Spec(m.Kd[0], m.Kd[1], m.Kd[2]).Clamp();
+        if (!r.IsBlack()) { s->kind[0] = BX_LAMBERTIAN; s->type[0] = BSDF_REFLECTION | BSDF_DIFFUSE; s->R[0] = r; s->n = 1; }
+    } else if (m.type == PBRTGPU_MAT_PLASTIC) { // plastic.cpp:42-66
+        Spec kd = Spec(m.Kd[0], m.Kd[1], m.Kd[2]).Clamp();
+        if (!kd.IsBlack()) { s->kind[0] = BX_LAMBERTIAN; s->type[0] = BSDF_REFLECTION | BSDF_DIFFUSE; s->R[0] = kd; s->n = 1; }
+        Spec ks = Spec(m.Ks[0], m.Ks[1], m.Ks[2]).Clamp();
+        if (!ks.IsBlack()) {
+            float e = 1.f / m.roughness;
+            if (e > 10000.f || isnan(e)) e = 10000.f;   // Blinn ctor, reflection.h:424-425
+            int i = s->n++;
+            s->kind[i] = BX_MICROFACET_BLINN; s->type[i] = BSDF_REFLECTION | BSDF_GLOSSY; s->R[i] = ks; s->exponent = e;
+        }
+    } else {                                     // measured.cpp:194-210
+        s->kind[0] = BX_IRREG_ISO; s->type[0] = BSDF_REFLECTION | BSDF_GLOSSY; s->R[0] = Spec(0.f); s->n = 1;
+        s->measured = m.measured;
+    }
+}
+DEV bool Matches(int type, int flags) { return (type & flags) == type; }
+
+DEV Spec FrDiel(float cosi, float cost, float etai, float etat) {   // reflection.cpp:60-67 (grey etas)
+    float Rparl = ((etat * cosi) - (etai * cost)) / ((etat * cosi) + (etai * cost));
+    float Rperp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
+    return Spec((Rparl * Rparl + Rperp * Rperp) / 2.f);
+}
+DEV Spec FresnelDielectric(float cosi, float eta_i, float eta_t) {   // reflection.cpp:115-135
+    cosi = Clampf(cosi, -1.f, 1.f);
+    bool entering = cosi > 0.f;
+    float ei = eta_i, et = eta_t;
+    if (!entering) { float t = ei; ei = et; et = t; }
+    float sint = ei / et * sqrtf(maxf(0.f, 1.f - cosi * cosi));
+    if (sint >= 1.f) return Spec(1.f);
+    float cost = sqrtf(maxf(0.f, 1.f - sint * sint));
+    return FrDiel(fabsf(cosi), cost, ei, et);
+}
+DEV float BlinnD(float exponent, const V3 &wh) {   // reflection.h:427-430
+    float costhetah = AbsCosTheta(wh);
+    return (exponent + 2) * INV_TWOPI_F * ref_powf(costhetah, exponent);
+}
+DEV float MicrofacetG(const V3 &wo, const V3 &wi, const V3 &wh) {   // reflection.h:403-410
+    float NdotWh = AbsCosTheta(wh);
+    float NdotWo = AbsCosTheta(wo);
+    float NdotWi = AbsCosTheta(wi);
+    float WOdotWh = AbsDot(wo, wh);
+    return minf(1.f, minf((2.f * NdotWh * NdotWo / WOdotWh), (2.f * NdotWh * NdotWi / WOdotWh)));
+}
+DEV V3 BRDFRemap(const V3 &wo, const V3 &wi) {   // reflection.cpp:247-256
+    float cosi = CosTheta(wi), coso = CosTheta(wo);
+    float sini = SinTheta(wi), sino = SinTheta(wo);
+    float phii = SphericalPhi(wi), phio = SphericalPhi(wo);
+    float dphi = phii - phio;
+    if (dphi < 0.f) dphi += 2.f * PI_F;
+    if (dphi > 2.f * PI_F) dphi -= 2.f * PI_F;
+    if (dphi > PI_F) dphi = 2.f * PI_F - dphi;
+    return V3(sini * sino, dphi / PI_F, cosi * coso);
+}
+
+// KdTree::Lookup with IrregIsoProc (core/kdtree.h:150-183, reflection.cpp:40-55).
+// The reference recurses "near child, far child, then this node"; the explicit
+// stack below visits nodes in exactly that order so the float accumulation of
+// weights matches bit for bit.
+DEV void KdGather(const DScene &sc, const PbrtGpuMeasured &m, const V3 &p, float maxDist2, Spec *vOut, float *sumW,
+                  int *nFound) {
+    Spec v(0.f);
+    float sumWeights = 0.f;
+    int found = 0;
+    uint32_t stack[40];
+    int sp = 0;
+    stack[sp++] = 0u;   // (node << 1) | visitedChildren
+    while (sp > 0) {
+        const uint32_t e = stack[--sp];
+        const uint32_t nodeNum = e >> 1;
+        if (!(e & 1u)) {
+            const PbrtGpuKdNode node = sc.kdNodes[m.firstNode + nodeNum];
+            const int axis = node.bits & 3u;
+            if (axis != 3) {
+                const uint32_t hasLeft = (node.bits >> 2) & 1u, rightChild = node.bits >> 3;
+                const float pa = p[axis];
+                const float dist2 = (pa - node.splitPos) * (pa - node.splitPos);
+                stack[sp++] = (nodeNum << 1) | 1u;
+                if (pa <= node.splitPos) {
+                    if (dist2 < maxDist2 && rightChild < m.nNodes) stack[sp++] = rightChild << 1;
+                    if (hasLeft) stack[sp++] = (nodeNum + 1) << 1;
+                } else {
+                    if (dist2 < maxDist2 && hasLeft) stack[sp++] = (nodeNum + 1) << 1;
+                    if (rightChild < m.nNodes) stack[sp++] = rightChild << 1;
+                }
+                continue;
+            }
+        }
+        const PbrtGpuBrdfSample s = sc.kdData[m.firstNode + nodeNum];
+        const float dist2 = DistanceSquared(V3(s.p[0], s.p[1], s.p[2]), p);
+        if (dist2 < maxDist2) {
+            const float weight = ref_expf(-100.f * dist2);
+            v = v + weight * Spec(s.v[0], s.v[1], s.v[2]);
+            sumWeights += weight;
+            ++found;
+        }
+    }
+    *vOut = v; *sumW = sumWeights; *nFound = found;
+}
+
+DEV Spec BxF(const DScene &sc, const BxSet &s, int i, const V3 &wo, const V3 &wi) {
+    if (s.kind[i] == BX_LAMBERTIAN) return s.R[i] * INV_PI_F;   // reflection.cpp:173-175
+    if (s.kind[i] == BX_MICROFACET_BLINN) {                     // Microfacet::f, reflection.cpp:211-222
+        float cosThetaO = AbsCosTheta(wo);
+        float cosThetaI = AbsCosTheta(wi);
+        if (cosThetaI == 0.f || cosThetaO == 0.f) return Spec(0.f);
+        V3 wh = wi + wo;
+        if (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f) return Spec(0.f);
+        wh = Normalize(wh);
+        float cosThetaH = Dot(wi, wh);
+        Spec F = FresnelDielectric(cosThetaH, 1.5f, 1.f);
+        return s.R[i] * BlinnD(s.exponent, wh) * MicrofacetG(wo, wi, wh) * F / (4.f * cosThetaI * cosThetaO);
+    }
+    // IrregIsotropicBRDF::f, reflection.cpp:259-272
+    V3 mpt = BRDFRemap(wo, wi);
+    float lastMaxDist2 = .001f;
+    const PbrtGpuMeasured md = sc.measured[s.measured];
+    while (true) {
+        Spec v;
+        float sumWeights;
+        int nFound;
+        KdGather(sc, md, mpt, lastMaxDist2, &v, &sumWeights, &nFound);
+        if (nFound > 2 || lastMaxDist2 > 1.5f) return v.Clamp() / sumWeights;
+        lastMaxDist2 *= 2.f;
+    }
+}
+DEV float BxPdf(const BxSet &s, int i, const V3 &wo, const V3 &wi) {
+    if (s.kind[i] == BX_MICROFACET_BLINN) {   // Microfacet::Pdf + Blinn::Pdf, reflection.cpp:340-343,365-374
+        if (!SameHemisphere(wo, wi)) return 0.f;
+        V3 wh = Normalize(wo + wi);
+        float costheta = AbsCosTheta(wh);
+        float blinn_pdf = ((s.exponent + 1.f) * ref_powf(costheta, s.exponent)) / (2.f * PI_F * 4.f * Dot(wo, wh));
+        if (Dot(wo, wh) <= 0.f) blinn_pdf = 0.f;
+        return blinn_pdf;
+    }
+    return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * INV_PI_F : 0.f;   // BxDF::Pdf, reflection.cpp:321-323
+}
+DEV Spec BxSample_f(const DScene &sc, const BxSet &s, int i, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
+    if (s.kind[i] == BX_MICROFACET_BLINN) {   // Microfacet::Sample_f + Blinn::Sample_f, reflection.cpp:332-363
+        float costheta = ref_powf(u1, 1.f / (s.exponent + 1));
+        float sintheta = sqrtf(maxf(0.f, 1.f - costheta * costheta));
+        float phi = u2 * 2.f * PI_F;
+        V3 wh = SphericalDirection(sintheta, costheta, phi);
+        if (!SameHemisphere(wo, wh)) wh = -wh;
+        *wi = -wo + 2.f * Dot(wo, wh) * wh;
+        float blinn_pdf = ((s.exponent + 1.f) * ref_powf(costheta, s.exponent)) / (2.f * PI_F * 4.f * Dot(wo, wh));
+        if (Dot(wo, wh) <= 0.f) blinn_pdf = 0.f;
+        *pdf = blinn_pdf;
+        if (!SameHemisphere(wo, *wi)) return Spec(0.f);
+        return BxF(sc, s, i, wo, *wi);
+    }
+    *wi = CosineSampleHemisphere(u1, u2);     // BxDF::Sample_f, reflection.cpp:311-318
+    if (wo.z < 0.f) wi->z *= -1.f;
+    *pdf = BxPdf(s, i, wo, *wi);
+    return BxF(sc, s, i, wo, *wi);
+}
+
+// BSDF::f, reflection.cpp:612-626
+DEV Spec BSDF_f(const DScene &sc, const ShadeCtx &c, const BxSet &s, const V3 &woW, const V3 &wiW, int flags) {
+    V3 wi = WorldToLocal(c, wiW), wo = WorldToLocal(c, woW);
+    if (Dot(wiW, c.ng) * Dot(woW, c.ng) > 0) flags &= ~BSDF_TRANSMISSION;
+    else flags &= ~BSDF_REFLECTION;
+    Spec f(0.f);
+    for (int i = 0; i < s.n; ++i)
+        if (Matches(s.type[i], flags)) f = f + BxF(sc, s, i, wo, wi);
+    return f;
+}
+// BSDF::Pdf, reflection.cpp:583-598
+DEV float BSDF_Pdf(const ShadeCtx &c, const BxSet &s, const V3 &woW, const V3 &wiW, int flags) {
+    if (s.n == 0) return 0.f;
+    V3 wo = WorldToLocal(c, woW), wi = WorldToLocal(c, wiW);
+    float pdf = 0.f;
+    int matchingComps = 0;
+    for (int i = 0; i < s.n; ++i)
+        if (Matches(s.type[i], flags)) {
+            ++matchingComps;
+            pdf += BxPdf(s, i, wo, wi);
+        }
+    return matchingComps > 0 ? pdf / matchingComps : 0.f;
+}
+// BSDF::Sample_f, reflection.cpp:522-580
+DEV Spec BSDF_Sample_f(const DScene &sc, const ShadeCtx &c, const BxSet &s, const V3 &woW, V3 *wiW, float uDir0,
+                       float uDir1, float uComponent, float *pdf, int flags, int *sampledType) {
+    int matchingComps = 0;
+    for (int i = 0; i < s.n; ++i) if (Matches(s.type[i], flags)) ++matchingComps;
+    if (matchingComps == 0) {
+        *pdf = 0.f;
+        *sampledType = 0;
+        return Spec(0.f);
+    }
+    int which = mini(Floor2Int(uComponent * matchingComps), matchingComps - 1);
+    int bx = -1;
+    int count = which;
+    for (int i = 0; i < s.n; ++i)
+        if (Matches(s.type[i], flags) && count-- == 0) { bx = i; break; }
+    V3 wo = WorldToLocal(c, woW);
+    V3 wi;
+    *pdf = 0.f;
+    Spec f = BxSample_f(sc, s, bx, wo, &wi, uDir0, uDir1, pdf);
+    if (*pdf == 0.f) {
+        *sampledType = 0;
+        return Spec(0.f);
+    }
+    *sampledType = s.type[bx];
+    *wiW = LocalToWorld(c, wi);
+    if (!(s.type[bx] & BSDF_SPECULAR) && matchingComps > 1)
+        for (int i = 0; i < s.n; ++i)
+            if (i != bx && Matches(s.type[i], flags)) *pdf += BxPdf(s, i, wo, wi);
+    if (matchingComps > 1) *pdf /= matchingComps;
+    if (!(s.type[bx] & BSDF_SPECULAR)) {
+        f = Spec(0.f);
+        if (Dot(*wiW, c.ng) * Dot(woW, c.ng) > 0) flags &= ~BSDF_TRANSMISSION;
+        else flags &= ~BSDF_REFLECTION;
+        for (int i = 0; i < s.n; ++i)
+            if (Matches(s.type[i], flags)) f = f + BxF(sc, s, i, wo, wi);
+    }
+    return f;
+}
+
+// ---- lights ---------------------------------------------------------------------
+// Shape::Pdf(p, wi), core/shape.cpp:86-99
+DEV float ShapePdf(const DScene &sc, const PbrtGpuQuadric &q, const V3 &p, const V3 &wi) {
+    DiffGeom dgLight;
+    Ray ray;
+    ray.o = p; ray.d = wi; ray.mint = 1e-3f; ray.maxt = INF_F;
+    float thit;
+    if (!QuadricIntersect(sc, q, ray, &thit, &dgLight)) return 0.f;
+    float pdf = DistanceSquared(p, RayAt(ray, thit)) / (AbsDot(dgLight.nn, -wi) * q.area);
+    if (isinf(pdf)) pdf = 0.f;
+    return pdf;
+}
+DEV V3 SphereSampleUniform(const DScene &sc, const PbrtGpuQuadric &q, float u1, float u2, V3 *ns) {   // sphere.cpp:226-231
+    const PbrtGpuXform &x = sc.xforms[q.xform];
+    V3 p = V3(0, 0, 0) + q.radius * UniformSampleSphere(u1, u2);
+    *ns = Normalize(XfNormal(x.mInv, V3(p.x, p.y, p.z)));
+    if (q.flags & PBRTGPU_SHAPE_REVERSE_ORIENT) *ns = *ns * -1.f;
+    return XfPoint(x.m, p);
+}
+DEV V3 SphereSample(const DScene &sc, const PbrtGpuQuadric &q, const V3 &p, float u1, float u2, V3 *ns) {   // sphere.cpp:236-261
+    const PbrtGpuXform &x = sc.xforms[q.xform];
+    V3 Pcenter = XfPoint(x.m, V3(0, 0, 0));
+    V3 wc = Normalize(Pcenter - p);
+    V3 wcX, wcY;
+    CoordinateSystem(wc, &wcX, &wcY);
+    if (DistanceSquared(p, Pcenter) - q.radius * q.radius < 1e-4f) return SphereSampleUniform(sc, q, u1, u2, ns);
+    float sinThetaMax2 = q.radius * q.radius / DistanceSquared(p, Pcenter);
+    float cosThetaMax = sqrtf(maxf(0.f, 1.f - sinThetaMax2));
+    DiffGeom dgSphere;
+    float thit;
+    Ray r;
+    r.o = p; r.d = UniformSampleCone(u1, u2, cosThetaMax, wcX, wcY, wc); r.mint = 1e-3f; r.maxt = INF_F;
+    if (!SphereIntersect(sc, q, r, &thit, &dgSphere)) thit = Dot(Pcenter - p, Normalize(r.d));
+    V3 ps = RayAt(r, thit);
+    *ns = Normalize(ps - Pcenter);
+    if (q.flags & PBRTGPU_SHAPE_REVERSE_ORIENT) *ns = *ns * -1.f;
+    return ps;
+}
+DEV float SpherePdf(const DScene &sc, const PbrtGpuQuadric &q, const V3 &p, const V3 &wi) {   // sphere.cpp:264-274
+    const PbrtGpuXform &x = sc.xforms[q.xform];
+    V3 Pcenter = XfPoint(x.m, V3(0, 0, 0));
+    if (DistanceSquared(p, Pcenter) - q.radius * q.radius < 1e-4f) return ShapePdf(sc, q, p, wi);
+    float sinThetaMax2 = q.radius * q.radius / DistanceSquared(p, Pcenter);
+    float cosThetaMax = sqrtf(maxf(0.f, 1.f - sinThetaMax2));
+    return UniformConePdf(cosThetaMax);
+}
+DEV V3 DiskSample(const DScene &sc, const PbrtGpuQuadric &q, float u1, float u2, V3 *Ns) {   // disk.cpp:148-156
+    const PbrtGpuXform &x = sc.xforms[q.xform];
+    V3 p;
+    ConcentricSampleDisk(u1, u2, &p.x, &p.y);
+    p.x *= q.radius;
+    p.y *= q.radius;
+    p.z = q.height;
+    *Ns = Normalize(XfNormal(x.mInv, V3(0, 0, 1)));
+    if (q.flags & PBRTGPU_SHAPE_REVERSE_ORIENT) *Ns = *Ns * -1.f;
+    return XfPoint(x.m, p);
+}
+// Light::Pdf: PointLight 0 (point.cpp:78-80); DiffuseAreaLight -> ShapeSet::Pdf (light.cpp:157-162)
+DEV float LightPdf(const DScene &sc, const PbrtGpuLight &l, const V3 &p, const V3 &wi) {
+    if (l.type == PBRTGPU_LIGHT_POINT) return 0.f;
+    float pdf = 0.f;
+    for (uint32_t i = 0; i < l.nShapes; ++i) {
+        const PbrtGpuLightShape ls = sc.lightShapes[l.firstShape + i];
+        const PbrtGpuQuadric &q = sc.quadrics[ls.index];
+        pdf += ls.area * (q.type == PBRTGPU_PRIM_SPHERE ? SpherePdf(sc, q, p, wi) : ShapePdf(sc, q, p, wi));
+    }
+    return pdf / l.sumArea;
+}
+// Light::Sample_L (point.cpp:50-57, diffuse.cpp:69-81) incl. VisibilityTester::SetSegment (light.h:87-92)
+DEV Spec LightSample_L(const DScene &sc, const PbrtGpuLight &l, const V3 &p, float pEpsilon, float uPos0, float uPos1,
+                       V3 *wi, float *pdf, Ray *vis) {
+    if (l.type == PBRTGPU_LIGHT_POINT) {
+        V3 lightPos(l.pos[0], l.pos[1], l.pos[2]);
+        *wi = Normalize(lightPos - p);
+        *pdf = 1.f;
+        float dist = Distance(p, lightPos);
+        vis->o = p; vis->d = (lightPos - p) / dist; vis->mint = pEpsilon; vis->maxt = dist * (1.f - 0.f);
+        return Spec(l.L[0], l.L[1], l.L[2]) / DistanceSquared(lightPos, p);
+    }
+    V3 ns;
+    const PbrtGpuLightShape lsh = sc.lightShapes[l.firstShape];
+    const PbrtGpuQuadric &q = sc.quadrics[lsh.index];
+    V3 ps = q.type == PBRTGPU_PRIM_SPHERE ? SphereSample(sc, q, p, uPos0, uPos1, &ns) : DiskSample(sc, q, uPos0, uPos1, &ns);
+    *wi = Normalize(ps - p);
+    *pdf = LightPdf(sc, l, p, *wi);
+    float dist = Distance(p, ps);
+    vis->o = p; vis->d = (ps - p) / dist; vis->mint = pEpsilon; vis->maxt = dist * (1.f - 1e-3f);
+    return Dot(ns, -*wi) > 0.f ? Spec(l.L[0], l.L[1], l.L[2]) : Spec(0.f);
+}
+
+}  // namespace dev

@@ -1,0 +1,53 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+import pbrt_v2_b200 as pb
+from pbrt_v2_b200 import scenes
+
+_cache = {}
+
+
+def host_scene(base, xres, yres, spp, ncores, maxdepth=None, crop=None, tag=""):
+    key = (base, xres, yres, spp, ncores, maxdepth, crop, tag)
+    if key not in _cache:
+        name = "%s-%dx%d-%dspp%s.pbrt" % (base, xres, yres, spp, tag)
+        path = scenes.variant(base, scenes.STAGED + "/" + name, xres, yres, spp, maxdepth=maxdepth, crop=crop)
+        _cache[key] = pb.HostScene(path, ncores=ncores)
+    return _cache[key]
+
+
+def random_rays(n, seed, bounds_lo, bounds_hi, inside_frac=0.5):
+    """aggregatetest-style rays (renderers/aggregatetest.cpp:61-119): random origins in/around
+    the scene bounds, random directions, a share of axis-aligned directions."""
+    rng = np.random.RandomState(seed)
+    lo, hi = np.asarray(bounds_lo, np.float32), np.asarray(bounds_hi, np.float32)
+    ext = hi - lo
+    rays = np.zeros(n, dtype=pb.RAY_DTYPE)
+    o = lo - ext + rng.rand(n, 3).astype(np.float32) * 3 * ext
+    inside = rng.rand(n) < inside_frac
+    o[inside] = lo + rng.rand(inside.sum(), 3).astype(np.float32) * ext
+    target = lo + rng.rand(n, 3).astype(np.float32) * ext
+    d = target - o
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20)
+    axis = rng.rand(n) < 0.05
+    k = rng.randint(0, 3, n)
+    da = np.zeros((n, 3), np.float32)
+    da[np.arange(n), k] = np.where(rng.rand(n) < 0.5, 1.0, -1.0)
+    d[axis] = da[axis]
+    rays["o"] = o
+    rays["d"] = d.astype(np.float32)
+    rays["mint"] = 0.0
+    rays["maxt"] = np.inf
+    short = rng.rand(n) < 0.2
+    rays["maxt"][short] = (rng.rand(short.sum()) * np.linalg.norm(ext)).astype(np.float32)
+    return rays
+
+
+def scene_bounds(hs):
+    """root node bounds of the flattened BVH (first 6 floats of nodes[0])."""
+    import ctypes as C
+    desc = C.cast(hs.desc_ptr, C.POINTER(C.c_uint32 * 4))   # nNodes, pad, ptr...
+    # PbrtGpuSceneDesc starts with {uint32 nNodes; (pad); const PbrtGpuBVHNode* nodes}
+    nodes_ptr = C.cast(hs.desc_ptr + 8, C.POINTER(C.c_void_p))[0]
+    b = np.ctypeslib.as_array(C.cast(nodes_ptr, C.POINTER(C.c_float)), shape=(6,)).copy()
+    return b[:3], b[3:]
