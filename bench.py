@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 path-tracing hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (reference arm: CPU)
+
+Metric (BASELINE.json): Msamples/s = camera samples (W*H*spp) per second of render
+phase.  Workload at every N: BASELINE.json configs[1] -- scenes/bunny.pbrt, path
+integrator, 1024 spp, 1024x1024, BVH accelerator -- one "step" = one full
+Renderer::Render of that image.  For N > 1 the image's render tasks are sharded
+across ranks (interleaved blocks of rows, no data-path collective) and the
+framebuffer is summed to rank 0 with one NCCL reduce; total work is fixed, so
+"scaling" is "strong".
+
+Prints ONE JSON line on rank 0 (see the keys below).  Numbers are device-timed
+(CUDA events on the launching stream), max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (staged base scene, xres, yres, spp)
+    "bunny-c2": ("bunny", 1024, 1024, 1024),            # BASELINE.json configs[1]
+    "killeroo-c1": ("killeroo-simple", 400, 400, 64),   # configs[0] (CPU-runnable case)
+    "killeroo-c3": ("killeroo-simple", 1920, 1080, 4096),
+}
+CPU_SAMPLE_SPP = 16     # bounded sample of the same workload for the CPU arms (cost is linear in spp)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def per_pixel_ncores(xres, yres):
+    """--ncores value that makes the reference create one render task per pixel:
+    nTasks = RoundUpPow2(max(32*ncores, nPixels/256)) >= nPixels (samplerrenderer.cpp:203-205)."""
+    npx = xres * yres
+    return max(1, (npx + 31) // 32)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_render_seconds(scene_path, ncores):
+    """Run the unmodified reference (oracle/_ref/bin/pbrt) and return its own render-phase time
+    (ProgressReporter's final '(N.Ns)', core/progressreporter.cpp:60-118) and the wall time."""
+    ref_bin = os.path.join(REPO, "oracle", "_ref", "bin", "pbrt")
+    cwd = os.path.dirname(scene_path)
+    t0 = time.time()
+    p = subprocess.run([ref_bin, "--ncores", str(ncores), os.path.basename(scene_path)], cwd=cwd,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, check=True)
+    wall = time.time() - t0
+    m = re.findall(r"\((\d+\.\d+)s\)", p.stdout)
+    return (float(m[-1]) if m else wall), wall
+
+
+def cpu_reference_rate(workload, threads):
+    """Msamples/s of the reference's multithreaded CPU path on a bounded sample of `workload`."""
+    from pbrt_v2_b200 import scenes
+    base, xres, yres, _ = WORKLOADS[workload]
+    path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-cpu-%s.pbrt" % workload), xres, yres, CPU_SAMPLE_SPP)
+    sec, wall = reference_render_seconds(path, threads)
+    nsamp = xres * yres * CPU_SAMPLE_SPP
+    return nsamp / max(sec, 1e-3) / 1e6, sec, wall
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, all host cores."""
+    if rank != 0:
+        return
+    workload = args.workload
+    base, xres, yres, spp = WORKLOADS[workload]
+    threads = os.cpu_count() or 1
+    ref_bin = os.path.join(REPO, "oracle", "_ref", "bin", "pbrt")
+    from pbrt_v2_b200 import scenes
+    scenes.stage()
+    if not os.path.exists(ref_bin) or not scenes.have_staged():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/pbrt or staged scenes missing (build() must run where /root/reference exists)"}))
+        return
+    for _ in range(args.warmup):
+        cpu_reference_rate(workload, threads)
+    secs = []
+    for _ in range(args.steps):
+        _, sec, _ = cpu_reference_rate(workload, threads)
+        secs.append(sec)
+    nsamp = xres * yres * CPU_SAMPLE_SPP
+    total = sum(secs)
+    value = nsamp * len(secs) / total / 1e6
+    sample = "%s at %d spp (1/%d of the %d-spp workload; cost is linear in spp), %dx%d, --ncores %d" % (
+        base, CPU_SAMPLE_SPP, spp // CPU_SAMPLE_SPP, spp, xres, yres, threads)
+    line = {
+        "impl": "reference", "metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(secs),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(workload, world, per_pixel=False),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(workload, world, per_pixel=True):
+    base, xres, yres, spp = WORKLOADS[workload]
+    return {
+        "workload": "scenes/%s.pbrt, SurfaceIntegrator \"path\" (maxdepth 5), Sampler \"lowdiscrepancy\" %d spp, "
+                    "%dx%d, Accelerator \"bvh\", box filter" % (base, spp, xres, yres),
+        "global_batch": xres * yres * spp, "parallelism": "tile%d" % world,
+        "tasks": ("one reference render task per pixel (--ncores %d)" % per_pixel_ncores(xres, yres)) if per_pixel
+                 else "reference default nTasks",
+        "l2": "256 MiB buffer rewritten between steps (L2 flush); per-step sample tables (>= 24 GB) stream through HBM",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bunny-c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override spp (development only; invalidates the number)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import pbrt_v2_b200 as pb
+    from pbrt_v2_b200 import scenes
+
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    rc = pb.gpu_lib().pbrtgpu_set_device(local_rank)
+    assert rc == 0, pb.gpu_lib().pbrtgpu_last_error()
+    dev = torch.device("cuda", local_rank)
+
+    scenes.stage()
+    if not scenes.have_staged():
+        raise SystemExit("fixture scenes missing: run __graft_entry__.build() where /root/reference exists")
+    base, xres, yres, spp = WORKLOADS[args.workload]
+    if args.spp:
+        spp = args.spp
+    path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-%s-r%d.pbrt" % (args.workload, rank)), xres, yres, spp)
+    hs = pb.HostScene(path, ncores=per_pixel_ncores(xres, yres))
+    rd = hs.render_desc()
+    rd.shardCount, rd.shardIndex = world, rank
+    rd.shardBlock = 4 * xres            # interleave blocks of 4 pixel rows across ranks
+    _, _, xc, yc = hs.film_extent()
+    nsamples = xc * yc * spp
+    scene_bytes = hs.scene_bytes()
+
+    gs = pb.GpuScene(hs)
+    film = torch.zeros((yc, xc, 4), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    host_film = torch.empty((yc, xc, 4), dtype=torch.float32, pin_memory=True)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_resident(want_stats=False):
+        st = gs.render_device(rd, film.data_ptr(), stream.cuda_stream, want_stats=want_stats)
+        if world > 1:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        return st
+
+    def step_e2e():
+        g2 = pb.GpuScene(hs)                       # host -> device copy of the flattened scene
+        g2.render_device(rd, film.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            host_film.copy_(film, non_blocking=True)   # device -> host read of the step's result
+        stream.synchronize()
+        g2.close()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- untimed counting pass (ray / node / primitive-test counters) + warm-up
+    gs.set_stats(1)
+    counted = step_resident(want_stats=True)
+    gs.set_stats(0)
+    counts = torch.tensor([counted.closestRays, counted.shadowRays, counted.nodesVisited, counted.primTests],
+                          dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    closest, shadow, nodes, prims = [float(x) for x in counts.tolist()]
+    for _ in range(max(0, args.warmup - 1)):
+        flush.fill_(1)
+        step_resident()
+
+    # ---- timed: K steps, device-resident inputs
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    path_ms, table_ms, launches = 0.0, 0.0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total_ms = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)                              # L2 flush between timed iterations (not timed)
+        e0.record(stream)
+        st = step_resident(want_stats=True)
+        e1.record(stream)
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        path_ms += st.traceMs
+        table_ms += st.tableMs
+        launches += int(st.kernelLaunches)
+    barrier()
+    t = torch.tensor([total_ms, path_ms, table_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, path_ms, table_ms = [float(x) for x in t.tolist()]
+    sampler.stop()
+    clocks = sampler.summary()
+
+    # ---- timed: K steps end to end (scene H2D + render + reduce + film D2H)
+    step_e2e()
+    barrier()
+    e2e_ms = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0.record(stream)
+        step_e2e()
+        e1.record(stream)
+        e1.synchronize()
+        e2e_ms += e0.elapsed_time(e1)
+    barrier()
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+
+    if rank == 0:
+        value = nsamples * args.steps / (total_ms * 1e-3) / 1e6
+        e2e_value = nsamples * args.steps / (e2e_ms * 1e-3) / 1e6
+        # algorithmic bytes: 32 B per BVH node whose bounds are tested + 48 B per
+        # primitive test (+36 B per shaded hit on a mesh with normals: none in bunny)
+        alg_bytes = 32.0 * nodes + 48.0 * prims
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg_bytes * args.steps / (path_ms * 1e-3) / 1e9 if path_ms > 0 else 0.0
+        n_path_launches = max(1, launches // 2)
+        line = {
+            "metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, world),
+            "e2e": {"value": e2e_value, "unit": "Msamples/s",
+                    "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": int(xc * yc * 16)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "kernel": "k_path<false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_sample": alg_bytes / nsamples,
+                "kernel_ms_per_launch": path_ms / n_path_launches,
+                "launches_per_step": n_path_launches / args.steps,
+                "note": "scene (BVH+triangles, %.1f MB) is L2-resident: the algorithmic-bytes roofline is an upper bound "
+                        "on useful traffic, not DRAM traffic" % (scene_bytes / 1e6),
+            },
+            "rays": {"closest_per_sample": closest / nsamples, "shadow_per_sample": shadow / nsamples,
+                     "nodes_per_ray": nodes / max(1.0, closest + shadow), "prim_tests_per_ray": prims / max(1.0, closest + shadow)},
+            "kernel_ms": {"k_path": path_ms / args.steps, "k_tables": table_ms / args.steps},
+        }
+        if spp != WORKLOADS[args.workload][3]:
+            line["INVALID"] = "spp overridden to %d (development run)" % spp
+        if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REPO, "oracle", "_ref", "bin", "pbrt")):
+            threads = os.cpu_count() or 1
+            v, sec, wall = cpu_reference_rate(args.workload, threads)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "Msamples/s", "cores": threads, "kind": "reference",
+                "sample": "%s %dx%d at %d spp (1/%d of the workload's spp; cost is linear in spp), reference binary "
+                          "--ncores %d, render phase %.1f s (wall %.1f s)" % (
+                              base, xres, yres, CPU_SAMPLE_SPP, max(1, WORKLOADS[args.workload][3] // CPU_SAMPLE_SPP),
+                              threads, sec, wall)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -176,6 +176,12 @@ typedef struct PbrtGpuRenderDesc {
      * how an image is sharded across GPUs.                                      */
     int32_t nTasks;
     int32_t taskBegin, taskEnd;
+    /* Optional interleaved sharding inside [taskBegin, taskEnd): only tasks t with
+     * (t / shardBlock) % shardCount == shardIndex are rendered.  shardCount <= 1
+     * (or 0) renders them all.  Interleaving blocks of rows balances cheap
+     * (background) and expensive (object) pixels across GPUs; tasks share nothing,
+     * so the sum of the shards' films is the one-GPU film.                       */
+    int32_t shardCount, shardIndex, shardBlock;
 } PbrtGpuRenderDesc;
 
 /* ImageFilm::Pixel {Lxyz[3], weightSum} (film/image.h:69-78), row-major over
@@ -214,6 +220,11 @@ const char *pbrtgpu_last_error(void);
 /* replaces: Scene / BVHAccel / GeometricPrimitive object graph (core/scene.h) */
 int  pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out);
 void pbrtgpu_scene_destroy(PbrtGpuScene *scene);
+/* replaces: the PBRT_PROBES_COUNTERS build switch (core/probes.h:219-395).  on != 0
+ * makes the following render calls run the counting instantiation of the path
+ * kernel and fill PbrtGpuStats.{closestRays,shadowRays,nodesVisited,primTests};
+ * timed runs leave it off.                                                     */
+int  pbrtgpu_set_stats(PbrtGpuScene *scene, int on);
 
 /* replaces: SamplerRenderer::Render (samplerrenderer.cpp:188-222) minus the
  * final WriteImage().  `pixels` is HOST memory (xPixelCount*yPixelCount);

@@ -1172,7 +1172,9 @@ int oracle_render(const PbrtGpuSceneDesc *scene, const PbrtGpuRenderDesc *rd, Pb
                 // same enqueue order as the reference: nTasks-1-i (samplerrenderer.cpp:212)
                 int i = next.fetch_add(1);
                 if (i >= rd->taskEnd) break;
-                R.RunTask(rd->taskBegin + (rd->taskEnd - 1 - i), &cnts[t]);
+                const int task = rd->taskBegin + (rd->taskEnd - 1 - i);
+                if (rd->shardCount > 1 && (task / std::max(1, rd->shardBlock)) % rd->shardCount != rd->shardIndex) continue;
+                R.RunTask(task, &cnts[t]);
             }
         });
     for (auto &th : threads) th.join();
@@ -1186,6 +1188,7 @@ int oracle_render(const PbrtGpuSceneDesc *scene, const PbrtGpuRenderDesc *rd, Pb
         // camera samples = pixels of the rendered tasks x spp
         uint64_t px = 0;
         for (int t = rd->taskBegin; t < rd->taskEnd; ++t) {
+            if (rd->shardCount > 1 && (t / std::max(1, rd->shardBlock)) % rd->shardCount != rd->shardIndex) continue;
             int x0, x1, y0, y1;
             R.ComputeSubWindow(t, rd->nTasks, &x0, &x1, &y0, &y1);
             px += (uint64_t)std::max(0, x1 - x0) * std::max(0, y1 - y0);

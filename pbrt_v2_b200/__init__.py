@@ -39,6 +39,7 @@ class RenderDesc(C.Structure):
         ("maxDepth", C.c_int32),
         ("nTasks", C.c_int32),
         ("taskBegin", C.c_int32), ("taskEnd", C.c_int32),
+        ("shardCount", C.c_int32), ("shardIndex", C.c_int32), ("shardBlock", C.c_int32),
     ]
 
 
@@ -90,6 +91,7 @@ def gpu_lib():
         lib.pbrtgpu_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.pbrtgpu_ld_samples.argtypes = [C.POINTER(RenderDesc), C.c_int, C.c_void_p]
         lib.pbrtgpu_set_device.argtypes = [C.c_int]
+        lib.pbrtgpu_set_stats.argtypes = [C.c_void_p, C.c_int]
         _gpu = lib
     return _gpu
 
@@ -113,6 +115,10 @@ def host_lib():
         lib.pbrthost_pixels_to_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pbrthost_write_image.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
         lib.pbrthost_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Stats)]
+        lib.pbrthost_scene_bytes.argtypes = [C.c_void_p]
+        lib.pbrthost_scene_bytes.restype = C.c_ulonglong
+        lib.pbrthost_scene_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint)] * 4
+        lib.pbrthost_scene_counts.restype = None
         _host = lib
     return _host
 
@@ -144,6 +150,14 @@ class HostScene(object):
     def desc_ptr(self):
         """const PbrtGpuSceneDesc* (valid while this object lives)."""
         return host_lib().pbrthost_scene_desc(self._h)
+
+    def scene_bytes(self):
+        return int(host_lib().pbrthost_scene_bytes(self._h))
+
+    def counts(self):
+        v = [C.c_uint() for _ in range(4)]
+        host_lib().pbrthost_scene_counts(self._h, *[C.byref(x) for x in v])
+        return dict(zip(("nodes", "primitives", "triangles", "lights"), (x.value for x in v)))
 
     def render_desc(self):
         rd = RenderDesc()
@@ -198,6 +212,10 @@ class GpuScene(object):
             self._h = None
 
     __del__ = close
+
+    def set_stats(self, on):
+        """switch the ray / node / primitive-test counters on (slower kernel instantiation)."""
+        _check(gpu_lib().pbrtgpu_set_stats(self._h, int(on)), "pbrtgpu_set_stats")
 
     def render(self, rd=None, out=None):
         """pbrtgpu_render into HOST pixels; returns (pixels, Stats)."""

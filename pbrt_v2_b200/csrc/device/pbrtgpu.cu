@@ -655,6 +655,8 @@ int ValidateRenderDesc(const PbrtGpuRenderDesc &rd) {
     if (rd.nTasks <= 0 || rd.taskBegin < 0 || rd.taskEnd > rd.nTasks || rd.taskBegin > rd.taskEnd)
         return Fail(PBRTGPU_EINVAL, "bad task range");
     if (rd.maxDepth < 0) return Fail(PBRTGPU_EINVAL, "bad maxDepth");
+    if (rd.shardCount > 1 && (rd.shardIndex < 0 || rd.shardIndex >= rd.shardCount))
+        return Fail(PBRTGPU_EINVAL, "bad shard index");
     return PBRTGPU_OK;
 }
 
@@ -834,7 +836,9 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     std::vector<TaskRec> tasks;
     int maxPixels = 0;
     uint64_t totalPixels = 0;
+    const int shardCount = std::max(1, rd->shardCount), shardBlock = std::max(1, rd->shardBlock);
     for (int t = rd->taskBegin; t < rd->taskEnd; ++t) {
+        if (shardCount > 1 && (t / shardBlock) % shardCount != rd->shardIndex) continue;
         TaskRec tr;
         tr.taskNum = t;
         ComputeSubWindow(ext, t, rd->nTasks, &tr.x0, &tr.x1, &tr.y0, &tr.y1);

@@ -38,6 +38,27 @@ void pbrthost_film_extent(PbrtHostScene *h, int *xStart, int *yStart, int *xCoun
     *xStart = f->xPixelStart; *yStart = f->yPixelStart; *xCount = f->xPixelCount; *yCount = f->yPixelCount;
 }
 
+// bytes of the flattened scene arrays (= what pbrtgpu_scene_create copies host->device)
+unsigned long long pbrthost_scene_bytes(PbrtHostScene *h) {
+    const PbrtGpuSceneDesc &d = h->ls.scene->desc;
+    unsigned long long b = 0;
+    b += (unsigned long long)d.nNodes * sizeof(PbrtGpuBVHNode);
+    b += (unsigned long long)d.nPrimitives * sizeof(PbrtGpuPrimitive);
+    b += (unsigned long long)d.nTriangles * sizeof(PbrtGpuTriangle);
+    b += (unsigned long long)d.nMeshes * sizeof(PbrtGpuMesh);
+    b += (unsigned long long)d.nVertices * 12ull * (1 + (d.N ? 1 : 0)) + (d.uv ? (unsigned long long)d.nVertices * 8ull : 0);
+    b += (unsigned long long)d.nQuadrics * sizeof(PbrtGpuQuadric) + (unsigned long long)d.nXforms * sizeof(PbrtGpuXform);
+    b += (unsigned long long)d.nMaterials * sizeof(PbrtGpuMaterial) + (unsigned long long)d.nMeasured * sizeof(PbrtGpuMeasured);
+    b += (unsigned long long)d.nKdNodes * (sizeof(PbrtGpuKdNode) + sizeof(PbrtGpuBrdfSample));
+    b += (unsigned long long)d.nLights * sizeof(PbrtGpuLight) + (unsigned long long)d.nLightShapes * sizeof(PbrtGpuLightShape);
+    return b;
+}
+
+void pbrthost_scene_counts(PbrtHostScene *h, unsigned *nNodes, unsigned *nPrims, unsigned *nTris, unsigned *nLights) {
+    const PbrtGpuSceneDesc &d = h->ls.scene->desc;
+    *nNodes = d.nNodes; *nPrims = d.nPrimitives; *nTris = d.nTriangles; *nLights = d.nLights;
+}
+
 // ImageFilm::WriteImage's XYZ->RGB / weight normalisation (film/image.cpp:178-205)
 int pbrthost_pixels_to_rgb(PbrtHostScene *h, const PbrtGpuPixel *pixels, float *rgb) {
     ImageFilm *f = h->ls.renderer->film.get();
