@@ -194,7 +194,8 @@ typedef struct PbrtGpuPixel {
 typedef struct PbrtGpuStats {
     double   renderMs;        /* CUDA-event time of the device work             */
     double   tableMs;         /* ... of which LD table generation               */
-    double   traceMs;         /* ... of which the path kernel                   */
+    double   traceMs;         /* ... of which path kernel phase 1 (table-driven bounces 0..2) */
+    double   tailMs;          /* ... of which path kernel phase 2 (RNG-driven tails + film)  */
     uint64_t cameraSamples;
     uint64_t closestRays, shadowRays;
     uint64_t nodesVisited;    /* BVH nodes whose bounds were tested             */

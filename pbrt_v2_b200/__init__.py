@@ -45,7 +45,7 @@ class RenderDesc(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [
-        ("renderMs", C.c_double), ("tableMs", C.c_double), ("traceMs", C.c_double),
+        ("renderMs", C.c_double), ("tableMs", C.c_double), ("traceMs", C.c_double), ("tailMs", C.c_double),
         ("cameraSamples", C.c_uint64),
         ("closestRays", C.c_uint64), ("shadowRays", C.c_uint64),
         ("nodesVisited", C.c_uint64), ("primTests", C.c_uint64),

@@ -50,6 +50,8 @@ struct BatchArgs {
     uint32_t *rngCur;    // [nBatch][624]
     uint32_t *rngNext;   // [nBatch][624]
     int *mti;            // [nBatch]
+    float4 *ls;          // [nBatch][spp]     finished radiance (xyz) + footprint/TAIL bits (w)
+    float4 *rec;         // [nBatch][spp][4]  parked bounce-3 vertices (phase 1 -> phase 2)
 };
 
 struct DeviceStats {
@@ -159,9 +161,27 @@ __global__ void k_expand_samples(BatchArgs a, int spp, float shutterOpen, float 
 }
 
 // ----------------------------------------------------------------------- k_path
+// The path integrator runs in two phases per pixel (DESIGN.md "Execution model"):
+//
+//   phase 1  one WARP per task-pixel, lanes = camera samples of that pixel.  Bounces
+//            0..2 draw every random number from the pixel's LD tables
+//            (path.cpp:71-76,86-88), so the spp samples of a pixel are independent
+//            there and run side by side: 32 nearly identical primary rays per warp.
+//            A sample either finishes (radiance stored in ls[s]) or reaches its
+//            bounce-3 vertex, where PathIntegrator::Li starts consuming the task's
+//            sequential RNG stream; it is then parked as a 64-byte record.
+//   phase 2  one THREAD per task-pixel walks ls[0..spp) in sample order: finished
+//            samples are added to the film (ImageFilm::AddSample order), parked
+//            ones are resumed with the RNG exactly where the previous sample's tail
+//            left it (UniformSampleOneLight 7 draws, BSDFSample 3, roulette 1).
+//
+// Both phases are one state machine with a single BVH-traversal site per loop
+// iteration, so the lanes of a warp traverse together whatever stage each is in.
 enum PathState {
     S_NEW_SAMPLE = 0, S_HIT_RESULT, S_SHADOW_RESULT, S_AFTER_LIGHT, S_MIS_RESULT, S_AFTER_DIRECT, S_END_SAMPLE, S_DONE
 };
+// ls[s].w bit field
+enum { LS_TAIL = 1, LS_LEFT = 2, LS_RIGHT = 4, LS_UP = 8, LS_DOWN = 16 };
 
 struct PathArgs {
     DScene sc;
@@ -172,10 +192,10 @@ struct PathArgs {
     int directFilm;   // 1: every AddSample goes straight to the film (multi-pixel tasks)
 };
 
-// ImageFilm::AddSample, film/image.cpp:77-137, box filter (all table weights are 1)
-DEV void FilmAdd(const PathArgs &a, int ownX, int ownY, float imageX, float imageY, const Spec &L, float acc[4],
-                 bool direct) {
-    const RenderParams &rp = a.rp;
+// Which pixels does ImageFilm::AddSample (film/image.cpp:77-96) touch for this sample?
+// With the 0.5 box filter: the sample's own pixel, plus a neighbour when the
+// sample sits exactly on a pixel edge or xPos + u rounded up to the next integer.
+DEV int FilmFootprint(const RenderParams &rp, int ownX, int ownY, float imageX, float imageY) {
     float dimageX = imageX - 0.5f;
     float dimageY = imageY - 0.5f;
     int x0 = Ceil2Int(dimageX - rp.filterXWidth);
@@ -186,19 +206,30 @@ DEV void FilmAdd(const PathArgs &a, int ownX, int ownY, float imageX, float imag
     x1 = mini(x1, rp.xPixelStart + rp.xPixelCount - 1);
     y0 = maxi(y0, rp.yPixelStart);
     y1 = mini(y1, rp.yPixelStart + rp.yPixelCount - 1);
-    if ((x1 - x0) < 0 || (y1 - y0) < 0) return;
+    int code = 0;
+    if (x0 < ownX) code |= LS_LEFT;
+    if (x1 > ownX) code |= LS_RIGHT;
+    if (y0 < ownY) code |= LS_UP;
+    if (y1 > ownY) code |= LS_DOWN;
+    return code;
+}
+
+// ImageFilm::AddSample, film/image.cpp:97-137, box filter (all table weights are 1)
+DEV void FilmAdd(const PathArgs &a, int ownX, int ownY, int code, const Spec &L, float acc[4], bool direct) {
+    const RenderParams &rp = a.rp;
     float xyz[3];   // RGBToXYZ, core/spectrum.h:58-62
     xyz[0] = 0.412453f * L.r + 0.357580f * L.g + 0.180423f * L.b;
     xyz[1] = 0.212671f * L.r + 0.715160f * L.g + 0.072169f * L.b;
     xyz[2] = 0.019334f * L.r + 0.119193f * L.g + 0.950227f * L.b;
+    const int y0 = ownY - ((code & LS_UP) ? 1 : 0), y1 = ownY + ((code & LS_DOWN) ? 1 : 0);
+    const int x0 = ownX - ((code & LS_LEFT) ? 1 : 0), x1 = ownX + ((code & LS_RIGHT) ? 1 : 0);
     for (int y = y0; y <= y1; ++y)
         for (int x = x0; x <= x1; ++x) {
             if (!direct && x == ownX && y == ownY) {
                 acc[0] += xyz[0]; acc[1] += xyz[1]; acc[2] += xyz[2]; acc[3] += 1.f;
             } else {
-                // a neighbour pixel (sample on a pixel edge, or imageX rounded up to the next
-                // integer): the reference does a plain += that can race with the owning task;
-                // atomics keep the sum complete, the order is as undefined as in the reference
+                // a neighbour pixel: the reference does a plain += that can race with the
+                // owning task; atomics keep the sum complete, the order is as undefined as there
                 PbrtGpuPixel *px = a.film + (size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart);
                 atomicAdd(&px->Lxyz[0], xyz[0]);
                 atomicAdd(&px->Lxyz[1], xyz[1]);
@@ -208,14 +239,22 @@ DEV void FilmAdd(const PathArgs &a, int ownX, int ownY, float imageX, float imag
         }
 }
 
-template <bool STATS>
+// samplerrenderer.cpp:119-133: NaN / negative / infinite luminance -> black
+DEV Spec SanitizeRadiance(const Spec &L) {
+    if (L.HasNaNs()) return Spec(0.f);
+    if ((double)L.y() < -1e-5) return Spec(0.f);
+    if (isinf(L.y())) return Spec(0.f);
+    return L;
+}
+
+template <int PHASE, bool STATS>
 __global__ void __launch_bounds__(128) k_path(PathArgs a) {
     __shared__ uint32_t smt[4][MT_N];
     const DScene &sc = a.sc;
     const RenderParams &rp = a.rp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int bi = PHASE == 1 ? (int)(blockIdx.x * 4 + warp) : (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int spp = rp.spp;
 
     bool valid = bi < a.b.nBatch;
@@ -228,7 +267,9 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
     const uint16_t *permBase = a.b.perm + slot * spp * PERM_STRIDE;
     const uint32_t *scr = a.b.scr + slot * SCR_STRIDE;
     const uint32_t *rngCur = a.b.rngCur + slot * MT_N, *rngNext = a.b.rngNext + slot * MT_N;
-    int mti = valid ? a.b.mti[bi] : 0;
+    float4 *lsBase = a.b.ls + slot * spp;
+    float4 *recBase = a.b.rec + slot * spp * 4;
+    int mti = (PHASE == 2 && valid) ? a.b.mti[bi] : 0;
     const bool direct = a.directFilm != 0;
 
     // draw `k` positions past mti (RNG::RandomUInt order), without advancing
@@ -239,7 +280,7 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
     auto rngF = [&](int k) -> float { return UIntToFloat(rngU(k)); };
 
     int state = valid ? S_NEW_SAMPLE : S_DONE;
-    int s = 0, bounces = 0;
+    int s = 0, bounces = 0, nextS = 0, code = 0;
     Ray ray;
     ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f;
     Hit hit;
@@ -252,16 +293,25 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
     V3 wo(0, 0, 1);
     int lightNum = 0;
     float bsU0 = 0.f, bsU1 = 0.f, bsUc = 0.f;   // USOL's BSDFSample (kept from S_HIT_RESULT to S_AFTER_LIGHT)
-    float imageX = 0.f, imageY = 0.f;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     TraceStats st;
     st.nodes = st.prims = 0;
     unsigned long long nClosest = 0, nShadow = 0, nShadedN = 0;
 
     for (;;) {
-        // ---- cooperative RNG top-up: make sure the <= 11 draws of a bounce are addressable
-        {
-            const bool need = (state == S_HIT_RESULT && found && bounces >= 3 && mti >= MT_N);
+        bool fresh = false;   // phase 1: this lane was handed a new sample index this iteration
+        if (PHASE == 1) {
+            // ---- hand the pixel's next camera samples to the idle lanes (warp-uniform counter)
+            const unsigned m = __ballot_sync(FULL, state == S_NEW_SAMPLE);
+            if (state == S_NEW_SAMPLE) {
+                s = nextS + __popc(m & ((1u << lane) - 1u));
+                if (s >= spp) state = S_DONE;
+                else fresh = true;
+            }
+            nextS += __popc(m);
+        } else {
+            // ---- cooperative RNG top-up: make sure the <= 11 draws of a bounce are addressable
+            const bool need = (state == S_HIT_RESULT && found && mti >= MT_N);
             unsigned m = __ballot_sync(FULL, need);
             while (m) {
                 const int l = __ffs(m) - 1;
@@ -289,6 +339,15 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
             if (!found) {
                 // SamplerRenderer::Li miss (bounce 0: sum of Light::Le == 0) / path.cpp:113-118
                 state = S_END_SAMPLE;
+            } else if (PHASE == 1 && bounces == 3) {
+                // ---- park the sample: from here on the path draws from the task's RNG stream
+                float4 *r = recBase + (size_t)s * 4;
+                r[0] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+                r[1] = make_float4(ray.d.x, ray.d.y, ray.d.z, hit.t);
+                r[2] = make_float4(T.r, T.g, T.b, __int_as_float(hit.prim));
+                r[3] = make_float4(hit.b1, hit.b2, hit.maxtIn, 0.f);
+                lsBase[s] = make_float4(L.r, L.g, L.b, __int_as_float(code | LS_TAIL));
+                state = S_NEW_SAMPLE;
             } else {
                 // ---- path.cpp:61-80: emitted light, BSDF, UniformSampleOneLight up to the shadow ray
                 BuildShadeCtx(sc, ray, hit, &ctx, STATS ? &nShadedN : nullptr);
@@ -437,53 +496,84 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
         }
 
         if (state == S_END_SAMPLE) {
-            // samplerrenderer.cpp:111-146: sanity checks, then ImageFilm::AddSample
-            Spec Ls = L;
-            if (Ls.HasNaNs()) Ls = Spec(0.f);
-            else if ((double)Ls.y() < -1e-5) Ls = Spec(0.f);
-            else if (isinf(Ls.y())) Ls = Spec(0.f);
-            FilmAdd(a, xPos, yPos, imageX, imageY, Ls, acc, direct);
-            ++s;
-            state = S_NEW_SAMPLE;
+            if (PHASE == 1) {
+                const Spec Ls = SanitizeRadiance(L);
+                lsBase[s] = make_float4(Ls.r, Ls.g, Ls.b, __int_as_float(code));
+                state = S_NEW_SAMPLE;   // next sample index is handed out at the top of the loop
+            } else {
+                // samplerrenderer.cpp:111-146: sanity checks, then ImageFilm::AddSample
+                FilmAdd(a, xPos, yPos, code, SanitizeRadiance(L), acc, direct);
+                ++s;
+                state = S_NEW_SAMPLE;
+            }
         }
 
         if (state == S_NEW_SAMPLE) {
-            if (s == spp) {
-                if (!direct) {
-                    PbrtGpuPixel *px = a.film + (size_t)(yPos - rp.yPixelStart) * rp.xPixelCount + (xPos - rp.xPixelStart);
-                    atomicAdd(&px->Lxyz[0], acc[0]);
-                    atomicAdd(&px->Lxyz[1], acc[1]);
-                    atomicAdd(&px->Lxyz[2], acc[2]);
-                    atomicAdd(&px->weightSum, acc[3]);
+            if (PHASE == 1) {
+                if (fresh) {
+                    // LDPixelSample's camera sample + PerspectiveCamera::GenerateRayDifferential (perspective.cpp:81-138)
+                    const uint16_t *row = permBase + (size_t)s * PERM_STRIDE;
+                    const uint32_t pi = row[0];
+                    const float imageX = xPos + VanDerCorput(pi, scr[0]);
+                    const float imageY = yPos + Sobol2(pi, scr[1]);
+                    code = FilmFootprint(rp, xPos, yPos, imageX, imageY);
+                    V3 Pcamera = XfPoint(rp.rasterToCamera, V3(imageX, imageY, 0));
+                    V3 dir = Normalize(V3(Pcamera.x, Pcamera.y, Pcamera.z));
+                    ray.o = V3(0, 0, 0); ray.d = dir; ray.mint = 0.f; ray.maxt = INF_F;
+                    if (rp.lensRadius > 0.f) {
+                        const uint32_t pl = row[1];
+                        float lensU, lensV;
+                        ConcentricSampleDisk(VanDerCorput(pl, scr[2]), Sobol2(pl, scr[3]), &lensU, &lensV);
+                        lensU *= rp.lensRadius;
+                        lensV *= rp.lensRadius;
+                        float ft = rp.focalDistance / ray.d.z;
+                        V3 Pfocus = RayAt(ray, ft);
+                        ray.o = V3(lensU, lensV, 0.f);
+                        ray.d = Normalize(Pfocus - ray.o);
+                    }
+                    ray.o = XfPoint(rp.cameraToWorld, ray.o);
+                    ray.d = XfVector(rp.cameraToWorld, ray.d);
+                    T = Spec(1.f); L = Spec(0.f);
+                    bounces = 0;
+                    wantTrace = true; anyHit = false;
+                    state = S_HIT_RESULT;
                 }
-                a.b.mti[bi] = mti;
-                state = S_DONE;
             } else {
-                // LDPixelSample's camera sample + PerspectiveCamera::GenerateRayDifferential (perspective.cpp:81-138)
-                const uint16_t *row = permBase + (size_t)s * PERM_STRIDE;
-                const uint32_t pi = row[0];
-                imageX = xPos + VanDerCorput(pi, scr[0]);
-                imageY = yPos + Sobol2(pi, scr[1]);
-                V3 Pcamera = XfPoint(rp.rasterToCamera, V3(imageX, imageY, 0));
-                V3 dir = Normalize(V3(Pcamera.x, Pcamera.y, Pcamera.z));
-                ray.o = V3(0, 0, 0); ray.d = dir; ray.mint = 0.f; ray.maxt = INF_F;
-                if (rp.lensRadius > 0.f) {
-                    const uint32_t pl = row[1];
-                    float lensU, lensV;
-                    ConcentricSampleDisk(VanDerCorput(pl, scr[2]), Sobol2(pl, scr[3]), &lensU, &lensV);
-                    lensU *= rp.lensRadius;
-                    lensV *= rp.lensRadius;
-                    float ft = rp.focalDistance / ray.d.z;
-                    V3 Pfocus = RayAt(ray, ft);
-                    ray.o = V3(lensU, lensV, 0.f);
-                    ray.d = Normalize(Pfocus - ray.o);
+                // walk ls[] in sample order: add finished samples, resume the next parked one
+                for (int k = 0; k < 64 && state == S_NEW_SAMPLE; ++k) {
+                    if (s == spp) {
+                        if (!direct) {
+                            PbrtGpuPixel *px = a.film + (size_t)(yPos - rp.yPixelStart) * rp.xPixelCount + (xPos - rp.xPixelStart);
+                            atomicAdd(&px->Lxyz[0], acc[0]);
+                            atomicAdd(&px->Lxyz[1], acc[1]);
+                            atomicAdd(&px->Lxyz[2], acc[2]);
+                            atomicAdd(&px->weightSum, acc[3]);
+                        }
+                        a.b.mti[bi] = mti;
+                        state = S_DONE;
+                        break;
+                    }
+                    const float4 v = __ldcs(lsBase + s);
+                    code = __float_as_int(v.w);
+                    if (code & LS_TAIL) {
+                        const float4 *r = recBase + (size_t)s * 4;
+                        const float4 r0 = __ldcs(r), r1 = __ldcs(r + 1), r2 = __ldcs(r + 2), r3 = __ldcs(r + 3);
+                        ray.o = V3(r0.x, r0.y, r0.z); ray.mint = r0.w;
+                        ray.d = V3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
+                        hit.t = r1.w;
+                        T = Spec(r2.x, r2.y, r2.z);
+                        hit.prim = __float_as_int(r2.w);
+                        hit.b1 = r3.x; hit.b2 = r3.y; hit.maxtIn = r3.z;
+                        L = Spec(v.x, v.y, v.z);
+                        code &= ~LS_TAIL;
+                        bounces = 3;
+                        found = true;
+                        state = S_HIT_RESULT;   // picked up (after the RNG top-up) next iteration
+                    } else {
+                        FilmAdd(a, xPos, yPos, code, Spec(v.x, v.y, v.z), acc, direct);
+                        ++s;
+                    }
                 }
-                ray.o = XfPoint(rp.cameraToWorld, ray.o);
-                ray.d = XfVector(rp.cameraToWorld, ray.d);
-                T = Spec(1.f); L = Spec(0.f);
-                bounces = 0;
-                wantTrace = true; anyHit = false;
-                state = S_HIT_RESULT;
             }
         }
 
@@ -599,12 +689,13 @@ struct PbrtGpuScene {
     DevBuf<uint16_t> perm;
     DevBuf<uint32_t> scr, rngCur, rngNext;
     DevBuf<int> mti;
+    DevBuf<float4> ls, rec;
     DevBuf<PbrtGpuPixel> film;
     DevBuf<DeviceStats> stats;
     DevBuf<PbrtGpuRay> rays;
     DevBuf<PbrtGpuHit> hits;
     DevBuf<uint8_t> occ;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool collectStats = false;
 };
 
@@ -801,7 +892,7 @@ int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
     d.materials = s->materials.p; d.measured = s->measured.p; d.kdNodes = s->kdNodes.p; d.kdData = s->kdData.p;
     d.lights = s->lights.p; d.lightShapes = s->lightShapes.p;
     d.nNodes = desc->nNodes; d.nPrims = desc->nPrimitives; d.nLights = desc->nLights;
-    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&s->ev[i]));
+    for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&s->ev[i]));
     s->collectStats = getenv("PBRTGPU_STATS") != nullptr;
     *out = s.release();
     return PBRTGPU_OK;
@@ -809,7 +900,7 @@ int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
 
 void pbrtgpu_scene_destroy(PbrtGpuScene *scene) {
     if (!scene) return;
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
         if (scene->ev[i]) cudaEventDestroy(scene->ev[i]);
     delete scene;
 }
@@ -862,7 +953,9 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     rp.xPixelCount = ext.xPixelCount; rp.yPixelCount = ext.yPixelCount;
     rp.spp = spp; rp.maxDepth = rd->maxDepth;
 
-    const size_t perTask = (size_t)spp * PERM_STRIDE * 2 + SCR_STRIDE * 4 + 2 * MT_N * 4 + 4 + sizeof(TaskRec);
+    // per task: permutation tables (64 B/sample) + finished radiance (16 B/sample) + parked
+    // bounce-3 vertices (64 B/sample, sparse) + scrambles + two MT19937 blocks
+    const size_t perTask = (size_t)spp * (PERM_STRIDE * 2 + 16 + 64) + SCR_STRIDE * 4 + 2 * MT_N * 4 + 4 + sizeof(TaskRec);
     size_t maxBatch = std::max<size_t>(1024, ScratchBudgetBytes() / perTask);
     maxBatch = std::min<size_t>(maxBatch, std::max<size_t>(tasks.size(), 1));
     CUDA_TRY(scene->tasks.Ensure(maxBatch));
@@ -871,13 +964,15 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     CUDA_TRY(scene->rngCur.Ensure(maxBatch * MT_N));
     CUDA_TRY(scene->rngNext.Ensure(maxBatch * MT_N));
     CUDA_TRY(scene->mti.Ensure(maxBatch));
+    CUDA_TRY(scene->ls.Ensure(maxBatch * spp));
+    CUDA_TRY(scene->rec.Ensure(maxBatch * spp * 4));
     CUDA_TRY(scene->stats.Ensure(1));
     const bool wantCounters = stats && scene->collectStats;
     if (wantCounters) CUDA_TRY(cudaMemsetAsync(scene->stats.p, 0, sizeof(DeviceStats), stream));
 
     const TableLaunch tl = PlanTables(spp);
     uint64_t launches = 0;
-    float tableMs = 0.f, traceMs = 0.f;
+    float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f;
     for (size_t begin = 0; begin < tasks.size(); begin += maxBatch) {
         const size_t nb = std::min(maxBatch, tasks.size() - begin);
         int rounds = 0;
@@ -887,7 +982,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
         BatchArgs b;
         b.tasks = scene->tasks.p; b.nBatch = (int)nb; b.round = 0;
         b.perm = scene->perm.p; b.scr = scene->scr.p; b.rngCur = scene->rngCur.p; b.rngNext = scene->rngNext.p;
-        b.mti = scene->mti.p;
+        b.mti = scene->mti.p; b.ls = scene->ls.p; b.rec = scene->rec.p;
         for (int r = 0; r < rounds; ++r) {
             b.round = r;
             if (stats) CUDA_TRY(cudaEventRecord(scene->ev[2], stream));
@@ -896,19 +991,26 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
             PathArgs pa;
             pa.sc = scene->d; pa.rp = rp; pa.b = b; pa.film = film; pa.stats = scene->stats.p;
             pa.directFilm = rounds > 1 ? 1 : 0;
-            const int blocks = (int)((nb + 127) / 128);
-            if (wantCounters) k_path<true><<<blocks, 128, 0, stream>>>(pa);
-            else k_path<false><<<blocks, 128, 0, stream>>>(pa);
+            const int blocks1 = (int)((nb + 3) / 4);       // phase 1: one warp per task-pixel
+            const int blocks2 = (int)((nb + 127) / 128);   // phase 2: one thread per task-pixel
+            if (wantCounters) k_path<1, true><<<blocks1, 128, 0, stream>>>(pa);
+            else k_path<1, false><<<blocks1, 128, 0, stream>>>(pa);
             CUDA_TRY(cudaGetLastError());
-            launches += 2;
+            if (stats) CUDA_TRY(cudaEventRecord(scene->ev[4], stream));
+            if (wantCounters) k_path<2, true><<<blocks2, 128, 0, stream>>>(pa);
+            else k_path<2, false><<<blocks2, 128, 0, stream>>>(pa);
+            CUDA_TRY(cudaGetLastError());
+            launches += 3;
             if (stats) {
                 CUDA_TRY(cudaEventRecord(scene->ev[1], stream));
                 CUDA_TRY(cudaEventSynchronize(scene->ev[1]));
                 float ms = 0.f;
                 CUDA_TRY(cudaEventElapsedTime(&ms, scene->ev[2], scene->ev[3]));
                 tableMs += ms;
-                CUDA_TRY(cudaEventElapsedTime(&ms, scene->ev[3], scene->ev[1]));
+                CUDA_TRY(cudaEventElapsedTime(&ms, scene->ev[3], scene->ev[4]));
                 traceMs += ms;
+                CUDA_TRY(cudaEventElapsedTime(&ms, scene->ev[4], scene->ev[1]));
+                tailMs += ms;
             }
         }
     }
@@ -921,6 +1023,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
         stats->renderMs = ms;
         stats->tableMs = tableMs;
         stats->traceMs = traceMs;
+        stats->tailMs = tailMs;
         stats->cameraSamples = totalPixels * (uint64_t)spp;
         stats->kernelLaunches = launches;
         if (wantCounters) {
