@@ -273,6 +273,53 @@ DEV void KdGather(const DScene &sc, const PbrtGpuMeasured &m, const V3 &p, float
     *vOut = v; *sumW = sumWeights; *nFound = found;
 }
 
+// Exact value of the 3rd-smallest squared distance from p to the kd-tree's points
+// (+inf if there are fewer than three).  IrregIsotropicBRDF::f (reflection.cpp:259-272)
+// doubles its search radius until a lookup finds more than two samples; that is the
+// first radius r2 in {.001 * 2^k} with (3rd-smallest dist2) < r2, so one k-nearest
+// query replaces the reference's repeated fixed-radius lookups and only the final
+// lookup (whose visiting order fixes the float summation order) has to be replayed.
+// Subtrees are pruned with the same float expression the reference uses for the
+// splitting-plane distance; a point beyond the plane cannot be closer than the plane.
+DEV float KdThirdNearest(const DScene &sc, const PbrtGpuMeasured &m, const V3 &p) {
+    float b0 = INF_F, b1 = INF_F, b2 = INF_F;
+    uint32_t stN[32];
+    float stD[32];
+    int sp = 0;
+    stN[0] = 0u; stD[0] = 0.f; sp = 1;
+    while (sp > 0) {
+        --sp;
+        if (!(stD[sp] < b2)) continue;
+        const uint32_t nodeNum = stN[sp];
+        const PbrtGpuKdNode node = sc.kdNodes[m.firstNode + nodeNum];
+        const PbrtGpuBrdfSample s = sc.kdData[m.firstNode + nodeNum];
+        const float d2 = DistanceSquared(V3(s.p[0], s.p[1], s.p[2]), p);
+        if (d2 < b2) {
+            if (d2 < b1) {
+                b2 = b1;
+                if (d2 < b0) { b1 = b0; b0 = d2; } else b1 = d2;
+            } else b2 = d2;
+        }
+        const int axis = node.bits & 3u;
+        if (axis != 3) {
+            const uint32_t hasLeft = (node.bits >> 2) & 1u, rightChild = node.bits >> 3;
+            const bool hasRight = rightChild < m.nNodes;
+            const float pa = p[axis];
+            const float plane2 = (pa - node.splitPos) * (pa - node.splitPos);
+            const bool leftFirst = pa <= node.splitPos;
+            // far child (pushed first, popped last) carries the plane distance as its bound
+            if (leftFirst) {
+                if (hasRight) { stN[sp] = rightChild; stD[sp] = plane2; ++sp; }
+                if (hasLeft) { stN[sp] = nodeNum + 1; stD[sp] = 0.f; ++sp; }
+            } else {
+                if (hasLeft) { stN[sp] = nodeNum + 1; stD[sp] = plane2; ++sp; }
+                if (hasRight) { stN[sp] = rightChild; stD[sp] = 0.f; ++sp; }
+            }
+        }
+    }
+    return b2;
+}
+
 DEV Spec BxF(const DScene &sc, const BxSet &s, int i, const V3 &wo, const V3 &wi) {
     if (s.kind[i] == BX_LAMBERTIAN) return s.R[i] * INV_PI_F;   // reflection.cpp:173-175
     if (s.kind[i] == BX_MICROFACET_BLINN) {                     // Microfacet::f, reflection.cpp:211-222
@@ -288,16 +335,15 @@ DEV Spec BxF(const DScene &sc, const BxSet &s, int i, const V3 &wo, const V3 &wi
     }
     // IrregIsotropicBRDF::f, reflection.cpp:259-272
     V3 mpt = BRDFRemap(wo, wi);
-    float lastMaxDist2 = .001f;
     const PbrtGpuMeasured md = sc.measured[s.measured];
-    while (true) {
-        Spec v;
-        float sumWeights;
-        int nFound;
-        KdGather(sc, md, mpt, lastMaxDist2, &v, &sumWeights, &nFound);
-        if (nFound > 2 || lastMaxDist2 > 1.5f) return v.Clamp() / sumWeights;
-        lastMaxDist2 *= 2.f;
-    }
+    const float d3 = KdThirdNearest(sc, md, mpt);
+    float lastMaxDist2 = .001f;
+    while (!(d3 < lastMaxDist2) && !(lastMaxDist2 > 1.5f)) lastMaxDist2 *= 2.f;   // nFound > 2 || lastMaxDist2 > 1.5f
+    Spec v;
+    float sumWeights;
+    int nFound;
+    KdGather(sc, md, mpt, lastMaxDist2, &v, &sumWeights, &nFound);
+    return v.Clamp() / sumWeights;
 }
 DEV float BxPdf(const BxSet &s, int i, const V3 &wo, const V3 &wi) {
     if (s.kind[i] == BX_MICROFACET_BLINN) {   // Microfacet::Pdf + Blinn::Pdf, reflection.cpp:340-343,365-374
@@ -310,8 +356,11 @@ DEV float BxPdf(const BxSet &s, int i, const V3 &wo, const V3 &wi) {
     }
     return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * INV_PI_F : 0.f;   // BxDF::Pdf, reflection.cpp:321-323
 }
-DEV Spec BxSample_f(const DScene &sc, const BxSet &s, int i, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
-    if (s.kind[i] == BX_MICROFACET_BLINN) {   // Microfacet::Sample_f + Blinn::Sample_f, reflection.cpp:332-363
+// BxDF::Sample_f without the f() it returns: BSDF::Sample_f (reflection.cpp:572-576) discards
+// that value for every non-specular BxDF and re-evaluates the sum of all matching components.
+//   Microfacet::Sample_f + Blinn::Sample_f, reflection.cpp:332-363;  BxDF::Sample_f, :311-318
+DEV void BxSampleDir(const BxSet &s, int i, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
+    if (s.kind[i] == BX_MICROFACET_BLINN) {
         float costheta = ref_powf(u1, 1.f / (s.exponent + 1));
         float sintheta = sqrtf(maxf(0.f, 1.f - costheta * costheta));
         float phi = u2 * 2.f * PI_F;
@@ -321,29 +370,16 @@ DEV Spec BxSample_f(const DScene &sc, const BxSet &s, int i, const V3 &wo, V3 *w
         float blinn_pdf = ((s.exponent + 1.f) * ref_powf(costheta, s.exponent)) / (2.f * PI_F * 4.f * Dot(wo, wh));
         if (Dot(wo, wh) <= 0.f) blinn_pdf = 0.f;
         *pdf = blinn_pdf;
-        if (!SameHemisphere(wo, *wi)) return Spec(0.f);
-        return BxF(sc, s, i, wo, *wi);
+        return;
     }
-    *wi = CosineSampleHemisphere(u1, u2);     // BxDF::Sample_f, reflection.cpp:311-318
+    *wi = CosineSampleHemisphere(u1, u2);
     if (wo.z < 0.f) wi->z *= -1.f;
     *pdf = BxPdf(s, i, wo, *wi);
-    return BxF(sc, s, i, wo, *wi);
 }
 
-// BSDF::f, reflection.cpp:612-626
-DEV Spec BSDF_f(const DScene &sc, const ShadeCtx &c, const BxSet &s, const V3 &woW, const V3 &wiW, int flags) {
-    V3 wi = WorldToLocal(c, wiW), wo = WorldToLocal(c, woW);
-    if (Dot(wiW, c.ng) * Dot(woW, c.ng) > 0) flags &= ~BSDF_TRANSMISSION;
-    else flags &= ~BSDF_REFLECTION;
-    Spec f(0.f);
-    for (int i = 0; i < s.n; ++i)
-        if (Matches(s.type[i], flags)) f = f + BxF(sc, s, i, wo, wi);
-    return f;
-}
-// BSDF::Pdf, reflection.cpp:583-598
-DEV float BSDF_Pdf(const ShadeCtx &c, const BxSet &s, const V3 &woW, const V3 &wiW, int flags) {
+// BSDF::Pdf (reflection.cpp:583-598) on already-local vectors
+DEV float BSDF_PdfLocal(const BxSet &s, const V3 &wo, const V3 &wi, int flags) {
     if (s.n == 0) return 0.f;
-    V3 wo = WorldToLocal(c, woW), wi = WorldToLocal(c, wiW);
     float pdf = 0.f;
     int matchingComps = 0;
     for (int i = 0; i < s.n; ++i)
@@ -353,16 +389,18 @@ DEV float BSDF_Pdf(const ShadeCtx &c, const BxSet &s, const V3 &woW, const V3 &w
         }
     return matchingComps > 0 ? pdf / matchingComps : 0.f;
 }
-// BSDF::Sample_f, reflection.cpp:522-580
-DEV Spec BSDF_Sample_f(const DScene &sc, const ShadeCtx &c, const BxSet &s, const V3 &woW, V3 *wiW, float uDir0,
-                       float uDir1, float uComponent, float *pdf, int flags, int *sampledType) {
+
+// BSDF::Sample_f (reflection.cpp:522-580) up to, but not including, the final
+// "f = sum of matching bxdfs[i]->f(wo, wi)": returns false where the reference returns a
+// black spectrum with pdf 0; otherwise the local wo/wi, the world wi, the combined pdf and
+// the flags (hemisphere-adjusted, :568-571) the caller hands to the evaluation site.
+DEV bool BSDF_SampleDir(const ShadeCtx &c, const BxSet &s, const V3 &woW, float uDir0, float uDir1, float uComponent,
+                        int flags, V3 *woOut, V3 *wiOut, V3 *wiW, float *pdf, int *sampledType, int *evalFlags) {
     int matchingComps = 0;
     for (int i = 0; i < s.n; ++i) if (Matches(s.type[i], flags)) ++matchingComps;
-    if (matchingComps == 0) {
-        *pdf = 0.f;
-        *sampledType = 0;
-        return Spec(0.f);
-    }
+    *pdf = 0.f;
+    *sampledType = 0;
+    if (matchingComps == 0) return false;
     int which = mini(Floor2Int(uComponent * matchingComps), matchingComps - 1);
     int bx = -1;
     int count = which;
@@ -370,26 +408,18 @@ DEV Spec BSDF_Sample_f(const DScene &sc, const ShadeCtx &c, const BxSet &s, cons
         if (Matches(s.type[i], flags) && count-- == 0) { bx = i; break; }
     V3 wo = WorldToLocal(c, woW);
     V3 wi;
-    *pdf = 0.f;
-    Spec f = BxSample_f(sc, s, bx, wo, &wi, uDir0, uDir1, pdf);
-    if (*pdf == 0.f) {
-        *sampledType = 0;
-        return Spec(0.f);
-    }
+    BxSampleDir(s, bx, wo, &wi, uDir0, uDir1, pdf);
+    if (*pdf == 0.f) return false;
     *sampledType = s.type[bx];
     *wiW = LocalToWorld(c, wi);
-    if (!(s.type[bx] & BSDF_SPECULAR) && matchingComps > 1)
+    if (matchingComps > 1)   // (no specular BxDF in scope)
         for (int i = 0; i < s.n; ++i)
             if (i != bx && Matches(s.type[i], flags)) *pdf += BxPdf(s, i, wo, wi);
     if (matchingComps > 1) *pdf /= matchingComps;
-    if (!(s.type[bx] & BSDF_SPECULAR)) {
-        f = Spec(0.f);
-        if (Dot(*wiW, c.ng) * Dot(woW, c.ng) > 0) flags &= ~BSDF_TRANSMISSION;
-        else flags &= ~BSDF_REFLECTION;
-        for (int i = 0; i < s.n; ++i)
-            if (Matches(s.type[i], flags)) f = f + BxF(sc, s, i, wo, wi);
-    }
-    return f;
+    if (Dot(*wiW, c.ng) * Dot(woW, c.ng) > 0) flags &= ~BSDF_TRANSMISSION;
+    else flags &= ~BSDF_REFLECTION;
+    *woOut = wo; *wiOut = wi; *evalFlags = flags;
+    return true;
 }
 
 // ---- lights ---------------------------------------------------------------------

@@ -178,7 +178,8 @@ __global__ void k_expand_samples(BatchArgs a, int spp, float shutterOpen, float 
 // Both phases are one state machine with a single BVH-traversal site per loop
 // iteration, so the lanes of a warp traverse together whatever stage each is in.
 enum PathState {
-    S_NEW_SAMPLE = 0, S_HIT_RESULT, S_SHADOW_RESULT, S_AFTER_LIGHT, S_MIS_RESULT, S_AFTER_DIRECT, S_END_SAMPLE, S_DONE
+    S_NEW_SAMPLE = 0, S_HIT_RESULT, S_SHADOW_RESULT, S_AFTER_LIGHT, S_MIS_RESULT, S_AFTER_DIRECT, S_END_SAMPLE, S_DONE,
+    S_E_LIGHT, S_E_MIS, S_E_PATH   // waiting for the BSDF value at the evaluation site
 };
 // ls[s].w bit field
 enum { LS_TAIL = 1, LS_LEFT = 2, LS_RIGHT = 4, LS_UP = 8, LS_DOWN = 16 };
@@ -293,6 +294,8 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
     V3 wo(0, 0, 1);
     int lightNum = 0;
     float bsU0 = 0.f, bsU1 = 0.f, bsUc = 0.f;   // USOL's BSDFSample (kept from S_HIT_RESULT to S_AFTER_LIGHT)
+    V3 wiW(0, 0, 1);                            // sampled incident direction (world)
+    float sPdf = 0.f, visMaxt = 0.f;            // its pdf; the shadow segment's maxt
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     TraceStats st;
     st.nodes = st.prims = 0;
@@ -334,7 +337,11 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
         if (!__any_sync(FULL, state != S_DONE)) break;
 
         bool wantTrace = false, anyHit = false;
+        bool evalReq = false;
+        V3 evalWo(0, 0, 1), evalWi(0, 0, 1);
+        int evalFlags = 0;
 
+        // ================= part A: consume the traversal result, run up to the next BSDF evaluation
         if (state == S_HIT_RESULT) {
             if (!found) {
                 // SamplerRenderer::Li miss (bounce 0: sum of Light::Le == 0) / path.cpp:113-118
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
                 lsBase[s] = make_float4(L.r, L.g, L.b, __int_as_float(code | LS_TAIL));
                 state = S_NEW_SAMPLE;
             } else {
-                // ---- path.cpp:61-80: emitted light, BSDF, UniformSampleOneLight up to the shadow ray
+                // ---- path.cpp:61-80: emitted light, BSDF, UniformSampleOneLight up to bsdf->f()
                 BuildShadeCtx(sc, ray, hit, &ctx, STATS ? &nShadedN : nullptr);
                 wo = -ray.d;
                 if (bounces == 0) L = L + T * HitLe(sc, ctx.areaLight, ctx.ng, wo);
@@ -379,65 +386,25 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
                     lightNum = mini(Floor2Int(lnU * nLights), nLights - 1);
                     const PbrtGpuLight &light = sc.lights[lightNum];
                     // ---- EstimateDirect, light-sampling half (integrator.cpp:123-142)
-                    V3 wi;
-                    float lightPdf;
                     Ray vis;
-                    Spec Li = LightSample_L(sc, light, ctx.p, ctx.rayEpsilon, lsU0, lsU1, &wi, &lightPdf, &vis);
+                    Spec Li = LightSample_L(sc, light, ctx.p, ctx.rayEpsilon, lsU0, lsU1, &wiW, &sPdf, &vis);
+                    visMaxt = vis.maxt;   // vis.o == p, vis.mint == rayEpsilon, vis.d == wi bit for bit
                     state = S_AFTER_LIGHT;
-                    if (lightPdf > 0.f && !Li.IsBlack()) {
-                        BxSet bx;
-                        MaterialBxDFs(sc, ctx.material, &bx);
-                        const int flags = BSDF_ALL & ~BSDF_SPECULAR;
-                        Spec f = BSDF_f(sc, ctx, bx, wo, wi, flags);
-                        if (!f.IsBlack()) {
-                            if (light.type == PBRTGPU_LIGHT_POINT)
-                                pend = f * Li * (AbsDot(wi, ctx.nn) / lightPdf);
-                            else {
-                                float bsdfPdf = BSDF_Pdf(ctx, bx, wo, wi, flags);
-                                float weight = PowerHeuristic(1, lightPdf, 1, bsdfPdf);
-                                pend = f * Li * (AbsDot(wi, ctx.nn) * weight / lightPdf);
-                            }
-                            ray = vis;
-                            wantTrace = true; anyHit = true;
-                            state = S_SHADOW_RESULT;
-                        }
+                    if (sPdf > 0.f && !Li.IsBlack()) {
+                        pend = Li;
+                        // Spectrum f = bsdf->f(wo, wi, flags)  -- BSDF::f, reflection.cpp:612-626
+                        evalWi = WorldToLocal(ctx, wiW); evalWo = WorldToLocal(ctx, wo);
+                        evalFlags = BSDF_ALL & ~BSDF_SPECULAR;
+                        if (Dot(wiW, ctx.ng) * Dot(wo, ctx.ng) > 0) evalFlags &= ~BSDF_TRANSMISSION;
+                        else evalFlags &= ~BSDF_REFLECTION;
+                        evalReq = true;
+                        state = S_E_LIGHT;
                     }
                 }
             }
         } else if (state == S_SHADOW_RESULT) {
             if (!found) Ld = Ld + pend;   // visibility.Unoccluded(scene), Transmittance == 1
             state = S_AFTER_LIGHT;
-        }
-
-        if (state == S_AFTER_LIGHT) {
-            // ---- EstimateDirect, BSDF-sampling half (integrator.cpp:145-172)
-            state = S_AFTER_DIRECT;
-            const PbrtGpuLight &light = sc.lights[lightNum];
-            if (light.type != PBRTGPU_LIGHT_POINT) {
-                BxSet bx;
-                MaterialBxDFs(sc, ctx.material, &bx);
-                const int flags = BSDF_ALL & ~BSDF_SPECULAR;
-                V3 wi;
-                float bsdfPdf;
-                int sampledType;
-                Spec f = BSDF_Sample_f(sc, ctx, bx, wo, &wi, bsU0, bsU1, bsUc, &bsdfPdf, flags, &sampledType);
-                if (!f.IsBlack() && bsdfPdf > 0.f) {
-                    float weight = 1.f;
-                    bool skip = false;
-                    if (!(sampledType & BSDF_SPECULAR)) {
-                        float lightPdf = LightPdf(sc, light, ctx.p, wi);
-                        if (lightPdf == 0.f) skip = true;   // `return Ld`
-                        else weight = PowerHeuristic(1, bsdfPdf, 1, lightPdf);
-                    }
-                    if (!skip) {
-                        // Li is either Lemit or black (diffuse.h:51-53), so the term can be formed now
-                        pend = f * Spec(light.L[0], light.L[1], light.L[2]) * AbsDot(wi, ctx.nn) * weight / bsdfPdf;
-                        ray.o = ctx.p; ray.d = wi; ray.mint = ctx.rayEpsilon; ray.maxt = INF_F;
-                        wantTrace = true; anyHit = false;
-                        state = S_MIS_RESULT;
-                    }
-                }
-            }
         } else if (state == S_MIS_RESULT) {
             if (found) {
                 DiffGeom dgl;
@@ -454,8 +421,24 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
             state = S_AFTER_DIRECT;
         }
 
+        if (state == S_AFTER_LIGHT) {
+            // ---- EstimateDirect, BSDF-sampling half (integrator.cpp:145-172): choose the direction
+            state = S_AFTER_DIRECT;
+            const PbrtGpuLight &light = sc.lights[lightNum];
+            if (light.type != PBRTGPU_LIGHT_POINT) {
+                BxSet bx;
+                MaterialBxDFs(sc, ctx.material, &bx);
+                int sampledType;
+                if (BSDF_SampleDir(ctx, bx, wo, bsU0, bsU1, bsUc, BSDF_ALL & ~BSDF_SPECULAR, &evalWo, &evalWi, &wiW,
+                                   &sPdf, &sampledType, &evalFlags)) {
+                    evalReq = true;
+                    state = S_E_MIS;
+                }
+            }
+        }
+
         if (state == S_AFTER_DIRECT) {
-            // ---- path.cpp:71-121: add direct light, sample the BSDF, Russian roulette, next ray
+            // ---- path.cpp:71-94: add direct light, choose the continuation direction
             L = L + T * ((float)(int)sc.nLights * Ld);
             float u0, u1, uc;
             if (bounces < 3) {
@@ -471,14 +454,62 @@ __global__ void __launch_bounds__(128) k_path(PathArgs a) {
             }
             BxSet bx;
             MaterialBxDFs(sc, ctx.material, &bx);
-            V3 wi;
-            float pdf;
-            int flags;
-            Spec f = BSDF_Sample_f(sc, ctx, bx, wo, &wi, u0, u1, uc, &pdf, BSDF_ALL, &flags);
+            int sampledType;
+            state = S_END_SAMPLE;   // f.IsBlack() || pdf == 0.  -> break
+            if (BSDF_SampleDir(ctx, bx, wo, u0, u1, uc, BSDF_ALL, &evalWo, &evalWi, &wiW, &sPdf, &sampledType, &evalFlags)) {
+                evalReq = true;
+                state = S_E_PATH;
+            }
+        }
+
+        // ================= the single BSDF-evaluation site (sum of matching BxDF::f, reflection.cpp:572-576,620-623)
+        Spec fEval(0.f);
+        if (evalReq) {
+            BxSet bx;
+            MaterialBxDFs(sc, ctx.material, &bx);
+            for (int i = 0; i < bx.n; ++i)
+                if (Matches(bx.type[i], evalFlags)) fEval = fEval + BxF(sc, bx, i, evalWo, evalWi);
+        }
+
+        // ================= part B: use the BSDF value, run up to the next ray
+        if (state == S_E_LIGHT) {
+            state = S_AFTER_LIGHT;   // (picked up by part A of the next iteration if no shadow ray is needed)
+            if (!fEval.IsBlack()) {
+                const PbrtGpuLight &light = sc.lights[lightNum];
+                if (light.type == PBRTGPU_LIGHT_POINT)
+                    pend = fEval * pend * (AbsDot(wiW, ctx.nn) / sPdf);
+                else {
+                    BxSet bx;
+                    MaterialBxDFs(sc, ctx.material, &bx);
+                    float bsdfPdf = BSDF_PdfLocal(bx, evalWo, evalWi, BSDF_ALL & ~BSDF_SPECULAR);
+                    float weight = PowerHeuristic(1, sPdf, 1, bsdfPdf);
+                    pend = fEval * pend * (AbsDot(wiW, ctx.nn) * weight / sPdf);
+                }
+                ray.o = ctx.p; ray.d = wiW; ray.mint = ctx.rayEpsilon; ray.maxt = visMaxt;
+                wantTrace = true; anyHit = true;
+                state = S_SHADOW_RESULT;
+            }
+        } else if (state == S_E_MIS) {
+            state = S_AFTER_DIRECT;   // (next iteration)
+            if (!fEval.IsBlack() && sPdf > 0.f) {
+                const PbrtGpuLight &light = sc.lights[lightNum];
+                // sampledType is never specular for the in-scope BxDFs
+                float lightPdf = LightPdf(sc, light, ctx.p, wiW);
+                if (lightPdf != 0.f) {   // else `return Ld`
+                    float weight = PowerHeuristic(1, sPdf, 1, lightPdf);
+                    // Li is either Lemit or black (diffuse.h:51-53), so the term can be formed now
+                    pend = fEval * Spec(light.L[0], light.L[1], light.L[2]) * AbsDot(wiW, ctx.nn) * weight / sPdf;
+                    ray.o = ctx.p; ray.d = wiW; ray.mint = ctx.rayEpsilon; ray.maxt = INF_F;
+                    wantTrace = true; anyHit = false;
+                    state = S_MIS_RESULT;
+                }
+            }
+        } else if (state == S_E_PATH) {
+            // ---- path.cpp:96-121: throughput, Russian roulette, next ray
             state = S_END_SAMPLE;
-            if (!(f.IsBlack() || pdf == 0.f)) {
-                T = T * (f * AbsDot(wi, ctx.nn) / pdf);
-                ray.o = ctx.p; ray.d = wi; ray.mint = ctx.rayEpsilon; ray.maxt = INF_F;
+            if (!fEval.IsBlack()) {
+                T = T * (fEval * AbsDot(wiW, ctx.nn) / sPdf);
+                ray.o = ctx.p; ray.d = wiW; ray.mint = ctx.rayEpsilon; ray.maxt = INF_F;
                 bool alive = true;
                 if (bounces > 3) {
                     float continueProbability = minf(.5f, T.y());

@@ -5,13 +5,18 @@ import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 cur_file = None
+cur_fn = ""
+FILTER = sys.argv[3] if len(sys.argv) > 3 else ""
 agg = {}
 hdr = None
 for r in rows:
     if not r: continue
     if r[0] == "File Path": cur_file = r[1].split("/")[-1]; continue
     if r[0] == "Line No": hdr = r; continue
-    if r[0] == "Function Name" or hdr is None: continue
+    if r[0] == "Function Name":
+        cur_fn = r[1]; continue
+    if hdr is None: continue
+    if FILTER and FILTER not in cur_fn: continue
     if not r[0].isdigit(): continue
     # source-line aggregate rows have '-' for Address
     if r[2] != "-": continue

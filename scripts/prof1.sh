@@ -13,6 +13,5 @@ for i in range(2):
     px, st = gs.render()
     print(st.as_dict())
 PY
-ncu --set full --clock-control none --import-source on -k regex:k_path -s 1 -c 1 -o gpurun_out/prof_path_bunny python /tmp/prof_run.py bunny 256 64 > gpurun_out/prof1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_tables -s 1 -c 1 -o gpurun_out/prof_tables_bunny python /tmp/prof_run.py bunny 256 1024 >> gpurun_out/prof1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_path -s 2 -c 2 -o gpurun_out/prof_path2_bunny python /tmp/prof_run.py bunny 256 64 > gpurun_out/prof1.log 2>&1
 tail -5 gpurun_out/prof1.log
