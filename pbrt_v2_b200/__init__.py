@@ -79,7 +79,7 @@ def gpu_lib():
     """libpbrtgpu.so (the CUDA hot path)."""
     global _gpu
     if _gpu is None:
-        lib = _load("libpbrtgpu.so")
+        lib = _load(os.environ.get("PBRTGPU_LIB", "libpbrtgpu.so"))   # (override: kernel A/B experiments)
         lib.pbrtgpu_last_error.restype = C.c_char_p
         lib.pbrtgpu_scene_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         lib.pbrtgpu_scene_destroy.argtypes = [C.c_void_p]

@@ -16,6 +16,26 @@
 #include <cuda_runtime.h>
 
 #define DEV __device__ __forceinline__
+// big, rarely-hot routines: one copy per kernel keeps the instruction footprint in cache
+#define DEV_NOINLINE __device__ __noinline__
+#ifndef PBRT_NI_LEVEL
+#define PBRT_NI_LEVEL 1   /* measured on B200: 1 (math only) beats 0, 2 and 3 */
+#endif
+#if PBRT_NI_LEVEL >= 1
+#define DEV_NI1 DEV_NOINLINE
+#else
+#define DEV_NI1 DEV
+#endif
+#if PBRT_NI_LEVEL >= 2
+#define DEV_NI2 DEV_NOINLINE
+#else
+#define DEV_NI2 DEV
+#endif
+#if PBRT_NI_LEVEL >= 3
+#define DEV_NI3 DEV_NOINLINE
+#else
+#define DEV_NI3 DEV
+#endif
 
 namespace dev {
 
@@ -128,11 +148,11 @@ DEV V3 XfNormal(const float *__restrict__ mInv, const V3 &n) {
 // arguments; agrees with glibc 2.39 on 99.9 % (sinf/cosf/powf), 99.99 % (expf),
 // 99.7 % (acosf), 84 % (atan2f, glibc's is not correctly rounded) of arguments,
 // and is within 1 ulp otherwise (measured, see DESIGN.md "libm").
-DEV float ref_sinf(float x) { return (float)sin((double)x); }
-DEV float ref_cosf(float x) { return (float)cos((double)x); }
-DEV float ref_expf(float x) { return (float)exp((double)x); }
-DEV float ref_powf(float x, float y) { return (float)pow((double)x, (double)y); }
-DEV float ref_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
-DEV float ref_acosf(float x) { return (float)acos((double)x); }
+DEV_NI1 float ref_sinf(float x) { return (float)sin((double)x); }
+DEV_NI1 float ref_cosf(float x) { return (float)cos((double)x); }
+DEV_NI1 float ref_expf(float x) { return (float)exp((double)x); }
+DEV_NI1 float ref_powf(float x, float y) { return (float)pow((double)x, (double)y); }
+DEV_NI1 float ref_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+DEV_NI1 float ref_acosf(float x) { return (float)acos((double)x); }
 
 }  // namespace dev

@@ -197,7 +197,7 @@ DEV bool DiskIntersect(const DScene &sc, const PbrtGpuQuadric &q, const Ray &r, 
     return true;
 }
 
-DEV bool QuadricIntersect(const DScene &sc, const PbrtGpuQuadric &q, const Ray &r, float *tHit, DiffGeom *dg) {
+DEV_NI2 bool QuadricIntersect(const DScene &sc, const PbrtGpuQuadric &q, const Ray &r, float *tHit, DiffGeom *dg) {
     return q.type == PBRTGPU_PRIM_SPHERE ? SphereIntersect(sc, q, r, tHit, dg) : DiskIntersect(sc, q, r, tHit, dg);
 }
 
@@ -286,7 +286,7 @@ DEV bool Traverse(const DScene &sc, Ray &ray, bool anyHit, Hit *hit, TraceStats 
 
 // Re-derive the winning primitive's DifferentialGeometry (what Shape::Intersect
 // filled in at the moment the hit was accepted) and its rayEpsilon.
-DEV void HitGeometry(const DScene &sc, const Ray &rayIn, const Hit &hit, DiffGeom *dg, float *rayEpsilon,
+DEV_NI3 void HitGeometry(const DScene &sc, const Ray &rayIn, const Hit &hit, DiffGeom *dg, float *rayEpsilon,
                      int *material, int *areaLight, uint4 *triOut, uint32_t *primType) {
     const float4 r0 = __ldg(sc.prims + 3 * hit.prim);
     const float4 r1 = __ldg(sc.prims + 3 * hit.prim + 1);

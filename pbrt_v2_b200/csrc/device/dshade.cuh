@@ -31,7 +31,7 @@ DEV V3 SphericalDirection(float sintheta, float costheta, float phi) {
     return V3(sintheta * ref_cosf(phi), sintheta * ref_sinf(phi), costheta);
 }
 
-DEV void ConcentricSampleDisk(float u1, float u2, float *dx, float *dy) {   // core/montecarlo.cpp:306-348
+DEV_NI3 void ConcentricSampleDisk(float u1, float u2, float *dx, float *dy) {   // core/montecarlo.cpp:306-348
     float r, theta;
     float sx = 2 * u1 - 1;
     float sy = 2 * u2 - 1;
@@ -359,7 +359,7 @@ DEV float BxPdf(const BxSet &s, int i, const V3 &wo, const V3 &wi) {
 // BxDF::Sample_f without the f() it returns: BSDF::Sample_f (reflection.cpp:572-576) discards
 // that value for every non-specular BxDF and re-evaluates the sum of all matching components.
 //   Microfacet::Sample_f + Blinn::Sample_f, reflection.cpp:332-363;  BxDF::Sample_f, :311-318
-DEV void BxSampleDir(const BxSet &s, int i, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
+DEV_NI3 void BxSampleDir(const BxSet &s, int i, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
     if (s.kind[i] == BX_MICROFACET_BLINN) {
         float costheta = ref_powf(u1, 1.f / (s.exponent + 1));
         float sintheta = sqrtf(maxf(0.f, 1.f - costheta * costheta));
@@ -480,7 +480,7 @@ DEV V3 DiskSample(const DScene &sc, const PbrtGpuQuadric &q, float u1, float u2,
     return XfPoint(x.m, p);
 }
 // Light::Pdf: PointLight 0 (point.cpp:78-80); DiffuseAreaLight -> ShapeSet::Pdf (light.cpp:157-162)
-DEV float LightPdf(const DScene &sc, const PbrtGpuLight &l, const V3 &p, const V3 &wi) {
+DEV_NI3 float LightPdf(const DScene &sc, const PbrtGpuLight &l, const V3 &p, const V3 &wi) {
     if (l.type == PBRTGPU_LIGHT_POINT) return 0.f;
     float pdf = 0.f;
     for (uint32_t i = 0; i < l.nShapes; ++i) {
