@@ -203,8 +203,8 @@ def main():
     path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-%s-r%d.pbrt" % (args.workload, rank)), xres, yres, spp)
     hs = pb.HostScene(path, ncores=per_pixel_ncores(xres, yres))
     rd = hs.render_desc()
-    rd.shardCount, rd.shardIndex = world, rank
-    rd.shardBlock = 4 * xres            # interleave blocks of 4 pixel rows across ranks
+    from pbrt_v2_b200.multigpu import shard_render_desc, reduce_film
+    shard_render_desc(rd, rank, world, xres)   # interleave blocks of 4 pixel rows across ranks
     _, _, xc, yc = hs.film_extent()
     nsamples = xc * yc * spp
     scene_bytes = hs.scene_bytes()
@@ -217,15 +217,13 @@ def main():
 
     def step_resident(want_stats=False):
         st = gs.render_device(rd, film.data_ptr(), stream.cuda_stream, want_stats=want_stats)
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        reduce_film(film, world)
         return st
 
     def step_e2e():
         g2 = pb.GpuScene(hs)                       # host -> device copy of the flattened scene
         g2.render_device(rd, film.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        reduce_film(film, world)
         if rank == 0:
             host_film.copy_(film, non_blocking=True)   # device -> host read of the step's result
         stream.synchronize()

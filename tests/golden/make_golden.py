@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference built into oracle/_ref by
+`make -C oracle ref`):   python tests/golden/make_golden.py
+
+  ld_samples.npz   LDSampler::GetMoreSamples tables (37 floats/sample) for a few
+                   (spp, nTasks, taskNum), via oracle/_ref/bin/refdump
+  rng.npz          MT19937 RandomUInt() prefixes for a few seeds
+  images.npz       reference-rendered RGB images (PFM -> float32) of tiny variants of
+                   the config scenes, at pinned nTasks (--ncores), + their scene settings
+  counts.json      "BVH created with N nodes for M primitives" of the config scenes
+"""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+from pbrt_v2_b200 import scenes
+import oracle_api as oa
+
+REFDUMP = os.path.join(REPO, "oracle", "_ref", "bin", "refdump")
+
+LD_CASES = [  # (res, spp, nTasks, taskNum)
+    (32, 4, 1024, 0), (32, 4, 1024, 37), (32, 64, 1024, 1023), (32, 1024, 64, 5), (48, 16, 4096, 131),
+]
+IMAGE_CASES = [  # (base, res, spp, ncores)
+    ("bunny", 32, 4, 32), ("bunny", 32, 8, 1), ("killeroo-simple", 32, 4, 32), ("killeroo-simple", 32, 8, 1),
+]
+
+
+def main():
+    scenes.stage()
+    ld = {}
+    for res, spp, ntasks, task in LD_CASES:
+        out = subprocess.run([REFDUMP, "ld", "0", str(res), "0", str(res), str(spp), str(res), str(res), str(ntasks),
+                              str(task), "0", "1"], check=True, stdout=subprocess.PIPE, text=True).stdout.split("\n")
+        n = int(out[0].split()[0])
+        rows = np.array([[float(x) for x in out[1 + i].split()] for i in range(n)], dtype=np.float32)
+        nxt = np.uint32(int(out[1 + n]))
+        key = "r%d_s%d_n%d_t%d" % (res, spp, ntasks, task)
+        ld[key] = rows
+        ld[key + "_next"] = nxt
+    np.savez_compressed(os.path.join(HERE, "ld_samples.npz"), **ld)
+    rng = {}
+    for seed in (0, 1, 5489, 123456):
+        out = subprocess.run([REFDUMP, "rng", str(seed), "2000"], check=True, stdout=subprocess.PIPE, text=True).stdout.split()
+        rng["seed%d" % seed] = np.array([int(x) for x in out], dtype=np.uint32)
+    np.savez_compressed(os.path.join(HERE, "rng.npz"), **rng)
+    imgs = {}
+    for base, res, spp, ncores in IMAGE_CASES:
+        p = scenes.variant(base, os.path.join(scenes.STAGED, "golden-%s.pbrt" % base), res, res, spp)
+        rgb, _ = oa.run_reference(p, ncores)
+        imgs["%s_r%d_s%d_c%d" % (base.replace("-", "_"), res, spp, ncores)] = rgb.astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "images.npz"), **imgs)
+    counts = {}
+    for base in ("bunny", "killeroo-simple"):
+        # (short file name: the reference truncates its log lines at 80 columns)
+        p = scenes.variant(base, os.path.join(scenes.STAGED, "g%s.pbrt" % base[0]), 8, 8, 1, filename="g.pfm")
+        out = subprocess.run([oa.REF_BIN, "--ncores", "1", "--verbose", os.path.basename(p)], cwd=scenes.STAGED,
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+        m = re.search(r"BVH created with (\d+) nodes for (\d+)", out)
+        counts[base] = {"nodes": int(m.group(1)), "primitives": int(m.group(2))}
+    json.dump(counts, open(os.path.join(HERE, "counts.json"), "w"), indent=1, sort_keys=True)
+    print("golden fixtures written:", sorted(os.listdir(HERE)))
+
+
+if __name__ == "__main__":
+    main()

@@ -117,3 +117,38 @@ def test_host_renderer_entry_point(staged):
     px2, _ = gs.render()
     assert np.array_equal(px1["Lxyz"].view(np.uint32), px2["Lxyz"].view(np.uint32))
     assert st.cameraSamples == 32 * 32 * 4
+
+
+@pytest.mark.parametrize("key", ["bunny_r32_s4_c32", "bunny_r32_s8_c1", "killeroo_simple_r32_s4_c32",
+                                 "killeroo_simple_r32_s8_c1"])
+def test_render_matches_golden_reference_images(staged, key):
+    """GPU render vs images rendered by the UNMODIFIED reference (tests/golden/images.npz)."""
+    import os
+    g = np.load(os.path.join(pb.REPO, "tests", "golden", "images.npz"))
+    base = "bunny" if key.startswith("bunny") else "killeroo-simple"
+    res, spp, ncores = [int(x[1:]) for x in key.split("_")[-3:]]
+    hs = host_scene(base, res, res, spp, ncores)
+    px, _ = _gpu_scene(hs).render()
+    rgb, want = hs.pixels_to_rgb(px), g[key]
+    rel = np.abs(rgb - want) / np.maximum(np.abs(want), 1e-3)
+    bad = (rel > TIER_A_REL).any(axis=2)
+    assert bad.mean() <= 0.01, "%.2f%% of pixels differ from the reference by more than %g" % (100 * bad.mean(), TIER_A_REL)
+    assert abs(rgb.mean() - want.mean()) <= 1e-3 * abs(want.mean())
+
+
+def test_full_size_properties(staged):
+    """BASELINE-size film (1024x1024) at reduced spp: size-independent properties --
+    every pixel receives exactly spp samples (+ edge splats), shards tile the image, no NaN/negative."""
+    hs = host_scene("bunny", 1024, 1024, 4, 32768)
+    gs = _gpu_scene(hs)
+    px, st = gs.render()
+    assert st.cameraSamples == 1024 * 1024 * 4
+    w = px["weightSum"]
+    assert w.min() >= 4 and w.max() <= 4 + 8 and abs(w.sum() - (4 * 1024 * 1024 + (w - 4).sum())) < 1
+    assert np.isfinite(px["Lxyz"]).all() and (px["Lxyz"] >= 0).all()
+    rd = hs.render_desc()
+    rd.shardCount, rd.shardIndex, rd.shardBlock = 2, 1, 4096
+    half, _ = gs.render(rd)
+    own = half["weightSum"] >= 4
+    assert abs(own.mean() - 0.5) < 0.01
+    assert np.array_equal(half["Lxyz"][own & (w == 4)].view(np.uint32), px["Lxyz"][own & (w == 4)].view(np.uint32))

@@ -1,0 +1,85 @@
+"""Pins the oracle (oracle/liboracle.so, the CPU restatement) against the reference:
+(a) committed golden vectors minted from the UNMODIFIED reference (tests/golden/,
+    generator: tests/golden/make_golden.py), and
+(b) where oracle/_ref/bin/pbrt exists, the reference binary run on the spot.
+Bit-exact except for the film pixels that receive samples from two different
+render tasks (edge splats, film/image.cpp:82-89,122-127), where the reference itself
+is order-dependent run to run."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import pbrt_v2_b200 as pb
+import oracle_api as oa
+from helpers import host_scene
+
+GOLD = os.path.join(pb.REPO, "tests", "golden")
+pytestmark = pytest.mark.skipif(not oa.have_oracle(), reason="oracle/liboracle.so not built")
+
+
+def test_rng_matches_reference_mt19937():
+    g = np.load(os.path.join(GOLD, "rng.npz"))
+    # the oracle exposes its RNG through the LD tables; check the MT19937 core via numpy's generator too
+    for key in g.files:
+        seed = int(key[4:])
+        want = g[key]
+        mt = np.random.RandomState()
+        # pbrt seeds with init_genrand(seed) == numpy's legacy seeding for 32-bit ints
+        mt.seed(seed)
+        got = mt.randint(0, 2**32, size=len(want), dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(got, want), "reference RNG is not plain MT19937 for seed %d" % seed
+
+
+def test_ld_tables_match_golden():
+    g = np.load(os.path.join(GOLD, "ld_samples.npz"))
+    cases = [k for k in g.files if not k.endswith("_next")]
+    assert len(cases) >= 5
+    for key in cases:
+        res, spp, ntasks, task = [int(x[1:]) for x in key.split("_")]
+        rd = pb.RenderDesc()
+        rd.xResolution = rd.yResolution = res
+        rd.cropWindow[:] = [0, 1, 0, 1]
+        rd.filterXWidth = rd.filterYWidth = 0.5
+        rd.samplesPerPixel = spp
+        rd.maxDepth = 5
+        rd.nTasks, rd.taskBegin, rd.taskEnd = ntasks, 0, ntasks
+        rd.shutterOpen, rd.shutterClose = 0.0, 1.0
+        got = oa.ld_samples(rd, task)
+        want = g[key]
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), key
+
+
+@pytest.mark.parametrize("key", ["bunny_r32_s4_c32", "bunny_r32_s8_c1", "killeroo_simple_r32_s4_c32",
+                                 "killeroo_simple_r32_s8_c1"])
+def test_oracle_image_matches_golden_reference_render(staged, key):
+    g = np.load(os.path.join(GOLD, "images.npz"))
+    base = "bunny" if key.startswith("bunny") else "killeroo-simple"
+    res, spp, ncores = [int(x[1:]) for x in key.split("_")[-3:]]
+    hs = host_scene(base, res, res, spp, ncores)
+    px, _ = oa.render(hs, threads=4)
+    rgb = hs.pixels_to_rgb(px)
+    want = g[key]
+    differ = (rgb.view(np.uint32) != want.view(np.uint32)).any(axis=2)
+    # multi-pixel tasks (c1): every pixel bit-exact; per-pixel tasks: only cross-task edge splats may differ
+    assert differ.sum() <= (0 if ncores == 1 else 4), "%d pixels differ from the reference render" % differ.sum()
+    np.testing.assert_allclose(rgb, want, rtol=2e-6, atol=0)
+
+
+def test_bvh_sizes_match_reference(staged):
+    counts = json.load(open(os.path.join(GOLD, "counts.json")))
+    for base, want in counts.items():
+        got = host_scene(base, 8, 8, 1, 1).counts()
+        assert got["nodes"] == want["nodes"] and got["primitives"] == want["primitives"], (base, got, want)
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("base,res,spp,ncores", [("bunny", 40, 8, 2), ("killeroo-simple", 40, 4, 2)])
+def test_oracle_bit_exact_vs_reference_binary(staged, base, res, spp, ncores):
+    hs = host_scene(base, res, res, spp, ncores, tag="-live")
+    px, _ = oa.render(hs, threads=4)
+    rgb = hs.pixels_to_rgb(px)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(rgb.view(np.uint32), ref.view(np.uint32))
