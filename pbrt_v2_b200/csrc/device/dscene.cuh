@@ -284,6 +284,76 @@ DEV bool Traverse(const DScene &sc, Ray &ray, bool anyHit, Hit *hit, TraceStats 
     return found;
 }
 
+// ---- step-wise traversal (wavefront trace kernel) ---------------------------------------
+// Same walk as Traverse<>, cut into single-node steps so that a persistent lane can pick up a new
+// ray from the queue the moment its current one finishes (no lane waits for its warp's longest ray).
+struct Trav {
+    Ray ray;
+    V3 invDir;
+    uint32_t nodeNum, todoOffset;
+    bool neg[3];
+    bool anyHit, found;
+    Hit hit;
+    uint32_t todo[64];
+};
+DEV void TravInit(Trav &t, const Ray &ray, bool anyHit) {
+    t.ray = ray;
+    t.invDir = V3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+    t.neg[0] = t.invDir.x < 0; t.neg[1] = t.invDir.y < 0; t.neg[2] = t.invDir.z < 0;
+    t.nodeNum = 0; t.todoOffset = 0;
+    t.anyHit = anyHit; t.found = false;
+    t.hit.prim = -1; t.hit.b1 = t.hit.b2 = 0.f; t.hit.maxtIn = 0.f; t.hit.t = 0.f;
+}
+// returns true when the ray is finished (result in t.found / t.hit / t.ray.maxt)
+template <bool STATS>
+DEV bool TravStep(const DScene &sc, Trav &t, TraceStats *st) {
+    const float4 n0 = __ldg(sc.nodes + 2 * t.nodeNum);
+    const float4 n1 = __ldg(sc.nodes + 2 * t.nodeNum + 1);
+    if (STATS) st->nodes++;
+    if (BoxTest(n0, n1, t.ray, t.invDir, t.neg)) {
+        const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
+        const uint32_t nPrims = meta & 0xffu;
+        if (nPrims > 0) {
+            for (uint32_t i = 0; i < nPrims; ++i) {
+                const uint32_t pi = offset + i;
+                const float4 r0 = __ldg(sc.prims + 3 * pi);
+                const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
+                const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
+                if (STATS) st->prims++;
+                const uint32_t type = __float_as_uint(r0.w);
+                float tt, b1 = 0.f, b2 = 0.f;
+                bool h;
+                if (type == PBRTGPU_PRIM_TRIANGLE)
+                    h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), t.ray, &tt, &b1, &b2);
+                else
+                    h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], t.ray, &tt, nullptr);
+                if (h) {
+                    t.hit.prim = (int)pi;
+                    t.found = true;
+                    if (t.anyHit) { t.hit.t = t.ray.maxt; return true; }
+                    t.hit.b1 = b1; t.hit.b2 = b2; t.hit.maxtIn = t.ray.maxt;
+                    t.ray.maxt = tt;
+                }
+            }
+            if (t.todoOffset == 0) { t.hit.t = t.ray.maxt; return true; }
+            t.nodeNum = t.todo[--t.todoOffset];
+        } else {
+            const uint32_t axis = (meta >> 8) & 0xffu;
+            if (t.neg[axis]) {
+                t.todo[t.todoOffset++] = t.nodeNum + 1;
+                t.nodeNum = offset;
+            } else {
+                t.todo[t.todoOffset++] = offset;
+                t.nodeNum = t.nodeNum + 1;
+            }
+        }
+    } else {
+        if (t.todoOffset == 0) { t.hit.t = t.ray.maxt; return true; }
+        t.nodeNum = t.todo[--t.todoOffset];
+    }
+    return false;
+}
+
 // Re-derive the winning primitive's DifferentialGeometry (what Shape::Intersect
 // filled in at the moment the hit was accepted) and its rayEpsilon.
 DEV_NI3 void HitGeometry(const DScene &sc, const Ray &rayIn, const Hit &hit, DiffGeom *dg, float *rayEpsilon,

@@ -59,16 +59,22 @@ struct DeviceStats {
 };
 
 // --------------------------------------------------------------------- k_tables
-// LDSampler::GetMoreSamples / LDPixelSample for one pixel of each task.
+// LDSampler::GetMoreSamples / LDPixelSample for one pixel of each task (one warp per task).
+//
+// The pixel's 37 + 52*spp draws are consumed array by array (drng.cuh): scramble word(s), spp
+// draws that the reference spends on 1-element shuffles (skipped: only the stream position moves),
+// spp Fisher-Yates draws.  Stage 1 turns the latter into swap targets `i + y % (spp - i)` and parks
+// them in the task's (not yet used) `rec` scratch; stage 2 runs the 26 inherently sequential
+// shuffles, one array per lane, on u16 index arrays in shared memory, with the targets prefetched
+// from global memory; stage 3 writes one 64-byte row of shuffled indices per camera sample.
 template <int WPB>
 __global__ void __launch_bounds__(32 * WPB) k_tables(BatchArgs a, int spp, int G) {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int stride = spp + 2;   // +2 u16 (one bank) of padding per array
-    const size_t warpWords = MT_N + (size_t)G * stride;   // mt + (T,P as u16 pairs -> G*stride words)
+    const size_t warpWords = MT_N + ((size_t)G * stride + 1) / 2;
     uint32_t *mt = smem + warp * warpWords;
-    uint16_t *T = reinterpret_cast<uint16_t *>(mt + MT_N);
-    uint16_t *P = T + (size_t)G * stride;
+    uint16_t *P = reinterpret_cast<uint16_t *>(mt + MT_N);
     const int bi = blockIdx.x * WPB + warp;
     if (bi >= a.nBatch) return;
     const TaskRec tr = a.tasks[bi];
@@ -88,56 +94,94 @@ __global__ void __launch_bounds__(32 * WPB) k_tables(BatchArgs a, int spp, int G
     }
     __syncwarp();
 
-    uint32_t consumed = 0;
     uint16_t *permOut = a.perm + (size_t)bi * spp * PERM_STRIDE;
     uint32_t *scrOut = a.scr + (size_t)bi * SCR_STRIDE;
-    for (int a0 = 0; a0 < N_ARRAYS; a0 += G) {
-        const int a1 = min(N_ARRAYS, a0 + G);
-        const uint32_t end = ArrayStart(a1, spp);
-        // stage 1: this group's slice of the pixel's draw stream -> scrambles + shuffle targets
-        while (consumed < end) {
+    uint16_t *Tg = reinterpret_cast<uint16_t *>(a.rec + (size_t)bi * spp * 4);   // [N_ARRAYS][spp] swap targets
+
+    // ---- stage 1: walk the draw stream
+    for (int arr = 0; arr < N_ARRAYS; ++arr) {
+        const int ns = (arr <= 1 || arr >= 17) ? 2 : 1;   // 2-D arrays draw two scramble words
+        for (int k = 0; k < ns; ++k) {
             if (mti >= MT_N) { WarpRegenMT(mt, lane); mti = 0; }
-            const uint32_t n = min((uint32_t)(MT_N - mti), end - consumed);
-            for (uint32_t j = lane; j < n; j += 32) {
+            if (lane == 0) scrOut[ScrambleSlot(arr) + k] = Temper(mt[mti]);
+            ++mti;
+        }
+        // Shuffle(samples + i, 1, dims, rng) for every pixel sample: `RandomUInt() % 1`, no effect
+        for (int n = spp; n > 0;) {
+            if (mti >= MT_N) { WarpRegenMT(mt, lane); mti = 0; }
+            const int take = min(n, MT_N - mti);
+            mti += take;
+            n -= take;
+        }
+        // Shuffle(samples, nPixel, dims, rng): other = i + RandomUInt() % (count - i), montecarlo.h:177
+        uint16_t *Ta = Tg + (size_t)arr * spp;
+        for (int i0 = 0; i0 < spp;) {
+            if (mti >= MT_N) { WarpRegenMT(mt, lane); mti = 0; }
+            const int take = min(spp - i0, MT_N - mti);
+            for (int j = lane; j < take; j += 32) {
+                const uint32_t i = (uint32_t)(i0 + j);
                 const uint32_t y = Temper(mt[mti + j]);
-                int arr, role;
-                uint32_t i;
-                ClassifyDraw(consumed + j, spp, &arr, &role, &i);
-                if (role == 0) scrOut[ScrambleSlot(arr) + i] = y;
-                else if (role == 2) T[(arr - a0) * stride + i] = (uint16_t)(i + y % (spp - i));   // montecarlo.h:177
+                Ta[i] = (uint16_t)(i + y % ((uint32_t)spp - i));
             }
-            __syncwarp();
-            mti += n;
-            consumed += n;
+            mti += take;
+            i0 += take;
         }
-        // stage 2: Fisher-Yates (Shuffle, montecarlo.h:174-181) of the identity, one array per lane
-        const int ng = a1 - a0;
-        for (int idx = lane; idx < ng * spp; idx += 32) {
-            const int l = idx / spp, i = idx - l * spp;
-            P[l * stride + i] = (uint16_t)i;
-        }
-        __syncwarp();
-        if (lane < ng) {
-            uint16_t *p = P + lane * stride;
-            const uint16_t *t = T + lane * stride;
-            for (int i = 0; i < spp; ++i) {
-                const int j = t[i];
-                const uint16_t tmp = p[i];
-                p[i] = p[j];
-                p[j] = tmp;
-            }
-        }
-        __syncwarp();
-        for (int s = lane; s < spp; s += 32)
-            for (int l = 0; l < ng; ++l) permOut[(size_t)s * PERM_STRIDE + a0 + l] = P[l * stride + s];
-        __syncwarp();
     }
-    // save the stream position: cur = block in use, next = the one after it
+    __syncwarp();
+    // the stream position after the tables: cur = block in use, next = the one after it
     for (int j = lane; j < MT_N; j += 32) cur[j] = mt[j];
     __syncwarp();
     WarpRegenMT(mt, lane);
     for (int j = lane; j < MT_N; j += 32) next[j] = mt[j];
     if (lane == 0) a.mti[bi] = mti;
+    __threadfence_block();
+    __syncwarp();
+
+    // ---- stages 2+3, G arrays at a time
+    for (int a0 = 0; a0 < N_ARRAYS; a0 += G) {
+        const int ng = min(N_ARRAYS, a0 + G) - a0;
+        for (int l = 0; l < ng; ++l)
+            for (int i = lane; i < spp; i += 32) P[l * stride + i] = (uint16_t)i;
+        __syncwarp();
+        if (lane < ng) {   // Fisher-Yates of the identity (Shuffle, montecarlo.h:174-181)
+            uint16_t *p = P + lane * stride;
+            const uint16_t *t = Tg + (size_t)(a0 + lane) * spp;
+            for (int i0 = 0; i0 < spp; i0 += 8) {   // spp is a power of two >= 1; targets fetched 8 ahead
+                uint16_t tj[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) tj[k] = (i0 + k < spp) ? __ldcg(t + i0 + k) : (uint16_t)0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + k;
+                    if (i < spp) {
+                        const int j = tj[k];
+                        const uint16_t tmp = p[i];
+                        p[i] = p[j];
+                        p[j] = tmp;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (ng == N_ARRAYS) {
+            // one 64-byte row per camera sample, assembled in registers: coalesced 128-bit stores
+            for (int s = lane; s < spp; s += 32) {
+                uint32_t w[16];
+#pragma unroll
+                for (int l = 0; l < 13; ++l) w[l] = (uint32_t)P[(2 * l) * stride + s] | ((uint32_t)P[(2 * l + 1) * stride + s] << 16);
+                w[13] = w[14] = w[15] = 0u;
+                uint4 *dst = reinterpret_cast<uint4 *>(permOut + (size_t)s * PERM_STRIDE);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+                dst[3] = make_uint4(w[12], w[13], w[14], w[15]);
+            }
+        } else {
+            for (int s = lane; s < spp; s += 32)
+                for (int l = 0; l < ng; ++l) permOut[(size_t)s * PERM_STRIDE + a0 + l] = P[l * stride + s];
+        }
+        __syncwarp();
+    }
 }
 
 // expand one task's tables into the reference's Sample layout (test hook)
@@ -343,195 +387,15 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
         }
         if (!__any_sync(FULL, state != S_DONE)) break;
 
-        bool wantTrace = false, anyHit = false;
-        bool evalReq = false;
-        V3 evalWo(0, 0, 1), evalWi(0, 0, 1);
-        int evalFlags = 0;
-
-        // ================= part A: consume the traversal result, run up to the next BSDF evaluation
-        if (state == S_HIT_RESULT) {
-            if (!found) {
-                // SamplerRenderer::Li miss (bounce 0: sum of Light::Le == 0) / path.cpp:113-118
-                state = S_END_SAMPLE;
-            } else if (PHASE == 1 && bounces == 3) {
-                // ---- park the sample: from here on the path draws from the task's RNG stream
-                float4 *r = recBase + (size_t)s * 4;
-                r[0] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
-                r[1] = make_float4(ray.d.x, ray.d.y, ray.d.z, hit.t);
-                r[2] = make_float4(T.r, T.g, T.b, __int_as_float(hit.prim));
-                r[3] = make_float4(hit.b1, hit.b2, hit.maxtIn, 0.f);
-                lsBase[s] = make_float4(L.r, L.g, L.b, __int_as_float(code | LS_TAIL));
-                state = S_NEW_SAMPLE;
-            } else {
-                // ---- path.cpp:61-80: emitted light, BSDF, UniformSampleOneLight up to bsdf->f()
-                BuildShadeCtx(sc, ray, hit, &ctx, STATS ? &nShadedN : nullptr);
-                wo = -ray.d;
-                if (bounces == 0) L = L + T * HitLe(sc, ctx.areaLight, ctx.ng, wo);
-                Ld = Spec(0.f);
-                const int nLights = (int)sc.nLights;
-                state = S_AFTER_DIRECT;
-                if (nLights > 0) {
-                    float lnU, lsU0, lsU1;
-                    if (bounces < 3) {   // path.cpp:71-76: table samples of depth `bounces`
-                        const uint16_t *row = permBase + (size_t)s * PERM_STRIDE;
-                        const int d = bounces;
-                        lnU = VanDerCorput(row[3 + 4 * d + 1], scr[5 + 4 * d + 1]);
-                        const uint32_t pl = row[17 + 3 * d + 0];
-                        lsU0 = VanDerCorput(pl, scr[19 + 2 * (3 * d + 0)]);
-                        lsU1 = Sobol2(pl, scr[20 + 2 * (3 * d + 0)]);
-                        const uint32_t pb = row[17 + 3 * d + 1];
-                        bsU0 = VanDerCorput(pb, scr[19 + 2 * (3 * d + 1)]);
-                        bsU1 = Sobol2(pb, scr[20 + 2 * (3 * d + 1)]);
-                        bsUc = VanDerCorput(row[3 + 4 * d + 2], scr[5 + 4 * d + 2]);
-                        // (light uComponent, oneD[4d+0], selects a shape of the ShapeSet: one shape in scope)
-                    } else {             // integrator.cpp:95,107-108: lightNum, LightSample(rng), BSDFSample(rng)
-                        lnU = rngF(0);
-                        lsU0 = rngF(1); lsU1 = rngF(2);
-                        bsU0 = rngF(4); bsU1 = rngF(5); bsUc = rngF(6);
-                        mti += 7;
-                    }
-                    lightNum = mini(Floor2Int(lnU * nLights), nLights - 1);
-                    const PbrtGpuLight &light = sc.lights[lightNum];
-                    // ---- EstimateDirect, light-sampling half (integrator.cpp:123-142)
-                    Ray vis;
-                    Spec Li = LightSample_L(sc, light, ctx.p, ctx.rayEpsilon, lsU0, lsU1, &wiW, &sPdf, &vis);
-                    visMaxt = vis.maxt;   // vis.o == p, vis.mint == rayEpsilon, vis.d == wi bit for bit
-                    state = S_AFTER_LIGHT;
-                    if (sPdf > 0.f && !Li.IsBlack()) {
-                        pend = Li;
-                        // Spectrum f = bsdf->f(wo, wi, flags)  -- BSDF::f, reflection.cpp:612-626
-                        evalWi = WorldToLocal(ctx, wiW); evalWo = WorldToLocal(ctx, wo);
-                        evalFlags = BSDF_ALL & ~BSDF_SPECULAR;
-                        if (Dot(wiW, ctx.ng) * Dot(wo, ctx.ng) > 0) evalFlags &= ~BSDF_TRANSMISSION;
-                        else evalFlags &= ~BSDF_REFLECTION;
-                        evalReq = true;
-                        state = S_E_LIGHT;
-                    }
-                }
-            }
-        } else if (state == S_SHADOW_RESULT) {
-            if (!found) Ld = Ld + pend;   // visibility.Unoccluded(scene), Transmittance == 1
-            state = S_AFTER_LIGHT;
-        } else if (state == S_MIS_RESULT) {
-            if (found) {
-                DiffGeom dgl;
-                float eps;
-                int mat, al;
-                uint4 tri;
-                uint32_t ptype;
-                HitGeometry(sc, ray, hit, &dgl, &eps, &mat, &al, &tri, &ptype);
-                // lightIsect.primitive->GetAreaLight() == light  &&  L(p, n, -wi) not black
-                const PbrtGpuLight &light = sc.lights[lightNum];
-                const bool emits = !Spec(light.L[0], light.L[1], light.L[2]).IsBlack();
-                if (al == lightNum && Dot(dgl.nn, -ray.d) > 0.f && emits) Ld = Ld + pend;
-            }
-            state = S_AFTER_DIRECT;
-        }
-
-        if (state == S_AFTER_LIGHT) {
-            // ---- EstimateDirect, BSDF-sampling half (integrator.cpp:145-172): choose the direction
-            state = S_AFTER_DIRECT;
-            const PbrtGpuLight &light = sc.lights[lightNum];
-            if (light.type != PBRTGPU_LIGHT_POINT) {
-                BxSet bx;
-                MaterialBxDFs(sc, ctx.material, &bx);
-                int sampledType;
-                if (BSDF_SampleDir(ctx, bx, wo, bsU0, bsU1, bsUc, BSDF_ALL & ~BSDF_SPECULAR, &evalWo, &evalWi, &wiW,
-                                   &sPdf, &sampledType, &evalFlags)) {
-                    evalReq = true;
-                    state = S_E_MIS;
-                }
-            }
-        }
-
-        if (state == S_AFTER_DIRECT) {
-            // ---- path.cpp:71-94: add direct light, choose the continuation direction
-            L = L + T * ((float)(int)sc.nLights * Ld);
-            float u0, u1, uc;
-            if (bounces < 3) {
-                const uint16_t *row = permBase + (size_t)s * PERM_STRIDE;
-                const int d = bounces;
-                const uint32_t pp = row[17 + 3 * d + 2];
-                u0 = VanDerCorput(pp, scr[19 + 2 * (3 * d + 2)]);
-                u1 = Sobol2(pp, scr[20 + 2 * (3 * d + 2)]);
-                uc = VanDerCorput(row[3 + 4 * d + 3], scr[5 + 4 * d + 3]);
-            } else {
-                u0 = rngF(0); u1 = rngF(1); uc = rngF(2);
-                mti += 3;
-            }
-            BxSet bx;
-            MaterialBxDFs(sc, ctx.material, &bx);
-            int sampledType;
-            state = S_END_SAMPLE;   // f.IsBlack() || pdf == 0.  -> break
-            if (BSDF_SampleDir(ctx, bx, wo, u0, u1, uc, BSDF_ALL, &evalWo, &evalWi, &wiW, &sPdf, &sampledType, &evalFlags)) {
-                evalReq = true;
-                state = S_E_PATH;
-            }
-        }
-
-        // ================= the single BSDF-evaluation site (sum of matching BxDF::f, reflection.cpp:572-576,620-623)
-        Spec fEval(0.f);
-        if (evalReq) {
-            BxSet bx;
-            MaterialBxDFs(sc, ctx.material, &bx);
-            for (int i = 0; i < bx.n; ++i)
-                if (Matches(bx.type[i], evalFlags)) fEval = fEval + BxF(sc, bx, i, evalWo, evalWi);
-        }
-
-        // ================= part B: use the BSDF value, run up to the next ray
-        if (state == S_E_LIGHT) {
-            state = S_AFTER_LIGHT;   // (picked up by part A of the next iteration if no shadow ray is needed)
-            if (!fEval.IsBlack()) {
-                const PbrtGpuLight &light = sc.lights[lightNum];
-                if (light.type == PBRTGPU_LIGHT_POINT)
-                    pend = fEval * pend * (AbsDot(wiW, ctx.nn) / sPdf);
-                else {
-                    BxSet bx;
-                    MaterialBxDFs(sc, ctx.material, &bx);
-                    float bsdfPdf = BSDF_PdfLocal(bx, evalWo, evalWi, BSDF_ALL & ~BSDF_SPECULAR);
-                    float weight = PowerHeuristic(1, sPdf, 1, bsdfPdf);
-                    pend = fEval * pend * (AbsDot(wiW, ctx.nn) * weight / sPdf);
-                }
-                ray.o = ctx.p; ray.d = wiW; ray.mint = ctx.rayEpsilon; ray.maxt = visMaxt;
-                wantTrace = true; anyHit = true;
-                state = S_SHADOW_RESULT;
-            }
-        } else if (state == S_E_MIS) {
-            state = S_AFTER_DIRECT;   // (next iteration)
-            if (!fEval.IsBlack() && sPdf > 0.f) {
-                const PbrtGpuLight &light = sc.lights[lightNum];
-                // sampledType is never specular for the in-scope BxDFs
-                float lightPdf = LightPdf(sc, light, ctx.p, wiW);
-                if (lightPdf != 0.f) {   // else `return Ld`
-                    float weight = PowerHeuristic(1, sPdf, 1, lightPdf);
-                    // Li is either Lemit or black (diffuse.h:51-53), so the term can be formed now
-                    pend = fEval * Spec(light.L[0], light.L[1], light.L[2]) * AbsDot(wiW, ctx.nn) * weight / sPdf;
-                    ray.o = ctx.p; ray.d = wiW; ray.mint = ctx.rayEpsilon; ray.maxt = INF_F;
-                    wantTrace = true; anyHit = false;
-                    state = S_MIS_RESULT;
-                }
-            }
-        } else if (state == S_E_PATH) {
-            // ---- path.cpp:96-121: throughput, Russian roulette, next ray
-            state = S_END_SAMPLE;
-            if (!fEval.IsBlack()) {
-                T = T * (fEval * AbsDot(wiW, ctx.nn) / sPdf);
-                ray.o = ctx.p; ray.d = wiW; ray.mint = ctx.rayEpsilon; ray.maxt = INF_F;
-                bool alive = true;
-                if (bounces > 3) {
-                    float continueProbability = minf(.5f, T.y());
-                    const float r = rngF(0);
-                    mti += 1;
-                    if (r > continueProbability) alive = false;
-                    else T = T / continueProbability;
-                }
-                if (alive && bounces != rp.maxDepth) {
-                    ++bounces;
-                    wantTrace = true; anyHit = false;
-                    state = S_HIT_RESULT;
-                }
-            }
-        }
+#define PATH_FEVAL_IN Spec(0.f)
+#define PATH_EVALWO_IN V3(0, 0, 1)
+#define PATH_EVALWI_IN V3(0, 0, 1)
+#define PATH_DEFER_MEASURED false
+#include "path_body.inc"
+#undef PATH_FEVAL_IN
+#undef PATH_EVALWO_IN
+#undef PATH_EVALWI_IN
+#undef PATH_DEFER_MEASURED
 
         if (state == S_END_SAMPLE) {
             if (PHASE == 1) {
@@ -639,6 +503,323 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
     }
 }
 
+// ------------------------------------------------------------------- wavefront
+// Phase 1 as a wavefront (the default): the same state machine, but every path lives in a pool slot
+// in HBM and each of its blocking requests is served by a kernel specialised for it:
+//   k_logic  one thread per pool slot: consume the previous result, run the state machine up to the
+//            next ray or (measured-BRDF) evaluation, park / finish / start camera samples
+//   k_trace  persistent lanes pull rays from the queue; a lane whose walk ends takes the next ray at
+//            once (no lane waits for its warp's longest walk)
+//   k_eval   kd-tree queries of IrregIsotropicBRDF::f for the queued requests
+// Slots are SoA float4 fields: field f of slot i is pool[f * P + i].
+enum {
+    F_RAY_O = 0,   // o.xyz, mint
+    F_RAY_D,       // d.xyz, maxt (in) / t (out)
+    F_HIT,         // prim, b1, b2, maxtIn
+    F_T,           // T.rgb, packed {state:8, bounces:8, lightNum:16}
+    F_L,           // L.rgb, code
+    F_LD,          // Ld.rgb, sPdf
+    F_PEND,        // pend.rgb, visMaxt
+    F_CTX_P,       // p.xyz, rayEpsilon
+    F_CTX_NN,      // nn.xyz, material | (areaLight+1) << 16
+    F_CTX_NG,      // ng.xyz, bsU0
+    F_CTX_SN,      // sn.xyz, bsU1
+    F_CTX_TN,      // tn.xyz, bsUc
+    F_WO,          // wo.xyz, task (batch index)
+    F_WI,          // wiW.xyz, sample index
+    F_EVAL_WO,     // evalWo.xyz, evalFlags
+    F_EVAL_WI,     // evalWi.xyz
+    F_FEVAL,       // fEval.rgb
+    F_COUNT
+};
+enum { C_TRACE_N = 0, C_EVAL_N, C_TRACE_CUR, C_EVAL_CUR, C_ALIVE, C_NEXT_SAMPLE, C_COUNT };
+
+struct WfArgs {
+    DScene sc;
+    RenderParams rp;
+    BatchArgs b;
+    float4 *pool;
+    uint32_t P;
+    uint32_t *traceQ;    // slot | anyHit << 31
+    uint32_t *evalQ;
+    unsigned *counters;  // C_*
+    unsigned totalSamples;
+    DeviceStats *stats;
+};
+
+DEV unsigned AggregatedAdd(unsigned *ctr) {   // warp-aggregated atomicAdd(ctr, 1) for the currently converged lanes
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(ctr, (unsigned)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.P) return;
+    const DScene &sc = a.sc;
+    const RenderParams &rp = a.rp;
+    const int spp = rp.spp;
+    const int PHASE = 1;
+    float4 *pool = a.pool;
+    const size_t P = a.P;
+#define FLD(f) pool[(size_t)(f) * P + slot]
+
+    const float4 fT = FLD(F_T);
+    const uint32_t packed = __float_as_uint(fT.w);
+    int state = packed & 0xffu;
+    if (state == S_DONE) return;
+    int bounces = (packed >> 8) & 0xffu;
+    int lightNum = packed >> 16;
+    Spec T(fT.x, fT.y, fT.z);
+
+    int s = 0, code = 0, bi = 0, mti = 0;
+    Ray ray;
+    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f;
+    Hit hit;
+    hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.maxtIn = 0.f;
+    bool found = false;
+    Spec L(0.f), Ld(0.f), pend(0.f), fLoaded(0.f);
+    ShadeCtx ctx;
+    ctx.p = ctx.nn = ctx.ng = ctx.sn = ctx.tn = V3(0, 0, 1);
+    ctx.material = 0; ctx.areaLight = -1; ctx.rayEpsilon = 0.f;
+    V3 wo(0, 0, 1), wiW(0, 0, 1), evalWoIn(0, 0, 1), evalWiIn(0, 0, 1);
+    float bsU0 = 0.f, bsU1 = 0.f, bsUc = 0.f, sPdf = 0.f, visMaxt = 0.f;
+    unsigned long long nShadedN = 0;
+
+    if (state != S_NEW_SAMPLE) {
+        const float4 fL = FLD(F_L), fWo = FLD(F_WO), fWi = FLD(F_WI);
+        L = Spec(fL.x, fL.y, fL.z); code = __float_as_int(fL.w);
+        wo = V3(fWo.x, fWo.y, fWo.z); bi = __float_as_int(fWo.w);
+        wiW = V3(fWi.x, fWi.y, fWi.z); s = __float_as_int(fWi.w);
+        const float4 r0 = FLD(F_RAY_O), r1 = FLD(F_RAY_D), h = FLD(F_HIT);
+        ray.o = V3(r0.x, r0.y, r0.z); ray.mint = r0.w;
+        ray.d = V3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
+        hit.prim = __float_as_int(h.x); hit.b1 = h.y; hit.b2 = h.z; hit.maxtIn = h.w; hit.t = r1.w;
+        found = hit.prim >= 0;
+        if (state != S_HIT_RESULT) {   // mid-vertex states need the shading context
+            const float4 c0 = FLD(F_CTX_P), c1 = FLD(F_CTX_NN), c2 = FLD(F_CTX_NG), c3 = FLD(F_CTX_SN), c4 = FLD(F_CTX_TN);
+            ctx.p = V3(c0.x, c0.y, c0.z); ctx.rayEpsilon = c0.w;
+            ctx.nn = V3(c1.x, c1.y, c1.z);
+            const uint32_t ml = __float_as_uint(c1.w);
+            ctx.material = (int)(ml & 0xffffu); ctx.areaLight = (int)(ml >> 16) - 1;
+            ctx.ng = V3(c2.x, c2.y, c2.z); bsU0 = c2.w;
+            ctx.sn = V3(c3.x, c3.y, c3.z); bsU1 = c3.w;
+            ctx.tn = V3(c4.x, c4.y, c4.z); bsUc = c4.w;
+            const float4 d0 = FLD(F_LD), d1 = FLD(F_PEND);
+            Ld = Spec(d0.x, d0.y, d0.z); sPdf = d0.w;
+            pend = Spec(d1.x, d1.y, d1.z); visMaxt = d1.w;
+            if (state == S_E_LIGHT || state == S_E_MIS || state == S_E_PATH) {
+                const float4 e0 = FLD(F_EVAL_WO), e1 = FLD(F_EVAL_WI), e2 = FLD(F_FEVAL);
+                evalWoIn = V3(e0.x, e0.y, e0.z); evalWiIn = V3(e1.x, e1.y, e1.z);
+                fLoaded = Spec(e2.x, e2.y, e2.z);
+            }
+        }
+    }
+
+    // per-task environment (re-derived whenever the slot starts a sample of another task)
+    const uint16_t *permBase = nullptr;
+    const uint32_t *scr = nullptr;
+    float4 *lsBase = nullptr, *recBase = nullptr;
+    int xPos = 0, yPos = 0;
+    auto bindTask = [&](int task) -> bool {
+        const TaskRec tr = a.b.tasks[task];
+        const int tw = tr.x1 - tr.x0;
+        if (a.b.round >= tw * (tr.y1 - tr.y0)) return false;
+        xPos = tr.x0 + a.b.round % tw;
+        yPos = tr.y0 + a.b.round / tw;
+        permBase = a.b.perm + (size_t)task * spp * PERM_STRIDE;
+        scr = a.b.scr + (size_t)task * SCR_STRIDE;
+        lsBase = a.b.ls + (size_t)task * spp;
+        recBase = a.b.rec + (size_t)task * spp * 4;
+        return true;
+    };
+    if (state != S_NEW_SAMPLE) bindTask(bi);
+    auto rngF = [&](int) -> float { return 0.f; };   // phase 1 never draws from the RNG stream
+
+    bool wantTraceOut = false, anyHitOut = false, deferOut = false;
+    V3 evalWoOut(0, 0, 1), evalWiOut(0, 0, 1);
+    int evalFlagsOut = 0;
+    for (;;) {
+#define PATH_FEVAL_IN fLoaded
+#define PATH_EVALWO_IN evalWoIn
+#define PATH_EVALWI_IN evalWiIn
+#define PATH_DEFER_MEASURED true
+#include "path_body.inc"
+#undef PATH_FEVAL_IN
+#undef PATH_EVALWO_IN
+#undef PATH_EVALWI_IN
+#undef PATH_DEFER_MEASURED
+        if (deferEval) {
+            deferOut = true;
+            evalWoOut = evalWo; evalWiOut = evalWi; evalFlagsOut = evalFlags;
+            break;
+        }
+        fLoaded = Spec(0.f);
+        if (state == S_END_SAMPLE) {
+            const Spec Ls = SanitizeRadiance(L);
+            lsBase[s] = make_float4(Ls.r, Ls.g, Ls.b, __int_as_float(code));
+            state = S_NEW_SAMPLE;
+        }
+        if (state == S_NEW_SAMPLE) {
+            // next camera sample of the batch: (task, sample) = (g / spp, g % spp)
+            bool have = false;
+            for (;;) {
+                const unsigned g = AggregatedAdd(a.counters + C_NEXT_SAMPLE);
+                if (g >= a.totalSamples) break;
+                bi = (int)(g / (unsigned)spp);
+                s = (int)(g - (unsigned)bi * (unsigned)spp);
+                if (bindTask(bi)) { have = true; break; }
+            }
+            if (!have) { state = S_DONE; break; }
+            // LDPixelSample's camera sample + PerspectiveCamera::GenerateRayDifferential (perspective.cpp:81-138)
+            const uint16_t *row = permBase + (size_t)s * PERM_STRIDE;
+            const uint32_t pi = row[0];
+            const float imageX = xPos + VanDerCorput(pi, scr[0]);
+            const float imageY = yPos + Sobol2(pi, scr[1]);
+            code = FilmFootprint(rp, xPos, yPos, imageX, imageY);
+            V3 Pcamera = XfPoint(rp.rasterToCamera, V3(imageX, imageY, 0));
+            V3 dir = Normalize(V3(Pcamera.x, Pcamera.y, Pcamera.z));
+            ray.o = V3(0, 0, 0); ray.d = dir; ray.mint = 0.f; ray.maxt = INF_F;
+            if (rp.lensRadius > 0.f) {
+                const uint32_t pl = row[1];
+                float lensU, lensV;
+                ConcentricSampleDisk(VanDerCorput(pl, scr[2]), Sobol2(pl, scr[3]), &lensU, &lensV);
+                lensU *= rp.lensRadius;
+                lensV *= rp.lensRadius;
+                float ft = rp.focalDistance / ray.d.z;
+                V3 Pfocus = RayAt(ray, ft);
+                ray.o = V3(lensU, lensV, 0.f);
+                ray.d = Normalize(Pfocus - ray.o);
+            }
+            ray.o = XfPoint(rp.cameraToWorld, ray.o);
+            ray.d = XfVector(rp.cameraToWorld, ray.d);
+            T = Spec(1.f); L = Spec(0.f);
+            bounces = 0;
+            wantTrace = true; anyHit = false;
+            state = S_HIT_RESULT;
+        }
+        if (wantTrace) { wantTraceOut = true; anyHitOut = anyHit; break; }
+        // otherwise the state is non-blocking (S_AFTER_LIGHT / S_AFTER_DIRECT): keep going
+    }
+
+    // ---- write the slot back and queue its request
+    FLD(F_T) = make_float4(T.r, T.g, T.b, __uint_as_float((uint32_t)state | ((uint32_t)bounces << 8) | ((uint32_t)lightNum << 16)));
+    if (state == S_DONE) return;
+    AggregatedAdd(a.counters + C_ALIVE);
+    FLD(F_L) = make_float4(L.r, L.g, L.b, __int_as_float(code));
+    FLD(F_WO) = make_float4(wo.x, wo.y, wo.z, __int_as_float(bi));
+    FLD(F_WI) = make_float4(wiW.x, wiW.y, wiW.z, __int_as_float(s));
+    if (state != S_HIT_RESULT) {
+        FLD(F_CTX_P) = make_float4(ctx.p.x, ctx.p.y, ctx.p.z, ctx.rayEpsilon);
+        FLD(F_CTX_NN) = make_float4(ctx.nn.x, ctx.nn.y, ctx.nn.z,
+                                   __uint_as_float((uint32_t)ctx.material | ((uint32_t)(ctx.areaLight + 1) << 16)));
+        FLD(F_CTX_NG) = make_float4(ctx.ng.x, ctx.ng.y, ctx.ng.z, bsU0);
+        FLD(F_CTX_SN) = make_float4(ctx.sn.x, ctx.sn.y, ctx.sn.z, bsU1);
+        FLD(F_CTX_TN) = make_float4(ctx.tn.x, ctx.tn.y, ctx.tn.z, bsUc);
+        FLD(F_LD) = make_float4(Ld.r, Ld.g, Ld.b, sPdf);
+        FLD(F_PEND) = make_float4(pend.r, pend.g, pend.b, visMaxt);
+    }
+    if (deferOut) {
+        FLD(F_EVAL_WO) = make_float4(evalWoOut.x, evalWoOut.y, evalWoOut.z, __int_as_float(evalFlagsOut));
+        FLD(F_EVAL_WI) = make_float4(evalWiOut.x, evalWiOut.y, evalWiOut.z, 0.f);
+        a.evalQ[AggregatedAdd(a.counters + C_EVAL_N)] = slot;
+    } else if (wantTraceOut) {
+        FLD(F_RAY_O) = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+        FLD(F_RAY_D) = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+        a.traceQ[AggregatedAdd(a.counters + C_TRACE_N)] = slot | (anyHitOut ? 0x80000000u : 0u);
+    }
+    if (STATS && nShadedN) atomicAdd(&a.stats->shadedN, nShadedN);
+#undef FLD
+}
+
+// persistent ray queue consumer
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_trace(WfArgs a) {
+    const DScene &sc = a.sc;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned n = a.counters[C_TRACE_N];
+    float4 *pool = a.pool;
+    const size_t P = a.P;
+    Trav t;
+    bool active = false;
+    uint32_t slot = 0;
+    TraceStats st;
+    st.nodes = st.prims = 0;
+    unsigned long long nClosest = 0, nShadow = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle) {
+            unsigned base = 0;
+            const int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(a.counters + C_TRACE_CUR, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (!active) {
+                const unsigned idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    const uint32_t q = a.traceQ[idx];
+                    slot = q & 0x7fffffffu;
+                    const float4 r0 = pool[(size_t)F_RAY_O * P + slot], r1 = pool[(size_t)F_RAY_D * P + slot];
+                    Ray ray;
+                    ray.o = V3(r0.x, r0.y, r0.z); ray.mint = r0.w;
+                    ray.d = V3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
+                    TravInit(t, ray, (q >> 31) != 0);
+                    if (STATS) { if (q >> 31) ++nShadow; else ++nClosest; }
+                    active = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) break;
+        // walk until a good share of the warp has finished, then refill
+        for (int it = 0; it < 64; ++it) {
+            if (active && TravStep<STATS>(sc, t, &st)) {
+                pool[(size_t)F_HIT * P + slot] = make_float4(__int_as_float(t.found ? t.hit.prim : -1), t.hit.b1, t.hit.b2, t.hit.maxtIn);
+                pool[(size_t)F_RAY_D * P + slot].w = t.ray.maxt;
+                active = false;
+            }
+            if (__popc(__ballot_sync(FULL, active)) < 24) break;
+        }
+    }
+    if (STATS) {
+        unsigned long long v[4] = {nClosest, nShadow, st.nodes, st.prims};
+        for (int k = 0; k < 4; ++k) {
+            unsigned long long x = v[k];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(FULL, x, o);
+            v[k] = x;
+        }
+        if (lane == 0) {
+            atomicAdd(&a.stats->closestRays, v[0]);
+            atomicAdd(&a.stats->shadowRays, v[1]);
+            atomicAdd(&a.stats->nodes, v[2]);
+            atomicAdd(&a.stats->prims, v[3]);
+        }
+    }
+}
+
+// measured-BRDF evaluations (IrregIsotropicBRDF::f) of the queued requests
+__global__ void __launch_bounds__(128) k_eval(WfArgs a) {
+    const unsigned n = a.counters[C_EVAL_N];
+    const size_t P = a.P;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const uint32_t slot = a.evalQ[idx];
+        const float4 c1 = a.pool[(size_t)F_CTX_NN * P + slot];
+        const float4 e0 = a.pool[(size_t)F_EVAL_WO * P + slot], e1 = a.pool[(size_t)F_EVAL_WI * P + slot];
+        const int material = (int)(__float_as_uint(c1.w) & 0xffffu);
+        const int flags = __float_as_int(e0.w);
+        BxSet bx;
+        MaterialBxDFs(a.sc, material, &bx);
+        Spec f(0.f);
+        for (int i = 0; i < bx.n; ++i)
+            if (Matches(bx.type[i], flags)) f = f + BxF(a.sc, bx, i, V3(e0.x, e0.y, e0.z), V3(e1.x, e1.y, e1.z));
+        a.pool[(size_t)F_FEVAL * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
+    }
+}
+
 // ------------------------------------------------------------- ray-batch kernels
 template <bool ANY>
 __global__ void k_intersect(DScene sc, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits, uint8_t *occ) {
@@ -728,6 +909,10 @@ struct PbrtGpuScene {
     DevBuf<uint32_t> scr, rngCur, rngNext;
     DevBuf<int> mti;
     DevBuf<float4> ls, rec;
+    DevBuf<float4> pool;              // wavefront path slots (F_COUNT fields x P)
+    DevBuf<uint32_t> traceQ, evalQ;
+    DevBuf<unsigned> counters;
+    unsigned *hostCounters = nullptr;  // pinned
     DevBuf<PbrtGpuPixel> film;
     DevBuf<DeviceStats> stats;
     DevBuf<PbrtGpuRay> rays;
@@ -735,6 +920,7 @@ struct PbrtGpuScene {
     DevBuf<uint8_t> occ;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool collectStats = false;
+    int nMeasuredMaterials = 0;
 };
 
 namespace {
@@ -795,12 +981,12 @@ struct TableLaunch {
 };
 TableLaunch PlanTables(int spp) {
     TableLaunch t;
-    const size_t perArray = (size_t)4 * (spp + 2);   // T + P, u16 each
+    const size_t perArray = (size_t)2 * (spp + 2);   // one u16 index array per (0,2)-sequence array
     const size_t budget = 56 * 1024;
     size_t g = (budget - MT_N * 4) / perArray;
-    t.G = (int)std::max<size_t>(1, std::min<size_t>(N_ARRAYS, g));
-    const size_t perWarp = MT_N * 4 + (size_t)t.G * perArray;
-    t.wpb = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / perWarp));
+    t.G = g >= N_ARRAYS ? N_ARRAYS : (int)std::max<size_t>(1, g);
+    const size_t perWarp = MT_N * 4 + ((size_t)t.G * perArray + 3) / 4 * 4;
+    t.wpb = (int)std::max<size_t>(1, std::min<size_t>(4, (226 * 1024) / perWarp));
     t.smemBytes = perWarp * t.wpb;
     return t;
 }
@@ -932,6 +1118,8 @@ int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
     d.nNodes = desc->nNodes; d.nPrims = desc->nPrimitives; d.nLights = desc->nLights;
     for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&s->ev[i]));
     s->collectStats = getenv("PBRTGPU_STATS") != nullptr;
+    for (uint32_t i = 0; i < desc->nMaterials; ++i)
+        if (desc->materials[i].type == PBRTGPU_MAT_MEASURED) s->nMeasuredMaterials++;
     *out = s.release();
     return PBRTGPU_OK;
 }
@@ -940,6 +1128,7 @@ void pbrtgpu_scene_destroy(PbrtGpuScene *scene) {
     if (!scene) return;
     for (int i = 0; i < 5; ++i)
         if (scene->ev[i]) cudaEventDestroy(scene->ev[i]);
+    if (scene->hostCounters) cudaFreeHost(scene->hostCounters);
     delete scene;
 }
 
@@ -1008,6 +1197,22 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     const bool wantCounters = stats && scene->collectStats;
     if (wantCounters) CUDA_TRY(cudaMemsetAsync(scene->stats.p, 0, sizeof(DeviceStats), stream));
 
+    // phase 1 runs as a wavefront over a pool of path slots unless PBRTGPU_WAVEFRONT=0
+    bool useWavefront = true;
+    { const char *e = getenv("PBRTGPU_WAVEFRONT"); if (e) useWavefront = atoi(e) != 0; }
+    size_t poolSize = (size_t)1 << 22;   // 4 Mi slots x 272 B = 1.1 GB (measured: +17 % over 1 Mi)
+    { const char *e = getenv("PBRTGPU_POOL"); if (e && atol(e) > 0) poolSize = (size_t)atol(e); }
+    poolSize = (poolSize + 127) / 128 * 128;
+    int nSM = 148;
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, scene->device);
+    bool hasMeasured = scene->measured.n > 0 && scene->nMeasuredMaterials > 0;
+    if (useWavefront) {
+        CUDA_TRY(scene->pool.Ensure(poolSize * F_COUNT));
+        CUDA_TRY(scene->traceQ.Ensure(poolSize));
+        CUDA_TRY(scene->evalQ.Ensure(poolSize));
+        CUDA_TRY(scene->counters.Ensure(C_COUNT));
+        if (!scene->hostCounters) CUDA_TRY(cudaMallocHost((void **)&scene->hostCounters, C_COUNT * sizeof(unsigned)));
+    }
     const TableLaunch tl = PlanTables(spp);
     uint64_t launches = 0;
     float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f;
@@ -1030,16 +1235,47 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
             pa.sc = scene->d; pa.rp = rp; pa.b = b; pa.film = film; pa.stats = scene->stats.p;
             pa.directFilm = rounds > 1 ? 1 : 0;
             { const char *e = getenv("PBRTGPU_LOCKSTEP"); pa.lockstep = e ? atoi(e) : 1; }
-            const int blocks1 = (int)((nb + 3) / 4);       // phase 1: one warp per task-pixel
+            const int blocks1 = (int)((nb + 3) / 4);       // phase 1 (megakernel form): one warp per task-pixel
             const int blocks2 = (int)((nb + 127) / 128);   // phase 2: one thread per task-pixel
-            if (wantCounters) k_path<1, true><<<blocks1, 128, 0, stream>>>(pa);
-            else k_path<1, false><<<blocks1, 128, 0, stream>>>(pa);
-            CUDA_TRY(cudaGetLastError());
+            if (!useWavefront) {
+                if (wantCounters) k_path<1, true><<<blocks1, 128, 0, stream>>>(pa);
+                else k_path<1, false><<<blocks1, 128, 0, stream>>>(pa);
+                CUDA_TRY(cudaGetLastError());
+                launches += 1;
+            } else {
+                // ---- phase 1 as a wavefront over a pool of path slots
+                WfArgs wa;
+                wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = scene->pool.p; wa.P = (uint32_t)poolSize;
+                wa.traceQ = scene->traceQ.p; wa.evalQ = scene->evalQ.p; wa.counters = scene->counters.p;
+                wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p;
+                CUDA_TRY(cudaMemsetAsync(scene->counters.p, 0, C_COUNT * sizeof(unsigned), stream));
+                // every slot starts in S_NEW_SAMPLE (= 0 in the packed state word)
+                CUDA_TRY(cudaMemsetAsync(scene->pool.p + (size_t)F_T * poolSize, 0, poolSize * sizeof(float4), stream));
+                const int lblocks = (int)((poolSize + 127) / 128);
+                const int tblocks = nSM * 8;
+                for (int iter = 0;; ++iter) {
+                    CUDA_TRY(cudaMemsetAsync(scene->counters.p, 0, C_NEXT_SAMPLE * sizeof(unsigned), stream));
+                    if (wantCounters) k_logic<true><<<lblocks, 128, 0, stream>>>(wa);
+                    else k_logic<false><<<lblocks, 128, 0, stream>>>(wa);
+                    if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
+                    if (wantCounters) k_trace<true><<<tblocks, 128, 0, stream>>>(wa);
+                    else k_trace<false><<<tblocks, 128, 0, stream>>>(wa);
+                    launches += hasMeasured ? 3 : 2;
+                    if ((iter & 7) == 7) {
+                        CUDA_TRY(cudaMemcpyAsync(scene->hostCounters, scene->counters.p, C_COUNT * sizeof(unsigned),
+                                                 cudaMemcpyDeviceToHost, stream));
+                        CUDA_TRY(cudaStreamSynchronize(stream));
+                        if (scene->hostCounters[C_ALIVE] == 0) break;
+                    }
+                    if (iter > 4000000) return Fail(PBRTGPU_ECUDA, "wavefront did not terminate");
+                }
+                CUDA_TRY(cudaGetLastError());
+            }
             if (stats) CUDA_TRY(cudaEventRecord(scene->ev[4], stream));
             if (wantCounters) k_path<2, true><<<blocks2, 128, 0, stream>>>(pa);
             else k_path<2, false><<<blocks2, 128, 0, stream>>>(pa);
             CUDA_TRY(cudaGetLastError());
-            launches += 3;
+            launches += 2;
             if (stats) {
                 CUDA_TRY(cudaEventRecord(scene->ev[1], stream));
                 CUDA_TRY(cudaEventSynchronize(scene->ev[1]));
@@ -1128,6 +1364,8 @@ int pbrtgpu_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
     DevBuf<uint32_t> scr, cur, next;
     DevBuf<int> mti;
     DevBuf<float> dout;
+    DevBuf<float4> rec;
+    CUDA_TRY(rec.Ensure((size_t)spp * 4));
     CUDA_TRY(tasks.Upload(&tr, 1));
     CUDA_TRY(perm.Ensure((size_t)spp * PERM_STRIDE));
     CUDA_TRY(scr.Ensure(SCR_STRIDE));
@@ -1137,7 +1375,7 @@ int pbrtgpu_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
     CUDA_TRY(dout.Ensure((size_t)spp * 37));
     BatchArgs b;
     b.tasks = tasks.p; b.nBatch = 1; b.round = 0; b.perm = perm.p; b.scr = scr.p; b.rngCur = cur.p; b.rngNext = next.p;
-    b.mti = mti.p;
+    b.mti = mti.p; b.ls = nullptr; b.rec = rec.p;
     const TableLaunch tl = PlanTables(spp);
     CUDA_TRY(LaunchTablesAny(b, spp, tl, nullptr));
     k_expand_samples<<<(spp + 127) / 128, 128>>>(b, spp, rd->shutterOpen, rd->shutterClose, dout.p);
