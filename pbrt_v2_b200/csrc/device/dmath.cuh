@@ -14,6 +14,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "refmath.h"
 
 #define DEV __device__ __forceinline__
 // big, rarely-hot routines: one copy per kernel keeps the instruction footprint in cache
@@ -140,19 +141,16 @@ DEV V3 XfNormal(const float *__restrict__ mInv, const V3 &n) {
               mInv[2] * x + mInv[6] * y + mInv[10] * z);
 }
 
-// ---- libm stand-ins ------------------------------------------------------------
-// The reference calls glibc's sinf/cosf/powf/expf/atan2f/acosf.
-// Those are NOT always correctly rounded, and neither are CUDA's; here every
-// call is routed through one place so the restatement can be tightened.  v1:
-// evaluate in double and round once -- correctly rounded except for ~1e-8 of
-// arguments; agrees with glibc 2.39 on 99.9 % (sinf/cosf/powf), 99.99 % (expf),
-// 99.7 % (acosf), 84 % (atan2f, glibc's is not correctly rounded) of arguments,
-// and is within 1 ulp otherwise (measured, see DESIGN.md "libm").
-DEV_NI1 float ref_sinf(float x) { return (float)sin((double)x); }
-DEV_NI1 float ref_cosf(float x) { return (float)cos((double)x); }
-DEV_NI1 float ref_expf(float x) { return (float)exp((double)x); }
-DEV_NI1 float ref_powf(float x, float y) { return (float)pow((double)x, (double)y); }
-DEV_NI1 float ref_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
-DEV_NI1 float ref_acosf(float x) { return (float)acos((double)x); }
+// ---- libm ---------------------------------------------------------------------
+// The reference calls glibc's sinf/cosf/powf/expf/atan2f/acosf; none of them is
+// correctly rounded, so refmath.h restates glibc 2.39's own algorithms.  Verified bit-identical to the
+// host libm on every float of the used ranges (tests/test_refmath.py: 0 mismatches for sinf/cosf/acosf/
+// atanf/atan2f/powf; expf differs on ~1 argument in 10^9 because the host's libm picks an FMA build).
+DEV_NI1 float ref_sinf(float x) { return refmath::ref_sinf(x); }
+DEV_NI1 float ref_cosf(float x) { return refmath::ref_cosf(x); }
+DEV_NI1 float ref_expf(float x) { return refmath::ref_expf(x); }
+DEV_NI1 float ref_powf(float x, float y) { return refmath::ref_powf(x, y); }
+DEV_NI1 float ref_atan2f(float y, float x) { return refmath::ref_atan2f(y, x); }
+DEV_NI1 float ref_acosf(float x) { return refmath::ref_acosf(x); }
 
 }  // namespace dev
