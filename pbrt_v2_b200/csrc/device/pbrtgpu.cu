@@ -532,7 +532,11 @@ enum {
     F_FEVAL,       // fEval.rgb
     F_COUNT
 };
-enum { C_TRACE_N = 0, C_EVAL_N, C_TRACE_CUR, C_EVAL_CUR, C_ALIVE, C_NEXT_SAMPLE, C_COUNT };
+// Request queues, one per resume state ("kind"), so that the lanes of a warp of k_logic are all in the same
+// state, k_trace sees shadow rays and extension rays in separate runs, and nothing iterates over retired slots.
+// Two sets are ping-ponged: iteration i of k_logic drains set i&1 and fills set (i+1)&1.
+enum { K_E_LIGHT = 0, K_E_MIS, K_E_PATH, K_HIT, K_SHADOW, K_MIS, K_COUNT };
+enum { C_QN = 0, C_TRACE_CUR = 2 * K_COUNT, C_EVAL_CUR, C_NEXT_SAMPLE, C_COUNT };
 
 struct WfArgs {
     DScene sc;
@@ -540,10 +544,10 @@ struct WfArgs {
     BatchArgs b;
     float4 *pool;
     uint32_t P;
-    uint32_t *traceQ;    // slot | anyHit << 31
-    uint32_t *evalQ;
-    unsigned *counters;  // C_*
+    uint32_t *q;         // [2 sets][K_COUNT][P] slot indices
+    unsigned *counters;  // C_QN + set * K_COUNT + kind: queue lengths; cursors; next camera sample
     unsigned totalSamples;
+    int iter;            // 0: every slot starts a camera sample
     DeviceStats *stats;
 };
 
@@ -559,24 +563,35 @@ DEV unsigned AggregatedAdd(unsigned *ctr) {   // warp-aggregated atomicAdd(ctr, 
 
 template <bool STATS>
 __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= a.P) return;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const DScene &sc = a.sc;
     const RenderParams &rp = a.rp;
     const int spp = rp.spp;
     const int PHASE = 1;
     float4 *pool = a.pool;
     const size_t P = a.P;
+    const int setIn = a.iter & 1, setOut = setIn ^ 1;
+    // which queue of the input set does this thread serve?
+    uint32_t slot;
+    int kindIn = -1;
+    if (a.iter == 0) {
+        if (idx >= a.P) return;
+        slot = idx;
+    } else {
+        uint32_t base = 0;
+        const unsigned *qn = a.counters + C_QN + setIn * K_COUNT;
+        for (int k = 0; k < K_COUNT; ++k) {
+            const uint32_t n = qn[k];
+            if (idx < base + n) { kindIn = k; break; }
+            base += n;
+        }
+        if (kindIn < 0) return;
+        slot = a.q[((size_t)setIn * K_COUNT + kindIn) * P + (idx - base)];
+    }
 #define FLD(f) pool[(size_t)(f) * P + slot]
 
-    const float4 fT = FLD(F_T);
-    const uint32_t packed = __float_as_uint(fT.w);
-    int state = packed & 0xffu;
-    if (state == S_DONE) return;
-    int bounces = (packed >> 8) & 0xffu;
-    int lightNum = packed >> 16;
-    Spec T(fT.x, fT.y, fT.z);
-
+    int state = S_NEW_SAMPLE, bounces = 0, lightNum = 0;
+    Spec T(1.f);
     int s = 0, code = 0, bi = 0, mti = 0;
     Ray ray;
     ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f;
@@ -590,18 +605,24 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
     V3 wo(0, 0, 1), wiW(0, 0, 1), evalWoIn(0, 0, 1), evalWiIn(0, 0, 1);
     float bsU0 = 0.f, bsU1 = 0.f, bsUc = 0.f, sPdf = 0.f, visMaxt = 0.f;
     unsigned long long nShadedN = 0;
+    bool ctxDirty = false;
 
-    if (state != S_NEW_SAMPLE) {
-        const float4 fL = FLD(F_L), fWo = FLD(F_WO), fWi = FLD(F_WI);
+    if (kindIn >= 0) {   // load only what this resume state reads
+        const float4 fT = FLD(F_T), fL = FLD(F_L), fWo = FLD(F_WO), fWi = FLD(F_WI);
+        const uint32_t packed = __float_as_uint(fT.w);
+        state = packed & 0xffu; bounces = (packed >> 8) & 0xffu; lightNum = packed >> 16;
+        T = Spec(fT.x, fT.y, fT.z);
         L = Spec(fL.x, fL.y, fL.z); code = __float_as_int(fL.w);
         wo = V3(fWo.x, fWo.y, fWo.z); bi = __float_as_int(fWo.w);
         wiW = V3(fWi.x, fWi.y, fWi.z); s = __float_as_int(fWi.w);
-        const float4 r0 = FLD(F_RAY_O), r1 = FLD(F_RAY_D), h = FLD(F_HIT);
-        ray.o = V3(r0.x, r0.y, r0.z); ray.mint = r0.w;
-        ray.d = V3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
-        hit.prim = __float_as_int(h.x); hit.b1 = h.y; hit.b2 = h.z; hit.maxtIn = h.w; hit.t = r1.w;
-        found = hit.prim >= 0;
-        if (state != S_HIT_RESULT) {   // mid-vertex states need the shading context
+        if (kindIn >= K_HIT) {   // a traversal result
+            const float4 r0 = FLD(F_RAY_O), r1 = FLD(F_RAY_D), h = FLD(F_HIT);
+            ray.o = V3(r0.x, r0.y, r0.z); ray.mint = r0.w;
+            ray.d = V3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
+            hit.prim = __float_as_int(h.x); hit.b1 = h.y; hit.b2 = h.z; hit.maxtIn = h.w; hit.t = r1.w;
+            found = hit.prim >= 0;
+        }
+        if (kindIn != K_HIT) {   // mid-vertex states need the shading context
             const float4 c0 = FLD(F_CTX_P), c1 = FLD(F_CTX_NN), c2 = FLD(F_CTX_NG), c3 = FLD(F_CTX_SN), c4 = FLD(F_CTX_TN);
             ctx.p = V3(c0.x, c0.y, c0.z); ctx.rayEpsilon = c0.w;
             ctx.nn = V3(c1.x, c1.y, c1.z);
@@ -613,7 +634,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
             const float4 d0 = FLD(F_LD), d1 = FLD(F_PEND);
             Ld = Spec(d0.x, d0.y, d0.z); sPdf = d0.w;
             pend = Spec(d1.x, d1.y, d1.z); visMaxt = d1.w;
-            if (state == S_E_LIGHT || state == S_E_MIS || state == S_E_PATH) {
+            if (kindIn <= K_E_PATH) {
                 const float4 e0 = FLD(F_EVAL_WO), e1 = FLD(F_EVAL_WI), e2 = FLD(F_FEVAL);
                 evalWoIn = V3(e0.x, e0.y, e0.z); evalWiIn = V3(e1.x, e1.y, e1.z);
                 fLoaded = Spec(e2.x, e2.y, e2.z);
@@ -641,6 +662,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
     if (state != S_NEW_SAMPLE) bindTask(bi);
     auto rngF = [&](int) -> float { return 0.f; };   // phase 1 never draws from the RNG stream
 
+    ctxDirty = (kindIn < 0 || kindIn == K_HIT);   // the context is (re)built only at a path vertex
     bool wantTraceOut = false, anyHitOut = false, deferOut = false;
     V3 evalWoOut(0, 0, 1), evalWiOut(0, 0, 1);
     int evalFlagsOut = 0;
@@ -707,32 +729,42 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
         // otherwise the state is non-blocking (S_AFTER_LIGHT / S_AFTER_DIRECT): keep going
     }
 
-    // ---- write the slot back and queue its request
+    // ---- write the slot back and queue its request under its resume state
+    if (state == S_DONE) return;   // no more camera samples: the slot retires (it is in no queue any more)
+    const int kindOut = state == S_E_LIGHT ? K_E_LIGHT : state == S_E_MIS ? K_E_MIS : state == S_E_PATH ? K_E_PATH
+                        : state == S_HIT_RESULT ? K_HIT : state == S_SHADOW_RESULT ? K_SHADOW : K_MIS;
     FLD(F_T) = make_float4(T.r, T.g, T.b, __uint_as_float((uint32_t)state | ((uint32_t)bounces << 8) | ((uint32_t)lightNum << 16)));
-    if (state == S_DONE) return;
-    AggregatedAdd(a.counters + C_ALIVE);
     FLD(F_L) = make_float4(L.r, L.g, L.b, __int_as_float(code));
     FLD(F_WO) = make_float4(wo.x, wo.y, wo.z, __int_as_float(bi));
     FLD(F_WI) = make_float4(wiW.x, wiW.y, wiW.z, __int_as_float(s));
-    if (state != S_HIT_RESULT) {
-        FLD(F_CTX_P) = make_float4(ctx.p.x, ctx.p.y, ctx.p.z, ctx.rayEpsilon);
-        FLD(F_CTX_NN) = make_float4(ctx.nn.x, ctx.nn.y, ctx.nn.z,
-                                   __uint_as_float((uint32_t)ctx.material | ((uint32_t)(ctx.areaLight + 1) << 16)));
-        FLD(F_CTX_NG) = make_float4(ctx.ng.x, ctx.ng.y, ctx.ng.z, bsU0);
-        FLD(F_CTX_SN) = make_float4(ctx.sn.x, ctx.sn.y, ctx.sn.z, bsU1);
-        FLD(F_CTX_TN) = make_float4(ctx.tn.x, ctx.tn.y, ctx.tn.z, bsUc);
+    if (kindOut != K_HIT) {
+        if (ctxDirty) {
+            FLD(F_CTX_P) = make_float4(ctx.p.x, ctx.p.y, ctx.p.z, ctx.rayEpsilon);
+            FLD(F_CTX_NN) = make_float4(ctx.nn.x, ctx.nn.y, ctx.nn.z,
+                                       __uint_as_float((uint32_t)ctx.material | ((uint32_t)(ctx.areaLight + 1) << 16)));
+            FLD(F_CTX_NG) = make_float4(ctx.ng.x, ctx.ng.y, ctx.ng.z, bsU0);
+            FLD(F_CTX_SN) = make_float4(ctx.sn.x, ctx.sn.y, ctx.sn.z, bsU1);
+            FLD(F_CTX_TN) = make_float4(ctx.tn.x, ctx.tn.y, ctx.tn.z, bsUc);
+        }
         FLD(F_LD) = make_float4(Ld.r, Ld.g, Ld.b, sPdf);
         FLD(F_PEND) = make_float4(pend.r, pend.g, pend.b, visMaxt);
     }
     if (deferOut) {
         FLD(F_EVAL_WO) = make_float4(evalWoOut.x, evalWoOut.y, evalWoOut.z, __int_as_float(evalFlagsOut));
         FLD(F_EVAL_WI) = make_float4(evalWiOut.x, evalWiOut.y, evalWiOut.z, 0.f);
-        a.evalQ[AggregatedAdd(a.counters + C_EVAL_N)] = slot;
-    } else if (wantTraceOut) {
+    } else {
         FLD(F_RAY_O) = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
         FLD(F_RAY_D) = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
-        a.traceQ[AggregatedAdd(a.counters + C_TRACE_N)] = slot | (anyHitOut ? 0x80000000u : 0u);
     }
+    {   // warp-aggregated push, one atomic per (warp, kind)
+        const unsigned peers = __match_any_sync(__activemask(), kindOut);
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(a.counters + C_QN + setOut * K_COUNT + kindOut, (unsigned)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        a.q[((size_t)setOut * K_COUNT + kindOut) * P + base + __popc(peers & ((1u << lane) - 1u))] = slot;
+    }
+    (void)wantTraceOut; (void)anyHitOut;
     if (STATS && nShadedN) atomicAdd(&a.stats->shadedN, nShadedN);
 #undef FLD
 }
@@ -743,9 +775,15 @@ __global__ void __launch_bounds__(128) k_trace(WfArgs a) {
     const DScene &sc = a.sc;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const unsigned n = a.counters[C_TRACE_N];
+    // this iteration's rays: the K_HIT, K_SHADOW and K_MIS queues of the set k_logic just filled, back to back
+    const int setOut = (a.iter & 1) ^ 1;
+    const unsigned *qn = a.counters + C_QN + setOut * K_COUNT;
+    const unsigned n0 = qn[K_HIT], n1 = n0 + qn[K_SHADOW], n = n1 + qn[K_MIS];
     float4 *pool = a.pool;
     const size_t P = a.P;
+    const uint32_t *qHit = a.q + ((size_t)setOut * K_COUNT + K_HIT) * P;
+    const uint32_t *qShadow = a.q + ((size_t)setOut * K_COUNT + K_SHADOW) * P;
+    const uint32_t *qMis = a.q + ((size_t)setOut * K_COUNT + K_MIS) * P;
     Trav t;
     bool active = false;
     uint32_t slot = 0;
@@ -762,14 +800,14 @@ __global__ void __launch_bounds__(128) k_trace(WfArgs a) {
             if (!active) {
                 const unsigned idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (idx < n) {
-                    const uint32_t q = a.traceQ[idx];
-                    slot = q & 0x7fffffffu;
+                    const bool any = idx >= n0 && idx < n1;
+                    slot = idx < n0 ? qHit[idx] : (idx < n1 ? qShadow[idx - n0] : qMis[idx - n1]);
                     const float4 r0 = pool[(size_t)F_RAY_O * P + slot], r1 = pool[(size_t)F_RAY_D * P + slot];
                     Ray ray;
                     ray.o = V3(r0.x, r0.y, r0.z); ray.mint = r0.w;
                     ray.d = V3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
-                    TravInit(t, ray, (q >> 31) != 0);
-                    if (STATS) { if (q >> 31) ++nShadow; else ++nClosest; }
+                    TravInit(t, ray, any);
+                    if (STATS) { if (any) ++nShadow; else ++nClosest; }
                     active = true;
                 }
             }
@@ -803,10 +841,13 @@ __global__ void __launch_bounds__(128) k_trace(WfArgs a) {
 
 // measured-BRDF evaluations (IrregIsotropicBRDF::f) of the queued requests
 __global__ void __launch_bounds__(128) k_eval(WfArgs a) {
-    const unsigned n = a.counters[C_EVAL_N];
+    const int setOut = (a.iter & 1) ^ 1;
+    const unsigned *qn = a.counters + C_QN + setOut * K_COUNT;
+    const unsigned n0 = qn[K_E_LIGHT], n1 = n0 + qn[K_E_MIS], n = n1 + qn[K_E_PATH];
     const size_t P = a.P;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-        const uint32_t slot = a.evalQ[idx];
+        const int kind = idx < n0 ? K_E_LIGHT : (idx < n1 ? K_E_MIS : K_E_PATH);
+        const uint32_t slot = a.q[((size_t)setOut * K_COUNT + kind) * P + (idx - (idx < n0 ? 0 : (idx < n1 ? n0 : n1)))];
         const float4 c1 = a.pool[(size_t)F_CTX_NN * P + slot];
         const float4 e0 = a.pool[(size_t)F_EVAL_WO * P + slot], e1 = a.pool[(size_t)F_EVAL_WI * P + slot];
         const int material = (int)(__float_as_uint(c1.w) & 0xffffu);
@@ -1208,8 +1249,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     bool hasMeasured = scene->measured.n > 0 && scene->nMeasuredMaterials > 0;
     if (useWavefront) {
         CUDA_TRY(scene->pool.Ensure(poolSize * F_COUNT));
-        CUDA_TRY(scene->traceQ.Ensure(poolSize));
-        CUDA_TRY(scene->evalQ.Ensure(poolSize));
+        CUDA_TRY(scene->traceQ.Ensure(poolSize * 2 * K_COUNT));   // request queues: 2 sets x K_COUNT kinds
         CUDA_TRY(scene->counters.Ensure(C_COUNT));
         if (!scene->hostCounters) CUDA_TRY(cudaMallocHost((void **)&scene->hostCounters, C_COUNT * sizeof(unsigned)));
     }
@@ -1246,15 +1286,17 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                 // ---- phase 1 as a wavefront over a pool of path slots
                 WfArgs wa;
                 wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = scene->pool.p; wa.P = (uint32_t)poolSize;
-                wa.traceQ = scene->traceQ.p; wa.evalQ = scene->evalQ.p; wa.counters = scene->counters.p;
+                wa.q = scene->traceQ.p; wa.counters = scene->counters.p;
                 wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p;
                 CUDA_TRY(cudaMemsetAsync(scene->counters.p, 0, C_COUNT * sizeof(unsigned), stream));
-                // every slot starts in S_NEW_SAMPLE (= 0 in the packed state word)
-                CUDA_TRY(cudaMemsetAsync(scene->pool.p + (size_t)F_T * poolSize, 0, poolSize * sizeof(float4), stream));
                 const int lblocks = (int)((poolSize + 127) / 128);
                 const int tblocks = nSM * 8;
                 for (int iter = 0;; ++iter) {
-                    CUDA_TRY(cudaMemsetAsync(scene->counters.p, 0, C_NEXT_SAMPLE * sizeof(unsigned), stream));
+                    wa.iter = iter;
+                    const int setOut = (iter & 1) ^ 1;
+                    // empty the queues k_logic is about to fill, and the consumers' cursors
+                    CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
+                    CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
                     if (wantCounters) k_logic<true><<<lblocks, 128, 0, stream>>>(wa);
                     else k_logic<false><<<lblocks, 128, 0, stream>>>(wa);
                     if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
@@ -1265,7 +1307,9 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                         CUDA_TRY(cudaMemcpyAsync(scene->hostCounters, scene->counters.p, C_COUNT * sizeof(unsigned),
                                                  cudaMemcpyDeviceToHost, stream));
                         CUDA_TRY(cudaStreamSynchronize(stream));
-                        if (scene->hostCounters[C_ALIVE] == 0) break;
+                        unsigned alive = 0;
+                        for (int k = 0; k < K_COUNT; ++k) alive += scene->hostCounters[C_QN + setOut * K_COUNT + k];
+                        if (alive == 0) break;
                     }
                     if (iter > 4000000) return Fail(PBRTGPU_ECUDA, "wavefront did not terminate");
                 }
