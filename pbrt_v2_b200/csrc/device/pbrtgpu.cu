@@ -16,6 +16,8 @@
 #include "dshade.cuh"
 #include "drng.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -52,6 +54,8 @@ struct BatchArgs {
     int *mti;            // [nBatch]
     float4 *ls;          // [nBatch][spp]     finished radiance (xyz) + footprint/TAIL bits (w)
     float4 *rec;         // [nBatch][spp][4]  parked bounce-3 vertices (phase 1 -> phase 2)
+    unsigned *tailCount; // [nBatch] 1 if the task parked any sample in phase 1: partition key for phase 2
+    const unsigned *order; // [nBatch] phase 2: thread i serves task order[i] (tasks with parked samples first) or null
 };
 
 struct DeviceStats {
@@ -301,10 +305,15 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
     const RenderParams &rp = a.rp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    const int bi = PHASE == 1 ? (int)(blockIdx.x * 4 + warp) : (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int ti = PHASE == 1 ? (int)(blockIdx.x * 4 + warp) : (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int spp = rp.spp;
+    // phase 2 serves the tasks that parked samples first (stable partition: image order is kept inside both
+    // groups, so neighbouring lanes still walk neighbouring pixels); warps of tail-free pixels only sum up.
+    // (Sorting by the parked-sample COUNT was measured too: +15 % on bunny, -37 % on killeroo, where nearly
+    // every pixel has tails and the sort only destroys ray coherence.)
+    const int bi = (PHASE == 2 && a.b.order && ti < a.b.nBatch) ? (int)a.b.order[ti] : ti;
 
-    bool valid = bi < a.b.nBatch;
+    bool valid = ti < a.b.nBatch;
     TaskRec tr = valid ? a.b.tasks[bi] : TaskRec{0, 0, 0, 0, 0};
     const int tw = tr.x1 - tr.x0;
     if (valid && a.b.round >= tw * (tr.y1 - tr.y0)) valid = false;
@@ -391,7 +400,9 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
 #define PATH_EVALWO_IN V3(0, 0, 1)
 #define PATH_EVALWI_IN V3(0, 0, 1)
 #define PATH_DEFER_MEASURED false
+#define PATH_COUNT_TAIL() atomicOr(a.b.tailCount + bi, 1u)
 #include "path_body.inc"
+#undef PATH_COUNT_TAIL
 #undef PATH_FEVAL_IN
 #undef PATH_EVALWO_IN
 #undef PATH_EVALWI_IN
@@ -671,7 +682,9 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
 #define PATH_EVALWO_IN evalWoIn
 #define PATH_EVALWI_IN evalWiIn
 #define PATH_DEFER_MEASURED true
+#define PATH_COUNT_TAIL() atomicOr(a.b.tailCount + bi, 1u)
 #include "path_body.inc"
+#undef PATH_COUNT_TAIL
 #undef PATH_FEVAL_IN
 #undef PATH_EVALWO_IN
 #undef PATH_EVALWI_IN
@@ -950,6 +963,8 @@ struct PbrtGpuScene {
     DevBuf<uint32_t> scr, rngCur, rngNext;
     DevBuf<int> mti;
     DevBuf<float4> ls, rec;
+    DevBuf<unsigned> tailCount, tailKeysOut, orderIn, orderOut;
+    DevBuf<unsigned char> sortTemp;
     DevBuf<float4> pool;              // wavefront path slots (F_COUNT fields x P)
     DevBuf<uint32_t> traceQ, evalQ;
     DevBuf<unsigned> counters;
@@ -1234,6 +1249,20 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     CUDA_TRY(scene->mti.Ensure(maxBatch));
     CUDA_TRY(scene->ls.Ensure(maxBatch * spp));
     CUDA_TRY(scene->rec.Ensure(maxBatch * spp * 4));
+    CUDA_TRY(scene->tailCount.Ensure(maxBatch));
+    CUDA_TRY(scene->tailKeysOut.Ensure(maxBatch));
+    CUDA_TRY(scene->orderIn.Ensure(maxBatch));
+    CUDA_TRY(scene->orderOut.Ensure(maxBatch));
+    {
+        std::vector<unsigned> iota(maxBatch);
+        for (size_t i = 0; i < maxBatch; ++i) iota[i] = (unsigned)i;
+        CUDA_TRY(cudaMemcpyAsync(scene->orderIn.p, iota.data(), maxBatch * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    size_t sortBytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, sortBytes, scene->tailCount.p, scene->tailKeysOut.p,
+                                              scene->orderIn.p, scene->orderOut.p, (int)maxBatch, 0, 1, stream);
+    CUDA_TRY(scene->sortTemp.Ensure(sortBytes + 16));
     CUDA_TRY(scene->stats.Ensure(1));
     const bool wantCounters = stats && scene->collectStats;
     if (wantCounters) CUDA_TRY(cudaMemsetAsync(scene->stats.p, 0, sizeof(DeviceStats), stream));
@@ -1266,11 +1295,13 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
         b.tasks = scene->tasks.p; b.nBatch = (int)nb; b.round = 0;
         b.perm = scene->perm.p; b.scr = scene->scr.p; b.rngCur = scene->rngCur.p; b.rngNext = scene->rngNext.p;
         b.mti = scene->mti.p; b.ls = scene->ls.p; b.rec = scene->rec.p;
+        b.tailCount = scene->tailCount.p; b.order = nullptr;
         for (int r = 0; r < rounds; ++r) {
             b.round = r;
             if (stats) CUDA_TRY(cudaEventRecord(scene->ev[2], stream));
             CUDA_TRY(LaunchTablesAny(b, spp, tl, stream));
             if (stats) CUDA_TRY(cudaEventRecord(scene->ev[3], stream));
+            CUDA_TRY(cudaMemsetAsync(scene->tailCount.p, 0, nb * sizeof(unsigned), stream));
             PathArgs pa;
             pa.sc = scene->d; pa.rp = rp; pa.b = b; pa.film = film; pa.stats = scene->stats.p;
             pa.directFilm = rounds > 1 ? 1 : 0;
@@ -1316,6 +1347,12 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                 CUDA_TRY(cudaGetLastError());
             }
             if (stats) CUDA_TRY(cudaEventRecord(scene->ev[4], stream));
+            {   // tasks with parked samples first
+                size_t tmp = scene->sortTemp.n;
+                cub::DeviceRadixSort::SortPairsDescending(scene->sortTemp.p, tmp, scene->tailCount.p, scene->tailKeysOut.p,
+                                                          scene->orderIn.p, scene->orderOut.p, (int)nb, 0, 1, stream);
+                pa.b.order = scene->orderOut.p;
+            }
             if (wantCounters) k_path<2, true><<<blocks2, 128, 0, stream>>>(pa);
             else k_path<2, false><<<blocks2, 128, 0, stream>>>(pa);
             CUDA_TRY(cudaGetLastError());
@@ -1419,7 +1456,7 @@ int pbrtgpu_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
     CUDA_TRY(dout.Ensure((size_t)spp * 37));
     BatchArgs b;
     b.tasks = tasks.p; b.nBatch = 1; b.round = 0; b.perm = perm.p; b.scr = scr.p; b.rngCur = cur.p; b.rngNext = next.p;
-    b.mti = mti.p; b.ls = nullptr; b.rec = rec.p;
+    b.mti = mti.p; b.ls = nullptr; b.rec = rec.p; b.tailCount = nullptr; b.order = nullptr;
     const TableLaunch tl = PlanTables(spp);
     CUDA_TRY(LaunchTablesAny(b, spp, tl, nullptr));
     k_expand_samples<<<(spp + 127) / 128, 128>>>(b, spp, rd->shutterOpen, rd->shutterClose, dout.p);
