@@ -33,7 +33,10 @@ WORKLOADS = {
     "bunny-c2": ("bunny", 1024, 1024, 1024),            # BASELINE.json configs[1]
     "killeroo-c1": ("killeroo-simple", 400, 400, 64),   # configs[0] (CPU-runnable case)
     "killeroo-c3": ("killeroo-simple", 1920, 1080, 4096),
+    # configs[4]: synthetic 10M-triangle random mesh, maxdepth 8 (HBM-resident: 1.3 GB of BVH + triangles)
+    "synthetic-c5": ("synthetic", 4096, 4096, 512),
 }
+SYNTHETIC_TRIS = 10000000
 CPU_SAMPLE_SPP = 16     # bounded sample of the same workload for the CPU arms (cost is linear in spp)
 
 
@@ -45,10 +48,34 @@ def env_int(name, default):
 
 
 def per_pixel_ncores(xres, yres):
-    """--ncores value that makes the reference create one render task per pixel:
-    nTasks = RoundUpPow2(max(32*ncores, nPixels/256)) >= nPixels (samplerrenderer.cpp:203-205)."""
+    """--ncores value that makes the reference create the finest task grid it can: one render task per pixel,
+    nTasks = RoundUpPow2(max(32*ncores, nPixels/256)) >= nPixels (samplerrenderer.cpp:203-205), unless that
+    overflows the int products of Sampler::ComputeSubWindow (sampler.cpp:58, 2*dx*ny < dy*nx) -- then the
+    largest power of two that does not (4096x4096: 2^18 tasks of 8x8 pixels)."""
     npx = xres * yres
-    return max(1, (npx + 31) // 32)
+    n = 1
+    while n < npx:
+        n *= 2
+    def overflows(count):
+        nx, ny = count, 1
+        while True:
+            if 2 * xres * ny > 0x7fffffff or yres * nx > 0x7fffffff:
+                return True
+            if not (nx % 2 == 0 and 2 * xres * ny < yres * nx):
+                return False
+            nx //= 2
+            ny *= 2
+    while n > 32 and overflows(n):
+        n //= 2
+    return max(1, n // 32)
+
+
+def tasks_note(xres, yres):
+    n = 32 * per_pixel_ncores(xres, yres)
+    if n >= xres * yres:
+        return "one reference render task per pixel (--ncores %d)" % (n // 32)
+    return "%d reference render tasks of %d pixels (--ncores %d; finer grids overflow Sampler::ComputeSubWindow's int products)" % (
+        n, xres * yres // n, n // 32)
 
 
 class ClockSampler(threading.Thread):
@@ -155,11 +182,12 @@ def run_reference_arm(args, rank, world):
 
 def workload_config(workload, world, per_pixel=True):
     base, xres, yres, spp = WORKLOADS[workload]
+    desc = ("scenes/%s.pbrt, SurfaceIntegrator \"path\" (maxdepth 5)" % base) if base != "synthetic" else \
+        "synthetic random-triangle scene (SURVEY 8d C5), SurfaceIntegrator \"path\" (maxdepth 8)"
     return {
-        "workload": "scenes/%s.pbrt, SurfaceIntegrator \"path\" (maxdepth 5), Sampler \"lowdiscrepancy\" %d spp, "
-                    "%dx%d, Accelerator \"bvh\", box filter" % (base, spp, xres, yres),
+        "workload": "%s, Sampler \"lowdiscrepancy\" %d spp, %dx%d, Accelerator \"bvh\", box filter" % (desc, spp, xres, yres),
         "global_batch": xres * yres * spp, "parallelism": "tile%d" % world,
-        "tasks": ("one reference render task per pixel (--ncores %d)" % per_pixel_ncores(xres, yres)) if per_pixel
+        "tasks": tasks_note(xres, yres) if per_pixel
                  else "reference default nTasks",
         "l2": "256 MiB buffer rewritten between steps (L2 flush); per-step sample tables (>= 24 GB) stream through HBM",
     }
@@ -173,6 +201,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bunny-c2", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override spp (development only; invalidates the number)")
+    ap.add_argument("--tris", type=int, default=SYNTHETIC_TRIS, help="triangle count of the synthetic workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -200,8 +229,11 @@ def main():
     base, xres, yres, spp = WORKLOADS[args.workload]
     if args.spp:
         spp = args.spp
-    path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-%s-r%d.pbrt" % (args.workload, rank)), xres, yres, spp)
-    hs = pb.HostScene(path, ncores=per_pixel_ncores(xres, yres))
+    if base == "synthetic":
+        hs = pb.HostScene.synthetic(args.tris, xres, yres, spp, maxdepth=8, ncores=per_pixel_ncores(xres, yres))
+    else:
+        path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-%s-r%d.pbrt" % (args.workload, rank)), xres, yres, spp)
+        hs = pb.HostScene(path, ncores=per_pixel_ncores(xres, yres))
     rd = hs.render_desc()
     from pbrt_v2_b200.multigpu import shard_render_desc, reduce_film
     shard_render_desc(rd, rank, world, xres)   # interleave blocks of 4 pixel rows across ranks
@@ -333,7 +365,7 @@ def main():
         }
         if spp != WORKLOADS[args.workload][3]:
             line["INVALID"] = "spp overridden to %d (development run)" % spp
-        if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REPO, "oracle", "_ref", "bin", "pbrt")):
+        if world == 1 and not args.no_cpu_baseline and base != "synthetic" and os.path.exists(os.path.join(REPO, "oracle", "_ref", "bin", "pbrt")):
             threads = os.cpu_count() or 1
             v, sec, wall = cpu_reference_rate(args.workload, threads)
             line["cpu_baseline"] = {

@@ -104,6 +104,9 @@ def host_lib():
         lib = _load("libpbrthost.so")
         lib.pbrthost_load.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
         lib.pbrthost_load.restype = C.c_void_p
+        lib.pbrthost_load_synthetic.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        lib.pbrthost_load_synthetic.restype = C.c_void_p
+        lib.pbrthost_write_synthetic.argtypes = [C.c_char_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
         lib.pbrthost_free.argtypes = [C.c_void_p]
         lib.pbrthost_free.restype = None
         lib.pbrthost_scene_desc.argtypes = [C.c_void_p]
@@ -131,13 +134,35 @@ def _check(rc, what):
 class HostScene(object):
     """A parsed + flattened scene (host memory only; no GPU needed)."""
 
-    def __init__(self, filename, ncores=0):
+    def __init__(self, filename, ncores=0, _handle=None):
         lib = host_lib()
+        if _handle is not None:
+            self._h, self.filename = _handle, filename
+            return
         err = C.create_string_buffer(1024)
         self._h = lib.pbrthost_load(os.fsencode(filename), int(ncores), err, len(err))
         if not self._h:
             raise PbrtGpuError("cannot load %s: %s" % (filename, err.value.decode()))
         self.filename = filename
+
+    @classmethod
+    def synthetic(cls, ntris, xres, yres, spp, maxdepth=8, ncores=0):
+        """BASELINE.json configs[4] (random-triangle scene), built directly in memory."""
+        err = C.create_string_buffer(1024)
+        h = host_lib().pbrthost_load_synthetic(int(ntris), int(xres), int(yres), int(spp), int(maxdepth), int(ncores),
+                                               err, len(err))
+        if not h:
+            raise PbrtGpuError("cannot build synthetic scene: %s" % err.value.decode())
+        return cls("<synthetic %d triangles>" % ntris, _handle=h)
+
+    @staticmethod
+    def write_synthetic(filename, ntris, xres, yres, spp, maxdepth=8, outfile="synthetic.pfm"):
+        """The same scene as pbrt text, for the unmodified reference."""
+        rc = host_lib().pbrthost_write_synthetic(os.fsencode(filename), int(ntris), int(xres), int(yres), int(spp),
+                                                 int(maxdepth), os.fsencode(outfile))
+        if rc:
+            raise PbrtGpuError("cannot write %s" % filename)
+        return filename
 
     def close(self):
         if getattr(self, "_h", None):

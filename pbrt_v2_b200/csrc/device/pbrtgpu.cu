@@ -265,8 +265,8 @@ DEV int FilmFootprint(const RenderParams &rp, int ownX, int ownY, float imageX, 
 }
 
 // ImageFilm::AddSample, film/image.cpp:97-137, box filter (all table weights are 1)
-DEV void FilmAdd(const PathArgs &a, int ownX, int ownY, int code, const Spec &L, float acc[4], bool direct) {
-    const RenderParams &rp = a.rp;
+DEV void FilmAdd(const RenderParams &rp, PbrtGpuPixel *film, int ownX, int ownY, int code, const Spec &L, float acc[4],
+                 bool direct) {
     float xyz[3];   // RGBToXYZ, core/spectrum.h:58-62
     xyz[0] = 0.412453f * L.r + 0.357580f * L.g + 0.180423f * L.b;
     xyz[1] = 0.212671f * L.r + 0.715160f * L.g + 0.072169f * L.b;
@@ -280,7 +280,7 @@ DEV void FilmAdd(const PathArgs &a, int ownX, int ownY, int code, const Spec &L,
             } else {
                 // a neighbour pixel: the reference does a plain += that can race with the
                 // owning task; atomics keep the sum complete, the order is as undefined as there
-                PbrtGpuPixel *px = a.film + (size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart);
+                PbrtGpuPixel *px = film + (size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart);
                 atomicAdd(&px->Lxyz[0], xyz[0]);
                 atomicAdd(&px->Lxyz[1], xyz[1]);
                 atomicAdd(&px->Lxyz[2], xyz[2]);
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
                 state = S_NEW_SAMPLE;   // next sample index is handed out at the top of the loop
             } else {
                 // samplerrenderer.cpp:111-146: sanity checks, then ImageFilm::AddSample
-                FilmAdd(a, xPos, yPos, code, SanitizeRadiance(L), acc, direct);
+                FilmAdd(rp, a.film, xPos, yPos, code, SanitizeRadiance(L), acc, direct);
                 ++s;
                 state = S_NEW_SAMPLE;
             }
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
                         found = true;
                         state = S_HIT_RESULT;   // picked up (after the RNG top-up) next iteration
                     } else {
-                        FilmAdd(a, xPos, yPos, code, Spec(v.x, v.y, v.z), acc, direct);
+                        FilmAdd(rp, a.film, xPos, yPos, code, Spec(v.x, v.y, v.z), acc, direct);
                         ++s;
                     }
                 }
@@ -541,12 +541,15 @@ enum {
     F_EVAL_WO,     // evalWo.xyz, evalFlags
     F_EVAL_WI,     // evalWi.xyz
     F_FEVAL,       // fEval.rgb
+    F_ACC,         // phase 2: the task's film accumulator {Lxyz, weightSum} (ImageFilm::Pixel of its current pixel)
     F_COUNT
 };
 // Request queues, one per resume state ("kind"), so that the lanes of a warp of k_logic are all in the same
 // state, k_trace sees shadow rays and extension rays in separate runs, and nothing iterates over retired slots.
 // Two sets are ping-ponged: iteration i of k_logic drains set i&1 and fills set (i+1)&1.
-enum { K_E_LIGHT = 0, K_E_MIS, K_E_PATH, K_HIT, K_SHADOW, K_MIS, K_COUNT };
+enum { K_E_LIGHT = 0, K_E_MIS, K_E_PATH, K_HIT, K_SHADOW, K_MIS,
+       K_RESUME,   // phase 2: a parked sample picked up while its task's RNG window needs a top-up (no ray to trace)
+       K_COUNT };
 enum { C_QN = 0, C_TRACE_CUR = 2 * K_COUNT, C_EVAL_CUR, C_NEXT_SAMPLE, C_COUNT };
 
 struct WfArgs {
@@ -559,6 +562,8 @@ struct WfArgs {
     unsigned *counters;  // C_QN + set * K_COUNT + kind: queue lengths; cursors; next camera sample
     unsigned totalSamples;
     int iter;            // 0: every slot starts a camera sample
+    PbrtGpuPixel *film;  // phase 2
+    int directFilm;
     DeviceStats *stats;
 };
 
@@ -572,21 +577,25 @@ DEV unsigned AggregatedAdd(unsigned *ctr) {   // warp-aggregated atomicAdd(ctr, 
     return base + __popc(m & ((1u << lane) - 1u));
 }
 
-template <bool STATS>
+// PHASE 1: slots are camera samples (bounces 0..2, table-driven).  PHASE 2: slot i is task-pixel i's chain of
+// parked samples, resumed one after the other with the task's sequential RNG stream; finished samples are added
+// to the film in sample order in between (what k_path<2> does per thread, here as a wavefront).
+template <int PHASE, bool STATS>
 __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
+    __shared__ uint32_t smt[PHASE == 2 ? 4 : 1][PHASE == 2 ? MT_N : 1];
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const DScene &sc = a.sc;
     const RenderParams &rp = a.rp;
     const int spp = rp.spp;
-    const int PHASE = 1;
     float4 *pool = a.pool;
     const size_t P = a.P;
     const int setIn = a.iter & 1, setOut = setIn ^ 1;
     // which queue of the input set does this thread serve?
-    uint32_t slot;
+    uint32_t slot = 0;
     int kindIn = -1;
+    bool live = true;
     if (a.iter == 0) {
-        if (idx >= a.P) return;
+        if (idx >= (PHASE == 1 ? a.P : (uint32_t)a.b.nBatch)) live = false;
         slot = idx;
     } else {
         uint32_t base = 0;
@@ -596,9 +605,10 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
             if (idx < base + n) { kindIn = k; break; }
             base += n;
         }
-        if (kindIn < 0) return;
-        slot = a.q[((size_t)setIn * K_COUNT + kindIn) * P + (idx - base)];
+        if (kindIn < 0) live = false;
+        else slot = a.q[((size_t)setIn * K_COUNT + kindIn) * P + (idx - base)];
     }
+    if (PHASE == 1 && !live) return;
 #define FLD(f) pool[(size_t)(f) * P + slot]
 
     int state = S_NEW_SAMPLE, bounces = 0, lightNum = 0;
@@ -617,8 +627,15 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
     float bsU0 = 0.f, bsU1 = 0.f, bsUc = 0.f, sPdf = 0.f, visMaxt = 0.f;
     unsigned long long nShadedN = 0;
     bool ctxDirty = false;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 
-    if (kindIn >= 0) {   // load only what this resume state reads
+    if (PHASE == 2 && live && kindIn < 0) {   // iteration 0: the task-pixel behind this slot
+        bi = a.b.order ? (int)a.b.order[idx] : (int)idx;
+        const TaskRec tr0 = a.b.tasks[bi];
+        if (a.b.round >= (tr0.x1 - tr0.x0) * (tr0.y1 - tr0.y0)) live = false;
+        else mti = a.b.mti[bi];
+    }
+    if (live && kindIn >= 0) {   // load only what this resume state reads
         const float4 fT = FLD(F_T), fL = FLD(F_L), fWo = FLD(F_WO), fWi = FLD(F_WI);
         const uint32_t packed = __float_as_uint(fT.w);
         state = packed & 0xffu; bounces = (packed >> 8) & 0xffu; lightNum = packed >> 16;
@@ -633,7 +650,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
             hit.prim = __float_as_int(h.x); hit.b1 = h.y; hit.b2 = h.z; hit.maxtIn = h.w; hit.t = r1.w;
             found = hit.prim >= 0;
         }
-        if (kindIn != K_HIT) {   // mid-vertex states need the shading context
+        if (kindIn != K_HIT && kindIn != K_RESUME) {   // mid-vertex states need the shading context
             const float4 c0 = FLD(F_CTX_P), c1 = FLD(F_CTX_NN), c2 = FLD(F_CTX_NG), c3 = FLD(F_CTX_SN), c4 = FLD(F_CTX_TN);
             ctx.p = V3(c0.x, c0.y, c0.z); ctx.rayEpsilon = c0.w;
             ctx.nn = V3(c1.x, c1.y, c1.z);
@@ -651,6 +668,36 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
                 fLoaded = Spec(e2.x, e2.y, e2.z);
             }
         }
+        if (PHASE == 2) {
+            const float4 ac = FLD(F_ACC);
+            acc[0] = ac.x; acc[1] = ac.y; acc[2] = ac.z; acc[3] = ac.w;
+            mti = a.b.mti[bi];
+        }
+    }
+    if (PHASE == 2) {
+        // cooperative RNG top-up before a bounce (<= 11 draws must be addressable), as in k_path<2>
+        const unsigned FULL = 0xffffffffu;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const bool need = live && state == S_HIT_RESULT && found && mti >= MT_N;
+        unsigned m = __ballot_sync(FULL, need);
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const int tb = __shfl_sync(FULL, bi, l);
+            uint32_t *c = a.b.rngCur + (size_t)tb * MT_N, *n = a.b.rngNext + (size_t)tb * MT_N;
+            uint32_t *mt = smt[warp];
+            for (int j = lane; j < MT_N; j += 32) {
+                const uint32_t v = __ldcg(n + j);
+                __stcg(c + j, v);
+                mt[j] = v;
+            }
+            __syncwarp();
+            WarpRegenMT(mt, lane);
+            for (int j = lane; j < MT_N; j += 32) __stcg(n + j, mt[j]);
+            __syncwarp();
+            if (lane == l) mti -= MT_N;
+        }
+        if (!live) return;
     }
 
     // per-task environment (re-derived whenever the slot starts a sample of another task)
@@ -670,10 +717,18 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
         recBase = a.b.rec + (size_t)task * spp * 4;
         return true;
     };
-    if (state != S_NEW_SAMPLE) bindTask(bi);
-    auto rngF = [&](int) -> float { return 0.f; };   // phase 1 never draws from the RNG stream
+    if (state != S_NEW_SAMPLE || PHASE == 2) bindTask(bi);
+    const uint32_t *rngCur = a.b.rngCur + (size_t)bi * MT_N, *rngNext = a.b.rngNext + (size_t)bi * MT_N;
+    // draw `k` positions past mti (RNG::RandomUInt order), without advancing; phase 1 never draws
+    auto rngF = [&](int k) -> float {
+        if (PHASE == 1) return 0.f;
+        const int j = mti + k;
+        return UIntToFloat(Temper(j < MT_N ? __ldcg(rngCur + j) : __ldcg(rngNext + (j - MT_N))));
+    };
+    const bool direct = a.directFilm != 0;
+    bool resumeOut = false;
 
-    ctxDirty = (kindIn < 0 || kindIn == K_HIT);   // the context is (re)built only at a path vertex
+    ctxDirty = (kindIn < 0 || kindIn == K_HIT || kindIn == K_RESUME);   // the context is (re)built only at a path vertex
     bool wantTraceOut = false, anyHitOut = false, deferOut = false;
     V3 evalWoOut(0, 0, 1), evalWiOut(0, 0, 1);
     int evalFlagsOut = 0;
@@ -695,6 +750,55 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
             break;
         }
         fLoaded = Spec(0.f);
+        if (PHASE == 2) {
+            if (state == S_END_SAMPLE) {
+                // samplerrenderer.cpp:111-146: sanity checks, then ImageFilm::AddSample
+                FilmAdd(rp, a.film, xPos, yPos, code, SanitizeRadiance(L), acc, direct);
+                ++s;
+                state = S_NEW_SAMPLE;
+            }
+            if (state == S_NEW_SAMPLE) {
+                // walk ls[] in sample order: add finished samples, resume the next parked one
+                while (state == S_NEW_SAMPLE) {
+                    if (s == spp) {
+                        if (!direct) {
+                            PbrtGpuPixel *px = a.film + (size_t)(yPos - rp.yPixelStart) * rp.xPixelCount + (xPos - rp.xPixelStart);
+                            atomicAdd(&px->Lxyz[0], acc[0]);
+                            atomicAdd(&px->Lxyz[1], acc[1]);
+                            atomicAdd(&px->Lxyz[2], acc[2]);
+                            atomicAdd(&px->weightSum, acc[3]);
+                        }
+                        a.b.mti[bi] = mti;
+                        state = S_DONE;
+                        break;
+                    }
+                    const float4 v = __ldcs(lsBase + s);
+                    code = __float_as_int(v.w);
+                    if (code & LS_TAIL) {
+                        const float4 *r = recBase + (size_t)s * 4;
+                        const float4 r0 = __ldcs(r), r1 = __ldcs(r + 1), r2 = __ldcs(r + 2), r3 = __ldcs(r + 3);
+                        ray.o = V3(r0.x, r0.y, r0.z); ray.mint = r0.w;
+                        ray.d = V3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
+                        hit.t = r1.w;
+                        T = Spec(r2.x, r2.y, r2.z);
+                        hit.prim = __float_as_int(r2.w);
+                        hit.b1 = r3.x; hit.b2 = r3.y; hit.maxtIn = r3.z;
+                        L = Spec(v.x, v.y, v.z);
+                        code &= ~LS_TAIL;
+                        bounces = 3;
+                        found = true;
+                        state = S_HIT_RESULT;
+                        ctxDirty = true;
+                    } else {
+                        FilmAdd(rp, a.film, xPos, yPos, code, Spec(v.x, v.y, v.z), acc, direct);
+                        ++s;
+                    }
+                }
+                if (state == S_DONE) break;
+                if (mti >= MT_N) { resumeOut = true; break; }   // RNG window must be topped up first (next iteration)
+                continue;                                       // shade the parked vertex right away
+            }
+        } else {
         if (state == S_END_SAMPLE) {
             const Spec Ls = SanitizeRadiance(L);
             lsBase[s] = make_float4(Ls.r, Ls.g, Ls.b, __int_as_float(code));
@@ -738,14 +842,20 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
             wantTrace = true; anyHit = false;
             state = S_HIT_RESULT;
         }
+        }
         if (wantTrace) { wantTraceOut = true; anyHitOut = anyHit; break; }
         // otherwise the state is non-blocking (S_AFTER_LIGHT / S_AFTER_DIRECT): keep going
     }
 
     // ---- write the slot back and queue its request under its resume state
     if (state == S_DONE) return;   // no more camera samples: the slot retires (it is in no queue any more)
-    const int kindOut = state == S_E_LIGHT ? K_E_LIGHT : state == S_E_MIS ? K_E_MIS : state == S_E_PATH ? K_E_PATH
-                        : state == S_HIT_RESULT ? K_HIT : state == S_SHADOW_RESULT ? K_SHADOW : K_MIS;
+    const int kindOut = resumeOut ? K_RESUME : state == S_E_LIGHT ? K_E_LIGHT : state == S_E_MIS ? K_E_MIS
+                        : state == S_E_PATH ? K_E_PATH : state == S_HIT_RESULT ? K_HIT
+                        : state == S_SHADOW_RESULT ? K_SHADOW : K_MIS;
+    if (PHASE == 2) {
+        FLD(F_ACC) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        a.b.mti[bi] = mti;
+    }
     FLD(F_T) = make_float4(T.r, T.g, T.b, __uint_as_float((uint32_t)state | ((uint32_t)bounces << 8) | ((uint32_t)lightNum << 16)));
     FLD(F_L) = make_float4(L.r, L.g, L.b, __int_as_float(code));
     FLD(F_WO) = make_float4(wo.x, wo.y, wo.z, __int_as_float(bi));
@@ -768,6 +878,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
     } else {
         FLD(F_RAY_O) = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
         FLD(F_RAY_D) = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+        if (resumeOut) FLD(F_HIT) = make_float4(__int_as_float(hit.prim), hit.b1, hit.b2, hit.maxtIn);
     }
     {   // warp-aggregated push, one atomic per (warp, kind)
         const unsigned peers = __match_any_sync(__activemask(), kindOut);
@@ -1026,6 +1137,20 @@ int ValidateRenderDesc(const PbrtGpuRenderDesc &rd) {
     if (rd.nTasks <= 0 || rd.taskBegin < 0 || rd.taskEnd > rd.nTasks || rd.taskBegin > rd.taskEnd)
         return Fail(PBRTGPU_EINVAL, "bad task range");
     if (rd.maxDepth < 0) return Fail(PBRTGPU_EINVAL, "bad maxDepth");
+    {   // Sampler::ComputeSubWindow multiplies in int (core/sampler.cpp:58: 2*dx*ny < dy*nx); a task grid that overflows
+        // it is undefined behaviour in the reference, so it is not a configuration parity can be defined for
+        const FilmExtent e = ComputeExtent(rd);
+        const long long dx = e.sx1 - e.sx0, dy = e.sy1 - e.sy0;
+        long long nx = rd.nTasks, ny = 1;
+        bool overflow = false;
+        for (;;) {
+            if (2 * dx * ny > 0x7fffffffLL || dy * nx > 0x7fffffffLL) { overflow = true; break; }
+            if (!((nx & 1) == 0 && 2 * dx * ny < dy * nx)) break;
+            nx >>= 1; ny <<= 1;
+        }
+        if (overflow)
+            return Fail(PBRTGPU_EINVAL, "nTasks x film extent overflows the int arithmetic of Sampler::ComputeSubWindow");
+    }
     if (rd.shardCount > 1 && (rd.shardIndex < 0 || rd.shardIndex >= rd.shardCount))
         return Fail(PBRTGPU_EINVAL, "bad shard index");
     return PBRTGPU_OK;
@@ -1241,6 +1366,12 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     const size_t perTask = (size_t)spp * (PERM_STRIDE * 2 + 16 + 64) + SCR_STRIDE * 4 + 2 * MT_N * 4 + 4 + sizeof(TaskRec);
     size_t maxBatch = std::max<size_t>(1024, ScratchBudgetBytes() / perTask);
     maxBatch = std::min<size_t>(maxBatch, std::max<size_t>(tasks.size(), 1));
+    {   // the tail wavefront keeps one pool slot per task of the batch
+        size_t ps = (size_t)1 << 22;
+        const char *e = getenv("PBRTGPU_POOL");
+        if (e && atol(e) > 0) ps = (size_t)atol(e);
+        maxBatch = std::min(maxBatch, ps);
+    }
     CUDA_TRY(scene->tasks.Ensure(maxBatch));
     CUDA_TRY(scene->perm.Ensure(maxBatch * spp * PERM_STRIDE));
     CUDA_TRY(scene->scr.Ensure(maxBatch * SCR_STRIDE));
@@ -1268,8 +1399,10 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     if (wantCounters) CUDA_TRY(cudaMemsetAsync(scene->stats.p, 0, sizeof(DeviceStats), stream));
 
     // phase 1 runs as a wavefront over a pool of path slots unless PBRTGPU_WAVEFRONT=0
-    bool useWavefront = true;
+    bool useWavefront = true, useWavefront2 = false;   // tail wavefront: measured slower than k_path<2> (profiles/), opt-in
     { const char *e = getenv("PBRTGPU_WAVEFRONT"); if (e) useWavefront = atoi(e) != 0; }
+    { const char *e = getenv("PBRTGPU_WAVEFRONT2"); if (e) useWavefront2 = atoi(e) != 0; }
+    if (!useWavefront) useWavefront2 = false;
     size_t poolSize = (size_t)1 << 22;   // 4 Mi slots x 272 B = 1.1 GB (measured: +17 % over 1 Mi)
     { const char *e = getenv("PBRTGPU_POOL"); if (e && atol(e) > 0) poolSize = (size_t)atol(e); }
     poolSize = (poolSize + 127) / 128 * 128;
@@ -1282,6 +1415,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
         CUDA_TRY(scene->counters.Ensure(C_COUNT));
         if (!scene->hostCounters) CUDA_TRY(cudaMallocHost((void **)&scene->hostCounters, C_COUNT * sizeof(unsigned)));
     }
+    const bool traceIters = getenv("PBRTGPU_TRACE_ITERS") != nullptr;   // debugging aid: queue occupancy on stderr
     const TableLaunch tl = PlanTables(spp);
     uint64_t launches = 0;
     float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f;
@@ -1319,6 +1453,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                 wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = scene->pool.p; wa.P = (uint32_t)poolSize;
                 wa.q = scene->traceQ.p; wa.counters = scene->counters.p;
                 wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p;
+                wa.film = film; wa.directFilm = 0;
                 CUDA_TRY(cudaMemsetAsync(scene->counters.p, 0, C_COUNT * sizeof(unsigned), stream));
                 const int lblocks = (int)((poolSize + 127) / 128);
                 const int tblocks = nSM * 8;
@@ -1328,8 +1463,8 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                     // empty the queues k_logic is about to fill, and the consumers' cursors
                     CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
                     CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
-                    if (wantCounters) k_logic<true><<<lblocks, 128, 0, stream>>>(wa);
-                    else k_logic<false><<<lblocks, 128, 0, stream>>>(wa);
+                    if (wantCounters) k_logic<1, true><<<lblocks, 128, 0, stream>>>(wa);
+                    else k_logic<1, false><<<lblocks, 128, 0, stream>>>(wa);
                     if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
                     if (wantCounters) k_trace<true><<<tblocks, 128, 0, stream>>>(wa);
                     else k_trace<false><<<tblocks, 128, 0, stream>>>(wa);
@@ -1340,6 +1475,12 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                         CUDA_TRY(cudaStreamSynchronize(stream));
                         unsigned alive = 0;
                         for (int k = 0; k < K_COUNT; ++k) alive += scene->hostCounters[C_QN + setOut * K_COUNT + k];
+                        if (traceIters)
+                            fprintf(stderr, "[pbrtgpu] batch@%zu round %d iter %d: queued %u (eval %u/%u/%u hit %u shadow %u mis %u) next sample %u of %u\n",
+                                    begin, r, iter, alive, scene->hostCounters[C_QN + setOut * K_COUNT + K_E_LIGHT],
+                                    scene->hostCounters[C_QN + setOut * K_COUNT + K_E_MIS], scene->hostCounters[C_QN + setOut * K_COUNT + K_E_PATH],
+                                    scene->hostCounters[C_QN + setOut * K_COUNT + K_HIT], scene->hostCounters[C_QN + setOut * K_COUNT + K_SHADOW],
+                                    scene->hostCounters[C_QN + setOut * K_COUNT + K_MIS], scene->hostCounters[C_NEXT_SAMPLE], wa.totalSamples);
                         if (alive == 0) break;
                     }
                     if (iter > 4000000) return Fail(PBRTGPU_ECUDA, "wavefront did not terminate");
@@ -1353,9 +1494,42 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                                                           scene->orderIn.p, scene->orderOut.p, (int)nb, 0, 1, stream);
                 pa.b.order = scene->orderOut.p;
             }
-            if (wantCounters) k_path<2, true><<<blocks2, 128, 0, stream>>>(pa);
-            else k_path<2, false><<<blocks2, 128, 0, stream>>>(pa);
-            CUDA_TRY(cudaGetLastError());
+            if (!useWavefront2) {
+                if (wantCounters) k_path<2, true><<<blocks2, 128, 0, stream>>>(pa);
+                else k_path<2, false><<<blocks2, 128, 0, stream>>>(pa);
+                CUDA_TRY(cudaGetLastError());
+            } else {
+                // ---- phase 2 as a wavefront: one slot per task-pixel chain
+                WfArgs wa;
+                wa.sc = scene->d; wa.rp = rp; wa.b = pa.b; wa.pool = scene->pool.p; wa.P = (uint32_t)poolSize;
+                wa.q = scene->traceQ.p; wa.counters = scene->counters.p;
+                wa.totalSamples = 0; wa.stats = scene->stats.p;
+                wa.film = film; wa.directFilm = pa.directFilm;
+                CUDA_TRY(cudaMemsetAsync(scene->counters.p, 0, C_COUNT * sizeof(unsigned), stream));
+                const int tblocks = nSM * 8;
+                for (int iter = 0;; ++iter) {
+                    wa.iter = iter;
+                    const int setOut = (iter & 1) ^ 1;
+                    CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
+                    CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
+                    if (wantCounters) k_logic<2, true><<<blocks2, 128, 0, stream>>>(wa);
+                    else k_logic<2, false><<<blocks2, 128, 0, stream>>>(wa);
+                    if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
+                    if (wantCounters) k_trace<true><<<tblocks, 128, 0, stream>>>(wa);
+                    else k_trace<false><<<tblocks, 128, 0, stream>>>(wa);
+                    launches += hasMeasured ? 3 : 2;
+                    if ((iter & 7) == 7) {
+                        CUDA_TRY(cudaMemcpyAsync(scene->hostCounters, scene->counters.p, C_COUNT * sizeof(unsigned),
+                                                 cudaMemcpyDeviceToHost, stream));
+                        CUDA_TRY(cudaStreamSynchronize(stream));
+                        unsigned alive = 0;
+                        for (int k = 0; k < K_COUNT; ++k) alive += scene->hostCounters[C_QN + setOut * K_COUNT + k];
+                        if (alive == 0) break;
+                    }
+                    if (iter > 40000000) return Fail(PBRTGPU_ECUDA, "tail wavefront did not terminate");
+                }
+                CUDA_TRY(cudaGetLastError());
+            }
             launches += 2;
             if (stats) {
                 CUDA_TRY(cudaEventRecord(scene->ev[1], stream));
@@ -1457,6 +1631,7 @@ int pbrtgpu_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
     BatchArgs b;
     b.tasks = tasks.p; b.nBatch = 1; b.round = 0; b.perm = perm.p; b.scr = scr.p; b.rngCur = cur.p; b.rngNext = next.p;
     b.mti = mti.p; b.ls = nullptr; b.rec = rec.p; b.tailCount = nullptr; b.order = nullptr;
+    const bool traceIters = getenv("PBRTGPU_TRACE_ITERS") != nullptr;   // debugging aid: queue occupancy on stderr
     const TableLaunch tl = PlanTables(spp);
     CUDA_TRY(LaunchTablesAny(b, spp, tl, nullptr));
     k_expand_samples<<<(spp + 127) / 128, 128>>>(b, spp, rd->shutterOpen, rd->shutterClose, dout.p);

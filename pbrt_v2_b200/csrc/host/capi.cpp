@@ -27,6 +27,32 @@ PbrtHostScene *pbrthost_load(const char *filename, int ncores, char *err, int er
     return h;
 }
 
+// the synthetic random-triangle scene of BASELINE.json configs[4], built without going through text
+PbrtHostScene *pbrthost_load_synthetic(long long ntris, int xres, int yres, int spp, int maxdepth, int ncores,
+                                       char *err, int errlen) {
+    PbrtHostScene *h = new PbrtHostScene;
+    Options opt;
+    opt.nCores = ncores;
+    SyntheticParams sp;
+    sp.nTriangles = ntris; sp.xres = xres; sp.yres = yres; sp.spp = spp; sp.maxDepth = maxdepth;
+    if (!LoadSyntheticScene(sp, opt, &h->ls)) {
+        if (err && errlen > 0) snprintf(err, errlen, "%s", h->ls.error.c_str());
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+// the same scene as pbrt text (for the unmodified reference)
+int pbrthost_write_synthetic(const char *filename, long long ntris, int xres, int yres, int spp, int maxdepth,
+                             const char *outfile) {
+    SyntheticParams sp;
+    sp.nTriangles = ntris; sp.xres = xres; sp.yres = yres; sp.spp = spp; sp.maxDepth = maxdepth;
+    sp.outfile = outfile;
+    std::string err;
+    return WriteSyntheticSceneFile(filename, sp, &err) ? 0 : 1;
+}
+
 void pbrthost_free(PbrtHostScene *h) { delete h; }
 
 const PbrtGpuSceneDesc *pbrthost_scene_desc(PbrtHostScene *h) { return &h->ls.scene->desc; }

@@ -636,4 +636,153 @@ bool LoadSceneFile(const std::string &filename, const Options &opt, LoadedScene 
     return true;
 }
 
+// ---------------------------------------------------------------- synthetic scene (config C5)
+// N random small triangles in [-1,1]^3 (pbrt RNG = MT19937, seed 1: per triangle the
+// centre c = 2u-1 (3 draws), edges e1, e2 = 0.02 (2u-1) (6 draws), vertices c, c+e1, c+e2, unindexed),
+// matte Kd .5, a 20x20 floor quad at y = -1.05, a disk area light L = 40 (radius 1, y = +3, facing -y),
+// a point light I = 5 at (0,0,4), camera LookAt 0 0 4.5  0 0 0  0 1 0, fov 40.
+// The generator either WRITES the scene as pbrt text (so the unmodified reference can render the same
+// scene; used for parity at small N) or builds the Scene directly through the same Api calls the parser
+// makes (used for the 10 M-triangle runs, where pbrt's text front end is the bottleneck and its float-typed
+// "integer indices" cannot even represent indices > 2^24).  Both routes produce bit-identical floats:
+// the text route prints them with %.9g.
+namespace {
+struct SynthRNG {   // RNG::RandomFloat, core/rng.cpp:43-107
+    uint32_t mt[624];
+    int mti;
+    explicit SynthRNG(uint32_t seed) {
+        mt[0] = seed;
+        for (mti = 1; mti < 624; mti++) mt[mti] = 1812433253u * (mt[mti - 1] ^ (mt[mti - 1] >> 30)) + (uint32_t)mti;
+    }
+    uint32_t U() {
+        if (mti >= 624) {
+            int kk;
+            uint32_t y;
+            for (kk = 0; kk < 624 - 397; kk++) { y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+            for (; kk < 623; kk++) { y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+            y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            mti = 0;
+        }
+        uint32_t y = mt[mti++];
+        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+        return y;
+    }
+    float F() { return (U() & 0xffffff) / float(1 << 24); }
+};
+const int kSynthTrisPerMesh = 1000000;   // keeps every vertex index below 2^24 (pbrt parses indices as floats)
+void SynthTriangle(SynthRNG &rng, V3 v[3]) {
+    V3 c;
+    c.x = 2.f * rng.F() - 1.f; c.y = 2.f * rng.F() - 1.f; c.z = 2.f * rng.F() - 1.f;
+    V3 e1, e2;
+    e1.x = 0.02f * (2.f * rng.F() - 1.f); e1.y = 0.02f * (2.f * rng.F() - 1.f); e1.z = 0.02f * (2.f * rng.F() - 1.f);
+    e2.x = 0.02f * (2.f * rng.F() - 1.f); e2.y = 0.02f * (2.f * rng.F() - 1.f); e2.z = 0.02f * (2.f * rng.F() - 1.f);
+    v[0] = c; v[1] = c + e1; v[2] = c + e2;
+}
+}  // namespace
+
+bool WriteSyntheticSceneFile(const std::string &filename, const SyntheticParams &sp, std::string *err) {
+    FILE *f = fopen(filename.c_str(), "w");
+    if (!f) { *err = "cannot write " + filename; return false; }
+    fprintf(f, "LookAt 0 0 4.5  0 0 0  0 1 0\nCamera \"perspective\" \"float fov\" [40]\n");
+    fprintf(f, "Film \"image\" \"integer xresolution\" [%d] \"integer yresolution\" [%d] \"string filename\" \"%s\"\n",
+            sp.xres, sp.yres, sp.outfile.c_str());
+    fprintf(f, "Sampler \"lowdiscrepancy\" \"integer pixelsamples\" [%d]\n", sp.spp);
+    fprintf(f, "SurfaceIntegrator \"path\" \"integer maxdepth\" [%d]\nWorldBegin\n", sp.maxDepth);
+    fprintf(f, "AttributeBegin\nAreaLightSource \"area\" \"color L\" [40 40 40]\nTranslate 0 3 0\nRotate 90 1 0 0\n"
+               "Shape \"disk\" \"float radius\" [1]\nAttributeEnd\n");
+    fprintf(f, "LightSource \"point\" \"color I\" [5 5 5] \"point from\" [0 0 4]\n");
+    fprintf(f, "Material \"matte\" \"color Kd\" [.5 .5 .5]\n");
+    fprintf(f, "Shape \"trianglemesh\" \"point P\" [-10 -1.05 -10  10 -1.05 -10  10 -1.05 10  -10 -1.05 10] "
+               "\"integer indices\" [0 1 2 2 3 0]\n");
+    SynthRNG rng(1);
+    for (long long t0 = 0; t0 < sp.nTriangles; t0 += kSynthTrisPerMesh) {
+        const int n = (int)std::min<long long>(kSynthTrisPerMesh, sp.nTriangles - t0);
+        fprintf(f, "Shape \"trianglemesh\" \"point P\" [\n");
+        for (int i = 0; i < n; ++i) {
+            V3 v[3];
+            SynthTriangle(rng, v);
+            fprintf(f, "%.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", v[0].x, v[0].y, v[0].z, v[1].x, v[1].y, v[1].z,
+                    v[2].x, v[2].y, v[2].z);
+        }
+        fprintf(f, "] \"integer indices\" [\n");
+        for (int i = 0; i < 3 * n; ++i) fprintf(f, "%d%c", i, (i % 24 == 23) ? '\n' : ' ');
+        fprintf(f, "]\n");
+    }
+    fprintf(f, "WorldEnd\n");
+    fclose(f);
+    return true;
+}
+
+bool LoadSyntheticScene(const SyntheticParams &sp, const Options &opt, LoadedScene *out) {
+    Api api;
+    api.opt = opt;
+    api.scene.reset(new Scene);
+    auto I = [](int v) { return std::vector<int>(1, v); };
+    auto F1 = [](float v) { return std::vector<float>(1, v); };
+    // LookAt / Camera / Film / Sampler / SurfaceIntegrator, exactly as the text route's directives
+    api.ForActive([&](Transform &t) { t = t * LookAt(V3(0, 0, 4.5f), V3(0, 0, 0), V3(0, 1, 0), nullptr); });
+    api.CameraName = "perspective";
+    api.CameraParams.floats["fov"] = F1(40.f);
+    api.CameraToWorld = InverseSet(api.curTransform);
+    api.namedCoordinateSystems["camera"] = api.CameraToWorld;
+    api.FilmParams.ints["xresolution"] = I(sp.xres);
+    api.FilmParams.ints["yresolution"] = I(sp.yres);
+    api.FilmParams.strings["filename"] = std::vector<std::string>(1, sp.outfile);
+    api.SamplerParams.ints["pixelsamples"] = I(sp.spp);
+    api.SurfIntegratorName = "path";
+    api.SurfIntegratorParams.ints["maxdepth"] = I(sp.maxDepth);
+    // WorldBegin
+    api.inWorld = true;
+    api.curTransform = TransformSet();
+    api.namedCoordinateSystems["world"] = api.curTransform;
+    {   // disk area light
+        api.pushedGraphicsStates.push_back(api.graphicsState);
+        api.pushedTransforms.push_back(api.curTransform);
+        api.graphicsState.areaLight = "area";
+        api.graphicsState.areaLightParams.spectra["L"] = std::vector<V3>(1, V3(40, 40, 40));
+        api.ForActive([&](Transform &t) { t = t * Translate(V3(0, 3, 0)); });
+        api.ForActive([&](Transform &t) { t = t * Rotate(90, V3(1, 0, 0)); });
+        ParamSet ps;
+        ps.floats["radius"] = F1(1.f);
+        if (!api.DoShape("disk", ps)) { out->error = api.error; return false; }
+        api.graphicsState = api.pushedGraphicsStates.back(); api.pushedGraphicsStates.pop_back();
+        api.curTransform = api.pushedTransforms.back(); api.pushedTransforms.pop_back();
+    }
+    {
+        ParamSet ps;
+        ps.spectra["I"] = std::vector<V3>(1, V3(5, 5, 5));
+        ps.points["from"] = std::vector<V3>(1, V3(0, 0, 4));
+        if (!api.DoLight("point", ps)) { out->error = api.error; return false; }
+    }
+    api.graphicsState.material = "matte";
+    api.graphicsState.materialParams = ParamSet();
+    api.graphicsState.materialParams.spectra["Kd"] = std::vector<V3>(1, V3(.5f, .5f, .5f));
+    {
+        ParamSet ps;
+        ps.points["P"] = {V3(-10, -1.05f, -10), V3(10, -1.05f, -10), V3(10, -1.05f, 10), V3(-10, -1.05f, 10)};
+        ps.ints["indices"] = {0, 1, 2, 2, 3, 0};
+        if (!api.DoShape("trianglemesh", ps)) { out->error = api.error; return false; }
+    }
+    SynthRNG rng(1);
+    for (long long t0 = 0; t0 < sp.nTriangles; t0 += kSynthTrisPerMesh) {
+        const int n = (int)std::min<long long>(kSynthTrisPerMesh, sp.nTriangles - t0);
+        ParamSet ps;
+        std::vector<V3> &P = ps.points["P"];
+        std::vector<int> &idx = ps.ints["indices"];
+        P.resize(3 * (size_t)n);
+        idx.resize(3 * (size_t)n);
+        for (int i = 0; i < n; ++i) {
+            V3 v[3];
+            SynthTriangle(rng, v);
+            P[3 * i] = v[0]; P[3 * i + 1] = v[1]; P[3 * i + 2] = v[2];
+        }
+        for (int i = 0; i < 3 * n; ++i) idx[i] = i;
+        if (!api.DoShape("trianglemesh", ps)) { out->error = api.error; return false; }
+    }
+    api.worldEnded = true;
+    if (!api.Finish(out)) { out->error = api.error; return false; }
+    return true;
+}
+
 }  // namespace pb

@@ -254,5 +254,14 @@ struct LoadedScene {
 // up to WorldEnd and builds Scene + Renderer; does NOT render.
 bool LoadSceneFile(const std::string &filename, const Options &opt, LoadedScene *out);
 
+// BASELINE.json configs[4]: the synthetic random-triangle scene
+struct SyntheticParams {
+    long long nTriangles = 10000000;
+    int xres = 4096, yres = 4096, spp = 512, maxDepth = 8;
+    std::string outfile = "synthetic.pfm";
+};
+bool WriteSyntheticSceneFile(const std::string &filename, const SyntheticParams &sp, std::string *err);
+bool LoadSyntheticScene(const SyntheticParams &sp, const Options &opt, LoadedScene *out);
+
 }  // namespace pb
 #endif

@@ -171,3 +171,14 @@ def test_full_size_properties(staged):
     own = half["weightSum"] >= 4
     assert abs(own.mean() - 0.5) < 0.01
     assert np.array_equal(half["Lxyz"][own & (w == 4)].view(np.uint32), px["Lxyz"][own & (w == 4)].view(np.uint32))
+
+
+def test_synthetic_scene_bit_exact(staged):
+    """BASELINE.json configs[4] generator (random small triangles, disk + point light, maxdepth 8) at a CI size."""
+    hs = pb.HostScene.synthetic(30000, 48, 48, 8, maxdepth=8, ncores=72)
+    px_gpu, st = _gpu_scene(hs).render()
+    px_cpu, _ = oa.render(hs, threads=2)
+    assert np.array_equal(px_gpu["weightSum"], px_cpu["weightSum"])
+    diff = (px_gpu["Lxyz"].view(np.uint32) != px_cpu["Lxyz"].view(np.uint32)).any(axis=2)
+    assert (diff & (px_cpu["weightSum"] == 8)).sum() <= 1
+    assert st.cameraSamples == 48 * 48 * 8

@@ -83,3 +83,19 @@ def test_oracle_bit_exact_vs_reference_binary(staged, base, res, spp, ncores):
     rgb = hs.pixels_to_rgb(px)
     ref, _ = oa.run_reference(hs.filename, ncores)
     assert np.array_equal(rgb.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+def test_synthetic_scene_text_and_direct_routes_match_reference(staged):
+    """the C5 generator: the in-memory build equals the text scene, and the oracle renders it bit-exactly
+    like the unmodified reference (multi-pixel tasks)."""
+    from pbrt_v2_b200 import scenes
+    path = pb.HostScene.write_synthetic(os.path.join(scenes.STAGED, "t-synth.pbrt"), 5000, 32, 32, 4, 8, "t-synth.pfm")
+    direct = pb.HostScene.synthetic(5000, 32, 32, 4, maxdepth=8, ncores=1)
+    text = pb.HostScene(path, ncores=1)
+    assert direct.counts() == text.counts() and direct.scene_bytes() == text.scene_bytes()
+    a, _ = oa.render(direct, threads=2)
+    b, _ = oa.render(text, threads=2)
+    assert np.array_equal(a["Lxyz"].view(np.uint32), b["Lxyz"].view(np.uint32))
+    ref, _ = oa.run_reference(path, 1)
+    assert np.array_equal(direct.pixels_to_rgb(a).view(np.uint32), ref.view(np.uint32))
