@@ -54,12 +54,13 @@ typedef struct PbrtGpuBVHNode {
 } PbrtGpuBVHNode;
 
 /* ---- primitives, in BVHAccel::primitives (leaf) order ---------------------- */
-enum { PBRTGPU_PRIM_TRIANGLE = 0, PBRTGPU_PRIM_SPHERE = 1, PBRTGPU_PRIM_DISK = 2 };
+enum { PBRTGPU_PRIM_TRIANGLE = 0, PBRTGPU_PRIM_SPHERE = 1, PBRTGPU_PRIM_DISK = 2,
+       PBRTGPU_PRIM_ANIMATED = 3   /* TransformedPrimitive: index into animated[], material/areaLight unused */ };
 
 /* GeometricPrimitive{shape, material, areaLight}, core/primitive.cpp:149-190 */
 typedef struct PbrtGpuPrimitive {
     uint32_t type;       /* PBRTGPU_PRIM_*                                      */
-    uint32_t index;      /* TRIANGLE: into triangles[]; else into quadrics[]    */
+    uint32_t index;      /* TRIANGLE: triangles[]; SPHERE/DISK: quadrics[]; ANIMATED: animated[] */
     int32_t  material;   /* into materials[]                                    */
     int32_t  areaLight;  /* into lights[] or -1 (GetAreaLight()==NULL)          */
 } PbrtGpuPrimitive;
@@ -94,6 +95,23 @@ typedef struct PbrtGpuQuadric {
     float height, innerRadius;               /* disk   */
     float area;            /* Shape::Area() evaluated on the host               */
 } PbrtGpuQuadric;
+
+/* TransformedPrimitive{primitive, WorldToPrimitive}, core/primitive.h:104-123, built by pbrtShape for a
+ * shape under an animated CTM (core/api.cpp:1011-1043).  The nested primitive is either its own
+ * BVHAccel(refined prims; default maxPrimsInNode 1, "sah") -- nNodes > 0, node and primitive offsets
+ * inside those nodes are relative to firstNode / firstPrimitive -- or a single primitive (nNodes == 0).
+ * start/end/T/R/S are AnimatedTransform's members (core/transform.h:321-326): the two
+ * world-to-primitive transforms and their Decompose() outputs (transform.cpp:328-368).                */
+typedef struct PbrtGpuAnimated {
+    PbrtGpuXform start, end;
+    float    startTime, endTime;     /* renderOptions->transformStartTime/EndTime (api.cpp:1031-1032) */
+    uint32_t actuallyAnimated;
+    float    T[2][3];
+    float    R[2][4];                /* quaternion (v.x, v.y, v.z, w)                      */
+    float    S[2][16];
+    uint32_t firstNode, nNodes;
+    uint32_t firstPrimitive, nPrimitives;
+} PbrtGpuAnimated;
 
 /* ---- materials (constant textures only), materials/{matte,plastic,measured} - */
 enum { PBRTGPU_MAT_MATTE = 0, PBRTGPU_MAT_PLASTIC = 1, PBRTGPU_MAT_MEASURED = 2 };
@@ -138,8 +156,8 @@ typedef struct PbrtGpuLightShape {
 
 /* ---- the flattened Scene --------------------------------------------------- */
 typedef struct PbrtGpuSceneDesc {
-    uint32_t nNodes;        const PbrtGpuBVHNode    *nodes;
-    uint32_t nPrimitives;   const PbrtGpuPrimitive  *primitives;
+    uint32_t nNodes;        const PbrtGpuBVHNode    *nodes;       /* scene BVH first (root = 0), nested BVHs after */
+    uint32_t nPrimitives;   const PbrtGpuPrimitive  *primitives;  /* scene BVH's leaf order first, nested after    */
     uint32_t nTriangles;    const PbrtGpuTriangle   *triangles;
     uint32_t nMeshes;       const PbrtGpuMesh       *meshes;
     uint32_t nVertices;     const float *P;   /* 3*nVertices                    */
@@ -153,6 +171,7 @@ typedef struct PbrtGpuSceneDesc {
                             const PbrtGpuBrdfSample *kdData;
     uint32_t nLights;       const PbrtGpuLight      *lights;
     uint32_t nLightShapes;  const PbrtGpuLightShape *lightShapes;
+    uint32_t nAnimated;     const PbrtGpuAnimated   *animated;    /* may be 0 / NULL                               */
 } PbrtGpuSceneDesc;
 
 /* ---- one Render() call ----------------------------------------------------- */
@@ -203,13 +222,13 @@ typedef struct PbrtGpuStats {
     uint64_t kernelLaunches;
 } PbrtGpuStats;
 
-typedef struct PbrtGpuRay { float o[3], d[3], mint, maxt; } PbrtGpuRay;
+typedef struct PbrtGpuRay { float o[3], d[3], mint, maxt, time; } PbrtGpuRay;   /* core/geometry.h:338-362 */
 typedef struct PbrtGpuHit {
     int32_t  hit;             /* 0/1                                            */
-    uint32_t primitive;       /* index into primitives[]                        */
+    uint32_t primitive;       /* index into primitives[] (the nested one under a TransformedPrimitive) */
     float    t;               /* ray.maxt after BVHAccel::Intersect             */
     float    b1, b2;          /* triangle barycentrics (0 for quadrics)         */
-    float    p[3], n[3];      /* dg.p, dg.nn                                    */
+    float    p[3], n[3];      /* dg.p, dg.nn (world space)                      */
 } PbrtGpuHit;
 
 typedef struct PbrtGpuScene PbrtGpuScene;

@@ -178,6 +178,9 @@ struct Intersection {   // core/intersection.h:45-62
     DiffGeom dg;
     uint32_t prim;
     float rayEpsilon;
+    bool instanced;   // hit under a TransformedPrimitive whose interpolated transform is not the identity
+    Xf w2p;           // ... that transform (isect->WorldToObject = WorldToObject * w2p, primitive.cpp:106)
+    Intersection() : prim(0), rayEpsilon(0.f), instanced(false) {}
 };
 
 struct SceneView {
@@ -325,9 +328,108 @@ struct SceneView {
         return q.type == PBRTGPU_PRIM_SPHERE ? SphereIntersect(q, r, tHit, rayEps, dg) : DiskIntersect(q, r, tHit, rayEps, dg);
     }
 
+    // Slerp, core/quaternion.cpp:99-111; quaternion = (v.x, v.y, v.z, w)
+    static void Slerp(float t, const float *q1, const float *q2, float *out) {
+        auto qdot = [](const float *a, const float *b) { return (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + a[3] * b[3]; };
+        auto qnormalize = [&](float *q) {   // quaternion.h:109-111: v /= f multiplies by 1/f, w /= f divides
+            float f = sqrtf(qdot(q, q));
+            float inv = 1.f / f;
+            q[0] *= inv; q[1] *= inv; q[2] *= inv;
+            q[3] /= f;
+        };
+        float cosTheta = qdot(q1, q2);
+        if (cosTheta > .9995f) {
+            for (int i = 0; i < 4; ++i) out[i] = q1[i] * (1.f - t) + q2[i] * t;
+            qnormalize(out);
+        } else {
+            float theta = acosf(Clampf(cosTheta, -1.f, 1.f));
+            float thetap = theta * t;
+            float qperp[4];
+            for (int i = 0; i < 4; ++i) qperp[i] = q2[i] - q1[i] * cosTheta;
+            qnormalize(qperp);
+            float c = cosf(thetap), sn = sinf(thetap);
+            for (int i = 0; i < 4; ++i) out[i] = q1[i] * c + qperp[i] * sn;
+        }
+    }
+    // AnimatedTransform::Interpolate, core/transform.cpp:371-396
+    static Xf Interpolate(const PbrtGpuAnimated &a, float time) {
+        Xf r;
+        if (!a.actuallyAnimated || time <= a.startTime) { memcpy(&r, &a.start, sizeof(r)); return r; }
+        if (time >= a.endTime) { memcpy(&r, &a.end, sizeof(r)); return r; }
+        float dt = (time - a.startTime) / (a.endTime - a.startTime);
+        float trans[3];
+        for (int i = 0; i < 3; ++i) trans[i] = (1.f - dt) * a.T[0][i] + dt * a.T[1][i];
+        float q[4];
+        Slerp(dt, a.R[0], a.R[1], q);
+        Xf scale;
+        MatIdentity(scale.m);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) scale.m[4 * i + j] = Lerp(dt, a.S[0][4 * i + j], a.S[1][4 * i + j]);
+        MatInverse(scale.m, scale.mInv);   // Transform(const Matrix4x4 &), transform.h:99-101
+        Xf tr;                             // Translate(), transform.cpp:160-170
+        MatIdentity(tr.m); MatIdentity(tr.mInv);
+        tr.m[3] = trans[0]; tr.m[7] = trans[1]; tr.m[11] = trans[2];
+        tr.mInv[3] = -trans[0]; tr.mInv[7] = -trans[1]; tr.mInv[11] = -trans[2];
+        Xf rot;                            // Quaternion::ToTransform, quaternion.cpp:39-58
+        {
+            const float x = q[0], y = q[1], z = q[2], w = q[3];
+            float xx = x * x, yy = y * y, zz = z * z;
+            float xy = x * y, xz = x * z, yz = y * z;
+            float wx = x * w, wy = y * w, wz = z * w;
+            float m[16];
+            MatIdentity(m);
+            m[0] = 1.f - 2.f * (yy + zz);
+            m[1] = 2.f * (xy + wz);
+            m[2] = 2.f * (xz - wy);
+            m[4] = 2.f * (xy - wz);
+            m[5] = 1.f - 2.f * (xx + zz);
+            m[6] = 2.f * (yz + wx);
+            m[8] = 2.f * (xz + wy);
+            m[9] = 2.f * (yz - wx);
+            m[10] = 1.f - 2.f * (xx + yy);
+            MatTranspose(m, rot.m);
+            memcpy(rot.mInv, m, sizeof(m));
+        }
+        return XfCompose(XfCompose(tr, rot), scale);
+    }
+
+    // TransformedPrimitive::Intersect, core/primitive.cpp:95-119
+    bool AnimatedIntersect(const PbrtGpuAnimated &a, const Ray &r, Intersection *isect, Counters *cnt, float *b1, float *b2) const {
+        Xf w2p = Interpolate(a, r.time);
+        Ray ray = r;
+        ray.o = XfPoint(w2p.m, r.o);
+        ray.d = XfVector(w2p.m, r.d);
+        bool hit;
+        if (a.nNodes > 0) hit = IntersectBVH(a.firstNode, a.firstPrimitive, ray, isect, cnt, b1, b2);
+        else hit = PrimIntersect(a.firstPrimitive, ray, isect, cnt, b1, b2);
+        if (!hit) return false;
+        r.maxt = ray.maxt;
+        isect->instanced = false;
+        if (!XfIsIdentity(w2p)) {
+            isect->instanced = true;
+            isect->w2p = w2p;
+            // PrimitiveToWorld = Inverse(w2p): points/vectors by w2p.mInv, normals by the transpose of w2p.m
+            isect->dg.p = XfPoint(w2p.mInv, isect->dg.p);
+            isect->dg.nn = Normalize(XfNormal(w2p.m, isect->dg.nn));
+            isect->dg.dpdu = XfVector(w2p.mInv, isect->dg.dpdu);
+            isect->dg.dpdv = XfVector(w2p.mInv, isect->dg.dpdv);
+        }
+        return true;
+    }
+    // TransformedPrimitive::IntersectP, core/primitive.cpp:122-124
+    bool AnimatedIntersectP(const PbrtGpuAnimated &a, const Ray &r, Counters *cnt) const {
+        Xf w2p = Interpolate(a, r.time);   // AnimatedTransform::operator()(Ray): same three cases (transform.cpp:416-427)
+        Ray ray = r;
+        ray.o = XfPoint(w2p.m, r.o);
+        ray.d = XfVector(w2p.m, r.d);
+        if (a.nNodes > 0) return IntersectPBVH(a.firstNode, a.firstPrimitive, ray, cnt);
+        return PrimIntersectP(a.firstPrimitive, ray, cnt);
+    }
+
     // GeometricPrimitive::Intersect, core/primitive.cpp:163-177
-    bool PrimIntersect(uint32_t pi, const Ray &r, Intersection *isect, float *b1 = nullptr, float *b2 = nullptr) const {
+    bool PrimIntersect(uint32_t pi, const Ray &r, Intersection *isect, Counters *cnt, float *b1 = nullptr, float *b2 = nullptr) const {
         const PbrtGpuPrimitive &p = d->primitives[pi];
+        if (p.type == PBRTGPU_PRIM_ANIMATED) return AnimatedIntersect(d->animated[p.index], r, isect, cnt, b1, b2);
         float thit, rayEpsilon;
         bool hit;
         if (p.type == PBRTGPU_PRIM_TRIANGLE) hit = TriIntersect(d->triangles[p.index], r, &thit, &rayEpsilon, &isect->dg, b1, b2);
@@ -338,11 +440,13 @@ struct SceneView {
         if (!hit) return false;
         isect->prim = pi;
         isect->rayEpsilon = rayEpsilon;
+        isect->instanced = false;
         r.maxt = thit;
         return true;
     }
-    bool PrimIntersectP(uint32_t pi, const Ray &r) const {
+    bool PrimIntersectP(uint32_t pi, const Ray &r, Counters *cnt) const {
         const PbrtGpuPrimitive &p = d->primitives[pi];
+        if (p.type == PBRTGPU_PRIM_ANIMATED) return AnimatedIntersectP(d->animated[p.index], r, cnt);
         float thit;
         if (p.type == PBRTGPU_PRIM_TRIANGLE) return TriIntersect(d->triangles[p.index], r, &thit, nullptr, nullptr);
         return QuadricIntersect(d->quadrics[p.index], r, &thit, nullptr, nullptr);
@@ -369,19 +473,28 @@ struct SceneView {
     // BVHAccel::Intersect, accelerators/bvh.cpp:403-454
     bool Intersect(const Ray &ray, Intersection *isect, Counters *cnt, float *b1 = nullptr, float *b2 = nullptr) const {
         if (cnt) cnt->closestRays++;
+        return IntersectBVH(0, 0, ray, isect, cnt, b1, b2);
+    }
+    bool IntersectP(const Ray &ray, Counters *cnt) const {
+        if (cnt) cnt->shadowRays++;
+        return IntersectPBVH(0, 0, ray, cnt);
+    }
+    // nodeBase / primBase: where this BVHAccel's nodes[] and primitives[] start in the flattened arrays
+    bool IntersectBVH(uint32_t nodeBase, uint32_t primBase, const Ray &ray, Intersection *isect, Counters *cnt,
+                      float *b1, float *b2) const {
         bool hit = false;
         Vec invDir(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
         uint32_t dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
         uint32_t todoOffset = 0, nodeNum = 0;
         uint32_t todo[64];
         while (true) {
-            const PbrtGpuBVHNode *node = &d->nodes[nodeNum];
+            const PbrtGpuBVHNode *node = &d->nodes[nodeBase + nodeNum];
             if (cnt) { cnt->nodesVisited++; cnt->closestNodes++; }
             if (BoxTest(*node, ray, invDir, dirIsNeg)) {
                 if (node->nPrimitives > 0) {
                     for (uint32_t i = 0; i < node->nPrimitives; ++i) {
                         if (cnt) { cnt->primTests++; cnt->closestPrims++; }
-                        if (PrimIntersect(node->offset + i, ray, isect, b1, b2)) hit = true;
+                        if (PrimIntersect(primBase + node->offset + i, ray, isect, cnt, b1, b2)) hit = true;
                     }
                     if (todoOffset == 0) break;
                     nodeNum = todo[--todoOffset];
@@ -402,20 +515,19 @@ struct SceneView {
         return hit;
     }
     // BVHAccel::IntersectP, accelerators/bvh.cpp:457-503
-    bool IntersectP(const Ray &ray, Counters *cnt) const {
-        if (cnt) cnt->shadowRays++;
+    bool IntersectPBVH(uint32_t nodeBase, uint32_t primBase, const Ray &ray, Counters *cnt) const {
         Vec invDir(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
         uint32_t dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
         uint32_t todo[64];
         uint32_t todoOffset = 0, nodeNum = 0;
         while (true) {
-            const PbrtGpuBVHNode *node = &d->nodes[nodeNum];
+            const PbrtGpuBVHNode *node = &d->nodes[nodeBase + nodeNum];
             if (cnt) cnt->nodesVisited++;
             if (BoxTest(*node, ray, invDir, dirIsNeg)) {
                 if (node->nPrimitives > 0) {
                     for (uint32_t i = 0; i < node->nPrimitives; ++i) {
                         if (cnt) cnt->primTests++;
-                        if (PrimIntersectP(node->offset + i, ray)) return true;
+                        if (PrimIntersectP(primBase + node->offset + i, ray, cnt)) return true;
                     }
                     if (todoOffset == 0) break;
                     nodeNum = todo[--todoOffset];
@@ -817,7 +929,14 @@ struct Renderer {
             if (!ok) b[0] = b[1] = b[2] = 1.f / 3.f;
             else b[0] = 1.f - b[1] - b[2];
         }
-        const PbrtGpuXform &o2w = sv.d->xforms[mesh.xform];
+        // obj2world = isect.ObjectToWorld; under a TransformedPrimitive that is Inverse(WorldToObject * w2p)
+        // (primitive.cpp:106-107), so its mInv -- what a Normal is transformed with -- is WorldToObject.m * w2p.m
+        PbrtGpuXform o2w = sv.d->xforms[mesh.xform];
+        if (isect.instanced) {
+            float wm[16];
+            MatMul(o2w.mInv, isect.w2p.m, wm);
+            memcpy(o2w.mInv, wm, sizeof(wm));
+        }
         Vec n0(sv.d->N + 3 * tri.v[0]), n1(sv.d->N + 3 * tri.v[1]), n2(sv.d->N + 3 * tri.v[2]);
         Vec ns = Normalize(XfNormal(o2w.mInv, b[0] * n0 + b[1] * n1 + b[2] * n2));
         Vec ss = Normalize(dg.dpdu);
@@ -1201,7 +1320,7 @@ int oracle_render(const PbrtGpuSceneDesc *scene, const PbrtGpuRenderDesc *rd, Pb
 int oracle_intersect(const PbrtGpuSceneDesc *scene, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits) {
     SceneView sv{scene};
     for (int i = 0; i < n; ++i) {
-        Ray r(Vec(rays[i].o), Vec(rays[i].d), rays[i].mint, rays[i].maxt);
+        Ray r(Vec(rays[i].o), Vec(rays[i].d), rays[i].mint, rays[i].maxt, rays[i].time);
         Intersection isect;
         float b1 = 0, b2 = 0;
         memset(&hits[i], 0, sizeof(PbrtGpuHit));
@@ -1222,7 +1341,7 @@ int oracle_intersect(const PbrtGpuSceneDesc *scene, const PbrtGpuRay *rays, int 
 int oracle_intersect_p(const PbrtGpuSceneDesc *scene, const PbrtGpuRay *rays, int n, uint8_t *occluded) {
     SceneView sv{scene};
     for (int i = 0; i < n; ++i) {
-        Ray r(Vec(rays[i].o), Vec(rays[i].d), rays[i].mint, rays[i].maxt);
+        Ray r(Vec(rays[i].o), Vec(rays[i].d), rays[i].mint, rays[i].maxt, rays[i].time);
         occluded[i] = sv.IntersectP(r, nullptr) ? 1 : 0;
     }
     return 0;

@@ -119,5 +119,79 @@ inline Vec XfNormal(const float *mInv, const Vec &n) {   // transform.h:241-246
                mInv[2] * x + mInv[6] * y + mInv[10] * z);
 }
 
+
+// ---- Matrix4x4 / Transform as row-major float[16] (core/transform.h:49-83,86-178) -- used by the
+// TransformedPrimitive restatement (AnimatedTransform::Interpolate runs per ray)
+struct Xf { float m[16], mInv[16]; };
+inline void MatIdentity(float *r) { for (int i = 0; i < 16; ++i) r[i] = (i % 5 == 0) ? 1.f : 0.f; }
+inline void MatMul(const float *m1, const float *m2, float *r) {   // Matrix4x4::Mul, transform.h:69-77
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            r[4 * i + j] = m1[4 * i] * m2[j] + m1[4 * i + 1] * m2[4 + j] + m1[4 * i + 2] * m2[8 + j] + m1[4 * i + 3] * m2[12 + j];
+}
+inline void MatTranspose(const float *m, float *r) {
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r[4 * i + j] = m[4 * j + i];
+}
+inline void MatInverse(const float *m, float *out) {   // Inverse(Matrix4x4), core/transform.cpp:76-136
+    int indxc[4], indxr[4];
+    int ipiv[4] = {0, 0, 0, 0};
+    float minv[4][4];
+    for (int i = 0; i < 16; ++i) minv[i / 4][i % 4] = m[i];
+    for (int i = 0; i < 4; i++) {
+        int irow = -1, icol = -1;
+        float big = 0.;
+        for (int j = 0; j < 4; j++) {
+            if (ipiv[j] != 1) {
+                for (int k = 0; k < 4; k++) {
+                    if (ipiv[k] == 0) {
+                        if (fabsf(minv[j][k]) >= big) {
+                            big = float(fabsf(minv[j][k]));
+                            irow = j;
+                            icol = k;
+                        }
+                    }
+                }
+            }
+        }
+        if (icol < 0) break;   // NaN matrix: the reference would index out of bounds here
+        ++ipiv[icol];
+        if (irow != icol)
+            for (int k = 0; k < 4; ++k) std::swap(minv[irow][k], minv[icol][k]);
+        indxr[i] = irow;
+        indxc[i] = icol;
+        float pivinv = 1.f / minv[icol][icol];
+        minv[icol][icol] = 1.f;
+        for (int j = 0; j < 4; j++) minv[icol][j] *= pivinv;
+        for (int j = 0; j < 4; j++) {
+            if (j != icol) {
+                float save = minv[j][icol];
+                minv[j][icol] = 0;
+                for (int k = 0; k < 4; k++) minv[j][k] -= minv[icol][k] * save;
+            }
+        }
+    }
+    for (int j = 3; j >= 0; j--) {
+        if (indxr[j] != indxc[j])
+            for (int k = 0; k < 4; k++) std::swap(minv[k][indxr[j]], minv[k][indxc[j]]);
+    }
+    for (int i = 0; i < 16; ++i) out[i] = minv[i / 4][i % 4];
+}
+inline Xf XfCompose(const Xf &a, const Xf &b) {   // Transform::operator*, transform.cpp:297-301
+    Xf r;
+    MatMul(a.m, b.m, r.m);
+    MatMul(b.mInv, a.mInv, r.mInv);
+    return r;
+}
+inline Xf XfInverse(const Xf &a) {
+    Xf r;
+    memcpy(r.m, a.mInv, sizeof(r.m));
+    memcpy(r.mInv, a.m, sizeof(r.m));
+    return r;
+}
+inline bool XfIsIdentity(const Xf &a) {   // transform.h:124-133 (checks m only)
+    for (int i = 0; i < 16; ++i) if (a.m[i] != ((i % 5 == 0) ? 1.f : 0.f)) return false;
+    return true;
+}
+
 }  // namespace orc
 #endif

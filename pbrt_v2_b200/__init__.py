@@ -57,7 +57,7 @@ class Stats(C.Structure):
 
 
 PIXEL_DTYPE = np.dtype([("Lxyz", np.float32, 3), ("weightSum", np.float32)])
-RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("mint", np.float32), ("maxt", np.float32)])
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("mint", np.float32), ("maxt", np.float32), ("time", np.float32)])
 HIT_DTYPE = np.dtype([("hit", np.int32), ("primitive", np.uint32), ("t", np.float32),
                       ("b1", np.float32), ("b2", np.float32), ("p", np.float32, 3), ("n", np.float32, 3)])
 SAMPLE_FLOATS = 37

@@ -10,11 +10,13 @@
 //           "12 B indices + 36 B positions" the reference touches per triangle
 //           test (trianglemesh.cpp:133-135) but pre-gathered, so a leaf test is
 //           three coalescable 128-bit loads instead of index -> vertex chasing:
-//           {p1.xyz, type} {p2.xyz, index} {p3.xyz, material | (areaLight+1)<<16}
+//           {p1.xyz, type | (owner+1)<<8} {p2.xyz, index} {p3.xyz, material | (areaLight+1)<<16}
+//           (owner = the TransformedPrimitive a nested primitive belongs to, -1 for the scene BVH's own)
 //   everything else (normals, uvs, quadrics, materials, kd-tree, lights) is
 //   touched only when a hit is shaded and stays in the PbrtGpu* POD form.
 #pragma once
 #include "dmath.cuh"
+#include "danim.cuh"
 #include "../../../include/pbrtgpu.h"
 
 namespace dev {
@@ -34,12 +36,14 @@ struct DScene {
     const PbrtGpuBrdfSample *kdData;
     const PbrtGpuLight *lights;
     const PbrtGpuLightShape *lightShapes;
-    uint32_t nNodes, nPrims, nLights;
+    const PbrtGpuAnimated *animated;   // TransformedPrimitives (null / 0 for static scenes)
+    uint32_t nNodes, nPrims, nLights, nAnimated;
 };
 
 struct Ray {
     V3 o, d;
     float mint, maxt;
+    float time;   // constant along a camera path (path.cpp:109, integrator.cpp:127,148); read by TransformedPrimitives only
 };
 DEV V3 RayAt(const Ray &r, float t) { return r.o + r.d * t; }   // geometry.h:333
 
@@ -227,34 +231,45 @@ DEV bool BoxTest(const float4 &n0, const float4 &n1, const Ray &ray, const V3 &i
     return (tmin < ray.maxt) && (tmax > ray.mint);
 }
 
-template <bool STATS>
-DEV bool Traverse(const DScene &sc, Ray &ray, bool anyHit, Hit *hit, TraceStats *st) {
-    hit->prim = -1;
+template <bool STATS> __device__ __noinline__ bool AnimatedIntersect(const DScene &sc, uint32_t index, Ray &ray, bool anyHit,
+                                                                      Hit *hit, TraceStats *st);
+
+// TOP: the scene's own BVH (nodes/primitives from 0); otherwise the BVH nested in a TransformedPrimitive,
+// whose node and primitive offsets are relative to nodeBase / primBase.
+template <bool STATS, bool TOP, bool ANIM>
+DEV bool TraverseBVH(const DScene &sc, uint32_t nodeBase, uint32_t primBase, Ray &ray, bool anyHit, Hit *hit, TraceStats *st) {
     V3 invDir(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
     bool neg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
     uint32_t todo[64];
     uint32_t todoOffset = 0, nodeNum = 0;
     bool found = false;
     while (true) {
-        const float4 n0 = __ldg(sc.nodes + 2 * nodeNum);
-        const float4 n1 = __ldg(sc.nodes + 2 * nodeNum + 1);
+        const float4 n0 = __ldg(sc.nodes + 2 * (nodeBase + nodeNum));
+        const float4 n1 = __ldg(sc.nodes + 2 * (nodeBase + nodeNum) + 1);
         if (STATS) st->nodes++;
         if (BoxTest(n0, n1, ray, invDir, neg)) {
             const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
             const uint32_t nPrims = meta & 0xffu;
             if (nPrims > 0) {
                 for (uint32_t i = 0; i < nPrims; ++i) {
-                    const uint32_t pi = offset + i;
+                    const uint32_t pi = primBase + offset + i;
                     const float4 r0 = __ldg(sc.prims + 3 * pi);
                     const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
                     const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
                     if (STATS) st->prims++;
-                    const uint32_t type = __float_as_uint(r0.w);
+                    const uint32_t type = __float_as_uint(r0.w) & 0xffu;
                     float t, b1 = 0.f, b2 = 0.f;
                     bool h;
                     if (type == PBRTGPU_PRIM_TRIANGLE)
                         h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), ray, &t, &b1, &b2);
-                    else
+                    else if (TOP && ANIM && type == PBRTGPU_PRIM_ANIMATED) {
+                        // TransformedPrimitive::Intersect fills the hit and shrinks ray.maxt itself
+                        if (AnimatedIntersect<STATS>(sc, __float_as_uint(r1.w), ray, anyHit, hit, st)) {
+                            if (anyHit) return true;
+                            found = true;
+                        }
+                        continue;
+                    } else
                         h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], ray, &t, nullptr);
                     if (h) {
                         if (anyHit) { hit->prim = (int)pi; return true; }
@@ -280,6 +295,57 @@ DEV bool Traverse(const DScene &sc, Ray &ray, bool anyHit, Hit *hit, TraceStats 
             nodeNum = todo[--todoOffset];
         }
     }
+    return found;
+}
+
+// one primitive tested directly (a TransformedPrimitive around a single refined primitive: no BVH, api.cpp:1040-1041)
+DEV bool SinglePrimTest(const DScene &sc, uint32_t pi, Ray &ray, bool anyHit, Hit *hit) {
+    const float4 r0 = __ldg(sc.prims + 3 * pi);
+    const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
+    const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
+    const uint32_t type = __float_as_uint(r0.w) & 0xffu;
+    float t, b1 = 0.f, b2 = 0.f;
+    bool h;
+    if (type == PBRTGPU_PRIM_TRIANGLE)
+        h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), ray, &t, &b1, &b2);
+    else
+        h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], ray, &t, nullptr);
+    if (!h) return false;
+    hit->prim = (int)pi;
+    if (anyHit) return true;
+    hit->b1 = b1; hit->b2 = b2; hit->maxtIn = ray.maxt;
+    ray.maxt = t;
+    return true;
+}
+
+// w2p(r): Transform::operator()(const Ray &), transform.h:253-262
+DEV void ToPrimitiveSpace(const DXf &w2p, const Ray &r, Ray *out) {
+    out->o = XfPoint(w2p.m, r.o);
+    out->d = XfVector(w2p.m, r.d);
+    out->mint = r.mint; out->maxt = r.maxt; out->time = r.time;
+}
+
+// TransformedPrimitive::Intersect / IntersectP, core/primitive.cpp:95-124 (the DifferentialGeometry is taken back
+// to world space in HitGeometry, when -- and if -- the hit is shaded)
+template <bool STATS>
+__device__ __noinline__ bool AnimatedIntersect(const DScene &sc, uint32_t index, Ray &r, bool anyHit, Hit *hit, TraceStats *st) {
+    const PbrtGpuAnimated *a = sc.animated + index;
+    DXf w2p;
+    AnimInterpolate(a, r.time, &w2p);
+    Ray ray;
+    ToPrimitiveSpace(w2p, r, &ray);
+    bool found;
+    if (a->nNodes > 0) found = TraverseBVH<STATS, false, false>(sc, a->firstNode, a->firstPrimitive, ray, anyHit, hit, st);
+    else found = SinglePrimTest(sc, a->firstPrimitive, ray, anyHit, hit);
+    if (found) r.maxt = ray.maxt;
+    return found;
+}
+
+// ANIM: the scene may contain TransformedPrimitives (instantiations without it carry no trace of them)
+template <bool STATS, bool ANIM>
+DEV bool Traverse(const DScene &sc, Ray &ray, bool anyHit, Hit *hit, TraceStats *st) {
+    hit->prim = -1;
+    const bool found = TraverseBVH<STATS, true, ANIM>(sc, 0u, 0u, ray, anyHit, hit, st);
     hit->t = ray.maxt;
     return found;
 }
@@ -288,96 +354,173 @@ DEV bool Traverse(const DScene &sc, Ray &ray, bool anyHit, Hit *hit, TraceStats 
 // Same walk as Traverse<>, cut into single-node steps so that a persistent lane can pick up a new
 // ray from the queue the moment its current one finishes (no lane waits for its warp's longest ray).
 struct Trav {
-    Ray ray;
+    Ray ray;            // in the space of the BVH being walked (primitive space inside a TransformedPrimitive)
     V3 invDir;
     uint32_t nodeNum, todoOffset;
     bool neg[3];
     bool anyHit, found;
     Hit hit;
+    // ---- TransformedPrimitive in progress (ANIM instantiation only)
+    int inst;                    // animated[] index or -1
+    uint32_t nodeBase, primBase; // of the BVH being walked
+    uint32_t todoBase;           // stack level at which the nested walk started
+    uint32_t leafNext, leafEnd;  // rest of the scene-BVH leaf that contained the TransformedPrimitive
+    V3 wo, wd;                   // the world-space ray
     uint32_t todo[64];
 };
+DEV void TravSetRay(Trav &t) {
+    t.invDir = V3(1.f / t.ray.d.x, 1.f / t.ray.d.y, 1.f / t.ray.d.z);
+    t.neg[0] = t.invDir.x < 0; t.neg[1] = t.invDir.y < 0; t.neg[2] = t.invDir.z < 0;
+}
 DEV void TravInit(Trav &t, const Ray &ray, bool anyHit) {
     t.ray = ray;
-    t.invDir = V3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
-    t.neg[0] = t.invDir.x < 0; t.neg[1] = t.invDir.y < 0; t.neg[2] = t.invDir.z < 0;
+    TravSetRay(t);
     t.nodeNum = 0; t.todoOffset = 0;
     t.anyHit = anyHit; t.found = false;
     t.hit.prim = -1; t.hit.b1 = t.hit.b2 = 0.f; t.hit.maxtIn = 0.f; t.hit.t = 0.f;
+    t.inst = -1; t.nodeBase = t.primBase = 0; t.todoBase = 0; t.leafNext = t.leafEnd = 0;
 }
 // returns true when the ray is finished (result in t.found / t.hit / t.ray.maxt)
-template <bool STATS>
+template <bool STATS, bool ANIM>
 DEV bool TravStep(const DScene &sc, Trav &t, TraceStats *st) {
-    const float4 n0 = __ldg(sc.nodes + 2 * t.nodeNum);
-    const float4 n1 = __ldg(sc.nodes + 2 * t.nodeNum + 1);
-    if (STATS) st->nodes++;
-    if (BoxTest(n0, n1, t.ray, t.invDir, t.neg)) {
-        const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
-        const uint32_t nPrims = meta & 0xffu;
-        if (nPrims > 0) {
-            for (uint32_t i = 0; i < nPrims; ++i) {
-                const uint32_t pi = offset + i;
-                const float4 r0 = __ldg(sc.prims + 3 * pi);
-                const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
-                const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
-                if (STATS) st->prims++;
-                const uint32_t type = __float_as_uint(r0.w);
-                float tt, b1 = 0.f, b2 = 0.f;
-                bool h;
-                if (type == PBRTGPU_PRIM_TRIANGLE)
-                    h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), t.ray, &tt, &b1, &b2);
-                else
-                    h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], t.ray, &tt, nullptr);
-                if (h) {
-                    t.hit.prim = (int)pi;
-                    t.found = true;
-                    if (t.anyHit) { t.hit.t = t.ray.maxt; return true; }
-                    t.hit.b1 = b1; t.hit.b2 = b2; t.hit.maxtIn = t.ray.maxt;
-                    t.ray.maxt = tt;
-                }
-            }
-            if (t.todoOffset == 0) { t.hit.t = t.ray.maxt; return true; }
-            t.nodeNum = t.todo[--t.todoOffset];
-        } else {
-            const uint32_t axis = (meta >> 8) & 0xffu;
-            if (t.neg[axis]) {
-                t.todo[t.todoOffset++] = t.nodeNum + 1;
-                t.nodeNum = offset;
+    uint32_t first = 0, end = 0;
+    bool leaf = false;
+    if (ANIM && t.inst < 0 && t.leafNext < t.leafEnd) {   // back from a TransformedPrimitive: the rest of that leaf
+        first = t.leafNext; end = t.leafEnd;
+        t.leafNext = t.leafEnd = 0;
+        leaf = true;
+    } else {
+        const uint32_t ni = (ANIM ? t.nodeBase : 0u) + t.nodeNum;
+        const float4 n0 = __ldg(sc.nodes + 2 * ni);
+        const float4 n1 = __ldg(sc.nodes + 2 * ni + 1);
+        if (STATS) st->nodes++;
+        if (BoxTest(n0, n1, t.ray, t.invDir, t.neg)) {
+            const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
+            const uint32_t nPrims = meta & 0xffu;
+            if (nPrims > 0) {
+                first = (ANIM ? t.primBase : 0u) + offset;
+                end = first + nPrims;
+                leaf = true;
             } else {
-                t.todo[t.todoOffset++] = offset;
-                t.nodeNum = t.nodeNum + 1;
+                const uint32_t axis = (meta >> 8) & 0xffu;
+                if (t.neg[axis]) {
+                    t.todo[t.todoOffset++] = t.nodeNum + 1;
+                    t.nodeNum = offset;
+                } else {
+                    t.todo[t.todoOffset++] = offset;
+                    t.nodeNum = t.nodeNum + 1;
+                }
+                return false;
             }
         }
-    } else {
-        if (t.todoOffset == 0) { t.hit.t = t.ray.maxt; return true; }
-        t.nodeNum = t.todo[--t.todoOffset];
     }
+    if (leaf) {
+        for (uint32_t pi = first; pi < end; ++pi) {
+            const float4 r0 = __ldg(sc.prims + 3 * pi);
+            const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
+            const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
+            if (STATS) st->prims++;
+            const uint32_t type = __float_as_uint(r0.w) & 0xffu;
+            float tt, b1 = 0.f, b2 = 0.f;
+            bool h;
+            if (type == PBRTGPU_PRIM_TRIANGLE)
+                h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), t.ray, &tt, &b1, &b2);
+            else if (ANIM && type == PBRTGPU_PRIM_ANIMATED) {
+                // TransformedPrimitive::Intersect(P): interpolate, go to primitive space, walk the nested BVH
+                const PbrtGpuAnimated *a = sc.animated + __float_as_uint(r1.w);
+                DXf w2p;
+                AnimInterpolate(a, t.ray.time, &w2p);
+                Ray rl;
+                ToPrimitiveSpace(w2p, t.ray, &rl);
+                if (a->nNodes == 0) {
+                    if (SinglePrimTest(sc, a->firstPrimitive, rl, t.anyHit, &t.hit)) {
+                        t.found = true;
+                        t.ray.maxt = rl.maxt;
+                        if (t.anyHit) { t.hit.t = t.ray.maxt; return true; }
+                    }
+                    continue;
+                }
+                t.wo = t.ray.o; t.wd = t.ray.d;
+                t.ray = rl;
+                TravSetRay(t);
+                t.inst = (int)__float_as_uint(r1.w);
+                t.nodeBase = a->firstNode; t.primBase = a->firstPrimitive;
+                t.todoBase = t.todoOffset;
+                t.leafNext = pi + 1; t.leafEnd = end;
+                if (t.leafNext == t.leafEnd) t.leafNext = t.leafEnd = 0;
+                t.nodeNum = 0;
+                return false;
+            } else
+                h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], t.ray, &tt, nullptr);
+            if (h) {
+                t.hit.prim = (int)pi;
+                t.found = true;
+                if (t.anyHit) { t.hit.t = t.ray.maxt; return true; }
+                t.hit.b1 = b1; t.hit.b2 = b2; t.hit.maxtIn = t.ray.maxt;
+                t.ray.maxt = tt;
+            }
+        }
+    }
+    // ---- next node from the stack
+    if (ANIM && t.inst >= 0) {
+        if (t.todoOffset > t.todoBase) {
+            t.nodeNum = t.todo[--t.todoOffset];
+            return false;
+        }
+        // the nested walk is over: back to world space (r.maxt = ray.maxt, primitive.cpp:102)
+        t.ray.o = t.wo; t.ray.d = t.wd;
+        TravSetRay(t);
+        t.inst = -1; t.nodeBase = t.primBase = 0;
+        if (t.leafNext < t.leafEnd) return false;   // the next step tests the rest of the leaf
+    }
+    if (t.todoOffset == 0) { t.hit.t = t.ray.maxt; return true; }
+    t.nodeNum = t.todo[--t.todoOffset];
     return false;
 }
 
 // Re-derive the winning primitive's DifferentialGeometry (what Shape::Intersect
 // filled in at the moment the hit was accepted) and its rayEpsilon.
-DEV_NI3 void HitGeometry(const DScene &sc, const Ray &rayIn, const Hit &hit, DiffGeom *dg, float *rayEpsilon,
-                     int *material, int *areaLight, uint4 *triOut, uint32_t *primType) {
+// Under a TransformedPrimitive the geometry is computed in primitive space with the transformed ray and then
+// taken to world space (primitive.cpp:104-117); *w2pOut receives the interpolated transform (what
+// isect->WorldToObject is multiplied by, primitive.cpp:106) and the return value says whether it applies.
+template <bool ANIM>
+DEV_NI3 bool HitGeometry(const DScene &sc, const Ray &rayIn, const Hit &hit, DiffGeom *dg, float *rayEpsilon,
+                     int *material, int *areaLight, uint4 *triOut, uint32_t *primType, DXf *w2p) {
     const float4 r0 = __ldg(sc.prims + 3 * hit.prim);
     const float4 r1 = __ldg(sc.prims + 3 * hit.prim + 1);
     const float4 r2 = __ldg(sc.prims + 3 * hit.prim + 2);
-    const uint32_t type = __float_as_uint(r0.w), index = __float_as_uint(r1.w), ml = __float_as_uint(r2.w);
+    const uint32_t tw = __float_as_uint(r0.w);
+    const uint32_t type = tw & 0xffu, index = __float_as_uint(r1.w), ml = __float_as_uint(r2.w);
+    const int owner = ANIM ? (int)(tw >> 8) - 1 : -1;
     *material = (int)(ml & 0xffffu);
     *areaLight = (int)(ml >> 16) - 1;
     *primType = type;
+    Ray ray = rayIn;
+    if (ANIM && owner >= 0) {
+        AnimInterpolate(sc.animated + owner, rayIn.time, w2p);
+        ToPrimitiveSpace(*w2p, rayIn, &ray);
+    }
     if (type == PBRTGPU_PRIM_TRIANGLE) {
         const uint4 tri = __ldg(sc.tris + index);
         *triOut = tri;
-        TriDG(sc, tri, V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), rayIn, hit.t, hit.b1, hit.b2, dg);
+        TriDG(sc, tri, V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), ray, hit.t, hit.b1, hit.b2, dg);
         *rayEpsilon = 1e-3f * hit.t;   // trianglemesh.cpp:206
     } else {
-        Ray r = rayIn;
-        r.maxt = hit.maxtIn;
+        ray.maxt = hit.maxtIn;
         float t;
-        QuadricIntersect(sc, sc.quadrics[index], r, &t, dg);
+        QuadricIntersect(sc, sc.quadrics[index], ray, &t, dg);
         *rayEpsilon = 5e-4f * t;       // sphere.cpp:143, disk.cpp:100
         *triOut = make_uint4(0, 0, 0, 0);
     }
+    if (ANIM && owner >= 0 && !MatIsIdentity(w2p->m)) {
+        // PrimitiveToWorld = Inverse(w2p): points and vectors by w2p.mInv, normals by the transpose of w2p.m
+        dg->p = XfPoint(w2p->mInv, dg->p);
+        dg->nn = Normalize(XfNormal(w2p->m, dg->nn));
+        dg->dpdu = XfVector(w2p->mInv, dg->dpdu);
+        dg->dpdv = XfVector(w2p->mInv, dg->dpdv);
+        return true;
+    }
+    return false;
 }
 
 }  // namespace dev

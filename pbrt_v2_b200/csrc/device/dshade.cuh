@@ -101,11 +101,13 @@ DEV V3 LocalToWorld(const ShadeCtx &c, const V3 &v) {
 
 // Intersection::GetBSDF -> GeometricPrimitive::GetBSDF -> Triangle::GetShadingGeometry
 // (shapes/trianglemesh.cpp:293-368) -> Material::GetBSDF -> BSDF ctor (reflection.cpp:601-609)
+template <bool ANIM>
 DEV void BuildShadeCtx(const DScene &sc, const Ray &rayIn, const Hit &hit, ShadeCtx *c, unsigned long long *shadedN) {
     DiffGeom dg;
     uint4 tri;
     uint32_t ptype;
-    HitGeometry(sc, rayIn, hit, &dg, &c->rayEpsilon, &c->material, &c->areaLight, &tri, &ptype);
+    DXf w2p;
+    const bool instanced = HitGeometry<ANIM>(sc, rayIn, hit, &dg, &c->rayEpsilon, &c->material, &c->areaLight, &tri, &ptype, &w2p);
     c->ng = dg.nn;
     DiffGeom dgs = dg;
     if (ptype == PBRTGPU_PRIM_TRIANGLE) {
@@ -129,7 +131,14 @@ DEV void BuildShadeCtx(const DScene &sc, const Ray &rayIn, const Hit &hit, Shade
                 if (!ok) b[0] = b[1] = b[2] = 1.f / 3.f;
                 else b[0] = 1.f - b[1] - b[2];
             }
+            // obj2world = isect.ObjectToWorld; under a TransformedPrimitive that is Inverse(WorldToObject * w2p)
+            // (primitive.cpp:106-107), whose mInv -- what transforms a Normal -- is WorldToObject.m * w2p.m
             const float *mInv = sc.xforms[mesh.xform].mInv;
+            float wm[16];
+            if (ANIM && instanced) {
+                MatMul(mInv, w2p.m, wm);
+                mInv = wm;
+            }
             V3 n0(__ldg(sc.N + 3 * tri.x), __ldg(sc.N + 3 * tri.x + 1), __ldg(sc.N + 3 * tri.x + 2));
             V3 n1(__ldg(sc.N + 3 * tri.y), __ldg(sc.N + 3 * tri.y + 1), __ldg(sc.N + 3 * tri.y + 2));
             V3 n2(__ldg(sc.N + 3 * tri.z), __ldg(sc.N + 3 * tri.z + 1), __ldg(sc.N + 3 * tri.z + 2));

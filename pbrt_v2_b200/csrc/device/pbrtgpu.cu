@@ -38,6 +38,7 @@ struct RenderParams {
     float rasterToCamera[16];
     float cameraToWorld[16];
     float lensRadius, focalDistance;
+    float shutterOpen, shutterClose;
     float filterXWidth, filterYWidth;
     int xPixelStart, yPixelStart, xPixelCount, yPixelCount;
     int spp, maxDepth;
@@ -297,7 +298,7 @@ DEV Spec SanitizeRadiance(const Spec &L) {
     return L;
 }
 
-template <int PHASE, bool STATS>
+template <int PHASE, bool STATS, bool ANIM>
 // 4 CTAs/SM (<= 128 registers): measured +9 % over the unconstrained 168-register build
 __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
     __shared__ uint32_t smt[4][MT_N];
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
     int state = valid ? S_NEW_SAMPLE : S_DONE;
     int s = 0, bounces = 0, nextS = 0, code = 0;
     Ray ray;
-    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f;
+    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f; ray.time = 0.f;
     Hit hit;
     hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.maxtIn = 0.f;
     bool found = false;
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
 #define PATH_EVALWO_IN V3(0, 0, 1)
 #define PATH_EVALWI_IN V3(0, 0, 1)
 #define PATH_DEFER_MEASURED false
+#define PATH_ANIM ANIM
 #define PATH_COUNT_TAIL() atomicOr(a.b.tailCount + bi, 1u)
 #include "path_body.inc"
 #undef PATH_COUNT_TAIL
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
 #undef PATH_EVALWO_IN
 #undef PATH_EVALWI_IN
 #undef PATH_DEFER_MEASURED
+#undef PATH_ANIM
 
         if (state == S_END_SAMPLE) {
             if (PHASE == 1) {
@@ -433,6 +436,7 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
                     V3 Pcamera = XfPoint(rp.rasterToCamera, V3(imageX, imageY, 0));
                     V3 dir = Normalize(V3(Pcamera.x, Pcamera.y, Pcamera.z));
                     ray.o = V3(0, 0, 0); ray.d = dir; ray.mint = 0.f; ray.maxt = INF_F;
+                    ray.time = Lerp(VanDerCorput(row[2], scr[4]), rp.shutterOpen, rp.shutterClose);   // montecarlo.cpp:243
                     if (rp.lensRadius > 0.f) {
                         const uint32_t pl = row[1];
                         float lensU, lensV;
@@ -477,6 +481,7 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
                         T = Spec(r2.x, r2.y, r2.z);
                         hit.prim = __float_as_int(r2.w);
                         hit.b1 = r3.x; hit.b2 = r3.y; hit.maxtIn = r3.z;
+                        ray.time = r3.w;
                         L = Spec(v.x, v.y, v.z);
                         code &= ~LS_TAIL;
                         bounces = 3;
@@ -493,7 +498,7 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
         // ---- the single traversal site
         if (wantTrace) {
             if (STATS) { if (anyHit) ++nShadow; else ++nClosest; }
-            found = Traverse<STATS>(sc, ray, anyHit, &hit, &st);
+            found = Traverse<STATS, ANIM>(sc, ray, anyHit, &hit, &st);
         }
     }
 
@@ -542,6 +547,7 @@ enum {
     F_EVAL_WI,     // evalWi.xyz
     F_FEVAL,       // fEval.rgb
     F_ACC,         // phase 2: the task's film accumulator {Lxyz, weightSum} (ImageFilm::Pixel of its current pixel)
+    F_TIME,        // ray.time of the camera path (scenes with TransformedPrimitives only)
     F_COUNT
 };
 // Request queues, one per resume state ("kind"), so that the lanes of a warp of k_logic are all in the same
@@ -580,7 +586,7 @@ DEV unsigned AggregatedAdd(unsigned *ctr) {   // warp-aggregated atomicAdd(ctr, 
 // PHASE 1: slots are camera samples (bounces 0..2, table-driven).  PHASE 2: slot i is task-pixel i's chain of
 // parked samples, resumed one after the other with the task's sequential RNG stream; finished samples are added
 // to the film in sample order in between (what k_path<2> does per thread, here as a wavefront).
-template <int PHASE, bool STATS>
+template <int PHASE, bool STATS, bool ANIM>
 __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
     __shared__ uint32_t smt[PHASE == 2 ? 4 : 1][PHASE == 2 ? MT_N : 1];
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -615,7 +621,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
     Spec T(1.f);
     int s = 0, code = 0, bi = 0, mti = 0;
     Ray ray;
-    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f;
+    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f; ray.time = 0.f;
     Hit hit;
     hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.maxtIn = 0.f;
     bool found = false;
@@ -673,6 +679,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
             acc[0] = ac.x; acc[1] = ac.y; acc[2] = ac.z; acc[3] = ac.w;
             mti = a.b.mti[bi];
         }
+        if (ANIM) ray.time = FLD(F_TIME).x;
     }
     if (PHASE == 2) {
         // cooperative RNG top-up before a bounce (<= 11 draws must be addressable), as in k_path<2>
@@ -737,6 +744,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
 #define PATH_EVALWO_IN evalWoIn
 #define PATH_EVALWI_IN evalWiIn
 #define PATH_DEFER_MEASURED true
+#define PATH_ANIM ANIM
 #define PATH_COUNT_TAIL() atomicOr(a.b.tailCount + bi, 1u)
 #include "path_body.inc"
 #undef PATH_COUNT_TAIL
@@ -744,6 +752,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
 #undef PATH_EVALWO_IN
 #undef PATH_EVALWI_IN
 #undef PATH_DEFER_MEASURED
+#undef PATH_ANIM
         if (deferEval) {
             deferOut = true;
             evalWoOut = evalWo; evalWiOut = evalWi; evalFlagsOut = evalFlags;
@@ -783,6 +792,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
                         T = Spec(r2.x, r2.y, r2.z);
                         hit.prim = __float_as_int(r2.w);
                         hit.b1 = r3.x; hit.b2 = r3.y; hit.maxtIn = r3.z;
+                        ray.time = r3.w;
                         L = Spec(v.x, v.y, v.z);
                         code &= ~LS_TAIL;
                         bounces = 3;
@@ -824,6 +834,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
             V3 Pcamera = XfPoint(rp.rasterToCamera, V3(imageX, imageY, 0));
             V3 dir = Normalize(V3(Pcamera.x, Pcamera.y, Pcamera.z));
             ray.o = V3(0, 0, 0); ray.d = dir; ray.mint = 0.f; ray.maxt = INF_F;
+                    ray.time = Lerp(VanDerCorput(row[2], scr[4]), rp.shutterOpen, rp.shutterClose);   // montecarlo.cpp:243
             if (rp.lensRadius > 0.f) {
                 const uint32_t pl = row[1];
                 float lensU, lensV;
@@ -856,6 +867,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
         FLD(F_ACC) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         a.b.mti[bi] = mti;
     }
+    if (ANIM) FLD(F_TIME) = make_float4(ray.time, 0.f, 0.f, 0.f);
     FLD(F_T) = make_float4(T.r, T.g, T.b, __uint_as_float((uint32_t)state | ((uint32_t)bounces << 8) | ((uint32_t)lightNum << 16)));
     FLD(F_L) = make_float4(L.r, L.g, L.b, __int_as_float(code));
     FLD(F_WO) = make_float4(wo.x, wo.y, wo.z, __int_as_float(bi));
@@ -894,7 +906,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
 }
 
 // persistent ray queue consumer
-template <bool STATS>
+template <bool STATS, bool ANIM>
 __global__ void __launch_bounds__(128) k_trace(WfArgs a) {
     const DScene &sc = a.sc;
     const unsigned FULL = 0xffffffffu;
@@ -930,6 +942,7 @@ __global__ void __launch_bounds__(128) k_trace(WfArgs a) {
                     Ray ray;
                     ray.o = V3(r0.x, r0.y, r0.z); ray.mint = r0.w;
                     ray.d = V3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
+                    ray.time = ANIM ? pool[(size_t)F_TIME * P + slot].x : 0.f;
                     TravInit(t, ray, any);
                     if (STATS) { if (any) ++nShadow; else ++nClosest; }
                     active = true;
@@ -939,7 +952,7 @@ __global__ void __launch_bounds__(128) k_trace(WfArgs a) {
         if (!__any_sync(FULL, active)) break;
         // walk until a good share of the warp has finished, then refill
         for (int it = 0; it < 64; ++it) {
-            if (active && TravStep<STATS>(sc, t, &st)) {
+            if (active && TravStep<STATS, ANIM>(sc, t, &st)) {
                 pool[(size_t)F_HIT * P + slot] = make_float4(__int_as_float(t.found ? t.hit.prim : -1), t.hit.b1, t.hit.b2, t.hit.maxtIn);
                 pool[(size_t)F_RAY_D * P + slot].w = t.ray.maxt;
                 active = false;
@@ -993,10 +1006,10 @@ __global__ void k_intersect(DScene sc, const PbrtGpuRay *rays, int n, PbrtGpuHit
     Ray ray;
     ray.o = V3(rays[i].o[0], rays[i].o[1], rays[i].o[2]);
     ray.d = V3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
-    ray.mint = rays[i].mint; ray.maxt = rays[i].maxt;
+    ray.mint = rays[i].mint; ray.maxt = rays[i].maxt; ray.time = rays[i].time;
     Hit hit;
     TraceStats st;
-    const bool found = Traverse<false>(sc, ray, ANY, &hit, &st);
+    const bool found = Traverse<false, true>(sc, ray, ANY, &hit, &st);
     if (ANY) { occ[i] = found ? 1 : 0; return; }
     PbrtGpuHit h;
     memset(&h, 0, sizeof(h));
@@ -1008,7 +1021,8 @@ __global__ void k_intersect(DScene sc, const PbrtGpuRay *rays, int n, PbrtGpuHit
         uint4 tri;
         uint32_t ptype;
         Ray r0 = ray;
-        HitGeometry(sc, r0, hit, &dg, &eps, &mat, &al, &tri, &ptype);
+        DXf w2p;
+        HitGeometry<true>(sc, r0, hit, &dg, &eps, &mat, &al, &tri, &ptype, &w2p);
         h.hit = 1; h.primitive = (uint32_t)hit.prim; h.b1 = hit.b1; h.b2 = hit.b2;
         h.p[0] = dg.p.x; h.p[1] = dg.p.y; h.p[2] = dg.p.z;
         h.n[0] = dg.nn.x; h.n[1] = dg.nn.y; h.n[2] = dg.nn.z;
@@ -1068,6 +1082,7 @@ struct PbrtGpuScene {
     DevBuf<PbrtGpuBrdfSample> kdData;
     DevBuf<PbrtGpuLight> lights;
     DevBuf<PbrtGpuLightShape> lightShapes;
+    DevBuf<PbrtGpuAnimated> animated;
     // per-render scratch, kept between calls
     DevBuf<TaskRec> tasks;
     DevBuf<uint16_t> perm;
@@ -1249,10 +1264,32 @@ int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
     // primitives: pre-gathered 48-byte records in leaf order
     {
         std::vector<float4> h(3 * (size_t)desc->nPrimitives);
+        // which TransformedPrimitive (if any) owns each nested primitive
+        std::vector<int> owner(desc->nPrimitives, -1);
+        if (desc->nAnimated > 255) return Fail(PBRTGPU_EUNSUPPORTED, "more than 255 TransformedPrimitives");
+        for (uint32_t k = 0; k < desc->nAnimated; ++k) {
+            const PbrtGpuAnimated &a = desc->animated[k];
+            if ((uint64_t)a.firstPrimitive + a.nPrimitives > desc->nPrimitives || (uint64_t)a.firstNode + a.nNodes > desc->nNodes ||
+                a.nPrimitives == 0 || (a.nNodes == 0 && a.nPrimitives != 1))
+                return Fail(PBRTGPU_EINVAL, "TransformedPrimitive range out of bounds");
+            for (uint32_t i = 0; i < a.nPrimitives; ++i) owner[a.firstPrimitive + i] = (int)k;
+        }
         for (uint32_t i = 0; i < desc->nPrimitives; ++i) {
             const PbrtGpuPrimitive &p = desc->primitives[i];
-            if (p.material < 0 || (uint32_t)p.material >= desc->nMaterials) return Fail(PBRTGPU_EINVAL, "primitive without material");
             float v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (p.type == PBRTGPU_PRIM_ANIMATED) {
+                if (p.index >= desc->nAnimated) return Fail(PBRTGPU_EINVAL, "animated index out of range");
+                if (owner[i] >= 0) return Fail(PBRTGPU_EUNSUPPORTED, "nested TransformedPrimitives are out of scope");
+                uint32_t w0 = p.type, w1 = p.index;
+                float f0, f1;
+                memcpy(&f0, &w0, 4); memcpy(&f1, &w1, 4);
+                h[3 * i] = make_float4(0, 0, 0, f0);
+                h[3 * i + 1] = make_float4(0, 0, 0, f1);
+                h[3 * i + 2] = make_float4(0, 0, 0, 0);
+                continue;
+            }
+            if (p.type > PBRTGPU_PRIM_ANIMATED) return Fail(PBRTGPU_EINVAL, "unknown primitive type");
+            if (p.material < 0 || (uint32_t)p.material >= desc->nMaterials) return Fail(PBRTGPU_EINVAL, "primitive without material");
             if (p.type == PBRTGPU_PRIM_TRIANGLE) {
                 if (p.index >= desc->nTriangles) return Fail(PBRTGPU_EINVAL, "triangle index out of range");
                 const PbrtGpuTriangle &t = desc->triangles[p.index];
@@ -1261,7 +1298,8 @@ int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
                     memcpy(v + 3 * k, desc->P + 3 * (size_t)t.v[k], 12);
                 }
             } else if (p.index >= desc->nQuadrics) return Fail(PBRTGPU_EINVAL, "quadric index out of range");
-            uint32_t w0 = p.type, w1 = p.index, w2 = (uint32_t)p.material | ((uint32_t)(p.areaLight + 1) << 16);
+            uint32_t w0 = p.type | ((uint32_t)(owner[i] + 1) << 8), w1 = p.index;
+            uint32_t w2 = (uint32_t)p.material | ((uint32_t)(p.areaLight + 1) << 16);
             float f0, f1, f2;
             memcpy(&f0, &w0, 4); memcpy(&f1, &w1, 4); memcpy(&f2, &w2, 4);
             h[3 * i] = make_float4(v[0], v[1], v[2], f0);
@@ -1287,6 +1325,7 @@ int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
     CUDA_TRY(s->kdData.Upload(desc->kdData, desc->nKdNodes));
     CUDA_TRY(s->lights.Upload(desc->lights, desc->nLights));
     CUDA_TRY(s->lightShapes.Upload(desc->lightShapes, desc->nLightShapes));
+    CUDA_TRY(s->animated.Upload(desc->animated, desc->nAnimated));
     for (uint32_t i = 0; i < desc->nMeshes; ++i) {
         if ((desc->meshes[i].flags & PBRTGPU_MESH_HAS_N) && !desc->N) return Fail(PBRTGPU_EINVAL, "mesh flags N but desc.N is null");
         if ((desc->meshes[i].flags & PBRTGPU_MESH_HAS_UV) && !desc->uv) return Fail(PBRTGPU_EINVAL, "mesh flags uv but desc.uv is null");
@@ -1295,8 +1334,8 @@ int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
     d.nodes = s->nodes.p; d.prims = s->prims.p; d.tris = s->tris.p; d.meshes = s->meshes.p;
     d.N = s->N.p; d.uv = s->uv.p; d.quadrics = s->quadrics.p; d.xforms = s->xforms.p;
     d.materials = s->materials.p; d.measured = s->measured.p; d.kdNodes = s->kdNodes.p; d.kdData = s->kdData.p;
-    d.lights = s->lights.p; d.lightShapes = s->lightShapes.p;
-    d.nNodes = desc->nNodes; d.nPrims = desc->nPrimitives; d.nLights = desc->nLights;
+    d.lights = s->lights.p; d.lightShapes = s->lightShapes.p; d.animated = s->animated.p;
+    d.nNodes = desc->nNodes; d.nPrims = desc->nPrimitives; d.nLights = desc->nLights; d.nAnimated = desc->nAnimated;
     for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&s->ev[i]));
     s->collectStats = getenv("PBRTGPU_STATS") != nullptr;
     for (uint32_t i = 0; i < desc->nMaterials; ++i)
@@ -1356,6 +1395,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     memcpy(rp.rasterToCamera, rd->rasterToCamera, sizeof(rp.rasterToCamera));
     memcpy(rp.cameraToWorld, rd->cameraToWorld, sizeof(rp.cameraToWorld));
     rp.lensRadius = rd->lensRadius; rp.focalDistance = rd->focalDistance;
+    rp.shutterOpen = rd->shutterOpen; rp.shutterClose = rd->shutterClose;
     rp.filterXWidth = rd->filterXWidth; rp.filterYWidth = rd->filterYWidth;
     rp.xPixelStart = ext.xPixelStart; rp.yPixelStart = ext.yPixelStart;
     rp.xPixelCount = ext.xPixelCount; rp.yPixelCount = ext.yPixelCount;
@@ -1443,8 +1483,13 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
             const int blocks1 = (int)((nb + 3) / 4);       // phase 1 (megakernel form): one warp per task-pixel
             const int blocks2 = (int)((nb + 127) / 128);   // phase 2: one thread per task-pixel
             if (!useWavefront) {
-                if (wantCounters) k_path<1, true><<<blocks1, 128, 0, stream>>>(pa);
-                else k_path<1, false><<<blocks1, 128, 0, stream>>>(pa);
+                if (scene->d.nAnimated) {
+                    if (wantCounters) k_path<1, true, true><<<blocks1, 128, 0, stream>>>(pa);
+                    else k_path<1, false, true><<<blocks1, 128, 0, stream>>>(pa);
+                } else {
+                    if (wantCounters) k_path<1, true, false><<<blocks1, 128, 0, stream>>>(pa);
+                    else k_path<1, false, false><<<blocks1, 128, 0, stream>>>(pa);
+                }
                 CUDA_TRY(cudaGetLastError());
                 launches += 1;
             } else {
@@ -1463,11 +1508,21 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                     // empty the queues k_logic is about to fill, and the consumers' cursors
                     CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
                     CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
-                    if (wantCounters) k_logic<1, true><<<lblocks, 128, 0, stream>>>(wa);
-                    else k_logic<1, false><<<lblocks, 128, 0, stream>>>(wa);
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_logic<1, true, true><<<lblocks, 128, 0, stream>>>(wa);
+                        else k_logic<1, false, true><<<lblocks, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_logic<1, true, false><<<lblocks, 128, 0, stream>>>(wa);
+                        else k_logic<1, false, false><<<lblocks, 128, 0, stream>>>(wa);
+                    }
                     if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
-                    if (wantCounters) k_trace<true><<<tblocks, 128, 0, stream>>>(wa);
-                    else k_trace<false><<<tblocks, 128, 0, stream>>>(wa);
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_trace<true, true><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_trace<false, true><<<tblocks, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_trace<true, false><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_trace<false, false><<<tblocks, 128, 0, stream>>>(wa);
+                    }
                     launches += hasMeasured ? 3 : 2;
                     if ((iter & 7) == 7) {
                         CUDA_TRY(cudaMemcpyAsync(scene->hostCounters, scene->counters.p, C_COUNT * sizeof(unsigned),
@@ -1495,8 +1550,13 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                 pa.b.order = scene->orderOut.p;
             }
             if (!useWavefront2) {
-                if (wantCounters) k_path<2, true><<<blocks2, 128, 0, stream>>>(pa);
-                else k_path<2, false><<<blocks2, 128, 0, stream>>>(pa);
+                if (scene->d.nAnimated) {
+                    if (wantCounters) k_path<2, true, true><<<blocks2, 128, 0, stream>>>(pa);
+                    else k_path<2, false, true><<<blocks2, 128, 0, stream>>>(pa);
+                } else {
+                    if (wantCounters) k_path<2, true, false><<<blocks2, 128, 0, stream>>>(pa);
+                    else k_path<2, false, false><<<blocks2, 128, 0, stream>>>(pa);
+                }
                 CUDA_TRY(cudaGetLastError());
             } else {
                 // ---- phase 2 as a wavefront: one slot per task-pixel chain
@@ -1512,11 +1572,21 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                     const int setOut = (iter & 1) ^ 1;
                     CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
                     CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
-                    if (wantCounters) k_logic<2, true><<<blocks2, 128, 0, stream>>>(wa);
-                    else k_logic<2, false><<<blocks2, 128, 0, stream>>>(wa);
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_logic<2, true, true><<<blocks2, 128, 0, stream>>>(wa);
+                        else k_logic<2, false, true><<<blocks2, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_logic<2, true, false><<<blocks2, 128, 0, stream>>>(wa);
+                        else k_logic<2, false, false><<<blocks2, 128, 0, stream>>>(wa);
+                    }
                     if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
-                    if (wantCounters) k_trace<true><<<tblocks, 128, 0, stream>>>(wa);
-                    else k_trace<false><<<tblocks, 128, 0, stream>>>(wa);
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_trace<true, true><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_trace<false, true><<<tblocks, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_trace<true, false><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_trace<false, false><<<tblocks, 128, 0, stream>>>(wa);
+                    }
                     launches += hasMeasured ? 3 : 2;
                     if ((iter & 7) == 7) {
                         CUDA_TRY(cudaMemcpyAsync(scene->hostCounters, scene->counters.p, C_COUNT * sizeof(unsigned),

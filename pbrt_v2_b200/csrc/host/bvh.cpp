@@ -146,6 +146,13 @@ struct Builder {
 // the input order of the build and must be kept.
 void FullyRefine(const GeometricPrimitive &gp, std::vector<RefinedPrim> *out,
                  std::vector<std::shared_ptr<Shape>> *owned) {
+    if (gp.animated) {   // TransformedPrimitive::CanIntersect() is true: handed over as it is
+        RefinedPrim r;
+        r.type = PBRTGPU_PRIM_ANIMATED;
+        r.animated = gp.animated.get();
+        out->push_back(r);
+        return;
+    }
     const Shape *s = gp.shape.get();
     auto emitMesh = [&](const TriangleMesh *m) {
         for (int i = m->ntris - 1; i >= 0; --i) {
@@ -208,6 +215,26 @@ GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, 
     nodes.reserve(2 * refined.size());
     Builder b{refined, info, primitives, nodes, maxPrimsInNode, splitMethod};
     b.Build(0, (uint32_t)refined.size());
+}
+
+TransformedPrimitive::TransformedPrimitive(const GeometricPrimitive &base, const AnimatedTransform &w2p)
+    : WorldToPrimitive(w2p) {
+    // api.cpp:1033-1043: "refine animated shape and create BVH if more than one shape created"
+    std::vector<GeometricPrimitive> one(1, base);
+    primitive.reset(new GpuBVHAccel(one));
+    if (primitive->primitives.size() == 1) primitive->nodes.clear();   // baseprim = refinedPrimitives[0]: no BVH around it
+}
+
+BBox TransformedPrimitive::WorldBound() const {   // primitive.h:116-118
+    BBox b;
+    if (!primitive->nodes.empty()) {   // BVHAccel::WorldBound, bvh.cpp:205-207
+        const PbrtGpuBVHNode &n = primitive->nodes[0];
+        b.pMin = V3(n.bmin[0], n.bmin[1], n.bmin[2]);
+        b.pMax = V3(n.bmax[0], n.bmax[1], n.bmax[2]);
+    } else if (!primitive->primitives.empty()) {
+        b = primitive->primitives[0].WorldBound();
+    }
+    return WorldToPrimitive.MotionBounds(b, true);
 }
 
 GpuBVHAccel *CreateGpuBVHAccelerator(const std::vector<GeometricPrimitive> &prims, const ParamSet &ps) {

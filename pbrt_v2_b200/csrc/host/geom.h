@@ -173,5 +173,30 @@ Transform LookAt(const V3 &pos, const V3 &look, const V3 &up, bool *ok);
 Transform Perspective(float fov, float znear, float zfar);
 bool SolveLinearSystem2x2(const float A[2][2], const float B[2], float *x0, float *x1);
 
+struct Quaternion {   // core/quaternion.h:44-92
+    V3 v;
+    float w;
+    Quaternion() : v(0, 0, 0), w(1.f) {}
+    Quaternion(const V3 &vv, float ww) : v(vv), w(ww) {}
+    explicit Quaternion(const Matrix4x4 &m);   // quaternion.cpp:61-96
+    Transform ToTransform() const;             // quaternion.cpp:39-58
+};
+Quaternion Slerp(float t, const Quaternion &q1, const Quaternion &q2);   // quaternion.cpp:99-111
+
+// core/transform.h:299-327, transform.cpp:328-413.  The per-ray Interpolate() of the hot path runs on
+// the device (device/danim.cuh); this host copy feeds Decompose's outputs to it and bounds the motion.
+struct AnimatedTransform {
+    float startTime, endTime;
+    Transform startTransform, endTransform;
+    bool actuallyAnimated;
+    V3 T[2];
+    Quaternion R[2];
+    Matrix4x4 S[2];
+    AnimatedTransform(const Transform &t1, float time1, const Transform &t2, float time2);
+    static void Decompose(const Matrix4x4 &m, V3 *T, Quaternion *R, Matrix4x4 *S);
+    void Interpolate(float time, Transform *t) const;
+    BBox MotionBounds(const BBox &b, bool useInverse) const;
+};
+
 }  // namespace pb
 #endif

@@ -291,10 +291,13 @@ int Api::MakeMaterial(const ParamSet &geomParams) {   // core/api.cpp:1062-1077,
 }
 
 bool Api::DoShape(const std::string &name, const ParamSet &params) {   // core/api.cpp:990-1059
-    if (curTransform.IsAnimated())
-        return Fail("animated shapes (TransformedPrimitive, config C4) are not implemented in this round");
+    const bool animated = curTransform.IsAnimated();
     const Transform *o2w, *w2o;
-    Cache().Lookup(curTransform.t[0], &o2w, &w2o);
+    if (!animated) Cache().Lookup(curTransform.t[0], &o2w, &w2o);
+    else {   // api.cpp:1017-1020: the shape of an animated primitive is made with the identity
+        Cache().Lookup(Transform(), &o2w, nullptr);
+        w2o = o2w;
+    }
     bool ro = graphicsState.reverseOrientation;
     std::shared_ptr<Shape> shape;
     if (name == "trianglemesh") {
@@ -324,6 +327,23 @@ bool Api::DoShape(const std::string &name, const ParamSet &params) {   // core/a
     if (!shape) return true;   // MakeShape returned NULL: ignored like api.cpp:1001
     int mtl = MakeMaterial(params);
     if (mtl < 0) return false;
+    if (animated) {   // api.cpp:1011-1043
+        if (!graphicsState.areaLight.empty())
+            fprintf(stderr, "Warning: Ignoring currently set area light when creating animated shape\n");
+        const Transform *w2o0, *w2o1;
+        Cache().Lookup(curTransform.t[0], nullptr, &w2o0);
+        Cache().Lookup(curTransform.t[1], nullptr, &w2o1);
+        AnimatedTransform animatedWorldToObject(*w2o0, transformStartTime, *w2o1, transformEndTime);
+        GeometricPrimitive base;
+        base.shape = shape;
+        base.material = mtl;
+        base.areaLight = -1;
+        GeometricPrimitive gp;
+        gp.animated.reset(new TransformedPrimitive(base, animatedWorldToObject));
+        if (gp.animated->primitive->primitives.empty()) return true;   // api.cpp:1037
+        primitives.push_back(gp);
+        return true;
+    }
     int area = -1;
     if (!graphicsState.areaLight.empty()) {   // api.cpp:1005-1008, lights/diffuse.cpp:58-66
         if (graphicsState.areaLight != "area" && graphicsState.areaLight != "diffuse")

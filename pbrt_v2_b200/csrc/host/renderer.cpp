@@ -99,12 +99,21 @@ bool Scene::Flatten(std::string *err) {
     std::map<std::pair<const Shape *, int>, uint32_t> triIndex;
     hasN = hasUV = false;
     // first pass: which optional vertex streams exist at all
+    // the scene BVH first, then the nested BVH (or single primitive) of every TransformedPrimitive
+    std::vector<const GpuBVHAccel *> units(1, &bvh);
+    std::map<const TransformedPrimitive *, uint32_t> animatedIndex;
     for (const RefinedPrim &rp : bvh.primitives)
-        if (rp.type == PBRTGPU_PRIM_TRIANGLE) {
-            const TriangleMesh *m = static_cast<const TriangleMesh *>(rp.shape);
-            if (!m->n.empty()) hasN = true;
-            if (!m->uvs.empty()) hasUV = true;
+        if (rp.type == PBRTGPU_PRIM_ANIMATED && !animatedIndex.count(rp.animated)) {
+            animatedIndex[rp.animated] = (uint32_t)units.size() - 1;
+            units.push_back(rp.animated->primitive.get());
         }
+    for (const GpuBVHAccel *u : units)
+        for (const RefinedPrim &rp : u->primitives)
+            if (rp.type == PBRTGPU_PRIM_TRIANGLE) {
+                const TriangleMesh *m = static_cast<const TriangleMesh *>(rp.shape);
+                if (!m->n.empty()) hasN = true;
+                if (!m->uvs.empty()) hasUV = true;
+            }
     auto meshOf = [&](const TriangleMesh *m) -> uint32_t {
         auto it = meshIndex.find(m);
         if (it != meshIndex.end()) return it->second;
@@ -151,13 +160,37 @@ bool Scene::Flatten(std::string *err) {
         return (uint32_t)fQuadrics.size() - 1;
     };
 
-    fPrims.reserve(bvh.primitives.size());
-    for (const RefinedPrim &rp : bvh.primitives) {
+    fAnimated.resize(units.size() - 1);
+    for (size_t ui = 0; ui < units.size(); ++ui) {
+    const GpuBVHAccel &unit = *units[ui];
+    if (ui > 0) {
+        PbrtGpuAnimated &ga = fAnimated[ui - 1];
+        ga.firstNode = (uint32_t)fNodes.size();        ga.nNodes = (uint32_t)unit.nodes.size();
+        ga.firstPrimitive = (uint32_t)fPrims.size();   ga.nPrimitives = (uint32_t)unit.primitives.size();
+    }
+    fNodes.insert(fNodes.end(), unit.nodes.begin(), unit.nodes.end());
+    for (const RefinedPrim &rp : unit.primitives) {
         PbrtGpuPrimitive gp;
         gp.type = rp.type;
         gp.material = rp.material;
         gp.areaLight = rp.areaLight;
-        if (rp.type == PBRTGPU_PRIM_TRIANGLE) {
+        if (rp.type == PBRTGPU_PRIM_ANIMATED) {
+            if (ui > 0) { *err = "nested TransformedPrimitives are outside the hot-path scope"; return false; }
+            const AnimatedTransform &at = rp.animated->WorldToPrimitive;
+            gp.index = animatedIndex[rp.animated];
+            PbrtGpuAnimated &ga = fAnimated[gp.index];
+            memcpy(ga.start.m, at.startTransform.m.m, sizeof(ga.start.m));
+            memcpy(ga.start.mInv, at.startTransform.mInv.m, sizeof(ga.start.mInv));
+            memcpy(ga.end.m, at.endTransform.m.m, sizeof(ga.end.m));
+            memcpy(ga.end.mInv, at.endTransform.mInv.m, sizeof(ga.end.mInv));
+            ga.startTime = at.startTime; ga.endTime = at.endTime;
+            ga.actuallyAnimated = at.actuallyAnimated ? 1u : 0u;
+            for (int k = 0; k < 2; ++k) {
+                ga.T[k][0] = at.T[k].x; ga.T[k][1] = at.T[k].y; ga.T[k][2] = at.T[k].z;
+                ga.R[k][0] = at.R[k].v.x; ga.R[k][1] = at.R[k].v.y; ga.R[k][2] = at.R[k].v.z; ga.R[k][3] = at.R[k].w;
+                memcpy(ga.S[k], at.S[k].m, sizeof(ga.S[k]));
+            }
+        } else if (rp.type == PBRTGPU_PRIM_TRIANGLE) {
             const TriangleMesh *m = static_cast<const TriangleMesh *>(rp.shape);
             uint32_t mi = meshOf(m);
             PbrtGpuTriangle t;
@@ -172,6 +205,7 @@ bool Scene::Flatten(std::string *err) {
             gp.index = quadricOf(rp.shape);
         }
         fPrims.push_back(gp);
+    }
     }
     for (const Material &m : materials) fMaterials.push_back(m.desc);
     for (const MeasuredData &md : measured) {
@@ -202,7 +236,7 @@ bool Scene::Flatten(std::string *err) {
     if (bvh.nodes.empty()) { *err = "scene has no primitives"; return false; }
 
     memset(&desc, 0, sizeof(desc));
-    desc.nNodes = (uint32_t)bvh.nodes.size();         desc.nodes = bvh.nodes.data();
+    desc.nNodes = (uint32_t)fNodes.size();            desc.nodes = fNodes.data();
     desc.nPrimitives = (uint32_t)fPrims.size();       desc.primitives = fPrims.data();
     desc.nTriangles = (uint32_t)fTris.size();         desc.triangles = fTris.data();
     desc.nMeshes = (uint32_t)fMeshes.size();          desc.meshes = fMeshes.data();
@@ -217,6 +251,7 @@ bool Scene::Flatten(std::string *err) {
     desc.kdData = fKdData.data();
     desc.nLights = (uint32_t)fLights.size();          desc.lights = fLights.data();
     desc.nLightShapes = (uint32_t)fLightShapes.size(); desc.lightShapes = fLightShapes.data();
+    desc.nAnimated = (uint32_t)fAnimated.size();      desc.animated = fAnimated.empty() ? nullptr : fAnimated.data();
     return true;
 }
 

@@ -122,10 +122,13 @@ struct Light {   // core/light.h:48-82; lights/point.h, lights/diffuse.h
 };
 
 // -------------------------------------------------------------- Primitives --
-struct GeometricPrimitive {   // core/primitive.h:81-101
+struct TransformedPrimitive;
+struct GeometricPrimitive {   // core/primitive.h:81-101 (or, with `animated` set, a TransformedPrimitive)
     std::shared_ptr<Shape> shape;
     int material;
     int areaLight;   // index into Scene::lights or -1
+    std::shared_ptr<TransformedPrimitive> animated;
+    GeometricPrimitive() : material(-1), areaLight(-1) {}
 };
 
 // refined, intersectable primitive handed to the accelerator
@@ -134,7 +137,10 @@ struct RefinedPrim {
     const Shape *shape;   // TriangleMesh (for triangles) or quadric
     int tri;              // triangle number within the mesh
     int material, areaLight;
-    BBox WorldBound() const;   // Triangle::WorldBound trianglemesh.cpp:118-124 / Shape::WorldBound
+    const TransformedPrimitive *animated;   // PBRTGPU_PRIM_ANIMATED
+    RefinedPrim() : type(0), shape(nullptr), tri(0), material(-1), areaLight(-1), animated(nullptr) {}
+    BBox WorldBound() const;   // Triangle::WorldBound trianglemesh.cpp:118-124 / Shape::WorldBound /
+                               // TransformedPrimitive::WorldBound primitive.h:116-118
 };
 
 // --------------------------------------------------------------- Aggregate --
@@ -155,6 +161,16 @@ struct GpuBVHAccel : Aggregate {
     std::vector<std::shared_ptr<Shape>> owned;   // meshes produced by refinement
 };
 GpuBVHAccel *CreateGpuBVHAccelerator(const std::vector<GeometricPrimitive> &prims, const ParamSet &ps);
+
+// core/primitive.h:104-123 as pbrtShape builds it for a shape under an animated CTM (api.cpp:1011-1043):
+// the shape is made with identity transforms, refined, and -- if that gave more than one primitive --
+// wrapped in its own BVHAccel with the constructor's DEFAULT arguments (maxPrimsInNode 1, "sah").
+struct TransformedPrimitive {
+    std::unique_ptr<GpuBVHAccel> primitive;   // `nodes` is empty when there is a single refined primitive
+    AnimatedTransform WorldToPrimitive;
+    TransformedPrimitive(const GeometricPrimitive &base, const AnimatedTransform &w2p);
+    BBox WorldBound() const;
+};
 
 // ------------------------------------------------------ Camera/Film/Sampler --
 struct ImageFilm {   // film/image.h:46-88, image.cpp:40-51
@@ -212,6 +228,8 @@ struct Scene {   // core/scene.h:45-70
     std::vector<PbrtGpuBrdfSample> fKdData;
     std::vector<PbrtGpuLight> fLights;
     std::vector<PbrtGpuLightShape> fLightShapes;
+    std::vector<PbrtGpuBVHNode> fNodes;
+    std::vector<PbrtGpuAnimated> fAnimated;
     PbrtGpuSceneDesc desc;
     bool hasN, hasUV;
     bool Flatten(std::string *err);

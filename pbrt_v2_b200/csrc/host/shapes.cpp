@@ -76,6 +76,7 @@ float Disk::Area() const {   // disk.cpp:133-136
 
 // -------------------------------------------------------------- RefinedPrim --
 BBox RefinedPrim::WorldBound() const {
+    if (type == PBRTGPU_PRIM_ANIMATED) return animated->WorldBound();
     if (type == PBRTGPU_PRIM_TRIANGLE) {   // Triangle::WorldBound, trianglemesh.cpp:118-124
         const TriangleMesh *m = static_cast<const TriangleMesh *>(shape);
         const V3 &p1 = m->p[m->vertexIndex[3 * tri]];

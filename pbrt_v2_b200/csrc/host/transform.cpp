@@ -153,4 +153,126 @@ bool Transform::HasScale() const {   // core/transform.h:134-141
     return notOne(la2) || notOne(lb2) || notOne(lc2);
 }
 
+// ---------------------------------------------------------------- Quaternion --
+Transform Quaternion::ToTransform() const {   // quaternion.cpp:39-58
+    float xx = v.x * v.x, yy = v.y * v.y, zz = v.z * v.z;
+    float xy = v.x * v.y, xz = v.x * v.z, yz = v.y * v.z;
+    float wx = v.x * w, wy = v.y * w, wz = v.z * w;
+    Matrix4x4 m;
+    m.m[0][0] = 1.f - 2.f * (yy + zz);
+    m.m[0][1] = 2.f * (xy + wz);
+    m.m[0][2] = 2.f * (xz - wy);
+    m.m[1][0] = 2.f * (xy - wz);
+    m.m[1][1] = 1.f - 2.f * (xx + zz);
+    m.m[1][2] = 2.f * (yz + wx);
+    m.m[2][0] = 2.f * (xz + wy);
+    m.m[2][1] = 2.f * (yz - wx);
+    m.m[2][2] = 1.f - 2.f * (xx + yy);
+    return Transform(Transpose(m), m);   // "transpose since we are left-handed"
+}
+
+Quaternion::Quaternion(const Matrix4x4 &m) {   // quaternion.cpp:61-96 (double-typed "+ 1.0" kept)
+    float trace = m.m[0][0] + m.m[1][1] + m.m[2][2];
+    if (trace > 0.f) {
+        float s = sqrtf((float)(trace + 1.0));
+        w = s / 2.0f;
+        s = 0.5f / s;
+        v.x = (m.m[2][1] - m.m[1][2]) * s;
+        v.y = (m.m[0][2] - m.m[2][0]) * s;
+        v.z = (m.m[1][0] - m.m[0][1]) * s;
+    } else {
+        const int nxt[3] = {1, 2, 0};
+        float q[3];
+        int i = 0;
+        if (m.m[1][1] > m.m[0][0]) i = 1;
+        if (m.m[2][2] > m.m[i][i]) i = 2;
+        int j = nxt[i];
+        int k = nxt[j];
+        float s = sqrtf((float)((m.m[i][i] - (m.m[j][j] + m.m[k][k])) + 1.0));
+        q[i] = s * 0.5f;
+        if (s != 0.f) s = 0.5f / s;
+        w = (m.m[k][j] - m.m[j][k]) * s;
+        q[j] = (m.m[j][i] + m.m[i][j]) * s;
+        q[k] = (m.m[k][i] + m.m[i][k]) * s;
+        v = V3(q[0], q[1], q[2]);
+    }
+}
+
+static inline float QDot(const Quaternion &a, const Quaternion &b) { return Dot(a.v, b.v) + a.w * b.w; }
+static inline Quaternion QMul(const Quaternion &q, float f) { return Quaternion(V3(q.v.x * f, q.v.y * f, q.v.z * f), q.w * f); }
+static inline Quaternion QAdd(const Quaternion &a, const Quaternion &b) { return Quaternion(a.v + b.v, a.w + b.w); }
+static inline Quaternion QSub(const Quaternion &a, const Quaternion &b) { return Quaternion(a.v - b.v, a.w - b.w); }
+static inline Quaternion QNormalize(const Quaternion &q) {   // quaternion.h:109-111: v by reciprocal, w by division
+    float f = sqrtf(QDot(q, q));
+    return Quaternion(q.v / f, q.w / f);
+}
+
+Quaternion Slerp(float t, const Quaternion &q1, const Quaternion &q2) {   // quaternion.cpp:99-111
+    float cosTheta = QDot(q1, q2);
+    if (cosTheta > .9995f) return QNormalize(QAdd(QMul(q1, 1.f - t), QMul(q2, t)));
+    float theta = acosf(Clampf(cosTheta, -1.f, 1.f));
+    float thetap = theta * t;
+    Quaternion qperp = QNormalize(QSub(q2, QMul(q1, cosTheta)));
+    return QAdd(QMul(q1, cosf(thetap)), QMul(qperp, sinf(thetap)));
+}
+
+// --------------------------------------------------------- AnimatedTransform --
+AnimatedTransform::AnimatedTransform(const Transform &t1, float time1, const Transform &t2, float time2)
+    : startTime(time1), endTime(time2), startTransform(t1), endTransform(t2), actuallyAnimated(t1 != t2) {
+    Decompose(startTransform.m, &T[0], &R[0], &S[0]);
+    Decompose(endTransform.m, &T[1], &R[1], &S[1]);
+}
+
+void AnimatedTransform::Decompose(const Matrix4x4 &m, V3 *T, Quaternion *Rquat, Matrix4x4 *S) {   // transform.cpp:328-368
+    T->x = m.m[0][3];
+    T->y = m.m[1][3];
+    T->z = m.m[2][3];
+    Matrix4x4 M = m;
+    for (int i = 0; i < 3; ++i) M.m[i][3] = M.m[3][i] = 0.f;
+    M.m[3][3] = 1.f;
+    float norm;
+    int count = 0;
+    Matrix4x4 R = M;
+    do {   // polar decomposition by averaging with the inverse transpose
+        Matrix4x4 Rnext;
+        Matrix4x4 Rit = Inverse(Transpose(R));
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) Rnext.m[i][j] = 0.5f * (R.m[i][j] + Rit.m[i][j]);
+        norm = 0.f;
+        for (int i = 0; i < 3; ++i) {
+            float n = fabsf(R.m[i][0] - Rnext.m[i][0]) + fabsf(R.m[i][1] - Rnext.m[i][1]) + fabsf(R.m[i][2] - Rnext.m[i][2]);
+            norm = std::max(norm, n);
+        }
+        R = Rnext;
+    } while (++count < 100 && norm > .0001f);
+    *Rquat = Quaternion(R);
+    *S = Matrix4x4::Mul(Inverse(R), M);
+}
+
+void AnimatedTransform::Interpolate(float time, Transform *t) const {   // transform.cpp:371-396
+    if (!actuallyAnimated || time <= startTime) { *t = startTransform; return; }
+    if (time >= endTime) { *t = endTransform; return; }
+    float dt = (time - startTime) / (endTime - startTime);
+    V3 trans = (1.f - dt) * T[0] + dt * T[1];
+    Quaternion rotate = Slerp(dt, R[0], R[1]);
+    Matrix4x4 scale;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) scale.m[i][j] = Lerp(dt, S[0].m[i][j], S[1].m[i][j]);
+    *t = Translate(trans) * rotate.ToTransform() * Transform(scale);
+}
+
+BBox AnimatedTransform::MotionBounds(const BBox &b, bool useInverse) const {   // transform.cpp:399-413
+    if (!actuallyAnimated) return useInverse ? Inverse(startTransform).Box(b) : startTransform.Box(b);
+    BBox ret;
+    const int nSteps = 128;
+    for (int i = 0; i < nSteps; ++i) {
+        Transform t;
+        float time = Lerp(float(i) / float(nSteps - 1), startTime, endTime);
+        Interpolate(time, &t);
+        if (useInverse) t = Inverse(t);
+        ret = Union(ret, t.Box(b));
+    }
+    return ret;
+}
+
 }  // namespace pb

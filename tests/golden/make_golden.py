@@ -33,6 +33,8 @@ LD_CASES = [  # (res, spp, nTasks, taskNum)
 ]
 IMAGE_CASES = [  # (base, res, spp, ncores)
     ("bunny", 32, 4, 32), ("bunny", 32, 8, 1), ("killeroo-simple", 32, 4, 32), ("killeroo-simple", 32, 8, 1),
+    # config C4's scene: two animated TransformedPrimitives, each over its own nested BVH
+    ("anim-killeroos-moving", 32, 4, 32), ("anim-killeroos-moving", 32, 8, 1),
 ]
 
 
@@ -55,7 +57,12 @@ def main():
         rng["seed%d" % seed] = np.array([int(x) for x in out], dtype=np.uint32)
     np.savez_compressed(os.path.join(HERE, "rng.npz"), **rng)
     imgs = {}
+    have = os.path.join(HERE, "images.npz")
+    if os.path.exists(have) and "--all" not in sys.argv:   # keep what is committed, mint only new cases
+        imgs = dict(np.load(have))
     for base, res, spp, ncores in IMAGE_CASES:
+        if "%s_r%d_s%d_c%d" % (base.replace("-", "_"), res, spp, ncores) in imgs:
+            continue
         p = scenes.variant(base, os.path.join(scenes.STAGED, "golden-%s.pbrt" % base), res, res, spp)
         rgb, _ = oa.run_reference(p, ncores)
         imgs["%s_r%d_s%d_c%d" % (base.replace("-", "_"), res, spp, ncores)] = rgb.astype(np.float32)

@@ -36,11 +36,16 @@ def test_ld_samples_bit_exact(staged, spp, ncores):
         assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), "LD tables differ for task %d" % task
 
 
-@pytest.mark.parametrize("base", ["bunny", "killeroo-simple"])
+@pytest.mark.parametrize("base", ["bunny", "killeroo-simple", "anim-killeroos-moving"])
 def test_intersect_bit_exact(staged, base):
     hs = host_scene(base, 32, 32, 4, 32)
     lo, hi = scene_bounds(hs)
+    if base.startswith("anim"):   # the scene's floor planes are 2000 units wide: aim at the moving killeroos
+        lo, hi = np.maximum(lo, [-300, -300, -150]).astype(np.float32), np.minimum(hi, [300, 300, 150]).astype(np.float32)
     rays = random_rays(200000, 7, lo, hi)
+    # ray.time: inside, at and beyond both ends of the [0,1] transform interval (AnimatedTransform::Interpolate's cases)
+    rays["time"] = np.random.RandomState(11).choice(np.array([-0.5, 0.0, 0.25, 0.5, 0.999, 1.0, 1.5], np.float32), len(rays))
+    rays["time"][::3] = np.random.RandomState(12).rand(len(rays[::3])).astype(np.float32)
     gs = _gpu_scene(hs)
     got = gs.intersect(rays)
     want = oa.intersect(hs, rays)
@@ -58,6 +63,11 @@ def test_intersect_bit_exact(staged, base):
     occ_want = oa.intersect_p(hs, rays)
     assert np.array_equal(occ_got, occ_want)
     assert h.mean() > 0.2, "ray set should hit geometry reasonably often"
+    if base.startswith("anim"):
+        nested = h & (want["primitive"] >= 7)   # the scene BVH holds 7 primitives; the rest live under a TransformedPrimitive
+        assert nested.mean() > 0.02, "ray set should reach the animated killeroos"
+        assert np.array_equal(got["p"][nested].view(np.uint32), want["p"][nested].view(np.uint32))
+        assert np.array_equal(got["n"][nested].view(np.uint32), want["n"][nested].view(np.uint32))
 
 
 def _compare_images(hs, px_gpu, px_cpu):
@@ -91,6 +101,7 @@ def test_render_matches_oracle(staged, base, res, spp, ncores):
 
 @pytest.mark.parametrize("base,res,spp,ncores", [
     ("bunny", 64, 16, 128), ("bunny", 64, 16, 1), ("killeroo-simple", 64, 16, 128), ("killeroo-simple", 48, 8, 2),
+    ("anim-killeroos-moving", 64, 16, 128), ("anim-killeroos-moving", 48, 8, 2),   # TransformedPrimitives (config C4)
 ])
 def test_render_bit_exact_vs_oracle(staged, base, res, spp, ncores):
     """With glibc's libm restated on the device (refmath.h) the film is bit-identical to the oracle's, except
@@ -139,12 +150,13 @@ def test_host_renderer_entry_point(staged):
 
 
 @pytest.mark.parametrize("key", ["bunny_r32_s4_c32", "bunny_r32_s8_c1", "killeroo_simple_r32_s4_c32",
-                                 "killeroo_simple_r32_s8_c1"])
+                                 "killeroo_simple_r32_s8_c1", "anim_killeroos_moving_r32_s4_c32",
+                                 "anim_killeroos_moving_r32_s8_c1"])
 def test_render_matches_golden_reference_images(staged, key):
     """GPU render vs images rendered by the UNMODIFIED reference (tests/golden/images.npz)."""
     import os
     g = np.load(os.path.join(pb.REPO, "tests", "golden", "images.npz"))
-    base = "bunny" if key.startswith("bunny") else "killeroo-simple"
+    base = "-".join(key.split("_")[:-3])
     res, spp, ncores = [int(x[1:]) for x in key.split("_")[-3:]]
     hs = host_scene(base, res, res, spp, ncores)
     px, _ = _gpu_scene(hs).render()

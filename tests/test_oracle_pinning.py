@@ -53,10 +53,11 @@ def test_ld_tables_match_golden():
 
 
 @pytest.mark.parametrize("key", ["bunny_r32_s4_c32", "bunny_r32_s8_c1", "killeroo_simple_r32_s4_c32",
-                                 "killeroo_simple_r32_s8_c1"])
+                                 "killeroo_simple_r32_s8_c1", "anim_killeroos_moving_r32_s4_c32",
+                                 "anim_killeroos_moving_r32_s8_c1"])
 def test_oracle_image_matches_golden_reference_render(staged, key):
     g = np.load(os.path.join(GOLD, "images.npz"))
-    base = "bunny" if key.startswith("bunny") else "killeroo-simple"
+    base = "-".join(key.split("_")[:-3])
     res, spp, ncores = [int(x[1:]) for x in key.split("_")[-3:]]
     hs = host_scene(base, res, res, spp, ncores)
     px, _ = oa.render(hs, threads=4)
@@ -76,7 +77,8 @@ def test_bvh_sizes_match_reference(staged):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
-@pytest.mark.parametrize("base,res,spp,ncores", [("bunny", 40, 8, 2), ("killeroo-simple", 40, 4, 2)])
+@pytest.mark.parametrize("base,res,spp,ncores", [("bunny", 40, 8, 2), ("killeroo-simple", 40, 4, 2),
+                                                 ("anim-killeroos-moving", 40, 4, 2)])
 def test_oracle_bit_exact_vs_reference_binary(staged, base, res, spp, ncores):
     hs = host_scene(base, res, res, spp, ncores, tag="-live")
     px, _ = oa.render(hs, threads=4)
