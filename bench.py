@@ -33,9 +33,13 @@ WORKLOADS = {
     "bunny-c2": ("bunny", 1024, 1024, 1024),            # BASELINE.json configs[1]
     "killeroo-c1": ("killeroo-simple", 400, 400, 64),   # configs[0] (CPU-runnable case)
     "killeroo-c3": ("killeroo-simple", 1920, 1080, 4096),
+    # configs[3]: two animated TransformedPrimitives (each its own nested BVH) of killeroos subdivided to
+    # 532 224 triangles (geometry copy with "integer nlevels" [3]), shutter 0..1
+    "anim-c4": ("anim-killeroos-moving", 1920, 1080, 1024),
     # configs[4]: synthetic 10M-triangle random mesh, maxdepth 8 (HBM-resident: 1.3 GB of BVH + triangles)
     "synthetic-c5": ("synthetic", 4096, 4096, 512),
 }
+WORKLOAD_NLEVELS = {"anim-c4": 3}
 SYNTHETIC_TRIS = 10000000
 CPU_SAMPLE_SPP = 16     # bounded sample of the same workload for the CPU arms (cost is linear in spp)
 
@@ -74,8 +78,8 @@ def tasks_note(xres, yres):
     n = 32 * per_pixel_ncores(xres, yres)
     if n >= xres * yres:
         return "one reference render task per pixel (--ncores %d)" % (n // 32)
-    return "%d reference render tasks of %d pixels (--ncores %d; finer grids overflow Sampler::ComputeSubWindow's int products)" % (
-        n, xres * yres // n, n // 32)
+    return "%d reference render tasks of ~%.3g pixels (--ncores %d; finer grids overflow Sampler::ComputeSubWindow's int products)" % (
+        n, xres * yres / n, n // 32)
 
 
 class ClockSampler(threading.Thread):
@@ -138,7 +142,8 @@ def cpu_reference_rate(workload, threads):
     """Msamples/s of the reference's multithreaded CPU path on a bounded sample of `workload`."""
     from pbrt_v2_b200 import scenes
     base, xres, yres, _ = WORKLOADS[workload]
-    path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-cpu-%s.pbrt" % workload), xres, yres, CPU_SAMPLE_SPP)
+    path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-cpu-%s.pbrt" % workload), xres, yres, CPU_SAMPLE_SPP,
+                          nlevels=WORKLOAD_NLEVELS.get(workload))
     sec, wall = reference_render_seconds(path, threads)
     nsamp = xres * yres * CPU_SAMPLE_SPP
     return nsamp / max(sec, 1e-3) / 1e6, sec, wall
@@ -182,7 +187,9 @@ def run_reference_arm(args, rank, world):
 
 def workload_config(workload, world, per_pixel=True):
     base, xres, yres, spp = WORKLOADS[workload]
-    desc = ("scenes/%s.pbrt, SurfaceIntegrator \"path\" (maxdepth 5)" % base) if base != "synthetic" else \
+    desc = ("scenes/%s.pbrt%s, SurfaceIntegrator \"path\" (maxdepth 5)" % (
+        base, (" with geometry/killeroo.pbrt at \"integer nlevels\" [%d]" % WORKLOAD_NLEVELS[workload]) if workload in WORKLOAD_NLEVELS else "")) \
+        if base != "synthetic" else \
         "synthetic random-triangle scene (SURVEY 8d C5), SurfaceIntegrator \"path\" (maxdepth 8)"
     return {
         "workload": "%s, Sampler \"lowdiscrepancy\" %d spp, %dx%d, Accelerator \"bvh\", box filter" % (desc, spp, xres, yres),
@@ -232,7 +239,8 @@ def main():
     if base == "synthetic":
         hs = pb.HostScene.synthetic(args.tris, xres, yres, spp, maxdepth=8, ncores=per_pixel_ncores(xres, yres))
     else:
-        path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-%s-r%d.pbrt" % (args.workload, rank)), xres, yres, spp)
+        path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-%s-r%d.pbrt" % (args.workload, rank)), xres, yres, spp,
+                              nlevels=WORKLOAD_NLEVELS.get(args.workload))
         hs = pb.HostScene(path, ncores=per_pixel_ncores(xres, yres))
     rd = hs.render_desc()
     from pbrt_v2_b200.multigpu import shard_render_desc, reduce_film
@@ -252,14 +260,15 @@ def main():
         reduce_film(film, world)
         return st
 
+    g2 = pb.GpuScene(hs)   # the end-to-end arm's own handle: every step re-uploads the scene into it
+
     def step_e2e():
-        g2 = pb.GpuScene(hs)                       # host -> device copy of the flattened scene
+        g2.update(hs)                              # host -> device copy of the flattened scene (the step's input)
         g2.render_device(rd, film.data_ptr(), stream.cuda_stream)
         reduce_film(film, world)
         if rank == 0:
             host_film.copy_(film, non_blocking=True)   # device -> host read of the step's result
         stream.synchronize()
-        g2.close()
 
     def barrier():
         if world > 1:

@@ -240,6 +240,10 @@ const char *pbrtgpu_last_error(void);
 /* replaces: Scene / BVHAccel / GeometricPrimitive object graph (core/scene.h) */
 int  pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out);
 void pbrtgpu_scene_destroy(PbrtGpuScene *scene);
+/* replaces: rebuilding the Scene when the world changes between frames (pbrtWorldEnd per frame,
+ * core/api.cpp:1150-1209).  Copies a new descriptor into the device buffers of an existing handle
+ * (reallocating only what grew); must not run concurrently with a render call on the same handle. */
+int  pbrtgpu_scene_update(PbrtGpuScene *scene, const PbrtGpuSceneDesc *desc);
 /* replaces: the PBRT_PROBES_COUNTERS build switch (core/probes.h:219-395).  on != 0
  * makes the following render calls run the counting instantiation of the path
  * kernel and fill PbrtGpuStats.{closestRays,shadowRays,nodesVisited,primTests};

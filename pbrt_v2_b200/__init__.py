@@ -83,6 +83,7 @@ def gpu_lib():
         lib.pbrtgpu_last_error.restype = C.c_char_p
         lib.pbrtgpu_scene_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         lib.pbrtgpu_scene_destroy.argtypes = [C.c_void_p]
+        lib.pbrtgpu_scene_update.argtypes = [C.c_void_p, C.c_void_p]
         lib.pbrtgpu_scene_destroy.restype = None
         lib.pbrtgpu_render.argtypes = [C.c_void_p, C.POINTER(RenderDesc), C.c_void_p, C.POINTER(Stats)]
         lib.pbrtgpu_render_device.argtypes = [C.c_void_p, C.POINTER(RenderDesc), C.c_void_p, C.c_void_p,
@@ -237,6 +238,11 @@ class GpuScene(object):
             self._h = None
 
     __del__ = close
+
+    def update(self, host_scene):
+        """pbrtgpu_scene_update: copy a (new) flattened scene into this handle's device buffers."""
+        _check(gpu_lib().pbrtgpu_scene_update(self._h, host_scene.desc_ptr), "pbrtgpu_scene_update")
+        self.host = host_scene
 
     def set_stats(self, on):
         """switch the ray / node / primitive-test counters on (slower kernel instantiation)."""

@@ -23,7 +23,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace dev;
@@ -1067,6 +1069,52 @@ template <typename T> struct DevBuf {
 
 }  // namespace
 
+// One lane = one CUDA stream + one set of scratch buffers (+ one host thread while a render call runs).
+struct Lane {
+    cudaStream_t stream = nullptr;
+    DevBuf<TaskRec> tasks;
+    DevBuf<uint16_t> perm;
+    DevBuf<uint32_t> scr, rngCur, rngNext;
+    DevBuf<int> mti;
+    DevBuf<float4> ls, rec;
+    DevBuf<unsigned> tailCount, tailKeysOut, orderIn, orderOut;
+    DevBuf<unsigned char> sortTemp;
+    DevBuf<float4> pool;              // wavefront path slots (F_COUNT fields x P)
+    DevBuf<uint32_t> traceQ;
+    DevBuf<unsigned> counters;
+    unsigned *hostCounters = nullptr;  // pinned
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Lane() {
+        for (int i = 0; i < 4; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+        if (hostCounters) cudaFreeHost(hostCounters);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+// Lanes outlive scene handles: released lanes wait here, per device, for the next render call.
+struct LaneCache {
+    std::mutex m;
+    std::vector<Lane *> free[64];
+};
+static LaneCache &Lanes() {
+    static LaneCache *c = new LaneCache;   // never destroyed: no cudaFree during process teardown
+    return *c;
+}
+static Lane *AcquireLane(int device) {
+    LaneCache &c = Lanes();
+    std::lock_guard<std::mutex> g(c.m);
+    std::vector<Lane *> &f = c.free[device & 63];
+    if (f.empty()) return new Lane;
+    Lane *l = f.back();
+    f.pop_back();
+    return l;
+}
+static void ReleaseLane(int device, Lane *l) {
+    LaneCache &c = Lanes();
+    std::lock_guard<std::mutex> g(c.m);
+    c.free[device & 63].push_back(l);
+}
+
 struct PbrtGpuScene {
     int device = 0;
     DScene d;
@@ -1083,24 +1131,16 @@ struct PbrtGpuScene {
     DevBuf<PbrtGpuLight> lights;
     DevBuf<PbrtGpuLightShape> lightShapes;
     DevBuf<PbrtGpuAnimated> animated;
-    // per-render scratch, kept between calls
-    DevBuf<TaskRec> tasks;
-    DevBuf<uint16_t> perm;
-    DevBuf<uint32_t> scr, rngCur, rngNext;
-    DevBuf<int> mti;
-    DevBuf<float4> ls, rec;
-    DevBuf<unsigned> tailCount, tailKeysOut, orderIn, orderOut;
-    DevBuf<unsigned char> sortTemp;
-    DevBuf<float4> pool;              // wavefront path slots (F_COUNT fields x P)
-    DevBuf<uint32_t> traceQ, evalQ;
-    DevBuf<unsigned> counters;
-    unsigned *hostCounters = nullptr;  // pinned
+    // per-render scratch: one Lane per concurrent batch pipeline (see pbrtgpu_render_device), borrowed from a
+    // process-wide cache so that a new scene handle does not pay for tens of GB of cudaMalloc again
+    static const int MAX_LANES = 4;
+    Lane *lanes[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<PbrtGpuPixel> film;
     DevBuf<DeviceStats> stats;
     DevBuf<PbrtGpuRay> rays;
     DevBuf<PbrtGpuHit> hits;
     DevBuf<uint8_t> occ;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // render start / end, the lanes' start gate
     bool collectStats = false;
     int nMeasuredMaterials = 0;
 };
@@ -1205,7 +1245,7 @@ cudaError_t LaunchTablesAny(const BatchArgs &b, int spp, const TableLaunch &tl, 
 
 size_t ScratchBudgetBytes() {
     const char *env = getenv("PBRTGPU_SCRATCH_GB");
-    double gb = env ? atof(env) : 24.0;
+    double gb = env ? atof(env) : 40.0;
     if (gb < 0.25) gb = 0.25;
     return (size_t)(gb * 1024.0 * 1024.0 * 1024.0);
 }
@@ -1227,11 +1267,8 @@ int pbrtgpu_set_device(int ordinal) {
 
 const char *pbrtgpu_last_error(void) { return g_lastError.c_str(); }
 
-int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
-    if (!desc || !out) return Fail(PBRTGPU_EINVAL, "null argument");
-    *out = nullptr;
-    if (pbrtgpu_device_count() <= 0)
-        return Fail(PBRTGPU_ENODEVICE, "no CUDA device visible; libpbrtgpu has no CPU fallback");
+// validates `desc` and copies it into the scene's device buffers (reused when large enough)
+static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
     if (desc->nNodes == 0 || desc->nPrimitives == 0) return Fail(PBRTGPU_EINVAL, "empty scene");
     if (desc->nMaterials > 65535 || desc->nLights > 65534) return Fail(PBRTGPU_EUNSUPPORTED, "too many materials/lights");
     for (uint32_t i = 0; i < desc->nLights; ++i)
@@ -1244,8 +1281,6 @@ int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
         if (m.type == PBRTGPU_MAT_MEASURED && (m.measured < 0 || (uint32_t)m.measured >= desc->nMeasured))
             return Fail(PBRTGPU_EINVAL, "measured material without data");
     }
-    std::unique_ptr<PbrtGpuScene> s(new PbrtGpuScene);
-    CUDA_TRY(cudaGetDevice(&s->device));
 
     // nodes: 32-byte LinearBVHNode -> two float4 (bit copy; the byte pair nPrimitives/axis lands in .w)
     {
@@ -1336,19 +1371,39 @@ int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
     d.materials = s->materials.p; d.measured = s->measured.p; d.kdNodes = s->kdNodes.p; d.kdData = s->kdData.p;
     d.lights = s->lights.p; d.lightShapes = s->lightShapes.p; d.animated = s->animated.p;
     d.nNodes = desc->nNodes; d.nPrims = desc->nPrimitives; d.nLights = desc->nLights; d.nAnimated = desc->nAnimated;
-    for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&s->ev[i]));
-    s->collectStats = getenv("PBRTGPU_STATS") != nullptr;
+    s->nMeasuredMaterials = 0;
     for (uint32_t i = 0; i < desc->nMaterials; ++i)
         if (desc->materials[i].type == PBRTGPU_MAT_MEASURED) s->nMeasuredMaterials++;
+    return PBRTGPU_OK;
+}
+
+int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
+    if (!desc || !out) return Fail(PBRTGPU_EINVAL, "null argument");
+    *out = nullptr;
+    if (pbrtgpu_device_count() <= 0)
+        return Fail(PBRTGPU_ENODEVICE, "no CUDA device visible; libpbrtgpu has no CPU fallback");
+    std::unique_ptr<PbrtGpuScene> s(new PbrtGpuScene);
+    CUDA_TRY(cudaGetDevice(&s->device));
+    int rc = UploadScene(s.get(), desc);
+    if (rc != PBRTGPU_OK) return rc;
+    s->collectStats = getenv("PBRTGPU_STATS") != nullptr;
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&s->ev[i]));
     *out = s.release();
     return PBRTGPU_OK;
 }
 
+int pbrtgpu_scene_update(PbrtGpuScene *scene, const PbrtGpuSceneDesc *desc) {
+    if (!scene || !desc) return Fail(PBRTGPU_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(scene->device));
+    return UploadScene(scene, desc);
+}
+
 void pbrtgpu_scene_destroy(PbrtGpuScene *scene) {
     if (!scene) return;
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 3; ++i)
         if (scene->ev[i]) cudaEventDestroy(scene->ev[i]);
-    if (scene->hostCounters) cudaFreeHost(scene->hostCounters);
+    for (int l = 0; l < PbrtGpuScene::MAX_LANES; ++l)
+        if (scene->lanes[l]) ReleaseLane(scene->device, scene->lanes[l]);
     delete scene;
 }
 
@@ -1360,6 +1415,252 @@ int pbrtgpu_set_stats(PbrtGpuScene *scene, int on) {
     scene->collectStats = on != 0;
     return PBRTGPU_OK;
 }
+
+}  // extern "C"
+
+namespace {
+
+// One lane = one CUDA stream + one set of scratch buffers + one host thread.  A render call deals its task
+// batches round-robin to the lanes; batches share nothing (own RNG streams, own pixels; edge splats are atomic),
+// so the lanes' kernels overlap on the device and fill the SMs the latency-bound tail / traversal kernels of a
+// single batch leave idle.
+struct LaneJob {
+    PbrtGpuScene *scene;
+    Lane *ln;
+    const std::vector<TaskRec> *tasks;
+    size_t maxBatch;
+    int laneIndex, nLanes;   // this lane renders batches laneIndex, laneIndex + nLanes, ...
+    RenderParams rp;
+    int spp;
+    PbrtGpuPixel *film;
+    bool timing, wantCounters;
+    // results
+    int rc = PBRTGPU_OK;
+    std::string err;
+    float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f;
+    uint64_t launches = 0;
+};
+
+int RunLane(LaneJob &job) {
+    PbrtGpuScene *scene = job.scene;
+    Lane *ln = job.ln;
+    CUDA_TRY(cudaSetDevice(scene->device));   // a new host thread starts on device 0
+    cudaStream_t stream = ln->stream;
+    const std::vector<TaskRec> &tasks = *job.tasks;
+    const int spp = job.spp;
+    const RenderParams &rp = job.rp;
+    PbrtGpuPixel *film = job.film;
+    const bool stats = job.timing, wantCounters = job.wantCounters;
+    const size_t maxBatch = job.maxBatch;
+    CUDA_TRY(cudaStreamWaitEvent(stream, scene->ev[2], 0));   // the film has been cleared
+    CUDA_TRY(ln->tasks.Ensure(maxBatch));
+    CUDA_TRY(ln->perm.Ensure(maxBatch * spp * PERM_STRIDE));
+    CUDA_TRY(ln->scr.Ensure(maxBatch * SCR_STRIDE));
+    CUDA_TRY(ln->rngCur.Ensure(maxBatch * MT_N));
+    CUDA_TRY(ln->rngNext.Ensure(maxBatch * MT_N));
+    CUDA_TRY(ln->mti.Ensure(maxBatch));
+    CUDA_TRY(ln->ls.Ensure(maxBatch * spp));
+    CUDA_TRY(ln->rec.Ensure(maxBatch * spp * 4));
+    CUDA_TRY(ln->tailCount.Ensure(maxBatch));
+    CUDA_TRY(ln->tailKeysOut.Ensure(maxBatch));
+    CUDA_TRY(ln->orderIn.Ensure(maxBatch));
+    CUDA_TRY(ln->orderOut.Ensure(maxBatch));
+    {
+        std::vector<unsigned> iota(maxBatch);
+        for (size_t i = 0; i < maxBatch; ++i) iota[i] = (unsigned)i;
+        CUDA_TRY(cudaMemcpyAsync(ln->orderIn.p, iota.data(), maxBatch * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    size_t sortBytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, sortBytes, ln->tailCount.p, ln->tailKeysOut.p,
+                                              ln->orderIn.p, ln->orderOut.p, (int)maxBatch, 0, 1, stream);
+    CUDA_TRY(ln->sortTemp.Ensure(sortBytes + 16));
+
+    // phase 1 runs as a wavefront over a pool of path slots unless PBRTGPU_WAVEFRONT=0
+    bool useWavefront = true, useWavefront2 = false;   // tail wavefront: measured slower than k_path<2> (profiles/), opt-in
+    { const char *e = getenv("PBRTGPU_WAVEFRONT"); if (e) useWavefront = atoi(e) != 0; }
+    { const char *e = getenv("PBRTGPU_WAVEFRONT2"); if (e) useWavefront2 = atoi(e) != 0; }
+    if (!useWavefront) useWavefront2 = false;
+    size_t poolSize = (size_t)1 << 22;   // 4 Mi slots x 272 B = 1.1 GB (measured: +17 % over 1 Mi)
+    { const char *e = getenv("PBRTGPU_POOL"); if (e && atol(e) > 0) poolSize = (size_t)atol(e); }
+    poolSize = (poolSize + 127) / 128 * 128;
+    int nSM = 148;
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, scene->device);
+    bool hasMeasured = scene->measured.n > 0 && scene->nMeasuredMaterials > 0;
+    if (useWavefront) {
+        CUDA_TRY(ln->pool.Ensure(poolSize * F_COUNT));
+        CUDA_TRY(ln->traceQ.Ensure(poolSize * 2 * K_COUNT));   // request queues: 2 sets x K_COUNT kinds
+        CUDA_TRY(ln->counters.Ensure(C_COUNT));
+        if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, C_COUNT * sizeof(unsigned)));
+    }
+    const bool traceIters = getenv("PBRTGPU_TRACE_ITERS") != nullptr;   // debugging aid: queue occupancy on stderr
+    const TableLaunch tl = PlanTables(spp);
+    uint64_t launches = 0;
+    float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f;
+    for (size_t bi = (size_t)job.laneIndex; bi * maxBatch < tasks.size(); bi += (size_t)job.nLanes) {
+        const size_t begin = bi * maxBatch;
+        const size_t nb = std::min(maxBatch, tasks.size() - begin);
+        int rounds = 0;
+        for (size_t i = 0; i < nb; ++i)
+            rounds = std::max(rounds, (tasks[begin + i].x1 - tasks[begin + i].x0) * (tasks[begin + i].y1 - tasks[begin + i].y0));
+        CUDA_TRY(cudaMemcpyAsync(ln->tasks.p, tasks.data() + begin, nb * sizeof(TaskRec), cudaMemcpyHostToDevice, stream));
+        BatchArgs b;
+        b.tasks = ln->tasks.p; b.nBatch = (int)nb; b.round = 0;
+        b.perm = ln->perm.p; b.scr = ln->scr.p; b.rngCur = ln->rngCur.p; b.rngNext = ln->rngNext.p;
+        b.mti = ln->mti.p; b.ls = ln->ls.p; b.rec = ln->rec.p;
+        b.tailCount = ln->tailCount.p; b.order = nullptr;
+        for (int r = 0; r < rounds; ++r) {
+            b.round = r;
+            if (stats) CUDA_TRY(cudaEventRecord(ln->ev[0], stream));
+            CUDA_TRY(LaunchTablesAny(b, spp, tl, stream));
+            if (stats) CUDA_TRY(cudaEventRecord(ln->ev[1], stream));
+            CUDA_TRY(cudaMemsetAsync(ln->tailCount.p, 0, nb * sizeof(unsigned), stream));
+            PathArgs pa;
+            pa.sc = scene->d; pa.rp = rp; pa.b = b; pa.film = film; pa.stats = scene->stats.p;
+            pa.directFilm = rounds > 1 ? 1 : 0;
+            { const char *e = getenv("PBRTGPU_LOCKSTEP"); pa.lockstep = e ? atoi(e) : 1; }
+            const int blocks1 = (int)((nb + 3) / 4);       // phase 1 (megakernel form): one warp per task-pixel
+            const int blocks2 = (int)((nb + 127) / 128);   // phase 2: one thread per task-pixel
+            if (!useWavefront) {
+                if (scene->d.nAnimated) {
+                    if (wantCounters) k_path<1, true, true><<<blocks1, 128, 0, stream>>>(pa);
+                    else k_path<1, false, true><<<blocks1, 128, 0, stream>>>(pa);
+                } else {
+                    if (wantCounters) k_path<1, true, false><<<blocks1, 128, 0, stream>>>(pa);
+                    else k_path<1, false, false><<<blocks1, 128, 0, stream>>>(pa);
+                }
+                CUDA_TRY(cudaGetLastError());
+                launches += 1;
+            } else {
+                // ---- phase 1 as a wavefront over a pool of path slots
+                WfArgs wa;
+                wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = ln->pool.p; wa.P = (uint32_t)poolSize;
+                wa.q = ln->traceQ.p; wa.counters = ln->counters.p;
+                wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p;
+                wa.film = film; wa.directFilm = 0;
+                CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, C_COUNT * sizeof(unsigned), stream));
+                const int lblocks = (int)((poolSize + 127) / 128);
+                const int tblocks = nSM * 8;
+                for (int iter = 0;; ++iter) {
+                    wa.iter = iter;
+                    const int setOut = (iter & 1) ^ 1;
+                    // empty the queues k_logic is about to fill, and the consumers' cursors
+                    CUDA_TRY(cudaMemsetAsync(ln->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
+                    CUDA_TRY(cudaMemsetAsync(ln->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_logic<1, true, true><<<lblocks, 128, 0, stream>>>(wa);
+                        else k_logic<1, false, true><<<lblocks, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_logic<1, true, false><<<lblocks, 128, 0, stream>>>(wa);
+                        else k_logic<1, false, false><<<lblocks, 128, 0, stream>>>(wa);
+                    }
+                    if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_trace<true, true><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_trace<false, true><<<tblocks, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_trace<true, false><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_trace<false, false><<<tblocks, 128, 0, stream>>>(wa);
+                    }
+                    launches += hasMeasured ? 3 : 2;
+                    if ((iter & 7) == 7) {
+                        CUDA_TRY(cudaMemcpyAsync(ln->hostCounters, ln->counters.p, C_COUNT * sizeof(unsigned),
+                                                 cudaMemcpyDeviceToHost, stream));
+                        CUDA_TRY(cudaStreamSynchronize(stream));
+                        unsigned alive = 0;
+                        for (int k = 0; k < K_COUNT; ++k) alive += ln->hostCounters[C_QN + setOut * K_COUNT + k];
+                        if (traceIters)
+                            fprintf(stderr, "[pbrtgpu] batch@%zu round %d iter %d: queued %u (eval %u/%u/%u hit %u shadow %u mis %u) next sample %u of %u\n",
+                                    begin, r, iter, alive, ln->hostCounters[C_QN + setOut * K_COUNT + K_E_LIGHT],
+                                    ln->hostCounters[C_QN + setOut * K_COUNT + K_E_MIS], ln->hostCounters[C_QN + setOut * K_COUNT + K_E_PATH],
+                                    ln->hostCounters[C_QN + setOut * K_COUNT + K_HIT], ln->hostCounters[C_QN + setOut * K_COUNT + K_SHADOW],
+                                    ln->hostCounters[C_QN + setOut * K_COUNT + K_MIS], ln->hostCounters[C_NEXT_SAMPLE], wa.totalSamples);
+                        if (alive == 0) break;
+                    }
+                    if (iter > 4000000) return Fail(PBRTGPU_ECUDA, "wavefront did not terminate");
+                }
+                CUDA_TRY(cudaGetLastError());
+            }
+            if (stats) CUDA_TRY(cudaEventRecord(ln->ev[2], stream));
+            {   // tasks with parked samples first
+                size_t tmp = ln->sortTemp.n;
+                cub::DeviceRadixSort::SortPairsDescending(ln->sortTemp.p, tmp, ln->tailCount.p, ln->tailKeysOut.p,
+                                                          ln->orderIn.p, ln->orderOut.p, (int)nb, 0, 1, stream);
+                pa.b.order = ln->orderOut.p;
+            }
+            if (!useWavefront2) {
+                if (scene->d.nAnimated) {
+                    if (wantCounters) k_path<2, true, true><<<blocks2, 128, 0, stream>>>(pa);
+                    else k_path<2, false, true><<<blocks2, 128, 0, stream>>>(pa);
+                } else {
+                    if (wantCounters) k_path<2, true, false><<<blocks2, 128, 0, stream>>>(pa);
+                    else k_path<2, false, false><<<blocks2, 128, 0, stream>>>(pa);
+                }
+                CUDA_TRY(cudaGetLastError());
+            } else {
+                // ---- phase 2 as a wavefront: one slot per task-pixel chain
+                WfArgs wa;
+                wa.sc = scene->d; wa.rp = rp; wa.b = pa.b; wa.pool = ln->pool.p; wa.P = (uint32_t)poolSize;
+                wa.q = ln->traceQ.p; wa.counters = ln->counters.p;
+                wa.totalSamples = 0; wa.stats = scene->stats.p;
+                wa.film = film; wa.directFilm = pa.directFilm;
+                CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, C_COUNT * sizeof(unsigned), stream));
+                const int tblocks = nSM * 8;
+                for (int iter = 0;; ++iter) {
+                    wa.iter = iter;
+                    const int setOut = (iter & 1) ^ 1;
+                    CUDA_TRY(cudaMemsetAsync(ln->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
+                    CUDA_TRY(cudaMemsetAsync(ln->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_logic<2, true, true><<<blocks2, 128, 0, stream>>>(wa);
+                        else k_logic<2, false, true><<<blocks2, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_logic<2, true, false><<<blocks2, 128, 0, stream>>>(wa);
+                        else k_logic<2, false, false><<<blocks2, 128, 0, stream>>>(wa);
+                    }
+                    if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_trace<true, true><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_trace<false, true><<<tblocks, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_trace<true, false><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_trace<false, false><<<tblocks, 128, 0, stream>>>(wa);
+                    }
+                    launches += hasMeasured ? 3 : 2;
+                    if ((iter & 7) == 7) {
+                        CUDA_TRY(cudaMemcpyAsync(ln->hostCounters, ln->counters.p, C_COUNT * sizeof(unsigned),
+                                                 cudaMemcpyDeviceToHost, stream));
+                        CUDA_TRY(cudaStreamSynchronize(stream));
+                        unsigned alive = 0;
+                        for (int k = 0; k < K_COUNT; ++k) alive += ln->hostCounters[C_QN + setOut * K_COUNT + k];
+                        if (alive == 0) break;
+                    }
+                    if (iter > 40000000) return Fail(PBRTGPU_ECUDA, "tail wavefront did not terminate");
+                }
+                CUDA_TRY(cudaGetLastError());
+            }
+            launches += 2;
+            if (stats) {
+                CUDA_TRY(cudaEventRecord(ln->ev[3], stream));
+                CUDA_TRY(cudaEventSynchronize(ln->ev[3]));
+                float ms = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&ms, ln->ev[0], ln->ev[1]));
+                tableMs += ms;
+                CUDA_TRY(cudaEventElapsedTime(&ms, ln->ev[1], ln->ev[2]));
+                traceMs += ms;
+                CUDA_TRY(cudaEventElapsedTime(&ms, ln->ev[2], ln->ev[3]));
+                tailMs += ms;
+            }
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    job.tableMs = tableMs; job.traceMs = traceMs; job.tailMs = tailMs; job.launches = launches;
+    return PBRTGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void *d_pixels, void *streamv,
                           PbrtGpuStats *stats) {
@@ -1404,215 +1705,54 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     // per task: permutation tables (64 B/sample) + finished radiance (16 B/sample) + parked
     // bounce-3 vertices (64 B/sample, sparse) + scrambles + two MT19937 blocks
     const size_t perTask = (size_t)spp * (PERM_STRIDE * 2 + 16 + 64) + SCR_STRIDE * 4 + 2 * MT_N * 4 + 4 + sizeof(TaskRec);
-    size_t maxBatch = std::max<size_t>(1024, ScratchBudgetBytes() / perTask);
-    maxBatch = std::min<size_t>(maxBatch, std::max<size_t>(tasks.size(), 1));
-    {   // the tail wavefront keeps one pool slot per task of the batch
-        size_t ps = (size_t)1 << 22;
-        const char *e = getenv("PBRTGPU_POOL");
-        if (e && atol(e) > 0) ps = (size_t)atol(e);
-        maxBatch = std::min(maxBatch, ps);
+    size_t poolSlots = (size_t)1 << 22;
+    { const char *e = getenv("PBRTGPU_POOL"); if (e && atol(e) > 0) poolSlots = (size_t)atol(e); }
+    // lanes: as many as keep every lane's wavefront pool full (measured on bunny/C2: 1 lane 210, 2 lanes 227,
+    // 4 lanes 245 Msamples/s; with less than a pool's worth of samples per lane and round extra lanes only add launches)
+    int nLanes = PbrtGpuScene::MAX_LANES;
+    { const char *e = getenv("PBRTGPU_LANES"); if (e) nLanes = atoi(e); }
+    nLanes = std::max(1, std::min(nLanes, (int)PbrtGpuScene::MAX_LANES));
+    if (!getenv("PBRTGPU_LANES"))
+        while (nLanes > 1 && tasks.size() / nLanes * (size_t)spp < poolSlots) --nLanes;
+    while (nLanes > 1 && tasks.size() < (size_t)nLanes * 1024) --nLanes;   // too little work to split further
+    size_t maxBatch = std::max<size_t>(1024, ScratchBudgetBytes() / (size_t)nLanes / perTask);
+    maxBatch = std::min(maxBatch, poolSlots);   // the tail wavefront keeps one pool slot per task of the batch
+    {   // a whole number of batches per lane, all of (nearly) the same size
+        size_t nBatches = (std::max<size_t>(tasks.size(), 1) + maxBatch - 1) / maxBatch;
+        nBatches = (nBatches + nLanes - 1) / nLanes * nLanes;
+        maxBatch = (std::max<size_t>(tasks.size(), 1) + nBatches - 1) / nBatches;
     }
-    CUDA_TRY(scene->tasks.Ensure(maxBatch));
-    CUDA_TRY(scene->perm.Ensure(maxBatch * spp * PERM_STRIDE));
-    CUDA_TRY(scene->scr.Ensure(maxBatch * SCR_STRIDE));
-    CUDA_TRY(scene->rngCur.Ensure(maxBatch * MT_N));
-    CUDA_TRY(scene->rngNext.Ensure(maxBatch * MT_N));
-    CUDA_TRY(scene->mti.Ensure(maxBatch));
-    CUDA_TRY(scene->ls.Ensure(maxBatch * spp));
-    CUDA_TRY(scene->rec.Ensure(maxBatch * spp * 4));
-    CUDA_TRY(scene->tailCount.Ensure(maxBatch));
-    CUDA_TRY(scene->tailKeysOut.Ensure(maxBatch));
-    CUDA_TRY(scene->orderIn.Ensure(maxBatch));
-    CUDA_TRY(scene->orderOut.Ensure(maxBatch));
-    {
-        std::vector<unsigned> iota(maxBatch);
-        for (size_t i = 0; i < maxBatch; ++i) iota[i] = (unsigned)i;
-        CUDA_TRY(cudaMemcpyAsync(scene->orderIn.p, iota.data(), maxBatch * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-    }
-    size_t sortBytes = 0;
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, sortBytes, scene->tailCount.p, scene->tailKeysOut.p,
-                                              scene->orderIn.p, scene->orderOut.p, (int)maxBatch, 0, 1, stream);
-    CUDA_TRY(scene->sortTemp.Ensure(sortBytes + 16));
     CUDA_TRY(scene->stats.Ensure(1));
     const bool wantCounters = stats && scene->collectStats;
     if (wantCounters) CUDA_TRY(cudaMemsetAsync(scene->stats.p, 0, sizeof(DeviceStats), stream));
-
-    // phase 1 runs as a wavefront over a pool of path slots unless PBRTGPU_WAVEFRONT=0
-    bool useWavefront = true, useWavefront2 = false;   // tail wavefront: measured slower than k_path<2> (profiles/), opt-in
-    { const char *e = getenv("PBRTGPU_WAVEFRONT"); if (e) useWavefront = atoi(e) != 0; }
-    { const char *e = getenv("PBRTGPU_WAVEFRONT2"); if (e) useWavefront2 = atoi(e) != 0; }
-    if (!useWavefront) useWavefront2 = false;
-    size_t poolSize = (size_t)1 << 22;   // 4 Mi slots x 272 B = 1.1 GB (measured: +17 % over 1 Mi)
-    { const char *e = getenv("PBRTGPU_POOL"); if (e && atol(e) > 0) poolSize = (size_t)atol(e); }
-    poolSize = (poolSize + 127) / 128 * 128;
-    int nSM = 148;
-    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, scene->device);
-    bool hasMeasured = scene->measured.n > 0 && scene->nMeasuredMaterials > 0;
-    if (useWavefront) {
-        CUDA_TRY(scene->pool.Ensure(poolSize * F_COUNT));
-        CUDA_TRY(scene->traceQ.Ensure(poolSize * 2 * K_COUNT));   // request queues: 2 sets x K_COUNT kinds
-        CUDA_TRY(scene->counters.Ensure(C_COUNT));
-        if (!scene->hostCounters) CUDA_TRY(cudaMallocHost((void **)&scene->hostCounters, C_COUNT * sizeof(unsigned)));
+    CUDA_TRY(cudaEventRecord(scene->ev[2], stream));
+    std::vector<LaneJob> jobs(nLanes);
+    for (int l = 0; l < nLanes; ++l) {
+        if (!scene->lanes[l]) scene->lanes[l] = AcquireLane(scene->device);
+        Lane &ln = *scene->lanes[l];
+        if (!ln.stream) CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i)
+            if (!ln.ev[i]) CUDA_TRY(cudaEventCreate(&ln.ev[i]));
+        LaneJob &j = jobs[l];
+        j.scene = scene; j.ln = &ln; j.tasks = &tasks; j.maxBatch = maxBatch; j.laneIndex = l; j.nLanes = nLanes;
+        j.rp = rp; j.spp = spp; j.film = film; j.timing = stats != nullptr; j.wantCounters = wantCounters;
     }
-    const bool traceIters = getenv("PBRTGPU_TRACE_ITERS") != nullptr;   // debugging aid: queue occupancy on stderr
-    const TableLaunch tl = PlanTables(spp);
+    {
+        auto run = [](LaneJob *j) {
+            j->rc = RunLane(*j);
+            if (j->rc != PBRTGPU_OK) j->err = g_lastError;   // thread-local: carry it back to the caller's thread
+        };
+        std::vector<std::thread> workers;
+        for (int l = 1; l < nLanes; ++l) workers.emplace_back(run, &jobs[l]);
+        run(&jobs[0]);
+        for (std::thread &w : workers) w.join();
+    }
     uint64_t launches = 0;
     float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f;
-    for (size_t begin = 0; begin < tasks.size(); begin += maxBatch) {
-        const size_t nb = std::min(maxBatch, tasks.size() - begin);
-        int rounds = 0;
-        for (size_t i = 0; i < nb; ++i)
-            rounds = std::max(rounds, (tasks[begin + i].x1 - tasks[begin + i].x0) * (tasks[begin + i].y1 - tasks[begin + i].y0));
-        CUDA_TRY(cudaMemcpyAsync(scene->tasks.p, tasks.data() + begin, nb * sizeof(TaskRec), cudaMemcpyHostToDevice, stream));
-        BatchArgs b;
-        b.tasks = scene->tasks.p; b.nBatch = (int)nb; b.round = 0;
-        b.perm = scene->perm.p; b.scr = scene->scr.p; b.rngCur = scene->rngCur.p; b.rngNext = scene->rngNext.p;
-        b.mti = scene->mti.p; b.ls = scene->ls.p; b.rec = scene->rec.p;
-        b.tailCount = scene->tailCount.p; b.order = nullptr;
-        for (int r = 0; r < rounds; ++r) {
-            b.round = r;
-            if (stats) CUDA_TRY(cudaEventRecord(scene->ev[2], stream));
-            CUDA_TRY(LaunchTablesAny(b, spp, tl, stream));
-            if (stats) CUDA_TRY(cudaEventRecord(scene->ev[3], stream));
-            CUDA_TRY(cudaMemsetAsync(scene->tailCount.p, 0, nb * sizeof(unsigned), stream));
-            PathArgs pa;
-            pa.sc = scene->d; pa.rp = rp; pa.b = b; pa.film = film; pa.stats = scene->stats.p;
-            pa.directFilm = rounds > 1 ? 1 : 0;
-            { const char *e = getenv("PBRTGPU_LOCKSTEP"); pa.lockstep = e ? atoi(e) : 1; }
-            const int blocks1 = (int)((nb + 3) / 4);       // phase 1 (megakernel form): one warp per task-pixel
-            const int blocks2 = (int)((nb + 127) / 128);   // phase 2: one thread per task-pixel
-            if (!useWavefront) {
-                if (scene->d.nAnimated) {
-                    if (wantCounters) k_path<1, true, true><<<blocks1, 128, 0, stream>>>(pa);
-                    else k_path<1, false, true><<<blocks1, 128, 0, stream>>>(pa);
-                } else {
-                    if (wantCounters) k_path<1, true, false><<<blocks1, 128, 0, stream>>>(pa);
-                    else k_path<1, false, false><<<blocks1, 128, 0, stream>>>(pa);
-                }
-                CUDA_TRY(cudaGetLastError());
-                launches += 1;
-            } else {
-                // ---- phase 1 as a wavefront over a pool of path slots
-                WfArgs wa;
-                wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = scene->pool.p; wa.P = (uint32_t)poolSize;
-                wa.q = scene->traceQ.p; wa.counters = scene->counters.p;
-                wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p;
-                wa.film = film; wa.directFilm = 0;
-                CUDA_TRY(cudaMemsetAsync(scene->counters.p, 0, C_COUNT * sizeof(unsigned), stream));
-                const int lblocks = (int)((poolSize + 127) / 128);
-                const int tblocks = nSM * 8;
-                for (int iter = 0;; ++iter) {
-                    wa.iter = iter;
-                    const int setOut = (iter & 1) ^ 1;
-                    // empty the queues k_logic is about to fill, and the consumers' cursors
-                    CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
-                    CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
-                    if (scene->d.nAnimated) {
-                        if (wantCounters) k_logic<1, true, true><<<lblocks, 128, 0, stream>>>(wa);
-                        else k_logic<1, false, true><<<lblocks, 128, 0, stream>>>(wa);
-                    } else {
-                        if (wantCounters) k_logic<1, true, false><<<lblocks, 128, 0, stream>>>(wa);
-                        else k_logic<1, false, false><<<lblocks, 128, 0, stream>>>(wa);
-                    }
-                    if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
-                    if (scene->d.nAnimated) {
-                        if (wantCounters) k_trace<true, true><<<tblocks, 128, 0, stream>>>(wa);
-                        else k_trace<false, true><<<tblocks, 128, 0, stream>>>(wa);
-                    } else {
-                        if (wantCounters) k_trace<true, false><<<tblocks, 128, 0, stream>>>(wa);
-                        else k_trace<false, false><<<tblocks, 128, 0, stream>>>(wa);
-                    }
-                    launches += hasMeasured ? 3 : 2;
-                    if ((iter & 7) == 7) {
-                        CUDA_TRY(cudaMemcpyAsync(scene->hostCounters, scene->counters.p, C_COUNT * sizeof(unsigned),
-                                                 cudaMemcpyDeviceToHost, stream));
-                        CUDA_TRY(cudaStreamSynchronize(stream));
-                        unsigned alive = 0;
-                        for (int k = 0; k < K_COUNT; ++k) alive += scene->hostCounters[C_QN + setOut * K_COUNT + k];
-                        if (traceIters)
-                            fprintf(stderr, "[pbrtgpu] batch@%zu round %d iter %d: queued %u (eval %u/%u/%u hit %u shadow %u mis %u) next sample %u of %u\n",
-                                    begin, r, iter, alive, scene->hostCounters[C_QN + setOut * K_COUNT + K_E_LIGHT],
-                                    scene->hostCounters[C_QN + setOut * K_COUNT + K_E_MIS], scene->hostCounters[C_QN + setOut * K_COUNT + K_E_PATH],
-                                    scene->hostCounters[C_QN + setOut * K_COUNT + K_HIT], scene->hostCounters[C_QN + setOut * K_COUNT + K_SHADOW],
-                                    scene->hostCounters[C_QN + setOut * K_COUNT + K_MIS], scene->hostCounters[C_NEXT_SAMPLE], wa.totalSamples);
-                        if (alive == 0) break;
-                    }
-                    if (iter > 4000000) return Fail(PBRTGPU_ECUDA, "wavefront did not terminate");
-                }
-                CUDA_TRY(cudaGetLastError());
-            }
-            if (stats) CUDA_TRY(cudaEventRecord(scene->ev[4], stream));
-            {   // tasks with parked samples first
-                size_t tmp = scene->sortTemp.n;
-                cub::DeviceRadixSort::SortPairsDescending(scene->sortTemp.p, tmp, scene->tailCount.p, scene->tailKeysOut.p,
-                                                          scene->orderIn.p, scene->orderOut.p, (int)nb, 0, 1, stream);
-                pa.b.order = scene->orderOut.p;
-            }
-            if (!useWavefront2) {
-                if (scene->d.nAnimated) {
-                    if (wantCounters) k_path<2, true, true><<<blocks2, 128, 0, stream>>>(pa);
-                    else k_path<2, false, true><<<blocks2, 128, 0, stream>>>(pa);
-                } else {
-                    if (wantCounters) k_path<2, true, false><<<blocks2, 128, 0, stream>>>(pa);
-                    else k_path<2, false, false><<<blocks2, 128, 0, stream>>>(pa);
-                }
-                CUDA_TRY(cudaGetLastError());
-            } else {
-                // ---- phase 2 as a wavefront: one slot per task-pixel chain
-                WfArgs wa;
-                wa.sc = scene->d; wa.rp = rp; wa.b = pa.b; wa.pool = scene->pool.p; wa.P = (uint32_t)poolSize;
-                wa.q = scene->traceQ.p; wa.counters = scene->counters.p;
-                wa.totalSamples = 0; wa.stats = scene->stats.p;
-                wa.film = film; wa.directFilm = pa.directFilm;
-                CUDA_TRY(cudaMemsetAsync(scene->counters.p, 0, C_COUNT * sizeof(unsigned), stream));
-                const int tblocks = nSM * 8;
-                for (int iter = 0;; ++iter) {
-                    wa.iter = iter;
-                    const int setOut = (iter & 1) ^ 1;
-                    CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
-                    CUDA_TRY(cudaMemsetAsync(scene->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
-                    if (scene->d.nAnimated) {
-                        if (wantCounters) k_logic<2, true, true><<<blocks2, 128, 0, stream>>>(wa);
-                        else k_logic<2, false, true><<<blocks2, 128, 0, stream>>>(wa);
-                    } else {
-                        if (wantCounters) k_logic<2, true, false><<<blocks2, 128, 0, stream>>>(wa);
-                        else k_logic<2, false, false><<<blocks2, 128, 0, stream>>>(wa);
-                    }
-                    if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
-                    if (scene->d.nAnimated) {
-                        if (wantCounters) k_trace<true, true><<<tblocks, 128, 0, stream>>>(wa);
-                        else k_trace<false, true><<<tblocks, 128, 0, stream>>>(wa);
-                    } else {
-                        if (wantCounters) k_trace<true, false><<<tblocks, 128, 0, stream>>>(wa);
-                        else k_trace<false, false><<<tblocks, 128, 0, stream>>>(wa);
-                    }
-                    launches += hasMeasured ? 3 : 2;
-                    if ((iter & 7) == 7) {
-                        CUDA_TRY(cudaMemcpyAsync(scene->hostCounters, scene->counters.p, C_COUNT * sizeof(unsigned),
-                                                 cudaMemcpyDeviceToHost, stream));
-                        CUDA_TRY(cudaStreamSynchronize(stream));
-                        unsigned alive = 0;
-                        for (int k = 0; k < K_COUNT; ++k) alive += scene->hostCounters[C_QN + setOut * K_COUNT + k];
-                        if (alive == 0) break;
-                    }
-                    if (iter > 40000000) return Fail(PBRTGPU_ECUDA, "tail wavefront did not terminate");
-                }
-                CUDA_TRY(cudaGetLastError());
-            }
-            launches += 2;
-            if (stats) {
-                CUDA_TRY(cudaEventRecord(scene->ev[1], stream));
-                CUDA_TRY(cudaEventSynchronize(scene->ev[1]));
-                float ms = 0.f;
-                CUDA_TRY(cudaEventElapsedTime(&ms, scene->ev[2], scene->ev[3]));
-                tableMs += ms;
-                CUDA_TRY(cudaEventElapsedTime(&ms, scene->ev[3], scene->ev[4]));
-                traceMs += ms;
-                CUDA_TRY(cudaEventElapsedTime(&ms, scene->ev[4], scene->ev[1]));
-                tailMs += ms;
-            }
-        }
+    for (const LaneJob &j : jobs) {
+        if (j.rc != PBRTGPU_OK) return Fail(j.rc, j.err);
+        launches += j.launches;
+        tableMs += j.tableMs; traceMs += j.traceMs; tailMs += j.tailMs;   // lanes overlap: the sum can exceed renderMs
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));

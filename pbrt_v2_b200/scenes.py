@@ -86,7 +86,16 @@ def variant(base, out_path, xres, yres, spp, integrator="path", maxdepth=None,
         out.append(ln)
     text = "\n".join(out)
     if nlevels is not None:
-        raise NotImplementedError("nlevels override needs a geometry copy")
+        # "use a copy of geometry/killeroo.pbrt with "integer nlevels" [3]"
+        geo_src = os.path.join(STAGED, "geometry", "killeroo.pbrt")
+        geo_dst = os.path.join(STAGED, "geometry", "killeroo-nl%d.pbrt" % nlevels)
+        if not os.path.exists(geo_dst):
+            g = open(geo_src).read()
+            g2, n = re.subn(r'"integer nlevels"\s*\[\s*\d+\s*\]', '"integer nlevels" [%d]' % nlevels, g, count=1)
+            assert n == 1, "no nlevels parameter in geometry/killeroo.pbrt"
+            with open(geo_dst, "w") as f:
+                f.write(g2)
+        text = text.replace("geometry/killeroo.pbrt", "geometry/killeroo-nl%d.pbrt" % nlevels)
     assert os.path.dirname(os.path.abspath(out_path)) == STAGED, \
         "variants must live in scenes/_staged so relative includes resolve"
     with open(out_path, "w") as f:

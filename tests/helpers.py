@@ -7,11 +7,12 @@ from pbrt_v2_b200 import scenes
 _cache = {}
 
 
-def host_scene(base, xres, yres, spp, ncores, maxdepth=None, crop=None, tag=""):
-    key = (base, xres, yres, spp, ncores, maxdepth, crop, tag)
+def host_scene(base, xres, yres, spp, ncores, maxdepth=None, crop=None, tag="", nlevels=None):
+    key = (base, xres, yres, spp, ncores, maxdepth, crop, tag, nlevels)
     if key not in _cache:
-        name = "%s-%dx%d-%dspp%s.pbrt" % (base, xres, yres, spp, tag)
-        path = scenes.variant(base, scenes.STAGED + "/" + name, xres, yres, spp, maxdepth=maxdepth, crop=crop)
+        name = "%s-%dx%d-%dspp%s%s.pbrt" % (base, xres, yres, spp, tag, "" if nlevels is None else "-nl%d" % nlevels)
+        path = scenes.variant(base, scenes.STAGED + "/" + name, xres, yres, spp, maxdepth=maxdepth, crop=crop,
+                              nlevels=nlevels)
         _cache[key] = pb.HostScene(path, ncores=ncores)
     return _cache[key]
 

@@ -139,6 +139,36 @@ def test_task_sharding_is_exact(staged):
     assert np.array_equal(b["Lxyz"][only_b].view(np.uint32), full["Lxyz"][only_b].view(np.uint32))
 
 
+def test_lanes_do_not_change_the_film(staged, monkeypatch):
+    """The render call deals its task batches to concurrent lanes (streams + host threads); batches share
+    nothing, so the film must not depend on the number of lanes (splat-receiving pixels aside)."""
+    hs = host_scene("killeroo-simple", 96, 96, 8, 288)   # 16384 tasks: enough for 4 lanes
+    gs = _gpu_scene(hs)
+    films = []
+    for lanes in ("1", "2", "4"):
+        monkeypatch.setenv("PBRTGPU_LANES", lanes)
+        monkeypatch.setenv("PBRTGPU_SCRATCH_GB", "0.25")   # several batches per lane
+        px, st = gs.render()
+        films.append(px)
+    own = films[0]["weightSum"] == 8
+    for f in films[1:]:
+        assert np.array_equal(f["weightSum"], films[0]["weightSum"])
+        assert np.array_equal(f["Lxyz"][own].view(np.uint32), films[0]["Lxyz"][own].view(np.uint32))
+
+
+def test_scene_update_reuses_the_handle(staged):
+    """pbrtgpu_scene_update: one handle, two different scenes in turn; films equal fresh handles' films."""
+    a, b = host_scene("bunny", 32, 32, 4, 32), host_scene("killeroo-simple", 32, 32, 4, 32)
+    want_a, _ = _gpu_scene(a).render()
+    want_b, _ = _gpu_scene(b).render()
+    gs = pb.GpuScene(a)
+    for hs, want in ((b, want_b), (a, want_a), (b, want_b)):
+        gs.update(hs)
+        got, _ = gs.render(hs.render_desc())
+        assert np.array_equal(got["Lxyz"].view(np.uint32), want["Lxyz"].view(np.uint32))
+    gs.close()
+
+
 def test_host_renderer_entry_point(staged):
     """GpuSamplerRenderer::Render (C++ host class -> C ABI) gives the same film as the direct call."""
     hs = host_scene("bunny", 32, 32, 4, 32)
