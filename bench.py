@@ -41,6 +41,8 @@ WORKLOADS = {
 }
 WORKLOAD_NLEVELS = {"anim-c4": 3}
 SYNTHETIC_TRIS = 10000000
+# dram__bytes_read.sum + dram__bytes_write.sum of one mid-render k_trace launch (ncu --set full, profiles/), per workload
+K_TRACE_DRAM_BYTES_PER_LAUNCH = {}
 CPU_SAMPLE_SPP = 16     # bounded sample of the same workload for the CPU arms (cost is linear in spp)
 
 
@@ -284,6 +286,15 @@ def main():
     if world > 1:
         dist.all_reduce(counts)
     closest, shadow, nodes, prims = [float(x) for x in counts.tolist()]
+    # ---- untimed roofline pass: the traversal kernel timed launch by launch (CUDA events on its stream) with the
+    # device to itself (one lane), + the tail kernel's exclusive time
+    gs.set_stats(2)
+    rl = step_resident(want_stats=True)
+    gs.set_stats(0)
+    rl_t = torch.tensor([rl.rayKernelMs, rl.tailMs, float(rl.rayKernelLaunches), rl.renderMs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rl_t, op=dist.ReduceOp.MAX)
+    ray_ms, tail_excl_ms, ray_launches, serial_ms = [float(x) for x in rl_t.tolist()]
     for _ in range(max(0, args.warmup - 1)):
         flush.fill_(1)
         step_resident()
@@ -344,10 +355,12 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # both phases of k_path walk the BVH; the counters cover both, so does the time
-        trace_ms = path_ms + tail_ms
-        achieved = alg_bytes * args.steps / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
-        n_path_launches = max(1, launches // 3)
+        # BVH traversal happens in k_trace (phase-1 wavefront) and inside k_path<2> (the RNG-driven tails); the
+        # node / primitive-test counters cover both, so the time does too: k_trace's launches timed one by one in
+        # the roofline pass + the tail kernel's exclusive time in that pass (it also shades, so this is conservative)
+        trace_ms = ray_ms + tail_excl_ms
+        achieved = alg_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        hbm_resident = scene_bytes > 100e6   # B200 L2: 126 MB
         line = {
             "metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -358,19 +371,29 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "k_path<1,false> + k_path<2,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
+                "bound": "hbm", "kernel": "k_trace (+ the traversals inside k_path<2>)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak if peak else None,
+                "traffic": K_TRACE_DRAM_BYTES_PER_LAUNCH.get(args.workload),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_sample": alg_bytes / nsamples,
-                "kernel_ms_per_launch": trace_ms / n_path_launches,
-                "launches_per_step": n_path_launches / args.steps,
-                "note": "scene (BVH+triangles, %.1f MB) is L2-resident: the algorithmic-bytes roofline is an upper bound "
-                        "on useful traffic, not DRAM traffic" % (scene_bytes / 1e6),
+                "algorithmic_bytes_per_launch": alg_bytes / max(1.0, ray_launches),
+                "kernel_ms_per_launch": ray_ms / max(1.0, ray_launches),
+                "launches_per_step": ray_launches,
+                "k_trace_ms_per_step": ray_ms, "k_path2_ms_per_step": tail_excl_ms, "serial_step_ms": serial_ms,
+                "k_trace_share_of_serial_step": ray_ms / serial_ms if serial_ms else None,
+                "how": "untimed extra pass on one lane: cudaEventRecord around every k_trace launch on its stream "
+                       "(pbrtgpu_set_stats(scene, 2)); in the timed steps the lanes' kernels overlap, so per-kernel "
+                       "durations are not separable there",
+                "note": ("scene (BVH+triangles, %.1f MB) exceeds the 126 MB L2: traversal streams from HBM" if hbm_resident else
+                         "scene (BVH+triangles, %.1f MB) is L2-resident: the algorithmic-bytes roofline is an upper bound "
+                         "on useful traffic, not DRAM traffic") % (scene_bytes / 1e6),
             },
             "rays": {"closest_per_sample": closest / nsamples, "shadow_per_sample": shadow / nsamples,
                      "nodes_per_ray": nodes / max(1.0, closest + shadow), "prim_tests_per_ray": prims / max(1.0, closest + shadow)},
+            # per-lane event times summed over the concurrent lanes (they overlap: the sum exceeds ms_per_step)
             "kernel_ms": {"k_path_phase1": path_ms / args.steps, "k_path_phase2": tail_ms / args.steps,
                           "k_tables": table_ms / args.steps},
+            "lanes": env_int("PBRTGPU_LANES", 4),
         }
         if spp != WORKLOADS[args.workload][3]:
             line["INVALID"] = "spp overridden to %d (development run)" % spp

@@ -220,6 +220,11 @@ typedef struct PbrtGpuStats {
     uint64_t nodesVisited;    /* BVH nodes whose bounds were tested             */
     uint64_t primTests;
     uint64_t kernelLaunches;
+    /* filled only under pbrtgpu_set_stats(scene, 2): the ray-traversal kernel (k_trace) timed launch by launch
+     * with CUDA events on its stream, for the roofline figure (the render then runs on ONE lane so that
+     * nothing else overlaps it) */
+    double   rayKernelMs;
+    uint64_t rayKernelLaunches;
 } PbrtGpuStats;
 
 typedef struct PbrtGpuRay { float o[3], d[3], mint, maxt, time; } PbrtGpuRay;   /* core/geometry.h:338-362 */
@@ -244,10 +249,11 @@ void pbrtgpu_scene_destroy(PbrtGpuScene *scene);
  * core/api.cpp:1150-1209).  Copies a new descriptor into the device buffers of an existing handle
  * (reallocating only what grew); must not run concurrently with a render call on the same handle. */
 int  pbrtgpu_scene_update(PbrtGpuScene *scene, const PbrtGpuSceneDesc *desc);
-/* replaces: the PBRT_PROBES_COUNTERS build switch (core/probes.h:219-395).  on != 0
+/* replaces: the PBRT_PROBES_COUNTERS build switch (core/probes.h:219-395).  on == 1
  * makes the following render calls run the counting instantiation of the path
- * kernel and fill PbrtGpuStats.{closestRays,shadowRays,nodesVisited,primTests};
- * timed runs leave it off.                                                     */
+ * kernels and fill PbrtGpuStats.{closestRays,shadowRays,nodesVisited,primTests};
+ * on == 2 times every launch of the traversal kernel instead (rayKernelMs);
+ * timed runs leave it off (0).                                                 */
 int  pbrtgpu_set_stats(PbrtGpuScene *scene, int on);
 
 /* replaces: SamplerRenderer::Render (samplerrenderer.cpp:188-222) minus the

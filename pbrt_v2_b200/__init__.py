@@ -50,6 +50,7 @@ class Stats(C.Structure):
         ("closestRays", C.c_uint64), ("shadowRays", C.c_uint64),
         ("nodesVisited", C.c_uint64), ("primTests", C.c_uint64),
         ("kernelLaunches", C.c_uint64),
+        ("rayKernelMs", C.c_double), ("rayKernelLaunches", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -908,6 +908,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
 }
 
 // persistent ray queue consumer
+#define TRACE_CHUNK 64
 template <bool STATS, bool ANIM>
 __global__ void __launch_bounds__(128) k_trace(WfArgs a) {
     const DScene &sc = a.sc;
@@ -928,16 +929,24 @@ __global__ void __launch_bounds__(128) k_trace(WfArgs a) {
     TraceStats st;
     st.nodes = st.prims = 0;
     unsigned long long nClosest = 0, nShadow = 0;
+    // Rays are handed out in chunks: a warp reserves TRACE_CHUNK queue entries with ONE atomic on the shared cursor
+    // and deals them to its lanes from registers (a per-refill atomic on one address was 40 % of this kernel's stall
+    // samples, profiles/r01_k_trace_*).  cPos/cEnd are warp-uniform.
+    unsigned cPos = 0, cEnd = 0;
+    bool exhausted = false;   // the cursor has passed the end of the queue
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, !active);
-        if (idle) {
-            unsigned base = 0;
-            const int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(a.counters + C_TRACE_CUR, (unsigned)__popc(idle));
-            base = __shfl_sync(FULL, base, leader);
+        if (idle && !(exhausted && cPos >= cEnd)) {
+            if (cPos >= cEnd) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(a.counters + C_TRACE_CUR, (unsigned)TRACE_CHUNK);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) { exhausted = true; cPos = cEnd = 0; }
+                else { cPos = base; cEnd = min(base + (unsigned)TRACE_CHUNK, n); }
+            }
             if (!active) {
-                const unsigned idx = base + __popc(idle & ((1u << lane) - 1u));
-                if (idx < n) {
+                const unsigned idx = cPos + __popc(idle & ((1u << lane) - 1u));
+                if (idx < cEnd) {
                     const bool any = idx >= n0 && idx < n1;
                     slot = idx < n0 ? qHit[idx] : (idx < n1 ? qShadow[idx - n0] : qMis[idx - n1]);
                     const float4 r0 = pool[(size_t)F_RAY_O * P + slot], r1 = pool[(size_t)F_RAY_D * P + slot];
@@ -950,16 +959,22 @@ __global__ void __launch_bounds__(128) k_trace(WfArgs a) {
                     active = true;
                 }
             }
+            cPos = min(cEnd, cPos + (unsigned)__popc(idle));
         }
-        if (!__any_sync(FULL, active)) break;
-        // walk until a good share of the warp has finished, then refill
+        const bool more = !(exhausted && cPos >= cEnd);   // could idle lanes still be given rays?
+        if (!__any_sync(FULL, active)) {
+            if (!more) break;
+            continue;
+        }
+        // walk until a good share of the warp has finished, then refill (nothing to refill with: walk on)
         for (int it = 0; it < 64; ++it) {
             if (active && TravStep<STATS, ANIM>(sc, t, &st)) {
                 pool[(size_t)F_HIT * P + slot] = make_float4(__int_as_float(t.found ? t.hit.prim : -1), t.hit.b1, t.hit.b2, t.hit.maxtIn);
                 pool[(size_t)F_RAY_D * P + slot].w = t.ray.maxt;
                 active = false;
             }
-            if (__popc(__ballot_sync(FULL, active)) < 24) break;
+            const int nActive = __popc(__ballot_sync(FULL, active));
+            if (nActive == 0 || (more && nActive < 24)) break;
         }
     }
     if (STATS) {
@@ -1141,7 +1156,7 @@ struct PbrtGpuScene {
     DevBuf<PbrtGpuHit> hits;
     DevBuf<uint8_t> occ;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // render start / end, the lanes' start gate
-    bool collectStats = false;
+    int collectStats = 0;   // 1: ray/node/primitive counters, 2: per-launch timing of the traversal kernel
     int nMeasuredMaterials = 0;
 };
 
@@ -1386,7 +1401,7 @@ int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
     CUDA_TRY(cudaGetDevice(&s->device));
     int rc = UploadScene(s.get(), desc);
     if (rc != PBRTGPU_OK) return rc;
-    s->collectStats = getenv("PBRTGPU_STATS") != nullptr;
+    s->collectStats = getenv("PBRTGPU_STATS") != nullptr ? 1 : 0;
     for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&s->ev[i]));
     *out = s.release();
     return PBRTGPU_OK;
@@ -1412,7 +1427,7 @@ void pbrtgpu_scene_destroy(PbrtGpuScene *scene) {
 // timed path runs the kernel instantiation without counters.
 int pbrtgpu_set_stats(PbrtGpuScene *scene, int on) {
     if (!scene) return Fail(PBRTGPU_EINVAL, "null scene");
-    scene->collectStats = on != 0;
+    scene->collectStats = on;
     return PBRTGPU_OK;
 }
 
@@ -1433,12 +1448,12 @@ struct LaneJob {
     RenderParams rp;
     int spp;
     PbrtGpuPixel *film;
-    bool timing, wantCounters;
+    bool timing, wantCounters, timeRays;
     // results
     int rc = PBRTGPU_OK;
     std::string err;
-    float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f;
-    uint64_t launches = 0;
+    float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f, rayMs = 0.f;
+    uint64_t launches = 0, rayLaunches = 0;
 };
 
 int RunLane(LaneJob &job) {
@@ -1450,8 +1465,20 @@ int RunLane(LaneJob &job) {
     const int spp = job.spp;
     const RenderParams &rp = job.rp;
     PbrtGpuPixel *film = job.film;
-    const bool stats = job.timing, wantCounters = job.wantCounters;
+    const bool stats = job.timing, wantCounters = job.wantCounters, timeRays = job.timeRays;
     const size_t maxBatch = job.maxBatch;
+    std::vector<cudaEvent_t> rayEvents;   // timeRays: a pair of events around every k_trace launch of a round
+    size_t rayEventsUsed = 0;
+    float rayMs = 0.f;
+    uint64_t rayLaunches = 0;
+    auto rayEvent = [&]() -> cudaEvent_t {
+        if (rayEventsUsed == rayEvents.size()) {
+            cudaEvent_t e = nullptr;
+            cudaEventCreate(&e);
+            rayEvents.push_back(e);
+        }
+        return rayEvents[rayEventsUsed++];
+    };
     CUDA_TRY(cudaStreamWaitEvent(stream, scene->ev[2], 0));   // the film has been cleared
     CUDA_TRY(ln->tasks.Ensure(maxBatch));
     CUDA_TRY(ln->perm.Ensure(maxBatch * spp * PERM_STRIDE));
@@ -1555,6 +1582,7 @@ int RunLane(LaneJob &job) {
                         else k_logic<1, false, false><<<lblocks, 128, 0, stream>>>(wa);
                     }
                     if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
+                    if (timeRays) CUDA_TRY(cudaEventRecord(rayEvent(), stream));
                     if (scene->d.nAnimated) {
                         if (wantCounters) k_trace<true, true><<<tblocks, 128, 0, stream>>>(wa);
                         else k_trace<false, true><<<tblocks, 128, 0, stream>>>(wa);
@@ -1562,6 +1590,7 @@ int RunLane(LaneJob &job) {
                         if (wantCounters) k_trace<true, false><<<tblocks, 128, 0, stream>>>(wa);
                         else k_trace<false, false><<<tblocks, 128, 0, stream>>>(wa);
                     }
+                    if (timeRays) CUDA_TRY(cudaEventRecord(rayEvent(), stream));
                     launches += hasMeasured ? 3 : 2;
                     if ((iter & 7) == 7) {
                         CUDA_TRY(cudaMemcpyAsync(ln->hostCounters, ln->counters.p, C_COUNT * sizeof(unsigned),
@@ -1650,11 +1679,19 @@ int RunLane(LaneJob &job) {
                 traceMs += ms;
                 CUDA_TRY(cudaEventElapsedTime(&ms, ln->ev[2], ln->ev[3]));
                 tailMs += ms;
+                for (size_t k = 0; k + 1 < rayEventsUsed; k += 2) {
+                    CUDA_TRY(cudaEventElapsedTime(&ms, rayEvents[k], rayEvents[k + 1]));
+                    rayMs += ms;
+                    ++rayLaunches;
+                }
+                rayEventsUsed = 0;
             }
         }
     }
     CUDA_TRY(cudaStreamSynchronize(stream));
     job.tableMs = tableMs; job.traceMs = traceMs; job.tailMs = tailMs; job.launches = launches;
+    job.rayMs = rayMs; job.rayLaunches = rayLaunches;
+    for (cudaEvent_t e : rayEvents) cudaEventDestroy(e);
     return PBRTGPU_OK;
 }
 
@@ -1705,6 +1742,8 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     // per task: permutation tables (64 B/sample) + finished radiance (16 B/sample) + parked
     // bounce-3 vertices (64 B/sample, sparse) + scrambles + two MT19937 blocks
     const size_t perTask = (size_t)spp * (PERM_STRIDE * 2 + 16 + 64) + SCR_STRIDE * 4 + 2 * MT_N * 4 + 4 + sizeof(TaskRec);
+    const bool wantCounters = stats && scene->collectStats == 1;
+    const bool timeRays = stats && scene->collectStats == 2;
     size_t poolSlots = (size_t)1 << 22;
     { const char *e = getenv("PBRTGPU_POOL"); if (e && atol(e) > 0) poolSlots = (size_t)atol(e); }
     // lanes: as many as keep every lane's wavefront pool full (measured on bunny/C2: 1 lane 210, 2 lanes 227,
@@ -1715,6 +1754,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     if (!getenv("PBRTGPU_LANES"))
         while (nLanes > 1 && tasks.size() / nLanes * (size_t)spp < poolSlots) --nLanes;
     while (nLanes > 1 && tasks.size() < (size_t)nLanes * 1024) --nLanes;   // too little work to split further
+    if (timeRays) nLanes = 1;   // the timed kernel must have the device to itself
     size_t maxBatch = std::max<size_t>(1024, ScratchBudgetBytes() / (size_t)nLanes / perTask);
     maxBatch = std::min(maxBatch, poolSlots);   // the tail wavefront keeps one pool slot per task of the batch
     {   // a whole number of batches per lane, all of (nearly) the same size
@@ -1723,7 +1763,6 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
         maxBatch = (std::max<size_t>(tasks.size(), 1) + nBatches - 1) / nBatches;
     }
     CUDA_TRY(scene->stats.Ensure(1));
-    const bool wantCounters = stats && scene->collectStats;
     if (wantCounters) CUDA_TRY(cudaMemsetAsync(scene->stats.p, 0, sizeof(DeviceStats), stream));
     CUDA_TRY(cudaEventRecord(scene->ev[2], stream));
     std::vector<LaneJob> jobs(nLanes);
@@ -1735,7 +1774,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
             if (!ln.ev[i]) CUDA_TRY(cudaEventCreate(&ln.ev[i]));
         LaneJob &j = jobs[l];
         j.scene = scene; j.ln = &ln; j.tasks = &tasks; j.maxBatch = maxBatch; j.laneIndex = l; j.nLanes = nLanes;
-        j.rp = rp; j.spp = spp; j.film = film; j.timing = stats != nullptr; j.wantCounters = wantCounters;
+        j.rp = rp; j.spp = spp; j.film = film; j.timing = stats != nullptr; j.wantCounters = wantCounters; j.timeRays = timeRays;
     }
     {
         auto run = [](LaneJob *j) {
@@ -1747,11 +1786,12 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
         run(&jobs[0]);
         for (std::thread &w : workers) w.join();
     }
-    uint64_t launches = 0;
-    float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f;
+    uint64_t launches = 0, rayLaunches = 0;
+    float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f, rayMs = 0.f;
     for (const LaneJob &j : jobs) {
         if (j.rc != PBRTGPU_OK) return Fail(j.rc, j.err);
         launches += j.launches;
+        rayMs += j.rayMs; rayLaunches += j.rayLaunches;
         tableMs += j.tableMs; traceMs += j.traceMs; tailMs += j.tailMs;   // lanes overlap: the sum can exceed renderMs
     }
     if (stats) {
@@ -1766,6 +1806,8 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
         stats->tailMs = tailMs;
         stats->cameraSamples = totalPixels * (uint64_t)spp;
         stats->kernelLaunches = launches;
+        stats->rayKernelMs = rayMs;
+        stats->rayKernelLaunches = rayLaunches;
         if (wantCounters) {
             DeviceStats ds;
             CUDA_TRY(cudaMemcpy(&ds, scene->stats.p, sizeof(ds), cudaMemcpyDeviceToHost));
