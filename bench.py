@@ -393,7 +393,7 @@ def main():
             # per-lane event times summed over the concurrent lanes (they overlap: the sum exceeds ms_per_step)
             "kernel_ms": {"k_path_phase1": path_ms / args.steps, "k_path_phase2": tail_ms / args.steps,
                           "k_tables": table_ms / args.steps},
-            "lanes": env_int("PBRTGPU_LANES", 4),
+            "lanes": env_int("PBRTGPU_LANES", 2),
         }
         if spp != WORKLOADS[args.workload][3]:
             line["INVALID"] = "spp overridden to %d (development run)" % spp

@@ -147,6 +147,7 @@ typedef struct PbrtGpuLight {
     uint32_t firstShape;  /* AREA: ShapeSet::shapes, into lightShapes[]         */
     uint32_t nShapes;     /* in scope: exactly 1 (sphere or disk)               */
     float    sumArea;     /* ShapeSet::sumArea                                  */
+    int32_t  nSamples;    /* Light::nSamples (core/light.h:53,78; "nsamples" of an area light); 0 reads as 1 */
 } PbrtGpuLight;
 typedef struct PbrtGpuLightShape {
     uint32_t type;        /* PBRTGPU_PRIM_SPHERE | PBRTGPU_PRIM_DISK            */
@@ -175,6 +176,11 @@ typedef struct PbrtGpuSceneDesc {
 } PbrtGpuSceneDesc;
 
 /* ---- one Render() call ----------------------------------------------------- */
+enum { PBRTGPU_INTEGRATOR_PATH = 0,            /* PathIntegrator, integrators/path.cpp            */
+       PBRTGPU_INTEGRATOR_DIRECTLIGHTING = 1   /* DirectLightingIntegrator, integrators/directlighting.cpp */ };
+enum { PBRTGPU_STRATEGY_ALL = 0, PBRTGPU_STRATEGY_ONE = 1 };   /* LightStrategy, directlighting.h:44 */
+#define PBRTGPU_MAX_SAMPLE_ARRAYS 32
+
 typedef struct PbrtGpuRenderDesc {
     /* PerspectiveCamera (cameras/perspective.cpp:41-49, core/camera.cpp:83-102) */
     float rasterToCamera[16];   /* RasterToCamera.m                             */
@@ -187,8 +193,19 @@ typedef struct PbrtGpuRenderDesc {
     float   filterXWidth, filterYWidth;   /* box filter only (filters/box.cpp)  */
     /* LDSampler (samplers/lowdiscrepancy.cpp:40-51): power of two              */
     int32_t samplesPerPixel;
-    /* PathIntegrator (integrators/path.cpp:125-128)                            */
+    /* PathIntegrator (integrators/path.cpp:125-128) / DirectLightingIntegrator
+     * (directlighting.cpp:120-133)                                              */
     int32_t maxDepth;
+    int32_t integrator;         /* PBRTGPU_INTEGRATOR_*                          */
+    int32_t lightStrategy;      /* DIRECTLIGHTING: PBRTGPU_STRATEGY_*            */
+    /* Sample::n1D / n2D (core/sampler.h:93-116) as the integrators' RequestSamples
+     * calls built them (surface integrator first, then EmissionIntegrator's two
+     * 1-D requests, samplerrenderer.cpp Sample ctor): how many values every
+     * pixel sample carries in each requested array.  They fix the LD tables'
+     * draw order (montecarlo.cpp:200-252).  PATH: 14 x {1}, 9 x {1}.             */
+    int32_t n1D, n2D;
+    uint16_t size1D[PBRTGPU_MAX_SAMPLE_ARRAYS];
+    uint16_t size2D[PBRTGPU_MAX_SAMPLE_ARRAYS];
     /* SamplerRenderer::Render task decomposition (samplerrenderer.cpp:203-205):
      * nTasks is a reference INPUT (it fixes which RNG stream feeds which
      * pixel); tasks [taskBegin, taskEnd) are rendered by this call, which is
@@ -274,9 +291,10 @@ int  pbrtgpu_intersect(PbrtGpuScene *scene, const PbrtGpuRay *rays, int n,
 int  pbrtgpu_intersect_p(PbrtGpuScene *scene, const PbrtGpuRay *rays, int n,
                          uint8_t *occluded);
 /* replaces: LDSampler::GetMoreSamples / LDPixelSample (montecarlo.cpp:200-252)
- * for the FIRST pixel of task `taskNum` (test hook).  out = spp rows of 37
- * floats: imageX,imageY,lensU,lensV,time, 14 1-D values, 9 2-D pairs (in
- * Sample::oneD / twoD order).                                                  */
+ * for the FIRST pixel of task `taskNum` (test hook).  out = spp rows of
+ * 5 + sum(size1D) + 2*sum(size2D) floats: imageX,imageY,lensU,lensV,time, the 1-D
+ * arrays' values, the 2-D arrays' pairs (Sample::oneD / twoD order) -- 37 floats
+ * for the path integrator's layout.                                            */
 int  pbrtgpu_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out);
 
 #ifdef __cplusplus

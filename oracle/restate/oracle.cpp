@@ -103,43 +103,66 @@ void LDShuffleScrambled2D(int nSamples, int nPixel, float *samples, RNG &rng) {
     Shuffle(samples, nPixel, 2 * nSamples, rng);
 }
 
-// struct Sample for PathIntegrator + EmissionIntegrator requests:
-//   1-D (core/sampler.h Add1D order; path.cpp:43-48, light.cpp:64-68,
-//   reflection.cpp:502-506, emission.cpp:41-42):
-//      per depth d<3: [4d+0] light.component [4d+1] lightNum [4d+2] bsdf.component [4d+3] path.component
-//      [12] emission tau  [13] emission scatter
-//   2-D: per depth d<3: [3d+0] light.pos [3d+1] bsdf.dir [3d+2] path.dir
-enum { N1D = 14, N2D = 9, SAMPLE_FLOATS = 5 + N1D + 2 * N2D };
+// struct Sample (core/sampler.h:93-116) with the integrators' requested arrays.  PathIntegrator +
+// EmissionIntegrator (path.cpp:43-48, light.cpp:64-68, reflection.cpp:502-506, emission.cpp:41-42):
+//   1-D per depth d<3: [4d+0] light.component [4d+1] lightNum [4d+2] bsdf.component [4d+3] path.component
+//       [12] emission tau  [13] emission scatter          2-D per depth d<3: [3d+0] light.pos [3d+1] bsdf.dir [3d+2] path.dir
+// DirectLightingIntegrator (directlighting.cpp:53-78), strategy "all", light i with n_i = RoundSize(nSamples):
+//   1-D [2i] light.component x n_i  [2i+1] bsdf.component x n_i, then tau, scatter;  2-D [2i] light.pos x n_i  [2i+1] bsdf.dir x n_i
+// strategy "one": 1-D [0] light.component [1] lightNum [2] bsdf.component, tau, scatter;  2-D [0] light.pos [1] bsdf.dir
+enum { MAX_ARRAYS = PBRTGPU_MAX_SAMPLE_ARRAYS };
+struct SampleLayout {
+    int n1D, n2D;
+    uint32_t size1D[MAX_ARRAYS], size2D[MAX_ARRAYS];
+    void FromDesc(const PbrtGpuRenderDesc *rd) {
+        n1D = rd->n1D; n2D = rd->n2D;
+        for (int i = 0; i < n1D; ++i) size1D[i] = rd->size1D[i];
+        for (int i = 0; i < n2D; ++i) size2D[i] = rd->size2D[i];
+    }
+    size_t Floats() const {   // per pixel sample, camera part included
+        size_t n = 5;
+        for (int i = 0; i < n1D; ++i) n += size1D[i];
+        for (int i = 0; i < n2D; ++i) n += 2 * size2D[i];
+        return n;
+    }
+};
 struct Sample {
     float imageX, imageY, lensU, lensV, time;
-    float oneD[N1D];
-    float twoD[N2D][2];
+    float *oneD[MAX_ARRAYS];
+    float *twoD[MAX_ARRAYS];
 };
 
-// LDPixelSample, core/montecarlo.cpp:200-252 (all n1D[i] == n2D[i] == 1 here)
-void LDPixelSample(int xPos, int yPos, float shutterOpen, float shutterClose, int nPixelSamples,
-                   Sample *samples, float *buf, RNG &rng) {
+// LDPixelSample, core/montecarlo.cpp:200-252.  `store`: Floats()-5 floats per pixel sample behind oneD/twoD.
+void LDPixelSample(const SampleLayout &lay, int xPos, int yPos, float shutterOpen, float shutterClose, int nPixelSamples,
+                   Sample *samples, float *store, float *buf, RNG &rng) {
     float *imageSamples = buf; buf += 2 * nPixelSamples;
     float *lensSamples = buf;  buf += 2 * nPixelSamples;
     float *timeSamples = buf;  buf += nPixelSamples;
-    float *oneDSamples[N1D], *twoDSamples[N2D];
-    for (int i = 0; i < N1D; ++i) { oneDSamples[i] = buf; buf += nPixelSamples; }
-    for (int i = 0; i < N2D; ++i) { twoDSamples[i] = buf; buf += 2 * nPixelSamples; }
+    float *oneDSamples[MAX_ARRAYS], *twoDSamples[MAX_ARRAYS];
+    for (int i = 0; i < lay.n1D; ++i) { oneDSamples[i] = buf; buf += lay.size1D[i] * nPixelSamples; }
+    for (int i = 0; i < lay.n2D; ++i) { twoDSamples[i] = buf; buf += 2 * lay.size2D[i] * nPixelSamples; }
     LDShuffleScrambled2D(1, nPixelSamples, imageSamples, rng);
     LDShuffleScrambled2D(1, nPixelSamples, lensSamples, rng);
     LDShuffleScrambled1D(1, nPixelSamples, timeSamples, rng);
-    for (int i = 0; i < N1D; ++i) LDShuffleScrambled1D(1, nPixelSamples, oneDSamples[i], rng);
-    for (int i = 0; i < N2D; ++i) LDShuffleScrambled2D(1, nPixelSamples, twoDSamples[i], rng);
+    for (int i = 0; i < lay.n1D; ++i) LDShuffleScrambled1D(lay.size1D[i], nPixelSamples, oneDSamples[i], rng);
+    for (int i = 0; i < lay.n2D; ++i) LDShuffleScrambled2D(lay.size2D[i], nPixelSamples, twoDSamples[i], rng);
+    const size_t per = lay.Floats() - 5;
     for (int i = 0; i < nPixelSamples; ++i) {
         samples[i].imageX = xPos + imageSamples[2 * i];
         samples[i].imageY = yPos + imageSamples[2 * i + 1];
         samples[i].time = Lerp(timeSamples[i], shutterOpen, shutterClose);
         samples[i].lensU = lensSamples[2 * i];
         samples[i].lensV = lensSamples[2 * i + 1];
-        for (int j = 0; j < N1D; ++j) samples[i].oneD[j] = oneDSamples[j][i];
-        for (int j = 0; j < N2D; ++j) {
-            samples[i].twoD[j][0] = twoDSamples[j][2 * i];
-            samples[i].twoD[j][1] = twoDSamples[j][2 * i + 1];
+        float *mem = store + per * i;
+        for (int j = 0; j < lay.n1D; ++j) {
+            samples[i].oneD[j] = mem;
+            int startSamp = lay.size1D[j] * i;
+            for (uint32_t k = 0; k < lay.size1D[j]; ++k) *mem++ = oneDSamples[j][startSamp + k];
+        }
+        for (int j = 0; j < lay.n2D; ++j) {
+            samples[i].twoD[j] = mem;
+            int startSamp = 2 * lay.size2D[j] * i;
+            for (uint32_t k = 0; k < 2 * lay.size2D[j]; ++k) *mem++ = twoDSamples[j][startSamp + k];
         }
     }
 }
@@ -1127,24 +1150,26 @@ struct Renderer {
         return Ld;
     }
 
-    // UniformSampleOneLight, core/integrator.cpp:82-114
+    // UniformSampleOneLight, core/integrator.cpp:82-114.  Table slots (indices into Sample::oneD / twoD, element 0)
+    // or -1 for all of them: LightSample(rng) / BSDFSample(rng) and rng.RandomFloat() for the light number
+    struct OneLightSlots { int lightNum, lightComp, lightPos, bsdfComp, bsdfDir; };
     Spec UniformSampleOneLight(const Vec &p, const Vec &n, const Vec &wo, float rayEpsilon, float time, const BSDF &bsdf,
-                               const Sample *sample, RNG &rng, int depthSlot, Counters *cnt) const {
+                               const Sample *sample, RNG &rng, const OneLightSlots *slots, Counters *cnt) const {
         int nLights = int(sv.d->nLights);
         if (nLights == 0) return Spec(0.);
         int lightNum;
-        if (depthSlot >= 0) lightNum = Floor2Int(sample->oneD[4 * depthSlot + 1] * nLights);
+        if (slots) lightNum = Floor2Int(sample->oneD[slots->lightNum][0] * nLights);
         else lightNum = Floor2Int(rng.RandomFloat() * nLights);
         lightNum = std::min(lightNum, nLights - 1);
         LightSample lightSample;
         BSDFSample bsdfSample;
-        if (depthSlot >= 0) {
-            lightSample.uPos[0] = sample->twoD[3 * depthSlot + 0][0];
-            lightSample.uPos[1] = sample->twoD[3 * depthSlot + 0][1];
-            lightSample.uComponent = sample->oneD[4 * depthSlot + 0];
-            bsdfSample.uDir[0] = sample->twoD[3 * depthSlot + 1][0];
-            bsdfSample.uDir[1] = sample->twoD[3 * depthSlot + 1][1];
-            bsdfSample.uComponent = sample->oneD[4 * depthSlot + 2];
+        if (slots) {
+            lightSample.uPos[0] = sample->twoD[slots->lightPos][0];
+            lightSample.uPos[1] = sample->twoD[slots->lightPos][1];
+            lightSample.uComponent = sample->oneD[slots->lightComp][0];
+            bsdfSample.uDir[0] = sample->twoD[slots->bsdfDir][0];
+            bsdfSample.uDir[1] = sample->twoD[slots->bsdfDir][1];
+            bsdfSample.uComponent = sample->oneD[slots->bsdfComp][0];
         } else {
             lightSample.uPos[0] = rng.RandomFloat();   // LightSample(RNG&), light.h:117-121
             lightSample.uPos[1] = rng.RandomFloat();
@@ -1155,6 +1180,56 @@ struct Renderer {
         }
         return (float)nLights * EstimateDirect(lightNum, p, n, wo, rayEpsilon, time, bsdf, lightSample, bsdfSample,
                                                BSDF_ALL & ~BSDF_SPECULAR, cnt);
+    }
+
+    // UniformSampleAllLights, core/integrator.cpp:47-79 (with sample offsets: directlighting "all")
+    Spec UniformSampleAllLights(const Vec &p, const Vec &n, const Vec &wo, float rayEpsilon, float time, const BSDF &bsdf,
+                                const Sample *sample, Counters *cnt) const {
+        Spec L(0.);
+        for (uint32_t i = 0; i < sv.d->nLights; ++i) {
+            int nSamples = (int)rd->size1D[2 * i];   // lightSampleOffsets[i].nSamples
+            Spec Ld(0.);
+            for (int j = 0; j < nSamples; ++j) {
+                LightSample lightSample;
+                BSDFSample bsdfSample;
+                lightSample.uPos[0] = sample->twoD[2 * i][2 * j];
+                lightSample.uPos[1] = sample->twoD[2 * i][2 * j + 1];
+                lightSample.uComponent = sample->oneD[2 * i][j];
+                bsdfSample.uDir[0] = sample->twoD[2 * i + 1][2 * j];
+                bsdfSample.uDir[1] = sample->twoD[2 * i + 1][2 * j + 1];
+                bsdfSample.uComponent = sample->oneD[2 * i + 1][j];
+                Ld += EstimateDirect((int)i, p, n, wo, rayEpsilon, time, bsdf, lightSample, bsdfSample,
+                                     BSDF_ALL & ~BSDF_SPECULAR, cnt);
+            }
+            L += Ld / (float)nSamples;   // Spectrum / float with an int argument, spectrum.h:170
+        }
+        return L;
+    }
+
+    // DirectLightingIntegrator::Li, integrators/directlighting.cpp:81-117 (ray.depth == 0: camera rays only, since
+    // no in-scope material has a specular component to spawn SpecularReflect / SpecularTransmit rays)
+    Spec DirectLi(const Ray &ray, const Intersection &isect, const Sample *sample, RNG &rng, Counters *cnt) const {
+        Spec L(0.f);
+        BSDF bsdf;
+        GetBSDF(isect, &bsdf, cnt);
+        Vec wo = -ray.d;
+        const Vec &p = bsdf.p;
+        const Vec &n = bsdf.nn;
+        L += Le(isect, wo);
+        if (sv.d->nLights > 0) {
+            if (rd->lightStrategy == PBRTGPU_STRATEGY_ALL)
+                L += UniformSampleAllLights(p, n, wo, isect.rayEpsilon, ray.time, bsdf, sample, cnt);
+            else {
+                const OneLightSlots slots = {1, 0, 0, 2, 1};
+                L += UniformSampleOneLight(p, n, wo, isect.rayEpsilon, ray.time, bsdf, sample, rng, &slots, cnt);
+            }
+        }
+        if (0 + 1 < rd->maxDepth) {
+            // SpecularReflect / SpecularTransmit (integrator.cpp:177-258): each builds BSDFSample(rng) -- three draws --
+            // before BSDF::Sample_f finds no BSDF_SPECULAR component and returns black with pdf 0
+            for (int k = 0; k < 6; ++k) rng.RandomFloat();
+        }
+        return L;
     }
 
     // PathIntegrator::Li, integrators/path.cpp:52-123
@@ -1172,15 +1247,16 @@ struct Renderer {
             const Vec &p = bsdf.p;
             const Vec &n = bsdf.nn;
             Vec wo = -ray.d;
-            if (bounces < SAMPLE_DEPTH)
-                L += pathThroughput * UniformSampleOneLight(p, n, wo, isectp->rayEpsilon, ray.time, bsdf, sample, rng, bounces, cnt);
-            else
-                L += pathThroughput * UniformSampleOneLight(p, n, wo, isectp->rayEpsilon, ray.time, bsdf, sample, rng, -1, cnt);
+            if (bounces < SAMPLE_DEPTH) {
+                const OneLightSlots slots = {4 * bounces + 1, 4 * bounces + 0, 3 * bounces + 0, 4 * bounces + 2, 3 * bounces + 1};
+                L += pathThroughput * UniformSampleOneLight(p, n, wo, isectp->rayEpsilon, ray.time, bsdf, sample, rng, &slots, cnt);
+            } else
+                L += pathThroughput * UniformSampleOneLight(p, n, wo, isectp->rayEpsilon, ray.time, bsdf, sample, rng, nullptr, cnt);
             BSDFSample outgoingBSDFSample;
             if (bounces < SAMPLE_DEPTH) {
                 outgoingBSDFSample.uDir[0] = sample->twoD[3 * bounces + 2][0];
                 outgoingBSDFSample.uDir[1] = sample->twoD[3 * bounces + 2][1];
-                outgoingBSDFSample.uComponent = sample->oneD[4 * bounces + 3];
+                outgoingBSDFSample.uComponent = sample->oneD[4 * bounces + 3][0];
             } else {
                 outgoingBSDFSample.uDir[0] = rng.RandomFloat();
                 outgoingBSDFSample.uDir[1] = rng.RandomFloat();
@@ -1241,19 +1317,23 @@ struct Renderer {
         if (x0 == x1 || y0 == y1) return;   // GetSubSampler returns NULL, lowdiscrepancy.cpp:62
         RNG rng((uint32_t)taskNum);
         const int spp = rd->samplesPerPixel;
+        SampleLayout lay;
+        lay.FromDesc(rd);
         std::vector<Sample> samples(spp);
-        std::vector<float> buf((size_t)SAMPLE_FLOATS * spp);
+        std::vector<float> buf(lay.Floats() * spp), store(lay.Floats() * spp);
         std::vector<Spec> Ls(spp);
+        const bool direct = rd->integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
         for (int yPos = y0; yPos < y1; ++yPos)
             for (int xPos = x0; xPos < x1; ++xPos) {
-                LDPixelSample(xPos, yPos, rd->shutterOpen, rd->shutterClose, spp, samples.data(), buf.data(), rng);
+                LDPixelSample(lay, xPos, yPos, rd->shutterOpen, rd->shutterClose, spp, samples.data(), store.data(), buf.data(), rng);
                 for (int i = 0; i < spp; ++i) {
                     Ray ray;
                     GenerateRay(samples[i], &ray);
                     // SamplerRenderer::Li, samplerrenderer.cpp:225-247 (volume integrator: T=1, Lvi=0)
                     Intersection isect;
                     Spec Li(0.f);
-                    if (sv.Intersect(ray, &isect, cnt)) Li = PathLi(ray, isect, &samples[i], rng, cnt);
+                    if (sv.Intersect(ray, &isect, cnt))
+                        Li = direct ? DirectLi(ray, isect, &samples[i], rng, cnt) : PathLi(ray, isect, &samples[i], rng, cnt);
                     Ls[i] = 1.f * (Spec(1.f) * Li + Spec(0.f));
                     if (Ls[i].HasNaNs()) Ls[i] = Spec(0.f);
                     else if (Ls[i].y() < -1e-5) Ls[i] = Spec(0.f);
@@ -1358,15 +1438,21 @@ int oracle_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
     if (x0 == x1 || y0 == y1) return 1;
     RNG rng((uint32_t)taskNum);
     const int spp = rd->samplesPerPixel;
+    SampleLayout lay;
+    lay.FromDesc(rd);
+    const size_t nf = lay.Floats();
     std::vector<Sample> samples(spp);
-    std::vector<float> buf((size_t)SAMPLE_FLOATS * spp);
-    LDPixelSample(x0, y0, rd->shutterOpen, rd->shutterClose, spp, samples.data(), buf.data(), rng);
+    std::vector<float> buf(nf * spp), store(nf * spp);
+    LDPixelSample(lay, x0, y0, rd->shutterOpen, rd->shutterClose, spp, samples.data(), store.data(), buf.data(), rng);
     for (int i = 0; i < spp; ++i) {
-        float *o = out + (size_t)SAMPLE_FLOATS * i;
+        float *o = out + nf * i;
         o[0] = samples[i].imageX; o[1] = samples[i].imageY; o[2] = samples[i].lensU; o[3] = samples[i].lensV;
         o[4] = samples[i].time;
-        for (int j = 0; j < N1D; ++j) o[5 + j] = samples[i].oneD[j];
-        for (int j = 0; j < N2D; ++j) { o[5 + N1D + 2 * j] = samples[i].twoD[j][0]; o[5 + N1D + 2 * j + 1] = samples[i].twoD[j][1]; }
+        o += 5;
+        for (int j = 0; j < lay.n1D; ++j)
+            for (uint32_t k = 0; k < lay.size1D[j]; ++k) *o++ = samples[i].oneD[j][k];
+        for (int j = 0; j < lay.n2D; ++j)
+            for (uint32_t k = 0; k < 2 * lay.size2D[j]; ++k) *o++ = samples[i].twoD[j][k];
     }
     return 0;
 }

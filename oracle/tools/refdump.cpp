@@ -7,6 +7,10 @@
 //   refdump ld   <x0> <x1> <y0> <y1> <spp> <xres> <yres> <nTasks> <taskNum> <shutterOpen> <shutterClose>
 //        first pixel of sub-sampler `taskNum`: spp rows of 37 floats
 //        (imageX imageY lensU lensV time, 14 one-D, 9 two-D pairs) + the RNG draw that follows
+//   refdump ldx  <the same 11 arguments> <n1D> <size>... <n2D> <size>...
+//        the same for an arbitrary Sample layout (e.g. DirectLightingIntegrator's per-light arrays): the requests are
+//        made through the reference's own Sample::Add1D / Add2D from a stub SurfaceIntegrator; every array's values
+//        are printed in Sample::oneD / twoD order
 //   refdump rng  <seed> <n>        n RandomUInt() values of RNG(seed)
 #include "pbrt.h"
 #include "rng.h"
@@ -14,10 +18,27 @@
 #include "samplers/lowdiscrepancy.h"
 #include "integrators/path.h"
 #include "integrators/emission.h"
+#include "integrator.h"
+#include "intersection.h"
+
+#include <vector>
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+
+// a SurfaceIntegrator that only requests sample arrays (what DirectLightingIntegrator::RequestSamples does through
+// LightSampleOffsets / BSDFSampleOffsets, light.cpp:64-68, reflection.cpp:502-506)
+class LayoutIntegrator : public SurfaceIntegrator {
+public:
+    std::vector<int> n1, n2;
+    void RequestSamples(Sampler *, Sample *sample, const Scene *) {
+        for (size_t i = 0; i < n1.size(); ++i) sample->Add1D(n1[i]);
+        for (size_t i = 0; i < n2.size(); ++i) sample->Add2D(n2[i]);
+    }
+    Spectrum Li(const Scene *, const Renderer *, const RayDifferential &, const Intersection &, const Sample *, RNG &,
+                MemoryArena &) const { return Spectrum(0.f); }
+};
 
 int main(int argc, char **argv) {
     if (argc >= 4 && !strcmp(argv[1], "rng")) {
@@ -53,6 +74,37 @@ int main(int argc, char **argv) {
         printf("%u\n", rng.RandomUInt());
         return 0;
     }
-    fprintf(stderr, "usage: refdump ld ... | refdump rng seed n\n");
+    if (argc >= 15 && !strcmp(argv[1], "ldx")) {
+        int x0 = atoi(argv[2]), x1 = atoi(argv[3]), y0 = atoi(argv[4]), y1 = atoi(argv[5]);
+        int spp = atoi(argv[6]);
+        int nTasks = atoi(argv[9]), taskNum = atoi(argv[10]);
+        float so = (float)atof(argv[11]), sc = (float)atof(argv[12]);
+        LayoutIntegrator surf;
+        int a = 13;
+        int c1 = atoi(argv[a++]);
+        for (int i = 0; i < c1; ++i) surf.n1.push_back(atoi(argv[a++]));
+        int c2 = atoi(argv[a++]);
+        for (int i = 0; i < c2; ++i) surf.n2.push_back(atoi(argv[a++]));
+        LDSampler mainSampler(x0, x1, y0, y1, spp, so, sc);
+        Sample *origSample = new Sample(&mainSampler, &surf, NULL, NULL);
+        Sampler *sub = mainSampler.GetSubSampler(taskNum, nTasks);
+        if (!sub) { printf("EMPTY\n"); return 0; }
+        RNG rng(taskNum);
+        Sample *samples = origSample->Duplicate(sub->MaximumSampleCount());
+        int n = sub->GetMoreSamples(samples, rng);
+        printf("%d %d %d\n", n, (int)origSample->n1D.size(), (int)origSample->n2D.size());
+        for (int i = 0; i < n; ++i) {
+            printf("%.9g %.9g %.9g %.9g %.9g", samples[i].imageX, samples[i].imageY, samples[i].lensU,
+                   samples[i].lensV, samples[i].time);
+            for (size_t j = 0; j < samples[i].n1D.size(); ++j)
+                for (uint32_t k = 0; k < samples[i].n1D[j]; ++k) printf(" %.9g", samples[i].oneD[j][k]);
+            for (size_t j = 0; j < samples[i].n2D.size(); ++j)
+                for (uint32_t k = 0; k < 2 * samples[i].n2D[j]; ++k) printf(" %.9g", samples[i].twoD[j][k]);
+            printf("\n");
+        }
+        printf("%u\n", rng.RandomUInt());
+        return 0;
+    }
+    fprintf(stderr, "usage: refdump ld ... | refdump ldx ... | refdump rng seed n\n");
     return 1;
 }

@@ -37,6 +37,9 @@ class RenderDesc(C.Structure):
         ("filterXWidth", C.c_float), ("filterYWidth", C.c_float),
         ("samplesPerPixel", C.c_int32),
         ("maxDepth", C.c_int32),
+        ("integrator", C.c_int32), ("lightStrategy", C.c_int32),
+        ("n1D", C.c_int32), ("n2D", C.c_int32),
+        ("size1D", C.c_uint16 * 32), ("size2D", C.c_uint16 * 32),
         ("nTasks", C.c_int32),
         ("taskBegin", C.c_int32), ("taskEnd", C.c_int32),
         ("shardCount", C.c_int32), ("shardIndex", C.c_int32), ("shardBlock", C.c_int32),
@@ -61,7 +64,23 @@ PIXEL_DTYPE = np.dtype([("Lxyz", np.float32, 3), ("weightSum", np.float32)])
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("mint", np.float32), ("maxt", np.float32), ("time", np.float32)])
 HIT_DTYPE = np.dtype([("hit", np.int32), ("primitive", np.uint32), ("t", np.float32),
                       ("b1", np.float32), ("b2", np.float32), ("p", np.float32, 3), ("n", np.float32, 3)])
-SAMPLE_FLOATS = 37
+SAMPLE_FLOATS = 37   # path integrator layout
+
+
+def set_path_layout(rd):
+    """Sample::n1D / n2D of PathIntegrator + EmissionIntegrator (path.cpp:41-49, emission.cpp:40-43)"""
+    rd.integrator, rd.lightStrategy = 0, 0
+    rd.n1D, rd.n2D = 14, 9
+    for i in range(14):
+        rd.size1D[i] = 1
+    for i in range(9):
+        rd.size2D[i] = 1
+    return rd
+
+
+def sample_floats(rd):
+    """floats per camera sample of pbrtgpu_ld_samples / oracle_ld_samples for rd's Sample layout"""
+    return 5 + sum(rd.size1D[i] for i in range(rd.n1D)) + 2 * sum(rd.size2D[i] for i in range(rd.n2D))
 
 _gpu = None
 _host = None
@@ -280,7 +299,7 @@ class GpuScene(object):
 
 def ld_samples(rd, task_num):
     """LDPixelSample for the first pixel of `task_num` on the GPU -> (spp, 37) float32."""
-    out = np.zeros((rd.samplesPerPixel, SAMPLE_FLOATS), dtype=np.float32)
+    out = np.zeros((rd.samplesPerPixel, sample_floats(rd)), dtype=np.float32)
     _check(gpu_lib().pbrtgpu_ld_samples(C.byref(rd), int(task_num), out.ctypes.data), "pbrtgpu_ld_samples")
     return out
 

@@ -31,7 +31,35 @@ constexpr int N_ARRAYS = 26;      // 2 + 1 + 14 + 9
 constexpr int N_1D = 14, N_2D = 9;
 constexpr int N_SCRAMBLES = 37;   // 2+2+1 + 14 + 18
 constexpr int PERM_STRIDE = 32;   // u16 per sample row (26 used) = 64 bytes
-constexpr int SCR_STRIDE = 40;
+constexpr int SCR_STRIDE = 104;   // scramble words per task: 5 + n1D + 2*n2D <= 5 + 32 + 64
+
+// Sample::n1D / n2D (core/sampler.h:93-116) and where each requested array sits in a camera sample's table
+// row and in the task's scramble block.  Rows: [0] image [1] lens [2] time, then the 1-D arrays' entries,
+// then the 2-D arrays'; every entry is a u16 index into the array's (0,2)-sequence (value = VanDerCorput /
+// Sobol2 of that index with the array's scramble words).  For the path integrator's 14 + 9 single-value
+// arrays this is the fixed layout the specialised k_tables writes (row1D[j] = 3+j, row2D[j] = 17+j).
+constexpr int MAX_SAMPLE_ARRAYS = 32;
+constexpr int MAX_TABLE_ARRAYS = 3 + 2 * MAX_SAMPLE_ARRAYS;
+constexpr int MAX_ARRAY_SAMPLES = 64;   // values per pixel sample in one array (a light's RoundSize(nsamples))
+struct SampleLayoutDev {
+    int rowStride;   // u16 entries per row, a multiple of 8
+    int n1D, n2D;
+    uint16_t size1D[MAX_SAMPLE_ARRAYS], size2D[MAX_SAMPLE_ARRAYS];
+    uint16_t row1D[MAX_SAMPLE_ARRAYS], row2D[MAX_SAMPLE_ARRAYS];
+    uint16_t scr1D[MAX_SAMPLE_ARRAYS], scr2D[MAX_SAMPLE_ARRAYS];
+};
+// the same, array by array in LDPixelSample's draw order (montecarlo.cpp:228-236), for the general table kernel
+struct TableArrays {
+    int nArrays;
+    int rowStride;
+    int tgtPerSample;                       // bytes of shuffle-target scratch per camera sample
+    uint16_t n[MAX_TABLE_ARRAYS];           // values per pixel sample
+    uint16_t row[MAX_TABLE_ARRAYS];         // first row entry
+    uint16_t scr[MAX_TABLE_ARRAYS];         // first scramble word
+    uint16_t tgtInner[MAX_TABLE_ARRAYS];    // per-sample byte offset of the in-block shuffle targets (u8 each, n > 1 only)
+    uint16_t tgtBlock[MAX_TABLE_ARRAYS];    // ... of the block shuffle targets (one u16)
+    uint8_t dims[MAX_TABLE_ARRAYS];         // 1 or 2 scramble words
+};
 
 DEV uint32_t Temper(uint32_t y) {   // rng.cpp:101-105
     y ^= (y >> 11);

@@ -44,6 +44,8 @@ struct RenderParams {
     float filterXWidth, filterYWidth;
     int xPixelStart, yPixelStart, xPixelCount, yPixelCount;
     int spp, maxDepth;
+    int integrator, lightStrategy;   // PBRTGPU_INTEGRATOR_*, PBRTGPU_STRATEGY_*
+    SampleLayoutDev lay;
 };
 
 struct BatchArgs {
@@ -192,23 +194,169 @@ __global__ void __launch_bounds__(32 * WPB) k_tables(BatchArgs a, int spp, int G
 }
 
 // expand one task's tables into the reference's Sample layout (test hook)
-__global__ void k_expand_samples(BatchArgs a, int spp, float shutterOpen, float shutterClose, float *out) {
+// ------------------------------------------------------------- k_tables_general
+// LDPixelSample for any Sample layout (arrays with more than one value per pixel sample: the light / BSDF
+// sample arrays DirectLightingIntegrator requests, directlighting.cpp:53-78).  Per array (montecarlo.h:300-325):
+// scramble word(s); for every pixel sample a Fisher-Yates shuffle of its n values (n draws each: skipped when
+// n == 1); one Fisher-Yates shuffle of the nPixelSamples blocks.  Stage 1 walks the draw stream and turns every
+// draw into its swap target (elementwise, so MT19937 block boundaries need no care); stage 2 runs the block
+// shuffles one array per lane (shared memory) and the in-block shuffles one block per lane (registers);
+// stage 3 writes, for camera sample s and value k, the original sequence index  b*n + inner_b[k]  (b = block
+// that ended up at position s).
+template <int WPB>
+__global__ void __launch_bounds__(32 * WPB) k_tables_general(BatchArgs a, int spp, int G, TableArrays L, uint8_t *tgtAll) {
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = spp + 2;
+    const size_t warpWords = MT_N + ((size_t)G * stride + 1) / 2;
+    uint32_t *mt = smem + warp * warpWords;
+    uint16_t *P = reinterpret_cast<uint16_t *>(mt + MT_N);
+    const int bi = blockIdx.x * WPB + warp;
+    if (bi >= a.nBatch) return;
+    const TaskRec tr = a.tasks[bi];
+    const int npx = (tr.x1 - tr.x0) * (tr.y1 - tr.y0);
+    if (a.round >= npx) return;
+
+    uint32_t *cur = a.rngCur + (size_t)bi * MT_N, *next = a.rngNext + (size_t)bi * MT_N;
+    int mti;
+    if (a.round == 0) {
+        if (lane == 0) SeedMT(mt, (uint32_t)tr.taskNum);
+        mti = MT_N;
+    } else {
+        mti = a.mti[bi];
+        const uint32_t *src = cur;
+        if (mti >= MT_N) { src = next; mti -= MT_N; }
+        for (int j = lane; j < MT_N; j += 32) mt[j] = __ldcg(src + j);
+    }
+    __syncwarp();
+
+    uint16_t *permOut = a.perm + (size_t)bi * spp * L.rowStride;
+    uint32_t *scrOut = a.scr + (size_t)bi * SCR_STRIDE;
+    uint8_t *tgt = tgtAll + (size_t)bi * spp * L.tgtPerSample;
+
+    // ---- stage 1: walk the draw stream
+    for (int arr = 0; arr < L.nArrays; ++arr) {
+        const int n = L.n[arr];
+        for (int k = 0; k < L.dims[arr]; ++k) {
+            if (mti >= MT_N) { WarpRegenMT(mt, lane); mti = 0; }
+            if (lane == 0) scrOut[L.scr[arr] + k] = Temper(mt[mti]);
+            ++mti;
+        }
+        if (n == 1) {   // Shuffle(samples + i, 1, dims, rng): `RandomUInt() % 1`, no effect
+            for (int left = spp; left > 0;) {
+                if (mti >= MT_N) { WarpRegenMT(mt, lane); mti = 0; }
+                const int take = min(left, MT_N - mti);
+                mti += take;
+                left -= take;
+            }
+        } else {        // Shuffle(samples + i * n, n, dims, rng) for pixel sample i: draw d = i*n + k swaps k with k + y % (n - k)
+            uint8_t *tin = tgt + (size_t)spp * L.tgtInner[arr];
+            const int total = spp * n;
+            for (int d0 = 0; d0 < total;) {
+                if (mti >= MT_N) { WarpRegenMT(mt, lane); mti = 0; }
+                const int take = min(total - d0, MT_N - mti);
+                for (int j = lane; j < take; j += 32) {
+                    const uint32_t d = (uint32_t)(d0 + j), k = d % (uint32_t)n;
+                    const uint32_t y = Temper(mt[mti + j]);
+                    tin[d] = (uint8_t)(k + y % ((uint32_t)n - k));
+                }
+                mti += take;
+                d0 += take;
+            }
+        }
+        uint16_t *Ta = reinterpret_cast<uint16_t *>(tgt + (size_t)spp * L.tgtBlock[arr]);
+        for (int i0 = 0; i0 < spp;) {   // Shuffle(samples, nPixel, dims * n, rng)
+            if (mti >= MT_N) { WarpRegenMT(mt, lane); mti = 0; }
+            const int take = min(spp - i0, MT_N - mti);
+            for (int j = lane; j < take; j += 32) {
+                const uint32_t i = (uint32_t)(i0 + j);
+                const uint32_t y = Temper(mt[mti + j]);
+                Ta[i] = (uint16_t)(i + y % ((uint32_t)spp - i));
+            }
+            mti += take;
+            i0 += take;
+        }
+    }
+    __syncwarp();
+    for (int j = lane; j < MT_N; j += 32) cur[j] = mt[j];
+    __syncwarp();
+    WarpRegenMT(mt, lane);
+    for (int j = lane; j < MT_N; j += 32) next[j] = mt[j];
+    if (lane == 0) a.mti[bi] = mti;
+    __threadfence_block();
+    __syncwarp();
+
+    // ---- stages 2+3, G arrays at a time
+    for (int a0 = 0; a0 < L.nArrays; a0 += G) {
+        const int ng = min(L.nArrays, a0 + G) - a0;
+        for (int l = 0; l < ng; ++l)
+            for (int i = lane; i < spp; i += 32) P[l * stride + i] = (uint16_t)i;
+        __syncwarp();
+        if (lane < ng) {   // block shuffle: Fisher-Yates of the identity
+            uint16_t *p = P + lane * stride;
+            const uint16_t *t = reinterpret_cast<const uint16_t *>(tgt + (size_t)spp * L.tgtBlock[a0 + lane]);
+            for (int i = 0; i < spp; ++i) {
+                const int j = __ldcg(t + i);
+                const uint16_t tmp = p[i];
+                p[i] = p[j];
+                p[j] = tmp;
+            }
+        }
+        for (int l = 0; l < ng; ++l) {   // in-block shuffles, one pixel sample per lane, in place over the targets
+            const int n = L.n[a0 + l];
+            if (n == 1) continue;
+            uint8_t *tin = tgt + (size_t)spp * L.tgtInner[a0 + l];
+            for (int i = lane; i < spp; i += 32) {
+                uint8_t p[MAX_ARRAY_SAMPLES];
+                for (int k = 0; k < n; ++k) p[k] = (uint8_t)k;
+                for (int k = 0; k < n; ++k) {
+                    const int j = __ldcg(tin + (size_t)i * n + k);
+                    const uint8_t tmp = p[k];
+                    p[k] = p[j];
+                    p[j] = tmp;
+                }
+                for (int k = 0; k < n; ++k) tin[(size_t)i * n + k] = p[k];
+            }
+        }
+        __threadfence_block();
+        __syncwarp();
+        for (int s = lane; s < spp; s += 32) {
+            uint16_t *row = permOut + (size_t)s * L.rowStride;
+            for (int l = 0; l < ng; ++l) {
+                const int n = L.n[a0 + l];
+                const uint32_t b = P[l * stride + s];
+                if (n == 1) row[L.row[a0 + l]] = (uint16_t)b;
+                else {
+                    const uint8_t *tin = tgt + (size_t)spp * L.tgtInner[a0 + l] + (size_t)b * n;
+                    for (int k = 0; k < n; ++k) row[L.row[a0 + l] + k] = (uint16_t)(b * (uint32_t)n + __ldcg(tin + k));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_expand_samples(BatchArgs a, int spp, float shutterOpen, float shutterClose, SampleLayoutDev L,
+                                 int floatsPerSample, float *out) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= spp) return;
     const TaskRec tr = a.tasks[0];
-    const uint16_t *row = a.perm + (size_t)s * PERM_STRIDE;
+    const uint16_t *row = a.perm + (size_t)s * L.rowStride;
     const uint32_t *scr = a.scr;
-    float *o = out + (size_t)s * 37;
+    float *o = out + (size_t)s * floatsPerSample;
     o[0] = tr.x0 + VanDerCorput(row[0], scr[0]);
     o[1] = tr.y0 + Sobol2(row[0], scr[1]);
     o[2] = VanDerCorput(row[1], scr[2]);
     o[3] = Sobol2(row[1], scr[3]);
     o[4] = Lerp(VanDerCorput(row[2], scr[4]), shutterOpen, shutterClose);
-    for (int j = 0; j < N_1D; ++j) o[5 + j] = VanDerCorput(row[3 + j], scr[5 + j]);
-    for (int j = 0; j < N_2D; ++j) {
-        o[5 + N_1D + 2 * j] = VanDerCorput(row[17 + j], scr[19 + 2 * j]);
-        o[5 + N_1D + 2 * j + 1] = Sobol2(row[17 + j], scr[20 + 2 * j]);
-    }
+    o += 5;
+    for (int j = 0; j < L.n1D; ++j)
+        for (int k = 0; k < L.size1D[j]; ++k) *o++ = VanDerCorput(row[L.row1D[j] + k], scr[L.scr1D[j]]);
+    for (int j = 0; j < L.n2D; ++j)
+        for (int k = 0; k < L.size2D[j]; ++k) {
+            *o++ = VanDerCorput(row[L.row2D[j] + k], scr[L.scr2D[j]]);
+            *o++ = Sobol2(row[L.row2D[j] + k], scr[L.scr2D[j] + 1]);
+        }
 }
 
 // ----------------------------------------------------------------------- k_path
@@ -230,10 +378,12 @@ __global__ void k_expand_samples(BatchArgs a, int spp, float shutterOpen, float 
 // iteration, so the lanes of a warp traverse together whatever stage each is in.
 enum PathState {
     S_NEW_SAMPLE = 0, S_HIT_RESULT, S_SHADOW_RESULT, S_AFTER_LIGHT, S_MIS_RESULT, S_AFTER_DIRECT, S_END_SAMPLE, S_DONE,
-    S_E_LIGHT, S_E_MIS, S_E_PATH   // waiting for the BSDF value at the evaluation site
+    S_E_LIGHT, S_E_MIS, S_E_PATH,   // waiting for the BSDF value at the evaluation site
+    S_DL_NEXT                       // DirectLightingIntegrator: next (light, sample) of the light loop
 };
 // ls[s].w bit field
-enum { LS_TAIL = 1, LS_LEFT = 2, LS_RIGHT = 4, LS_UP = 8, LS_DOWN = 16 };
+enum { LS_TAIL = 1, LS_LEFT = 2, LS_RIGHT = 4, LS_UP = 8, LS_DOWN = 16,
+       LS_HIT = 32 };   // directlighting: the camera ray hit something (6 RNG draws follow, see k_film_direct)
 
 struct PathArgs {
     DScene sc;
@@ -355,6 +505,11 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
     V3 wiW(0, 0, 1);                            // sampled incident direction (world)
     float sPdf = 0.f, visMaxt = 0.f;            // its pdf; the shadow segment's maxt
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int dlI = 0, dlJ = 0;                 // (DirectLightingIntegrator state of path_body.inc: unused, PATH_INTEG == 0 here)
+    Spec dlSum(0.f), dlAll(0.f);
+    const int rowStride = PERM_STRIDE;
+    bool ctxDirty = false;
+    (void)ctxDirty;
     TraceStats st;
     st.nodes = st.prims = 0;
     unsigned long long nClosest = 0, nShadow = 0, nShadedN = 0;
@@ -404,6 +559,7 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
 #define PATH_EVALWI_IN V3(0, 0, 1)
 #define PATH_DEFER_MEASURED false
 #define PATH_ANIM ANIM
+#define PATH_INTEG 0
 #define PATH_COUNT_TAIL() atomicOr(a.b.tailCount + bi, 1u)
 #include "path_body.inc"
 #undef PATH_COUNT_TAIL
@@ -412,6 +568,7 @@ __global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
 #undef PATH_EVALWI_IN
 #undef PATH_DEFER_MEASURED
 #undef PATH_ANIM
+#undef PATH_INTEG
 
         if (state == S_END_SAMPLE) {
             if (PHASE == 1) {
@@ -550,6 +707,8 @@ enum {
     F_FEVAL,       // fEval.rgb
     F_ACC,         // phase 2: the task's film accumulator {Lxyz, weightSum} (ImageFilm::Pixel of its current pixel)
     F_TIME,        // ray.time of the camera path (scenes with TransformedPrimitives only)
+    F_DL_SUM,      // directlighting: Ld summed over this light's samples so far, packed {light:16, sample:16}
+    F_DL_ALL,      // directlighting: UniformSampleAllLights' L so far
     F_COUNT
 };
 // Request queues, one per resume state ("kind"), so that the lanes of a warp of k_logic are all in the same
@@ -588,7 +747,7 @@ DEV unsigned AggregatedAdd(unsigned *ctr) {   // warp-aggregated atomicAdd(ctr, 
 // PHASE 1: slots are camera samples (bounces 0..2, table-driven).  PHASE 2: slot i is task-pixel i's chain of
 // parked samples, resumed one after the other with the task's sequential RNG stream; finished samples are added
 // to the film in sample order in between (what k_path<2> does per thread, here as a wavefront).
-template <int PHASE, bool STATS, bool ANIM>
+template <int PHASE, bool STATS, bool ANIM, int INTEG>
 __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
     __shared__ uint32_t smt[PHASE == 2 ? 4 : 1][PHASE == 2 ? MT_N : 1];
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -636,6 +795,9 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
     unsigned long long nShadedN = 0;
     bool ctxDirty = false;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int dlI = 0, dlJ = 0;                  // DirectLightingIntegrator's light loop
+    Spec dlSum(0.f), dlAll(0.f);
+    const int rowStride = INTEG == PBRTGPU_INTEGRATOR_DIRECTLIGHTING ? rp.lay.rowStride : PERM_STRIDE;
 
     if (PHASE == 2 && live && kindIn < 0) {   // iteration 0: the task-pixel behind this slot
         bi = a.b.order ? (int)a.b.order[idx] : (int)idx;
@@ -682,6 +844,11 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
             mti = a.b.mti[bi];
         }
         if (ANIM) ray.time = FLD(F_TIME).x;
+        if (INTEG == PBRTGPU_INTEGRATOR_DIRECTLIGHTING) {
+            const float4 d0 = FLD(F_DL_SUM), d1 = FLD(F_DL_ALL);
+            dlSum = Spec(d0.x, d0.y, d0.z); dlAll = Spec(d1.x, d1.y, d1.z);
+            dlI = (int)(__float_as_uint(d0.w) & 0xffffu); dlJ = (int)(__float_as_uint(d0.w) >> 16);
+        }
     }
     if (PHASE == 2) {
         // cooperative RNG top-up before a bounce (<= 11 draws must be addressable), as in k_path<2>
@@ -720,7 +887,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
         if (a.b.round >= tw * (tr.y1 - tr.y0)) return false;
         xPos = tr.x0 + a.b.round % tw;
         yPos = tr.y0 + a.b.round / tw;
-        permBase = a.b.perm + (size_t)task * spp * PERM_STRIDE;
+        permBase = a.b.perm + (size_t)task * spp * rowStride;
         scr = a.b.scr + (size_t)task * SCR_STRIDE;
         lsBase = a.b.ls + (size_t)task * spp;
         recBase = a.b.rec + (size_t)task * spp * 4;
@@ -747,6 +914,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
 #define PATH_EVALWI_IN evalWiIn
 #define PATH_DEFER_MEASURED true
 #define PATH_ANIM ANIM
+#define PATH_INTEG INTEG
 #define PATH_COUNT_TAIL() atomicOr(a.b.tailCount + bi, 1u)
 #include "path_body.inc"
 #undef PATH_COUNT_TAIL
@@ -755,6 +923,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
 #undef PATH_EVALWI_IN
 #undef PATH_DEFER_MEASURED
 #undef PATH_ANIM
+#undef PATH_INTEG
         if (deferEval) {
             deferOut = true;
             evalWoOut = evalWo; evalWiOut = evalWi; evalFlagsOut = evalFlags;
@@ -828,7 +997,7 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
             }
             if (!have) { state = S_DONE; break; }
             // LDPixelSample's camera sample + PerspectiveCamera::GenerateRayDifferential (perspective.cpp:81-138)
-            const uint16_t *row = permBase + (size_t)s * PERM_STRIDE;
+            const uint16_t *row = permBase + (size_t)s * rowStride;
             const uint32_t pi = row[0];
             const float imageX = xPos + VanDerCorput(pi, scr[0]);
             const float imageY = yPos + Sobol2(pi, scr[1]);
@@ -870,6 +1039,10 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
         a.b.mti[bi] = mti;
     }
     if (ANIM) FLD(F_TIME) = make_float4(ray.time, 0.f, 0.f, 0.f);
+    if (INTEG == PBRTGPU_INTEGRATOR_DIRECTLIGHTING) {
+        FLD(F_DL_SUM) = make_float4(dlSum.r, dlSum.g, dlSum.b, __uint_as_float((uint32_t)dlI | ((uint32_t)dlJ << 16)));
+        FLD(F_DL_ALL) = make_float4(dlAll.r, dlAll.g, dlAll.b, 0.f);
+    }
     FLD(F_T) = make_float4(T.r, T.g, T.b, __uint_as_float((uint32_t)state | ((uint32_t)bounces << 8) | ((uint32_t)lightNum << 16)));
     FLD(F_L) = make_float4(L.r, L.g, L.b, __int_as_float(code));
     FLD(F_WO) = make_float4(wo.x, wo.y, wo.z, __int_as_float(bi));
@@ -905,6 +1078,72 @@ __global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
     (void)wantTraceOut; (void)anyHitOut;
     if (STATS && nShadedN) atomicAdd(&a.stats->shadedN, nShadedN);
 #undef FLD
+}
+
+// DirectLightingIntegrator's "phase 2": the samples of a pixel are added to the film in sample order
+// (samplerrenderer.cpp:147-157) and the task's RNG moves past the draws SpecularReflect / SpecularTransmit made for
+// every camera ray that hit (BSDFSample(rng) twice = 6 draws, integrator.cpp:184,227; only when depth + 1 < maxDepth,
+// directlighting.cpp:108).  One thread per task-pixel; the stream position is advanced block by block,
+// warp-cooperatively, only when another pixel of the task follows (`advance`).
+__global__ void __launch_bounds__(128) k_film_direct(PathArgs a, int advance) {
+    __shared__ uint32_t smt[4][MT_N];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+    const RenderParams &rp = a.rp;
+    const int spp = rp.spp;
+    bool live = bi < a.b.nBatch;
+    int mti = 0;
+    if (live) {
+        const TaskRec tr = a.b.tasks[bi];
+        const int tw = tr.x1 - tr.x0;
+        if (a.b.round >= tw * (tr.y1 - tr.y0)) live = false;
+        else {
+            const int xPos = tr.x0 + a.b.round % tw, yPos = tr.y0 + a.b.round / tw;
+            const float4 *ls = a.b.ls + (size_t)bi * spp;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            int hits = 0;
+            const bool direct = a.directFilm != 0;
+            for (int s = 0; s < spp; ++s) {
+                const float4 v = __ldcs(ls + s);
+                const int code = __float_as_int(v.w);
+                hits += (code & LS_HIT) ? 1 : 0;
+                FilmAdd(rp, a.film, xPos, yPos, code & ~LS_HIT, Spec(v.x, v.y, v.z), acc, direct);
+            }
+            if (!direct) {
+                PbrtGpuPixel *px = a.film + (size_t)(yPos - rp.yPixelStart) * rp.xPixelCount + (xPos - rp.xPixelStart);
+                atomicAdd(&px->Lxyz[0], acc[0]);
+                atomicAdd(&px->Lxyz[1], acc[1]);
+                atomicAdd(&px->Lxyz[2], acc[2]);
+                atomicAdd(&px->weightSum, acc[3]);
+            }
+            mti = a.b.mti[bi] + ((0 + 1 < rp.maxDepth) ? 6 * hits : 0);
+        }
+    }
+    if (!advance) return;
+    // bring the two-block window (cur, next) forward until mti lies in [0, 2 * MT_N) again (what k_tables expects)
+    for (;;) {
+        unsigned m = __ballot_sync(FULL, live && mti >= MT_N);
+        if (!m) break;
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const int tb = __shfl_sync(FULL, bi, l);
+            uint32_t *c = a.b.rngCur + (size_t)tb * MT_N, *n = a.b.rngNext + (size_t)tb * MT_N;
+            uint32_t *mt = smt[warp];
+            for (int j = lane; j < MT_N; j += 32) {
+                const uint32_t v = __ldcg(n + j);
+                __stcg(c + j, v);
+                mt[j] = v;
+            }
+            __syncwarp();
+            WarpRegenMT(mt, lane);
+            for (int j = lane; j < MT_N; j += 32) __stcg(n + j, mt[j]);
+            __syncwarp();
+            if (lane == l) mti -= MT_N;
+        }
+    }
+    if (live) a.b.mti[bi] = mti;
 }
 
 // persistent ray queue consumer
@@ -1094,6 +1333,7 @@ struct Lane {
     DevBuf<float4> ls, rec;
     DevBuf<unsigned> tailCount, tailKeysOut, orderIn, orderOut;
     DevBuf<unsigned char> sortTemp;
+    DevBuf<uint8_t> tgt;              // general table kernel: shuffle targets
     DevBuf<float4> pool;              // wavefront path slots (F_COUNT fields x P)
     DevBuf<uint32_t> traceQ;
     DevBuf<unsigned> counters;
@@ -1197,6 +1437,47 @@ void ComputeSubWindow(const FilmExtent &e, int num, int count, int *x0, int *x1,
     *y1 = HFloor2Int(HLerp(ty1, e.sy0, e.sy1));
 }
 
+// Sample layout of a render descriptor -> row / scramble positions (drng.cuh)
+bool IsPathLayout(const PbrtGpuRenderDesc &rd) {
+    if (rd.n1D != N_1D || rd.n2D != N_2D) return false;
+    for (int i = 0; i < rd.n1D; ++i) if (rd.size1D[i] != 1) return false;
+    for (int i = 0; i < rd.n2D; ++i) if (rd.size2D[i] != 1) return false;
+    return true;
+}
+void BuildLayout(const PbrtGpuRenderDesc &rd, SampleLayoutDev *L, TableArrays *T) {
+    memset(L, 0, sizeof(*L));
+    memset(T, 0, sizeof(*T));
+    L->n1D = rd.n1D; L->n2D = rd.n2D;
+    int row = 3, scr = 5, arr = 0, tgt = 0;
+    auto add = [&](int n, int dims, int rowAt, int scrAt) {
+        T->n[arr] = (uint16_t)n; T->dims[arr] = (uint8_t)dims; T->row[arr] = (uint16_t)rowAt; T->scr[arr] = (uint16_t)scrAt;
+        T->tgtInner[arr] = (uint16_t)tgt;
+        if (n > 1) tgt += (n + 1) & ~1;
+        T->tgtBlock[arr] = (uint16_t)tgt;
+        tgt += 2;
+        ++arr;
+    };
+    add(1, 2, 0, 0); add(1, 2, 1, 2); add(1, 1, 2, 4);   // image, lens, time (montecarlo.cpp:228-230)
+    for (int j = 0; j < rd.n1D; ++j) {
+        L->size1D[j] = rd.size1D[j]; L->row1D[j] = (uint16_t)row; L->scr1D[j] = (uint16_t)scr;
+        add(rd.size1D[j], 1, row, scr);
+        row += rd.size1D[j]; scr += 1;
+    }
+    for (int j = 0; j < rd.n2D; ++j) {
+        L->size2D[j] = rd.size2D[j]; L->row2D[j] = (uint16_t)row; L->scr2D[j] = (uint16_t)scr;
+        add(rd.size2D[j], 2, row, scr);
+        row += rd.size2D[j]; scr += 2;
+    }
+    L->rowStride = (row + 7) / 8 * 8;
+    T->nArrays = arr; T->rowStride = L->rowStride; T->tgtPerSample = tgt;
+}
+int FloatsPerSample(const PbrtGpuRenderDesc &rd) {
+    int n = 5;
+    for (int j = 0; j < rd.n1D; ++j) n += rd.size1D[j];
+    for (int j = 0; j < rd.n2D; ++j) n += 2 * rd.size2D[j];
+    return n;
+}
+
 int ValidateRenderDesc(const PbrtGpuRenderDesc &rd) {
     if (rd.xResolution <= 0 || rd.yResolution <= 0) return Fail(PBRTGPU_EINVAL, "bad film resolution");
     const int spp = rd.samplesPerPixel;
@@ -1207,6 +1488,17 @@ int ValidateRenderDesc(const PbrtGpuRenderDesc &rd) {
     if (rd.nTasks <= 0 || rd.taskBegin < 0 || rd.taskEnd > rd.nTasks || rd.taskBegin > rd.taskEnd)
         return Fail(PBRTGPU_EINVAL, "bad task range");
     if (rd.maxDepth < 0) return Fail(PBRTGPU_EINVAL, "bad maxDepth");
+    if (rd.integrator != PBRTGPU_INTEGRATOR_PATH && rd.integrator != PBRTGPU_INTEGRATOR_DIRECTLIGHTING)
+        return Fail(PBRTGPU_EUNSUPPORTED, "unknown surface integrator");
+    if (rd.n1D < 0 || rd.n1D > PBRTGPU_MAX_SAMPLE_ARRAYS || rd.n2D < 0 || rd.n2D > PBRTGPU_MAX_SAMPLE_ARRAYS)
+        return Fail(PBRTGPU_EINVAL, "bad sample-array counts");
+    for (int i = 0; i < rd.n1D + rd.n2D; ++i) {
+        const int n = i < rd.n1D ? rd.size1D[i] : rd.size2D[i - rd.n1D];
+        if (n < 1 || n > MAX_ARRAY_SAMPLES) return Fail(PBRTGPU_EUNSUPPORTED, "a sample array asks for 0 or more than 64 values per pixel sample");
+        if ((long long)n * spp > 65536) return Fail(PBRTGPU_EUNSUPPORTED, "samplesPerPixel x array size exceeds the 16-bit table index");
+    }
+    if (rd.integrator == PBRTGPU_INTEGRATOR_PATH && !IsPathLayout(rd))
+        return Fail(PBRTGPU_EINVAL, "PathIntegrator's Sample layout is 14 one-value 1-D and 9 one-value 2-D arrays (path.cpp:41-49)");
     {   // Sampler::ComputeSubWindow multiplies in int (core/sampler.cpp:58: 2*dx*ny < dy*nx); a task grid that overflows
         // it is undefined behaviour in the reference, so it is not a configuration parity can be defined for
         const FilmExtent e = ComputeExtent(rd);
@@ -1255,6 +1547,35 @@ cudaError_t LaunchTablesAny(const BatchArgs &b, int spp, const TableLaunch &tl, 
     case 3: return LaunchTables<3>(b, spp, tl, stream);
     case 2: return LaunchTables<2>(b, spp, tl, stream);
     default: return LaunchTables<1>(b, spp, tl, stream);
+    }
+}
+
+TableLaunch PlanTablesGeneral(int spp, int nArrays) {
+    TableLaunch t;
+    const size_t perArray = (size_t)2 * (spp + 2);
+    const size_t budget = 56 * 1024;
+    size_t g = (budget - MT_N * 4) / perArray;
+    t.G = (int)std::max<size_t>(1, std::min<size_t>(g, (size_t)std::min(32, nArrays)));   // one array per lane in the block shuffle
+    const size_t perWarp = MT_N * 4 + ((size_t)t.G * perArray + 3) / 4 * 4;
+    t.wpb = (int)std::max<size_t>(1, std::min<size_t>(4, (226 * 1024) / perWarp));
+    t.smemBytes = perWarp * t.wpb;
+    return t;
+}
+template <int WPB> cudaError_t LaunchTablesGeneral(const BatchArgs &b, int spp, const TableLaunch &tl, const TableArrays &T,
+                                                   uint8_t *tgt, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(k_tables_general<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smemBytes);
+    if (e != cudaSuccess) return e;
+    const int blocks = (b.nBatch + WPB - 1) / WPB;
+    k_tables_general<WPB><<<blocks, 32 * WPB, tl.smemBytes, stream>>>(b, spp, tl.G, T, tgt);
+    return cudaGetLastError();
+}
+cudaError_t LaunchTablesGeneralAny(const BatchArgs &b, int spp, const TableLaunch &tl, const TableArrays &T, uint8_t *tgt,
+                                   cudaStream_t stream) {
+    switch (tl.wpb) {
+    case 4: return LaunchTablesGeneral<4>(b, spp, tl, T, tgt, stream);
+    case 3: return LaunchTablesGeneral<3>(b, spp, tl, T, tgt, stream);
+    case 2: return LaunchTablesGeneral<2>(b, spp, tl, T, tgt, stream);
+    default: return LaunchTablesGeneral<1>(b, spp, tl, T, tgt, stream);
     }
 }
 
@@ -1449,6 +1770,8 @@ struct LaneJob {
     int spp;
     PbrtGpuPixel *film;
     bool timing, wantCounters, timeRays;
+    TableArrays tables;      // the Sample layout, array by array
+    bool pathLayout;         // ... is PathIntegrator's: the specialised table kernel applies
     // results
     int rc = PBRTGPU_OK;
     std::string err;
@@ -1481,13 +1804,15 @@ int RunLane(LaneJob &job) {
     };
     CUDA_TRY(cudaStreamWaitEvent(stream, scene->ev[2], 0));   // the film has been cleared
     CUDA_TRY(ln->tasks.Ensure(maxBatch));
-    CUDA_TRY(ln->perm.Ensure(maxBatch * spp * PERM_STRIDE));
+    const bool direct = rp.integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
+    CUDA_TRY(ln->perm.Ensure(maxBatch * spp * (size_t)rp.lay.rowStride));
+    if (!job.pathLayout) CUDA_TRY(ln->tgt.Ensure(maxBatch * spp * (size_t)job.tables.tgtPerSample + 16));
     CUDA_TRY(ln->scr.Ensure(maxBatch * SCR_STRIDE));
     CUDA_TRY(ln->rngCur.Ensure(maxBatch * MT_N));
     CUDA_TRY(ln->rngNext.Ensure(maxBatch * MT_N));
     CUDA_TRY(ln->mti.Ensure(maxBatch));
     CUDA_TRY(ln->ls.Ensure(maxBatch * spp));
-    CUDA_TRY(ln->rec.Ensure(maxBatch * spp * 4));
+    CUDA_TRY(ln->rec.Ensure(direct ? 4 : maxBatch * spp * 4));   // parked bounce-3 vertices: PathIntegrator only
     CUDA_TRY(ln->tailCount.Ensure(maxBatch));
     CUDA_TRY(ln->tailKeysOut.Ensure(maxBatch));
     CUDA_TRY(ln->orderIn.Ensure(maxBatch));
@@ -1521,7 +1846,8 @@ int RunLane(LaneJob &job) {
         if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, C_COUNT * sizeof(unsigned)));
     }
     const bool traceIters = getenv("PBRTGPU_TRACE_ITERS") != nullptr;   // debugging aid: queue occupancy on stderr
-    const TableLaunch tl = PlanTables(spp);
+    const TableLaunch tl = job.pathLayout ? PlanTables(spp) : PlanTablesGeneral(spp, job.tables.nArrays);
+    if (direct && !useWavefront) return Fail(PBRTGPU_EUNSUPPORTED, "DirectLightingIntegrator runs on the wavefront only (PBRTGPU_WAVEFRONT=0 is a PathIntegrator A/B switch)");
     uint64_t launches = 0;
     float tableMs = 0.f, traceMs = 0.f, tailMs = 0.f;
     for (size_t bi = (size_t)job.laneIndex; bi * maxBatch < tasks.size(); bi += (size_t)job.nLanes) {
@@ -1539,7 +1865,8 @@ int RunLane(LaneJob &job) {
         for (int r = 0; r < rounds; ++r) {
             b.round = r;
             if (stats) CUDA_TRY(cudaEventRecord(ln->ev[0], stream));
-            CUDA_TRY(LaunchTablesAny(b, spp, tl, stream));
+            if (job.pathLayout) CUDA_TRY(LaunchTablesAny(b, spp, tl, stream));
+            else CUDA_TRY(LaunchTablesGeneralAny(b, spp, tl, job.tables, ln->tgt.p, stream));
             if (stats) CUDA_TRY(cudaEventRecord(ln->ev[1], stream));
             CUDA_TRY(cudaMemsetAsync(ln->tailCount.p, 0, nb * sizeof(unsigned), stream));
             PathArgs pa;
@@ -1574,12 +1901,15 @@ int RunLane(LaneJob &job) {
                     // empty the queues k_logic is about to fill, and the consumers' cursors
                     CUDA_TRY(cudaMemsetAsync(ln->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
                     CUDA_TRY(cudaMemsetAsync(ln->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
-                    if (scene->d.nAnimated) {
-                        if (wantCounters) k_logic<1, true, true><<<lblocks, 128, 0, stream>>>(wa);
-                        else k_logic<1, false, true><<<lblocks, 128, 0, stream>>>(wa);
+                    if (direct) {   // DirectLightingIntegrator: one instantiation (TransformedPrimitives handled at run time)
+                        if (wantCounters) k_logic<1, true, true, 1><<<lblocks, 128, 0, stream>>>(wa);
+                        else k_logic<1, false, true, 1><<<lblocks, 128, 0, stream>>>(wa);
+                    } else if (scene->d.nAnimated) {
+                        if (wantCounters) k_logic<1, true, true, 0><<<lblocks, 128, 0, stream>>>(wa);
+                        else k_logic<1, false, true, 0><<<lblocks, 128, 0, stream>>>(wa);
                     } else {
-                        if (wantCounters) k_logic<1, true, false><<<lblocks, 128, 0, stream>>>(wa);
-                        else k_logic<1, false, false><<<lblocks, 128, 0, stream>>>(wa);
+                        if (wantCounters) k_logic<1, true, false, 0><<<lblocks, 128, 0, stream>>>(wa);
+                        else k_logic<1, false, false, 0><<<lblocks, 128, 0, stream>>>(wa);
                     }
                     if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
                     if (timeRays) CUDA_TRY(cudaEventRecord(rayEvent(), stream));
@@ -1617,7 +1947,10 @@ int RunLane(LaneJob &job) {
                                                           ln->orderIn.p, ln->orderOut.p, (int)nb, 0, 1, stream);
                 pa.b.order = ln->orderOut.p;
             }
-            if (!useWavefront2) {
+            if (direct) {
+                k_film_direct<<<blocks2, 128, 0, stream>>>(pa, r + 1 < rounds ? 1 : 0);
+                CUDA_TRY(cudaGetLastError());
+            } else if (!useWavefront2) {
                 if (scene->d.nAnimated) {
                     if (wantCounters) k_path<2, true, true><<<blocks2, 128, 0, stream>>>(pa);
                     else k_path<2, false, true><<<blocks2, 128, 0, stream>>>(pa);
@@ -1641,11 +1974,11 @@ int RunLane(LaneJob &job) {
                     CUDA_TRY(cudaMemsetAsync(ln->counters.p + C_QN + setOut * K_COUNT, 0, K_COUNT * sizeof(unsigned), stream));
                     CUDA_TRY(cudaMemsetAsync(ln->counters.p + C_TRACE_CUR, 0, 2 * sizeof(unsigned), stream));
                     if (scene->d.nAnimated) {
-                        if (wantCounters) k_logic<2, true, true><<<blocks2, 128, 0, stream>>>(wa);
-                        else k_logic<2, false, true><<<blocks2, 128, 0, stream>>>(wa);
+                        if (wantCounters) k_logic<2, true, true, 0><<<blocks2, 128, 0, stream>>>(wa);
+                        else k_logic<2, false, true, 0><<<blocks2, 128, 0, stream>>>(wa);
                     } else {
-                        if (wantCounters) k_logic<2, true, false><<<blocks2, 128, 0, stream>>>(wa);
-                        else k_logic<2, false, false><<<blocks2, 128, 0, stream>>>(wa);
+                        if (wantCounters) k_logic<2, true, false, 0><<<blocks2, 128, 0, stream>>>(wa);
+                        else k_logic<2, false, false, 0><<<blocks2, 128, 0, stream>>>(wa);
                     }
                     if (hasMeasured) k_eval<<<tblocks, 128, 0, stream>>>(wa);
                     if (scene->d.nAnimated) {
@@ -1738,17 +2071,36 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     rp.xPixelStart = ext.xPixelStart; rp.yPixelStart = ext.yPixelStart;
     rp.xPixelCount = ext.xPixelCount; rp.yPixelCount = ext.yPixelCount;
     rp.spp = spp; rp.maxDepth = rd->maxDepth;
+    rp.integrator = rd->integrator; rp.lightStrategy = rd->lightStrategy;
 
     // per task: permutation tables (64 B/sample) + finished radiance (16 B/sample) + parked
     // bounce-3 vertices (64 B/sample, sparse) + scrambles + two MT19937 blocks
-    const size_t perTask = (size_t)spp * (PERM_STRIDE * 2 + 16 + 64) + SCR_STRIDE * 4 + 2 * MT_N * 4 + 4 + sizeof(TaskRec);
+    TableArrays tables;
+    BuildLayout(*rd, &rp.lay, &tables);
+    const bool pathLayout = IsPathLayout(*rd);
+    const bool directInteg = rd->integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
+    if (directInteg) {   // the layout must be what DirectLightingIntegrator::RequestSamples builds for this scene's lights
+        const int nl = (int)scene->d.nLights;
+        const bool all = rd->lightStrategy == PBRTGPU_STRATEGY_ALL;
+        if (rd->lightStrategy != PBRTGPU_STRATEGY_ALL && rd->lightStrategy != PBRTGPU_STRATEGY_ONE)
+            return Fail(PBRTGPU_EINVAL, "bad lightStrategy");
+        if (all ? (rd->n1D != 2 * nl + 2 || rd->n2D != 2 * nl) : (rd->n1D != 5 || rd->n2D != 2))
+            return Fail(PBRTGPU_EINVAL, "Sample layout does not match DirectLightingIntegrator::RequestSamples for this scene (directlighting.cpp:53-78)");
+        for (int i = 0; i < (all ? nl : 0); ++i)
+            if (rd->size1D[2 * i] != rd->size1D[2 * i + 1] || rd->size1D[2 * i] != rd->size2D[2 * i] || rd->size1D[2 * i] != rd->size2D[2 * i + 1])
+                return Fail(PBRTGPU_EINVAL, "a light's four sample arrays must have the same size (light.cpp:64-68, reflection.cpp:502-506)");
+    }
+    const size_t perTask = (size_t)spp * ((size_t)rp.lay.rowStride * 2 + 16 + (directInteg ? 0 : 64) + (pathLayout ? 0 : tables.tgtPerSample)) +
+                           SCR_STRIDE * 4 + 2 * MT_N * 4 + 4 + sizeof(TaskRec);
     const bool wantCounters = stats && scene->collectStats == 1;
     const bool timeRays = stats && scene->collectStats == 2;
     size_t poolSlots = (size_t)1 << 22;
     { const char *e = getenv("PBRTGPU_POOL"); if (e && atol(e) > 0) poolSlots = (size_t)atol(e); }
-    // lanes: as many as keep every lane's wavefront pool full (measured on bunny/C2: 1 lane 210, 2 lanes 227,
-    // 4 lanes 245 Msamples/s; with less than a pool's worth of samples per lane and round extra lanes only add launches)
-    int nLanes = PbrtGpuScene::MAX_LANES;
+    // lanes: the kernels' register allocations fill the SMs, so lanes cannot overlap two full-size kernels; what they
+    // hide is each other's low-occupancy stretches (the tail kernel, the wavefront's drain at the end of a batch).
+    // Measured on C2 (bunny 1024x1024): 128 spp 1/2/3/4 lanes = 210/227/240/250 Msamples/s, 1024 spp 1/2/4 lanes =
+    // 197/219/188 (more lanes = smaller batches = more, equally long, tail launches).  Default 2.
+    int nLanes = 2;
     { const char *e = getenv("PBRTGPU_LANES"); if (e) nLanes = atoi(e); }
     nLanes = std::max(1, std::min(nLanes, (int)PbrtGpuScene::MAX_LANES));
     if (!getenv("PBRTGPU_LANES"))
@@ -1775,6 +2127,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
         LaneJob &j = jobs[l];
         j.scene = scene; j.ln = &ln; j.tasks = &tasks; j.maxBatch = maxBatch; j.laneIndex = l; j.nLanes = nLanes;
         j.rp = rp; j.spp = spp; j.film = film; j.timing = stats != nullptr; j.wantCounters = wantCounters; j.timeRays = timeRays;
+        j.tables = tables; j.pathLayout = pathLayout;
     }
     {
         auto run = [](LaneJob *j) {
@@ -1872,23 +2225,29 @@ int pbrtgpu_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
     DevBuf<int> mti;
     DevBuf<float> dout;
     DevBuf<float4> rec;
+    DevBuf<uint8_t> tgt;
+    SampleLayoutDev L;
+    TableArrays T;
+    BuildLayout(*rd, &L, &T);
+    const bool pathLayout = IsPathLayout(*rd);
+    const int nf = FloatsPerSample(*rd);
     CUDA_TRY(rec.Ensure((size_t)spp * 4));
+    CUDA_TRY(tgt.Ensure((size_t)spp * T.tgtPerSample + 16));
     CUDA_TRY(tasks.Upload(&tr, 1));
-    CUDA_TRY(perm.Ensure((size_t)spp * PERM_STRIDE));
+    CUDA_TRY(perm.Ensure((size_t)spp * L.rowStride));
     CUDA_TRY(scr.Ensure(SCR_STRIDE));
     CUDA_TRY(cur.Ensure(MT_N));
     CUDA_TRY(next.Ensure(MT_N));
     CUDA_TRY(mti.Ensure(1));
-    CUDA_TRY(dout.Ensure((size_t)spp * 37));
+    CUDA_TRY(dout.Ensure((size_t)spp * nf));
     BatchArgs b;
     b.tasks = tasks.p; b.nBatch = 1; b.round = 0; b.perm = perm.p; b.scr = scr.p; b.rngCur = cur.p; b.rngNext = next.p;
     b.mti = mti.p; b.ls = nullptr; b.rec = rec.p; b.tailCount = nullptr; b.order = nullptr;
-    const bool traceIters = getenv("PBRTGPU_TRACE_ITERS") != nullptr;   // debugging aid: queue occupancy on stderr
-    const TableLaunch tl = PlanTables(spp);
-    CUDA_TRY(LaunchTablesAny(b, spp, tl, nullptr));
-    k_expand_samples<<<(spp + 127) / 128, 128>>>(b, spp, rd->shutterOpen, rd->shutterClose, dout.p);
+    if (pathLayout) CUDA_TRY(LaunchTablesAny(b, spp, PlanTables(spp), nullptr));
+    else CUDA_TRY(LaunchTablesGeneralAny(b, spp, PlanTablesGeneral(spp, T.nArrays), T, tgt.p, nullptr));
+    k_expand_samples<<<(spp + 127) / 128, 128>>>(b, spp, rd->shutterOpen, rd->shutterClose, L, nf, dout.p);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpy(out, dout.p, (size_t)spp * 37 * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out, dout.p, (size_t)spp * nf * sizeof(float), cudaMemcpyDeviceToHost));
     return PBRTGPU_OK;
 }
 

@@ -355,6 +355,7 @@ bool Api::DoShape(const std::string &name, const ParamSet &params) {   // core/a
         V3 sc = ap.FindOneSpectrum("scale", V3(1, 1, 1));
         Light lt;
         lt.desc.type = PBRTGPU_LIGHT_DIFFUSE_AREA;
+        lt.desc.nSamples = std::max(1, ap.FindOneInt("nsamples", 1));   // diffuse.cpp:63, light.h:53
         lt.desc.L[0] = L.x * sc.x; lt.desc.L[1] = L.y * sc.y; lt.desc.L[2] = L.z * sc.z;
         lt.shape = shape.get();
         scene->lights.push_back(lt);
@@ -377,6 +378,7 @@ bool Api::DoLight(const std::string &name, const ParamSet &params) {   // core/a
     Transform l2w = Translate(V3(P.x, P.y, P.z)) * curTransform.t[0];
     Light lt;
     lt.desc.type = PBRTGPU_LIGHT_POINT;
+    lt.desc.nSamples = 1;   // Light(l2w) default, light.h:52
     lt.desc.L[0] = I.x * sc.x; lt.desc.L[1] = I.y * sc.y; lt.desc.L[2] = I.z * sc.z;
     V3 pos = l2w.Pt(V3(0, 0, 0));
     lt.desc.pos[0] = pos.x; lt.desc.pos[1] = pos.y; lt.desc.pos[2] = pos.z;
@@ -437,10 +439,25 @@ bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
                                  &r->sampler.yPixelEnd);
     }
     // --- integrators (api.cpp:533-563) ---
-    if (SurfIntegratorName != "path" && SurfIntegratorName != "gpupath")
-        return Fail("surface integrator \"" + SurfIntegratorName + "\" is not on the hot path (use \"path\")");
-    r->surfaceIntegrator.reset(new GpuPathIntegrator(SurfIntegratorParams.FindOneInt("maxdepth", 5)));
+    if (SurfIntegratorName == "path" || SurfIntegratorName == "gpupath")
+        r->surfaceIntegrator.reset(new GpuPathIntegrator(SurfIntegratorParams.FindOneInt("maxdepth", 5)));
+    else if (SurfIntegratorName == "directlighting") {   // directlighting.cpp:120-133
+        int maxDepth = SurfIntegratorParams.FindOneInt("maxdepth", 5);
+        std::string st = SurfIntegratorParams.FindOneString("strategy", "all");
+        int strategy = PBRTGPU_STRATEGY_ALL;
+        if (st == "one") strategy = PBRTGPU_STRATEGY_ONE;
+        else if (st != "all")
+            fprintf(stderr, "Warning: Strategy \"%s\" for direct lighting unknown. Using \"all\".\n", st.c_str());
+        r->surfaceIntegrator.reset(new GpuDirectLightingIntegrator(strategy, maxDepth));
+    } else
+        return Fail("surface integrator \"" + SurfIntegratorName + "\" is outside the scope (path, directlighting)");
     if (VolIntegratorName != "emission") return Fail("volume integrator \"" + VolIntegratorName + "\" is out of scope");
+    // Sample::Sample (core/sampler.cpp:84-92): surface integrator's requests, then the volume integrator's
+    r->surfaceIntegrator->RequestSamples(*scene, &r->n1D, &r->n2D);
+    r->n1D.push_back(1);   // EmissionIntegrator::RequestSamples (emission.cpp:40-43): tauSampleOffset
+    r->n1D.push_back(1);   //                                                       scatterSampleOffset
+    if (r->n1D.size() > PBRTGPU_MAX_SAMPLE_ARRAYS || r->n2D.size() > PBRTGPU_MAX_SAMPLE_ARRAYS)
+        return Fail("too many lights for the sample-array table of the C ABI (PBRTGPU_MAX_SAMPLE_ARRAYS)");
     if (RendererName != "sampler" && RendererName != "gpusampler")
         return Fail("renderer \"" + RendererName + "\" is out of scope (sampler)");
     // --- accelerator (api.cpp:580-594, 1186-1207) ---

@@ -255,6 +255,39 @@ bool Scene::Flatten(std::string *err) {
     return true;
 }
 
+// -------------------------------------------------------------- Integrators --
+void GpuPathIntegrator::RequestSamples(const Scene &, std::vector<uint16_t> *n1D, std::vector<uint16_t> *n2D) const {
+    // path.cpp:41-49: for SAMPLE_DEPTH (3) depths: LightSampleOffsets(1), Add1D(1) lightNum, BSDFSampleOffsets(1),
+    // BSDFSampleOffsets(1) for the path direction
+    for (int i = 0; i < 3; ++i) {
+        n1D->push_back(1); n2D->push_back(1);   // light: component, pos  (light.cpp:64-68)
+        n1D->push_back(1);                      // lightNum
+        n1D->push_back(1); n2D->push_back(1);   // bsdf: component, dir   (reflection.cpp:502-506)
+        n1D->push_back(1); n2D->push_back(1);   // path: component, dir
+    }
+}
+
+static uint16_t RoundSize(int size) {   // LDSampler::RoundSize = RoundUpPow2, lowdiscrepancy.h:56
+    uint32_t v = (uint32_t)std::max(1, size);
+    v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; v++;
+    return (uint16_t)std::min<uint32_t>(v, 32768u);
+}
+
+void GpuDirectLightingIntegrator::RequestSamples(const Scene &scene, std::vector<uint16_t> *n1D,
+                                                 std::vector<uint16_t> *n2D) const {   // directlighting.cpp:53-78
+    if (strategy == PBRTGPU_STRATEGY_ALL) {
+        for (const Light &l : scene.lights) {
+            uint16_t n = RoundSize(l.desc.nSamples);
+            n1D->push_back(n); n2D->push_back(n);   // LightSampleOffsets(nSamples, sample)
+            n1D->push_back(n); n2D->push_back(n);   // BSDFSampleOffsets(nSamples, sample)
+        }
+    } else {
+        n1D->push_back(1); n2D->push_back(1);       // LightSampleOffsets(1, sample)
+        n1D->push_back(1);                          // lightNumOffset
+        n1D->push_back(1); n2D->push_back(1);       // BSDFSampleOffsets(1, sample)
+    }
+}
+
 // ------------------------------------------------------- GpuSamplerRenderer --
 static int NumSystemCores(int nCores) {   // core/parallel.cpp:878-886
     if (nCores > 0) return nCores;
@@ -285,6 +318,13 @@ void GpuSamplerRenderer::FillRenderDesc(PbrtGpuRenderDesc *rd) const {
     rd->filterYWidth = film->filterYWidth;
     rd->samplesPerPixel = sampler.samplesPerPixel;
     rd->maxDepth = surfaceIntegrator->maxDepth;
+    rd->integrator = surfaceIntegrator->kind;
+    rd->lightStrategy = surfaceIntegrator->kind == PBRTGPU_INTEGRATOR_DIRECTLIGHTING
+                            ? static_cast<const GpuDirectLightingIntegrator *>(surfaceIntegrator.get())->strategy : 0;
+    rd->n1D = (int32_t)std::min<size_t>(n1D.size(), PBRTGPU_MAX_SAMPLE_ARRAYS);
+    rd->n2D = (int32_t)std::min<size_t>(n2D.size(), PBRTGPU_MAX_SAMPLE_ARRAYS);
+    for (int i = 0; i < rd->n1D; ++i) rd->size1D[i] = n1D[i];
+    for (int i = 0; i < rd->n2D; ++i) rd->size2D[i] = n2D[i];
     rd->nTasks = TaskCount();
     rd->taskBegin = 0;
     rd->taskEnd = rd->nTasks;

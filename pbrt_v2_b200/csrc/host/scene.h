@@ -197,15 +197,28 @@ struct LDSampler {   // samplers/lowdiscrepancy.h
 };
 
 // ------------------------------------------------------------ Integrators --
+struct Scene;
 struct SurfaceIntegrator {   // core/integrator.h:51-70
+    int kind;       // PBRTGPU_INTEGRATOR_*
+    int maxDepth;
+    SurfaceIntegrator(int k, int md) : kind(k), maxDepth(md) {}
     virtual ~SurfaceIntegrator() {}
+    // Integrator::RequestSamples: appends this integrator's Add1D / Add2D calls (array sizes) in call order
+    virtual void RequestSamples(const Scene &scene, std::vector<uint16_t> *n1D, std::vector<uint16_t> *n2D) const = 0;
 };
 // Drop-in for PathIntegrator (integrators/path.h:44-63): same parameter
 // ("maxdepth", default 5), same RequestSamples layout (3 depths x {light 1D+2D,
 // lightNum 1D, bsdf 1D+2D, path 1D+2D}); Li() runs on the GPU.
 struct GpuPathIntegrator : SurfaceIntegrator {
-    explicit GpuPathIntegrator(int md) : maxDepth(md) {}
-    int maxDepth;
+    explicit GpuPathIntegrator(int md) : SurfaceIntegrator(PBRTGPU_INTEGRATOR_PATH, md) {}
+    void RequestSamples(const Scene &scene, std::vector<uint16_t> *n1D, std::vector<uint16_t> *n2D) const override;
+};
+// Drop-in for DirectLightingIntegrator (integrators/directlighting.h:47-70): parameters "maxdepth" (5) and
+// "strategy" ("all" | "one"), RequestSamples as directlighting.cpp:53-78 with LDSampler::RoundSize.
+struct GpuDirectLightingIntegrator : SurfaceIntegrator {
+    int strategy;   // PBRTGPU_STRATEGY_*
+    GpuDirectLightingIntegrator(int st, int md) : SurfaceIntegrator(PBRTGPU_INTEGRATOR_DIRECTLIGHTING, md), strategy(st) {}
+    void RequestSamples(const Scene &scene, std::vector<uint16_t> *n1D, std::vector<uint16_t> *n2D) const override;
 };
 
 // -------------------------------------------------------------------- Scene --
@@ -247,7 +260,8 @@ struct GpuSamplerRenderer : Renderer {
     LDSampler sampler;
     std::unique_ptr<PerspectiveCamera> camera;
     std::unique_ptr<ImageFilm> film;
-    std::unique_ptr<GpuPathIntegrator> surfaceIntegrator;
+    std::unique_ptr<SurfaceIntegrator> surfaceIntegrator;
+    std::vector<uint16_t> n1D, n2D;   // Sample::n1D / n2D after both integrators' RequestSamples (sampler.cpp:89-91)
     int nCores;           // PbrtOptions.nCores (--ncores); 0 = hardware
     bool writeImage;
     PbrtGpuStats lastStats;

@@ -53,7 +53,7 @@ def _film(xres, yres, filename, crop):
 
 
 def variant(base, out_path, xres, yres, spp, integrator="path", maxdepth=None,
-            crop=None, filename=None, nlevels=None):
+            crop=None, filename=None, nlevels=None, strategy=None):
     """Write a config variant of staged scene `base` ('killeroo-simple' | 'bunny').
 
     The variant lives next to the staged base so that relative Include /
@@ -66,6 +66,8 @@ def variant(base, out_path, xres, yres, spp, integrator="path", maxdepth=None,
     integ = 'SurfaceIntegrator "%s"' % integrator
     if maxdepth is not None:
         integ += ' "integer maxdepth" [%d]' % maxdepth
+    if strategy is not None:
+        integ += ' "string strategy" "%s"' % strategy
     sampler = 'Sampler "lowdiscrepancy" "integer pixelsamples" [%d]' % spp
     # drop the Film / Sampler / SurfaceIntegrator directives (incl. their
     # continuation lines) and re-emit ours in front of WorldBegin

@@ -31,10 +31,20 @@ REFDUMP = os.path.join(REPO, "oracle", "_ref", "bin", "refdump")
 LD_CASES = [  # (res, spp, nTasks, taskNum)
     (32, 4, 1024, 0), (32, 4, 1024, 37), (32, 64, 1024, 1023), (32, 1024, 64, 5), (48, 16, 4096, 131),
 ]
+LDX_CASES = [  # (res, spp, nTasks, taskNum, n1D sizes, n2D sizes): DirectLightingIntegrator layouts (+ the 2 emission 1-D requests)
+    (32, 4, 1024, 5, [8, 8, 1, 1], [8, 8]),            # killeroo-simple.pbrt as shipped: one area light, nsamples 8
+    (32, 16, 64, 3, [1, 1, 4, 4, 1, 1], [1, 1, 4, 4]),  # bunny.pbrt under directlighting: point light + area light, nsamples 4
+    (32, 64, 1024, 1000, [1, 1, 1, 1, 1], [1, 1]),      # strategy "one"
+    (48, 1024, 64, 7, [16, 16, 1, 1], [16, 16]),
+]
 IMAGE_CASES = [  # (base, res, spp, ncores)
     ("bunny", 32, 4, 32), ("bunny", 32, 8, 1), ("killeroo-simple", 32, 4, 32), ("killeroo-simple", 32, 8, 1),
     # config C4's scene: two animated TransformedPrimitives, each over its own nested BVH
     ("anim-killeroos-moving", 32, 4, 32), ("anim-killeroos-moving", 32, 8, 1),
+    # DirectLightingIntegrator (what the shipped scene files ask for): 5th field = integrator, 6th = strategy
+    ("killeroo-simple", 32, 4, 32, "directlighting", None), ("killeroo-simple", 32, 8, 1, "directlighting", None),
+    ("bunny", 32, 4, 32, "directlighting", None), ("bunny", 32, 8, 1, "directlighting", "one"),
+    ("anim-killeroos-moving", 32, 4, 1, "directlighting", None),
 ]
 
 
@@ -51,6 +61,18 @@ def main():
         ld[key] = rows
         ld[key + "_next"] = nxt
     np.savez_compressed(os.path.join(HERE, "ld_samples.npz"), **ld)
+    ldx = {}
+    for ci, (res, spp, ntasks, task, s1, s2) in enumerate(LDX_CASES):
+        args = [REFDUMP, "ldx", "0", str(res), "0", str(res), str(spp), str(res), str(res), str(ntasks), str(task), "0", "1",
+                str(len(s1))] + [str(x) for x in s1] + [str(len(s2))] + [str(x) for x in s2]
+        out = subprocess.run(args, check=True, stdout=subprocess.PIPE, text=True).stdout.split("\n")
+        n = int(out[0].split()[0])
+        rows = np.array([[float(x) for x in out[1 + i].split()] for i in range(n)], dtype=np.float32)
+        key = "case%d" % ci
+        ldx[key] = rows
+        ldx[key + "_meta"] = np.array([res, spp, ntasks, task, len(s1)] + s1 + [len(s2)] + s2, dtype=np.int64)
+        ldx[key + "_next"] = np.uint32(int(out[1 + n]))
+    np.savez_compressed(os.path.join(HERE, "ld_samples_general.npz"), **ldx)
     rng = {}
     for seed in (0, 1, 5489, 123456):
         out = subprocess.run([REFDUMP, "rng", str(seed), "2000"], check=True, stdout=subprocess.PIPE, text=True).stdout.split()
@@ -60,12 +82,19 @@ def main():
     have = os.path.join(HERE, "images.npz")
     if os.path.exists(have) and "--all" not in sys.argv:   # keep what is committed, mint only new cases
         imgs = dict(np.load(have))
-    for base, res, spp, ncores in IMAGE_CASES:
-        if "%s_r%d_s%d_c%d" % (base.replace("-", "_"), res, spp, ncores) in imgs:
+    for case in IMAGE_CASES:
+        base, res, spp, ncores = case[:4]
+        integ = case[4] if len(case) > 4 else "path"
+        strategy = case[5] if len(case) > 5 else None
+        key = "%s_r%d_s%d_c%d" % (base.replace("-", "_"), res, spp, ncores)
+        if integ != "path":
+            key = "%s_%s_%s" % (integ if strategy is None else integ + strategy, "x", key)
+        if key in imgs:
             continue
-        p = scenes.variant(base, os.path.join(scenes.STAGED, "golden-%s.pbrt" % base), res, res, spp)
+        p = scenes.variant(base, os.path.join(scenes.STAGED, "golden-%s.pbrt" % base), res, res, spp, integrator=integ,
+                           strategy=strategy)
         rgb, _ = oa.run_reference(p, ncores)
-        imgs["%s_r%d_s%d_c%d" % (base.replace("-", "_"), res, spp, ncores)] = rgb.astype(np.float32)
+        imgs[key] = rgb.astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "images.npz"), **imgs)
     counts = {}
     for base in ("bunny", "killeroo-simple"):

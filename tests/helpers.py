@@ -7,12 +7,14 @@ from pbrt_v2_b200 import scenes
 _cache = {}
 
 
-def host_scene(base, xres, yres, spp, ncores, maxdepth=None, crop=None, tag="", nlevels=None):
-    key = (base, xres, yres, spp, ncores, maxdepth, crop, tag, nlevels)
+def host_scene(base, xres, yres, spp, ncores, maxdepth=None, crop=None, tag="", nlevels=None, integrator="path",
+               strategy=None):
+    key = (base, xres, yres, spp, ncores, maxdepth, crop, tag, nlevels, integrator, strategy)
     if key not in _cache:
-        name = "%s-%dx%d-%dspp%s%s.pbrt" % (base, xres, yres, spp, tag, "" if nlevels is None else "-nl%d" % nlevels)
+        name = "%s-%dx%d-%dspp%s%s%s.pbrt" % (base, xres, yres, spp, tag, "" if nlevels is None else "-nl%d" % nlevels,
+                                              "" if integrator == "path" else "-%s%s" % (integrator, strategy or ""))
         path = scenes.variant(base, scenes.STAGED + "/" + name, xres, yres, spp, maxdepth=maxdepth, crop=crop,
-                              nlevels=nlevels)
+                              nlevels=nlevels, integrator=integrator, strategy=strategy)
         _cache[key] = pb.HostScene(path, ncores=ncores)
     return _cache[key]
 
@@ -52,3 +54,39 @@ def scene_bounds(hs):
     nodes_ptr = C.cast(hs.desc_ptr + 8, C.POINTER(C.c_void_p))[0]
     b = np.ctypeslib.as_array(C.cast(nodes_ptr, C.POINTER(C.c_float)), shape=(6,)).copy()
     return b[:3], b[3:]
+
+
+def golden_image_case(key):
+    """(base, res, spp, ncores, integrator, strategy) of a tests/golden/images.npz key"""
+    integrator, strategy = "path", None
+    if "_x_" in key:
+        head, key = key.split("_x_")
+        integrator = "directlighting"
+        strategy = head[len("directlighting"):] or None
+    parts = key.split("_")
+    res, spp, ncores = [int(x[1:]) for x in parts[-3:]]
+    return "-".join(parts[:-3]), res, spp, ncores, integrator, strategy
+
+
+def layout_rd(meta):
+    """RenderDesc of a tests/golden/ld_samples_general.npz case (its `_meta` vector)"""
+    m = [int(x) for x in meta]
+    res, spp, ntasks, task, c1 = m[:5]
+    s1 = m[5:5 + c1]
+    c2 = m[5 + c1]
+    s2 = m[6 + c1:6 + c1 + c2]
+    rd = pb.RenderDesc()
+    rd.xResolution = rd.yResolution = res
+    rd.cropWindow[:] = [0, 1, 0, 1]
+    rd.filterXWidth = rd.filterYWidth = 0.5
+    rd.samplesPerPixel = spp
+    rd.maxDepth = 5
+    rd.integrator = 1
+    rd.nTasks, rd.taskBegin, rd.taskEnd = ntasks, 0, ntasks
+    rd.shutterOpen, rd.shutterClose = 0.0, 1.0
+    rd.n1D, rd.n2D = c1, c2
+    for i, v in enumerate(s1):
+        rd.size1D[i] = v
+    for i, v in enumerate(s2):
+        rd.size2D[i] = v
+    return rd, task

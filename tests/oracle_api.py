@@ -70,7 +70,7 @@ def intersect_p(host_scene, rays):
 
 
 def ld_samples(rd, task_num):
-    out = np.zeros((rd.samplesPerPixel, pb.SAMPLE_FLOATS), dtype=np.float32)
+    out = np.zeros((rd.samplesPerPixel, pb.sample_floats(rd)), dtype=np.float32)
     rc = lib().oracle_ld_samples(C.byref(rd), int(task_num), out.ctypes.data)
     assert rc == 0, "empty task window"
     return out

@@ -36,6 +36,21 @@ def test_ld_samples_bit_exact(staged, spp, ncores):
         assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), "LD tables differ for task %d" % task
 
 
+def test_ld_samples_general_layouts_bit_exact():
+    """k_tables_general (arrays with several values per pixel sample: DirectLightingIntegrator's layouts) against
+    the vectors minted from the reference's own Sample / LDSampler classes, and against the oracle."""
+    import os
+    from helpers import layout_rd
+    g = np.load(os.path.join(pb.REPO, "tests", "golden", "ld_samples_general.npz"))
+    for key in [k for k in g.files if not k.endswith("_next") and not k.endswith("_meta")]:
+        rd, task = layout_rd(g[key + "_meta"])
+        got = pb.ld_samples(rd, task)
+        assert got.shape == g[key].shape
+        assert np.array_equal(got.view(np.uint32), g[key].view(np.uint32)), key
+        for t in (0, rd.nTasks - 1):
+            assert np.array_equal(pb.ld_samples(rd, t).view(np.uint32), oa.ld_samples(rd, t).view(np.uint32))
+
+
 @pytest.mark.parametrize("base", ["bunny", "killeroo-simple", "anim-killeroos-moving"])
 def test_intersect_bit_exact(staged, base):
     hs = host_scene(base, 32, 32, 4, 32)
@@ -99,15 +114,20 @@ def test_render_matches_oracle(staged, base, res, spp, ncores):
     assert st.cameraSamples == cnt.cameraSamples
 
 
-@pytest.mark.parametrize("base,res,spp,ncores", [
-    ("bunny", 64, 16, 128), ("bunny", 64, 16, 1), ("killeroo-simple", 64, 16, 128), ("killeroo-simple", 48, 8, 2),
-    ("anim-killeroos-moving", 64, 16, 128), ("anim-killeroos-moving", 48, 8, 2),   # TransformedPrimitives (config C4)
+@pytest.mark.parametrize("base,res,spp,ncores,integrator,strategy", [
+    ("bunny", 64, 16, 128, "path", None), ("bunny", 64, 16, 1, "path", None),
+    ("killeroo-simple", 64, 16, 128, "path", None), ("killeroo-simple", 48, 8, 2, "path", None),
+    ("anim-killeroos-moving", 64, 16, 128, "path", None), ("anim-killeroos-moving", 48, 8, 2, "path", None),   # config C4
+    # DirectLightingIntegrator: strategies "all" (per-light sample arrays) and "one", per-pixel and multi-pixel tasks
+    ("killeroo-simple", 64, 16, 128, "directlighting", None), ("killeroo-simple", 48, 8, 2, "directlighting", None),
+    ("bunny", 64, 8, 128, "directlighting", None), ("bunny", 48, 16, 1, "directlighting", None),
+    ("bunny", 48, 8, 2, "directlighting", "one"), ("anim-killeroos-moving", 48, 8, 2, "directlighting", None),
 ])
-def test_render_bit_exact_vs_oracle(staged, base, res, spp, ncores):
+def test_render_bit_exact_vs_oracle(staged, base, res, spp, ncores, integrator, strategy):
     """With glibc's libm restated on the device (refmath.h) the film is bit-identical to the oracle's, except
     (a) pixels that receive an edge splat from another task (order-dependent in the reference itself) and
     (b) the ~1e-9 of expf arguments where the host libm's FMA build rounds differently."""
-    hs = host_scene(base, res, res, spp, ncores)
+    hs = host_scene(base, res, res, spp, ncores, integrator=integrator, strategy=strategy)
     px_gpu, _ = _gpu_scene(hs).render()
     px_cpu, _ = oa.render(hs, threads=1)
     assert np.array_equal(px_gpu["weightSum"], px_cpu["weightSum"])
@@ -181,14 +201,17 @@ def test_host_renderer_entry_point(staged):
 
 @pytest.mark.parametrize("key", ["bunny_r32_s4_c32", "bunny_r32_s8_c1", "killeroo_simple_r32_s4_c32",
                                  "killeroo_simple_r32_s8_c1", "anim_killeroos_moving_r32_s4_c32",
-                                 "anim_killeroos_moving_r32_s8_c1"])
+                                 "anim_killeroos_moving_r32_s8_c1",
+                                 "directlighting_x_killeroo_simple_r32_s4_c32", "directlighting_x_killeroo_simple_r32_s8_c1",
+                                 "directlighting_x_bunny_r32_s4_c32", "directlightingone_x_bunny_r32_s8_c1",
+                                 "directlighting_x_anim_killeroos_moving_r32_s4_c1"])
 def test_render_matches_golden_reference_images(staged, key):
     """GPU render vs images rendered by the UNMODIFIED reference (tests/golden/images.npz)."""
     import os
     g = np.load(os.path.join(pb.REPO, "tests", "golden", "images.npz"))
-    base = "-".join(key.split("_")[:-3])
-    res, spp, ncores = [int(x[1:]) for x in key.split("_")[-3:]]
-    hs = host_scene(base, res, res, spp, ncores)
+    from helpers import golden_image_case
+    base, res, spp, ncores, integrator, strategy = golden_image_case(key)
+    hs = host_scene(base, res, res, spp, ncores, integrator=integrator, strategy=strategy)
     px, _ = _gpu_scene(hs).render()
     rgb, want = hs.pixels_to_rgb(px), g[key]
     rel = np.abs(rgb - want) / np.maximum(np.abs(want), 1e-3)

@@ -49,7 +49,7 @@ def test_crop_window_extent(staged):
 
 
 @pytest.mark.parametrize("text,needle", [
-    ('SurfaceIntegrator "directlighting"', "not on the hot path"),
+    ('SurfaceIntegrator "whitted"', "outside the scope"),
     ('Sampler "random"', "out of scope"),
     ('Material "glass"', "outside the hot-path scope"),
     ('Texture "t" "float" "constant"', "outside the hot-path scope"),

@@ -38,7 +38,7 @@ def test_ld_tables_match_golden():
     assert len(cases) >= 5
     for key in cases:
         res, spp, ntasks, task = [int(x[1:]) for x in key.split("_")]
-        rd = pb.RenderDesc()
+        rd = pb.set_path_layout(pb.RenderDesc())
         rd.xResolution = rd.yResolution = res
         rd.cropWindow[:] = [0, 1, 0, 1]
         rd.filterXWidth = rd.filterYWidth = 0.5
@@ -52,20 +52,39 @@ def test_ld_tables_match_golden():
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), key
 
 
-@pytest.mark.parametrize("key", ["bunny_r32_s4_c32", "bunny_r32_s8_c1", "killeroo_simple_r32_s4_c32",
-                                 "killeroo_simple_r32_s8_c1", "anim_killeroos_moving_r32_s4_c32",
-                                 "anim_killeroos_moving_r32_s8_c1"])
+def test_oracle_ld_samples_general_layouts_match_golden():
+    """LDPixelSample with arrays of more than one value per pixel sample (DirectLightingIntegrator's layouts),
+    against vectors minted from the reference's own Sample / LDSampler classes (refdump ldx)."""
+    from helpers import layout_rd
+    g = np.load(os.path.join(GOLD, "ld_samples_general.npz"))
+    cases = [k for k in g.files if not k.endswith("_next") and not k.endswith("_meta")]
+    assert len(cases) >= 4
+    for key in cases:
+        rd, task = layout_rd(g[key + "_meta"])
+        got = oa.ld_samples(rd, task)
+        assert got.shape == g[key].shape
+        assert np.array_equal(got.view(np.uint32), g[key].view(np.uint32)), key
+
+
+GOLDEN_IMAGES = ["bunny_r32_s4_c32", "bunny_r32_s8_c1", "killeroo_simple_r32_s4_c32", "killeroo_simple_r32_s8_c1",
+                 "anim_killeroos_moving_r32_s4_c32", "anim_killeroos_moving_r32_s8_c1",
+                 "directlighting_x_killeroo_simple_r32_s4_c32", "directlighting_x_killeroo_simple_r32_s8_c1",
+                 "directlighting_x_bunny_r32_s4_c32", "directlightingone_x_bunny_r32_s8_c1",
+                 "directlighting_x_anim_killeroos_moving_r32_s4_c1"]
+
+
+@pytest.mark.parametrize("key", GOLDEN_IMAGES)
 def test_oracle_image_matches_golden_reference_render(staged, key):
     g = np.load(os.path.join(GOLD, "images.npz"))
-    base = "-".join(key.split("_")[:-3])
-    res, spp, ncores = [int(x[1:]) for x in key.split("_")[-3:]]
-    hs = host_scene(base, res, res, spp, ncores)
+    from helpers import golden_image_case
+    base, res, spp, ncores, integrator, strategy = golden_image_case(key)
+    hs = host_scene(base, res, res, spp, ncores, integrator=integrator, strategy=strategy)
     px, _ = oa.render(hs, threads=4)
     rgb = hs.pixels_to_rgb(px)
     want = g[key]
     differ = (rgb.view(np.uint32) != want.view(np.uint32)).any(axis=2)
     # multi-pixel tasks (c1): every pixel bit-exact; per-pixel tasks: only cross-task edge splats may differ
-    assert differ.sum() <= (0 if ncores == 1 else 4), "%d pixels differ from the reference render" % differ.sum()
+    assert differ.sum() <= (0 if ncores <= 1 else 4), "%d pixels differ from the reference render" % differ.sum()
     np.testing.assert_allclose(rgb, want, rtol=2e-6, atol=0)
 
 
@@ -77,10 +96,11 @@ def test_bvh_sizes_match_reference(staged):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
-@pytest.mark.parametrize("base,res,spp,ncores", [("bunny", 40, 8, 2), ("killeroo-simple", 40, 4, 2),
-                                                 ("anim-killeroos-moving", 40, 4, 2)])
-def test_oracle_bit_exact_vs_reference_binary(staged, base, res, spp, ncores):
-    hs = host_scene(base, res, res, spp, ncores, tag="-live")
+@pytest.mark.parametrize("base,res,spp,ncores,integrator", [
+    ("bunny", 40, 8, 2, "path"), ("killeroo-simple", 40, 4, 2, "path"), ("anim-killeroos-moving", 40, 4, 2, "path"),
+    ("killeroo-simple", 40, 4, 2, "directlighting"), ("bunny", 40, 4, 2, "directlighting")])
+def test_oracle_bit_exact_vs_reference_binary(staged, base, res, spp, ncores, integrator):
+    hs = host_scene(base, res, res, spp, ncores, tag="-live", integrator=integrator)
     px, _ = oa.render(hs, threads=4)
     rgb = hs.pixels_to_rgb(px)
     ref, _ = oa.run_reference(hs.filename, ncores)
