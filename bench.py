@@ -36,13 +36,19 @@ WORKLOADS = {
     # configs[3]: two animated TransformedPrimitives (each its own nested BVH) of killeroos subdivided to
     # 532 224 triangles (geometry copy with "integer nlevels" [3]), shutter 0..1
     "anim-c4": ("anim-killeroos-moving", 1920, 1080, 1024),
+    # scenes/killeroo-simple.pbrt exactly as shipped (SurfaceIntegrator "directlighting", strategy
+    # "all", area light with 8 samples: 17 rays per camera sample), 700x700, 64 spp
+    "killeroo-dl": ("killeroo-simple", 700, 700, 64),
     # configs[4]: synthetic 10M-triangle random mesh, maxdepth 8 (HBM-resident: 1.3 GB of BVH + triangles)
     "synthetic-c5": ("synthetic", 4096, 4096, 512),
 }
 WORKLOAD_NLEVELS = {"anim-c4": 3}
+WORKLOAD_INTEGRATOR = {"killeroo-dl": "directlighting"}
 SYNTHETIC_TRIS = 10000000
 # dram__bytes_read.sum + dram__bytes_write.sum of one mid-render k_trace launch (ncu --set full, profiles/), per workload
-K_TRACE_DRAM_BYTES_PER_LAUNCH = {}
+K_TRACE_DRAM_BYTES_PER_LAUNCH = {
+    "bunny-c2": 208541696 + 118836992,   # profiles/r01_k_trace_ncu_full.txt (launch 200 of a 128-spp run: a full 4 Mi-slot pool, as at 1024 spp)
+}
 CPU_SAMPLE_SPP = 16     # bounded sample of the same workload for the CPU arms (cost is linear in spp)
 
 
@@ -145,7 +151,7 @@ def cpu_reference_rate(workload, threads):
     from pbrt_v2_b200 import scenes
     base, xres, yres, _ = WORKLOADS[workload]
     path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-cpu-%s.pbrt" % workload), xres, yres, CPU_SAMPLE_SPP,
-                          nlevels=WORKLOAD_NLEVELS.get(workload))
+                          nlevels=WORKLOAD_NLEVELS.get(workload), integrator=WORKLOAD_INTEGRATOR.get(workload, "path"))
     sec, wall = reference_render_seconds(path, threads)
     nsamp = xres * yres * CPU_SAMPLE_SPP
     return nsamp / max(sec, 1e-3) / 1e6, sec, wall
@@ -189,8 +195,9 @@ def run_reference_arm(args, rank, world):
 
 def workload_config(workload, world, per_pixel=True):
     base, xres, yres, spp = WORKLOADS[workload]
-    desc = ("scenes/%s.pbrt%s, SurfaceIntegrator \"path\" (maxdepth 5)" % (
-        base, (" with geometry/killeroo.pbrt at \"integer nlevels\" [%d]" % WORKLOAD_NLEVELS[workload]) if workload in WORKLOAD_NLEVELS else "")) \
+    desc = ("scenes/%s.pbrt%s, SurfaceIntegrator \"%s\" (maxdepth 5)" % (
+        base, (" with geometry/killeroo.pbrt at \"integer nlevels\" [%d]" % WORKLOAD_NLEVELS[workload]) if workload in WORKLOAD_NLEVELS else "",
+        WORKLOAD_INTEGRATOR.get(workload, "path"))) \
         if base != "synthetic" else \
         "synthetic random-triangle scene (SURVEY 8d C5), SurfaceIntegrator \"path\" (maxdepth 8)"
     return {
@@ -198,7 +205,7 @@ def workload_config(workload, world, per_pixel=True):
         "global_batch": xres * yres * spp, "parallelism": "tile%d" % world,
         "tasks": tasks_note(xres, yres) if per_pixel
                  else "reference default nTasks",
-        "l2": "256 MiB buffer rewritten between steps (L2 flush); per-step sample tables (>= 24 GB) stream through HBM",
+        "l2": "256 MiB buffer rewritten between steps (L2 flush); the per-step sample tables (64 B per camera sample, 69 GB at C2) stream through HBM",
     }
 
 
@@ -242,7 +249,8 @@ def main():
         hs = pb.HostScene.synthetic(args.tris, xres, yres, spp, maxdepth=8, ncores=per_pixel_ncores(xres, yres))
     else:
         path = scenes.variant(base, os.path.join(scenes.STAGED, "bench-%s-r%d.pbrt" % (args.workload, rank)), xres, yres, spp,
-                              nlevels=WORKLOAD_NLEVELS.get(args.workload))
+                              nlevels=WORKLOAD_NLEVELS.get(args.workload),
+                              integrator=WORKLOAD_INTEGRATOR.get(args.workload, "path"))
         hs = pb.HostScene(path, ncores=per_pixel_ncores(xres, yres))
     rd = hs.render_desc()
     from pbrt_v2_b200.multigpu import shard_render_desc, reduce_film
