@@ -193,8 +193,10 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
-def workload_config(workload, world, per_pixel=True):
+def workload_config(workload, world, per_pixel=True, spp_override=None):
     base, xres, yres, spp = WORKLOADS[workload]
+    if spp_override:
+        spp = spp_override
     desc = ("scenes/%s.pbrt%s, SurfaceIntegrator \"%s\" (maxdepth 5)" % (
         base, (" with geometry/killeroo.pbrt at \"integer nlevels\" [%d]" % WORKLOAD_NLEVELS[workload]) if workload in WORKLOAD_NLEVELS else "",
         WORKLOAD_INTEGRATOR.get(workload, "path"))) \
@@ -373,7 +375,7 @@ def main():
             "metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, world),
+            "config": workload_config(args.workload, world, spp_override=spp),
             "e2e": {"value": e2e_value, "unit": "Msamples/s",
                     "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": int(xc * yc * 16)},
             "gpu_launches": launches,
