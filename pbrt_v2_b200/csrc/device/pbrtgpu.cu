@@ -376,6 +376,21 @@ __global__ void k_expand_samples(BatchArgs a, int spp, float shutterOpen, float 
 //
 // Both phases are one state machine with a single BVH-traversal site per loop
 // iteration, so the lanes of a warp traverse together whatever stage each is in.
+// resident blocks per SM the register allocator must allow (A/B knobs; the defaults are the measured best on C2 at
+// 256 spp: k_logic 4 -> 5: 221 -> 214 Msamples/s; k_path 4 -> 5: 220; k_trace unbounded (79 regs, 6 blocks) -> 7 (72 regs)
+// with k_eval -> 8: 221 -> 232; k_trace -> 8 (64 regs): 234, within noise of 7)
+#ifndef K_PATH_MIN_BLOCKS
+#define K_PATH_MIN_BLOCKS 4
+#endif
+#ifndef K_LOGIC_MIN_BLOCKS
+#define K_LOGIC_MIN_BLOCKS 4
+#endif
+#ifndef K_TRACE_MIN_BLOCKS
+#define K_TRACE_MIN_BLOCKS 7
+#endif
+#ifndef K_EVAL_MIN_BLOCKS
+#define K_EVAL_MIN_BLOCKS 8
+#endif
 enum PathState {
     S_NEW_SAMPLE = 0, S_HIT_RESULT, S_SHADOW_RESULT, S_AFTER_LIGHT, S_MIS_RESULT, S_AFTER_DIRECT, S_END_SAMPLE, S_DONE,
     S_E_LIGHT, S_E_MIS, S_E_PATH,   // waiting for the BSDF value at the evaluation site
@@ -452,7 +467,7 @@ DEV Spec SanitizeRadiance(const Spec &L) {
 
 template <int PHASE, bool STATS, bool ANIM>
 // 4 CTAs/SM (<= 128 registers): measured +9 % over the unconstrained 168-register build
-__global__ void __launch_bounds__(128, 4) k_path(PathArgs a) {
+__global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(PathArgs a) {
     __shared__ uint32_t smt[4][MT_N];
     const DScene &sc = a.sc;
     const RenderParams &rp = a.rp;
@@ -748,7 +763,7 @@ DEV unsigned AggregatedAdd(unsigned *ctr) {   // warp-aggregated atomicAdd(ctr, 
 // parked samples, resumed one after the other with the task's sequential RNG stream; finished samples are added
 // to the film in sample order in between (what k_path<2> does per thread, here as a wavefront).
 template <int PHASE, bool STATS, bool ANIM, int INTEG>
-__global__ void __launch_bounds__(128, 4) k_logic(WfArgs a) {
+__global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
     __shared__ uint32_t smt[PHASE == 2 ? 4 : 1][PHASE == 2 ? MT_N : 1];
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const DScene &sc = a.sc;
@@ -1149,7 +1164,7 @@ __global__ void __launch_bounds__(128) k_film_direct(PathArgs a, int advance) {
 // persistent ray queue consumer
 #define TRACE_CHUNK 64
 template <bool STATS, bool ANIM>
-__global__ void __launch_bounds__(128) k_trace(WfArgs a) {
+__global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(WfArgs a) {
     const DScene &sc = a.sc;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -1233,7 +1248,7 @@ __global__ void __launch_bounds__(128) k_trace(WfArgs a) {
 }
 
 // measured-BRDF evaluations (IrregIsotropicBRDF::f) of the queued requests
-__global__ void __launch_bounds__(128) k_eval(WfArgs a) {
+__global__ void __launch_bounds__(128, K_EVAL_MIN_BLOCKS) k_eval(WfArgs a) {
     const int setOut = (a.iter & 1) ^ 1;
     const unsigned *qn = a.counters + C_QN + setOut * K_COUNT;
     const unsigned n0 = qn[K_E_LIGHT], n1 = n0 + qn[K_E_MIS], n = n1 + qn[K_E_PATH];
