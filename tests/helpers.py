@@ -90,3 +90,31 @@ def layout_rd(meta):
     for i, v in enumerate(s2):
         rd.size2D[i] = v
     return rd, task
+
+
+# scene-file variants beyond resolution / spp / integrator: (name, base, xres, yres, spp, ncores, variant kwargs, text edits)
+VARIANTS = [
+    ("dof", "bunny", 40, 40, 4, 2, {},
+     [('Camera "perspective"', 'Camera "perspective" "float lensradius" [0.02] "float focaldistance" [0.6]')]),
+    ("maxdepth1", "killeroo-simple", 40, 40, 4, 2, {"maxdepth": 1}, []),
+    ("maxdepth8", "killeroo-simple", 40, 40, 4, 2, {"maxdepth": 8}, []),
+    ("nonsquare-crop", "bunny", 48, 32, 4, 3, {"crop": (0.1, 0.9, 0.25, 0.8)}, []),
+    ("directlighting-maxdepth1", "killeroo-simple", 40, 40, 4, 2, {"maxdepth": 1, "integrator": "directlighting"}, []),
+    ("shutter", "anim-killeroos-moving", 40, 40, 4, 2, {},
+     [('Camera "perspective"', 'Camera "perspective" "float shutteropen" [0.25] "float shutterclose" [0.5]')]),
+]
+
+
+def variant_scene(name):
+    """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
+    key = ("variant", name)
+    if key not in _cache:
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS if v[0] == name][0]
+        path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
+        text = open(path).read()
+        for a, b in edits:
+            assert a in text
+            text = text.replace(a, b)
+        open(path, "w").write(text)
+        _cache[key] = (pb.HostScene(path, ncores=ncores), ncores)
+    return _cache[key]

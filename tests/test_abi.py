@@ -79,3 +79,34 @@ def test_product_never_loads_the_oracle():
                 text = open(os.path.join(root, f), errors="ignore").read()
                 assert "liboracle" not in text and "oracle_api" not in text and "oracle/" not in text.replace("(oracle/", "").replace("``oracle/``", ""), \
                     "%s mentions the oracle" % os.path.join(root, f)
+
+
+def _rd(res=64, spp=4, ntasks=1024):
+    rd = pb.set_path_layout(pb.RenderDesc())
+    rd.xResolution = rd.yResolution = res
+    rd.cropWindow[:] = [0, 1, 0, 1]
+    rd.filterXWidth = rd.filterYWidth = 0.5
+    rd.samplesPerPixel = spp
+    rd.maxDepth = 5
+    rd.nTasks, rd.taskBegin, rd.taskEnd = ntasks, 0, ntasks
+    rd.shutterOpen, rd.shutterClose = 0.0, 1.0
+    return rd
+
+
+def test_render_desc_validation_precedes_the_device():
+    """Descriptor errors are reported as such (EINVAL / EUNSUPPORTED) even on a box without a GPU."""
+    cases = []
+    rd = _rd(res=4096, ntasks=1 << 24)            # dy * nx overflows int in Sampler::ComputeSubWindow (sampler.cpp:58)
+    cases.append((rd, "ComputeSubWindow"))
+    rd = _rd(); rd.size1D[3] = 2                  # not PathIntegrator's Sample layout
+    cases.append((rd, "Sample layout"))
+    rd = _rd(spp=3)                               # LDSampler rounds to powers of two
+    cases.append((rd, "power of two"))
+    rd = _rd(); rd.integrator = 7
+    cases.append((rd, "integrator"))
+    rd = _rd(); rd.filterXWidth = 2.0             # wide filters need cross-task splats
+    cases.append((rd, "filters wider"))
+    for rd, needle in cases:
+        with pytest.raises(pb.PbrtGpuError) as e:
+            pb.ld_samples(rd, 0)
+        assert needle in str(e.value), str(e.value)

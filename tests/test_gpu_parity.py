@@ -139,6 +139,19 @@ def test_render_bit_exact_vs_oracle(staged, base, res, spp, ncores, integrator, 
     np.testing.assert_allclose(px_gpu["Lxyz"][~splat & ~diff], px_cpu["Lxyz"][~splat & ~diff], rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("name", ["dof", "maxdepth1", "maxdepth8", "nonsquare-crop", "directlighting-maxdepth1", "shutter"])
+def test_render_variants_bit_exact_vs_oracle(staged, name):
+    """the scene-file variants the oracle is pinned on against the reference binary (tests/helpers.py VARIANTS)"""
+    from helpers import variant_scene
+    hs, _ = variant_scene(name)
+    px_gpu, _ = _gpu_scene(hs).render()
+    px_cpu, _ = oa.render(hs, threads=1)
+    assert np.array_equal(px_gpu["weightSum"], px_cpu["weightSum"])
+    own = px_cpu["weightSum"] == hs.render_desc().samplesPerPixel   # (pixels that received an edge splat: order-dependent)
+    assert own.mean() > 0.99
+    assert np.array_equal(px_gpu["Lxyz"][own].view(np.uint32), px_cpu["Lxyz"][own].view(np.uint32))
+
+
 def test_task_sharding_is_exact(staged):
     """rendering [0,n/2) and [n/2,n) separately sums to the one-shot render (multi-GPU split)."""
     hs = host_scene("bunny", 48, 48, 8, 72)   # nTasks = 4096 > 2304 pixels: some tasks are empty

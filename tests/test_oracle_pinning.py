@@ -108,6 +108,18 @@ def test_oracle_bit_exact_vs_reference_binary(staged, base, res, spp, ncores, in
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["dof", "maxdepth1", "maxdepth8", "nonsquare-crop", "directlighting-maxdepth1", "shutter"])
+def test_oracle_bit_exact_vs_reference_binary_on_variants(staged, name):
+    """thin-lens camera (perspective.cpp:100-113), maxdepth 1 / 8, a non-square cropped film, directlighting without the
+    SpecularReflect/Transmit draws (maxdepth 1), a shutter interval inside the transform interval (animated scene)"""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 def test_synthetic_scene_text_and_direct_routes_match_reference(staged):
     """the C5 generator: the in-memory build equals the text scene, and the oracle renders it bit-exactly
     like the unmodified reference (multi-pixel tasks)."""
