@@ -1418,6 +1418,118 @@ int oracle_intersect(const PbrtGpuSceneDesc *scene, const PbrtGpuRay *rays, int 
     return 0;
 }
 
+// AggregateTest::Render, renderers/aggregatetest.cpp:60-119 -- the reference's own accelerator check: random rays
+// (RNG with its default seed; origins in the grown scene box or at the last hit point, directions uniform on the sphere
+// with occasional axis-aligned ones, ray epsilon 0 / last hit's / 1e-3), the accelerator against an exhaustive loop over
+// the refined primitives, each gated by its world bound (BBox::IntersectP, geometry.cpp:68-86); a primitive that is hit
+// although its bound is missed makes the case "inconsistent" and it is not reported.  The rays and the exhaustive
+// answers (hit flag, ray.maxt) are returned so that the same set can be sent through other implementations; the return
+// value is the number of "Disagreement" warnings the reference would print (static scenes only: no MotionBounds here).
+struct Box3 { Vec lo, hi; };
+static Box3 UnionPt(const Box3 &b, const Vec &p) {
+    Box3 r;
+    r.lo = Vec(std::min(b.lo.x, p.x), std::min(b.lo.y, p.y), std::min(b.lo.z, p.z));
+    r.hi = Vec(std::max(b.hi.x, p.x), std::max(b.hi.y, p.y), std::max(b.hi.z, p.z));
+    return r;
+}
+static Box3 PrimWorldBound(const PbrtGpuSceneDesc *d, uint32_t pi) {
+    const PbrtGpuPrimitive &p = d->primitives[pi];
+    Box3 b;
+    if (p.type == PBRTGPU_PRIM_TRIANGLE) {   // Triangle::WorldBound, trianglemesh.cpp:118-124: Union(BBox(p1, p2), p3)
+        const PbrtGpuTriangle &t = d->triangles[p.index];
+        Vec p1(d->P + 3 * t.v[0]), p2(d->P + 3 * t.v[1]), p3(d->P + 3 * t.v[2]);
+        b.lo = Vec(std::min(p1.x, p2.x), std::min(p1.y, p2.y), std::min(p1.z, p2.z));
+        b.hi = Vec(std::max(p1.x, p2.x), std::max(p1.y, p2.y), std::max(p1.z, p2.z));
+        return UnionPt(b, p3);
+    }
+    const PbrtGpuQuadric &q = d->quadrics[p.index];   // Shape::WorldBound = ObjectToWorld(ObjectBound()), shape.cpp:52-54
+    Vec lo, hi;
+    if (q.type == PBRTGPU_PRIM_SPHERE) { lo = Vec(-q.radius, -q.radius, q.zmin); hi = Vec(q.radius, q.radius, q.zmax); }
+    else { lo = Vec(-q.radius, -q.radius, q.height); hi = Vec(q.radius, q.radius, q.height); }
+    const float *m = d->xforms[q.xform].m;
+    auto M = [&](float x, float y, float z) {   // Transform::operator()(const Point &): the returning version
+        float xp = m[0] * x + m[1] * y + m[2] * z + m[3], yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+        float zp = m[8] * x + m[9] * y + m[10] * z + m[11], wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+        if (wp == 1.) return Vec(xp, yp, zp);
+        return Vec(xp, yp, zp) / wp;
+    };
+    Vec c0 = M(lo.x, lo.y, lo.z);   // Transform::operator()(const BBox &), transform.cpp:283-294
+    b.lo = c0; b.hi = c0;
+    b = UnionPt(b, M(hi.x, lo.y, lo.z)); b = UnionPt(b, M(lo.x, hi.y, lo.z)); b = UnionPt(b, M(lo.x, lo.y, hi.z));
+    b = UnionPt(b, M(lo.x, hi.y, hi.z)); b = UnionPt(b, M(hi.x, hi.y, lo.z)); b = UnionPt(b, M(hi.x, lo.y, hi.z));
+    b = UnionPt(b, M(hi.x, hi.y, hi.z));
+    return b;
+}
+static bool BoxIntersectP(const Box3 &b, const Ray &ray) {   // BBox::IntersectP, geometry.cpp:68-86
+    float t0 = ray.mint, t1 = ray.maxt;
+    for (int i = 0; i < 3; ++i) {
+        float invRayDir = 1.f / ray.d[i];
+        float tNear = (b.lo[i] - ray.o[i]) * invRayDir;
+        float tFar = (b.hi[i] - ray.o[i]) * invRayDir;
+        if (tNear > tFar) std::swap(tNear, tFar);
+        t0 = tNear > t0 ? tNear : t0;
+        t1 = tFar < t1 ? tFar : t1;
+        if (t0 > t1) return false;
+    }
+    return true;
+}
+
+int oracle_aggregate_test(const PbrtGpuSceneDesc *scene, int nIterations, PbrtGpuRay *raysOut, uint8_t *hitOut, float *tOut) {
+    SceneView sv{scene};
+    if (scene->nAnimated) return -1;
+    RNG rng(5489u);   // RNG(uint32_t seed = 5489UL), core/rng.h:47
+    const uint32_t nTop = scene->nPrimitives;
+    std::vector<Box3> bboxes(nTop);
+    for (uint32_t j = 0; j < nTop; ++j) bboxes[j] = PrimWorldBound(scene, j);
+    Vec bmin(scene->nodes[0].bmin), bmax(scene->nodes[0].bmax);   // scene->WorldBound() = BVHAccel::WorldBound
+    {   // bbox.Expand(extent of the largest axis), aggregatetest.cpp:65-66
+        Vec d = bmax - bmin;
+        int ax = (d.x > d.y && d.x > d.z) ? 0 : (d.y > d.z ? 1 : 2);
+        float delta = bmax[ax] - bmin[ax];
+        bmin = bmin - Vec(delta, delta, delta);
+        bmax = bmax + Vec(delta, delta, delta);
+    }
+    Vec lastHit(0, 0, 0);
+    float lastEps = 0.f;
+    int disagreements = 0;
+    for (int i = 0; i < nIterations; ++i) {
+        // the reference draws inside argument lists (aggregatetest.cpp:74-80); g++ on x86-64 evaluates them right to
+        // left, so z is drawn first and UniformSampleSphere's u2 before u1 -- pinned by the reference binary's own output
+        const float rz = rng.RandomFloat(), ry = rng.RandomFloat(), rx = rng.RandomFloat();
+        Vec org(Lerp(rx, bmin.x, bmax.x), Lerp(ry, bmin.y, bmax.y), Lerp(rz, bmin.z, bmax.z));
+        if ((rng.RandomUInt() % 4) == 0) org = lastHit;
+        const float u2 = rng.RandomFloat(), u1 = rng.RandomFloat();
+        Vec dir = UniformSampleSphere(u1, u2);
+        if ((rng.RandomUInt() % 32) == 0) dir.x = dir.y = 0.f;
+        else if ((rng.RandomUInt() % 32) == 0) dir.x = dir.z = 0.f;
+        else if ((rng.RandomUInt() % 32) == 0) dir.y = dir.z = 0.f;
+        float eps = 0.f;
+        if (rng.RandomFloat() < .25) eps = lastEps;
+        else if (rng.RandomFloat() < .25) eps = 1e-3f;
+        Ray rayAccel(org, dir, eps), rayAll(org, dir, eps);
+        Intersection isectAccel, isectAll;
+        bool hitAccel = sv.Intersect(rayAccel, &isectAccel, nullptr);
+        bool hitAll = false, inconsistentBounds = false;
+        for (uint32_t j = 0; j < nTop; ++j) {
+            if (BoxIntersectP(bboxes[j], rayAll)) hitAll |= sv.PrimIntersect(j, rayAll, &isectAll, nullptr);
+            else if (sv.PrimIntersect(j, rayAll, &isectAll, nullptr)) inconsistentBounds = true;
+        }
+        if (!inconsistentBounds && (hitAccel != hitAll || rayAccel.maxt != rayAll.maxt)) ++disagreements;
+        if (raysOut) {
+            PbrtGpuRay &r = raysOut[i];
+            r.o[0] = org.x; r.o[1] = org.y; r.o[2] = org.z; r.d[0] = dir.x; r.d[1] = dir.y; r.d[2] = dir.z;
+            r.mint = eps; r.maxt = INF_F; r.time = 0.f;
+            hitOut[i] = hitAll ? 1 : 0;
+            tOut[i] = rayAll.maxt;
+        }
+        if (hitAll) {
+            lastHit = rayAll(rayAll.maxt);
+            lastEps = isectAll.rayEpsilon;
+        }
+    }
+    return disagreements;
+}
+
 int oracle_intersect_p(const PbrtGpuSceneDesc *scene, const PbrtGpuRay *rays, int n, uint8_t *occluded) {
     SceneView sv{scene};
     for (int i = 0; i < n; ++i) {

@@ -105,6 +105,23 @@ def main():
         m = re.search(r"BVH created with (\d+) nodes for (\d+)", out)
         counts[base] = {"nodes": int(m.group(1)), "primitives": int(m.group(2))}
     json.dump(counts, open(os.path.join(HERE, "counts.json"), "w"), indent=1, sort_keys=True)
+    # Renderer "aggregatetest" (renderers/aggregatetest.cpp): the reference's accelerator check prints one
+    # "Disagreement" warning per ray where BVHAccel and the exhaustive loop differ (rays that start on a flat
+    # primitive with mint == 0); their number and the rays themselves are the known answer
+    agg = {}
+    for base in ("bunny", "killeroo-simple"):
+        n = 20000
+        p = scenes.variant(base, os.path.join(scenes.STAGED, "golden-agg-%s.pbrt" % base), 32, 32, 4)
+        text = open(p).read().replace("WorldBegin", 'Renderer "aggregatetest" "integer niters" [%d]\nWorldBegin' % n, 1)
+        open(p, "w").write(text)
+        out = subprocess.run([oa.REF_BIN, "--ncores", "1", os.path.basename(p)], cwd=scenes.STAGED, stdout=subprocess.PIPE,
+                             stderr=subprocess.STDOUT, text=True).stdout
+        flat = re.sub(r"\s+", " ", out)
+        rays = re.findall(r"Ray: org \[([^\]]+)\], dir \[([^\]]+)\], mint = (\S+)", flat)
+        hx = lambda t: [float.fromhex(x.strip()) for x in t.split(",")]
+        agg[base] = {"niters": n, "disagreements": len(rays),
+                     "first_rays": [{"o": hx(a), "d": hx(b), "mint": float.fromhex(c)} for a, b, c in rays[:50]]}
+    json.dump(agg, open(os.path.join(HERE, "aggregatetest.json"), "w"), indent=1, sort_keys=True)
     print("golden fixtures written:", sorted(os.listdir(HERE)))
 
 

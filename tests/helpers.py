@@ -118,3 +118,18 @@ def variant_scene(name):
         open(path, "w").write(text)
         _cache[key] = (pb.HostScene(path, ncores=ncores), ncores)
     return _cache[key]
+
+
+def exrdiff(im1, im2):
+    """The reference's own "same image" metric (tools/exrdiff.cpp:74-96) over RGB float images: channels that are zero in
+    both are skipped; relative difference |a-b|/a above 0.5 % counts as small, above 5 % as big.  exrdiff without -d
+    fails on any small or big difference.  Returns (smallDiff, bigDiff, avgDelta)."""
+    a, b = np.asarray(im1, np.float32).ravel(), np.asarray(im2, np.float32).ravel()
+    keep = ~((a == 0) & (b == 0))
+    a, b = a[keep], b[keep]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.abs(a - b) / a
+    n = max(1, im1.size)
+    avg1, avg2 = float(a.astype(np.float64).sum()) / n, float(b.astype(np.float64).sum()) / n
+    avg_delta = (avg1 - avg2) / min(avg1, avg2) if min(avg1, avg2) != 0 else 0.0
+    return int((d > .005).sum()), int((d > .05).sum()), avg_delta

@@ -32,6 +32,7 @@ def lib():
         l.oracle_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         l.oracle_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         l.oracle_ld_samples.argtypes = [C.POINTER(pb.RenderDesc), C.c_int, C.c_void_p]
+        l.oracle_aggregate_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         l.oracle_task_window.argtypes = [C.POINTER(pb.RenderDesc), C.c_int, C.POINTER(C.c_int * 4)]
         _lib = l
     return _lib
@@ -67,6 +68,15 @@ def intersect_p(host_scene, rays):
     occ = np.zeros(len(rays), dtype=np.uint8)
     lib().oracle_intersect_p(host_scene.desc_ptr, rays.ctypes.data, len(rays), occ.ctypes.data)
     return occ
+
+
+def aggregate_test(host_scene, n):
+    """renderers/aggregatetest.cpp restated: returns (disagreements BVH vs exhaustive, rays, hit, t)"""
+    rays = np.zeros(n, dtype=pb.RAY_DTYPE)
+    hit = np.zeros(n, dtype=np.uint8)
+    t = np.zeros(n, dtype=np.float32)
+    bad = lib().oracle_aggregate_test(host_scene.desc_ptr, int(n), rays.ctypes.data, hit.ctypes.data, t.ctypes.data)
+    return bad, rays, hit, t
 
 
 def ld_samples(rd, task_num):
