@@ -103,13 +103,24 @@ VARIANTS = [
     ("shutter", "anim-killeroos-moving", 40, 40, 4, 2, {},
      [('Camera "perspective"', 'Camera "perspective" "float shutteropen" [0.25] "float shutterclose" [0.5]')]),
 ]
+# edge cases (pinned oracle-vs-reference on the CPU; not yet part of the GPU suite): one sample per pixel, a 1x1 film,
+# maxdepth 0, scenes without lights under both integrators
+EDGE_VARIANTS = [
+    ("spp1", "bunny", 24, 24, 1, 1, {}, []),
+    ("film1x1", "killeroo-simple", 1, 1, 4, 1, {}, []),
+    ("maxdepth0", "killeroo-simple", 24, 24, 4, 2, {"maxdepth": 0}, []),
+    ("nolights", "bunny", 24, 24, 4, 2, {},
+     [('LightSource "point" "color I" [ .7 .7 .7 ]', ''), ('AreaLightSource "area" "color L" [15 15 15 ] "integer nsamples"  [4]', '')]),
+    ("nolights-directlighting", "bunny", 24, 24, 4, 2, {"integrator": "directlighting"},
+     [('LightSource "point" "color I" [ .7 .7 .7 ]', ''), ('AreaLightSource "area" "color L" [15 15 15 ] "integer nsamples"  [4]', '')]),
+]
 
 
 def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

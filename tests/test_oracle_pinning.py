@@ -141,7 +141,8 @@ def test_oracle_bit_exact_vs_reference_binary(staged, base, res, spp, ncores, in
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
-@pytest.mark.parametrize("name", ["dof", "maxdepth1", "maxdepth8", "nonsquare-crop", "directlighting-maxdepth1", "shutter"])
+@pytest.mark.parametrize("name", ["dof", "maxdepth1", "maxdepth8", "nonsquare-crop", "directlighting-maxdepth1", "shutter",
+                                  "spp1", "film1x1", "maxdepth0", "nolights", "nolights-directlighting"])
 def test_oracle_bit_exact_vs_reference_binary_on_variants(staged, name):
     """thin-lens camera (perspective.cpp:100-113), maxdepth 1 / 8, a non-square cropped film, directlighting without the
     SpecularReflect/Transmit draws (maxdepth 1), a shutter interval inside the transform interval (animated scene)"""
