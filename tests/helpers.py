@@ -103,8 +103,7 @@ VARIANTS = [
     ("shutter", "anim-killeroos-moving", 40, 40, 4, 2, {},
      [('Camera "perspective"', 'Camera "perspective" "float shutteropen" [0.25] "float shutterclose" [0.5]')]),
 ]
-# edge cases (pinned oracle-vs-reference on the CPU; not yet part of the GPU suite): one sample per pixel, a 1x1 film,
-# maxdepth 0, scenes without lights under both integrators
+# edge cases: one sample per pixel, a 1x1 film, maxdepth 0, scenes without lights under both integrators
 EDGE_VARIANTS = [
     ("spp1", "bunny", 24, 24, 1, 1, {}, []),
     ("film1x1", "killeroo-simple", 1, 1, 4, 1, {}, []),

@@ -139,7 +139,8 @@ def test_render_bit_exact_vs_oracle(staged, base, res, spp, ncores, integrator, 
     np.testing.assert_allclose(px_gpu["Lxyz"][~splat & ~diff], px_cpu["Lxyz"][~splat & ~diff], rtol=0, atol=0)
 
 
-@pytest.mark.parametrize("name", ["dof", "maxdepth1", "maxdepth8", "nonsquare-crop", "directlighting-maxdepth1", "shutter"])
+@pytest.mark.parametrize("name", ["dof", "maxdepth1", "maxdepth8", "nonsquare-crop", "directlighting-maxdepth1", "shutter",
+                                  "spp1", "film1x1", "maxdepth0", "nolights", "nolights-directlighting"])
 def test_render_variants_bit_exact_vs_oracle(staged, name):
     """the scene-file variants the oracle is pinned on against the reference binary (tests/helpers.py VARIANTS)"""
     from helpers import variant_scene
@@ -148,7 +149,7 @@ def test_render_variants_bit_exact_vs_oracle(staged, name):
     px_cpu, _ = oa.render(hs, threads=1)
     assert np.array_equal(px_gpu["weightSum"], px_cpu["weightSum"])
     own = px_cpu["weightSum"] == hs.render_desc().samplesPerPixel   # (pixels that received an edge splat: order-dependent)
-    assert own.mean() > 0.99
+    assert own.mean() > 0.99 or own.size == 1
     assert np.array_equal(px_gpu["Lxyz"][own].view(np.uint32), px_cpu["Lxyz"][own].view(np.uint32))
 
 
