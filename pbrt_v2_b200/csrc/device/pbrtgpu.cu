@@ -1,18 +1,21 @@
 // pbrtgpu.cu -- CUDA kernels and C ABI (include/pbrtgpu.h) of the B200 path-tracing
 // hot path.  sm_100a only; no CPU fallback anywhere in this file.
 //
-// Work decomposition (DESIGN.md "Execution model"):
-//   unit        = one reference render task (SamplerRendererTask, its own MT19937
-//                 stream seeded with taskNum, samplerrenderer.cpp:72-73)
-//   k_tables    = one WARP per task: generates the LD sample tables of the task's
-//                 current pixel (LDPixelSample) and advances the task's RNG state
-//   k_path      = one THREAD per task: runs the pixel's spp camera samples one after
-//                 the other (the RNG offset of sample i+1 depends on how many
-//                 draws the tail of sample i's path consumed), as a state machine
-//                 with a single BVH-traversal site per loop iteration so that all
-//                 lanes of a warp traverse together whatever stage they are in
-//   rounds      = tasks with more than one pixel alternate k_tables / k_path once
-//                 per pixel (pixel p+1's tables start where pixel p's paths stopped)
+// Work decomposition:
+//   unit        = one reference render task (SamplerRendererTask, its own MT19937 stream seeded with taskNum,
+//                 samplerrenderer.cpp:72-73); a batch of tasks is processed pixel by pixel ("rounds")
+//   k_tables / k_tables_general
+//               = one WARP per task: the LD sample tables of the task's current pixel (LDPixelSample) and the task's
+//                 RNG position after them
+//   phase 1     = everything that draws from the tables only (PathIntegrator: bounces 0..2; DirectLightingIntegrator:
+//                 all of Li): a wavefront over a pool of path slots -- k_logic (state machine, path_body.inc),
+//                 k_eval (measured-BRDF kd-tree queries), k_trace (persistent BVH walk) -- with one request queue per
+//                 resume state.  PathIntegrator samples that reach bounce 3 are parked (`rec`)
+//   phase 2     = k_path<2>: one THREAD per task resumes the parked samples in sample order with the task's RNG (the
+//                 offset of one tail depends on how many draws the previous one consumed) and adds all samples to the
+//                 film in order; DirectLightingIntegrator: k_film_direct (film + the RNG draws of SpecularReflect/Transmit)
+//   lanes       = batches are dealt to concurrent lanes (stream + scratch + host thread), see pbrtgpu_render_device
+//   k_path<1>   = the megakernel form of phase 1 (one warp per pixel), kept as the A/B baseline (PBRTGPU_WAVEFRONT=0)
 #include "dshade.cuh"
 #include "drng.cuh"
 
