@@ -1539,6 +1539,33 @@ int oracle_intersect_p(const PbrtGpuSceneDesc *scene, const PbrtGpuRay *rays, in
     return 0;
 }
 
+// The BxDF restatements evaluated on the direction pairs `refdump bxdf` (the reference's own classes) prints:
+// out = n rows of 15 floats: lambert f, pdf | blinn f, pdf | blinn Sample_f wi.xyz, pdf, f | lambert Sample_f wi.xyz, pdf |
+// FresnelDielectric(1.5, 1)(wo.z)
+int oracle_bxdf_test(float exponent, int n, const float *wo, const float *wi, const float *u, float *out) {
+    BSDF bsdf;
+    bsdf.sv = nullptr;
+    if (exponent > 10000.f || std::isnan(exponent)) exponent = 10000.f;   // Blinn ctor, reflection.h:424-425
+    BxDF lambert{BX_LAMBERTIAN, BSDF_REFLECTION | BSDF_DIFFUSE, Spec(0.5f), 0.f, -1};
+    BxDF blinn{BX_MICROFACET_BLINN, BSDF_REFLECTION | BSDF_GLOSSY, Spec(0.5f), exponent, -1};
+    for (int i = 0; i < n; ++i) {
+        Vec o(wo + 3 * i), w(wi + 3 * i);
+        float *r = out + 15 * i;
+        r[0] = bsdf.BxF(lambert, o, w).c[0]; r[1] = bsdf.BxPdf(lambert, o, w);
+        r[2] = bsdf.BxF(blinn, o, w).c[0];   r[3] = bsdf.BxPdf(blinn, o, w);
+        Vec ws;
+        float pdf = 0.f;
+        Spec f = bsdf.BxSample_f(blinn, o, &ws, u[2 * i], u[2 * i + 1], &pdf);
+        r[4] = ws.x; r[5] = ws.y; r[6] = ws.z; r[7] = pdf; r[8] = f.c[0];
+        pdf = 0.f;
+        bsdf.BxSample_f(lambert, o, &ws, u[2 * i], u[2 * i + 1], &pdf);
+        r[9] = ws.x; r[10] = ws.y; r[11] = ws.z; r[12] = pdf;
+        r[13] = BSDF::FresnelDielectricEvaluate(o.z, 1.5f, 1.f).c[0];
+        r[14] = 0.f;
+    }
+    return 0;
+}
+
 // spp rows of 37 floats for the first pixel of task `taskNum`
 int oracle_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
     Renderer R;

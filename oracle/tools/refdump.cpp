@@ -11,6 +11,10 @@
 //        the same for an arbitrary Sample layout (e.g. DirectLightingIntegrator's per-light arrays): the requests are
 //        made through the reference's own Sample::Add1D / Add2D from a stub SurfaceIntegrator; every array's values
 //        are printed in Sample::oneD / twoD order
+//   refdump bxdf <exponent> <n> <seed>
+//        the reference's own Lambertian / Microfacet(Blinn, FresnelDielectric(1.5, 1)) / FresnelDielectric classes on n
+//        random direction pairs (tools/bsdftest.cpp exercises the same classes): per test
+//        wo wi u1 u2 | lambert f, pdf | blinn f, pdf | blinn Sample_f wi, pdf, f | lambert Sample_f wi, pdf | Fr(cos)
 //   refdump rng  <seed> <n>        n RandomUInt() values of RNG(seed)
 #include "pbrt.h"
 #include "rng.h"
@@ -20,6 +24,8 @@
 #include "integrators/emission.h"
 #include "integrator.h"
 #include "intersection.h"
+#include "reflection.h"
+#include "montecarlo.h"
 
 #include <vector>
 
@@ -72,6 +78,34 @@ int main(int argc, char **argv) {
             printf("\n");
         }
         printf("%u\n", rng.RandomUInt());
+        return 0;
+    }
+    if (argc >= 5 && !strcmp(argv[1], "bxdf")) {
+        float exponent = (float)atof(argv[2]);
+        int n = atoi(argv[3]);
+        RNG rng((uint32_t)strtoul(argv[4], NULL, 10));
+        Spectrum R(0.5f);
+        Lambertian lambert(R);
+        FresnelDielectric fresnel(1.5f, 1.f);
+        Blinn blinn(exponent);
+        Microfacet micro(R, &fresnel, &blinn);
+        for (int i = 0; i < n; ++i) {
+            // every random number is drawn in its own statement: no dependence on argument evaluation order
+            float a = rng.RandomFloat(), b = rng.RandomFloat(), c = rng.RandomFloat(), d = rng.RandomFloat();
+            float u1 = rng.RandomFloat(), u2 = rng.RandomFloat();
+            Vector wo = UniformSampleSphere(a, b), wi = UniformSampleSphere(c, d);
+            float rgb[3];
+            printf("%a %a %a %a %a %a %a %a", wo.x, wo.y, wo.z, wi.x, wi.y, wi.z, u1, u2);
+            lambert.f(wo, wi).ToRGB(rgb); printf(" %a %a", rgb[0], lambert.Pdf(wo, wi));
+            micro.f(wo, wi).ToRGB(rgb);   printf(" %a %a", rgb[0], micro.Pdf(wo, wi));
+            Vector ws; float pdf = 0.f;
+            Spectrum f = micro.Sample_f(wo, &ws, u1, u2, &pdf);
+            f.ToRGB(rgb); printf(" %a %a %a %a %a", ws.x, ws.y, ws.z, pdf, rgb[0]);
+            pdf = 0.f;
+            f = lambert.Sample_f(wo, &ws, u1, u2, &pdf);
+            printf(" %a %a %a %a", ws.x, ws.y, ws.z, pdf);
+            fresnel.Evaluate(wo.z).ToRGB(rgb); printf(" %a\n", rgb[0]);
+        }
         return 0;
     }
     if (argc >= 15 && !strcmp(argv[1], "ldx")) {

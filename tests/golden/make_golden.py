@@ -78,6 +78,15 @@ def main():
         out = subprocess.run([REFDUMP, "rng", str(seed), "2000"], check=True, stdout=subprocess.PIPE, text=True).stdout.split()
         rng["seed%d" % seed] = np.array([int(x) for x in out], dtype=np.uint32)
     np.savez_compressed(os.path.join(HERE, "rng.npz"), **rng)
+    # the reference's own BxDF classes on random direction pairs (what tools/bsdftest.cpp exercises): refdump bxdf
+    bx = {}
+    for exponent, seed in ((40.0, 7), (1.0 / 0.15, 8), (20000.0, 9)):
+        out = subprocess.run([REFDUMP, "bxdf", repr(exponent), "2000", str(seed)], check=True, stdout=subprocess.PIPE,
+                             text=True).stdout.strip().split("\n")
+        rows = np.array([[float.fromhex(x) for x in ln.split()] for ln in out], dtype=np.float32)
+        bx["e%d" % seed] = rows
+        bx["e%d_exponent" % seed] = np.float32(exponent)
+    np.savez_compressed(os.path.join(HERE, "bxdf.npz"), **bx)
     imgs = {}
     have = os.path.join(HERE, "images.npz")
     if os.path.exists(have) and "--all" not in sys.argv:   # keep what is committed, mint only new cases

@@ -79,6 +79,16 @@ def aggregate_test(host_scene, n):
     return bad, rays, hit, t
 
 
+def bxdf_test(exponent, wo, wi, u):
+    """oracle BxDF restatements on given direction pairs -> (n, 15) float32 (see oracle_bxdf_test)"""
+    wo, wi, u = [np.ascontiguousarray(a, np.float32) for a in (wo, wi, u)]
+    out = np.zeros((len(wo), 15), np.float32)
+    l = lib()
+    l.oracle_bxdf_test.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.oracle_bxdf_test(float(exponent), len(wo), wo.ctypes.data, wi.ctypes.data, u.ctypes.data, out.ctypes.data)
+    return out
+
+
 def ld_samples(rd, task_num):
     out = np.zeros((rd.samplesPerPixel, pb.sample_floats(rd)), dtype=np.float32)
     rc = lib().oracle_ld_samples(C.byref(rd), int(task_num), out.ctypes.data)

@@ -109,6 +109,22 @@ def test_aggregatetest_matches_reference_output(staged, base):
     assert walk_disagrees.sum() >= bad   # (= bad + the "inconsistent bounds" cases the reference does not report)
 
 
+def test_bxdf_restatements_match_reference_classes():
+    """Lambertian, Microfacet(Blinn) f / Pdf / Sample_f and FresnelDielectric(1.5, 1) against values printed by the
+    reference's own classes (refdump bxdf; tools/bsdftest.cpp exercises the same ones), bit for bit, incl. powf."""
+    g = np.load(os.path.join(GOLD, "bxdf.npz"))
+    for key in [k for k in g.files if not k.endswith("_exponent")]:
+        rows = g[key]
+        got = oa.bxdf_test(float(g[key + "_exponent"]), rows[:, 0:3], rows[:, 3:6], rows[:, 6:8])
+        want = rows[:, 8:22]
+        for c, name in enumerate(["lambert f", "lambert pdf", "blinn f", "blinn pdf", "blinn wi.x", "blinn wi.y", "blinn wi.z",
+                                  "blinn sample pdf", "blinn sample f", "lambert wi.x", "lambert wi.y", "lambert wi.z",
+                                  "lambert sample pdf", "fresnel"]):
+            same = got[:, c].view(np.uint32) == want[:, c].view(np.uint32)
+            both_nan = np.isnan(got[:, c]) & np.isnan(want[:, c])
+            assert (same | both_nan).all(), "%s: %s differs on %d of %d" % (key, name, (~(same | both_nan)).sum(), len(same))
+
+
 def test_exrdiff_metric_on_golden_images(staged):
     """tools/exrdiff.cpp's thresholds (the reference's definition of "same image") on oracle vs reference renders"""
     from helpers import exrdiff, golden_image_case
