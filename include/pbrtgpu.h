@@ -114,7 +114,10 @@ typedef struct PbrtGpuAnimated {
 } PbrtGpuAnimated;
 
 /* ---- materials (constant textures only), materials/{matte,plastic,measured} - */
-enum { PBRTGPU_MAT_MATTE = 0, PBRTGPU_MAT_PLASTIC = 1, PBRTGPU_MAT_MEASURED = 2 };
+enum { PBRTGPU_MAT_MATTE = 0, PBRTGPU_MAT_PLASTIC = 1, PBRTGPU_MAT_MEASURED = 2,
+       /* SURVEY 8(f) rank 4, host front end + oracle only so far: pbrtgpu_scene_create answers PBRTGPU_EUNSUPPORTED.
+        * MIRROR (materials/mirror.cpp): Ks = Kr.  GLASS (materials/glass.cpp): Ks = Kr, Kd = Kt, roughness = index. */
+       PBRTGPU_MAT_MIRROR = 3, PBRTGPU_MAT_GLASS = 4 };
 typedef struct PbrtGpuMaterial {
     uint32_t type;
     float Kd[3];

@@ -647,7 +647,9 @@ inline float PowerHeuristic(int nf, float fPdf, int ng, float gPdf) {   // monte
     return (f * f) / (f * f + g * g);
 }
 
-enum BxDFKind { BX_LAMBERTIAN, BX_MICROFACET_BLINN, BX_IRREG_ISO };
+enum BxDFKind { BX_LAMBERTIAN, BX_MICROFACET_BLINN, BX_IRREG_ISO,
+                BX_SPECULAR_REFLECTION,     // exponent = eta_t of its FresnelDielectric(1, eta_t), or 0 for FresnelNoOp
+                BX_SPECULAR_TRANSMISSION }; // exponent = eta_t (etai = 1)
 struct BxDF {
     BxDFKind kind;
     int type;         // BxDFType flags
@@ -749,6 +751,9 @@ struct BSDF {
 
     Spec BxF(const BxDF &b, const Vec &wo, const Vec &wi) const {
         switch (b.kind) {
+        case BX_SPECULAR_REFLECTION:    // reflection.h:317-319
+        case BX_SPECULAR_TRANSMISSION:  // reflection.h:339-341
+            return Spec(0.f);
         case BX_LAMBERTIAN: return b.R * INV_PI_F;   // reflection.cpp:173-175
         case BX_MICROFACET_BLINN: {                  // Microfacet::f, reflection.cpp:211-222
             float cosThetaO = AbsCosTheta(wo);
@@ -777,6 +782,7 @@ struct BSDF {
         return Spec(0.f);
     }
     float BxPdf(const BxDF &b, const Vec &wo, const Vec &wi) const {
+        if (b.kind == BX_SPECULAR_REFLECTION || b.kind == BX_SPECULAR_TRANSMISSION) return 0.f;   // reflection.h:322-324,344-346
         if (b.kind == BX_MICROFACET_BLINN) {   // Microfacet::Pdf + Blinn::Pdf, reflection.cpp:340-343,365-374
             if (!SameHemisphere(wo, wi)) return 0.f;
             Vec wh = Normalize(wo + wi);
@@ -789,6 +795,28 @@ struct BSDF {
         return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * INV_PI_F : 0.f;
     }
     Spec BxSample_f(const BxDF &b, const Vec &wo, Vec *wi, float u1, float u2, float *pdf) const {
+        if (b.kind == BX_SPECULAR_REFLECTION) {   // SpecularReflection::Sample_f, reflection.cpp:138-144
+            *wi = Vec(-wo.x, -wo.y, wo.z);
+            *pdf = 1.f;
+            Spec F = b.exponent == 0.f ? Spec(1.f) : FresnelDielectricEvaluate(CosTheta(wo), 1.f, b.exponent);
+            return F * b.R / AbsCosTheta(*wi);
+        }
+        if (b.kind == BX_SPECULAR_TRANSMISSION) {   // SpecularTransmission::Sample_f, reflection.cpp:147-170
+            bool entering = CosTheta(wo) > 0.;
+            float ei = 1.f, et = b.exponent;
+            if (!entering) std::swap(ei, et);
+            float sini2 = SinTheta2(wo);
+            float eta = ei / et;
+            float sint2 = eta * eta * sini2;
+            if (sint2 >= 1.) return Spec(0.f);   // total internal reflection (*pdf stays as the caller set it: 0)
+            float cost = sqrtf(std::max(0.f, 1.f - sint2));
+            if (entering) cost = -cost;
+            float sintOverSini = eta;
+            *wi = Vec(sintOverSini * -wo.x, sintOverSini * -wo.y, cost);
+            *pdf = 1.f;
+            Spec F = FresnelDielectricEvaluate(CosTheta(wo), 1.f, b.exponent);
+            return (Spec(1.f) - F) * b.R / AbsCosTheta(*wi);
+        }
         if (b.kind == BX_MICROFACET_BLINN) {   // Microfacet::Sample_f + Blinn::Sample_f, reflection.cpp:332-363
             float costheta = powf(u1, 1.f / (b.exponent + 1));
             float sintheta = sqrtf(std::max(0.f, 1.f - costheta * costheta));
@@ -997,6 +1025,14 @@ struct Renderer {
                 if (e > 10000.f || std::isnan(e)) e = 10000.f;   // Blinn ctor, reflection.h:424-425
                 bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_MICROFACET_BLINN, BSDF_REFLECTION | BSDF_GLOSSY, ks, e, -1};
             }
+        } else if (m.type == PBRTGPU_MAT_MIRROR) {   // mirror.cpp:41-53: SpecularReflection(R, FresnelNoOp)
+            Spec r = Spec(m.Ks).Clamp();
+            if (!r.IsBlack()) bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_SPECULAR_REFLECTION, BSDF_REFLECTION | BSDF_SPECULAR, r, 0.f, -1};
+        } else if (m.type == PBRTGPU_MAT_GLASS) {    // glass.cpp:41-57
+            float ior = m.roughness;
+            Spec r = Spec(m.Ks).Clamp(), t = Spec(m.Kd).Clamp();
+            if (!r.IsBlack()) bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_SPECULAR_REFLECTION, BSDF_REFLECTION | BSDF_SPECULAR, r, ior, -1};
+            if (!t.IsBlack()) bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_SPECULAR_TRANSMISSION, BSDF_TRANSMISSION | BSDF_SPECULAR, t, ior, -1};
         } else {
             bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_IRREG_ISO, BSDF_REFLECTION | BSDF_GLOSSY, Spec(0.f), 0.f, m.measured};
         }
@@ -1206,9 +1242,34 @@ struct Renderer {
         return L;
     }
 
-    // DirectLightingIntegrator::Li, integrators/directlighting.cpp:81-117 (ray.depth == 0: camera rays only, since
-    // no in-scope material has a specular component to spawn SpecularReflect / SpecularTransmit rays)
-    Spec DirectLi(const Ray &ray, const Intersection &isect, const Sample *sample, RNG &rng, Counters *cnt) const {
+    // SpecularReflect / SpecularTransmit, core/integrator.cpp:177-258 (ray differentials only feed texture filtering:
+    // omitted).  BSDFSample(rng) draws its three numbers BEFORE BSDF::Sample_f looks for a specular component.
+    Spec SpecularBounce(const Ray &ray, const BSDF &bsdf, RNG &rng, const Intersection &isect, const Sample *sample,
+                        int depth, int flags, Counters *cnt) const {
+        Vec wo = -ray.d, wi;
+        float pdf;
+        const Vec &p = bsdf.p;
+        const Vec &n = bsdf.nn;
+        BSDFSample bs;
+        bs.uDir[0] = rng.RandomFloat();   // reflection.h:135-139
+        bs.uDir[1] = rng.RandomFloat();
+        bs.uComponent = rng.RandomFloat();
+        Spec f = bsdf.Sample_f(wo, &wi, bs, &pdf, flags, nullptr);
+        Spec L(0.f);
+        if (pdf > 0.f && !f.IsBlack() && AbsDot(wi, n) != 0.f) {
+            Ray rd(p, wi, isect.rayEpsilon, INF_F, ray.time);   // RayDifferential(p, wi, parent, eps): depth + 1
+            // SamplerRenderer::Li, samplerrenderer.cpp:225-247 (no volume: T = 1, Lvi = 0; area/point lights' Le(ray) = 0)
+            Intersection next;
+            Spec Li(0.f);
+            if (sv.Intersect(rd, &next, cnt)) Li = DirectLi(rd, next, sample, rng, cnt, depth + 1);
+            Li = Spec(1.f) * Li + Spec(0.f);
+            L = f * Li * AbsDot(wi, n) / pdf;
+        }
+        return L;
+    }
+
+    // DirectLightingIntegrator::Li, integrators/directlighting.cpp:81-117
+    Spec DirectLi(const Ray &ray, const Intersection &isect, const Sample *sample, RNG &rng, Counters *cnt, int depth = 0) const {
         Spec L(0.f);
         BSDF bsdf;
         GetBSDF(isect, &bsdf, cnt);
@@ -1224,10 +1285,9 @@ struct Renderer {
                 L += UniformSampleOneLight(p, n, wo, isect.rayEpsilon, ray.time, bsdf, sample, rng, &slots, cnt);
             }
         }
-        if (0 + 1 < rd->maxDepth) {
-            // SpecularReflect / SpecularTransmit (integrator.cpp:177-258): each builds BSDFSample(rng) -- three draws --
-            // before BSDF::Sample_f finds no BSDF_SPECULAR component and returns black with pdf 0
-            for (int k = 0; k < 6; ++k) rng.RandomFloat();
+        if (depth + 1 < rd->maxDepth) {
+            L += SpecularBounce(ray, bsdf, rng, isect, sample, depth, BSDF_REFLECTION | BSDF_SPECULAR, cnt);
+            L += SpecularBounce(ray, bsdf, rng, isect, sample, depth, BSDF_TRANSMISSION | BSDF_SPECULAR, cnt);
         }
         return L;
     }

@@ -260,6 +260,17 @@ int Api::MakeMaterial(const ParamSet &geomParams) {   // core/api.cpp:1062-1077,
         m.desc.Kd[0] = kd.x; m.desc.Kd[1] = kd.y; m.desc.Kd[2] = kd.z;
         m.desc.Ks[0] = ks.x; m.desc.Ks[1] = ks.y; m.desc.Ks[2] = ks.z;
         m.desc.roughness = TexFloat(geomParams, mp, "roughness", .1f);
+    } else if (name == "mirror") {   // materials/mirror.cpp:56-61
+        m.desc.type = PBRTGPU_MAT_MIRROR;
+        V3 kr = TexSpectrum(geomParams, mp, "Kr", V3(0.9f, 0.9f, 0.9f));
+        m.desc.Ks[0] = kr.x; m.desc.Ks[1] = kr.y; m.desc.Ks[2] = kr.z;
+    } else if (name == "glass") {    // materials/glass.cpp:60-67
+        m.desc.type = PBRTGPU_MAT_GLASS;
+        V3 kr = TexSpectrum(geomParams, mp, "Kr", V3(1.f, 1.f, 1.f));
+        V3 kt = TexSpectrum(geomParams, mp, "Kt", V3(1.f, 1.f, 1.f));
+        m.desc.Ks[0] = kr.x; m.desc.Ks[1] = kr.y; m.desc.Ks[2] = kr.z;
+        m.desc.Kd[0] = kt.x; m.desc.Kd[1] = kt.y; m.desc.Kd[2] = kt.z;
+        m.desc.roughness = TexFloat(geomParams, mp, "index", 1.5f);
     } else if (name == "measured") {   // materials/measured.cpp:213-217
         m.desc.type = PBRTGPU_MAT_MEASURED;
         std::string fn = geomParams.FindOneString("filename", mp.FindOneString("filename", ""));
@@ -280,7 +291,7 @@ int Api::MakeMaterial(const ParamSet &geomParams) {   // core/api.cpp:1062-1077,
         }
         m.desc.measured = idx;
     } else {
-        Fail("material \"" + name + "\" is outside the hot-path scope (matte, plastic, measured)");
+        Fail("material \"" + name + "\" is outside the hot-path scope (matte, plastic, measured; mirror and glass up to the oracle)");
         return -1;
     }
     // identical descriptors share one slot

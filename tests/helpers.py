@@ -115,11 +115,29 @@ EDGE_VARIANTS = [
 ]
 
 
+_M1 = 'Material "plastic" "color Kd" [.4 .2 .2] "color Ks" [.5 .5 .5]\n        "float roughness" [.025]'
+_M2 = 'Material "plastic" "color Ks" [.3 .3 .3] "color Kd" [.4 .5 .4]\n        "float roughness" [.15] '
+_FLOOR = 'Material "matte" "color Kd" [.5 .5 .8]'
+# SURVEY 8(f) rank 4, specular materials: host front end + oracle so far (the device answers PBRTGPU_EUNSUPPORTED)
+SPECULAR_VARIANTS = [
+    ("path-glass-mirror", "killeroo-simple", 40, 40, 4, 2, {}, [(_M1, 'Material "glass"'), (_M2, 'Material "mirror"')]),
+    ("path-glass-params-mirror-floor", "killeroo-simple", 40, 40, 4, 2, {"maxdepth": 8},
+     [(_M1, 'Material "glass" "color Kr" [.8 .9 1] "color Kt" [.9 .7 .6] "float index" [1.33]'),
+      (_FLOOR, 'Material "mirror" "color Kr" [.7 .7 .7]')]),
+    ("direct-glass-mirror", "killeroo-simple", 40, 40, 4, 2, {"integrator": "directlighting"},
+     [(_M1, 'Material "glass"'), (_M2, 'Material "mirror"')]),
+    ("direct-mirror-floor-maxdepth3", "killeroo-simple", 40, 40, 4, 2, {"integrator": "directlighting", "maxdepth": 3},
+     [(_FLOOR, 'Material "mirror"'), (_M1, 'Material "glass" "float index" [1.2]')]),
+    ("direct-one-glass", "killeroo-simple", 40, 40, 4, 1, {"integrator": "directlighting", "strategy": "one"},
+     [(_M1, 'Material "glass"')]),
+]
+
+
 def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

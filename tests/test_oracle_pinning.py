@@ -170,6 +170,20 @@ def test_oracle_bit_exact_vs_reference_binary_on_variants(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["path-glass-mirror", "path-glass-params-mirror-floor", "direct-glass-mirror",
+                                  "direct-mirror-floor-maxdepth3", "direct-one-glass"])
+def test_oracle_specular_materials_bit_exact_vs_reference_binary(staged, name):
+    """mirror / glass (SpecularReflection, SpecularTransmission; materials/mirror.cpp, glass.cpp): the specularBounce
+    branches of PathIntegrator (path.cpp:63,98) and the recursive SpecularReflect / SpecularTransmit rays of
+    DirectLightingIntegrator (integrator.cpp:177-258)"""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 def test_synthetic_scene_text_and_direct_routes_match_reference(staged):
     """the C5 generator: the in-memory build equals the text scene, and the oracle renders it bit-exactly
     like the unmodified reference (multi-pixel tasks)."""
