@@ -1599,6 +1599,59 @@ int oracle_intersect_p(const PbrtGpuSceneDesc *scene, const PbrtGpuRay *rays, in
     return 0;
 }
 
+// Shading quantities at the first hit of each ray, for function-level comparison with the device code compiled for the
+// host (tests/native/device_on_host.cpp).  u: 6 floats per ray (light uPos0 uPos1, bsdf uDir0 uDir1 uComponent, light
+// pick).  out: 36 floats per ray, zeros on a miss:
+//   0-2 p  3-5 nn  6-8 sn  9-11 tn  12-14 ng  15 rayEpsilon | light sample: 16-18 wi 19 pdf 20-22 Li 23 visibility maxt
+//   24-26 f(wo, wi, ALL & ~SPECULAR) 27 Pdf | BSDF::Sample_f(ALL): 28-30 f 31-33 wi 34 pdf | 35 light pdf of that wi
+int oracle_shade_test(const PbrtGpuSceneDesc *scene, const PbrtGpuRay *rays, int n, const float *u, float *out) {
+    Renderer R;
+    PbrtGpuRenderDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.xResolution = rd.yResolution = 1; rd.cropWindow[1] = rd.cropWindow[3] = 1.f; rd.nTasks = 1;
+    R.Init(scene, &rd, nullptr);
+    const int nLights = (int)scene->nLights;
+    for (int i = 0; i < n; ++i) {
+        float *o = out + 36 * (size_t)i;
+        for (int k = 0; k < 36; ++k) o[k] = 0.f;
+        Ray ray(Vec(rays[i].o), Vec(rays[i].d), rays[i].mint, rays[i].maxt, rays[i].time);
+        Intersection isect;
+        if (!R.sv.Intersect(ray, &isect, nullptr)) continue;
+        BSDF bsdf;
+        R.GetBSDF(isect, &bsdf, nullptr);
+        Vec wo = -ray.d;
+        auto put = [&](int at, const Vec &v) { o[at] = v.x; o[at + 1] = v.y; o[at + 2] = v.z; };
+        put(0, bsdf.p); put(3, bsdf.nn); put(6, bsdf.sn); put(9, bsdf.tn); put(12, bsdf.ng);
+        o[15] = isect.rayEpsilon;
+        if (nLights == 0) continue;
+        const float *uu = u + 6 * (size_t)i;
+        const int lightNum = std::min(Floor2Int(uu[5] * nLights), nLights - 1);
+        const PbrtGpuLight &light = scene->lights[lightNum];
+        LightSample ls;
+        ls.uPos[0] = uu[0]; ls.uPos[1] = uu[1]; ls.uComponent = 0.f;
+        Vec wi;
+        float lightPdf;
+        Ray vis;
+        Spec Li = R.Sample_L(light, bsdf.p, isect.rayEpsilon, ls, ray.time, &wi, &lightPdf, &vis);
+        put(16, wi); o[19] = lightPdf; o[20] = Li.c[0]; o[21] = Li.c[1]; o[22] = Li.c[2]; o[23] = vis.maxt;
+        Spec f = bsdf.f(wo, wi, BSDF_ALL & ~BSDF_SPECULAR);
+        o[24] = f.c[0]; o[25] = f.c[1]; o[26] = f.c[2];
+        o[27] = bsdf.Pdf(wo, wi, BSDF_ALL & ~BSDF_SPECULAR);
+        BSDFSample bs;
+        bs.uDir[0] = uu[2]; bs.uDir[1] = uu[3]; bs.uComponent = uu[4];
+        Vec wi2;
+        float pdf2 = 0.f;
+        int sampled = 0;
+        Spec f2 = bsdf.Sample_f(wo, &wi2, bs, &pdf2, BSDF_ALL, &sampled);
+        if (pdf2 != 0.f) {
+            o[28] = f2.c[0]; o[29] = f2.c[1]; o[30] = f2.c[2];
+            put(31, wi2); o[34] = pdf2;
+            o[35] = R.LightPdf(light, bsdf.p, wi2);
+        }
+    }
+    return 0;
+}
+
 // The BxDF restatements evaluated on the direction pairs `refdump bxdf` (the reference's own classes) prints:
 // out = n rows of 15 floats: lambert f, pdf | blinn f, pdf | blinn Sample_f wi.xyz, pdf, f | lambert Sample_f wi.xyz, pdf |
 // FresnelDielectric(1.5, 1)(wo.z)
