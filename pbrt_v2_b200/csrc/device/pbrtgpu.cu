@@ -18,6 +18,7 @@
 //   k_path<1>   = the megakernel form of phase 1 (one warp per pixel), kept as the A/B baseline (PBRTGPU_WAVEFRONT=0)
 #include "dshade.cuh"
 #include "drng.cuh"
+#include "dpath.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -37,18 +38,6 @@ using namespace dev;
 struct TaskRec {
     int taskNum;
     int x0, x1, y0, y1;   // Sampler::ComputeSubWindow tile
-};
-
-struct RenderParams {
-    float rasterToCamera[16];
-    float cameraToWorld[16];
-    float lensRadius, focalDistance;
-    float shutterOpen, shutterClose;
-    float filterXWidth, filterYWidth;
-    int xPixelStart, yPixelStart, xPixelCount, yPixelCount;
-    int spp, maxDepth;
-    int integrator, lightStrategy;   // PBRTGPU_INTEGRATOR_*, PBRTGPU_STRATEGY_*
-    SampleLayoutDev lay;
 };
 
 struct BatchArgs {
@@ -394,15 +383,6 @@ __global__ void k_expand_samples(BatchArgs a, int spp, float shutterOpen, float 
 #ifndef K_EVAL_MIN_BLOCKS
 #define K_EVAL_MIN_BLOCKS 8
 #endif
-enum PathState {
-    S_NEW_SAMPLE = 0, S_HIT_RESULT, S_SHADOW_RESULT, S_AFTER_LIGHT, S_MIS_RESULT, S_AFTER_DIRECT, S_END_SAMPLE, S_DONE,
-    S_E_LIGHT, S_E_MIS, S_E_PATH,   // waiting for the BSDF value at the evaluation site
-    S_DL_NEXT                       // DirectLightingIntegrator: next (light, sample) of the light loop
-};
-// ls[s].w bit field
-enum { LS_TAIL = 1, LS_LEFT = 2, LS_RIGHT = 4, LS_UP = 8, LS_DOWN = 16,
-       LS_HIT = 32 };   // directlighting: the camera ray hit something (6 RNG draws follow, see k_film_direct)
-
 struct PathArgs {
     DScene sc;
     RenderParams rp;
@@ -412,28 +392,6 @@ struct PathArgs {
     int directFilm;   // 1: every AddSample goes straight to the film (multi-pixel tasks)
     int lockstep;     // phase 1: hand out camera samples 32 at a time (see k_path)
 };
-
-// Which pixels does ImageFilm::AddSample (film/image.cpp:77-96) touch for this sample?
-// With the 0.5 box filter: the sample's own pixel, plus a neighbour when the
-// sample sits exactly on a pixel edge or xPos + u rounded up to the next integer.
-DEV int FilmFootprint(const RenderParams &rp, int ownX, int ownY, float imageX, float imageY) {
-    float dimageX = imageX - 0.5f;
-    float dimageY = imageY - 0.5f;
-    int x0 = Ceil2Int(dimageX - rp.filterXWidth);
-    int x1 = Floor2Int(dimageX + rp.filterXWidth);
-    int y0 = Ceil2Int(dimageY - rp.filterYWidth);
-    int y1 = Floor2Int(dimageY + rp.filterYWidth);
-    x0 = maxi(x0, rp.xPixelStart);
-    x1 = mini(x1, rp.xPixelStart + rp.xPixelCount - 1);
-    y0 = maxi(y0, rp.yPixelStart);
-    y1 = mini(y1, rp.yPixelStart + rp.yPixelCount - 1);
-    int code = 0;
-    if (x0 < ownX) code |= LS_LEFT;
-    if (x1 > ownX) code |= LS_RIGHT;
-    if (y0 < ownY) code |= LS_UP;
-    if (y1 > ownY) code |= LS_DOWN;
-    return code;
-}
 
 // ImageFilm::AddSample, film/image.cpp:97-137, box filter (all table weights are 1)
 DEV void FilmAdd(const RenderParams &rp, PbrtGpuPixel *film, int ownX, int ownY, int code, const Spec &L, float acc[4],
@@ -460,13 +418,6 @@ DEV void FilmAdd(const RenderParams &rp, PbrtGpuPixel *film, int ownX, int ownY,
         }
 }
 
-// samplerrenderer.cpp:119-133: NaN / negative / infinite luminance -> black
-DEV Spec SanitizeRadiance(const Spec &L) {
-    if (L.HasNaNs()) return Spec(0.f);
-    if ((double)L.y() < -1e-5) return Spec(0.f);
-    if (isinf(L.y())) return Spec(0.f);
-    return L;
-}
 
 template <int PHASE, bool STATS, bool ANIM>
 // 4 CTAs/SM (<= 128 registers): measured +9 % over the unconstrained 168-register build

@@ -32,6 +32,7 @@ static inline void __syncwarp(unsigned = 0xffffffffu) {}
 
 #include "../../pbrt_v2_b200/csrc/device/dscene.cuh"
 #include "../../pbrt_v2_b200/csrc/device/dshade.cuh"
+#include "../../pbrt_v2_b200/csrc/device/dpath.cuh"
 
 using namespace dev;
 
@@ -83,7 +84,232 @@ void Pack(const PbrtGpuSceneDesc *desc, HostScene *h) {
 }
 }  // namespace
 
+namespace {
+
+// the task's MT19937 stream (core/rng.cpp), tempered, addressable ahead of the read position like the device's
+// two-block window: draws at [pos, pos + k) can be looked at before `pos` moves
+struct Stream {
+    uint32_t mt[MT_N];
+    int idx;
+    std::vector<uint32_t> out;
+    explicit Stream(uint32_t seed) { SeedMT(mt, seed); idx = MT_N; }
+    void Regen() {
+        for (int k = 0; k < MT_N; ++k) {
+            uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % MT_N] & 0x7fffffffu);
+            mt[k] = mt[(k + MT_M) % MT_N] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        idx = 0;
+    }
+    uint32_t At(size_t i) {
+        while (out.size() <= i) {
+            if (idx >= MT_N) Regen();
+            out.push_back(Temper(mt[idx++]));
+        }
+        return out[i];
+    }
+};
+
+// Sampler::ComputeSubWindow / ImageFilm extent, as the host code of pbrtgpu.cu computes them
+struct Extent { int xs, ys, xc, yc, sx0, sx1, sy0, sy1; };
+Extent ComputeExtentH(const PbrtGpuRenderDesc &rd) {
+    Extent e;
+    e.xs = (int)ceilf(rd.xResolution * rd.cropWindow[0]);
+    e.xc = std::max(1, (int)ceilf(rd.xResolution * rd.cropWindow[1]) - e.xs);
+    e.ys = (int)ceilf(rd.yResolution * rd.cropWindow[2]);
+    e.yc = std::max(1, (int)ceilf(rd.yResolution * rd.cropWindow[3]) - e.ys);
+    e.sx0 = (int)floorf(e.xs + 0.5f - rd.filterXWidth);
+    e.sx1 = (int)ceilf(e.xs - 0.5f + e.xc + rd.filterXWidth);
+    e.sy0 = (int)floorf(e.ys + 0.5f - rd.filterYWidth);
+    e.sy1 = (int)ceilf(e.ys - 0.5f + e.yc + rd.filterYWidth);
+    return e;
+}
+void SubWindow(const Extent &e, int num, int count, int *x0, int *x1, int *y0, int *y1) {
+    int dx = e.sx1 - e.sx0, dy = e.sy1 - e.sy0;
+    int nx = count, ny = 1;
+    while ((nx & 0x1) == 0 && 2 * dx * ny < dy * nx) { nx >>= 1; ny <<= 1; }
+    int xo = num % nx, yo = num / nx;
+    float tx0 = float(xo) / float(nx), tx1 = float(xo + 1) / float(nx);
+    float ty0 = float(yo) / float(ny), ty1 = float(yo + 1) / float(ny);
+    auto lerp = [](float t, float a, float b) { return (1.f - t) * a + t * b; };
+    *x0 = (int)floorf(lerp(tx0, e.sx0, e.sx1)); *x1 = (int)floorf(lerp(tx1, e.sx0, e.sx1));
+    *y0 = (int)floorf(lerp(ty0, e.sy0, e.sy1)); *y1 = (int)floorf(lerp(ty1, e.sy0, e.sy1));
+}
+
+// the Sample layout -> row / scramble positions, as BuildLayout in pbrtgpu.cu lays them out
+void LayoutH(const PbrtGpuRenderDesc &rd, SampleLayoutDev *L) {
+    memset(L, 0, sizeof(*L));
+    L->n1D = rd.n1D; L->n2D = rd.n2D;
+    int row = 3, scr = 5;
+    for (int j = 0; j < rd.n1D; ++j) { L->size1D[j] = rd.size1D[j]; L->row1D[j] = (uint16_t)row; L->scr1D[j] = (uint16_t)scr; row += rd.size1D[j]; scr += 1; }
+    for (int j = 0; j < rd.n2D; ++j) { L->size2D[j] = rd.size2D[j]; L->row2D[j] = (uint16_t)row; L->scr2D[j] = (uint16_t)scr; row += rd.size2D[j]; scr += 2; }
+    L->rowStride = (row + 7) / 8 * 8;
+}
+
+// LDPixelSample (montecarlo.cpp:200-252) on sequence INDICES: what k_tables / k_tables_general leave in a task's rows
+void TablesH(const SampleLayoutDev &L, int spp, Stream &rng, int *pos, std::vector<uint16_t> *rows, uint32_t *scr) {
+    rows->assign((size_t)spp * L.rowStride, 0);
+    auto array = [&](int n, int dims, int rowAt, int scrAt) {
+        for (int k = 0; k < dims; ++k) scr[scrAt + k] = rng.At((*pos)++);
+        std::vector<uint32_t> idx((size_t)spp * n);
+        for (size_t i = 0; i < idx.size(); ++i) idx[i] = (uint32_t)i;
+        for (int i = 0; i < spp; ++i)   // Shuffle(samples + i * n, n, dims, rng)
+            for (int k = 0; k < n; ++k) {
+                uint32_t other = k + rng.At((*pos)++) % (uint32_t)(n - k);
+                std::swap(idx[(size_t)i * n + k], idx[(size_t)i * n + other]);
+            }
+        for (int i = 0; i < spp; ++i) {   // Shuffle(samples, nPixel, dims * n, rng)
+            uint32_t other = i + rng.At((*pos)++) % (uint32_t)(spp - i);
+            for (int k = 0; k < n; ++k) std::swap(idx[(size_t)i * n + k], idx[(size_t)other * n + k]);
+        }
+        for (int i = 0; i < spp; ++i)
+            for (int k = 0; k < n; ++k) (*rows)[(size_t)i * L.rowStride + rowAt + k] = (uint16_t)idx[(size_t)i * n + k];
+    };
+    array(1, 2, 0, 0); array(1, 2, 1, 2); array(1, 1, 2, 4);
+    for (int j = 0; j < L.n1D; ++j) array(L.size1D[j], 1, L.row1D[j], L.scr1D[j]);
+    for (int j = 0; j < L.n2D; ++j) array(L.size2D[j], 2, L.row2D[j], L.scr2D[j]);
+}
+
+// One task, pixel by pixel, sample by sample: the path state machine (path_body.inc) run to the end of every
+// camera path by a single host thread -- the tables for bounces < 3, the task's stream after that, exactly what the
+// kernels do in two phases.
+template <int INTEG>
+void RunTaskH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc &rd, int taskNum, const Extent &ext,
+              PbrtGpuPixel *film) {
+    constexpr int PHASE = 2;
+    constexpr bool STATS = false;
+    int wx0, wx1, wy0, wy1;
+    SubWindow(ext, taskNum, rd.nTasks, &wx0, &wx1, &wy0, &wy1);
+    if (wx0 == wx1 || wy0 == wy1) return;
+    Stream rng((uint32_t)taskNum);
+    int mti = 0;   // position in the task's stream
+    const int spp = rp.spp;
+    const int rowStride = rp.lay.rowStride;
+    std::vector<uint16_t> rows;
+    uint32_t scrBuf[SCR_STRIDE];
+    float4 *lsBase = nullptr, *recBase = nullptr;   // (phase-1 outputs: unused, PHASE == 2)
+    auto rngF = [&](int k) -> float { return UIntToFloat(rng.At((size_t)(mti + k))); };
+    for (int yPos = wy0; yPos < wy1; ++yPos)
+        for (int xPos = wx0; xPos < wx1; ++xPos) {
+            TablesH(rp.lay, spp, rng, &mti, &rows, scrBuf);
+            const uint16_t *permBase = rows.data();
+            const uint32_t *scr = scrBuf;
+            for (int s = 0; s < spp; ++s) {
+                int state = S_NEW_SAMPLE, bounces = 0, code = 0, lightNum = 0;
+                Ray ray;
+                ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f; ray.time = 0.f;
+                Hit hit;
+                hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.maxtIn = 0.f;
+                bool found = false;
+                Spec T(1.f), L(0.f), Ld(0.f), pend(0.f);
+                ShadeCtx ctx;
+                ctx.p = ctx.nn = ctx.ng = ctx.sn = ctx.tn = V3(0, 0, 1);
+                ctx.material = 0; ctx.areaLight = -1; ctx.rayEpsilon = 0.f;
+                V3 wo(0, 0, 1), wiW(0, 0, 1);
+                float bsU0 = 0.f, bsU1 = 0.f, bsUc = 0.f, sPdf = 0.f, visMaxt = 0.f;
+                unsigned long long nShadedN = 0;
+                int dlI = 0, dlJ = 0;
+                Spec dlSum(0.f), dlAll(0.f);
+                bool ctxDirty = false;
+                (void)ctxDirty; (void)nShadedN;
+                TraceStats st;
+                st.nodes = st.prims = 0;
+                bool first = true;
+                for (;;) {
+#define PATH_FEVAL_IN Spec(0.f)
+#define PATH_EVALWO_IN V3(0, 0, 1)
+#define PATH_EVALWI_IN V3(0, 0, 1)
+#define PATH_DEFER_MEASURED false
+#define PATH_ANIM true
+#define PATH_INTEG INTEG
+#define PATH_COUNT_TAIL() ((void)0)
+#include "../../pbrt_v2_b200/csrc/device/path_body.inc"
+#undef PATH_COUNT_TAIL
+#undef PATH_FEVAL_IN
+#undef PATH_EVALWO_IN
+#undef PATH_EVALWI_IN
+#undef PATH_DEFER_MEASURED
+#undef PATH_ANIM
+#undef PATH_INTEG
+                    (void)deferEval;
+                    if (state == S_END_SAMPLE) break;
+                    if (state == S_NEW_SAMPLE && first) {
+                        // the camera ray, as in k_logic / k_path (perspective.cpp:81-138)
+                        first = false;
+                        const uint16_t *row = permBase + (size_t)s * rowStride;
+                        const uint32_t pi = row[0];
+                        const float imageX = xPos + VanDerCorput(pi, scr[0]);
+                        const float imageY = yPos + Sobol2(pi, scr[1]);
+                        code = FilmFootprint(rp, xPos, yPos, imageX, imageY);
+                        V3 Pcamera = XfPoint(rp.rasterToCamera, V3(imageX, imageY, 0));
+                        V3 dir = Normalize(V3(Pcamera.x, Pcamera.y, Pcamera.z));
+                        ray.o = V3(0, 0, 0); ray.d = dir; ray.mint = 0.f; ray.maxt = INF_F;
+                        ray.time = Lerp(VanDerCorput(row[2], scr[4]), rp.shutterOpen, rp.shutterClose);
+                        if (rp.lensRadius > 0.f) {
+                            const uint32_t pl = row[1];
+                            float lensU, lensV;
+                            ConcentricSampleDisk(VanDerCorput(pl, scr[2]), Sobol2(pl, scr[3]), &lensU, &lensV);
+                            lensU *= rp.lensRadius;
+                            lensV *= rp.lensRadius;
+                            float ft = rp.focalDistance / ray.d.z;
+                            V3 Pfocus = RayAt(ray, ft);
+                            ray.o = V3(lensU, lensV, 0.f);
+                            ray.d = Normalize(Pfocus - ray.o);
+                        }
+                        ray.o = XfPoint(rp.cameraToWorld, ray.o);
+                        ray.d = XfVector(rp.cameraToWorld, ray.d);
+                        T = Spec(1.f); L = Spec(0.f);
+                        bounces = 0;
+                        wantTrace = true; anyHit = false;
+                        state = S_HIT_RESULT;
+                    }
+                    if (wantTrace) found = Traverse<false, true>(sc, ray, anyHit, &hit, &st);
+                }
+                // DirectLightingIntegrator: SpecularReflect/Transmit's BSDFSample(rng) draws (what k_film_direct accounts for)
+                if (INTEG == PBRTGPU_INTEGRATOR_DIRECTLIGHTING && (code & LS_HIT) && 0 + 1 < rp.maxDepth) mti += 6;
+                // ImageFilm::AddSample through the footprint bits (FilmAdd in pbrtgpu.cu, without atomics)
+                const Spec Ls = SanitizeRadiance(L);
+                float xyz[3];
+                xyz[0] = 0.412453f * Ls.r + 0.357580f * Ls.g + 0.180423f * Ls.b;
+                xyz[1] = 0.212671f * Ls.r + 0.715160f * Ls.g + 0.072169f * Ls.b;
+                xyz[2] = 0.019334f * Ls.r + 0.119193f * Ls.g + 0.950227f * Ls.b;
+                const int fy0 = yPos - ((code & LS_UP) ? 1 : 0), fy1 = yPos + ((code & LS_DOWN) ? 1 : 0);
+                const int fx0 = xPos - ((code & LS_LEFT) ? 1 : 0), fx1 = xPos + ((code & LS_RIGHT) ? 1 : 0);
+                for (int y = fy0; y <= fy1; ++y)
+                    for (int x = fx0; x <= fx1; ++x) {
+                        PbrtGpuPixel &px = film[(size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart)];
+                        px.Lxyz[0] += xyz[0]; px.Lxyz[1] += xyz[1]; px.Lxyz[2] += xyz[2]; px.weightSum += 1.f;
+                    }
+            }
+        }
+}
+
+}  // namespace
+
 extern "C" {
+
+// pbrtgpu_render's result computed by one host thread running the device state machine (see RunTaskH)
+int doh_render(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc *rd, PbrtGpuPixel *pixels) {
+    HostScene hs;
+    Pack(desc, &hs);
+    const Extent ext = ComputeExtentH(*rd);
+    RenderParams rp;
+    memset(&rp, 0, sizeof(rp));
+    memcpy(rp.rasterToCamera, rd->rasterToCamera, sizeof(rp.rasterToCamera));
+    memcpy(rp.cameraToWorld, rd->cameraToWorld, sizeof(rp.cameraToWorld));
+    rp.lensRadius = rd->lensRadius; rp.focalDistance = rd->focalDistance;
+    rp.shutterOpen = rd->shutterOpen; rp.shutterClose = rd->shutterClose;
+    rp.filterXWidth = rd->filterXWidth; rp.filterYWidth = rd->filterYWidth;
+    rp.xPixelStart = ext.xs; rp.yPixelStart = ext.ys; rp.xPixelCount = ext.xc; rp.yPixelCount = ext.yc;
+    rp.spp = rd->samplesPerPixel; rp.maxDepth = rd->maxDepth;
+    rp.integrator = rd->integrator; rp.lightStrategy = rd->lightStrategy;
+    LayoutH(*rd, &rp.lay);
+    memset(pixels, 0, sizeof(PbrtGpuPixel) * (size_t)ext.xc * ext.yc);
+    for (int t = rd->taskBegin; t < rd->taskEnd; ++t) {
+        if (rd->integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING) RunTaskH<1>(hs.d, rp, *rd, t, ext, pixels);
+        else RunTaskH<0>(hs.d, rp, *rd, t, ext, pixels);
+    }
+    return 0;
+}
 
 // k_intersect<false>'s body (device/pbrtgpu.cu) on the host: BVHAccel::Intersect + the hit's differential geometry
 int doh_intersect(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits, int stepwise) {

@@ -2,7 +2,9 @@
 (tests/native/device_on_host.cpp: g++ with the CUDA intrinsics shimmed, no FMA contraction) and compared with the oracle
 bit for bit: BVH walks in both forms (Traverse<>, the wavefront's TravStep<>), TransformedPrimitives, hit geometry, and
 the shading steps of the path state machine (shading frame, light sampling, BSDF::f / Pdf / Sample_f incl. the measured
-BRDF's k-nearest + gather form).  No GPU needed: this is the CPU-stage guard for edits to the device arithmetic."""
+BRDF's k-nearest + gather form), and finally whole renders: path_body.inc -- the state machine the kernels include --
+run to the end of every camera path by one host thread (both integrators, all scene-file variants).  No GPU needed:
+this is the CPU-stage guard for edits to the device code's arithmetic and control flow (not its kernel plumbing)."""
 import ctypes as C
 import os
 import subprocess
@@ -27,6 +29,7 @@ def doh(tmp_path_factory):
     lib.doh_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.doh_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.doh_shade_test.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
     return lib
 
 
@@ -72,3 +75,30 @@ def test_device_shading_on_host_matches_oracle(staged, doh, base):
     assert (a[:, 15] != 0).mean() > 0.2 and (a[:, 34] != 0).mean() > 0.1   # hits shaded, BSDF samples drawn
     same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
     assert same.all(), "columns differing: %s" % np.nonzero(~same.all(axis=0))[0].tolist()
+
+
+RENDER_CASES = [("bunny", 32, 8, 32, "path", None), ("bunny", 32, 8, 1, "path", None), ("killeroo-simple", 32, 8, 2, "path", None),
+                ("anim-killeroos-moving", 32, 4, 2, "path", None), ("killeroo-simple", 32, 4, 2, "directlighting", None),
+                ("bunny", 32, 8, 1, "directlighting", None), ("bunny", 32, 4, 2, "directlighting", "one"),
+                ("anim-killeroos-moving", 32, 4, 1, "directlighting", None)]
+
+
+def _same_film(doh, hs):
+    rd = hs.render_desc()
+    px = hs.new_pixels()
+    doh.doh_render(hs.desc_ptr, C.byref(rd), px.ctypes.data)
+    ref, _ = oa.render(hs, threads=4)
+    assert np.array_equal(px["weightSum"], ref["weightSum"])
+    own = ref["weightSum"] == rd.samplesPerPixel   # (splat receivers: the reference's own order dependence)
+    assert np.array_equal(px["Lxyz"][own].view(np.uint32), ref["Lxyz"][own].view(np.uint32))
+
+
+@pytest.mark.parametrize("base,res,spp,ncores,integrator,strategy", RENDER_CASES)
+def test_device_state_machine_on_host_renders_like_the_oracle(staged, doh, base, res, spp, ncores, integrator, strategy):
+    _same_film(doh, host_scene(base, res, res, spp, ncores, integrator=integrator, strategy=strategy))
+
+
+def test_device_state_machine_on_host_variants(staged, doh):
+    from helpers import VARIANTS, EDGE_VARIANTS, variant_scene
+    for v in VARIANTS + EDGE_VARIANTS:
+        _same_film(doh, variant_scene(v[0])[0])
