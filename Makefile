@@ -17,12 +17,15 @@ HOSTFLAGS := -O2 -std=c++17 -ffp-contract=off -fPIC -Wall -Wno-unused-function
 HOSTSRC   := transform parser shapes bvh measured renderer render_call capi
 HOSTOBJ   := $(patsubst %,build/host/%.o,$(HOSTSRC))
 DEVSRC    := $(wildcard $(DEVDIR)/*.cu)
-DEVHDR    := $(wildcard $(DEVDIR)/*.cuh) include/pbrtgpu.h
+DEVHDR    := $(wildcard $(DEVDIR)/*.cuh) $(wildcard $(DEVDIR)/*.inc) $(wildcard $(DEVDIR)/*.h) include/pbrtgpu.h
+# extra -D switches for kernel experiments, e.g.  make NVDEFS=-DPBRT_SPECULAR=1  (see device/dshade.cuh) or
+# -DK_TRACE_MIN_BLOCKS=8; the shipped library is built with none
+NVDEFS    ?=
 
 all: $(PKG)/libpbrtgpu.so $(PKG)/libpbrthost.so $(PKG)/pbrt_b200 oracle
 
 $(PKG)/libpbrtgpu.so: $(DEVSRC) $(DEVHDR)
-	$(NVCC) $(NVFLAGS) -shared $(DEVSRC) -o $@ 2> build/ptxas.log || (cat build/ptxas.log; false)
+	$(NVCC) $(NVFLAGS) $(NVDEFS) -shared $(DEVSRC) -o $@ 2> build/ptxas.log || (cat build/ptxas.log; false)
 	@grep -E "registers|spill|error" build/ptxas.log | sort | uniq -c | sort -rn | head -20 || true
 
 build/host/%.o: $(HOSTDIR)/%.cpp $(HOSTDIR)/scene.h $(HOSTDIR)/geom.h include/pbrtgpu.h

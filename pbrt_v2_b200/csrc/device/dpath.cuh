@@ -25,7 +25,8 @@ enum PathState {
 };
 // ls[s].w bit field
 enum { LS_TAIL = 1, LS_LEFT = 2, LS_RIGHT = 4, LS_UP = 8, LS_DOWN = 16,
-       LS_HIT = 32 };   // directlighting: the camera ray hit something (6 RNG draws follow, see k_film_direct)
+       LS_HIT = 32,     // directlighting: the camera ray hit something (6 RNG draws follow, see k_film_direct)
+       LS_SPEC = 64 };  // PBRT_SPECULAR builds: the parked vertex was reached by a specular bounce (path.cpp:62-63)
 
 // Which pixels does ImageFilm::AddSample (film/image.cpp:77-96) touch for this sample?
 // With the 0.5 box filter: the sample's own pixel, plus a neighbour when the

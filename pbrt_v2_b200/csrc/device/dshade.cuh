@@ -17,6 +17,15 @@ enum {
     BSDF_ALL = BSDF_ALL_REFLECTION | BSDF_ALL_TRANSMISSION
 };
 enum { BX_LAMBERTIAN = 0, BX_MICROFACET_BLINN = 1, BX_IRREG_ISO = 2 };
+// specular BxDFs (mirror / glass).  The code under PBRT_SPECULAR is verified on the CPU through the
+// host-compiled state machine (tests/native/device_on_host.cpp, built with -DPBRT_SPECULAR=1) but has not run on a GPU
+// yet; the shipped library is compiled without it (byte-identical kernels) and pbrtgpu_scene_create refuses the materials.
+#ifndef PBRT_SPECULAR
+#define PBRT_SPECULAR 0
+#endif
+#if PBRT_SPECULAR
+enum { BX_SPECULAR_REFLECTION = 3, BX_SPECULAR_TRANSMISSION = 4 };   // BxSet.exponent: eta_t of the dielectric, 0 = FresnelNoOp
+#endif
 
 DEV float CosTheta(const V3 &w) { return w.z; }
 DEV float AbsCosTheta(const V3 &w) { return fabsf(w.z); }
@@ -193,6 +202,19 @@ DEV void MaterialBxDFs(const DScene &sc, int material, BxSet *s) {
             int i = s->n++;
             s->kind[i] = BX_MICROFACET_BLINN; s->type[i] = BSDF_REFLECTION | BSDF_GLOSSY; s->R[i] = ks; s->exponent = e;
         }
+#if PBRT_SPECULAR
+    } else if (m.type == PBRTGPU_MAT_MIRROR) {  // mirror.cpp:41-53: SpecularReflection(R, FresnelNoOp); Ks holds Kr
+        Spec r = Spec(m.Ks[0], m.Ks[1], m.Ks[2]).Clamp();
+        if (!r.IsBlack()) { s->kind[0] = BX_SPECULAR_REFLECTION; s->type[0] = BSDF_REFLECTION | BSDF_SPECULAR; s->R[0] = r; s->n = 1; }
+    } else if (m.type == PBRTGPU_MAT_GLASS) {   // glass.cpp:41-57: Ks = Kr, Kd = Kt, roughness = index
+        s->exponent = m.roughness;
+        Spec r = Spec(m.Ks[0], m.Ks[1], m.Ks[2]).Clamp(), t = Spec(m.Kd[0], m.Kd[1], m.Kd[2]).Clamp();
+        if (!r.IsBlack()) { s->kind[0] = BX_SPECULAR_REFLECTION; s->type[0] = BSDF_REFLECTION | BSDF_SPECULAR; s->R[0] = r; s->n = 1; }
+        if (!t.IsBlack()) {
+            int i = s->n++;
+            s->kind[i] = BX_SPECULAR_TRANSMISSION; s->type[i] = BSDF_TRANSMISSION | BSDF_SPECULAR; s->R[i] = t;
+        }
+#endif
     } else {                                     // measured.cpp:194-210
         s->kind[0] = BX_IRREG_ISO; s->type[0] = BSDF_REFLECTION | BSDF_GLOSSY; s->R[0] = Spec(0.f); s->n = 1;
         s->measured = m.measured;
@@ -330,6 +352,9 @@ DEV float KdThirdNearest(const DScene &sc, const PbrtGpuMeasured &m, const V3 &p
 }
 
 DEV Spec BxF(const DScene &sc, const BxSet &s, int i, const V3 &wo, const V3 &wi) {
+#if PBRT_SPECULAR
+    if (s.kind[i] == BX_SPECULAR_REFLECTION || s.kind[i] == BX_SPECULAR_TRANSMISSION) return Spec(0.f);   // reflection.h:317-319,339-341
+#endif
     if (s.kind[i] == BX_LAMBERTIAN) return s.R[i] * INV_PI_F;   // reflection.cpp:173-175
     if (s.kind[i] == BX_MICROFACET_BLINN) {                     // Microfacet::f, reflection.cpp:211-222
         float cosThetaO = AbsCosTheta(wo);
@@ -355,6 +380,9 @@ DEV Spec BxF(const DScene &sc, const BxSet &s, int i, const V3 &wo, const V3 &wi
     return v.Clamp() / sumWeights;
 }
 DEV float BxPdf(const BxSet &s, int i, const V3 &wo, const V3 &wi) {
+#if PBRT_SPECULAR
+    if (s.kind[i] == BX_SPECULAR_REFLECTION || s.kind[i] == BX_SPECULAR_TRANSMISSION) return 0.f;   // reflection.h:322-324,344-346
+#endif
     if (s.kind[i] == BX_MICROFACET_BLINN) {   // Microfacet::Pdf + Blinn::Pdf, reflection.cpp:340-343,365-374
         if (!SameHemisphere(wo, wi)) return 0.f;
         V3 wh = Normalize(wo + wi);
@@ -386,6 +414,33 @@ DEV_NI3 void BxSampleDir(const BxSet &s, int i, const V3 &wo, V3 *wi, float u1, 
     *pdf = BxPdf(s, i, wo, *wi);
 }
 
+#if PBRT_SPECULAR
+// SpecularReflection::Sample_f / SpecularTransmission::Sample_f, reflection.cpp:138-170: direction, pdf and the value
+// BSDF::Sample_f returns as it is for a specular component (:572)
+DEV Spec SpecularSample(const BxSet &s, int i, const V3 &wo, V3 *wi, float *pdf) {
+    if (s.kind[i] == BX_SPECULAR_REFLECTION) {
+        *wi = V3(-wo.x, -wo.y, wo.z);
+        *pdf = 1.f;
+        Spec F = s.exponent == 0.f ? Spec(1.f) : FresnelDielectric(CosTheta(wo), 1.f, s.exponent);
+        return F * s.R[i] / AbsCosTheta(*wi);
+    }
+    bool entering = CosTheta(wo) > 0.f;
+    float ei = 1.f, et = s.exponent;
+    if (!entering) { float t = ei; ei = et; et = t; }
+    float sini2 = SinTheta2(wo);
+    float eta = ei / et;
+    float sint2 = eta * eta * sini2;
+    if (sint2 >= 1.f) return Spec(0.f);   // total internal reflection: *pdf keeps the caller's 0
+    float cost = sqrtf(maxf(0.f, 1.f - sint2));
+    if (entering) cost = -cost;
+    float sintOverSini = eta;
+    *wi = V3(sintOverSini * -wo.x, sintOverSini * -wo.y, cost);
+    *pdf = 1.f;
+    Spec F = FresnelDielectric(CosTheta(wo), 1.f, s.exponent);
+    return (Spec(1.f) - F) * s.R[i] / AbsCosTheta(*wi);
+}
+#endif
+
 // BSDF::Pdf (reflection.cpp:583-598) on already-local vectors
 DEV float BSDF_PdfLocal(const BxSet &s, const V3 &wo, const V3 &wi, int flags) {
     if (s.n == 0) return 0.f;
@@ -404,7 +459,11 @@ DEV float BSDF_PdfLocal(const BxSet &s, const V3 &wo, const V3 &wi, int flags) {
 // black spectrum with pdf 0; otherwise the local wo/wi, the world wi, the combined pdf and
 // the flags (hemisphere-adjusted, :568-571) the caller hands to the evaluation site.
 DEV bool BSDF_SampleDir(const ShadeCtx &c, const BxSet &s, const V3 &woW, float uDir0, float uDir1, float uComponent,
-                        int flags, V3 *woOut, V3 *wiOut, V3 *wiW, float *pdf, int *sampledType, int *evalFlags) {
+                        int flags, V3 *woOut, V3 *wiOut, V3 *wiW, float *pdf, int *sampledType, int *evalFlags
+#if PBRT_SPECULAR
+                        , Spec *specF   // the value to use when *sampledType has BSDF_SPECULAR
+#endif
+                        ) {
     int matchingComps = 0;
     for (int i = 0; i < s.n; ++i) if (Matches(s.type[i], flags)) ++matchingComps;
     *pdf = 0.f;
@@ -417,11 +476,19 @@ DEV bool BSDF_SampleDir(const ShadeCtx &c, const BxSet &s, const V3 &woW, float 
         if (Matches(s.type[i], flags) && count-- == 0) { bx = i; break; }
     V3 wo = WorldToLocal(c, woW);
     V3 wi;
+#if PBRT_SPECULAR
+    const bool specular = (s.type[bx] & BSDF_SPECULAR) != 0;
+    if (specular) *specF = SpecularSample(s, bx, wo, &wi, pdf);
+    else
+#endif
     BxSampleDir(s, bx, wo, &wi, uDir0, uDir1, pdf);
     if (*pdf == 0.f) return false;
     *sampledType = s.type[bx];
     *wiW = LocalToWorld(c, wi);
-    if (matchingComps > 1)   // (no specular BxDF in scope)
+#if PBRT_SPECULAR
+    if (!specular)
+#endif
+    if (matchingComps > 1)   // (reflection.cpp:560-564: only for a non-specular sampled component)
         for (int i = 0; i < s.n; ++i)
             if (i != bx && Matches(s.type[i], flags)) *pdf += BxPdf(s, i, wo, wi);
     if (matchingComps > 1) *pdf /= matchingComps;

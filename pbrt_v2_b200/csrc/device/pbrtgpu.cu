@@ -474,6 +474,9 @@ __global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(PathArgs a) {
     V3 wiW(0, 0, 1);                            // sampled incident direction (world)
     float sPdf = 0.f, visMaxt = 0.f;            // its pdf; the shadow segment's maxt
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#if PBRT_SPECULAR
+    bool specularBounce = false;          // path.cpp:53; travels with a parked sample as LS_SPEC
+#endif
     int dlI = 0, dlJ = 0;                 // (DirectLightingIntegrator state of path_body.inc: unused, PATH_INTEG == 0 here)
     Spec dlSum(0.f), dlAll(0.f);
     const int rowStride = PERM_STRIDE;
@@ -579,6 +582,9 @@ __global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(PathArgs a) {
                     ray.o = XfPoint(rp.cameraToWorld, ray.o);
                     ray.d = XfVector(rp.cameraToWorld, ray.d);
                     T = Spec(1.f); L = Spec(0.f);
+#if PBRT_SPECULAR
+                    specularBounce = false;
+#endif
                     bounces = 0;
                     wantTrace = true; anyHit = false;
                     state = S_HIT_RESULT;
@@ -611,6 +617,10 @@ __global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(PathArgs a) {
                         hit.b1 = r3.x; hit.b2 = r3.y; hit.maxtIn = r3.z;
                         ray.time = r3.w;
                         L = Spec(v.x, v.y, v.z);
+#if PBRT_SPECULAR
+                        specularBounce = (code & LS_SPEC) != 0;
+                        code &= ~LS_SPEC;
+#endif
                         code &= ~LS_TAIL;
                         bounces = 3;
                         found = true;
@@ -764,6 +774,9 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
     unsigned long long nShadedN = 0;
     bool ctxDirty = false;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#if PBRT_SPECULAR
+    bool specularBounce = false;           // path.cpp:53; bit 31 of the packed state word between iterations
+#endif
     int dlI = 0, dlJ = 0;                  // DirectLightingIntegrator's light loop
     Spec dlSum(0.f), dlAll(0.f);
     const int rowStride = INTEG == PBRTGPU_INTEGRATOR_DIRECTLIGHTING ? rp.lay.rowStride : PERM_STRIDE;
@@ -777,7 +790,12 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
     if (live && kindIn >= 0) {   // load only what this resume state reads
         const float4 fT = FLD(F_T), fL = FLD(F_L), fWo = FLD(F_WO), fWi = FLD(F_WI);
         const uint32_t packed = __float_as_uint(fT.w);
+#if PBRT_SPECULAR
+        state = packed & 0xffu; bounces = (packed >> 8) & 0xffu; lightNum = (packed >> 16) & 0x7fffu;
+        specularBounce = (packed >> 31) != 0;
+#else
         state = packed & 0xffu; bounces = (packed >> 8) & 0xffu; lightNum = packed >> 16;
+#endif
         T = Spec(fT.x, fT.y, fT.z);
         L = Spec(fL.x, fL.y, fL.z); code = __float_as_int(fL.w);
         wo = V3(fWo.x, fWo.y, fWo.z); bi = __float_as_int(fWo.w);
@@ -934,6 +952,10 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
                         hit.b1 = r3.x; hit.b2 = r3.y; hit.maxtIn = r3.z;
                         ray.time = r3.w;
                         L = Spec(v.x, v.y, v.z);
+#if PBRT_SPECULAR
+                        specularBounce = (code & LS_SPEC) != 0;
+                        code &= ~LS_SPEC;
+#endif
                         code &= ~LS_TAIL;
                         bounces = 3;
                         found = true;
@@ -989,6 +1011,9 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
             ray.o = XfPoint(rp.cameraToWorld, ray.o);
             ray.d = XfVector(rp.cameraToWorld, ray.d);
             T = Spec(1.f); L = Spec(0.f);
+#if PBRT_SPECULAR
+            specularBounce = false;
+#endif
             bounces = 0;
             wantTrace = true; anyHit = false;
             state = S_HIT_RESULT;
@@ -1012,7 +1037,12 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
         FLD(F_DL_SUM) = make_float4(dlSum.r, dlSum.g, dlSum.b, __uint_as_float((uint32_t)dlI | ((uint32_t)dlJ << 16)));
         FLD(F_DL_ALL) = make_float4(dlAll.r, dlAll.g, dlAll.b, 0.f);
     }
+#if PBRT_SPECULAR
+    FLD(F_T) = make_float4(T.r, T.g, T.b, __uint_as_float((uint32_t)state | ((uint32_t)bounces << 8) | ((uint32_t)lightNum << 16) |
+                                                          (specularBounce ? 0x80000000u : 0u)));
+#else
     FLD(F_T) = make_float4(T.r, T.g, T.b, __uint_as_float((uint32_t)state | ((uint32_t)bounces << 8) | ((uint32_t)lightNum << 16)));
+#endif
     FLD(F_L) = make_float4(L.r, L.g, L.b, __int_as_float(code));
     FLD(F_WO) = make_float4(wo.x, wo.y, wo.z, __int_as_float(bi));
     FLD(F_WI) = make_float4(wiW.x, wiW.y, wiW.z, __int_as_float(s));
@@ -1367,6 +1397,7 @@ struct PbrtGpuScene {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // render start / end, the lanes' start gate
     int collectStats = 0;   // 1: ray/node/primitive counters, 2: per-launch timing of the traversal kernel
     int nMeasuredMaterials = 0;
+    int nSpecularMaterials = 0;
 };
 
 namespace {
@@ -1581,8 +1612,10 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
             return Fail(PBRTGPU_EUNSUPPORTED, "area lights over more than one shape are out of scope");
     for (uint32_t i = 0; i < desc->nMaterials; ++i) {
         const PbrtGpuMaterial &m = desc->materials[i];
+#if !PBRT_SPECULAR
         if (m.type == PBRTGPU_MAT_MIRROR || m.type == PBRTGPU_MAT_GLASS)
             return Fail(PBRTGPU_EUNSUPPORTED, "specular materials (mirror, glass) are restated in the oracle only: not on the device yet");
+#endif
         if (m.type > PBRTGPU_MAT_GLASS) return Fail(PBRTGPU_EINVAL, "unknown material type");
         if (m.type == PBRTGPU_MAT_MATTE && m.sigma != 0.f) return Fail(PBRTGPU_EUNSUPPORTED, "Oren-Nayar (sigma != 0) is out of scope");
         if (m.type == PBRTGPU_MAT_MEASURED && (m.measured < 0 || (uint32_t)m.measured >= desc->nMeasured))
@@ -1679,8 +1712,11 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
     d.lights = s->lights.p; d.lightShapes = s->lightShapes.p; d.animated = s->animated.p;
     d.nNodes = desc->nNodes; d.nPrims = desc->nPrimitives; d.nLights = desc->nLights; d.nAnimated = desc->nAnimated;
     s->nMeasuredMaterials = 0;
-    for (uint32_t i = 0; i < desc->nMaterials; ++i)
+    s->nSpecularMaterials = 0;
+    for (uint32_t i = 0; i < desc->nMaterials; ++i) {
         if (desc->materials[i].type == PBRTGPU_MAT_MEASURED) s->nMeasuredMaterials++;
+        if (desc->materials[i].type == PBRTGPU_MAT_MIRROR || desc->materials[i].type == PBRTGPU_MAT_GLASS) s->nSpecularMaterials++;
+    }
     return PBRTGPU_OK;
 }
 
@@ -2050,6 +2086,11 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     BuildLayout(*rd, &rp.lay, &tables);
     const bool pathLayout = IsPathLayout(*rd);
     const bool directInteg = rd->integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
+#if PBRT_SPECULAR
+    if (directInteg && scene->nSpecularMaterials)
+        return Fail(PBRTGPU_EUNSUPPORTED, "DirectLightingIntegrator with specular materials needs the recursive SpecularReflect/Transmit rays: not on the device yet");
+    if (scene->nSpecularMaterials && scene->d.nLights > 32767) return Fail(PBRTGPU_EUNSUPPORTED, "too many lights");
+#endif
     if (directInteg) {   // the layout must be what DirectLightingIntegrator::RequestSamples builds for this scene's lights
         const int nl = (int)scene->d.nLights;
         const bool all = rd->lightStrategy == PBRTGPU_STRATEGY_ALL;

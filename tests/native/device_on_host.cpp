@@ -210,7 +210,8 @@ void RunTaskH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
                 int dlI = 0, dlJ = 0;
                 Spec dlSum(0.f), dlAll(0.f);
                 bool ctxDirty = false;
-                (void)ctxDirty; (void)nShadedN;
+                bool specularBounce = false;   // (PBRT_SPECULAR builds: path.cpp:53)
+                (void)ctxDirty; (void)nShadedN; (void)specularBounce;
                 TraceStats st;
                 st.nodes = st.prims = 0;
                 bool first = true;
@@ -424,10 +425,18 @@ int doh_shade_test(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, 
             V3 evalWo, evalWi, wi2;
             float pdf2;
             int sampledType, evalFlags;
+#if PBRT_SPECULAR
+            Spec specF(0.f);
+            if (BSDF_SampleDir(ctx, bx, wo, uu[2], uu[3], uu[4], BSDF_ALL, &evalWo, &evalWi, &wi2, &pdf2, &sampledType, &evalFlags, &specF)) {
+#else
             if (BSDF_SampleDir(ctx, bx, wo, uu[2], uu[3], uu[4], BSDF_ALL, &evalWo, &evalWi, &wi2, &pdf2, &sampledType, &evalFlags)) {
+#endif
                 Spec f(0.f);
                 for (int k = 0; k < bx.n; ++k)
                     if (Matches(bx.type[k], evalFlags)) f = f + BxF(sc, bx, k, evalWo, evalWi);
+#if PBRT_SPECULAR
+                if (sampledType & BSDF_SPECULAR) f = specF;
+#endif
                 o[28] = f.r; o[29] = f.g; o[30] = f.b;
                 put(31, wi2); o[34] = pdf2;
                 o[35] = LightPdf(sc, light, ctx.p, wi2);
