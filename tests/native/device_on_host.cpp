@@ -3,7 +3,12 @@
 // the CPU test stage can compare the product's own arithmetic with the oracle, bit for bit, without a GPU: a guard for
 // edits made while no GPU is at hand.  It is never linked into the product; only tests/ load it.
 //
+// Build with -fvisibility=hidden -Wl,-Bsymbolic (tests/test_device_on_host.py does): libpbrtgpu.so exports host stubs of
+// the same dev:: functions (nvcc emits them for __device__ code), and a process that has the product library loaded
+// must not bind this harness's calls to those stubs.
+//
 // The shims below give the handful of CUDA intrinsics the headers use their plain C++ meaning.
+#define DOH_EXPORT extern "C" __attribute__((visibility("default")))
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -289,7 +294,7 @@ void RunTaskH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
 extern "C" {
 
 // pbrtgpu_render's result computed by one host thread running the device state machine (see RunTaskH)
-int doh_render(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc *rd, PbrtGpuPixel *pixels) {
+DOH_EXPORT int doh_render(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc *rd, PbrtGpuPixel *pixels) {
     HostScene hs;
     Pack(desc, &hs);
     const Extent ext = ComputeExtentH(*rd);
@@ -313,7 +318,7 @@ int doh_render(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc *rd, PbrtGp
 }
 
 // k_intersect<false>'s body (device/pbrtgpu.cu) on the host: BVHAccel::Intersect + the hit's differential geometry
-int doh_intersect(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits, int stepwise) {
+DOH_EXPORT int doh_intersect(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits, int stepwise) {
     HostScene hs;
     Pack(desc, &hs);
     const DScene &sc = hs.d;
@@ -353,7 +358,7 @@ int doh_intersect(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, P
     return 0;
 }
 
-int doh_intersect_p(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, uint8_t *occ, int stepwise) {
+DOH_EXPORT int doh_intersect_p(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, uint8_t *occ, int stepwise) {
     HostScene hs;
     Pack(desc, &hs);
     const DScene &sc = hs.d;
@@ -377,7 +382,7 @@ int doh_intersect_p(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n,
 }
 
 // the shading steps of path_body.inc at the first hit of each ray, laid out like oracle_shade_test's output
-int doh_shade_test(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, const float *u, float *out) {
+DOH_EXPORT int doh_shade_test(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, const float *u, float *out) {
     HostScene hs;
     Pack(desc, &hs);
     const DScene &sc = hs.d;

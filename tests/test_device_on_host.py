@@ -23,8 +23,9 @@ pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_
 def _build(tmp_path_factory, name, defines=()):
     so = str(tmp_path_factory.mktemp(name) / ("lib%s.so" % name))
     src = os.path.join(pb.REPO, "tests", "native", "device_on_host.cpp")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I" + CUDA_INC] + list(defines) +
-                   [src, "-o", so], check=True)
+    # hidden visibility + -Bsymbolic: see the note at the top of device_on_host.cpp
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic",
+                    "-I" + CUDA_INC] + list(defines) + [src, "-o", so], check=True)
     return C.CDLL(so)
 
 
