@@ -218,7 +218,7 @@ GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, 
 }
 
 TransformedPrimitive::TransformedPrimitive(const GeometricPrimitive &base, const AnimatedTransform &w2p)
-    : WorldToPrimitive(w2p) {
+    : shape(base.shape), WorldToPrimitive(w2p) {
     // api.cpp:1033-1043: "refine animated shape and create BVH if more than one shape created"
     std::vector<GeometricPrimitive> one(1, base);
     primitive.reset(new GpuBVHAccel(one));

@@ -166,6 +166,7 @@ GpuBVHAccel *CreateGpuBVHAccelerator(const std::vector<GeometricPrimitive> &prim
 // the shape is made with identity transforms, refined, and -- if that gave more than one primitive --
 // wrapped in its own BVHAccel with the constructor's DEFAULT arguments (maxPrimsInNode 1, "sah").
 struct TransformedPrimitive {
+    std::shared_ptr<Shape> shape;             // keeps the shape alive: the refined primitives point into it
     std::unique_ptr<GpuBVHAccel> primitive;   // `nodes` is empty when there is a single refined primitive
     AnimatedTransform WorldToPrimitive;
     TransformedPrimitive(const GeometricPrimitive &base, const AnimatedTransform &w2p);

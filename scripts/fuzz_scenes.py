@@ -1,0 +1,142 @@
+#!/usr/bin/env python
+"""Random in-scope scenes: the unmodified reference binary vs the oracle vs the device code compiled for the host
+(tests/native/device_on_host.cpp).  CPU only.  usage: fuzz_scenes.py [n] [seed0]"""
+import ctypes as C, os, subprocess, sys
+import numpy as np
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests"))
+import pbrt_v2_b200 as pb
+from pbrt_v2_b200 import scenes
+import oracle_api as oa
+
+def fl(a): return " ".join("%.6g" % x for x in a)
+
+def gen(rng, path, animated=None):
+    L = []
+    eye = rng.uniform(-1, 1, 3); eye = eye / np.linalg.norm(eye) * rng.uniform(3, 6)
+    L.append("LookAt %s  %s  0 1 0" % (fl(eye), fl(rng.uniform(-.3, .3, 3))))
+    cam = 'Camera "perspective" "float fov" [%g]' % rng.uniform(30, 60)
+    if rng.rand() < .3: cam += ' "float lensradius" [%g] "float focaldistance" [%g]' % (rng.uniform(.01, .1), rng.uniform(2, 6))
+    L.append(cam)
+    xr, yr = rng.choice([16, 24, 32]), rng.choice([16, 24])
+    spp = int(rng.choice([1, 2, 4, 8]))
+    L.append('Film "image" "integer xresolution" [%d] "integer yresolution" [%d] "string filename" "fz.pfm"' % (xr, yr))
+    L.append('Sampler "lowdiscrepancy" "integer pixelsamples" [%d]' % spp)
+    integ = rng.choice(["path", "directlighting"])
+    s = 'SurfaceIntegrator "%s" "integer maxdepth" [%d]' % (integ, rng.choice([1, 2, 3, 5, 7]))
+    if integ == "directlighting" and rng.rand() < .4: s += ' "string strategy" "one"'
+    L.append(s)
+    L.append("WorldBegin")
+    def xform():
+        t = []
+        if rng.rand() < .8: t.append("Translate %s" % fl(rng.uniform(-1.2, 1.2, 3)))
+        if rng.rand() < .6: t.append("Rotate %g %s" % (rng.uniform(-180, 180), fl(rng.uniform(-1, 1, 3) + 1e-3)))
+        if rng.rand() < .5:
+            sc = rng.uniform(.4, 1.6, 3) if rng.rand() < .5 else np.repeat(rng.uniform(.4, 1.6), 3)
+            if rng.rand() < .25: sc[rng.randint(3)] *= -1     # swaps handedness
+            t.append("Scale %s" % fl(sc))
+        return t
+    def material():
+        k = rng.rand()
+        if k < .4: return 'Material "matte" "color Kd" [%s]' % fl(rng.uniform(0, 1, 3))
+        if k < .8: return 'Material "plastic" "color Kd" [%s] "color Ks" [%s] "float roughness" [%g]' % (
+            fl(rng.uniform(0, .6, 3)), fl(rng.uniform(0, .6, 3)), rng.choice([.5, .1, .03, 1e-5]))
+        return 'Material "measured" "string filename" "brdfs/mystique.brdf"'
+    def shape():
+        k = rng.rand()
+        if k < .35:
+            r = rng.uniform(.2, .7)
+            s = 'Shape "sphere" "float radius" [%g]' % r
+            if rng.rand() < .4: s += ' "float zmin" [%g] "float zmax" [%g]' % (-r * rng.uniform(.2, 1), r * rng.uniform(.2, 1))
+            if rng.rand() < .3: s += ' "float phimax" [%g]' % rng.uniform(90, 330)
+            return s
+        if k < .55:
+            s = 'Shape "disk" "float radius" [%g] "float height" [%g]' % (rng.uniform(.3, .9), rng.uniform(-.3, .3))
+            if rng.rand() < .4: s += ' "float innerradius" [%g]' % rng.uniform(.05, .25)
+            if rng.rand() < .3: s += ' "float phimax" [%g]' % rng.uniform(90, 330)
+            return s
+        nv = rng.randint(4, 9)
+        P = rng.uniform(-.8, .8, (nv, 3))
+        nt = rng.randint(2, 7)
+        idx = np.array([rng.choice(nv, 3, replace=False) for _ in range(nt)])
+        s = 'Shape "trianglemesh" "integer indices" [%s] "point P" [%s]' % (fl(idx.ravel()), fl(P.ravel()))
+        if rng.rand() < .5:
+            N = rng.uniform(-1, 1, (nv, 3)); N /= np.linalg.norm(N, axis=1, keepdims=True)
+            s += ' "normal N" [%s]' % fl(N.ravel())
+        if rng.rand() < .5: s += ' "float uv" [%s]' % fl(rng.uniform(0, 1, nv * 2))
+        return s
+    for _ in range(rng.randint(0, 3)):
+        L.append('LightSource "point" "color I" [%s] "point from" [%s]' % (fl(rng.uniform(1, 8, 3)), fl(rng.uniform(-3, 3, 3))))
+    for _ in range(rng.randint(0, 3)):
+        L.append("AttributeBegin")
+        L += xform()
+        if rng.rand() < .3: L.append("ReverseOrientation")
+        L.append('AreaLightSource "area" "color L" [%s] "integer nsamples" [%d]' % (fl(rng.uniform(2, 20, 3)), rng.choice([1, 2, 3, 4, 8])))
+        L.append(material())
+        L.append('Shape "sphere" "float radius" [%g]' % rng.uniform(.1, .4) if rng.rand() < .5 else
+                 'Shape "disk" "float radius" [%g]' % rng.uniform(.2, .6))
+        L.append("AttributeEnd")
+    L.append('Material "matte" "color Kd" [.6 .6 .6]')
+    L.append('Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-4 -1.5 -4  4 -1.5 -4  4 -1.5 4  -4 -1.5 4]')
+    if animated is None:
+        animated = len(sys.argv) > 3 and sys.argv[3] == "animated"
+    for _ in range(rng.randint(2, 7)):
+        L.append("AttributeBegin")
+        L += xform()
+        if animated and rng.rand() < .5:   # a TransformedPrimitive: the two CTMs differ (api.cpp:1011-1043)
+            L.append("ActiveTransform %s" % rng.choice(["StartTime", "EndTime"]))
+            k = rng.rand()
+            if k < .5: L.append("Translate %s" % fl(rng.uniform(-.6, .6, 3)))
+            if k > .3: L.append("Rotate %g %s" % (rng.uniform(-170, 170), fl(rng.uniform(-1, 1, 3) + 1e-3)))
+            if rng.rand() < .3: L.append("Scale %s" % fl(rng.uniform(.6, 1.5, 3)))
+            L.append("ActiveTransform All")
+            if rng.rand() < .5: L += xform()
+        if rng.rand() < .2: L.append("ReverseOrientation")
+        L.append(material())
+        L.append(shape())
+        L.append("AttributeEnd")
+    L.append("WorldEnd")
+    open(path, "w").write("\n".join(L) + "\n")
+    return spp
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    scenes.stage()
+    so = "/tmp/libdoh_fuzz.so"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic",
+                    "-I/usr/local/cuda/include", os.path.join(REPO, "tests/native/device_on_host.cpp"), "-o", so], check=True)
+    doh = C.CDLL(so)
+    doh.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+    bad = 0
+    for k in range(n):
+        seed = seed0 + k
+        rng = np.random.RandomState(seed)
+        path = os.path.join(scenes.STAGED, "fuzz-%d.pbrt" % seed)
+        spp = gen(rng, path)
+        ncores = int(rng.choice([1, 2, 64]))
+        try:
+            hs = pb.HostScene(path, ncores=ncores)
+        except pb.PbrtGpuError as e:
+            print("seed %d: host front end: %s" % (seed, str(e)[:120])); continue
+        try:
+            ref, _ = oa.run_reference(path, ncores, timeout=120)
+        except Exception as e:
+            print("seed %d: reference failed: %r" % (seed, e)); continue
+        px, _ = oa.render(hs, threads=1)
+        o = hs.pixels_to_rgb(px)
+        rd = hs.render_desc()
+        px2 = hs.new_pixels()
+        doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
+        own = px["weightSum"] == spp
+        d_ref = int((o.view(np.uint32) != ref.view(np.uint32)).any(axis=2)[own].sum()) if o.shape == ref.shape else -1
+        d_dev = int((px2["Lxyz"].view(np.uint32) != px["Lxyz"].view(np.uint32)).any(axis=2)[own].sum())
+        w_dev = bool(np.array_equal(px2["weightSum"], px["weightSum"]))
+        flag = "" if (d_ref == 0 and d_dev == 0 and w_dev) else "   <<<<<<"
+        bad += bool(flag)
+        print("seed %d: %dx%d spp %d ncores %d integ %d  oracle-vs-reference %d  device-on-host-vs-oracle %d (weights %s)  mean %.4g%s" % (
+            seed, rd.xResolution, rd.yResolution, spp, ncores, rd.integrator, d_ref, d_dev, w_dev, float(ref.mean()), flag), flush=True)
+    print("mismatching scenes:", bad)
+
+if __name__ == "__main__":
+    main()

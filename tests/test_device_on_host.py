@@ -120,3 +120,29 @@ def test_specular_device_code_on_host(staged, tmp_path_factory):
     for name in ("path-glass-mirror", "path-glass-params-mirror-floor", "maxdepth8", "dof"):
         _same_film(lib, variant_scene(name)[0])
     _same_film(lib, host_scene("bunny", 32, 32, 8, 2))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("seed,animated", [(3, False), (4, False), (21, False), (25, False), (1000, True), (1003, True), (1010, True), (1017, True)])
+def test_random_scenes_three_way(staged, doh, seed, animated):
+    """scripts/fuzz_scenes.py: random in-scope scenes (partial spheres, annuli, meshes with/without normals and uvs, several
+    point and area lights, non-uniform / handedness-swapping / animated transforms, both integrators, thin lens): the
+    unmodified reference binary, the oracle and the device code compiled for the host must give the same film."""
+    import sys
+    sys.path.insert(0, os.path.join(pb.REPO, "scripts"))
+    import fuzz_scenes
+    from pbrt_v2_b200 import scenes
+    rng = np.random.RandomState(seed)
+    path = os.path.join(scenes.STAGED, "fuzz-%d.pbrt" % seed)
+    spp = fuzz_scenes.gen(rng, path, animated=animated)
+    ncores = int(rng.choice([1, 2, 64]))
+    hs = pb.HostScene(path, ncores=ncores)
+    ref, _ = oa.run_reference(path, ncores, timeout=300)
+    px, _ = oa.render(hs, threads=1)
+    own = px["weightSum"] == spp
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32)[own], ref.view(np.uint32)[own])
+    rd = hs.render_desc()
+    px2 = hs.new_pixels()
+    doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
+    assert np.array_equal(px2["weightSum"], px["weightSum"])
+    assert np.array_equal(px2["Lxyz"].view(np.uint32)[own], px["Lxyz"].view(np.uint32)[own])
