@@ -20,7 +20,7 @@ Matrix4x4 Transpose(const Matrix4x4 &a) {   // core/transform.cpp:68-73
 Matrix4x4 Inverse(const Matrix4x4 &src) {
     float a[4][4];
     memcpy(a, src.m, sizeof(a));
-    int pivotRow[4], pivotCol[4];
+    int pivotRow[4] = {0, 0, 0, 0}, pivotCol[4] = {0, 0, 0, 0};
     int used[4] = {0, 0, 0, 0};
     for (int step = 0; step < 4; ++step) {
         int r = -1, c = -1;
@@ -38,6 +38,10 @@ Matrix4x4 Inverse(const Matrix4x4 &src) {
                     fprintf(stderr, "pbrt_b200: singular matrix in Inverse()\n");
                 }
             }
+        }
+        if (c < 0) {   // a matrix of NaNs: no pivot candidate compares >= 0 (the reference indexes out of bounds here)
+            fprintf(stderr, "pbrt_b200: singular matrix in Inverse()\n");
+            break;
         }
         ++used[c];
         if (r != c)
