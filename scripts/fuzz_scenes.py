@@ -13,6 +13,7 @@ def fl(a): return " ".join("%.6g" % x for x in a)
 
 def gen(rng, path, animated=None):
     L = []
+    outname = os.path.splitext(os.path.basename(path))[0] + ".pfm"   # unique per scene: campaigns may run side by side
     eye = rng.uniform(-1, 1, 3); eye = eye / np.linalg.norm(eye) * rng.uniform(3, 6)
     L.append("LookAt %s  %s  0 1 0" % (fl(eye), fl(rng.uniform(-.3, .3, 3))))
     cam = 'Camera "perspective" "float fov" [%g]' % rng.uniform(30, 60)
@@ -20,7 +21,11 @@ def gen(rng, path, animated=None):
     L.append(cam)
     xr, yr = rng.choice([16, 24, 32]), rng.choice([16, 24])
     spp = int(rng.choice([1, 2, 4, 8]))
-    L.append('Film "image" "integer xresolution" [%d] "integer yresolution" [%d] "string filename" "fz.pfm"' % (xr, yr))
+    film = 'Film "image" "integer xresolution" [%d] "integer yresolution" [%d] "string filename" "%s"' % (xr, yr, outname)
+    if len(sys.argv) > 3 and "crop" in sys.argv[3] and rng.rand() < .5:
+        a, b = sorted(rng.uniform(0, 1, 2)); c, d = sorted(rng.uniform(0, 1, 2))
+        film += ' "float cropwindow" [%g %g %g %g]' % (a, max(b, a + .2), c, max(d, c + .2))
+    L.append(film)
     L.append('Sampler "lowdiscrepancy" "integer pixelsamples" [%d]' % spp)
     integ = rng.choice(["path", "directlighting"])
     s = 'SurfaceIntegrator "%s" "integer maxdepth" [%d]' % (integ, rng.choice([1, 2, 3, 5, 7]))
@@ -60,6 +65,18 @@ def gen(rng, path, animated=None):
             if rng.rand() < .4: s += ' "float innerradius" [%g]' % rng.uniform(.05, .25)
             if rng.rand() < .3: s += ' "float phimax" [%g]' % rng.uniform(90, 330)
             return s
+        if len(sys.argv) > 3 and "subdiv" in sys.argv[3] and rng.rand() < .5:
+            # LoopSubdiv (shapes/loopsubdiv.cpp): a closed octahedron or an open hexagonal fan (boundary rules), jittered
+            if rng.rand() < .5:
+                P = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], float) * rng.uniform(.3, .7)
+                idx = [0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5]
+            else:
+                ang = np.arange(6) * np.pi / 3
+                P = np.vstack([[0, 0, 0], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)]) * rng.uniform(.4, .8)
+                idx = sum([[0, 1 + k, 1 + (k + 1) % 6] for k in range(6 if rng.rand() < .5 else 4)], [])
+            P = P + rng.uniform(-.05, .05, P.shape)
+            return 'Shape "loopsubdiv" "integer nlevels" [%d] "integer indices" [%s] "point P" [%s]' % (
+                rng.randint(1, 4), fl(idx), fl(P.ravel()))
         nv = rng.randint(4, 9)
         P = rng.uniform(-.8, .8, (nv, 3))
         nt = rng.randint(2, 7)
