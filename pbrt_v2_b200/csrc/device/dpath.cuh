@@ -21,7 +21,19 @@ struct RenderParams {
 enum PathState {
     S_NEW_SAMPLE = 0, S_HIT_RESULT, S_SHADOW_RESULT, S_AFTER_LIGHT, S_MIS_RESULT, S_AFTER_DIRECT, S_END_SAMPLE, S_DONE,
     S_E_LIGHT, S_E_MIS, S_E_PATH,   // waiting for the BSDF value at the evaluation site
-    S_DL_NEXT                       // DirectLightingIntegrator: next (light, sample) of the light loop
+    S_DL_NEXT,                      // DirectLightingIntegrator: next (light, sample) of the light loop
+    S_SPEC_NEXT                     // ... next of SpecularReflect / SpecularTransmit at this node (PBRT_SPECULAR builds)
+};
+// PBRT_SPECULAR builds: one frame per ancestor of the node being shaded in DirectLightingIntegrator's recursion
+// (integrator.cpp:177-258): the parent's radiance so far and what the child's result is multiplied with
+constexpr int DL_MAX_DEPTH = 8;
+struct DlFrame {
+    Spec L, f;
+    float absDot, pdf;
+    int stage;        // 0: the SpecularReflect child is in flight, 1: the SpecularTransmit child
+    V3 p, nn, ng, sn, tn, wo;
+    int material, areaLight;
+    float rayEpsilon;
 };
 // ls[s].w bit field
 enum { LS_TAIL = 1, LS_LEFT = 2, LS_RIGHT = 4, LS_UP = 8, LS_DOWN = 16,

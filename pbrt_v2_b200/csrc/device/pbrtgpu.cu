@@ -476,6 +476,10 @@ __global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(PathArgs a) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #if PBRT_SPECULAR
     bool specularBounce = false;          // path.cpp:53; travels with a parked sample as LS_SPEC
+    int dlDepth = 0, dlStage = 0, dlNodes = 0;   // (DirectLightingIntegrator's recursion: unused, PATH_INTEG == 0 here)
+    bool dlReturn = false;
+    DlFrame dlFrames[1];
+    (void)dlStage; (void)dlNodes; (void)dlReturn; (void)dlFrames;
 #endif
     int dlI = 0, dlJ = 0;                 // (DirectLightingIntegrator state of path_body.inc: unused, PATH_INTEG == 0 here)
     Spec dlSum(0.f), dlAll(0.f);
@@ -776,6 +780,13 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #if PBRT_SPECULAR
     bool specularBounce = false;           // path.cpp:53; bit 31 of the packed state word between iterations
+    // DirectLightingIntegrator's SpecularReflect / SpecularTransmit recursion: the state machine (path_body.inc) is
+    // complete and verified on the host, but the frames do not travel with the slot yet -- pbrtgpu_render refuses
+    // directlighting over specular materials until they do
+    int dlDepth = 0, dlStage = 0, dlNodes = 0;
+    bool dlReturn = false;
+    DlFrame dlFrames[DL_MAX_DEPTH];
+    (void)dlNodes;
 #endif
     int dlI = 0, dlJ = 0;                  // DirectLightingIntegrator's light loop
     Spec dlSum(0.f), dlAll(0.f);

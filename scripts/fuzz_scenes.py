@@ -151,10 +151,7 @@ def main():
         o = hs.pixels_to_rgb(px)
         rd = hs.render_desc()
         px2 = hs.new_pixels()
-        if spec and rd.integrator == 1:   # the device state machine has no SpecularReflect/Transmit recursion yet
-            px2 = px.copy()
-        else:
-            doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
+        doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
         own = px["weightSum"] == spp
         d_ref = int((o.view(np.uint32) != ref.view(np.uint32)).any(axis=2)[own].sum()) if o.shape == ref.shape else -1
         d_dev = int((px2["Lxyz"].view(np.uint32) != px["Lxyz"].view(np.uint32)).any(axis=2)[own].sum())

@@ -216,7 +216,11 @@ void RunTaskH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
                 Spec dlSum(0.f), dlAll(0.f);
                 bool ctxDirty = false;
                 bool specularBounce = false;   // (PBRT_SPECULAR builds: path.cpp:53)
-                (void)ctxDirty; (void)nShadedN; (void)specularBounce;
+                int dlDepth = 0, dlStage = 0, dlNodes = 0;   // (PBRT_SPECULAR builds: the recursion of DirectLightingIntegrator)
+                bool dlReturn = false;
+                DlFrame dlFrames[DL_MAX_DEPTH];
+                (void)ctxDirty; (void)nShadedN; (void)specularBounce; (void)dlDepth; (void)dlStage; (void)dlNodes; (void)dlReturn;
+                (void)dlFrames;
                 TraceStats st;
                 st.nodes = st.prims = 0;
                 bool first = true;
@@ -271,7 +275,11 @@ void RunTaskH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
                     if (wantTrace) found = Traverse<false, true>(sc, ray, anyHit, &hit, &st);
                 }
                 // DirectLightingIntegrator: SpecularReflect/Transmit's BSDFSample(rng) draws (what k_film_direct accounts for)
+#if PBRT_SPECULAR
+                if (INTEG == PBRTGPU_INTEGRATOR_DIRECTLIGHTING) mti += 6 * dlNodes;   // every node that made the two specular calls
+#else
                 if (INTEG == PBRTGPU_INTEGRATOR_DIRECTLIGHTING && (code & LS_HIT) && 0 + 1 < rp.maxDepth) mti += 6;
+#endif
                 // ImageFilm::AddSample through the footprint bits (FilmAdd in pbrtgpu.cu, without atomics)
                 const Spec Ls = SanitizeRadiance(L);
                 float xyz[3];

@@ -117,9 +117,12 @@ def test_specular_device_code_on_host(staged, tmp_path_factory):
     from helpers import variant_scene
     lib = _build(tmp_path_factory, "device_on_host_specular", ["-DPBRT_SPECULAR=1"])
     lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
-    for name in ("path-glass-mirror", "path-glass-params-mirror-floor", "maxdepth8", "dof"):
+    for name in ("path-glass-mirror", "path-glass-params-mirror-floor", "maxdepth8", "dof",
+                 # DirectLightingIntegrator's recursive SpecularReflect / SpecularTransmit rays (a per-path frame stack)
+                 "direct-glass-mirror", "direct-mirror-floor-maxdepth3", "direct-one-glass", "directlighting-maxdepth1"):
         _same_film(lib, variant_scene(name)[0])
     _same_film(lib, host_scene("bunny", 32, 32, 8, 2))
+    _same_film(lib, host_scene("killeroo-simple", 32, 32, 4, 2, integrator="directlighting"))
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
