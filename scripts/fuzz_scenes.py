@@ -158,6 +158,9 @@ def main():
         w_dev = bool(np.array_equal(px2["weightSum"], px["weightSum"]))
         flag = "" if (d_ref == 0 and d_dev == 0 and w_dev) else "   <<<<<<"
         bad += bool(flag)
+        if not flag:   # keep only the scenes worth looking at
+            for f in (path, os.path.splitext(path)[0] + ".pfm"):
+                if os.path.exists(f): os.remove(f)
         print("seed %d: %dx%d spp %d ncores %d integ %d  oracle-vs-reference %d  device-on-host-vs-oracle %d (weights %s)  mean %.4g%s" % (
             seed, rd.xResolution, rd.yResolution, spp, ncores, rd.integrator, d_ref, d_dev, w_dev, float(ref.mean()), flag), flush=True)
     print("mismatching scenes:", bad)
