@@ -1679,8 +1679,10 @@ int oracle_bxdf_test(float exponent, int n, const float *wo, const float *wi, co
     return 0;
 }
 
-// spp rows of 37 floats for the first pixel of task `taskNum`
-int oracle_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
+// spp rows of sample values for pixel number `pixelIndex` (row-major in the task's window) of task `taskNum`, the task's RNG
+// having served LDPixelSample for the pixels before it and nothing else (no integrator draws in between) -- what the LD
+// table kernels produce when run round after round on their own
+int oracle_ld_samples_seq(const PbrtGpuRenderDesc *rd, int taskNum, int pixelIndex, float *out) {
     Renderer R;
     PbrtGpuSceneDesc dummy;
     memset(&dummy, 0, sizeof(dummy));
@@ -1695,7 +1697,10 @@ int oracle_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
     const size_t nf = lay.Floats();
     std::vector<Sample> samples(spp);
     std::vector<float> buf(nf * spp), store(nf * spp);
-    LDPixelSample(lay, x0, y0, rd->shutterOpen, rd->shutterClose, spp, samples.data(), store.data(), buf.data(), rng);
+    if (pixelIndex < 0 || pixelIndex >= (x1 - x0) * (y1 - y0)) return 2;
+    for (int p = 0; p <= pixelIndex; ++p)
+        LDPixelSample(lay, x0 + p % (x1 - x0), y0 + p / (x1 - x0), rd->shutterOpen, rd->shutterClose, spp, samples.data(),
+                      store.data(), buf.data(), rng);
     for (int i = 0; i < spp; ++i) {
         float *o = out + nf * i;
         o[0] = samples[i].imageX; o[1] = samples[i].imageY; o[2] = samples[i].lensU; o[3] = samples[i].lensV;
@@ -1708,6 +1713,9 @@ int oracle_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) {
     }
     return 0;
 }
+
+// ... for the first pixel of the task
+int oracle_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out) { return oracle_ld_samples_seq(rd, taskNum, 0, out); }
 
 int oracle_task_window(const PbrtGpuRenderDesc *rd, int taskNum, int *win) {
     Renderer R;

@@ -89,10 +89,13 @@ def bxdf_test(exponent, wo, wi, u):
     return out
 
 
-def ld_samples(rd, task_num):
+def ld_samples(rd, task_num, pixel_index=0):
+    """LDPixelSample's values for pixel `pixel_index` of the task (the pixels before it sampled first, no integrator draws)"""
     out = np.zeros((rd.samplesPerPixel, pb.sample_floats(rd)), dtype=np.float32)
-    rc = lib().oracle_ld_samples(C.byref(rd), int(task_num), out.ctypes.data)
-    assert rc == 0, "empty task window"
+    f = lib().oracle_ld_samples_seq
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rc = f(C.addressof(rd), int(task_num), int(pixel_index), out.ctypes.data)
+    assert rc == 0, "empty task window or pixel outside it"
     return out
 
 
