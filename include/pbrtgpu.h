@@ -300,6 +300,25 @@ int  pbrtgpu_intersect_p(PbrtGpuScene *scene, const PbrtGpuRay *rays, int n,
  * for the path integrator's layout.                                            */
 int  pbrtgpu_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, float *out);
 
+/* replaces: BVHAccel::BVHAccel's build -- recursiveBuild + flattenBVHTree (accelerators/bvh.cpp:153-202, 210-380,
+ * 383-399) -- for the FullyRefine'd primitives whose world bounds are `bounds` (nPrimitives x 6 floats: pMin xyz,
+ * pMax xyz, in the order BVHAccel received the primitives).  Builds on the current device and returns to HOST memory
+ *   nodes[0 .. *nNodes)      the LinearBVHNode array in flattenBVHTree's depth-first order (capacity 2*nPrimitives - 1);
+ *   order[0 .. nPrimitives)  BVHAccel::primitives after the build: primitives[i] = input primitive order[i].
+ * The tree is the one the reference builds from the same input (same split decisions, same std::partition /
+ * std::nth_element permutations, same flattening); node bounds may differ in the sign of a zero coordinate only.
+ * splitMethod: PBRTGPU_SPLIT_SAH ("sah", the default of CreateBVHAccelerator, bvh.cpp:506-511); "middle" and "equal"
+ * answer PBRTGPU_EUNSUPPORTED.  maxPrimsInNode 1..255.  Bounds that are not finite answer PBRTGPU_EINVAL (the
+ * reference's SAH bucket index is undefined for them).                                                             */
+enum { PBRTGPU_SPLIT_MIDDLE = 0, PBRTGPU_SPLIT_EQUAL_COUNTS = 1, PBRTGPU_SPLIT_SAH = 2 };   /* bvh.h:56 */
+typedef struct PbrtGpuBuildStats {
+    double   buildMs;         /* CUDA-event time of the build, copies included  */
+    uint32_t nLevels;         /* depth of the tree + 1                          */
+    uint32_t reserved;
+} PbrtGpuBuildStats;
+int  pbrtgpu_bvh_build(const float *bounds, uint32_t nPrimitives, uint32_t maxPrimsInNode, int splitMethod,
+                       PbrtGpuBVHNode *nodes, uint32_t *nNodes, uint32_t *order, PbrtGpuBuildStats *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,15 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class BuildStats(C.Structure):
+    """PbrtGpuBuildStats"""
+    _fields_ = [("buildMs", C.c_double), ("nLevels", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+# PbrtGpuBVHNode = LinearBVHNode (accelerators/bvh.cpp:113-123)
+NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("offset", np.uint32), ("nPrimitives", np.uint8),
+                       ("axis", np.uint8), ("pad", np.uint8, 2)])
+SPLIT_MIDDLE, SPLIT_EQUAL_COUNTS, SPLIT_SAH = 0, 1, 2
 PIXEL_DTYPE = np.dtype([("Lxyz", np.float32, 3), ("weightSum", np.float32)])
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("mint", np.float32), ("maxt", np.float32), ("time", np.float32)])
 HIT_DTYPE = np.dtype([("hit", np.int32), ("primitive", np.uint32), ("t", np.float32),
@@ -113,6 +122,8 @@ def gpu_lib():
         lib.pbrtgpu_ld_samples.argtypes = [C.POINTER(RenderDesc), C.c_int, C.c_void_p]
         lib.pbrtgpu_set_device.argtypes = [C.c_int]
         lib.pbrtgpu_set_stats.argtypes = [C.c_void_p, C.c_int]
+        lib.pbrtgpu_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.POINTER(C.c_uint32),
+                                          C.c_void_p, C.POINTER(BuildStats)]
         _gpu = lib
     return _gpu
 
@@ -143,6 +154,12 @@ def host_lib():
         lib.pbrthost_scene_bytes.restype = C.c_ulonglong
         lib.pbrthost_scene_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint)] * 4
         lib.pbrthost_scene_counts.restype = None
+        lib.pbrthost_build_input.argtypes = [C.c_void_p, C.c_void_p]
+        lib.pbrthost_build_input.restype = C.c_uint
+        lib.pbrthost_scene_nodes.argtypes = [C.c_void_p, C.c_void_p]
+        lib.pbrthost_scene_nodes.restype = None
+        lib.pbrthost_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.POINTER(C.c_uint32),
+                                           C.c_void_p]
         _host = lib
     return _host
 
@@ -204,6 +221,20 @@ class HostScene(object):
         v = [C.c_uint() for _ in range(4)]
         host_lib().pbrthost_scene_counts(self._h, *[C.byref(x) for x in v])
         return dict(zip(("nodes", "primitives", "triangles", "lights"), (x.value for x in v)))
+
+    def build_input(self):
+        """the BVH build's input: world bounds of the refined primitives in the order BVHAccel gets them, (n, 6) float32
+        pMin xyz, pMax xyz.  Only kept by scenes loaded after keep_build_input(True)."""
+        n = host_lib().pbrthost_build_input(self._h, None)
+        out = np.zeros((n, 6), np.float32)
+        host_lib().pbrthost_build_input(self._h, out.ctypes.data)
+        return out
+
+    def nodes(self):
+        """the top-level accelerator's flattened LinearBVHNode array"""
+        out = np.zeros(self.counts()["nodes"], NODE_DTYPE)
+        host_lib().pbrthost_scene_nodes(self._h, out.ctypes.data)
+        return out
 
     def render_desc(self):
         rd = RenderDesc()
@@ -302,6 +333,36 @@ def ld_samples(rd, task_num):
     out = np.zeros((rd.samplesPerPixel, sample_floats(rd)), dtype=np.float32)
     _check(gpu_lib().pbrtgpu_ld_samples(C.byref(rd), int(task_num), out.ctypes.data), "pbrtgpu_ld_samples")
     return out
+
+
+def _bvh_build(fn, bounds, max_prims_in_node, split_method, stats):
+    bounds = np.ascontiguousarray(bounds, np.float32).reshape(-1, 6)
+    n = len(bounds)
+    nodes = np.zeros(max(2 * n, 1), NODE_DTYPE)
+    order = np.zeros(max(n, 1), np.uint32)
+    nn = C.c_uint32()
+    args = [bounds.ctypes.data, n, int(max_prims_in_node), int(split_method), nodes.ctypes.data, C.byref(nn), order.ctypes.data]
+    return fn(*(args + ([C.byref(stats)] if stats is not None else []))), nodes, nn, order[:n]
+
+
+def bvh_build(bounds, max_prims_in_node=4, split_method=SPLIT_SAH):
+    """BVHAccel's build on the GPU (pbrtgpu_bvh_build) -> (nodes, order, BuildStats)"""
+    st = BuildStats()
+    rc, nodes, nn, order = _bvh_build(gpu_lib().pbrtgpu_bvh_build, bounds, max_prims_in_node, split_method, st)
+    _check(rc, "pbrtgpu_bvh_build")
+    return nodes[:nn.value].copy(), order, st
+
+
+def host_bvh_build(bounds, max_prims_in_node=4, split_method=SPLIT_SAH):
+    """the same build by the host front end's recursive builder (pbrthost_bvh_build) -> (nodes, order)"""
+    rc, nodes, nn, order = _bvh_build(host_lib().pbrthost_bvh_build, bounds, max_prims_in_node, split_method, None)
+    if rc:
+        raise PbrtGpuError("pbrthost_bvh_build: bad arguments")
+    return nodes[:nn.value].copy(), order
+
+
+def keep_build_input(on=True):
+    host_lib().pbrthost_keep_build_input(int(on))
 
 
 def device_count():

@@ -1229,6 +1229,9 @@ size_t ScratchBudgetBytes() {
 
 extern "C" {
 
+// (internal, for the library's other translation units: records the thread's last-error text)
+int pbrtgpu_set_error_text(int code, const char *text) { return Fail(code, text ? text : ""); }
+
 int pbrtgpu_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

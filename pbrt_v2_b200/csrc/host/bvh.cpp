@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace pb {
 
@@ -26,9 +27,8 @@ struct PrimInfo {   // BVHPrimitiveInfo, bvh.cpp:40-49
 };
 
 struct Builder {
-    const std::vector<RefinedPrim> &prims;
     std::vector<PrimInfo> &info;
-    std::vector<RefinedPrim> &ordered;
+    std::vector<uint32_t> &ordered;   // orderedPrims, as indices into the input primitives
     std::vector<PbrtGpuBVHNode> &nodes;
     uint32_t maxPrimsInNode;
     int splitMethod;
@@ -45,7 +45,7 @@ struct Builder {
     }
     uint32_t MakeLeaf(uint32_t nodeIdx, uint32_t start, uint32_t end, const BBox &bbox) {
         uint32_t first = (uint32_t)ordered.size();
-        for (uint32_t i = start; i < end; ++i) ordered.push_back(prims[info[i].primitiveNumber]);
+        for (uint32_t i = start; i < end; ++i) ordered.push_back((uint32_t)info[i].primitiveNumber);
         PbrtGpuBVHNode &n = nodes[nodeIdx];
         SetBounds(n, bbox);
         n.offset = first;
@@ -189,7 +189,9 @@ void FullyRefine(const GeometricPrimitive &gp, std::vector<RefinedPrim> *out,
 
 }  // namespace
 
-GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, const std::string &sm) {
+bool g_keepBuildInput = false;
+
+GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, const std::string &sm, const std::string &builder) {
     // BVHAccel::BVHAccel, bvh.cpp:153-202
     maxPrimsInNode = std::min(255u, mp);
     std::vector<RefinedPrim> refined;
@@ -202,19 +204,53 @@ GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, 
         splitMethod = 2;
     }
     if (refined.empty()) return;
-    std::vector<PrimInfo> info;
-    info.reserve(refined.size());
+    std::vector<float> bounds(refined.size() * 6);
     for (size_t i = 0; i < refined.size(); ++i) {
+        const BBox b = refined[i].WorldBound();
+        float *o = &bounds[6 * i];
+        o[0] = b.pMin.x; o[1] = b.pMin.y; o[2] = b.pMin.z; o[3] = b.pMax.x; o[4] = b.pMax.y; o[5] = b.pMax.z;
+    }
+    std::vector<uint32_t> order;
+    if (builder == "gpu") {   // the same tree, built on the device (include/pbrtgpu.h: pbrtgpu_bvh_build)
+        nodes.resize(2 * refined.size());
+        order.resize(refined.size());
+        uint32_t nNodes = 0;
+        const int rc = pbrtgpu_bvh_build(bounds.data(), (uint32_t)refined.size(), maxPrimsInNode, splitMethod, nodes.data(), &nNodes,
+                                         order.data(), nullptr);
+        if (rc != PBRTGPU_OK) {
+            buildError = std::string("BVH build on the device failed: ") + pbrtgpu_last_error();
+            nodes.clear();
+            return;
+        }
+        nodes.resize(nNodes);
+    } else {
+        BuildBVHOnHost(bounds.data(), (uint32_t)refined.size(), maxPrimsInNode, splitMethod, &nodes, &order);
+    }
+    primitives.reserve(refined.size());
+    for (uint32_t i : order) primitives.push_back(refined[i]);
+    if (g_keepBuildInput) buildInput.swap(bounds);
+}
+
+void BuildBVHOnHost(const float *bounds, uint32_t n, uint32_t maxPrimsInNode, int splitMethod, std::vector<PbrtGpuBVHNode> *nodes,
+                    std::vector<uint32_t> *order) {
+    nodes->clear();
+    order->clear();
+    if (n == 0) return;
+    std::vector<PrimInfo> info;
+    info.reserve(n);
+    for (uint32_t i = 0; i < n; ++i) {
         PrimInfo pi;
         pi.primitiveNumber = (int)i;
-        pi.bounds = refined[i].WorldBound();
+        const float *b = bounds + 6 * (size_t)i;
+        pi.bounds.pMin = V3(b[0], b[1], b[2]);
+        pi.bounds.pMax = V3(b[3], b[4], b[5]);
         pi.centroid = .5f * pi.bounds.pMin + .5f * pi.bounds.pMax;   // bvh.cpp:44-46
         info.push_back(pi);
     }
-    primitives.reserve(refined.size());
-    nodes.reserve(2 * refined.size());
-    Builder b{refined, info, primitives, nodes, maxPrimsInNode, splitMethod};
-    b.Build(0, (uint32_t)refined.size());
+    order->reserve(n);
+    nodes->reserve(2 * (size_t)n);
+    Builder b{info, *order, *nodes, maxPrimsInNode, splitMethod};
+    b.Build(0, n);
 }
 
 TransformedPrimitive::TransformedPrimitive(const GeometricPrimitive &base, const AnimatedTransform &w2p)
@@ -241,7 +277,19 @@ GpuBVHAccel *CreateGpuBVHAccelerator(const std::vector<GeometricPrimitive> &prim
     // CreateBVHAccelerator, bvh.cpp:506-511
     std::string splitMethod = ps.FindOneString("splitmethod", "sah");
     uint32_t maxPrimsInNode = ps.FindOneInt("maxnodeprims", 4);
-    return new GpuBVHAccel(prims, maxPrimsInNode, splitMethod);
+    // "string builder" [ "host" | "gpu" ] (also PBRTGPU_BVH_BUILDER in the environment): where the tree is built.  The
+    // result is the same tree; "host" stays the default until the device build has been timed against it.
+    const char *env = getenv("PBRTGPU_BVH_BUILDER");
+    std::string builder = ps.FindOneString("builder", env ? env : "host");
+    if (builder != "host" && builder != "gpu") {
+        fprintf(stderr, "Warning: BVH builder \"%s\" unknown.  Using \"host\".\n", builder.c_str());
+        builder = "host";
+    }
+    if (builder == "gpu" && splitMethod != "sah") {
+        fprintf(stderr, "Warning: only splitmethod \"sah\" is built on the device.  Using the host build.\n");
+        builder = "host";
+    }
+    return new GpuBVHAccel(prims, maxPrimsInNode, splitMethod, builder);
 }
 
 }  // namespace pb

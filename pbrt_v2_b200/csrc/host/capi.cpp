@@ -114,4 +114,33 @@ int pbrthost_render(PbrtHostScene *h, int writeImage, PbrtGpuPixel *pixelsOut, P
     return 0;
 }
 
+// test / bench hooks: the input of the top-level accelerator's build -- the world bounds of the refined primitives in the
+// order BVHAccel receives them -- kept by scenes loaded after pbrthost_keep_build_input(1); returns the primitive count
+void pbrthost_keep_build_input(int on) { g_keepBuildInput = on != 0; }
+unsigned pbrthost_build_input(PbrtHostScene *h, float *out) {
+    const GpuBVHAccel *a = h->ls.scene->aggregate.get();
+    if (out && !a->buildInput.empty()) memcpy(out, a->buildInput.data(), a->buildInput.size() * sizeof(float));
+    return (unsigned)(a->buildInput.size() / 6);
+}
+// ... and its flattened node array
+void pbrthost_scene_nodes(PbrtHostScene *h, PbrtGpuBVHNode *out) {
+    const GpuBVHAccel *a = h->ls.scene->aggregate.get();
+    if (!a->nodes.empty()) memcpy(out, a->nodes.data(), a->nodes.size() * sizeof(PbrtGpuBVHNode));
+}
+
+// the host front end's BVH build (BVHAccel::recursiveBuild + flattenBVHTree as the reference runs them, bvh.cpp) on raw
+// primitive bounds: same arguments and results as pbrtgpu_bvh_build, which it is the comparison partner and the timing
+// baseline of.  nodes: capacity 2n - 1.
+int pbrthost_bvh_build(const float *bounds, uint32_t n, uint32_t maxPrimsInNode, int splitMethod, PbrtGpuBVHNode *nodes,
+                       uint32_t *nNodes, uint32_t *order) {
+    if (splitMethod < 0 || splitMethod > 2 || maxPrimsInNode < 1 || maxPrimsInNode > 255) return 1;
+    std::vector<PbrtGpuBVHNode> nv;
+    std::vector<uint32_t> ov;
+    BuildBVHOnHost(bounds, n, maxPrimsInNode, splitMethod, &nv, &ov);
+    *nNodes = (uint32_t)nv.size();
+    if (!nv.empty()) memcpy(nodes, nv.data(), nv.size() * sizeof(PbrtGpuBVHNode));
+    if (!ov.empty()) memcpy(order, ov.data(), ov.size() * sizeof(uint32_t));
+    return 0;
+}
+
 }  // extern "C"

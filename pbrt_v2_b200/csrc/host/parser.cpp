@@ -474,7 +474,9 @@ bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
     // --- accelerator (api.cpp:580-594, 1186-1207) ---
     if (AcceleratorName != "bvh" && AcceleratorName != "gpubvh")
         return Fail("accelerator \"" + AcceleratorName + "\" is out of scope (bvh)");
-    scene->aggregate.reset(CreateGpuBVHAccelerator(primitives, AcceleratorParams));
+    GpuBVHAccel *accel = CreateGpuBVHAccelerator(primitives, AcceleratorParams);
+    scene->aggregate.reset(accel);
+    if (!accel->buildError.empty()) return Fail(accel->buildError);
     std::string err;
     if (!scene->Flatten(&err)) return Fail(err);
     out->scene = std::move(scene);

@@ -153,13 +153,19 @@ struct Aggregate {   // core/primitive.h:126-134
 // per-ray Intersect / IntersectP run on the GPU.
 struct GpuBVHAccel : Aggregate {
     GpuBVHAccel(const std::vector<GeometricPrimitive> &prims, uint32_t maxPrims = 1,
-                const std::string &splitMethod = "sah");
+                const std::string &splitMethod = "sah", const std::string &builder = "host");
     uint32_t maxPrimsInNode;
     int splitMethod;   // 0 middle, 1 equal counts, 2 sah
     std::vector<RefinedPrim> primitives;    // in leaf order (BVHAccel::primitives after the swap)
     std::vector<PbrtGpuBVHNode> nodes;      // depth-first, bvh.cpp:383-399
     std::vector<std::shared_ptr<Shape>> owned;   // meshes produced by refinement
+    std::vector<float> buildInput;          // the build's input bounds (n x 6), kept only under g_keepBuildInput (test hook)
+    std::string buildError;                 // set when the device build was asked for and failed (no silent fallback)
 };
+extern bool g_keepBuildInput;
+// recursiveBuild + flattenBVHTree on primitive bounds (n x 6 floats); order = BVHAccel::primitives as input indices
+void BuildBVHOnHost(const float *bounds, uint32_t n, uint32_t maxPrimsInNode, int splitMethod, std::vector<PbrtGpuBVHNode> *nodes,
+                    std::vector<uint32_t> *order);
 GpuBVHAccel *CreateGpuBVHAccelerator(const std::vector<GeometricPrimitive> &prims, const ParamSet &ps);
 
 // core/primitive.h:104-123 as pbrtShape builds it for a shape under an animated CTM (api.cpp:1011-1043):
