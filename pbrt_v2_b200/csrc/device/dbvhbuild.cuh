@@ -73,7 +73,7 @@ struct State {
     const float *bounds;      // [n][6] pMin xyz, pMax xyz (BVHPrimitiveInfo::bounds, bvh.cpp:40-49)
     uint32_t *idx;            // [n] BVHPrimitiveInfo::primitiveNumber, permuted in place like buildData
     int32_t *nodeOf;          // [n] node that owns the position on the current level, -1 once it is in a leaf
-    uint8_t *flag;            // [n] partition predicate
+    uint8_t *flag;            // [n rounded up to SCAN_CHUNK] partition predicate, 0 in the padding
     uint32_t *prefix;         // [n + 1] exclusive prefix sum of flag
     uint32_t *sum1, *sum2;    // scan partials: per SCAN_CHUNK flags, per SCAN_CHUNK sum1 entries
     uint32_t *pairR;          // [n] position of the k-th misplaced element of the right part (from the right), at [start + k]
@@ -296,9 +296,9 @@ BVHB_GLOBAL void k_sah(State s, uint32_t levelBase, uint32_t levelCount) {
 }
 
 // the partition predicate of every position (CompareToBucket, bvh.cpp:126-145); 0 outside partitioned nodes
-BVHB_GLOBAL void k_flags(State s) {
-    for (uint32_t i = BVHB_THREAD_ID; i < s.n; i += BVHB_THREADS) {
-        const int32_t node = s.nodeOf[i];
+BVHB_GLOBAL void k_flags(State s, uint32_t nPadded) {
+    for (uint32_t i = BVHB_THREAD_ID; i < nPadded; i += BVHB_THREADS) {   // (the padding up to a whole scan chunk stays 0)
+        const int32_t node = i < s.n ? s.nodeOf[i] : -1;
         uint8_t f = 0;
         if (node >= 0 && s.kind[node] == KIND_PARTITION) {
             const int dim = s.dim[node];
@@ -312,9 +312,12 @@ BVHB_GLOBAL void k_flags(State s) {
 // ---- exclusive prefix sum of flag[0..n) into prefix[0..n], in chunks (no intra-block cooperation needed) ----
 BVHB_GLOBAL void k_scan_sum_flags(State s, uint32_t nChunks) {
     for (uint32_t c = BVHB_THREAD_ID; c < nChunks; c += BVHB_THREADS) {
-        const uint32_t a = c * SCAN_CHUNK, b = (a + SCAN_CHUNK < s.n) ? a + SCAN_CHUNK : s.n;
+        const uint4 *w = reinterpret_cast<const uint4 *>(s.flag + (size_t)c * SCAN_CHUNK);   // flags are 0 / 1 bytes
         uint32_t sum = 0;
-        for (uint32_t i = a; i < b; ++i) sum += s.flag[i];
+        for (int k = 0; k < SCAN_CHUNK / 16; ++k) {
+            const uint4 v = w[k];
+            sum += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        }
         s.sum1[c] = sum;
     }
 }
@@ -464,7 +467,7 @@ inline int Build(const float *hostBounds, uint32_t n, uint32_t maxPrimsInNode, P
     const size_t maxBucketNodes = (size_t)n / 5 + 1;   // nodes of one level with more than 4 primitives
     float *dBounds = nullptr;
     PbrtGpuBVHNode *dOut = nullptr;
-    bool ok = buf.Get(&dBounds, (size_t)n * 6) && buf.Get(&s.idx, n) && buf.Get(&s.nodeOf, n) && buf.Get(&s.flag, n) &&
+    bool ok = buf.Get(&dBounds, (size_t)n * 6) && buf.Get(&s.idx, n) && buf.Get(&s.nodeOf, n) && buf.Get(&s.flag, (size_t)nChunks * SCAN_CHUNK) &&
               buf.Get(&s.prefix, (size_t)n + 1) && buf.Get(&s.sum1, nChunks) && buf.Get(&s.sum2, nSuper) && buf.Get(&s.pairR, n) &&
               buf.Get(&s.start, maxNodes) && buf.Get(&s.end, maxNodes) && buf.Get(&s.mid, maxNodes) &&
               buf.Get(&s.left, maxNodes) && buf.Get(&s.bbKey, maxNodes * 6) && buf.Get(&s.cbKey, maxNodes * 6) &&
@@ -489,7 +492,7 @@ inline int Build(const float *hostBounds, uint32_t n, uint32_t maxPrimsInNode, P
         BVHB_LAUNCH(k_decide, count, stream, s, base, count);
         BVHB_LAUNCH(k_bucket, n, stream, s);
         BVHB_LAUNCH(k_sah, count, stream, s, base, count);
-        BVHB_LAUNCH(k_flags, n, stream, s);
+        BVHB_LAUNCH(k_flags, nChunks * SCAN_CHUNK, stream, s, nChunks * SCAN_CHUNK);
         BVHB_LAUNCH(k_scan_sum_flags, nChunks, stream, s, nChunks);
         BVHB_LAUNCH(k_scan_sum_sums, nSuper, stream, s, nChunks, nSuper);
         BVHB_LAUNCH(k_scan_top, 1, stream, s, nSuper);

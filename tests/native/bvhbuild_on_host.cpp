@@ -17,6 +17,7 @@ static uint3 threadIdx, blockIdx;
 static dim3 blockDim, gridDim;
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
 static inline uint32_t atomicMin(uint32_t *p, uint32_t v) { const uint32_t o = *p; if (v < o) *p = v; return o; }
 static inline uint32_t atomicMax(uint32_t *p, uint32_t v) { const uint32_t o = *p; if (v > o) *p = v; return o; }
