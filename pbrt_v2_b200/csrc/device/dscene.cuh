@@ -18,6 +18,24 @@
 #include "dmath.cuh"
 #include "danim.cuh"
 #include "../../../include/pbrtgpu.h"
+#if defined(PBRT_PAIR_NODES) && PBRT_PAIR_NODES
+#include <cstring>
+#include <vector>
+#endif
+
+// Round-2 experiment, OFF in the shipped kernels (the default build is textually unchanged): sibling-pair node layout.
+// The reference's walk loads one 32-byte node per visit and learns only then whether the ray misses it; with the two
+// children of every interior node side by side in one 64-byte record, one load serves the near child's test (which the
+// reference performs next anyway) and the far child's.  The far child's test is the same arithmetic done earlier: its
+// outcome can only change through the final `tmin < ray.maxt` (maxt shrinks), so a far child that fails now is never
+// pushed, and one that passes is pushed WITH its tmin and re-compared against the then-current maxt when popped --
+// exactly the decision BVHAccel::Intersect takes at that moment (bvh.cpp:126-148, 403-454).  Same nodes entered, same
+// primitives tested in the same order, same result; fewer dependent loads.  Verified on the CPU
+// (tests/test_device_on_host.py builds the harness with -DPBRT_PAIR_NODES=1 too); the counting (STATS) instantiations
+// always take the reference-shaped walk, so the algorithmic byte counts do not change.
+#ifndef PBRT_PAIR_NODES
+#define PBRT_PAIR_NODES 0
+#endif
 
 namespace dev {
 
@@ -38,6 +56,11 @@ struct DScene {
     const PbrtGpuLightShape *lightShapes;
     const PbrtGpuAnimated *animated;   // TransformedPrimitives (null / 0 for static scenes)
     uint32_t nNodes, nPrims, nLights, nAnimated;
+#if PBRT_PAIR_NODES
+    const float4 *pairs;          // 4 x float4 per interior node: both children's node records ({box, ref, meta} each);
+                                  // ref = the child's own pair index (interior) or its primitive offset (leaf)
+    const uint32_t *pairOfNode;   // [nNodes] pair index of an interior node (used for the roots only)
+#endif
 };
 
 struct Ray {
@@ -234,10 +257,143 @@ DEV bool BoxTest(const float4 &n0, const float4 &n1, const Ray &ray, const V3 &i
 template <bool STATS> __device__ __noinline__ bool AnimatedIntersect(const DScene &sc, uint32_t index, Ray &ray, bool anyHit,
                                                                       Hit *hit, TraceStats *st);
 
+#if PBRT_PAIR_NODES
+// host side: the pair records of a flattened scene (scene BVH first, nested BVHs by their PbrtGpuAnimated ranges)
+inline void BuildNodePairs(const PbrtGpuSceneDesc *desc, std::vector<float4> *pairs, std::vector<uint32_t> *pairOfNode) {
+    const uint32_t n = desc->nNodes;
+    std::vector<uint32_t> base(n, 0u);
+    for (uint32_t k = 0; k < desc->nAnimated; ++k)
+        for (uint32_t i = 0; i < desc->animated[k].nNodes; ++i) base[desc->animated[k].firstNode + i] = desc->animated[k].firstNode;
+    pairOfNode->assign(n, 0xffffffffu);
+    uint32_t nPairs = 0;
+    for (uint32_t i = 0; i < n; ++i)
+        if (desc->nodes[i].nPrimitives == 0) (*pairOfNode)[i] = nPairs++;
+    pairs->assign(4 * (size_t)nPairs, make_float4(0.f, 0.f, 0.f, 0.f));
+    auto record = [&](uint32_t child, float4 *out) {
+        const PbrtGpuBVHNode &c = desc->nodes[child];
+        const uint32_t ref = c.nPrimitives ? c.offset : (*pairOfNode)[child];
+        const uint32_t meta = (uint32_t)c.nPrimitives | ((uint32_t)c.axis << 8);
+        float rf, mf;
+        memcpy(&rf, &ref, 4);
+        memcpy(&mf, &meta, 4);
+        out[0] = make_float4(c.bmin[0], c.bmin[1], c.bmin[2], c.bmax[0]);
+        out[1] = make_float4(c.bmax[1], c.bmax[2], rf, mf);
+    };
+    for (uint32_t i = 0; i < n; ++i) {
+        if (desc->nodes[i].nPrimitives) continue;
+        float4 *rec = pairs->data() + 4 * (size_t)(*pairOfNode)[i];
+        record(i + 1, rec);                                   // first child: the next node (bvh.cpp:392)
+        record(base[i] + desc->nodes[i].offset, rec + 2);     // second child: secondChildOffset (bvh.cpp:394)
+    }
+}
+
+// BoxTest without its last line: false if the slabs miss whatever maxt is, else *tminOut for the `tmin < maxt` that decides
+DEV bool BoxTestDeferred(const float4 &n0, const float4 &n1, const Ray &ray, const V3 &invDir, const bool neg[3], float *tminOut) {
+    float tmin = ((neg[0] ? n0.w : n0.x) - ray.o.x) * invDir.x;
+    float tmax = ((neg[0] ? n0.x : n0.w) - ray.o.x) * invDir.x;
+    float tymin = ((neg[1] ? n1.x : n0.y) - ray.o.y) * invDir.y;
+    float tymax = ((neg[1] ? n0.y : n1.x) - ray.o.y) * invDir.y;
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = ((neg[2] ? n1.y : n0.z) - ray.o.z) * invDir.z;
+    float tzmax = ((neg[2] ? n0.z : n1.y) - ray.o.z) * invDir.z;
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) tmax = tzmax;
+    *tminOut = tmin;
+    return tmax > ray.mint;
+}
+
+template <bool TOP, bool ANIM>
+DEV bool TraverseBVHPairs(const DScene &sc, uint32_t nodeBase, uint32_t primBase, Ray &ray, bool anyHit, Hit *hit) {
+    V3 invDir(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+    bool neg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
+    uint32_t todoRef[64], todoMeta[64];
+    float todoT[64];
+    uint32_t todoOffset = 0;
+    bool found = false;
+    uint32_t ref, meta;
+    {   // the root is nobody's child: its own record
+        const float4 n0 = __ldg(sc.nodes + 2 * nodeBase);
+        const float4 n1 = __ldg(sc.nodes + 2 * nodeBase + 1);
+        if (!BoxTest(n0, n1, ray, invDir, neg)) return false;
+        meta = __float_as_uint(n1.w);
+        ref = (meta & 0xffu) ? __float_as_uint(n1.z) : __ldg(sc.pairOfNode + nodeBase);
+    }
+    while (true) {
+        const uint32_t nPrims = meta & 0xffu;
+        bool descend = false;
+        if (nPrims > 0) {
+            for (uint32_t i = 0; i < nPrims; ++i) {
+                const uint32_t pi = primBase + ref + i;
+                const float4 r0 = __ldg(sc.prims + 3 * pi);
+                const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
+                const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
+                const uint32_t type = __float_as_uint(r0.w) & 0xffu;
+                float t, b1 = 0.f, b2 = 0.f;
+                bool h;
+                if (type == PBRTGPU_PRIM_TRIANGLE)
+                    h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), ray, &t, &b1, &b2);
+                else if (TOP && ANIM && type == PBRTGPU_PRIM_ANIMATED) {
+                    if (AnimatedIntersect<false>(sc, __float_as_uint(r1.w), ray, anyHit, hit, nullptr)) {
+                        if (anyHit) return true;
+                        found = true;
+                    }
+                    continue;
+                } else
+                    h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], ray, &t, nullptr);
+                if (h) {
+                    if (anyHit) { hit->prim = (int)pi; return true; }
+                    hit->prim = (int)pi; hit->b1 = b1; hit->b2 = b2; hit->maxtIn = ray.maxt;
+                    ray.maxt = t;
+                    found = true;
+                }
+            }
+        } else {
+            const float4 *p = sc.pairs + 4 * (size_t)ref;
+            const float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
+            const bool secondFirst = neg[(meta >> 8) & 0xffu];   // bvh.cpp:436-444: the far child waits on the stack
+            const float4 &N0 = secondFirst ? b0 : a0, &N1 = secondFirst ? b1 : a1;
+            const float4 &F0 = secondFirst ? a0 : b0, &F1 = secondFirst ? a1 : b1;
+            const bool hitNear = BoxTest(N0, N1, ray, invDir, neg);
+            float tFar = 0.f;
+            const bool hitFar = BoxTestDeferred(F0, F1, ray, invDir, neg, &tFar) && tFar < ray.maxt;
+            if (hitNear) {
+                if (hitFar) {
+                    todoRef[todoOffset] = __float_as_uint(F1.z); todoMeta[todoOffset] = __float_as_uint(F1.w); todoT[todoOffset] = tFar;
+                    ++todoOffset;
+                }
+                ref = __float_as_uint(N1.z); meta = __float_as_uint(N1.w);
+                descend = true;
+            } else if (hitFar) {
+                ref = __float_as_uint(F1.z); meta = __float_as_uint(F1.w);
+                descend = true;
+            }
+        }
+        if (descend) continue;
+        bool got = false;
+        while (todoOffset > 0) {
+            --todoOffset;
+            if (todoT[todoOffset] < ray.maxt) {   // the far child's own box test, with the maxt of this moment
+                ref = todoRef[todoOffset]; meta = todoMeta[todoOffset];
+                got = true;
+                break;
+            }
+        }
+        if (!got) break;
+    }
+    return found;
+}
+#endif   // PBRT_PAIR_NODES
+
 // TOP: the scene's own BVH (nodes/primitives from 0); otherwise the BVH nested in a TransformedPrimitive,
 // whose node and primitive offsets are relative to nodeBase / primBase.
 template <bool STATS, bool TOP, bool ANIM>
 DEV bool TraverseBVH(const DScene &sc, uint32_t nodeBase, uint32_t primBase, Ray &ray, bool anyHit, Hit *hit, TraceStats *st) {
+#if PBRT_PAIR_NODES
+    if (!STATS) return TraverseBVHPairs<TOP, ANIM>(sc, nodeBase, primBase, ray, anyHit, hit);
+#endif
     V3 invDir(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
     bool neg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
     uint32_t todo[64];
@@ -367,6 +523,13 @@ struct Trav {
     uint32_t leafNext, leafEnd;  // rest of the scene-BVH leaf that contained the TransformedPrimitive
     V3 wo, wd;                   // the world-space ray
     uint32_t todo[64];
+#if PBRT_PAIR_NODES
+    // pair walk: the node to enter next (it has passed its box test) or `needRoot`; todo[] holds the refs
+    uint32_t curRef, curMeta;
+    bool needRoot;
+    uint32_t todoMeta[64];
+    float todoT[64];
+#endif
 };
 DEV void TravSetRay(Trav &t) {
     t.invDir = V3(1.f / t.ray.d.x, 1.f / t.ray.d.y, 1.f / t.ray.d.z);
@@ -379,10 +542,139 @@ DEV void TravInit(Trav &t, const Ray &ray, bool anyHit) {
     t.anyHit = anyHit; t.found = false;
     t.hit.prim = -1; t.hit.b1 = t.hit.b2 = 0.f; t.hit.maxtIn = 0.f; t.hit.t = 0.f;
     t.inst = -1; t.nodeBase = t.primBase = 0; t.todoBase = 0; t.leafNext = t.leafEnd = 0;
+#if PBRT_PAIR_NODES
+    t.curRef = t.curMeta = 0; t.needRoot = true;
+#endif
 }
+#if PBRT_PAIR_NODES
+// TravStep over the pair layout: one step = the root's test, one interior node (both children tested), or one leaf
+template <bool ANIM>
+DEV bool TravStepPairs(const DScene &sc, Trav &t) {
+    uint32_t first = 0, end = 0;
+    bool leaf = false;
+    if (ANIM && t.inst < 0 && t.leafNext < t.leafEnd) {   // back from a TransformedPrimitive: the rest of that leaf
+        first = t.leafNext; end = t.leafEnd;
+        t.leafNext = t.leafEnd = 0;
+        leaf = true;
+    } else if (t.needRoot) {
+        t.needRoot = false;
+        const uint32_t ni = ANIM ? t.nodeBase : 0u;
+        const float4 n0 = __ldg(sc.nodes + 2 * ni);
+        const float4 n1 = __ldg(sc.nodes + 2 * ni + 1);
+        if (BoxTest(n0, n1, t.ray, t.invDir, t.neg)) {
+            t.curMeta = __float_as_uint(n1.w);
+            t.curRef = (t.curMeta & 0xffu) ? __float_as_uint(n1.z) : __ldg(sc.pairOfNode + ni);
+            return false;
+        }
+    } else {
+        const uint32_t nPrims = t.curMeta & 0xffu;
+        if (nPrims > 0) {
+            first = (ANIM ? t.primBase : 0u) + t.curRef;
+            end = first + nPrims;
+            leaf = true;
+        } else {
+            const float4 *p = sc.pairs + 4 * (size_t)t.curRef;
+            const float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
+            const bool secondFirst = t.neg[(t.curMeta >> 8) & 0xffu];
+            const float4 &N0 = secondFirst ? b0 : a0, &N1 = secondFirst ? b1 : a1;
+            const float4 &F0 = secondFirst ? a0 : b0, &F1 = secondFirst ? a1 : b1;
+            const bool hitNear = BoxTest(N0, N1, t.ray, t.invDir, t.neg);
+            float tFar = 0.f;
+            const bool hitFar = BoxTestDeferred(F0, F1, t.ray, t.invDir, t.neg, &tFar) && tFar < t.ray.maxt;
+            if (hitNear) {
+                if (hitFar) {
+                    t.todo[t.todoOffset] = __float_as_uint(F1.z); t.todoMeta[t.todoOffset] = __float_as_uint(F1.w);
+                    t.todoT[t.todoOffset] = tFar;
+                    ++t.todoOffset;
+                }
+                t.curRef = __float_as_uint(N1.z); t.curMeta = __float_as_uint(N1.w);
+                return false;
+            }
+            if (hitFar) {
+                t.curRef = __float_as_uint(F1.z); t.curMeta = __float_as_uint(F1.w);
+                return false;
+            }
+        }
+    }
+    if (leaf) {
+        for (uint32_t pi = first; pi < end; ++pi) {
+            const float4 r0 = __ldg(sc.prims + 3 * pi);
+            const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
+            const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
+            const uint32_t type = __float_as_uint(r0.w) & 0xffu;
+            float tt, b1 = 0.f, b2 = 0.f;
+            bool h;
+            if (type == PBRTGPU_PRIM_TRIANGLE)
+                h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), t.ray, &tt, &b1, &b2);
+            else if (ANIM && type == PBRTGPU_PRIM_ANIMATED) {
+                const PbrtGpuAnimated *a = sc.animated + __float_as_uint(r1.w);
+                DXf w2p;
+                AnimInterpolate(a, t.ray.time, &w2p);
+                Ray rl;
+                ToPrimitiveSpace(w2p, t.ray, &rl);
+                if (a->nNodes == 0) {
+                    if (SinglePrimTest(sc, a->firstPrimitive, rl, t.anyHit, &t.hit)) {
+                        t.found = true;
+                        t.ray.maxt = rl.maxt;
+                        if (t.anyHit) { t.hit.t = t.ray.maxt; return true; }
+                    }
+                    continue;
+                }
+                t.wo = t.ray.o; t.wd = t.ray.d;
+                t.ray = rl;
+                TravSetRay(t);
+                t.inst = (int)__float_as_uint(r1.w);
+                t.nodeBase = a->firstNode; t.primBase = a->firstPrimitive;
+                t.todoBase = t.todoOffset;
+                t.leafNext = pi + 1; t.leafEnd = end;
+                if (t.leafNext == t.leafEnd) t.leafNext = t.leafEnd = 0;
+                t.needRoot = true;
+                return false;
+            } else
+                h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], t.ray, &tt, nullptr);
+            if (h) {
+                t.hit.prim = (int)pi;
+                t.found = true;
+                if (t.anyHit) { t.hit.t = t.ray.maxt; return true; }
+                t.hit.b1 = b1; t.hit.b2 = b2; t.hit.maxtIn = t.ray.maxt;
+                t.ray.maxt = tt;
+            }
+        }
+    }
+    // ---- next node from the stack: entries whose tmin no longer beats maxt fail the box test they were waiting for
+    const uint32_t floor = (ANIM && t.inst >= 0) ? t.todoBase : 0u;
+    while (t.todoOffset > floor) {
+        --t.todoOffset;
+        if (t.todoT[t.todoOffset] < t.ray.maxt) {
+            t.curRef = t.todo[t.todoOffset]; t.curMeta = t.todoMeta[t.todoOffset];
+            return false;
+        }
+    }
+    if (ANIM && t.inst >= 0) {
+        // the nested walk is over: back to world space (r.maxt = ray.maxt, primitive.cpp:102)
+        t.ray.o = t.wo; t.ray.d = t.wd;
+        TravSetRay(t);
+        t.inst = -1; t.nodeBase = t.primBase = 0;
+        if (t.leafNext < t.leafEnd) return false;   // the next step tests the rest of the leaf
+        while (t.todoOffset > 0) {
+            --t.todoOffset;
+            if (t.todoT[t.todoOffset] < t.ray.maxt) {
+                t.curRef = t.todo[t.todoOffset]; t.curMeta = t.todoMeta[t.todoOffset];
+                return false;
+            }
+        }
+    }
+    t.hit.t = t.ray.maxt;
+    return true;
+}
+#endif   // PBRT_PAIR_NODES
+
 // returns true when the ray is finished (result in t.found / t.hit / t.ray.maxt)
 template <bool STATS, bool ANIM>
 DEV bool TravStep(const DScene &sc, Trav &t, TraceStats *st) {
+#if PBRT_PAIR_NODES
+    if (!STATS) return TravStepPairs<ANIM>(sc, t);
+#endif
     uint32_t first = 0, end = 0;
     bool leaf = false;
     if (ANIM && t.inst < 0 && t.leafNext < t.leafEnd) {   // back from a TransformedPrimitive: the rest of that leaf

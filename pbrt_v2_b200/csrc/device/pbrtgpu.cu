@@ -1080,6 +1080,10 @@ struct PbrtGpuScene {
     int device = 0;
     DScene d;
     DevBuf<float4> nodes, prims;
+#if PBRT_PAIR_NODES
+    DevBuf<float4> pairs;
+    DevBuf<uint32_t> pairOfNode;
+#endif
     DevBuf<uint4> tris;
     DevBuf<PbrtGpuMesh> meshes;
     DevBuf<float> N, uv;
@@ -1278,6 +1282,15 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
         }
         CUDA_TRY(s->nodes.Upload(h.data(), h.size()));
     }
+#if PBRT_PAIR_NODES
+    {
+        std::vector<float4> pairs;
+        std::vector<uint32_t> pairOfNode;
+        BuildNodePairs(desc, &pairs, &pairOfNode);
+        CUDA_TRY(s->pairs.Upload(pairs.data(), pairs.size()));
+        CUDA_TRY(s->pairOfNode.Upload(pairOfNode.data(), pairOfNode.size()));
+    }
+#endif
     // primitives: pre-gathered 48-byte records in leaf order
     {
         std::vector<float4> h(3 * (size_t)desc->nPrimitives);
@@ -1349,6 +1362,9 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
     }
     DScene &d = s->d;
     d.nodes = s->nodes.p; d.prims = s->prims.p; d.tris = s->tris.p; d.meshes = s->meshes.p;
+#if PBRT_PAIR_NODES
+    d.pairs = s->pairs.p; d.pairOfNode = s->pairOfNode.p;
+#endif
     d.N = s->N.p; d.uv = s->uv.p; d.quadrics = s->quadrics.p; d.xforms = s->xforms.p;
     d.materials = s->materials.p; d.measured = s->measured.p; d.kdNodes = s->kdNodes.p; d.kdData = s->kdData.p;
     d.lights = s->lights.p; d.lightShapes = s->lightShapes.p; d.animated = s->animated.p;

@@ -44,6 +44,10 @@ using namespace dev;
 namespace {
 struct HostScene {
     std::vector<float4> nodes, prims;
+#if PBRT_PAIR_NODES
+    std::vector<float4> pairs;
+    std::vector<uint32_t> pairOfNode;
+#endif
     std::vector<uint4> tris;
     DScene d;
 };
@@ -82,6 +86,10 @@ void Pack(const PbrtGpuSceneDesc *desc, HostScene *h) {
     DScene &d = h->d;
     memset(&d, 0, sizeof(d));
     d.nodes = h->nodes.data(); d.prims = h->prims.data(); d.tris = h->tris.data(); d.meshes = desc->meshes;
+#if PBRT_PAIR_NODES
+    BuildNodePairs(desc, &h->pairs, &h->pairOfNode);
+    d.pairs = h->pairs.data(); d.pairOfNode = h->pairOfNode.data();
+#endif
     d.N = desc->N; d.uv = desc->uv; d.quadrics = desc->quadrics; d.xforms = desc->xforms; d.materials = desc->materials;
     d.measured = desc->measured; d.kdNodes = desc->kdNodes; d.kdData = desc->kdData; d.lights = desc->lights;
     d.lightShapes = desc->lightShapes; d.animated = desc->animated;

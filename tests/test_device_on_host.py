@@ -125,6 +125,37 @@ def test_specular_device_code_on_host(staged, tmp_path_factory):
     _same_film(lib, host_scene("killeroo-simple", 32, 32, 4, 2, integrator="directlighting"))
 
 
+def test_pair_node_walk_on_host(staged, tmp_path_factory):
+    """The sibling-pair node layout (-DPBRT_PAIR_NODES=1, device/dscene.cuh: a round-2 kernel experiment that is not in the
+    shipped kernels) must walk the tree exactly like the reference-shaped loop: same hits, same `t`, same films -- both the
+    whole-ray walk (k_path, pbrtgpu_intersect) and the step-wise one (k_trace), static and animated scenes."""
+    from helpers import variant_scene
+    lib = _build(tmp_path_factory, "device_on_host_pairs", ["-DPBRT_PAIR_NODES=1"])
+    lib.doh_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.doh_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+    for base in ("bunny", "killeroo-simple", "anim-killeroos-moving"):
+        hs = host_scene(base, 32, 32, 4, 32)
+        rays = _rays(hs, base, 100000, 11)
+        want, occ_want = oa.intersect(hs, rays), oa.intersect_p(hs, rays)
+        for stepwise in (0, 1):
+            got = np.zeros(len(rays), dtype=pb.HIT_DTYPE)
+            occ = np.zeros(len(rays), np.uint8)
+            lib.doh_intersect(hs.desc_ptr, rays.ctypes.data, len(rays), got.ctypes.data, stepwise)
+            lib.doh_intersect_p(hs.desc_ptr, rays.ctypes.data, len(rays), occ.ctypes.data, stepwise)
+            assert np.array_equal(got["hit"], want["hit"]) and np.array_equal(occ, occ_want), (base, stepwise)
+            assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), (base, stepwise)
+            h = want["hit"] == 1
+            for f in ("primitive", "b1", "b2", "p", "n"):
+                assert np.array_equal(got[f][h].view(np.uint32), want[f][h].view(np.uint32)), (base, stepwise, f)
+    for case in RENDER_CASES[:5]:
+        base, res, spp, ncores, integrator, strategy = case
+        _same_film(lib, host_scene(base, res, res, spp, ncores, integrator=integrator, strategy=strategy))
+    for name in ("shutter", "maxdepth8", "dof"):
+        _same_film(lib, variant_scene(name)[0])
+    _same_film(lib, host_scene("anim-killeroos-moving", 32, 32, 4, 2, nlevels=3))   # TransformedPrimitives three deep
+
+
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 @pytest.mark.parametrize("seed,animated", [(3, False), (4, False), (21, False), (25, False), (1000, True), (1003, True), (1010, True), (1017, True)])
 def test_random_scenes_three_way(staged, doh, seed, animated):
