@@ -91,6 +91,45 @@ def test_device_build_on_host_matches_recursive_build(emu, kind):
         assert leaves > 1   # the multi-primitive leaf branches were really taken
 
 
+def test_small_ranges_exhaustively(emu):
+    """every key pattern of 2..5 primitives on a 3-value grid along x (ties included): libstdc++'s nth_element for <= 4
+    elements (introselect round + insertion sort) and the first SAH partition above it, restated in the kernels"""
+    import itertools
+    f32 = np.float32
+    checked = 0
+    for n in (2, 3, 4, 5):
+        for xs in itertools.product((0.0, 1.0, 2.0), repeat=n):
+            if len(set(xs)) == 1:
+                continue   # (degenerate centroid bounds: covered by "dup")
+            c = np.zeros((n, 3), f32)
+            c[:, 0] = xs
+            c[:, 1] = np.arange(n) * 0.125   # distinct boxes, x stays the widest axis
+            e = np.full((n, 3), 0.25, f32)
+            b = np.concatenate([c - e, c + e], 1).astype(f32)
+            for maxp in (1, 4):
+                want_nodes, want_order = pb.host_bvh_build(b, maxp)
+                nodes, order, _ = emu_build(emu, b, maxp)
+                assert np.array_equal(order, want_order) and same_tree(nodes, want_nodes), (xs, maxp)
+                checked += 1
+    assert checked > 600
+
+
+def test_random_campaign(emu):
+    rs = np.random.RandomState(77)
+    for it in range(400):
+        n = int(rs.randint(1, 400))
+        kind = KINDS[rs.randint(len(KINDS))]
+        b = boxes(kind, n, rs)
+        if rs.rand() < .3:   # mixtures: part of another family, shuffled in
+            b2 = boxes(KINDS[rs.randint(len(KINDS))], n, rs)
+            m = rs.rand(n) < .5
+            b[m] = b2[m]
+        maxp = int(rs.choice([1, 2, 3, 4, 8, 255]))
+        want_nodes, want_order = pb.host_bvh_build(b, maxp)
+        nodes, order, _ = emu_build(emu, b, maxp, int(rs.choice([0, 1, 2])), int(rs.randint(2)))
+        assert np.array_equal(order, want_order) and same_tree(nodes, want_nodes), (it, kind, n, maxp)
+
+
 def test_tree_invariants_and_levels(emu):
     rs = np.random.RandomState(5)
     n = 300000   # (several levels of scan partials)
