@@ -39,8 +39,9 @@ def test_repeated_builds_are_identical():
 def test_config_scene_built_on_device_is_the_same_scene(staged, base, monkeypatch):
     host = host_scene(base, 48, 48, 4, 8)
     monkeypatch.setenv("PBRTGPU_BVH_BUILDER", "gpu")
-    dev = host_scene(base, 48, 48, 4, 8)
+    dev = host_scene(base, 48, 48, 4, 8, tag="-devbuilt")   # (the tag keeps helpers' scene cache from returning `host`)
     monkeypatch.delenv("PBRTGPU_BVH_BUILDER")
+    assert dev is not host
     assert same_tree(dev.nodes(), host.nodes())
     px_h, _ = host.render()
     px_d, _ = dev.render()
