@@ -125,10 +125,12 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     scenes.stage()
-    so = "/tmp/libdoh_fuzz.so"
+    # optional third argument: kernel build flags to fuzz, e.g. "specular", "pairs", "specular+pairs"
     spec = len(sys.argv) > 3 and "specular" in sys.argv[3]
+    pairs = len(sys.argv) > 3 and "pairs" in sys.argv[3]
+    so = "/tmp/libdoh_fuzz%s%s.so" % ("_spec" if spec else "", "_pairs" if pairs else "")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic",
-                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) +
+                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) + (["-DPBRT_PAIR_NODES=1"] if pairs else []) +
                    [os.path.join(REPO, "tests/native/device_on_host.cpp"), "-o", so], check=True)
     doh = C.CDLL(so)
     doh.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
