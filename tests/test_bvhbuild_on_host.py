@@ -181,3 +181,15 @@ def test_entry_point_validates_before_touching_the_device():
     if pb.device_count() == 0:
         with pytest.raises(pb.PbrtGpuError, match="no CPU fallback"):
             pb.bvh_build(b)
+
+
+def test_front_end_builder_option_has_no_silent_fallback(staged, monkeypatch):
+    """Accelerator "bvh" "string builder" "gpu" (or PBRTGPU_BVH_BUILDER=gpu) must build on the device or fail: on a box
+    without a GPU the scene does not load, and the message says why"""
+    if pb.device_count() > 0:
+        pytest.skip("a CUDA device is present: covered by test_zz_gpu_bvhbuild.py")
+    monkeypatch.setenv("PBRTGPU_BVH_BUILDER", "gpu")
+    with pytest.raises(pb.PbrtGpuError, match="no CUDA device"):
+        host_scene("bunny", 24, 24, 4, 2, tag="-devbuilt-cpu")
+    monkeypatch.setenv("PBRTGPU_BVH_BUILDER", "host")
+    assert host_scene("bunny", 24, 24, 4, 2, tag="-hostbuilt").counts()["nodes"] > 0
