@@ -22,7 +22,21 @@ DEVHDR    := $(wildcard $(DEVDIR)/*.cuh) $(wildcard $(DEVDIR)/*.inc) $(wildcard 
 # -DK_TRACE_MIN_BLOCKS=8; the shipped library is built with none
 NVDEFS    ?=
 
-all: $(PKG)/libpbrtgpu.so $(PKG)/libpbrthost.so $(PKG)/pbrt_b200 oracle
+# kernel experiments that are CPU-verified but not yet timed on a GPU: built next to the product library so that a GPU
+# visit (bench.py's "extras", scripts/r2_*.sh) can A/B them without compiling on the box.  Nothing loads them by default.
+VARIANTS  := $(PKG)/ab/libpbrtgpu_pairs.so $(PKG)/ab/libpbrtgpu_specular.so
+
+all: $(PKG)/libpbrtgpu.so $(PKG)/libpbrthost.so $(PKG)/pbrt_b200 oracle variants
+
+variants: $(VARIANTS)
+
+$(PKG)/ab/libpbrtgpu_pairs.so: $(DEVSRC) $(DEVHDR)
+	@mkdir -p $(PKG)/ab build
+	$(NVCC) $(NVFLAGS) -DPBRT_PAIR_NODES=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_pairs.log || (cat build/ptxas_pairs.log; false)
+
+$(PKG)/ab/libpbrtgpu_specular.so: $(DEVSRC) $(DEVHDR)
+	@mkdir -p $(PKG)/ab build
+	$(NVCC) $(NVFLAGS) -DPBRT_SPECULAR=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_specular.log || (cat build/ptxas_specular.log; false)
 
 $(PKG)/libpbrtgpu.so: $(DEVSRC) $(DEVHDR)
 	$(NVCC) $(NVFLAGS) $(NVDEFS) -shared $(DEVSRC) -o $@ 2> build/ptxas.log || (cat build/ptxas.log; false)
@@ -42,7 +56,7 @@ oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -rf build $(PKG)/*.so $(PKG)/pbrt_b200
+	rm -rf build $(PKG)/*.so $(PKG)/ab $(PKG)/pbrt_b200
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle variants clean

@@ -13,7 +13,9 @@ framebuffer is summed to rank 0 with one NCCL reduce; total work is fixed, so
 "scaling" is "strong".
 
 Prints ONE JSON line on rank 0 (see the keys below).  Numbers are device-timed
-(CUDA events on the launching stream), max over ranks.
+(CUDA events on the launching stream), max over ranks.  At N = 1 the line also
+carries "extras": untimed side measurements taken after everything else, each in
+its own process (run_extras; --no-extras skips them).
 """
 import argparse
 import ctypes as C
@@ -211,6 +213,61 @@ def workload_config(workload, world, per_pixel=True, spp_override=None):
     }
 
 
+def run_extras():
+    """Side measurements of work that is in the repo but not (yet) on the measured path, taken AFTER the timed regions, each
+    in its own process (a fault there cannot touch the line above) and with a timeout.  They cost about a minute.
+      bvh_build   pbrtgpu_bvh_build against the host front end's recursive build (scripts/bench_bvhbuild.py)
+      variants    the kernel-experiment libraries built by `make variants` (pbrt_v2_b200/ab/), each against the product
+                  library on the same reduced-spp workload: throughput and whether the film is byte-identical"""
+    import subprocess
+    out = {}
+    env = dict(os.environ)
+    env.setdefault("PBRTGPU_SCRATCH_GB", "16")   # the parent still holds its own scratch
+    try:
+        r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "bench_bvhbuild.py"), "--n", "2000000", "--reps", "2"],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, env=env, cwd=REPO)
+        rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+        out["bvh_build"] = rows if rows else {"error": (r.stderr or "no output").strip()[-300:]}
+    except Exception as e:   # noqa: BLE001
+        out["bvh_build"] = {"error": repr(e)[:300]}
+
+    def ab_line(lib):
+        e = dict(env)
+        if lib:
+            e["PBRTGPU_LIB"] = lib
+        r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--spp", "64", "--steps", "2", "--warmup", "2",
+                            "--no-cpu-baseline", "--no-extras", "--film-hash"],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, env=e, cwd=REPO)
+        rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+        if not rows:
+            raise RuntimeError((r.stderr or "no output").strip()[-300:])
+        d = rows[-1]
+        return {"value": d["value"], "film_md5": d.get("film_md5"), "kernel_ms": d.get("kernel_ms"),
+                "k_trace_ms_per_step": d["roofline"].get("k_trace_ms_per_step"),
+                "k_path2_ms_per_step": d["roofline"].get("k_path2_ms_per_step")}
+
+    variants = {}
+    libs = [(n, "ab/libpbrtgpu_%s.so" % n) for n in ("pairs", "specular")
+            if os.path.exists(os.path.join(REPO, "pbrt_v2_b200", "ab", "libpbrtgpu_%s.so" % n))]
+    if libs:
+        try:
+            base = ab_line(None)
+            variants["product"] = base
+            for name, lib in libs:
+                try:
+                    v = ab_line(lib)
+                    v["same_film_as_product"] = v["film_md5"] == base["film_md5"]
+                    v["speedup_vs_product"] = v["value"] / base["value"] if base["value"] else None
+                    variants[name] = v
+                except Exception as e:   # noqa: BLE001
+                    variants[name] = {"error": repr(e)[:300]}
+        except Exception as e:   # noqa: BLE001
+            variants["product"] = {"error": repr(e)[:300]}
+        variants["workload"] = "bunny-c2 at 64 spp, 2 steps (development size: the numbers compare libraries, nothing else)"
+    out["variants"] = variants
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,6 +278,8 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override spp (development only; invalidates the number)")
     ap.add_argument("--tris", type=int, default=SYNTHETIC_TRIS, help="triangle count of the synthetic workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the untimed side measurements appended under \"extras\"")
+    ap.add_argument("--film-hash", action="store_true", help="add an md5 of the last film to the line (A/B runs)")
     args = ap.parse_args()
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -416,6 +475,11 @@ def main():
                           "--ncores %d, render phase %.1f s (wall %.1f s)" % (
                               base, xres, yres, CPU_SAMPLE_SPP, max(1, WORKLOADS[args.workload][3] // CPU_SAMPLE_SPP),
                               threads, sec, wall)}
+        if args.film_hash:
+            import hashlib
+            line["film_md5"] = hashlib.md5(film.cpu().numpy().tobytes()).hexdigest()
+        if world == 1 and not args.no_extras and "INVALID" not in line:
+            line["extras"] = run_extras()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

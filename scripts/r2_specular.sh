@@ -2,9 +2,8 @@
 # on a GPU), check its parity and what it costs the headline.  Run on the GPU box:  bash scripts/r2_specular.sh
 set -x
 mkdir -p pbrt_v2_b200/ab gpurun_out
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -prec-div=true \
-    -prec-sqrt=true -ftz=false -Xcompiler -fPIC -shared -DPBRT_SPECULAR=1 pbrt_v2_b200/csrc/device/pbrtgpu.cu \
-    -o pbrt_v2_b200/ab/libpbrtgpu_specular.so
+# (built by `make variants` / __graft_entry__.build() and shipped with the snapshot; compiled here only if missing)
+[ -f pbrt_v2_b200/ab/libpbrtgpu_specular.so ] || make variants
 PBRTGPU_LIB=ab/libpbrtgpu_specular.so python -m pytest tests/test_gpu_specular.py tests/test_gpu_parity.py -q -m gpu \
     --deselect tests/test_gpu_parity.py::test_specular_materials_are_refused_loudly 2>&1 | tail -5 | tee gpurun_out/r2_specular_tests.txt
 for lib in libpbrtgpu.so ab/libpbrtgpu_specular.so; do
