@@ -221,11 +221,15 @@ def run_extras():
                   library on the same reduced-spp workload: throughput and whether the film is byte-identical"""
     import subprocess
     out = {}
+    deadline = time.time() + 240.0   # all of it together: a stuck child must not cost the line above
+
+    def left():
+        return max(1.0, min(120.0, deadline - time.time()))
     env = dict(os.environ)
     env.setdefault("PBRTGPU_SCRATCH_GB", "16")   # the parent still holds its own scratch
     try:
         r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "bench_bvhbuild.py"), "--n", "2000000", "--reps", "2"],
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, env=env, cwd=REPO)
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=left(), env=env, cwd=REPO)
         rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
         out["bvh_build"] = rows if rows else {"error": (r.stderr or "no output").strip()[-300:]}
     except Exception as e:   # noqa: BLE001
@@ -237,7 +241,7 @@ def run_extras():
             e["PBRTGPU_LIB"] = lib
         r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--spp", "64", "--steps", "2", "--warmup", "2",
                             "--no-cpu-baseline", "--no-extras", "--film-hash"],
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, env=e, cwd=REPO)
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=left(), env=e, cwd=REPO)
         rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
         if not rows:
             raise RuntimeError((r.stderr or "no output").strip()[-300:])
@@ -254,6 +258,9 @@ def run_extras():
             base = ab_line(None)
             variants["product"] = base
             for name, lib in libs:
+                if deadline - time.time() < 30.0:
+                    variants[name] = {"error": "skipped: the extras' time budget was used up"}
+                    continue
                 try:
                     v = ab_line(lib)
                     v["same_film_as_product"] = v["film_md5"] == base["film_md5"]
