@@ -39,6 +39,7 @@ $(PKG)/ab/libpbrtgpu_specular.so: $(DEVSRC) $(DEVHDR)
 	$(NVCC) $(NVFLAGS) -DPBRT_SPECULAR=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_specular.log || (cat build/ptxas_specular.log; false)
 
 $(PKG)/libpbrtgpu.so: $(DEVSRC) $(DEVHDR)
+	@mkdir -p build
 	$(NVCC) $(NVFLAGS) $(NVDEFS) -shared $(DEVSRC) -o $@ 2> build/ptxas.log || (cat build/ptxas.log; false)
 	@grep -E "registers|spill|error" build/ptxas.log | sort | uniq -c | sort -rn | head -20 || true
 
