@@ -319,6 +319,24 @@ typedef struct PbrtGpuBuildStats {
 int  pbrtgpu_bvh_build(const float *bounds, uint32_t nPrimitives, uint32_t maxPrimsInNode, int splitMethod,
                        PbrtGpuBVHNode *nodes, uint32_t *nNodes, uint32_t *order, PbrtGpuBuildStats *stats);
 
+/* replaces: LoopSubdiv::Refine (shapes/loopsubdiv.cpp:221-422) -- the subdivision levels, the limit-surface positions
+ * and normals, the triangle list.  Input: what the LoopSubdiv constructor builds (loopsubdiv.cpp:156-216), the SDVertex /
+ * SDFace arrays as indices; that topology pass over the control mesh stays on the host.  Output, to HOST memory: the
+ * arguments of the TriangleMesh Refine creates (loopsubdiv.cpp:404-422) -- P (limit positions), N (limit normals, not
+ * normalised, as the reference leaves them), vertex indices -- identical to the reference's, element for element.
+ * Sizes: pbrtgpu_loopsubdiv_counts.  The control mesh must be a manifold (an edge in at most two faces, neighbour links
+ * reciprocal), which the reference's algorithm assumes as well: anything else answers PBRTGPU_EINVAL.               */
+typedef struct PbrtGpuSubdivMesh {
+    uint32_t nVertices, nFaces;
+    const float   *P;          /* nVertices x 3: SDVertex::P                                   */
+    const int32_t *startFace;  /* nVertices: SDVertex::startFace (-1: no face uses the vertex) */
+    const uint8_t *vflags;     /* nVertices: bit 0 SDVertex::boundary, bit 1 SDVertex::regular */
+    const int32_t *faceV;      /* nFaces x 3: SDFace::v                                        */
+    const int32_t *faceF;      /* nFaces x 3: SDFace::f (-1: no neighbour across edge k)       */
+} PbrtGpuSubdivMesh;
+int  pbrtgpu_loopsubdiv_counts(const PbrtGpuSubdivMesh *mesh, int nLevels, uint32_t *nVerticesOut, uint32_t *nTrianglesOut);
+int  pbrtgpu_loopsubdiv_refine(const PbrtGpuSubdivMesh *mesh, int nLevels, float *P, float *N, int32_t *vertexIndices);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,12 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class SubdivMesh(C.Structure):
+    """PbrtGpuSubdivMesh"""
+    _fields_ = [("nVertices", C.c_uint32), ("nFaces", C.c_uint32), ("P", C.c_void_p), ("startFace", C.c_void_p),
+                ("vflags", C.c_void_p), ("faceV", C.c_void_p), ("faceF", C.c_void_p)]
+
+
 class BuildStats(C.Structure):
     """PbrtGpuBuildStats"""
     _fields_ = [("buildMs", C.c_double), ("nLevels", C.c_uint32), ("reserved", C.c_uint32)]
@@ -122,6 +128,8 @@ def gpu_lib():
         lib.pbrtgpu_ld_samples.argtypes = [C.POINTER(RenderDesc), C.c_int, C.c_void_p]
         lib.pbrtgpu_set_device.argtypes = [C.c_int]
         lib.pbrtgpu_set_stats.argtypes = [C.c_void_p, C.c_int]
+        lib.pbrtgpu_loopsubdiv_counts.argtypes = [C.POINTER(SubdivMesh), C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        lib.pbrtgpu_loopsubdiv_refine.argtypes = [C.POINTER(SubdivMesh), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pbrtgpu_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.POINTER(C.c_uint32),
                                           C.c_void_p, C.POINTER(BuildStats)]
         _gpu = lib
@@ -158,6 +166,9 @@ def host_lib():
         lib.pbrthost_build_input.restype = C.c_uint
         lib.pbrthost_scene_nodes.argtypes = [C.c_void_p, C.c_void_p]
         lib.pbrthost_scene_nodes.restype = None
+        lib.pbrthost_loopsubdiv_topology.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 6
+        lib.pbrthost_loopsubdiv_refine.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint32),
+                                                   C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pbrthost_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.POINTER(C.c_uint32),
                                            C.c_void_p]
         _host = lib
@@ -359,6 +370,47 @@ def host_bvh_build(bounds, max_prims_in_node=4, split_method=SPLIT_SAH):
     if rc:
         raise PbrtGpuError("pbrthost_bvh_build: bad arguments")
     return nodes[:nn.value].copy(), order
+
+
+class ControlMesh(object):
+    """A LoopSubdiv control mesh with the constructor's topology (loopsubdiv.cpp:156-216) as PbrtGpuSubdivMesh arrays."""
+
+    def __init__(self, indices, P):
+        self.indices = np.ascontiguousarray(indices, np.int32).reshape(-1, 3)
+        self.P = np.ascontiguousarray(P, np.float32).reshape(-1, 3)
+        nv, nf = len(self.P), len(self.indices)
+        self.startFace = np.zeros(nv, np.int32)
+        self.vflags = np.zeros(nv, np.uint8)
+        self.faceV = np.zeros((nf, 3), np.int32)
+        self.faceF = np.zeros((nf, 3), np.int32)
+        host_lib().pbrthost_loopsubdiv_topology(nv, nf, self.indices.ctypes.data, self.P.ctypes.data, self.startFace.ctypes.data,
+                                                self.vflags.ctypes.data, self.faceV.ctypes.data, self.faceF.ctypes.data)
+        self.desc = SubdivMesh(nv, nf, self.P.ctypes.data, self.startFace.ctypes.data, self.vflags.ctypes.data,
+                               self.faceV.ctypes.data, self.faceF.ctypes.data)
+
+    def counts(self, nlevels):
+        """(vertices, triangles) of the refined mesh (pbrtgpu_loopsubdiv_counts: validation + arithmetic, no device needed)"""
+        nv, nt = C.c_uint32(), C.c_uint32()
+        _check(gpu_lib().pbrtgpu_loopsubdiv_counts(C.byref(self.desc), int(nlevels), C.byref(nv), C.byref(nt)), "pbrtgpu_loopsubdiv_counts")
+        return nv.value, nt.value
+
+    def refine(self, nlevels):
+        """LoopSubdiv::Refine on the GPU -> (P limit, N limit, vertex indices)"""
+        nv, nt = self.counts(nlevels)
+        P, N, idx = np.zeros((nv, 3), np.float32), np.zeros((nv, 3), np.float32), np.zeros((nt, 3), np.int32)
+        _check(gpu_lib().pbrtgpu_loopsubdiv_refine(C.byref(self.desc), int(nlevels), P.ctypes.data, N.ctypes.data, idx.ctypes.data),
+               "pbrtgpu_loopsubdiv_refine")
+        return P, N, idx
+
+    def host_refine(self, nlevels):
+        """the same by the host front end's LoopSubdiv::Refine"""
+        nv, nt = C.c_uint32(), C.c_uint32()
+        args = [len(self.P), len(self.indices), self.indices.ctypes.data, self.P.ctypes.data, int(nlevels), C.byref(nv), C.byref(nt)]
+        if host_lib().pbrthost_loopsubdiv_refine(*(args + [None, None, None])):
+            raise PbrtGpuError("pbrthost_loopsubdiv_refine failed")
+        P, N, idx = np.zeros((nv.value, 3), np.float32), np.zeros((nv.value, 3), np.float32), np.zeros((nt.value, 3), np.int32)
+        host_lib().pbrthost_loopsubdiv_refine(*(args + [P.ctypes.data, N.ctypes.data, idx.ctypes.data]))
+        return P, N, idx
 
 
 def keep_build_input(on=True):

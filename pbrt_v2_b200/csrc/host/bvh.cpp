@@ -145,7 +145,7 @@ struct Builder {
 // mesh's triangles reach the accelerator in REVERSE index order; that order is
 // the input order of the build and must be kept.
 void FullyRefine(const GeometricPrimitive &gp, std::vector<RefinedPrim> *out,
-                 std::vector<std::shared_ptr<Shape>> *owned) {
+                 std::vector<std::shared_ptr<Shape>> *owned, std::string *err) {
     if (gp.animated) {   // TransformedPrimitive::CanIntersect() is true: handed over as it is
         RefinedPrim r;
         r.type = PBRTGPU_PRIM_ANIMATED;
@@ -169,6 +169,7 @@ void FullyRefine(const GeometricPrimitive &gp, std::vector<RefinedPrim> *out,
     case Shape::TRIANGLE_MESH: emitMesh(static_cast<const TriangleMesh *>(s)); break;
     case Shape::LOOP_SUBDIV: {
         std::shared_ptr<Shape> mesh(static_cast<const LoopSubdiv *>(s)->Refine());
+        if (!mesh) { *err = static_cast<const LoopSubdiv *>(s)->refineError; break; }
         owned->push_back(mesh);
         emitMesh(static_cast<const TriangleMesh *>(mesh.get()));
         break;
@@ -195,7 +196,8 @@ GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, 
     // BVHAccel::BVHAccel, bvh.cpp:153-202
     maxPrimsInNode = std::min(255u, mp);
     std::vector<RefinedPrim> refined;
-    for (const GeometricPrimitive &gp : p) FullyRefine(gp, &refined, &owned);
+    for (const GeometricPrimitive &gp : p) FullyRefine(gp, &refined, &owned, &buildError);
+    if (!buildError.empty()) return;
     if (sm == "sah") splitMethod = 2;
     else if (sm == "middle") splitMethod = 0;
     else if (sm == "equal") splitMethod = 1;

@@ -143,4 +143,42 @@ int pbrthost_bvh_build(const float *bounds, uint32_t n, uint32_t maxPrimsInNode,
     return 0;
 }
 
+// LoopSubdiv on raw arrays (test hooks and the comparison partner of pbrtgpu_loopsubdiv_refine).
+// topology: the constructor's pass (loopsubdiv.cpp:156-216) -> the index arrays of PbrtGpuSubdivMesh
+int pbrthost_loopsubdiv_topology(int nVertices, int nFaces, const int *indices, const float *P, int32_t *startFace, uint8_t *vflags,
+                                 int32_t *faceV, int32_t *faceF) {
+    std::vector<V3> Pv(nVertices);
+    for (int i = 0; i < nVertices; ++i) Pv[i] = V3(P[3 * i], P[3 * i + 1], P[3 * i + 2]);
+    Transform identity;
+    LoopSubdiv ls(&identity, &identity, false, nFaces, nVertices, indices, Pv.data(), 0);
+    std::vector<int32_t> sf, fv, ff;
+    std::vector<uint8_t> vf;
+    ls.Topology(&sf, &vf, &fv, &ff);
+    memcpy(startFace, sf.data(), sf.size() * 4);
+    memcpy(vflags, vf.data(), vf.size());
+    memcpy(faceV, fv.data(), fv.size() * 4);
+    memcpy(faceF, ff.data(), ff.size() * 4);
+    return 0;
+}
+// refine: the host front end's LoopSubdiv::Refine; first call with null outputs for the sizes
+int pbrthost_loopsubdiv_refine(int nVertices, int nFaces, const int *indices, const float *P, int nLevels, uint32_t *nvOut,
+                               uint32_t *ntOut, float *Pout, float *Nout, int32_t *indicesOut) {
+    std::vector<V3> Pv(nVertices);
+    for (int i = 0; i < nVertices; ++i) Pv[i] = V3(P[3 * i], P[3 * i + 1], P[3 * i + 2]);
+    Transform identity;
+    LoopSubdiv ls(&identity, &identity, false, nFaces, nVertices, indices, Pv.data(), nLevels);
+    std::unique_ptr<TriangleMesh> m(ls.Refine());
+    if (!m) return 1;
+    *nvOut = (uint32_t)m->nverts;
+    *ntOut = (uint32_t)m->ntris;
+    if (!Pout) return 0;
+    // TriangleMesh keeps P in world space (identity here) and N as given
+    for (int i = 0; i < m->nverts; ++i) {
+        Pout[3 * i] = m->p[i].x; Pout[3 * i + 1] = m->p[i].y; Pout[3 * i + 2] = m->p[i].z;
+        Nout[3 * i] = m->n[i].x; Nout[3 * i + 1] = m->n[i].y; Nout[3 * i + 2] = m->n[i].z;
+    }
+    for (int i = 0; i < 3 * m->ntris; ++i) indicesOut[i] = m->vertexIndex[i];
+    return 0;
+}
+
 }  // extern "C"

@@ -329,9 +329,16 @@ bool Api::DoShape(const std::string &name, const ParamSet &params) {   // core/a
         int nlevels = params.FindOneInt("nlevels", 3);
         const std::vector<int> *vi = params.FindInt("indices");
         const std::vector<V3> *P = params.FindPoint("P");
-        if (vi && P)
-            shape.reset(new LoopSubdiv(o2w, w2o, ro, (int)vi->size() / 3, (int)P->size(), vi->data(),
-                                       P->data(), nlevels));
+        if (vi && P) {
+            LoopSubdiv *ls = new LoopSubdiv(o2w, w2o, ro, (int)vi->size() / 3, (int)P->size(), vi->data(), P->data(), nlevels);
+            // "string refiner" [ "host" | "gpu" ] (also PBRTGPU_SUBDIV in the environment): where Refine() runs
+            const char *env = getenv("PBRTGPU_SUBDIV");
+            const std::string refiner = params.FindOneString("refiner", env ? env : "host");
+            if (refiner != "host" && refiner != "gpu")
+                fprintf(stderr, "Warning: loopsubdiv refiner \"%s\" unknown.  Using \"host\".\n", refiner.c_str());
+            ls->refineOnDevice = refiner == "gpu";
+            shape.reset(ls);
+        }
     } else {
         return Fail("shape \"" + name + "\" is outside the hot-path scope");
     }
@@ -351,6 +358,7 @@ bool Api::DoShape(const std::string &name, const ParamSet &params) {   // core/a
         base.areaLight = -1;
         GeometricPrimitive gp;
         gp.animated.reset(new TransformedPrimitive(base, animatedWorldToObject));
+        if (!gp.animated->primitive->buildError.empty()) return Fail(gp.animated->primitive->buildError);
         if (gp.animated->primitive->primitives.empty()) return true;   // api.cpp:1037
         primitives.push_back(gp);
         return true;

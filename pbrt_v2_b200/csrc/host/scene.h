@@ -100,7 +100,13 @@ struct LoopSubdiv : Shape {   // shapes/loopsubdiv.h -- refined to a TriangleMes
     LoopSubdiv(const Transform *o2w, const Transform *w2o, bool ro, int nfaces, int nvertices,
                const int *vi, const V3 *P, int nl);
     bool CanIntersect() const override { return false; }
-    TriangleMesh *Refine() const;   // shapes/loopsubdiv.cpp:240-446
+    TriangleMesh *Refine() const;   // shapes/loopsubdiv.cpp:240-446; null (and refineError set) if the device refine failed
+    bool refineOnDevice = false;    // "string refiner" "gpu" / PBRTGPU_SUBDIV=gpu
+    mutable std::string refineError;
+    // the constructor's topology pass (loopsubdiv.cpp:156-216) as PbrtGpuSubdivMesh's index arrays
+    void Topology(std::vector<int32_t> *startFace, std::vector<uint8_t> *vflags, std::vector<int32_t> *faceV,
+                  std::vector<int32_t> *faceF) const;
+    TriangleMesh *RefineOnDevice(std::string *err) const;
 };
 
 // --------------------------------------------------------------- Materials --

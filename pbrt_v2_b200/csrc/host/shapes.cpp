@@ -192,9 +192,10 @@ LoopSubdiv::LoopSubdiv(const Transform *o2w, const Transform *w2o, bool ro, int 
     P.assign(Pin, Pin + nvertices);
 }
 
-TriangleMesh *LoopSubdiv::Refine() const {
-    // ---- control mesh topology, loopsubdiv.cpp:156-216 ----
-    Mesh cur;
+namespace {
+// LoopSubdiv::LoopSubdiv's topology pass, loopsubdiv.cpp:156-216
+void ControlTopology(const std::vector<int> &indices, const std::vector<V3> &P, Mesh *out) {
+    Mesh &cur = *out;
     int nverts = (int)P.size(), nfaces = (int)indices.size() / 3;
     cur.V.resize(nverts);
     for (int i = 0; i < nverts; ++i) cur.V[i].P = P[i];
@@ -231,6 +232,57 @@ TriangleMesh *LoopSubdiv::Refine() const {
         else if (cur.V[i].boundary && val == 4) cur.V[i].regular = true;
         else cur.V[i].regular = false;
     }
+}
+}  // namespace
+
+// the control mesh as the index arrays of include/pbrtgpu.h's PbrtGpuSubdivMesh
+void LoopSubdiv::Topology(std::vector<int32_t> *startFace, std::vector<uint8_t> *vflags, std::vector<int32_t> *faceV,
+                          std::vector<int32_t> *faceF) const {
+    Mesh cur;
+    ControlTopology(indices, P, &cur);
+    startFace->resize(cur.V.size());
+    vflags->resize(cur.V.size());
+    for (size_t i = 0; i < cur.V.size(); ++i) {
+        (*startFace)[i] = cur.V[i].startFace;
+        (*vflags)[i] = (uint8_t)((cur.V[i].boundary ? 1 : 0) | (cur.V[i].regular ? 2 : 0));
+    }
+    faceV->resize(3 * cur.F.size());
+    faceF->resize(3 * cur.F.size());
+    for (size_t j = 0; j < cur.F.size(); ++j)
+        for (int k = 0; k < 3; ++k) { (*faceV)[3 * j + k] = cur.F[j].v[k]; (*faceF)[3 * j + k] = cur.F[j].f[k]; }
+}
+
+// LoopSubdiv::Refine on the device (include/pbrtgpu.h: pbrtgpu_loopsubdiv_refine): same TriangleMesh
+TriangleMesh *LoopSubdiv::RefineOnDevice(std::string *err) const {
+    std::vector<int32_t> startFace, faceV, faceF;
+    std::vector<uint8_t> vflags;
+    Topology(&startFace, &vflags, &faceV, &faceF);
+    std::vector<float> Pin(3 * P.size());
+    for (size_t i = 0; i < P.size(); ++i) { Pin[3 * i] = P[i].x; Pin[3 * i + 1] = P[i].y; Pin[3 * i + 2] = P[i].z; }
+    PbrtGpuSubdivMesh m;
+    m.nVertices = (uint32_t)P.size(); m.nFaces = (uint32_t)(indices.size() / 3);
+    m.P = Pin.data(); m.startFace = startFace.data(); m.vflags = vflags.data(); m.faceV = faceV.data(); m.faceF = faceF.data();
+    uint32_t nv = 0, nt = 0;
+    if (pbrtgpu_loopsubdiv_counts(&m, nLevels, &nv, &nt) != PBRTGPU_OK) { *err = pbrtgpu_last_error(); return nullptr; }
+    std::vector<float> Pl(3 * (size_t)nv), Nl(3 * (size_t)nv);
+    std::vector<int32_t> verts(3 * (size_t)nt);
+    if (pbrtgpu_loopsubdiv_refine(&m, nLevels, Pl.data(), Nl.data(), verts.data()) != PBRTGPU_OK) { *err = pbrtgpu_last_error(); return nullptr; }
+    std::vector<V3> Pv(nv), Nv(nv);
+    for (uint32_t i = 0; i < nv; ++i) { Pv[i] = V3(Pl[3 * i], Pl[3 * i + 1], Pl[3 * i + 2]); Nv[i] = V3(Nl[3 * i], Nl[3 * i + 1], Nl[3 * i + 2]); }
+    return new TriangleMesh(ObjectToWorld, WorldToObject, ReverseOrientation, (int)nt, (int)nv, verts.data(), Pv.data(), Nv.data(), nullptr);
+}
+
+TriangleMesh *LoopSubdiv::Refine() const {
+    // "string refiner" "gpu" on the shape, or PBRTGPU_SUBDIV=gpu: the levels run on the device.  No silent fallback.
+    if (refineOnDevice) {
+        std::string err;
+        TriangleMesh *mesh = RefineOnDevice(&err);
+        if (!mesh) refineError = "LoopSubdiv on the device failed: " + err;
+        return mesh;   // null on failure: the accelerator's build reports refineError
+    }
+    // ---- control mesh topology, loopsubdiv.cpp:156-216 ----
+    Mesh cur;
+    ControlTopology(indices, P, &cur);
 
     // ---- subdivision levels, loopsubdiv.cpp:240-345 ----
     for (int level = 0; level < nLevels; ++level) {
