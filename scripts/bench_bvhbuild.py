@@ -1,5 +1,5 @@
-"""Times pbrtgpu_bvh_build against the host front end's recursive build on the same input and checks that the trees are
-the same.  Inputs: the BASELINE scenes' own build inputs and random triangles' bounds at C5 size.  One JSON line per case.
+"""Scene-preparation kernels against the host front end: times pbrtgpu_bvh_build against the host front end's recursive build on the same input and checks that the trees are
+the same (and pbrtgpu_loopsubdiv_refine against LoopSubdiv::Refine on the killeroo control mesh).  Inputs: the BASELINE scenes' own build inputs and random triangles' bounds at C5 size.  One JSON line per case.
 Run on a GPU box:  python scripts/bench_bvhbuild.py [--n 10000000]"""
 import argparse
 import json
@@ -37,6 +37,36 @@ def case(name, bounds, maxp, reps):
                       "same_tree": bool(np.array_equal(order, want_order) and same_tree(nodes, want_nodes))}), flush=True)
 
 
+def subdiv_case(nlevels, reps):
+    """LoopSubdiv::Refine of the killeroo control mesh (scenes/geometry/killeroo.pbrt): device vs host front end"""
+    import re
+    from pbrt_v2_b200 import scenes
+    text = open(os.path.join(scenes.STAGED, "geometry", "killeroo.pbrt")).read()
+    m = re.search(r'Shape "loopsubdiv".*?"integer indices"\s*\[([^\]]*)\]\s*"point P"\s*\[([^\]]*)\]', text, re.S)
+    cm = pb.ControlMesh(np.array(m.group(1).split(), np.int32).reshape(-1, 3), np.array(m.group(2).split(), np.float32).reshape(-1, 3))
+    t0 = time.time()
+    want = cm.host_refine(nlevels)
+    host_s = time.time() - t0
+    cm.refine(0)
+    wall = []
+    for _ in range(reps):
+        t0 = time.time()
+        got = cm.refine(nlevels)
+        wall.append(time.time() - t0)
+    same = bool(np.array_equal(got[2], want[2]) and np.array_equal(got[0], want[0], equal_nan=True) and
+                np.array_equal(got[1], want[1], equal_nan=True))
+    print(json.dumps({"case": "loopsubdiv killeroo nlevels %d" % nlevels, "control_faces": len(cm.indices), "triangles": len(want[2]),
+                      "host_refine_s": round(host_s, 3), "device_call_wall_ms": round(1e3 * min(wall), 3),
+                      "speedup_vs_host": round(host_s / min(wall), 1), "same_mesh": same}), flush=True)
+
+
+def guard(name, fn):
+    try:
+        fn()
+    except Exception as e:   # noqa: BLE001  (one failing case must not hide the others)
+        print(json.dumps({"case": name, "error": repr(e)[:300]}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=10000000, help="random-triangle case size (BASELINE C5: 10 M)")
@@ -50,11 +80,13 @@ def main():
             pb.keep_build_input(True)
             hs = host_scene(base, 32, 32, 4, 32)
             pb.keep_build_input(False)
-            case(base, hs.build_input(), 4, a.reps)
+            guard(base, lambda: case(base, hs.build_input(), 4, a.reps))
+        for nlevels in (1, 3):
+            guard("loopsubdiv killeroo nlevels %d" % nlevels, lambda: subdiv_case(nlevels, a.reps))
     rs = np.random.RandomState(1)
     c = rs.rand(a.n, 3).astype(np.float32) * 2 - 1
     e = (rs.rand(a.n, 3).astype(np.float32) * 0.01).astype(np.float32)
-    case("random-%d" % a.n, np.concatenate([c - e, c + e], 1).astype(np.float32), 4, a.reps)
+    guard("random-%d" % a.n, lambda: case("random-%d" % a.n, np.concatenate([c - e, c + e], 1).astype(np.float32), 4, a.reps))
 
 
 if __name__ == "__main__":
