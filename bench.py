@@ -216,7 +216,7 @@ def workload_config(workload, world, per_pixel=True, spp_override=None):
 def run_extras():
     """Side measurements of work that is in the repo but not (yet) on the measured path, taken AFTER the timed regions, each
     in its own process (a fault there cannot touch the line above) and with a timeout.  They cost about a minute.
-      bvh_build   pbrtgpu_bvh_build against the host front end's recursive build (scripts/bench_bvhbuild.py)
+      scene_prep  pbrtgpu_bvh_build and pbrtgpu_loopsubdiv_refine against the host front end (scripts/bench_bvhbuild.py)
       variants    the kernel-experiment libraries built by `make variants` (pbrt_v2_b200/ab/), each against the product
                   library on the same reduced-spp workload: throughput and whether the film is byte-identical"""
     import subprocess
@@ -231,9 +231,9 @@ def run_extras():
         r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "bench_bvhbuild.py"), "--n", "2000000", "--reps", "2"],
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=left(), env=env, cwd=REPO)
         rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
-        out["bvh_build"] = rows if rows else {"error": (r.stderr or "no output").strip()[-300:]}
+        out["scene_prep"] = rows if rows else {"error": (r.stderr or "no output").strip()[-300:]}
     except Exception as e:   # noqa: BLE001
-        out["bvh_build"] = {"error": repr(e)[:300]}
+        out["scene_prep"] = {"error": repr(e)[:300]}
 
     def ab_line(lib):
         e = dict(env)
