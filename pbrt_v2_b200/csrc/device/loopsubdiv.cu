@@ -81,7 +81,7 @@ extern "C" int pbrtgpu_loopsubdiv_counts(const PbrtGpuSubdivMesh *mesh, int nLev
     if (const char *why = ValidateSubdivMesh(*mesh, nLevels))
         return pbrtgpu_set_error_text(PBRTGPU_EINVAL, (std::string("pbrtgpu_loopsubdiv: ") + why).c_str());
     uint64_t nv = 0, nf = 0;
-    if (!FinalCounts(*mesh, nLevels, &nv, &nf)) return pbrtgpu_set_error_text(PBRTGPU_EINVAL, "pbrtgpu_loopsubdiv: refined mesh too large");
+    if (!FinalCounts(*mesh, nLevels, &nv, &nf)) return pbrtgpu_set_error_text(PBRTGPU_EINVAL, "pbrtgpu_loopsubdiv: the neighbour links do not describe a manifold, or the refined mesh exceeds 2^31 indices");
     *nVerticesOut = (uint32_t)nv;
     *nTrianglesOut = (uint32_t)nf;
     return PBRTGPU_OK;
@@ -92,7 +92,7 @@ extern "C" int pbrtgpu_loopsubdiv_refine(const PbrtGpuSubdivMesh *mesh, int nLev
     if (const char *why = ValidateSubdivMesh(*mesh, nLevels))
         return pbrtgpu_set_error_text(PBRTGPU_EINVAL, (std::string("pbrtgpu_loopsubdiv: ") + why).c_str());
     uint64_t nv = 0, nf = 0;
-    if (!FinalCounts(*mesh, nLevels, &nv, &nf)) return pbrtgpu_set_error_text(PBRTGPU_EINVAL, "pbrtgpu_loopsubdiv: refined mesh too large");
+    if (!FinalCounts(*mesh, nLevels, &nv, &nf)) return pbrtgpu_set_error_text(PBRTGPU_EINVAL, "pbrtgpu_loopsubdiv: the neighbour links do not describe a manifold, or the refined mesh exceeds 2^31 indices");
     int nDev = 0;
     if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
         return pbrtgpu_set_error_text(PBRTGPU_ENODEVICE, "no CUDA device visible; libpbrtgpu has no CPU fallback");
