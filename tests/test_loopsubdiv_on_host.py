@@ -100,6 +100,29 @@ def test_device_refine_on_host_matches_host_refine(emu, name, mesh):
         assert np.isfinite(want[0]).all()
 
 
+def test_random_campaign(emu):
+    rs = np.random.RandomState(2024)
+    cases = 0
+    for it in range(120):
+        kind = rs.randint(4)
+        if kind == 0:
+            mesh = grid(int(rs.randint(1, 9)), int(rs.randint(1, 9)), rs, holes=float(rs.choice([0, 0, .1, .3])))
+        elif kind == 1:
+            mesh = fan(int(rs.randint(3, 20)), True, rs, centre_z=float(rs.rand()))
+        elif kind == 2:
+            mesh = fan(int(rs.randint(1, 15)), False, rs)
+        else:
+            mesh = closed_solid("oct", rs)
+        if not mesh[0]:
+            continue
+        cm = pb.ControlMesh(*mesh)
+        for nlevels in (1, 2, 3):
+            got = emu_refine(emu, cm, nlevels, int(rs.choice([0, 1, 2])), int(rs.randint(2)))
+            assert same_mesh(got, cm.host_refine(nlevels)), (it, kind, nlevels)
+            cases += 1
+    assert cases > 300
+
+
 def _killeroo_control_mesh():
     from pbrt_v2_b200 import scenes
     scenes.stage()
