@@ -9,7 +9,7 @@ PBRTGPU_LIB=ab/libpbrtgpu_pairs.so python -m pytest tests/test_gpu_parity.py -q 
 # then the headline, the denser mesh and the animated scene (nested walks), both libraries back to back
 for wl in bunny-c2 killeroo-c1 anim-c4; do
   for lib in libpbrtgpu.so ab/libpbrtgpu_pairs.so; do
-    PBRTGPU_LIB=$lib python bench.py --workload $wl --spp 64 --steps 2 --warmup 1 --no-cpu-baseline 2>&1 | tail -1 | \
+    PBRTGPU_LIB=$lib python bench.py --workload $wl --spp 64 --steps 2 --warmup 1 --no-cpu-baseline --no-extras 2>&1 | tail -1 | \
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$wl', '$lib', round(d['value'],1), d.get('kernel_ms'))" | tee -a gpurun_out/r2_pairs_bench.txt
   done
 done
