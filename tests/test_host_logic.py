@@ -69,6 +69,30 @@ def test_out_of_scope_directives_fail_loudly(staged, text, needle):
     assert needle in str(e.value)
 
 
+def test_scene_preparation_options_are_parsed(staged, capfd):
+    """Accelerator "bvh" "string builder" and Shape "loopsubdiv" "string refiner": "host" is the default and gives the
+    same scene; an unknown value warns and uses the host; "gpu" without a device fails the load (no silent fallback)"""
+    src = open(scenes.variant("killeroo-simple", os.path.join(scenes.STAGED, "t-opt.pbrt"), 8, 8, 1)).read()
+    assert 'Accelerator' not in src   # (the shipped scenes leave the accelerator at its default)
+
+    def load(accel, env=None):
+        p = os.path.join(scenes.STAGED, "t-opt2.pbrt")
+        open(p, "w").write(src.replace("WorldBegin", accel + "\nWorldBegin", 1))
+        return pb.HostScene(p, ncores=1)
+    base = load("")
+    for accel in ('Accelerator "bvh" "string builder" "host"', 'Accelerator "bvh" "string builder" "fpga"'):
+        hs = load(accel)
+        assert hs.nodes().tobytes() == base.nodes().tobytes()
+    assert 'BVH builder "fpga" unknown' in capfd.readouterr().err
+    if pb.device_count() == 0:
+        with pytest.raises(pb.PbrtGpuError, match="no CUDA device"):
+            load('Accelerator "bvh" "string builder" "gpu"')
+    # middle / equal splits are host-only: asking for the device build there warns and builds on the host
+    hs = load('Accelerator "bvh" "string splitmethod" "middle" "string builder" "gpu"')
+    assert hs.counts()["nodes"] > 0
+    assert "only splitmethod" in capfd.readouterr().err
+
+
 def test_flattened_bvh_invariants(staged):
     """depth-first layout: left child = node+1, second child > node; every primitive in exactly one leaf."""
     hs = host_scene("killeroo-simple", 8, 8, 1, 1)
