@@ -239,7 +239,7 @@ def run_extras():
         e = dict(env)
         if lib:
             e["PBRTGPU_LIB"] = lib
-        r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--spp", "64", "--steps", "2", "--warmup", "2",
+        r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--spp", "128", "--steps", "2", "--warmup", "2",
                             "--no-cpu-baseline", "--no-extras", "--film-hash"],
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=left(), env=e, cwd=REPO)
         rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
@@ -270,7 +270,7 @@ def run_extras():
                     variants[name] = {"error": repr(e)[:300]}
         except Exception as e:   # noqa: BLE001
             variants["product"] = {"error": repr(e)[:300]}
-        variants["workload"] = "bunny-c2 at 64 spp, 2 steps (development size: the numbers compare libraries, nothing else)"
+        variants["workload"] = "bunny-c2 at 128 spp, 2 steps (development size: the numbers compare libraries, nothing else)"
     out["variants"] = variants
     out["seconds"] = round(time.time() - (deadline - 240.0), 1)
     return out
