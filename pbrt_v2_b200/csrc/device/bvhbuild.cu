@@ -46,7 +46,8 @@ extern "C" int pbrtgpu_bvh_build(const float *bounds, uint32_t nPrimitives, uint
                                       "run std::nth_element over whole ranges)");
     if (maxPrimsInNode < 1 || maxPrimsInNode > 255)
         return pbrtgpu_set_error_text(PBRTGPU_EINVAL, "pbrtgpu_bvh_build: maxPrimsInNode must be 1..255 (BVHAccel clamps to 255, bvh.cpp:155)");
-    if (nPrimitives > 0x7fffffffu) return pbrtgpu_set_error_text(PBRTGPU_EINVAL, "pbrtgpu_bvh_build: too many primitives");
+    if (nPrimitives > 300000000u)   // 32-bit indexing of the per-node key arrays (6 keys x 2n nodes)
+        return pbrtgpu_set_error_text(PBRTGPU_EINVAL, "pbrtgpu_bvh_build: more than 3e8 primitives");
     for (size_t i = 0; i < (size_t)nPrimitives * 6; ++i)
         if (!std::isfinite(bounds[i]))   // (an infinite extent makes the reference's bucket index int(NaN): undefined there too)
             return pbrtgpu_set_error_text(PBRTGPU_EINVAL, "pbrtgpu_bvh_build: a primitive's bounds are not finite");
