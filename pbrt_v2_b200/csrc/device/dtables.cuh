@@ -10,6 +10,11 @@
 
 using namespace dev;   // (the kernels live in the global namespace, like the rest of pbrtgpu.cu)
 
+// Round-2 experiment, OFF in the shipped kernels: k_tables' Fisher-Yates chains two steps at a time (see stage 2).
+#ifndef PBRT_TABLES_PAIRED
+#define PBRT_TABLES_PAIRED 0
+#endif
+
 struct TaskRec {
     int taskNum;
     int x0, x1, y0, y1;   // Sampler::ComputeSubWindow tile
@@ -122,6 +127,32 @@ __global__ void __launch_bounds__(32 * WPB) k_tables(BatchArgs a, int spp, int G
                 uint16_t tj[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) tj[k] = (i0 + k < spp) ? __ldcg(t + i0 + k) : (uint16_t)0;
+#if PBRT_TABLES_PAIRED
+                // two steps per shared-memory round trip: all four loads first, then the values step k+1 would have seen
+                // after step k's stores are patched in registers (step k puts `a` at j0: that is position i+1 if
+                // j0 == i+1, and it is what step k+1 finds at j1 if j1 == j0), then the four stores in program order
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    const int i = i0 + k;
+                    if (i + 1 < spp) {
+                        const int j0 = tj[k], j1 = tj[k + 1];
+                        const uint16_t a = p[i], b = p[j0];
+                        uint16_t c = p[i + 1], d = p[j1];
+                        if (j0 == i + 1) c = a;
+                        if (j1 == j0) d = a;
+                        if (j1 == i + 1) d = c;
+                        p[i] = b;
+                        p[j0] = a;
+                        p[i + 1] = d;
+                        p[j1] = c;
+                    } else if (i < spp) {   // spp == 1
+                        const int j = tj[k];
+                        const uint16_t tmp = p[i];
+                        p[i] = p[j];
+                        p[j] = tmp;
+                    }
+                }
+#else
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int i = i0 + k;
@@ -132,6 +163,7 @@ __global__ void __launch_bounds__(32 * WPB) k_tables(BatchArgs a, int spp, int G
                         p[j] = tmp;
                     }
                 }
+#endif
             }
         }
         __syncwarp();

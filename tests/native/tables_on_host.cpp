@@ -64,6 +64,8 @@ template <typename K> void LaunchWarp(K kernel) {   // one block of one warp: <<
 
 }  // namespace
 
+DOH_EXPORT int toh_paired_build(void) { return PBRT_TABLES_PAIRED; }   // which variant of the kernel source this harness holds
+
 // pbrtgpu_ld_samples with the table kernel executed by the warp emulation.  general != 0 forces k_tables_general even for
 // the path integrator's layout; rounds > 0 additionally runs that many further pixels of the task first (the RNG state
 // handed from pixel to pixel through rngCur / rngNext / mti) and returns the LAST pixel's samples -- without path tails

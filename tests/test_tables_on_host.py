@@ -18,15 +18,19 @@ CUDA_INC = "/usr/local/cuda/include"
 pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")), reason="CUDA headers not installed")
 
 
-@pytest.fixture(scope="module")
-def toh(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("toh") / "libtables_on_host.so")
+def _build(tmp_path_factory, name, defines=()):
+    so = str(tmp_path_factory.mktemp(name) / ("lib%s.so" % name))
     src = os.path.join(pb.REPO, "tests", "native", "tables_on_host.cpp")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic",
-                    "-pthread", "-I" + CUDA_INC, src, "-o", so], check=True)
+                    "-pthread", "-I" + CUDA_INC] + list(defines) + [src, "-o", so], check=True)
     lib = C.CDLL(so)
     lib.toh_ld_samples.argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 4 + [C.c_int, C.c_int, C.c_void_p]
     return lib
+
+
+@pytest.fixture(scope="module")
+def toh(tmp_path_factory):
+    return _build(tmp_path_factory, "tables_on_host")
 
 
 def _path_rd(spp, res=64, ntasks=16):
@@ -94,3 +98,16 @@ def test_large_arrays_and_spp_in_general_kernel(toh):
     assert _same(_run(toh, rd, 1), oa.ld_samples(rd, 1))   # 32 x 2048 = 65536 table entries: the 16-bit index limit
     rd.samplesPerPixel = 256
     assert _same(_run(toh, rd, 1, rounds=2), oa.ld_samples(rd, 1, 2))
+
+
+def test_paired_shuffle_steps_give_the_same_tables(tmp_path_factory):
+    """-DPBRT_TABLES_PAIRED=1 (a round-2 kernel experiment, not in the shipped kernels): k_tables runs its Fisher-Yates
+    chains two steps per shared-memory round trip, patching in registers what the second step would have read after the
+    first one's stores.  Same tables, bit for bit, incl. spp 1 (no pair) and the grouped path of 2048 spp."""
+    lib = _build(tmp_path_factory, "tables_on_host_paired", ["-DPBRT_TABLES_PAIRED=1"])
+    assert lib.toh_paired_build() == 1
+    for spp, tasks, rounds in [(1, [0, 3], 2), (2, [1], 3), (4, [2], 1), (8, [5], 0), (32, [0, 7], 1), (256, [4], 0), (1024, [6], 0),
+                               (2048, [3], 0)]:
+        rd = _path_rd(spp)
+        for task in tasks:
+            assert _same(_run(lib, rd, task, rounds=rounds), oa.ld_samples(rd, task, rounds)), (spp, task)
