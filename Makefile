@@ -25,7 +25,7 @@ NVDEFS    ?=
 # kernel experiments that are CPU-verified but not yet timed on a GPU: built next to the product library so that a GPU
 # visit (bench.py's "extras", scripts/r2_*.sh) can A/B them without compiling on the box.  Nothing loads them by default.
 VARIANTS  := $(PKG)/ab/libpbrtgpu_pairs.so $(PKG)/ab/libpbrtgpu_pairs6.so $(PKG)/ab/libpbrtgpu_specular.so \
-             $(PKG)/ab/libpbrtgpu_tables2.so
+             $(PKG)/ab/libpbrtgpu_tables2.so $(PKG)/ab/libpbrtgpu_pairs_tables2.so
 
 all: $(PKG)/libpbrtgpu.so $(PKG)/libpbrthost.so $(PKG)/pbrt_b200 oracle variants
 
@@ -44,6 +44,11 @@ $(PKG)/ab/libpbrtgpu_pairs6.so: $(DEVSRC) $(DEVHDR)
 $(PKG)/ab/libpbrtgpu_tables2.so: $(DEVSRC) $(DEVHDR)
 	@mkdir -p $(PKG)/ab build
 	$(NVCC) $(NVFLAGS) -DPBRT_TABLES_PAIRED=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_tables2.log || (cat build/ptxas_tables2.log; false)
+
+# ... both experiments together (are their gains additive?)
+$(PKG)/ab/libpbrtgpu_pairs_tables2.so: $(DEVSRC) $(DEVHDR)
+	@mkdir -p $(PKG)/ab build
+	$(NVCC) $(NVFLAGS) -DPBRT_PAIR_NODES=1 -DPBRT_TABLES_PAIRED=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_pairs_tables2.log || (cat build/ptxas_pairs_tables2.log; false)
 
 $(PKG)/ab/libpbrtgpu_specular.so: $(DEVSRC) $(DEVHDR)
 	@mkdir -p $(PKG)/ab build
