@@ -487,7 +487,10 @@ def main():
             import hashlib
             line["film_md5"] = hashlib.md5(film.cpu().numpy().tobytes()).hexdigest()
         if world == 1 and not args.no_extras and "INVALID" not in line:
-            line["extras"] = run_extras()
+            try:
+                line["extras"] = run_extras()
+            except BaseException as e:   # noqa: BLE001  (nothing in there may cost the line)
+                line["extras"] = {"error": repr(e)[:300]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
