@@ -221,7 +221,7 @@ def run_extras():
                   library on the same reduced-spp workload: throughput and whether the film is byte-identical"""
     import subprocess
     out = {}
-    deadline = time.time() + 240.0   # all of it together: a stuck child must not cost the line above
+    deadline = time.time() + 200.0   # all of it together: a stuck child must not cost the line above
 
     def left():
         return max(1.0, min(120.0, deadline - time.time()))
@@ -272,7 +272,7 @@ def run_extras():
             variants["product"] = {"error": repr(e)[:300]}
         variants["workload"] = "bunny-c2 at 128 spp, 2 steps (development size: the numbers compare libraries, nothing else)"
     out["variants"] = variants
-    out["seconds"] = round(time.time() - (deadline - 240.0), 1)
+    out["seconds"] = round(time.time() - (deadline - 200.0), 1)
     return out
 
 
