@@ -235,12 +235,12 @@ def run_extras():
     except Exception as e:   # noqa: BLE001
         out["scene_prep"] = {"error": repr(e)[:300]}
 
-    def ab_line(lib):
+    def ab_line(lib, workload="bunny-c2", spp=128):
         e = dict(env)
         if lib:
             e["PBRTGPU_LIB"] = lib
-        r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--spp", "128", "--steps", "2", "--warmup", "2",
-                            "--no-cpu-baseline", "--no-extras", "--film-hash"],
+        r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--workload", workload, "--spp", str(spp), "--steps", "2",
+                            "--warmup", "2", "--no-cpu-baseline", "--no-extras", "--film-hash"],
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=left(), env=e, cwd=REPO)
         rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
         if not rows:
@@ -251,7 +251,7 @@ def run_extras():
                 "k_path2_ms_per_step": d["roofline"].get("k_path2_ms_per_step")}
 
     variants = {}
-    libs = [(n, "ab/libpbrtgpu_%s.so" % n) for n in ("pairs", "tables2", "pairs_tables2", "pairs6", "specular")
+    libs = [(n, "ab/libpbrtgpu_%s.so" % n) for n in ("pairs", "tables2", "pairs_tables2", "specular", "pairs6")
             if os.path.exists(os.path.join(REPO, "pbrt_v2_b200", "ab", "libpbrtgpu_%s.so" % n))]
     if libs:
         try:
@@ -270,6 +270,14 @@ def run_extras():
                     variants[name] = {"error": repr(e)[:300]}
         except Exception as e:   # noqa: BLE001
             variants["product"] = {"error": repr(e)[:300]}
+        # the pair-node walk once more where rays enter nested BVHs (TransformedPrimitives): the animated config at 16 spp
+        if any(n == "pairs" for n, _ in libs) and deadline - time.time() > 60.0:
+            try:
+                a0, a1 = ab_line(None, "anim-c4", 16), ab_line("ab/libpbrtgpu_pairs.so", "anim-c4", 16)
+                variants["pairs_on_anim-c4_16spp"] = {"product": a0["value"], "pairs": a1["value"],
+                                                      "same_film_as_product": a0["film_md5"] == a1["film_md5"]}
+            except Exception as e:   # noqa: BLE001
+                variants["pairs_on_anim-c4_16spp"] = {"error": repr(e)[:300]}
         variants["workload"] = "bunny-c2 at 128 spp, 2 steps (development size: the numbers compare libraries, nothing else)"
     out["variants"] = variants
     out["seconds"] = round(time.time() - (deadline - 200.0), 1)
