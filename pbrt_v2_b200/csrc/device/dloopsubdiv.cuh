@@ -69,38 +69,42 @@ DEV int OtherVert(const Mesh &m, int f, int v0, int v1) {   // loopsubdiv.h:121-
     }
     return -1;
 }
+// (every walk around a vertex is capped at the face count: flags that do not match the links -- which the entry point
+// cannot rule out without doing the walks itself -- then give a wrong mesh, never a kernel that does not return)
 DEV int Valence(const Mesh &m, int vert) {   // SDVertex::valence, loopsubdiv.cpp:117-136
     const int start = m.start[vert];
+    const int cap = (int)m.nf;
     int f = start;
     if (!(m.vflags[vert] & VF_BOUNDARY)) {
         int nf = 1;
-        while ((f = NextFace(m, f, vert)) != start) ++nf;
+        while ((f = NextFace(m, f, vert)) != start && f != -1 && nf <= cap) ++nf;
         return nf;
     }
     int nf = 1;
-    while ((f = NextFace(m, f, vert)) != -1) ++nf;
+    while ((f = NextFace(m, f, vert)) != -1 && nf <= cap) ++nf;
     f = start;
-    while ((f = PrevFace(m, f, vert)) != -1) ++nf;
+    while ((f = PrevFace(m, f, vert)) != -1 && nf <= 2 * cap) ++nf;
     return nf + 1;
 }
 // SDVertex::oneRing (loopsubdiv.cpp:458-479) without the array: fn(k, P of the k-th ring vertex), in its order
 template <typename F> DEV void ForRing(const Mesh &m, int vert, F fn) {
     int k = 0;
+    const int cap = (int)m.nf;
     if (!(m.vflags[vert] & VF_BOUNDARY)) {
         const int start = m.start[vert];
         int face = start;
         do {
             fn(k++, GetP(m, NextVert(m, face, vert)));
             face = NextFace(m, face, vert);
-        } while (face != start);
+        } while (face != start && face != -1 && k <= cap);
     } else {
-        int face = m.start[vert], f2;
-        while ((f2 = NextFace(m, face, vert)) != -1) face = f2;
+        int face = m.start[vert], f2, guard = 0;
+        while ((f2 = NextFace(m, face, vert)) != -1 && guard++ <= cap) face = f2;
         fn(k++, GetP(m, NextVert(m, face, vert)));
         do {
             fn(k++, GetP(m, PrevVert(m, face, vert)));
             face = PrevFace(m, face, vert);
-        } while (face != -1);
+        } while (face != -1 && k <= cap + 1);
     }
 }
 DEV V3 WeightOneRing(const Mesh &m, int vert, float beta) {   // loopsubdiv.cpp:447-456
