@@ -206,7 +206,7 @@ BVHB_GLOBAL void k_decide(State s, uint32_t levelBase, uint32_t levelCount) {
         s.left[node] = 0;
         s.dim[node] = 0;
         s.mid[node] = (st + en) / 2;
-        if (np == 1) { s.kind[node] = KIND_LEAF; continue; }
+        if (np <= 1) { s.kind[node] = KIND_LEAF; continue; }   // (np == 0 cannot arise: every split leaves both sides non-empty)
         float d[3];
         for (int k = 0; k < 3; ++k) d[k] = KeyFloat(s.cbKey[6 * node + 3 + k]) - KeyFloat(s.cbKey[6 * node + k]);
         const int dim = (d[0] > d[1] && d[0] > d[2]) ? 0 : (d[1] > d[2] ? 1 : 2);   // BBox::MaximumExtent
@@ -507,6 +507,7 @@ inline int Build(const float *hostBounds, uint32_t n, uint32_t maxPrimsInNode, P
         if (!BVHB_D2H(&total, s.nodeCount, 4, stream)) return 1;
         const uint32_t nextBase = base + count;
         if (total == nextBase) break;
+        if (levelBase.size() > (size_t)n + 1) return 1;   // deeper than a chain of n nodes: cannot be a tree
         levelBase.push_back(nextBase);
         levelCount.push_back(total - nextBase);
     }
