@@ -24,8 +24,8 @@ NVDEFS    ?=
 
 # kernel experiments that are CPU-verified but not yet timed on a GPU: built next to the product library so that a GPU
 # visit (bench.py's "extras", scripts/r2_*.sh) can A/B them without compiling on the box.  Nothing loads them by default.
-VARIANTS  := $(PKG)/ab/libpbrtgpu_pairs.so $(PKG)/ab/libpbrtgpu_pairs6.so $(PKG)/ab/libpbrtgpu_specular.so \
-             $(PKG)/ab/libpbrtgpu_tables2.so $(PKG)/ab/libpbrtgpu_pairs_tables2.so
+VARIANTS  := $(PKG)/ab/libpbrtgpu_pairs.so $(PKG)/ab/libpbrtgpu_specular.so \
+             $(PKG)/ab/libpbrtgpu_tables2.so $(PKG)/ab/libpbrtgpu_pairs_tables2.so $(PKG)/ab/libpbrtgpu_kdrec.so
 
 all: $(PKG)/libpbrtgpu.so $(PKG)/libpbrthost.so $(PKG)/pbrt_b200 oracle variants
 
@@ -35,15 +35,15 @@ $(PKG)/ab/libpbrtgpu_pairs.so: $(DEVSRC) $(DEVHDR)
 	@mkdir -p $(PKG)/ab build
 	$(NVCC) $(NVFLAGS) -DPBRT_PAIR_NODES=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_pairs.log || (cat build/ptxas_pairs.log; false)
 
-# ... the same with one block fewer per SM for k_trace (80 registers instead of 72: the pair walk keeps three stack arrays)
-$(PKG)/ab/libpbrtgpu_pairs6.so: $(DEVSRC) $(DEVHDR)
-	@mkdir -p $(PKG)/ab build
-	$(NVCC) $(NVFLAGS) -DPBRT_PAIR_NODES=1 -DK_TRACE_MIN_BLOCKS=6 -shared $(DEVSRC) -o $@ 2> build/ptxas_pairs6.log || (cat build/ptxas_pairs6.log; false)
-
 # k_tables with two Fisher-Yates steps per shared-memory round trip (device/dtables.cuh)
 $(PKG)/ab/libpbrtgpu_tables2.so: $(DEVSRC) $(DEVHDR)
 	@mkdir -p $(PKG)/ab build
 	$(NVCC) $(NVFLAGS) -DPBRT_TABLES_PAIRED=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_tables2.log || (cat build/ptxas_tables2.log; false)
+
+# the measured-BRDF kd-tree as one 32-byte record per node (device/dscene.cuh, dshade.cuh)
+$(PKG)/ab/libpbrtgpu_kdrec.so: $(DEVSRC) $(DEVHDR)
+	@mkdir -p $(PKG)/ab build
+	$(NVCC) $(NVFLAGS) -DPBRT_KD_INTERLEAVED=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_kdrec.log || (cat build/ptxas_kdrec.log; false)
 
 # ... both experiments together (are their gains additive?)
 $(PKG)/ab/libpbrtgpu_pairs_tables2.so: $(DEVSRC) $(DEVHDR)

@@ -251,7 +251,7 @@ def run_extras():
                 "k_path2_ms_per_step": d["roofline"].get("k_path2_ms_per_step")}
 
     variants = {}
-    libs = [(n, "ab/libpbrtgpu_%s.so" % n) for n in ("pairs", "tables2", "pairs_tables2", "specular", "pairs6")
+    libs = [(n, "ab/libpbrtgpu_%s.so" % n) for n in ("pairs", "tables2", "kdrec", "pairs_tables2", "specular")
             if os.path.exists(os.path.join(REPO, "pbrt_v2_b200", "ab", "libpbrtgpu_%s.so" % n))]
     if libs:
         try:

@@ -18,7 +18,7 @@
 #include "dmath.cuh"
 #include "danim.cuh"
 #include "../../../include/pbrtgpu.h"
-#if defined(PBRT_PAIR_NODES) && PBRT_PAIR_NODES
+#if (defined(PBRT_PAIR_NODES) && PBRT_PAIR_NODES) || (defined(PBRT_KD_INTERLEAVED) && PBRT_KD_INTERLEAVED)
 #include <cstring>
 #include <vector>
 #endif
@@ -35,6 +35,12 @@
 // always take the reference-shaped walk, so the algorithmic byte counts do not change.
 #ifndef PBRT_PAIR_NODES
 #define PBRT_PAIR_NODES 0
+#endif
+// Round-2 experiment, OFF in the shipped kernels: the measured-BRDF kd-tree as ONE 32-byte record per node ({splitPos,
+// bits, p.xy} {p.z, v.rgb}: two 128-bit loads) instead of a node array and a sample array of 4-byte-aligned structs
+// (eight 32-bit loads per visit).  Same values, same visiting order.
+#ifndef PBRT_KD_INTERLEAVED
+#define PBRT_KD_INTERLEAVED 0
 #endif
 
 namespace dev {
@@ -56,6 +62,9 @@ struct DScene {
     const PbrtGpuLightShape *lightShapes;
     const PbrtGpuAnimated *animated;   // TransformedPrimitives (null / 0 for static scenes)
     uint32_t nNodes, nPrims, nLights, nAnimated;
+#if PBRT_KD_INTERLEAVED
+    const float4 *kdRec;          // 2 x float4 per kd node: {splitPos, bits, p.x, p.y} {p.z, v.r, v.g, v.b}
+#endif
 #if PBRT_PAIR_NODES
     const float4 *pairs;          // 4 x float4 per interior node: both children's node records ({box, ref, meta} each);
                                   // ref = the child's own pair index (interior) or its primitive offset (leaf)
@@ -256,6 +265,21 @@ DEV bool BoxTest(const float4 &n0, const float4 &n1, const Ray &ray, const V3 &i
 
 template <bool STATS> __device__ __noinline__ bool AnimatedIntersect(const DScene &sc, uint32_t index, Ray &ray, bool anyHit,
                                                                       Hit *hit, TraceStats *st);
+
+#if PBRT_KD_INTERLEAVED
+// host side: the interleaved kd records of a flattened scene
+inline void BuildKdRecords(const PbrtGpuSceneDesc *desc, std::vector<float4> *rec) {
+    rec->resize(2 * (size_t)desc->nKdNodes);
+    for (uint32_t i = 0; i < desc->nKdNodes; ++i) {
+        const PbrtGpuKdNode &n = desc->kdNodes[i];
+        const PbrtGpuBrdfSample &b = desc->kdData[i];
+        float bits;
+        memcpy(&bits, &n.bits, 4);
+        (*rec)[2 * (size_t)i] = make_float4(n.splitPos, bits, b.p[0], b.p[1]);
+        (*rec)[2 * (size_t)i + 1] = make_float4(b.p[2], b.v[0], b.v[1], b.v[2]);
+    }
+}
+#endif
 
 #if PBRT_PAIR_NODES
 // host side: the pair records of a flattened scene (scene BVH first, nested BVHs by their PbrtGpuAnimated ranges)

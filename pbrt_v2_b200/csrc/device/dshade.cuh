@@ -275,7 +275,13 @@ DEV void KdGather(const DScene &sc, const PbrtGpuMeasured &m, const V3 &p, float
         const uint32_t e = stack[--sp];
         const uint32_t nodeNum = e >> 1;
         if (!(e & 1u)) {
+#if PBRT_KD_INTERLEAVED
+            const float4 k0 = __ldg(sc.kdRec + 2 * (size_t)(m.firstNode + nodeNum));
+            PbrtGpuKdNode node;
+            node.splitPos = k0.x; node.bits = __float_as_uint(k0.y);
+#else
             const PbrtGpuKdNode node = sc.kdNodes[m.firstNode + nodeNum];
+#endif
             const int axis = node.bits & 3u;
             if (axis != 3) {
                 const uint32_t hasLeft = (node.bits >> 2) & 1u, rightChild = node.bits >> 3;
@@ -292,7 +298,15 @@ DEV void KdGather(const DScene &sc, const PbrtGpuMeasured &m, const V3 &p, float
                 continue;
             }
         }
+#if PBRT_KD_INTERLEAVED
+        PbrtGpuBrdfSample s;
+        {
+            const float4 k0 = __ldg(sc.kdRec + 2 * (size_t)(m.firstNode + nodeNum)), k1 = __ldg(sc.kdRec + 2 * (size_t)(m.firstNode + nodeNum) + 1);
+            s.p[0] = k0.z; s.p[1] = k0.w; s.p[2] = k1.x; s.v[0] = k1.y; s.v[1] = k1.z; s.v[2] = k1.w;
+        }
+#else
         const PbrtGpuBrdfSample s = sc.kdData[m.firstNode + nodeNum];
+#endif
         const float dist2 = DistanceSquared(V3(s.p[0], s.p[1], s.p[2]), p);
         if (dist2 < maxDist2) {
             const float weight = ref_expf(-100.f * dist2);
@@ -322,8 +336,19 @@ DEV float KdThirdNearest(const DScene &sc, const PbrtGpuMeasured &m, const V3 &p
         --sp;
         if (!(stD[sp] < b2)) continue;
         const uint32_t nodeNum = stN[sp];
+#if PBRT_KD_INTERLEAVED
+        PbrtGpuKdNode node;
+        PbrtGpuBrdfSample s;
+        {   // (the third-nearest search needs the positions only: p.z is the first word of the second half)
+            const float4 k0 = __ldg(sc.kdRec + 2 * (size_t)(m.firstNode + nodeNum));
+            node.splitPos = k0.x; node.bits = __float_as_uint(k0.y);
+            s.p[0] = k0.z; s.p[1] = k0.w;
+            s.p[2] = __ldg(reinterpret_cast<const float *>(sc.kdRec + 2 * (size_t)(m.firstNode + nodeNum) + 1));
+        }
+#else
         const PbrtGpuKdNode node = sc.kdNodes[m.firstNode + nodeNum];
         const PbrtGpuBrdfSample s = sc.kdData[m.firstNode + nodeNum];
+#endif
         const float d2 = DistanceSquared(V3(s.p[0], s.p[1], s.p[2]), p);
         if (d2 < b2) {
             if (d2 < b1) {

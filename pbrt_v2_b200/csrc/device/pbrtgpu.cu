@@ -1093,6 +1093,9 @@ struct PbrtGpuScene {
     DevBuf<PbrtGpuMeasured> measured;
     DevBuf<PbrtGpuKdNode> kdNodes;
     DevBuf<PbrtGpuBrdfSample> kdData;
+#if PBRT_KD_INTERLEAVED
+    DevBuf<float4> kdRec;
+#endif
     DevBuf<PbrtGpuLight> lights;
     DevBuf<PbrtGpuLightShape> lightShapes;
     DevBuf<PbrtGpuAnimated> animated;
@@ -1353,6 +1356,13 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
     CUDA_TRY(s->measured.Upload(desc->measured, desc->nMeasured));
     CUDA_TRY(s->kdNodes.Upload(desc->kdNodes, desc->nKdNodes));
     CUDA_TRY(s->kdData.Upload(desc->kdData, desc->nKdNodes));
+#if PBRT_KD_INTERLEAVED
+    {
+        std::vector<float4> rec;
+        BuildKdRecords(desc, &rec);
+        CUDA_TRY(s->kdRec.Upload(rec.data(), rec.size()));
+    }
+#endif
     CUDA_TRY(s->lights.Upload(desc->lights, desc->nLights));
     CUDA_TRY(s->lightShapes.Upload(desc->lightShapes, desc->nLightShapes));
     CUDA_TRY(s->animated.Upload(desc->animated, desc->nAnimated));
@@ -1364,6 +1374,9 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
     d.nodes = s->nodes.p; d.prims = s->prims.p; d.tris = s->tris.p; d.meshes = s->meshes.p;
 #if PBRT_PAIR_NODES
     d.pairs = s->pairs.p; d.pairOfNode = s->pairOfNode.p;
+#endif
+#if PBRT_KD_INTERLEAVED
+    d.kdRec = s->kdRec.p;
 #endif
     d.N = s->N.p; d.uv = s->uv.p; d.quadrics = s->quadrics.p; d.xforms = s->xforms.p;
     d.materials = s->materials.p; d.measured = s->measured.p; d.kdNodes = s->kdNodes.p; d.kdData = s->kdData.p;

@@ -48,6 +48,9 @@ struct HostScene {
     std::vector<float4> pairs;
     std::vector<uint32_t> pairOfNode;
 #endif
+#if PBRT_KD_INTERLEAVED
+    std::vector<float4> kdRec;
+#endif
     std::vector<uint4> tris;
     DScene d;
 };
@@ -86,6 +89,10 @@ void Pack(const PbrtGpuSceneDesc *desc, HostScene *h) {
     DScene &d = h->d;
     memset(&d, 0, sizeof(d));
     d.nodes = h->nodes.data(); d.prims = h->prims.data(); d.tris = h->tris.data(); d.meshes = desc->meshes;
+#if PBRT_KD_INTERLEAVED
+    BuildKdRecords(desc, &h->kdRec);
+    d.kdRec = h->kdRec.data();
+#endif
 #if PBRT_PAIR_NODES
     BuildNodePairs(desc, &h->pairs, &h->pairOfNode);
     d.pairs = h->pairs.data(); d.pairOfNode = h->pairOfNode.data();

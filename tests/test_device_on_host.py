@@ -156,6 +156,27 @@ def test_pair_node_walk_on_host(staged, tmp_path_factory):
     _same_film(lib, host_scene("anim-killeroos-moving", 32, 32, 4, 2, nlevels=3))   # TransformedPrimitives three deep
 
 
+def test_interleaved_kd_records_on_host(staged, tmp_path_factory):
+    """-DPBRT_KD_INTERLEAVED=1 (a round-2 kernel experiment, not in the shipped kernels): the measured-BRDF kd-tree read as
+    one 32-byte record per node.  IrregIsotropicBRDF::f and whole films over the bunny's measured material must not move."""
+    lib = _build(tmp_path_factory, "device_on_host_kdrec", ["-DPBRT_KD_INTERLEAVED=1"])
+    lib.doh_shade_test.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+    hs = host_scene("bunny", 32, 32, 4, 32)
+    n = 60000
+    rays = _rays(hs, "bunny", n, 13)
+    u = np.random.RandomState(5).rand(n, 6).astype(np.float32)
+    a, b = np.zeros((n, 36), np.float32), np.zeros((n, 36), np.float32)
+    oa.lib().oracle_shade_test.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    oa.lib().oracle_shade_test(hs.desc_ptr, rays.ctypes.data, n, u.ctypes.data, a.ctypes.data)
+    lib.doh_shade_test(hs.desc_ptr, rays.ctypes.data, n, u.ctypes.data, b.ctypes.data)
+    assert (a[:, 24:27] != 0).any(axis=1).mean() > 0.05   # BSDF values over the measured material were produced
+    same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+    assert same.all(), "columns differing: %s" % np.nonzero(~same.all(axis=0))[0].tolist()
+    _same_film(lib, host_scene("bunny", 32, 32, 8, 32))
+    _same_film(lib, host_scene("bunny", 32, 32, 8, 1, integrator="directlighting"))
+
+
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 @pytest.mark.parametrize("seed,animated", [(3, False), (4, False), (21, False), (25, False), (1000, True), (1003, True), (1010, True), (1017, True)])
 def test_random_scenes_three_way(staged, doh, seed, animated):

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 CASES = [
     ("pairs", ["tests/test_gpu_parity.py"], []),
     ("tables2", ["tests/test_gpu_parity.py"], []),
+    ("kdrec", ["tests/test_gpu_parity.py"], []),
     ("pairs_tables2", ["tests/test_gpu_parity.py"], []),
     # the specular build must still reproduce every non-specular scene, and render mirror / glass like the oracle
     ("specular", ["tests/test_gpu_parity.py", "tests/test_gpu_specular.py"],
