@@ -22,37 +22,20 @@ DEVHDR    := $(wildcard $(DEVDIR)/*.cuh) $(wildcard $(DEVDIR)/*.inc) $(wildcard 
 # -DK_TRACE_MIN_BLOCKS=8; the shipped library is built with none
 NVDEFS    ?=
 
-# kernel experiments that are CPU-verified but not yet timed on a GPU: built next to the product library so that a GPU
-# visit (bench.py's "extras", scripts/r2_*.sh) can A/B them without compiling on the box.  Nothing loads them by default.
-VARIANTS  := $(PKG)/ab/libpbrtgpu_pairs.so $(PKG)/ab/libpbrtgpu_specular.so \
-             $(PKG)/ab/libpbrtgpu_tables2.so $(PKG)/ab/libpbrtgpu_pairs_tables2.so $(PKG)/ab/libpbrtgpu_kdrec.so
+# kernel experiments, built next to the product library so that a GPU visit can A/B them without compiling on the box
+# (scripts/ab_variants.py; tests/test_zz_gpu_variants.py runs the parity suite over them).  Nothing loads them by default.
+#   make variants VARIANT_NAMES="pairs foo"   with   VARIANT_DEFS_foo := -DSOMETHING=1
+VARIANT_NAMES ?= pairs
+VARIANT_DEFS_pairs := -DPBRT_PAIR_NODES=1
+VARIANTS  := $(patsubst %,$(PKG)/ab/libpbrtgpu_%.so,$(VARIANT_NAMES))
 
 all: $(PKG)/libpbrtgpu.so $(PKG)/libpbrthost.so $(PKG)/pbrt_b200 oracle variants
 
 variants: $(VARIANTS)
 
-$(PKG)/ab/libpbrtgpu_pairs.so: $(DEVSRC) $(DEVHDR)
+$(PKG)/ab/libpbrtgpu_%.so: $(DEVSRC) $(DEVHDR)
 	@mkdir -p $(PKG)/ab build
-	$(NVCC) $(NVFLAGS) -DPBRT_PAIR_NODES=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_pairs.log || (cat build/ptxas_pairs.log; false)
-
-# k_tables with two Fisher-Yates steps per shared-memory round trip (device/dtables.cuh)
-$(PKG)/ab/libpbrtgpu_tables2.so: $(DEVSRC) $(DEVHDR)
-	@mkdir -p $(PKG)/ab build
-	$(NVCC) $(NVFLAGS) -DPBRT_TABLES_PAIRED=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_tables2.log || (cat build/ptxas_tables2.log; false)
-
-# the measured-BRDF kd-tree as one 32-byte record per node (device/dscene.cuh, dshade.cuh)
-$(PKG)/ab/libpbrtgpu_kdrec.so: $(DEVSRC) $(DEVHDR)
-	@mkdir -p $(PKG)/ab build
-	$(NVCC) $(NVFLAGS) -DPBRT_KD_INTERLEAVED=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_kdrec.log || (cat build/ptxas_kdrec.log; false)
-
-# ... both experiments together (are their gains additive?)
-$(PKG)/ab/libpbrtgpu_pairs_tables2.so: $(DEVSRC) $(DEVHDR)
-	@mkdir -p $(PKG)/ab build
-	$(NVCC) $(NVFLAGS) -DPBRT_PAIR_NODES=1 -DPBRT_TABLES_PAIRED=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_pairs_tables2.log || (cat build/ptxas_pairs_tables2.log; false)
-
-$(PKG)/ab/libpbrtgpu_specular.so: $(DEVSRC) $(DEVHDR)
-	@mkdir -p $(PKG)/ab build
-	$(NVCC) $(NVFLAGS) -DPBRT_SPECULAR=1 -shared $(DEVSRC) -o $@ 2> build/ptxas_specular.log || (cat build/ptxas_specular.log; false)
+	$(NVCC) $(NVFLAGS) $(VARIANT_DEFS_$*) -shared $(DEVSRC) -o $@ 2> build/ptxas_$*.log || (cat build/ptxas_$*.log; false)
 
 $(PKG)/libpbrtgpu.so: $(DEVSRC) $(DEVHDR)
 	@mkdir -p build

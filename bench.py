@@ -13,9 +13,8 @@ framebuffer is summed to rank 0 with one NCCL reduce; total work is fixed, so
 "scaling" is "strong".
 
 Prints ONE JSON line on rank 0 (see the keys below).  Numbers are device-timed
-(CUDA events on the launching stream), max over ranks.  At N = 1 the line also
-carries "extras": untimed side measurements taken after everything else, each in
-its own process (run_extras; --no-extras skips them).
+(CUDA events on the launching stream), max over ranks.  Side measurements (kernel
+variants, scene-preparation kernels) are NOT part of this command: scripts/ab_variants.py.
 """
 import argparse
 import ctypes as C
@@ -135,6 +134,30 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Threads the CPU arms may really use: the affinity mask, capped by the cgroup CPU quota (a leased box can show 128
+    CPUs in os.cpu_count() and still be throttled to a fraction of them: BENCH_r01 vs SCALE_r01 differed 5.8x on the same
+    binary).  Returns (threads, detail)."""
+    n_aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:   # cgroup v2
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:
+        try:   # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    n = n_aff
+    if quota is not None:
+        n = max(1, min(n_aff, int(quota + 0.5)))
+    return n, {"os_cpu_count": os.cpu_count(), "sched_affinity": n_aff, "cgroup_cpu_quota": quota, "threads_used": n}
+
+
 def reference_render_seconds(scene_path, ncores):
     """Run the unmodified reference (oracle/_ref/bin/pbrt) and return its own render-phase time
     (ProgressReporter's final '(N.Ns)', core/progressreporter.cpp:60-118) and the wall time."""
@@ -165,7 +188,7 @@ def run_reference_arm(args, rank, world):
         return
     workload = args.workload
     base, xres, yres, spp = WORKLOADS[workload]
-    threads = os.cpu_count() or 1
+    threads, thread_detail = host_threads()
     ref_bin = os.path.join(REPO, "oracle", "_ref", "bin", "pbrt")
     from pbrt_v2_b200 import scenes
     scenes.stage()
@@ -187,15 +210,17 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(secs),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(workload, world, per_pixel=False),
-        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "reference", "sample": sample},
+        # the config names what this arm RAN: the bounded sample (CPU_SAMPLE_SPP of the workload's spp), default nTasks
+        "config": workload_config(workload, world, per_pixel=False, spp_override=CPU_SAMPLE_SPP, sample_of=spp),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "reference", "sample": sample,
+                         "host": thread_detail},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(workload, world, per_pixel=True, spp_override=None):
+def workload_config(workload, world, per_pixel=True, spp_override=None, sample_of=None):
     base, xres, yres, spp = WORKLOADS[workload]
     if spp_override:
         spp = spp_override
@@ -204,84 +229,15 @@ def workload_config(workload, world, per_pixel=True, spp_override=None):
         WORKLOAD_INTEGRATOR.get(workload, "path"))) \
         if base != "synthetic" else \
         "synthetic random-triangle scene (SURVEY 8d C5), SurfaceIntegrator \"path\" (maxdepth 8)"
+    sample_note = (" (a %d-spp sample of the %d-spp workload: cost is linear in spp)" % (spp, sample_of)) if sample_of else ""
     return {
-        "workload": "%s, Sampler \"lowdiscrepancy\" %d spp, %dx%d, Accelerator \"bvh\", box filter" % (desc, spp, xres, yres),
+        "workload": "%s, Sampler \"lowdiscrepancy\" %d spp%s, %dx%d, Accelerator \"bvh\", box filter" % (
+            desc, spp, sample_note, xres, yres),
         "global_batch": xres * yres * spp, "parallelism": "tile%d" % world,
         "tasks": tasks_note(xres, yres) if per_pixel
                  else "reference default nTasks",
         "l2": "256 MiB buffer rewritten between steps (L2 flush); the per-step sample tables (64 B per camera sample, 69 GB at C2) stream through HBM",
     }
-
-
-def run_extras():
-    """Side measurements of work that is in the repo but not (yet) on the measured path, taken AFTER the timed regions, each
-    in its own process (a fault there cannot touch the line above) and with a timeout.  They cost about a minute.
-      scene_prep  pbrtgpu_bvh_build and pbrtgpu_loopsubdiv_refine against the host front end (scripts/bench_bvhbuild.py)
-      variants    the kernel-experiment libraries built by `make variants` (pbrt_v2_b200/ab/), each against the product
-                  library on the same reduced-spp workload: throughput and whether the film is byte-identical"""
-    import subprocess
-    out = {}
-    deadline = time.time() + 200.0   # all of it together: a stuck child must not cost the line above
-
-    def left():
-        return max(1.0, min(120.0, deadline - time.time()))
-    env = dict(os.environ)
-    env.setdefault("PBRTGPU_SCRATCH_GB", "16")   # the parent still holds its own scratch
-    try:
-        r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "bench_bvhbuild.py"), "--n", "2000000", "--reps", "2"],
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=left(), env=env, cwd=REPO)
-        rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
-        out["scene_prep"] = rows if rows else {"error": (r.stderr or "no output").strip()[-300:]}
-    except Exception as e:   # noqa: BLE001
-        out["scene_prep"] = {"error": repr(e)[:300]}
-
-    def ab_line(lib, workload="bunny-c2", spp=128):
-        e = dict(env)
-        if lib:
-            e["PBRTGPU_LIB"] = lib
-        r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--workload", workload, "--spp", str(spp), "--steps", "2",
-                            "--warmup", "2", "--no-cpu-baseline", "--no-extras", "--film-hash"],
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=left(), env=e, cwd=REPO)
-        rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
-        if not rows:
-            raise RuntimeError((r.stderr or "no output").strip()[-300:])
-        d = rows[-1]
-        return {"value": d["value"], "film_md5": d.get("film_md5"), "kernel_ms": d.get("kernel_ms"),
-                "k_trace_ms_per_step": d["roofline"].get("k_trace_ms_per_step"),
-                "k_path2_ms_per_step": d["roofline"].get("k_path2_ms_per_step")}
-
-    variants = {}
-    libs = [(n, "ab/libpbrtgpu_%s.so" % n) for n in ("pairs", "tables2", "kdrec", "pairs_tables2", "specular")
-            if os.path.exists(os.path.join(REPO, "pbrt_v2_b200", "ab", "libpbrtgpu_%s.so" % n))]
-    if libs:
-        try:
-            base = ab_line(None)
-            variants["product"] = base
-            for name, lib in libs:
-                if deadline - time.time() < 30.0:
-                    variants[name] = {"error": "skipped: the extras' time budget was used up"}
-                    continue
-                try:
-                    v = ab_line(lib)
-                    v["same_film_as_product"] = v["film_md5"] == base["film_md5"]
-                    v["speedup_vs_product"] = v["value"] / base["value"] if base["value"] else None
-                    variants[name] = v
-                except Exception as e:   # noqa: BLE001
-                    variants[name] = {"error": repr(e)[:300]}
-        except Exception as e:   # noqa: BLE001
-            variants["product"] = {"error": repr(e)[:300]}
-        # the pair-node walk once more where rays enter nested BVHs (TransformedPrimitives): the animated config at 16 spp
-        if any(n == "pairs" for n, _ in libs) and deadline - time.time() > 60.0:
-            try:
-                a0, a1 = ab_line(None, "anim-c4", 16), ab_line("ab/libpbrtgpu_pairs.so", "anim-c4", 16)
-                variants["pairs_on_anim-c4_16spp"] = {"product": a0["value"], "pairs": a1["value"],
-                                                      "same_film_as_product": a0["film_md5"] == a1["film_md5"]}
-            except Exception as e:   # noqa: BLE001
-                variants["pairs_on_anim-c4_16spp"] = {"error": repr(e)[:300]}
-        variants["workload"] = "bunny-c2 at 128 spp, 2 steps (development size: the numbers compare libraries, nothing else)"
-    out["variants"] = variants
-    out["seconds"] = round(time.time() - (deadline - 200.0), 1)
-    return out
 
 
 def main():
@@ -294,8 +250,11 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override spp (development only; invalidates the number)")
     ap.add_argument("--tris", type=int, default=SYNTHETIC_TRIS, help="triangle count of the synthetic workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the untimed side measurements appended under \"extras\"")
-    ap.add_argument("--film-hash", action="store_true", help="add an md5 of the last film to the line (A/B runs)")
+    ap.add_argument("--no-extras", action="store_true", help="(accepted for old scripts; side measurements now live in scripts/ab_variants.py)")
+    ap.add_argument("--film-out", default="", help="save the last film as .npy (A/B runs: scripts/ab_variants.py compares "
+                                                   "the pixels no other task splats into, bit for bit)")
+    ap.add_argument("--economy", action="store_true",
+                    help="large configs: the counting pass and the per-launch timing pass stand in for the warm-up steps")
     args = ap.parse_args()
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -349,12 +308,17 @@ def main():
 
     g2 = pb.GpuScene(hs)   # the end-to-end arm's own handle: every step re-uploads the scene into it
 
+    host_px = host_film.numpy().view(pb.PIXEL_DTYPE).reshape(yc, xc)   # the caller's (pinned) HOST pixel buffer
+
     def step_e2e():
         g2.update(hs)                              # host -> device copy of the flattened scene (the step's input)
-        g2.render_device(rd, film.data_ptr(), stream.cuda_stream)
-        reduce_film(film, world)
-        if rank == 0:
-            host_film.copy_(film, non_blocking=True)   # device -> host read of the step's result
+        if world == 1:
+            g2.render(rd, out=host_px)             # pbrtgpu_render: the host-buffer entry point (film D2H inside)
+        else:
+            g2.render_device(rd, film.data_ptr(), stream.cuda_stream)
+            reduce_film(film, world)
+            if rank == 0:
+                host_film.copy_(film, non_blocking=True)   # device -> host read of the step's result
         stream.synchronize()
 
     def barrier():
@@ -380,7 +344,8 @@ def main():
     if world > 1:
         dist.all_reduce(rl_t, op=dist.ReduceOp.MAX)
     ray_ms, tail_excl_ms, ray_launches, serial_ms = [float(x) for x in rl_t.tolist()]
-    for _ in range(max(0, args.warmup - 1)):
+    # (the two passes above are full steps of the same work: with --economy they stand in for two warm-up steps)
+    for _ in range(max(0, args.warmup - (2 if args.economy else 1))):
         flush.fill_(1)
         step_resident()
 
@@ -412,7 +377,8 @@ def main():
     clocks = sampler.summary()
 
     # ---- timed: K steps end to end (scene H2D + render + reduce + film D2H)
-    step_e2e()
+    if not args.economy:
+        step_e2e()
     barrier()
     e2e_ms = 0.0
     for _ in range(args.steps):
@@ -443,8 +409,11 @@ def main():
         # BVH traversal happens in k_trace (phase-1 wavefront) and inside k_path<2> (the RNG-driven tails); the
         # node / primitive-test counters cover both, so the time does too: k_trace's launches timed one by one in
         # the roofline pass + the tail kernel's exclusive time in that pass (it also shades, so this is conservative)
+        # Per GPU: the counters are summed over ranks, the times are one rank's (max over ranks), the peak is one GPU's.
         trace_ms = ray_ms + tail_excl_ms
-        achieved = alg_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        alg_bytes_gpu = alg_bytes / world
+        achieved = alg_bytes_gpu / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        step_achieved = alg_bytes_gpu / (total_ms / args.steps * 1e-3) / 1e9
         hbm_resident = scene_bytes > 100e6   # B200 L2: 126 MB
         line = {
             "metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -452,16 +421,21 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload, world, spp_override=spp),
             "e2e": {"value": e2e_value, "unit": "Msamples/s",
-                    "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": int(xc * yc * 16)},
+                    "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": int(xc * yc * 16),
+                    "through": "pbrtgpu_scene_update + pbrtgpu_render (host pixel buffer)" if world == 1 else
+                               "pbrtgpu_scene_update + pbrtgpu_render_device + NCCL reduce + film D2H"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "kernel": "k_trace (+ the traversals inside k_path<2>)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if peak else None,
+                "per": "GPU (algorithmic bytes of all ranks / n_gpus, over one rank's kernel time)",
+                # the same bytes over the whole timed step (tables, shading, film included): what the throughput implies
+                "step_achieved": step_achieved, "step_frac": step_achieved / peak if peak else None,
                 "traffic": K_TRACE_DRAM_BYTES_PER_LAUNCH.get(args.workload),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_sample": alg_bytes / nsamples,
-                "algorithmic_bytes_per_launch": alg_bytes / max(1.0, ray_launches),
+                "algorithmic_bytes_per_launch": alg_bytes_gpu / max(1.0, ray_launches),
                 "kernel_ms_per_launch": ray_ms / max(1.0, ray_launches),
                 "launches_per_step": ray_launches,
                 "k_trace_ms_per_step": ray_ms, "k_path2_ms_per_step": tail_excl_ms, "serial_step_ms": serial_ms,
@@ -483,22 +457,16 @@ def main():
         if spp != WORKLOADS[args.workload][3]:
             line["INVALID"] = "spp overridden to %d (development run)" % spp
         if world == 1 and not args.no_cpu_baseline and base != "synthetic" and os.path.exists(os.path.join(REPO, "oracle", "_ref", "bin", "pbrt")):
-            threads = os.cpu_count() or 1
+            threads, thread_detail = host_threads()
             v, sec, wall = cpu_reference_rate(args.workload, threads)
             line["cpu_baseline"] = {
-                "value": v, "unit": "Msamples/s", "cores": threads, "kind": "reference",
+                "value": v, "unit": "Msamples/s", "cores": threads, "kind": "reference", "host": thread_detail,
                 "sample": "%s %dx%d at %d spp (1/%d of the workload's spp; cost is linear in spp), reference binary "
                           "--ncores %d, render phase %.1f s (wall %.1f s)" % (
                               base, xres, yres, CPU_SAMPLE_SPP, max(1, WORKLOADS[args.workload][3] // CPU_SAMPLE_SPP),
                               threads, sec, wall)}
-        if args.film_hash:
-            import hashlib
-            line["film_md5"] = hashlib.md5(film.cpu().numpy().tobytes()).hexdigest()
-        if world == 1 and not args.no_extras and "INVALID" not in line:
-            try:
-                line["extras"] = run_extras()
-            except BaseException as e:   # noqa: BLE001  (nothing in there may cost the line)
-                line["extras"] = {"error": repr(e)[:300]}
+        if args.film_out:
+            np.save(args.film_out, film.cpu().numpy())
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -17,11 +17,11 @@ enum {
     BSDF_ALL = BSDF_ALL_REFLECTION | BSDF_ALL_TRANSMISSION
 };
 enum { BX_LAMBERTIAN = 0, BX_MICROFACET_BLINN = 1, BX_IRREG_ISO = 2 };
-// specular BxDFs (mirror / glass).  The code under PBRT_SPECULAR is verified on the CPU through the
-// host-compiled state machine (tests/native/device_on_host.cpp, built with -DPBRT_SPECULAR=1) but has not run on a GPU
-// yet; the shipped library is compiled without it (byte-identical kernels) and pbrtgpu_scene_create refuses the materials.
+// specular BxDFs (mirror / glass).  On since round 2 (GPU parity: tests/test_gpu_specular.py; round 1
+// carried it as the variant library ab/libpbrtgpu_specular.so, which reproduced the oracle on the B200).
+// -DPBRT_SPECULAR=0 builds the kernels without it.
 #ifndef PBRT_SPECULAR
-#define PBRT_SPECULAR 0
+#define PBRT_SPECULAR 1
 #endif
 #if PBRT_SPECULAR
 enum { BX_SPECULAR_REFLECTION = 3, BX_SPECULAR_TRANSMISSION = 4 };   // BxSet.exponent: eta_t of the dielectric, 0 = FresnelNoOp

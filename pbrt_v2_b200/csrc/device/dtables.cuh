@@ -31,7 +31,9 @@ struct BatchArgs {
     int *mti;            // [nBatch]
     float4 *ls;          // [nBatch][spp]     finished radiance (xyz) + footprint/TAIL bits (w)
     float4 *rec;         // [nBatch][spp][4]  parked bounce-3 vertices (phase 1 -> phase 2)
-    unsigned *tailCount; // [nBatch] 1 if the task parked any sample in phase 1: partition key for phase 2
+    unsigned *tailCount; // [nBatch] number of samples the task parked in phase 1 (sort key of phase 2)
+    uint32_t *tailMask;  // [nBatch][maskWords] bit s: sample s of the task's current pixel is parked (null: not kept)
+    int maskWords;       // max(1, spp / 32)
     const unsigned *order; // [nBatch] phase 2: thread i serves task order[i] (tasks with parked samples first) or null
 };
 

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(PathArgs a) {
 #define PATH_DEFER_MEASURED false
 #define PATH_ANIM ANIM
 #define PATH_INTEG 0
-#define PATH_COUNT_TAIL() atomicOr(a.b.tailCount + bi, 1u)
+#define PATH_COUNT_TAIL() (atomicAdd(a.b.tailCount + bi, 1u), a.b.tailMask ? (void)atomicOr(a.b.tailMask + (size_t)bi * a.b.maskWords + (s >> 5), 1u << (s & 31)) : (void)0)
 #include "path_body.inc"
 #undef PATH_COUNT_TAIL
 #undef PATH_FEVAL_IN
@@ -356,6 +356,8 @@ __global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(PathArgs a) {
         }
     }
 }
+
+#include "kvertex.cuh"
 
 // ------------------------------------------------------------------- wavefront
 // Phase 1 as a wavefront (the default): the same state machine, but every path lives in a pool slot
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
 #define PATH_DEFER_MEASURED true
 #define PATH_ANIM ANIM
 #define PATH_INTEG INTEG
-#define PATH_COUNT_TAIL() atomicOr(a.b.tailCount + bi, 1u)
+#define PATH_COUNT_TAIL() (atomicAdd(a.b.tailCount + bi, 1u), a.b.tailMask ? (void)atomicOr(a.b.tailMask + (size_t)bi * a.b.maskWords + (s >> 5), 1u << (s & 31)) : (void)0)
 #include "path_body.inc"
 #undef PATH_COUNT_TAIL
 #undef PATH_FEVAL_IN
@@ -1037,7 +1039,8 @@ struct Lane {
     DevBuf<uint32_t> scr, rngCur, rngNext;
     DevBuf<int> mti;
     DevBuf<float4> ls, rec;
-    DevBuf<unsigned> tailCount, tailKeysOut, orderIn, orderOut;
+    DevBuf<unsigned> tailCount, tailKeysOut, orderIn, orderOut, tailFlag, workCounter;
+    DevBuf<uint32_t> tailMask;        // [task][max(1, spp / 32)] parked-sample bits of the task's current pixel
     DevBuf<unsigned char> sortTemp;
     DevBuf<uint8_t> tgt;              // general table kernel: shuffle targets
     DevBuf<float4> pool;              // wavefront path slots (F_COUNT fields x P)
@@ -1222,6 +1225,35 @@ cudaError_t LaunchTablesGeneralAny(const BatchArgs &b, int spp, const TableLaunc
     case 3: return LaunchTablesGeneral<3>(b, spp, tl, T, tgt, stream);
     case 2: return LaunchTablesGeneral<2>(b, spp, tl, T, tgt, stream);
     default: return LaunchTablesGeneral<1>(b, spp, tl, T, tgt, stream);
+    }
+}
+
+// Development switches, read once per render CALL (never inside its batch / round / iteration loops).
+struct RenderConfig {
+    bool wavefront = true;     // PBRTGPU_WAVEFRONT=0: phase 1 as the one-warp-per-pixel megakernel k_path<1> (A/B baseline)
+    bool wavefront2 = false;   // PBRTGPU_WAVEFRONT2=1: phase 2 as a wavefront (measured slower)
+    int vertex = 3;            // PBRTGPU_VERTEX bit 0: phase 1 by k_vertex<1>, bit 1: phase 2 by k_vertex<2> + k_film
+    int tailSort = 2;          // PBRTGPU_TAIL_SORT 0: chains in task order, 2: longest chain first
+    int lockstep = 1;
+    size_t pool = (size_t)1 << 22;
+    int lanes = 0;             // 0: automatic
+    bool traceIters = false;
+    int vertexBlocksPerSM = K_VERTEX_MIN_BLOCKS;
+};
+RenderConfig ReadConfig() {
+    {
+        RenderConfig c;
+        if (const char *e = getenv("PBRTGPU_WAVEFRONT")) c.wavefront = atoi(e) != 0;
+        if (const char *e = getenv("PBRTGPU_WAVEFRONT2")) c.wavefront2 = atoi(e) != 0;
+        if (const char *e = getenv("PBRTGPU_VERTEX")) c.vertex = atoi(e);
+        if (const char *e = getenv("PBRTGPU_TAIL_SORT")) c.tailSort = atoi(e);
+        if (const char *e = getenv("PBRTGPU_LOCKSTEP")) c.lockstep = atoi(e);
+        if (const char *e = getenv("PBRTGPU_POOL")) { if (atol(e) > 0) c.pool = (size_t)atol(e); }
+        if (const char *e = getenv("PBRTGPU_LANES")) c.lanes = atoi(e);
+        if (const char *e = getenv("PBRTGPU_VERTEX_BLOCKS")) { if (atoi(e) > 0) c.vertexBlocksPerSM = atoi(e); }
+        c.traceIters = getenv("PBRTGPU_TRACE_ITERS") != nullptr;
+        if (!c.wavefront) c.wavefront2 = false;
+        return c;
     }
 }
 
@@ -1448,6 +1480,7 @@ struct LaneJob {
     int spp;
     PbrtGpuPixel *film;
     bool timing, wantCounters, timeRays;
+    RenderConfig cfg;
     TableArrays tables;      // the Sample layout, array by array
     bool pathLayout;         // ... is PathIntegrator's: the specialised table kernel applies
     // results
@@ -1482,7 +1515,6 @@ int RunLane(LaneJob &job) {
     };
     CUDA_TRY(cudaStreamWaitEvent(stream, scene->ev[2], 0));   // the film has been cleared
     CUDA_TRY(ln->tasks.Ensure(maxBatch));
-    const bool direct = rp.integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
     CUDA_TRY(ln->perm.Ensure(maxBatch * spp * (size_t)rp.lay.rowStride));
     if (!job.pathLayout) CUDA_TRY(ln->tgt.Ensure(maxBatch * spp * (size_t)job.tables.tgtPerSample + 16));
     CUDA_TRY(ln->scr.Ensure(maxBatch * SCR_STRIDE));
@@ -1490,7 +1522,7 @@ int RunLane(LaneJob &job) {
     CUDA_TRY(ln->rngNext.Ensure(maxBatch * MT_N));
     CUDA_TRY(ln->mti.Ensure(maxBatch));
     CUDA_TRY(ln->ls.Ensure(maxBatch * spp));
-    CUDA_TRY(ln->rec.Ensure(direct ? 4 : maxBatch * spp * 4));   // parked bounce-3 vertices: PathIntegrator only
+    CUDA_TRY(ln->rec.Ensure(rp.integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING ? 4 : maxBatch * spp * 4));   // parked bounce-3 vertices: PathIntegrator only
     CUDA_TRY(ln->tailCount.Ensure(maxBatch));
     CUDA_TRY(ln->tailKeysOut.Ensure(maxBatch));
     CUDA_TRY(ln->orderIn.Ensure(maxBatch));
@@ -1503,17 +1535,21 @@ int RunLane(LaneJob &job) {
     }
     size_t sortBytes = 0;
     cub::DeviceRadixSort::SortPairsDescending(nullptr, sortBytes, ln->tailCount.p, ln->tailKeysOut.p,
-                                              ln->orderIn.p, ln->orderOut.p, (int)maxBatch, 0, 1, stream);
+                                              ln->orderIn.p, ln->orderOut.p, (int)maxBatch, 0, 14, stream);
     CUDA_TRY(ln->sortTemp.Ensure(sortBytes + 16));
 
-    // phase 1 runs as a wavefront over a pool of path slots unless PBRTGPU_WAVEFRONT=0
-    bool useWavefront = true, useWavefront2 = false;   // tail wavefront: measured slower than k_path<2> (profiles/), opt-in
-    { const char *e = getenv("PBRTGPU_WAVEFRONT"); if (e) useWavefront = atoi(e) != 0; }
-    { const char *e = getenv("PBRTGPU_WAVEFRONT2"); if (e) useWavefront2 = atoi(e) != 0; }
-    if (!useWavefront) useWavefront2 = false;
-    size_t poolSize = (size_t)1 << 22;   // 4 Mi slots x 272 B = 1.1 GB (measured: +17 % over 1 Mi)
-    { const char *e = getenv("PBRTGPU_POOL"); if (e && atol(e) > 0) poolSize = (size_t)atol(e); }
+    // PathIntegrator: both phases by the vertex-synchronous kernel (k_vertex) unless PBRTGPU_VERTEX says otherwise;
+    // DirectLightingIntegrator: the wavefront (k_logic / k_eval / k_trace)
+    const RenderConfig &cfg = job.cfg;
+    const bool direct = rp.integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
+    const bool vertex1 = !direct && (cfg.vertex & 1), vertex2 = !direct && (cfg.vertex & 2);
+    const bool useWavefront = cfg.wavefront && !vertex1, useWavefront2 = cfg.wavefront2 && useWavefront && !vertex2;
+    size_t poolSize = cfg.pool;   // 4 Mi slots x 272 B = 1.1 GB (measured: +17 % over 1 Mi)
     poolSize = (poolSize + 127) / 128 * 128;
+    const int maskWords = std::max(1, spp / 32);
+    CUDA_TRY(ln->tailMask.Ensure(maxBatch * (size_t)maskWords));
+    CUDA_TRY(ln->tailFlag.Ensure(maxBatch));
+    CUDA_TRY(ln->workCounter.Ensure(4));
     int nSM = 148;
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, scene->device);
     bool hasMeasured = scene->measured.n > 0 && scene->nMeasuredMaterials > 0;
@@ -1523,7 +1559,7 @@ int RunLane(LaneJob &job) {
         CUDA_TRY(ln->counters.Ensure(C_COUNT));
         if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, C_COUNT * sizeof(unsigned)));
     }
-    const bool traceIters = getenv("PBRTGPU_TRACE_ITERS") != nullptr;   // debugging aid: queue occupancy on stderr
+    const bool traceIters = cfg.traceIters;   // debugging aid: queue occupancy on stderr
     const TableLaunch tl = job.pathLayout ? PlanTables(spp) : PlanTablesGeneral(spp, job.tables.nArrays);
     if (direct && !useWavefront) return Fail(PBRTGPU_EUNSUPPORTED, "DirectLightingIntegrator runs on the wavefront only (PBRTGPU_WAVEFRONT=0 is a PathIntegrator A/B switch)");
     uint64_t launches = 0;
@@ -1540,6 +1576,7 @@ int RunLane(LaneJob &job) {
         b.perm = ln->perm.p; b.scr = ln->scr.p; b.rngCur = ln->rngCur.p; b.rngNext = ln->rngNext.p;
         b.mti = ln->mti.p; b.ls = ln->ls.p; b.rec = ln->rec.p;
         b.tailCount = ln->tailCount.p; b.order = nullptr;
+        b.tailMask = ln->tailMask.p; b.maskWords = maskWords;
         for (int r = 0; r < rounds; ++r) {
             b.round = r;
             if (stats) CUDA_TRY(cudaEventRecord(ln->ev[0], stream));
@@ -1547,13 +1584,31 @@ int RunLane(LaneJob &job) {
             else CUDA_TRY(LaunchTablesGeneralAny(b, spp, tl, job.tables, ln->tgt.p, stream));
             if (stats) CUDA_TRY(cudaEventRecord(ln->ev[1], stream));
             CUDA_TRY(cudaMemsetAsync(ln->tailCount.p, 0, nb * sizeof(unsigned), stream));
+            CUDA_TRY(cudaMemsetAsync(ln->tailMask.p, 0, nb * (size_t)maskWords * sizeof(uint32_t), stream));
             PathArgs pa;
             pa.sc = scene->d; pa.rp = rp; pa.b = b; pa.film = film; pa.stats = scene->stats.p;
             pa.directFilm = rounds > 1 ? 1 : 0;
-            { const char *e = getenv("PBRTGPU_LOCKSTEP"); pa.lockstep = e ? atoi(e) : 1; }
+            pa.lockstep = cfg.lockstep;
+            VxArgs va;
+            va.sc = scene->d; va.rp = rp; va.b = b; va.workCounter = ln->workCounter.p;
+            va.totalSamples = (unsigned)(nb * (size_t)spp); va.sortedCount = nullptr; va.stats = scene->stats.p;
+            const int vblocks = nSM * cfg.vertexBlocksPerSM;   // persistent: every warp pulls work until none is left
             const int blocks1 = (int)((nb + 3) / 4);       // phase 1 (megakernel form): one warp per task-pixel
             const int blocks2 = (int)((nb + 127) / 128);   // phase 2: one thread per task-pixel
-            if (!useWavefront) {
+            if (vertex1) {
+                if (timeRays) CUDA_TRY(cudaEventRecord(rayEvent(), stream));
+                CUDA_TRY(cudaMemsetAsync(ln->workCounter.p, 0, sizeof(unsigned), stream));
+                if (scene->d.nAnimated) {
+                    if (wantCounters) k_vertex<1, true, true><<<vblocks, 128, 0, stream>>>(va);
+                    else k_vertex<1, false, true><<<vblocks, 128, 0, stream>>>(va);
+                } else {
+                    if (wantCounters) k_vertex<1, true, false><<<vblocks, 128, 0, stream>>>(va);
+                    else k_vertex<1, false, false><<<vblocks, 128, 0, stream>>>(va);
+                }
+                CUDA_TRY(cudaGetLastError());
+                if (timeRays) CUDA_TRY(cudaEventRecord(rayEvent(), stream));
+                launches += 1;
+            } else if (!useWavefront) {
                 if (scene->d.nAnimated) {
                     if (wantCounters) k_path<1, true, true><<<blocks1, 128, 0, stream>>>(pa);
                     else k_path<1, false, true><<<blocks1, 128, 0, stream>>>(pa);
@@ -1619,13 +1674,36 @@ int RunLane(LaneJob &job) {
                 CUDA_TRY(cudaGetLastError());
             }
             if (stats) CUDA_TRY(cudaEventRecord(ln->ev[2], stream));
-            {   // tasks with parked samples first
+            if (vertex2) {
+                // ---- phase 2, vertex-synchronous: chains handed out longest first, then the film in sample order
+                if (cfg.tailSort) {
+                    size_t tmp = ln->sortTemp.n;
+                    cub::DeviceRadixSort::SortPairsDescending(ln->sortTemp.p, tmp, ln->tailCount.p, ln->tailKeysOut.p,
+                                                              ln->orderIn.p, ln->orderOut.p, (int)nb, 0, 14, stream);
+                    va.b.order = ln->orderOut.p;
+                    va.sortedCount = ln->tailKeysOut.p;
+                }
+                CUDA_TRY(cudaMemsetAsync(ln->workCounter.p, 0, sizeof(unsigned), stream));
+                if (scene->d.nAnimated) {
+                    if (wantCounters) k_vertex<2, true, true><<<vblocks, 128, 0, stream>>>(va);
+                    else k_vertex<2, false, true><<<vblocks, 128, 0, stream>>>(va);
+                } else {
+                    if (wantCounters) k_vertex<2, true, false><<<vblocks, 128, 0, stream>>>(va);
+                    else k_vertex<2, false, false><<<vblocks, 128, 0, stream>>>(va);
+                }
+                CUDA_TRY(cudaGetLastError());
+                k_film<<<blocks2, 128, 0, stream>>>(pa);
+                CUDA_TRY(cudaGetLastError());
+                launches += 1;
+            } else if (!direct) {   // thread-per-task tails: tasks with parked samples first
+                k_tail_flags<<<(int)((nb + 255) / 256), 256, 0, stream>>>(ln->tailCount.p, ln->tailFlag.p, (int)nb);
                 size_t tmp = ln->sortTemp.n;
-                cub::DeviceRadixSort::SortPairsDescending(ln->sortTemp.p, tmp, ln->tailCount.p, ln->tailKeysOut.p,
+                cub::DeviceRadixSort::SortPairsDescending(ln->sortTemp.p, tmp, ln->tailFlag.p, ln->tailKeysOut.p,
                                                           ln->orderIn.p, ln->orderOut.p, (int)nb, 0, 1, stream);
                 pa.b.order = ln->orderOut.p;
             }
-            if (direct) {
+            if (vertex2) {
+            } else if (direct) {
                 k_film_direct<<<blocks2, 128, 0, stream>>>(pa, r + 1 < rounds ? 1 : 0);
                 CUDA_TRY(cudaGetLastError());
             } else if (!useWavefront2) {
@@ -1774,19 +1852,18 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
                 return Fail(PBRTGPU_EINVAL, "a light's four sample arrays must have the same size (light.cpp:64-68, reflection.cpp:502-506)");
     }
     const size_t perTask = (size_t)spp * ((size_t)rp.lay.rowStride * 2 + 16 + (directInteg ? 0 : 64) + (pathLayout ? 0 : tables.tgtPerSample)) +
-                           SCR_STRIDE * 4 + 2 * MT_N * 4 + 4 + sizeof(TaskRec);
+                           SCR_STRIDE * 4 + 2 * MT_N * 4 + 4 + sizeof(TaskRec) + (size_t)std::max(1, spp / 32) * 4;
     const bool wantCounters = stats && scene->collectStats == 1;
     const bool timeRays = stats && scene->collectStats == 2;
-    size_t poolSlots = (size_t)1 << 22;
-    { const char *e = getenv("PBRTGPU_POOL"); if (e && atol(e) > 0) poolSlots = (size_t)atol(e); }
+    const RenderConfig cfg = ReadConfig();
+    const size_t poolSlots = cfg.pool;
     // lanes: the kernels' register allocations fill the SMs, so lanes cannot overlap two full-size kernels; what they
     // hide is each other's low-occupancy stretches (the tail kernel, the wavefront's drain at the end of a batch).
     // Measured on C2 (bunny 1024x1024): 128 spp 1/2/3/4 lanes = 210/227/240/250 Msamples/s, 1024 spp 1/2/4 lanes =
     // 197/219/188 (more lanes = smaller batches = more, equally long, tail launches).  Default 2.
-    int nLanes = 2;
-    { const char *e = getenv("PBRTGPU_LANES"); if (e) nLanes = atoi(e); }
+    int nLanes = cfg.lanes > 0 ? cfg.lanes : 2;
     nLanes = std::max(1, std::min(nLanes, (int)PbrtGpuScene::MAX_LANES));
-    if (!getenv("PBRTGPU_LANES"))
+    if (cfg.lanes <= 0)
         while (nLanes > 1 && tasks.size() / nLanes * (size_t)spp < poolSlots) --nLanes;
     while (nLanes > 1 && tasks.size() < (size_t)nLanes * 1024) --nLanes;   // too little work to split further
     if (timeRays) nLanes = 1;   // the timed kernel must have the device to itself
@@ -1810,7 +1887,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
         LaneJob &j = jobs[l];
         j.scene = scene; j.ln = &ln; j.tasks = &tasks; j.maxBatch = maxBatch; j.laneIndex = l; j.nLanes = nLanes;
         j.rp = rp; j.spp = spp; j.film = film; j.timing = stats != nullptr; j.wantCounters = wantCounters; j.timeRays = timeRays;
-        j.tables = tables; j.pathLayout = pathLayout;
+        j.tables = tables; j.pathLayout = pathLayout; j.cfg = cfg;
     }
     {
         auto run = [](LaneJob *j) {

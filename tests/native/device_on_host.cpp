@@ -38,10 +38,12 @@ static inline void __syncwarp(unsigned = 0xffffffffu) {}
 #include "../../pbrt_v2_b200/csrc/device/dscene.cuh"
 #include "../../pbrt_v2_b200/csrc/device/dshade.cuh"
 #include "../../pbrt_v2_b200/csrc/device/dpath.cuh"
+#include "../../pbrt_v2_b200/csrc/device/dvertex.cuh"
 
 using namespace dev;
 
 namespace {
+int g_vertexForm = 0;
 struct HostScene {
     std::vector<float4> nodes, prims;
 #if PBRT_PAIR_NODES
@@ -312,6 +314,97 @@ void RunTaskH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
         }
 }
 
+// The same task through the VERTEX form of PathIntegrator::Li (dvertex.cuh: VertexA -> the three BSDF values -> VertexB ->
+// the three rays back to back), which is what the vertex-synchronous kernels (k_vertex) execute per lane.
+void RunTaskVertexH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc &rd, int taskNum, const Extent &ext,
+                    PbrtGpuPixel *film) {
+    int wx0, wx1, wy0, wy1;
+    SubWindow(ext, taskNum, rd.nTasks, &wx0, &wx1, &wy0, &wy1);
+    if (wx0 == wx1 || wy0 == wy1) return;
+    Stream rng((uint32_t)taskNum);
+    int mti = 0;
+    const int spp = rp.spp;
+    std::vector<uint16_t> rows;
+    uint32_t scrBuf[SCR_STRIDE];
+    auto rngF = [&](int k) -> float { return UIntToFloat(rng.At((size_t)(mti + k))); };
+    for (int yPos = wy0; yPos < wy1; ++yPos)
+        for (int xPos = wx0; xPos < wx1; ++xPos) {
+            TablesH(rp.lay, spp, rng, &mti, &rows, scrBuf);
+            for (int s = 0; s < spp; ++s) {
+                const uint16_t *row = rows.data() + (size_t)s * rp.lay.rowStride;
+                Ray ray;
+                const int code = CameraRay(rp, row, scrBuf, xPos, yPos, &ray);
+                Spec T(1.f), L(0.f);
+                int bounces = 0;
+                bool afterSpecular = false;
+                Hit hit;
+                TraceStats st;
+                st.nodes = st.prims = 0;
+                bool found = Traverse<false, true>(sc, ray, false, &hit, &st);
+                while (found) {
+                    VertexRandoms u;
+                    const int nLights = (int)sc.nLights;
+                    int k0 = 0;
+                    if (bounces < 3) VertexRandomsFromTables(row, scrBuf, bounces, &u);
+                    else {
+                        if (nLights > 0) {
+                            u.lnU = rngF(0); u.lsU0 = rngF(1); u.lsU1 = rngF(2);
+                            u.bsU0 = rngF(4); u.bsU1 = rngF(5); u.bsUc = rngF(6);
+                            k0 = 7;
+                        } else u.lnU = u.lsU0 = u.lsU1 = u.bsU0 = u.bsU1 = u.bsUc = 0.f;
+                        u.pU0 = rngF(k0); u.pU1 = rngF(k0 + 1); u.pUc = rngF(k0 + 2);
+                    }
+                    ShadeCtx ctx;
+                    Vertex v;
+                    VertexA<true>(sc, ray, hit, bounces, afterSpecular, u, T, L, ctx, &v, nullptr);
+                    Spec f[3] = {Spec(0.f), Spec(0.f), Spec(0.f)};
+                    for (int e = 0; e < 3; ++e) {
+#if PBRT_SPECULAR
+                        if (e == VX_PATH && v.specSampled) continue;
+#endif
+                        if (v.need[e]) f[e] = VertexEval(sc, v.material, v.evalWo, v.evalWi[e], v.evalFlags[e]);
+                    }
+                    bool rrDrawn = false;
+                    const float rrU = bounces > 3 ? rngF(k0 + 3) : 0.f;
+                    const bool cont = VertexB(f, bounces, rp.maxDepth, T, rrU, &v, &rrDrawn);
+                    if (bounces >= 3) mti += k0 + 3 + (rrDrawn ? 1 : 0);
+                    Spec Ld(0.f);
+                    if (v.ray[VX_LIGHT]) {
+                        Ray r; r.o = v.p; r.d = v.wiW[VX_LIGHT]; r.mint = v.eps; r.maxt = v.visMaxt; r.time = ray.time;
+                        Hit h;
+                        if (!Traverse<false, true>(sc, r, true, &h, &st)) Ld = Ld + v.pendS;
+                    }
+                    if (v.ray[VX_MIS]) {
+                        Ray r; r.o = v.p; r.d = v.wiW[VX_MIS]; r.mint = v.eps; r.maxt = INF_F; r.time = ray.time;
+                        Hit h;
+                        if (Traverse<false, true>(sc, r, false, &h, &st) && MisHitIsLight<true>(sc, r, h, v.lightNum)) Ld = Ld + v.pendM;
+                    }
+                    L = L + T * ((float)nLights * Ld);
+                    T = v.Tnew;
+                    if (!cont) break;
+#if PBRT_SPECULAR
+                    afterSpecular = v.specSampled;
+#endif
+                    ++bounces;
+                    ray.o = v.p; ray.d = v.wiW[VX_PATH]; ray.mint = v.eps; ray.maxt = INF_F;
+                    found = Traverse<false, true>(sc, ray, false, &hit, &st);
+                }
+                const Spec Ls = SanitizeRadiance(L);
+                float xyz[3];
+                xyz[0] = 0.412453f * Ls.r + 0.357580f * Ls.g + 0.180423f * Ls.b;
+                xyz[1] = 0.212671f * Ls.r + 0.715160f * Ls.g + 0.072169f * Ls.b;
+                xyz[2] = 0.019334f * Ls.r + 0.119193f * Ls.g + 0.950227f * Ls.b;
+                const int fy0 = yPos - ((code & LS_UP) ? 1 : 0), fy1 = yPos + ((code & LS_DOWN) ? 1 : 0);
+                const int fx0 = xPos - ((code & LS_LEFT) ? 1 : 0), fx1 = xPos + ((code & LS_RIGHT) ? 1 : 0);
+                for (int y = fy0; y <= fy1; ++y)
+                    for (int x = fx0; x <= fx1; ++x) {
+                        PbrtGpuPixel &px = film[(size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart)];
+                        px.Lxyz[0] += xyz[0]; px.Lxyz[1] += xyz[1]; px.Lxyz[2] += xyz[2]; px.weightSum += 1.f;
+                    }
+            }
+        }
+}
+
 }  // namespace
 
 extern "C" {
@@ -335,10 +428,14 @@ DOH_EXPORT int doh_render(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc 
     memset(pixels, 0, sizeof(PbrtGpuPixel) * (size_t)ext.xc * ext.yc);
     for (int t = rd->taskBegin; t < rd->taskEnd; ++t) {
         if (rd->integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING) RunTaskH<1>(hs.d, rp, *rd, t, ext, pixels);
+        else if (g_vertexForm) RunTaskVertexH(hs.d, rp, *rd, t, ext, pixels);
         else RunTaskH<0>(hs.d, rp, *rd, t, ext, pixels);
     }
     return 0;
 }
+
+// PathIntegrator renders through the vertex form (dvertex.cuh) instead of the state machine (path_body.inc)
+DOH_EXPORT void doh_set_vertex_form(int on) { g_vertexForm = on; }
 
 // k_intersect<false>'s body (device/pbrtgpu.cu) on the host: BVHAccel::Intersect + the hit's differential geometry
 DOH_EXPORT int doh_intersect(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits, int stepwise) {

@@ -104,6 +104,24 @@ def test_device_state_machine_on_host_renders_like_the_oracle(staged, doh, base,
     _same_film(doh, host_scene(base, res, res, spp, ncores, integrator=integrator, strategy=strategy))
 
 
+def test_vertex_form_on_host_renders_like_the_oracle(staged, doh):
+    """dvertex.cuh (VertexA -> the three BSDF values at one site -> VertexB -> shadow, MIS and path ray back to back): the
+    per-lane program of the vertex-synchronous kernels k_vertex<1|2>, run by one host thread for whole films -- every
+    PathIntegrator case and scene-file variant, specular materials included."""
+    from helpers import VARIANTS, EDGE_VARIANTS, SPECULAR_VARIANTS, variant_scene
+    doh.doh_set_vertex_form(1)
+    try:
+        for base, res, spp, ncores, integrator, strategy in RENDER_CASES:
+            if integrator == "path":
+                _same_film(doh, host_scene(base, res, res, spp, ncores))
+        for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS:
+            if v[6].get("integrator", "path") == "path":
+                _same_film(doh, variant_scene(v[0])[0])
+        _same_film(doh, host_scene("anim-killeroos-moving", 32, 32, 4, 2, nlevels=3))
+    finally:
+        doh.doh_set_vertex_form(0)
+
+
 def test_device_state_machine_on_host_variants(staged, doh):
     from helpers import VARIANTS, EDGE_VARIANTS, variant_scene
     for v in VARIANTS + EDGE_VARIANTS:

@@ -153,15 +153,6 @@ def test_render_variants_bit_exact_vs_oracle(staged, name):
     assert np.array_equal(px_gpu["Lxyz"][own].view(np.uint32), px_cpu["Lxyz"][own].view(np.uint32))
 
 
-def test_specular_materials_are_refused_loudly(staged):
-    """mirror / glass exist in the host front end and the oracle only: the device must say so, not approximate."""
-    from helpers import variant_scene
-    hs, _ = variant_scene("path-glass-mirror")
-    with pytest.raises(pb.PbrtGpuError) as e:
-        pb.GpuScene(hs)
-    assert "specular materials" in str(e.value)
-
-
 def test_task_sharding_is_exact(staged):
     """rendering [0,n/2) and [n/2,n) separately sums to the one-shot render (multi-GPU split)."""
     hs = host_scene("bunny", 48, 48, 8, 72)   # nTasks = 4096 > 2304 pixels: some tasks are empty

@@ -1,10 +1,6 @@
-"""GPU parity of the specular-material device code, which ships DISABLED (compile flag PBRT_SPECULAR, see
-device/dshade.cuh): these tests run only when PBRTGPU_LIB points at a library built with it, e.g.
-
-    make NVDEFS=-DPBRT_SPECULAR=1 ...   or   scripts/r2_specular.sh   (builds pbrt_v2_b200/ab/libpbrtgpu_specular.so)
-    PBRTGPU_LIB=ab/libpbrtgpu_specular.so python -m pytest tests/test_gpu_specular.py -m gpu
-
-With the shipped library they are skipped (and test_gpu_parity.py checks that it refuses the materials)."""
+"""GPU parity of the specular materials (mirror, glass: SpecularReflection / SpecularTransmission, the specularBounce
+branches of PathIntegrator::Li, path.cpp:62-63,98,114; materials/mirror.cpp:41-53, glass.cpp:41-57), in the shipped
+library since round 2."""
 import os
 
 import numpy as np
@@ -14,8 +10,7 @@ import pbrt_v2_b200 as pb
 import oracle_api as oa
 from helpers import variant_scene
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif("specular" not in os.environ.get("PBRTGPU_LIB", ""), reason="needs a PBRT_SPECULAR build (PBRTGPU_LIB)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["path-glass-mirror", "path-glass-params-mirror-floor"])

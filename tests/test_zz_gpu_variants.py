@@ -1,7 +1,7 @@
-"""The kernel-experiment libraries of `make variants` (pbrt_v2_b200/ab/) against the GPU parity suite, each in its own
-process with PBRTGPU_LIB pointing at it.  They are CPU-verified experiments that have not been timed or run on hardware
-yet and are NOT part of the product (nothing loads them by default), so their outcome is reported without deciding the
-suite: xpassed = the variant reproduces the oracle on the GPU, xfailed = it does not (yet)."""
+"""The kernel-experiment libraries of `make variants` (pbrt_v2_b200/ab/) and the product library under its development
+switches (the kernels the default path replaced), each against the GPU parity suite in its own process.  They are NOT the
+product path (nothing selects them by default), so their outcome is reported without deciding the suite: xpassed = the
+variant reproduces the oracle on the GPU, xfailed = it does not."""
 import os
 import subprocess
 import sys
@@ -12,25 +12,27 @@ import pbrt_v2_b200 as pb
 
 pytestmark = pytest.mark.gpu
 
+# (library or None = the product library, extra environment, test files)
 CASES = [
-    ("pairs", ["tests/test_gpu_parity.py"], []),
-    ("tables2", ["tests/test_gpu_parity.py"], []),
-    ("kdrec", ["tests/test_gpu_parity.py"], []),
-    ("pairs_tables2", ["tests/test_gpu_parity.py"], []),
-    # the specular build must still reproduce every non-specular scene, and render mirror / glass like the oracle
-    ("specular", ["tests/test_gpu_parity.py", "tests/test_gpu_specular.py"],
-     ["--deselect", "tests/test_gpu_parity.py::test_specular_materials_are_refused_loudly"]),
+    ("pairs", "ab/libpbrtgpu_pairs.so", {}, ["tests/test_gpu_parity.py"]),
+    # the kernels the vertex-synchronous path replaced stay selectable (A/B baselines): they must still reproduce the oracle
+    ("wavefront+k_path2", None, {"PBRTGPU_VERTEX": "0"}, ["tests/test_gpu_parity.py", "tests/test_gpu_specular.py"]),
+    ("megakernel+k_path2", None, {"PBRTGPU_VERTEX": "0", "PBRTGPU_WAVEFRONT": "0"}, ["tests/test_gpu_parity.py"]),
+    ("vertex1+k_path2", None, {"PBRTGPU_VERTEX": "1"}, ["tests/test_gpu_parity.py"]),
+    ("wavefront+vertex2", None, {"PBRTGPU_VERTEX": "2"}, ["tests/test_gpu_parity.py"]),
+    ("vertex-unsorted-chains", None, {"PBRTGPU_TAIL_SORT": "0"}, ["tests/test_gpu_parity.py"]),
 ]
 
 
-@pytest.mark.xfail(strict=False, reason="kernel experiment: CPU-verified, first hardware run; not part of the product")
-@pytest.mark.parametrize("name,files,extra", CASES, ids=[c[0] for c in CASES])
-def test_variant_library_reproduces_the_oracle(name, files, extra):
-    lib = os.path.join("ab", "libpbrtgpu_%s.so" % name)
-    if not os.path.exists(os.path.join(pb.REPO, "pbrt_v2_b200", lib)):
+@pytest.mark.xfail(strict=False, reason="kernel experiment / A-B baseline: not the product path")
+@pytest.mark.parametrize("name,lib,extra_env,files", CASES, ids=[c[0] for c in CASES])
+def test_variant_library_reproduces_the_oracle(name, lib, extra_env, files):
+    if lib and not os.path.exists(os.path.join(pb.REPO, "pbrt_v2_b200", lib)):
         pytest.skip("variant library not built (make variants)")
-    env = dict(os.environ, PBRTGPU_LIB=lib, PBRTGPU_SCRATCH_GB="16")
-    r = subprocess.run([sys.executable, "-m", "pytest"] + files + ["-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + extra,
+    env = dict(os.environ, PBRTGPU_SCRATCH_GB="16", **extra_env)
+    if lib:
+        env["PBRTGPU_LIB"] = lib
+    r = subprocess.run([sys.executable, "-m", "pytest"] + files + ["-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"],
                        cwd=pb.REPO, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     tail = "\n".join(r.stdout.splitlines()[-15:])
     print("\n[%s]\n%s" % (name, tail))
