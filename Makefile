@@ -25,8 +25,13 @@ NVDEFS    ?=
 # kernel experiments, built next to the product library so that a GPU visit can A/B them without compiling on the box
 # (scripts/ab_variants.py; tests/test_zz_gpu_variants.py runs the parity suite over them).  Nothing loads them by default.
 #   make variants VARIANT_NAMES="pairs foo"   with   VARIANT_DEFS_foo := -DSOMETHING=1
-VARIANT_NAMES ?= pairs
+VARIANT_NAMES ?= pairs top10 sstack top9_sstack
 VARIANT_DEFS_pairs := -DPBRT_PAIR_NODES=1
+# north_star kernel items as A/B variants: top 10 levels of the scene BVH staged in shared memory by a TMA bulk copy;
+# the first 32 traversal-stack entries in shared memory
+VARIANT_DEFS_top10 := -DPBRT_TOP_LEVELS=10
+VARIANT_DEFS_sstack := -DPBRT_SMEM_STACK=32
+VARIANT_DEFS_top9_sstack := -DPBRT_TOP_LEVELS=9 -DPBRT_SMEM_STACK=32
 VARIANTS  := $(patsubst %,$(PKG)/ab/libpbrtgpu_%.so,$(VARIANT_NAMES))
 
 all: $(PKG)/libpbrtgpu.so $(PKG)/libpbrthost.so $(PKG)/pbrt_b200 oracle variants
@@ -47,10 +52,10 @@ build/host/%.o: $(HOSTDIR)/%.cpp $(HOSTDIR)/scene.h $(HOSTDIR)/geom.h include/pb
 	$(CXX) $(HOSTFLAGS) -c $< -o $@
 
 $(PKG)/libpbrthost.so: $(HOSTOBJ) $(PKG)/libpbrtgpu.so
-	$(CXX) -shared $(HOSTOBJ) -o $@ -L$(PKG) -lpbrtgpu -Wl,-rpath,'$$ORIGIN' -lpthread
+	$(CXX) -shared $(HOSTOBJ) -o $@ -L$(PKG) -lpbrtgpu -Wl,-rpath,'$$ORIGIN' -lpthread -ldl
 
 $(PKG)/pbrt_b200: build/host/main.o $(PKG)/libpbrthost.so
-	$(CXX) build/host/main.o -o $@ -L$(PKG) -lpbrthost -lpbrtgpu -Wl,-rpath,'$$ORIGIN' -lpthread
+	$(CXX) build/host/main.o -o $@ -L$(PKG) -lpbrthost -lpbrtgpu -Wl,-rpath,'$$ORIGIN' -lpthread -ldl
 
 oracle:
 	$(MAKE) -C oracle all

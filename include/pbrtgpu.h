@@ -287,6 +287,25 @@ int  pbrtgpu_render(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd,
 int  pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd,
                            void *d_pixels, void *stream, PbrtGpuStats *stats);
 
+/* ---- one Render() over several GPUs (one process per GPU) ---------------------------------------------------------
+ * replaces: nothing in the reference (pbrt-v2 is single-process); it is what SURVEY 8(e) asks of the drop-in renderer.
+ * A communicator is an NCCL communicator owned by the library (libnccl.so.2 is loaded at run time: the build does not
+ * link it).  Rank 0 obtains a unique id, the host distributes its PBRTGPU_COMM_ID_BYTES to every rank by whatever means
+ * it has (the CLI uses a rendezvous file, bench.py torch.distributed), every rank then creates the communicator on ITS
+ * current device.  pbrtgpu_render_sharded renders this rank's share of [taskBegin, taskEnd) -- blocks of `shardBlock`
+ * consecutive tasks dealt round-robin to the ranks (rd->shardCount / shardIndex are overwritten from the communicator;
+ * shardBlock 0 = four rows of one-pixel tasks) -- and sums the per-rank films onto rank 0 with ONE ncclReduce (float
+ * sum over 4 floats per pixel: pixels owned by another rank contribute zeros, edge splats that cross an ownership
+ * border add up, which a gather of owned tiles would lose).  `pixels` (HOST memory) receives the whole film on rank 0;
+ * other ranks may pass NULL.                                                                                        */
+#define PBRTGPU_COMM_ID_BYTES 128
+typedef struct PbrtGpuComm PbrtGpuComm;
+int  pbrtgpu_comm_unique_id(void *id);
+int  pbrtgpu_comm_create(const void *id, int rank, int worldSize, PbrtGpuComm **out);
+void pbrtgpu_comm_destroy(PbrtGpuComm *comm);
+int  pbrtgpu_render_sharded(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, PbrtGpuComm *comm,
+                            PbrtGpuPixel *pixels, PbrtGpuStats *stats);
+
 /* replaces: BVHAccel::Intersect (bvh.cpp:403-454) over a ray batch             */
 int  pbrtgpu_intersect(PbrtGpuScene *scene, const PbrtGpuRay *rays, int n,
                        PbrtGpuHit *hits);

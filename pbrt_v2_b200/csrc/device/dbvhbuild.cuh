@@ -107,8 +107,8 @@ BVHB_GLOBAL void k_init_level(State s, uint32_t levelBase, uint32_t levelCount) 
     for (uint32_t t = BVHB_THREAD_ID; t < levelCount; t += BVHB_THREADS) {
         const uint32_t node = levelBase + t;
         for (int k = 0; k < 3; ++k) {
-            s.bbKey[6 * node + k] = s.cbKey[6 * node + k] = BVHB_KEY_POS_INF;
-            s.bbKey[6 * node + 3 + k] = s.cbKey[6 * node + 3 + k] = BVHB_KEY_NEG_INF;
+            s.bbKey[6 * (size_t)node + k] = s.cbKey[6 * (size_t)node + k] = BVHB_KEY_POS_INF;
+            s.bbKey[6 * (size_t)node + 3 + k] = s.cbKey[6 * (size_t)node + 3 + k] = BVHB_KEY_NEG_INF;
         }
         if (t == 0) *s.sahCount = 0;
     }
@@ -125,10 +125,10 @@ BVHB_GLOBAL void k_reduce(State s) {
         if (node != cur) {
             if (cur >= 0)
                 for (int k = 0; k < 3; ++k) {
-                    atomicMin(&s.bbKey[6 * cur + k], FloatKey(bl[k]));
-                    atomicMax(&s.bbKey[6 * cur + 3 + k], FloatKey(bh[k]));
-                    atomicMin(&s.cbKey[6 * cur + k], FloatKey(cl[k]));
-                    atomicMax(&s.cbKey[6 * cur + 3 + k], FloatKey(ch[k]));
+                    atomicMin(&s.bbKey[6 * (size_t)cur + k], FloatKey(bl[k]));
+                    atomicMax(&s.bbKey[6 * (size_t)cur + 3 + k], FloatKey(bh[k]));
+                    atomicMin(&s.cbKey[6 * (size_t)cur + k], FloatKey(cl[k]));
+                    atomicMax(&s.cbKey[6 * (size_t)cur + 3 + k], FloatKey(ch[k]));
                 }
             cur = node;
             for (int k = 0; k < 3; ++k) {
@@ -208,11 +208,11 @@ BVHB_GLOBAL void k_decide(State s, uint32_t levelBase, uint32_t levelCount) {
         s.mid[node] = (st + en) / 2;
         if (np <= 1) { s.kind[node] = KIND_LEAF; continue; }   // (np == 0 cannot arise: every split leaves both sides non-empty)
         float d[3];
-        for (int k = 0; k < 3; ++k) d[k] = KeyFloat(s.cbKey[6 * node + 3 + k]) - KeyFloat(s.cbKey[6 * node + k]);
+        for (int k = 0; k < 3; ++k) d[k] = KeyFloat(s.cbKey[6 * (size_t)node + 3 + k]) - KeyFloat(s.cbKey[6 * (size_t)node + k]);
         const int dim = (d[0] > d[1] && d[0] > d[2]) ? 0 : (d[1] > d[2] ? 1 : 2);   // BBox::MaximumExtent
         s.dim[node] = (uint8_t)dim;
-        if (s.cbKey[6 * node + 3 + dim] == s.cbKey[6 * node + dim] ||
-            KeyFloat(s.cbKey[6 * node + 3 + dim]) == KeyFloat(s.cbKey[6 * node + dim])) {   // bvh.cpp:239-261 (-0 == +0 too)
+        if (s.cbKey[6 * (size_t)node + 3 + dim] == s.cbKey[6 * (size_t)node + dim] ||
+            KeyFloat(s.cbKey[6 * (size_t)node + 3 + dim]) == KeyFloat(s.cbKey[6 * (size_t)node + dim])) {   // bvh.cpp:239-261 (-0 == +0 too)
             s.kind[node] = np <= s.maxPrimsInNode ? KIND_LEAF : KIND_MIDSPLIT;
             if (s.kind[node] == KIND_LEAF) s.dim[node] = 0;
             continue;
@@ -241,7 +241,7 @@ BVHB_GLOBAL void k_bucket(State s) {
         const int32_t node = s.nodeOf[i];
         if (node < 0 || s.kind[node] != KIND_SAH_PENDING) continue;
         const int dim = s.dim[node];
-        const float cmin = KeyFloat(s.cbKey[6 * node + dim]), cmax = KeyFloat(s.cbKey[6 * node + 3 + dim]);
+        const float cmin = KeyFloat(s.cbKey[6 * (size_t)node + dim]), cmax = KeyFloat(s.cbKey[6 * (size_t)node + 3 + dim]);
         const float *b = s.bounds + (size_t)s.idx[i] * 6;
         const int bk = BucketOf(Centroid(b, dim), cmin, cmax);
         const size_t slot = (size_t)s.sahSlot[node] * N_BUCKETS + bk;
@@ -260,7 +260,7 @@ BVHB_GLOBAL void k_sah(State s, uint32_t levelBase, uint32_t levelCount) {
         if (s.kind[node] != KIND_SAH_PENDING) continue;
         const uint32_t np = s.end[node] - s.start[node];
         Box bbox;
-        for (int k = 0; k < 3; ++k) { bbox.lo[k] = KeyFloat(s.bbKey[6 * node + k]); bbox.hi[k] = KeyFloat(s.bbKey[6 * node + 3 + k]); }
+        for (int k = 0; k < 3; ++k) { bbox.lo[k] = KeyFloat(s.bbKey[6 * (size_t)node + k]); bbox.hi[k] = KeyFloat(s.bbKey[6 * (size_t)node + 3 + k]); }
         const float invArea = SurfaceArea(bbox);
         float minCost = 0.f;
         uint32_t minCostSplit = 0;
@@ -302,7 +302,7 @@ BVHB_GLOBAL void k_flags(State s, uint32_t nPadded) {
         uint8_t f = 0;
         if (node >= 0 && s.kind[node] == KIND_PARTITION) {
             const int dim = s.dim[node];
-            const float cmin = KeyFloat(s.cbKey[6 * node + dim]), cmax = KeyFloat(s.cbKey[6 * node + 3 + dim]);
+            const float cmin = KeyFloat(s.cbKey[6 * (size_t)node + dim]), cmax = KeyFloat(s.cbKey[6 * (size_t)node + 3 + dim]);
             f = BucketOf(Centroid(s.bounds + (size_t)s.idx[i] * 6, dim), cmin, cmax) <= (int)s.minCostSplit[node];
         }
         s.flag[i] = f;
@@ -419,7 +419,7 @@ BVHB_GLOBAL void k_preorder(State s, uint32_t levelBase, uint32_t levelCount) {
 BVHB_GLOBAL void k_emit(State s, uint32_t nNodes, PbrtGpuBVHNode *out) {
     for (uint32_t node = BVHB_THREAD_ID; node < nNodes; node += BVHB_THREADS) {
         PbrtGpuBVHNode o;
-        for (int k = 0; k < 3; ++k) { o.bmin[k] = KeyFloat(s.bbKey[6 * node + k]); o.bmax[k] = KeyFloat(s.bbKey[6 * node + 3 + k]); }
+        for (int k = 0; k < 3; ++k) { o.bmin[k] = KeyFloat(s.bbKey[6 * (size_t)node + k]); o.bmax[k] = KeyFloat(s.bbKey[6 * (size_t)node + 3 + k]); }
         if (s.kind[node] == KIND_LEAF) {
             o.offset = s.start[node];                                   // primitivesOffset
             o.nPrimitives = (uint8_t)(s.end[node] - s.start[node]);

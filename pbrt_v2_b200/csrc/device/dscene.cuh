@@ -42,6 +42,21 @@
 #define PBRT_KD_INTERLEAVED 1
 #endif
 
+// Top of the scene BVH in shared memory (north_star: "the top of the BVH staged in shared memory via TMA").  Every ray
+// starts at the root, so the first levels are the hottest lines of the node array; a persistent kernel copies them once
+// per CTA (one cp.async.bulk = SASS UBLKCP, completion on an mbarrier) and the walk reads them with LDS instead of
+// LDG while its heap index stays inside the table.  0 = off (every node from global memory / L1).
+#ifndef PBRT_TOP_LEVELS
+#define PBRT_TOP_LEVELS 0
+#endif
+// Traversal stack in shared memory (north_star: "short per-thread traversal stacks in registers/shared"): the first
+// PBRT_SMEM_STACK entries of the walk's todo[] live in the CTA's shared memory, entry-major (entry i of thread t at
+// [i * 128 + t]: conflict-free whatever the lanes' depths are); deeper entries spill to the local array.  0 = off.
+#ifndef PBRT_SMEM_STACK
+#define PBRT_SMEM_STACK 0
+#endif
+#define PBRT_TOP_SLOTS ((1u << PBRT_TOP_LEVELS) - 1u)
+
 namespace dev {
 
 struct DScene {
@@ -61,6 +76,10 @@ struct DScene {
     const PbrtGpuLightShape *lightShapes;
     const PbrtGpuAnimated *animated;   // TransformedPrimitives (null / 0 for static scenes)
     uint32_t nNodes, nPrims, nLights, nAnimated;
+    // the top PBRT_TOP_LEVELS levels of the scene BVH once more, in HEAP order (slot h-1 holds the node with heap index h:
+    // root 1, first child 2h, second child 2h+1; slots without a node stay zero): one contiguous block that the persistent
+    // kernels copy into shared memory with a TMA bulk copy (cp.async.bulk) -- see TopNodes below
+    const float4 *topNodes;
 #if PBRT_KD_INTERLEAVED
     const float4 *kdRec;          // 2 x float4 per kd node: {splitPos, bits, p.x, p.y} {p.z, v.r, v.g, v.b}
 #endif
@@ -265,6 +284,27 @@ DEV bool BoxTest(const float4 &n0, const float4 &n1, const Ray &ray, const V3 &i
 template <bool STATS> __device__ __noinline__ bool AnimatedIntersect(const DScene &sc, uint32_t index, Ray &ray, bool anyHit,
                                                                       Hit *hit, TraceStats *st);
 
+// host side: the heap-ordered copy of the first `levels` levels of the scene BVH (2 x float4 per slot, like `nodes`)
+inline void BuildTopNodes(const PbrtGpuSceneDesc *desc, int levels, std::vector<float4> *top) {
+    const uint32_t slots = levels > 0 ? (1u << levels) - 1u : 0u;
+    top->assign(2 * (size_t)slots + 2, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (!slots || !desc->nNodes) return;
+    std::vector<uint32_t> nodeOf(slots + 1, 0xffffffffu);
+    nodeOf[1] = 0;
+    for (uint32_t h = 1; h <= slots; ++h) {
+        const uint32_t ni = nodeOf[h];
+        if (ni == 0xffffffffu) continue;
+        const PbrtGpuBVHNode &n = desc->nodes[ni];
+        const uint32_t meta = (uint32_t)n.nPrimitives | ((uint32_t)n.axis << 8);
+        float off, mf;
+        memcpy(&off, &n.offset, 4);
+        memcpy(&mf, &meta, 4);
+        (*top)[2 * (size_t)(h - 1)] = make_float4(n.bmin[0], n.bmin[1], n.bmin[2], n.bmax[0]);
+        (*top)[2 * (size_t)(h - 1) + 1] = make_float4(n.bmax[1], n.bmax[2], off, mf);
+        if (n.nPrimitives == 0 && 2 * h + 1 <= slots) { nodeOf[2 * h] = ni + 1; nodeOf[2 * h + 1] = n.offset; }
+    }
+}
+
 #if PBRT_KD_INTERLEAVED
 // host side: the interleaved kd records of a flattened scene
 inline void BuildKdRecords(const PbrtGpuSceneDesc *desc, std::vector<float4> *rec) {
@@ -413,68 +453,115 @@ DEV bool TraverseBVHPairs(const DScene &sc, uint32_t nodeBase, uint32_t primBase
 // TOP: the scene's own BVH (nodes/primitives from 0); otherwise the BVH nested in a TransformedPrimitive,
 // whose node and primitive offsets are relative to nodeBase / primBase.
 template <bool STATS, bool TOP, bool ANIM>
-DEV bool TraverseBVH(const DScene &sc, uint32_t nodeBase, uint32_t primBase, Ray &ray, bool anyHit, Hit *hit, TraceStats *st) {
+DEV bool TraverseBVH(const DScene &sc, uint32_t nodeBase, uint32_t primBase, Ray &ray, bool anyHit, Hit *hit, TraceStats *st,
+                     const float4 *smemTop = nullptr, uint32_t *smemStack = nullptr) {
 #if PBRT_PAIR_NODES
     if (!STATS) return TraverseBVHPairs<TOP, ANIM>(sc, nodeBase, primBase, ray, anyHit, hit);
+#endif
+#if PBRT_TOP_LEVELS
+    // heap index of the node to test next while it lies inside the shared-memory table, else 0; todoHeap shadows todo[]
+    uint32_t heap = (TOP && smemTop) ? 1u : 0u;
+    uint16_t todoHeap[64];
+#endif
+#if PBRT_SMEM_STACK
+    uint32_t *const todoS = smemStack;   // this thread's column: entry i at todoS[i * 128]
+#define TODO_PUSH(v) do { if (todoS && todoOffset < PBRT_SMEM_STACK) todoS[todoOffset * 128] = (v); else todo[todoOffset] = (v); ++todoOffset; } while (0)
+#define TODO_POP() ((--todoOffset, (todoS && todoOffset < PBRT_SMEM_STACK)) ? todoS[todoOffset * 128] : todo[todoOffset])
+#else
+#define TODO_PUSH(v) (todo[todoOffset++] = (v))
+#define TODO_POP() (todo[--todoOffset])
 #endif
     V3 invDir(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
     bool neg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
     uint32_t todo[64];
     uint32_t todoOffset = 0, nodeNum = 0;
     bool found = false;
+    // "while-while" form of the reference's loop (Aila & Laine 2009): the inner loop walks interior nodes until THIS ray
+    // reaches a leaf whose box it hits (or runs out of nodes); the lanes of a warp leave it one by one and reconverge
+    // behind it, so the primitive tests below run with every lane that has a leaf instead of being serialised against the
+    // other lanes' node tests.  Per ray nothing moves: same nodes, same order, same maxt at every test.
     while (true) {
-        const float4 n0 = __ldg(sc.nodes + 2 * (nodeBase + nodeNum));
-        const float4 n1 = __ldg(sc.nodes + 2 * (nodeBase + nodeNum) + 1);
-        if (STATS) st->nodes++;
-        if (BoxTest(n0, n1, ray, invDir, neg)) {
-            const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
-            const uint32_t nPrims = meta & 0xffu;
-            if (nPrims > 0) {
-                for (uint32_t i = 0; i < nPrims; ++i) {
-                    const uint32_t pi = primBase + offset + i;
-                    const float4 r0 = __ldg(sc.prims + 3 * pi);
-                    const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
-                    const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
-                    if (STATS) st->prims++;
-                    const uint32_t type = __float_as_uint(r0.w) & 0xffu;
-                    float t, b1 = 0.f, b2 = 0.f;
-                    bool h;
-                    if (type == PBRTGPU_PRIM_TRIANGLE)
-                        h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), ray, &t, &b1, &b2);
-                    else if (TOP && ANIM && type == PBRTGPU_PRIM_ANIMATED) {
-                        // TransformedPrimitive::Intersect fills the hit and shrinks ray.maxt itself
-                        if (AnimatedIntersect<STATS>(sc, __float_as_uint(r1.w), ray, anyHit, hit, st)) {
-                            if (anyHit) return true;
-                            found = true;
-                        }
-                        continue;
-                    } else
-                        h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], ray, &t, nullptr);
-                    if (h) {
-                        if (anyHit) { hit->prim = (int)pi; return true; }
-                        hit->prim = (int)pi; hit->b1 = b1; hit->b2 = b2; hit->maxtIn = ray.maxt;
-                        ray.maxt = t;   // GeometricPrimitive::Intersect, primitive.cpp:175
-                        found = true;
-                    }
-                }
-                if (todoOffset == 0) break;
-                nodeNum = todo[--todoOffset];
-            } else {
+        uint32_t leafOffset = 0, leafCount = 0;
+        bool done = false;
+        while (true) {
+            float4 n0, n1;
+#if PBRT_TOP_LEVELS
+            if (heap) { n0 = smemTop[2 * (heap - 1)]; n1 = smemTop[2 * (heap - 1) + 1]; }
+            else
+#endif
+            {
+                n0 = __ldg(sc.nodes + 2 * (nodeBase + nodeNum));
+                n1 = __ldg(sc.nodes + 2 * (nodeBase + nodeNum) + 1);
+            }
+            if (STATS) st->nodes++;
+            if (BoxTest(n0, n1, ray, invDir, neg)) {
+                const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
+                const uint32_t nPrims = meta & 0xffu;
+                if (nPrims > 0) { leafOffset = offset; leafCount = nPrims; break; }
                 const uint32_t axis = (meta >> 8) & 0xffu;
+#if PBRT_TOP_LEVELS
+                const uint32_t kids = (heap && 2 * heap + 1 <= PBRT_TOP_SLOTS) ? 2 * heap : 0u;   // heap index of the first child
+#endif
                 if (neg[axis]) {
-                    todo[todoOffset++] = nodeNum + 1;
+#if PBRT_TOP_LEVELS
+                    todoHeap[todoOffset] = (uint16_t)kids;
+                    heap = kids ? kids + 1 : 0u;
+#endif
+                    TODO_PUSH(nodeNum + 1);
                     nodeNum = offset;
                 } else {
-                    todo[todoOffset++] = offset;
+#if PBRT_TOP_LEVELS
+                    todoHeap[todoOffset] = (uint16_t)(kids ? kids + 1 : 0u);
+                    heap = kids;
+#endif
+                    TODO_PUSH(offset);
                     nodeNum = nodeNum + 1;
                 }
+            } else {
+                if (todoOffset == 0) { done = true; break; }
+                nodeNum = TODO_POP();
+#if PBRT_TOP_LEVELS
+                heap = todoHeap[todoOffset];
+#endif
             }
-        } else {
-            if (todoOffset == 0) break;
-            nodeNum = todo[--todoOffset];
         }
+        if (done) break;
+        for (uint32_t i = 0; i < leafCount; ++i) {
+            const uint32_t pi = primBase + leafOffset + i;
+            const float4 r0 = __ldg(sc.prims + 3 * pi);
+            const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
+            const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
+            if (STATS) st->prims++;
+            const uint32_t type = __float_as_uint(r0.w) & 0xffu;
+            float t, b1 = 0.f, b2 = 0.f;
+            bool h;
+            if (type == PBRTGPU_PRIM_TRIANGLE)
+                h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), ray, &t, &b1, &b2);
+            else if (TOP && ANIM && type == PBRTGPU_PRIM_ANIMATED) {
+                // TransformedPrimitive::Intersect fills the hit and shrinks ray.maxt itself
+                if (AnimatedIntersect<STATS>(sc, __float_as_uint(r1.w), ray, anyHit, hit, st)) {
+                    if (anyHit) return true;
+                    found = true;
+                }
+                continue;
+            } else
+                h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], ray, &t, nullptr);
+            if (h) {
+                if (anyHit) { hit->prim = (int)pi; return true; }
+                hit->prim = (int)pi; hit->b1 = b1; hit->b2 = b2; hit->maxtIn = ray.maxt;
+                ray.maxt = t;   // GeometricPrimitive::Intersect, primitive.cpp:175
+                found = true;
+            }
+        }
+        if (todoOffset == 0) break;
+        nodeNum = TODO_POP();
+#if PBRT_TOP_LEVELS
+        heap = todoHeap[todoOffset];
+#endif
     }
     return found;
+#undef TODO_PUSH
+#undef TODO_POP
 }
 
 // one primitive tested directly (a TransformedPrimitive around a single refined primitive: no BVH, api.cpp:1040-1041)
@@ -522,9 +609,10 @@ __device__ __noinline__ bool AnimatedIntersect(const DScene &sc, uint32_t index,
 
 // ANIM: the scene may contain TransformedPrimitives (instantiations without it carry no trace of them)
 template <bool STATS, bool ANIM>
-DEV bool Traverse(const DScene &sc, Ray &ray, bool anyHit, Hit *hit, TraceStats *st) {
+DEV bool Traverse(const DScene &sc, Ray &ray, bool anyHit, Hit *hit, TraceStats *st, const float4 *smemTop = nullptr,
+                  uint32_t *smemStack = nullptr) {
     hit->prim = -1;
-    const bool found = TraverseBVH<STATS, true, ANIM>(sc, 0u, 0u, ray, anyHit, hit, st);
+    const bool found = TraverseBVH<STATS, true, ANIM>(sc, 0u, 0u, ray, anyHit, hit, st, smemTop, smemStack);
     hit->t = ray.maxt;
     return found;
 }
@@ -545,6 +633,14 @@ struct Trav {
     uint32_t todoBase;           // stack level at which the nested walk started
     uint32_t leafNext, leafEnd;  // rest of the scene-BVH leaf that contained the TransformedPrimitive
     V3 wo, wd;                   // the world-space ray
+    uint32_t leafFirst, leafLast; // the leaf TravDescend stopped in front of (primitive range)
+#if PBRT_SMEM_STACK
+    uint32_t *sstk;              // this thread's column of the CTA's shared-memory stack (entry i at sstk[i * 128]) or null
+#endif
+#if PBRT_TOP_LEVELS
+    uint32_t heap;               // heap index of nodeNum while it lies inside the shared-memory top table, else 0
+    uint16_t todoHeap[64];
+#endif
     uint32_t todo[64];
 #if PBRT_PAIR_NODES
     // pair walk: the node to enter next (it has passed its box test) or `needRoot`; todo[] holds the refs
@@ -565,6 +661,10 @@ DEV void TravInit(Trav &t, const Ray &ray, bool anyHit) {
     t.anyHit = anyHit; t.found = false;
     t.hit.prim = -1; t.hit.b1 = t.hit.b2 = 0.f; t.hit.maxtIn = 0.f; t.hit.t = 0.f;
     t.inst = -1; t.nodeBase = t.primBase = 0; t.todoBase = 0; t.leafNext = t.leafEnd = 0;
+    t.leafFirst = t.leafLast = 0;
+#if PBRT_TOP_LEVELS
+    t.heap = 1;
+#endif
 #if PBRT_PAIR_NODES
     t.curRef = t.curMeta = 0; t.needRoot = true;
 #endif
@@ -692,104 +792,160 @@ DEV bool TravStepPairs(const DScene &sc, Trav &t) {
 }
 #endif   // PBRT_PAIR_NODES
 
-// returns true when the ray is finished (result in t.found / t.hit / t.ray.maxt)
-template <bool STATS, bool ANIM>
-DEV bool TravStep(const DScene &sc, Trav &t, TraceStats *st) {
-#if PBRT_PAIR_NODES
-    if (!STATS) return TravStepPairs<ANIM>(sc, t);
+// ---- the step-wise walk in two halves (the wavefront trace kernel's "while-while" loop) ------------------------
+// TravDescend walks interior nodes until the ray stands before a leaf whose box it hits (1), is finished (2), or has
+// used up `maxSteps` node tests (0); TravLeaf tests that leaf's primitives and pops the next node (true: finished).
+// k_trace runs the two as separate warp-wide phases: all lanes descend, reconverge, then every lane that has a leaf
+// tests it -- the primitive tests (double-precision cross products) no longer serialise against the other lanes' node
+// tests.  Per ray the sequence of node tests, primitive tests and maxt updates is BVHAccel::Intersect's, as before.
+#if PBRT_SMEM_STACK
+#define TRAV_PUSH(t, v) do { if ((t).sstk && (t).todoOffset < PBRT_SMEM_STACK) (t).sstk[(t).todoOffset * 128] = (v); else (t).todo[(t).todoOffset] = (v); ++(t).todoOffset; } while (0)
+#define TRAV_POP(t) ((--(t).todoOffset, ((t).sstk && (t).todoOffset < PBRT_SMEM_STACK)) ? (t).sstk[(t).todoOffset * 128] : (t).todo[(t).todoOffset])
+#else
+#define TRAV_PUSH(t, v) ((t).todo[(t).todoOffset++] = (v))
+#define TRAV_POP(t) ((t).todo[--(t).todoOffset])
 #endif
-    uint32_t first = 0, end = 0;
-    bool leaf = false;
-    if (ANIM && t.inst < 0 && t.leafNext < t.leafEnd) {   // back from a TransformedPrimitive: the rest of that leaf
-        first = t.leafNext; end = t.leafEnd;
-        t.leafNext = t.leafEnd = 0;
-        leaf = true;
-    } else {
-        const uint32_t ni = (ANIM ? t.nodeBase : 0u) + t.nodeNum;
-        const float4 n0 = __ldg(sc.nodes + 2 * ni);
-        const float4 n1 = __ldg(sc.nodes + 2 * ni + 1);
-        if (STATS) st->nodes++;
-        if (BoxTest(n0, n1, t.ray, t.invDir, t.neg)) {
-            const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
-            const uint32_t nPrims = meta & 0xffu;
-            if (nPrims > 0) {
-                first = (ANIM ? t.primBase : 0u) + offset;
-                end = first + nPrims;
-                leaf = true;
-            } else {
-                const uint32_t axis = (meta >> 8) & 0xffu;
-                if (t.neg[axis]) {
-                    t.todo[t.todoOffset++] = t.nodeNum + 1;
-                    t.nodeNum = offset;
-                } else {
-                    t.todo[t.todoOffset++] = offset;
-                    t.nodeNum = t.nodeNum + 1;
-                }
-                return false;
-            }
-        }
-    }
-    if (leaf) {
-        for (uint32_t pi = first; pi < end; ++pi) {
-            const float4 r0 = __ldg(sc.prims + 3 * pi);
-            const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
-            const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
-            if (STATS) st->prims++;
-            const uint32_t type = __float_as_uint(r0.w) & 0xffu;
-            float tt, b1 = 0.f, b2 = 0.f;
-            bool h;
-            if (type == PBRTGPU_PRIM_TRIANGLE)
-                h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), t.ray, &tt, &b1, &b2);
-            else if (ANIM && type == PBRTGPU_PRIM_ANIMATED) {
-                // TransformedPrimitive::Intersect(P): interpolate, go to primitive space, walk the nested BVH
-                const PbrtGpuAnimated *a = sc.animated + __float_as_uint(r1.w);
-                DXf w2p;
-                AnimInterpolate(a, t.ray.time, &w2p);
-                Ray rl;
-                ToPrimitiveSpace(w2p, t.ray, &rl);
-                if (a->nNodes == 0) {
-                    if (SinglePrimTest(sc, a->firstPrimitive, rl, t.anyHit, &t.hit)) {
-                        t.found = true;
-                        t.ray.maxt = rl.maxt;
-                        if (t.anyHit) { t.hit.t = t.ray.maxt; return true; }
-                    }
-                    continue;
-                }
-                t.wo = t.ray.o; t.wd = t.ray.d;
-                t.ray = rl;
-                TravSetRay(t);
-                t.inst = (int)__float_as_uint(r1.w);
-                t.nodeBase = a->firstNode; t.primBase = a->firstPrimitive;
-                t.todoBase = t.todoOffset;
-                t.leafNext = pi + 1; t.leafEnd = end;
-                if (t.leafNext == t.leafEnd) t.leafNext = t.leafEnd = 0;
-                t.nodeNum = 0;
-                return false;
-            } else
-                h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], t.ray, &tt, nullptr);
-            if (h) {
-                t.hit.prim = (int)pi;
-                t.found = true;
-                if (t.anyHit) { t.hit.t = t.ray.maxt; return true; }
-                t.hit.b1 = b1; t.hit.b2 = b2; t.hit.maxtIn = t.ray.maxt;
-                t.ray.maxt = tt;
-            }
-        }
-    }
-    // ---- next node from the stack
+
+// the next node from the stack; true when there is none left (the ray is finished: result in t.found / t.hit / t.ray.maxt)
+template <bool ANIM>
+DEV bool TravPop(Trav &t) {
     if (ANIM && t.inst >= 0) {
         if (t.todoOffset > t.todoBase) {
-            t.nodeNum = t.todo[--t.todoOffset];
+            t.nodeNum = TRAV_POP(t);
+#if PBRT_TOP_LEVELS
+            t.heap = 0;
+#endif
             return false;
         }
         // the nested walk is over: back to world space (r.maxt = ray.maxt, primitive.cpp:102)
         t.ray.o = t.wo; t.ray.d = t.wd;
         TravSetRay(t);
         t.inst = -1; t.nodeBase = t.primBase = 0;
-        if (t.leafNext < t.leafEnd) return false;   // the next step tests the rest of the leaf
+        if (t.leafNext < t.leafEnd) return false;   // the rest of the scene-BVH leaf comes first
     }
     if (t.todoOffset == 0) { t.hit.t = t.ray.maxt; return true; }
-    t.nodeNum = t.todo[--t.todoOffset];
+    t.nodeNum = TRAV_POP(t);
+#if PBRT_TOP_LEVELS
+    t.heap = t.todoHeap[t.todoOffset];
+#endif
+    return false;
+}
+
+template <bool STATS, bool ANIM>
+DEV int TravDescend(const DScene &sc, Trav &t, TraceStats *st, int maxSteps, const float4 *smemTop = nullptr) {
+    for (int k = 0; k < maxSteps; ++k) {
+        if (ANIM && t.inst < 0 && t.leafNext < t.leafEnd) {   // back from a TransformedPrimitive: the rest of that leaf
+            t.leafFirst = t.leafNext; t.leafLast = t.leafEnd;
+            t.leafNext = t.leafEnd = 0;
+            return 1;
+        }
+        const uint32_t ni = (ANIM ? t.nodeBase : 0u) + t.nodeNum;
+        float4 n0, n1;
+#if PBRT_TOP_LEVELS
+        if (smemTop && t.heap) { n0 = smemTop[2 * (t.heap - 1)]; n1 = smemTop[2 * (t.heap - 1) + 1]; }
+        else
+#endif
+        {
+            n0 = __ldg(sc.nodes + 2 * ni);
+            n1 = __ldg(sc.nodes + 2 * ni + 1);
+        }
+        if (STATS) st->nodes++;
+        if (BoxTest(n0, n1, t.ray, t.invDir, t.neg)) {
+            const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
+            const uint32_t nPrims = meta & 0xffu;
+            if (nPrims > 0) {
+                t.leafFirst = (ANIM ? t.primBase : 0u) + offset;
+                t.leafLast = t.leafFirst + nPrims;
+                return 1;
+            }
+            const uint32_t axis = (meta >> 8) & 0xffu;
+#if PBRT_TOP_LEVELS
+            const uint32_t kids = (t.heap && 2 * t.heap + 1 <= PBRT_TOP_SLOTS) ? 2 * t.heap : 0u;
+#endif
+            if (t.neg[axis]) {
+#if PBRT_TOP_LEVELS
+                t.todoHeap[t.todoOffset] = (uint16_t)kids;
+                t.heap = kids ? kids + 1 : 0u;
+#endif
+                TRAV_PUSH(t, t.nodeNum + 1);
+                t.nodeNum = offset;
+            } else {
+#if PBRT_TOP_LEVELS
+                t.todoHeap[t.todoOffset] = (uint16_t)(kids ? kids + 1 : 0u);
+                t.heap = kids;
+#endif
+                TRAV_PUSH(t, offset);
+                t.nodeNum = t.nodeNum + 1;
+            }
+        } else if (TravPop<ANIM>(t))
+            return 2;
+    }
+    return 0;
+}
+
+template <bool STATS, bool ANIM>
+DEV bool TravLeaf(const DScene &sc, Trav &t, TraceStats *st) {
+    const uint32_t end = t.leafLast;
+    for (uint32_t pi = t.leafFirst; pi < end; ++pi) {
+        const float4 r0 = __ldg(sc.prims + 3 * pi);
+        const float4 r1 = __ldg(sc.prims + 3 * pi + 1);
+        const float4 r2 = __ldg(sc.prims + 3 * pi + 2);
+        if (STATS) st->prims++;
+        const uint32_t type = __float_as_uint(r0.w) & 0xffu;
+        float tt, b1 = 0.f, b2 = 0.f;
+        bool h;
+        if (type == PBRTGPU_PRIM_TRIANGLE)
+            h = TriTest(V3(r0.x, r0.y, r0.z), V3(r1.x, r1.y, r1.z), V3(r2.x, r2.y, r2.z), t.ray, &tt, &b1, &b2);
+        else if (ANIM && type == PBRTGPU_PRIM_ANIMATED) {
+            // TransformedPrimitive::Intersect(P): interpolate, go to primitive space, walk the nested BVH
+            const PbrtGpuAnimated *a = sc.animated + __float_as_uint(r1.w);
+            DXf w2p;
+            AnimInterpolate(a, t.ray.time, &w2p);
+            Ray rl;
+            ToPrimitiveSpace(w2p, t.ray, &rl);
+            if (a->nNodes == 0) {
+                if (SinglePrimTest(sc, a->firstPrimitive, rl, t.anyHit, &t.hit)) {
+                    t.found = true;
+                    t.ray.maxt = rl.maxt;
+                    if (t.anyHit) { t.hit.t = t.ray.maxt; return true; }
+                }
+                continue;
+            }
+            t.wo = t.ray.o; t.wd = t.ray.d;
+            t.ray = rl;
+            TravSetRay(t);
+            t.inst = (int)__float_as_uint(r1.w);
+            t.nodeBase = a->firstNode; t.primBase = a->firstPrimitive;
+            t.todoBase = t.todoOffset;
+            t.leafNext = pi + 1; t.leafEnd = end;
+            if (t.leafNext == t.leafEnd) t.leafNext = t.leafEnd = 0;
+            t.nodeNum = 0;
+#if PBRT_TOP_LEVELS
+            t.heap = 0;
+#endif
+            return false;   // (descend into the nested BVH next)
+        } else
+            h = QuadricIntersect(sc, sc.quadrics[__float_as_uint(r1.w)], t.ray, &tt, nullptr);
+        if (h) {
+            t.hit.prim = (int)pi;
+            t.found = true;
+            if (t.anyHit) { t.hit.t = t.ray.maxt; return true; }
+            t.hit.b1 = b1; t.hit.b2 = b2; t.hit.maxtIn = t.ray.maxt;
+            t.ray.maxt = tt;
+        }
+    }
+    return TravPop<ANIM>(t);
+}
+
+// one node test (+ the leaf it leads to): the walk in single steps.  true when the ray is finished.
+template <bool STATS, bool ANIM>
+DEV bool TravStep(const DScene &sc, Trav &t, TraceStats *st) {
+#if PBRT_PAIR_NODES
+    if (!STATS) return TravStepPairs<ANIM>(sc, t);
+#endif
+    const int r = TravDescend<STATS, ANIM>(sc, t, st, 1);
+    if (r == 2) return true;
+    if (r == 1) return TravLeaf<STATS, ANIM>(sc, t, st);
     return false;
 }
 

@@ -31,6 +31,29 @@ struct VxArgs {
     DeviceStats *stats;
 };
 
+#if PBRT_TOP_LEVELS
+// One TMA bulk copy (cp.async.bulk.shared::cluster.global, SASS UBLKCP) of the heap-ordered top of the scene BVH into the
+// CTA's shared memory; completion is signalled on an mbarrier that every thread of the CTA then waits on.
+DEV void StageTopNodes(float4 *dst, uint64_t *mbar, const float4 *src) {
+    constexpr uint32_t bytes = PBRT_TOP_SLOTS * 32u;
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar), ds = (uint32_t)__cvta_generic_to_shared(dst);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(ds), "l"(src), "r"(bytes), "r"(mb) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mb) : "memory");
+}
+#endif
+
 DEV unsigned AggregatedAddV(unsigned *ctr) {   // warp-aggregated atomicAdd(ctr, 1) for the currently converged lanes
     const unsigned m = __activemask();
     const int lane = threadIdx.x & 31;
@@ -47,6 +70,20 @@ __global__ void __launch_bounds__(128, K_VERTEX_MIN_BLOCKS) k_vertex(VxArgs a) {
     const DScene &sc = a.sc;
     const RenderParams &rp = a.rp;
     const unsigned FULL = 0xffffffffu;
+#if PBRT_TOP_LEVELS
+    __shared__ __align__(128) float4 sTop[2 * PBRT_TOP_SLOTS];
+    __shared__ __align__(8) uint64_t sTopBar;
+    StageTopNodes(sTop, &sTopBar, sc.topNodes);
+    const float4 *smemTop = sTop;
+#else
+    const float4 *smemTop = nullptr;
+#endif
+#if PBRT_SMEM_STACK
+    __shared__ uint32_t sStack[PBRT_SMEM_STACK * 128];
+    uint32_t *smemStack = sStack + threadIdx.x;
+#else
+    uint32_t *smemStack = nullptr;
+#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int spp = rp.spp;
     const int nLights = (int)sc.nLights;
@@ -247,7 +284,7 @@ __global__ void __launch_bounds__(128, K_VERTEX_MIN_BLOCKS) k_vertex(VxArgs a) {
                 }
                 Hit h;
                 if (STATS) { if (r == 0) ++nShadow; else ++nClosest; }
-                const bool found = Traverse<STATS, ANIM>(sc, q, r == 0, &h, &st);   // the single traversal site
+                const bool found = Traverse<STATS, ANIM>(sc, q, r == 0, &h, &st, smemTop, smemStack);   // the single traversal site
                 if (r == 0) { if (!found) Ld = Ld + v.pendS; }   // visibility.Unoccluded(scene), Transmittance == 1
                 else if (r == 1) { if (found && MisHitIsLight<ANIM>(sc, q, h, v.lightNum)) Ld = Ld + v.pendM; }
                 else { atVertex = found; hit = h; ray.maxt = q.maxt; }

@@ -856,6 +856,12 @@ __global__ void __launch_bounds__(128) k_film_direct(PathArgs a, int advance) {
 
 // persistent ray queue consumer
 #define TRACE_CHUNK 64
+#ifndef TRACE_DESCEND_STEPS
+#define TRACE_DESCEND_STEPS 12   // node tests per lane before the warp looks at its leaves / refills
+#endif
+#ifndef TRACE_REFILL_BELOW
+#define TRACE_REFILL_BELOW 24    // refill the warp from the queue when fewer lanes than this are still walking
+#endif
 template <bool STATS, bool ANIM>
 __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(WfArgs a) {
     const DScene &sc = a.sc;
@@ -871,7 +877,20 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(WfArgs a) {
     const uint32_t *qShadow = a.q + ((size_t)setOut * K_COUNT + K_SHADOW) * P;
     const uint32_t *qMis = a.q + ((size_t)setOut * K_COUNT + K_MIS) * P;
     Trav t;
+#if PBRT_SMEM_STACK
+    __shared__ uint32_t sStack[PBRT_SMEM_STACK * 128];
+    t.sstk = sStack + threadIdx.x;
+#endif
+#if PBRT_TOP_LEVELS
+    __shared__ __align__(128) float4 sTop[2 * PBRT_TOP_SLOTS];
+    __shared__ __align__(8) uint64_t sTopBar;
+    StageTopNodes(sTop, &sTopBar, sc.topNodes);
+    const float4 *smemTop = sTop;
+#else
+    const float4 *smemTop = nullptr;
+#endif
     bool active = false;
+    bool leaf = false;        // the lane stands before a leaf (TravDescend returned 1)
     uint32_t slot = 0;
     TraceStats st;
     st.nodes = st.prims = 0;
@@ -903,7 +922,7 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(WfArgs a) {
                     ray.time = ANIM ? pool[(size_t)F_TIME * P + slot].x : 0.f;
                     TravInit(t, ray, any);
                     if (STATS) { if (any) ++nShadow; else ++nClosest; }
-                    active = true;
+                    active = true; leaf = false;
                 }
             }
             cPos = min(cEnd, cPos + (unsigned)__popc(idle));
@@ -914,14 +933,32 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(WfArgs a) {
             continue;
         }
         // walk until a good share of the warp has finished, then refill (nothing to refill with: walk on)
+#if PBRT_PAIR_NODES
         for (int it = 0; it < 64; ++it) {
-            if (active && TravStep<STATS, ANIM>(sc, t, &st)) {
+            bool fin = active && TravStep<STATS, ANIM>(sc, t, &st);
+#else
+        for (int it = 0; it < 8; ++it) {
+            // "while-while": every lane descends to its next leaf (bounded, so that finished lanes are refilled in time),
+            // the warp reconverges, then the lanes that stand before a leaf test its primitives together
+            bool fin = false;
+            if (active && !leaf) {
+                const int r = TravDescend<STATS, ANIM>(sc, t, &st, TRACE_DESCEND_STEPS, smemTop);
+                leaf = r == 1;
+                fin = r == 2;
+            }
+            __syncwarp();
+            if (active && leaf) {
+                leaf = false;
+                fin = TravLeaf<STATS, ANIM>(sc, t, &st);
+            }
+#endif
+            if (fin) {
                 pool[(size_t)F_HIT * P + slot] = make_float4(__int_as_float(t.found ? t.hit.prim : -1), t.hit.b1, t.hit.b2, t.hit.maxtIn);
                 pool[(size_t)F_RAY_D * P + slot].w = t.ray.maxt;
                 active = false;
             }
             const int nActive = __popc(__ballot_sync(FULL, active));
-            if (nActive == 0 || (more && nActive < 24)) break;
+            if (nActive == 0 || (more && nActive < TRACE_REFILL_BELOW)) break;
         }
     }
     if (STATS) {
@@ -1087,6 +1124,7 @@ struct PbrtGpuScene {
     DevBuf<float4> pairs;
     DevBuf<uint32_t> pairOfNode;
 #endif
+    DevBuf<float4> topNodes;
     DevBuf<uint4> tris;
     DevBuf<PbrtGpuMesh> meshes;
     DevBuf<float> N, uv;
@@ -1115,6 +1153,7 @@ struct PbrtGpuScene {
     int collectStats = 0;   // 1: ray/node/primitive counters, 2: per-launch timing of the traversal kernel
     int nMeasuredMaterials = 0;
     int nSpecularMaterials = 0;
+    bool valid = false;     // false while an upload is in progress or after one failed half way
 };
 
 namespace {
@@ -1232,7 +1271,11 @@ cudaError_t LaunchTablesGeneralAny(const BatchArgs &b, int spp, const TableLaunc
 struct RenderConfig {
     bool wavefront = true;     // PBRTGPU_WAVEFRONT=0: phase 1 as the one-warp-per-pixel megakernel k_path<1> (A/B baseline)
     bool wavefront2 = false;   // PBRTGPU_WAVEFRONT2=1: phase 2 as a wavefront (measured slower)
-    int vertex = 3;            // PBRTGPU_VERTEX bit 0: phase 1 by k_vertex<1>, bit 1: phase 2 by k_vertex<2> + k_film
+    // PBRTGPU_VERTEX bit 0: phase 1 by k_vertex<1>, bit 1: phase 2 by k_vertex<2> + k_film.  Measured on C2 (bunny 1024x1024,
+    // 1024 spp, one lane; profiles/r02_*): phase 1 wavefront 3.2 s vs k_vertex<1> 4.8 s (8.2 of 32 lanes active: a camera
+    // sample's 0..3 evaluations and 0..3 rays per vertex are too uneven for lock-step lanes; the wavefront compacts them),
+    // phase 2 k_path<2> 814 ms vs k_vertex<2> + k_film 567 ms.  Default: wavefront phase 1, vertex-synchronous phase 2.
+    int vertex = 2;
     int tailSort = 2;          // PBRTGPU_TAIL_SORT 0: chains in task order, 2: longest chain first
     int lockstep = 1;
     size_t pool = (size_t)1 << 22;
@@ -1284,24 +1327,106 @@ int pbrtgpu_set_device(int ordinal) {
 
 const char *pbrtgpu_last_error(void) { return g_lastError.c_str(); }
 
-// validates `desc` and copies it into the scene's device buffers (reused when large enough)
-static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
+// Everything pbrtgpu_scene_create / _update promise to answer with PBRTGPU_EINVAL / EUNSUPPORTED, checked BEFORE any device
+// buffer is touched: a failed update leaves the handle exactly as it was.  Every index the kernels follow is
+// range-checked here, so a consumer other than the in-tree host front end cannot make them read out of bounds.
+static int ValidateSceneDesc(const PbrtGpuSceneDesc *desc) {
     if (desc->nNodes == 0 || desc->nPrimitives == 0) return Fail(PBRTGPU_EINVAL, "empty scene");
+    if (!desc->nodes || !desc->primitives) return Fail(PBRTGPU_EINVAL, "null node / primitive array");
     if (desc->nMaterials > 65535 || desc->nLights > 65534) return Fail(PBRTGPU_EUNSUPPORTED, "too many materials/lights");
-    for (uint32_t i = 0; i < desc->nLights; ++i)
-        if (desc->lights[i].type == PBRTGPU_LIGHT_DIFFUSE_AREA && desc->lights[i].nShapes != 1)
-            return Fail(PBRTGPU_EUNSUPPORTED, "area lights over more than one shape are out of scope");
+    if (desc->nAnimated > 255) return Fail(PBRTGPU_EUNSUPPORTED, "more than 255 TransformedPrimitives");
+    for (uint32_t i = 0; i < desc->nLights; ++i) {
+        const PbrtGpuLight &l = desc->lights[i];
+        if (l.type == PBRTGPU_LIGHT_DIFFUSE_AREA) {
+            if (l.nShapes != 1) return Fail(PBRTGPU_EUNSUPPORTED, "area lights over more than one shape are out of scope");
+            if ((uint64_t)l.firstShape + l.nShapes > desc->nLightShapes) return Fail(PBRTGPU_EINVAL, "light shape range out of bounds");
+        }
+    }
+    for (uint32_t i = 0; i < desc->nLightShapes; ++i)
+        if (desc->lightShapes[i].index >= desc->nQuadrics) return Fail(PBRTGPU_EINVAL, "light shape index out of range");
     for (uint32_t i = 0; i < desc->nMaterials; ++i) {
         const PbrtGpuMaterial &m = desc->materials[i];
 #if !PBRT_SPECULAR
         if (m.type == PBRTGPU_MAT_MIRROR || m.type == PBRTGPU_MAT_GLASS)
-            return Fail(PBRTGPU_EUNSUPPORTED, "specular materials (mirror, glass) are restated in the oracle only: not on the device yet");
+            return Fail(PBRTGPU_EUNSUPPORTED, "specular materials (mirror, glass): this library was built with PBRT_SPECULAR=0");
 #endif
         if (m.type > PBRTGPU_MAT_GLASS) return Fail(PBRTGPU_EINVAL, "unknown material type");
         if (m.type == PBRTGPU_MAT_MATTE && m.sigma != 0.f) return Fail(PBRTGPU_EUNSUPPORTED, "Oren-Nayar (sigma != 0) is out of scope");
         if (m.type == PBRTGPU_MAT_MEASURED && (m.measured < 0 || (uint32_t)m.measured >= desc->nMeasured))
             return Fail(PBRTGPU_EINVAL, "measured material without data");
     }
+    for (uint32_t i = 0; i < desc->nMeasured; ++i) {
+        const PbrtGpuMeasured &m = desc->measured[i];
+        if ((uint64_t)m.firstNode + m.nNodes > desc->nKdNodes || m.nNodes == 0) return Fail(PBRTGPU_EINVAL, "measured kd-tree range out of bounds");
+        for (uint32_t k = 0; k < m.nNodes; ++k) {
+            const uint32_t bits = desc->kdNodes[m.firstNode + k].bits;
+            // (rightChild >= nNodes means "no right child", kdtree.h:56; a left child is the next node)
+            if ((bits & 3u) != 3u && ((bits >> 2) & 1u) && k + 1 >= m.nNodes) return Fail(PBRTGPU_EINVAL, "kd node's left child out of range");
+        }
+    }
+    for (uint32_t i = 0; i < desc->nMeshes; ++i) {
+        if (desc->meshes[i].xform >= desc->nXforms) return Fail(PBRTGPU_EINVAL, "mesh transform index out of range");
+        if ((desc->meshes[i].flags & PBRTGPU_MESH_HAS_N) && !desc->N) return Fail(PBRTGPU_EINVAL, "mesh flags N but desc.N is null");
+        if ((desc->meshes[i].flags & PBRTGPU_MESH_HAS_UV) && !desc->uv) return Fail(PBRTGPU_EINVAL, "mesh flags uv but desc.uv is null");
+    }
+    for (uint32_t i = 0; i < desc->nQuadrics; ++i)
+        if (desc->quadrics[i].xform >= desc->nXforms) return Fail(PBRTGPU_EINVAL, "quadric transform index out of range");
+    for (uint32_t i = 0; i < desc->nTriangles; ++i) {
+        const PbrtGpuTriangle &t = desc->triangles[i];
+        if (t.mesh >= desc->nMeshes) return Fail(PBRTGPU_EINVAL, "triangle mesh index out of range");
+        for (int k = 0; k < 3; ++k)
+            if (t.v[k] >= desc->nVertices) return Fail(PBRTGPU_EINVAL, "vertex index out of range");
+    }
+    std::vector<uint8_t> nested(desc->nPrimitives, 0);
+    std::vector<uint32_t> nodeBase(desc->nNodes, 0u), nodeEnd(desc->nNodes, 0u), primBase(desc->nNodes, 0u), primEnd(desc->nNodes, 0u);
+    uint32_t topNodes = desc->nNodes, topPrims = desc->nPrimitives;
+    for (uint32_t k = 0; k < desc->nAnimated; ++k) {
+        const PbrtGpuAnimated &a = desc->animated[k];
+        if ((uint64_t)a.firstPrimitive + a.nPrimitives > desc->nPrimitives || (uint64_t)a.firstNode + a.nNodes > desc->nNodes ||
+            a.nPrimitives == 0 || (a.nNodes == 0 && a.nPrimitives != 1))
+            return Fail(PBRTGPU_EINVAL, "TransformedPrimitive range out of bounds");
+        for (uint32_t i = 0; i < a.nPrimitives; ++i) nested[a.firstPrimitive + i] = 1;
+        for (uint32_t i = 0; i < a.nNodes; ++i) {
+            nodeBase[a.firstNode + i] = a.firstNode; nodeEnd[a.firstNode + i] = a.firstNode + a.nNodes;
+            primBase[a.firstNode + i] = a.firstPrimitive; primEnd[a.firstNode + i] = a.firstPrimitive + a.nPrimitives;
+        }
+        if (a.nNodes) topNodes = std::min(topNodes, a.firstNode);
+        topPrims = std::min(topPrims, a.firstPrimitive);
+    }
+    for (uint32_t i = 0; i < topNodes; ++i) { nodeEnd[i] = topNodes; primEnd[i] = topPrims; }
+    for (uint32_t i = 0; i < desc->nNodes; ++i) {   // child / primitive offsets are relative to the BVH the node belongs to
+        const PbrtGpuBVHNode &n = desc->nodes[i];
+        if (nodeEnd[i] == 0) continue;   // (a node outside every BVH range is never reached)
+        if (n.nPrimitives) {
+            if ((uint64_t)primBase[i] + n.offset + n.nPrimitives > primEnd[i]) return Fail(PBRTGPU_EINVAL, "BVH leaf's primitive range out of bounds");
+        } else {
+            if ((uint64_t)nodeBase[i] + n.offset >= nodeEnd[i] || i + 1 >= nodeEnd[i]) return Fail(PBRTGPU_EINVAL, "BVH child offset out of bounds");
+            if (n.axis > 2) return Fail(PBRTGPU_EINVAL, "BVH split axis out of range");
+        }
+    }
+    for (uint32_t i = 0; i < desc->nPrimitives; ++i) {
+        const PbrtGpuPrimitive &p = desc->primitives[i];
+        if (p.type == PBRTGPU_PRIM_ANIMATED) {
+            if (p.index >= desc->nAnimated) return Fail(PBRTGPU_EINVAL, "animated index out of range");
+            if (nested[i]) return Fail(PBRTGPU_EUNSUPPORTED, "nested TransformedPrimitives are out of scope");
+            continue;
+        }
+        if (p.type > PBRTGPU_PRIM_ANIMATED) return Fail(PBRTGPU_EINVAL, "unknown primitive type");
+        if (p.material < 0 || (uint32_t)p.material >= desc->nMaterials) return Fail(PBRTGPU_EINVAL, "primitive without material");
+        if (p.areaLight < -1 || p.areaLight >= (int)desc->nLights) return Fail(PBRTGPU_EINVAL, "primitive's area light out of range");
+        if (p.type == PBRTGPU_PRIM_TRIANGLE) {
+            if (p.index >= desc->nTriangles) return Fail(PBRTGPU_EINVAL, "triangle index out of range");
+        } else if (p.index >= desc->nQuadrics) return Fail(PBRTGPU_EINVAL, "quadric index out of range");
+    }
+    return PBRTGPU_OK;
+}
+
+// copies a validated `desc` into the scene's device buffers (reused when large enough).  A CUDA failure half way leaves the
+// handle marked invalid (render / intersect refuse it) until a later update succeeds.
+static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
+    int vrc = ValidateSceneDesc(desc);
+    if (vrc != PBRTGPU_OK) return vrc;
+    s->valid = false;
 
     // nodes: 32-byte LinearBVHNode -> two float4 (bit copy; the byte pair nPrimitives/axis lands in .w)
     {
@@ -1317,6 +1442,11 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
         }
         CUDA_TRY(s->nodes.Upload(h.data(), h.size()));
     }
+    {
+        std::vector<float4> top;
+        BuildTopNodes(desc, PBRT_TOP_LEVELS, &top);
+        CUDA_TRY(s->topNodes.Upload(top.data(), top.size()));
+    }
 #if PBRT_PAIR_NODES
     {
         std::vector<float4> pairs;
@@ -1331,20 +1461,14 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
         std::vector<float4> h(3 * (size_t)desc->nPrimitives);
         // which TransformedPrimitive (if any) owns each nested primitive
         std::vector<int> owner(desc->nPrimitives, -1);
-        if (desc->nAnimated > 255) return Fail(PBRTGPU_EUNSUPPORTED, "more than 255 TransformedPrimitives");
         for (uint32_t k = 0; k < desc->nAnimated; ++k) {
             const PbrtGpuAnimated &a = desc->animated[k];
-            if ((uint64_t)a.firstPrimitive + a.nPrimitives > desc->nPrimitives || (uint64_t)a.firstNode + a.nNodes > desc->nNodes ||
-                a.nPrimitives == 0 || (a.nNodes == 0 && a.nPrimitives != 1))
-                return Fail(PBRTGPU_EINVAL, "TransformedPrimitive range out of bounds");
             for (uint32_t i = 0; i < a.nPrimitives; ++i) owner[a.firstPrimitive + i] = (int)k;
         }
         for (uint32_t i = 0; i < desc->nPrimitives; ++i) {
             const PbrtGpuPrimitive &p = desc->primitives[i];
             float v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (p.type == PBRTGPU_PRIM_ANIMATED) {
-                if (p.index >= desc->nAnimated) return Fail(PBRTGPU_EINVAL, "animated index out of range");
-                if (owner[i] >= 0) return Fail(PBRTGPU_EUNSUPPORTED, "nested TransformedPrimitives are out of scope");
                 uint32_t w0 = p.type, w1 = p.index;
                 float f0, f1;
                 memcpy(&f0, &w0, 4); memcpy(&f1, &w1, 4);
@@ -1353,16 +1477,10 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
                 h[3 * i + 2] = make_float4(0, 0, 0, 0);
                 continue;
             }
-            if (p.type > PBRTGPU_PRIM_ANIMATED) return Fail(PBRTGPU_EINVAL, "unknown primitive type");
-            if (p.material < 0 || (uint32_t)p.material >= desc->nMaterials) return Fail(PBRTGPU_EINVAL, "primitive without material");
             if (p.type == PBRTGPU_PRIM_TRIANGLE) {
-                if (p.index >= desc->nTriangles) return Fail(PBRTGPU_EINVAL, "triangle index out of range");
                 const PbrtGpuTriangle &t = desc->triangles[p.index];
-                for (int k = 0; k < 3; ++k) {
-                    if (t.v[k] >= desc->nVertices) return Fail(PBRTGPU_EINVAL, "vertex index out of range");
-                    memcpy(v + 3 * k, desc->P + 3 * (size_t)t.v[k], 12);
-                }
-            } else if (p.index >= desc->nQuadrics) return Fail(PBRTGPU_EINVAL, "quadric index out of range");
+                for (int k = 0; k < 3; ++k) memcpy(v + 3 * k, desc->P + 3 * (size_t)t.v[k], 12);
+            }
             uint32_t w0 = p.type | ((uint32_t)(owner[i] + 1) << 8), w1 = p.index;
             uint32_t w2 = (uint32_t)p.material | ((uint32_t)(p.areaLight + 1) << 16);
             float f0, f1, f2;
@@ -1398,12 +1516,9 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
     CUDA_TRY(s->lights.Upload(desc->lights, desc->nLights));
     CUDA_TRY(s->lightShapes.Upload(desc->lightShapes, desc->nLightShapes));
     CUDA_TRY(s->animated.Upload(desc->animated, desc->nAnimated));
-    for (uint32_t i = 0; i < desc->nMeshes; ++i) {
-        if ((desc->meshes[i].flags & PBRTGPU_MESH_HAS_N) && !desc->N) return Fail(PBRTGPU_EINVAL, "mesh flags N but desc.N is null");
-        if ((desc->meshes[i].flags & PBRTGPU_MESH_HAS_UV) && !desc->uv) return Fail(PBRTGPU_EINVAL, "mesh flags uv but desc.uv is null");
-    }
     DScene &d = s->d;
     d.nodes = s->nodes.p; d.prims = s->prims.p; d.tris = s->tris.p; d.meshes = s->meshes.p;
+    d.topNodes = s->topNodes.p;
 #if PBRT_PAIR_NODES
     d.pairs = s->pairs.p; d.pairOfNode = s->pairOfNode.p;
 #endif
@@ -1420,6 +1535,7 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
         if (desc->materials[i].type == PBRTGPU_MAT_MEASURED) s->nMeasuredMaterials++;
         if (desc->materials[i].type == PBRTGPU_MAT_MIRROR || desc->materials[i].type == PBRTGPU_MAT_GLASS) s->nSpecularMaterials++;
     }
+    s->valid = true;
     return PBRTGPU_OK;
 }
 
@@ -1791,6 +1907,7 @@ extern "C" {
 int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void *d_pixels, void *streamv,
                           PbrtGpuStats *stats) {
     if (!scene || !rd || !d_pixels) return Fail(PBRTGPU_EINVAL, "null argument");
+    if (!scene->valid) return Fail(PBRTGPU_EINVAL, "the scene handle is invalid: its last pbrtgpu_scene_update failed on the device");
     int rc = ValidateRenderDesc(*rd);
     if (rc != PBRTGPU_OK) return rc;
     cudaStream_t stream = (cudaStream_t)streamv;
@@ -1945,8 +2062,38 @@ int pbrtgpu_render(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, PbrtGpuPixe
     return PBRTGPU_OK;
 }
 
+// (comm.cu)
+int PbrtGpuCommReduceToRoot(PbrtGpuComm *c, float *buf, size_t count, cudaStream_t stream);
+int PbrtGpuCommRank(const PbrtGpuComm *c);
+int PbrtGpuCommWorld(const PbrtGpuComm *c);
+
+int pbrtgpu_render_sharded(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rdIn, PbrtGpuComm *comm, PbrtGpuPixel *pixels,
+                           PbrtGpuStats *stats) {
+    if (!scene || !rdIn || !comm) return Fail(PBRTGPU_EINVAL, "null argument");
+    const int rank = PbrtGpuCommRank(comm), world = PbrtGpuCommWorld(comm);
+    if (rank == 0 && !pixels) return Fail(PBRTGPU_EINVAL, "rank 0 needs a pixel buffer");
+    PbrtGpuRenderDesc rd = *rdIn;
+    rd.shardCount = world; rd.shardIndex = rank;
+    if (rd.shardBlock <= 0) rd.shardBlock = std::max(1, 4 * rd.xResolution);
+    int rc = ValidateRenderDesc(rd);
+    if (rc != PBRTGPU_OK) return rc;
+    const FilmExtent ext = ComputeExtent(rd);
+    const size_t nFilm = (size_t)ext.xPixelCount * ext.yPixelCount;
+    CUDA_TRY(scene->film.Ensure(nFilm));
+    PbrtGpuStats local;
+    rc = pbrtgpu_render_device(scene, &rd, scene->film.p, nullptr, stats ? stats : &local);
+    if (rc != PBRTGPU_OK) return rc;
+    // the exchange step: one reduce of the 16 B/pixel film to rank 0 (its time is part of the caller's e2e, not of renderMs)
+    rc = PbrtGpuCommReduceToRoot(comm, reinterpret_cast<float *>(scene->film.p), nFilm * 4, nullptr);
+    if (rc != PBRTGPU_OK) return rc;
+    if (rank == 0) CUDA_TRY(cudaMemcpy(pixels, scene->film.p, nFilm * sizeof(PbrtGpuPixel), cudaMemcpyDeviceToHost));
+    else CUDA_TRY(cudaStreamSynchronize(nullptr));
+    return PBRTGPU_OK;
+}
+
 int pbrtgpu_intersect(PbrtGpuScene *scene, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits) {
     if (!scene || (!rays && n) || (!hits && n) || n < 0) return Fail(PBRTGPU_EINVAL, "bad argument");
+    if (!scene->valid) return Fail(PBRTGPU_EINVAL, "the scene handle is invalid");
     if (n == 0) return PBRTGPU_OK;
     CUDA_TRY(scene->rays.Upload(rays, n));
     CUDA_TRY(scene->hits.Ensure(n));
@@ -1958,6 +2105,7 @@ int pbrtgpu_intersect(PbrtGpuScene *scene, const PbrtGpuRay *rays, int n, PbrtGp
 
 int pbrtgpu_intersect_p(PbrtGpuScene *scene, const PbrtGpuRay *rays, int n, uint8_t *occluded) {
     if (!scene || (!rays && n) || (!occluded && n) || n < 0) return Fail(PBRTGPU_EINVAL, "bad argument");
+    if (!scene->valid) return Fail(PBRTGPU_EINVAL, "the scene handle is invalid");
     if (n == 0) return PBRTGPU_OK;
     CUDA_TRY(scene->rays.Upload(rays, n));
     CUDA_TRY(scene->occ.Ensure(n));

@@ -413,7 +413,7 @@ bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
     if (FilmName != "image") return Fail("film \"" + FilmName + "\" unknown");
     std::string filename = FilmParams.FindOneString("filename", "");
     if (!opt.imageFile.empty() && filename.empty()) filename = opt.imageFile;
-    if (filename.empty()) filename = "pbrt.pfm";
+    if (filename.empty()) filename = "pbrt.tga";   // film/image.cpp:267-271 (the default of a build without OpenEXR)
     int xres = FilmParams.FindOneInt("xresolution", 640);
     int yres = FilmParams.FindOneInt("yresolution", 480);
     float crop[4] = {0, 1, 0, 1};

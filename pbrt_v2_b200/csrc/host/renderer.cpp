@@ -2,6 +2,9 @@
 // scene flattening into the PbrtGpuSceneDesc POD arrays, the single
 // pbrtgpu_render() call, and ImageFilm::WriteImage (PFM).
 #include "scene.h"
+#include <unistd.h>
+#include <cctype>
+#include <cmath>
 
 #include <cstdio>
 #include <map>
@@ -49,17 +52,60 @@ void ImageFilm::ToRGB(std::vector<float> *rgbOut) const {   // film/image.cpp:17
     }
 }
 
-bool ImageFilm::WriteImage() const {
+static bool WritePFM(const std::string &name, const std::vector<float> &rgb, int w, int h) {
     // PFM, bottom-to-top rows, little-endian (negative scale): core/imageio.cpp:419-455
-    std::vector<float> rgb;
-    ToRGB(&rgb);
-    FILE *fp = fopen(filename.c_str(), "wb");
-    if (!fp) { fprintf(stderr, "Error: unable to open output file \"%s\"\n", filename.c_str()); return false; }
-    fprintf(fp, "PF\n%d %d\n-1.000000\n", xPixelCount, yPixelCount);
-    for (int y = yPixelCount - 1; y >= 0; --y)
-        fwrite(&rgb[(size_t)3 * y * xPixelCount], sizeof(float), (size_t)3 * xPixelCount, fp);
+    FILE *fp = fopen(name.c_str(), "wb");
+    if (!fp) { fprintf(stderr, "Error: unable to open output file \"%s\"\n", name.c_str()); return false; }
+    fprintf(fp, "PF\n%d %d\n-1.000000\n", w, h);
+    for (int y = h - 1; y >= 0; --y)
+        fwrite(&rgb[(size_t)3 * y * w], sizeof(float), (size_t)3 * w, fp);
     fclose(fp);
     return true;
+}
+
+static bool WriteTGA(const std::string &name, const std::vector<float> &rgb, int w, int h) {
+    // WriteImageTGA (core/imageio.cpp:200-225): 24-bit uncompressed BGR, top-to-bottom rows, gamma 2.2, written the way
+    // tga_write_bgr fills the header (core/targa.c:566-620)
+    FILE *fp = fopen(name.c_str(), "wb");
+    if (!fp) { fprintf(stderr, "Error: unable to open output file \"%s\"\n", name.c_str()); return false; }
+    unsigned char hdr[18] = {0};
+    hdr[2] = 2;                                      // TGA_IMAGE_TYPE_BGR
+    hdr[12] = (unsigned char)(w & 0xff); hdr[13] = (unsigned char)((w >> 8) & 0xff);
+    hdr[14] = (unsigned char)(h & 0xff); hdr[15] = (unsigned char)((h >> 8) & 0xff);
+    hdr[16] = 24;
+    hdr[17] = 0x20;                                  // TGA_T_TO_B_BIT
+    fwrite(hdr, 1, sizeof(hdr), fp);
+    std::vector<unsigned char> row((size_t)3 * w);
+    auto toByte = [](float v) -> unsigned char {
+        float b = 255.f * powf(v, 1.f / 2.2f);
+        b = b < 0.f ? 0.f : (b > 255.f ? 255.f : b);   // Clamp (NaN from a negative base stays NaN in the reference: -> 0 here)
+        return (unsigned char)(b == b ? b : 0.f);
+    };
+    for (int y = 0; y < h; ++y) {
+        for (int x = 0; x < w; ++x) {
+            const float *p = &rgb[3 * ((size_t)y * w + x)];
+            row[3 * x] = toByte(p[2]); row[3 * x + 1] = toByte(p[1]); row[3 * x + 2] = toByte(p[0]);
+        }
+        fwrite(row.data(), 1, row.size(), fp);
+    }
+    fclose(fp);
+    return true;
+}
+
+bool ImageFilm::WriteImage() const {
+    // ::WriteImage picks the format by the suffix (core/imageio.cpp:85-140); this build has PFM and TGA.  A name this
+    // front end cannot honour (.exr needs OpenEXR, .png lodepng) is NOT written under that name with other contents:
+    // the float image goes to "<name>.pfm" and a warning says so.
+    std::vector<float> rgb;
+    ToRGB(&rgb);
+    std::string suffix = filename.size() >= 5 ? filename.substr(filename.size() - 4) : std::string();
+    for (char &c : suffix) c = (char)tolower((unsigned char)c);
+    if (suffix == ".pfm") return WritePFM(filename, rgb, xPixelCount, yPixelCount);
+    if (suffix == ".tga") return WriteTGA(filename, rgb, xPixelCount, yPixelCount);
+    const std::string alt = filename + ".pfm";
+    fprintf(stderr, "Warning: this build writes .pfm and .tga images; \"%s\" is written as \"%s\" (float RGB, lossless)\n",
+            filename.c_str(), alt.c_str());
+    return WritePFM(alt, rgb, xPixelCount, yPixelCount);
 }
 
 // -------------------------------------------------------- PerspectiveCamera --
@@ -291,8 +337,10 @@ void GpuDirectLightingIntegrator::RequestSamples(const Scene &scene, std::vector
 // ------------------------------------------------------- GpuSamplerRenderer --
 static int NumSystemCores(int nCores) {   // core/parallel.cpp:878-886
     if (nCores > 0) return nCores;
-    unsigned n = std::thread::hardware_concurrency();
-    return n ? (int)n : 1;
+    // sysconf(_SC_NPROCESSORS_ONLN), as the reference: it ignores the affinity mask / cpuset, unlike
+    // std::thread::hardware_concurrency(); nTasks -- and with it the image -- must not depend on taskset
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
 }
 
 int GpuSamplerRenderer::TaskCount() const {   // samplerrenderer.cpp:203-205

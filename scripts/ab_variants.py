@@ -20,6 +20,7 @@ import tempfile
 import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
 
 
 def run_arm(lib, extra_env, workload, spp, steps, tmp, tag, timeout):

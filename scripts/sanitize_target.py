@@ -28,7 +28,12 @@ for base, r, spp, ncores, integ in cases:
         rays = random_rays(20000, 3, lo, hi)
         print("  intersect", int(gs.intersect(rays)["hit"].sum()), "occluded", int(gs.intersect_p(rays).sum()))
         rd = hs.render_desc()
-        print("  ld_samples", float(pb.ld_samples(rd, 0).sum()))
+        for t in range(rd.nTasks):   # the first task with a non-empty pixel window
+            try:
+                print("  ld_samples of task", t, float(pb.ld_samples(rd, t).sum()))
+                break
+            except pb.PbrtGpuError:
+                continue
     gs.close()
 hs, _ = variant_scene("path-glass-mirror")
 px, st = pb.GpuScene(hs).render()

@@ -54,8 +54,11 @@ struct HostScene {
     std::vector<float4> kdRec;
 #endif
     std::vector<uint4> tris;
+    std::vector<float4> top;   // heap-ordered top of the scene BVH (what the kernels stage in shared memory)
     DScene d;
 };
+// -DPBRT_TOP_LEVELS=n builds: the walks read the first n levels from the heap-ordered table, as the kernels do from shared memory
+#define DOH_TOP(sc) (PBRT_TOP_LEVELS ? (sc).topNodes : nullptr)
 // the same packing as pbrtgpu_scene_create (device/pbrtgpu.cu): nodes -> 2 x float4, primitives -> 3 x float4
 void Pack(const PbrtGpuSceneDesc *desc, HostScene *h) {
     h->nodes.resize(2 * (size_t)desc->nNodes);
@@ -91,6 +94,8 @@ void Pack(const PbrtGpuSceneDesc *desc, HostScene *h) {
     DScene &d = h->d;
     memset(&d, 0, sizeof(d));
     d.nodes = h->nodes.data(); d.prims = h->prims.data(); d.tris = h->tris.data(); d.meshes = desc->meshes;
+    BuildTopNodes(desc, PBRT_TOP_LEVELS, &h->top);
+    d.topNodes = h->top.data();
 #if PBRT_KD_INTERLEAVED
     BuildKdRecords(desc, &h->kdRec);
     d.kdRec = h->kdRec.data();
@@ -289,7 +294,7 @@ void RunTaskH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
                         wantTrace = true; anyHit = false;
                         state = S_HIT_RESULT;
                     }
-                    if (wantTrace) found = Traverse<false, true>(sc, ray, anyHit, &hit, &st);
+                    if (wantTrace) found = Traverse<false, true>(sc, ray, anyHit, &hit, &st, DOH_TOP(sc));
                 }
                 // DirectLightingIntegrator: SpecularReflect/Transmit's BSDFSample(rng) draws (what k_film_direct accounts for)
 #if PBRT_SPECULAR
@@ -340,7 +345,7 @@ void RunTaskVertexH(const DScene &sc, const RenderParams &rp, const PbrtGpuRende
                 Hit hit;
                 TraceStats st;
                 st.nodes = st.prims = 0;
-                bool found = Traverse<false, true>(sc, ray, false, &hit, &st);
+                bool found = Traverse<false, true>(sc, ray, false, &hit, &st, DOH_TOP(sc));
                 while (found) {
                     VertexRandoms u;
                     const int nLights = (int)sc.nLights;
@@ -372,12 +377,12 @@ void RunTaskVertexH(const DScene &sc, const RenderParams &rp, const PbrtGpuRende
                     if (v.ray[VX_LIGHT]) {
                         Ray r; r.o = v.p; r.d = v.wiW[VX_LIGHT]; r.mint = v.eps; r.maxt = v.visMaxt; r.time = ray.time;
                         Hit h;
-                        if (!Traverse<false, true>(sc, r, true, &h, &st)) Ld = Ld + v.pendS;
+                        if (!Traverse<false, true>(sc, r, true, &h, &st, DOH_TOP(sc))) Ld = Ld + v.pendS;
                     }
                     if (v.ray[VX_MIS]) {
                         Ray r; r.o = v.p; r.d = v.wiW[VX_MIS]; r.mint = v.eps; r.maxt = INF_F; r.time = ray.time;
                         Hit h;
-                        if (Traverse<false, true>(sc, r, false, &h, &st) && MisHitIsLight<true>(sc, r, h, v.lightNum)) Ld = Ld + v.pendM;
+                        if (Traverse<false, true>(sc, r, false, &h, &st, DOH_TOP(sc)) && MisHitIsLight<true>(sc, r, h, v.lightNum)) Ld = Ld + v.pendM;
                     }
                     L = L + T * ((float)nLights * Ld);
                     T = v.Tnew;
@@ -387,7 +392,7 @@ void RunTaskVertexH(const DScene &sc, const RenderParams &rp, const PbrtGpuRende
 #endif
                     ++bounces;
                     ray.o = v.p; ray.d = v.wiW[VX_PATH]; ray.mint = v.eps; ray.maxt = INF_F;
-                    found = Traverse<false, true>(sc, ray, false, &hit, &st);
+                    found = Traverse<false, true>(sc, ray, false, &hit, &st, DOH_TOP(sc));
                 }
                 const Spec Ls = SanitizeRadiance(L);
                 float xyz[3];
@@ -454,10 +459,20 @@ DOH_EXPORT int doh_intersect(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *ray
         if (stepwise) {   // the wavefront's step-wise walk (k_trace)
             Trav t;
             TravInit(t, ray, false);
+#if PBRT_SMEM_STACK
+            static uint32_t fakeShared[PBRT_SMEM_STACK * 128];
+            t.sstk = fakeShared + 5;
+#endif
+            if (stepwise == 2) {   // k_trace's two-phase loop: bounded descents, then the leaf
+                for (;;) {
+                    const int r = TravDescend<false, true>(sc, t, &st, 3, DOH_TOP(sc));
+                    if (r == 2 || (r == 1 && TravLeaf<false, true>(sc, t, &st))) break;
+                }
+            } else
             while (!TravStep<false, true>(sc, t, &st)) {}
             found = t.found; hit = t.hit; ray.maxt = t.ray.maxt;
         } else
-            found = Traverse<false, true>(sc, ray, false, &hit, &st);
+            found = Traverse<false, true>(sc, ray, false, &hit, &st, DOH_TOP(sc));
         PbrtGpuHit h;
         memset(&h, 0, sizeof(h));
         h.t = ray.maxt;
@@ -493,10 +508,20 @@ DOH_EXPORT int doh_intersect_p(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *r
         if (stepwise) {
             Trav t;
             TravInit(t, ray, true);
+#if PBRT_SMEM_STACK
+            static uint32_t fakeShared[PBRT_SMEM_STACK * 128];
+            t.sstk = fakeShared + 7;
+#endif
+            if (stepwise == 2) {
+                for (;;) {
+                    const int r = TravDescend<false, true>(sc, t, &st, 3, DOH_TOP(sc));
+                    if (r == 2 || (r == 1 && TravLeaf<false, true>(sc, t, &st))) break;
+                }
+            } else
             while (!TravStep<false, true>(sc, t, &st)) {}
             occ[i] = t.found ? 1 : 0;
         } else
-            occ[i] = Traverse<false, true>(sc, ray, true, &hit, &st) ? 1 : 0;
+            occ[i] = Traverse<false, true>(sc, ray, true, &hit, &st, DOH_TOP(sc)) ? 1 : 0;
     }
     return 0;
 }
@@ -517,7 +542,7 @@ DOH_EXPORT int doh_shade_test(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *ra
         Hit hit;
         TraceStats st;
         st.nodes = st.prims = 0;
-        if (!Traverse<false, true>(sc, ray, false, &hit, &st)) continue;
+        if (!Traverse<false, true>(sc, ray, false, &hit, &st, DOH_TOP(sc))) continue;
         ShadeCtx ctx;
         BuildShadeCtx<true>(sc, ray, hit, &ctx, nullptr);
         const V3 wo = -ray.d;

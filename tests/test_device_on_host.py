@@ -50,7 +50,7 @@ def _rays(hs, base, n, seed):
 
 
 @pytest.mark.parametrize("base", ["bunny", "killeroo-simple", "anim-killeroos-moving"])
-@pytest.mark.parametrize("stepwise", [0, 1])
+@pytest.mark.parametrize("stepwise", [0, 1, 2])   # whole walk; single steps; k_trace's descend / leaf halves
 def test_device_traversal_on_host_matches_oracle(staged, doh, base, stepwise):
     hs = host_scene(base, 32, 32, 4, 32)
     rays = _rays(hs, base, 100000, 7)
@@ -141,6 +141,33 @@ def test_specular_device_code_on_host(staged, tmp_path_factory):
         _same_film(lib, variant_scene(name)[0])
     _same_film(lib, host_scene("bunny", 32, 32, 8, 2))
     _same_film(lib, host_scene("killeroo-simple", 32, 32, 4, 2, integrator="directlighting"))
+
+
+def test_shared_memory_stack_and_top_table_on_host(staged, tmp_path_factory):
+    """-DPBRT_TOP_LEVELS / -DPBRT_SMEM_STACK (north_star kernel items, built as A/B variants: the top levels of the scene BVH
+    read from a heap-ordered table -- shared memory on the device, filled by one TMA bulk copy -- and the first stack
+    entries kept in a per-thread column of shared memory): the walks must not change."""
+    lib = _build(tmp_path_factory, "device_on_host_top", ["-DPBRT_TOP_LEVELS=10", "-DPBRT_SMEM_STACK=4"])
+    lib.doh_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.doh_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+    for base, nl in (("bunny", None), ("killeroo-simple", None), ("anim-killeroos-moving", 3)):
+        hs = host_scene(base, 32, 32, 4, 32, nlevels=nl)
+        rays = _rays(hs, base, 60000, 17)
+        want, occ_want = oa.intersect(hs, rays), oa.intersect_p(hs, rays)
+        for stepwise in (0, 2):
+            got = np.zeros(len(rays), dtype=pb.HIT_DTYPE)
+            occ = np.zeros(len(rays), np.uint8)
+            lib.doh_intersect(hs.desc_ptr, rays.ctypes.data, len(rays), got.ctypes.data, stepwise)
+            lib.doh_intersect_p(hs.desc_ptr, rays.ctypes.data, len(rays), occ.ctypes.data, stepwise)
+            assert np.array_equal(got["hit"], want["hit"]) and np.array_equal(occ, occ_want), (base, stepwise)
+            assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), (base, stepwise)
+            h = want["hit"] == 1
+            for f in ("primitive", "b1", "b2", "p", "n"):
+                assert np.array_equal(got[f][h].view(np.uint32), want[f][h].view(np.uint32)), (base, stepwise, f)
+    lib.doh_set_vertex_form(1)
+    _same_film(lib, host_scene("bunny", 32, 32, 8, 32))
+    _same_film(lib, host_scene("anim-killeroos-moving", 32, 32, 4, 2))
 
 
 def test_pair_node_walk_on_host(staged, tmp_path_factory):
