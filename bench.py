@@ -289,8 +289,13 @@ def main():
                               integrator=WORKLOAD_INTEGRATOR.get(args.workload, "path"))
         hs = pb.HostScene(path, ncores=per_pixel_ncores(xres, yres))
     rd = hs.render_desc()
-    from pbrt_v2_b200.multigpu import shard_render_desc, reduce_film
+    from pbrt_v2_b200.multigpu import shard_render_desc
     shard_render_desc(rd, rank, world, xres)   # interleave blocks of 4 pixel rows across ranks
+    comm = None
+    if world > 1:   # the library's own NCCL communicator (pbrtgpu_comm_*): the exchange step lives in the host plugin
+        ids = [pb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = pb.Comm(ids[0], rank, world)
     _, _, xc, yc = hs.film_extent()
     nsamples = xc * yc * spp
     scene_bytes = hs.scene_bytes()
@@ -302,8 +307,9 @@ def main():
     stream = torch.cuda.current_stream(dev)
 
     def step_resident(want_stats=False):
-        st = gs.render_device(rd, film.data_ptr(), stream.cuda_stream, want_stats=want_stats)
-        reduce_film(film, world)
+        if world == 1:
+            return gs.render_device(rd, film.data_ptr(), stream.cuda_stream, want_stats=want_stats)
+        _, st = gs.render_sharded(rd, comm, fetch=False)   # shard + render + ncclReduce to rank 0, film stays on the device
         return st
 
     g2 = pb.GpuScene(hs)   # the end-to-end arm's own handle: every step re-uploads the scene into it
@@ -315,10 +321,7 @@ def main():
         if world == 1:
             g2.render(rd, out=host_px)             # pbrtgpu_render: the host-buffer entry point (film D2H inside)
         else:
-            g2.render_device(rd, film.data_ptr(), stream.cuda_stream)
-            reduce_film(film, world)
-            if rank == 0:
-                host_film.copy_(film, non_blocking=True)   # device -> host read of the step's result
+            g2.render_sharded(rd, comm, out=host_px if rank == 0 else None)   # + ncclReduce + rank 0's film D2H inside
         stream.synchronize()
 
     def barrier():
@@ -423,7 +426,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Msamples/s",
                     "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": int(xc * yc * 16),
                     "through": "pbrtgpu_scene_update + pbrtgpu_render (host pixel buffer)" if world == 1 else
-                               "pbrtgpu_scene_update + pbrtgpu_render_device + NCCL reduce + film D2H"},
+                               "pbrtgpu_scene_update + pbrtgpu_render_sharded (ncclReduce inside the library, host pixel buffer on rank 0)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
@@ -466,7 +469,7 @@ def main():
                               base, xres, yres, CPU_SAMPLE_SPP, max(1, WORKLOADS[args.workload][3] // CPU_SAMPLE_SPP),
                               threads, sec, wall)}
         if args.film_out:
-            np.save(args.film_out, film.cpu().numpy())
+            np.save(args.film_out, film.cpu().numpy() if world == 1 else host_film.numpy())
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -297,7 +297,8 @@ int  pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd,
  * shardBlock 0 = four rows of one-pixel tasks) -- and sums the per-rank films onto rank 0 with ONE ncclReduce (float
  * sum over 4 floats per pixel: pixels owned by another rank contribute zeros, edge splats that cross an ownership
  * border add up, which a gather of owned tiles would lose).  `pixels` (HOST memory) receives the whole film on rank 0;
- * other ranks may pass NULL.                                                                                        */
+ * other ranks may pass NULL (so may rank 0: the summed film then stays on the device, which is what a benchmark of the
+ * device-resident rate wants).                                                                                        */
 #define PBRTGPU_COMM_ID_BYTES 128
 typedef struct PbrtGpuComm PbrtGpuComm;
 int  pbrtgpu_comm_unique_id(void *id);

@@ -126,6 +126,11 @@ def gpu_lib():
         lib.pbrtgpu_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.pbrtgpu_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.pbrtgpu_ld_samples.argtypes = [C.POINTER(RenderDesc), C.c_int, C.c_void_p]
+        lib.pbrtgpu_comm_unique_id.argtypes = [C.c_void_p]
+        lib.pbrtgpu_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        lib.pbrtgpu_comm_destroy.argtypes = [C.c_void_p]
+        lib.pbrtgpu_comm_destroy.restype = None
+        lib.pbrtgpu_render_sharded.argtypes = [C.c_void_p, C.POINTER(RenderDesc), C.c_void_p, C.c_void_p, C.POINTER(Stats)]
         lib.pbrtgpu_set_device.argtypes = [C.c_int]
         lib.pbrtgpu_set_stats.argtypes = [C.c_void_p, C.c_int]
         lib.pbrtgpu_loopsubdiv_counts.argtypes = [C.POINTER(SubdivMesh), C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -318,6 +323,15 @@ class GpuScene(object):
         _check(gpu_lib().pbrtgpu_render(self._h, C.byref(rd), px.ctypes.data, C.byref(st)), "pbrtgpu_render")
         return px, st
 
+    def render_sharded(self, rd, comm, out=None, fetch=True):
+        """pbrtgpu_render_sharded: this rank's share of the tasks + the library's NCCL reduce; rank 0 gets the film
+        (fetch=False: the summed film stays on the device)."""
+        px = out if out is not None else (self.host.new_pixels() if (comm.rank == 0 and fetch) else None)
+        st = Stats()
+        _check(gpu_lib().pbrtgpu_render_sharded(self._h, C.byref(rd), comm._h, px.ctypes.data if px is not None else None,
+                                                C.byref(st)), "pbrtgpu_render_sharded")
+        return px, st
+
     def render_device(self, rd, device_ptr, stream=None, want_stats=False):
         """pbrtgpu_render_device into DEVICE memory (e.g. a torch tensor's data_ptr())."""
         st = Stats() if want_stats else None
@@ -337,6 +351,33 @@ class GpuScene(object):
         occ = np.zeros(len(rays), dtype=np.uint8)
         _check(gpu_lib().pbrtgpu_intersect_p(self._h, rays.ctypes.data, len(rays), occ.ctypes.data), "pbrtgpu_intersect_p")
         return occ
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """rank 0: the 128-byte id every rank needs to join the communicator (pbrtgpu_comm_unique_id)"""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(gpu_lib().pbrtgpu_comm_unique_id(buf), "pbrtgpu_comm_unique_id")
+    return buf.raw
+
+
+class Comm(object):
+    """The library's NCCL communicator (pbrtgpu_comm_create) on the current device."""
+
+    def __init__(self, unique_id, rank, world):
+        assert len(unique_id) == COMM_ID_BYTES
+        h = C.c_void_p()
+        _check(gpu_lib().pbrtgpu_comm_create(unique_id, int(rank), int(world), C.byref(h)), "pbrtgpu_comm_create")
+        self._h, self.rank, self.world = h, int(rank), int(world)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            gpu_lib().pbrtgpu_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 def ld_samples(rd, task_num):

@@ -46,20 +46,31 @@ struct BatchArgs {
 // them in the task's (not yet used) `rec` scratch; stage 2 runs the 26 inherently sequential
 // shuffles, one array per lane, on u16 index arrays in shared memory, with the targets prefetched
 // from global memory; stage 3 writes one 64-byte row of shuffled indices per camera sample.
+//
+// `stages` selects what a launch does: 1 = stage 1 only (needs one MT19937 block of shared memory per warp: many warps
+// per SM, which hides the latencies of the block regeneration and of the modulo), 2 = stages 2 + 3 only (needs the index
+// arrays: 2 KB of shared memory per chain at 1024 spp, so few warps per SM whatever the rest does), 3 = all in one launch.
+// The render path launches 1 then 2 (ncu, profiles/r02_k_tables_*: in one launch the whole kernel ran at 4 warps per SM).
 template <int WPB>
-__global__ void __launch_bounds__(32 * WPB) k_tables(BatchArgs a, int spp, int G) {
+__global__ void __launch_bounds__(32 * WPB) k_tables(BatchArgs a, int spp, int G, int stages = 3) {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int stride = spp + 2;   // +2 u16 (one bank) of padding per array
-    const size_t warpWords = MT_N + ((size_t)G * stride + 1) / 2;
+    const size_t mtWords = (stages & 1) ? MT_N : 0;
+    const size_t warpWords = mtWords + ((stages & 2) ? ((size_t)G * stride + 1) / 2 : 0);
     uint32_t *mt = smem + warp * warpWords;
-    uint16_t *P = reinterpret_cast<uint16_t *>(mt + MT_N);
+    uint16_t *P = reinterpret_cast<uint16_t *>(mt + mtWords);
     const int bi = blockIdx.x * WPB + warp;
     if (bi >= a.nBatch) return;
     const TaskRec tr = a.tasks[bi];
     const int npx = (tr.x1 - tr.x0) * (tr.y1 - tr.y0);
     if (a.round >= npx) return;
 
+    uint16_t *permOut = a.perm + (size_t)bi * spp * PERM_STRIDE;
+    uint32_t *scrOut = a.scr + (size_t)bi * SCR_STRIDE;
+    uint16_t *Tg = reinterpret_cast<uint16_t *>(a.rec + (size_t)bi * spp * 4);   // [N_ARRAYS][spp] swap targets
+
+    if (stages & 1) {
     uint32_t *cur = a.rngCur + (size_t)bi * MT_N, *next = a.rngNext + (size_t)bi * MT_N;
     int mti;
     if (a.round == 0) {   // RNG rng(taskNum), samplerrenderer.cpp:73
@@ -72,10 +83,6 @@ __global__ void __launch_bounds__(32 * WPB) k_tables(BatchArgs a, int spp, int G
         for (int j = lane; j < MT_N; j += 32) mt[j] = __ldcg(src + j);
     }
     __syncwarp();
-
-    uint16_t *permOut = a.perm + (size_t)bi * spp * PERM_STRIDE;
-    uint32_t *scrOut = a.scr + (size_t)bi * SCR_STRIDE;
-    uint16_t *Tg = reinterpret_cast<uint16_t *>(a.rec + (size_t)bi * spp * 4);   // [N_ARRAYS][spp] swap targets
 
     // ---- stage 1: walk the draw stream
     for (int arr = 0; arr < N_ARRAYS; ++arr) {
@@ -115,6 +122,8 @@ __global__ void __launch_bounds__(32 * WPB) k_tables(BatchArgs a, int spp, int G
     if (lane == 0) a.mti[bi] = mti;
     __threadfence_block();
     __syncwarp();
+    }   // stage 1
+    if (!(stages & 2)) return;
 
     // ---- stages 2+3, G arrays at a time
     for (int a0 = 0; a0 < N_ARRAYS; a0 += G) {
@@ -125,10 +134,29 @@ __global__ void __launch_bounds__(32 * WPB) k_tables(BatchArgs a, int spp, int G
         if (lane < ng) {   // Fisher-Yates of the identity (Shuffle, montecarlo.h:174-181)
             uint16_t *p = P + lane * stride;
             const uint16_t *t = Tg + (size_t)(a0 + lane) * spp;
-            for (int i0 = 0; i0 < spp; i0 += 8) {   // spp is a power of two >= 1; targets fetched 8 ahead
+            // spp is a power of two >= 1.  The swap targets come from global memory eight at a time (one 128-bit load)
+            // and TWO groups ahead of the chain: the chain itself is ~40 cycles per step of shared-memory round trips, a
+            // group's load ~600 cycles away -- fetched only when needed it tripled the time per step (profiles/r02_k_tables_*)
+            const bool wide = spp >= 8;
+            uint4 q1 = make_uint4(0, 0, 0, 0), q2 = make_uint4(0, 0, 0, 0);
+            if (wide) {
+                q1 = __ldcg(reinterpret_cast<const uint4 *>(t));
+                if (8 < spp) q2 = __ldcg(reinterpret_cast<const uint4 *>(t + 8));
+            }
+            for (int i0 = 0; i0 < spp; i0 += 8) {
                 uint16_t tj[8];
+                if (wide) {
+                    const uint4 q = q1;
+                    q1 = q2;
+                    if (i0 + 16 < spp) q2 = __ldcg(reinterpret_cast<const uint4 *>(t + i0 + 16));
+                    tj[0] = (uint16_t)(q.x & 0xffffu); tj[1] = (uint16_t)(q.x >> 16);
+                    tj[2] = (uint16_t)(q.y & 0xffffu); tj[3] = (uint16_t)(q.y >> 16);
+                    tj[4] = (uint16_t)(q.z & 0xffffu); tj[5] = (uint16_t)(q.z >> 16);
+                    tj[6] = (uint16_t)(q.w & 0xffffu); tj[7] = (uint16_t)(q.w >> 16);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) tj[k] = (i0 + k < spp) ? __ldcg(t + i0 + k) : (uint16_t)0;
+                    for (int k = 0; k < 8; ++k) tj[k] = (i0 + k < spp) ? __ldcg(t + i0 + k) : (uint16_t)0;
+                }
 #if PBRT_TABLES_PAIRED
                 // two steps per shared-memory round trip: all four loads first, then the values step k+1 would have seen
                 // after step k's stores are patched in registers (step k puts `a` at j0: that is position i+1 if
@@ -403,13 +431,15 @@ struct TableLaunch {
     int G, wpb;
     size_t smemBytes;
 };
-inline TableLaunch PlanTables(int spp) {
+// stages: 3 = the one-launch form (an MT19937 block + the index arrays per warp), 2 = stages 2 + 3 only (index arrays only)
+inline TableLaunch PlanTables(int spp, int stages = 3) {
     TableLaunch t;
     const size_t perArray = (size_t)2 * (spp + 2);   // one u16 index array per (0,2)-sequence array
     const size_t budget = 56 * 1024;
-    size_t g = (budget - MT_N * 4) / perArray;
+    const size_t mtBytes = (stages & 1) ? MT_N * 4 : 0;
+    size_t g = (budget - mtBytes) / perArray;
     t.G = g >= N_ARRAYS ? N_ARRAYS : (int)std::max<size_t>(1, g);
-    const size_t perWarp = MT_N * 4 + ((size_t)t.G * perArray + 3) / 4 * 4;
+    const size_t perWarp = mtBytes + ((size_t)t.G * perArray + 3) / 4 * 4;
     t.wpb = (int)std::max<size_t>(1, std::min<size_t>(4, (226 * 1024) / perWarp));
     t.smemBytes = perWarp * t.wpb;
     return t;

@@ -233,7 +233,9 @@ __global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(PathArgs a) {
 #define PATH_ANIM ANIM
 #define PATH_INTEG 0
 #define PATH_COUNT_TAIL() (atomicAdd(a.b.tailCount + bi, 1u), a.b.tailMask ? (void)atomicOr(a.b.tailMask + (size_t)bi * a.b.maskWords + (s >> 5), 1u << (s & 31)) : (void)0)
+#define PATH_DL_FRAME(i) dlFrames[((i), 0)]
 #include "path_body.inc"
+#undef PATH_DL_FRAME
 #undef PATH_COUNT_TAIL
 #undef PATH_FEVAL_IN
 #undef PATH_EVALWO_IN
@@ -413,6 +415,7 @@ struct WfArgs {
     PbrtGpuPixel *film;  // phase 2
     int directFilm;
     DeviceStats *stats;
+    DlFrame *dlFrames;   // [P][DL_MAX_DEPTH] DirectLightingIntegrator over specular materials, else null
 };
 
 DEV unsigned AggregatedAdd(unsigned *ctr) {   // warp-aggregated atomicAdd(ctr, 1) for the currently converged lanes
@@ -478,13 +481,11 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #if PBRT_SPECULAR
     bool specularBounce = false;           // path.cpp:53; bit 31 of the packed state word between iterations
-    // DirectLightingIntegrator's SpecularReflect / SpecularTransmit recursion: the state machine (path_body.inc) is
-    // complete and verified on the host, but the frames do not travel with the slot yet -- pbrtgpu_render refuses
-    // directlighting over specular materials until they do
+    // DirectLightingIntegrator's SpecularReflect / SpecularTransmit recursion (integrator.cpp:177-258) as a post-order walk:
+    // depth / stage / return flag / drawing-node count travel in F_DL_ALL.w, the frames of the ancestors live in the
+    // slot's column of a.dlFrames (global memory: only scenes with specular materials have any)
     int dlDepth = 0, dlStage = 0, dlNodes = 0;
     bool dlReturn = false;
-    DlFrame dlFrames[DL_MAX_DEPTH];
-    (void)dlNodes;
 #endif
     int dlI = 0, dlJ = 0;                  // DirectLightingIntegrator's light loop
     Spec dlSum(0.f), dlAll(0.f);
@@ -544,6 +545,10 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
             const float4 d0 = FLD(F_DL_SUM), d1 = FLD(F_DL_ALL);
             dlSum = Spec(d0.x, d0.y, d0.z); dlAll = Spec(d1.x, d1.y, d1.z);
             dlI = (int)(__float_as_uint(d0.w) & 0xffffu); dlJ = (int)(__float_as_uint(d0.w) >> 16);
+#if PBRT_SPECULAR
+            const uint32_t rw = __float_as_uint(d1.w);
+            dlDepth = (int)(rw & 0xfu); dlStage = (int)((rw >> 4) & 0x3u); dlReturn = ((rw >> 6) & 1u) != 0; dlNodes = (int)(rw >> 8);
+#endif
         }
     }
     if (PHASE == 2) {
@@ -612,7 +617,9 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
 #define PATH_ANIM ANIM
 #define PATH_INTEG INTEG
 #define PATH_COUNT_TAIL() (atomicAdd(a.b.tailCount + bi, 1u), a.b.tailMask ? (void)atomicOr(a.b.tailMask + (size_t)bi * a.b.maskWords + (s >> 5), 1u << (s & 31)) : (void)0)
+#define PATH_DL_FRAME(i) a.dlFrames[(size_t)slot * DL_MAX_DEPTH + (size_t)(i)]
 #include "path_body.inc"
+#undef PATH_DL_FRAME
 #undef PATH_COUNT_TAIL
 #undef PATH_FEVAL_IN
 #undef PATH_EVALWO_IN
@@ -682,6 +689,12 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
         } else {
         if (state == S_END_SAMPLE) {
             const Spec Ls = SanitizeRadiance(L);
+#if PBRT_SPECULAR
+            // DirectLightingIntegrator: the number of Li nodes that made the two specular calls (6 RNG draws each) rides in
+            // the code word's upper bits to k_film_direct
+            if (INTEG == PBRTGPU_INTEGRATOR_DIRECTLIGHTING) code |= dlNodes << 8;
+            dlDepth = dlStage = dlNodes = 0; dlReturn = false;
+#endif
             lsBase[s] = make_float4(Ls.r, Ls.g, Ls.b, __int_as_float(code));
             state = S_NEW_SAMPLE;
         }
@@ -744,7 +757,12 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
     if (ANIM) FLD(F_TIME) = make_float4(ray.time, 0.f, 0.f, 0.f);
     if (INTEG == PBRTGPU_INTEGRATOR_DIRECTLIGHTING) {
         FLD(F_DL_SUM) = make_float4(dlSum.r, dlSum.g, dlSum.b, __uint_as_float((uint32_t)dlI | ((uint32_t)dlJ << 16)));
+#if PBRT_SPECULAR
+        FLD(F_DL_ALL) = make_float4(dlAll.r, dlAll.g, dlAll.b, __uint_as_float((uint32_t)dlDepth | ((uint32_t)dlStage << 4) |
+                                                                                   (dlReturn ? 0x40u : 0u) | ((uint32_t)dlNodes << 8)));
+#else
         FLD(F_DL_ALL) = make_float4(dlAll.r, dlAll.g, dlAll.b, 0.f);
+#endif
     }
 #if PBRT_SPECULAR
     FLD(F_T) = make_float4(T.r, T.g, T.b, __uint_as_float((uint32_t)state | ((uint32_t)bounces << 8) | ((uint32_t)lightNum << 16) |
@@ -815,8 +833,12 @@ __global__ void __launch_bounds__(128) k_film_direct(PathArgs a, int advance) {
             for (int s = 0; s < spp; ++s) {
                 const float4 v = __ldcs(ls + s);
                 const int code = __float_as_int(v.w);
-                hits += (code & LS_HIT) ? 1 : 0;
-                FilmAdd(rp, a.film, xPos, yPos, code & ~LS_HIT, Spec(v.x, v.y, v.z), acc, direct);
+#if PBRT_SPECULAR
+                hits += code >> 8;   // Li nodes that drew (the camera vertex and, under mirror / glass, its specular descendants)
+#else
+                hits += ((code & LS_HIT) && 0 + 1 < rp.maxDepth) ? 1 : 0;
+#endif
+                FilmAdd(rp, a.film, xPos, yPos, code & (LS_LEFT | LS_RIGHT | LS_UP | LS_DOWN), Spec(v.x, v.y, v.z), acc, direct);
             }
             if (!direct) {
                 PbrtGpuPixel *px = a.film + (size_t)(yPos - rp.yPixelStart) * rp.xPixelCount + (xPos - rp.xPixelStart);
@@ -825,7 +847,7 @@ __global__ void __launch_bounds__(128) k_film_direct(PathArgs a, int advance) {
                 atomicAdd(&px->Lxyz[2], acc[2]);
                 atomicAdd(&px->weightSum, acc[3]);
             }
-            mti = a.b.mti[bi] + ((0 + 1 < rp.maxDepth) ? 6 * hits : 0);
+            mti = a.b.mti[bi] + 6 * hits;
         }
     }
     if (!advance) return;
@@ -1082,6 +1104,7 @@ struct Lane {
     DevBuf<uint8_t> tgt;              // general table kernel: shuffle targets
     DevBuf<float4> pool;              // wavefront path slots (F_COUNT fields x P)
     DevBuf<uint32_t> traceQ;
+    DevBuf<DlFrame> dlFrames;         // DirectLightingIntegrator over specular materials: [P][DL_MAX_DEPTH]
     DevBuf<unsigned> counters;
     unsigned *hostCounters = nullptr;  // pinned
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1233,19 +1256,26 @@ int ValidateRenderDesc(const PbrtGpuRenderDesc &rd) {
     return PBRTGPU_OK;
 }
 
-template <int WPB> cudaError_t LaunchTables(const BatchArgs &b, int spp, const TableLaunch &tl, cudaStream_t stream) {
+template <int WPB> cudaError_t LaunchTables(const BatchArgs &b, int spp, const TableLaunch &tl, int stages, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(k_tables<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smemBytes);
     if (e != cudaSuccess) return e;
     const int blocks = (b.nBatch + WPB - 1) / WPB;
-    k_tables<WPB><<<blocks, 32 * WPB, tl.smemBytes, stream>>>(b, spp, tl.G);
+    k_tables<WPB><<<blocks, 32 * WPB, tl.smemBytes, stream>>>(b, spp, tl.G, stages);
     return cudaGetLastError();
 }
-cudaError_t LaunchTablesAny(const BatchArgs &b, int spp, const TableLaunch &tl, cudaStream_t stream) {
+// PathIntegrator's tables in two launches: the draw-stream walk with eight warps per block (one MT19937 block of shared
+// memory each), then the shuffles + row assembly with as many warps as the index arrays leave room for
+cudaError_t LaunchTablesAny(const BatchArgs &b, int spp, const TableLaunch &, cudaStream_t stream) {
+    TableLaunch s1;
+    s1.G = 0; s1.wpb = 8; s1.smemBytes = (size_t)8 * MT_N * 4;
+    cudaError_t e = LaunchTables<8>(b, spp, s1, 1, stream);
+    if (e != cudaSuccess) return e;
+    const TableLaunch tl = PlanTables(spp, 2);
     switch (tl.wpb) {
-    case 4: return LaunchTables<4>(b, spp, tl, stream);
-    case 3: return LaunchTables<3>(b, spp, tl, stream);
-    case 2: return LaunchTables<2>(b, spp, tl, stream);
-    default: return LaunchTables<1>(b, spp, tl, stream);
+    case 4: return LaunchTables<4>(b, spp, tl, 2, stream);
+    case 3: return LaunchTables<3>(b, spp, tl, 2, stream);
+    case 2: return LaunchTables<2>(b, spp, tl, 2, stream);
+    default: return LaunchTables<1>(b, spp, tl, 2, stream);
     }
 }
 
@@ -1661,6 +1691,8 @@ int RunLane(LaneJob &job) {
     const bool vertex1 = !direct && (cfg.vertex & 1), vertex2 = !direct && (cfg.vertex & 2);
     const bool useWavefront = cfg.wavefront && !vertex1, useWavefront2 = cfg.wavefront2 && useWavefront && !vertex2;
     size_t poolSize = cfg.pool;   // 4 Mi slots x 272 B = 1.1 GB (measured: +17 % over 1 Mi)
+    const bool dlSpecular = direct && scene->nSpecularMaterials > 0;
+    if (dlSpecular) poolSize = std::min<size_t>(poolSize, (size_t)1 << 20);   // + 960 B of recursion frames per slot
     poolSize = (poolSize + 127) / 128 * 128;
     const int maskWords = std::max(1, spp / 32);
     CUDA_TRY(ln->tailMask.Ensure(maxBatch * (size_t)maskWords));
@@ -1673,6 +1705,7 @@ int RunLane(LaneJob &job) {
         CUDA_TRY(ln->pool.Ensure(poolSize * F_COUNT));
         CUDA_TRY(ln->traceQ.Ensure(poolSize * 2 * K_COUNT));   // request queues: 2 sets x K_COUNT kinds
         CUDA_TRY(ln->counters.Ensure(C_COUNT));
+        if (dlSpecular) CUDA_TRY(ln->dlFrames.Ensure(poolSize * DL_MAX_DEPTH));
         if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, C_COUNT * sizeof(unsigned)));
     }
     const bool traceIters = cfg.traceIters;   // debugging aid: queue occupancy on stderr
@@ -1741,6 +1774,7 @@ int RunLane(LaneJob &job) {
                 wa.q = ln->traceQ.p; wa.counters = ln->counters.p;
                 wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p;
                 wa.film = film; wa.directFilm = 0;
+                wa.dlFrames = dlSpecular ? ln->dlFrames.p : nullptr;
                 CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, C_COUNT * sizeof(unsigned), stream));
                 const int lblocks = (int)((poolSize + 127) / 128);
                 const int tblocks = nSM * 8;
@@ -1837,7 +1871,7 @@ int RunLane(LaneJob &job) {
                 wa.sc = scene->d; wa.rp = rp; wa.b = pa.b; wa.pool = ln->pool.p; wa.P = (uint32_t)poolSize;
                 wa.q = ln->traceQ.p; wa.counters = ln->counters.p;
                 wa.totalSamples = 0; wa.stats = scene->stats.p;
-                wa.film = film; wa.directFilm = pa.directFilm;
+                wa.film = film; wa.directFilm = pa.directFilm; wa.dlFrames = nullptr;
                 CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, C_COUNT * sizeof(unsigned), stream));
                 const int tblocks = nSM * 8;
                 for (int iter = 0;; ++iter) {
@@ -1953,8 +1987,8 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     const bool pathLayout = IsPathLayout(*rd);
     const bool directInteg = rd->integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
 #if PBRT_SPECULAR
-    if (directInteg && scene->nSpecularMaterials)
-        return Fail(PBRTGPU_EUNSUPPORTED, "DirectLightingIntegrator with specular materials needs the recursive SpecularReflect/Transmit rays: not on the device yet");
+    if (directInteg && scene->nSpecularMaterials && rd->maxDepth > DL_MAX_DEPTH)
+        return Fail(PBRTGPU_EUNSUPPORTED, "DirectLightingIntegrator over specular materials: maxdepth beyond the 8 recursion frames a path slot carries");
     if (scene->nSpecularMaterials && scene->d.nLights > 32767) return Fail(PBRTGPU_EUNSUPPORTED, "too many lights");
 #endif
     if (directInteg) {   // the layout must be what DirectLightingIntegrator::RequestSamples builds for this scene's lights
@@ -2071,7 +2105,6 @@ int pbrtgpu_render_sharded(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rdIn, P
                            PbrtGpuStats *stats) {
     if (!scene || !rdIn || !comm) return Fail(PBRTGPU_EINVAL, "null argument");
     const int rank = PbrtGpuCommRank(comm), world = PbrtGpuCommWorld(comm);
-    if (rank == 0 && !pixels) return Fail(PBRTGPU_EINVAL, "rank 0 needs a pixel buffer");
     PbrtGpuRenderDesc rd = *rdIn;
     rd.shardCount = world; rd.shardIndex = rank;
     if (rd.shardBlock <= 0) rd.shardBlock = std::max(1, 4 * rd.xResolution);
@@ -2086,7 +2119,7 @@ int pbrtgpu_render_sharded(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rdIn, P
     // the exchange step: one reduce of the 16 B/pixel film to rank 0 (its time is part of the caller's e2e, not of renderMs)
     rc = PbrtGpuCommReduceToRoot(comm, reinterpret_cast<float *>(scene->film.p), nFilm * 4, nullptr);
     if (rc != PBRTGPU_OK) return rc;
-    if (rank == 0) CUDA_TRY(cudaMemcpy(pixels, scene->film.p, nFilm * sizeof(PbrtGpuPixel), cudaMemcpyDeviceToHost));
+    if (rank == 0 && pixels) CUDA_TRY(cudaMemcpy(pixels, scene->film.p, nFilm * sizeof(PbrtGpuPixel), cudaMemcpyDeviceToHost));
     else CUDA_TRY(cudaStreamSynchronize(nullptr));
     return PBRTGPU_OK;
 }

@@ -17,13 +17,16 @@ bool GpuSamplerRenderer::Render(Scene *scene) {
     }
     PbrtGpuRenderDesc rd;
     FillRenderDesc(&rd);
-    rc = pbrtgpu_render(gs, &rd, film->pixels.data(), &lastStats);
+    // several GPUs: every rank renders its share of the task list, the films are summed onto rank 0 by the
+    // library's NCCL reduce, rank 0 owns the image
+    if (comm) rc = pbrtgpu_render_sharded(gs, &rd, comm, film->pixels.data(), &lastStats);
+    else rc = pbrtgpu_render(gs, &rd, film->pixels.data(), &lastStats);
     pbrtgpu_scene_destroy(gs);
     if (rc != PBRTGPU_OK) {
         fprintf(stderr, "Error: pbrtgpu_render failed (%d): %s\n", rc, pbrtgpu_last_error());
         return false;
     }
-    if (writeImage) return film->WriteImage();
+    if (writeImage && (!comm || commRank == 0)) return film->WriteImage();
     return true;
 }
 

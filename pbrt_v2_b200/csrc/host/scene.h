@@ -278,7 +278,9 @@ struct GpuSamplerRenderer : Renderer {
     int nCores;           // PbrtOptions.nCores (--ncores); 0 = hardware
     bool writeImage;
     PbrtGpuStats lastStats;
-    GpuSamplerRenderer() : nCores(0), writeImage(true) { memset(&lastStats, 0, sizeof(lastStats)); }
+    PbrtGpuComm *comm;    // several GPUs: the library's NCCL communicator (not owned) or null; rank 0 owns the image
+    int commRank;
+    GpuSamplerRenderer() : nCores(0), writeImage(true), comm(nullptr), commRank(0) { memset(&lastStats, 0, sizeof(lastStats)); }
     int TaskCount() const;                       // samplerrenderer.cpp:203-205
     void FillRenderDesc(PbrtGpuRenderDesc *rd) const;
     bool Render(Scene *scene) override;          // samplerrenderer.cpp:188-222

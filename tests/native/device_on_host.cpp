@@ -254,7 +254,9 @@ void RunTaskH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
 #define PATH_ANIM true
 #define PATH_INTEG INTEG
 #define PATH_COUNT_TAIL() ((void)0)
+#define PATH_DL_FRAME(i) dlFrames[i]
 #include "../../pbrt_v2_b200/csrc/device/path_body.inc"
+#undef PATH_DL_FRAME
 #undef PATH_COUNT_TAIL
 #undef PATH_FEVAL_IN
 #undef PATH_EVALWO_IN

@@ -32,7 +32,7 @@ alignas(16) uint32_t smem[64 * 1024];          // `extern __shared__ uint32_t sm
 static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&g_warpBarrier); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
-template <typename T> static inline T __ldcg(const T *p) { return *(const volatile T *)p; }
+template <typename T> static inline T __ldcg(const T *p) { T v; memcpy(&v, p, sizeof(T)); std::atomic_signal_fence(std::memory_order_seq_cst); return v; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
@@ -64,7 +64,10 @@ template <typename K> void LaunchWarp(K kernel) {   // one block of one warp: <<
 
 }  // namespace
 
-DOH_EXPORT int toh_paired_build(void) { return PBRT_TABLES_PAIRED; }   // which variant of the kernel source this harness holds
+DOH_EXPORT int toh_paired_build(void) { return PBRT_TABLES_PAIRED; }
+static int g_split = 0;
+// 1: run k_tables the way the render path launches it -- the stream walk (stages 1) and the shuffles (stages 2) as two launches
+DOH_EXPORT void toh_set_split(int on) { g_split = on; }   // which variant of the kernel source this harness holds
 
 // pbrtgpu_ld_samples with the table kernel executed by the warp emulation.  general != 0 forces k_tables_general even for
 // the path integrator's layout; rounds > 0 additionally runs that many further pixels of the task first (the RNG state
@@ -94,7 +97,11 @@ DOH_EXPORT int toh_ld_samples(const PbrtGpuRenderDesc *rd, int taskNum, int x0, 
     for (int r = 0; r <= rounds; ++r) {
         b.round = r;
         if (useGeneral) LaunchWarp([&]() { k_tables_general<1>(b, spp, G, T, tgt.data()); });
-        else LaunchWarp([&]() { k_tables<1>(b, spp, G); });
+        else if (g_split) {
+            const int G2 = PlanTables(spp, 2).G;
+            LaunchWarp([&]() { k_tables<1>(b, spp, 0, 1); });
+            LaunchWarp([&]() { k_tables<1>(b, spp, G2, 2); });
+        } else LaunchWarp([&]() { k_tables<1>(b, spp, G); });
     }
     const int tw = x1 - x0;
     tr.x0 = x0 + rounds % tw; tr.y0 = y0 + rounds / tw;   // ExpandSample offsets by the pixel in tasks[0]

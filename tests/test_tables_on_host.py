@@ -65,6 +65,21 @@ def test_path_table_kernel_matches_oracle(toh, spp):
         assert _same(_run(toh, rd, task), oa.ld_samples(rd, task)), (spp, task)
 
 
+@pytest.mark.parametrize("spp", [1, 2, 4, 8, 16, 32, 256, 1024, 2048, 4096, 8192])
+def test_path_table_kernel_in_two_launches_matches_oracle(toh, spp):
+    """the render path's form: the draw-stream walk (stages = 1) and the shuffles + rows (stages = 2) as separate launches,
+    the latter with its own shared-memory plan; also across pixels (the RNG state handed on through rngCur / rngNext / mti)"""
+    toh.toh_set_split(1)
+    try:
+        rd = _path_rd(spp)
+        for task in ([0, 5] if spp <= 1024 else [3]):
+            assert _same(_run(toh, rd, task), oa.ld_samples(rd, task)), (spp, task)
+        if spp in (4, 32, 2048):
+            assert _same(_run(toh, rd, 2, rounds=3), oa.ld_samples(rd, 2, 3))
+    finally:
+        toh.toh_set_split(0)
+
+
 @pytest.mark.parametrize("spp", [1, 8, 128, 2048])
 def test_general_table_kernel_on_path_layout_matches_oracle(toh, spp):
     rd = _path_rd(spp)
