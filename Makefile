@@ -25,11 +25,13 @@ NVDEFS    ?=
 # kernel experiments, built next to the product library so that a GPU visit can A/B them without compiling on the box
 # (scripts/ab_variants.py; tests/test_zz_gpu_variants.py runs the parity suite over them).  Nothing loads them by default.
 #   make variants VARIANT_NAMES="pairs foo"   with   VARIANT_DEFS_foo := -DSOMETHING=1
-VARIANT_NAMES ?= pairs top10 sstack top9_sstack
+VARIANT_NAMES ?= pairs ww ww_sstack sstack top9_sstack
 VARIANT_DEFS_pairs := -DPBRT_PAIR_NODES=1
-# north_star kernel items as A/B variants: top 10 levels of the scene BVH staged in shared memory by a TMA bulk copy;
-# the first 32 traversal-stack entries in shared memory
-VARIANT_DEFS_top10 := -DPBRT_TOP_LEVELS=10
+# the trace kernels' walk as a warp-uniform while-while (kcommon.cuh PBRT_TRACE_LOOP); north_star kernel items as A/B
+# variants: the first 32 traversal-stack entries in shared memory; the top 9 levels of the scene BVH staged in shared memory
+# by a TMA bulk copy
+VARIANT_DEFS_ww := -DPBRT_TRACE_LOOP=1
+VARIANT_DEFS_ww_sstack := -DPBRT_TRACE_LOOP=1 -DPBRT_SMEM_STACK=32
 VARIANT_DEFS_sstack := -DPBRT_SMEM_STACK=32
 VARIANT_DEFS_top9_sstack := -DPBRT_TOP_LEVELS=9 -DPBRT_SMEM_STACK=32
 VARIANTS  := $(patsubst %,$(PKG)/ab/libpbrtgpu_%.so,$(VARIANT_NAMES))

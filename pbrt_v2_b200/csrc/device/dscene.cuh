@@ -939,11 +939,11 @@ DEV bool TravLeaf(const DScene &sc, Trav &t, TraceStats *st) {
 
 // one node test (+ the leaf it leads to): the walk in single steps.  true when the ray is finished.
 template <bool STATS, bool ANIM>
-DEV bool TravStep(const DScene &sc, Trav &t, TraceStats *st) {
+DEV bool TravStep(const DScene &sc, Trav &t, TraceStats *st, const float4 *smemTop = nullptr) {
 #if PBRT_PAIR_NODES
     if (!STATS) return TravStepPairs<ANIM>(sc, t);
 #endif
-    const int r = TravDescend<STATS, ANIM>(sc, t, st, 1);
+    const int r = TravDescend<STATS, ANIM>(sc, t, st, 1, smemTop);
     if (r == 2) return true;
     if (r == 1) return TravLeaf<STATS, ANIM>(sc, t, st);
     return false;

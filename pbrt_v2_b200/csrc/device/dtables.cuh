@@ -7,6 +7,7 @@
 #include "../../../include/pbrtgpu.h"
 #include "dmath.cuh"
 #include "drng.cuh"
+#include "kcommon.cuh"
 
 using namespace dev;   // (the kernels live in the global namespace, like the rest of pbrtgpu.cu)
 
@@ -14,28 +15,6 @@ using namespace dev;   // (the kernels live in the global namespace, like the re
 #ifndef PBRT_TABLES_PAIRED
 #define PBRT_TABLES_PAIRED 0
 #endif
-
-struct TaskRec {
-    int taskNum;
-    int x0, x1, y0, y1;   // Sampler::ComputeSubWindow tile
-};
-
-struct BatchArgs {
-    const TaskRec *tasks;
-    int nBatch;
-    int round;
-    uint16_t *perm;      // [nBatch][spp][PERM_STRIDE]
-    uint32_t *scr;       // [nBatch][SCR_STRIDE]
-    uint32_t *rngCur;    // [nBatch][624]
-    uint32_t *rngNext;   // [nBatch][624]
-    int *mti;            // [nBatch]
-    float4 *ls;          // [nBatch][spp]     finished radiance (xyz) + footprint/TAIL bits (w)
-    float4 *rec;         // [nBatch][spp][4]  parked bounce-3 vertices (phase 1 -> phase 2)
-    unsigned *tailCount; // [nBatch] number of samples the task parked in phase 1 (sort key of phase 2)
-    uint32_t *tailMask;  // [nBatch][maskWords] bit s: sample s of the task's current pixel is parked (null: not kept)
-    int maskWords;       // max(1, spp / 32)
-    const unsigned *order; // [nBatch] phase 2: thread i serves task order[i] (tasks with parked samples first) or null
-};
 
 // --------------------------------------------------------------------- k_tables
 // LDSampler::GetMoreSamples / LDPixelSample for one pixel of each task (one warp per task).

@@ -16,6 +16,7 @@
 // k_film: ImageFilm::AddSample for every sample of every task-pixel, in sample order (what k_path<2> did inline).
 #pragma once
 #include "dvertex.cuh"
+#include "kcommon.cuh"
 
 #ifndef K_VERTEX_MIN_BLOCKS
 #define K_VERTEX_MIN_BLOCKS 4
@@ -53,16 +54,6 @@ DEV void StageTopNodes(float4 *dst, uint64_t *mbar, const float4 *src) {
                      : "=r"(done) : "r"(mb) : "memory");
 }
 #endif
-
-DEV unsigned AggregatedAddV(unsigned *ctr) {   // warp-aggregated atomicAdd(ctr, 1) for the currently converged lanes
-    const unsigned m = __activemask();
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(ctr, (unsigned)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    return base + __popc(m & ((1u << lane) - 1u));
-}
 
 template <int PHASE, bool STATS, bool ANIM>
 __global__ void __launch_bounds__(128, K_VERTEX_MIN_BLOCKS) k_vertex(VxArgs a) {

@@ -1,0 +1,409 @@
+// kwave.cuh -- phase 1 of PathIntegrator as a VERTEX wavefront (included by pbrtgpu.cu; the default since round 2).
+//
+// The first wavefront (k_logic / k_eval / k_trace, still what DirectLightingIntegrator runs on) cuts PathIntegrator::Li at
+// every blocking request: a path vertex costs up to three BSDF evaluations and three rays, one after the other, and each of
+// those six hand-overs moves the whole 288-byte slot through HBM (profiles/r01_k_logic_ncu_full.txt: 2 KB of state traffic
+// per camera sample, more than the scene bytes the sample touches).  The vertex-synchronous megakernel (kvertex.cuh) showed
+// that the three directions of a vertex -- light sample, MIS sample, continuation -- depend on the shading context and the
+// vertex's random numbers only (dvertex.cuh), so they can be chosen together; it lost to the wavefront because its lanes
+// idle through each other's stages (8 of 32 active).  This file puts that schedule on the wavefront's compaction:
+//
+//   k_wshade   one thread per path slot, ONE pass per path vertex: finish the previous vertex with its three ray results
+//              (VertexB: L += T * nLights * Ld, T = Tnew), then -- path ray missed / path over: write the sample's radiance
+//              and take the next camera sample of the batch; bounce 3 reached: park the sample for phase 2; else VertexA:
+//              shade, choose the three directions, write the vertex record.  BSDF values of analytic materials are computed
+//              on the spot and their rays queued; measured-BRDF directions go to the evaluation queue
+//   k_weval    persistent lanes over the evaluation queue: IrregIsotropicBRDF::f per (slot, direction); a direction whose
+//              value is not black gets its ray queued
+//   k_wtrace   persistent lanes over the three ray queues (shadow, MIS, path rays in separate runs): BVHAccel::IntersectP /
+//              Intersect step-wise as in k_trace; the MIS ray's "did it land on the sampled light" test happens here
+// so a vertex moves its state through HBM once (~420 B in k_wshade, 48 B per evaluation, 48 B per ray) instead of six times.
+// Every float expression is dvertex.cuh's (shared with k_vertex and the host-compiled harness): same operands, same
+// operation order per quantity, so the film is the same film.
+#pragma once
+#include "dvertex.cuh"
+#include "kcommon.cuh"
+#include "drng.cuh"
+
+#ifndef K_WSHADE_MIN_BLOCKS
+#define K_WSHADE_MIN_BLOCKS 4
+#endif
+#ifndef K_WEVAL_MIN_BLOCKS
+#define K_WEVAL_MIN_BLOCKS 8
+#endif
+
+// slot fields (SoA float4: field f of slot i is pool[f * P + i])
+enum {
+    W_P = 0,   // origin of the vertex's rays: p.xyz, rayEpsilon            (camera ray: o.xyz, 0)
+    W_D0,      // light sample:  wiW.xyz, visMaxt            -> .w = 1 if the shadow ray was blocked
+    W_D1,      // MIS sample:    wiW.xyz, lightNum (int)     -> .w = 1 if the ray landed on that light, facing it
+    W_D2,      // continuation / camera ray: d.xyz, -        -> .w = t of the hit
+    W_HIT,     // path ray result: prim (-1: none), b1, b2, maxtIn
+    W_EWO,     // evalWo.xyz, material
+    W_EW0,     // evalWi[k].xyz, evalFlags[k] | (ray allowed << 16)
+    W_EW1,
+    W_EW2,
+    W_F0,      // BSDF values f[k].rgb
+    W_F1,
+    W_F2,
+    W_T,       // T.rgb (before the vertex), packed bits (WB_*)
+    W_L,       // L.rgb, film-footprint code
+    W_ID,      // task (batch index), sample, ray.time, pdfP
+    W_V0,      // Li.rgb, scalarL
+    W_V1,      // absM, weightM, pdfM, absP
+    W_V2,      // specF.rgb (PBRT_SPECULAR), -
+    W_COUNT
+};
+// W_T.w
+enum { WB_BOUNCES = 0x3, WB_VERTEX = 0x4, WB_AFTER_SPEC = 0x8, WB_SPEC_SAMPLED = 0x10, WB_NEED0 = 0x20, WB_NEED1 = 0x40,
+       WB_NEED2 = 0x80, WB_RETIRED = 0x100, WB_LIGHT_SHIFT = 16 };
+// counters
+enum { WC_RAYS = 0 /* 3 */, WC_EVALS = 3, WC_TRACE_CUR, WC_EVAL_CUR,
+       WC_LIVE,          // slots that hold a camera path after k_wshade (0: the batch is done)
+       WC_NEXT_SAMPLE,   // (everything before it is reset every iteration)
+       WC_COUNT };
+#define W_RAY_ALLOWED 0x10000
+
+struct WvArgs {
+    DScene sc;
+    RenderParams rp;
+    BatchArgs b;
+    float4 *pool;
+    uint32_t P;
+    uint32_t *qRay;      // [3][P] slots with a shadow / MIS / path ray to trace this iteration
+    uint32_t *qEval;     // [3 * P] (slot << 2) | direction
+    unsigned *counters;  // WC_*
+    unsigned totalSamples;
+    int iter;            // 0: every slot starts with a camera sample
+    DeviceStats *stats;
+};
+
+DEV void WvPushRay(const WvArgs &a, int kind, uint32_t slot) {
+    const unsigned i = AggregatedAddV(a.counters + WC_RAYS + kind);
+    a.qRay[(size_t)kind * a.P + i] = slot;
+}
+
+// ----------------------------------------------------------------------------------------------------------- k_wshade
+template <bool STATS, bool ANIM>
+__global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(WvArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.P) return;
+    const DScene &sc = a.sc;
+    const RenderParams &rp = a.rp;
+    const int spp = rp.spp;
+    const size_t P = a.P;
+    float4 *pool = a.pool;
+    const int nLights = (int)sc.nLights;
+#define WF(f) pool[(size_t)(f) * P + slot]
+
+    Ray ray;
+    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f; ray.time = 0.f;
+    Hit hit;
+    hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.maxtIn = 0.f;
+    Spec T(1.f), L(0.f);
+    int bounces = 0, s = 0, bi = 0, code = 0;
+    bool afterSpecular = false;
+    bool have = false;       // the slot holds a camera path whose path ray has been traced
+    bool atVertex = false;   // ... and hit something
+    unsigned long long nShadedN = 0;
+
+    if (a.iter > 0) {
+        const float4 fT = WF(W_T);
+        const uint32_t bits = __float_as_uint(fT.w);
+        if (bits & WB_RETIRED) return;
+        const float4 fL = WF(W_L), fId = WF(W_ID), fP = WF(W_P), fD2 = WF(W_D2), fH = WF(W_HIT);
+        T = Spec(fT.x, fT.y, fT.z);
+        L = Spec(fL.x, fL.y, fL.z); code = __float_as_int(fL.w);
+        bi = __float_as_int(fId.x); s = __float_as_int(fId.y); ray.time = fId.z;
+        bounces = (int)(bits & WB_BOUNCES);
+        afterSpecular = (bits & WB_AFTER_SPEC) != 0;
+        bool pathTraced = true;
+        if (bits & WB_VERTEX) {
+            // ---- the second half of the previous vertex (dvertex.cuh VertexB) with the BSDF values and the ray results
+            const float4 f0 = WF(W_F0), f1 = WF(W_F1), f2 = WF(W_F2), v0 = WF(W_V0), v1 = WF(W_V1);
+            Vertex v;
+            v.need[0] = (bits & WB_NEED0) != 0; v.need[1] = (bits & WB_NEED1) != 0; v.need[2] = (bits & WB_NEED2) != 0;
+            v.Li = Spec(v0.x, v0.y, v0.z); v.scalarL = v0.w;
+            v.absM = v1.x; v.weightM = v1.y; v.pdfM = v1.z; v.absP = v1.w; v.pdfP = fId.w;
+            const int lightNum = (int)(bits >> WB_LIGHT_SHIFT);
+            v.Lemit = Spec(0.f);
+            if (v.need[1]) { const PbrtGpuLight &light = sc.lights[lightNum]; v.Lemit = Spec(light.L[0], light.L[1], light.L[2]); }
+#if PBRT_SPECULAR
+            v.specSampled = (bits & WB_SPEC_SAMPLED) != 0;
+            v.specF = Spec(0.f);
+            if (v.specSampled) { const float4 v2 = WF(W_V2); v.specF = Spec(v2.x, v2.y, v2.z); }
+#endif
+            const Spec f[3] = {Spec(f0.x, f0.y, f0.z), Spec(f1.x, f1.y, f1.z), Spec(f2.x, f2.y, f2.z)};
+            bool rrDrawn = false;
+            const bool cont = VertexB(f, bounces, rp.maxDepth, T, 0.f, &v, &rrDrawn);   // (bounces <= 2: no Russian roulette)
+            Spec Ld(0.f);
+            if (v.ray[VX_LIGHT] && WF(W_D0).w == 0.f) Ld = Ld + v.pendS;    // visibility.Unoccluded(scene)
+            if (v.ray[VX_MIS] && WF(W_D1).w == 1.f) Ld = Ld + v.pendM;      // the MIS ray landed on the light
+            L = L + T * ((float)nLights * Ld);                              // path.cpp:71-80
+            T = v.Tnew;
+            if (cont) {
+#if PBRT_SPECULAR
+                afterSpecular = v.specSampled;
+#endif
+                ++bounces;
+            } else
+                pathTraced = false;   // PathIntegrator::Li returned at this vertex
+        }
+        have = true;
+        if (pathTraced) {
+            ray.o = V3(fP.x, fP.y, fP.z); ray.mint = fP.w;
+            ray.d = V3(fD2.x, fD2.y, fD2.z); ray.maxt = fD2.w;
+            hit.prim = __float_as_int(fH.x); hit.b1 = fH.y; hit.b2 = fH.z; hit.maxtIn = fH.w; hit.t = fD2.w;
+            atVertex = hit.prim >= 0;
+        }
+        if (!atVertex) {
+            // the path is over (no continuation, or the ray left the scene: path.cpp:113-118 adds nothing for the in-scope
+            // lights); samplerrenderer.cpp:119-133 sanity checks
+            const Spec Ls = SanitizeRadiance(L);
+            a.b.ls[(size_t)bi * spp + s] = make_float4(Ls.r, Ls.g, Ls.b, __int_as_float(code));
+            have = false;
+        } else if (bounces == 3) {
+            // ---- park the sample: from here on the path draws from the task's RNG stream (phase 2)
+            float4 *r = a.b.rec + ((size_t)bi * spp + s) * 4;
+            r[0] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+            r[1] = make_float4(ray.d.x, ray.d.y, ray.d.z, hit.t);
+            r[2] = make_float4(T.r, T.g, T.b, __int_as_float(hit.prim));
+            r[3] = make_float4(hit.b1, hit.b2, hit.maxtIn, ray.time);
+            a.b.ls[(size_t)bi * spp + s] = make_float4(L.r, L.g, L.b, __int_as_float(code | LS_TAIL | (afterSpecular ? LS_SPEC : 0)));
+            atomicAdd(a.b.tailCount + bi, 1u);
+            atomicOr(a.b.tailMask + (size_t)bi * a.b.maskWords + (s >> 5), 1u << (s & 31));
+            have = false;
+        }
+    }
+
+    if (!have) {
+        // ---- the next camera sample of the batch: (task, sample) = (g / spp, g % spp)
+        bool got = false;
+        for (;;) {
+            const unsigned g = AggregatedAddV(a.counters + WC_NEXT_SAMPLE);
+            if (g >= a.totalSamples) break;
+            bi = (int)(g / (unsigned)spp);
+            s = (int)(g - (unsigned)bi * (unsigned)spp);
+            const TaskRec tr = a.b.tasks[bi];
+            const int tw = tr.x1 - tr.x0;
+            if (a.b.round >= tw * (tr.y1 - tr.y0)) continue;   // (this task has no pixel in this round)
+            const int xPos = tr.x0 + a.b.round % tw, yPos = tr.y0 + a.b.round / tw;
+            const uint16_t *row = a.b.perm + ((size_t)bi * spp + s) * PERM_STRIDE;
+            code = CameraRay(rp, row, a.b.scr + (size_t)bi * SCR_STRIDE, xPos, yPos, &ray);
+            got = true;
+            break;
+        }
+        if (!got) {
+            WF(W_T) = make_float4(0.f, 0.f, 0.f, __uint_as_float(WB_RETIRED));
+            return;
+        }
+        AggregatedAddV(a.counters + WC_LIVE);
+        WF(W_P) = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+        WF(W_D2) = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+        WF(W_T) = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
+        WF(W_L) = make_float4(0.f, 0.f, 0.f, __int_as_float(code));
+        WF(W_ID) = make_float4(__int_as_float(bi), __int_as_float(s), ray.time, 0.f);
+        WvPushRay(a, VX_PATH, slot);
+        return;
+    }
+
+    AggregatedAddV(a.counters + WC_LIVE);
+    // ---- a vertex to shade: VertexA, the record, the requests
+    VertexRandoms u;
+    VertexRandomsFromTables(a.b.perm + ((size_t)bi * spp + s) * PERM_STRIDE, a.b.scr + (size_t)bi * SCR_STRIDE, bounces, &u);
+    Vertex v;
+    {
+        ShadeCtx ctx;
+        VertexA<ANIM>(sc, ray, hit, bounces, afterSpecular, u, T, L, ctx, &v, STATS ? &nShadedN : nullptr);
+    }
+    const bool pathAllowed = bounces != rp.maxDepth;
+    uint32_t bits = (uint32_t)bounces | WB_VERTEX | (afterSpecular ? WB_AFTER_SPEC : 0u) |
+                    (v.need[0] ? WB_NEED0 : 0u) | (v.need[1] ? WB_NEED1 : 0u) | (v.need[2] ? WB_NEED2 : 0u) |
+                    ((uint32_t)v.lightNum << WB_LIGHT_SHIFT);
+#if PBRT_SPECULAR
+    if (v.specSampled) bits |= WB_SPEC_SAMPLED;
+#endif
+    WF(W_P) = make_float4(v.p.x, v.p.y, v.p.z, v.eps);
+    WF(W_T) = make_float4(T.r, T.g, T.b, __uint_as_float(bits));
+    WF(W_L) = make_float4(L.r, L.g, L.b, __int_as_float(code));
+    WF(W_ID) = make_float4(__int_as_float(bi), __int_as_float(s), ray.time, v.pdfP);
+    WF(W_V0) = make_float4(v.Li.r, v.Li.g, v.Li.b, v.scalarL);
+    WF(W_V1) = make_float4(v.absM, v.weightM, v.pdfM, v.absP);
+    if (v.need[VX_LIGHT]) WF(W_D0) = make_float4(v.wiW[VX_LIGHT].x, v.wiW[VX_LIGHT].y, v.wiW[VX_LIGHT].z, v.visMaxt);
+    if (v.need[VX_MIS]) WF(W_D1) = make_float4(v.wiW[VX_MIS].x, v.wiW[VX_MIS].y, v.wiW[VX_MIS].z, __int_as_float(v.lightNum));
+    if (v.need[VX_PATH]) WF(W_D2) = make_float4(v.wiW[VX_PATH].x, v.wiW[VX_PATH].y, v.wiW[VX_PATH].z, INF_F);
+#if PBRT_SPECULAR
+    if (v.specSampled) WF(W_V2) = make_float4(v.specF.r, v.specF.g, v.specF.b, 0.f);
+#endif
+    const bool measured = sc.materials[v.material].type == PBRTGPU_MAT_MEASURED;
+    bool wroteWo = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (!v.need[k]) continue;
+        const bool allowed = k != VX_PATH || pathAllowed;
+#if PBRT_SPECULAR
+        if (k == VX_PATH && v.specSampled) {   // the value is specF (BSDF::Sample_f, reflection.cpp:572): nothing to evaluate
+            if (allowed && !v.specF.IsBlack()) WvPushRay(a, k, slot);
+            continue;
+        }
+#endif
+        if (measured) {
+            if (!wroteWo) { WF(W_EWO) = make_float4(v.evalWo.x, v.evalWo.y, v.evalWo.z, __int_as_float(v.material)); wroteWo = true; }
+            WF(W_EW0 + k) = make_float4(v.evalWi[k].x, v.evalWi[k].y, v.evalWi[k].z,
+                                        __int_as_float(v.evalFlags[k] | (allowed ? W_RAY_ALLOWED : 0)));
+            const unsigned i = AggregatedAddV(a.counters + WC_EVALS);
+            a.qEval[i] = (slot << 2) | (uint32_t)k;
+        } else {
+            const Spec f = VertexEval(sc, v.material, v.evalWo, v.evalWi[k], v.evalFlags[k]);
+            WF(W_F0 + k) = make_float4(f.r, f.g, f.b, 0.f);
+            if (allowed && !f.IsBlack()) WvPushRay(a, k, slot);
+        }
+    }
+    if (STATS && nShadedN) atomicAdd(&a.stats->shadedN, nShadedN);
+#undef WF
+}
+
+// ------------------------------------------------------------------------------------------------------------ k_weval
+// measured-BRDF values (IrregIsotropicBRDF::f) of the queued (slot, direction) requests
+__global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(WvArgs a) {
+    const unsigned n = a.counters[WC_EVALS];
+    const size_t P = a.P;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const uint32_t e = a.qEval[idx];
+        const uint32_t slot = e >> 2;
+        const int k = (int)(e & 3u);
+        const float4 wo = a.pool[(size_t)W_EWO * P + slot], wi = a.pool[(size_t)(W_EW0 + k) * P + slot];
+        const int word = __float_as_int(wi.w);
+        const Spec f = VertexEval(a.sc, __float_as_int(wo.w), V3(wo.x, wo.y, wo.z), V3(wi.x, wi.y, wi.z), word & 0xffff);
+        a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
+        if ((word & W_RAY_ALLOWED) && !f.IsBlack()) WvPushRay(a, k, slot);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------- k_wtrace
+// persistent ray-queue consumer: k_trace's loop (chunked hand-out, while-while walk) over the vertex wavefront's records
+template <bool STATS, bool ANIM>
+__global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_wtrace(WvArgs a) {
+    const DScene &sc = a.sc;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // this iteration's rays: the shadow, MIS and path queues back to back
+    const unsigned n0 = a.counters[WC_RAYS + VX_LIGHT], n1 = n0 + a.counters[WC_RAYS + VX_MIS], n = n1 + a.counters[WC_RAYS + VX_PATH];
+    float4 *pool = a.pool;
+    const size_t P = a.P;
+    const uint32_t *q0 = a.qRay, *q1 = a.qRay + P, *q2 = a.qRay + 2 * P;
+    Trav t;
+#if PBRT_SMEM_STACK
+    __shared__ uint32_t sStack[PBRT_SMEM_STACK * 128];
+    t.sstk = sStack + threadIdx.x;
+#endif
+#if PBRT_TOP_LEVELS
+    __shared__ __align__(128) float4 sTop[2 * PBRT_TOP_SLOTS];
+    __shared__ __align__(8) uint64_t sTopBar;
+    StageTopNodes(sTop, &sTopBar, sc.topNodes);
+    const float4 *smemTop = sTop;
+#else
+    const float4 *smemTop = nullptr;
+#endif
+    bool active = false;
+    bool leaf = false;        // the lane stands before a leaf (TravDescend returned 1)
+    uint32_t slot = 0;
+    int kind = 0, lightNum = 0;
+    Ray wray;                 // the ray as queued (world space): MisHitIsLight needs it after the walk
+    wray.o = V3(0, 0, 0); wray.d = V3(0, 0, 1); wray.mint = 0.f; wray.maxt = 0.f; wray.time = 0.f;
+    TraceStats st;
+    st.nodes = st.prims = 0;
+    unsigned long long nClosest = 0, nShadow = 0;
+    unsigned cPos = 0, cEnd = 0;   // the warp's reserved chunk of queue entries (warp-uniform)
+    bool exhausted = false;        // the cursor has passed the end of the queue
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && !(exhausted && cPos >= cEnd)) {
+            if (cPos >= cEnd) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(a.counters + WC_TRACE_CUR, (unsigned)TRACE_CHUNK);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) { exhausted = true; cPos = cEnd = 0; }
+                else { cPos = base; cEnd = min(base + (unsigned)TRACE_CHUNK, n); }
+            }
+            if (!active) {
+                const unsigned idx = cPos + __popc(idle & ((1u << lane) - 1u));
+                if (idx < cEnd) {
+                    kind = idx < n0 ? VX_LIGHT : (idx < n1 ? VX_MIS : VX_PATH);
+                    slot = kind == VX_LIGHT ? q0[idx] : (kind == VX_MIS ? q1[idx - n0] : q2[idx - n1]);
+                    const float4 r0 = pool[(size_t)W_P * P + slot], r1 = pool[(size_t)(W_D0 + kind) * P + slot];
+                    wray.o = V3(r0.x, r0.y, r0.z); wray.mint = r0.w;
+                    wray.d = V3(r1.x, r1.y, r1.z);
+                    wray.maxt = kind == VX_LIGHT ? r1.w : INF_F;
+                    lightNum = kind == VX_MIS ? __float_as_int(r1.w) : 0;
+                    wray.time = ANIM ? pool[(size_t)W_ID * P + slot].z : 0.f;
+                    TravInit(t, wray, kind == VX_LIGHT);
+                    if (STATS) { if (kind == VX_LIGHT) ++nShadow; else ++nClosest; }
+                    active = true; leaf = false;
+                }
+            }
+            cPos = min(cEnd, cPos + (unsigned)__popc(idle));
+        }
+        const bool more = !(exhausted && cPos >= cEnd);   // could idle lanes still be given rays?
+        if (!__any_sync(FULL, active)) {
+            if (!more) break;
+            continue;
+        }
+#if PBRT_TRACE_LOOP == 0 || PBRT_PAIR_NODES
+        for (int it = 0; it < 64; ++it) {
+            const bool fin = active && TravStep<STATS, ANIM>(sc, t, &st, smemTop);
+#else
+        for (int it = 0; it < 8; ++it) {
+            bool fin = false;
+            for (int k = 0; k < TRACE_DESCEND_STEPS; ++k) {   // the warp's loop: every round ends in a vote
+                const bool walking = active && !leaf && !fin;
+                if (!__any_sync(FULL, walking)) break;
+                if (walking) {
+                    const int r = TravDescend<STATS, ANIM>(sc, t, &st, 1, smemTop);
+                    leaf = r == 1;
+                    fin = r == 2;
+                }
+            }
+            if (active && leaf) {
+                leaf = false;
+                fin = TravLeaf<STATS, ANIM>(sc, t, &st);
+            }
+#endif
+            if (fin) {
+                if (kind == VX_LIGHT)
+                    pool[(size_t)W_D0 * P + slot].w = t.found ? 1.f : 0.f;
+                else if (kind == VX_MIS) {
+                    bool onLight = false;
+                    if (t.found) {
+                        Ray q = wray;
+                        q.maxt = t.ray.maxt;
+                        Hit h = t.hit;
+                        h.t = t.ray.maxt;
+                        onLight = MisHitIsLight<ANIM>(sc, q, h, lightNum);
+                    }
+                    pool[(size_t)W_D1 * P + slot].w = onLight ? 1.f : 0.f;
+                } else {
+                    pool[(size_t)W_HIT * P + slot] = make_float4(__int_as_float(t.found ? t.hit.prim : -1), t.hit.b1, t.hit.b2, t.hit.maxtIn);
+                    pool[(size_t)W_D2 * P + slot].w = t.ray.maxt;
+                }
+                active = false;
+            }
+            const int nActive = __popc(__ballot_sync(FULL, active));
+            if (nActive == 0 || (more && nActive < TRACE_REFILL_BELOW)) break;
+        }
+    }
+    if (STATS) {
+        unsigned long long v[4] = {nClosest, nShadow, st.nodes, st.prims};
+        for (int k = 0; k < 4; ++k) {
+            unsigned long long x = v[k];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(FULL, x, o);
+            v[k] = x;
+        }
+        if (lane == 0) {
+            atomicAdd(&a.stats->closestRays, v[0]);
+            atomicAdd(&a.stats->shadowRays, v[1]);
+            atomicAdd(&a.stats->nodes, v[2]);
+            atomicAdd(&a.stats->prims, v[3]);
+        }
+    }
+}

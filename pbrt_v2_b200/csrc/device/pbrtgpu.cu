@@ -20,6 +20,7 @@
 #include "drng.cuh"
 #include "dpath.cuh"
 #include "dtables.cuh"
+#include "kcommon.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -36,10 +37,6 @@
 using namespace dev;
 
 // ===================================================================== device
-struct DeviceStats {
-    unsigned long long closestRays, shadowRays, nodes, prims, shadedN, cameraSamples;
-};
-
 __global__ void k_expand_samples(BatchArgs a, int spp, float shutterOpen, float shutterClose, SampleLayoutDev L,
                                  int floatsPerSample, float *out) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,9 +69,6 @@ __global__ void k_expand_samples(BatchArgs a, int spp, float shutterOpen, float 
 #endif
 #ifndef K_LOGIC_MIN_BLOCKS
 #define K_LOGIC_MIN_BLOCKS 4
-#endif
-#ifndef K_TRACE_MIN_BLOCKS
-#define K_TRACE_MIN_BLOCKS 7
 #endif
 #ifndef K_EVAL_MIN_BLOCKS
 #define K_EVAL_MIN_BLOCKS 8
@@ -876,14 +870,7 @@ __global__ void __launch_bounds__(128) k_film_direct(PathArgs a, int advance) {
     if (live) a.b.mti[bi] = mti;
 }
 
-// persistent ray queue consumer
-#define TRACE_CHUNK 64
-#ifndef TRACE_DESCEND_STEPS
-#define TRACE_DESCEND_STEPS 12   // node tests per lane before the warp looks at its leaves / refills
-#endif
-#ifndef TRACE_REFILL_BELOW
-#define TRACE_REFILL_BELOW 24    // refill the warp from the queue when fewer lanes than this are still walking
-#endif
+// persistent ray queue consumer (tuning constants: kcommon.cuh)
 template <bool STATS, bool ANIM>
 __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(WfArgs a) {
     const DScene &sc = a.sc;
@@ -955,20 +942,21 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(WfArgs a) {
             continue;
         }
         // walk until a good share of the warp has finished, then refill (nothing to refill with: walk on)
-#if PBRT_PAIR_NODES
+#if PBRT_TRACE_LOOP == 0 || PBRT_PAIR_NODES
         for (int it = 0; it < 64; ++it) {
-            bool fin = active && TravStep<STATS, ANIM>(sc, t, &st);
+            const bool fin = active && TravStep<STATS, ANIM>(sc, t, &st, smemTop);
 #else
         for (int it = 0; it < 8; ++it) {
-            // "while-while": every lane descends to its next leaf (bounded, so that finished lanes are refilled in time),
-            // the warp reconverges, then the lanes that stand before a leaf test its primitives together
             bool fin = false;
-            if (active && !leaf) {
-                const int r = TravDescend<STATS, ANIM>(sc, t, &st, TRACE_DESCEND_STEPS, smemTop);
-                leaf = r == 1;
-                fin = r == 2;
+            for (int k = 0; k < TRACE_DESCEND_STEPS; ++k) {   // the warp's loop: every round ends in a vote
+                const bool walking = active && !leaf && !fin;
+                if (!__any_sync(FULL, walking)) break;
+                if (walking) {
+                    const int r = TravDescend<STATS, ANIM>(sc, t, &st, 1, smemTop);
+                    leaf = r == 1;
+                    fin = r == 2;
+                }
             }
-            __syncwarp();
             if (active && leaf) {
                 leaf = false;
                 fin = TravLeaf<STATS, ANIM>(sc, t, &st);
@@ -998,6 +986,8 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(WfArgs a) {
         }
     }
 }
+
+#include "kwave.cuh"
 
 // measured-BRDF evaluations (IrregIsotropicBRDF::f) of the queued requests
 __global__ void __launch_bounds__(128, K_EVAL_MIN_BLOCKS) k_eval(WfArgs a) {
@@ -1104,6 +1094,7 @@ struct Lane {
     DevBuf<uint8_t> tgt;              // general table kernel: shuffle targets
     DevBuf<float4> pool;              // wavefront path slots (F_COUNT fields x P)
     DevBuf<uint32_t> traceQ;
+    DevBuf<uint32_t> evalQ;           // vertex wavefront: (slot, direction) evaluation requests
     DevBuf<DlFrame> dlFrames;         // DirectLightingIntegrator over specular materials: [P][DL_MAX_DEPTH]
     DevBuf<unsigned> counters;
     unsigned *hostCounters = nullptr;  // pinned
@@ -1306,6 +1297,9 @@ struct RenderConfig {
     // sample's 0..3 evaluations and 0..3 rays per vertex are too uneven for lock-step lanes; the wavefront compacts them),
     // phase 2 k_path<2> 814 ms vs k_vertex<2> + k_film 567 ms.  Default: wavefront phase 1, vertex-synchronous phase 2.
     int vertex = 2;
+    // PBRTGPU_WAVE=0: PathIntegrator's phase 1 on the request-granular wavefront (k_logic / k_eval / k_trace) instead of the
+    // vertex wavefront (kwave.cuh: k_wshade / k_weval / k_wtrace)
+    bool wave = true;
     int tailSort = 2;          // PBRTGPU_TAIL_SORT 0: chains in task order, 2: longest chain first
     int lockstep = 1;
     size_t pool = (size_t)1 << 22;
@@ -1319,6 +1313,7 @@ RenderConfig ReadConfig() {
         if (const char *e = getenv("PBRTGPU_WAVEFRONT")) c.wavefront = atoi(e) != 0;
         if (const char *e = getenv("PBRTGPU_WAVEFRONT2")) c.wavefront2 = atoi(e) != 0;
         if (const char *e = getenv("PBRTGPU_VERTEX")) c.vertex = atoi(e);
+        if (const char *e = getenv("PBRTGPU_WAVE")) c.wave = atoi(e) != 0;
         if (const char *e = getenv("PBRTGPU_TAIL_SORT")) c.tailSort = atoi(e);
         if (const char *e = getenv("PBRTGPU_LOCKSTEP")) c.lockstep = atoi(e);
         if (const char *e = getenv("PBRTGPU_POOL")) { if (atol(e) > 0) c.pool = (size_t)atol(e); }
@@ -1689,7 +1684,8 @@ int RunLane(LaneJob &job) {
     const RenderConfig &cfg = job.cfg;
     const bool direct = rp.integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
     const bool vertex1 = !direct && (cfg.vertex & 1), vertex2 = !direct && (cfg.vertex & 2);
-    const bool useWavefront = cfg.wavefront && !vertex1, useWavefront2 = cfg.wavefront2 && useWavefront && !vertex2;
+    const bool wave1 = !direct && cfg.wave && cfg.wavefront && !vertex1;   // phase 1 on the vertex wavefront (kwave.cuh)
+    const bool useWavefront = cfg.wavefront && !vertex1 && !wave1, useWavefront2 = cfg.wavefront2 && useWavefront && !vertex2;
     size_t poolSize = cfg.pool;   // 4 Mi slots x 272 B = 1.1 GB (measured: +17 % over 1 Mi)
     const bool dlSpecular = direct && scene->nSpecularMaterials > 0;
     if (dlSpecular) poolSize = std::min<size_t>(poolSize, (size_t)1 << 20);   // + 960 B of recursion frames per slot
@@ -1707,6 +1703,13 @@ int RunLane(LaneJob &job) {
         CUDA_TRY(ln->counters.Ensure(C_COUNT));
         if (dlSpecular) CUDA_TRY(ln->dlFrames.Ensure(poolSize * DL_MAX_DEPTH));
         if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, C_COUNT * sizeof(unsigned)));
+    }
+    if (wave1) {
+        CUDA_TRY(ln->pool.Ensure(poolSize * std::max<size_t>(W_COUNT, useWavefront2 ? F_COUNT : 0)));
+        CUDA_TRY(ln->traceQ.Ensure(poolSize * 3));
+        CUDA_TRY(ln->evalQ.Ensure(poolSize * 3));
+        CUDA_TRY(ln->counters.Ensure(std::max<int>(WC_COUNT, C_COUNT)));
+        if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, std::max<int>(WC_COUNT, C_COUNT) * sizeof(unsigned)));
     }
     const bool traceIters = cfg.traceIters;   // debugging aid: queue occupancy on stderr
     const TableLaunch tl = job.pathLayout ? PlanTables(spp) : PlanTablesGeneral(spp, job.tables.nArrays);
@@ -1757,6 +1760,50 @@ int RunLane(LaneJob &job) {
                 CUDA_TRY(cudaGetLastError());
                 if (timeRays) CUDA_TRY(cudaEventRecord(rayEvent(), stream));
                 launches += 1;
+            } else if (wave1) {
+                // ---- phase 1 as a vertex wavefront: one k_wshade pass per path vertex
+                WvArgs wa;
+                wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = ln->pool.p; wa.P = (uint32_t)poolSize;
+                wa.qRay = ln->traceQ.p; wa.qEval = ln->evalQ.p; wa.counters = ln->counters.p;
+                wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p;
+                CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_COUNT * sizeof(unsigned), stream));
+                const int sblocks = (int)((poolSize + 127) / 128);
+                const int tblocks = nSM * 8;
+                for (int iter = 0;; ++iter) {
+                    wa.iter = iter;
+                    // empty the queues k_wshade is about to fill, the consumers' cursors and the live-slot count
+                    CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_NEXT_SAMPLE * sizeof(unsigned), stream));
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_wshade<true, true><<<sblocks, 128, 0, stream>>>(wa);
+                        else k_wshade<false, true><<<sblocks, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_wshade<true, false><<<sblocks, 128, 0, stream>>>(wa);
+                        else k_wshade<false, false><<<sblocks, 128, 0, stream>>>(wa);
+                    }
+                    if (hasMeasured) k_weval<<<tblocks, 128, 0, stream>>>(wa);
+                    if (timeRays) CUDA_TRY(cudaEventRecord(rayEvent(), stream));
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_wtrace<true, true><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_wtrace<false, true><<<tblocks, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_wtrace<true, false><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_wtrace<false, false><<<tblocks, 128, 0, stream>>>(wa);
+                    }
+                    if (timeRays) CUDA_TRY(cudaEventRecord(rayEvent(), stream));
+                    launches += hasMeasured ? 3 : 2;
+                    if ((iter & 7) == 7) {
+                        CUDA_TRY(cudaMemcpyAsync(ln->hostCounters, ln->counters.p, WC_COUNT * sizeof(unsigned),
+                                                 cudaMemcpyDeviceToHost, stream));
+                        CUDA_TRY(cudaStreamSynchronize(stream));
+                        if (traceIters)
+                            fprintf(stderr, "[pbrtgpu] batch@%zu round %d iter %d: live %u rays %u/%u/%u evals %u next sample %u of %u\n",
+                                    begin, r, iter, ln->hostCounters[WC_LIVE], ln->hostCounters[WC_RAYS], ln->hostCounters[WC_RAYS + 1],
+                                    ln->hostCounters[WC_RAYS + 2], ln->hostCounters[WC_EVALS], ln->hostCounters[WC_NEXT_SAMPLE], wa.totalSamples);
+                        if (ln->hostCounters[WC_LIVE] == 0) break;
+                    }
+                    if (iter > 4000000) return Fail(PBRTGPU_ECUDA, "vertex wavefront did not terminate");
+                }
+                CUDA_TRY(cudaGetLastError());
             } else if (!useWavefront) {
                 if (scene->d.nAnimated) {
                     if (wantCounters) k_path<1, true, true><<<blocks1, 128, 0, stream>>>(pa);

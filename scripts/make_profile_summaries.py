@@ -14,7 +14,7 @@ RAW = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'lau
        'smsp__warp_issue_stalled_no_instruction_per_warp_active.pct', 'smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct',
        'smsp__warp_issue_stalled_barrier_per_warp_active.pct', 'smsp__warp_issue_stalled_not_selected_per_warp_active.pct',
        'smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct']
-for k in ("k_trace", "k_logic", "k_eval", "k_path", "k_tables"):
+for k in ("k_trace", "k_logic", "k_eval", "k_path", "k_tables", "k_vertex", "k_wshade", "k_weval", "k_wtrace"):
     raw = os.path.join(G, "full_%s_raw.csv" % k)
     if not os.path.exists(raw):
         continue

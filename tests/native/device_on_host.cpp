@@ -34,11 +34,33 @@ static inline unsigned __brev(unsigned x) {
     return x;
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
+// ---- the vertex-wavefront kernels (kwave.cuh) run with launches as loops, one "thread" at a time: a thread is alone in its
+// warp (every warp-wide primitive sees just the calling lane), which is a schedule the kernels must be correct under
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+static thread_local uint3 threadIdx, blockIdx;
+static thread_local dim3 blockDim, gridDim;
+static inline unsigned doh_lane_bit() { return 1u << (threadIdx.x & 31); }
+static inline unsigned __activemask() { return doh_lane_bit(); }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? doh_lane_bit() : 0u; }
+static inline int __any_sync(unsigned, int p) { return p != 0; }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, int) { return T(0) * v; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+template <typename T> static inline T __ldcg(const T *p) { return *p; }
+using std::min;
+using std::max;
 
 #include "../../pbrt_v2_b200/csrc/device/dscene.cuh"
 #include "../../pbrt_v2_b200/csrc/device/dshade.cuh"
 #include "../../pbrt_v2_b200/csrc/device/dpath.cuh"
 #include "../../pbrt_v2_b200/csrc/device/dvertex.cuh"
+#include "../../pbrt_v2_b200/csrc/device/kwave.cuh"
 
 using namespace dev;
 
@@ -412,6 +434,166 @@ void RunTaskVertexH(const DScene &sc, const RenderParams &rp, const PbrtGpuRende
         }
 }
 
+// A batch of tasks through the VERTEX WAVEFRONT kernels themselves (kwave.cuh: k_wshade / k_weval / k_wtrace, the product's
+// phase 1 of PathIntegrator), launches as loops over a pool of `P` path slots; then the tails (bounce 3 on, the task's RNG
+// stream) and the film in sample order, as k_vertex<2> + k_film do.  Pixel by pixel ("rounds") so that a task's stream
+// position is handed from one pixel's tails to the next pixel's tables.
+// `leadersOnly`: kernels whose warps elect lane 0 (k_wtrace's chunk reservation) run as warps of one lane, lane 0
+template <typename K> void LaunchH(unsigned threads, K kernel, bool leadersOnly = false) {
+    blockDim = dim3(128, 1, 1);
+    gridDim = dim3((threads + 127) / 128, 1, 1);
+    for (unsigned i = 0; i < gridDim.x * 128u; ++i) {
+        if (leadersOnly && (i & 31u)) continue;
+        blockIdx.x = i / 128; threadIdx.x = i % 128;
+        kernel();
+    }
+    threadIdx.x = blockIdx.x = 0;
+}
+void RunWaveH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc &rd, const Extent &ext, PbrtGpuPixel *film,
+              uint32_t P) {
+    std::vector<TaskRec> tasks;
+    int rounds = 0;
+    for (int t = rd.taskBegin; t < rd.taskEnd; ++t) {
+        TaskRec tr;
+        tr.taskNum = t;
+        SubWindow(ext, t, rd.nTasks, &tr.x0, &tr.x1, &tr.y0, &tr.y1);
+        if (tr.x0 == tr.x1 || tr.y0 == tr.y1) continue;
+        tasks.push_back(tr);
+        rounds = std::max(rounds, (tr.x1 - tr.x0) * (tr.y1 - tr.y0));
+    }
+    const size_t nb = tasks.size();
+    if (!nb) return;
+    const int spp = rp.spp;
+    const int maskWords = std::max(1, spp / 32);
+    std::vector<Stream> rng;
+    for (size_t i = 0; i < nb; ++i) rng.emplace_back((uint32_t)tasks[i].taskNum);
+    std::vector<int> mti(nb, 0);
+    std::vector<uint16_t> perm(nb * spp * PERM_STRIDE);
+    std::vector<uint32_t> scr(nb * SCR_STRIDE);
+    std::vector<float4> ls(nb * spp), rec(nb * spp * 4), pool((size_t)W_COUNT * P);
+    std::vector<unsigned> tailCount(nb), counters(WC_COUNT);
+    std::vector<uint32_t> tailMask(nb * maskWords), qRay(3 * (size_t)P), qEval(3 * (size_t)P);
+    const bool hasMeasured = sc.measured != nullptr;
+    for (int r = 0; r < rounds; ++r) {
+        for (size_t i = 0; i < nb; ++i) {   // k_tables
+            const TaskRec &tr = tasks[i];
+            if (r >= (tr.x1 - tr.x0) * (tr.y1 - tr.y0)) continue;
+            std::vector<uint16_t> rows;
+            TablesH(rp.lay, spp, rng[i], &mti[i], &rows, scr.data() + i * SCR_STRIDE);
+            for (int s = 0; s < spp; ++s)
+                memcpy(perm.data() + (i * spp + s) * PERM_STRIDE, rows.data() + (size_t)s * rp.lay.rowStride,
+                       sizeof(uint16_t) * std::min<int>(PERM_STRIDE, rp.lay.rowStride));
+        }
+        std::fill(tailCount.begin(), tailCount.end(), 0u);
+        std::fill(tailMask.begin(), tailMask.end(), 0u);
+        WvArgs wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.sc = sc; wa.rp = rp;
+        wa.b.tasks = tasks.data(); wa.b.nBatch = (int)nb; wa.b.round = r;
+        wa.b.perm = perm.data(); wa.b.scr = scr.data(); wa.b.ls = ls.data(); wa.b.rec = rec.data();
+        wa.b.tailCount = tailCount.data(); wa.b.tailMask = tailMask.data(); wa.b.maskWords = maskWords;
+        wa.pool = pool.data(); wa.P = P; wa.qRay = qRay.data(); wa.qEval = qEval.data(); wa.counters = counters.data();
+        wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = nullptr;
+        std::fill(counters.begin(), counters.end(), 0u);
+        for (int iter = 0;; ++iter) {
+            wa.iter = iter;
+            for (int k = 0; k < WC_NEXT_SAMPLE; ++k) counters[k] = 0;
+            LaunchH(P, [&]() { k_wshade<false, true>(wa); });
+            if (hasMeasured) LaunchH(1, [&]() { k_weval(wa); });
+            LaunchH(1, [&]() { k_wtrace<false, true>(wa); }, true);
+            if (counters[WC_LIVE] == 0) break;
+        }
+        // ---- phase 2 + film: every task's current pixel, samples in order
+        for (size_t i = 0; i < nb; ++i) {
+            const TaskRec &tr = tasks[i];
+            const int tw = tr.x1 - tr.x0;
+            if (r >= tw * (tr.y1 - tr.y0)) continue;
+            const int xPos = tr.x0 + r % tw, yPos = tr.y0 + r / tw;
+            const uint16_t *rowBase = perm.data() + i * spp * PERM_STRIDE;
+            (void)rowBase;
+            auto rngF = [&](int k) -> float { return UIntToFloat(rng[i].At((size_t)(mti[i] + k))); };
+            for (int s = 0; s < spp; ++s) {
+                const float4 v = ls[i * spp + s];
+                int code = __float_as_int(v.w);
+                Spec L(v.x, v.y, v.z);
+                if (code & LS_TAIL) {
+                    const float4 *q = rec.data() + (i * spp + s) * 4;
+                    Ray ray;
+                    ray.o = V3(q[0].x, q[0].y, q[0].z); ray.mint = q[0].w;
+                    ray.d = V3(q[1].x, q[1].y, q[1].z); ray.maxt = q[1].w;
+                    Hit hit;
+                    hit.t = q[1].w; hit.prim = __float_as_int(q[2].w); hit.b1 = q[3].x; hit.b2 = q[3].y; hit.maxtIn = q[3].z;
+                    ray.time = q[3].w;
+                    Spec T(q[2].x, q[2].y, q[2].z);
+                    bool afterSpecular = (code & LS_SPEC) != 0;
+                    code &= ~(LS_SPEC | LS_TAIL);
+                    int bounces = 3;
+                    bool found = true;
+                    TraceStats st;
+                    st.nodes = st.prims = 0;
+                    const int nLights = (int)sc.nLights;
+                    while (found) {
+                        VertexRandoms u;
+                        int k0 = 0;
+                        if (nLights > 0) {
+                            u.lnU = rngF(0); u.lsU0 = rngF(1); u.lsU1 = rngF(2);
+                            u.bsU0 = rngF(4); u.bsU1 = rngF(5); u.bsUc = rngF(6);
+                            k0 = 7;
+                        } else u.lnU = u.lsU0 = u.lsU1 = u.bsU0 = u.bsU1 = u.bsUc = 0.f;
+                        u.pU0 = rngF(k0); u.pU1 = rngF(k0 + 1); u.pUc = rngF(k0 + 2);
+                        ShadeCtx ctx;
+                        Vertex vx;
+                        VertexA<true>(sc, ray, hit, bounces, afterSpecular, u, T, L, ctx, &vx, nullptr);
+                        Spec f[3] = {Spec(0.f), Spec(0.f), Spec(0.f)};
+                        for (int e = 0; e < 3; ++e) {
+#if PBRT_SPECULAR
+                            if (e == VX_PATH && vx.specSampled) continue;
+#endif
+                            if (vx.need[e]) f[e] = VertexEval(sc, vx.material, vx.evalWo, vx.evalWi[e], vx.evalFlags[e]);
+                        }
+                        bool rrDrawn = false;
+                        const float rrU = bounces > 3 ? rngF(k0 + 3) : 0.f;
+                        const bool cont = VertexB(f, bounces, rp.maxDepth, T, rrU, &vx, &rrDrawn);
+                        mti[i] += k0 + 3 + (rrDrawn ? 1 : 0);
+                        Spec Ld(0.f);
+                        if (vx.ray[VX_LIGHT]) {
+                            Ray q2; q2.o = vx.p; q2.d = vx.wiW[VX_LIGHT]; q2.mint = vx.eps; q2.maxt = vx.visMaxt; q2.time = ray.time;
+                            Hit h;
+                            if (!Traverse<false, true>(sc, q2, true, &h, &st, DOH_TOP(sc))) Ld = Ld + vx.pendS;
+                        }
+                        if (vx.ray[VX_MIS]) {
+                            Ray q2; q2.o = vx.p; q2.d = vx.wiW[VX_MIS]; q2.mint = vx.eps; q2.maxt = INF_F; q2.time = ray.time;
+                            Hit h;
+                            if (Traverse<false, true>(sc, q2, false, &h, &st, DOH_TOP(sc)) && MisHitIsLight<true>(sc, q2, h, vx.lightNum)) Ld = Ld + vx.pendM;
+                        }
+                        L = L + T * ((float)nLights * Ld);
+                        T = vx.Tnew;
+                        if (!cont) break;
+#if PBRT_SPECULAR
+                        afterSpecular = vx.specSampled;
+#endif
+                        ++bounces;
+                        ray.o = vx.p; ray.d = vx.wiW[VX_PATH]; ray.mint = vx.eps; ray.maxt = INF_F;
+                        found = Traverse<false, true>(sc, ray, false, &hit, &st, DOH_TOP(sc));
+                    }
+                    L = SanitizeRadiance(L);
+                }
+                float xyz[3];
+                xyz[0] = 0.412453f * L.r + 0.357580f * L.g + 0.180423f * L.b;
+                xyz[1] = 0.212671f * L.r + 0.715160f * L.g + 0.072169f * L.b;
+                xyz[2] = 0.019334f * L.r + 0.119193f * L.g + 0.950227f * L.b;
+                const int fy0 = yPos - ((code & LS_UP) ? 1 : 0), fy1 = yPos + ((code & LS_DOWN) ? 1 : 0);
+                const int fx0 = xPos - ((code & LS_LEFT) ? 1 : 0), fx1 = xPos + ((code & LS_RIGHT) ? 1 : 0);
+                for (int y = fy0; y <= fy1; ++y)
+                    for (int x = fx0; x <= fx1; ++x) {
+                        PbrtGpuPixel &px = film[(size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart)];
+                        px.Lxyz[0] += xyz[0]; px.Lxyz[1] += xyz[1]; px.Lxyz[2] += xyz[2]; px.weightSum += 1.f;
+                    }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -433,6 +615,10 @@ DOH_EXPORT int doh_render(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc 
     rp.integrator = rd->integrator; rp.lightStrategy = rd->lightStrategy;
     LayoutH(*rd, &rp.lay);
     memset(pixels, 0, sizeof(PbrtGpuPixel) * (size_t)ext.xc * ext.yc);
+    if (g_vertexForm >= 2 && rd->integrator != PBRTGPU_INTEGRATOR_DIRECTLIGHTING) {
+        RunWaveH(hs.d, rp, *rd, ext, pixels, (uint32_t)g_vertexForm);   // (the value is the pool size: small pools force slot reuse)
+        return 0;
+    }
     for (int t = rd->taskBegin; t < rd->taskEnd; ++t) {
         if (rd->integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING) RunTaskH<1>(hs.d, rp, *rd, t, ext, pixels);
         else if (g_vertexForm) RunTaskVertexH(hs.d, rp, *rd, t, ext, pixels);
@@ -441,7 +627,8 @@ DOH_EXPORT int doh_render(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc 
     return 0;
 }
 
-// PathIntegrator renders through the vertex form (dvertex.cuh) instead of the state machine (path_body.inc)
+// PathIntegrator renders through the vertex form (dvertex.cuh) instead of the state machine (path_body.inc); a value >= 2
+// runs the vertex-wavefront kernels (kwave.cuh) over a pool of that many path slots
 DOH_EXPORT void doh_set_vertex_form(int on) { g_vertexForm = on; }
 
 // k_intersect<false>'s body (device/pbrtgpu.cu) on the host: BVHAccel::Intersect + the hit's differential geometry

@@ -122,6 +122,27 @@ def test_vertex_form_on_host_renders_like_the_oracle(staged, doh):
         doh.doh_set_vertex_form(0)
 
 
+def test_vertex_wavefront_kernels_on_host_render_like_the_oracle(staged, doh):
+    """kwave.cuh -- k_wshade / k_weval / k_wtrace, the product's phase 1 of PathIntegrator -- executed on the host with
+    launches as loops over a pool of path slots (3 slots: every slot is reused many times and retires while others still
+    run; 1000: most slots never leave their first sample), tails and film as k_vertex<2> / k_film: whole films against the
+    oracle for every PathIntegrator case and scene-file variant, multi-pixel tasks (rounds) and specular materials included."""
+    from helpers import VARIANTS, EDGE_VARIANTS, SPECULAR_VARIANTS, variant_scene
+    try:
+        for pool in (3, 1000):
+            doh.doh_set_vertex_form(pool)
+            for base, res, spp, ncores, integrator, strategy in RENDER_CASES:
+                if integrator == "path":
+                    _same_film(doh, host_scene(base, res, res, spp, ncores))
+            for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS:
+                if v[6].get("integrator", "path") == "path":
+                    _same_film(doh, variant_scene(v[0])[0])
+        doh.doh_set_vertex_form(64)
+        _same_film(doh, host_scene("anim-killeroos-moving", 32, 32, 4, 2, nlevels=3))
+    finally:
+        doh.doh_set_vertex_form(0)
+
+
 def test_device_state_machine_on_host_variants(staged, doh):
     from helpers import VARIANTS, EDGE_VARIANTS, variant_scene
     for v in VARIANTS + EDGE_VARIANTS:

@@ -51,7 +51,11 @@ def _compare_subrange(hs, gs, rd, begin, end, spp, min_own=0.25):
     px_gpu, st = gs.render(rd)
     px_cpu, cnt = oa.render(hs, rd)
     assert st.cameraSamples == cnt.cameraSamples and cnt.cameraSamples > 0
-    assert np.array_equal(px_gpu["weightSum"], px_cpu["weightSum"]), "sample counts per pixel differ"
+    if not np.array_equal(px_gpu["weightSum"], px_cpu["weightSum"]):
+        ys, xs = np.nonzero(px_gpu["weightSum"] != px_cpu["weightSum"])
+        raise AssertionError("sample counts differ on %d pixels in tasks [%d, %d): first (x, y, gpu, cpu) = %s" % (
+            len(xs), begin, end, [(int(x), int(y), float(px_gpu["weightSum"][y, x]), float(px_cpu["weightSum"][y, x]))
+                                  for x, y in list(zip(xs, ys))[:6]]))
     touched = px_cpu["weightSum"] > 0
     own = px_cpu["weightSum"] == spp
     assert own.sum() >= min_own * touched.sum()
