@@ -78,9 +78,19 @@ struct WvArgs {
     DeviceStats *stats;
 };
 
+// `kind` must be the same for all converged lanes (a compile-time constant at the call site)
 DEV void WvPushRay(const WvArgs &a, int kind, uint32_t slot) {
     const unsigned i = AggregatedAddV(a.counters + WC_RAYS + kind);
     a.qRay[(size_t)kind * a.P + i] = slot;
+}
+// ... any kind per lane: one atomic per (warp, kind)
+DEV void WvPushRayAny(const WvArgs &a, int kind, uint32_t slot) {
+    const unsigned peers = __match_any_sync(__activemask(), kind);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(a.counters + WC_RAYS + kind, (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    a.qRay[(size_t)kind * a.P + base + __popc(peers & ((1u << lane) - 1u))] = slot;
 }
 
 // ----------------------------------------------------------------------------------------------------------- k_wshade
@@ -264,7 +274,164 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(WvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------ k_weval
-// measured-BRDF values (IrregIsotropicBRDF::f) of the queued (slot, direction) requests
+// measured-BRDF values (IrregIsotropicBRDF::f, reflection.cpp:259-272) of the queued (slot, direction) requests.
+//
+// dshade.cuh's BxF does it per thread in two kd-tree walks of data-dependent length -- the exact third-nearest distance
+// (which fixes the radius the reference's doubling search ends on), then the gather at that radius in the reference's
+// visiting order -- and a warp of such threads ran with 8.8 of 32 lanes active (profiles/r01_k_eval_ncu_full.txt).  Here
+// the lanes are persistent and both walks are ONE node step per lane and warp iteration: a lane's state is the entry it
+// processes next, a step loads that node's 32-byte record and yields the next entry (a child entered directly, or the
+// stack top), a lane whose gather ends writes its value and takes the next request at the following refill.
+//   entry = node << 1 | flag.  third-nearest walk: flag = "far child of this node, if the splitting plane is still closer
+//   than the third-best distance" (the plane distance is recomputed from the parent's record when the entry is popped: no
+//   float stack).  gather: flag = "children done: process the node itself" (KdTree::privateLookup's order, kdtree.h:150-183:
+//   near child, far child, node).
+#if PBRT_KD_INTERLEAVED
+#define WEVAL_STACK 48
+__global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(WvArgs a) {
+    const DScene &sc = a.sc;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned n = a.counters[WC_EVALS];
+    const size_t P = a.P;
+    int mode = 0;             // 0: idle, 1: third-nearest walk, 2: gather
+    uint32_t slot = 0, cur = 0, first = 0, nNodes = 0;
+    int k = 0, word = 0, sp = 0;
+    V3 p(0, 0, 0);
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, maxDist2 = 0.f, sumW = 0.f;
+    Spec v(0.f);
+    uint32_t stk[WEVAL_STACK];
+    unsigned cPos = 0, cEnd = 0;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, mode == 0);
+        if (idle && !(exhausted && cPos >= cEnd)) {
+            if (cPos >= cEnd) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(a.counters + WC_EVAL_CUR, 32u);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) { exhausted = true; cPos = cEnd = 0; }
+                else { cPos = base; cEnd = min(base + 32u, n); }
+            }
+            if (mode == 0) {
+                const unsigned idx = cPos + __popc(idle & ((1u << lane) - 1u));
+                if (idx < cEnd) {
+                    const uint32_t e = a.qEval[idx];
+                    slot = e >> 2;
+                    k = (int)(e & 3u);
+                    const float4 wo = a.pool[(size_t)W_EWO * P + slot], wi = a.pool[(size_t)(W_EW0 + k) * P + slot];
+                    word = __float_as_int(wi.w);
+                    const PbrtGpuMaterial &m = sc.materials[__float_as_int(wo.w)];
+                    bool walk = false;
+                    Spec f(0.f);
+                    if (m.type == PBRTGPU_MAT_MEASURED) {
+                        // the BSDF's one component (measured.cpp:194-210) takes part if its type matches the flags
+                        if (Matches(BSDF_REFLECTION | BSDF_GLOSSY, word & 0xffff)) {
+                            const PbrtGpuMeasured md = sc.measured[m.measured];
+                            first = md.firstNode; nNodes = md.nNodes;
+                            p = BRDFRemap(V3(wo.x, wo.y, wo.z), V3(wi.x, wi.y, wi.z));
+                            b0 = b1 = b2 = INF_F;
+                            cur = 0u; sp = 0;
+                            walk = true;
+                        }
+                    } else   // (k_wshade evaluates analytic materials itself; kept for completeness)
+                        f = VertexEval(sc, __float_as_int(wo.w), V3(wo.x, wo.y, wo.z), V3(wi.x, wi.y, wi.z), word & 0xffff);
+                    if (walk) mode = 1;
+                    else {
+                        a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
+                        if ((word & W_RAY_ALLOWED) && !f.IsBlack()) WvPushRayAny(a, k, slot);
+                    }
+                }
+            }
+            cPos = min(cEnd, cPos + (unsigned)__popc(idle));
+        }
+        const bool more = !(exhausted && cPos >= cEnd);
+        if (!__any_sync(FULL, mode != 0)) {
+            if (!more) break;
+            continue;
+        }
+        for (int it = 0; it < 64; ++it) {
+            if (mode != 0) {
+                const uint32_t node = cur >> 1;
+                const bool flag = (cur & 1u) != 0;
+                const float4 *rec = sc.kdRec + 2 * (size_t)(first + node);
+                const float4 k0 = __ldg(rec);
+                const float splitPos = k0.x;
+                const uint32_t bits = __float_as_uint(k0.y);
+                const int axis = (int)(bits & 3u);
+                const bool hasLeft = ((bits >> 2) & 1u) != 0;
+                const uint32_t rightChild = bits >> 3;
+                const bool hasRight = rightChild < nNodes;
+                const float pa = p[axis == 3 ? 0 : axis];
+                const float plane2 = (pa - splitPos) * (pa - splitPos);
+                const bool leftFirst = pa <= splitPos;
+                const bool nearExists = axis != 3 && (leftFirst ? hasLeft : hasRight);
+                const bool farExists = axis != 3 && (leftFirst ? hasRight : hasLeft);
+                const uint32_t nearChild = leftFirst ? node + 1 : rightChild, farChild = leftFirst ? rightChild : node + 1;
+                bool pop = false, finished = false;
+                if (mode == 1) {
+                    // ---- exact third-smallest squared distance (the pruning is conservative: any visiting order gives it)
+                    if (!flag) {
+                        const float pz = __ldg(reinterpret_cast<const float *>(rec + 1));
+                        const float d2 = DistanceSquared(V3(k0.z, k0.w, pz), p);
+                        if (d2 < b2) {
+                            if (d2 < b1) {
+                                b2 = b1;
+                                if (d2 < b0) { b1 = b0; b0 = d2; } else b1 = d2;
+                            } else b2 = d2;
+                        }
+                        if (farExists) stk[sp++] = cur | 1u;
+                        if (nearExists) cur = nearChild << 1;
+                        else pop = true;
+                    } else if (plane2 < b2) cur = farChild << 1;
+                    else pop = true;
+                    if (pop) {
+                        if (sp > 0) cur = stk[--sp];
+                        else {
+                            // reflection.cpp:261-271: the radius doubles until a lookup finds more than two samples
+                            float r2 = .001f;
+                            while (!(b2 < r2) && !(r2 > 1.5f)) r2 *= 2.f;
+                            maxDist2 = r2;
+                            v = Spec(0.f); sumW = 0.f;
+                            mode = 2; cur = 0u; sp = 0;
+                        }
+                    }
+                } else {
+                    // ---- the gather at that radius, in KdTree::privateLookup's order
+                    bool process = flag || axis == 3;
+                    if (!process) {
+                        stk[sp++] = cur | 1u;
+                        if (farExists && plane2 < maxDist2) stk[sp++] = farChild << 1;
+                        if (nearExists) cur = nearChild << 1;
+                        else pop = true;
+                    } else {
+                        const float4 k1 = __ldg(rec + 1);
+                        const float d2 = DistanceSquared(V3(k0.z, k0.w, k1.x), p);
+                        if (d2 < maxDist2) {   // IrregIsoProc, reflection.cpp:40-55
+                            const float weight = ref_expf(-100.f * d2);
+                            v = v + weight * Spec(k1.y, k1.z, k1.w);
+                            sumW += weight;
+                        }
+                        pop = true;
+                    }
+                    if (pop) {
+                        if (sp > 0) cur = stk[--sp];
+                        else finished = true;
+                    }
+                }
+                if (finished) {
+                    const Spec f = v.Clamp() / sumW;
+                    a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
+                    if ((word & W_RAY_ALLOWED) && !f.IsBlack()) WvPushRayAny(a, k, slot);
+                    mode = 0;
+                }
+            }
+            const int nActive = __popc(__ballot_sync(FULL, mode != 0));
+            if (nActive == 0 || (more && nActive < 24)) break;
+        }
+    }
+}
+#else
 __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(WvArgs a) {
     const unsigned n = a.counters[WC_EVALS];
     const size_t P = a.P;
@@ -276,9 +443,10 @@ __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(WvArgs a) {
         const int word = __float_as_int(wi.w);
         const Spec f = VertexEval(a.sc, __float_as_int(wo.w), V3(wo.x, wo.y, wo.z), V3(wi.x, wi.y, wi.z), word & 0xffff);
         a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
-        if ((word & W_RAY_ALLOWED) && !f.IsBlack()) WvPushRay(a, k, slot);
+        if ((word & W_RAY_ALLOWED) && !f.IsBlack()) WvPushRayAny(a, k, slot);
     }
 }
+#endif
 
 // ----------------------------------------------------------------------------------------------------------- k_wtrace
 // persistent ray-queue consumer: k_trace's loop (chunked hand-out, while-while walk) over the vertex wavefront's records
@@ -297,11 +465,13 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_wtrace(WvArgs a) {
     __shared__ uint32_t sStack[PBRT_SMEM_STACK * 128];
     t.sstk = sStack + threadIdx.x;
 #endif
-#if PBRT_TOP_LEVELS
+#if PBRT_TOP_LEVELS && defined(__CUDACC__)
     __shared__ __align__(128) float4 sTop[2 * PBRT_TOP_SLOTS];
     __shared__ __align__(8) uint64_t sTopBar;
     StageTopNodes(sTop, &sTopBar, sc.topNodes);
     const float4 *smemTop = sTop;
+#elif PBRT_TOP_LEVELS
+    const float4 *smemTop = sc.topNodes;   // (host-compiled harness: the table itself)
 #else
     const float4 *smemTop = nullptr;
 #endif

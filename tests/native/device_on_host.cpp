@@ -44,6 +44,7 @@ static inline unsigned doh_lane_bit() { return 1u << (threadIdx.x & 31); }
 static inline unsigned __activemask() { return doh_lane_bit(); }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? doh_lane_bit() : 0u; }
 static inline int __any_sync(unsigned, int p) { return p != 0; }
+template <typename T> static inline unsigned __match_any_sync(unsigned, T) { return doh_lane_bit(); }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 template <typename T> static inline T __shfl_down_sync(unsigned, T v, int) { return T(0) * v; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
@@ -499,7 +500,7 @@ void RunWaveH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
             wa.iter = iter;
             for (int k = 0; k < WC_NEXT_SAMPLE; ++k) counters[k] = 0;
             LaunchH(P, [&]() { k_wshade<false, true>(wa); });
-            if (hasMeasured) LaunchH(1, [&]() { k_weval(wa); });
+            if (hasMeasured) LaunchH(1, [&]() { k_weval(wa); }, PBRT_KD_INTERLEAVED != 0);   // (the persistent form elects lane 0)
             LaunchH(1, [&]() { k_wtrace<false, true>(wa); }, true);
             if (counters[WC_LIVE] == 0) break;
         }
