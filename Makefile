@@ -25,15 +25,18 @@ NVDEFS    ?=
 # kernel experiments, built next to the product library so that a GPU visit can A/B them without compiling on the box
 # (scripts/ab_variants.py; tests/test_zz_gpu_variants.py runs the parity suite over them).  Nothing loads them by default.
 #   make variants VARIANT_NAMES="pairs foo"   with   VARIANT_DEFS_foo := -DSOMETHING=1
-VARIANT_NAMES ?= pairs ww ww_sstack sstack top9_sstack
+VARIANT_NAMES ?= ws5 ws6 we10
+# Kernel experiments of the current round (the earlier ones and their verdicts: profiles/README.md).  Traversal variants
+# that lost on the B200 and can still be built:  pairs (-DPBRT_PAIR_NODES=1), ww (-DPBRT_TRACE_LOOP=1),
+# sstack (-DPBRT_SMEM_STACK=32), top9_sstack (-DPBRT_TOP_LEVELS=9 -DPBRT_SMEM_STACK=32)
 VARIANT_DEFS_pairs := -DPBRT_PAIR_NODES=1
-# the trace kernels' walk as a warp-uniform while-while (kcommon.cuh PBRT_TRACE_LOOP); north_star kernel items as A/B
-# variants: the first 32 traversal-stack entries in shared memory; the top 9 levels of the scene BVH staged in shared memory
-# by a TMA bulk copy
 VARIANT_DEFS_ww := -DPBRT_TRACE_LOOP=1
-VARIANT_DEFS_ww_sstack := -DPBRT_TRACE_LOOP=1 -DPBRT_SMEM_STACK=32
 VARIANT_DEFS_sstack := -DPBRT_SMEM_STACK=32
 VARIANT_DEFS_top9_sstack := -DPBRT_TOP_LEVELS=9 -DPBRT_SMEM_STACK=32
+# register bounds of the vertex wavefront's kernels
+VARIANT_DEFS_ws5 := -DK_WSHADE_MIN_BLOCKS=5
+VARIANT_DEFS_ws6 := -DK_WSHADE_MIN_BLOCKS=6
+VARIANT_DEFS_we10 := -DK_WEVAL_MIN_BLOCKS=10
 VARIANTS  := $(patsubst %,$(PKG)/ab/libpbrtgpu_%.so,$(VARIANT_NAMES))
 
 all: $(PKG)/libpbrtgpu.so $(PKG)/libpbrthost.so $(PKG)/pbrt_b200 oracle variants

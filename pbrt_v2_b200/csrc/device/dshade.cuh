@@ -176,47 +176,54 @@ DEV Spec HitLe(const DScene &sc, int areaLight, const V3 &ngeom, const V3 &w) {
 }
 
 // ---- BxDFs ----------------------------------------------------------------------
-struct BxSet {   // the BSDF's component list, implied by the material
-    int n;
-    int kind[2];
-    int type[2];
-    Spec R[2];
+struct BxSet {   // the BSDF's component list, implied by the material.  Scalars with select accessors, not arrays: a
+    int n;       // dynamically indexed member array would put every BxSet (and whatever holds one) into local memory
+    int kind0, kind1;
+    int type0, type1;
+    Spec R0, R1;
     float exponent;
     int measured;
+    DEV int kind(int i) const { return i == 0 ? kind0 : kind1; }
+    DEV int type(int i) const { return i == 0 ? type0 : type1; }
+    DEV Spec R(int i) const { return i == 0 ? R0 : R1; }
+    DEV void set(int i, int k, int t, const Spec &r) {
+        if (i == 0) { kind0 = k; type0 = t; R0 = r; } else { kind1 = k; type1 = t; R1 = r; }
+    }
 };
 DEV void MaterialBxDFs(const DScene &sc, int material, BxSet *s) {
     const PbrtGpuMaterial &m = sc.materials[material];
     s->n = 0;
+    s->kind0 = s->kind1 = 0; s->type0 = s->type1 = 0; s->R0 = Spec(0.f); s->R1 = Spec(0.f);
     s->exponent = 0.f;
     s->measured = -1;
     if (m.type == PBRTGPU_MAT_MATTE) {          // matte.cpp:42-63 (sigma == 0)
         Spec r = Spec(m.Kd[0], m.Kd[1], m.Kd[2]).Clamp();
-        if (!r.IsBlack()) { s->kind[0] = BX_LAMBERTIAN; s->type[0] = BSDF_REFLECTION | BSDF_DIFFUSE; s->R[0] = r; s->n = 1; }
+        if (!r.IsBlack()) { s->set(0, BX_LAMBERTIAN, BSDF_REFLECTION | BSDF_DIFFUSE, r); s->n = 1; }
     } else if (m.type == PBRTGPU_MAT_PLASTIC) { // plastic.cpp:42-66
         Spec kd = Spec(m.Kd[0], m.Kd[1], m.Kd[2]).Clamp();
-        if (!kd.IsBlack()) { s->kind[0] = BX_LAMBERTIAN; s->type[0] = BSDF_REFLECTION | BSDF_DIFFUSE; s->R[0] = kd; s->n = 1; }
+        if (!kd.IsBlack()) { s->set(0, BX_LAMBERTIAN, BSDF_REFLECTION | BSDF_DIFFUSE, kd); s->n = 1; }
         Spec ks = Spec(m.Ks[0], m.Ks[1], m.Ks[2]).Clamp();
         if (!ks.IsBlack()) {
             float e = 1.f / m.roughness;
             if (e > 10000.f || isnan(e)) e = 10000.f;   // Blinn ctor, reflection.h:424-425
             int i = s->n++;
-            s->kind[i] = BX_MICROFACET_BLINN; s->type[i] = BSDF_REFLECTION | BSDF_GLOSSY; s->R[i] = ks; s->exponent = e;
+            s->set(i, BX_MICROFACET_BLINN, BSDF_REFLECTION | BSDF_GLOSSY, ks); s->exponent = e;
         }
 #if PBRT_SPECULAR
     } else if (m.type == PBRTGPU_MAT_MIRROR) {  // mirror.cpp:41-53: SpecularReflection(R, FresnelNoOp); Ks holds Kr
         Spec r = Spec(m.Ks[0], m.Ks[1], m.Ks[2]).Clamp();
-        if (!r.IsBlack()) { s->kind[0] = BX_SPECULAR_REFLECTION; s->type[0] = BSDF_REFLECTION | BSDF_SPECULAR; s->R[0] = r; s->n = 1; }
+        if (!r.IsBlack()) { s->set(0, BX_SPECULAR_REFLECTION, BSDF_REFLECTION | BSDF_SPECULAR, r); s->n = 1; }
     } else if (m.type == PBRTGPU_MAT_GLASS) {   // glass.cpp:41-57: Ks = Kr, Kd = Kt, roughness = index
         s->exponent = m.roughness;
         Spec r = Spec(m.Ks[0], m.Ks[1], m.Ks[2]).Clamp(), t = Spec(m.Kd[0], m.Kd[1], m.Kd[2]).Clamp();
-        if (!r.IsBlack()) { s->kind[0] = BX_SPECULAR_REFLECTION; s->type[0] = BSDF_REFLECTION | BSDF_SPECULAR; s->R[0] = r; s->n = 1; }
+        if (!r.IsBlack()) { s->set(0, BX_SPECULAR_REFLECTION, BSDF_REFLECTION | BSDF_SPECULAR, r); s->n = 1; }
         if (!t.IsBlack()) {
             int i = s->n++;
-            s->kind[i] = BX_SPECULAR_TRANSMISSION; s->type[i] = BSDF_TRANSMISSION | BSDF_SPECULAR; s->R[i] = t;
+            s->set(i, BX_SPECULAR_TRANSMISSION, BSDF_TRANSMISSION | BSDF_SPECULAR, t);
         }
 #endif
     } else {                                     // measured.cpp:194-210
-        s->kind[0] = BX_IRREG_ISO; s->type[0] = BSDF_REFLECTION | BSDF_GLOSSY; s->R[0] = Spec(0.f); s->n = 1;
+        s->set(0, BX_IRREG_ISO, BSDF_REFLECTION | BSDF_GLOSSY, Spec(0.f)); s->n = 1;
         s->measured = m.measured;
     }
 }
@@ -376,22 +383,25 @@ DEV float KdThirdNearest(const DScene &sc, const PbrtGpuMeasured &m, const V3 &p
     return b2;
 }
 
-DEV Spec BxF(const DScene &sc, const BxSet &s, int i, const V3 &wo, const V3 &wi) {
+// the analytic BxDFs' f(wo, wi)
+DEV Spec BxFAnalytic(const BxSet &s, int i, const V3 &wo, const V3 &wi) {
 #if PBRT_SPECULAR
-    if (s.kind[i] == BX_SPECULAR_REFLECTION || s.kind[i] == BX_SPECULAR_TRANSMISSION) return Spec(0.f);   // reflection.h:317-319,339-341
+    if (s.kind(i) == BX_SPECULAR_REFLECTION || s.kind(i) == BX_SPECULAR_TRANSMISSION) return Spec(0.f);   // reflection.h:317-319,339-341
 #endif
-    if (s.kind[i] == BX_LAMBERTIAN) return s.R[i] * INV_PI_F;   // reflection.cpp:173-175
-    if (s.kind[i] == BX_MICROFACET_BLINN) {                     // Microfacet::f, reflection.cpp:211-222
-        float cosThetaO = AbsCosTheta(wo);
-        float cosThetaI = AbsCosTheta(wi);
-        if (cosThetaI == 0.f || cosThetaO == 0.f) return Spec(0.f);
-        V3 wh = wi + wo;
-        if (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f) return Spec(0.f);
-        wh = Normalize(wh);
-        float cosThetaH = Dot(wi, wh);
-        Spec F = FresnelDielectric(cosThetaH, 1.5f, 1.f);
-        return s.R[i] * BlinnD(s.exponent, wh) * MicrofacetG(wo, wi, wh) * F / (4.f * cosThetaI * cosThetaO);
-    }
+    if (s.kind(i) == BX_LAMBERTIAN) return s.R(i) * INV_PI_F;   // reflection.cpp:173-175
+    // Microfacet::f, reflection.cpp:211-222
+    float cosThetaO = AbsCosTheta(wo);
+    float cosThetaI = AbsCosTheta(wi);
+    if (cosThetaI == 0.f || cosThetaO == 0.f) return Spec(0.f);
+    V3 wh = wi + wo;
+    if (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f) return Spec(0.f);
+    wh = Normalize(wh);
+    float cosThetaH = Dot(wi, wh);
+    Spec F = FresnelDielectric(cosThetaH, 1.5f, 1.f);
+    return s.R(i) * BlinnD(s.exponent, wh) * MicrofacetG(wo, wi, wh) * F / (4.f * cosThetaI * cosThetaO);
+}
+DEV Spec BxF(const DScene &sc, const BxSet &s, int i, const V3 &wo, const V3 &wi) {
+    if (s.kind(i) != BX_IRREG_ISO) return BxFAnalytic(s, i, wo, wi);
     // IrregIsotropicBRDF::f, reflection.cpp:259-272
     V3 mpt = BRDFRemap(wo, wi);
     const PbrtGpuMeasured md = sc.measured[s.measured];
@@ -406,9 +416,9 @@ DEV Spec BxF(const DScene &sc, const BxSet &s, int i, const V3 &wo, const V3 &wi
 }
 DEV float BxPdf(const BxSet &s, int i, const V3 &wo, const V3 &wi) {
 #if PBRT_SPECULAR
-    if (s.kind[i] == BX_SPECULAR_REFLECTION || s.kind[i] == BX_SPECULAR_TRANSMISSION) return 0.f;   // reflection.h:322-324,344-346
+    if (s.kind(i) == BX_SPECULAR_REFLECTION || s.kind(i) == BX_SPECULAR_TRANSMISSION) return 0.f;   // reflection.h:322-324,344-346
 #endif
-    if (s.kind[i] == BX_MICROFACET_BLINN) {   // Microfacet::Pdf + Blinn::Pdf, reflection.cpp:340-343,365-374
+    if (s.kind(i) == BX_MICROFACET_BLINN) {   // Microfacet::Pdf + Blinn::Pdf, reflection.cpp:340-343,365-374
         if (!SameHemisphere(wo, wi)) return 0.f;
         V3 wh = Normalize(wo + wi);
         float costheta = AbsCosTheta(wh);
@@ -422,7 +432,7 @@ DEV float BxPdf(const BxSet &s, int i, const V3 &wo, const V3 &wi) {
 // that value for every non-specular BxDF and re-evaluates the sum of all matching components.
 //   Microfacet::Sample_f + Blinn::Sample_f, reflection.cpp:332-363;  BxDF::Sample_f, :311-318
 DEV_NI3 void BxSampleDir(const BxSet &s, int i, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
-    if (s.kind[i] == BX_MICROFACET_BLINN) {
+    if (s.kind(i) == BX_MICROFACET_BLINN) {
         float costheta = ref_powf(u1, 1.f / (s.exponent + 1));
         float sintheta = sqrtf(maxf(0.f, 1.f - costheta * costheta));
         float phi = u2 * 2.f * PI_F;
@@ -443,11 +453,11 @@ DEV_NI3 void BxSampleDir(const BxSet &s, int i, const V3 &wo, V3 *wi, float u1, 
 // SpecularReflection::Sample_f / SpecularTransmission::Sample_f, reflection.cpp:138-170: direction, pdf and the value
 // BSDF::Sample_f returns as it is for a specular component (:572)
 DEV Spec SpecularSample(const BxSet &s, int i, const V3 &wo, V3 *wi, float *pdf) {
-    if (s.kind[i] == BX_SPECULAR_REFLECTION) {
+    if (s.kind(i) == BX_SPECULAR_REFLECTION) {
         *wi = V3(-wo.x, -wo.y, wo.z);
         *pdf = 1.f;
         Spec F = s.exponent == 0.f ? Spec(1.f) : FresnelDielectric(CosTheta(wo), 1.f, s.exponent);
-        return F * s.R[i] / AbsCosTheta(*wi);
+        return F * s.R(i) / AbsCosTheta(*wi);
     }
     bool entering = CosTheta(wo) > 0.f;
     float ei = 1.f, et = s.exponent;
@@ -462,7 +472,7 @@ DEV Spec SpecularSample(const BxSet &s, int i, const V3 &wo, V3 *wi, float *pdf)
     *wi = V3(sintOverSini * -wo.x, sintOverSini * -wo.y, cost);
     *pdf = 1.f;
     Spec F = FresnelDielectric(CosTheta(wo), 1.f, s.exponent);
-    return (Spec(1.f) - F) * s.R[i] / AbsCosTheta(*wi);
+    return (Spec(1.f) - F) * s.R(i) / AbsCosTheta(*wi);
 }
 #endif
 
@@ -472,7 +482,7 @@ DEV float BSDF_PdfLocal(const BxSet &s, const V3 &wo, const V3 &wi, int flags) {
     float pdf = 0.f;
     int matchingComps = 0;
     for (int i = 0; i < s.n; ++i)
-        if (Matches(s.type[i], flags)) {
+        if (Matches(s.type(i), flags)) {
             ++matchingComps;
             pdf += BxPdf(s, i, wo, wi);
         }
@@ -490,7 +500,7 @@ DEV bool BSDF_SampleDir(const ShadeCtx &c, const BxSet &s, const V3 &woW, float 
 #endif
                         ) {
     int matchingComps = 0;
-    for (int i = 0; i < s.n; ++i) if (Matches(s.type[i], flags)) ++matchingComps;
+    for (int i = 0; i < s.n; ++i) if (Matches(s.type(i), flags)) ++matchingComps;
     *pdf = 0.f;
     *sampledType = 0;
     if (matchingComps == 0) return false;
@@ -498,24 +508,24 @@ DEV bool BSDF_SampleDir(const ShadeCtx &c, const BxSet &s, const V3 &woW, float 
     int bx = -1;
     int count = which;
     for (int i = 0; i < s.n; ++i)
-        if (Matches(s.type[i], flags) && count-- == 0) { bx = i; break; }
+        if (Matches(s.type(i), flags) && count-- == 0) { bx = i; break; }
     V3 wo = WorldToLocal(c, woW);
     V3 wi;
 #if PBRT_SPECULAR
-    const bool specular = (s.type[bx] & BSDF_SPECULAR) != 0;
+    const bool specular = (s.type(bx) & BSDF_SPECULAR) != 0;
     if (specular) *specF = SpecularSample(s, bx, wo, &wi, pdf);
     else
 #endif
     BxSampleDir(s, bx, wo, &wi, uDir0, uDir1, pdf);
     if (*pdf == 0.f) return false;
-    *sampledType = s.type[bx];
+    *sampledType = s.type(bx);
     *wiW = LocalToWorld(c, wi);
 #if PBRT_SPECULAR
     if (!specular)
 #endif
     if (matchingComps > 1)   // (reflection.cpp:560-564: only for a non-specular sampled component)
         for (int i = 0; i < s.n; ++i)
-            if (i != bx && Matches(s.type[i], flags)) *pdf += BxPdf(s, i, wo, wi);
+            if (i != bx && Matches(s.type(i), flags)) *pdf += BxPdf(s, i, wo, wi);
     if (matchingComps > 1) *pdf /= matchingComps;
     if (Dot(*wiW, c.ng) * Dot(woW, c.ng) > 0) flags &= ~BSDF_TRANSMISSION;
     else flags &= ~BSDF_REFLECTION;

@@ -155,12 +155,22 @@ DEV void VertexA(const DScene &sc, const Ray &ray, const Hit &hit, int bounces, 
 }
 
 // The evaluation site: the sum of the matching BxDF::f (reflection.cpp:572-576, 620-623) for one direction.
-DEV_NOINLINE Spec VertexEval(const DScene &sc, int material, const V3 &wo, const V3 &wi, int flags) {
+// (vectors by value: a reference parameter of a non-inlined function forces the caller's whole Vertex into local memory)
+DEV_NOINLINE Spec VertexEval(const DScene &sc, int material, V3 wo, V3 wi, int flags) {
     BxSet bx;
     MaterialBxDFs(sc, material, &bx);
     Spec f(0.f);
     for (int i = 0; i < bx.n; ++i)
-        if (Matches(bx.type[i], flags)) f = f + BxF(sc, bx, i, wo, wi);
+        if (Matches(bx.type(i), flags)) f = f + BxF(sc, bx, i, wo, wi);
+    return f;
+}
+// ... for a material without a measured BRDF (matte, plastic, mirror, glass): inlined, no kd-tree stacks in the caller's frame
+DEV Spec VertexEvalAnalytic(const DScene &sc, int material, const V3 &wo, const V3 &wi, int flags) {
+    BxSet bx;
+    MaterialBxDFs(sc, material, &bx);
+    Spec f(0.f);
+    for (int i = 0; i < bx.n; ++i)
+        if (Matches(bx.type(i), flags)) f = f + BxFAnalytic(bx, i, wo, wi);
     return f;
 }
 

@@ -8,6 +8,12 @@
 
 using namespace dev;   // (the kernels live in the global namespace)
 
+#ifndef __CUDACC__
+#ifndef __grid_constant__
+#define __grid_constant__
+#endif
+#endif
+
 struct TaskRec {
     int taskNum;
     int x0, x1, y0, y1;   // Sampler::ComputeSubWindow tile

@@ -56,7 +56,7 @@ DEV void StageTopNodes(float4 *dst, uint64_t *mbar, const float4 *src) {
 #endif
 
 template <int PHASE, bool STATS, bool ANIM>
-__global__ void __launch_bounds__(128, K_VERTEX_MIN_BLOCKS) k_vertex(VxArgs a) {
+__global__ void __launch_bounds__(128, K_VERTEX_MIN_BLOCKS) k_vertex(const __grid_constant__ VxArgs a) {
     __shared__ uint32_t smt[PHASE == 2 ? 4 : 1][PHASE == 2 ? MT_N : 1];
     const DScene &sc = a.sc;
     const RenderParams &rp = a.rp;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(128, K_VERTEX_MIN_BLOCKS) k_vertex(VxArgs a) {
 // ImageFilm::AddSample for the samples of every task's current pixel, in sample order (samplerrenderer.cpp:147-157):
 // one thread per task-pixel.  `direct`: multi-pixel tasks add every sample straight to the film (a neighbour pixel of the
 // same task may already have splatted into it: the reference's order is splat first, then this pixel's samples).
-__global__ void __launch_bounds__(128) k_film(PathArgs a) {
+__global__ void __launch_bounds__(128) k_film(const __grid_constant__ PathArgs a) {
     const int bi = blockIdx.x * blockDim.x + threadIdx.x;
     if (bi >= a.b.nBatch) return;
     const RenderParams &rp = a.rp;

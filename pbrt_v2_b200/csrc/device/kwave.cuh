@@ -95,7 +95,7 @@ DEV void WvPushRayAny(const WvArgs &a, int kind, uint32_t slot) {
 
 // ----------------------------------------------------------------------------------------------------------- k_wshade
 template <bool STATS, bool ANIM>
-__global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(WvArgs a) {
+__global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __grid_constant__ WvArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= a.P) return;
     const DScene &sc = a.sc;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(WvArgs a) {
             const unsigned i = AggregatedAddV(a.counters + WC_EVALS);
             a.qEval[i] = (slot << 2) | (uint32_t)k;
         } else {
-            const Spec f = VertexEval(sc, v.material, v.evalWo, v.evalWi[k], v.evalFlags[k]);
+            const Spec f = VertexEvalAnalytic(sc, v.material, v.evalWo, v.evalWi[k], v.evalFlags[k]);
             WF(W_F0 + k) = make_float4(f.r, f.g, f.b, 0.f);
             if (allowed && !f.IsBlack()) WvPushRay(a, k, slot);
         }
@@ -288,14 +288,14 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(WvArgs a) {
 //   near child, far child, node).
 #if PBRT_KD_INTERLEAVED
 #define WEVAL_STACK 48
-__global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(WvArgs a) {
+__global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(const __grid_constant__ WvArgs a) {
     const DScene &sc = a.sc;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned n = a.counters[WC_EVALS];
     const size_t P = a.P;
     int mode = 0;             // 0: idle, 1: third-nearest walk, 2: gather
-    uint32_t slot = 0, cur = 0, first = 0, nNodes = 0;
+    uint32_t slot = 0, cur = 0, first_ = 0, nNodes = 0;   // first_: the tree's first node in kdRec
     int k = 0, word = 0, sp = 0;
     V3 p(0, 0, 0);
     float b0 = 0.f, b1 = 0.f, b2 = 0.f, maxDist2 = 0.f, sumW = 0.f;
@@ -328,14 +328,14 @@ __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(WvArgs a) {
                         // the BSDF's one component (measured.cpp:194-210) takes part if its type matches the flags
                         if (Matches(BSDF_REFLECTION | BSDF_GLOSSY, word & 0xffff)) {
                             const PbrtGpuMeasured md = sc.measured[m.measured];
-                            first = md.firstNode; nNodes = md.nNodes;
+                            first_ = md.firstNode; nNodes = md.nNodes;
                             p = BRDFRemap(V3(wo.x, wo.y, wo.z), V3(wi.x, wi.y, wi.z));
                             b0 = b1 = b2 = INF_F;
                             cur = 0u; sp = 0;
                             walk = true;
                         }
                     } else   // (k_wshade evaluates analytic materials itself; kept for completeness)
-                        f = VertexEval(sc, __float_as_int(wo.w), V3(wo.x, wo.y, wo.z), V3(wi.x, wi.y, wi.z), word & 0xffff);
+                        f = VertexEvalAnalytic(sc, __float_as_int(wo.w), V3(wo.x, wo.y, wo.z), V3(wi.x, wi.y, wi.z), word & 0xffff);
                     if (walk) mode = 1;
                     else {
                         a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
@@ -352,87 +352,73 @@ __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(WvArgs a) {
         }
         for (int it = 0; it < 64; ++it) {
             if (mode != 0) {
+                // ---- one node step, the two walks on one instruction stream (selects, not branches: a branchy form of this
+                // body ran with 10 of 32 lanes active, profiles/r02b_k_weval_ncu_full.txt)
                 const uint32_t node = cur >> 1;
-                const bool flag = (cur & 1u) != 0;
-                const float4 *rec = sc.kdRec + 2 * (size_t)(first + node);
-                const float4 k0 = __ldg(rec);
+                const bool first = (cur & 1u) == 0;   // first arrival at the node (else: its flagged entry came off the stack)
+                const bool knn = mode == 1;
+                const float4 *rec = sc.kdRec + 2 * (size_t)(first_ + node);
+                const float4 k0 = __ldg(rec), k1 = __ldg(rec + 1);
                 const float splitPos = k0.x;
                 const uint32_t bits = __float_as_uint(k0.y);
                 const int axis = (int)(bits & 3u);
+                const bool interior = axis != 3;
                 const bool hasLeft = ((bits >> 2) & 1u) != 0;
                 const uint32_t rightChild = bits >> 3;
                 const bool hasRight = rightChild < nNodes;
-                const float pa = p[axis == 3 ? 0 : axis];
+                const float pa = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);   // (a leaf's value is not looked at)
                 const float plane2 = (pa - splitPos) * (pa - splitPos);
                 const bool leftFirst = pa <= splitPos;
-                const bool nearExists = axis != 3 && (leftFirst ? hasLeft : hasRight);
-                const bool farExists = axis != 3 && (leftFirst ? hasRight : hasLeft);
+                const bool nearExists = interior && (leftFirst ? hasLeft : hasRight);
+                const bool farExists = interior && (leftFirst ? hasRight : hasLeft);
                 const uint32_t nearChild = leftFirst ? node + 1 : rightChild, farChild = leftFirst ? rightChild : node + 1;
-                bool pop = false, finished = false;
-                if (mode == 1) {
-                    // ---- exact third-smallest squared distance (the pruning is conservative: any visiting order gives it)
-                    if (!flag) {
-                        const float pz = __ldg(reinterpret_cast<const float *>(rec + 1));
-                        const float d2 = DistanceSquared(V3(k0.z, k0.w, pz), p);
-                        if (d2 < b2) {
-                            if (d2 < b1) {
-                                b2 = b1;
-                                if (d2 < b0) { b1 = b0; b0 = d2; } else b1 = d2;
-                            } else b2 = d2;
-                        }
-                        if (farExists) stk[sp++] = cur | 1u;
-                        if (nearExists) cur = nearChild << 1;
-                        else pop = true;
-                    } else if (plane2 < b2) cur = farChild << 1;
-                    else pop = true;
-                    if (pop) {
-                        if (sp > 0) cur = stk[--sp];
-                        else {
-                            // reflection.cpp:261-271: the radius doubles until a lookup finds more than two samples
-                            float r2 = .001f;
-                            while (!(b2 < r2) && !(r2 > 1.5f)) r2 *= 2.f;
-                            maxDist2 = r2;
-                            v = Spec(0.f); sumW = 0.f;
-                            mode = 2; cur = 0u; sp = 0;
-                        }
-                    }
-                } else {
-                    // ---- the gather at that radius, in KdTree::privateLookup's order
-                    bool process = flag || axis == 3;
-                    if (!process) {
-                        stk[sp++] = cur | 1u;
-                        if (farExists && plane2 < maxDist2) stk[sp++] = farChild << 1;
-                        if (nearExists) cur = nearChild << 1;
-                        else pop = true;
-                    } else {
-                        const float4 k1 = __ldg(rec + 1);
-                        const float d2 = DistanceSquared(V3(k0.z, k0.w, k1.x), p);
-                        if (d2 < maxDist2) {   // IrregIsoProc, reflection.cpp:40-55
-                            const float weight = ref_expf(-100.f * d2);
-                            v = v + weight * Spec(k1.y, k1.z, k1.w);
-                            sumW += weight;
-                        }
-                        pop = true;
-                    }
-                    if (pop) {
-                        if (sp > 0) cur = stk[--sp];
-                        else finished = true;
-                    }
+                const float d2 = DistanceSquared(V3(k0.z, k0.w, k1.x), p);
+                // third-nearest walk, first arrival: the node's own point enters the three best (d2 < b0 implies d2 < b1 < b2)
+                const bool c2 = knn && first && d2 < b2, c1 = c2 && d2 < b1, c0 = c1 && d2 < b0;
+                b2 = c2 ? (c1 ? b1 : d2) : b2;
+                b1 = c1 ? (c0 ? b0 : d2) : b1;
+                b0 = c0 ? d2 : b0;
+                // gather, second arrival (or a leaf): the node's own point is processed (IrregIsoProc, reflection.cpp:40-55)
+                if (!knn && (!first || !interior) && d2 < maxDist2) {
+                    const float weight = ref_expf(-100.f * d2);
+                    v = v + weight * Spec(k1.y, k1.z, k1.w);
+                    sumW += weight;
                 }
-                if (finished) {
-                    const Spec f = v.Clamp() / sumW;
-                    a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
-                    if ((word & W_RAY_ALLOWED) && !f.IsBlack()) WvPushRayAny(a, k, slot);
-                    mode = 0;
+                // what goes on the stack: the entry to come back to (third-nearest: "my far child, if its plane is still
+                // close enough then"; gather: "my own point"), and -- gather only -- the far child itself
+                if (first && interior && (!knn || farExists)) stk[sp++] = cur | 1u;
+                if (!knn && first && farExists && plane2 < maxDist2) stk[sp++] = farChild << 1;
+                // where to go: the near child; the far child of a popped third-nearest entry; else whatever the stack holds
+                uint32_t next = 0u;
+                bool have = false;
+                if (first && nearExists) { next = nearChild << 1; have = true; }
+                if (knn && !first && plane2 < b2) { next = farChild << 1; have = true; }
+                if (!have && sp > 0) { next = stk[--sp]; have = true; }
+                cur = next;
+                if (!have) {
+                    if (knn) {
+                        // reflection.cpp:261-271: the radius doubles until a lookup finds more than two samples
+                        float r2 = .001f;
+                        while (!(b2 < r2) && !(r2 > 1.5f)) r2 *= 2.f;
+                        maxDist2 = r2;
+                        v = Spec(0.f); sumW = 0.f;
+                        mode = 2; cur = 0u; sp = 0;
+                    } else {
+                        const Spec f = v.Clamp() / sumW;
+                        a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
+                        if ((word & W_RAY_ALLOWED) && !f.IsBlack()) WvPushRayAny(a, k, slot);
+                        mode = 0;
+                    }
                 }
             }
+            if ((it & 1) == 0) continue;   // a vote every second step
             const int nActive = __popc(__ballot_sync(FULL, mode != 0));
             if (nActive == 0 || (more && nActive < 24)) break;
         }
     }
 }
 #else
-__global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(WvArgs a) {
+__global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(const __grid_constant__ WvArgs a) {
     const unsigned n = a.counters[WC_EVALS];
     const size_t P = a.P;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
@@ -451,7 +437,7 @@ __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(WvArgs a) {
 // ----------------------------------------------------------------------------------------------------------- k_wtrace
 // persistent ray-queue consumer: k_trace's loop (chunked hand-out, while-while walk) over the vertex wavefront's records
 template <bool STATS, bool ANIM>
-__global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_wtrace(WvArgs a) {
+__global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_wtrace(const __grid_constant__ WvArgs a) {
     const DScene &sc = a.sc;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;

@@ -111,7 +111,7 @@ DEV void FilmAdd(const RenderParams &rp, PbrtGpuPixel *film, int ownX, int ownY,
 
 template <int PHASE, bool STATS, bool ANIM>
 // 4 CTAs/SM (<= 128 registers): measured +9 % over the unconstrained 168-register build
-__global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(PathArgs a) {
+__global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(const __grid_constant__ PathArgs a) {
     __shared__ uint32_t smt[4][MT_N];
     const DScene &sc = a.sc;
     const RenderParams &rp = a.rp;
@@ -426,7 +426,7 @@ DEV unsigned AggregatedAdd(unsigned *ctr) {   // warp-aggregated atomicAdd(ctr, 
 // parked samples, resumed one after the other with the task's sequential RNG stream; finished samples are added
 // to the film in sample order in between (what k_path<2> does per thread, here as a wavefront).
 template <int PHASE, bool STATS, bool ANIM, int INTEG>
-__global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
+__global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(const __grid_constant__ WfArgs a) {
     __shared__ uint32_t smt[PHASE == 2 ? 4 : 1][PHASE == 2 ? MT_N : 1];
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const DScene &sc = a.sc;
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(WfArgs a) {
 // every camera ray that hit (BSDFSample(rng) twice = 6 draws, integrator.cpp:184,227; only when depth + 1 < maxDepth,
 // directlighting.cpp:108).  One thread per task-pixel; the stream position is advanced block by block,
 // warp-cooperatively, only when another pixel of the task follows (`advance`).
-__global__ void __launch_bounds__(128) k_film_direct(PathArgs a, int advance) {
+__global__ void __launch_bounds__(128) k_film_direct(const __grid_constant__ PathArgs a, int advance) {
     __shared__ uint32_t smt[4][MT_N];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -872,7 +872,7 @@ __global__ void __launch_bounds__(128) k_film_direct(PathArgs a, int advance) {
 
 // persistent ray queue consumer (tuning constants: kcommon.cuh)
 template <bool STATS, bool ANIM>
-__global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(WfArgs a) {
+__global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ WfArgs a) {
     const DScene &sc = a.sc;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -990,7 +990,7 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(WfArgs a) {
 #include "kwave.cuh"
 
 // measured-BRDF evaluations (IrregIsotropicBRDF::f) of the queued requests
-__global__ void __launch_bounds__(128, K_EVAL_MIN_BLOCKS) k_eval(WfArgs a) {
+__global__ void __launch_bounds__(128, K_EVAL_MIN_BLOCKS) k_eval(const __grid_constant__ WfArgs a) {
     const int setOut = (a.iter & 1) ^ 1;
     const unsigned *qn = a.counters + C_QN + setOut * K_COUNT;
     const unsigned n0 = qn[K_E_LIGHT], n1 = n0 + qn[K_E_MIS], n = n1 + qn[K_E_PATH];
@@ -1006,14 +1006,14 @@ __global__ void __launch_bounds__(128, K_EVAL_MIN_BLOCKS) k_eval(WfArgs a) {
         MaterialBxDFs(a.sc, material, &bx);
         Spec f(0.f);
         for (int i = 0; i < bx.n; ++i)
-            if (Matches(bx.type[i], flags)) f = f + BxF(a.sc, bx, i, V3(e0.x, e0.y, e0.z), V3(e1.x, e1.y, e1.z));
+            if (Matches(bx.type(i), flags)) f = f + BxF(a.sc, bx, i, V3(e0.x, e0.y, e0.z), V3(e1.x, e1.y, e1.z));
         a.pool[(size_t)F_FEVAL * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
     }
 }
 
 // ------------------------------------------------------------- ray-batch kernels
 template <bool ANY>
-__global__ void k_intersect(DScene sc, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits, uint8_t *occ) {
+__global__ void k_intersect(const __grid_constant__ DScene sc, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits, uint8_t *occ) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Ray ray;
@@ -1387,6 +1387,21 @@ static int ValidateSceneDesc(const PbrtGpuSceneDesc *desc) {
             const uint32_t bits = desc->kdNodes[m.firstNode + k].bits;
             // (rightChild >= nNodes means "no right child", kdtree.h:56; a left child is the next node)
             if ((bits & 3u) != 3u && ((bits >> 2) & 1u) && k + 1 >= m.nNodes) return Fail(PBRTGPU_EINVAL, "kd node's left child out of range");
+            // children come after their parent (KdTree::recursiveBuild numbers the nodes in preorder, kdtree.h:93-118):
+            // the device walks rely on it to terminate
+            if ((bits & 3u) != 3u && (bits >> 3) < m.nNodes && (bits >> 3) <= k) return Fail(PBRTGPU_EINVAL, "kd node's right child does not follow it");
+        }
+        {   // depth: the evaluation kernels keep two stack entries per level (k_weval: WEVAL_STACK, dshade.cuh KdGather: 40)
+            std::vector<uint8_t> depth(m.nNodes, 0);
+            depth[0] = 1;
+            for (uint32_t k = 0; k < m.nNodes; ++k) {
+                const uint32_t bits = desc->kdNodes[m.firstNode + k].bits;
+                if (depth[k] == 0) continue;   // (unreachable node)
+                if (depth[k] > 18) return Fail(PBRTGPU_EUNSUPPORTED, "measured-BRDF kd-tree deeper than 18 levels (not a median-split tree)");
+                if ((bits & 3u) == 3u) continue;
+                if ((bits >> 2) & 1u) depth[k + 1] = (uint8_t)(depth[k] + 1);
+                if ((bits >> 3) < m.nNodes) depth[bits >> 3] = (uint8_t)(depth[k] + 1);
+            }
         }
     }
     for (uint32_t i = 0; i < desc->nMeshes; ++i) {

@@ -249,8 +249,9 @@ RM_FN float ref_powf(float x, float y) {   // e_powf.c
 RM_FN float rm_fabsf(float x) { return asfloat(asuint(x) & 0x7fffffffu); }
 
 RM_FN float ref_atanf(float x) {   // s_atanf.c
-    const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
-    const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    // atanhi[id], atanlo[id] as selects: an indexed local array is re-initialised in local memory on every call
+#define RM_ATANHI(id) ((id) == 0 ? 4.6364760399e-01f : (id) == 1 ? 7.8539812565e-01f : (id) == 2 ? 9.8279368877e-01f : 1.5707962513e+00f)
+#define RM_ATANLO(id) ((id) == 0 ? 5.0121582440e-09f : (id) == 1 ? 3.7748947079e-08f : (id) == 2 ? 3.4473217170e-08f : 7.5497894159e-08f)
     const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f, aT2 = 1.4285714924e-01f, aT3 = -1.1111110449e-01f,
                 aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f, aT6 = 6.6610731184e-02f, aT7 = -5.8335702866e-02f,
                 aT8 = 4.9768779427e-02f, aT9 = -3.6531571299e-02f, aT10 = 1.6285819933e-02f;
@@ -260,8 +261,8 @@ RM_FN float ref_atanf(float x) {   // s_atanf.c
     ix = hx & 0x7fffffff;
     if (ix >= 0x4c000000) {   // |x| >= 2^25
         if (ix > 0x7f800000) return x + x;
-        if (hx > 0) return atanhi[3] + atanlo[3];
-        else return -atanhi[3] - atanlo[3];
+        if (hx > 0) return RM_ATANHI(3) + RM_ATANLO(3);
+        else return -RM_ATANHI(3) - RM_ATANLO(3);
     }
     if (ix < 0x3ee00000) {   // |x| < 0.4375
         if (ix < 0x31000000) return x;   // |x| < 2^-29
@@ -281,7 +282,7 @@ RM_FN float ref_atanf(float x) {   // s_atanf.c
     s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
     s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
     if (id < 0) return x - x * (s1 + s2);
-    z = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+    z = RM_ATANHI(id) - ((x * (s1 + s2) - RM_ATANLO(id)) - x);
     return (hx < 0) ? -z : z;
 }
 

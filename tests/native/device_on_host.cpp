@@ -757,7 +757,7 @@ DOH_EXPORT int doh_shade_test(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *ra
             else flags &= ~BSDF_REFLECTION;
             Spec f(0.f);
             for (int k = 0; k < bx.n; ++k)
-                if (Matches(bx.type[k], flags)) f = f + BxF(sc, bx, k, evalWo, evalWi);
+                if (Matches(bx.type(k), flags)) f = f + BxF(sc, bx, k, evalWo, evalWi);
             o[24] = f.r; o[25] = f.g; o[26] = f.b;
             o[27] = BSDF_PdfLocal(bx, evalWo, evalWi, BSDF_ALL & ~BSDF_SPECULAR);
         }
@@ -773,7 +773,7 @@ DOH_EXPORT int doh_shade_test(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *ra
 #endif
                 Spec f(0.f);
                 for (int k = 0; k < bx.n; ++k)
-                    if (Matches(bx.type[k], evalFlags)) f = f + BxF(sc, bx, k, evalWo, evalWi);
+                    if (Matches(bx.type(k), evalFlags)) f = f + BxF(sc, bx, k, evalWo, evalWi);
 #if PBRT_SPECULAR
                 if (sampledType & BSDF_SPECULAR) f = specF;
 #endif
