@@ -25,7 +25,7 @@ NVDEFS    ?=
 # kernel experiments, built next to the product library so that a GPU visit can A/B them without compiling on the box
 # (scripts/ab_variants.py; tests/test_zz_gpu_variants.py runs the parity suite over them).  Nothing loads them by default.
 #   make variants VARIANT_NAMES="pairs foo"   with   VARIANT_DEFS_foo := -DSOMETHING=1
-VARIANT_NAMES ?= ws5 ws6 we10
+VARIANT_NAMES ?= ws6 ws6_lb8 ws6_lb12 ws6_lb20
 # Kernel experiments of the current round (the earlier ones and their verdicts: profiles/README.md).  Traversal variants
 # that lost on the B200 and can still be built:  pairs (-DPBRT_PAIR_NODES=1), ww (-DPBRT_TRACE_LOOP=1),
 # sstack (-DPBRT_SMEM_STACK=32), top9_sstack (-DPBRT_TOP_LEVELS=9 -DPBRT_SMEM_STACK=32)
@@ -37,6 +37,10 @@ VARIANT_DEFS_top9_sstack := -DPBRT_TOP_LEVELS=9 -DPBRT_SMEM_STACK=32
 VARIANT_DEFS_ws5 := -DK_WSHADE_MIN_BLOCKS=5
 VARIANT_DEFS_ws6 := -DK_WSHADE_MIN_BLOCKS=6
 VARIANT_DEFS_we10 := -DK_WEVAL_MIN_BLOCKS=10
+# leaf tests in batches of >= n lanes (PBRT_TRACE_LOOP 2), on top of ws6
+VARIANT_DEFS_ws6_lb8 := -DK_WSHADE_MIN_BLOCKS=6 -DPBRT_TRACE_LOOP=2 -DPBRT_LEAF_BATCH=8
+VARIANT_DEFS_ws6_lb12 := -DK_WSHADE_MIN_BLOCKS=6 -DPBRT_TRACE_LOOP=2 -DPBRT_LEAF_BATCH=12
+VARIANT_DEFS_ws6_lb20 := -DK_WSHADE_MIN_BLOCKS=6 -DPBRT_TRACE_LOOP=2 -DPBRT_LEAF_BATCH=20
 VARIANTS  := $(patsubst %,$(PKG)/ab/libpbrtgpu_%.so,$(VARIANT_NAMES))
 
 all: $(PKG)/libpbrtgpu.so $(PKG)/libpbrthost.so $(PKG)/pbrt_b200 oracle variants

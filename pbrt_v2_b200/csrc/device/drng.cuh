@@ -100,6 +100,31 @@ DEV void WarpRegenMT(uint32_t *mt, int lane) {
     }
 }
 
+// A task's two-block MT19937 window (cur = the block in use, next = the one after it) one block forward, by the lanes of
+// one warp; `mt` is a block of shared memory of theirs.  (A host compiler sees the one-thread form: the CPU test stage
+// runs the kernels one thread at a time, tests/native/device_on_host.cpp.)
+DEV void WarpAdvanceWindow(uint32_t *cur, uint32_t *next, uint32_t *mt, int lane) {
+#ifdef __CUDACC__
+    for (int j = lane; j < MT_N; j += 32) {
+        const uint32_t v = __ldcg(next + j);
+        __stcg(cur + j, v);
+        mt[j] = v;
+    }
+    __syncwarp();
+    WarpRegenMT(mt, lane);
+    for (int j = lane; j < MT_N; j += 32) __stcg(next + j, mt[j]);
+    __syncwarp();
+#else
+    (void)lane;
+    for (int j = 0; j < MT_N; ++j) { cur[j] = next[j]; mt[j] = next[j]; }
+    for (int k = 0; k < MT_N; ++k) {
+        const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % MT_N] & 0x7fffffffu);
+        mt[k] = mt[(k + MT_M) % MT_N] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    for (int j = 0; j < MT_N; ++j) next[j] = mt[j];
+#endif
+}
+
 // RNG::Seed, rng.cpp:43-55 (sequential by nature; one lane)
 DEV void SeedMT(uint32_t *mt, uint32_t seed) {
     mt[0] = seed;

@@ -174,6 +174,19 @@ DEV Spec VertexEvalAnalytic(const DScene &sc, int material, const V3 &wo, const 
     return f;
 }
 
+// Does the path sample with BSDF value `fp` lead to a continuation ray (maxDepth aside)?  VertexB's test, for the kernels
+// that queue the ray before VertexB runs (kwave.cuh): the value is not black and, when `roulette` (bounces > 3), the path
+// survives path.cpp:103-108 -- the same expressions on the same operands as in VertexB below.
+DEV bool PathSampleAlive(const Spec &fp, const Spec &T, float absP, float pdfP, bool roulette, float rrU) {
+    if (fp.IsBlack()) return false;
+    if (roulette) {
+        const Spec Tn = T * (fp * absP / pdfP);
+        const float continueProbability = minf(.5f, Tn.y());
+        if (rrU > continueProbability) return false;
+    }
+    return true;
+}
+
 // Part B: with the three BSDF values, the terms the rays carry and the new throughput.  `rrU` is the Russian-roulette
 // draw (looked at only when bounces > 3 and the path sample's f is not black: *rrDrawn says whether it was consumed).
 // Returns true when the path continues (ray[VX_PATH]); `bounces` is NOT advanced here.

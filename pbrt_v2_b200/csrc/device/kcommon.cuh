@@ -63,8 +63,12 @@ DEV unsigned AggregatedAddV(unsigned *ctr) {
 //      one box test, then the lanes that stand before a leaf test its primitives together.  (The first form of this,
 //      with the descend loop inside a per-lane function, let the lanes drift apart: 4.1 of 32 active and 5.3 ms instead of
 //      0.87 ms per launch, profiles/r02a_k_trace_ncu_full.txt -- the loop must be the WARP's, with a vote per round.)
+//   2  one box test per walking lane and iteration as in 0, but leaves are tested in batches: see the kernels
 #ifndef PBRT_TRACE_LOOP
 #define PBRT_TRACE_LOOP 0
+#endif
+#ifndef PBRT_LEAF_BATCH
+#define PBRT_LEAF_BATCH 12
 #endif
 #ifndef TRACE_DESCEND_STEPS
 #define TRACE_DESCEND_STEPS 12   // node tests per lane before the warp looks at its leaves / refills

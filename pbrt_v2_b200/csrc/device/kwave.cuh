@@ -52,17 +52,19 @@ enum {
     W_V0,      // Li.rgb, scalarL
     W_V1,      // absM, weightM, pdfM, absP
     W_V2,      // specF.rgb (PBRT_SPECULAR), -
+    W_CH,      // phase 2, the slot's task chain: mti, tail-mask word index, its remaining bits, the vertex's roulette draw
     W_COUNT
 };
-// W_T.w
-enum { WB_BOUNCES = 0x3, WB_VERTEX = 0x4, WB_AFTER_SPEC = 0x8, WB_SPEC_SAMPLED = 0x10, WB_NEED0 = 0x20, WB_NEED1 = 0x40,
-       WB_NEED2 = 0x80, WB_RETIRED = 0x100, WB_LIGHT_SHIFT = 16 };
+// W_T.w: flags, bounces (8 bits), lightNum (16 bits)
+enum { WB_VERTEX = 0x1, WB_AFTER_SPEC = 0x2, WB_SPEC_SAMPLED = 0x4, WB_NEED0 = 0x8, WB_NEED1 = 0x10, WB_NEED2 = 0x20,
+       WB_RETIRED = 0x40, WB_BOUNCES_SHIFT = 8, WB_LIGHT_SHIFT = 16 };
 // counters
 enum { WC_RAYS = 0 /* 3 */, WC_EVALS = 3, WC_TRACE_CUR, WC_EVAL_CUR,
        WC_LIVE,          // slots that hold a camera path after k_wshade (0: the batch is done)
        WC_NEXT_SAMPLE,   // (everything before it is reset every iteration)
        WC_COUNT };
 #define W_RAY_ALLOWED 0x10000
+#define W_RR 0x20000   // (direction 2, phase 2) the path ray also has to survive Russian roulette: see k_weval
 
 struct WvArgs {
     DScene sc;
@@ -94,17 +96,25 @@ DEV void WvPushRayAny(const WvArgs &a, int kind, uint32_t slot) {
 }
 
 // ----------------------------------------------------------------------------------------------------------- k_wshade
-template <bool STATS, bool ANIM>
+// PHASE 1: slots are camera samples (bounces 0..2, random numbers from the tables), handed out by a global counter.
+// PHASE 2: slot c is task chain c -- the parked samples of one task-pixel in sample order, each resumed with the task's RNG
+//          exactly where the previous one stopped (7 + 3 + [1] draws per vertex, path.cpp:86-108) -- so the chains advance
+//          one vertex per iteration side by side and the iteration count is the longest chain's vertex count; what
+//          k_vertex<2> did with one lane per chain and 5 of 32 lanes active (profiles/r02a_k_vertex_ncu_full.txt).
+template <int PHASE, bool STATS, bool ANIM>
 __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __grid_constant__ WvArgs a) {
+    __shared__ uint32_t smt[PHASE == 2 ? 4 : 1][PHASE == 2 ? MT_N : 1];
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= a.P) return;
     const DScene &sc = a.sc;
     const RenderParams &rp = a.rp;
     const int spp = rp.spp;
     const size_t P = a.P;
     float4 *pool = a.pool;
     const int nLights = (int)sc.nLights;
+    const int k0 = nLights > 0 ? 7 : 0;   // PHASE 2: draws of UniformSampleOneLight before the path's BSDFSample
 #define WF(f) pool[(size_t)(f) * P + slot]
+    bool live = slot < (PHASE == 1 ? a.P : (uint32_t)a.b.nBatch);
+    if (PHASE == 1 && !live) return;
 
     Ray ray;
     ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f; ray.time = 0.f;
@@ -115,18 +125,40 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
     bool afterSpecular = false;
     bool have = false;       // the slot holds a camera path whose path ray has been traced
     bool atVertex = false;   // ... and hit something
+    int mti = 0, mw = 0;     // PHASE 2: the chain's RNG position, the tail-mask word being walked
+    uint32_t mbits = 0;      //          ... and its remaining bits
     unsigned long long nShadedN = 0;
 
-    if (a.iter > 0) {
+    if (a.iter == 0) {
+        if (PHASE == 2 && live) {
+            bi = a.b.order ? (int)a.b.order[slot] : (int)slot;
+            const TaskRec tr = a.b.tasks[bi];
+            if (a.b.round >= (tr.x1 - tr.x0) * (tr.y1 - tr.y0) || a.b.tailCount[bi] == 0) {
+                WF(W_T) = make_float4(0.f, 0.f, 0.f, __uint_as_float(WB_RETIRED));
+                live = false;
+            } else {
+                mti = a.b.mti[bi];
+                mbits = __ldcg(a.b.tailMask + (size_t)bi * a.b.maskWords);
+            }
+        }
+    } else if (live) {
         const float4 fT = WF(W_T);
         const uint32_t bits = __float_as_uint(fT.w);
-        if (bits & WB_RETIRED) return;
+        if (bits & WB_RETIRED) {
+            if (PHASE == 1) return;
+            live = false;
+        } else {
         const float4 fL = WF(W_L), fId = WF(W_ID), fP = WF(W_P), fD2 = WF(W_D2), fH = WF(W_HIT);
         T = Spec(fT.x, fT.y, fT.z);
         L = Spec(fL.x, fL.y, fL.z); code = __float_as_int(fL.w);
         bi = __float_as_int(fId.x); s = __float_as_int(fId.y); ray.time = fId.z;
-        bounces = (int)(bits & WB_BOUNCES);
+        bounces = (int)((bits >> WB_BOUNCES_SHIFT) & 0xffu);
         afterSpecular = (bits & WB_AFTER_SPEC) != 0;
+        float rrU = 0.f;
+        if (PHASE == 2) {
+            const float4 ch = WF(W_CH);
+            mti = __float_as_int(ch.x); mw = __float_as_int(ch.y); mbits = __float_as_uint(ch.z); rrU = ch.w;
+        }
         bool pathTraced = true;
         if (bits & WB_VERTEX) {
             // ---- the second half of the previous vertex (dvertex.cuh VertexB) with the BSDF values and the ray results
@@ -145,7 +177,8 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
 #endif
             const Spec f[3] = {Spec(f0.x, f0.y, f0.z), Spec(f1.x, f1.y, f1.z), Spec(f2.x, f2.y, f2.z)};
             bool rrDrawn = false;
-            const bool cont = VertexB(f, bounces, rp.maxDepth, T, 0.f, &v, &rrDrawn);   // (bounces <= 2: no Russian roulette)
+            const bool cont = VertexB(f, bounces, rp.maxDepth, T, rrU, &v, &rrDrawn);   // (PHASE 1, bounces <= 2: no roulette)
+            if (PHASE == 2) mti += k0 + 3 + (rrDrawn ? 1 : 0);
             Spec Ld(0.f);
             if (v.ray[VX_LIGHT] && WF(W_D0).w == 0.f) Ld = Ld + v.pendS;    // visibility.Unoccluded(scene)
             if (v.ray[VX_MIS] && WF(W_D1).w == 1.f) Ld = Ld + v.pendM;      // the MIS ray landed on the light
@@ -172,7 +205,7 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
             const Spec Ls = SanitizeRadiance(L);
             a.b.ls[(size_t)bi * spp + s] = make_float4(Ls.r, Ls.g, Ls.b, __int_as_float(code));
             have = false;
-        } else if (bounces == 3) {
+        } else if (PHASE == 1 && bounces == 3) {
             // ---- park the sample: from here on the path draws from the task's RNG stream (phase 2)
             float4 *r = a.b.rec + ((size_t)bi * spp + s) * 4;
             r[0] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
@@ -184,9 +217,10 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
             atomicOr(a.b.tailMask + (size_t)bi * a.b.maskWords + (s >> 5), 1u << (s & 31));
             have = false;
         }
+        }
     }
 
-    if (!have) {
+    if (PHASE == 1 && !have) {
         // ---- the next camera sample of the batch: (task, sample) = (g / spp, g % spp)
         bool got = false;
         for (;;) {
@@ -216,18 +250,76 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
         WvPushRay(a, VX_PATH, slot);
         return;
     }
+    if (PHASE == 2) {
+        if (live && !have) {
+            // ---- the chain's next parked sample (a bounce-3 vertex: nothing to trace first), or the end of the chain
+            while (mbits == 0 && mw + 1 < a.b.maskWords) { ++mw; mbits = __ldcg(a.b.tailMask + (size_t)bi * a.b.maskWords + mw); }
+            if (mbits == 0) {
+                a.b.mti[bi] = mti;   // the task's stream position for its next pixel
+                WF(W_T) = make_float4(0.f, 0.f, 0.f, __uint_as_float(WB_RETIRED));
+                live = false;
+            } else {
+                s = mw * 32 + (__ffs(mbits) - 1);
+                mbits &= mbits - 1;
+                const float4 lv = __ldcs(a.b.ls + (size_t)bi * spp + s);
+                const float4 *r = a.b.rec + ((size_t)bi * spp + s) * 4;
+                const float4 r0 = __ldcs(r), r1 = __ldcs(r + 1), r2 = __ldcs(r + 2), r3 = __ldcs(r + 3);
+                ray.o = V3(r0.x, r0.y, r0.z); ray.mint = r0.w;
+                ray.d = V3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
+                hit.t = r1.w;
+                T = Spec(r2.x, r2.y, r2.z);
+                hit.prim = __float_as_int(r2.w);
+                hit.b1 = r3.x; hit.b2 = r3.y; hit.maxtIn = r3.z;
+                ray.time = r3.w;
+                L = Spec(lv.x, lv.y, lv.z);
+                code = __float_as_int(lv.w);
+                afterSpecular = (code & LS_SPEC) != 0;
+                code &= ~(LS_SPEC | LS_TAIL);
+                bounces = 3;
+                have = true; atVertex = true;
+            }
+        }
+        // ---- cooperative RNG top-up: the <= 11 draws of the vertex must be addressable in the two-block window
+        const unsigned FULL = 0xffffffffu;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned m = __ballot_sync(FULL, live && mti >= MT_N);
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const int tb = __shfl_sync(FULL, bi, l);
+            WarpAdvanceWindow(a.b.rngCur + (size_t)tb * MT_N, a.b.rngNext + (size_t)tb * MT_N, smt[warp], lane);
+            if (lane == l) mti -= MT_N;
+        }
+        if (!live) return;
+    }
 
     AggregatedAddV(a.counters + WC_LIVE);
     // ---- a vertex to shade: VertexA, the record, the requests
     VertexRandoms u;
-    VertexRandomsFromTables(a.b.perm + ((size_t)bi * spp + s) * PERM_STRIDE, a.b.scr + (size_t)bi * SCR_STRIDE, bounces, &u);
+    float rrU = 0.f;
+    if (PHASE == 1)
+        VertexRandomsFromTables(a.b.perm + ((size_t)bi * spp + s) * PERM_STRIDE, a.b.scr + (size_t)bi * SCR_STRIDE, bounces, &u);
+    else {
+        const uint32_t *rc = a.b.rngCur + (size_t)bi * MT_N, *rn = a.b.rngNext + (size_t)bi * MT_N;
+        auto rngF = [&](int k) -> float {
+            const int j = mti + k;
+            return UIntToFloat(Temper(j < MT_N ? __ldcg(rc + j) : __ldcg(rn + (j - MT_N))));
+        };
+        if (nLights > 0) {   // integrator.cpp:95,107-108: lightNum, LightSample(rng), BSDFSample(rng)
+            u.lnU = rngF(0); u.lsU0 = rngF(1); u.lsU1 = rngF(2);
+            u.bsU0 = rngF(4); u.bsU1 = rngF(5); u.bsUc = rngF(6);
+        } else u.lnU = u.lsU0 = u.lsU1 = u.bsU0 = u.bsU1 = u.bsUc = 0.f;
+        u.pU0 = rngF(k0); u.pU1 = rngF(k0 + 1); u.pUc = rngF(k0 + 2);   // path.cpp:90
+        if (bounces > 3) rrU = rngF(k0 + 3);                            // path.cpp:104 (looked at only if the sample's f is not black)
+    }
     Vertex v;
     {
         ShadeCtx ctx;
         VertexA<ANIM>(sc, ray, hit, bounces, afterSpecular, u, T, L, ctx, &v, STATS ? &nShadedN : nullptr);
     }
     const bool pathAllowed = bounces != rp.maxDepth;
-    uint32_t bits = (uint32_t)bounces | WB_VERTEX | (afterSpecular ? WB_AFTER_SPEC : 0u) |
+    const bool roulette = PHASE == 2 && bounces > 3;
+    uint32_t bits = ((uint32_t)bounces << WB_BOUNCES_SHIFT) | WB_VERTEX | (afterSpecular ? WB_AFTER_SPEC : 0u) |
                     (v.need[0] ? WB_NEED0 : 0u) | (v.need[1] ? WB_NEED1 : 0u) | (v.need[2] ? WB_NEED2 : 0u) |
                     ((uint32_t)v.lightNum << WB_LIGHT_SHIFT);
 #if PBRT_SPECULAR
@@ -239,6 +331,7 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
     WF(W_ID) = make_float4(__int_as_float(bi), __int_as_float(s), ray.time, v.pdfP);
     WF(W_V0) = make_float4(v.Li.r, v.Li.g, v.Li.b, v.scalarL);
     WF(W_V1) = make_float4(v.absM, v.weightM, v.pdfM, v.absP);
+    if (PHASE == 2) WF(W_CH) = make_float4(__int_as_float(mti), __int_as_float(mw), __uint_as_float(mbits), rrU);
     if (v.need[VX_LIGHT]) WF(W_D0) = make_float4(v.wiW[VX_LIGHT].x, v.wiW[VX_LIGHT].y, v.wiW[VX_LIGHT].z, v.visMaxt);
     if (v.need[VX_MIS]) WF(W_D1) = make_float4(v.wiW[VX_MIS].x, v.wiW[VX_MIS].y, v.wiW[VX_MIS].z, __int_as_float(v.lightNum));
     if (v.need[VX_PATH]) WF(W_D2) = make_float4(v.wiW[VX_PATH].x, v.wiW[VX_PATH].y, v.wiW[VX_PATH].z, INF_F);
@@ -253,24 +346,36 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
         const bool allowed = k != VX_PATH || pathAllowed;
 #if PBRT_SPECULAR
         if (k == VX_PATH && v.specSampled) {   // the value is specF (BSDF::Sample_f, reflection.cpp:572): nothing to evaluate
-            if (allowed && !v.specF.IsBlack()) WvPushRay(a, k, slot);
+            if (allowed && PathSampleAlive(v.specF, T, v.absP, v.pdfP, roulette, rrU)) WvPushRay(a, k, slot);
             continue;
         }
 #endif
         if (measured) {
             if (!wroteWo) { WF(W_EWO) = make_float4(v.evalWo.x, v.evalWo.y, v.evalWo.z, __int_as_float(v.material)); wroteWo = true; }
             WF(W_EW0 + k) = make_float4(v.evalWi[k].x, v.evalWi[k].y, v.evalWi[k].z,
-                                        __int_as_float(v.evalFlags[k] | (allowed ? W_RAY_ALLOWED : 0)));
+                                        __int_as_float(v.evalFlags[k] | (allowed ? W_RAY_ALLOWED : 0) |
+                                                       ((k == VX_PATH && roulette) ? W_RR : 0)));
             const unsigned i = AggregatedAddV(a.counters + WC_EVALS);
             a.qEval[i] = (slot << 2) | (uint32_t)k;
         } else {
             const Spec f = VertexEvalAnalytic(sc, v.material, v.evalWo, v.evalWi[k], v.evalFlags[k]);
             WF(W_F0 + k) = make_float4(f.r, f.g, f.b, 0.f);
-            if (allowed && !f.IsBlack()) WvPushRay(a, k, slot);
+            if (allowed && (k == VX_PATH ? PathSampleAlive(f, T, v.absP, v.pdfP, roulette, rrU) : !f.IsBlack())) WvPushRay(a, k, slot);
         }
     }
     if (STATS && nShadedN) atomicAdd(&a.stats->shadedN, nShadedN);
 #undef WF
+}
+
+// k_weval's "does direction k get its ray" test: the value is not black and -- the path sample from bounce 4 on -- the path
+// survives VertexB's Russian roulette (the same expressions on the same operands)
+DEV bool WvRayWanted(const WvArgs &a, uint32_t slot, int k, int word, const Spec &f) {
+    if (!(word & W_RAY_ALLOWED)) return false;
+    if (!(word & W_RR)) return !f.IsBlack();
+    const size_t P = a.P;
+    const float4 fT = a.pool[(size_t)W_T * P + slot];
+    return PathSampleAlive(f, Spec(fT.x, fT.y, fT.z), a.pool[(size_t)W_V1 * P + slot].w, a.pool[(size_t)W_ID * P + slot].w, true,
+                           a.pool[(size_t)W_CH * P + slot].w);
 }
 
 // ------------------------------------------------------------------------------------------------------------ k_weval
@@ -339,7 +444,7 @@ __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(const __grid_
                     if (walk) mode = 1;
                     else {
                         a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
-                        if ((word & W_RAY_ALLOWED) && !f.IsBlack()) WvPushRayAny(a, k, slot);
+                        if (WvRayWanted(a, slot, k, word, f)) WvPushRayAny(a, k, slot);
                     }
                 }
             }
@@ -406,7 +511,7 @@ __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(const __grid_
                     } else {
                         const Spec f = v.Clamp() / sumW;
                         a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
-                        if ((word & W_RAY_ALLOWED) && !f.IsBlack()) WvPushRayAny(a, k, slot);
+                        if (WvRayWanted(a, slot, k, word, f)) WvPushRayAny(a, k, slot);
                         mode = 0;
                     }
                 }
@@ -429,7 +534,7 @@ __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(const __grid_
         const int word = __float_as_int(wi.w);
         const Spec f = VertexEval(a.sc, __float_as_int(wo.w), V3(wo.x, wo.y, wo.z), V3(wi.x, wi.y, wi.z), word & 0xffff);
         a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
-        if ((word & W_RAY_ALLOWED) && !f.IsBlack()) WvPushRayAny(a, k, slot);
+        if (WvRayWanted(a, slot, k, word, f)) WvPushRayAny(a, k, slot);
     }
 }
 #endif
@@ -508,6 +613,25 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_wtrace(const __grid
 #if PBRT_TRACE_LOOP == 0 || PBRT_PAIR_NODES
         for (int it = 0; it < 64; ++it) {
             const bool fin = active && TravStep<STATS, ANIM>(sc, t, &st, smemTop);
+#elif PBRT_TRACE_LOOP == 2
+        for (int it = 0; it < 64; ++it) {
+            // one box test per walking lane; a lane that reaches a leaf waits until PBRT_LEAF_BATCH lanes stand before one (or
+            // nobody walks any more), then those lanes test their primitives together (the double-precision cross products of
+            // a lone leaf test no longer run with 5 of 32 lanes, profiles/r02b_k_wtrace_ncu_full.txt)
+            bool fin = false;
+            if (active && !leaf) {
+                const int r = TravDescend<STATS, ANIM>(sc, t, &st, 1, smemTop);
+                leaf = r == 1;
+                fin = r == 2;
+            }
+            const unsigned atLeaf = __ballot_sync(FULL, active && leaf);
+            const unsigned walking = __ballot_sync(FULL, active && !leaf && !fin);
+            if (atLeaf && (__popc(atLeaf) >= PBRT_LEAF_BATCH || !walking)) {
+                if (active && leaf) {
+                    leaf = false;
+                    fin = TravLeaf<STATS, ANIM>(sc, t, &st);
+                }
+            }
 #else
         for (int it = 0; it < 8; ++it) {
             bool fin = false;

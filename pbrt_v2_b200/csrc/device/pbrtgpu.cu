@@ -945,6 +945,25 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_trace(const __grid_
 #if PBRT_TRACE_LOOP == 0 || PBRT_PAIR_NODES
         for (int it = 0; it < 64; ++it) {
             const bool fin = active && TravStep<STATS, ANIM>(sc, t, &st, smemTop);
+#elif PBRT_TRACE_LOOP == 2
+        for (int it = 0; it < 64; ++it) {
+            // one box test per walking lane; a lane that reaches a leaf waits until PBRT_LEAF_BATCH lanes stand before one (or
+            // nobody walks any more), then those lanes test their primitives together (the double-precision cross products of
+            // a lone leaf test no longer run with 5 of 32 lanes, profiles/r02b_k_wtrace_ncu_full.txt)
+            bool fin = false;
+            if (active && !leaf) {
+                const int r = TravDescend<STATS, ANIM>(sc, t, &st, 1, smemTop);
+                leaf = r == 1;
+                fin = r == 2;
+            }
+            const unsigned atLeaf = __ballot_sync(FULL, active && leaf);
+            const unsigned walking = __ballot_sync(FULL, active && !leaf && !fin);
+            if (atLeaf && (__popc(atLeaf) >= PBRT_LEAF_BATCH || !walking)) {
+                if (active && leaf) {
+                    leaf = false;
+                    fin = TravLeaf<STATS, ANIM>(sc, t, &st);
+                }
+            }
 #else
         for (int it = 0; it < 8; ++it) {
             bool fin = false;
@@ -1299,7 +1318,8 @@ struct RenderConfig {
     int vertex = 2;
     // PBRTGPU_WAVE=0: PathIntegrator's phase 1 on the request-granular wavefront (k_logic / k_eval / k_trace) instead of the
     // vertex wavefront (kwave.cuh: k_wshade / k_weval / k_wtrace)
-    bool wave = true;
+    // bit 1: phase 2 (the task chains) on it as well instead of k_vertex<2>
+    int wave = 3;
     int tailSort = 2;          // PBRTGPU_TAIL_SORT 0: chains in task order, 2: longest chain first
     int lockstep = 1;
     size_t pool = (size_t)1 << 22;
@@ -1313,7 +1333,7 @@ RenderConfig ReadConfig() {
         if (const char *e = getenv("PBRTGPU_WAVEFRONT")) c.wavefront = atoi(e) != 0;
         if (const char *e = getenv("PBRTGPU_WAVEFRONT2")) c.wavefront2 = atoi(e) != 0;
         if (const char *e = getenv("PBRTGPU_VERTEX")) c.vertex = atoi(e);
-        if (const char *e = getenv("PBRTGPU_WAVE")) c.wave = atoi(e) != 0;
+        if (const char *e = getenv("PBRTGPU_WAVE")) c.wave = atoi(e);
         if (const char *e = getenv("PBRTGPU_TAIL_SORT")) c.tailSort = atoi(e);
         if (const char *e = getenv("PBRTGPU_LOCKSTEP")) c.lockstep = atoi(e);
         if (const char *e = getenv("PBRTGPU_POOL")) { if (atol(e) > 0) c.pool = (size_t)atol(e); }
@@ -1699,7 +1719,8 @@ int RunLane(LaneJob &job) {
     const RenderConfig &cfg = job.cfg;
     const bool direct = rp.integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
     const bool vertex1 = !direct && (cfg.vertex & 1), vertex2 = !direct && (cfg.vertex & 2);
-    const bool wave1 = !direct && cfg.wave && cfg.wavefront && !vertex1;   // phase 1 on the vertex wavefront (kwave.cuh)
+    const bool wave1 = !direct && (cfg.wave & 1) && cfg.wavefront && !vertex1;
+    const bool wave2 = !direct && (cfg.wave & 2) && cfg.wavefront;   // phase 2 on the vertex wavefront   // phase 1 on the vertex wavefront (kwave.cuh)
     const bool useWavefront = cfg.wavefront && !vertex1 && !wave1, useWavefront2 = cfg.wavefront2 && useWavefront && !vertex2;
     size_t poolSize = cfg.pool;   // 4 Mi slots x 272 B = 1.1 GB (measured: +17 % over 1 Mi)
     const bool dlSpecular = direct && scene->nSpecularMaterials > 0;
@@ -1719,10 +1740,10 @@ int RunLane(LaneJob &job) {
         if (dlSpecular) CUDA_TRY(ln->dlFrames.Ensure(poolSize * DL_MAX_DEPTH));
         if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, C_COUNT * sizeof(unsigned)));
     }
-    if (wave1) {
-        CUDA_TRY(ln->pool.Ensure(poolSize * std::max<size_t>(W_COUNT, useWavefront2 ? F_COUNT : 0)));
-        CUDA_TRY(ln->traceQ.Ensure(poolSize * 3));
-        CUDA_TRY(ln->evalQ.Ensure(poolSize * 3));
+    if (wave1 || wave2) {
+        CUDA_TRY(ln->pool.Ensure(std::max(poolSize, maxBatch) * std::max<size_t>(W_COUNT, F_COUNT)));
+        CUDA_TRY(ln->traceQ.Ensure(std::max(poolSize, maxBatch) * 3));
+        CUDA_TRY(ln->evalQ.Ensure(std::max(poolSize, maxBatch) * 3));
         CUDA_TRY(ln->counters.Ensure(std::max<int>(WC_COUNT, C_COUNT)));
         if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, std::max<int>(WC_COUNT, C_COUNT) * sizeof(unsigned)));
     }
@@ -1789,11 +1810,11 @@ int RunLane(LaneJob &job) {
                     // empty the queues k_wshade is about to fill, the consumers' cursors and the live-slot count
                     CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_NEXT_SAMPLE * sizeof(unsigned), stream));
                     if (scene->d.nAnimated) {
-                        if (wantCounters) k_wshade<true, true><<<sblocks, 128, 0, stream>>>(wa);
-                        else k_wshade<false, true><<<sblocks, 128, 0, stream>>>(wa);
+                        if (wantCounters) k_wshade<1, true, true><<<sblocks, 128, 0, stream>>>(wa);
+                        else k_wshade<1, false, true><<<sblocks, 128, 0, stream>>>(wa);
                     } else {
-                        if (wantCounters) k_wshade<true, false><<<sblocks, 128, 0, stream>>>(wa);
-                        else k_wshade<false, false><<<sblocks, 128, 0, stream>>>(wa);
+                        if (wantCounters) k_wshade<1, true, false><<<sblocks, 128, 0, stream>>>(wa);
+                        else k_wshade<1, false, false><<<sblocks, 128, 0, stream>>>(wa);
                     }
                     if (hasMeasured) k_weval<<<tblocks, 128, 0, stream>>>(wa);
                     if (timeRays) CUDA_TRY(cudaEventRecord(rayEvent(), stream));
@@ -1886,7 +1907,46 @@ int RunLane(LaneJob &job) {
                 CUDA_TRY(cudaGetLastError());
             }
             if (stats) CUDA_TRY(cudaEventRecord(ln->ev[2], stream));
-            if (vertex2) {
+            if (wave2) {
+                // ---- phase 2 as a vertex wavefront over the task chains (slot c = chain c), then the film in sample order
+                WvArgs wa;
+                wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = ln->pool.p; wa.P = (uint32_t)std::max(poolSize, maxBatch);
+                wa.qRay = ln->traceQ.p; wa.qEval = ln->evalQ.p; wa.counters = ln->counters.p;
+                wa.totalSamples = 0; wa.stats = scene->stats.p;
+                const int cblocks = (int)((nb + 127) / 128);
+                const int tblocks = nSM * 8;
+                for (int iter = 0;; ++iter) {
+                    wa.iter = iter;
+                    CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_NEXT_SAMPLE * sizeof(unsigned), stream));
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_wshade<2, true, true><<<cblocks, 128, 0, stream>>>(wa);
+                        else k_wshade<2, false, true><<<cblocks, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_wshade<2, true, false><<<cblocks, 128, 0, stream>>>(wa);
+                        else k_wshade<2, false, false><<<cblocks, 128, 0, stream>>>(wa);
+                    }
+                    if (hasMeasured) k_weval<<<tblocks, 128, 0, stream>>>(wa);
+                    if (scene->d.nAnimated) {
+                        if (wantCounters) k_wtrace<true, true><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_wtrace<false, true><<<tblocks, 128, 0, stream>>>(wa);
+                    } else {
+                        if (wantCounters) k_wtrace<true, false><<<tblocks, 128, 0, stream>>>(wa);
+                        else k_wtrace<false, false><<<tblocks, 128, 0, stream>>>(wa);
+                    }
+                    launches += hasMeasured ? 3 : 2;
+                    if ((iter & 7) == 7) {
+                        CUDA_TRY(cudaMemcpyAsync(ln->hostCounters, ln->counters.p, WC_COUNT * sizeof(unsigned),
+                                                 cudaMemcpyDeviceToHost, stream));
+                        CUDA_TRY(cudaStreamSynchronize(stream));
+                        if (ln->hostCounters[WC_LIVE] == 0) break;
+                    }
+                    if (iter > 40000000) return Fail(PBRTGPU_ECUDA, "chain wavefront did not terminate");
+                }
+                CUDA_TRY(cudaGetLastError());
+                k_film<<<blocks2, 128, 0, stream>>>(pa);
+                CUDA_TRY(cudaGetLastError());
+                launches += 1;
+            } else if (vertex2) {
                 // ---- phase 2, vertex-synchronous: chains handed out longest first, then the film in sample order
                 if (cfg.tailSort) {
                     size_t tmp = ln->sortTemp.n;
@@ -1914,7 +1974,7 @@ int RunLane(LaneJob &job) {
                                                           ln->orderIn.p, ln->orderOut.p, (int)nb, 0, 1, stream);
                 pa.b.order = ln->orderOut.p;
             }
-            if (vertex2) {
+            if (vertex2 || wave2) {
             } else if (direct) {
                 k_film_direct<<<blocks2, 128, 0, stream>>>(pa, r + 1 < rounds ? 1 : 0);
                 CUDA_TRY(cudaGetLastError());

@@ -54,6 +54,7 @@ static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long 
 static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 template <typename T> static inline T __ldcs(const T *p) { return *p; }
 template <typename T> static inline T __ldcg(const T *p) { return *p; }
+template <typename T> static inline void __stcg(T *p, T v) { *p = v; }
 using std::min;
 using std::max;
 
@@ -140,23 +141,22 @@ namespace {
 // two-block window: draws at [pos, pos + k) can be looked at before `pos` moves
 struct Stream {
     uint32_t mt[MT_N];
-    int idx;
-    std::vector<uint32_t> out;
-    explicit Stream(uint32_t seed) { SeedMT(mt, seed); idx = MT_N; }
+    std::vector<std::vector<uint32_t>> blocks;   // block b: the raw state words the draws [b * 624, (b + 1) * 624) are tempered from
+    explicit Stream(uint32_t seed) { SeedMT(mt, seed); }
     void Regen() {
         for (int k = 0; k < MT_N; ++k) {
             uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % MT_N] & 0x7fffffffu);
             mt[k] = mt[(k + MT_M) % MT_N] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
         }
-        idx = 0;
     }
-    uint32_t At(size_t i) {
-        while (out.size() <= i) {
-            if (idx >= MT_N) Regen();
-            out.push_back(Temper(mt[idx++]));
+    const std::vector<uint32_t> &Block(size_t b) {
+        while (blocks.size() <= b) {
+            Regen();
+            blocks.emplace_back(mt, mt + MT_N);
         }
-        return out[i];
+        return blocks[b];
     }
+    uint32_t At(size_t i) { return Temper(Block(i / MT_N)[i % MT_N]); }
 };
 
 // Sampler::ComputeSubWindow / ImageFilm extent, as the host code of pbrtgpu.cu computes them
@@ -499,86 +499,49 @@ void RunWaveH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
         for (int iter = 0;; ++iter) {
             wa.iter = iter;
             for (int k = 0; k < WC_NEXT_SAMPLE; ++k) counters[k] = 0;
-            LaunchH(P, [&]() { k_wshade<false, true>(wa); });
+            LaunchH(P, [&]() { k_wshade<1, false, true>(wa); });
             if (hasMeasured) LaunchH(1, [&]() { k_weval(wa); }, PBRT_KD_INTERLEAVED != 0);   // (the persistent form elects lane 0)
             LaunchH(1, [&]() { k_wtrace<false, true>(wa); }, true);
             if (counters[WC_LIVE] == 0) break;
         }
-        // ---- phase 2 + film: every task's current pixel, samples in order
+        // ---- phase 2: the task chains on the same kernels (k_wshade<2>), each chain's RNG window in the kernels' format
+        std::vector<uint32_t> cur(nb * MT_N), next(nb * MT_N);
+        std::vector<size_t> baseBlock(nb);
+        std::vector<int> mtiDev(nb);
+        for (size_t i = 0; i < nb; ++i) {
+            baseBlock[i] = (size_t)mti[i] / MT_N;
+            mtiDev[i] = mti[i] % MT_N;
+            memcpy(cur.data() + i * MT_N, rng[i].Block(baseBlock[i]).data(), MT_N * 4);
+            memcpy(next.data() + i * MT_N, rng[i].Block(baseBlock[i] + 1).data(), MT_N * 4);
+        }
+        wa.b.rngCur = cur.data(); wa.b.rngNext = next.data(); wa.b.mti = mtiDev.data(); wa.b.order = nullptr;
+        wa.P = std::max<uint32_t>(P, (uint32_t)nb);
+        std::vector<float4> pool2((size_t)W_COUNT * wa.P);
+        std::vector<uint32_t> qRay2(3 * (size_t)wa.P), qEval2(3 * (size_t)wa.P);
+        wa.pool = pool2.data(); wa.qRay = qRay2.data(); wa.qEval = qEval2.data();
+        for (int iter = 0;; ++iter) {
+            wa.iter = iter;
+            for (int k = 0; k < WC_NEXT_SAMPLE; ++k) counters[k] = 0;
+            LaunchH((unsigned)nb, [&]() { k_wshade<2, false, true>(wa); });
+            if (hasMeasured) LaunchH(1, [&]() { k_weval(wa); }, PBRT_KD_INTERLEAVED != 0);
+            LaunchH(1, [&]() { k_wtrace<false, true>(wa); }, true);
+            if (counters[WC_LIVE] == 0) break;
+        }
+        for (size_t i = 0; i < nb; ++i) {   // where the chain left its task's stream: the window may have moved on by whole blocks
+            size_t moved = 0;
+            while (memcmp(cur.data() + i * MT_N, rng[i].Block(baseBlock[i] + moved).data(), MT_N * 4) != 0) ++moved;
+            mti[i] = (int)((baseBlock[i] + moved) * MT_N) + mtiDev[i];
+        }
+        // ---- the film: every task's current pixel, samples in order (k_film)
         for (size_t i = 0; i < nb; ++i) {
             const TaskRec &tr = tasks[i];
             const int tw = tr.x1 - tr.x0;
             if (r >= tw * (tr.y1 - tr.y0)) continue;
             const int xPos = tr.x0 + r % tw, yPos = tr.y0 + r / tw;
-            const uint16_t *rowBase = perm.data() + i * spp * PERM_STRIDE;
-            (void)rowBase;
-            auto rngF = [&](int k) -> float { return UIntToFloat(rng[i].At((size_t)(mti[i] + k))); };
             for (int s = 0; s < spp; ++s) {
                 const float4 v = ls[i * spp + s];
-                int code = __float_as_int(v.w);
-                Spec L(v.x, v.y, v.z);
-                if (code & LS_TAIL) {
-                    const float4 *q = rec.data() + (i * spp + s) * 4;
-                    Ray ray;
-                    ray.o = V3(q[0].x, q[0].y, q[0].z); ray.mint = q[0].w;
-                    ray.d = V3(q[1].x, q[1].y, q[1].z); ray.maxt = q[1].w;
-                    Hit hit;
-                    hit.t = q[1].w; hit.prim = __float_as_int(q[2].w); hit.b1 = q[3].x; hit.b2 = q[3].y; hit.maxtIn = q[3].z;
-                    ray.time = q[3].w;
-                    Spec T(q[2].x, q[2].y, q[2].z);
-                    bool afterSpecular = (code & LS_SPEC) != 0;
-                    code &= ~(LS_SPEC | LS_TAIL);
-                    int bounces = 3;
-                    bool found = true;
-                    TraceStats st;
-                    st.nodes = st.prims = 0;
-                    const int nLights = (int)sc.nLights;
-                    while (found) {
-                        VertexRandoms u;
-                        int k0 = 0;
-                        if (nLights > 0) {
-                            u.lnU = rngF(0); u.lsU0 = rngF(1); u.lsU1 = rngF(2);
-                            u.bsU0 = rngF(4); u.bsU1 = rngF(5); u.bsUc = rngF(6);
-                            k0 = 7;
-                        } else u.lnU = u.lsU0 = u.lsU1 = u.bsU0 = u.bsU1 = u.bsUc = 0.f;
-                        u.pU0 = rngF(k0); u.pU1 = rngF(k0 + 1); u.pUc = rngF(k0 + 2);
-                        ShadeCtx ctx;
-                        Vertex vx;
-                        VertexA<true>(sc, ray, hit, bounces, afterSpecular, u, T, L, ctx, &vx, nullptr);
-                        Spec f[3] = {Spec(0.f), Spec(0.f), Spec(0.f)};
-                        for (int e = 0; e < 3; ++e) {
-#if PBRT_SPECULAR
-                            if (e == VX_PATH && vx.specSampled) continue;
-#endif
-                            if (vx.need[e]) f[e] = VertexEval(sc, vx.material, vx.evalWo, vx.evalWi[e], vx.evalFlags[e]);
-                        }
-                        bool rrDrawn = false;
-                        const float rrU = bounces > 3 ? rngF(k0 + 3) : 0.f;
-                        const bool cont = VertexB(f, bounces, rp.maxDepth, T, rrU, &vx, &rrDrawn);
-                        mti[i] += k0 + 3 + (rrDrawn ? 1 : 0);
-                        Spec Ld(0.f);
-                        if (vx.ray[VX_LIGHT]) {
-                            Ray q2; q2.o = vx.p; q2.d = vx.wiW[VX_LIGHT]; q2.mint = vx.eps; q2.maxt = vx.visMaxt; q2.time = ray.time;
-                            Hit h;
-                            if (!Traverse<false, true>(sc, q2, true, &h, &st, DOH_TOP(sc))) Ld = Ld + vx.pendS;
-                        }
-                        if (vx.ray[VX_MIS]) {
-                            Ray q2; q2.o = vx.p; q2.d = vx.wiW[VX_MIS]; q2.mint = vx.eps; q2.maxt = INF_F; q2.time = ray.time;
-                            Hit h;
-                            if (Traverse<false, true>(sc, q2, false, &h, &st, DOH_TOP(sc)) && MisHitIsLight<true>(sc, q2, h, vx.lightNum)) Ld = Ld + vx.pendM;
-                        }
-                        L = L + T * ((float)nLights * Ld);
-                        T = vx.Tnew;
-                        if (!cont) break;
-#if PBRT_SPECULAR
-                        afterSpecular = vx.specSampled;
-#endif
-                        ++bounces;
-                        ray.o = vx.p; ray.d = vx.wiW[VX_PATH]; ray.mint = vx.eps; ray.maxt = INF_F;
-                        found = Traverse<false, true>(sc, ray, false, &hit, &st, DOH_TOP(sc));
-                    }
-                    L = SanitizeRadiance(L);
-                }
+                const int code = __float_as_int(v.w);
+                const Spec L(v.x, v.y, v.z);
                 float xyz[3];
                 xyz[0] = 0.412453f * L.r + 0.357580f * L.g + 0.180423f * L.b;
                 xyz[1] = 0.212671f * L.r + 0.715160f * L.g + 0.072169f * L.b;

@@ -15,12 +15,13 @@ pytestmark = pytest.mark.gpu
 # (library or None = the product library, extra environment, test files)
 CASES = [
     ("pairs", "ab/libpbrtgpu_pairs.so", {}, ["tests/test_gpu_parity.py"]),
-    # the kernels the vertex-synchronous path replaced stay selectable (A/B baselines): they must still reproduce the oracle
-    ("wavefront+k_path2", None, {"PBRTGPU_VERTEX": "0"}, ["tests/test_gpu_parity.py", "tests/test_gpu_specular.py"]),
-    ("megakernel+k_path2", None, {"PBRTGPU_VERTEX": "0", "PBRTGPU_WAVEFRONT": "0"}, ["tests/test_gpu_parity.py"]),
-    ("vertex1+k_path2", None, {"PBRTGPU_VERTEX": "1"}, ["tests/test_gpu_parity.py"]),
-    ("wavefront+vertex2", None, {"PBRTGPU_VERTEX": "2"}, ["tests/test_gpu_parity.py"]),
-    ("vertex-unsorted-chains", None, {"PBRTGPU_TAIL_SORT": "0"}, ["tests/test_gpu_parity.py"]),
+    # the kernels the vertex wavefront (kwave.cuh) replaced stay selectable (A/B baselines): they must still reproduce the oracle
+    ("request-wavefront+vertex2", None, {"PBRTGPU_WAVE": "0"}, ["tests/test_gpu_parity.py", "tests/test_gpu_specular.py"]),
+    ("vertex-wavefront+vertex2", None, {"PBRTGPU_WAVE": "1"}, ["tests/test_gpu_parity.py", "tests/test_gpu_specular.py"]),
+    ("request-wavefront+chain-wavefront", None, {"PBRTGPU_WAVE": "2"}, ["tests/test_gpu_parity.py"]),
+    ("request-wavefront+k_path2", None, {"PBRTGPU_WAVE": "0", "PBRTGPU_VERTEX": "0"}, ["tests/test_gpu_parity.py"]),
+    ("megakernel+k_path2", None, {"PBRTGPU_WAVE": "0", "PBRTGPU_VERTEX": "0", "PBRTGPU_WAVEFRONT": "0"}, ["tests/test_gpu_parity.py"]),
+    ("vertex1+vertex2", None, {"PBRTGPU_WAVE": "0", "PBRTGPU_VERTEX": "3"}, ["tests/test_gpu_parity.py"]),
 ]
 
 
