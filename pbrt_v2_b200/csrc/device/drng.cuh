@@ -75,9 +75,20 @@ DEV float VanDerCorput(uint32_t n, uint32_t scramble) {   // montecarlo.h:281-29
     n ^= scramble;
     return minf(((n >> 8) & 0xffffff) / float(1 << 24), ONE_MINUS_EPS);
 }
-DEV float Sobol2(uint32_t n, uint32_t scramble) {   // montecarlo.h:293-297
-    for (uint32_t v = 1u << 31; n != 0; n >>= 1, v ^= v >> 1)
-        if (n & 0x1) scramble ^= v;
+// montecarlo.h:293-297 XORs v_i over the set bits i of n, v_0 = 1 << 31, v_(i+1) = v_i ^ (v_i >> 1): with a right shift read
+// as multiplication by x, v_i = (1 + x)^i, so the sum is the polynomial n(y) over GF(2) evaluated at y = 1 + x -- a Taylor
+// shift, five butterfly steps because (1 + x)^(2^k) = 1 + x^(2^k) -- written most significant bit first.  Same word for
+// every n (tests/test_device_on_host.py::test_sobol2_closed_form checks it against the loop); no data-dependent trip count.
+DEV uint32_t Sobol2Word(uint32_t n) {
+    n ^= (n >> 1) & 0x55555555u;
+    n ^= (n >> 2) & 0x33333333u;
+    n ^= (n >> 4) & 0x0f0f0f0fu;
+    n ^= (n >> 8) & 0x00ff00ffu;
+    n ^= (n >> 16) & 0x0000ffffu;
+    return __brev(n);
+}
+DEV float Sobol2(uint32_t n, uint32_t scramble) {
+    scramble ^= Sobol2Word(n);
     return minf(((scramble >> 8) & 0xffffff) / float(1 << 24), ONE_MINUS_EPS);
 }
 

@@ -90,10 +90,16 @@ struct DScene {
 #endif
 };
 
+// TransformedPrimitives whose interpolated transforms a path slot of the vertex wavefront carries (kwave.cuh)
+constexpr uint32_t ANIM_CACHE_MAX = 2;
 struct Ray {
     V3 o, d;
     float mint, maxt;
     float time;   // constant along a camera path (path.cpp:109, integrator.cpp:127,148); read by TransformedPrimitives only
+    // AnimatedTransform::Interpolate(time) of the scene's first ANIM_CACHE_MAX TransformedPrimitives, computed once per camera
+    // sample instead of once per ray and instance (8 float4 each -- m, mInv row by row -- `xfStride` float4 apart), or null
+    const float4 *xfCache = nullptr;
+    uint32_t xfStride = 0;
 };
 DEV V3 RayAt(const Ray &r, float t) { return r.o + r.d * t; }   // geometry.h:333
 
@@ -589,6 +595,35 @@ DEV void ToPrimitiveSpace(const DXf &w2p, const Ray &r, Ray *out) {
     out->o = XfPoint(w2p.m, r.o);
     out->d = XfVector(w2p.m, r.d);
     out->mint = r.mint; out->maxt = r.maxt; out->time = r.time;
+    out->xfCache = r.xfCache; out->xfStride = r.xfStride;
+}
+
+// WorldToPrimitive.Interpolate(ray.time) of TransformedPrimitive `index` (primitive.cpp:97,112): from the ray's cache if it
+// has one -- the same function's result, stored when the camera sample (and with it ray.time) was chosen -- else computed
+DEV void RayW2P(const DScene &sc, uint32_t index, const Ray &r, DXf *out) {
+    if (r.xfCache && index < ANIM_CACHE_MAX) {
+        const float4 *c = r.xfCache + (size_t)index * 8 * r.xfStride;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float4 a = c[(size_t)e * r.xfStride], b = c[(size_t)(4 + e) * r.xfStride];
+            out->m[4 * e] = a.x; out->m[4 * e + 1] = a.y; out->m[4 * e + 2] = a.z; out->m[4 * e + 3] = a.w;
+            out->mInv[4 * e] = b.x; out->mInv[4 * e + 1] = b.y; out->mInv[4 * e + 2] = b.z; out->mInv[4 * e + 3] = b.w;
+        }
+    } else
+        AnimInterpolate(sc.animated + index, r.time, out);
+}
+// ... and filling such a cache (`dst` = the slot's first cache field)
+DEV void FillXfCache(const DScene &sc, float time, float4 *dst, uint32_t stride) {
+    for (uint32_t i = 0; i < sc.nAnimated && i < ANIM_CACHE_MAX; ++i) {
+        DXf x;
+        AnimInterpolate(sc.animated + i, time, &x);
+        float4 *c = dst + (size_t)i * 8 * stride;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            c[(size_t)e * stride] = make_float4(x.m[4 * e], x.m[4 * e + 1], x.m[4 * e + 2], x.m[4 * e + 3]);
+            c[(size_t)(4 + e) * stride] = make_float4(x.mInv[4 * e], x.mInv[4 * e + 1], x.mInv[4 * e + 2], x.mInv[4 * e + 3]);
+        }
+    }
 }
 
 // TransformedPrimitive::Intersect / IntersectP, core/primitive.cpp:95-124 (the DifferentialGeometry is taken back
@@ -597,7 +632,7 @@ template <bool STATS>
 __device__ __noinline__ bool AnimatedIntersect(const DScene &sc, uint32_t index, Ray &r, bool anyHit, Hit *hit, TraceStats *st) {
     const PbrtGpuAnimated *a = sc.animated + index;
     DXf w2p;
-    AnimInterpolate(a, r.time, &w2p);
+    RayW2P(sc, index, r, &w2p);
     Ray ray;
     ToPrimitiveSpace(w2p, r, &ray);
     bool found;
@@ -732,7 +767,7 @@ DEV bool TravStepPairs(const DScene &sc, Trav &t) {
             else if (ANIM && type == PBRTGPU_PRIM_ANIMATED) {
                 const PbrtGpuAnimated *a = sc.animated + __float_as_uint(r1.w);
                 DXf w2p;
-                AnimInterpolate(a, t.ray.time, &w2p);
+                RayW2P(sc, __float_as_uint(r1.w), t.ray, &w2p);
                 Ray rl;
                 ToPrimitiveSpace(w2p, t.ray, &rl);
                 if (a->nNodes == 0) {
@@ -900,7 +935,7 @@ DEV bool TravLeaf(const DScene &sc, Trav &t, TraceStats *st) {
             // TransformedPrimitive::Intersect(P): interpolate, go to primitive space, walk the nested BVH
             const PbrtGpuAnimated *a = sc.animated + __float_as_uint(r1.w);
             DXf w2p;
-            AnimInterpolate(a, t.ray.time, &w2p);
+            RayW2P(sc, __float_as_uint(r1.w), t.ray, &w2p);
             Ray rl;
             ToPrimitiveSpace(w2p, t.ray, &rl);
             if (a->nNodes == 0) {
@@ -968,7 +1003,7 @@ DEV_NI3 bool HitGeometry(const DScene &sc, const Ray &rayIn, const Hit &hit, Dif
     *primType = type;
     Ray ray = rayIn;
     if (ANIM && owner >= 0) {
-        AnimInterpolate(sc.animated + owner, rayIn.time, w2p);
+        RayW2P(sc, (uint32_t)owner, rayIn, w2p);
         ToPrimitiveSpace(*w2p, rayIn, &ray);
     }
     if (type == PBRTGPU_PRIM_TRIANGLE) {

@@ -53,7 +53,11 @@ enum {
     W_V1,      // absM, weightM, pdfM, absP
     W_V2,      // specF.rgb (PBRT_SPECULAR), -
     W_CH,      // phase 2, the slot's task chain: mti, tail-mask word index, its remaining bits, the vertex's roulette draw
-    W_COUNT
+    W_COUNT,
+    // scenes with TransformedPrimitives: AnimatedTransform::Interpolate(ray.time) of the first ANIM_CACHE_MAX instances, filled
+    // when the slot takes a camera sample (ray.time is constant along the path): 8 float4 each (dscene.cuh RayW2P)
+    W_AX = W_COUNT,
+    W_COUNT_ANIM = W_COUNT + 8 * ANIM_CACHE_MAX
 };
 // W_T.w: flags, bounces (8 bits), lightNum (16 bits)
 enum { WB_VERTEX = 0x1, WB_AFTER_SPEC = 0x2, WB_SPEC_SAMPLED = 0x4, WB_NEED0 = 0x8, WB_NEED1 = 0x10, WB_NEED2 = 0x20,
@@ -62,6 +66,7 @@ enum { WB_VERTEX = 0x1, WB_AFTER_SPEC = 0x2, WB_SPEC_SAMPLED = 0x4, WB_NEED0 = 0
 enum { WC_RAYS = 0 /* 3 */, WC_EVALS = 3, WC_TRACE_CUR, WC_EVAL_CUR,
        WC_LIVE,          // slots that hold a camera path after k_wshade (0: the batch is done)
        WC_NEXT_SAMPLE,   // (everything before it is reset every iteration)
+       WC_LIVE2,         // phase 2: WC_LIVE and WC_LIVE2 are the lengths of the two live-chain lists (ping-pong, see k_wshade<2>)
        WC_COUNT };
 #define W_RAY_ALLOWED 0x10000
 #define W_RR 0x20000   // (direction 2, phase 2) the path ray also has to survive Russian roulette: see k_weval
@@ -78,7 +83,10 @@ struct WvArgs {
     unsigned totalSamples;
     int iter;            // 0: every slot starts with a camera sample
     DeviceStats *stats;
+    uint32_t *liveList;  // phase 2: [2][nBatch] the chains still running, compacted: iteration i reads list i & 1 (from
+                         // iteration 1 on) and writes list (i + 1) & 1, so the kernels shrink with the number of live chains
 };
+DEV int WvLiveCounter(int list) { return list ? WC_LIVE2 : WC_LIVE; }
 
 // `kind` must be the same for all converged lanes (a compile-time constant at the call site)
 DEV void WvPushRay(const WvArgs &a, int kind, uint32_t slot) {
@@ -104,7 +112,15 @@ DEV void WvPushRayAny(const WvArgs &a, int kind, uint32_t slot) {
 template <int PHASE, bool STATS, bool ANIM>
 __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __grid_constant__ WvArgs a) {
     __shared__ uint32_t smt[PHASE == 2 ? 4 : 1][PHASE == 2 ? MT_N : 1];
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t slot = tid;
+    bool live;
+    if (PHASE == 1) live = tid < a.P;
+    else if (a.iter == 0) live = tid < (uint32_t)a.b.nBatch;
+    else {   // the chains that were still running after the previous iteration
+        live = tid < a.counters[WvLiveCounter(a.iter & 1)];
+        slot = live ? a.liveList[(size_t)(a.iter & 1) * a.b.nBatch + tid] : 0u;
+    }
     const DScene &sc = a.sc;
     const RenderParams &rp = a.rp;
     const int spp = rp.spp;
@@ -113,11 +129,11 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
     const int nLights = (int)sc.nLights;
     const int k0 = nLights > 0 ? 7 : 0;   // PHASE 2: draws of UniformSampleOneLight before the path's BSDFSample
 #define WF(f) pool[(size_t)(f) * P + slot]
-    bool live = slot < (PHASE == 1 ? a.P : (uint32_t)a.b.nBatch);
     if (PHASE == 1 && !live) return;
 
     Ray ray;
     ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f; ray.time = 0.f;
+    if (ANIM) { ray.xfCache = pool + (size_t)W_AX * P + slot; ray.xfStride = a.P; }
     Hit hit;
     hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.maxtIn = 0.f;
     Spec T(1.f), L(0.f);
@@ -242,6 +258,7 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
             return;
         }
         AggregatedAddV(a.counters + WC_LIVE);
+        if (ANIM) FillXfCache(sc, ray.time, &WF(W_AX), a.P);
         WF(W_P) = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
         WF(W_D2) = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
         WF(W_T) = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
@@ -271,6 +288,7 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
                 hit.prim = __float_as_int(r2.w);
                 hit.b1 = r3.x; hit.b2 = r3.y; hit.maxtIn = r3.z;
                 ray.time = r3.w;
+                if (ANIM) FillXfCache(sc, ray.time, &WF(W_AX), a.P);
                 L = Spec(lv.x, lv.y, lv.z);
                 code = __float_as_int(lv.w);
                 afterSpecular = (code & LS_SPEC) != 0;
@@ -293,7 +311,8 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
         if (!live) return;
     }
 
-    AggregatedAddV(a.counters + WC_LIVE);
+    if (PHASE == 1) AggregatedAddV(a.counters + WC_LIVE);
+    else a.liveList[(size_t)((a.iter + 1) & 1) * a.b.nBatch + AggregatedAddV(a.counters + WvLiveCounter((a.iter + 1) & 1))] = slot;
     // ---- a vertex to shade: VertexA, the record, the requests
     VertexRandoms u;
     float rrU = 0.f;
@@ -598,6 +617,7 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_wtrace(const __grid
                     wray.maxt = kind == VX_LIGHT ? r1.w : INF_F;
                     lightNum = kind == VX_MIS ? __float_as_int(r1.w) : 0;
                     wray.time = ANIM ? pool[(size_t)W_ID * P + slot].z : 0.f;
+                    if (ANIM) { wray.xfCache = pool + (size_t)W_AX * P + slot; wray.xfStride = a.P; }
                     TravInit(t, wray, kind == VX_LIGHT);
                     if (STATS) { if (kind == VX_LIGHT) ++nShadow; else ++nClosest; }
                     active = true; leaf = false;

@@ -1114,6 +1114,7 @@ struct Lane {
     DevBuf<float4> pool;              // wavefront path slots (F_COUNT fields x P)
     DevBuf<uint32_t> traceQ;
     DevBuf<uint32_t> evalQ;           // vertex wavefront: (slot, direction) evaluation requests
+    DevBuf<uint32_t> liveList;        // chain wavefront: [2][maxBatch] live chains, compacted
     DevBuf<DlFrame> dlFrames;         // DirectLightingIntegrator over specular materials: [P][DL_MAX_DEPTH]
     DevBuf<unsigned> counters;
     unsigned *hostCounters = nullptr;  // pinned
@@ -1327,6 +1328,7 @@ struct RenderConfig {
     bool traceIters = false;
     int vertexBlocksPerSM = K_VERTEX_MIN_BLOCKS;
 };
+inline int WvLiveCounterHost(int list) { return list ? WC_LIVE2 : WC_LIVE; }
 RenderConfig ReadConfig() {
     {
         RenderConfig c;
@@ -1741,9 +1743,10 @@ int RunLane(LaneJob &job) {
         if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, C_COUNT * sizeof(unsigned)));
     }
     if (wave1 || wave2) {
-        CUDA_TRY(ln->pool.Ensure(std::max(poolSize, maxBatch) * std::max<size_t>(W_COUNT, F_COUNT)));
+        CUDA_TRY(ln->pool.Ensure(std::max(poolSize, maxBatch) * std::max<size_t>(scene->d.nAnimated ? W_COUNT_ANIM : W_COUNT, F_COUNT)));
         CUDA_TRY(ln->traceQ.Ensure(std::max(poolSize, maxBatch) * 3));
         CUDA_TRY(ln->evalQ.Ensure(std::max(poolSize, maxBatch) * 3));
+        CUDA_TRY(ln->liveList.Ensure(maxBatch * 2));
         CUDA_TRY(ln->counters.Ensure(std::max<int>(WC_COUNT, C_COUNT)));
         if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, std::max<int>(WC_COUNT, C_COUNT) * sizeof(unsigned)));
     }
@@ -1801,7 +1804,7 @@ int RunLane(LaneJob &job) {
                 WvArgs wa;
                 wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = ln->pool.p; wa.P = (uint32_t)poolSize;
                 wa.qRay = ln->traceQ.p; wa.qEval = ln->evalQ.p; wa.counters = ln->counters.p;
-                wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p;
+                wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p; wa.liveList = nullptr;
                 CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_COUNT * sizeof(unsigned), stream));
                 const int sblocks = (int)((poolSize + 127) / 128);
                 const int tblocks = nSM * 8;
@@ -1913,11 +1916,18 @@ int RunLane(LaneJob &job) {
                 wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = ln->pool.p; wa.P = (uint32_t)std::max(poolSize, maxBatch);
                 wa.qRay = ln->traceQ.p; wa.qEval = ln->evalQ.p; wa.counters = ln->counters.p;
                 wa.totalSamples = 0; wa.stats = scene->stats.p;
-                const int cblocks = (int)((nb + 127) / 128);
-                const int tblocks = nSM * 8;
+                wa.liveList = ln->liveList.p;
+                // the kernels shrink with the number of live chains: the grids follow the count read back every 8 iterations
+                // (it only falls in between); an empty persistent kernel at full size costs 6 - 16 us, and a chain wavefront
+                // runs as many iterations as its longest chain has vertices (profiles/r02d_launches.csv)
+                size_t liveEst = nb;
                 for (int iter = 0;; ++iter) {
                     wa.iter = iter;
-                    CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_NEXT_SAMPLE * sizeof(unsigned), stream));
+                    const int cblocks = (int)((liveEst + 127) / 128);
+                    const int tblocks = (int)std::min<size_t>((size_t)nSM * 8, std::max<size_t>(1, (liveEst * 3 + 255) / 256));
+                    // empty the queues, the cursors and the live list this iteration writes (its length: WC_LIVE / WC_LIVE2)
+                    CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_LIVE * sizeof(unsigned), stream));
+                    CUDA_TRY(cudaMemsetAsync(ln->counters.p + WvLiveCounterHost((iter + 1) & 1), 0, sizeof(unsigned), stream));
                     if (scene->d.nAnimated) {
                         if (wantCounters) k_wshade<2, true, true><<<cblocks, 128, 0, stream>>>(wa);
                         else k_wshade<2, false, true><<<cblocks, 128, 0, stream>>>(wa);
@@ -1938,7 +1948,8 @@ int RunLane(LaneJob &job) {
                         CUDA_TRY(cudaMemcpyAsync(ln->hostCounters, ln->counters.p, WC_COUNT * sizeof(unsigned),
                                                  cudaMemcpyDeviceToHost, stream));
                         CUDA_TRY(cudaStreamSynchronize(stream));
-                        if (ln->hostCounters[WC_LIVE] == 0) break;
+                        liveEst = ln->hostCounters[WvLiveCounterHost((iter + 1) & 1)];
+                        if (liveEst == 0) break;
                     }
                     if (iter > 40000000) return Fail(PBRTGPU_ECUDA, "chain wavefront did not terminate");
                 }

@@ -471,7 +471,7 @@ void RunWaveH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
     std::vector<int> mti(nb, 0);
     std::vector<uint16_t> perm(nb * spp * PERM_STRIDE);
     std::vector<uint32_t> scr(nb * SCR_STRIDE);
-    std::vector<float4> ls(nb * spp), rec(nb * spp * 4), pool((size_t)W_COUNT * P);
+    std::vector<float4> ls(nb * spp), rec(nb * spp * 4), pool((size_t)W_COUNT_ANIM * P);
     std::vector<unsigned> tailCount(nb), counters(WC_COUNT);
     std::vector<uint32_t> tailMask(nb * maskWords), qRay(3 * (size_t)P), qEval(3 * (size_t)P);
     const bool hasMeasured = sc.measured != nullptr;
@@ -516,16 +516,19 @@ void RunWaveH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
         }
         wa.b.rngCur = cur.data(); wa.b.rngNext = next.data(); wa.b.mti = mtiDev.data(); wa.b.order = nullptr;
         wa.P = std::max<uint32_t>(P, (uint32_t)nb);
-        std::vector<float4> pool2((size_t)W_COUNT * wa.P);
+        std::vector<float4> pool2((size_t)W_COUNT_ANIM * wa.P);
         std::vector<uint32_t> qRay2(3 * (size_t)wa.P), qEval2(3 * (size_t)wa.P);
         wa.pool = pool2.data(); wa.qRay = qRay2.data(); wa.qEval = qEval2.data();
+        std::vector<uint32_t> liveList(2 * nb);
+        wa.liveList = liveList.data();
         for (int iter = 0;; ++iter) {
             wa.iter = iter;
-            for (int k = 0; k < WC_NEXT_SAMPLE; ++k) counters[k] = 0;
+            for (int k = 0; k < WC_LIVE; ++k) counters[k] = 0;
+            counters[WvLiveCounter((iter + 1) & 1)] = 0;
             LaunchH((unsigned)nb, [&]() { k_wshade<2, false, true>(wa); });
             if (hasMeasured) LaunchH(1, [&]() { k_weval(wa); }, PBRT_KD_INTERLEAVED != 0);
             LaunchH(1, [&]() { k_wtrace<false, true>(wa); }, true);
-            if (counters[WC_LIVE] == 0) break;
+            if (counters[WvLiveCounter((iter + 1) & 1)] == 0) break;
         }
         for (size_t i = 0; i < nb; ++i) {   // where the chain left its task's stream: the window may have moved on by whole blocks
             size_t moved = 0;
@@ -590,6 +593,9 @@ DOH_EXPORT int doh_render(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc 
     }
     return 0;
 }
+
+// drng.cuh's closed form of the Sobol' (0,2)-sequence word, for the test that compares it with montecarlo.h's loop
+DOH_EXPORT uint32_t doh_sobol2_word(uint32_t n) { return Sobol2Word(n); }
 
 // PathIntegrator renders through the vertex form (dvertex.cuh) instead of the state machine (path_body.inc); a value >= 2
 // runs the vertex-wavefront kernels (kwave.cuh) over a pool of that many path slots

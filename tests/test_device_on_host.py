@@ -143,6 +143,26 @@ def test_vertex_wavefront_kernels_on_host_render_like_the_oracle(staged, doh):
         doh.doh_set_vertex_form(0)
 
 
+def test_sobol2_closed_form(doh):
+    """drng.cuh computes Sobol2's XOR of direction numbers (montecarlo.h:293-297) as a five-step GF(2) Taylor shift + bit
+    reversal: the same word as the reference's loop for every index the tables can hold and for random 32-bit words."""
+    doh.doh_sobol2_word.restype = C.c_uint32
+    doh.doh_sobol2_word.argtypes = [C.c_uint32]
+
+    def loop(n):
+        s, v = 0, 1 << 31
+        while n:
+            if n & 1:
+                s ^= v
+            n >>= 1
+            v ^= v >> 1
+        return s
+    rs = np.random.RandomState(5)
+    cases = list(range(0, 70000)) + [int(x) for x in rs.randint(0, 2 ** 32, 30000, dtype=np.uint64)] + [2 ** 32 - 1, 2 ** 31]
+    for n in cases:
+        assert doh.doh_sobol2_word(n) == loop(n), n
+
+
 def test_device_state_machine_on_host_variants(staged, doh):
     from helpers import VARIANTS, EDGE_VARIANTS, variant_scene
     for v in VARIANTS + EDGE_VARIANTS:
