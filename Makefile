@@ -25,7 +25,7 @@ NVDEFS    ?=
 # kernel experiments, built next to the product library so that a GPU visit can A/B them without compiling on the box
 # (scripts/ab_variants.py; tests/test_zz_gpu_variants.py runs the parity suite over them).  Nothing loads them by default.
 #   make variants VARIANT_NAMES="pairs foo"   with   VARIANT_DEFS_foo := -DSOMETHING=1
-VARIANT_NAMES ?= ws6
+VARIANT_NAMES ?=
 # Kernel experiments of the current round (the earlier ones and their verdicts: profiles/README.md).  Traversal variants
 # that lost on the B200 and can still be built:  pairs (-DPBRT_PAIR_NODES=1), ww (-DPBRT_TRACE_LOOP=1),
 # sstack (-DPBRT_SMEM_STACK=32), top9_sstack (-DPBRT_TOP_LEVELS=9 -DPBRT_SMEM_STACK=32)

@@ -46,9 +46,9 @@ WORKLOADS = {
 WORKLOAD_NLEVELS = {"anim-c4": 3}
 WORKLOAD_INTEGRATOR = {"killeroo-dl": "directlighting"}
 SYNTHETIC_TRIS = 10000000
-# dram__bytes_read.sum + dram__bytes_write.sum of one mid-render k_trace launch (ncu --set full, profiles/), per workload
+# dram__bytes_read.sum + dram__bytes_write.sum of one mid-render k_wtrace launch (ncu --set full, profiles/), per workload
 K_TRACE_DRAM_BYTES_PER_LAUNCH = {
-    "bunny-c2": 208541696 + 118836992,   # profiles/r01_k_trace_ncu_full.txt (launch 200 of a 128-spp run: a full 4 Mi-slot pool, as at 1024 spp)
+    "bunny-c2": 341647872 + 191812352,   # profiles/r02b_k_wtrace_ncu_full.txt (launch 60 of a 256-spp run: a full 4 Mi-slot pool, as at 1024 spp)
 }
 CPU_SAMPLE_SPP = 16     # bounded sample of the same workload for the CPU arms (cost is linear in spp)
 
@@ -409,9 +409,9 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # BVH traversal happens in k_trace (phase-1 wavefront) and inside k_path<2> (the RNG-driven tails); the
-        # node / primitive-test counters cover both, so the time does too: k_trace's launches timed one by one in
-        # the roofline pass + the tail kernel's exclusive time in that pass (it also shades, so this is conservative)
+        # BVH traversal happens in k_wtrace (phase 1, the vertex wavefront) and inside k_vertex<2> (phase 2, the RNG-driven
+        # task chains); the node / primitive-test counters cover both, so the time does too: k_wtrace's launches timed one
+        # by one in the roofline pass + the phase-2 kernel's exclusive time in that pass (it also shades: conservative)
         # Per GPU: the counters are summed over ranks, the times are one rank's (max over ranks), the peak is one GPU's.
         trace_ms = ray_ms + tail_excl_ms
         alg_bytes_gpu = alg_bytes / world
@@ -430,7 +430,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "k_trace (+ the traversals inside k_path<2>)", "achieved": achieved, "peak": peak,
+                "bound": "hbm", "kernel": "k_wtrace (+ the traversals inside k_vertex<2>)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if peak else None,
                 "per": "GPU (algorithmic bytes of all ranks / n_gpus, over one rank's kernel time)",
                 # the same bytes over the whole timed step (tables, shading, film included): what the throughput implies
@@ -443,7 +443,7 @@ def main():
                 "launches_per_step": ray_launches,
                 "k_trace_ms_per_step": ray_ms, "k_path2_ms_per_step": tail_excl_ms, "serial_step_ms": serial_ms,
                 "k_trace_share_of_serial_step": ray_ms / serial_ms if serial_ms else None,
-                "how": "untimed extra pass on one lane: cudaEventRecord around every k_trace launch on its stream "
+                "how": "untimed extra pass on one lane: cudaEventRecord around every k_wtrace launch on its stream "
                        "(pbrtgpu_set_stats(scene, 2)); in the timed steps the lanes' kernels overlap, so per-kernel "
                        "durations are not separable there",
                 "note": ("scene (BVH+triangles, %.1f MB) exceeds the 126 MB L2: traversal streams from HBM" if hbm_resident else

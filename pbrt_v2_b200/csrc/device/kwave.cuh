@@ -25,8 +25,10 @@
 #include "kcommon.cuh"
 #include "drng.cuh"
 
+// resident blocks per SM the register allocator must allow.  k_wshade: 4 (128 registers) / 5 (96) / 6 (80, 550 B of spills):
+// 6 measured +6.8 %, +0.5 %, +4.2 % on C2 in three visits (profiles/r02c_ab_wave2.json, r02d_ab_wave3.json, r02e_ab_wave4.json)
 #ifndef K_WSHADE_MIN_BLOCKS
-#define K_WSHADE_MIN_BLOCKS 4
+#define K_WSHADE_MIN_BLOCKS 6
 #endif
 #ifndef K_WEVAL_MIN_BLOCKS
 #define K_WEVAL_MIN_BLOCKS 8
@@ -67,7 +69,8 @@ enum { WC_RAYS = 0 /* 3 */, WC_EVALS = 3, WC_TRACE_CUR, WC_EVAL_CUR,
        WC_LIVE,          // slots that hold a camera path after k_wshade (0: the batch is done)
        WC_NEXT_SAMPLE,   // (everything before it is reset every iteration)
        WC_LIVE2,         // phase 2: WC_LIVE and WC_LIVE2 are the lengths of the two live-chain lists (ping-pong, see k_wshade<2>)
-       WC_COUNT };
+       WC_SORT,          // phase 1: lengths of the sorted slot lists, [set][kind] (4 counters, see WvArgs::sortList)
+       WC_COUNT = WC_SORT + 4 };
 #define W_RAY_ALLOWED 0x10000
 #define W_RR 0x20000   // (direction 2, phase 2) the path ray also has to survive Russian roulette: see k_weval
 
@@ -83,10 +86,19 @@ struct WvArgs {
     unsigned totalSamples;
     int iter;            // 0: every slot starts with a camera sample
     DeviceStats *stats;
+    uint32_t *sortList;  // phase 1: [2 sets][2 kinds][P] or null
     uint32_t *liveList;  // phase 2: [2][nBatch] the chains still running, compacted: iteration i reads list i & 1 (from
                          // iteration 1 on) and writes list (i + 1) & 1, so the kernels shrink with the number of live chains
 };
 DEV int WvLiveCounter(int list) { return list ? WC_LIVE2 : WC_LIVE; }
+// Phase 1, slots sorted by what k_wshade will do with them next (null: thread i serves slot i).  Every live slot is put on
+// exactly one list of set (iter + 1) & 1 during iteration `iter` -- by whoever learns its fate: k_wtrace when its path ray
+// comes back (hit, and not the bounce-3 vertex that is only parked: SORT_VERTEX; else SORT_OTHER), k_wshade / k_weval when
+// they decide that no path ray will be traced (SORT_OTHER: the sample ends at the next pass) -- and k_wshade of iteration
+// iter + 1 serves list SORT_VERTEX, then SORT_OTHER: its warps are all shading a vertex, or all finishing a sample and
+// starting a camera ray, instead of a mix that ran with 7 of 32 lanes active (profiles/r02c_k_wshade_ncu_full.txt).
+enum { SORT_VERTEX = 0, SORT_OTHER = 1 };
+DEV void WvSortPush(const WvArgs &a, int kind, uint32_t slot);
 
 // `kind` must be the same for all converged lanes (a compile-time constant at the call site)
 DEV void WvPushRay(const WvArgs &a, int kind, uint32_t slot) {
@@ -103,6 +115,18 @@ DEV void WvPushRayAny(const WvArgs &a, int kind, uint32_t slot) {
     a.qRay[(size_t)kind * a.P + base + __popc(peers & ((1u << lane) - 1u))] = slot;
 }
 
+// (all converged lanes must pass the same `kind`: a compile-time constant or a per-lane value pushed through match_any)
+DEV void WvSortPush(const WvArgs &a, int kind, uint32_t slot) {
+    if (!a.sortList) return;
+    const int set = (a.iter + 1) & 1;
+    const unsigned peers = __match_any_sync(__activemask(), kind);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(a.counters + WC_SORT + set * 2 + kind, (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    a.sortList[((size_t)set * 2 + kind) * a.P + base + __popc(peers & ((1u << lane) - 1u))] = slot;
+}
+
 // ----------------------------------------------------------------------------------------------------------- k_wshade
 // PHASE 1: slots are camera samples (bounces 0..2, random numbers from the tables), handed out by a global counter.
 // PHASE 2: slot c is task chain c -- the parked samples of one task-pixel in sample order, each resumed with the task's RNG
@@ -115,8 +139,16 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t slot = tid;
     bool live;
-    if (PHASE == 1) live = tid < a.P;
-    else if (a.iter == 0) live = tid < (uint32_t)a.b.nBatch;
+    if (PHASE == 1) {
+        live = tid < a.P;
+        if (a.sortList && a.iter > 0) {   // the sorted lists of this iteration: vertices to shade first, then the rest
+            const int set = a.iter & 1;
+            const unsigned nV = a.counters[WC_SORT + set * 2 + SORT_VERTEX], nO = a.counters[WC_SORT + set * 2 + SORT_OTHER];
+            live = tid < nV + nO;
+            if (live) slot = tid < nV ? a.sortList[((size_t)set * 2 + SORT_VERTEX) * a.P + tid]
+                                      : a.sortList[((size_t)set * 2 + SORT_OTHER) * a.P + (tid - nV)];
+        }
+    } else if (a.iter == 0) live = tid < (uint32_t)a.b.nBatch;
     else {   // the chains that were still running after the previous iteration
         live = tid < a.counters[WvLiveCounter(a.iter & 1)];
         slot = live ? a.liveList[(size_t)(a.iter & 1) * a.b.nBatch + tid] : 0u;
@@ -366,6 +398,7 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
 #if PBRT_SPECULAR
         if (k == VX_PATH && v.specSampled) {   // the value is specF (BSDF::Sample_f, reflection.cpp:572): nothing to evaluate
             if (allowed && PathSampleAlive(v.specF, T, v.absP, v.pdfP, roulette, rrU)) WvPushRay(a, k, slot);
+            else if (PHASE == 1) WvSortPush(a, SORT_OTHER, slot);
             continue;
         }
 #endif
@@ -380,8 +413,10 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
             const Spec f = VertexEvalAnalytic(sc, v.material, v.evalWo, v.evalWi[k], v.evalFlags[k]);
             WF(W_F0 + k) = make_float4(f.r, f.g, f.b, 0.f);
             if (allowed && (k == VX_PATH ? PathSampleAlive(f, T, v.absP, v.pdfP, roulette, rrU) : !f.IsBlack())) WvPushRay(a, k, slot);
+            else if (PHASE == 1 && k == VX_PATH) WvSortPush(a, SORT_OTHER, slot);
         }
     }
+    if (PHASE == 1 && !v.need[VX_PATH]) WvSortPush(a, SORT_OTHER, slot);   // no continuation direction at all
     if (STATS && nShadedN) atomicAdd(&a.stats->shadedN, nShadedN);
 #undef WF
 }
@@ -464,6 +499,7 @@ __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(const __grid_
                     else {
                         a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
                         if (WvRayWanted(a, slot, k, word, f)) WvPushRayAny(a, k, slot);
+                        else if (k == VX_PATH) WvSortPush(a, SORT_OTHER, slot);
                     }
                 }
             }
@@ -531,6 +567,7 @@ __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(const __grid_
                         const Spec f = v.Clamp() / sumW;
                         a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
                         if (WvRayWanted(a, slot, k, word, f)) WvPushRayAny(a, k, slot);
+                        else if (k == VX_PATH) WvSortPush(a, SORT_OTHER, slot);
                         mode = 0;
                     }
                 }
@@ -554,6 +591,7 @@ __global__ void __launch_bounds__(128, K_WEVAL_MIN_BLOCKS) k_weval(const __grid_
         const Spec f = VertexEval(a.sc, __float_as_int(wo.w), V3(wo.x, wo.y, wo.z), V3(wi.x, wi.y, wi.z), word & 0xffff);
         a.pool[(size_t)(W_F0 + k) * P + slot] = make_float4(f.r, f.g, f.b, 0.f);
         if (WvRayWanted(a, slot, k, word, f)) WvPushRayAny(a, k, slot);
+                        else if (k == VX_PATH) WvSortPush(a, SORT_OTHER, slot);
     }
 }
 #endif
@@ -685,6 +723,11 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_wtrace(const __grid
                 } else {
                     pool[(size_t)W_HIT * P + slot] = make_float4(__int_as_float(t.found ? t.hit.prim : -1), t.hit.b1, t.hit.b2, t.hit.maxtIn);
                     pool[(size_t)W_D2 * P + slot].w = t.ray.maxt;
+                    if (a.sortList) {   // a vertex to shade next (not the bounce-3 vertex, which is only parked)?
+                        const uint32_t bits = __float_as_uint(pool[(size_t)W_T * P + slot].w);
+                        const bool park = (bits & WB_VERTEX) && ((bits >> WB_BOUNCES_SHIFT) & 0xffu) == 2u;
+                        WvSortPush(a, (t.found && !park) ? SORT_VERTEX : SORT_OTHER, slot);
+                    }
                 }
                 active = false;
             }

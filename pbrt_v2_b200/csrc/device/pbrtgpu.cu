@@ -1115,6 +1115,7 @@ struct Lane {
     DevBuf<uint32_t> traceQ;
     DevBuf<uint32_t> evalQ;           // vertex wavefront: (slot, direction) evaluation requests
     DevBuf<uint32_t> liveList;        // chain wavefront: [2][maxBatch] live chains, compacted
+    DevBuf<uint32_t> sortList;        // vertex wavefront: [2][2][P] slots sorted by their next action
     DevBuf<DlFrame> dlFrames;         // DirectLightingIntegrator over specular materials: [P][DL_MAX_DEPTH]
     DevBuf<unsigned> counters;
     unsigned *hostCounters = nullptr;  // pinned
@@ -1319,8 +1320,12 @@ struct RenderConfig {
     int vertex = 2;
     // PBRTGPU_WAVE=0: PathIntegrator's phase 1 on the request-granular wavefront (k_logic / k_eval / k_trace) instead of the
     // vertex wavefront (kwave.cuh: k_wshade / k_weval / k_wtrace)
-    // bit 1: phase 2 (the task chains) on it as well instead of k_vertex<2>
-    int wave = 3;
+    // bit 1: phase 2 (the task chains) on it as well instead of k_vertex<2>.  Measured on C2, one GPU (profiles/r02d_*, r02e_*):
+    // k_vertex<2> 541 ms per step, the chain wavefront 794 ms -- every iteration costs the LATENCY of one vertex (one shade,
+    // one kd-tree evaluation, one ray: ~150 us even for a single chain, r02e_launches.csv) and a batch runs as many
+    // iterations as its longest chain has vertices; the megakernel's lanes pay only their own chain's latency.  Default 1.
+    int wave = 1;
+    bool wsort = true;         // PBRTGPU_WSORT=0: k_wshade<1> serves slot i with thread i instead of the slots sorted by next action
     int tailSort = 2;          // PBRTGPU_TAIL_SORT 0: chains in task order, 2: longest chain first
     int lockstep = 1;
     size_t pool = (size_t)1 << 22;
@@ -1336,6 +1341,7 @@ RenderConfig ReadConfig() {
         if (const char *e = getenv("PBRTGPU_WAVEFRONT2")) c.wavefront2 = atoi(e) != 0;
         if (const char *e = getenv("PBRTGPU_VERTEX")) c.vertex = atoi(e);
         if (const char *e = getenv("PBRTGPU_WAVE")) c.wave = atoi(e);
+        if (const char *e = getenv("PBRTGPU_WSORT")) c.wsort = atoi(e) != 0;
         if (const char *e = getenv("PBRTGPU_TAIL_SORT")) c.tailSort = atoi(e);
         if (const char *e = getenv("PBRTGPU_LOCKSTEP")) c.lockstep = atoi(e);
         if (const char *e = getenv("PBRTGPU_POOL")) { if (atol(e) > 0) c.pool = (size_t)atol(e); }
@@ -1747,6 +1753,7 @@ int RunLane(LaneJob &job) {
         CUDA_TRY(ln->traceQ.Ensure(std::max(poolSize, maxBatch) * 3));
         CUDA_TRY(ln->evalQ.Ensure(std::max(poolSize, maxBatch) * 3));
         CUDA_TRY(ln->liveList.Ensure(maxBatch * 2));
+        if (cfg.wsort) CUDA_TRY(ln->sortList.Ensure(poolSize * 4));
         CUDA_TRY(ln->counters.Ensure(std::max<int>(WC_COUNT, C_COUNT)));
         if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, std::max<int>(WC_COUNT, C_COUNT) * sizeof(unsigned)));
     }
@@ -1805,13 +1812,16 @@ int RunLane(LaneJob &job) {
                 wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = ln->pool.p; wa.P = (uint32_t)poolSize;
                 wa.qRay = ln->traceQ.p; wa.qEval = ln->evalQ.p; wa.counters = ln->counters.p;
                 wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p; wa.liveList = nullptr;
+                wa.sortList = cfg.wsort ? ln->sortList.p : nullptr;
                 CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_COUNT * sizeof(unsigned), stream));
                 const int sblocks = (int)((poolSize + 127) / 128);
                 const int tblocks = nSM * 8;
                 for (int iter = 0;; ++iter) {
                     wa.iter = iter;
-                    // empty the queues k_wshade is about to fill, the consumers' cursors and the live-slot count
+                    // empty the queues k_wshade is about to fill, the consumers' cursors, the live-slot count and the sorted
+                    // lists this iteration writes
                     CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_NEXT_SAMPLE * sizeof(unsigned), stream));
+                    if (cfg.wsort) CUDA_TRY(cudaMemsetAsync(ln->counters.p + WC_SORT + ((iter + 1) & 1) * 2, 0, 2 * sizeof(unsigned), stream));
                     if (scene->d.nAnimated) {
                         if (wantCounters) k_wshade<1, true, true><<<sblocks, 128, 0, stream>>>(wa);
                         else k_wshade<1, false, true><<<sblocks, 128, 0, stream>>>(wa);
@@ -1916,7 +1926,7 @@ int RunLane(LaneJob &job) {
                 wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = ln->pool.p; wa.P = (uint32_t)std::max(poolSize, maxBatch);
                 wa.qRay = ln->traceQ.p; wa.qEval = ln->evalQ.p; wa.counters = ln->counters.p;
                 wa.totalSamples = 0; wa.stats = scene->stats.p;
-                wa.liveList = ln->liveList.p;
+                wa.liveList = ln->liveList.p; wa.sortList = nullptr;
                 // the kernels shrink with the number of live chains: the grids follow the count read back every 8 iterations
                 // (it only falls in between); an empty persistent kernel at full size costs 6 - 16 us, and a chain wavefront
                 // runs as many iterations as its longest chain has vertices (profiles/r02d_launches.csv)

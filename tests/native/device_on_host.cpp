@@ -68,6 +68,7 @@ using namespace dev;
 
 namespace {
 int g_vertexForm = 0;
+int g_waveSort = 1;   // the vertex wavefront's phase 1 with its slots sorted by next action (WvArgs::sortList)
 struct HostScene {
     std::vector<float4> nodes, prims;
 #if PBRT_PAIR_NODES
@@ -496,9 +497,13 @@ void RunWaveH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
         wa.pool = pool.data(); wa.P = P; wa.qRay = qRay.data(); wa.qEval = qEval.data(); wa.counters = counters.data();
         wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = nullptr;
         std::fill(counters.begin(), counters.end(), 0u);
+        std::vector<uint32_t> sortList(4 * (size_t)P);
+        wa.sortList = g_waveSort ? sortList.data() : nullptr;
+        wa.liveList = nullptr;
         for (int iter = 0;; ++iter) {
             wa.iter = iter;
             for (int k = 0; k < WC_NEXT_SAMPLE; ++k) counters[k] = 0;
+            counters[WC_SORT + ((iter + 1) & 1) * 2] = counters[WC_SORT + ((iter + 1) & 1) * 2 + 1] = 0;
             LaunchH(P, [&]() { k_wshade<1, false, true>(wa); });
             if (hasMeasured) LaunchH(1, [&]() { k_weval(wa); }, PBRT_KD_INTERLEAVED != 0);   // (the persistent form elects lane 0)
             LaunchH(1, [&]() { k_wtrace<false, true>(wa); }, true);
@@ -520,7 +525,7 @@ void RunWaveH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
         std::vector<uint32_t> qRay2(3 * (size_t)wa.P), qEval2(3 * (size_t)wa.P);
         wa.pool = pool2.data(); wa.qRay = qRay2.data(); wa.qEval = qEval2.data();
         std::vector<uint32_t> liveList(2 * nb);
-        wa.liveList = liveList.data();
+        wa.liveList = liveList.data(); wa.sortList = nullptr;
         for (int iter = 0;; ++iter) {
             wa.iter = iter;
             for (int k = 0; k < WC_LIVE; ++k) counters[k] = 0;
@@ -600,6 +605,7 @@ DOH_EXPORT uint32_t doh_sobol2_word(uint32_t n) { return Sobol2Word(n); }
 // PathIntegrator renders through the vertex form (dvertex.cuh) instead of the state machine (path_body.inc); a value >= 2
 // runs the vertex-wavefront kernels (kwave.cuh) over a pool of that many path slots
 DOH_EXPORT void doh_set_vertex_form(int on) { g_vertexForm = on; }
+DOH_EXPORT void doh_set_wave_sort(int on) { g_waveSort = on; }
 
 // k_intersect<false>'s body (device/pbrtgpu.cu) on the host: BVHAccel::Intersect + the hit's differential geometry
 DOH_EXPORT int doh_intersect(const PbrtGpuSceneDesc *desc, const PbrtGpuRay *rays, int n, PbrtGpuHit *hits, int stepwise) {

@@ -15,9 +15,11 @@ pytestmark = pytest.mark.gpu
 # (library or None = the product library, extra environment, test files)
 CASES = [
     ("pairs", "ab/libpbrtgpu_pairs.so", {}, ["tests/test_gpu_parity.py"]),
-    # the kernels the vertex wavefront (kwave.cuh) replaced stay selectable (A/B baselines): they must still reproduce the oracle
+    # what the default path (vertex wavefront sorted by next action + k_vertex<2>) replaced or did not adopt stays
+    # selectable (A/B baselines): every combination must still reproduce the oracle
+    ("vertex-wavefront-unsorted", None, {"PBRTGPU_WSORT": "0"}, ["tests/test_gpu_parity.py", "tests/test_gpu_specular.py"]),
+    ("vertex-wavefront+chain-wavefront", None, {"PBRTGPU_WAVE": "3"}, ["tests/test_gpu_parity.py", "tests/test_gpu_specular.py"]),
     ("request-wavefront+vertex2", None, {"PBRTGPU_WAVE": "0"}, ["tests/test_gpu_parity.py", "tests/test_gpu_specular.py"]),
-    ("vertex-wavefront+vertex2", None, {"PBRTGPU_WAVE": "1"}, ["tests/test_gpu_parity.py", "tests/test_gpu_specular.py"]),
     ("request-wavefront+chain-wavefront", None, {"PBRTGPU_WAVE": "2"}, ["tests/test_gpu_parity.py"]),
     ("request-wavefront+k_path2", None, {"PBRTGPU_WAVE": "0", "PBRTGPU_VERTEX": "0"}, ["tests/test_gpu_parity.py"]),
     ("megakernel+k_path2", None, {"PBRTGPU_WAVE": "0", "PBRTGPU_VERTEX": "0", "PBRTGPU_WAVEFRONT": "0"}, ["tests/test_gpu_parity.py"]),
