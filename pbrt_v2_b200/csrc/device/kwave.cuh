@@ -69,8 +69,8 @@ enum { WC_RAYS = 0 /* 3 */, WC_EVALS = 3, WC_TRACE_CUR, WC_EVAL_CUR,
        WC_LIVE,          // slots that hold a camera path after k_wshade (0: the batch is done)
        WC_NEXT_SAMPLE,   // (everything before it is reset every iteration)
        WC_LIVE2,         // phase 2: WC_LIVE and WC_LIVE2 are the lengths of the two live-chain lists (ping-pong, see k_wshade<2>)
-       WC_SORT,          // phase 1: lengths of the sorted slot lists, [set][kind] (4 counters, see WvArgs::sortList)
-       WC_COUNT = WC_SORT + 4 };
+       WC_SORT,          // phase 1: lengths of the two sorted slot lists (see WvArgs::sortList)
+       WC_COUNT = WC_SORT + 2 };
 #define W_RAY_ALLOWED 0x10000
 #define W_RR 0x20000   // (direction 2, phase 2) the path ray also has to survive Russian roulette: see k_weval
 
@@ -86,17 +86,21 @@ struct WvArgs {
     unsigned totalSamples;
     int iter;            // 0: every slot starts with a camera sample
     DeviceStats *stats;
-    uint32_t *sortList;  // phase 1: [2 sets][2 kinds][P] or null
+    uint32_t *sortList;  // phase 1: [2 kinds][P] or null
+    uint8_t *sortClass;  //          [P rounded up to 1024] 0: none, 1 + SORT_* : the slot's class of this iteration
     uint32_t *liveList;  // phase 2: [2][nBatch] the chains still running, compacted: iteration i reads list i & 1 (from
                          // iteration 1 on) and writes list (i + 1) & 1, so the kernels shrink with the number of live chains
 };
 DEV int WvLiveCounter(int list) { return list ? WC_LIVE2 : WC_LIVE; }
-// Phase 1, slots sorted by what k_wshade will do with them next (null: thread i serves slot i).  Every live slot is put on
-// exactly one list of set (iter + 1) & 1 during iteration `iter` -- by whoever learns its fate: k_wtrace when its path ray
-// comes back (hit, and not the bounce-3 vertex that is only parked: SORT_VERTEX; else SORT_OTHER), k_wshade / k_weval when
-// they decide that no path ray will be traced (SORT_OTHER: the sample ends at the next pass) -- and k_wshade of iteration
-// iter + 1 serves list SORT_VERTEX, then SORT_OTHER: its warps are all shading a vertex, or all finishing a sample and
-// starting a camera ray, instead of a mix that ran with 7 of 32 lanes active (profiles/r02c_k_wshade_ncu_full.txt).
+// Phase 1, slots sorted by what k_wshade will do with them next (null: thread i serves slot i).  Every live slot gets
+// exactly one class during an iteration -- from whoever learns its fate: k_wtrace when its path ray comes back (hit, and
+// not the bounce-3 vertex that is only parked: SORT_VERTEX; else SORT_OTHER), k_wshade / k_weval when they decide that no
+// path ray will be traced (SORT_OTHER: the sample ends at the next pass) -- k_wcompact turns the class bytes into two slot
+// lists, and k_wshade of the next iteration serves list SORT_VERTEX, then SORT_OTHER: its warps are all shading a vertex,
+// or all finishing a sample and starting a camera ray, instead of a mix that ran with 7 of 32 lanes active
+// (profiles/r02c_k_wshade_ncu_full.txt).  The lists keep the slots of every 1024-slot block in ascending order, so
+// neighbouring threads still read neighbouring slots (lists appended to in completion order scattered every slot access:
+// k_wtrace 228 -> 284 ms per step, profiles/r02f_ab_wsort.json).
 enum { SORT_VERTEX = 0, SORT_OTHER = 1 };
 DEV void WvSortPush(const WvArgs &a, int kind, uint32_t slot);
 
@@ -115,16 +119,59 @@ DEV void WvPushRayAny(const WvArgs &a, int kind, uint32_t slot) {
     a.qRay[(size_t)kind * a.P + base + __popc(peers & ((1u << lane) - 1u))] = slot;
 }
 
-// (all converged lanes must pass the same `kind`: a compile-time constant or a per-lane value pushed through match_any)
 DEV void WvSortPush(const WvArgs &a, int kind, uint32_t slot) {
-    if (!a.sortList) return;
-    const int set = (a.iter + 1) & 1;
-    const unsigned peers = __match_any_sync(__activemask(), kind);
-    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(a.counters + WC_SORT + set * 2 + kind, (unsigned)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    a.sortList[((size_t)set * 2 + kind) * a.P + base + __popc(peers & ((1u << lane) - 1u))] = slot;
+    if (a.sortList) a.sortClass[slot] = (uint8_t)(1 + kind);
+}
+
+// Class bytes -> slot lists.  One block per 1024 consecutive slots (a thread reads its four class bytes as one word), a
+// block-wide exclusive scan of the per-thread counts, one atomicAdd per block and list for the block's range, the slots
+// written in ascending order inside it; the class bytes are cleared for the next iteration.
+#define WCOMPACT_THREADS 256
+__global__ void __launch_bounds__(WCOMPACT_THREADS) k_wcompact(const __grid_constant__ WvArgs a) {
+#ifdef __CUDACC__
+    __shared__ unsigned warpV[WCOMPACT_THREADS / 32], warpO[WCOMPACT_THREADS / 32], baseV, baseO;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t first = (blockIdx.x * WCOMPACT_THREADS + threadIdx.x) * 4u;
+    uint32_t *word = reinterpret_cast<uint32_t *>(a.sortClass) + (first >> 2);
+    const uint32_t w = first < a.P ? *word : 0u;
+    if (w) *word = 0u;
+    unsigned cV = 0, cO = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t c = (w >> (8 * k)) & 0xffu;
+        cV += c == 1u + SORT_VERTEX; cO += c == 1u + SORT_OTHER;
+    }
+    unsigned sV = cV, sO = cO;   // inclusive warp scans
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(FULL, sV, o), q = __shfl_up_sync(FULL, sO, o);
+        if (lane >= o) { sV += v; sO += q; }
+    }
+    if (lane == 31) { warpV[warp] = sV; warpO[warp] = sO; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tV = 0, tO = 0;
+        for (int i = 0; i < WCOMPACT_THREADS / 32; ++i) { const unsigned v = warpV[i], q = warpO[i]; warpV[i] = tV; warpO[i] = tO; tV += v; tO += q; }
+        baseV = tV ? atomicAdd(a.counters + WC_SORT + SORT_VERTEX, tV) : 0u;
+        baseO = tO ? atomicAdd(a.counters + WC_SORT + SORT_OTHER, tO) : 0u;
+    }
+    __syncthreads();
+    unsigned oV = baseV + warpV[warp] + sV - cV, oO = baseO + warpO[warp] + sO - cO;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t c = (w >> (8 * k)) & 0xffu;
+        if (c == 1u + SORT_VERTEX) a.sortList[(size_t)SORT_VERTEX * a.P + oV++] = first + k;
+        else if (c == 1u + SORT_OTHER) a.sortList[(size_t)SORT_OTHER * a.P + oO++] = first + k;
+    }
+#else   // (host-compiled harness: one thread does it all)
+    if (blockIdx.x || threadIdx.x) return;
+    for (uint32_t slot = 0; slot < a.P; ++slot) {
+        const uint8_t c = a.sortClass[slot];
+        a.sortClass[slot] = 0;
+        if (c) a.sortList[(size_t)(c - 1) * a.P + a.counters[WC_SORT + (c - 1)]++] = slot;
+    }
+#endif
 }
 
 // ----------------------------------------------------------------------------------------------------------- k_wshade
@@ -141,12 +188,10 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
     bool live;
     if (PHASE == 1) {
         live = tid < a.P;
-        if (a.sortList && a.iter > 0) {   // the sorted lists of this iteration: vertices to shade first, then the rest
-            const int set = a.iter & 1;
-            const unsigned nV = a.counters[WC_SORT + set * 2 + SORT_VERTEX], nO = a.counters[WC_SORT + set * 2 + SORT_OTHER];
+        if (a.sortList && a.iter > 0) {   // the sorted lists k_wcompact left: vertices to shade first, then the rest
+            const unsigned nV = a.counters[WC_SORT + SORT_VERTEX], nO = a.counters[WC_SORT + SORT_OTHER];
             live = tid < nV + nO;
-            if (live) slot = tid < nV ? a.sortList[((size_t)set * 2 + SORT_VERTEX) * a.P + tid]
-                                      : a.sortList[((size_t)set * 2 + SORT_OTHER) * a.P + (tid - nV)];
+            if (live) slot = tid < nV ? a.sortList[(size_t)SORT_VERTEX * a.P + tid] : a.sortList[(size_t)SORT_OTHER * a.P + (tid - nV)];
         }
     } else if (a.iter == 0) live = tid < (uint32_t)a.b.nBatch;
     else {   // the chains that were still running after the previous iteration

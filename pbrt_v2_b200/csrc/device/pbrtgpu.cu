@@ -1115,7 +1115,8 @@ struct Lane {
     DevBuf<uint32_t> traceQ;
     DevBuf<uint32_t> evalQ;           // vertex wavefront: (slot, direction) evaluation requests
     DevBuf<uint32_t> liveList;        // chain wavefront: [2][maxBatch] live chains, compacted
-    DevBuf<uint32_t> sortList;        // vertex wavefront: [2][2][P] slots sorted by their next action
+    DevBuf<uint32_t> sortList;        // vertex wavefront: [2][P] slots sorted by their next action
+    DevBuf<uint8_t> sortClass;        // ... and the class bytes the lists are built from
     DevBuf<DlFrame> dlFrames;         // DirectLightingIntegrator over specular materials: [P][DL_MAX_DEPTH]
     DevBuf<unsigned> counters;
     unsigned *hostCounters = nullptr;  // pinned
@@ -1753,7 +1754,13 @@ int RunLane(LaneJob &job) {
         CUDA_TRY(ln->traceQ.Ensure(std::max(poolSize, maxBatch) * 3));
         CUDA_TRY(ln->evalQ.Ensure(std::max(poolSize, maxBatch) * 3));
         CUDA_TRY(ln->liveList.Ensure(maxBatch * 2));
-        if (cfg.wsort) CUDA_TRY(ln->sortList.Ensure(poolSize * 4));
+        if (cfg.wsort) {
+            const size_t nClass = (poolSize + 1023) / 1024 * 1024;
+            const bool fresh = ln->sortClass.n < nClass;
+            CUDA_TRY(ln->sortList.Ensure(poolSize * 2));
+            CUDA_TRY(ln->sortClass.Ensure(nClass));
+            if (fresh) CUDA_TRY(cudaMemsetAsync(ln->sortClass.p, 0, ln->sortClass.n, stream));
+        }
         CUDA_TRY(ln->counters.Ensure(std::max<int>(WC_COUNT, C_COUNT)));
         if (!ln->hostCounters) CUDA_TRY(cudaMallocHost((void **)&ln->hostCounters, std::max<int>(WC_COUNT, C_COUNT) * sizeof(unsigned)));
     }
@@ -1812,7 +1819,8 @@ int RunLane(LaneJob &job) {
                 wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = ln->pool.p; wa.P = (uint32_t)poolSize;
                 wa.qRay = ln->traceQ.p; wa.qEval = ln->evalQ.p; wa.counters = ln->counters.p;
                 wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = scene->stats.p; wa.liveList = nullptr;
-                wa.sortList = cfg.wsort ? ln->sortList.p : nullptr;
+                wa.sortList = cfg.wsort ? ln->sortList.p : nullptr; wa.sortClass = ln->sortClass.p;
+                if (cfg.wsort) CUDA_TRY(cudaMemsetAsync(ln->sortClass.p, 0, ln->sortClass.n, stream));   // (a batch that ended early leaves none, but be sure)
                 CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_COUNT * sizeof(unsigned), stream));
                 const int sblocks = (int)((poolSize + 127) / 128);
                 const int tblocks = nSM * 8;
@@ -1821,7 +1829,7 @@ int RunLane(LaneJob &job) {
                     // empty the queues k_wshade is about to fill, the consumers' cursors, the live-slot count and the sorted
                     // lists this iteration writes
                     CUDA_TRY(cudaMemsetAsync(ln->counters.p, 0, WC_NEXT_SAMPLE * sizeof(unsigned), stream));
-                    if (cfg.wsort) CUDA_TRY(cudaMemsetAsync(ln->counters.p + WC_SORT + ((iter + 1) & 1) * 2, 0, 2 * sizeof(unsigned), stream));
+
                     if (scene->d.nAnimated) {
                         if (wantCounters) k_wshade<1, true, true><<<sblocks, 128, 0, stream>>>(wa);
                         else k_wshade<1, false, true><<<sblocks, 128, 0, stream>>>(wa);
@@ -1840,6 +1848,11 @@ int RunLane(LaneJob &job) {
                     }
                     if (timeRays) CUDA_TRY(cudaEventRecord(rayEvent(), stream));
                     launches += hasMeasured ? 3 : 2;
+                    if (cfg.wsort) {   // this iteration's class bytes -> the slot lists of the next
+                        CUDA_TRY(cudaMemsetAsync(ln->counters.p + WC_SORT, 0, 2 * sizeof(unsigned), stream));
+                        k_wcompact<<<(int)((poolSize + 1023) / 1024), WCOMPACT_THREADS, 0, stream>>>(wa);
+                        launches += 1;
+                    }
                     if ((iter & 7) == 7) {
                         CUDA_TRY(cudaMemcpyAsync(ln->hostCounters, ln->counters.p, WC_COUNT * sizeof(unsigned),
                                                  cudaMemcpyDeviceToHost, stream));
@@ -1926,7 +1939,7 @@ int RunLane(LaneJob &job) {
                 wa.sc = scene->d; wa.rp = rp; wa.b = b; wa.pool = ln->pool.p; wa.P = (uint32_t)std::max(poolSize, maxBatch);
                 wa.qRay = ln->traceQ.p; wa.qEval = ln->evalQ.p; wa.counters = ln->counters.p;
                 wa.totalSamples = 0; wa.stats = scene->stats.p;
-                wa.liveList = ln->liveList.p; wa.sortList = nullptr;
+                wa.liveList = ln->liveList.p; wa.sortList = nullptr; wa.sortClass = nullptr;
                 // the kernels shrink with the number of live chains: the grids follow the count read back every 8 iterations
                 // (it only falls in between); an empty persistent kernel at full size costs 6 - 16 us, and a chain wavefront
                 // runs as many iterations as its longest chain has vertices (profiles/r02d_launches.csv)

@@ -497,16 +497,21 @@ void RunWaveH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
         wa.pool = pool.data(); wa.P = P; wa.qRay = qRay.data(); wa.qEval = qEval.data(); wa.counters = counters.data();
         wa.totalSamples = (unsigned)(nb * (size_t)spp); wa.stats = nullptr;
         std::fill(counters.begin(), counters.end(), 0u);
-        std::vector<uint32_t> sortList(4 * (size_t)P);
+        std::vector<uint32_t> sortList(2 * (size_t)P);
+        std::vector<uint8_t> sortClass(((size_t)P + 1023) / 1024 * 1024, 0);
         wa.sortList = g_waveSort ? sortList.data() : nullptr;
+        wa.sortClass = sortClass.data();
         wa.liveList = nullptr;
         for (int iter = 0;; ++iter) {
             wa.iter = iter;
             for (int k = 0; k < WC_NEXT_SAMPLE; ++k) counters[k] = 0;
-            counters[WC_SORT + ((iter + 1) & 1) * 2] = counters[WC_SORT + ((iter + 1) & 1) * 2 + 1] = 0;
             LaunchH(P, [&]() { k_wshade<1, false, true>(wa); });
             if (hasMeasured) LaunchH(1, [&]() { k_weval(wa); }, PBRT_KD_INTERLEAVED != 0);   // (the persistent form elects lane 0)
             LaunchH(1, [&]() { k_wtrace<false, true>(wa); }, true);
+            if (g_waveSort) {
+                counters[WC_SORT] = counters[WC_SORT + 1] = 0;
+                LaunchH(1, [&]() { k_wcompact(wa); });
+            }
             if (counters[WC_LIVE] == 0) break;
         }
         // ---- phase 2: the task chains on the same kernels (k_wshade<2>), each chain's RNG window in the kernels' format
@@ -525,7 +530,7 @@ void RunWaveH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
         std::vector<uint32_t> qRay2(3 * (size_t)wa.P), qEval2(3 * (size_t)wa.P);
         wa.pool = pool2.data(); wa.qRay = qRay2.data(); wa.qEval = qEval2.data();
         std::vector<uint32_t> liveList(2 * nb);
-        wa.liveList = liveList.data(); wa.sortList = nullptr;
+        wa.liveList = liveList.data(); wa.sortList = nullptr; wa.sortClass = nullptr;
         for (int iter = 0;; ++iter) {
             wa.iter = iter;
             for (int k = 0; k < WC_LIVE; ++k) counters[k] = 0;
