@@ -40,17 +40,6 @@ struct DeviceStats {
     unsigned long long closestRays, shadowRays, nodes, prims, shadedN, cameraSamples;
 };
 
-// warp-aggregated atomicAdd(ctr, 1) for the currently converged lanes
-DEV unsigned AggregatedAddV(unsigned *ctr) {
-    const unsigned m = __activemask();
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(ctr, (unsigned)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    return base + __popc(m & ((1u << lane) - 1u));
-}
-
 // persistent ray-queue consumers (k_trace, k_wtrace)
 #ifndef K_TRACE_MIN_BLOCKS
 #define K_TRACE_MIN_BLOCKS 7

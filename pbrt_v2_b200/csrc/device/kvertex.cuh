@@ -17,6 +17,7 @@
 #pragma once
 #include "dvertex.cuh"
 #include "kcommon.cuh"
+#include "kwarp.cuh"
 
 #ifndef K_VERTEX_MIN_BLOCKS
 #define K_VERTEX_MIN_BLOCKS 4

@@ -17,12 +17,16 @@
 //              value is not black gets its ray queued
 //   k_wtrace   persistent lanes over the three ray queues (shadow, MIS, path rays in separate runs): BVHAccel::IntersectP /
 //              Intersect step-wise as in k_trace; the MIS ray's "did it land on the sampled light" test happens here
+//   k_wcompact class bytes (written by whoever learns a slot's fate) -> slot lists sorted by next action: k_wshade's warps are
+//              all shading a vertex or all finishing a sample, and neighbouring threads still read neighbouring slots
 // so a vertex moves its state through HBM once (~420 B in k_wshade, 48 B per evaluation, 48 B per ray) instead of six times.
+// k_wshade<2> runs phase 2 (the task chains) on the same kernels (PBRTGPU_WAVE=3; not the default: see pbrtgpu.cu RenderConfig).
 // Every float expression is dvertex.cuh's (shared with k_vertex and the host-compiled harness): same operands, same
 // operation order per quantity, so the film is the same film.
 #pragma once
 #include "dvertex.cuh"
 #include "kcommon.cuh"
+#include "kwarp.cuh"
 #include "drng.cuh"
 
 // resident blocks per SM the register allocator must allow.  k_wshade: 4 (128 registers) / 5 (96) / 6 (80, 550 B of spills):
