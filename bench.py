@@ -48,7 +48,7 @@ WORKLOAD_INTEGRATOR = {"killeroo-dl": "directlighting"}
 SYNTHETIC_TRIS = 10000000
 # dram__bytes_read.sum + dram__bytes_write.sum of one mid-render k_wtrace launch (ncu --set full, profiles/), per workload
 K_TRACE_DRAM_BYTES_PER_LAUNCH = {
-    "bunny-c2": 341647872 + 191812352,   # profiles/r02b_k_wtrace_ncu_full.txt (launch 60 of a 256-spp run: a full 4 Mi-slot pool, as at 1024 spp)
+    "bunny-c2": 635614976 + 241986048,   # profiles/r02g_k_wtrace_ncu_full.txt (launch 60 of a 256-spp run: a full 4 Mi-slot pool, as at 1024 spp)
 }
 CPU_SAMPLE_SPP = 16     # bounded sample of the same workload for the CPU arms (cost is linear in spp)
 

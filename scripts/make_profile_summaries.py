@@ -21,7 +21,7 @@ for k in ("k_trace", "k_logic", "k_eval", "k_path", "k_tables", "k_vertex", "k_w
     rows = list(csv.reader(open(raw)))
     H, U, V = rows[0], rows[1], rows[2]
     out = ["ncu --set full --clock-control none --import-source on -k regex:%s -c 1 (one mid-render launch), command:" % k,
-           "    python bench.py --spp 128 --steps 1 --warmup 1 --no-cpu-baseline      (BASELINE configs[1] scene, 1024x1024)",
+           "    python bench.py --spp 256 --steps 1 --warmup 1 --no-cpu-baseline      (BASELINE configs[1] scene, 1024x1024; round 1 used --spp 128)",
            "kernel: " + V[H.index("Kernel Name")], ""]
     for m in RAW:
         if m in H:
