@@ -255,6 +255,9 @@ def main():
                                                    "the pixels no other task splats into, bit for bit)")
     ap.add_argument("--economy", action="store_true",
                     help="large configs: the counting pass and the per-launch timing pass stand in for the warm-up steps")
+    ap.add_argument("--lean", action="store_true",
+                    help="(with --economy) no per-launch timing pass and no end-to-end region: the counting pass is the warm-up; "
+                         "the line carries value + step_frac only and says so")
     args = ap.parse_args()
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -340,10 +343,13 @@ def main():
     closest, shadow, nodes, prims = [float(x) for x in counts.tolist()]
     # ---- untimed roofline pass: the traversal kernel timed launch by launch (CUDA events on its stream) with the
     # device to itself (one lane), + the tail kernel's exclusive time
-    gs.set_stats(2)
-    rl = step_resident(want_stats=True)
-    gs.set_stats(0)
-    rl_t = torch.tensor([rl.rayKernelMs, rl.tailMs, float(rl.rayKernelLaunches), rl.renderMs], dtype=torch.float64, device=dev)
+    if args.lean:
+        rl_t = torch.zeros(4, dtype=torch.float64, device=dev)
+    else:
+        gs.set_stats(2)
+        rl = step_resident(want_stats=True)
+        gs.set_stats(0)
+        rl_t = torch.tensor([rl.rayKernelMs, rl.tailMs, float(rl.rayKernelLaunches), rl.renderMs], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(rl_t, op=dist.ReduceOp.MAX)
     ray_ms, tail_excl_ms, ray_launches, serial_ms = [float(x) for x in rl_t.tolist()]
@@ -384,7 +390,7 @@ def main():
         step_e2e()
     barrier()
     e2e_ms = 0.0
-    for _ in range(args.steps):
+    for _ in range(0 if args.lean else args.steps):
         flush.fill_(1)
         e0.record(stream)
         step_e2e()
@@ -399,7 +405,7 @@ def main():
 
     if rank == 0:
         value = nsamples * args.steps / (total_ms * 1e-3) / 1e6
-        e2e_value = nsamples * args.steps / (e2e_ms * 1e-3) / 1e6
+        e2e_value = nsamples * args.steps / (e2e_ms * 1e-3) / 1e6 if e2e_ms > 0 else None
         # algorithmic bytes: 32 B per BVH node whose bounds are tested + 48 B per
         # primitive test (+36 B per shaded hit on a mesh with normals: none in bunny)
         alg_bytes = 32.0 * nodes + 48.0 * prims
@@ -430,8 +436,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "k_wtrace (+ the traversals inside k_vertex<2>)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak if peak else None,
+                "bound": "hbm", "kernel": "k_wtrace (+ the traversals inside k_vertex<2>)", "achieved": achieved if trace_ms > 0 else None, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak if (peak and trace_ms > 0) else None,
                 "per": "GPU (algorithmic bytes of all ranks / n_gpus, over one rank's kernel time)",
                 # the same bytes over the whole timed step (tables, shading, film included): what the throughput implies
                 "step_achieved": step_achieved, "step_frac": step_achieved / peak if peak else None,
@@ -459,6 +465,9 @@ def main():
         }
         if spp != WORKLOADS[args.workload][3]:
             line["INVALID"] = "spp overridden to %d (development run)" % spp
+        if args.lean:
+            line["lean"] = ("--lean run (GPU budget): no per-launch timing pass (roofline.frac / kernel times absent, step_frac stands) "
+                            "and no end-to-end region (e2e.value null); warm-up = the counting pass")
         if world == 1 and not args.no_cpu_baseline and base != "synthetic" and os.path.exists(os.path.join(REPO, "oracle", "_ref", "bin", "pbrt")):
             threads, thread_detail = host_threads()
             v, sec, wall = cpu_reference_rate(args.workload, threads)

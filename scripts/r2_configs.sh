@@ -16,3 +16,8 @@ case "$1" in
       cut -c1-1800 gpurun_out/bench_c5_n8.json ;;
 esac
 tail -5 gpurun_out/c*_err.txt
+# c3lean: configs[2] with the GPU minutes that were left at the end of round 2 (no per-launch timing pass, no e2e region)
+if [ "$1" = c3lean ]; then
+  timeout 170 python bench.py --workload killeroo-c3 --steps 1 --warmup 1 --economy --lean --no-cpu-baseline 2>gpurun_out/c3_err.txt | tail -1 > gpurun_out/bench_c3.json
+  cut -c1-1500 gpurun_out/bench_c3.json; tail -3 gpurun_out/c3_err.txt
+fi
