@@ -16,6 +16,14 @@
 //        random direction pairs (tools/bsdftest.cpp exercises the same classes): per test
 //        wo wi u1 u2 | lambert f, pdf | blinn f, pdf | blinn Sample_f wi, pdf, f | lambert Sample_f wi, pdf | Fr(cos)
 //   refdump rng  <seed> <n>        n RandomUInt() values of RNG(seed)
+//   refdump bvh  <bounds.bin> <maxPrimsInNode> <out.bin>
+//        the reference's own BVHAccel (split method "sah") over n box primitives (bounds.bin: n x 6 float32 = pMin, pMax):
+//        out.bin = uint32 nNodes, the LinearBVHNode array as it lies in memory (32 bytes per node, bvh.cpp:113-123), then
+//        n uint32: the input index of the primitive at each position of the accelerator's reordered primitive list
+//   refdump loopsubdiv <mesh.bin> <nlevels> <out.bin>
+//        the reference's own LoopSubdiv::Refine (mesh.bin: int32 nTriangles, nVertices, 3*nt int32 indices, 3*nv float32 P;
+//        identity transform): out.bin = uint32 nv, nt, then 3*nv float32 P, 3*nv float32 N, 3*nt int32 indices of the
+//        TriangleMesh it creates
 #include "pbrt.h"
 #include "rng.h"
 #include "sampler.h"
@@ -28,10 +36,51 @@
 #include "montecarlo.h"
 
 #include <vector>
+#include <map>
+#include <set>
+#include <string>
+#include <algorithm>
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+
+#include "primitive.h"
+#include "shape.h"
+#include "paramset.h"
+// the accelerator's node array and the refined mesh are private / protected members of the reference's classes: this TOOL
+// reads them where they lie (the library it links is the unmodified build; access specifiers do not change a layout)
+#define private public
+#define protected public
+#include "accelerators/bvh.h"
+#include "shapes/trianglemesh.h"
+#include "shapes/loopsubdiv.h"
+#undef private
+#undef protected
+
+// a primitive that is nothing but its bounds: all BVHAccel's construction looks at (bvh.cpp:153-202)
+class BoxPrimitive : public Primitive {
+public:
+    BoxPrimitive(const BBox &b, uint32_t i) : bounds(b), index(i) {}
+    BBox WorldBound() const { return bounds; }
+    bool Intersect(const Ray &, Intersection *) const { return false; }
+    bool IntersectP(const Ray &) const { return false; }
+    const AreaLight *GetAreaLight() const { return NULL; }
+    BSDF *GetBSDF(const DifferentialGeometry &, const Transform &, MemoryArena &) const { return NULL; }
+    BSSRDF *GetBSSRDF(const DifferentialGeometry &, const Transform &, MemoryArena &) const { return NULL; }
+    BBox bounds;
+    uint32_t index;
+};
+struct DumpedNode {   // LinearBVHNode, accelerators/bvh.cpp:113-123 (defined in the .cpp: restated here to size the dump)
+    float bounds[6];
+    uint32_t offset;
+    uint8_t nPrimitives, axis, pad[2];
+};
+static uint32_t CountNodes(const DumpedNode *nodes, uint32_t i) {   // depth-first layout: a subtree is a contiguous range
+    if (nodes[i].nPrimitives) return 1;
+    const uint32_t left = CountNodes(nodes, i + 1);
+    return 1 + left + CountNodes(nodes, nodes[i].offset);
+}
 
 // a SurfaceIntegrator that only requests sample arrays (what DirectLightingIntegrator::RequestSamples does through
 // LightSampleOffsets / BSDFSampleOffsets, light.cpp:64-68, reflection.cpp:502-506)
@@ -47,6 +96,60 @@ public:
 };
 
 int main(int argc, char **argv) {
+    if (argc >= 5 && !strcmp(argv[1], "bvh")) {
+        FILE *f = fopen(argv[2], "rb");
+        if (!f) return 2;
+        std::vector<float> b;
+        float v[6];
+        while (fread(v, sizeof(float), 6, f) == 6) b.insert(b.end(), v, v + 6);
+        fclose(f);
+        const uint32_t n = (uint32_t)(b.size() / 6);
+        vector<Reference<Primitive> > prims;
+        for (uint32_t i = 0; i < n; ++i)
+            prims.push_back(new BoxPrimitive(BBox(Point(b[6 * i], b[6 * i + 1], b[6 * i + 2]), Point(b[6 * i + 3], b[6 * i + 4], b[6 * i + 5])), i));
+        BVHAccel accel(prims, (uint32_t)atoi(argv[3]), "sah");
+        static_assert(sizeof(DumpedNode) == 32, "LinearBVHNode is 32 bytes");
+        const DumpedNode *nodes = reinterpret_cast<const DumpedNode *>(accel.nodes);
+        const uint32_t nNodes = n ? CountNodes(nodes, 0) : 0;
+        FILE *o = fopen(argv[4], "wb");
+        if (!o) return 2;
+        fwrite(&nNodes, 4, 1, o);
+        fwrite(nodes, sizeof(DumpedNode), nNodes, o);
+        for (size_t i = 0; i < accel.primitives.size(); ++i) {
+            const uint32_t idx = static_cast<const BoxPrimitive *>(accel.primitives[i].GetPtr())->index;
+            fwrite(&idx, 4, 1, o);
+        }
+        fclose(o);
+        return 0;
+    }
+    if (argc >= 5 && !strcmp(argv[1], "loopsubdiv")) {
+        FILE *f = fopen(argv[2], "rb");
+        if (!f) return 2;
+        int nt = 0, nv = 0;
+        if (fread(&nt, 4, 1, f) != 1 || fread(&nv, 4, 1, f) != 1) return 2;
+        std::vector<int> vi(3 * (size_t)nt);
+        std::vector<float> P(3 * (size_t)nv);
+        if (fread(vi.data(), 4, vi.size(), f) != vi.size() || fread(P.data(), 4, P.size(), f) != P.size()) return 2;
+        fclose(f);
+        std::vector<Point> pts(nv);
+        for (int i = 0; i < nv; ++i) pts[i] = Point(P[3 * i], P[3 * i + 1], P[3 * i + 2]);
+        Transform identity;
+        LoopSubdiv subdiv(&identity, &identity, false, nt, nv, vi.data(), pts.data(), atoi(argv[3]));
+        vector<Reference<Shape> > refined;
+        subdiv.Refine(refined);
+        if (refined.size() != 1) return 3;
+        const TriangleMesh *mesh = static_cast<const TriangleMesh *>(refined[0].GetPtr());
+        FILE *o = fopen(argv[4], "wb");
+        if (!o) return 2;
+        const uint32_t onv = (uint32_t)mesh->nverts, ont = (uint32_t)mesh->ntris;
+        fwrite(&onv, 4, 1, o);
+        fwrite(&ont, 4, 1, o);
+        fwrite(mesh->p, sizeof(Point), onv, o);
+        fwrite(mesh->n, sizeof(Normal), onv, o);
+        fwrite(mesh->vertexIndex, sizeof(int), 3 * (size_t)ont, o);
+        fclose(o);
+        return 0;
+    }
     if (argc >= 4 && !strcmp(argv[1], "rng")) {
         RNG rng((uint32_t)strtoul(argv[2], NULL, 10));
         int n = atoi(argv[3]);

@@ -1729,7 +1729,8 @@ int RunLane(LaneJob &job) {
     const bool direct = rp.integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
     const bool vertex1 = !direct && (cfg.vertex & 1), vertex2 = !direct && (cfg.vertex & 2);
     const bool wave1 = !direct && (cfg.wave & 1) && cfg.wavefront && !vertex1;
-    const bool wave2 = !direct && (cfg.wave & 2) && cfg.wavefront;   // phase 2 on the vertex wavefront   // phase 1 on the vertex wavefront (kwave.cuh)
+    // phase 2 on the vertex wavefront (its slot word keeps the bounce index in 8 bits: deeper paths stay with k_vertex<2>)
+    const bool wave2 = !direct && (cfg.wave & 2) && cfg.wavefront && rp.maxDepth <= 250;   // phase 1 on the vertex wavefront (kwave.cuh)
     const bool useWavefront = cfg.wavefront && !vertex1 && !wave1, useWavefront2 = cfg.wavefront2 && useWavefront && !vertex2;
     size_t poolSize = cfg.pool;   // 4 Mi slots x 272 B = 1.1 GB (measured: +17 % over 1 Mi)
     const bool dlSpecular = direct && scene->nSpecularMaterials > 0;

@@ -1,0 +1,111 @@
+"""Direct pins of the two scene-preparation builders on the reference's OWN arrays (missing #8): the
+accelerator's `LinearBVHNode[]` + reordered primitive list (accelerators/bvh.cpp:153-202, 383-399) and the TriangleMesh that
+`LoopSubdiv::Refine` creates (shapes/loopsubdiv.cpp:221-422), dumped by oracle/_ref/bin/refdump (`bvh`, `loopsubdiv` modes:
+our tool linked against the unmodified reference library) -- committed as tests/golden/builders.npz
+(tests/golden/make_builder_golden.py), and taken live on the config scenes' inputs where the reference is built.
+
+Pinned here: the host front end's builders (host/bvh.cpp, host/shapes.cpp).  The device builders are compared with those,
+input for input, by test_bvhbuild_on_host.py / test_loopsubdiv_on_host.py (CPU) and tests/test_zz_gpu_*.py (GPU), and one
+case each is compared with the reference's dump directly below."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import pbrt_v2_b200 as pb
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_builder_golden as mg   # noqa: E402
+
+GOLDEN = np.load(os.path.join(HERE, "golden", "builders.npz"))
+live = pytest.mark.skipif(not os.path.exists(mg.REFDUMP), reason="the reference is not built here (oracle/_ref)")
+
+
+def same_tree(ours, our_order, ref, ref_order):
+    """Our NODE_DTYPE records + primitive order against the reference's LinearBVHNode dump + reordered primitive list: every
+    node's bounds, interior nodes' axis and second-child offset, leaves' primitive count and CONTENT (the input
+    indices of its primitives, in order).
+
+    What is NOT compared is where a leaf's block lies in the reordered primitive array: the reference builds both children
+    inside one call's argument list -- `node->InitInterior(dim, recursiveBuild(.. start, mid ..), recursiveBuild(.. mid, end ..))`,
+    bvh.cpp:257-261, 367-373 -- and C++ leaves the order of the two unspecified: the g++ build this pin runs against builds
+    the RIGHT child first (the first leaf in depth-first order gets the largest primitivesOffset), a left-to-right compiler
+    gives the order the front end uses.  The walk visits the same primitives in the same order either way."""
+    if len(ours) != len(ref) or len(our_order) != len(ref_order):
+        return False
+    # (bounds by value: where a box face lies at zero the builders may keep -0 or +0 -- std::min / std::max return their first
+    # argument on a tie and the operand order of a Union is not part of what is pinned; bounds only enter comparisons)
+    if not (np.array_equal(ours["bmin"], ref["bmin"]) and np.array_equal(ours["bmax"], ref["bmax"]) and
+            np.array_equal(ours["nPrimitives"], ref["nPrimitives"])):
+        return False
+    interior = ref["nPrimitives"] == 0
+    if not (np.array_equal(ours["axis"][interior], ref["axis"][interior]) and np.array_equal(ours["offset"][interior], ref["offset"][interior])):
+        return False
+    for i in np.nonzero(~interior)[0]:
+        n = int(ref["nPrimitives"][i])
+        a, b = int(ours["offset"][i]), int(ref["offset"][i])
+        if not np.array_equal(our_order[a:a + n], ref_order[b:b + n]):
+            return False
+    # (and with g++'s right-first evaluation the reference's blocks are ours mirrored: leaf k from the front = leaf k from the back)
+    return True
+
+
+def same_mesh(ours, ref):
+    return (np.array_equal(ours[2], ref[2]) and ours[0].shape == ref[0].shape and np.array_equal(ours[0], ref[0], equal_nan=True) and
+            np.array_equal(ours[1], ref[1], equal_nan=True))
+
+
+def test_host_bvh_build_is_the_references_tree_golden():
+    keys = sorted(k[:-7] for k in GOLDEN.files if k.startswith("bvh_") and k.endswith("_bounds"))
+    assert len(keys) >= 32
+    multi = 0
+    for k in keys:
+        maxp = int(k.rsplit("_", 1)[1])
+        nodes, order = pb.host_bvh_build(GOLDEN[k + "_bounds"], maxp)
+        assert same_tree(nodes, order, GOLDEN[k + "_nodes"], GOLDEN[k + "_order"]), k
+        multi = max(multi, int(nodes["nPrimitives"].max()))
+    assert multi > 1   # multi-primitive leaves are among the pinned trees
+
+
+def test_host_loopsubdiv_refine_is_the_references_mesh_golden():
+    keys = sorted(k[:-4] for k in GOLDEN.files if k.startswith("subdiv_") and k.endswith("_idx"))
+    assert len(keys) >= 30
+    for k in keys:
+        levels = int(k.rsplit("_L", 1)[1])
+        cm = pb.ControlMesh(GOLDEN[k + "_idx"], GOLDEN[k + "_P"])
+        assert same_mesh(cm.host_refine(levels), (GOLDEN[k + "_rP"], GOLDEN[k + "_rN"], GOLDEN[k + "_ridx"])), k
+
+
+@live
+@pytest.mark.parametrize("base", ["bunny", "killeroo-simple"])
+def test_scene_accelerator_is_the_references_tree_live(staged, base):
+    """the config scenes' own build input (69 k / 66 k refined primitives in the order BVHAccel gets them; the killeroo's are
+    the refined loopsubdiv mesh): the reference's BVHAccel over those bounds IS the accelerator the front end built for the
+    scene (maxPrimsInNode 4), and with maxPrimsInNode 1 (what nested TransformedPrimitive BVHs use) the builders agree too"""
+    from helpers import host_scene
+    pb.keep_build_input(True)
+    try:
+        hs = host_scene(base, 16, 16, 4, 1, tag="-pin")
+    finally:
+        pb.keep_build_input(False)
+    b = hs.build_input()
+    assert len(b) > 60000
+    for maxp in (4, 1):
+        ref_nodes, ref_order = mg.ref_bvh(b, maxp)
+        nodes, order = pb.host_bvh_build(b, maxp)
+        assert same_tree(nodes, order, ref_nodes, ref_order), (base, maxp)
+        if maxp == 4:   # ... and that IS the accelerator the front end built for the scene
+            sn = hs.nodes()
+            assert all(np.array_equal(sn[f], nodes[f]) for f in ("bmin", "bmax", "offset", "nPrimitives", "axis")), base
+
+
+@live
+def test_host_loopsubdiv_refine_is_the_references_mesh_live(staged):
+    """the killeroo's control mesh at the shipped nlevels (1), at configs[3]'s (3) and in between"""
+    from test_loopsubdiv_on_host import _killeroo_control_mesh
+    idx, P = _killeroo_control_mesh()
+    cm = pb.ControlMesh(idx, P)
+    for levels in (1, 2, 3):
+        assert same_mesh(cm.host_refine(levels), mg.ref_loopsubdiv(idx, P, levels)), levels
