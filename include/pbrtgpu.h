@@ -117,7 +117,11 @@ typedef struct PbrtGpuAnimated {
 enum { PBRTGPU_MAT_MATTE = 0, PBRTGPU_MAT_PLASTIC = 1, PBRTGPU_MAT_MEASURED = 2,
        /* SURVEY 8(f) rank 4, host front end + oracle only so far: pbrtgpu_scene_create answers PBRTGPU_EUNSUPPORTED.
         * MIRROR (materials/mirror.cpp): Ks = Kr.  GLASS (materials/glass.cpp): Ks = Kr, Kd = Kt, roughness = index. */
-       PBRTGPU_MAT_MIRROR = 3, PBRTGPU_MAT_GLASS = 4 };
+       PBRTGPU_MAT_MIRROR = 3, PBRTGPU_MAT_GLASS = 4,
+       /* METAL (materials/metal.cpp): Microfacet(1, FresnelConductor(eta, k), Blinn(1 / roughness)); Kd = eta, Ks = k (RGB).
+        * Host front end + oracle (pinned on the reference binary) + device code behind -DPBRT_METAL=1; the shipped
+        * library answers PBRTGPU_EUNSUPPORTED until that code has run on a GPU. */
+       PBRTGPU_MAT_METAL = 5 };
 typedef struct PbrtGpuMaterial {
     uint32_t type;
     float Kd[3];

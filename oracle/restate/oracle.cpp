@@ -656,6 +656,8 @@ struct BxDF {
     Spec R;
     float exponent;   // Blinn
     int measured;     // IrregIsotropicBRDF kd-tree
+    bool conductor = false;        // Microfacet's Fresnel term: FresnelConductor(eta, k) (metal) instead of FresnelDielectric(1.5, 1)
+    Spec eta = Spec(0.f), k = Spec(0.f);
 };
 
 struct BSDFSample { float uDir[2], uComponent; };
@@ -717,6 +719,13 @@ struct BSDF {
         Spec Rperp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
         return (Rparl * Rparl + Rperp * Rperp) / 2.f;
     }
+    static Spec FrCond(float cosi, const Spec &eta, const Spec &k) {   // reflection.cpp:70-79
+        Spec tmp = (eta * eta + k * k) * cosi * cosi;
+        Spec Rparl2 = (tmp - (2.f * eta * cosi) + Spec(1.f)) / (tmp + (2.f * eta * cosi) + Spec(1.f));
+        Spec tmp_f = eta * eta + k * k;
+        Spec Rperp2 = (tmp_f - (2.f * eta * cosi) + Spec(cosi * cosi)) / (tmp_f + (2.f * eta * cosi) + Spec(cosi * cosi));
+        return (Rparl2 + Rperp2) / 2.f;
+    }
     static Spec FresnelDielectricEvaluate(float cosi, float eta_i, float eta_t) {   // reflection.cpp:115-135
         cosi = Clampf(cosi, -1.f, 1.f);
         bool entering = cosi > 0.;
@@ -763,7 +772,8 @@ struct BSDF {
             if (wh.x == 0. && wh.y == 0. && wh.z == 0.) return Spec(0.f);
             wh = Normalize(wh);
             float cosThetaH = Dot(wi, wh);
-            Spec F = FresnelDielectricEvaluate(cosThetaH, 1.5f, 1.f);
+            // plastic.cpp:61: FresnelDielectric(1.5, 1); metal.cpp:63-65: FresnelConductor(eta, k), Evaluate = FrCond(|cosi|, ..)
+            Spec F = b.conductor ? FrCond(fabsf(cosThetaH), b.eta, b.k) : FresnelDielectricEvaluate(cosThetaH, 1.5f, 1.f);
             return b.R * BlinnD(b.exponent, wh) * MicrofacetG(wo, wi, wh) * F / (4.f * cosThetaI * cosThetaO);
         }
         case BX_IRREG_ISO: {                         // IrregIsotropicBRDF::f, reflection.cpp:259-272
@@ -1025,6 +1035,12 @@ struct Renderer {
                 if (e > 10000.f || std::isnan(e)) e = 10000.f;   // Blinn ctor, reflection.h:424-425
                 bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_MICROFACET_BLINN, BSDF_REFLECTION | BSDF_GLOSSY, ks, e, -1};
             }
+        } else if (m.type == PBRTGPU_MAT_METAL) {    // metal.cpp:51-67: Microfacet(1., FresnelConductor(eta, k), Blinn(1 / rough))
+            float e = 1.f / m.roughness;
+            if (e > 10000.f || std::isnan(e)) e = 10000.f;   // Blinn ctor, reflection.h:424-425
+            BxDF b{BX_MICROFACET_BLINN, BSDF_REFLECTION | BSDF_GLOSSY, Spec(1.f), e, -1};
+            b.conductor = true; b.eta = Spec(m.Kd); b.k = Spec(m.Ks);
+            bsdf->bxdfs[bsdf->nBxDFs++] = b;
         } else if (m.type == PBRTGPU_MAT_MIRROR) {   // mirror.cpp:41-53: SpecularReflection(R, FresnelNoOp)
             Spec r = Spec(m.Ks).Clamp();
             if (!r.IsBlack()) bsdf->bxdfs[bsdf->nBxDFs++] = BxDF{BX_SPECULAR_REFLECTION, BSDF_REFLECTION | BSDF_SPECULAR, r, 0.f, -1};

@@ -20,6 +20,8 @@
 //        the reference's own BVHAccel (split method "sah") over n box primitives (bounds.bin: n x 6 float32 = pMin, pMax):
 //        out.bin = uint32 nNodes, the LinearBVHNode array as it lies in memory (32 bytes per node, bvh.cpp:113-123), then
 //        n uint32: the input index of the primitive at each position of the accelerator's reordered primitive list
+//   refdump metal
+//        the RGB coefficients of the default MetalMaterial's eta and k (copper) and its roughness, as hex floats
 //   refdump loopsubdiv <mesh.bin> <nlevels> <out.bin>
 //        the reference's own LoopSubdiv::Refine (mesh.bin: int32 nTriangles, nVertices, 3*nt int32 indices, 3*nv float32 P;
 //        identity transform): out.bin = uint32 nv, nt, then 3*nv float32 P, 3*nv float32 N, 3*nt int32 indices of the
@@ -55,8 +57,10 @@
 #include "accelerators/bvh.h"
 #include "shapes/trianglemesh.h"
 #include "shapes/loopsubdiv.h"
+#include "materials/metal.h"
 #undef private
 #undef protected
+#include "texture.h"
 
 // a primitive that is nothing but its bounds: all BVHAccel's construction looks at (bvh.cpp:153-202)
 class BoxPrimitive : public Primitive {
@@ -96,6 +100,23 @@ public:
 };
 
 int main(int argc, char **argv) {
+    if (argc >= 2 && !strcmp(argv[1], "metal")) {
+        // the default MetalMaterial (materials/metal.cpp:101-112): RGBSpectrum::FromSampled of copper's n and k
+        ParamSet geom, mat;
+        std::map<string, Reference<Texture<float> > > ft;
+        std::map<string, Reference<Texture<Spectrum> > > st;
+        TextureParams tp(geom, mat, ft, st);
+        Transform identity;
+        MetalMaterial *m = CreateMetalMaterial(identity, tp);
+        DifferentialGeometry dg;
+        float rgb[3];
+        m->eta->Evaluate(dg).ToRGB(rgb);
+        printf("eta %a %a %a\n", rgb[0], rgb[1], rgb[2]);
+        m->k->Evaluate(dg).ToRGB(rgb);
+        printf("k %a %a %a\n", rgb[0], rgb[1], rgb[2]);
+        printf("roughness %a\n", m->roughness->Evaluate(dg));
+        return 0;
+    }
     if (argc >= 5 && !strcmp(argv[1], "bvh")) {
         FILE *f = fopen(argv[2], "rb");
         if (!f) return 2;

@@ -1404,7 +1404,11 @@ static int ValidateSceneDesc(const PbrtGpuSceneDesc *desc) {
         if (m.type == PBRTGPU_MAT_MIRROR || m.type == PBRTGPU_MAT_GLASS)
             return Fail(PBRTGPU_EUNSUPPORTED, "specular materials (mirror, glass): this library was built with PBRT_SPECULAR=0");
 #endif
-        if (m.type > PBRTGPU_MAT_GLASS) return Fail(PBRTGPU_EINVAL, "unknown material type");
+#if !PBRT_METAL
+        if (m.type == PBRTGPU_MAT_METAL)
+            return Fail(PBRTGPU_EUNSUPPORTED, "metal material: this library was built with PBRT_METAL=0 (the device code has not run on a GPU yet)");
+#endif
+        if (m.type > PBRTGPU_MAT_METAL) return Fail(PBRTGPU_EINVAL, "unknown material type");
         if (m.type == PBRTGPU_MAT_MATTE && m.sigma != 0.f) return Fail(PBRTGPU_EUNSUPPORTED, "Oren-Nayar (sigma != 0) is out of scope");
         if (m.type == PBRTGPU_MAT_MEASURED && (m.measured < 0 || (uint32_t)m.measured >= desc->nMeasured))
             return Fail(PBRTGPU_EINVAL, "measured material without data");

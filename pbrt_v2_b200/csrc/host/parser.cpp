@@ -271,6 +271,16 @@ int Api::MakeMaterial(const ParamSet &geomParams) {   // core/api.cpp:1062-1077,
         m.desc.Ks[0] = kr.x; m.desc.Ks[1] = kr.y; m.desc.Ks[2] = kr.z;
         m.desc.Kd[0] = kt.x; m.desc.Kd[1] = kt.y; m.desc.Kd[2] = kt.z;
         m.desc.roughness = TexFloat(geomParams, mp, "index", 1.5f);
+    } else if (name == "metal") {    // materials/metal.cpp:101-112
+        m.desc.type = PBRTGPU_MAT_METAL;
+        // defaults: RGBSpectrum::FromSampled of copper's measured n and k (metal.cpp:70-105) -- the RGB coefficients the
+        // reference computes, read out of it by `oracle/_ref/bin/refdump metal` (spectrum-typed parameters, i.e. sampled
+        // SPDs, are not read by this front end: "rgb" / "color" values or these defaults)
+        V3 eta = TexSpectrum(geomParams, mp, "eta", V3(0x1.9a73d8p-3f, 0x1.d91c9cp-1f, 0x1.1a2ad8p+0f));
+        V3 k = TexSpectrum(geomParams, mp, "k", V3(0x1.f4db58p+1f, 0x1.39f6acp+1f, 0x1.1233ap+1f));
+        m.desc.Kd[0] = eta.x; m.desc.Kd[1] = eta.y; m.desc.Kd[2] = eta.z;
+        m.desc.Ks[0] = k.x; m.desc.Ks[1] = k.y; m.desc.Ks[2] = k.z;
+        m.desc.roughness = TexFloat(geomParams, mp, "roughness", .01f);
     } else if (name == "measured") {   // materials/measured.cpp:213-217
         m.desc.type = PBRTGPU_MAT_MEASURED;
         std::string fn = geomParams.FindOneString("filename", mp.FindOneString("filename", ""));
@@ -291,7 +301,7 @@ int Api::MakeMaterial(const ParamSet &geomParams) {   // core/api.cpp:1062-1077,
         }
         m.desc.measured = idx;
     } else {
-        Fail("material \"" + name + "\" is outside the hot-path scope (matte, plastic, measured; mirror and glass up to the oracle)");
+        Fail("material \"" + name + "\" is outside the hot-path scope (matte, plastic, measured, mirror, glass, metal)");
         return -1;
     }
     // identical descriptors share one slot

@@ -133,11 +133,23 @@ SPECULAR_VARIANTS = [
 ]
 
 
+# SURVEY 8(f) rank 4, MetalMaterial: host front end + oracle (pinned on the reference binary) + device code behind
+# -DPBRT_METAL=1 (host-verified; the shipped library answers PBRTGPU_EUNSUPPORTED)
+METAL_VARIANTS = [
+    ("path-metal-copper", "killeroo-simple", 40, 40, 4, 2, {}, [(_M1, 'Material "metal"')]),
+    ("path-metal-params-floor", "killeroo-simple", 40, 40, 4, 2, {"maxdepth": 8},
+     [(_M2, 'Material "metal" "color eta" [.14 .37 1.44] "color k" [3.98 2.38 1.6] "float roughness" [.08]'),
+      (_FLOOR, 'Material "metal" "float roughness" [.3]')]),
+    ("direct-metal", "killeroo-simple", 40, 40, 4, 2, {"integrator": "directlighting"},
+     [(_M1, 'Material "metal" "float roughness" [.05]'), (_M2, 'Material "metal"')]),
+]
+
+
 def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

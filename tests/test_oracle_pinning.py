@@ -184,6 +184,19 @@ def test_oracle_specular_materials_bit_exact_vs_reference_binary(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["path-metal-copper", "path-metal-params-floor", "direct-metal"])
+def test_oracle_metal_material_bit_exact_vs_reference_binary(staged, name):
+    """MetalMaterial (materials/metal.cpp): Microfacet(1, FresnelConductor(eta, k), Blinn(1 / roughness)) -- the default
+    copper coefficients (RGBSpectrum::FromSampled of the measured n and k, read out of the reference by `refdump metal`),
+    rgb-valued eta / k, both integrators"""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 def test_synthetic_scene_text_and_direct_routes_match_reference(staged):
     """the C5 generator: the in-memory build equals the text scene, and the oracle renders it bit-exactly
     like the unmodified reference (multi-pixel tasks)."""
