@@ -274,7 +274,7 @@ int Api::MakeMaterial(const ParamSet &geomParams) {   // core/api.cpp:1062-1077,
     } else if (name == "metal") {    // materials/metal.cpp:101-112
         m.desc.type = PBRTGPU_MAT_METAL;
         // defaults: RGBSpectrum::FromSampled of copper's measured n and k (metal.cpp:70-105) -- the RGB coefficients the
-        // reference computes, read out of it by `oracle/_ref/bin/refdump metal` (spectrum-typed parameters, i.e. sampled
+        // reference computes, read out of it by the test tool `refdump metal` (spectrum-typed parameters, i.e. sampled
         // SPDs, are not read by this front end: "rgb" / "color" values or these defaults)
         V3 eta = TexSpectrum(geomParams, mp, "eta", V3(0x1.9a73d8p-3f, 0x1.d91c9cp-1f, 0x1.1a2ad8p+0f));
         V3 k = TexSpectrum(geomParams, mp, "k", V3(0x1.f4db58p+1f, 0x1.39f6acp+1f, 0x1.1233ap+1f));

@@ -45,3 +45,28 @@ def test_directlighting_recursion_deeper_than_the_slot_is_refused(staged):
     with pytest.raises(pb.PbrtGpuError) as e:
         pb.GpuScene(hs).render(rd)
     assert "recursion frames" in str(e.value)
+
+
+# ---- MetalMaterial: device code behind -DPBRT_METAL=1 (host-verified, tests/test_device_on_host.py); first GPU run next round
+def _metal_build():
+    return "metal" in os.environ.get("PBRTGPU_LIB", "")
+
+
+@pytest.mark.skipif(_metal_build(), reason="a PBRT_METAL build accepts the material")
+def test_metal_is_refused_by_the_shipped_library(staged):
+    """no silent fallback: the shipped kernels carry no FresnelConductor code, so a scene with a metal material is an error"""
+    hs, _ = variant_scene("path-metal-copper")
+    with pytest.raises(pb.PbrtGpuError) as e:
+        pb.GpuScene(hs)
+    assert "PBRT_METAL" in str(e.value)
+
+
+@pytest.mark.skipif(not _metal_build(), reason="needs a PBRT_METAL build: make variants VARIANT_NAMES=metal; PBRTGPU_LIB=ab/libpbrtgpu_metal.so")
+@pytest.mark.parametrize("name", ["path-metal-copper", "path-metal-params-floor", "direct-metal"])
+def test_metal_bit_exact_vs_oracle(staged, name):
+    hs, _ = variant_scene(name)
+    px_gpu, _ = pb.GpuScene(hs).render()
+    px_cpu, _ = oa.render(hs, threads=2)
+    assert np.array_equal(px_gpu["weightSum"], px_cpu["weightSum"])
+    own = px_cpu["weightSum"] == hs.render_desc().samplesPerPixel
+    assert np.array_equal(px_gpu["Lxyz"][own].view(np.uint32), px_cpu["Lxyz"][own].view(np.uint32))

@@ -51,7 +51,8 @@ def test_crop_window_extent(staged):
 @pytest.mark.parametrize("text,needle", [
     ('SurfaceIntegrator "whitted"', "outside the scope"),
     ('Sampler "random"', "out of scope"),
-    ('Material "metal"', "outside the hot-path scope"),
+    ('Material "uber"', "outside the hot-path scope"),
+    ('Material "metal" "spectrum eta" "spds/Au.eta.spd"', "not supported by this front end"),
     ('Texture "t" "float" "constant"', "outside the hot-path scope"),
 ])
 def test_out_of_scope_directives_fail_loudly(staged, text, needle):
