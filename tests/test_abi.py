@@ -110,3 +110,17 @@ def test_render_desc_validation_precedes_the_device():
         with pytest.raises(pb.PbrtGpuError) as e:
             pb.ld_samples(rd, 0)
         assert needle in str(e.value), str(e.value)
+
+
+def test_render_kernels_are_the_gpu_verified_ones():
+    """No GPU here: what guards the kernels between GPU visits is their SASS.  scripts/sass_fingerprint.sh holds the md5 of
+    pbrtgpu.cu's cubin as it ran the round's last full GPU visit (profiles/r02g_*); experiments that are meant to be
+    compiled out (-DPBRT_METAL=0 ...) must not move it.  (A deliberate kernel change updates the fingerprint together with a
+    GPU run.)"""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not installed")
+    r = subprocess.run(["bash", os.path.join(pb.REPO, "scripts", "sass_fingerprint.sh")], cwd=pb.REPO, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
