@@ -1,6 +1,9 @@
 #!/usr/bin/env python
 """Random in-scope scenes: the unmodified reference binary vs the oracle vs the device code compiled for the host
-(tests/native/device_on_host.cpp).  CPU only.  usage: fuzz_scenes.py [n] [seed0]"""
+(tests/native/device_on_host.cpp).  CPU only.  usage: fuzz_scenes.py [n] [seed0] [flags]
+flags (joined with +): specular, metal (materials; metal builds the harness with -DPBRT_METAL=1), pairs (-DPBRT_PAIR_NODES=1),
+crop, wave (PathIntegrator scenes run through the vertex-wavefront KERNELS -- kwave.cuh's k_wshade / k_weval / k_wtrace /
+k_wcompact, launches as loops -- over a pool of 3, 17 or 4096 slots instead of the state machine)"""
 import ctypes as C, os, subprocess, sys
 import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -42,7 +45,12 @@ def gen(rng, path, animated=None):
             t.append("Scale %s" % fl(sc))
         return t
     specular = len(sys.argv) > 3 and "specular" in sys.argv[3]
+    metal = len(sys.argv) > 3 and "metal" in sys.argv[3]
     def material():
+        if metal and rng.rand() < .3:
+            if rng.rand() < .4: return 'Material "metal" "float roughness" [%g]' % rng.choice([.01, .05, .3])
+            return 'Material "metal" "color eta" [%s] "color k" [%s] "float roughness" [%g]' % (
+                fl(rng.uniform(.1, 2, 3)), fl(rng.uniform(1, 5, 3)), rng.choice([.5, .1, .02, 1e-5]))
         if specular and rng.rand() < .4:
             if rng.rand() < .5: return 'Material "mirror" "color Kr" [%s]' % fl(rng.uniform(.3, 1, 3))
             return 'Material "glass" "color Kr" [%s] "color Kt" [%s] "float index" [%g]' % (
@@ -128,9 +136,11 @@ def main():
     # optional third argument: kernel build flags to fuzz, e.g. "specular", "pairs", "specular+pairs"
     spec = len(sys.argv) > 3 and "specular" in sys.argv[3]
     pairs = len(sys.argv) > 3 and "pairs" in sys.argv[3]
-    so = "/tmp/libdoh_fuzz%s%s.so" % ("_spec" if spec else "", "_pairs" if pairs else "")
+    metal = len(sys.argv) > 3 and "metal" in sys.argv[3]
+    wave = len(sys.argv) > 3 and "wave" in sys.argv[3]
+    so = "/tmp/libdoh_fuzz%s%s%s.so" % ("_spec" if spec else "", "_pairs" if pairs else "", "_metal" if metal else "")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic",
-                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) + (["-DPBRT_PAIR_NODES=1"] if pairs else []) +
+                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) + (["-DPBRT_PAIR_NODES=1"] if pairs else []) + (["-DPBRT_METAL=1"] if metal else []) +
                    [os.path.join(REPO, "tests/native/device_on_host.cpp"), "-o", so], check=True)
     doh = C.CDLL(so)
     doh.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
@@ -153,6 +163,7 @@ def main():
         o = hs.pixels_to_rgb(px)
         rd = hs.render_desc()
         px2 = hs.new_pixels()
+        doh.doh_set_vertex_form(int(rng.choice([3, 17, 4096])) if wave else 0)
         doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
         own = px["weightSum"] == spp
         d_ref = int((o.view(np.uint32) != ref.view(np.uint32)).any(axis=2)[own].sum()) if o.shape == ref.shape else -1
