@@ -115,7 +115,7 @@ typedef struct PbrtGpuAnimated {
 
 /* ---- materials (constant textures only), materials/{matte,plastic,measured} - */
 enum { PBRTGPU_MAT_MATTE = 0, PBRTGPU_MAT_PLASTIC = 1, PBRTGPU_MAT_MEASURED = 2,
-       /* SURVEY 8(f) rank 4, host front end + oracle only so far: pbrtgpu_scene_create answers PBRTGPU_EUNSUPPORTED.
+       /* SURVEY 8(f) rank 4, on the device since round 2 (both integrators).
         * MIRROR (materials/mirror.cpp): Ks = Kr.  GLASS (materials/glass.cpp): Ks = Kr, Kd = Kt, roughness = index. */
        PBRTGPU_MAT_MIRROR = 3, PBRTGPU_MAT_GLASS = 4,
        /* METAL (materials/metal.cpp): Microfacet(1, FresnelConductor(eta, k), Blinn(1 / roughness)); Kd = eta, Ks = k (RGB).
