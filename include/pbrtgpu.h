@@ -146,12 +146,15 @@ typedef struct PbrtGpuMeasured {
 } PbrtGpuMeasured;
 
 /* ---- lights, lights/{point,diffuse}.cpp, core/light.cpp:114-171 ------------ */
-enum { PBRTGPU_LIGHT_POINT = 0, PBRTGPU_LIGHT_DIFFUSE_AREA = 1 };
+enum { PBRTGPU_LIGHT_POINT = 0, PBRTGPU_LIGHT_DIFFUSE_AREA = 1,
+       /* InfiniteAreaLight (lights/infinite.cpp) with a constant radiance (no "mapname": a 1x1 radiance map).  Host front end
+        * + oracle (pinned on the reference binary) only: pbrtgpu_scene_create answers PBRTGPU_EUNSUPPORTED. */
+       PBRTGPU_LIGHT_INFINITE = 2 };
 typedef struct PbrtGpuLight {
     uint32_t type;
-    float    L[3];        /* POINT: Intensity; AREA: Lemit                      */
+    float    L[3];        /* POINT: Intensity; AREA: Lemit; INFINITE: L * scale  */
     float    pos[3];      /* POINT: lightPos (world)                            */
-    uint32_t firstShape;  /* AREA: ShapeSet::shapes, into lightShapes[]         */
+    uint32_t firstShape;  /* AREA: ShapeSet::shapes, into lightShapes[]; INFINITE: LightToWorld, into xforms[] */
     uint32_t nShapes;     /* in scope: exactly 1 (sphere or disk)               */
     float    sumArea;     /* ShapeSet::sumArea                                  */
     int32_t  nSamples;    /* Light::nSamples (core/light.h:53,78; "nsamples" of an area light); 0 reads as 1 */

@@ -587,6 +587,7 @@ inline float AbsCosTheta(const Vec &w) { return fabsf(w.z); }
 inline float SinTheta2(const Vec &w) { return std::max(0.f, 1.f - CosTheta(w) * CosTheta(w)); }
 inline float SinTheta(const Vec &w) { return sqrtf(SinTheta2(w)); }
 inline bool SameHemisphere(const Vec &w, const Vec &wp) { return w.z * wp.z > 0.f; }
+inline float SphericalTheta(const Vec &v) { return acosf(Clampf(v.z, -1.f, 1.f)); }   // geometry.h:640-642
 inline float SphericalPhi(const Vec &v) {   // geometry.h:644-647
     float p = atan2f(v.y, v.x);
     return (p < 0.f) ? p + 2.f * PI_F : p;
@@ -1122,9 +1123,60 @@ struct Renderer {
         return XfPoint(x.m, p);
     }
 
-    // ShapeSet::Pdf(p, wi), core/light.cpp:157-162 (one shape)
+    // ---- InfiniteAreaLight over a 1x1 radiance map (lights/infinite.cpp:67-104 without "mapname": texels[0] = L) ----
+    // MIPMap::Lookup(s, t, width = 0) (core/mipmap.h:239-255): level = nLevels - 1 + Log2(1e-8) < 0 -> triangle(0, s, t)
+    // (:259-269): bilinear weights over four reads of the one texel (TEXTURE_REPEAT wraps every index to 0)
+    static Spec InfiniteLookup(const PbrtGpuLight &l, float s, float t) {
+        s = s * 1 - 0.5f;   // pyramid[0]->uSize() == vSize() == 1
+        t = t * 1 - 0.5f;
+        int s0 = Floor2Int(s), t0 = Floor2Int(t);
+        float ds = s - s0, dt = t - t0;
+        Spec texel(l.L);
+        return (1.f - ds) * (1.f - dt) * texel + (1.f - ds) * dt * texel + ds * (1.f - dt) * texel + ds * dt * texel;
+    }
+    // Light::Le(ray) (core/light.cpp:59-61: black) / InfiniteAreaLight::Le (infinite.cpp:114-119)
+    Spec LightLe(const PbrtGpuLight &l, const Ray &r) const {
+        if (l.type != PBRTGPU_LIGHT_INFINITE) return Spec(0.f);
+        Vec wh = Normalize(XfVector(sv.d->xforms[l.firstShape].mInv, r.d));   // WorldToLight(r.d)
+        float s = SphericalPhi(wh) * INV_TWOPI_F;
+        float t = SphericalTheta(wh) * INV_PI_F;
+        return InfiniteLookup(l, s, t);
+    }
+    Spec EscapedLe(const Ray &r) const {   // "for every light: L += light->Le(ray)" (samplerrenderer.cpp:239-242, path.cpp:114-116)
+        Spec L(0.f);
+        for (uint32_t i = 0; i < sv.d->nLights; ++i) L += LightLe(sv.d->lights[i], r);
+        return L;
+    }
+    // the sampling distribution of the 1x1 map (infinite.cpp:88-103, montecarlo.h:99-167): one function value
+    // f = L.y() * sinf(pi * .5); Distribution1D over it: cdf = {0, 1} (or {0, 1} by the funcInt == 0 branch), funcInt = f
+    static float InfiniteFunc(const PbrtGpuLight &l) { return Spec(l.L).y() * sinf(PI_F * float(0 + .5f) / float(1)); }
+    // Distribution2D::SampleContinuous(u0, u1, uv, &pdf) over that function
+    static void InfiniteSampleContinuous(const PbrtGpuLight &l, float u0, float u1, float uv[2], float *pdf) {
+        const float f = InfiniteFunc(l);
+        // pMarginal->SampleContinuous(u1): offset 0, du = (u1 - cdf[0]) / (cdf[1] - cdf[0]), pdf = func[0] / funcInt
+        float pdf1 = f / f;        // marginal: func[0] = the row's funcInt = f, funcInt = f / 1 = f
+        uv[1] = (0 + (u1 - 0.f) / (1.f - 0.f)) / 1;
+        float pdf0 = f / f;
+        uv[0] = (0 + (u0 - 0.f) / (1.f - 0.f)) / 1;
+        *pdf = pdf0 * pdf1;
+    }
+    // Distribution2D::Pdf(u, v), montecarlo.h:158-166
+    static float InfiniteMapPdf(const PbrtGpuLight &l, float, float) {
+        const float f = InfiniteFunc(l);
+        if (f * f == 0.f) return 0.f;
+        return (f * f) / (f * f);
+    }
+
+    // ShapeSet::Pdf(p, wi), core/light.cpp:157-162 (one shape); InfiniteAreaLight::Pdf, infinite.cpp:229-239
     float LightPdf(const PbrtGpuLight &l, const Vec &p, const Vec &wi) const {
         if (l.type == PBRTGPU_LIGHT_POINT) return 0.;
+        if (l.type == PBRTGPU_LIGHT_INFINITE) {
+            Vec w = XfVector(sv.d->xforms[l.firstShape].mInv, wi);
+            float theta = SphericalTheta(w), phi = SphericalPhi(w);
+            float sintheta = sinf(theta);
+            if (sintheta == 0.f) return 0.f;
+            return InfiniteMapPdf(l, phi * INV_TWOPI_F, theta * INV_PI_F) / (2.f * PI_F * PI_F * sintheta);
+        }
         float pdf = 0.f;
         for (uint32_t i = 0; i < l.nShapes; ++i) {
             const PbrtGpuLightShape &ls = sv.d->lightShapes[l.firstShape + i];
@@ -1144,6 +1196,19 @@ struct Renderer {
             float dist = Distance(p, lightPos);
             *vis = Ray(p, (lightPos - p) / dist, pEpsilon, dist * (1.f - 0.f), time);
             return Spec(l.L) / DistanceSquared(lightPos, p);
+        }
+        if (l.type == PBRTGPU_LIGHT_INFINITE) {   // infinite.cpp:195-226
+            float uv[2], mapPdf;
+            InfiniteSampleContinuous(l, ls.uPos[0], ls.uPos[1], uv, &mapPdf);
+            if (mapPdf == 0.f) { *pdf = 0.f; return Spec(0.f); }
+            float theta = uv[1] * PI_F, phi = uv[0] * 2.f * PI_F;
+            float costheta = cosf(theta), sintheta = sinf(theta);
+            float sinphi = sinf(phi), cosphi = cosf(phi);
+            *wi = XfVector(sv.d->xforms[l.firstShape].m, Vec(sintheta * cosphi, sintheta * sinphi, costheta));
+            *pdf = mapPdf / (2.f * PI_F * PI_F * sintheta);
+            if (sintheta == 0.f) *pdf = 0.f;
+            *vis = Ray(p, *wi, pEpsilon, INF_F, time);   // VisibilityTester::SetRay, light.h:93-96
+            return InfiniteLookup(l, uv[0], uv[1]);
         }
         Vec ns;
         // ShapeSet::Sample(p, ls, Ns), light.cpp:142-146: SampleDiscrete over one shape is always 0
@@ -1195,7 +1260,8 @@ struct Renderer {
                 Ray ray(p, wi, rayEpsilon, INF_F, time);
                 if (sv.Intersect(ray, &lightIsect, cnt)) {
                     if (sv.d->primitives[lightIsect.prim].areaLight == lightIdx) Li = Le(lightIsect, -wi);
-                }   // else light->Le(ray) == 0 for area lights
+                } else
+                    Li = LightLe(light, ray);   // black for area lights
                 if (!Li.IsBlack()) Ld += f * Li * AbsDot(wi, n) * weight / bsdfPdf;
             }
         }
@@ -1278,6 +1344,7 @@ struct Renderer {
             Intersection next;
             Spec Li(0.f);
             if (sv.Intersect(rd, &next, cnt)) Li = DirectLi(rd, next, sample, rng, cnt, depth + 1);
+            else Li += EscapedLe(rd);   // samplerrenderer.cpp:238-242
             Li = Spec(1.f) * Li + Spec(0.f);
             L = f * Li * AbsDot(wi, n) / pdf;
         }
@@ -1352,7 +1419,11 @@ struct Renderer {
                 pathThroughput /= continueProbability;
             }
             if (bounces == rd->maxDepth) break;
-            if (!sv.Intersect(ray, &localIsect, cnt)) break;   // (specularBounce: lights' Le(ray) == 0)
+            if (!sv.Intersect(ray, &localIsect, cnt)) {
+                if (specularBounce)
+                    for (uint32_t i = 0; i < sv.d->nLights; ++i) L += pathThroughput * LightLe(sv.d->lights[i], ray);   // path.cpp:113-117
+                break;
+            }
             isectp = &localIsect;
         }
         return L;
@@ -1410,6 +1481,8 @@ struct Renderer {
                     Spec Li(0.f);
                     if (sv.Intersect(ray, &isect, cnt))
                         Li = direct ? DirectLi(ray, isect, &samples[i], rng, cnt) : PathLi(ray, isect, &samples[i], rng, cnt);
+                    else
+                        Li += EscapedLe(ray);   // "Handle ray that doesn't intersect any geometry"
                     Ls[i] = 1.f * (Spec(1.f) * Li + Spec(0.f));
                     if (Ls[i].HasNaNs()) Ls[i] = Spec(0.f);
                     else if (Ls[i].y() < -1e-5) Ls[i] = Spec(0.f);

@@ -1391,6 +1391,9 @@ static int ValidateSceneDesc(const PbrtGpuSceneDesc *desc) {
     if (desc->nAnimated > 255) return Fail(PBRTGPU_EUNSUPPORTED, "more than 255 TransformedPrimitives");
     for (uint32_t i = 0; i < desc->nLights; ++i) {
         const PbrtGpuLight &l = desc->lights[i];
+        if (l.type == PBRTGPU_LIGHT_INFINITE)
+            return Fail(PBRTGPU_EUNSUPPORTED, "infinite area lights: host front end and oracle only so far (no device code)");
+        if (l.type > PBRTGPU_LIGHT_INFINITE) return Fail(PBRTGPU_EINVAL, "unknown light type");
         if (l.type == PBRTGPU_LIGHT_DIFFUSE_AREA) {
             if (l.nShapes != 1) return Fail(PBRTGPU_EUNSUPPORTED, "area lights over more than one shape are out of scope");
             if ((uint64_t)l.firstShape + l.nShapes > desc->nLightShapes) return Fail(PBRTGPU_EINVAL, "light shape range out of bounds");

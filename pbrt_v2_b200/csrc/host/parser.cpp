@@ -399,7 +399,20 @@ bool Api::DoShape(const std::string &name, const ParamSet &params) {   // core/a
 }
 
 bool Api::DoLight(const std::string &name, const ParamSet &params) {   // core/api.cpp:956-967
-    if (name != "point") return Fail("light \"" + name + "\" is outside the hot-path scope (point, area)");
+    if (name == "infinite" || name == "exinfinite") {   // lights/infinite.cpp:256-265 (api.cpp:549-551: both names)
+        V3 L = params.FindOneSpectrum("L", V3(1, 1, 1));
+        V3 sc = params.FindOneSpectrum("scale", V3(1, 1, 1));
+        if (!params.FindOneString("mapname", "").empty())
+            return Fail("infinite light: environment maps (\"mapname\") are outside the hot-path scope (constant radiance only)");
+        Light lt;
+        lt.desc.type = PBRTGPU_LIGHT_INFINITE;
+        lt.desc.nSamples = std::max(1, params.FindOneInt("nsamples", 1));   // Light ctor, light.cpp:46-51
+        lt.desc.L[0] = L.x * sc.x; lt.desc.L[1] = L.y * sc.y; lt.desc.L[2] = L.z * sc.z;
+        lt.lightToWorld = curTransform.t[0];
+        scene->lights.push_back(lt);
+        return true;
+    }
+    if (name != "point") return Fail("light \"" + name + "\" is outside the hot-path scope (point, area, infinite)");
     // lights/point.cpp:68-75 and :41-46
     V3 I = params.FindOneSpectrum("I", V3(1, 1, 1));
     V3 sc = params.FindOneSpectrum("scale", V3(1, 1, 1));

@@ -276,7 +276,8 @@ bool Scene::Flatten(std::string *err) {
             sumArea += ls.area;
             gl.sumArea = sumArea;
             fLightShapes.push_back(ls);
-        }
+        } else if (gl.type == PBRTGPU_LIGHT_INFINITE)
+            gl.firstShape = xformOf(&l.lightToWorld);
         fLights.push_back(gl);
     }
     if (bvh.nodes.empty()) { *err = "scene has no primitives"; return false; }

@@ -124,6 +124,7 @@ bool LoadIrregIsotropicBRDF(const std::string &filename, MeasuredData *out, std:
 struct Light {   // core/light.h:48-82; lights/point.h, lights/diffuse.h
     PbrtGpuLight desc;
     const Shape *shape;   // DiffuseAreaLight: the ShapeSet's (single) shape
+    Transform lightToWorld;   // InfiniteAreaLight: Light::LightToWorld (core/light.h:57-60)
     Light() : shape(nullptr) { memset(&desc, 0, sizeof(desc)); }
 };
 

@@ -145,11 +145,26 @@ METAL_VARIANTS = [
 ]
 
 
+# SURVEY 8(f) rank 4, InfiniteAreaLight with a constant radiance: host front end + oracle (pinned on the reference binary); the
+# device answers PBRTGPU_EUNSUPPORTED
+_WB = "WorldBegin"
+_INF1 = _WB + '\nAttributeBegin\nRotate 35 1 .2 0\nLightSource "infinite" "color L" [.4 .5 .7]\nAttributeEnd\n'
+_INF2 = _WB + '\nLightSource "infinite" "color L" [.2 .2 .2] "color scale" [2 1 .5] "integer nsamples" [4]\n'
+INFINITE_VARIANTS = [
+    ("path-infinite", "killeroo-simple", 40, 40, 4, 2, {}, [(_WB, _INF1)]),
+    ("path-infinite-specular", "killeroo-simple", 40, 40, 4, 2, {"maxdepth": 8},
+     [(_WB, _INF2), (_M1, 'Material "glass"'), (_M2, 'Material "mirror"')]),
+    ("direct-infinite", "killeroo-simple", 40, 40, 4, 2, {"integrator": "directlighting"}, [(_WB, _INF2), (_M2, 'Material "mirror"')]),
+    ("direct-one-infinite", "bunny", 40, 40, 4, 1, {"integrator": "directlighting", "strategy": "one"}, [(_WB, _INF1)]),
+    ("path-infinite-bunny", "bunny", 40, 40, 8, 64, {}, [(_WB, _INF1)]),
+]
+
+
 def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

@@ -197,6 +197,21 @@ def test_oracle_metal_material_bit_exact_vs_reference_binary(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["path-infinite", "path-infinite-specular", "direct-infinite", "direct-one-infinite",
+                                  "path-infinite-bunny"])
+def test_oracle_infinite_light_bit_exact_vs_reference_binary(staged, name):
+    """InfiniteAreaLight with a constant radiance (lights/infinite.cpp over its 1x1 map: MIPMap::Lookup's bilinear weights,
+    Distribution2D sampling, Pdf): Le of escaping camera rays (samplerrenderer.cpp:238-242), of escaping specular bounces
+    (path.cpp:113-117, and through SpecularReflect / SpecularTransmit under directlighting), of escaping MIS rays
+    (integrator.cpp:163-164), the light sample itself; rotated light-to-world transform, nsamples, both strategies"""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 def test_synthetic_scene_text_and_direct_routes_match_reference(staged):
     """the C5 generator: the in-memory build equals the text scene, and the oracle renders it bit-exactly
     like the unmodified reference (multi-pixel tasks)."""
