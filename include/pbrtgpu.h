@@ -200,7 +200,7 @@ typedef struct PbrtGpuRenderDesc {
     /* ImageFilm (film/image.cpp:40-51) */
     int32_t xResolution, yResolution;
     float   cropWindow[4];
-    float   filterXWidth, filterYWidth;   /* box filter only (filters/box.cpp)  */
+    float   filterXWidth, filterYWidth;   /* Filter::xWidth / yWidth; the weights: filterTable below */
     /* LDSampler (samplers/lowdiscrepancy.cpp:40-51): power of two              */
     int32_t samplesPerPixel;
     /* PathIntegrator (integrators/path.cpp:125-128) / DirectLightingIntegrator
@@ -228,6 +228,13 @@ typedef struct PbrtGpuRenderDesc {
      * (background) and expensive (object) pixels across GPUs; tasks share nothing,
      * so the sum of the shards' films is the one-GPU film.                       */
     int32_t shardCount, shardIndex, shardBlock;
+    /* The pixel filter as ImageFilm holds it (film/image.cpp:57-69): Filter::Evaluate at the 16 x 16 table positions
+     * ((i + .5) * width / 16), row = y.  hasFilterTable == 0 reads as the box filter (every weight 1).  Filters wider than
+     * half a pixel (gaussian, mitchell, sinc, triangle, wide boxes) make every sample splat into neighbouring tasks' pixels:
+     * host front end + oracle (pinned on the reference binary at --ncores 1, where the reference's own sums are ordered);
+     * the device entry points answer PBRTGPU_EUNSUPPORTED for them.  (Appended in round 2: earlier offsets are unchanged.) */
+    int32_t hasFilterTable;
+    float   filterTable[256];
 } PbrtGpuRenderDesc;
 
 /* ImageFilm::Pixel {Lxyz[3], weightSum} (film/image.h:69-78), row-major over

@@ -1446,9 +1446,21 @@ struct Renderer {
         xyz[0] = 0.412453f * L.c[0] + 0.357580f * L.c[1] + 0.180423f * L.c[2];
         xyz[1] = 0.212671f * L.c[0] + 0.715160f * L.c[1] + 0.072169f * L.c[2];
         xyz[2] = 0.019334f * L.c[0] + 0.119193f * L.c[1] + 0.950227f * L.c[2];
-        const float filterWt = 1.f;
+        // filter table offsets, image.cpp:101-112 (Filter::invXWidth = 1.f / xWidth, filter.h:47-49)
+        const float invXWidth = 1.f / rd->filterXWidth, invYWidth = 1.f / rd->filterYWidth;
+        int ifx[64], ify[64];
+        if (x1 - x0 >= 64 || y1 - y0 >= 64) return;   // (filters wider than 32 pixels: not a configuration anyone renders)
+        for (int x = x0; x <= x1; ++x) {
+            float fx = fabsf((x - dimageX) * invXWidth * 16);
+            ifx[x - x0] = std::min(Floor2Int(fx), 16 - 1);
+        }
+        for (int y = y0; y <= y1; ++y) {
+            float fy = fabsf((y - dimageY) * invYWidth * 16);
+            ify[y - y0] = std::min(Floor2Int(fy), 16 - 1);
+        }
         for (int y = y0; y <= y1; ++y)
             for (int x = x0; x <= x1; ++x) {
+                const float filterWt = rd->hasFilterTable ? rd->filterTable[ify[y - y0] * 16 + ifx[x - x0]] : 1.f;
                 PbrtGpuPixel &pixel = pixels[(size_t)(y - yPixelStart) * xPixelCount + (x - xPixelStart)];
                 pixel.Lxyz[0] += filterWt * xyz[0];   // non-atomic, like the reference (image.cpp:122-127)
                 pixel.Lxyz[1] += filterWt * xyz[1];

@@ -43,6 +43,7 @@ class RenderDesc(C.Structure):
         ("nTasks", C.c_int32),
         ("taskBegin", C.c_int32), ("taskEnd", C.c_int32),
         ("shardCount", C.c_int32), ("shardIndex", C.c_int32), ("shardBlock", C.c_int32),
+        ("hasFilterTable", C.c_int32), ("filterTable", C.c_float * 256),
     ]
 
 

@@ -1236,6 +1236,9 @@ int ValidateRenderDesc(const PbrtGpuRenderDesc &rd) {
     if (spp > 8192) return Fail(PBRTGPU_EUNSUPPORTED, "samplesPerPixel > 8192 does not fit the table kernel's shared memory");
     if (rd.filterXWidth > 0.5f || rd.filterYWidth > 0.5f)
         return Fail(PBRTGPU_EUNSUPPORTED, "filters wider than the 0.5 box need cross-task splats (out of scope)");
+    if (rd.hasFilterTable)
+        for (int i = 0; i < 256; ++i)
+            if (rd.filterTable[i] != 1.f) return Fail(PBRTGPU_EUNSUPPORTED, "pixel filters other than the box filter are rendered by the oracle only");
     if (rd.nTasks <= 0 || rd.taskBegin < 0 || rd.taskEnd > rd.nTasks || rd.taskBegin > rd.taskEnd)
         return Fail(PBRTGPU_EINVAL, "bad task range");
     if (rd.maxDepth < 0) return Fail(PBRTGPU_EINVAL, "bad maxDepth");

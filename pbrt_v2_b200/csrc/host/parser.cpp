@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <functional>
 #include <set>
 #include <sstream>
 
@@ -430,9 +431,51 @@ bool Api::DoLight(const std::string &name, const ParamSet &params) {   // core/a
 
 bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
     // --- film + filter + camera (api.cpp:1272-1281, film/image.cpp:220-258) ---
-    if (FilterName != "box") return Fail("pixel filter \"" + FilterName + "\" is out of scope (box only)");
-    float fxw = FilterParams.FindOneFloat("xwidth", 0.5f), fyw = FilterParams.FindOneFloat("ywidth", 0.5f);
-    if (fxw > 0.5f || fyw > 0.5f) return Fail("box filter wider than 0.5 needs cross-task splats: out of scope");
+    // MakeFilter, core/api.cpp:572-589; filters/{box,gaussian,mitchell,sinc,triangle}.cpp.  Filters wider than half a pixel
+    // are rendered by the oracle only (the device entry points refuse them): see PbrtGpuRenderDesc::filterTable
+    float fxw, fyw;
+    std::function<float(float, float)> evaluate;
+    if (FilterName == "box") {
+        fxw = FilterParams.FindOneFloat("xwidth", 0.5f); fyw = FilterParams.FindOneFloat("ywidth", 0.5f);
+        evaluate = [](float, float) { return 1.f; };
+    } else if (FilterName == "gaussian") {   // gaussian.h:47-58
+        fxw = FilterParams.FindOneFloat("xwidth", 2.f); fyw = FilterParams.FindOneFloat("ywidth", 2.f);
+        const float alpha = FilterParams.FindOneFloat("alpha", 2.f);
+        const float expX = expf(-alpha * fxw * fxw), expY = expf(-alpha * fyw * fyw);
+        auto gaussian = [alpha](float d, float expv) { return std::max(0.f, float(expf(-alpha * d * d) - expv)); };
+        evaluate = [=](float x, float y) { return gaussian(x, expX) * gaussian(y, expY); };
+    } else if (FilterName == "mitchell") {   // mitchell.h:47-63
+        fxw = FilterParams.FindOneFloat("xwidth", 2.f); fyw = FilterParams.FindOneFloat("ywidth", 2.f);
+        const float B = FilterParams.FindOneFloat("B", 1.f / 3.f), C = FilterParams.FindOneFloat("C", 1.f / 3.f);
+        const float invX = 1.f / fxw, invY = 1.f / fyw;
+        auto mitchell1D = [B, C](float x) {
+            x = fabsf(2.f * x);
+            if (x > 1.f)
+                return ((-B - 6 * C) * x * x * x + (6 * B + 30 * C) * x * x + (-12 * B - 48 * C) * x + (8 * B + 24 * C)) * (1.f / 6.f);
+            else
+                return ((12 - 9 * B - 6 * C) * x * x * x + (-18 + 12 * B + 6 * C) * x * x + (6 - 2 * B)) * (1.f / 6.f);
+        };
+        evaluate = [=](float x, float y) { return mitchell1D(x * invX) * mitchell1D(y * invY); };
+    } else if (FilterName == "sinc") {       // sinc.h:47-59
+        fxw = FilterParams.FindOneFloat("xwidth", 4.f); fyw = FilterParams.FindOneFloat("ywidth", 4.f);
+        const float tau = FilterParams.FindOneFloat("tau", 3.f);
+        const float invX = 1.f / fxw, invY = 1.f / fyw;
+        auto sinc1D = [tau](float x) {
+            x = fabsf(x);
+            if (x < 1e-5) return 1.f;
+            if (x > 1.) return 0.f;
+            x *= kPi;
+            float sinc = sinf(x) / x;
+            float lanczos = sinf(x * tau) / (x * tau);
+            return sinc * lanczos;
+        };
+        evaluate = [=](float x, float y) { return sinc1D(x * invX) * sinc1D(y * invY); };
+    } else if (FilterName == "triangle") {   // triangle.cpp:39-42
+        fxw = FilterParams.FindOneFloat("xwidth", 2.f); fyw = FilterParams.FindOneFloat("ywidth", 2.f);
+        const float xw = fxw, yw = fyw;
+        evaluate = [=](float x, float y) { return std::max(0.f, xw - fabsf(x)) * std::max(0.f, yw - fabsf(y)); };
+    } else
+        return Fail("pixel filter \"" + FilterName + "\" unknown");
     if (FilmName != "image") return Fail("film \"" + FilmName + "\" unknown");
     std::string filename = FilmParams.FindOneString("filename", "");
     if (!opt.imageFile.empty() && filename.empty()) filename = opt.imageFile;
@@ -450,6 +493,13 @@ bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
     std::unique_ptr<GpuSamplerRenderer> r(new GpuSamplerRenderer);
     r->nCores = opt.nCores;
     r->film.reset(new ImageFilm(xres, yres, fxw, fyw, crop, filename));
+    for (int y = 0; y < 16; ++y) {   // film/image.cpp:57-69 (FILTER_TABLE_SIZE 16)
+        float fy = ((float)y + .5f) * fyw / 16;
+        for (int x = 0; x < 16; ++x) {
+            float fx = ((float)x + .5f) * fxw / 16;
+            r->film->filterTable[16 * y + x] = evaluate(fx, fy);
+        }
+    }
     if (CameraName != "perspective") return Fail("camera \"" + CameraName + "\" is out of scope (perspective)");
     if (CameraToWorld.IsAnimated()) return Fail("animated cameras are out of scope");
     {   // cameras/perspective.cpp:141-180

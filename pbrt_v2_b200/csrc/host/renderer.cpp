@@ -15,6 +15,7 @@ namespace pb {
 // ---------------------------------------------------------------- ImageFilm --
 ImageFilm::ImageFilm(int xres, int yres, float fxw, float fyw, const float crop[4], const std::string &fn)
     : xResolution(xres), yResolution(yres), filterXWidth(fxw), filterYWidth(fyw), filename(fn) {
+    for (int i = 0; i < 256; ++i) filterTable[i] = 1.f;   // BoxFilter::Evaluate (filters/box.cpp:39-41); others: parser.cpp
     // film/image.cpp:40-51
     memcpy(cropWindow, crop, 4 * sizeof(float));
     xPixelStart = (int)ceilf(xResolution * cropWindow[0]);
@@ -363,6 +364,8 @@ void GpuSamplerRenderer::FillRenderDesc(PbrtGpuRenderDesc *rd) const {
     rd->xResolution = film->xResolution;
     rd->yResolution = film->yResolution;
     memcpy(rd->cropWindow, film->cropWindow, sizeof(rd->cropWindow));
+    rd->hasFilterTable = 1;
+    memcpy(rd->filterTable, film->filterTable, sizeof(rd->filterTable));
     rd->filterXWidth = film->filterXWidth;
     rd->filterYWidth = film->filterYWidth;
     rd->samplesPerPixel = sampler.samplesPerPixel;

@@ -191,6 +191,7 @@ struct ImageFilm {   // film/image.h:46-88, image.cpp:40-51
     int xResolution, yResolution;
     float cropWindow[4];
     float filterXWidth, filterYWidth;
+    float filterTable[256];   // Filter::Evaluate at the table positions (image.cpp:57-69); box: all 1
     std::string filename;
     int xPixelStart, yPixelStart, xPixelCount, yPixelCount;
     std::vector<PbrtGpuPixel> pixels;

@@ -160,11 +160,24 @@ INFINITE_VARIANTS = [
 ]
 
 
+# SURVEY 8(f) rank 4, pixel filters wider than half a pixel (every sample splats into neighbouring tasks' pixels): host front
+# end + oracle, pinned on the reference binary at --ncores 1 (one worker thread runs the tasks in ascending order: the
+# reference's own sums are ordered only there); the device entry points answer PBRTGPU_EUNSUPPORTED
+_FILM = 'Film "image"'
+FILTER_VARIANTS = [
+    ("filter-gaussian", "killeroo-simple", 36, 28, 4, 1, {}, [(_FILM, 'PixelFilter "gaussian"\n' + _FILM)]),
+    ("filter-mitchell", "killeroo-simple", 36, 28, 4, 1, {}, [(_FILM, 'PixelFilter "mitchell" "float B" [.2] "float C" [.4] "float xwidth" [3]\n' + _FILM)]),
+    ("filter-triangle-crop", "bunny", 40, 40, 4, 1, {"crop": (0.2, 0.8, 0.1, 0.7)}, [(_FILM, 'PixelFilter "triangle" "float xwidth" [1.5] "float ywidth" [2.5]\n' + _FILM)]),
+    ("filter-sinc", "killeroo-simple", 32, 32, 2, 1, {"integrator": "directlighting"}, [(_FILM, 'PixelFilter "sinc"\n' + _FILM)]),
+    ("filter-widebox", "bunny", 32, 32, 4, 1, {}, [(_FILM, 'PixelFilter "box" "float xwidth" [1.5] "float ywidth" [.75]\n' + _FILM)]),
+]
+
+
 def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

@@ -212,6 +212,21 @@ def test_oracle_infinite_light_bit_exact_vs_reference_binary(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["filter-gaussian", "filter-mitchell", "filter-triangle-crop", "filter-sinc", "filter-widebox"])
+def test_oracle_wide_pixel_filters_bit_exact_vs_reference_binary(staged, name):
+    """gaussian / mitchell / triangle / sinc / wide box filters (filters/*.cpp; ImageFilm's 16 x 16 weight table and the
+    sample's raster extent, film/image.cpp:57-69, 77-112; the sample extent grows with the filter, :157-166): every pixel
+    of the image, bit for bit, at --ncores 1 -- one worker thread runs the tasks in ascending order, so the reference's own
+    float sums are ordered; the oracle adds in the same order with one thread."""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    assert ncores == 1
+    px, _ = oa.render(hs, threads=1)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 def test_synthetic_scene_text_and_direct_routes_match_reference(staged):
     """the C5 generator: the in-memory build equals the text scene, and the oracle renders it bit-exactly
     like the unmodified reference (multi-pixel tasks)."""
