@@ -33,6 +33,13 @@ enum { BX_SPECULAR_REFLECTION = 3, BX_SPECULAR_TRANSMISSION = 4 };   // BxSet.ex
 #ifndef PBRT_METAL
 #define PBRT_METAL 0
 #endif
+// InfiniteAreaLight with a constant radiance (lights/infinite.cpp over its 1x1 map), PathIntegrator only,
+// on the vertex-form kernels (kwave.cuh, kvertex.cuh).  Off in the shipped kernels for the same reason as PBRT_METAL: CPU-
+// verified against the oracle through the host-compiled kernels (-DPBRT_INFINITE=1), never run on a GPU; with 0 the code is
+// unchanged and pbrtgpu_scene_create answers PBRTGPU_EUNSUPPORTED for a scene with such a light.
+#ifndef PBRT_INFINITE
+#define PBRT_INFINITE 0
+#endif
 
 DEV float CosTheta(const V3 &w) { return w.z; }
 DEV float AbsCosTheta(const V3 &w) { return fabsf(w.z); }
@@ -624,9 +631,43 @@ DEV V3 DiskSample(const DScene &sc, const PbrtGpuQuadric &q, float u1, float u2,
     if (q.flags & PBRTGPU_SHAPE_REVERSE_ORIENT) *Ns = *Ns * -1.f;
     return XfPoint(x.m, p);
 }
+#if PBRT_INFINITE
+DEV float SphericalTheta(const V3 &v) { return ref_acosf(Clampf(v.z, -1.f, 1.f)); }   // geometry.h:640-642
+// MIPMap::Lookup(s, t, width = 0) over the 1x1 radiance map (core/mipmap.h:239-269): level < 0 -> triangle(0, s, t), four
+// bilinear weights over the one texel (TEXTURE_REPEAT wraps every index to 0)
+DEV Spec InfiniteLookup(const PbrtGpuLight &l, float s, float t) {
+    s = s * 1 - 0.5f;
+    t = t * 1 - 0.5f;
+    const int s0 = Floor2Int(s), t0 = Floor2Int(t);
+    const float ds = s - s0, dt = t - t0;
+    const Spec texel(l.L[0], l.L[1], l.L[2]);
+    return (1.f - ds) * (1.f - dt) * texel + (1.f - ds) * dt * texel + ds * (1.f - dt) * texel + ds * dt * texel;
+}
+// Light::Le(ray): black (core/light.cpp:59-61) except InfiniteAreaLight::Le (infinite.cpp:114-119)
+DEV Spec LightLe(const DScene &sc, const PbrtGpuLight &l, const V3 &d) {
+    if (l.type != PBRTGPU_LIGHT_INFINITE) return Spec(0.f);
+    const V3 wh = Normalize(XfVector(sc.xforms[l.firstShape].mInv, d));   // WorldToLight(r.d)
+    const float s = SphericalPhi(wh) * INV_TWOPI_F;
+    const float t = SphericalTheta(wh) * INV_PI_F;
+    return InfiniteLookup(l, s, t);
+}
+// the one value of the sampling distribution's function (infinite.cpp:88-99: img[0] = Lookup(0, 0, 1).y() * sinf(pi * .5))
+DEV float InfiniteFunc(const PbrtGpuLight &l) { return Spec(l.L[0], l.L[1], l.L[2]).y() * ref_sinf(PI_F * float(0 + .5f) / float(1)); }
+#endif
 // Light::Pdf: PointLight 0 (point.cpp:78-80); DiffuseAreaLight -> ShapeSet::Pdf (light.cpp:157-162)
 DEV_NI3 float LightPdf(const DScene &sc, const PbrtGpuLight &l, const V3 &p, const V3 &wi) {
     if (l.type == PBRTGPU_LIGHT_POINT) return 0.f;
+#if PBRT_INFINITE
+    if (l.type == PBRTGPU_LIGHT_INFINITE) {   // infinite.cpp:229-239; Distribution2D::Pdf over one cell, montecarlo.h:158-166
+        const V3 w = XfVector(sc.xforms[l.firstShape].mInv, wi);
+        const float theta = SphericalTheta(w);
+        const float sintheta = ref_sinf(theta);
+        if (sintheta == 0.f) return 0.f;
+        const float f = InfiniteFunc(l);
+        const float mapPdf = (f * f == 0.f) ? 0.f : (f * f) / (f * f);
+        return mapPdf / (2.f * PI_F * PI_F * sintheta);
+    }
+#endif
     float pdf = 0.f;
     for (uint32_t i = 0; i < l.nShapes; ++i) {
         const PbrtGpuLightShape ls = sc.lightShapes[l.firstShape + i];
@@ -646,6 +687,25 @@ DEV Spec LightSample_L(const DScene &sc, const PbrtGpuLight &l, const V3 &p, flo
         vis->o = p; vis->d = (lightPos - p) / dist; vis->mint = pEpsilon; vis->maxt = dist * (1.f - 0.f);
         return Spec(l.L[0], l.L[1], l.L[2]) / DistanceSquared(lightPos, p);
     }
+#if PBRT_INFINITE
+    if (l.type == PBRTGPU_LIGHT_INFINITE) {   // infinite.cpp:195-226; Distribution2D::SampleContinuous over one cell: uv = u
+        const float f = InfiniteFunc(l);
+        const float pdf1 = f / f, pdf0 = f / f;
+        const float uv1 = (0 + (uPos1 - 0.f) / (1.f - 0.f)) / 1, uv0 = (0 + (uPos0 - 0.f) / (1.f - 0.f)) / 1;
+        const float mapPdf = pdf0 * pdf1;
+        vis->o = p; vis->d = V3(0, 0, 1); vis->mint = pEpsilon; vis->maxt = INF_F;
+        *wi = V3(0, 0, 1);
+        if (mapPdf == 0.f) { *pdf = 0.f; return Spec(0.f); }
+        const float theta = uv1 * PI_F, phi = uv0 * 2.f * PI_F;
+        const float costheta = ref_cosf(theta), sintheta = ref_sinf(theta);
+        const float sinphi = ref_sinf(phi), cosphi = ref_cosf(phi);
+        *wi = XfVector(sc.xforms[l.firstShape].m, V3(sintheta * cosphi, sintheta * sinphi, costheta));
+        *pdf = mapPdf / (2.f * PI_F * PI_F * sintheta);
+        if (sintheta == 0.f) *pdf = 0.f;
+        vis->d = *wi;   // VisibilityTester::SetRay(p, eps, wi, time): unbounded
+        return InfiniteLookup(l, uv0, uv1);
+    }
+#endif
     V3 ns;
     const PbrtGpuLightShape lsh = sc.lightShapes[l.firstShape];
     const PbrtGpuQuadric &q = sc.quadrics[lsh.index];

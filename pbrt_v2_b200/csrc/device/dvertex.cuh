@@ -128,6 +128,10 @@ DEV void VertexA(const DScene &sc, const Ray &ray, const Hit &hit, int bounces, 
                         v->weightM = PowerHeuristic(1, pdfM, 1, lightPdf);
                         v->pdfM = pdfM;
                         v->Lemit = Spec(light.L[0], light.L[1], light.L[2]);   // Li is Lemit or black (diffuse.h:51-53)
+#if PBRT_INFINITE
+                        // an infinite light contributes when the MIS ray ESCAPES: Li = light->Le(ray) (integrator.cpp:163-164)
+                        if (light.type == PBRTGPU_LIGHT_INFINITE) v->Lemit = LightLe(sc, light, wiM);
+#endif
                     }
                 }
             }
@@ -237,6 +241,26 @@ DEV bool MisHitIsLight(const DScene &sc, const Ray &ray, const Hit &hit, int lig
     const PbrtGpuLight &light = sc.lights[lightNum];
     const bool emits = !Spec(light.L[0], light.L[1], light.L[2]).IsBlack();
     return al == lightNum && Dot(dgl.nn, -ray.d) > 0.f && emits;
+}
+
+// Does the MIS ray's outcome add its term (integrator.cpp:158-169)?  Area light: the ray hit that light, facing it; infinite
+// light (PBRT_INFINITE builds): the ray escaped.
+template <bool ANIM>
+DEV bool MisRayContributes(const DScene &sc, const Ray &ray, const Hit &hit, bool found, int lightNum) {
+#if PBRT_INFINITE
+    if (sc.lights[lightNum].type == PBRTGPU_LIGHT_INFINITE) return !found;
+#endif
+    return found && MisHitIsLight<ANIM>(sc, ray, hit, lightNum);
+}
+// What a path ray that left the scene adds (PBRT_INFINITE builds; else nothing): the camera ray, every light's Le
+// (samplerrenderer.cpp:238-242); a ray sampled from a specular component, T * Le per light (path.cpp:113-117)
+DEV void EscapedRadiance(const DScene &sc, const V3 &d, bool cameraRay, bool afterSpecular, const Spec &T, Spec &L) {
+#if PBRT_INFINITE
+    if (cameraRay) { for (uint32_t i = 0; i < sc.nLights; ++i) L = L + LightLe(sc, sc.lights[i], d); }
+    else if (afterSpecular) { for (uint32_t i = 0; i < sc.nLights; ++i) L = L + T * LightLe(sc, sc.lights[i], d); }
+#else
+    (void)sc; (void)d; (void)cameraRay; (void)afterSpecular; (void)T; (void)L;
+#endif
 }
 
 // the random numbers of a vertex at depth `d` < 3 from the camera sample's table row (path.cpp:71-76, 86-88)

@@ -278,8 +278,16 @@ __global__ void __launch_bounds__(128, K_VERTEX_MIN_BLOCKS) k_vertex(const __gri
                 if (STATS) { if (r == 0) ++nShadow; else ++nClosest; }
                 const bool found = Traverse<STATS, ANIM>(sc, q, r == 0, &h, &st, smemTop, smemStack);   // the single traversal site
                 if (r == 0) { if (!found) Ld = Ld + v.pendS; }   // visibility.Unoccluded(scene), Transmittance == 1
+#if PBRT_INFINITE
+                else if (r == 1) { if (MisRayContributes<ANIM>(sc, q, h, found, v.lightNum)) Ld = Ld + v.pendM; }
+                else {
+                    atVertex = found; hit = h; ray.maxt = q.maxt;
+                    if (!found) EscapedRadiance(sc, ray.d, !doVertex, afterSpecular, T, L);   // (a camera ray has no vertex behind it)
+                }
+#else
                 else if (r == 1) { if (found && MisHitIsLight<ANIM>(sc, q, h, v.lightNum)) Ld = Ld + v.pendM; }
                 else { atVertex = found; hit = h; ray.maxt = q.maxt; }
+#endif
             }
         }
 

@@ -266,7 +266,13 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
             v.absM = v1.x; v.weightM = v1.y; v.pdfM = v1.z; v.absP = v1.w; v.pdfP = fId.w;
             const int lightNum = (int)(bits >> WB_LIGHT_SHIFT);
             v.Lemit = Spec(0.f);
-            if (v.need[1]) { const PbrtGpuLight &light = sc.lights[lightNum]; v.Lemit = Spec(light.L[0], light.L[1], light.L[2]); }
+            if (v.need[1]) {
+                const PbrtGpuLight &light = sc.lights[lightNum];
+                v.Lemit = Spec(light.L[0], light.L[1], light.L[2]);
+#if PBRT_INFINITE
+                if (light.type == PBRTGPU_LIGHT_INFINITE) { const float4 d1 = WF(W_D1); v.Lemit = LightLe(sc, light, V3(d1.x, d1.y, d1.z)); }
+#endif
+            }
 #if PBRT_SPECULAR
             v.specSampled = (bits & WB_SPEC_SAMPLED) != 0;
             v.specF = Spec(0.f);
@@ -297,8 +303,11 @@ __global__ void __launch_bounds__(128, K_WSHADE_MIN_BLOCKS) k_wshade(const __gri
             atVertex = hit.prim >= 0;
         }
         if (!atVertex) {
-            // the path is over (no continuation, or the ray left the scene: path.cpp:113-118 adds nothing for the in-scope
-            // lights); samplerrenderer.cpp:119-133 sanity checks
+            // the path is over: no continuation, or the ray left the scene (which adds nothing for point / area lights:
+            // path.cpp:113-118, samplerrenderer.cpp:238-242; infinite lights: EscapedRadiance); samplerrenderer.cpp:119-133 checks
+#if PBRT_INFINITE
+            if (pathTraced) EscapedRadiance(sc, ray.d, !(bits & WB_VERTEX), afterSpecular, T, L);
+#endif
             const Spec Ls = SanitizeRadiance(L);
             a.b.ls[(size_t)bi * spp + s] = make_float4(Ls.r, Ls.g, Ls.b, __int_as_float(code));
             have = false;
@@ -760,6 +769,14 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_wtrace(const __grid
                 if (kind == VX_LIGHT)
                     pool[(size_t)W_D0 * P + slot].w = t.found ? 1.f : 0.f;
                 else if (kind == VX_MIS) {
+#if PBRT_INFINITE
+                    Ray q = wray;
+                    q.maxt = t.ray.maxt;
+                    Hit h = t.hit;
+                    h.t = t.ray.maxt;
+                    const bool counts = MisRayContributes<ANIM>(sc, q, h, t.found, lightNum);   // landed on the light / escaped to it
+                    pool[(size_t)W_D1 * P + slot].w = counts ? 1.f : 0.f;
+#else
                     bool onLight = false;
                     if (t.found) {
                         Ray q = wray;
@@ -769,6 +786,7 @@ __global__ void __launch_bounds__(128, K_TRACE_MIN_BLOCKS) k_wtrace(const __grid
                         onLight = MisHitIsLight<ANIM>(sc, q, h, lightNum);
                     }
                     pool[(size_t)W_D1 * P + slot].w = onLight ? 1.f : 0.f;
+#endif
                 } else {
                     pool[(size_t)W_HIT * P + slot] = make_float4(__int_as_float(t.found ? t.hit.prim : -1), t.hit.b1, t.hit.b2, t.hit.maxtIn);
                     pool[(size_t)W_D2 * P + slot].w = t.ray.maxt;

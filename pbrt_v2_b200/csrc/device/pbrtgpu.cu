@@ -1189,6 +1189,7 @@ struct PbrtGpuScene {
     int collectStats = 0;   // 1: ray/node/primitive counters, 2: per-launch timing of the traversal kernel
     int nMeasuredMaterials = 0;
     int nSpecularMaterials = 0;
+    int nInfiniteLights = 0;
     bool valid = false;     // false while an upload is in progress or after one failed half way
 };
 
@@ -1394,8 +1395,12 @@ static int ValidateSceneDesc(const PbrtGpuSceneDesc *desc) {
     if (desc->nAnimated > 255) return Fail(PBRTGPU_EUNSUPPORTED, "more than 255 TransformedPrimitives");
     for (uint32_t i = 0; i < desc->nLights; ++i) {
         const PbrtGpuLight &l = desc->lights[i];
+#if PBRT_INFINITE
+        if (l.type == PBRTGPU_LIGHT_INFINITE && l.firstShape >= desc->nXforms) return Fail(PBRTGPU_EINVAL, "infinite light's transform index out of range");
+#else
         if (l.type == PBRTGPU_LIGHT_INFINITE)
-            return Fail(PBRTGPU_EUNSUPPORTED, "infinite area lights: host front end and oracle only so far (no device code)");
+            return Fail(PBRTGPU_EUNSUPPORTED, "infinite area lights: this library was built with PBRT_INFINITE=0 (the device code has not run on a GPU yet)");
+#endif
         if (l.type > PBRTGPU_LIGHT_INFINITE) return Fail(PBRTGPU_EINVAL, "unknown light type");
         if (l.type == PBRTGPU_LIGHT_DIFFUSE_AREA) {
             if (l.nShapes != 1) return Fail(PBRTGPU_EUNSUPPORTED, "area lights over more than one shape are out of scope");
@@ -1613,6 +1618,9 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
     for (uint32_t i = 0; i < desc->nMaterials; ++i) {
         if (desc->materials[i].type == PBRTGPU_MAT_MEASURED) s->nMeasuredMaterials++;
         if (desc->materials[i].type == PBRTGPU_MAT_MIRROR || desc->materials[i].type == PBRTGPU_MAT_GLASS) s->nSpecularMaterials++;
+    s->nInfiniteLights = 0;
+    for (uint32_t i = 0; i < desc->nLights; ++i)
+        if (desc->lights[i].type == PBRTGPU_LIGHT_INFINITE) s->nInfiniteLights++;
     }
     s->valid = true;
     return PBRTGPU_OK;
@@ -2174,6 +2182,11 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     const bool wantCounters = stats && scene->collectStats == 1;
     const bool timeRays = stats && scene->collectStats == 2;
     const RenderConfig cfg = ReadConfig();
+    if (scene->nInfiniteLights) {   // (PBRT_INFINITE builds) only the vertex-form kernels add Le for rays that leave the scene
+        const bool vertexForm1 = (cfg.wave & 1) || (cfg.vertex & 1), vertexForm2 = (cfg.wave & 2) || (cfg.vertex & 2);
+        if (directInteg || !cfg.wavefront || !vertexForm1 || !vertexForm2 || cfg.wavefront2)
+            return Fail(PBRTGPU_EUNSUPPORTED, "infinite area lights: PathIntegrator on the vertex-form kernels only (not DirectLightingIntegrator, not the state-machine kernels)");
+    }
     const size_t poolSlots = cfg.pool;
     // lanes: the kernels' register allocations fill the SMs, so lanes cannot overlap two full-size kernels; what they
     // hide is each other's low-occupancy stretches (the tail kernel, the wavefront's drain at the end of a batch).

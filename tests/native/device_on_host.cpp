@@ -372,6 +372,7 @@ void RunTaskVertexH(const DScene &sc, const RenderParams &rp, const PbrtGpuRende
                 TraceStats st;
                 st.nodes = st.prims = 0;
                 bool found = Traverse<false, true>(sc, ray, false, &hit, &st, DOH_TOP(sc));
+                if (!found) EscapedRadiance(sc, ray.d, true, false, T, L);
                 while (found) {
                     VertexRandoms u;
                     const int nLights = (int)sc.nLights;
@@ -408,7 +409,8 @@ void RunTaskVertexH(const DScene &sc, const RenderParams &rp, const PbrtGpuRende
                     if (v.ray[VX_MIS]) {
                         Ray r; r.o = v.p; r.d = v.wiW[VX_MIS]; r.mint = v.eps; r.maxt = INF_F; r.time = ray.time;
                         Hit h;
-                        if (Traverse<false, true>(sc, r, false, &h, &st, DOH_TOP(sc)) && MisHitIsLight<true>(sc, r, h, v.lightNum)) Ld = Ld + v.pendM;
+                        const bool fnd = Traverse<false, true>(sc, r, false, &h, &st, DOH_TOP(sc));
+                        if (MisRayContributes<true>(sc, r, h, fnd, v.lightNum)) Ld = Ld + v.pendM;
                     }
                     L = L + T * ((float)nLights * Ld);
                     T = v.Tnew;
@@ -419,6 +421,7 @@ void RunTaskVertexH(const DScene &sc, const RenderParams &rp, const PbrtGpuRende
                     ++bounces;
                     ray.o = v.p; ray.d = v.wiW[VX_PATH]; ray.mint = v.eps; ray.maxt = INF_F;
                     found = Traverse<false, true>(sc, ray, false, &hit, &st, DOH_TOP(sc));
+                    if (!found) EscapedRadiance(sc, ray.d, false, afterSpecular, T, L);
                 }
                 const Spec Ls = SanitizeRadiance(L);
                 float xyz[3];

@@ -231,6 +231,24 @@ def test_metal_device_code_on_host(staged, tmp_path_factory):
     _same_film(lib, host_scene("killeroo-simple", 32, 32, 4, 2))
 
 
+def test_infinite_light_device_code_on_host(staged, tmp_path_factory):
+    """InfiniteAreaLight (constant radiance) on the device, PathIntegrator, vertex-form kernels only (dshade.cuh / dvertex.cuh /
+    kwave.cuh / kvertex.cuh under -DPBRT_INFINITE=1): not in the shipped kernels (never run on a GPU).  Compiled for the host
+    and rendered against the oracle -- pinned on the reference binary for the same scenes (test_oracle_pinning.py) -- through
+    the vertex form and through the vertex-wavefront kernels over small and large pools; scenes without such a light must
+    not move."""
+    from helpers import INFINITE_VARIANTS, variant_scene
+    lib = _build(tmp_path_factory, "device_on_host_infinite", ["-DPBRT_INFINITE=1"])
+    lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+    for form in (1, 3, 64, 4096):   # vertex form; the wave kernels over 3, 64 and 4096 slots
+        lib.doh_set_vertex_form(form)
+        for v in INFINITE_VARIANTS:
+            if v[6].get("integrator", "path") == "path":
+                _same_film(lib, variant_scene(v[0])[0])
+        _same_film(lib, host_scene("bunny", 24, 24, 4, 8))
+    lib.doh_set_vertex_form(0)
+
+
 def test_pair_node_walk_on_host(staged, tmp_path_factory):
     """The sibling-pair node layout (-DPBRT_PAIR_NODES=1, device/dscene.cuh: a round-2 kernel experiment that is not in the
     shipped kernels) must walk the tree exactly like the reference-shaped loop: same hits, same `t`, same films -- both the

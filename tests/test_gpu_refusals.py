@@ -1,13 +1,32 @@
 """No silent fallbacks: what the oracle and the host front end can do but the kernels cannot yet (SURVEY 8(f) rank 4 rest)
 must be refused by the device entry points with PBRTGPU_EUNSUPPORTED, not rendered differently."""
+import os
+
+import numpy as np
 import pytest
 
 import pbrt_v2_b200 as pb
+import oracle_api as oa
 from helpers import variant_scene
 
 pytestmark = pytest.mark.gpu
+F4_BUILD = "f4" in os.environ.get("PBRTGPU_LIB", "")   # make variants VARIANT_NAMES=f4: -DPBRT_METAL=1 -DPBRT_INFINITE=1
 
 
+@pytest.mark.skipif(not F4_BUILD, reason="needs PBRTGPU_LIB=ab/libpbrtgpu_f4.so (make variants VARIANT_NAMES=f4)")
+@pytest.mark.parametrize("name", ["path-infinite", "path-infinite-specular", "path-infinite-bunny", "path-metal-copper",
+                                  "path-metal-params-floor"])
+def test_f4_build_bit_exact_vs_oracle(staged, name):
+    """first GPU run of the gated device code for infinite lights and metal (host-verified: tests/test_device_on_host.py)"""
+    hs, _ = variant_scene(name)
+    px_gpu, _ = pb.GpuScene(hs).render()
+    px_cpu, _ = oa.render(hs, threads=2)
+    assert np.array_equal(px_gpu["weightSum"], px_cpu["weightSum"])
+    own = px_cpu["weightSum"] == hs.render_desc().samplesPerPixel
+    assert np.array_equal(px_gpu["Lxyz"][own].view(np.uint32), px_cpu["Lxyz"][own].view(np.uint32))
+
+
+@pytest.mark.skipif(F4_BUILD, reason="a PBRT_INFINITE build accepts the light")
 def test_infinite_area_light_is_refused(staged):
     hs, _ = variant_scene("path-infinite")
     with pytest.raises(pb.PbrtGpuError) as e:
