@@ -2,7 +2,8 @@
 """Random in-scope scenes: the unmodified reference binary vs the oracle vs the device code compiled for the host
 (tests/native/device_on_host.cpp).  CPU only.  usage: fuzz_scenes.py [n] [seed0] [flags]
 flags (joined with +): specular, metal (materials; metal builds the harness with -DPBRT_METAL=1), pairs (-DPBRT_PAIR_NODES=1),
-crop, wave (PathIntegrator scenes run through the vertex-wavefront KERNELS -- kwave.cuh's k_wshade / k_weval / k_wtrace /
+crop, infinite (constant-radiance InfiniteAreaLights; the harness is built with -DPBRT_INFINITE=1, whose device code covers
+PathIntegrator: directlighting scenes with such a light are compared reference-vs-oracle only), wave (PathIntegrator scenes run through the vertex-wavefront KERNELS -- kwave.cuh's k_wshade / k_weval / k_wtrace /
 k_wcompact, launches as loops -- over a pool of 3, 17 or 4096 slots instead of the state machine)"""
 import ctypes as C, os, subprocess, sys
 import numpy as np
@@ -35,6 +36,11 @@ def gen(rng, path, animated=None):
     if integ == "directlighting" and rng.rand() < .4: s += ' "string strategy" "one"'
     L.append(s)
     L.append("WorldBegin")
+    if len(sys.argv) > 3 and "infinite" in sys.argv[3] and rng.rand() < .4:   # constant-radiance InfiniteAreaLight, rotated
+        L.append("AttributeBegin")
+        L.append("Rotate %g %s" % (rng.uniform(-180, 180), fl(rng.uniform(-1, 1, 3) + 1e-3)))
+        L.append('LightSource "infinite" "color L" [%s] "integer nsamples" [%d]' % (fl(rng.uniform(0, .8, 3)), rng.choice([1, 2, 4])))
+        L.append("AttributeEnd")
     def xform():
         t = []
         if rng.rand() < .8: t.append("Translate %s" % fl(rng.uniform(-1.2, 1.2, 3)))
@@ -138,9 +144,10 @@ def main():
     pairs = len(sys.argv) > 3 and "pairs" in sys.argv[3]
     metal = len(sys.argv) > 3 and "metal" in sys.argv[3]
     wave = len(sys.argv) > 3 and "wave" in sys.argv[3]
-    so = "/tmp/libdoh_fuzz%s%s%s.so" % ("_spec" if spec else "", "_pairs" if pairs else "", "_metal" if metal else "")
+    infinite = len(sys.argv) > 3 and "infinite" in sys.argv[3]
+    so = "/tmp/libdoh_fuzz%s%s%s%s.so" % ("_spec" if spec else "", "_pairs" if pairs else "", "_metal" if metal else "", "_inf" if infinite else "")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic",
-                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) + (["-DPBRT_PAIR_NODES=1"] if pairs else []) + (["-DPBRT_METAL=1"] if metal else []) +
+                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) + (["-DPBRT_PAIR_NODES=1"] if pairs else []) + (["-DPBRT_METAL=1"] if metal else []) + (["-DPBRT_INFINITE=1"] if infinite else []) +
                    [os.path.join(REPO, "tests/native/device_on_host.cpp"), "-o", so], check=True)
     doh = C.CDLL(so)
     doh.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
@@ -163,8 +170,13 @@ def main():
         o = hs.pixels_to_rgb(px)
         rd = hs.render_desc()
         px2 = hs.new_pixels()
-        doh.doh_set_vertex_form(int(rng.choice([3, 17, 4096])) if wave else 0)
-        doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
+        has_inf = 'LightSource "infinite"' in open(path).read()
+        if has_inf and rd.integrator != 0:
+            px2 = px.copy()   # (no device code for infinite lights under directlighting: reference vs oracle only)
+        else:
+            # infinite lights live in the vertex-form code only: vertex form (1) or the wave kernels
+            doh.doh_set_vertex_form(int(rng.choice([3, 17, 4096])) if wave else (1 if has_inf else 0))
+            doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
         own = px["weightSum"] == spp
         d_ref = int((o.view(np.uint32) != ref.view(np.uint32)).any(axis=2)[own].sum()) if o.shape == ref.shape else -1
         d_dev = int((px2["Lxyz"].view(np.uint32) != px["Lxyz"].view(np.uint32)).any(axis=2)[own].sum())
