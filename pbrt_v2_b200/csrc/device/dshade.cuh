@@ -33,8 +33,8 @@ enum { BX_SPECULAR_REFLECTION = 3, BX_SPECULAR_TRANSMISSION = 4 };   // BxSet.ex
 #ifndef PBRT_METAL
 #define PBRT_METAL 0
 #endif
-// InfiniteAreaLight with a constant radiance (lights/infinite.cpp over its 1x1 map), PathIntegrator only,
-// on the vertex-form kernels (kwave.cuh, kvertex.cuh).  Off in the shipped kernels for the same reason as PBRT_METAL: CPU-
+// InfiniteAreaLight with a constant radiance (lights/infinite.cpp over its 1x1 map), both integrators, every
+// kernel form (path_body.inc, dvertex.cuh, kwave.cuh, kvertex.cuh).  Off in the shipped kernels for the same reason as PBRT_METAL: CPU-
 // verified against the oracle through the host-compiled kernels (-DPBRT_INFINITE=1), never run on a GPU; with 0 the code is
 // unchanged and pbrtgpu_scene_create answers PBRTGPU_EUNSUPPORTED for a scene with such a light.
 #ifndef PBRT_INFINITE
@@ -716,5 +716,17 @@ DEV Spec LightSample_L(const DScene &sc, const PbrtGpuLight &l, const V3 &p, flo
     vis->o = p; vis->d = (ps - p) / dist; vis->mint = pEpsilon; vis->maxt = dist * (1.f - 1e-3f);
     return Dot(ns, -*wi) > 0.f ? Spec(l.L[0], l.L[1], l.L[2]) : Spec(0.f);
 }
+
+// What a path ray that left the scene adds (PBRT_INFINITE builds; else nothing): the camera ray, every light's Le
+// (samplerrenderer.cpp:238-242); a ray sampled from a specular component, T * Le per light (path.cpp:113-117)
+DEV void EscapedRadiance(const DScene &sc, const V3 &d, bool cameraRay, bool afterSpecular, const Spec &T, Spec &L) {
+#if PBRT_INFINITE
+    if (cameraRay) { for (uint32_t i = 0; i < sc.nLights; ++i) L = L + LightLe(sc, sc.lights[i], d); }
+    else if (afterSpecular) { for (uint32_t i = 0; i < sc.nLights; ++i) L = L + T * LightLe(sc, sc.lights[i], d); }
+#else
+    (void)sc; (void)d; (void)cameraRay; (void)afterSpecular; (void)T; (void)L;
+#endif
+}
+
 
 }  // namespace dev

@@ -252,17 +252,6 @@ DEV bool MisRayContributes(const DScene &sc, const Ray &ray, const Hit &hit, boo
 #endif
     return found && MisHitIsLight<ANIM>(sc, ray, hit, lightNum);
 }
-// What a path ray that left the scene adds (PBRT_INFINITE builds; else nothing): the camera ray, every light's Le
-// (samplerrenderer.cpp:238-242); a ray sampled from a specular component, T * Le per light (path.cpp:113-117)
-DEV void EscapedRadiance(const DScene &sc, const V3 &d, bool cameraRay, bool afterSpecular, const Spec &T, Spec &L) {
-#if PBRT_INFINITE
-    if (cameraRay) { for (uint32_t i = 0; i < sc.nLights; ++i) L = L + LightLe(sc, sc.lights[i], d); }
-    else if (afterSpecular) { for (uint32_t i = 0; i < sc.nLights; ++i) L = L + T * LightLe(sc, sc.lights[i], d); }
-#else
-    (void)sc; (void)d; (void)cameraRay; (void)afterSpecular; (void)T; (void)L;
-#endif
-}
-
 // the random numbers of a vertex at depth `d` < 3 from the camera sample's table row (path.cpp:71-76, 86-88)
 DEV void VertexRandomsFromTables(const uint16_t *row, const uint32_t *scr, int d, VertexRandoms *u) {
     u->lnU = VanDerCorput(row[3 + 4 * d + 1], scr[5 + 4 * d + 1]);

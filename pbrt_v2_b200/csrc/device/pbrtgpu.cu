@@ -2182,11 +2182,6 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     const bool wantCounters = stats && scene->collectStats == 1;
     const bool timeRays = stats && scene->collectStats == 2;
     const RenderConfig cfg = ReadConfig();
-    if (scene->nInfiniteLights) {   // (PBRT_INFINITE builds) only the vertex-form kernels add Le for rays that leave the scene
-        const bool vertexForm1 = (cfg.wave & 1) || (cfg.vertex & 1), vertexForm2 = (cfg.wave & 2) || (cfg.vertex & 2);
-        if (directInteg || !cfg.wavefront || !vertexForm1 || !vertexForm2 || cfg.wavefront2)
-            return Fail(PBRTGPU_EUNSUPPORTED, "infinite area lights: PathIntegrator on the vertex-form kernels only (not DirectLightingIntegrator, not the state-machine kernels)");
-    }
     const size_t poolSlots = cfg.pool;
     // lanes: the kernels' register allocations fill the SMs, so lanes cannot overlap two full-size kernels; what they
     // hide is each other's low-occupancy stretches (the tail kernel, the wavefront's drain at the end of a batch).

@@ -2,8 +2,7 @@
 """Random in-scope scenes: the unmodified reference binary vs the oracle vs the device code compiled for the host
 (tests/native/device_on_host.cpp).  CPU only.  usage: fuzz_scenes.py [n] [seed0] [flags]
 flags (joined with +): specular, metal (materials; metal builds the harness with -DPBRT_METAL=1), pairs (-DPBRT_PAIR_NODES=1),
-crop, infinite (constant-radiance InfiniteAreaLights; the harness is built with -DPBRT_INFINITE=1, whose device code covers
-PathIntegrator: directlighting scenes with such a light are compared reference-vs-oracle only), wave (PathIntegrator scenes run through the vertex-wavefront KERNELS -- kwave.cuh's k_wshade / k_weval / k_wtrace /
+crop, infinite (constant-radiance InfiniteAreaLights; the harness is built with -DPBRT_INFINITE=1), wave (PathIntegrator scenes run through the vertex-wavefront KERNELS -- kwave.cuh's k_wshade / k_weval / k_wtrace /
 k_wcompact, launches as loops -- over a pool of 3, 17 or 4096 slots instead of the state machine)"""
 import ctypes as C, os, subprocess, sys
 import numpy as np
@@ -170,13 +169,8 @@ def main():
         o = hs.pixels_to_rgb(px)
         rd = hs.render_desc()
         px2 = hs.new_pixels()
-        has_inf = 'LightSource "infinite"' in open(path).read()
-        if has_inf and rd.integrator != 0:
-            px2 = px.copy()   # (no device code for infinite lights under directlighting: reference vs oracle only)
-        else:
-            # infinite lights live in the vertex-form code only: vertex form (1) or the wave kernels
-            doh.doh_set_vertex_form(int(rng.choice([3, 17, 4096])) if wave else (1 if has_inf else 0))
-            doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
+        doh.doh_set_vertex_form(int(rng.choice([3, 17, 4096])) if wave else 0)
+        doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
         own = px["weightSum"] == spp
         d_ref = int((o.view(np.uint32) != ref.view(np.uint32)).any(axis=2)[own].sum()) if o.shape == ref.shape else -1
         d_dev = int((px2["Lxyz"].view(np.uint32) != px["Lxyz"].view(np.uint32)).any(axis=2)[own].sum())

@@ -232,7 +232,7 @@ def test_metal_device_code_on_host(staged, tmp_path_factory):
 
 
 def test_infinite_light_device_code_on_host(staged, tmp_path_factory):
-    """InfiniteAreaLight (constant radiance) on the device, PathIntegrator, vertex-form kernels only (dshade.cuh / dvertex.cuh /
+    """InfiniteAreaLight (constant radiance) on the device, both integrators (dshade.cuh / dvertex.cuh / path_body.inc /
     kwave.cuh / kvertex.cuh under -DPBRT_INFINITE=1): not in the shipped kernels (never run on a GPU).  Compiled for the host
     and rendered against the oracle -- pinned on the reference binary for the same scenes (test_oracle_pinning.py) -- through
     the vertex form and through the vertex-wavefront kernels over small and large pools; scenes without such a light must
@@ -240,6 +240,8 @@ def test_infinite_light_device_code_on_host(staged, tmp_path_factory):
     from helpers import INFINITE_VARIANTS, variant_scene
     lib = _build(tmp_path_factory, "device_on_host_infinite", ["-DPBRT_INFINITE=1"])
     lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+    for v in INFINITE_VARIANTS:   # the state machine (path_body.inc): both integrators, incl. the specular recursion's children
+        _same_film(lib, variant_scene(v[0])[0])
     for form in (1, 3, 64, 4096):   # vertex form; the wave kernels over 3, 64 and 4096 slots
         lib.doh_set_vertex_form(form)
         for v in INFINITE_VARIANTS:

@@ -14,8 +14,8 @@ F4_BUILD = "f4" in os.environ.get("PBRTGPU_LIB", "")   # make variants VARIANT_N
 
 
 @pytest.mark.skipif(not F4_BUILD, reason="needs PBRTGPU_LIB=ab/libpbrtgpu_f4.so (make variants VARIANT_NAMES=f4)")
-@pytest.mark.parametrize("name", ["path-infinite", "path-infinite-specular", "path-infinite-bunny", "path-metal-copper",
-                                  "path-metal-params-floor"])
+@pytest.mark.parametrize("name", ["path-infinite", "path-infinite-specular", "path-infinite-bunny", "direct-infinite",
+                                  "direct-one-infinite", "path-metal-copper", "path-metal-params-floor", "direct-metal"])
 def test_f4_build_bit_exact_vs_oracle(staged, name):
     """first GPU run of the gated device code for infinite lights and metal (host-verified: tests/test_device_on_host.py)"""
     hs, _ = variant_scene(name)
