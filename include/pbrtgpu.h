@@ -232,7 +232,9 @@ typedef struct PbrtGpuRenderDesc {
      * ((i + .5) * width / 16), row = y.  hasFilterTable == 0 reads as the box filter (every weight 1).  Filters wider than
      * half a pixel (gaussian, mitchell, sinc, triangle, wide boxes) make every sample splat into neighbouring tasks' pixels:
      * host front end + oracle (pinned on the reference binary at --ncores 1, where the reference's own sums are ordered);
-     * the device entry points answer PBRTGPU_EUNSUPPORTED for them.  (Appended in round 2: earlier offsets are unchanged.) */
+     * the device entry points answer PBRTGPU_EUNSUPPORTED for them unless the library was built with -DPBRT_FILTER=1
+     * (atomic adds: sums complete, order undefined as in the reference above one thread; host-verified, not yet run on a
+     * GPU).  (Appended in round 2: earlier offsets are unchanged.) */
     int32_t hasFilterTable;
     float   filterTable[256];
 } PbrtGpuRenderDesc;

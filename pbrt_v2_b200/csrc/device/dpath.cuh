@@ -4,6 +4,13 @@
 #include "dmath.cuh"
 #include "drng.cuh"
 
+// pixel filters other than the 0.5 box (filters/*.cpp through ImageFilm's 16x16 weight table).  Off in
+// the shipped kernels (the code below never ran on a GPU: the round's GPU budget ended first); the host-compiled harness
+// builds it with -DPBRT_FILTER=1 and compares whole films with the oracle.
+#ifndef PBRT_FILTER
+#define PBRT_FILTER 0
+#endif
+
 namespace dev {
 
 struct RenderParams {
@@ -16,6 +23,9 @@ struct RenderParams {
     int spp, maxDepth;
     int integrator, lightStrategy;   // PBRTGPU_INTEGRATOR_*, PBRTGPU_STRATEGY_*
     SampleLayoutDev lay;
+#if PBRT_FILTER
+    const float *filterTable;   // ImageFilm::filterTable (16 x 16 weights) in device memory; NULL: the 0.5 box (FilmAdd)
+#endif
 };
 
 enum PathState {
@@ -61,6 +71,57 @@ DEV int FilmFootprint(const RenderParams &rp, int ownX, int ownY, float imageX, 
     if (y1 > ownY) code |= LS_DOWN;
     return code;
 }
+
+#if PBRT_FILTER
+// ImageFilm::AddSample (film/image.cpp:77-137) for any filter table and width.  Every pixel of the footprint is another
+// task's pixel as likely as not: all adds are atomic, and their order is as undefined as in the reference, which takes its
+// AtomicAdd branch (image.cpp:128-134) for exactly these filters.  In one thread (the host harness, tasks in order) the
+// order is the reference's --ncores 1 order and the film is bit-identical.
+DEV void FilmAddFiltered(const RenderParams &rp, PbrtGpuPixel *film, float imageX, float imageY, const Spec &L) {
+    const float dimageX = imageX - 0.5f;
+    const float dimageY = imageY - 0.5f;
+    int x0 = Ceil2Int(dimageX - rp.filterXWidth);
+    int x1 = Floor2Int(dimageX + rp.filterXWidth);
+    int y0 = Ceil2Int(dimageY - rp.filterYWidth);
+    int y1 = Floor2Int(dimageY + rp.filterYWidth);
+    x0 = maxi(x0, rp.xPixelStart);
+    x1 = mini(x1, rp.xPixelStart + rp.xPixelCount - 1);
+    y0 = maxi(y0, rp.yPixelStart);
+    y1 = mini(y1, rp.yPixelStart + rp.yPixelCount - 1);
+    if ((x1 - x0) < 0 || (y1 - y0) < 0) return;
+    if (x1 - x0 >= 64 || y1 - y0 >= 64) return;   // the oracle's limit (its offset arrays hold 64 entries)
+    float xyz[3];   // RGBToXYZ, core/spectrum.h:58-62
+    xyz[0] = 0.412453f * L.r + 0.357580f * L.g + 0.180423f * L.b;
+    xyz[1] = 0.212671f * L.r + 0.715160f * L.g + 0.072169f * L.b;
+    xyz[2] = 0.019334f * L.r + 0.119193f * L.g + 0.950227f * L.b;
+    const float invXWidth = 1.f / rp.filterXWidth, invYWidth = 1.f / rp.filterYWidth;   // filter.h:47-49
+    for (int y = y0; y <= y1; ++y) {
+        const float fy = fabsf((y - dimageY) * invYWidth * 16);
+        const int ify = mini(Floor2Int(fy), 16 - 1);
+        for (int x = x0; x <= x1; ++x) {
+            const float fx = fabsf((x - dimageX) * invXWidth * 16);
+            const int ifx = mini(Floor2Int(fx), 16 - 1);
+            const float filterWt = rp.filterTable[ify * 16 + ifx];
+            PbrtGpuPixel *px = film + (size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart);
+            atomicAdd(&px->Lxyz[0], filterWt * xyz[0]);
+            atomicAdd(&px->Lxyz[1], filterWt * xyz[1]);
+            atomicAdd(&px->Lxyz[2], filterWt * xyz[2]);
+            atomicAdd(&px->weightSum, filterWt);
+        }
+    }
+}
+// The same, for sample `row` of a task-pixel whose radiance waited in ls[]: the image position again from the pixel's
+// LD tables (LDPixelSample's first two dimensions, as CameraRay computes them)
+DEV void FilmAddFilteredRow(const RenderParams &rp, PbrtGpuPixel *film, const uint16_t *row, const uint32_t *scr, int xPos,
+                            int yPos, const Spec &L) {
+    const uint32_t pi = row[0];
+    FilmAddFiltered(rp, film, xPos + VanDerCorput(pi, scr[0]), yPos + Sobol2(pi, scr[1]), L);
+}
+// u16 entries per table row of the render's integrator (PathIntegrator: fixed layout; directlighting: per scene)
+DEV int FilmRowStride(const RenderParams &rp) {
+    return rp.integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING ? rp.lay.rowStride : PERM_STRIDE;
+}
+#endif
 
 // samplerrenderer.cpp:119-133: NaN / negative / infinite luminance -> black
 DEV Spec SanitizeRadiance(const Spec &L) {

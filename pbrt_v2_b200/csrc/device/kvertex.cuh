@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(128) k_film(const __grid_constant__ PathArgs a
     const bool direct = a.directFilm != 0;
     for (int s = 0; s < spp; ++s) {
         const float4 v = __ldcs(ls + s);
-        FilmAdd(rp, a.film, xPos, yPos, __float_as_int(v.w) & (LS_LEFT | LS_RIGHT | LS_UP | LS_DOWN), Spec(v.x, v.y, v.z), acc, direct);
+        FILM_ADD(a.b.perm + ((size_t)bi * spp + s) * PERM_STRIDE, a.b.scr + (size_t)bi * SCR_STRIDE,
+                 __float_as_int(v.w) & (LS_LEFT | LS_RIGHT | LS_UP | LS_DOWN), Spec(v.x, v.y, v.z));
     }
     if (!direct) {
         PbrtGpuPixel *px = a.film + (size_t)(yPos - rp.yPixelStart) * rp.xPixelCount + (xPos - rp.xPixelStart);

@@ -108,6 +108,17 @@ DEV void FilmAdd(const RenderParams &rp, PbrtGpuPixel *film, int ownX, int ownY,
         }
 }
 
+// one sample into the film at the sites below (xPos, yPos, acc, direct, rp, a in scope): through the weight table when the
+// render has one (PBRT_FILTER builds), else the 0.5 box's footprint bits
+#if PBRT_FILTER
+#define FILM_ADD(row, scr, code, L)                                                                     \
+    do {                                                                                                \
+        if (rp.filterTable) FilmAddFilteredRow(rp, a.film, (row), (scr), xPos, yPos, (L));              \
+        else FilmAdd(rp, a.film, xPos, yPos, (code), (L), acc, direct);                                 \
+    } while (0)
+#else
+#define FILM_ADD(row, scr, code, L) FilmAdd(rp, a.film, xPos, yPos, (code), (L), acc, direct)
+#endif
 
 template <int PHASE, bool STATS, bool ANIM>
 // 4 CTAs/SM (<= 128 registers): measured +9 % over the unconstrained 168-register build
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(const __grid_co
                 state = S_NEW_SAMPLE;   // next sample index is handed out at the top of the loop
             } else {
                 // samplerrenderer.cpp:111-146: sanity checks, then ImageFilm::AddSample
-                FilmAdd(rp, a.film, xPos, yPos, code, SanitizeRadiance(L), acc, direct);
+                FILM_ADD(permBase + (size_t)s * PERM_STRIDE, scr, code, SanitizeRadiance(L));
                 ++s;
                 state = S_NEW_SAMPLE;
             }
@@ -322,7 +333,7 @@ __global__ void __launch_bounds__(128, K_PATH_MIN_BLOCKS) k_path(const __grid_co
                         found = true;
                         state = S_HIT_RESULT;   // picked up (after the RNG top-up) next iteration
                     } else {
-                        FilmAdd(rp, a.film, xPos, yPos, code, Spec(v.x, v.y, v.z), acc, direct);
+                        FILM_ADD(permBase + (size_t)s * PERM_STRIDE, scr, code, Spec(v.x, v.y, v.z));
                         ++s;
                     }
                 }
@@ -630,7 +641,7 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(const __grid_
         if (PHASE == 2) {
             if (state == S_END_SAMPLE) {
                 // samplerrenderer.cpp:111-146: sanity checks, then ImageFilm::AddSample
-                FilmAdd(rp, a.film, xPos, yPos, code, SanitizeRadiance(L), acc, direct);
+                FILM_ADD(permBase + (size_t)s * rowStride, scr, code, SanitizeRadiance(L));
                 ++s;
                 state = S_NEW_SAMPLE;
             }
@@ -672,7 +683,7 @@ __global__ void __launch_bounds__(128, K_LOGIC_MIN_BLOCKS) k_logic(const __grid_
                         state = S_HIT_RESULT;
                         ctxDirty = true;
                     } else {
-                        FilmAdd(rp, a.film, xPos, yPos, code, Spec(v.x, v.y, v.z), acc, direct);
+                        FILM_ADD(permBase + (size_t)s * rowStride, scr, code, Spec(v.x, v.y, v.z));
                         ++s;
                     }
                 }
@@ -832,7 +843,8 @@ __global__ void __launch_bounds__(128) k_film_direct(const __grid_constant__ Pat
 #else
                 hits += ((code & LS_HIT) && 0 + 1 < rp.maxDepth) ? 1 : 0;
 #endif
-                FilmAdd(rp, a.film, xPos, yPos, code & (LS_LEFT | LS_RIGHT | LS_UP | LS_DOWN), Spec(v.x, v.y, v.z), acc, direct);
+                FILM_ADD(a.b.perm + ((size_t)bi * spp + s) * rp.lay.rowStride, a.b.scr + (size_t)bi * SCR_STRIDE,
+                         code & (LS_LEFT | LS_RIGHT | LS_UP | LS_DOWN), Spec(v.x, v.y, v.z));
             }
             if (!direct) {
                 PbrtGpuPixel *px = a.film + (size_t)(yPos - rp.yPixelStart) * rp.xPixelCount + (xPos - rp.xPixelStart);
@@ -1190,6 +1202,9 @@ struct PbrtGpuScene {
     int nMeasuredMaterials = 0;
     int nSpecularMaterials = 0;
     int nInfiniteLights = 0;
+#if PBRT_FILTER
+    DevBuf<float> filterTable;   // the current render's ImageFilm::filterTable (RenderParams::filterTable)
+#endif
     bool valid = false;     // false while an upload is in progress or after one failed half way
 };
 
@@ -1235,11 +1250,17 @@ int ValidateRenderDesc(const PbrtGpuRenderDesc &rd) {
     const int spp = rd.samplesPerPixel;
     if (spp <= 0 || (spp & (spp - 1))) return Fail(PBRTGPU_EINVAL, "samplesPerPixel must be a power of two (LDSampler)");
     if (spp > 8192) return Fail(PBRTGPU_EUNSUPPORTED, "samplesPerPixel > 8192 does not fit the table kernel's shared memory");
+#if PBRT_FILTER
+    if (!(rd.filterXWidth > 0.f) || !(rd.filterYWidth > 0.f)) return Fail(PBRTGPU_EINVAL, "bad filter width");
+    if (rd.filterXWidth > 31.f || rd.filterYWidth > 31.f)
+        return Fail(PBRTGPU_EUNSUPPORTED, "filters wider than 31 pixels exceed the film code's 64-pixel footprint");
+#else
     if (rd.filterXWidth > 0.5f || rd.filterYWidth > 0.5f)
         return Fail(PBRTGPU_EUNSUPPORTED, "filters wider than the 0.5 box need cross-task splats (out of scope)");
     if (rd.hasFilterTable)
         for (int i = 0; i < 256; ++i)
             if (rd.filterTable[i] != 1.f) return Fail(PBRTGPU_EUNSUPPORTED, "pixel filters other than the box filter are rendered by the oracle only");
+#endif
     if (rd.nTasks <= 0 || rd.taskBegin < 0 || rd.taskEnd > rd.nTasks || rd.taskBegin > rd.taskEnd)
         return Fail(PBRTGPU_EINVAL, "bad task range");
     if (rd.maxDepth < 0) return Fail(PBRTGPU_EINVAL, "bad maxDepth");
@@ -1812,6 +1833,9 @@ int RunLane(LaneJob &job) {
             PathArgs pa;
             pa.sc = scene->d; pa.rp = rp; pa.b = b; pa.film = film; pa.stats = scene->stats.p;
             pa.directFilm = rounds > 1 ? 1 : 0;
+#if PBRT_FILTER
+            if (rp.filterTable) pa.directFilm = 1;   // no own-pixel accumulator: the pixel may lie outside the film
+#endif
             pa.lockstep = cfg.lockstep;
             VxArgs va;
             va.sc = scene->d; va.rp = rp; va.b = b; va.workCounter = ln->workCounter.p;
@@ -2154,6 +2178,21 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     rp.xPixelCount = ext.xPixelCount; rp.yPixelCount = ext.yPixelCount;
     rp.spp = spp; rp.maxDepth = rd->maxDepth;
     rp.integrator = rd->integrator; rp.lightStrategy = rd->lightStrategy;
+#if PBRT_FILTER
+    {   // the 0.5 box keeps its footprint-bit path (FilmAdd); everything else goes through the weight table
+        bool box = rd->filterXWidth <= 0.5f && rd->filterYWidth <= 0.5f;
+        float table[256];
+        for (int i = 0; i < 256; ++i) {
+            table[i] = rd->hasFilterTable ? rd->filterTable[i] : 1.f;
+            if (table[i] != 1.f) box = false;
+        }
+        rp.filterTable = nullptr;
+        if (!box) {
+            CUDA_TRY(scene->filterTable.Upload(table, 256));
+            rp.filterTable = scene->filterTable.p;
+        }
+    }
+#endif
 
     // per task: permutation tables (64 B/sample) + finished radiance (16 B/sample) + parked
     // bounce-3 vertices (64 B/sample, sparse) + scrambles + two MT19937 blocks

@@ -432,7 +432,7 @@ bool Api::DoLight(const std::string &name, const ParamSet &params) {   // core/a
 bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
     // --- film + filter + camera (api.cpp:1272-1281, film/image.cpp:220-258) ---
     // MakeFilter, core/api.cpp:572-589; filters/{box,gaussian,mitchell,sinc,triangle}.cpp.  Filters wider than half a pixel
-    // are rendered by the oracle only (the device entry points refuse them): see PbrtGpuRenderDesc::filterTable
+    // reach the kernels as ImageFilm's weight table (PbrtGpuRenderDesc::filterTable; the shipped build refuses them)
     float fxw, fyw;
     std::function<float(float, float)> evaluate;
     if (FilterName == "box") {

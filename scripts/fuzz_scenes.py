@@ -2,7 +2,9 @@
 """Random in-scope scenes: the unmodified reference binary vs the oracle vs the device code compiled for the host
 (tests/native/device_on_host.cpp).  CPU only.  usage: fuzz_scenes.py [n] [seed0] [flags]
 flags (joined with +): specular, metal (materials; metal builds the harness with -DPBRT_METAL=1), pairs (-DPBRT_PAIR_NODES=1),
-crop, infinite (constant-radiance InfiniteAreaLights; the harness is built with -DPBRT_INFINITE=1), wave (PathIntegrator scenes run through the vertex-wavefront KERNELS -- kwave.cuh's k_wshade / k_weval / k_wtrace /
+crop, infinite (constant-radiance InfiniteAreaLights; the harness is built with -DPBRT_INFINITE=1), filter (a random
+PixelFilter on half of the scenes, harness built with -DPBRT_FILTER=1: such scenes run on one core -- the only order the
+reference defines for them -- through the state machine, and EVERY pixel is compared), wave (PathIntegrator scenes run through the vertex-wavefront KERNELS -- kwave.cuh's k_wshade / k_weval / k_wtrace /
 k_wcompact, launches as loops -- over a pool of 3, 17 or 4096 slots instead of the state machine)"""
 import ctypes as C, os, subprocess, sys
 import numpy as np
@@ -28,6 +30,14 @@ def gen(rng, path, animated=None):
     if len(sys.argv) > 3 and "crop" in sys.argv[3] and rng.rand() < .5:
         a, b = sorted(rng.uniform(0, 1, 2)); c, d = sorted(rng.uniform(0, 1, 2))
         film += ' "float cropwindow" [%g %g %g %g]' % (a, max(b, a + .2), c, max(d, c + .2))
+    if len(sys.argv) > 3 and "filter" in sys.argv[3] and rng.rand() < .5:
+        name = rng.choice(["box", "gaussian", "mitchell", "sinc", "triangle"])
+        f = 'PixelFilter "%s"' % name
+        if rng.rand() < .6: f += ' "float xwidth" [%g] "float ywidth" [%g]' % (rng.uniform(.3, 3.5), rng.uniform(.3, 3.5))
+        if name == "gaussian" and rng.rand() < .5: f += ' "float alpha" [%g]' % rng.uniform(.5, 4)
+        if name == "mitchell" and rng.rand() < .5: f += ' "float B" [%g] "float C" [%g]' % (rng.uniform(0, 1), rng.uniform(0, 1))
+        if name == "sinc" and rng.rand() < .5: f += ' "float tau" [%g]' % rng.uniform(1, 5)
+        L.append(f)
     L.append(film)
     L.append('Sampler "lowdiscrepancy" "integer pixelsamples" [%d]' % spp)
     integ = rng.choice(["path", "directlighting"])
@@ -144,9 +154,10 @@ def main():
     metal = len(sys.argv) > 3 and "metal" in sys.argv[3]
     wave = len(sys.argv) > 3 and "wave" in sys.argv[3]
     infinite = len(sys.argv) > 3 and "infinite" in sys.argv[3]
-    so = "/tmp/libdoh_fuzz%s%s%s%s.so" % ("_spec" if spec else "", "_pairs" if pairs else "", "_metal" if metal else "", "_inf" if infinite else "")
+    filt = len(sys.argv) > 3 and "filter" in sys.argv[3]
+    so = "/tmp/libdoh_fuzz%s%s%s%s%s.so" % ("_spec" if spec else "", "_pairs" if pairs else "", "_metal" if metal else "", "_inf" if infinite else "", "_filt" if filt else "")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic",
-                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) + (["-DPBRT_PAIR_NODES=1"] if pairs else []) + (["-DPBRT_METAL=1"] if metal else []) + (["-DPBRT_INFINITE=1"] if infinite else []) +
+                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) + (["-DPBRT_PAIR_NODES=1"] if pairs else []) + (["-DPBRT_METAL=1"] if metal else []) + (["-DPBRT_INFINITE=1"] if infinite else []) + (["-DPBRT_FILTER=1"] if filt else []) +
                    [os.path.join(REPO, "tests/native/device_on_host.cpp"), "-o", so], check=True)
     doh = C.CDLL(so)
     doh.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
@@ -157,6 +168,8 @@ def main():
         path = os.path.join(scenes.STAGED, "fuzz-%d.pbrt" % seed)
         spp = gen(rng, path)
         ncores = int(rng.choice([1, 2, 64]))
+        filtered = "PixelFilter" in open(path).read()
+        if filtered: ncores = 1
         try:
             hs = pb.HostScene(path, ncores=ncores)
         except pb.PbrtGpuError as e:
@@ -169,12 +182,13 @@ def main():
         o = hs.pixels_to_rgb(px)
         rd = hs.render_desc()
         px2 = hs.new_pixels()
-        doh.doh_set_vertex_form(int(rng.choice([3, 17, 4096])) if wave else 0)
+        doh.doh_set_vertex_form(int(rng.choice([3, 17, 4096])) if wave and not filtered else 0)
         doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
         own = px["weightSum"] == spp
+        if filtered: own = np.ones_like(own)
         d_ref = int((o.view(np.uint32) != ref.view(np.uint32)).any(axis=2)[own].sum()) if o.shape == ref.shape else -1
         d_dev = int((px2["Lxyz"].view(np.uint32) != px["Lxyz"].view(np.uint32)).any(axis=2)[own].sum())
-        w_dev = bool(np.array_equal(px2["weightSum"], px["weightSum"]))
+        w_dev = bool(np.array_equal(px2["weightSum"].view(np.uint32), px["weightSum"].view(np.uint32)))
         flag = "" if (d_ref == 0 and d_dev == 0 and w_dev) else "   <<<<<<"
         bad += bool(flag)
         if not flag:   # keep only the scenes worth looking at

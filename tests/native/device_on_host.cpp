@@ -50,6 +50,7 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int) { ret
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+static inline float atomicAdd(float *p, float v) { float o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 template <typename T> static inline T __ldcs(const T *p) { return *p; }
@@ -197,6 +198,27 @@ void LayoutH(const PbrtGpuRenderDesc &rd, SampleLayoutDev *L) {
 }
 
 // LDPixelSample (montecarlo.cpp:200-252) on sequence INDICES: what k_tables / k_tables_general leave in a task's rows
+// ImageFilm::AddSample: through the footprint bits for the 0.5 box (FilmAdd in pbrtgpu.cu, without atomics), through the
+// weight table otherwise (dpath.cuh FilmAddFilteredRow, PBRT_FILTER builds: the device code itself)
+void FilmAddH(const RenderParams &rp, PbrtGpuPixel *film, int xPos, int yPos, int code, const uint16_t *row, const uint32_t *scr,
+              const Spec &Ls) {
+#if PBRT_FILTER
+    if (rp.filterTable) { FilmAddFilteredRow(rp, film, row, scr, xPos, yPos, Ls); return; }
+#endif
+    (void)row; (void)scr;
+    float xyz[3];
+    xyz[0] = 0.412453f * Ls.r + 0.357580f * Ls.g + 0.180423f * Ls.b;
+    xyz[1] = 0.212671f * Ls.r + 0.715160f * Ls.g + 0.072169f * Ls.b;
+    xyz[2] = 0.019334f * Ls.r + 0.119193f * Ls.g + 0.950227f * Ls.b;
+    const int fy0 = yPos - ((code & LS_UP) ? 1 : 0), fy1 = yPos + ((code & LS_DOWN) ? 1 : 0);
+    const int fx0 = xPos - ((code & LS_LEFT) ? 1 : 0), fx1 = xPos + ((code & LS_RIGHT) ? 1 : 0);
+    for (int y = fy0; y <= fy1; ++y)
+        for (int x = fx0; x <= fx1; ++x) {
+            PbrtGpuPixel &px = film[(size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart)];
+            px.Lxyz[0] += xyz[0]; px.Lxyz[1] += xyz[1]; px.Lxyz[2] += xyz[2]; px.weightSum += 1.f;
+        }
+}
+
 void TablesH(const SampleLayoutDev &L, int spp, Stream &rng, int *pos, std::vector<uint16_t> *rows, uint32_t *scr) {
     rows->assign((size_t)spp * L.rowStride, 0);
     auto array = [&](int n, int dims, int rowAt, int scrAt) {
@@ -330,17 +352,7 @@ void RunTaskH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
 #endif
                 // ImageFilm::AddSample through the footprint bits (FilmAdd in pbrtgpu.cu, without atomics)
                 const Spec Ls = SanitizeRadiance(L);
-                float xyz[3];
-                xyz[0] = 0.412453f * Ls.r + 0.357580f * Ls.g + 0.180423f * Ls.b;
-                xyz[1] = 0.212671f * Ls.r + 0.715160f * Ls.g + 0.072169f * Ls.b;
-                xyz[2] = 0.019334f * Ls.r + 0.119193f * Ls.g + 0.950227f * Ls.b;
-                const int fy0 = yPos - ((code & LS_UP) ? 1 : 0), fy1 = yPos + ((code & LS_DOWN) ? 1 : 0);
-                const int fx0 = xPos - ((code & LS_LEFT) ? 1 : 0), fx1 = xPos + ((code & LS_RIGHT) ? 1 : 0);
-                for (int y = fy0; y <= fy1; ++y)
-                    for (int x = fx0; x <= fx1; ++x) {
-                        PbrtGpuPixel &px = film[(size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart)];
-                        px.Lxyz[0] += xyz[0]; px.Lxyz[1] += xyz[1]; px.Lxyz[2] += xyz[2]; px.weightSum += 1.f;
-                    }
+                FilmAddH(rp, film, xPos, yPos, code, permBase + (size_t)s * rowStride, scr, Ls);
             }
         }
 }
@@ -424,17 +436,7 @@ void RunTaskVertexH(const DScene &sc, const RenderParams &rp, const PbrtGpuRende
                     if (!found) EscapedRadiance(sc, ray.d, false, afterSpecular, T, L);
                 }
                 const Spec Ls = SanitizeRadiance(L);
-                float xyz[3];
-                xyz[0] = 0.412453f * Ls.r + 0.357580f * Ls.g + 0.180423f * Ls.b;
-                xyz[1] = 0.212671f * Ls.r + 0.715160f * Ls.g + 0.072169f * Ls.b;
-                xyz[2] = 0.019334f * Ls.r + 0.119193f * Ls.g + 0.950227f * Ls.b;
-                const int fy0 = yPos - ((code & LS_UP) ? 1 : 0), fy1 = yPos + ((code & LS_DOWN) ? 1 : 0);
-                const int fx0 = xPos - ((code & LS_LEFT) ? 1 : 0), fx1 = xPos + ((code & LS_RIGHT) ? 1 : 0);
-                for (int y = fy0; y <= fy1; ++y)
-                    for (int x = fx0; x <= fx1; ++x) {
-                        PbrtGpuPixel &px = film[(size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart)];
-                        px.Lxyz[0] += xyz[0]; px.Lxyz[1] += xyz[1]; px.Lxyz[2] += xyz[2]; px.weightSum += 1.f;
-                    }
+                FilmAddH(rp, film, xPos, yPos, code, row, scrBuf, Ls);
             }
         }
 }
@@ -557,18 +559,8 @@ void RunWaveH(const DScene &sc, const RenderParams &rp, const PbrtGpuRenderDesc 
             for (int s = 0; s < spp; ++s) {
                 const float4 v = ls[i * spp + s];
                 const int code = __float_as_int(v.w);
-                const Spec L(v.x, v.y, v.z);
-                float xyz[3];
-                xyz[0] = 0.412453f * L.r + 0.357580f * L.g + 0.180423f * L.b;
-                xyz[1] = 0.212671f * L.r + 0.715160f * L.g + 0.072169f * L.b;
-                xyz[2] = 0.019334f * L.r + 0.119193f * L.g + 0.950227f * L.b;
-                const int fy0 = yPos - ((code & LS_UP) ? 1 : 0), fy1 = yPos + ((code & LS_DOWN) ? 1 : 0);
-                const int fx0 = xPos - ((code & LS_LEFT) ? 1 : 0), fx1 = xPos + ((code & LS_RIGHT) ? 1 : 0);
-                for (int y = fy0; y <= fy1; ++y)
-                    for (int x = fx0; x <= fx1; ++x) {
-                        PbrtGpuPixel &px = film[(size_t)(y - rp.yPixelStart) * rp.xPixelCount + (x - rp.xPixelStart)];
-                        px.Lxyz[0] += xyz[0]; px.Lxyz[1] += xyz[1]; px.Lxyz[2] += xyz[2]; px.weightSum += 1.f;
-                    }
+                FilmAddH(rp, film, xPos, yPos, code, perm.data() + (i * spp + s) * PERM_STRIDE, scr.data() + i * SCR_STRIDE,
+                         Spec(v.x, v.y, v.z));
             }
         }
     }
@@ -594,12 +586,23 @@ DOH_EXPORT int doh_render(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc 
     rp.spp = rd->samplesPerPixel; rp.maxDepth = rd->maxDepth;
     rp.integrator = rd->integrator; rp.lightStrategy = rd->lightStrategy;
     LayoutH(*rd, &rp.lay);
+#if PBRT_FILTER
+    {   // as pbrtgpu_render_device: the 0.5 box keeps the footprint bits, everything else reads the table
+        static float table[256];
+        bool box = rd->filterXWidth <= 0.5f && rd->filterYWidth <= 0.5f;
+        for (int i = 0; i < 256; ++i) {
+            table[i] = rd->hasFilterTable ? rd->filterTable[i] : 1.f;
+            if (table[i] != 1.f) box = false;
+        }
+        rp.filterTable = box ? nullptr : table;
+    }
+#endif
     memset(pixels, 0, sizeof(PbrtGpuPixel) * (size_t)ext.xc * ext.yc);
     if (g_vertexForm >= 2 && rd->integrator != PBRTGPU_INTEGRATOR_DIRECTLIGHTING) {
         RunWaveH(hs.d, rp, *rd, ext, pixels, (uint32_t)g_vertexForm);   // (the value is the pool size: small pools force slot reuse)
         return 0;
     }
-    for (int t = rd->taskBegin; t < rd->taskEnd; ++t) {
+    for (int t = rd->taskEnd - 1; t >= rd->taskBegin; --t) {   // the reference's one-thread order (samplerrenderer.cpp:212)
         if (rd->integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING) RunTaskH<1>(hs.d, rp, *rd, t, ext, pixels);
         else if (g_vertexForm) RunTaskVertexH(hs.d, rp, *rd, t, ext, pixels);
         else RunTaskH<0>(hs.d, rp, *rd, t, ext, pixels);

@@ -251,6 +251,46 @@ def test_infinite_light_device_code_on_host(staged, tmp_path_factory):
     lib.doh_set_vertex_form(0)
 
 
+def test_pixel_filter_device_code_on_host(staged, tmp_path_factory):
+    """ImageFilm::AddSample through the 16 x 16 weight table (dpath.cuh FilmAddFiltered under -DPBRT_FILTER=1: gaussian,
+    mitchell, triangle, sinc, wide box; not in the shipped kernels, never run on a GPU).  One host thread adding task by task
+    IS the reference's --ncores 1 order, so the state machine and the vertex form must give the oracle's one-thread film bit
+    for bit, every pixel (the oracle is pinned on the reference binary for the same scenes, test_oracle_pinning.py).  The wave
+    kernels add pixel round by pixel round over all tasks -- an order the reference only has above one thread, where it is
+    undefined -- so their films are compared to rounding."""
+    from helpers import FILTER_VARIANTS, variant_scene
+    lib = _build(tmp_path_factory, "device_on_host_filter", ["-DPBRT_FILTER=1"])
+    lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+
+    def films(hs):
+        rd = hs.render_desc()
+        px = hs.new_pixels()
+        lib.doh_render(hs.desc_ptr, C.byref(rd), px.ctypes.data)
+        ref, _ = oa.render(hs, threads=1)
+        return px, ref
+
+    for form in (0, 1):
+        lib.doh_set_vertex_form(form)
+        for v in FILTER_VARIANTS:
+            if form == 1 and v[6].get("integrator", "path") != "path":
+                continue
+            px, ref = films(variant_scene(v[0])[0])
+            assert np.array_equal(px["weightSum"].view(np.uint32), ref["weightSum"].view(np.uint32)), (form, v[0])
+            assert np.array_equal(px["Lxyz"].view(np.uint32), ref["Lxyz"].view(np.uint32)), (form, v[0])
+        _same_film(lib, host_scene("bunny", 24, 24, 4, 8))   # the 0.5 box keeps its footprint-bit path
+    for form in (3, 4096):
+        lib.doh_set_vertex_form(form)
+        for v in FILTER_VARIANTS:
+            if v[6].get("integrator", "path") != "path":
+                continue
+            px, ref = films(variant_scene(v[0])[0])
+            for f in ("weightSum", "Lxyz"):
+                scale = np.abs(ref[f]).max()
+                assert np.abs(px[f].astype(np.float64) - ref[f]).max() <= 4e-6 * scale, (form, v[0], f)
+        _same_film(lib, host_scene("bunny", 24, 24, 4, 8))
+    lib.doh_set_vertex_form(0)
+
+
 def test_pair_node_walk_on_host(staged, tmp_path_factory):
     """The sibling-pair node layout (-DPBRT_PAIR_NODES=1, device/dscene.cuh: a round-2 kernel experiment that is not in the
     shipped kernels) must walk the tree exactly like the reference-shaped loop: same hits, same `t`, same films -- both the
