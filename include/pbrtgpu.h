@@ -147,18 +147,32 @@ typedef struct PbrtGpuMeasured {
 
 /* ---- lights, lights/{point,diffuse}.cpp, core/light.cpp:114-171 ------------ */
 enum { PBRTGPU_LIGHT_POINT = 0, PBRTGPU_LIGHT_DIFFUSE_AREA = 1,
-       /* InfiniteAreaLight (lights/infinite.cpp) with a constant radiance (no "mapname": a 1x1 radiance map).  Host front end
-        * + oracle (pinned on the reference binary) only: pbrtgpu_scene_create answers PBRTGPU_EUNSUPPORTED. */
+       /* InfiniteAreaLight (lights/infinite.cpp): radiance map + sampling distribution in envMaps[] (a 1x1 map without
+        * "mapname").  Host front end + oracle (pinned on the reference binary); the shipped kernels do not hold the code
+        * (PBRT_INFINITE=0): pbrtgpu_scene_create answers PBRTGPU_EUNSUPPORTED. */
        PBRTGPU_LIGHT_INFINITE = 2 };
 typedef struct PbrtGpuLight {
     uint32_t type;
     float    L[3];        /* POINT: Intensity; AREA: Lemit; INFINITE: L * scale  */
     float    pos[3];      /* POINT: lightPos (world)                            */
     uint32_t firstShape;  /* AREA: ShapeSet::shapes, into lightShapes[]; INFINITE: LightToWorld, into xforms[] */
-    uint32_t nShapes;     /* in scope: exactly 1 (sphere or disk)               */
+    uint32_t nShapes;     /* AREA: in scope exactly 1 (sphere or disk); INFINITE: index into envMaps[] */
     float    sumArea;     /* ShapeSet::sumArea                                  */
     int32_t  nSamples;    /* Light::nSamples (core/light.h:53,78; "nsamples" of an area light); 0 reads as 1 */
 } PbrtGpuLight;
+/* InfiniteAreaLight's members as its constructor leaves them (lights/infinite.cpp:67-104): level 0 of the radiance MIPMap
+ * (texels already times L * scale, resampled to a power of two like core/mipmap.h:118-168) and the Distribution2D over
+ * luminance x sin(theta) of the filtered map (core/montecarlo.h:54-80, montecarlo.cpp:358-370).  All offsets into envData[]. */
+typedef struct PbrtGpuEnvMap {
+    uint32_t width, height;   /* MIPMap::Width() / Height(): pyramid[0], a power of two each            */
+    uint32_t texels;          /* 3 * width * height floats, RGB, row t = 0 first (image file order)     */
+    uint32_t nu, nv;          /* Distribution2D: the image file's own resolution                        */
+    uint32_t func;            /* nu * nv: pConditionalV[v]->func[u]                                     */
+    uint32_t cdf;             /* nv * (nu + 1): pConditionalV[v]->cdf                                   */
+    uint32_t funcInt;         /* nv: pConditionalV[v]->funcInt == pMarginal->func[v]                    */
+    uint32_t margCdf;         /* nv + 1: pMarginal->cdf                                                 */
+    float    margFuncInt;     /* pMarginal->funcInt                                                     */
+} PbrtGpuEnvMap;
 typedef struct PbrtGpuLightShape {
     uint32_t type;        /* PBRTGPU_PRIM_SPHERE | PBRTGPU_PRIM_DISK            */
     uint32_t index;       /* into quadrics[]                                    */
@@ -183,6 +197,9 @@ typedef struct PbrtGpuSceneDesc {
     uint32_t nLights;       const PbrtGpuLight      *lights;
     uint32_t nLightShapes;  const PbrtGpuLightShape *lightShapes;
     uint32_t nAnimated;     const PbrtGpuAnimated   *animated;    /* may be 0 / NULL                               */
+    /* (appended in round 2: earlier offsets are unchanged) one entry per InfiniteAreaLight */
+    uint32_t nEnvMaps;      const PbrtGpuEnvMap     *envMaps;     /* may be 0 / NULL                               */
+    uint32_t nEnvData;      const float             *envData;
 } PbrtGpuSceneDesc;
 
 /* ---- one Render() call ----------------------------------------------------- */

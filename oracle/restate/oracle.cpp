@@ -1123,16 +1123,29 @@ struct Renderer {
         return XfPoint(x.m, p);
     }
 
-    // ---- InfiniteAreaLight over a 1x1 radiance map (lights/infinite.cpp:67-104 without "mapname": texels[0] = L) ----
+    // ---- InfiniteAreaLight (lights/infinite.cpp): radiance map level 0 + Distribution2D arrive ready-made in envMaps[] ----
+    // (what the constructor computes, infinite.cpp:67-104, is host front-end work: pbrt_v2_b200/csrc/host/envmap.cpp)
     // MIPMap::Lookup(s, t, width = 0) (core/mipmap.h:239-255): level = nLevels - 1 + Log2(1e-8) < 0 -> triangle(0, s, t)
-    // (:259-269): bilinear weights over four reads of the one texel (TEXTURE_REPEAT wraps every index to 0)
-    static Spec InfiniteLookup(const PbrtGpuLight &l, float s, float t) {
-        s = s * 1 - 0.5f;   // pyramid[0]->uSize() == vSize() == 1
-        t = t * 1 - 0.5f;
+    // (:259-269): bilinear over level 0, TEXTURE_REPEAT wraps every index (Texel, :203-228; Mod, pbrt.h:237-242)
+    static int Mod(int a, int b) {
+        int n = int(a / b);
+        a -= n * b;
+        if (a < 0) a += b;
+        return a;
+    }
+    Spec EnvTexel(const PbrtGpuEnvMap &m, int s, int t) const {
+        s = Mod(s, (int)m.width);
+        t = Mod(t, (int)m.height);
+        return Spec(sv.d->envData + m.texels + 3 * ((size_t)t * m.width + s));
+    }
+    Spec InfiniteLookup(const PbrtGpuLight &l, float s, float t) const {
+        const PbrtGpuEnvMap &m = sv.d->envMaps[l.nShapes];
+        s = s * m.width - 0.5f;
+        t = t * m.height - 0.5f;
         int s0 = Floor2Int(s), t0 = Floor2Int(t);
         float ds = s - s0, dt = t - t0;
-        Spec texel(l.L);
-        return (1.f - ds) * (1.f - dt) * texel + (1.f - ds) * dt * texel + ds * (1.f - dt) * texel + ds * dt * texel;
+        return (1.f - ds) * (1.f - dt) * EnvTexel(m, s0, t0) + (1.f - ds) * dt * EnvTexel(m, s0, t0 + 1) +
+               ds * (1.f - dt) * EnvTexel(m, s0 + 1, t0) + ds * dt * EnvTexel(m, s0 + 1, t0 + 1);
     }
     // Light::Le(ray) (core/light.cpp:59-61: black) / InfiniteAreaLight::Le (infinite.cpp:114-119)
     Spec LightLe(const PbrtGpuLight &l, const Ray &r) const {
@@ -1147,24 +1160,34 @@ struct Renderer {
         for (uint32_t i = 0; i < sv.d->nLights; ++i) L += LightLe(sv.d->lights[i], r);
         return L;
     }
-    // the sampling distribution of the 1x1 map (infinite.cpp:88-103, montecarlo.h:99-167): one function value
-    // f = L.y() * sinf(pi * .5); Distribution1D over it: cdf = {0, 1} (or {0, 1} by the funcInt == 0 branch), funcInt = f
-    static float InfiniteFunc(const PbrtGpuLight &l) { return Spec(l.L).y() * sinf(PI_F * float(0 + .5f) / float(1)); }
-    // Distribution2D::SampleContinuous(u0, u1, uv, &pdf) over that function
-    static void InfiniteSampleContinuous(const PbrtGpuLight &l, float u0, float u1, float uv[2], float *pdf) {
-        const float f = InfiniteFunc(l);
-        // pMarginal->SampleContinuous(u1): offset 0, du = (u1 - cdf[0]) / (cdf[1] - cdf[0]), pdf = func[0] / funcInt
-        float pdf1 = f / f;        // marginal: func[0] = the row's funcInt = f, funcInt = f / 1 = f
-        uv[1] = (0 + (u1 - 0.f) / (1.f - 0.f)) / 1;
-        float pdf0 = f / f;
-        uv[0] = (0 + (u0 - 0.f) / (1.f - 0.f)) / 1;
-        *pdf = pdf0 * pdf1;
+    // Distribution1D::SampleContinuous(u, &pdf, &off), montecarlo.h:81-97 (std::upper_bound: first cdf entry > u)
+    static float SampleContinuous1D(const float *func, const float *cdf, float funcInt, int count, float u, float *pdf, int *off) {
+        const float *ptr = std::upper_bound(cdf, cdf + count + 1, u);
+        int offset = std::max(0, int(ptr - cdf - 1));
+        if (off) *off = offset;
+        float du = (u - cdf[offset]) / (cdf[offset + 1] - cdf[offset]);
+        if (pdf) *pdf = func[offset] / funcInt;
+        return (offset + du) / count;
     }
-    // Distribution2D::Pdf(u, v), montecarlo.h:158-166
-    static float InfiniteMapPdf(const PbrtGpuLight &l, float, float) {
-        const float f = InfiniteFunc(l);
-        if (f * f == 0.f) return 0.f;
-        return (f * f) / (f * f);
+    // Distribution2D::SampleContinuous(u0, u1, uv, &pdf), montecarlo.h:146-153
+    void InfiniteSampleContinuous(const PbrtGpuLight &l, float u0, float u1, float uv[2], float *pdf) const {
+        const PbrtGpuEnvMap &m = sv.d->envMaps[l.nShapes];
+        const float *e = sv.d->envData;
+        float pdfs[2];
+        int v;
+        uv[1] = SampleContinuous1D(e + m.funcInt, e + m.margCdf, m.margFuncInt, (int)m.nv, u1, &pdfs[1], &v);
+        uv[0] = SampleContinuous1D(e + m.func + (size_t)v * m.nu, e + m.cdf + (size_t)v * (m.nu + 1), e[m.funcInt + v], (int)m.nu, u0,
+                                   &pdfs[0], nullptr);
+        *pdf = pdfs[0] * pdfs[1];
+    }
+    // Distribution2D::Pdf(u, v), montecarlo.h:154-162 (Float2Int truncates, pbrt.h:296-298)
+    float InfiniteMapPdf(const PbrtGpuLight &l, float u, float v) const {
+        const PbrtGpuEnvMap &m = sv.d->envMaps[l.nShapes];
+        const float *e = sv.d->envData;
+        int iu = std::min(std::max((int)(u * (int)m.nu), 0), (int)m.nu - 1);
+        int iv = std::min(std::max((int)(v * (int)m.nv), 0), (int)m.nv - 1);
+        if (e[m.funcInt + iv] * m.margFuncInt == 0.f) return 0.f;
+        return (e[m.func + (size_t)iv * m.nu + iu] * e[m.funcInt + iv]) / (e[m.funcInt + iv] * m.margFuncInt);
     }
 
     // ShapeSet::Pdf(p, wi), core/light.cpp:157-162 (one shape); InfiniteAreaLight::Pdf, infinite.cpp:229-239

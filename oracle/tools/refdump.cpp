@@ -22,11 +22,28 @@
 //        n uint32: the input index of the primitive at each position of the accelerator's reordered primitive list
 //   refdump metal
 //        the RGB coefficients of the default MetalMaterial's eta and k (copper) and its roughness, as hex floats
+//   refdump envmap <map.pfm | -> <Lr> <Lg> <Lb> <out.bin>
+//        the reference's own InfiniteAreaLight(identity, L, 1, map) ("-": no map): out.bin = uint32 width, height of
+//        radianceMap (level 0), nu, nv of the distribution; 3*width*height float32 level-0 texels (Texel(0, s, t), row t
+//        first); nu*nv func; nv*(nu+1) conditional cdf; nv conditional funcInt; nv+1 marginal cdf; 1 marginal funcInt
 //   refdump loopsubdiv <mesh.bin> <nlevels> <out.bin>
 //        the reference's own LoopSubdiv::Refine (mesh.bin: int32 nTriangles, nVertices, 3*nt int32 indices, 3*nv float32 P;
 //        identity transform): out.bin = uint32 nv, nt, then 3*nv float32 P, 3*nv float32 N, 3*nt int32 indices of the
 //        TriangleMesh it creates
+#include <vector>
+#include <map>
+#include <set>
+#include <string>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
 #include "pbrt.h"
+// Distribution1D / 2D keep their arrays private: this TOOL reads them where they lie (see the note further down)
+#define private public
+#include "montecarlo.h"
+#undef private
 #include "rng.h"
 #include "sampler.h"
 #include "samplers/lowdiscrepancy.h"
@@ -58,6 +75,7 @@
 #include "shapes/trianglemesh.h"
 #include "shapes/loopsubdiv.h"
 #include "materials/metal.h"
+#include "lights/infinite.h"
 #undef private
 #undef protected
 #include "texture.h"
@@ -115,6 +133,31 @@ int main(int argc, char **argv) {
         m->k->Evaluate(dg).ToRGB(rgb);
         printf("k %a %a %a\n", rgb[0], rgb[1], rgb[2]);
         printf("roughness %a\n", m->roughness->Evaluate(dg));
+        return 0;
+    }
+    if (argc >= 7 && !strcmp(argv[1], "envmap")) {
+        float rgb[3] = {(float)atof(argv[3]), (float)atof(argv[4]), (float)atof(argv[5])};
+        InfiniteAreaLight light(Transform(), Spectrum::FromRGB(rgb), 1, strcmp(argv[2], "-") ? argv[2] : "");
+        const MIPMap<RGBSpectrum> *m = light.radianceMap;
+        const Distribution2D *d = light.distribution;
+        FILE *f = fopen(argv[6], "wb");
+        if (!f) return 1;
+        const uint32_t w = m->Width(), h = m->Height();
+        const uint32_t nu = (uint32_t)d->pConditionalV[0]->count, nv = (uint32_t)d->pMarginal->count;
+        const uint32_t head[4] = {w, h, nu, nv};
+        fwrite(head, 4, 4, f);
+        for (uint32_t t = 0; t < h; ++t)
+            for (uint32_t s = 0; s < w; ++s) {
+                float c[3];
+                m->Texel(0, (int)s, (int)t).ToRGB(c);
+                fwrite(c, 4, 3, f);
+            }
+        for (uint32_t v = 0; v < nv; ++v) fwrite(d->pConditionalV[v]->func, 4, nu, f);
+        for (uint32_t v = 0; v < nv; ++v) fwrite(d->pConditionalV[v]->cdf, 4, nu + 1, f);
+        for (uint32_t v = 0; v < nv; ++v) fwrite(&d->pConditionalV[v]->funcInt, 4, 1, f);
+        fwrite(d->pMarginal->cdf, 4, nv + 1, f);
+        fwrite(&d->pMarginal->funcInt, 4, 1, f);
+        fclose(f);
         return 0;
     }
     if (argc >= 5 && !strcmp(argv[1], "bvh")) {

@@ -177,6 +177,8 @@ def host_lib():
                                                    C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pbrthost_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.POINTER(C.c_uint32),
                                            C.c_void_p]
+        lib.pbrthost_envmap_build.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pbrthost_envmap_build.restype = C.c_ulonglong
         _host = lib
     return _host
 
@@ -412,6 +414,34 @@ def host_bvh_build(bounds, max_prims_in_node=4, split_method=SPLIT_SAH):
     if rc:
         raise PbrtGpuError("pbrthost_bvh_build: bad arguments")
     return nodes[:nn.value].copy(), order
+
+
+def host_envmap_build(pfm, L):
+    """InfiniteAreaLight's constructor by the host front end (csrc/host/envmap.cpp) -> dict of the PbrtGpuEnvMap arrays:
+    width, height, nu, nv, texels [height, width, 3], func [nv, nu], cdf [nv, nu + 1], funcInt [nv], margCdf [nv + 1],
+    margFuncInt"""
+    L = np.ascontiguousarray(L, np.float32)
+    head = np.zeros(4, np.uint32)
+    name = pfm.encode() if pfm else None
+    n = host_lib().pbrthost_envmap_build(name, L.ctypes.data, head.ctypes.data, None)
+    if not n:
+        raise PbrtGpuError("pbrthost_envmap_build: cannot read %r" % pfm)
+    buf = np.zeros(n, np.float32)
+    host_lib().pbrthost_envmap_build(name, L.ctypes.data, head.ctypes.data, buf.ctypes.data)
+    return parse_envmap_dump(head, buf)
+
+
+def parse_envmap_dump(head, buf):
+    """the layout shared by pbrthost_envmap_build and `refdump envmap`"""
+    w, h, nu, nv = [int(x) for x in head]
+    out, at = {"width": w, "height": h, "nu": nu, "nv": nv}, 0
+    for key, shape in (("texels", (h, w, 3)), ("func", (nv, nu)), ("cdf", (nv, nu + 1)), ("funcInt", (nv,)), ("margCdf", (nv + 1,)),
+                       ("margFuncInt", (1,))):
+        n = int(np.prod(shape))
+        out[key] = buf[at:at + n].reshape(shape).copy()
+        at += n
+    assert at == len(buf)
+    return out
 
 
 class ControlMesh(object):

@@ -143,6 +143,29 @@ int pbrthost_bvh_build(const float *bounds, uint32_t n, uint32_t maxPrimsInNode,
     return 0;
 }
 
+// InfiniteAreaLight's constructor on a .pfm file (NULL / "": no map, one texel = L) -> the arrays a PbrtGpuEnvMap points at,
+// in the layout of `refdump envmap` (oracle/tools/refdump.cpp), its comparison partner: uint32 width, height, nu, nv; level-0
+// texels; func; conditional cdfs; conditional funcInts; marginal cdf; marginal funcInt.  Returns the float count written
+// after the 4-word head (out may be NULL to size the buffer), 0 on a read error.
+unsigned long long pbrthost_envmap_build(const char *pfm, const float L[3], uint32_t head[4], float *out) {
+    std::vector<float> rgb;
+    int w = 1, h = 1;
+    const bool haveMap = pfm && *pfm;
+    std::string err;
+    if (haveMap && !ReadImagePFM(pfm, &w, &h, &rgb, &err)) return 0;
+    EnvMap em;
+    BuildEnvMap(L, w, h, haveMap ? rgb.data() : nullptr, &em);
+    head[0] = (uint32_t)em.width; head[1] = (uint32_t)em.height; head[2] = (uint32_t)em.nu; head[3] = (uint32_t)em.nv;
+    const std::vector<float> *parts[5] = {&em.texels, &em.func, &em.cdf, &em.funcInt, &em.margCdf};
+    unsigned long long n = 0;
+    for (const std::vector<float> *v : parts) {
+        if (out) memcpy(out + n, v->data(), v->size() * sizeof(float));
+        n += v->size();
+    }
+    if (out) out[n] = em.margFuncInt;
+    return n + 1;
+}
+
 // LoopSubdiv on raw arrays (test hooks and the comparison partner of pbrtgpu_loopsubdiv_refine).
 // topology: the constructor's pass (loopsubdiv.cpp:156-216) -> the index arrays of PbrtGpuSubdivMesh
 int pbrthost_loopsubdiv_topology(int nVertices, int nFaces, const int *indices, const float *P, int32_t *startFace, uint8_t *vflags,

@@ -277,8 +277,26 @@ bool Scene::Flatten(std::string *err) {
             sumArea += ls.area;
             gl.sumArea = sumArea;
             fLightShapes.push_back(ls);
-        } else if (gl.type == PBRTGPU_LIGHT_INFINITE)
+        } else if (gl.type == PBRTGPU_LIGHT_INFINITE) {
             gl.firstShape = xformOf(&l.lightToWorld);
+            const EnvMap &em = *l.envMap;
+            auto append = [&](const std::vector<float> &v) {
+                const uint32_t at = (uint32_t)fEnvData.size();
+                fEnvData.insert(fEnvData.end(), v.begin(), v.end());
+                return at;
+            };
+            PbrtGpuEnvMap ge;
+            ge.width = (uint32_t)em.width; ge.height = (uint32_t)em.height;
+            ge.texels = append(em.texels);
+            ge.nu = (uint32_t)em.nu; ge.nv = (uint32_t)em.nv;
+            ge.func = append(em.func);
+            ge.cdf = append(em.cdf);
+            ge.funcInt = append(em.funcInt);
+            ge.margCdf = append(em.margCdf);
+            ge.margFuncInt = em.margFuncInt;
+            gl.nShapes = (uint32_t)fEnvMaps.size();
+            fEnvMaps.push_back(ge);
+        }
         fLights.push_back(gl);
     }
     if (bvh.nodes.empty()) { *err = "scene has no primitives"; return false; }
@@ -298,6 +316,8 @@ bool Scene::Flatten(std::string *err) {
     desc.nKdNodes = (uint32_t)fKdNodes.size();        desc.kdNodes = fKdNodes.data();
     desc.kdData = fKdData.data();
     desc.nLights = (uint32_t)fLights.size();          desc.lights = fLights.data();
+    desc.nEnvMaps = (uint32_t)fEnvMaps.size();        desc.envMaps = fEnvMaps.empty() ? nullptr : fEnvMaps.data();
+    desc.nEnvData = (uint32_t)fEnvData.size();        desc.envData = fEnvData.empty() ? nullptr : fEnvData.data();
     desc.nLightShapes = (uint32_t)fLightShapes.size(); desc.lightShapes = fLightShapes.data();
     desc.nAnimated = (uint32_t)fAnimated.size();      desc.animated = fAnimated.empty() ? nullptr : fAnimated.data();
     return true;

@@ -121,10 +121,22 @@ struct MeasuredData {   // materials/measured.cpp:85-135 + core/kdtree.h:101-147
 bool LoadIrregIsotropicBRDF(const std::string &filename, MeasuredData *out, std::string *err);
 
 // ------------------------------------------------------------------ Lights --
+// InfiniteAreaLight::radianceMap (level 0) and ::distribution as the constructor leaves them (envmap.cpp)
+struct EnvMap {
+    int width = 0, height = 0;   // level 0 of the MIPMap: powers of two
+    std::vector<float> texels;   // 3 * width * height
+    int nu = 0, nv = 0;          // the image file's resolution = the distribution's
+    std::vector<float> func, cdf, funcInt, margCdf;
+    float margFuncInt = 0.f;
+};
+bool ReadImagePFM(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);
+void BuildEnvMap(const float L[3], int width, int height, const float *rgb, EnvMap *out);
+
 struct Light {   // core/light.h:48-82; lights/point.h, lights/diffuse.h
     PbrtGpuLight desc;
     const Shape *shape;   // DiffuseAreaLight: the ShapeSet's (single) shape
     Transform lightToWorld;   // InfiniteAreaLight: Light::LightToWorld (core/light.h:57-60)
+    std::shared_ptr<EnvMap> envMap;   // InfiniteAreaLight
     Light() : shape(nullptr) { memset(&desc, 0, sizeof(desc)); }
 };
 
@@ -256,6 +268,8 @@ struct Scene {   // core/scene.h:45-70
     std::vector<PbrtGpuBrdfSample> fKdData;
     std::vector<PbrtGpuLight> fLights;
     std::vector<PbrtGpuLightShape> fLightShapes;
+    std::vector<PbrtGpuEnvMap> fEnvMaps;
+    std::vector<float> fEnvData;
     std::vector<PbrtGpuBVHNode> fNodes;
     std::vector<PbrtGpuAnimated> fAnimated;
     PbrtGpuSceneDesc desc;

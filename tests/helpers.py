@@ -1,4 +1,5 @@
 """Shared helpers for the parity tests."""
+import os
 import numpy as np
 
 import pbrt_v2_b200 as pb
@@ -159,6 +160,43 @@ INFINITE_VARIANTS = [
     ("path-infinite-bunny", "bunny", 40, 40, 8, 64, {}, [(_WB, _INF1)]),
 ]
 
+# ... with a radiance map ("mapname"): .pfm files written next to the staged scene by variant_scene (ENV_MAPS: file name ->
+# width, height, seed, channels, PFM scale word: negative = little-endian data, |scale| multiplies).  Powers of two and not
+# (MIPMap's Lanczos resampling; the distribution keeps the file's resolution), RGB and grey, both byte orders, 1x1.
+ENV_MAPS = {
+    "env-16x8.pfm": (16, 8, 1, 3, -1.0),
+    "env-12x7.pfm": (12, 7, 2, 3, -1.0),
+    "env-grey-8x8-be.pfm": (8, 8, 3, 1, 2.0),
+    "env-32x16.pfm": (32, 16, 4, 3, -0.5),
+    "env-1x1.pfm": (1, 1, 5, 3, -1.0),
+    "env-5x3.pfm": (5, 3, 6, 3, -1.0),
+}
+def _inf_map(fn, extra=""):
+    return _WB + '\nAttributeBegin\nRotate 35 1 .2 0\nLightSource "infinite" "string mapname" "%s"%s\nAttributeEnd\n' % (fn, extra)
+ENVMAP_VARIANTS = [
+    ("path-envmap-pow2", "killeroo-simple", 40, 40, 4, 2, {}, [(_WB, _inf_map("env-16x8.pfm"))]),
+    ("path-envmap-npot-specular", "killeroo-simple", 40, 40, 4, 2, {"maxdepth": 8},
+     [(_WB, _inf_map("env-12x7.pfm", ' "color L" [.5 .6 .9] "integer nsamples" [2]')), (_M1, 'Material "glass"'), (_M2, 'Material "mirror"')]),
+    ("direct-envmap-npot", "killeroo-simple", 40, 40, 4, 2, {"integrator": "directlighting"},
+     [(_WB, _inf_map("env-5x3.pfm", ' "integer nsamples" [4]')), (_M2, 'Material "mirror"')]),
+    ("direct-one-envmap-grey", "bunny", 40, 40, 4, 1, {"integrator": "directlighting", "strategy": "one"},
+     [(_WB, _inf_map("env-grey-8x8-be.pfm", ' "color scale" [.2 .3 .25]'))]),
+    ("path-envmap-bunny", "bunny", 40, 40, 8, 64, {}, [(_WB, _inf_map("env-32x16.pfm"))]),
+    ("path-envmap-1x1", "bunny", 32, 32, 4, 2, {}, [(_WB, _inf_map("env-1x1.pfm"))]),
+]
+
+
+def write_env_pfm(path, w, h, seed, channels, scale):
+    """a small HDR-ish radiance map: log-normal texels, one very bright one, a black row"""
+    rng = np.random.RandomState(seed)
+    a = np.exp(rng.randn(h, w, channels)).astype(np.float32) * 0.3
+    a[rng.randint(h), rng.randint(w)] = 25.0
+    if h > 2:
+        a[h - 1] = 0.0
+    with open(path, "wb") as f:
+        f.write(("PF" if channels == 3 else "Pf").encode() + b"\n%d %d\n%g\n" % (w, h, scale))
+        f.write(a.astype("<f4" if scale < 0 else ">f4").tobytes())
+
 
 # SURVEY 8(f) rank 4, pixel filters wider than half a pixel (every sample splats into neighbouring tasks' pixels): host front
 # end + oracle, pinned on the reference binary at --ncores 1 (one worker thread runs the tasks in ascending order: the
@@ -177,13 +215,16 @@ def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:
             assert a in text
             text = text.replace(a, b)
         open(path, "w").write(text)
+        for fn, spec in ENV_MAPS.items():
+            if fn in text:
+                write_env_pfm(os.path.join(scenes.STAGED, fn), *spec)
         _cache[key] = (pb.HostScene(path, ncores=ncores), ncores)
     return _cache[key]
 

@@ -18,6 +18,7 @@ import pbrt_v2_b200 as pb
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
 import make_builder_golden as mg   # noqa: E402
+import make_envmap_golden as me   # noqa: E402
 
 GOLDEN = np.load(os.path.join(HERE, "golden", "builders.npz"))
 live = pytest.mark.skipif(not os.path.exists(mg.REFDUMP), reason="the reference is not built here (oracle/_ref)")
@@ -109,3 +110,39 @@ def test_host_loopsubdiv_refine_is_the_references_mesh_live(staged):
     cm = pb.ControlMesh(idx, P)
     for levels in (1, 2, 3):
         assert same_mesh(cm.host_refine(levels), mg.ref_loopsubdiv(idx, P, levels)), levels
+
+
+# ---- InfiniteAreaLight's constructor (lights/infinite.cpp:67-104): host/envmap.cpp against the reference's own members ----
+def _same_envmap(mine, head, data):
+    ref = pb.parse_envmap_dump(head, data)
+    for k in ("width", "height", "nu", "nv"):
+        assert mine[k] == ref[k], k
+    for k in ("texels", "func", "cdf", "funcInt", "margCdf", "margFuncInt"):
+        assert np.array_equal(mine[k].view(np.uint32), ref[k].view(np.uint32)), k
+
+
+def test_host_envmap_build_is_the_references_light_golden(tmp_path):
+    """radianceMap level 0 (ReadImagePFM -> x L -> MIPMap: Lanczos resampling for the 12x7 and 5x3 files) and the
+    Distribution2D over the filtered luminance x sin(theta), bit for bit: RGB / grey files, both byte orders, a scale word"""
+    g = np.load(os.path.join(HERE, "golden", "envmaps.npz"))
+    names = sorted(k[:-4] for k in g.files if k.endswith("_pfm"))
+    assert len(names) >= 6
+    for k in names:
+        path = str(tmp_path / (k + ".pfm"))
+        open(path, "wb").write(g[k + "_pfm"].tobytes())
+        _same_envmap(pb.host_envmap_build(path, g[k + "_L"]), g[k + "_head"], g[k + "_data"])
+    _same_envmap(pb.host_envmap_build(None, g["nomap_L"]), g["nomap_head"], g["nomap_data"])
+
+
+@live
+def test_host_envmap_build_is_the_references_light_live(tmp_path):
+    """random resolutions up to 70 x 40 (one- and two-sided resampling, single rows and columns)"""
+    from helpers import write_env_pfm
+    rs = np.random.RandomState(7)
+    sizes = [(1, 2), (2, 1), (3, 1), (1, 5), (7, 1), (64, 32), (17, 9), (70, 40), (33, 8), (8, 33)]
+    sizes += [(int(rs.randint(1, 40)), int(rs.randint(1, 24))) for _ in range(14)]
+    for i, (w, h) in enumerate(sizes):
+        path = str(tmp_path / ("m%d.pfm" % i))
+        write_env_pfm(path, w, h, 100 + i, 3 if i % 3 else 1, [-1.0, 1.0, -2.5][i % 3])
+        L = rs.uniform(0, 2, 3).astype(np.float32)
+        _same_envmap(pb.host_envmap_build(path, L), *me.ref_envmap(path, L))

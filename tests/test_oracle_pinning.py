@@ -212,12 +212,28 @@ def test_oracle_infinite_light_bit_exact_vs_reference_binary(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["path-envmap-pow2", "path-envmap-npot-specular", "direct-envmap-npot", "direct-one-envmap-grey",
+                                  "path-envmap-bunny", "path-envmap-1x1"])
+def test_oracle_environment_maps_bit_exact_vs_reference_binary(staged, name):
+    """InfiniteAreaLight with "mapname" (.pfm): the host front end restates the constructor (ReadImagePFM, texels x L x scale,
+    MIPMap's Lanczos resampling to a power of two and its pyramid, the filtered luminance x sin(theta) image, Distribution2D
+    -- pbrt_v2_b200/csrc/host/envmap.cpp), the oracle the per-ray work (bilinear MIPMap::Lookup over level 0 with
+    TEXTURE_REPEAT, Distribution2D::SampleContinuous / Pdf).  Power-of-two and other resolutions, RGB and grey files, both byte
+    orders and a scale word, a 1x1 file, L and scale on top; both integrators and strategies."""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 @pytest.mark.parametrize("name", ["filter-gaussian", "filter-mitchell", "filter-triangle-crop", "filter-sinc", "filter-widebox"])
 def test_oracle_wide_pixel_filters_bit_exact_vs_reference_binary(staged, name):
     """gaussian / mitchell / triangle / sinc / wide box filters (filters/*.cpp; ImageFilm's 16 x 16 weight table and the
     sample's raster extent, film/image.cpp:57-69, 77-112; the sample extent grows with the filter, :157-166): every pixel
-    of the image, bit for bit, at --ncores 1 -- one worker thread runs the tasks in ascending order, so the reference's own
-    float sums are ordered; the oracle adds in the same order with one thread."""
+    of the image, bit for bit, at --ncores 1 -- EnqueueTasks then runs the tasks inline in enqueue order, nTasks-1 down to 0
+    (parallel.cpp:800-805), so the reference's own float sums are ordered; the oracle adds in the same order with one thread."""
     from helpers import variant_scene
     hs, ncores = variant_scene(name)
     assert ncores == 1
