@@ -59,6 +59,10 @@
 
 namespace dev {
 
+#ifndef PBRT_INFINITE
+#define PBRT_INFINITE 0   // InfiniteAreaLight device code, see dshade.cuh
+#endif
+
 struct DScene {
     const float4 *nodes;
     const float4 *prims;
@@ -80,6 +84,10 @@ struct DScene {
     // root 1, first child 2h, second child 2h+1; slots without a node stay zero): one contiguous block that the persistent
     // kernels copy into shared memory with a TMA bulk copy (cp.async.bulk) -- see TopNodes below
     const float4 *topNodes;
+#if PBRT_INFINITE
+    const PbrtGpuEnvMap *envMaps;   // InfiniteAreaLights' radiance maps and sampling distributions (PbrtGpuLight::nShapes indexes)
+    const float *envData;
+#endif
 #if PBRT_KD_INTERLEAVED
     const float4 *kdRec;          // 2 x float4 per kd node: {splitPos, bits, p.x, p.y} {p.z, v.r, v.g, v.b}
 #endif

@@ -33,7 +33,7 @@ enum { BX_SPECULAR_REFLECTION = 3, BX_SPECULAR_TRANSMISSION = 4 };   // BxSet.ex
 #ifndef PBRT_METAL
 #define PBRT_METAL 0
 #endif
-// InfiniteAreaLight with a constant radiance (lights/infinite.cpp over its 1x1 map), both integrators, every
+// InfiniteAreaLight (lights/infinite.cpp: radiance map + Distribution2D, PbrtGpuEnvMap), both integrators, every
 // kernel form (path_body.inc, dvertex.cuh, kwave.cuh, kvertex.cuh).  Off in the shipped kernels for the same reason as PBRT_METAL: CPU-
 // verified against the oracle through the host-compiled kernels (-DPBRT_INFINITE=1), never run on a GPU; with 0 the code is
 // unchanged and pbrtgpu_scene_create answers PBRTGPU_EUNSUPPORTED for a scene with such a light.
@@ -633,15 +633,23 @@ DEV V3 DiskSample(const DScene &sc, const PbrtGpuQuadric &q, float u1, float u2,
 }
 #if PBRT_INFINITE
 DEV float SphericalTheta(const V3 &v) { return ref_acosf(Clampf(v.z, -1.f, 1.f)); }   // geometry.h:640-642
-// MIPMap::Lookup(s, t, width = 0) over the 1x1 radiance map (core/mipmap.h:239-269): level < 0 -> triangle(0, s, t), four
-// bilinear weights over the one texel (TEXTURE_REPEAT wraps every index to 0)
-DEV Spec InfiniteLookup(const PbrtGpuLight &l, float s, float t) {
-    s = s * 1 - 0.5f;
-    t = t * 1 - 0.5f;
+// MIPMap::Lookup(s, t, width = 0) (core/mipmap.h:239-269): level < 0 -> triangle(0, s, t), bilinear over level 0 of the
+// radiance map; TEXTURE_REPEAT wraps every index (Texel, :203-228).  Level 0 is a power of two in both directions
+// (mipmap.h:118-168; checked at upload): Mod(a, b) (pbrt.h:237-242, the non-negative remainder) is a & (b - 1)
+DEV Spec EnvTexel(const DScene &sc, const PbrtGpuEnvMap &m, int s, int t) {
+    s &= (int)m.width - 1;
+    t &= (int)m.height - 1;
+    const float *p = sc.envData + m.texels + 3 * ((size_t)t * m.width + s);
+    return Spec(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+DEV Spec InfiniteLookup(const DScene &sc, const PbrtGpuLight &l, float s, float t) {
+    const PbrtGpuEnvMap &m = sc.envMaps[l.nShapes];
+    s = s * m.width - 0.5f;
+    t = t * m.height - 0.5f;
     const int s0 = Floor2Int(s), t0 = Floor2Int(t);
     const float ds = s - s0, dt = t - t0;
-    const Spec texel(l.L[0], l.L[1], l.L[2]);
-    return (1.f - ds) * (1.f - dt) * texel + (1.f - ds) * dt * texel + ds * (1.f - dt) * texel + ds * dt * texel;
+    return (1.f - ds) * (1.f - dt) * EnvTexel(sc, m, s0, t0) + (1.f - ds) * dt * EnvTexel(sc, m, s0, t0 + 1) +
+           ds * (1.f - dt) * EnvTexel(sc, m, s0 + 1, t0) + ds * dt * EnvTexel(sc, m, s0 + 1, t0 + 1);
 }
 // Light::Le(ray): black (core/light.cpp:59-61) except InfiniteAreaLight::Le (infinite.cpp:114-119)
 DEV Spec LightLe(const DScene &sc, const PbrtGpuLight &l, const V3 &d) {
@@ -649,23 +657,45 @@ DEV Spec LightLe(const DScene &sc, const PbrtGpuLight &l, const V3 &d) {
     const V3 wh = Normalize(XfVector(sc.xforms[l.firstShape].mInv, d));   // WorldToLight(r.d)
     const float s = SphericalPhi(wh) * INV_TWOPI_F;
     const float t = SphericalTheta(wh) * INV_PI_F;
-    return InfiniteLookup(l, s, t);
+    return InfiniteLookup(sc, l, s, t);
 }
-// the one value of the sampling distribution's function (infinite.cpp:88-99: img[0] = Lookup(0, 0, 1).y() * sinf(pi * .5))
-DEV float InfiniteFunc(const PbrtGpuLight &l) { return Spec(l.L[0], l.L[1], l.L[2]).y() * ref_sinf(PI_F * float(0 + .5f) / float(1)); }
+// Distribution1D::SampleContinuous(u, &pdf, &off), montecarlo.h:81-97.  std::upper_bound over the count + 1 cdf entries:
+// the first one greater than u
+DEV float SampleContinuous1D(const float *func, const float *cdf, float funcInt, int count, float u, float *pdf, int *off) {
+    int lo = 0, len = count + 1;
+    while (len > 0) {
+        const int half = len >> 1;
+        if (!(u < __ldg(cdf + lo + half))) { lo += half + 1; len -= half + 1; }
+        else len = half;
+    }
+    const int offset = maxi(0, lo - 1);
+    *off = offset;
+    const float c0 = __ldg(cdf + offset);
+    const float du = (u - c0) / (__ldg(cdf + offset + 1) - c0);
+    *pdf = __ldg(func + offset) / funcInt;
+    return (offset + du) / count;
+}
+// Distribution2D::Pdf(u, v), montecarlo.h:154-162 (Float2Int truncates)
+DEV float InfiniteMapPdf(const DScene &sc, const PbrtGpuLight &l, float u, float v) {
+    const PbrtGpuEnvMap &m = sc.envMaps[l.nShapes];
+    const float *e = sc.envData;
+    const int iu = mini(maxi((int)(u * (int)m.nu), 0), (int)m.nu - 1);
+    const int iv = mini(maxi((int)(v * (int)m.nv), 0), (int)m.nv - 1);
+    const float fi = __ldg(e + m.funcInt + iv);
+    if (fi * m.margFuncInt == 0.f) return 0.f;
+    return (__ldg(e + m.func + (size_t)iv * m.nu + iu) * fi) / (fi * m.margFuncInt);
+}
 #endif
 // Light::Pdf: PointLight 0 (point.cpp:78-80); DiffuseAreaLight -> ShapeSet::Pdf (light.cpp:157-162)
 DEV_NI3 float LightPdf(const DScene &sc, const PbrtGpuLight &l, const V3 &p, const V3 &wi) {
     if (l.type == PBRTGPU_LIGHT_POINT) return 0.f;
 #if PBRT_INFINITE
-    if (l.type == PBRTGPU_LIGHT_INFINITE) {   // infinite.cpp:229-239; Distribution2D::Pdf over one cell, montecarlo.h:158-166
+    if (l.type == PBRTGPU_LIGHT_INFINITE) {   // infinite.cpp:229-239
         const V3 w = XfVector(sc.xforms[l.firstShape].mInv, wi);
-        const float theta = SphericalTheta(w);
+        const float theta = SphericalTheta(w), phi = SphericalPhi(w);
         const float sintheta = ref_sinf(theta);
         if (sintheta == 0.f) return 0.f;
-        const float f = InfiniteFunc(l);
-        const float mapPdf = (f * f == 0.f) ? 0.f : (f * f) / (f * f);
-        return mapPdf / (2.f * PI_F * PI_F * sintheta);
+        return InfiniteMapPdf(sc, l, phi * INV_TWOPI_F, theta * INV_PI_F) / (2.f * PI_F * PI_F * sintheta);
     }
 #endif
     float pdf = 0.f;
@@ -688,10 +718,14 @@ DEV Spec LightSample_L(const DScene &sc, const PbrtGpuLight &l, const V3 &p, flo
         return Spec(l.L[0], l.L[1], l.L[2]) / DistanceSquared(lightPos, p);
     }
 #if PBRT_INFINITE
-    if (l.type == PBRTGPU_LIGHT_INFINITE) {   // infinite.cpp:195-226; Distribution2D::SampleContinuous over one cell: uv = u
-        const float f = InfiniteFunc(l);
-        const float pdf1 = f / f, pdf0 = f / f;
-        const float uv1 = (0 + (uPos1 - 0.f) / (1.f - 0.f)) / 1, uv0 = (0 + (uPos0 - 0.f) / (1.f - 0.f)) / 1;
+    if (l.type == PBRTGPU_LIGHT_INFINITE) {   // infinite.cpp:195-226; Distribution2D::SampleContinuous, montecarlo.h:146-153
+        const PbrtGpuEnvMap &m = sc.envMaps[l.nShapes];
+        const float *e = sc.envData;
+        float pdf0, pdf1;
+        int v, unused;
+        const float uv1 = SampleContinuous1D(e + m.funcInt, e + m.margCdf, m.margFuncInt, (int)m.nv, uPos1, &pdf1, &v);
+        const float uv0 = SampleContinuous1D(e + m.func + (size_t)v * m.nu, e + m.cdf + (size_t)v * (m.nu + 1), __ldg(e + m.funcInt + v),
+                                             (int)m.nu, uPos0, &pdf0, &unused);
         const float mapPdf = pdf0 * pdf1;
         vis->o = p; vis->d = V3(0, 0, 1); vis->mint = pEpsilon; vis->maxt = INF_F;
         *wi = V3(0, 0, 1);
@@ -703,7 +737,7 @@ DEV Spec LightSample_L(const DScene &sc, const PbrtGpuLight &l, const V3 &p, flo
         *pdf = mapPdf / (2.f * PI_F * PI_F * sintheta);
         if (sintheta == 0.f) *pdf = 0.f;
         vis->d = *wi;   // VisibilityTester::SetRay(p, eps, wi, time): unbounded
-        return InfiniteLookup(l, uv0, uv1);
+        return InfiniteLookup(sc, l, uv0, uv1);
     }
 #endif
     V3 ns;

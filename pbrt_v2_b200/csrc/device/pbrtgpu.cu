@@ -1186,6 +1186,10 @@ struct PbrtGpuScene {
     DevBuf<float4> kdRec;
 #endif
     DevBuf<PbrtGpuLight> lights;
+#if PBRT_INFINITE
+    DevBuf<PbrtGpuEnvMap> envMaps;
+    DevBuf<float> envData;
+#endif
     DevBuf<PbrtGpuLightShape> lightShapes;
     DevBuf<PbrtGpuAnimated> animated;
     // per-render scratch: one Lane per concurrent batch pipeline (see pbrtgpu_render_device), borrowed from a
@@ -1257,6 +1261,9 @@ int ValidateRenderDesc(const PbrtGpuRenderDesc &rd) {
 #else
     if (rd.filterXWidth > 0.5f || rd.filterYWidth > 0.5f)
         return Fail(PBRTGPU_EUNSUPPORTED, "filters wider than the 0.5 box need cross-task splats (out of scope)");
+    // (narrower boxes leave some samples without any pixel, image.cpp:85-91: the footprint bits of FilmAdd cannot say that)
+    if (rd.filterXWidth != 0.5f || rd.filterYWidth != 0.5f)
+        return Fail(PBRTGPU_EUNSUPPORTED, "filters narrower than the 0.5 box are rendered by PBRT_FILTER builds only");
     if (rd.hasFilterTable)
         for (int i = 0; i < 256; ++i)
             if (rd.filterTable[i] != 1.f) return Fail(PBRTGPU_EUNSUPPORTED, "pixel filters other than the box filter are rendered by the oracle only");
@@ -1417,7 +1424,19 @@ static int ValidateSceneDesc(const PbrtGpuSceneDesc *desc) {
     for (uint32_t i = 0; i < desc->nLights; ++i) {
         const PbrtGpuLight &l = desc->lights[i];
 #if PBRT_INFINITE
-        if (l.type == PBRTGPU_LIGHT_INFINITE && l.firstShape >= desc->nXforms) return Fail(PBRTGPU_EINVAL, "infinite light's transform index out of range");
+        if (l.type == PBRTGPU_LIGHT_INFINITE) {
+            if (l.firstShape >= desc->nXforms) return Fail(PBRTGPU_EINVAL, "infinite light's transform index out of range");
+            if (l.nShapes >= desc->nEnvMaps || !desc->envMaps || !desc->envData) return Fail(PBRTGPU_EINVAL, "infinite light's environment map index out of range");
+            const PbrtGpuEnvMap &m = desc->envMaps[l.nShapes];
+            auto pow2 = [](uint32_t v) { return v && !(v & (v - 1)); };
+            if (!pow2(m.width) || !pow2(m.height) || m.width > 65536 || m.height > 65536)
+                return Fail(PBRTGPU_EINVAL, "environment map: level 0 must be a power of two in both directions");
+            if (m.nu < 1 || m.nv < 1 || m.nu > 65536 || m.nv > 65536) return Fail(PBRTGPU_EINVAL, "environment map: bad distribution size");
+            const uint64_t n = desc->nEnvData, nu = m.nu, nv = m.nv;
+            if (m.texels + 3ull * m.width * m.height > n || m.func + nu * nv > n || m.cdf + nv * (nu + 1) > n || m.funcInt + nv > n ||
+                m.margCdf + nv + 1 > n)
+                return Fail(PBRTGPU_EINVAL, "environment map: array range out of bounds");
+        }
 #else
         if (l.type == PBRTGPU_LIGHT_INFINITE)
             return Fail(PBRTGPU_EUNSUPPORTED, "infinite area lights: this library was built with PBRT_INFINITE=0 (the device code has not run on a GPU yet)");
@@ -1619,6 +1638,10 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
     }
 #endif
     CUDA_TRY(s->lights.Upload(desc->lights, desc->nLights));
+#if PBRT_INFINITE
+    CUDA_TRY(s->envMaps.Upload(desc->envMaps, desc->nEnvMaps));
+    CUDA_TRY(s->envData.Upload(desc->envData, desc->nEnvData));
+#endif
     CUDA_TRY(s->lightShapes.Upload(desc->lightShapes, desc->nLightShapes));
     CUDA_TRY(s->animated.Upload(desc->animated, desc->nAnimated));
     DScene &d = s->d;
@@ -1633,6 +1656,9 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
     d.N = s->N.p; d.uv = s->uv.p; d.quadrics = s->quadrics.p; d.xforms = s->xforms.p;
     d.materials = s->materials.p; d.measured = s->measured.p; d.kdNodes = s->kdNodes.p; d.kdData = s->kdData.p;
     d.lights = s->lights.p; d.lightShapes = s->lightShapes.p; d.animated = s->animated.p;
+#if PBRT_INFINITE
+    d.envMaps = s->envMaps.p; d.envData = s->envData.p;
+#endif
     d.nNodes = desc->nNodes; d.nPrims = desc->nPrimitives; d.nLights = desc->nLights; d.nAnimated = desc->nAnimated;
     s->nMeasuredMaterials = 0;
     s->nSpecularMaterials = 0;
@@ -2180,7 +2206,7 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     rp.integrator = rd->integrator; rp.lightStrategy = rd->lightStrategy;
 #if PBRT_FILTER
     {   // the 0.5 box keeps its footprint-bit path (FilmAdd); everything else goes through the weight table
-        bool box = rd->filterXWidth <= 0.5f && rd->filterYWidth <= 0.5f;
+        bool box = rd->filterXWidth == 0.5f && rd->filterYWidth == 0.5f;
         float table[256];
         for (int i = 0; i < 256; ++i) {
             table[i] = rd->hasFilterTable ? rd->filterTable[i] : 1.f;

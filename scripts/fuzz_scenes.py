@@ -2,7 +2,7 @@
 """Random in-scope scenes: the unmodified reference binary vs the oracle vs the device code compiled for the host
 (tests/native/device_on_host.cpp).  CPU only.  usage: fuzz_scenes.py [n] [seed0] [flags]
 flags (joined with +): specular, metal (materials; metal builds the harness with -DPBRT_METAL=1), pairs (-DPBRT_PAIR_NODES=1),
-crop, infinite (constant-radiance InfiniteAreaLights; the harness is built with -DPBRT_INFINITE=1), filter (a random
+crop, infinite (InfiniteAreaLights, constant or over a random .pfm radiance map; the harness is built with -DPBRT_INFINITE=1), filter (a random
 PixelFilter on half of the scenes, harness built with -DPBRT_FILTER=1: such scenes run on one core -- the only order the
 reference defines for them -- through the state machine, and EVERY pixel is compared), wave (PathIntegrator scenes run through the vertex-wavefront KERNELS -- kwave.cuh's k_wshade / k_weval / k_wtrace /
 k_wcompact, launches as loops -- over a pool of 3, 17 or 4096 slots instead of the state machine)"""
@@ -48,7 +48,14 @@ def gen(rng, path, animated=None):
     if len(sys.argv) > 3 and "infinite" in sys.argv[3] and rng.rand() < .4:   # constant-radiance InfiniteAreaLight, rotated
         L.append("AttributeBegin")
         L.append("Rotate %g %s" % (rng.uniform(-180, 180), fl(rng.uniform(-1, 1, 3) + 1e-3)))
-        L.append('LightSource "infinite" "color L" [%s] "integer nsamples" [%d]' % (fl(rng.uniform(0, .8, 3)), rng.choice([1, 2, 4])))
+        light = 'LightSource "infinite" "color L" [%s] "integer nsamples" [%d]' % (fl(rng.uniform(0, .8, 3)), rng.choice([1, 2, 4]))
+        if rng.rand() < .6:   # a radiance map: random resolution (mostly not a power of two), RGB or grey, either byte order
+            from helpers import write_env_pfm
+            mapname = os.path.splitext(os.path.basename(path))[0] + "-env.pfm"
+            write_env_pfm(os.path.join(os.path.dirname(path), mapname), int(rng.randint(1, 24)), int(rng.randint(1, 14)),
+                          int(rng.randint(1 << 30)), int(rng.choice([1, 3])), float(rng.choice([-1.0, 1.0, -0.5, 3.0])))
+            light += ' "string mapname" "%s"' % mapname
+        L.append(light)
         L.append("AttributeEnd")
     def xform():
         t = []
@@ -192,7 +199,7 @@ def main():
         flag = "" if (d_ref == 0 and d_dev == 0 and w_dev) else "   <<<<<<"
         bad += bool(flag)
         if not flag:   # keep only the scenes worth looking at
-            for f in (path, os.path.splitext(path)[0] + ".pfm"):
+            for f in (path, os.path.splitext(path)[0] + ".pfm", os.path.splitext(path)[0] + "-env.pfm"):
                 if os.path.exists(f): os.remove(f)
         print("seed %d: %dx%d spp %d ncores %d integ %d  oracle-vs-reference %d  device-on-host-vs-oracle %d (weights %s)  mean %.4g%s" % (
             seed, rd.xResolution, rd.yResolution, spp, ncores, rd.integrator, d_ref, d_dev, w_dev, float(ref.mean()), flag), flush=True)

@@ -208,6 +208,8 @@ FILTER_VARIANTS = [
     ("filter-triangle-crop", "bunny", 40, 40, 4, 1, {"crop": (0.2, 0.8, 0.1, 0.7)}, [(_FILM, 'PixelFilter "triangle" "float xwidth" [1.5] "float ywidth" [2.5]\n' + _FILM)]),
     ("filter-sinc", "killeroo-simple", 32, 32, 2, 1, {"integrator": "directlighting"}, [(_FILM, 'PixelFilter "sinc"\n' + _FILM)]),
     ("filter-widebox", "bunny", 32, 32, 4, 1, {}, [(_FILM, 'PixelFilter "box" "float xwidth" [1.5] "float ywidth" [.75]\n' + _FILM)]),
+    # narrower than half a pixel: some samples touch no pixel at all (image.cpp:85-91), found by scripts/fuzz_scenes.py
+    ("filter-narrowbox", "bunny", 32, 32, 4, 1, {}, [(_FILM, 'PixelFilter "box" "float xwidth" [.45] "float ywidth" [.3]\n' + _FILM)]),
 ]
 
 

@@ -133,6 +133,9 @@ void Pack(const PbrtGpuSceneDesc *desc, HostScene *h) {
     d.N = desc->N; d.uv = desc->uv; d.quadrics = desc->quadrics; d.xforms = desc->xforms; d.materials = desc->materials;
     d.measured = desc->measured; d.kdNodes = desc->kdNodes; d.kdData = desc->kdData; d.lights = desc->lights;
     d.lightShapes = desc->lightShapes; d.animated = desc->animated;
+#if PBRT_INFINITE
+    d.envMaps = desc->envMaps; d.envData = desc->envData;
+#endif
     d.nNodes = desc->nNodes; d.nPrims = desc->nPrimitives; d.nLights = desc->nLights; d.nAnimated = desc->nAnimated;
 }
 }  // namespace
@@ -589,7 +592,7 @@ DOH_EXPORT int doh_render(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc 
 #if PBRT_FILTER
     {   // as pbrtgpu_render_device: the 0.5 box keeps the footprint bits, everything else reads the table
         static float table[256];
-        bool box = rd->filterXWidth <= 0.5f && rd->filterYWidth <= 0.5f;
+        bool box = rd->filterXWidth == 0.5f && rd->filterYWidth == 0.5f;
         for (int i = 0; i < 256; ++i) {
             table[i] = rd->hasFilterTable ? rd->filterTable[i] : 1.f;
             if (table[i] != 1.f) box = false;

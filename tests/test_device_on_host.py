@@ -237,14 +237,16 @@ def test_infinite_light_device_code_on_host(staged, tmp_path_factory):
     and rendered against the oracle -- pinned on the reference binary for the same scenes (test_oracle_pinning.py) -- through
     the vertex form and through the vertex-wavefront kernels over small and large pools; scenes without such a light must
     not move."""
-    from helpers import INFINITE_VARIANTS, variant_scene
+    from helpers import INFINITE_VARIANTS, ENVMAP_VARIANTS, variant_scene
     lib = _build(tmp_path_factory, "device_on_host_infinite", ["-DPBRT_INFINITE=1"])
     lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
-    for v in INFINITE_VARIANTS:   # the state machine (path_body.inc): both integrators, incl. the specular recursion's children
+    # constant radiance and radiance maps ("mapname": bilinear MIPMap::Lookup over level 0, Distribution2D sampling / pdf)
+    variants = INFINITE_VARIANTS + ENVMAP_VARIANTS
+    for v in variants:   # the state machine (path_body.inc): both integrators, incl. the specular recursion's children
         _same_film(lib, variant_scene(v[0])[0])
     for form in (1, 3, 64, 4096):   # vertex form; the wave kernels over 3, 64 and 4096 slots
         lib.doh_set_vertex_form(form)
-        for v in INFINITE_VARIANTS:
+        for v in variants:
             if v[6].get("integrator", "path") == "path":
                 _same_film(lib, variant_scene(v[0])[0])
         _same_film(lib, host_scene("bunny", 24, 24, 4, 8))

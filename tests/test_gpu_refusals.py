@@ -16,7 +16,9 @@ F4_BUILD = "f4" in os.environ.get("PBRTGPU_LIB", "")
 
 @pytest.mark.skipif(not F4_BUILD, reason="needs PBRTGPU_LIB=ab/libpbrtgpu_f4.so (make variants VARIANT_NAMES=f4)")
 @pytest.mark.parametrize("name", ["path-infinite", "path-infinite-specular", "path-infinite-bunny", "direct-infinite",
-                                  "direct-one-infinite", "path-metal-copper", "path-metal-params-floor", "direct-metal"])
+                                  "direct-one-infinite", "path-envmap-pow2", "path-envmap-npot-specular", "direct-envmap-npot",
+                                  "direct-one-envmap-grey", "path-envmap-bunny", "path-metal-copper", "path-metal-params-floor",
+                                  "direct-metal"])
 def test_f4_build_bit_exact_vs_oracle(staged, name):
     """first GPU run of the gated device code for infinite lights and metal (host-verified: tests/test_device_on_host.py)"""
     hs, _ = variant_scene(name)
@@ -36,7 +38,7 @@ def test_infinite_area_light_is_refused(staged):
 
 
 @pytest.mark.skipif(not F4_BUILD, reason="needs PBRTGPU_LIB=ab/libpbrtgpu_f4.so (make variants VARIANT_NAMES=f4)")
-@pytest.mark.parametrize("name", ["filter-gaussian", "filter-mitchell", "filter-triangle-crop", "filter-sinc", "filter-widebox"])
+@pytest.mark.parametrize("name", ["filter-gaussian", "filter-mitchell", "filter-triangle-crop", "filter-sinc", "filter-widebox", "filter-narrowbox"])
 def test_f4_build_pixel_filters_vs_oracle(staged, name):
     """first GPU run of ImageFilm::AddSample through the weight table (dpath.cuh FilmAddFiltered; bit-exact on the host in the
     reference's one-thread order, tests/test_device_on_host.py).  On the device the order of the atomic adds into a pixel
@@ -51,7 +53,7 @@ def test_f4_build_pixel_filters_vs_oracle(staged, name):
 
 
 @pytest.mark.skipif(F4_BUILD, reason="a PBRT_FILTER build renders them")
-@pytest.mark.parametrize("name", ["filter-gaussian", "filter-widebox"])
+@pytest.mark.parametrize("name", ["filter-gaussian", "filter-widebox", "filter-narrowbox"])
 def test_wide_pixel_filters_are_refused(staged, name):
     hs, _ = variant_scene(name)
     gs = pb.GpuScene(hs)           # the scene itself is fine

@@ -228,7 +228,7 @@ def test_oracle_environment_maps_bit_exact_vs_reference_binary(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
-@pytest.mark.parametrize("name", ["filter-gaussian", "filter-mitchell", "filter-triangle-crop", "filter-sinc", "filter-widebox"])
+@pytest.mark.parametrize("name", ["filter-gaussian", "filter-mitchell", "filter-triangle-crop", "filter-sinc", "filter-widebox", "filter-narrowbox"])
 def test_oracle_wide_pixel_filters_bit_exact_vs_reference_binary(staged, name):
     """gaussian / mitchell / triangle / sinc / wide box filters (filters/*.cpp; ImageFilm's 16 x 16 weight table and the
     sample's raster extent, film/image.cpp:57-69, 77-112; the sample extent grows with the filter, :157-166): every pixel
