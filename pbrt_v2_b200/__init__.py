@@ -416,6 +416,21 @@ def host_bvh_build(bounds, max_prims_in_node=4, split_method=SPLIT_SAH):
     return nodes[:nn.value].copy(), order
 
 
+def write_binary_mesh(path, indices, P, N=None, uv=None):
+    """the `"string binfile"` form of a trianglemesh / loopsubdiv's arrays (csrc/host/parser.cpp LoadBinaryMesh)"""
+    indices = np.ascontiguousarray(indices, "<i4").ravel()
+    P = np.ascontiguousarray(P, "<f4").reshape(-1, 3)
+    flags = (1 if N is not None else 0) | (2 if uv is not None else 0)
+    with open(path, "wb") as f:
+        f.write(b"PBRTMESH" + np.array([flags, len(indices), len(P)], "<u4").tobytes())
+        f.write(indices.tobytes())
+        f.write(P.tobytes())
+        if N is not None:
+            f.write(np.ascontiguousarray(N, "<f4").reshape(len(P), 3).tobytes())
+        if uv is not None:
+            f.write(np.ascontiguousarray(uv, "<f4").reshape(len(P), 2).tobytes())
+
+
 def host_envmap_build(pfm, L):
     """InfiniteAreaLight's constructor by the host front end (csrc/host/envmap.cpp) -> dict of the PbrtGpuEnvMap arrays:
     width, height, nu, nv, texels [height, width, 3], func [nv, nu], cdf [nv, nu + 1], funcInt [nv], margCdf [nv + 1],

@@ -312,7 +312,52 @@ int Api::MakeMaterial(const ParamSet &geomParams) {   // core/api.cpp:1062-1077,
     return (int)scene->materials.size() - 1;
 }
 
-bool Api::DoShape(const std::string &name, const ParamSet &params) {   // core/api.cpp:990-1059
+// "string binfile": the mesh arrays of a trianglemesh / loopsubdiv from a binary file instead of the parameter list (SURVEY 8(f)
+// rank 3: no text parsing, no per-number allocations for multi-million-triangle meshes).  Not a reference format: the arrays
+// land in the same ParamSet slots the text form fills ("indices", "P", "N", "uv"), so everything downstream is the same code.
+// Layout (little-endian): "PBRTMESH", uint32 flags (1: normals, 2: uvs), uint32 nIndices, uint32 nVertices, int32 indices[],
+// float P[3 nv], float N[3 nv] if flagged, float uv[2 nv] if flagged.  pbrt_v2_b200.write_binary_mesh writes it.
+static bool LoadBinaryMesh(const std::string &fn, ParamSet *ps, std::string *err) {
+    FILE *f = fopen(fn.c_str(), "rb");
+    if (!f) { *err = "cannot open binary mesh " + fn; return false; }
+    char magic[8];
+    uint32_t head[3];
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "PBRTMESH", 8) == 0 && fread(head, 4, 3, f) == 3;
+    const uint32_t flags = head[0], ni = head[1], nv = head[2];
+    if (ok && (ni > (1u << 31) - 1 || nv > (1u << 30) || (flags & ~3u))) ok = false;
+    if (ok) {
+        std::vector<int> &idx = ps->ints["indices"];
+        idx.resize(ni);
+        ok = fread(idx.data(), 4, ni, f) == ni;
+        auto readV3 = [&](std::vector<V3> *dst) {
+            std::vector<float> raw((size_t)3 * nv);
+            if (fread(raw.data(), 4, raw.size(), f) != raw.size()) return false;
+            dst->resize(nv);
+            for (uint32_t i = 0; i < nv; ++i) (*dst)[i] = V3(raw[3 * i], raw[3 * i + 1], raw[3 * i + 2]);
+            return true;
+        };
+        ok = ok && readV3(&ps->points["P"]);
+        if (ok && (flags & 1u)) ok = readV3(&ps->normals["N"]);
+        if (ok && (flags & 2u)) {
+            std::vector<float> &uv = ps->floats["uv"];
+            uv.resize((size_t)2 * nv);
+            ok = fread(uv.data(), 4, uv.size(), f) == uv.size();
+        }
+    }
+    fclose(f);
+    if (!ok) *err = "malformed binary mesh " + fn;
+    return ok;
+}
+
+bool Api::DoShape(const std::string &name, const ParamSet &paramsIn) {   // core/api.cpp:990-1059
+    ParamSet withMesh;
+    const std::string binfile = paramsIn.FindOneString("binfile", "");
+    if (!binfile.empty() && (name == "trianglemesh" || name == "loopsubdiv")) {
+        withMesh = paramsIn;
+        std::string err;
+        if (!LoadBinaryMesh(ResolvePath(baseDir, binfile), &withMesh, &err)) return Fail(err);
+    }
+    const ParamSet &params = binfile.empty() ? paramsIn : withMesh;
     const bool animated = curTransform.IsAnimated();
     const Transform *o2w, *w2o;
     if (!animated) Cache().Lookup(curTransform.t[0], &o2w, &w2o);

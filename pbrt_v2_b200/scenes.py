@@ -103,3 +103,63 @@ def variant(base, out_path, xres, yres, spp, integrator="path", maxdepth=None,
     with open(out_path, "w") as f:
         f.write(text)
     return out_path
+
+
+# ---- binary mesh ingestion ---------------------------------------------------------------------------
+_PARAM = re.compile(r'\s*"(\w+)\s+(\w+)"\s*')
+
+
+def _shape_params(text, pos):
+    """the parameter list that follows a Shape directive's name at text[pos:] -> ([(type, name, raw value text)], end)"""
+    params = []
+    while True:
+        m = _PARAM.match(text, pos)
+        if not m:
+            return params, pos
+        p = m.end()
+        if text[p] == "[":
+            e = text.index("]", p) + 1
+        elif text[p] == '"':
+            e = text.index('"', p + 1) + 1
+        else:
+            e = re.compile(r"\S+").match(text, p).end()
+        params.append((m.group(1), m.group(2), text[p:e]))
+        pos = e
+
+
+def binarize(scene_in, scene_out, min_triangles=64):
+    """Rewrite a scene file so that its large trianglemesh / loopsubdiv shapes read their arrays from binary files
+    (`"string binfile"`, parser.cpp LoadBinaryMesh; written next to scene_out).  Include files are expanded in place.
+    Returns the number of shapes converted."""
+    import numpy as np
+    from . import write_binary_mesh
+    base = os.path.dirname(os.path.abspath(scene_in))
+
+    def expand(path):
+        text = "\n".join(line.split("#", 1)[0] for line in open(path).read().split("\n"))
+        return re.sub(r'Include\s+"([^"]+)"', lambda m: expand(os.path.join(base, m.group(1))), text)
+
+    text = expand(scene_in)
+    out, pos, n = [], 0, 0
+    stem = os.path.splitext(os.path.abspath(scene_out))[0]
+    for m in re.finditer(r'Shape\s+"(trianglemesh|loopsubdiv)"', text):
+        params, end = _shape_params(text, m.end())
+        arrays = {(t, k): v for t, k, v in params}
+        idx = arrays.get(("integer", "indices"))
+        P = arrays.get(("point", "P"))
+        if idx is None or P is None or idx.count(" ") < 3 * min_triangles:
+            continue
+        num = lambda v, dt: np.array(v.strip("[]").split(), dt)
+        N = arrays.get(("normal", "N"))
+        uv = arrays.get(("float", "uv"), arrays.get(("float", "st")))
+        binfile = "%s-mesh%d.bin" % (stem, n)
+        write_binary_mesh(binfile, num(idx, np.int32), num(P, np.float32), None if N is None else num(N, np.float32),
+                          None if uv is None else num(uv, np.float32))
+        keep = " ".join('"%s %s" %s' % (t, k, v) for t, k, v in params
+                        if (t, k) not in (("integer", "indices"), ("point", "P"), ("normal", "N"), ("float", "uv"), ("float", "st")))
+        out.append(text[pos:m.end()] + ' "string binfile" "%s" %s\n' % (os.path.basename(binfile), keep))
+        pos, n = end, n + 1
+    out.append(text[pos:])
+    with open(scene_out, "w") as f:
+        f.write("".join(out))
+    return n

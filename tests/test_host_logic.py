@@ -158,3 +158,34 @@ def test_world_size_2_gloo_shard_and_reduce(staged, tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(w), pb.REPO],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert "GLOO_OK" in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("base", ["bunny", "killeroo-simple"])
+def test_binary_mesh_ingestion_builds_the_same_scene(staged, base):
+    """`"string binfile"` (mesh arrays from a binary file instead of the parameter list; trianglemesh for
+    the bunny, loopsubdiv control meshes for the killeroo): same flattened scene -- node array bit for bit -- and the same film"""
+    src = scenes.variant(base, os.path.join(scenes.STAGED, "binmesh-src-%s.pbrt" % base), 20, 20, 2)
+    dst = os.path.join(scenes.STAGED, "binmesh-%s.pbrt" % base)
+    assert scenes.binarize(src, dst) >= 1
+    assert '"string binfile"' in open(dst).read()
+    a, b = pb.HostScene(src, ncores=2), pb.HostScene(dst, ncores=2)
+    assert a.counts() == b.counts() and a.scene_bytes() == b.scene_bytes()
+    assert np.array_equal(a.nodes().view(np.uint8), b.nodes().view(np.uint8))
+    pa, _ = oa.render(a, threads=4)
+    pbin, _ = oa.render(b, threads=4)
+    assert np.array_equal(pa.view(np.uint8), pbin.view(np.uint8))
+
+
+def test_malformed_binary_mesh_is_refused(staged, tmp_path):
+    scene = os.path.join(scenes.STAGED, "binmesh-bad.pbrt")
+    text = open(scenes.variant("bunny", scene, 8, 8, 1)).read()
+    text = text.replace("WorldEnd", 'Shape "trianglemesh" "string binfile" "%s"\nWorldEnd' % str(tmp_path / "m.bin"))
+    open(scene, "w").write(text)
+    for payload in (None, b"NOTAMESH" + b"\0" * 64, b"PBRTMESH" + np.array([0, 3, 3], "<u4").tobytes() + b"\0" * 8):
+        if payload is not None:
+            open(tmp_path / "m.bin", "wb").write(payload)
+        with pytest.raises(pb.PbrtGpuError) as e:
+            pb.HostScene(scene, ncores=1)
+        assert "binary mesh" in str(e.value)
+    pb.write_binary_mesh(str(tmp_path / "m.bin"), [0, 1, 2], [[0, 0, 0], [1, 0, 0], [0, 1, 0]])
+    assert pb.HostScene(scene, ncores=1).counts()["triangles"] == pb.HostScene(scenes.variant("bunny", scene + ".ref.pbrt", 8, 8, 1), ncores=1).counts()["triangles"] + 1
