@@ -14,7 +14,7 @@ NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
 # host code must not contract to FMA either (no -march=native)
 HOSTFLAGS := -O2 -std=c++17 -ffp-contract=off -fPIC -Wall -Wno-unused-function
 
-HOSTSRC   := transform parser shapes bvh measured envmap renderer render_call capi
+HOSTSRC   := transform parser shapes bvh measured envmap exr renderer render_call capi
 HOSTOBJ   := $(patsubst %,build/host/%.o,$(HOSTSRC))
 DEVSRC    := $(wildcard $(DEVDIR)/*.cu)
 DEVHDR    := $(wildcard $(DEVDIR)/*.cuh) $(wildcard $(DEVDIR)/*.inc) $(wildcard $(DEVDIR)/*.h) include/pbrtgpu.h
@@ -66,7 +66,7 @@ build/host/%.o: $(HOSTDIR)/%.cpp $(HOSTDIR)/scene.h $(HOSTDIR)/geom.h include/pb
 	$(CXX) $(HOSTFLAGS) -c $< -o $@
 
 $(PKG)/libpbrthost.so: $(HOSTOBJ) $(PKG)/libpbrtgpu.so
-	$(CXX) -shared $(HOSTOBJ) -o $@ -L$(PKG) -lpbrtgpu -Wl,-rpath,'$$ORIGIN' -lpthread -ldl
+	$(CXX) -shared $(HOSTOBJ) -o $@ -L$(PKG) -lpbrtgpu -Wl,-rpath,'$$ORIGIN' -lpthread -ldl -lz
 
 $(PKG)/pbrt_b200: build/host/main.o $(PKG)/libpbrthost.so
 	$(CXX) build/host/main.o -o $@ -L$(PKG) -lpbrthost -lpbrtgpu -Wl,-rpath,'$$ORIGIN' -lpthread -ldl

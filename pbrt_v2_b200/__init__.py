@@ -179,6 +179,7 @@ def host_lib():
                                            C.c_void_p]
         lib.pbrthost_envmap_build.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pbrthost_envmap_build.restype = C.c_ulonglong
+        lib.pbrthost_read_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
         _host = lib
     return _host
 
@@ -429,6 +430,16 @@ def write_binary_mesh(path, indices, P, N=None, uv=None):
             f.write(np.ascontiguousarray(N, "<f4").reshape(len(P), 3).tobytes())
         if uv is not None:
             f.write(np.ascontiguousarray(uv, "<f4").reshape(len(P), 2).tobytes())
+
+
+def host_read_image(filename):
+    """the host front end's ReadImage (.pfm, .exr) -> float32 [height, width, 3]"""
+    w, h = C.c_int(), C.c_int()
+    if host_lib().pbrthost_read_image(filename.encode(), C.byref(w), C.byref(h), None):
+        raise PbrtGpuError("cannot read image %r" % filename)
+    out = np.zeros((h.value, w.value, 3), np.float32)
+    host_lib().pbrthost_read_image(filename.encode(), C.byref(w), C.byref(h), out.ctypes.data)
+    return out
 
 
 def host_envmap_build(pfm, L):

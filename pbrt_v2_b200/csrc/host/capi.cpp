@@ -77,6 +77,7 @@ unsigned long long pbrthost_scene_bytes(PbrtHostScene *h) {
     b += (unsigned long long)d.nMaterials * sizeof(PbrtGpuMaterial) + (unsigned long long)d.nMeasured * sizeof(PbrtGpuMeasured);
     b += (unsigned long long)d.nKdNodes * (sizeof(PbrtGpuKdNode) + sizeof(PbrtGpuBrdfSample));
     b += (unsigned long long)d.nLights * sizeof(PbrtGpuLight) + (unsigned long long)d.nLightShapes * sizeof(PbrtGpuLightShape);
+    b += (unsigned long long)d.nEnvMaps * sizeof(PbrtGpuEnvMap) + (unsigned long long)d.nEnvData * sizeof(float);
     return b;
 }
 
@@ -152,7 +153,7 @@ unsigned long long pbrthost_envmap_build(const char *pfm, const float L[3], uint
     int w = 1, h = 1;
     const bool haveMap = pfm && *pfm;
     std::string err;
-    if (haveMap && !ReadImagePFM(pfm, &w, &h, &rgb, &err)) return 0;
+    if (haveMap && !ReadImage(pfm, &w, &h, &rgb, &err)) return 0;
     EnvMap em;
     BuildEnvMap(L, w, h, haveMap ? rgb.data() : nullptr, &em);
     head[0] = (uint32_t)em.width; head[1] = (uint32_t)em.height; head[2] = (uint32_t)em.nu; head[3] = (uint32_t)em.nv;
@@ -164,6 +165,15 @@ unsigned long long pbrthost_envmap_build(const char *pfm, const float L[3], uint
     }
     if (out) out[n] = em.margFuncInt;
     return n + 1;
+}
+
+// ReadImage (core/imageio.cpp:58-81) for .pfm / .exr: RGB float triples, rows in the reference's order.  out NULL: sizes only.
+int pbrthost_read_image(const char *filename, int *width, int *height, float *out) {
+    std::vector<float> rgb;
+    std::string err;
+    if (!ReadImage(filename, width, height, &rgb, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    if (out) memcpy(out, rgb.data(), rgb.size() * sizeof(float));
+    return 0;
 }
 
 // LoopSubdiv on raw arrays (test hooks and the comparison partner of pbrtgpu_loopsubdiv_refine).

@@ -246,6 +246,15 @@ bool ReadImagePFM(const std::string &filename, int *xres, int *yres, std::vector
     return true;
 }
 
+bool ReadImage(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err) {
+    const std::string suffix = filename.size() >= 5 ? filename.substr(filename.size() - 4) : "";
+    if (suffix == ".pfm" || suffix == ".PFM") return ReadImagePFM(filename, xres, yres, rgb, err);
+    if (suffix == ".exr" || suffix == ".EXR") return ReadImageEXR(filename, xres, yres, rgb, err);
+    // (.tga: the reference reads those through its bundled targa.c; not restated)
+    *err = "image files are read from .pfm and .exr only: " + filename;
+    return false;
+}
+
 // InfiniteAreaLight::InfiniteAreaLight, lights/infinite.cpp:67-104.  `rgb` NULL: no map, one texel = L
 void BuildEnvMap(const float L[3], int width, int height, const float *rgb, EnvMap *out) {
     std::vector<Rgb> texels((size_t)width * height);

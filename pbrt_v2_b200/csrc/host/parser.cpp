@@ -452,18 +452,15 @@ bool Api::DoLight(const std::string &name, const ParamSet &params) {   // core/a
         lt.desc.type = PBRTGPU_LIGHT_INFINITE;
         lt.desc.nSamples = std::max(1, params.FindOneInt("nsamples", 1));   // Light ctor, light.cpp:46-51
         lt.desc.L[0] = L.x * sc.x; lt.desc.L[1] = L.y * sc.y; lt.desc.L[2] = L.z * sc.z;
-        // "mapname": ReadImage (core/imageio.cpp:58-81).  PFM is read here; TGA and EXR files are refused rather than
-        // guessed at (the reference itself, built without OpenEXR, turns an .exr into one grey texel)
+        // "mapname": ReadImage (core/imageio.cpp:58-81).  .pfm and .exr are read here (envmap.cpp, exr.cpp); .tga files
+        // are refused rather than guessed at
         std::string mapname = params.FindOneString("mapname", "");
         std::vector<float> rgb;
         int w = 1, h = 1;
         if (!mapname.empty()) {
             mapname = ResolvePath(baseDir, mapname);
-            const std::string suffix = mapname.size() >= 5 ? mapname.substr(mapname.size() - 4) : "";
-            if (suffix != ".pfm" && suffix != ".PFM")
-                return Fail("infinite light: environment maps are read from .pfm files only: " + mapname);
             std::string err;
-            if (!ReadImagePFM(mapname, &w, &h, &rgb, &err)) return Fail("infinite light: " + err);
+            if (!ReadImage(mapname, &w, &h, &rgb, &err)) return Fail("infinite light: " + err);
         }
         lt.envMap = std::make_shared<EnvMap>();
         BuildEnvMap(lt.desc.L, w, h, mapname.empty() ? nullptr : rgb.data(), lt.envMap.get());

@@ -130,6 +130,9 @@ struct EnvMap {
     float margFuncInt = 0.f;
 };
 bool ReadImagePFM(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);
+bool ReadImageEXR(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);   // exr.cpp
+// ReadImage (core/imageio.cpp:58-81) for the formats read here: by suffix, .pfm / .exr; anything else is an error
+bool ReadImage(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);
 void BuildEnvMap(const float L[3], int width, int height, const float *rgb, EnvMap *out);
 
 struct Light {   // core/light.h:48-82; lights/point.h, lights/diffuse.h
