@@ -14,7 +14,7 @@ NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
 # host code must not contract to FMA either (no -march=native)
 HOSTFLAGS := -O2 -std=c++17 -ffp-contract=off -fPIC -Wall -Wno-unused-function
 
-HOSTSRC   := transform parser shapes bvh measured envmap exr renderer render_call capi
+HOSTSRC   := transform parser shapes bvh measured envmap exr tga renderer render_call capi
 HOSTOBJ   := $(patsubst %,build/host/%.o,$(HOSTSRC))
 DEVSRC    := $(wildcard $(DEVDIR)/*.cu)
 DEVHDR    := $(wildcard $(DEVDIR)/*.cuh) $(wildcard $(DEVDIR)/*.inc) $(wildcard $(DEVDIR)/*.h) include/pbrtgpu.h

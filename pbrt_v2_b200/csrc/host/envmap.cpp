@@ -250,8 +250,8 @@ bool ReadImage(const std::string &filename, int *xres, int *yres, std::vector<fl
     const std::string suffix = filename.size() >= 5 ? filename.substr(filename.size() - 4) : "";
     if (suffix == ".pfm" || suffix == ".PFM") return ReadImagePFM(filename, xres, yres, rgb, err);
     if (suffix == ".exr" || suffix == ".EXR") return ReadImageEXR(filename, xres, yres, rgb, err);
-    // (.tga: the reference reads those through its bundled targa.c; not restated)
-    *err = "image files are read from .pfm and .exr only: " + filename;
+    if (suffix == ".tga" || suffix == ".TGA") return ReadImageTGA(filename, xres, yres, rgb, err);
+    *err = "image files are read from .pfm, .tga and .exr only: " + filename;
     return false;
 }
 

@@ -452,8 +452,7 @@ bool Api::DoLight(const std::string &name, const ParamSet &params) {   // core/a
         lt.desc.type = PBRTGPU_LIGHT_INFINITE;
         lt.desc.nSamples = std::max(1, params.FindOneInt("nsamples", 1));   // Light ctor, light.cpp:46-51
         lt.desc.L[0] = L.x * sc.x; lt.desc.L[1] = L.y * sc.y; lt.desc.L[2] = L.z * sc.z;
-        // "mapname": ReadImage (core/imageio.cpp:58-81).  .pfm and .exr are read here (envmap.cpp, exr.cpp); .tga files
-        // are refused rather than guessed at
+        // "mapname": ReadImage (core/imageio.cpp:58-81): .pfm, .tga and .exr (envmap.cpp, tga.cpp, exr.cpp)
         std::string mapname = params.FindOneString("mapname", "");
         std::vector<float> rgb;
         int w = 1, h = 1;

@@ -131,7 +131,8 @@ struct EnvMap {
 };
 bool ReadImagePFM(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);
 bool ReadImageEXR(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);   // exr.cpp
-// ReadImage (core/imageio.cpp:58-81) for the formats read here: by suffix, .pfm / .exr; anything else is an error
+bool ReadImageTGA(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);   // tga.cpp
+// ReadImage (core/imageio.cpp:58-81): by suffix, .pfm / .tga / .exr; anything else is an error
 bool ReadImage(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);
 void BuildEnvMap(const float L[3], int width, int height, const float *rgb, EnvMap *out);
 

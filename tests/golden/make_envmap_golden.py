@@ -2,7 +2,7 @@
 """Golden vectors for InfiniteAreaLight's constructor, minted from the UNMODIFIED reference's own members
 (oracle/_ref/bin/refdump envmap: radianceMap level 0, the Distribution2D's arrays; run where /root/reference exists):
 
-  envmaps.npz   <name>_pfm: the .pfm file's bytes; <name>_L: L x scale; <name>_{head,data}: the dump
+  envmaps.npz   <name>_pfm / <name>_tga: the image file's bytes; <name>_L: L x scale; <name>_{head,data}: the dump
                 (layout: pbrt_v2_b200.parse_envmap_dump)
 """
 import os
@@ -38,6 +38,15 @@ def main():
             L = np.array([[1, 1, 1], [.5, .6, .9], [2, .25, 0]][i % 3], np.float32)
             key = fn[:-4].replace("-", "_")
             out[key + "_pfm"] = np.frombuffer(open(path, "rb").read(), np.uint8)
+            out[key + "_L"] = L
+            out[key + "_head"], out[key + "_data"] = ref_envmap(path, L)
+        from helpers import TGA_MAPS, write_tga
+        for fn, spec in sorted(TGA_MAPS.items()):
+            path = os.path.join(tmp, fn)
+            write_tga(path, *spec)
+            L = np.array([1.5, 1, 2], np.float32)
+            key = fn[:-4].replace("-", "_")
+            out[key + "_tga"] = np.frombuffer(open(path, "rb").read(), np.uint8)
             out[key + "_L"] = L
             out[key + "_head"], out[key + "_data"] = ref_envmap(path, L)
         out["nomap_L"] = np.array([.4, .5, .7], np.float32)

@@ -183,6 +183,10 @@ ENVMAP_VARIANTS = [
      [(_WB, _inf_map("env-grey-8x8-be.pfm", ' "color scale" [.2 .3 .25]'))]),
     ("path-envmap-bunny", "bunny", 40, 40, 8, 64, {}, [(_WB, _inf_map("env-32x16.pfm"))]),
     ("path-envmap-1x1", "bunny", 32, 32, 4, 2, {}, [(_WB, _inf_map("env-1x1.pfm"))]),
+    # Targa files (ReadImageTGA over targa.c: restated in csrc/host/tga.cpp)
+    ("path-envmap-tga", "bunny", 32, 32, 4, 2, {}, [(_WB, _inf_map("env-bgra-rle-td-16x8.tga", ' "color L" [3 3 3]'))]),
+    ("direct-envmap-tga-mapped", "killeroo-simple", 32, 32, 4, 2, {"integrator": "directlighting"},
+     [(_WB, _inf_map("env-mapped-12x6.tga", ' "color L" [2 2 2] "integer nsamples" [2]'))]),
 ]
 
 
@@ -196,6 +200,59 @@ def write_env_pfm(path, w, h, seed, channels, scale):
     with open(path, "wb") as f:
         f.write(("PF" if channels == 3 else "Pf").encode() + b"\n%d %d\n%g\n" % (w, h, scale))
         f.write(a.astype("<f4" if scale < 0 else ">f4").tobytes())
+
+
+def write_tga(path, w, h, seed, kind="bgr", rle=False, top_down=False, right_left=False, alpha=False, map_origin=0):
+    """a Targa file of one of the kinds ReadImageTGA interprets: "bgr" (24 / 32 bit with alpha), "mono" (8 bit),
+    "mapped" (8-bit indices into a 24 / 32-bit colour map whose first entry is index map_origin); raw or RLE packets;
+    any scan direction.  Long constant runs make the RLE packets real."""
+    rng = np.random.RandomState(seed)
+    bpp = {"bgr": 4 if alpha else 3, "mono": 1, "mapped": 1}[kind]
+    cmap = b""
+    if kind == "mapped":
+        n = 37
+        mbpp = 4 if alpha else 3
+        cmap = rng.randint(0, 256, (n, mbpp)).astype(np.uint8).tobytes()
+        px = rng.randint(map_origin, map_origin + n, (h, w, 1)).astype(np.uint8)
+    else:
+        px = rng.randint(0, 256, (h, w, bpp)).astype(np.uint8)
+    px[h // 2, : max(1, w - 1)] = px[h // 2, 0]
+    flat = px.reshape(-1, bpp)
+    if rle:
+        data, i, n = bytearray(), 0, len(flat)
+        while i < n:
+            j = i + 1
+            while j < n and j - i < 128 and (flat[j] == flat[i]).all():
+                j += 1
+            if j - i > 1:
+                data += bytes([0x80 | (j - i - 1)]) + flat[i].tobytes()
+            else:
+                j = i + 1
+                while j < n and j - i < 128 and not (j + 1 < n and (flat[j] == flat[j + 1]).all()):
+                    j += 1
+                data += bytes([j - i - 1]) + flat[i:j].tobytes()
+            i = j
+        data = bytes(data)
+    else:
+        data = flat.tobytes()
+    typ = {"bgr": 2, "mono": 3, "mapped": 1}[kind] + (8 if rle else 0)
+    ident = b"id!"
+    head = bytes([len(ident), 1 if kind == "mapped" else 0, typ])
+    head += np.array([map_origin if kind == "mapped" else 0, 37 if kind == "mapped" else 0], "<u2").tobytes()
+    head += bytes([(32 if alpha else 24) if kind == "mapped" else 0])
+    head += np.array([0, 0, w, h], "<u2").tobytes() + bytes([8 * bpp, (0x20 if top_down else 0) | (0x10 if right_left else 0) | (8 if alpha and kind == "bgr" else 0)])
+    with open(path, "wb") as f:
+        f.write(head + ident + cmap + data)
+
+
+TGA_MAPS = {   # file name -> write_tga arguments after the path
+    "env-bgr-9x5.tga": (9, 5, 11, "bgr"),
+    "env-bgra-rle-td-16x8.tga": (16, 8, 12, "bgr", True, True, False, True),
+    "env-mono-rl-7x4.tga": (7, 4, 13, "mono", False, False, True),
+    "env-mono-rle-8x8.tga": (8, 8, 14, "mono", True, True, True),
+    "env-mapped-12x6.tga": (12, 6, 15, "mapped", False, False, False, False, 3),
+    "env-mapped-rle-a-5x9.tga": (5, 9, 16, "mapped", True, True, False, True, 0),
+}
 
 
 # SURVEY 8(f) rank 4, pixel filters wider than half a pixel (every sample splats into neighbouring tasks' pixels): host front
@@ -227,6 +284,9 @@ def variant_scene(name):
         for fn, spec in ENV_MAPS.items():
             if fn in text:
                 write_env_pfm(os.path.join(scenes.STAGED, fn), *spec)
+        for fn, spec in TGA_MAPS.items():
+            if fn in text:
+                write_tga(os.path.join(scenes.STAGED, fn), *spec)
         _cache[key] = (pb.HostScene(path, ncores=ncores), ncores)
     return _cache[key]
 

@@ -125,11 +125,12 @@ def test_host_envmap_build_is_the_references_light_golden(tmp_path):
     """radianceMap level 0 (ReadImagePFM -> x L -> MIPMap: Lanczos resampling for the 12x7 and 5x3 files) and the
     Distribution2D over the filtered luminance x sin(theta), bit for bit: RGB / grey files, both byte orders, a scale word"""
     g = np.load(os.path.join(HERE, "golden", "envmaps.npz"))
-    names = sorted(k[:-4] for k in g.files if k.endswith("_pfm"))
-    assert len(names) >= 6
-    for k in names:
-        path = str(tmp_path / (k + ".pfm"))
-        open(path, "wb").write(g[k + "_pfm"].tobytes())
+    names = sorted(k for k in g.files if k.endswith("_pfm") or k.endswith("_tga"))
+    assert len(names) >= 12
+    for key in names:   # (Targa files: ReadImageTGA over targa.c -- raw / RLE, grey, BGR(A), colour-mapped, all scan directions)
+        k, ext = key[:-4], key[-3:]
+        path = str(tmp_path / (k + "." + ext))
+        open(path, "wb").write(g[key].tobytes())
         _same_envmap(pb.host_envmap_build(path, g[k + "_L"]), g[k + "_head"], g[k + "_data"])
     _same_envmap(pb.host_envmap_build(None, g["nomap_L"]), g["nomap_head"], g["nomap_data"])
 
@@ -144,5 +145,13 @@ def test_host_envmap_build_is_the_references_light_live(tmp_path):
     for i, (w, h) in enumerate(sizes):
         path = str(tmp_path / ("m%d.pfm" % i))
         write_env_pfm(path, w, h, 100 + i, 3 if i % 3 else 1, [-1.0, 1.0, -2.5][i % 3])
+        L = rs.uniform(0, 2, 3).astype(np.float32)
+        _same_envmap(pb.host_envmap_build(path, L), *me.ref_envmap(path, L))
+    from helpers import write_tga
+    for i in range(24):   # Targa: every kind x raw / RLE x the four scan directions
+        kind = ["bgr", "mono", "mapped"][i % 3]
+        path = str(tmp_path / ("t%d.tga" % i))
+        write_tga(path, int(rs.randint(1, 20)), int(rs.randint(1, 12)), 200 + i, kind, bool(i & 1), bool(i & 2), bool(i & 4),
+                  bool(i & 8) and kind != "mono", int(rs.randint(0, 5)))
         L = rs.uniform(0, 2, 3).astype(np.float32)
         _same_envmap(pb.host_envmap_build(path, L), *me.ref_envmap(path, L))

@@ -213,7 +213,7 @@ def test_oracle_infinite_light_bit_exact_vs_reference_binary(staged, name):
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 @pytest.mark.parametrize("name", ["path-envmap-pow2", "path-envmap-npot-specular", "direct-envmap-npot", "direct-one-envmap-grey",
-                                  "path-envmap-bunny", "path-envmap-1x1"])
+                                  "path-envmap-bunny", "path-envmap-1x1", "path-envmap-tga", "direct-envmap-tga-mapped"])
 def test_oracle_environment_maps_bit_exact_vs_reference_binary(staged, name):
     """InfiniteAreaLight with "mapname" (.pfm): the host front end restates the constructor (ReadImagePFM, texels x L x scale,
     MIPMap's Lanczos resampling to a power of two and its pyramid, the filtered luminance x sin(theta) image, Distribution2D
