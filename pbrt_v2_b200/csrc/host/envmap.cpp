@@ -222,6 +222,13 @@ bool ReadImagePFM(const std::string &filename, int *xres, int *yres, std::vector
     if (sscanf(buffer, "%f", &scale) != 1) return fail();
     if (width <= 0 || height <= 0 || (long long)width * height > (1ll << 28)) return fail();
     const size_t nFloats = (size_t)nChannels * width * height;
+    {   // (the data must be there before memory is set aside for it)
+        const long at = ftell(fp);
+        fseek(fp, 0, SEEK_END);
+        const long end = ftell(fp);
+        fseek(fp, at, SEEK_SET);
+        if (at < 0 || end < at || (size_t)(end - at) < nFloats * sizeof(float)) return fail();
+    }
     std::vector<float> data(nFloats);
     if (fread(data.data(), sizeof(float), nFloats, fp) != nFloats) return fail();
     const bool fileLittleEndian = scale < 0.f;

@@ -171,6 +171,8 @@ bool ReadImageEXR(const std::string &filename, int *xres, int *yres, std::vector
         lineBytes += (size_t)c.bytes * (size_t)width;
     }
     if (!offsetOf.count("R") && !offsetOf.count("G") && !offsetOf.count("B")) return fail("no R, G or B channel (luminance-only files are not supported)");
+    // (deflate expands at most ~1032 : 1, the RLE here 128 : 1: a data window the file cannot possibly fill is a corrupt header)
+    if ((double)lineBytes * (double)height > 1100.0 * (double)d.size()) return fail("data window larger than the file can hold");
     const size_t nChunks = (size_t)((height + linesPerBlock - 1) / linesPerBlock);
     if (p + 8 * nChunks > d.size()) return fail("truncated offset table");
     rgb->assign((size_t)3 * width * height, 0.f);   // a missing colour channel reads as 0 (RgbaInputFile's fill value)

@@ -62,6 +62,7 @@ bool ReadImageTGA(const std::string &filename, int *xres, int *yres, std::vector
         p += (size_t)mapLength * mapBpp;
     }
     const size_t bpp = depth / 8, nPixels = (size_t)width * height;
+    if ((double)nPixels * (double)bpp > 130.0 * (double)d.size()) return fail("premature end of file");   // (RLE: at most 128 : 1)
     std::vector<uint8_t> pix(nPixels * bpp);
     if (!rle) {
         if (p + pix.size() > d.size()) return fail("premature end of file");

@@ -169,13 +169,20 @@ def test_device_state_machine_on_host_variants(staged, doh):
         _same_film(doh, variant_scene(v[0])[0])
 
 
-def test_specular_device_code_on_host(staged, tmp_path_factory):
-    """The device code for mirror / glass (SpecularReflection / SpecularTransmission, the specularBounce branches of the
-    path state machine) exists under -DPBRT_SPECULAR=1 but is not in the shipped kernels yet (it has not been measured on
-    a GPU).  Here it is compiled for the host and rendered against the oracle; the non-specular scenes must not move."""
-    from helpers import variant_scene
-    lib = _build(tmp_path_factory, "device_on_host_specular", ["-DPBRT_SPECULAR=1"])
+@pytest.fixture(scope="module")
+def doh_f4(tmp_path_factory):
+    """the harness with every gated SURVEY 8(f) rank 4 feature on, as `make variants VARIANT_NAMES=f4` builds the library"""
+    lib = _build(tmp_path_factory, "device_on_host_f4", ["-DPBRT_METAL=1", "-DPBRT_INFINITE=1", "-DPBRT_FILTER=1"])
     lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+    return lib
+
+
+def test_specular_device_code_on_host(staged, doh):
+    """The device code for mirror / glass (SpecularReflection / SpecularTransmission, the specularBounce branches of the
+    path state machine; PBRT_SPECULAR, on in the shipped kernels since round 2), compiled for the host and rendered against
+    the oracle; the non-specular scenes must not move."""
+    from helpers import variant_scene
+    lib = doh
     for name in ("path-glass-mirror", "path-glass-params-mirror-floor", "maxdepth8", "dof",
                  # DirectLightingIntegrator's recursive SpecularReflect / SpecularTransmit rays (a per-path frame stack)
                  "direct-glass-mirror", "direct-mirror-floor-maxdepth3", "direct-one-glass", "directlighting-maxdepth1"):
@@ -211,15 +218,14 @@ def test_shared_memory_stack_and_top_table_on_host(staged, tmp_path_factory):
     _same_film(lib, host_scene("anim-killeroos-moving", 32, 32, 4, 2))
 
 
-def test_metal_device_code_on_host(staged, tmp_path_factory):
+def test_metal_device_code_on_host(staged, doh_f4):
     """MetalMaterial on the device (dshade.cuh under -DPBRT_METAL=1: the Blinn microfacet BRDF with FrCond as its Fresnel term)
     is not in the shipped kernels yet (written after the round's GPU budget was spent).  Here it is compiled for the host and
     rendered against the oracle -- which is pinned on the reference binary for the same scenes (test_oracle_pinning.py) --
     through the state machine (both integrators), the vertex form and the vertex-wavefront kernels; a scene without metal
     must not move."""
     from helpers import METAL_VARIANTS, variant_scene
-    lib = _build(tmp_path_factory, "device_on_host_metal", ["-DPBRT_METAL=1"])
-    lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+    lib = doh_f4
     for v in METAL_VARIANTS:
         _same_film(lib, variant_scene(v[0])[0])
     for form in (1, 5, 1000):   # vertex form; the wave kernels over 5 and 1000 slots
@@ -231,15 +237,14 @@ def test_metal_device_code_on_host(staged, tmp_path_factory):
     _same_film(lib, host_scene("killeroo-simple", 32, 32, 4, 2))
 
 
-def test_infinite_light_device_code_on_host(staged, tmp_path_factory):
+def test_infinite_light_device_code_on_host(staged, doh_f4):
     """InfiniteAreaLight (constant radiance) on the device, both integrators (dshade.cuh / dvertex.cuh / path_body.inc /
     kwave.cuh / kvertex.cuh under -DPBRT_INFINITE=1): not in the shipped kernels (never run on a GPU).  Compiled for the host
     and rendered against the oracle -- pinned on the reference binary for the same scenes (test_oracle_pinning.py) -- through
     the vertex form and through the vertex-wavefront kernels over small and large pools; scenes without such a light must
     not move."""
     from helpers import INFINITE_VARIANTS, ENVMAP_VARIANTS, variant_scene
-    lib = _build(tmp_path_factory, "device_on_host_infinite", ["-DPBRT_INFINITE=1"])
-    lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+    lib = doh_f4
     # constant radiance and radiance maps ("mapname": bilinear MIPMap::Lookup over level 0, Distribution2D sampling / pdf)
     variants = INFINITE_VARIANTS + ENVMAP_VARIANTS
     for v in variants:   # the state machine (path_body.inc): both integrators, incl. the specular recursion's children
@@ -253,7 +258,7 @@ def test_infinite_light_device_code_on_host(staged, tmp_path_factory):
     lib.doh_set_vertex_form(0)
 
 
-def test_pixel_filter_device_code_on_host(staged, tmp_path_factory):
+def test_pixel_filter_device_code_on_host(staged, doh_f4):
     """ImageFilm::AddSample through the 16 x 16 weight table (dpath.cuh FilmAddFiltered under -DPBRT_FILTER=1: gaussian,
     mitchell, triangle, sinc, wide box; not in the shipped kernels, never run on a GPU).  One host thread adding task by task
     IS the reference's --ncores 1 order, so the state machine and the vertex form must give the oracle's one-thread film bit
@@ -261,8 +266,7 @@ def test_pixel_filter_device_code_on_host(staged, tmp_path_factory):
     kernels add pixel round by pixel round over all tasks -- an order the reference only has above one thread, where it is
     undefined -- so their films are compared to rounding."""
     from helpers import FILTER_VARIANTS, variant_scene
-    lib = _build(tmp_path_factory, "device_on_host_filter", ["-DPBRT_FILTER=1"])
-    lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
+    lib = doh_f4
 
     def films(hs):
         rd = hs.render_desc()
@@ -325,9 +329,10 @@ def test_pair_node_walk_on_host(staged, tmp_path_factory):
 
 
 def test_interleaved_kd_records_on_host(staged, tmp_path_factory):
-    """-DPBRT_KD_INTERLEAVED=1 (a round-2 kernel experiment, not in the shipped kernels): the measured-BRDF kd-tree read as
-    one 32-byte record per node.  IrregIsotropicBRDF::f and whole films over the bunny's measured material must not move."""
-    lib = _build(tmp_path_factory, "device_on_host_kdrec", ["-DPBRT_KD_INTERLEAVED=1"])
+    """The measured-BRDF kd-tree is read as one 32-byte record per node in the shipped kernels (PBRT_KD_INTERLEAVED=1, what
+    every other test here compiles); -DPBRT_KD_INTERLEAVED=0 keeps the reference-shaped split layout (node array + sample
+    array) as the A/B partner.  IrregIsotropicBRDF::f and whole films over the bunny's measured material must not move."""
+    lib = _build(tmp_path_factory, "device_on_host_kdsplit", ["-DPBRT_KD_INTERLEAVED=0"])
     lib.doh_shade_test.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
     hs = host_scene("bunny", 32, 32, 4, 32)
