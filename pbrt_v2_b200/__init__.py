@@ -150,6 +150,8 @@ def host_lib():
         lib = _load("libpbrthost.so")
         lib.pbrthost_load.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
         lib.pbrthost_load.restype = C.c_void_p
+        lib.pbrthost_load_options.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        lib.pbrthost_load_options.restype = C.c_void_p
         lib.pbrthost_load_synthetic.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
         lib.pbrthost_load_synthetic.restype = C.c_void_p
         lib.pbrthost_write_synthetic.argtypes = [C.c_char_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
@@ -192,13 +194,13 @@ def _check(rc, what):
 class HostScene(object):
     """A parsed + flattened scene (host memory only; no GPU needed)."""
 
-    def __init__(self, filename, ncores=0, _handle=None):
+    def __init__(self, filename, ncores=0, _handle=None, quick=False):
         lib = host_lib()
         if _handle is not None:
             self._h, self.filename = _handle, filename
             return
         err = C.create_string_buffer(1024)
-        self._h = lib.pbrthost_load(os.fsencode(filename), int(ncores), err, len(err))
+        self._h = lib.pbrthost_load_options(os.fsencode(filename), int(ncores), int(bool(quick)), err, len(err))
         if not self._h:
             raise PbrtGpuError("cannot load %s: %s" % (filename, err.value.decode()))
         self.filename = filename

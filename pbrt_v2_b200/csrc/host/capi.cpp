@@ -15,9 +15,11 @@ struct PbrtHostScene {
     LoadedScene ls;
 };
 
-PbrtHostScene *pbrthost_load(const char *filename, int ncores, char *err, int errlen) {
+// ncores, quick: PbrtOptions.nCores (--ncores), PbrtOptions.quickRender (--quick), core/pbrt.h:126-138
+PbrtHostScene *pbrthost_load_options(const char *filename, int ncores, int quick, char *err, int errlen) {
     PbrtHostScene *h = new PbrtHostScene;
     Options opt;
+    opt.quickRender = quick != 0;
     opt.nCores = ncores;
     if (!LoadSceneFile(filename, opt, &h->ls)) {
         if (err && errlen > 0) snprintf(err, errlen, "%s", h->ls.error.c_str());
@@ -25,6 +27,10 @@ PbrtHostScene *pbrthost_load(const char *filename, int ncores, char *err, int er
         return nullptr;
     }
     return h;
+}
+
+PbrtHostScene *pbrthost_load(const char *filename, int ncores, char *err, int errlen) {
+    return pbrthost_load_options(filename, ncores, 0, err, errlen);
 }
 
 // the synthetic random-triangle scene of BASELINE.json configs[4], built without going through text

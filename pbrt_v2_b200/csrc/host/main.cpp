@@ -50,10 +50,11 @@ int main(int argc, char *argv[]) {
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) localRank = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--rendezvous") && i + 1 < argc) rendezvous = argv[++i];
         else if (!strcmp(argv[i], "--outfile")) opt.imageFile = argv[++i];
+        else if (!strcmp(argv[i], "--quick")) opt.quickRender = true;
         else if (!strcmp(argv[i], "--quiet")) opt.quiet = true;
         else if (!strcmp(argv[i], "--verbose")) {}
         else if (!strcmp(argv[i], "--help") || !strcmp(argv[i], "-h")) {
-            printf("usage: pbrt_b200 [--ncores n] [--outfile filename] [--quiet] [--rank r --world n --rendezvous file [--device d]] <filename.pbrt> ...\n");
+            printf("usage: pbrt_b200 [--ncores n] [--outfile filename] [--quick] [--quiet] [--rank r --world n --rendezvous file [--device d]] <filename.pbrt> ...\n");
             return 0;
         } else files.push_back(argv[i]);
     }

@@ -430,7 +430,9 @@ bool Api::DoShape(const std::string &name, const ParamSet &paramsIn) {   // core
         V3 sc = ap.FindOneSpectrum("scale", V3(1, 1, 1));
         Light lt;
         lt.desc.type = PBRTGPU_LIGHT_DIFFUSE_AREA;
-        lt.desc.nSamples = std::max(1, ap.FindOneInt("nsamples", 1));   // diffuse.cpp:63, light.h:53
+        int nSamples = ap.FindOneInt("nsamples", 1);
+        if (opt.quickRender) nSamples = std::max(1, nSamples / 4);   // diffuse.cpp:64
+        lt.desc.nSamples = std::max(1, nSamples);   // diffuse.cpp:63, light.h:53
         lt.desc.L[0] = L.x * sc.x; lt.desc.L[1] = L.y * sc.y; lt.desc.L[2] = L.z * sc.z;
         lt.shape = shape.get();
         scene->lights.push_back(lt);
@@ -450,7 +452,9 @@ bool Api::DoLight(const std::string &name, const ParamSet &params) {   // core/a
         V3 sc = params.FindOneSpectrum("scale", V3(1, 1, 1));
         Light lt;
         lt.desc.type = PBRTGPU_LIGHT_INFINITE;
-        lt.desc.nSamples = std::max(1, params.FindOneInt("nsamples", 1));   // Light ctor, light.cpp:46-51
+        int nSamples = params.FindOneInt("nsamples", 1);
+        if (opt.quickRender) nSamples = std::max(1, nSamples / 4);   // infinite.cpp:190
+        lt.desc.nSamples = std::max(1, nSamples);   // Light ctor, light.cpp:46-51
         lt.desc.L[0] = L.x * sc.x; lt.desc.L[1] = L.y * sc.y; lt.desc.L[2] = L.z * sc.z;
         // "mapname": ReadImage (core/imageio.cpp:58-81): .pfm, .tga and .exr (envmap.cpp, tga.cpp, exr.cpp)
         std::string mapname = params.FindOneString("mapname", "");
@@ -536,6 +540,8 @@ bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
     if (filename.empty()) filename = "pbrt.tga";   // film/image.cpp:267-271 (the default of a build without OpenEXR)
     int xres = FilmParams.FindOneInt("xresolution", 640);
     int yres = FilmParams.FindOneInt("yresolution", 480);
+    if (opt.quickRender) xres = std::max(1, xres / 4);   // film/image.cpp:244-245
+    if (opt.quickRender) yres = std::max(1, yres / 4);
     float crop[4] = {0, 1, 0, 1};
     const std::vector<float> *cr = FilmParams.FindFloat("cropwindow");
     if (cr && cr->size() == 4) {
@@ -578,6 +584,7 @@ bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
     if (SamplerName != "lowdiscrepancy") return Fail("sampler \"" + SamplerName + "\" is out of scope (lowdiscrepancy)");
     {
         int nsamp = SamplerParams.FindOneInt("pixelsamples", 4);
+        if (opt.quickRender) nsamp = 1;   // lowdiscrepancy.cpp:88
         uint32_t v = (uint32_t)nsamp;   // RoundUpPow2, core/pbrt.h:271-277
         v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; v++;
         r->sampler.samplesPerPixel = (int)v;

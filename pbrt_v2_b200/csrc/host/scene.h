@@ -310,6 +310,7 @@ struct GpuSamplerRenderer : Renderer {
 struct Options {   // core/pbrt.h:126-138
     int nCores = 0;
     bool quiet = false;
+    bool quickRender = false;   // --quick: film resolution / 4, one pixel sample, light samples / 4
     std::string imageFile;
 };
 struct LoadedScene {

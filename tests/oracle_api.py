@@ -114,7 +114,7 @@ def read_pfm(path):
     return data.reshape(h, w, 3)[::-1].copy()   # rows are stored bottom-to-top
 
 
-def run_reference(scene_path, ncores, timeout=3600):
+def run_reference(scene_path, ncores, timeout=3600, extra_args=()):
     """Run the UNMODIFIED reference on `scene_path` (cwd = scene dir); returns (rgb, seconds)."""
     import re, time
     cwd = os.path.dirname(os.path.abspath(scene_path))
@@ -124,7 +124,7 @@ def run_reference(scene_path, ncores, timeout=3600):
     if os.path.exists(outp):
         os.remove(outp)
     t0 = time.time()
-    subprocess.run([REF_BIN, "--ncores", str(ncores), "--quiet", os.path.basename(scene_path)], cwd=cwd,
+    subprocess.run([REF_BIN, "--ncores", str(ncores), "--quiet"] + list(extra_args) + [os.path.basename(scene_path)], cwd=cwd,
                    check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout)
     dt = time.time() - t0
     return read_pfm(outp), dt

@@ -170,6 +170,21 @@ def test_oracle_bit_exact_vs_reference_binary_on_variants(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["direct-infinite", "path-infinite-bunny", "direct-envmap-npot"])
+def test_quick_render_option_matches_reference_binary(staged, name):
+    """--quick (PbrtOptions.quickRender): film resolution / 4 (film/image.cpp:244-245), one pixel sample
+    (lowdiscrepancy.cpp:88), light samples / 4 (diffuse.cpp:64, infinite.cpp:190)"""
+    from helpers import variant_scene
+    hs0, ncores = variant_scene(name)
+    hs = pb.HostScene(hs0.filename, ncores=ncores, quick=True)
+    rd = hs.render_desc()
+    assert (rd.xResolution, rd.yResolution, rd.samplesPerPixel) == (10, 10, 1)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores, extra_args=["--quick"])
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 @pytest.mark.parametrize("name", ["path-glass-mirror", "path-glass-params-mirror-floor", "direct-glass-mirror",
                                   "direct-mirror-floor-maxdepth3", "direct-one-glass"])
 def test_oracle_specular_materials_bit_exact_vs_reference_binary(staged, name):
