@@ -182,6 +182,7 @@ def host_lib():
         lib.pbrthost_envmap_build.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pbrthost_envmap_build.restype = C.c_ulonglong
         lib.pbrthost_read_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+        lib.pbrthost_write_exr.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         _host = lib
     return _host
 
@@ -442,6 +443,13 @@ def host_read_image(filename):
     out = np.zeros((h.value, w.value, 3), np.float32)
     host_lib().pbrthost_read_image(filename.encode(), C.byref(w), C.byref(h), out.ctypes.data)
     return out
+
+
+def host_write_exr(filename, rgb):
+    """the host front end's WriteImageEXR on a float32 [height, width, 3] image"""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    if host_lib().pbrthost_write_exr(filename.encode(), rgb.ctypes.data, rgb.shape[1], rgb.shape[0]):
+        raise PbrtGpuError("cannot write %r" % filename)
 
 
 def host_envmap_build(pfm, L):

@@ -182,6 +182,12 @@ int pbrthost_read_image(const char *filename, int *width, int *height, float *ou
     return 0;
 }
 
+// WriteImageEXR (core/imageio.cpp:170-193) on a raw float RGB image (data window = display window)
+int pbrthost_write_exr(const char *filename, const float *rgb, int width, int height) {
+    std::vector<float> v(rgb, rgb + (size_t)3 * width * height);
+    return WriteImageEXR(filename, v, width, height, width, height, 0, 0) ? 0 : 1;
+}
+
 // LoopSubdiv on raw arrays (test hooks and the comparison partner of pbrtgpu_loopsubdiv_refine).
 // topology: the constructor's pass (loopsubdiv.cpp:156-216) -> the index arrays of PbrtGpuSubdivMesh
 int pbrthost_loopsubdiv_topology(int nVertices, int nFaces, const int *indices, const float *P, int32_t *startFace, uint8_t *vflags,

@@ -225,4 +225,93 @@ bool ReadImageEXR(const std::string &filename, int *xres, int *yres, std::vector
     return true;
 }
 
+
+// WriteImageEXR (core/imageio.cpp:170-193): what RgbaOutputFile(name, displayWindow, dataWindow, WRITE_RGBA) stores -- HALF
+// A, B, G, R channels over the data window (the crop region inside the full-resolution display window), alpha 1 --
+// as a scan-line file with ZIP compression (the OpenEXR library's default would be PIZ; any reader takes either).
+// float -> half as the library's `half` does it: round to nearest even, overflow to infinity.
+static uint16_t FloatToHalf(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+    const uint32_t absx = x & 0x7fffffffu;
+    if (absx >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (absx > 0x7f800000u ? 0x200u | ((absx >> 13) & 0x3ffu) : 0u));   // inf / NaN
+    if (absx >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);                 // rounds up to 65536 or beyond: infinity
+    if (absx < 0x33000001u) return sign;                                      // at most half of the smallest subnormal: zero
+    int e = (int)(absx >> 23) - 127;
+    uint32_t m = (absx & 0x7fffffu) | 0x800000u;
+    int shift;   // bits dropped from the 24-bit significand
+    uint32_t base;
+    if (e < -14) { shift = 13 + (-14 - e); base = 0; }                       // subnormal half
+    else { shift = 13; base = (uint32_t)(e + 15) << 10; m &= 0x7fffffu; }
+    const uint32_t kept = m >> shift, rem = m & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+    uint32_t h = base + kept;
+    if (rem > halfway || (rem == halfway && (h & 1u))) ++h;                    // carries ripple into the exponent correctly
+    return (uint16_t)(sign | h);
+}
+
+bool WriteImageEXR(const std::string &name, const std::vector<float> &rgb, int xRes, int yRes, int totalXRes, int totalYRes,
+                   int xOffset, int yOffset) {
+    std::vector<uint8_t> out;
+    auto put = [&](const void *p, size_t n) { out.insert(out.end(), (const uint8_t *)p, (const uint8_t *)p + n); };
+    auto put32 = [&](int32_t v) { put(&v, 4); };
+    auto attr = [&](const char *nm, const char *type, const void *v, int32_t n) {
+        put(nm, strlen(nm) + 1); put(type, strlen(type) + 1); put32(n); put(v, (size_t)n);
+    };
+    put32(20000630); put32(2);
+    {
+        std::vector<uint8_t> ch;
+        for (const char *c : {"A", "B", "G", "R"}) {
+            ch.push_back((uint8_t)c[0]); ch.push_back(0);
+            const int32_t rec[4] = {1, 0, 1, 1};   // HALF, pLinear 0 (+ 3 reserved bytes), xSampling, ySampling
+            ch.insert(ch.end(), (const uint8_t *)rec, (const uint8_t *)rec + 16);
+        }
+        ch.push_back(0);
+        attr("channels", "chlist", ch.data(), (int32_t)ch.size());
+    }
+    const uint8_t zip = 3, increasingY = 0;
+    attr("compression", "compression", &zip, 1);
+    const int32_t dataWindow[4] = {xOffset, yOffset, xOffset + xRes - 1, yOffset + yRes - 1};
+    const int32_t displayWindow[4] = {0, 0, totalXRes - 1, totalYRes - 1};
+    attr("dataWindow", "box2i", dataWindow, 16);
+    attr("displayWindow", "box2i", displayWindow, 16);
+    attr("lineOrder", "lineOrder", &increasingY, 1);
+    const float one = 1.f, centre[2] = {0.f, 0.f};
+    attr("pixelAspectRatio", "float", &one, 4);
+    attr("screenWindowCenter", "v2f", centre, 8);
+    attr("screenWindowWidth", "float", &one, 4);
+    out.push_back(0);
+    const int nChunks = (yRes + 15) / 16;
+    const size_t tableAt = out.size();
+    out.resize(out.size() + 8 * (size_t)nChunks);
+    const uint16_t alpha = FloatToHalf(1.f);
+    std::vector<uint8_t> raw, tmp, comp;
+    for (int c = 0; c < nChunks; ++c) {
+        const int y0 = 16 * c, lines = std::min(16, yRes - y0);
+        raw.clear();
+        for (int y = y0; y < y0 + lines; ++y)
+            for (int k = 0; k < 4; ++k)   // A, B, G, R: one channel after the other inside a scan line
+                for (int x = 0; x < xRes; ++x) {
+                    const uint16_t h = k == 0 ? alpha : FloatToHalf(rgb[3 * ((size_t)y * xRes + x) + (3 - k)]);
+                    raw.push_back((uint8_t)(h & 0xff)); raw.push_back((uint8_t)(h >> 8));
+                }
+        tmp.resize(raw.size());   // even bytes first, then odd bytes; then the delta predictor
+        for (size_t i = 0, a = 0, b = (raw.size() + 1) / 2; i < raw.size(); ++i) tmp[(i & 1) ? b++ : a++] = raw[i];
+        for (size_t i = tmp.size(); i-- > 1;) tmp[i] = (uint8_t)(tmp[i] - tmp[i - 1] + 128);
+        uLongf n = compressBound((uLong)tmp.size());
+        comp.resize(n);
+        const bool packed = compress(comp.data(), &n, tmp.data(), (uLong)tmp.size()) == Z_OK && n < raw.size();
+        const uint64_t at = out.size();
+        memcpy(out.data() + tableAt + 8 * (size_t)c, &at, 8);
+        put32(yOffset + y0);
+        put32((int32_t)(packed ? n : raw.size()));
+        if (packed) put(comp.data(), n); else put(raw.data(), raw.size());
+    }
+    FILE *f = fopen(name.c_str(), "wb");
+    if (!f) { fprintf(stderr, "Error: Unable to write image file \"%s\"\n", name.c_str()); return false; }
+    const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    fclose(f);
+    return ok;
+}
+
 }  // namespace pb

@@ -94,17 +94,18 @@ static bool WriteTGA(const std::string &name, const std::vector<float> &rgb, int
 }
 
 bool ImageFilm::WriteImage() const {
-    // ::WriteImage picks the format by the suffix (core/imageio.cpp:85-140); this build has PFM and TGA.  A name this
-    // front end cannot honour (.exr needs OpenEXR, .png lodepng) is NOT written under that name with other contents:
-    // the float image goes to "<name>.pfm" and a warning says so.
+    // ::WriteImage picks the format by the suffix (core/imageio.cpp:85-140); this build has PFM, TGA and EXR (exr.cpp).  A
+    // name this front end cannot honour (.png) is NOT written under that name with other contents: the float image goes to
+    // "<name>.pfm" and a warning says so.
     std::vector<float> rgb;
     ToRGB(&rgb);
     std::string suffix = filename.size() >= 5 ? filename.substr(filename.size() - 4) : std::string();
     for (char &c : suffix) c = (char)tolower((unsigned char)c);
     if (suffix == ".pfm") return WritePFM(filename, rgb, xPixelCount, yPixelCount);
     if (suffix == ".tga") return WriteTGA(filename, rgb, xPixelCount, yPixelCount);
+    if (suffix == ".exr") return WriteImageEXR(filename, rgb, xPixelCount, yPixelCount, xResolution, yResolution, xPixelStart, yPixelStart);
     const std::string alt = filename + ".pfm";
-    fprintf(stderr, "Warning: this build writes .pfm and .tga images; \"%s\" is written as \"%s\" (float RGB, lossless)\n",
+    fprintf(stderr, "Warning: this build writes .pfm, .tga and .exr images; \"%s\" is written as \"%s\" (float RGB, lossless)\n",
             filename.c_str(), alt.c_str());
     return WritePFM(alt, rgb, xPixelCount, yPixelCount);
 }

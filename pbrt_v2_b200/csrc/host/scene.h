@@ -131,6 +131,8 @@ struct EnvMap {
 };
 bool ReadImagePFM(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);
 bool ReadImageEXR(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);   // exr.cpp
+bool WriteImageEXR(const std::string &name, const std::vector<float> &rgb, int xRes, int yRes, int totalXRes, int totalYRes,
+                   int xOffset, int yOffset);   // exr.cpp
 bool ReadImageTGA(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);   // tga.cpp
 // ReadImage (core/imageio.cpp:58-81): by suffix, .pfm / .tga / .exr; anything else is an error
 bool ReadImage(const std::string &filename, int *xres, int *yres, std::vector<float> *rgb, std::string *err);
