@@ -284,6 +284,7 @@ def main():
     base, xres, yres, spp = WORKLOADS[args.workload]
     if args.spp:
         spp = args.spp
+    t_prep = time.perf_counter()
     if base == "synthetic":
         hs = pb.HostScene.synthetic(args.tris, xres, yres, spp, maxdepth=8, ncores=per_pixel_ncores(xres, yres))
     else:
@@ -291,6 +292,7 @@ def main():
                               nlevels=WORKLOAD_NLEVELS.get(args.workload),
                               integrator=WORKLOAD_INTEGRATOR.get(args.workload, "path"))
         hs = pb.HostScene(path, ncores=per_pixel_ncores(xres, yres))
+    prep_host_s = time.perf_counter() - t_prep   # parse + Loop subdivision + BVH build + flattening, on the host
     rd = hs.render_desc()
     from pbrt_v2_b200.multigpu import shard_render_desc
     shard_render_desc(rd, rank, world, xres)   # interleave blocks of 4 pixel rows across ranks
@@ -303,7 +305,10 @@ def main():
     nsamples = xc * yc * spp
     scene_bytes = hs.scene_bytes()
 
-    gs = pb.GpuScene(hs)
+    t_up = time.perf_counter()
+    gs = pb.GpuScene(hs)             # pbrtgpu_scene_create: validation + the host -> device copy of the flattened scene
+    torch.cuda.synchronize(dev)
+    prep_upload_s = time.perf_counter() - t_up
     film = torch.zeros((yc, xc, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     host_film = torch.empty((yc, xc, 4), dtype=torch.float32, pin_memory=True)
@@ -434,6 +439,9 @@ def main():
                     "through": "pbrtgpu_scene_update + pbrtgpu_render (host pixel buffer)" if world == 1 else
                                "pbrtgpu_scene_update + pbrtgpu_render_sharded (ncclReduce inside the library, host pixel buffer on rank 0)"},
             "gpu_launches": launches,
+            # outside the timed region, once per scene: what the step's input cost to prepare (rank 0's wall clock)
+            "scene_prep": {"host_s": prep_host_s, "scene_create_s": prep_upload_s, "scene_bytes": scene_bytes,
+                           "what": "host: parse + LoopSubdiv::Refine + BVHAccel build + flattening; scene_create: validation + upload"},
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "kernel": "k_wtrace (+ the traversals inside k_vertex<2>)", "achieved": achieved if trace_ms > 0 else None, "peak": peak,
