@@ -525,5 +525,10 @@ def keep_build_input(on=True):
     host_lib().pbrthost_keep_build_input(int(on))
 
 
+def set_bvh_parallel_min(n=1 << 17):
+    """host BVH builds of at least n primitives fork their subtrees onto several threads (same tree either way)"""
+    host_lib().pbrthost_set_bvh_parallel_min(int(n))
+
+
 def device_count():
     return gpu_lib().pbrtgpu_device_count()

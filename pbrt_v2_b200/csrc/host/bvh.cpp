@@ -15,6 +15,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
+#include <memory>
+#include <thread>
 
 namespace pb {
 
@@ -28,8 +31,7 @@ struct PrimInfo {   // BVHPrimitiveInfo, bvh.cpp:40-49
 
 struct Builder {
     std::vector<PrimInfo> &info;
-    std::vector<uint32_t> &ordered;   // orderedPrims, as indices into the input primitives
-    std::vector<PbrtGpuBVHNode> &nodes;
+    std::vector<PbrtGpuBVHNode> &nodes;   // this builder's subtree in depth-first order; child offsets count from nodes[0]
     uint32_t maxPrimsInNode;
     int splitMethod;
 
@@ -43,9 +45,11 @@ struct Builder {
         b.pMax = V3(n.bmax[0], n.bmax[1], n.bmax[2]);
         return b;
     }
+    // A leaf appends its range to orderedPrims (bvh.cpp:232-236).  Leaves are reached left to right and their ranges tile
+    // [0, n), so orderedPrims.size() at that moment IS `start`, and orderedPrims as a whole is the build array in its final
+    // order: the driver copies it once at the end.  (That is what lets subtrees be built independently of each other.)
     uint32_t MakeLeaf(uint32_t nodeIdx, uint32_t start, uint32_t end, const BBox &bbox) {
-        uint32_t first = (uint32_t)ordered.size();
-        for (uint32_t i = start; i < end; ++i) ordered.push_back((uint32_t)info[i].primitiveNumber);
+        uint32_t first = start;
         PbrtGpuBVHNode &n = nodes[nodeIdx];
         SetBounds(n, bbox);
         n.offset = first;
@@ -73,17 +77,29 @@ struct Builder {
         nodes.push_back(PbrtGpuBVHNode());
         memset(&nodes[nodeIdx], 0, sizeof(PbrtGpuBVHNode));
         BBox bbox;
+        int dim;
+        uint32_t mid;
+        if (!Decide(start, end, &bbox, &dim, &mid)) return MakeLeaf(nodeIdx, start, end, bbox);
+        return MakeInterior(nodeIdx, dim, start, mid, end);
+    }
+    // What recursiveBuild decides for [start, end) before it recurses: leaf (false; *bbox set) or interior (true; the range
+    // partitioned around *mid along *dim)
+    bool Decide(uint32_t start, uint32_t end, BBox *bboxOut, int *dimOut, uint32_t *midOut) {
+        BBox bbox;
         for (uint32_t i = start; i < end; ++i) bbox = Union(bbox, info[i].bounds);
+        *bboxOut = bbox;
         uint32_t nPrimitives = end - start;
-        if (nPrimitives == 1) return MakeLeaf(nodeIdx, start, end, bbox);
+        if (nPrimitives == 1) return false;
 
         BBox centroidBounds;
         for (uint32_t i = start; i < end; ++i) centroidBounds = Union(centroidBounds, info[i].centroid);
         int dim = centroidBounds.MaximumExtent();
         uint32_t mid = (start + end) / 2;
+        *dimOut = dim;
         if (centroidBounds.pMax[dim] == centroidBounds.pMin[dim]) {   // bvh.cpp:239-261
-            if (nPrimitives <= maxPrimsInNode) return MakeLeaf(nodeIdx, start, end, bbox);
-            return MakeInterior(nodeIdx, dim, start, mid, end);
+            if (nPrimitives <= maxPrimsInNode) return false;
+            *midOut = mid;
+            return true;
         }
         PrimInfo *base = info.data();
         auto equalCounts = [&]() {   // bvh.cpp:280-286
@@ -134,10 +150,94 @@ struct Builder {
                 });
                 mid = (uint32_t)(pmid - base);
             } else {
-                return MakeLeaf(nodeIdx, start, end, bbox);
+                return false;
             }
         }
-        return MakeInterior(nodeIdx, dim, start, mid, end);
+        *midOut = mid;
+        return true;
+    }
+};
+
+// The same tree with its subtrees built side by side.  recursiveBuild's work on [start, end) touches that range of the
+// build array only and -- see MakeLeaf -- nothing it emits depends on what was built before it except the position of its
+// nodes in the depth-first array.  So: the top `depth` levels fork (each call decides its node, then its two halves run
+// on two threads), every range below is built by an ordinary Builder into its own node array, and the pieces are
+// stitched together in preorder with their child offsets rebased.
+struct ParallelBuild {
+    struct Tree {
+        std::vector<PbrtGpuBVHNode> piece;   // a serially built subtree (or a single leaf); empty for a forked interior node
+        int dim = 0;
+        std::unique_ptr<Tree> child[2];
+    };
+    std::vector<PrimInfo> &info;
+    uint32_t maxPrimsInNode;
+    int splitMethod;
+    uint32_t serialBelow;   // ranges of at most this many primitives are not forked
+
+    std::unique_ptr<Tree> Build(uint32_t start, uint32_t end, int depth) {
+        std::unique_ptr<Tree> t(new Tree);
+        Builder b{info, t->piece, maxPrimsInNode, splitMethod};
+        if (depth <= 0 || end - start <= serialBelow) {
+            t->piece.reserve(2 * (size_t)(end - start));
+            b.Build(start, end);
+            return t;
+        }
+        BBox bbox;
+        uint32_t mid = 0;
+        if (!b.Decide(start, end, &bbox, &t->dim, &mid)) {
+            t->piece.push_back(PbrtGpuBVHNode());
+            memset(&t->piece[0], 0, sizeof(PbrtGpuBVHNode));
+            b.MakeLeaf(0, start, end, bbox);
+            return t;
+        }
+        std::thread left([&]() { t->child[0] = Build(start, mid, depth - 1); });
+        t->child[1] = Build(mid, end, depth - 1);
+        left.join();
+        return t;
+    }
+    // preorder positions first (a piece's size is known, a forked node takes one slot), then every piece is copied to its
+    // place -- second-child offsets rebased -- on its own thread, and the forked nodes are filled in bottom-up
+    struct Placed { const Tree *t; uint32_t base; };
+    static uint32_t Place(const Tree &t, uint32_t base, std::vector<Placed> *pieces, std::vector<Placed> *forks) {
+        if (!t.child[0]) {
+            pieces->push_back(Placed{&t, base});
+            return base + (uint32_t)t.piece.size();
+        }
+        forks->push_back(Placed{&t, base});
+        const uint32_t c1 = Place(*t.child[0], base + 1, pieces, forks);
+        return Place(*t.child[1], c1, pieces, forks);
+    }
+    static uint32_t SizeOf(const Tree &t) {
+        return t.child[0] ? 1 + SizeOf(*t.child[0]) + SizeOf(*t.child[1]) : (uint32_t)t.piece.size();
+    }
+    static void Stitch(const Tree &t, std::vector<PbrtGpuBVHNode> *out) {
+        std::vector<Placed> pieces, forks;
+        const uint32_t total = Place(t, 0, &pieces, &forks);
+        out->resize(total);
+        PbrtGpuBVHNode *o = out->data();
+        auto copyPiece = [o](const Placed &p) {
+            PbrtGpuBVHNode *dst = o + p.base;
+            memcpy(dst, p.t->piece.data(), p.t->piece.size() * sizeof(PbrtGpuBVHNode));
+            if (p.base)
+                for (size_t i = 0; i < p.t->piece.size(); ++i)
+                    if (dst[i].nPrimitives == 0) dst[i].offset += p.base;   // interior: second child's index
+        };
+        const unsigned nThreads = std::min<unsigned>((unsigned)pieces.size(), std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> workers;
+        for (unsigned w = 1; w < nThreads; ++w)
+            workers.emplace_back([&, w]() { for (size_t k = w; k < pieces.size(); k += nThreads) copyPiece(pieces[k]); });
+        for (size_t k = 0; k < pieces.size(); k += std::max(1u, nThreads)) copyPiece(pieces[k]);
+        for (std::thread &w : workers) w.join();
+        for (size_t k = forks.size(); k-- > 0;) {   // preorder list walked backwards: children before parents
+            const Placed &f = forks[k];
+            const uint32_t c1 = f.base + 1 + SizeOf(*f.t->child[0]);
+            PbrtGpuBVHNode &n = o[f.base];   // BVHBuildNode::InitInterior, bvh.cpp:60-66
+            memset(&n, 0, sizeof(n));
+            Builder::SetBounds(n, Union(Builder::GetBounds(o[f.base + 1]), Builder::GetBounds(o[c1])));
+            n.offset = c1;
+            n.nPrimitives = 0;
+            n.axis = (uint8_t)f.t->dim;
+        }
     }
 };
 
@@ -191,6 +291,7 @@ void FullyRefine(const GeometricPrimitive &gp, std::vector<RefinedPrim> *out,
 }  // namespace
 
 bool g_keepBuildInput = false;
+uint32_t g_bvhParallelMin = 1u << 17;   // builds of at least this many primitives run their subtrees on several threads
 
 GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, const std::string &sm, const std::string &builder) {
     // BVHAccel::BVHAccel, bvh.cpp:153-202
@@ -249,10 +350,24 @@ void BuildBVHOnHost(const float *bounds, uint32_t n, uint32_t maxPrimsInNode, in
         pi.centroid = .5f * pi.bounds.pMin + .5f * pi.bounds.pMax;   // bvh.cpp:44-46
         info.push_back(pi);
     }
-    order->reserve(n);
     nodes->reserve(2 * (size_t)n);
-    Builder b{info, *order, *nodes, maxPrimsInNode, splitMethod};
-    b.Build(0, n);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (n >= g_bvhParallelMin && hw > 1) {
+        int depth = 1;
+        while ((1u << depth) < 2 * hw && depth < 7) ++depth;   // ~2 pieces per hardware thread, at most 128
+        ParallelBuild pb{info, maxPrimsInNode, splitMethod, std::max(1u, g_bvhParallelMin / 64)};
+        auto T0 = std::chrono::steady_clock::now();
+        std::unique_ptr<ParallelBuild::Tree> t = pb.Build(0, n, depth);
+        auto T1 = std::chrono::steady_clock::now();
+        ParallelBuild::Stitch(*t, nodes);
+        auto T2 = std::chrono::steady_clock::now();
+        if (getenv("PBRTGPU_BVH_TIMING")) fprintf(stderr, "host bvh: build %.3f s, stitch %.3f s, depth %d\n", std::chrono::duration<double>(T1 - T0).count(), std::chrono::duration<double>(T2 - T1).count(), depth);
+    } else {
+        Builder b{info, *nodes, maxPrimsInNode, splitMethod};
+        b.Build(0, n);
+    }
+    order->resize(n);   // orderedPrims: the build array in its final order (see Builder::MakeLeaf)
+    for (uint32_t i = 0; i < n; ++i) (*order)[i] = (uint32_t)info[i].primitiveNumber;
 }
 
 TransformedPrimitive::TransformedPrimitive(const GeometricPrimitive &base, const AnimatedTransform &w2p)

@@ -124,6 +124,8 @@ int pbrthost_render(PbrtHostScene *h, int writeImage, PbrtGpuPixel *pixelsOut, P
 // test / bench hooks: the input of the top-level accelerator's build -- the world bounds of the refined primitives in the
 // order BVHAccel receives them -- kept by scenes loaded after pbrthost_keep_build_input(1); returns the primitive count
 void pbrthost_keep_build_input(int on) { g_keepBuildInput = on != 0; }
+// builds of at least n primitives run their subtrees on several threads (default 131072; tests force it down to 2)
+void pbrthost_set_bvh_parallel_min(unsigned n) { g_bvhParallelMin = n ? n : 1u; }
 unsigned pbrthost_build_input(PbrtHostScene *h, float *out) {
     const GpuBVHAccel *a = h->ls.scene->aggregate.get();
     if (out && !a->buildInput.empty()) memcpy(out, a->buildInput.data(), a->buildInput.size() * sizeof(float));

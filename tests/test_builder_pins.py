@@ -58,7 +58,16 @@ def same_mesh(ours, ref):
             np.array_equal(ours[1], ref[1], equal_nan=True))
 
 
-def test_host_bvh_build_is_the_references_tree_golden():
+@pytest.fixture(params=[1 << 30, 2], ids=["serial", "forked"])
+def build_mode(request):
+    """the host build as one recursion, and with its subtrees forked onto threads from the root down (host/bvh.cpp
+    ParallelBuild; production builds fork above 131 072 primitives): the same tree either way"""
+    pb.set_bvh_parallel_min(request.param)
+    yield request.param
+    pb.set_bvh_parallel_min()
+
+
+def test_host_bvh_build_is_the_references_tree_golden(build_mode):
     keys = sorted(k[:-7] for k in GOLDEN.files if k.startswith("bvh_") and k.endswith("_bounds"))
     assert len(keys) >= 32
     multi = 0
@@ -68,6 +77,25 @@ def test_host_bvh_build_is_the_references_tree_golden():
         assert same_tree(nodes, order, GOLDEN[k + "_nodes"], GOLDEN[k + "_order"]), k
         multi = max(multi, int(nodes["nPrimitives"].max()))
     assert multi > 1   # multi-primitive leaves are among the pinned trees
+
+
+@pytest.mark.parametrize("split", [pb.SPLIT_SAH, 0, 1])
+def test_forked_host_build_is_the_serial_build(split):
+    """every split method ("sah", "middle" = 0, "equal" = 1), random and degenerate inputs, leaf sizes 1 / 4 / 255: node array and
+    primitive order byte for byte"""
+    from test_bvhbuild_on_host import boxes, KINDS
+    rs = np.random.RandomState(11)
+    for kind in KINDS:
+        for n, maxp in [(2, 1), (37, 4), (1000, 1), (5000, 4), (3000, 255)]:
+            b = boxes(kind, n, rs)
+            pb.set_bvh_parallel_min(1 << 30)
+            n0, o0 = pb.host_bvh_build(b, maxp, split)
+            pb.set_bvh_parallel_min(2)
+            try:
+                n1, o1 = pb.host_bvh_build(b, maxp, split)
+            finally:
+                pb.set_bvh_parallel_min()
+            assert np.array_equal(n0.view(np.uint8), n1.view(np.uint8)) and np.array_equal(o0, o1), (kind, n, maxp)
 
 
 def test_host_loopsubdiv_refine_is_the_references_mesh_golden():
@@ -81,7 +109,7 @@ def test_host_loopsubdiv_refine_is_the_references_mesh_golden():
 
 @live
 @pytest.mark.parametrize("base", ["bunny", "killeroo-simple"])
-def test_scene_accelerator_is_the_references_tree_live(staged, base):
+def test_scene_accelerator_is_the_references_tree_live(staged, base, build_mode):
     """the config scenes' own build input (69 k / 66 k refined primitives in the order BVHAccel gets them; the killeroo's are
     the refined loopsubdiv mesh): the reference's BVHAccel over those bounds IS the accelerator the front end built for the
     scene (maxPrimsInNode 4), and with maxPrimsInNode 1 (what nested TransformedPrimitive BVHs use) the builders agree too"""
