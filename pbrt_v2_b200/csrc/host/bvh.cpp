@@ -291,13 +291,22 @@ void FullyRefine(const GeometricPrimitive &gp, std::vector<RefinedPrim> *out,
 }  // namespace
 
 bool g_keepBuildInput = false;
+static double NowSeconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+PrepTimer::PrepTimer(const char *w) : what(w), t0(getenv("PBRTGPU_PREP_TIMING") ? NowSeconds() : -1.) {}
+void PrepTimer::Stop() {
+    if (t0 >= 0.) fprintf(stderr, "scene preparation: %-30s %.3f s\n", what, NowSeconds() - t0);
+    t0 = -1.;
+}
 uint32_t g_bvhParallelMin = 1u << 17;   // builds of at least this many primitives run their subtrees on several threads
 
 GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, const std::string &sm, const std::string &builder) {
     // BVHAccel::BVHAccel, bvh.cpp:153-202
     maxPrimsInNode = std::min(255u, mp);
     std::vector<RefinedPrim> refined;
-    for (const GeometricPrimitive &gp : p) FullyRefine(gp, &refined, &owned, &buildError);
+    {
+        PrepTimer t("FullyRefine");
+        for (const GeometricPrimitive &gp : p) FullyRefine(gp, &refined, &owned, &buildError);
+    }
     if (!buildError.empty()) return;
     if (sm == "sah") splitMethod = 2;
     else if (sm == "middle") splitMethod = 0;
@@ -308,12 +317,15 @@ GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, 
     }
     if (refined.empty()) return;
     std::vector<float> bounds(refined.size() * 6);
+    PrepTimer tb("WorldBound of every primitive");
     for (size_t i = 0; i < refined.size(); ++i) {
         const BBox b = refined[i].WorldBound();
         float *o = &bounds[6 * i];
         o[0] = b.pMin.x; o[1] = b.pMin.y; o[2] = b.pMin.z; o[3] = b.pMax.x; o[4] = b.pMax.y; o[5] = b.pMax.z;
     }
+    tb.Stop();
     std::vector<uint32_t> order;
+    PrepTimer tbuild("BVH build");
     if (builder == "gpu") {   // the same tree, built on the device (include/pbrtgpu.h: pbrtgpu_bvh_build)
         nodes.resize(2 * refined.size());
         order.resize(refined.size());
@@ -329,6 +341,8 @@ GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, 
     } else {
         BuildBVHOnHost(bounds.data(), (uint32_t)refined.size(), maxPrimsInNode, splitMethod, &nodes, &order);
     }
+    tbuild.Stop();
+    PrepTimer tr("reordered primitive list");
     primitives.reserve(refined.size());
     for (uint32_t i : order) primitives.push_back(refined[i]);
     if (g_keepBuildInput) buildInput.swap(bounds);

@@ -957,6 +957,7 @@ bool LoadSyntheticScene(const SyntheticParams &sp, const Options &opt, LoadedSce
         if (!api.DoShape("trianglemesh", ps)) { out->error = api.error; return false; }
     }
     SynthRNG rng(1);
+    PrepTimer tgen("synthetic triangles + meshes");
     for (long long t0 = 0; t0 < sp.nTriangles; t0 += kSynthTrisPerMesh) {
         const int n = (int)std::min<long long>(kSynthTrisPerMesh, sp.nTriangles - t0);
         ParamSet ps;
@@ -972,6 +973,7 @@ bool LoadSyntheticScene(const SyntheticParams &sp, const Options &opt, LoadedSce
         for (int i = 0; i < 3 * n; ++i) idx[i] = i;
         if (!api.DoShape("trianglemesh", ps)) { out->error = api.error; return false; }
     }
+    tgen.Stop();
     api.worldEnded = true;
     if (!api.Finish(out)) { out->error = api.error; return false; }
     return true;

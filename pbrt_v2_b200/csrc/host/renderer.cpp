@@ -127,6 +127,7 @@ PerspectiveCamera::PerspectiveCamera(const Transform &cam2world, const float scr
 
 // ------------------------------------------------------------------ Flatten --
 bool Scene::Flatten(std::string *err) {
+    PrepTimer timer("Flatten");
     const GpuBVHAccel &bvh = *aggregate;
     std::map<const Transform *, uint32_t> xformIndex;
     auto xformOf = [&](const Transform *t) -> uint32_t {
@@ -144,7 +145,6 @@ bool Scene::Flatten(std::string *err) {
                (s->TransformSwapsHandedness ? PBRTGPU_SHAPE_SWAPS_HANDED : 0u);
     };
     std::map<const Shape *, uint32_t> meshIndex, quadricIndex;
-    std::map<std::pair<const Shape *, int>, uint32_t> triIndex;
     hasN = hasUV = false;
     // first pass: which optional vertex streams exist at all
     // the scene BVH first, then the nested BVH (or single primitive) of every TransformedPrimitive
@@ -208,6 +208,25 @@ bool Scene::Flatten(std::string *err) {
         return (uint32_t)fQuadrics.size() - 1;
     };
 
+    {   // the arrays' final sizes are known: no growth by doubling (at 10 M triangles that is gigabytes of copying)
+        size_t nNodes = 0, nPrims = 0, nTris = 0, nVerts = 0;
+        std::map<const Shape *, bool> seenMesh;
+        for (const GpuBVHAccel *u : units) {
+            nNodes += u->nodes.size();
+            nPrims += u->primitives.size();
+            for (const RefinedPrim &rp : u->primitives)
+                if (rp.type == PBRTGPU_PRIM_TRIANGLE) {
+                    ++nTris;
+                    if (!seenMesh.count(rp.shape)) {
+                        seenMesh[rp.shape] = true;
+                        nVerts += (size_t)static_cast<const TriangleMesh *>(rp.shape)->nverts;
+                    }
+                }
+        }
+        fNodes.reserve(nNodes); fPrims.reserve(nPrims); fTris.reserve(nTris); fP.reserve(3 * nVerts);
+        if (hasN) fN.reserve(3 * nVerts);
+        if (hasUV) fUV.reserve(2 * nVerts);
+    }
     fAnimated.resize(units.size() - 1);
     for (size_t ui = 0; ui < units.size(); ++ui) {
     const GpuBVHAccel &unit = *units[ui];

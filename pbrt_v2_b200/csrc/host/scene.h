@@ -188,6 +188,14 @@ struct GpuBVHAccel : Aggregate {
     std::string buildError;                 // set when the device build was asked for and failed (no silent fallback)
 };
 extern bool g_keepBuildInput;
+// PBRTGPU_PREP_TIMING=1 in the environment: wall clock of the scene-preparation phases on stderr
+struct PrepTimer {
+    const char *what;
+    double t0;
+    explicit PrepTimer(const char *w);
+    ~PrepTimer() { Stop(); }
+    void Stop();
+};
 extern uint32_t g_bvhParallelMin;   // bvh.cpp: smallest build that forks its subtrees onto several threads
 // recursiveBuild + flattenBVHTree on primitive bounds (n x 6 floats); order = BVHAccel::primitives as input indices
 void BuildBVHOnHost(const float *bounds, uint32_t n, uint32_t maxPrimsInNode, int splitMethod, std::vector<PbrtGpuBVHNode> *nodes,
