@@ -127,6 +127,23 @@ def test_sharded_oracle_render_sums_to_full(staged):
     np.testing.assert_allclose(acc["Lxyz"], full["Lxyz"], rtol=1e-6)
 
 
+def test_sharded_render_with_a_wide_filter_sums_to_full(staged):
+    """every sample of a wide filter splats into other tasks' -- other shards' -- pixels: the shards' films still add up to the
+    one-process film, to the rounding of the sums (the reduce is a plain sum of films; ncclReduce in the library)"""
+    from helpers import variant_scene
+    from pbrt_v2_b200.multigpu import shard_render_desc
+    hs, _ = variant_scene("filter-mitchell")
+    full, _ = oa.render(hs, threads=1)
+    acc = None
+    for r in range(4):
+        rd = shard_render_desc(hs.render_desc(), r, 4, hs.render_desc().xResolution, rows_per_block=2)
+        part, _ = oa.render(hs, rd, threads=1)
+        acc = part if acc is None else np.rec.fromarrays([acc["Lxyz"] + part["Lxyz"], acc["weightSum"] + part["weightSum"]],
+                                                         dtype=pb.PIXEL_DTYPE)
+    for f in ("weightSum", "Lxyz"):
+        assert np.abs(acc[f].astype(np.float64) - full[f]).max() <= 4e-6 * np.abs(full[f]).max(), f
+
+
 _GLOO_WORKER = r'''
 import os, sys
 import numpy as np, torch, torch.distributed as dist
