@@ -325,6 +325,14 @@ static bool LoadBinaryMesh(const std::string &fn, ParamSet *ps, std::string *err
     bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "PBRTMESH", 8) == 0 && fread(head, 4, 3, f) == 3;
     const uint32_t flags = head[0], ni = head[1], nv = head[2];
     if (ok && (ni > (1u << 31) - 1 || nv > (1u << 30) || (flags & ~3u))) ok = false;
+    if (ok) {   // the arrays must be there before memory is set aside for them
+        const unsigned long long need = 4ull * ni + 12ull * nv + ((flags & 1u) ? 12ull * nv : 0) + ((flags & 2u) ? 8ull * nv : 0);
+        const long at = ftell(f);
+        fseek(f, 0, SEEK_END);
+        const long end = ftell(f);
+        fseek(f, at, SEEK_SET);
+        if (at < 0 || end < at || (unsigned long long)(end - at) < need) ok = false;
+    }
     if (ok) {
         std::vector<int> &idx = ps->ints["indices"];
         idx.resize(ni);
