@@ -16,7 +16,7 @@ def main():
     host = os.path.join(REPO, "pbrt_v2_b200", "csrc", "host")
     subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
                     "-I" + os.path.join(REPO, "include"), os.path.join(REPO, "tests/native/san/main_images.cpp")] +
-                   [os.path.join(host, f) for f in ("envmap.cpp", "tga.cpp", "exr.cpp")] + ["-lz", "-o", exe], check=True)
+                   [os.path.join(host, f) for f in ("envmap.cpp", "tga.cpp", "exr.cpp", "measured.cpp")] + ["-lz", "-o", exe], check=True)
     seeds = []
     for fn, spec in ENV_MAPS.items():
         write_env_pfm(os.path.join(tmp, fn), *spec); seeds.append(os.path.join(tmp, fn))
@@ -29,6 +29,14 @@ def main():
         ch = {"R": (1, img[..., 0]), "G": (1, img[..., 1]), "B": (1, img[..., 2])}
         if c & 1: ch["A"] = (2, np.ones(img.shape[:2], np.float32))
         write_exr(p, ch, c); seeds.append(p)
+    from pbrt_v2_b200 import scenes
+    brdf = os.path.join(scenes.STAGED, "brdfs", "mystique.brdf")
+    if os.path.exists(brdf):   # the measured-BRDF reader (a text file of floats, materials/measured.cpp:85-135): the first 400 records
+        tok = [t for line in open(brdf) for t in line.split("#")[0].split()][:20000]
+        nw = int(float(tok[0]))
+        keep = tok[:1 + nw + 400 * (4 + nw)]
+        open(os.path.join(tmp, "s.brdf"), "w").write("\n".join(keep) + "\n")
+        seeds.append(os.path.join(tmp, "s.brdf"))
     subprocess.run([exe] + seeds, check=True)
     batch, done = [], 0
     for k in range(n):
