@@ -394,6 +394,8 @@ bool Api::DoShape(const std::string &name, const ParamSet &paramsIn) {   // core
         const std::vector<int> *vi = params.FindInt("indices");
         const std::vector<V3> *P = params.FindPoint("P");
         if (vi && P) {
+            for (int idx : *vi)   // (the reference does not check, loopsubdiv.cpp:166-174, and reads out of bounds)
+                if (idx < 0 || idx >= (int)P->size()) return Fail("loopsubdiv has an out-of-bounds vertex index");
             LoopSubdiv *ls = new LoopSubdiv(o2w, w2o, ro, (int)vi->size() / 3, (int)P->size(), vi->data(), P->data(), nlevels);
             // "string refiner" [ "host" | "gpu" ] (also PBRTGPU_SUBDIV in the environment): where Refine() runs
             const char *env = getenv("PBRTGPU_SUBDIV");
@@ -550,6 +552,8 @@ bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
     int yres = FilmParams.FindOneInt("yresolution", 480);
     if (opt.quickRender) xres = std::max(1, xres / 4);   // film/image.cpp:244-245
     if (opt.quickRender) yres = std::max(1, yres / 4);
+    // (the reference takes any integers here and fails later, in int arithmetic or in an allocation)
+    if (xres <= 0 || yres <= 0 || (long long)xres * yres > (1ll << 28)) return Fail("film resolution out of range");
     float crop[4] = {0, 1, 0, 1};
     const std::vector<float> *cr = FilmParams.FindFloat("cropwindow");
     if (cr && cr->size() == 4) {

@@ -36,7 +36,7 @@ TriangleMesh *CreateTriangleMeshShape(const Transform *o2w, const Transform *w2o
     const std::vector<V3> *N = params.FindNormal("N");
     if (N && (int)N->size() != npi) N = nullptr;
     for (int idx : *vi)
-        if (idx >= npi) {
+        if (idx < 0 || idx >= npi) {   // (the reference checks the upper bound only, trianglemesh.cpp:386-391, and reads out of bounds below 0)
             fprintf(stderr, "trianglemesh has out of-bounds vertex index %d (%d \"P\" values were given)\n", idx, npi);
             return nullptr;
         }
