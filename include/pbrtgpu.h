@@ -295,6 +295,10 @@ int  pbrtgpu_device_count(void);
 int  pbrtgpu_set_device(int ordinal);
 const char *pbrtgpu_last_error(void);
 
+/* The checks pbrtgpu_scene_create / pbrtgpu_scene_update run before anything is copied, on their own (no device needed):
+ * PBRTGPU_OK, or the PBRTGPU_EINVAL / PBRTGPU_EUNSUPPORTED the create call would answer.  A descriptor that passes keeps
+ * every index the kernels follow inside its array, every walk finite and inside its stack. */
+int  pbrtgpu_scene_validate(const PbrtGpuSceneDesc *desc);
 /* replaces: Scene / BVHAccel / GeometricPrimitive object graph (core/scene.h) */
 int  pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out);
 void pbrtgpu_scene_destroy(PbrtGpuScene *scene);

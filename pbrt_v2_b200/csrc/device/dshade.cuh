@@ -668,7 +668,9 @@ DEV float SampleContinuous1D(const float *func, const float *cdf, float funcInt,
         if (!(u < __ldg(cdf + lo + half))) { lo += half + 1; len -= half + 1; }
         else len = half;
     }
-    const int offset = maxi(0, lo - 1);
+    // (a cdf whose last entry is not above u -- NaNs, a descriptor that did not come from the constructor -- would put
+    // the segment one past the end: stay inside the arrays; a well-formed cdf ends in 1 > u and never takes the clamp)
+    const int offset = mini(maxi(0, lo - 1), count - 1);
     *off = offset;
     const float c0 = __ldg(cdf + offset);
     const float du = (u - c0) / (__ldg(cdf + offset + 1) - c0);

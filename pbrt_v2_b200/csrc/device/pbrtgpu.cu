@@ -1518,6 +1518,13 @@ static int ValidateSceneDesc(const PbrtGpuSceneDesc *desc) {
         topPrims = std::min(topPrims, a.firstPrimitive);
     }
     for (uint32_t i = 0; i < topNodes; ++i) { nodeEnd[i] = topNodes; primEnd[i] = topPrims; }
+    // depth of every node below its BVH's root (0: not reached yet).  flattenBVHTree numbers the nodes in preorder
+    // (bvh.cpp:383-399): both children come after their parent, which is what makes one forward pass enough here and
+    // what lets the walks terminate; the walks keep one stack entry per level (todo[64], bvh.cpp:410, as in the reference)
+    std::vector<uint8_t> depth(desc->nNodes, 0);
+    depth[0] = 1;
+    for (uint32_t k = 0; k < desc->nAnimated; ++k)
+        if (desc->animated[k].nNodes) depth[desc->animated[k].firstNode] = 1;
     for (uint32_t i = 0; i < desc->nNodes; ++i) {   // child / primitive offsets are relative to the BVH the node belongs to
         const PbrtGpuBVHNode &n = desc->nodes[i];
         if (nodeEnd[i] == 0) continue;   // (a node outside every BVH range is never reached)
@@ -1526,6 +1533,13 @@ static int ValidateSceneDesc(const PbrtGpuSceneDesc *desc) {
         } else {
             if ((uint64_t)nodeBase[i] + n.offset >= nodeEnd[i] || i + 1 >= nodeEnd[i]) return Fail(PBRTGPU_EINVAL, "BVH child offset out of bounds");
             if (n.axis > 2) return Fail(PBRTGPU_EINVAL, "BVH split axis out of range");
+            const uint32_t second = nodeBase[i] + n.offset;
+            if (second <= i + 1) return Fail(PBRTGPU_EINVAL, "BVH second child does not follow the first child's subtree");
+            if (depth[i]) {
+                if (depth[i] >= 64) return Fail(PBRTGPU_EUNSUPPORTED, "BVH deeper than 64 levels (the traversal stack of the reference and of the kernels)");
+                depth[i + 1] = std::max<uint8_t>(depth[i + 1], (uint8_t)(depth[i] + 1));
+                depth[second] = std::max<uint8_t>(depth[second], (uint8_t)(depth[i] + 1));
+            }
         }
     }
     for (uint32_t i = 0; i < desc->nPrimitives; ++i) {
@@ -1671,6 +1685,11 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
     }
     s->valid = true;
     return PBRTGPU_OK;
+}
+
+int pbrtgpu_scene_validate(const PbrtGpuSceneDesc *desc) {
+    if (!desc) return Fail(PBRTGPU_EINVAL, "null argument");
+    return ValidateSceneDesc(desc);
 }
 
 int pbrtgpu_scene_create(const PbrtGpuSceneDesc *desc, PbrtGpuScene **out) {
