@@ -187,6 +187,27 @@ def host_lib():
     return _host
 
 
+class SceneDesc(C.Structure):
+    """include/pbrtgpu.h PbrtGpuSceneDesc, for tools that inspect or rewrite a descriptor (HostScene.desc_ptr points at one)"""
+    _fields_ = [("nNodes", C.c_uint32), ("nodes", C.c_void_p), ("nPrimitives", C.c_uint32), ("primitives", C.c_void_p),
+                ("nTriangles", C.c_uint32), ("triangles", C.c_void_p), ("nMeshes", C.c_uint32), ("meshes", C.c_void_p),
+                ("nVertices", C.c_uint32), ("P", C.c_void_p), ("N", C.c_void_p), ("uv", C.c_void_p),
+                ("nQuadrics", C.c_uint32), ("quadrics", C.c_void_p), ("nXforms", C.c_uint32), ("xforms", C.c_void_p),
+                ("nMaterials", C.c_uint32), ("materials", C.c_void_p), ("nMeasured", C.c_uint32), ("measured", C.c_void_p),
+                ("nKdNodes", C.c_uint32), ("kdNodes", C.c_void_p), ("kdData", C.c_void_p),
+                ("nLights", C.c_uint32), ("lights", C.c_void_p), ("nLightShapes", C.c_uint32), ("lightShapes", C.c_void_p),
+                ("nAnimated", C.c_uint32), ("animated", C.c_void_p), ("nEnvMaps", C.c_uint32), ("envMaps", C.c_void_p),
+                ("nEnvData", C.c_uint32), ("envData", C.c_void_p)]
+
+
+def scene_validate(desc_ptr):
+    """pbrtgpu_scene_validate: (code, message) -- the checks pbrtgpu_scene_create runs first, without a device"""
+    lib = gpu_lib()
+    lib.pbrtgpu_scene_validate.argtypes = [C.c_void_p]
+    rc = lib.pbrtgpu_scene_validate(desc_ptr)
+    return rc, (lib.pbrtgpu_last_error().decode() if rc else "")
+
+
 def _check(rc, what):
     if rc != 0:
         raise PbrtGpuError("%s failed (code %d): %s" % (what, rc, gpu_lib().pbrtgpu_last_error().decode()))

@@ -26,16 +26,7 @@ ELEMS = ["PbrtGpuBVHNode", "PbrtGpuPrimitive", "PbrtGpuTriangle", "PbrtGpuMesh",
          "PbrtGpuMeasured", "PbrtGpuKdNode", "PbrtGpuBrdfSample", "PbrtGpuLight", "PbrtGpuLightShape", "PbrtGpuAnimated", "PbrtGpuEnvMap"]
 
 
-class SceneDesc(C.Structure):   # include/pbrtgpu.h PbrtGpuSceneDesc
-    _fields_ = [("nNodes", C.c_uint32), ("nodes", C.c_void_p), ("nPrimitives", C.c_uint32), ("primitives", C.c_void_p),
-                ("nTriangles", C.c_uint32), ("triangles", C.c_void_p), ("nMeshes", C.c_uint32), ("meshes", C.c_void_p),
-                ("nVertices", C.c_uint32), ("P", C.c_void_p), ("N", C.c_void_p), ("uv", C.c_void_p),
-                ("nQuadrics", C.c_uint32), ("quadrics", C.c_void_p), ("nXforms", C.c_uint32), ("xforms", C.c_void_p),
-                ("nMaterials", C.c_uint32), ("materials", C.c_void_p), ("nMeasured", C.c_uint32), ("measured", C.c_void_p),
-                ("nKdNodes", C.c_uint32), ("kdNodes", C.c_void_p), ("kdData", C.c_void_p),
-                ("nLights", C.c_uint32), ("lights", C.c_void_p), ("nLightShapes", C.c_uint32), ("lightShapes", C.c_void_p),
-                ("nAnimated", C.c_uint32), ("animated", C.c_void_p), ("nEnvMaps", C.c_uint32), ("envMaps", C.c_void_p),
-                ("nEnvData", C.c_uint32), ("envData", C.c_void_p)]
+SceneDesc = pb.SceneDesc
 
 
 def main():

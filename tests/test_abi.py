@@ -124,3 +124,48 @@ def test_render_kernels_are_the_gpu_verified_ones():
     r = subprocess.run(["bash", os.path.join(pb.REPO, "scripts", "sass_fingerprint.sh")], cwd=pb.REPO, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
+
+
+def test_scene_validate_refuses_malformed_descriptors(staged):
+    """pbrtgpu_scene_validate (the checks of pbrtgpu_scene_create, no device needed): a front-end descriptor passes; indices
+    past their arrays, a BVH whose second child does not follow the first child's subtree, a BVH deeper than the 64-entry
+    traversal stack are PBRTGPU_EINVAL / PBRTGPU_EUNSUPPORTED (scripts/fuzz_descriptors.py is the broad version of this)"""
+    import ctypes as C
+    from helpers import host_scene
+    hs = host_scene("bunny", 16, 16, 1, 1)
+    assert pb.scene_validate(hs.desc_ptr)[0] == 0
+    src = pb.SceneDesc.from_address(hs.desc_ptr)
+
+    def mutated(field, count, dtype, edit):
+        d = pb.SceneDesc()
+        C.memmove(C.byref(d), hs.desc_ptr, C.sizeof(pb.SceneDesc))
+        a = np.empty(getattr(src, count), dtype)
+        C.memmove(a.ctypes.data, getattr(src, field), a.nbytes)
+        edit(a)
+        setattr(d, field, a.ctypes.data)
+        rc, msg = pb.scene_validate(C.addressof(d))
+        return rc, msg
+
+    tri = np.dtype([("v", np.uint32, 3), ("mesh", np.uint32)])
+    rc, msg = mutated("triangles", "nTriangles", tri, lambda a: a["v"].__setitem__((5, 1), src.nVertices))
+    assert rc != 0 and "vertex index" in msg
+    rc, msg = mutated("triangles", "nTriangles", tri, lambda a: a["mesh"].__setitem__(7, 99))
+    assert rc != 0 and "mesh index" in msg
+
+    def second_child_first(a):
+        i = int(np.nonzero(a["nPrimitives"] == 0)[0][3])
+        a["offset"][i] = i + 1
+    rc, msg = mutated("nodes", "nNodes", pb.NODE_DTYPE, second_child_first)
+    assert rc != 0 and "second child" in msg
+
+    def chain(a):   # a 70-level comb: every interior node's first child is the next interior node
+        n = len(a)
+        for i in range(70):
+            a["nPrimitives"][i] = 0
+            a["axis"][i] = 0
+            a["offset"][i] = n - 1 - i      # second child: some later node
+        for i in range(n - 71, n):
+            a["nPrimitives"][i] = 1
+            a["offset"][i] = 0
+    rc, msg = mutated("nodes", "nNodes", pb.NODE_DTYPE, chain)
+    assert rc != 0 and ("deeper than 64" in msg or "out of bounds" in msg)
