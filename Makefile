@@ -39,9 +39,10 @@ VARIANT_DEFS_ws6 := -DK_WSHADE_MIN_BLOCKS=6
 VARIANT_DEFS_we10 := -DK_WEVAL_MIN_BLOCKS=10
 # MetalMaterial on the device (host-verified; first GPU run: PBRTGPU_LIB=ab/libpbrtgpu_metal.so pytest tests/test_gpu_specular.py -m gpu)
 VARIANT_DEFS_metal := -DPBRT_METAL=1
-# ... plus InfiniteAreaLight (constant radiance) and pixel filters through the weight table: the whole of SURVEY 8(f) rank 4.
+# ... plus InfiniteAreaLight and pixel filters through the weight table: the whole of SURVEY 8(f) rank 4 -- and the
+# zero-initialised pivot arrays of MatInverse (danim.cuh PBRT_SAFE_INVERSE).
 # PBRTGPU_LIB=ab/libpbrtgpu_f4.so pytest tests/test_gpu_refusals.py tests/test_gpu_specular.py -m gpu
-VARIANT_DEFS_f4 := -DPBRT_METAL=1 -DPBRT_INFINITE=1 -DPBRT_FILTER=1
+VARIANT_DEFS_f4 := -DPBRT_METAL=1 -DPBRT_INFINITE=1 -DPBRT_FILTER=1 -DPBRT_SAFE_INVERSE=1
 # leaf tests in batches of >= n lanes (PBRT_TRACE_LOOP 2), on top of ws6
 VARIANT_DEFS_ws6_lb8 := -DK_WSHADE_MIN_BLOCKS=6 -DPBRT_TRACE_LOOP=2 -DPBRT_LEAF_BATCH=8
 VARIANT_DEFS_ws6_lb12 := -DK_WSHADE_MIN_BLOCKS=6 -DPBRT_TRACE_LOOP=2 -DPBRT_LEAF_BATCH=12

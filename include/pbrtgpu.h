@@ -313,6 +313,14 @@ int  pbrtgpu_scene_update(PbrtGpuScene *scene, const PbrtGpuSceneDesc *desc);
  * timed runs leave it off (0).                                                 */
 int  pbrtgpu_set_stats(PbrtGpuScene *scene, int on);
 
+/* The checks every render call runs on its descriptor first, on their own (no device needed), and the film's pixel
+ * extent -- ImageFilm::xPixelStart, yPixelStart, xPixelCount, yPixelCount (film/image.cpp:40-51) -- that a caller sizes
+ * `pixels` with.                                                                */
+int  pbrtgpu_render_validate(const PbrtGpuRenderDesc *rd);
+/* ... and with the scene it is for: the Sample layout against the scene's lights (DirectLightingIntegrator::RequestSamples,
+ * directlighting.cpp:53-78), recursion depth against specular materials -- everything a render call refuses. */
+int  pbrtgpu_render_validate_scene(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc *rd);
+int  pbrtgpu_film_extent(const PbrtGpuRenderDesc *rd, int32_t extent[4]);
 /* replaces: SamplerRenderer::Render (samplerrenderer.cpp:188-222) minus the
  * final WriteImage().  `pixels` is HOST memory (xPixelCount*yPixelCount);
  * pixels of tasks outside [taskBegin,taskEnd) are left zero.                   */

@@ -27,7 +27,20 @@ DEV void MatMul(const float *m1, const float *m2, float *r) {   // Matrix4x4::Mu
 }
 // Inverse(const Matrix4x4 &), core/transform.cpp:76-136: full-pivot Gauss-Jordan, same visiting order
 __device__ __noinline__ void MatInverse(const float *m, float *out) {
+    // A matrix that turns into NaNs half way -- an interpolated transform that is singular at the ray's time -- leaves the
+    // loop below early, and the un-scrambling loop then indexes with whatever indxr / indxc held (the reference is no better
+    // off: its pivot search ends with icol = -1 and `++ipiv[icol]` writes below the array, transform.cpp:82-104).  Found by
+    // scripts/fuzz_descriptors.py after the round's last GPU visit: the zero-initialisation is behind PBRT_SAFE_INVERSE
+    // (on in the f4 variant and the host harnesses) until the kernels that contain it have run on a GPU -- it re-allocates
+    // registers across every ANIM instantiation.  Non-finite transforms and shutter times are refused at validation.
+#ifndef PBRT_SAFE_INVERSE
+#define PBRT_SAFE_INVERSE 0
+#endif
+#if PBRT_SAFE_INVERSE
+    int indxc[4] = {0, 0, 0, 0}, indxr[4] = {0, 0, 0, 0};
+#else
     int indxc[4], indxr[4];
+#endif
     int ipiv[4] = {0, 0, 0, 0};
     float a[4][4];
     for (int i = 0; i < 16; ++i) a[i >> 2][i & 3] = m[i];

@@ -25,6 +25,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1251,6 +1252,18 @@ void ComputeSubWindow(const FilmExtent &e, int num, int count, int *x0, int *x1,
 
 int ValidateRenderDesc(const PbrtGpuRenderDesc &rd) {
     if (rd.xResolution <= 0 || rd.yResolution <= 0) return Fail(PBRTGPU_EINVAL, "bad film resolution");
+    if (rd.xResolution > 65536 || rd.yResolution > 65536 || (long long)rd.xResolution * rd.yResolution > (1ll << 28))
+        return Fail(PBRTGPU_EUNSUPPORTED, "film resolution beyond 2^28 pixels");
+    // ImageFilm's crop window is four numbers in [0, 1], low <= high (CreateImageFilm clamps and orders what the scene file
+    // says, film/image.cpp:246-257); the film extent is computed from them in int
+    for (int i = 0; i < 4; ++i)
+        if (!(rd.cropWindow[i] >= 0.f && rd.cropWindow[i] <= 1.f)) return Fail(PBRTGPU_EINVAL, "bad crop window");
+    if (rd.cropWindow[0] > rd.cropWindow[1] || rd.cropWindow[2] > rd.cropWindow[3]) return Fail(PBRTGPU_EINVAL, "bad crop window");
+    {   // camera: every ray's origin, direction and time come out of these
+        bool finite = std::isfinite(rd.lensRadius) && std::isfinite(rd.focalDistance) && std::isfinite(rd.shutterOpen) && std::isfinite(rd.shutterClose);
+        for (int i = 0; i < 16; ++i) finite = finite && std::isfinite(rd.rasterToCamera[i]) && std::isfinite(rd.cameraToWorld[i]);
+        if (!finite) return Fail(PBRTGPU_EINVAL, "non-finite camera parameter");
+    }
     const int spp = rd.samplesPerPixel;
     if (spp <= 0 || (spp & (spp - 1))) return Fail(PBRTGPU_EINVAL, "samplesPerPixel must be a power of two (LDSampler)");
     if (spp > 8192) return Fail(PBRTGPU_EUNSUPPORTED, "samplesPerPixel > 8192 does not fit the table kernel's shared memory");
@@ -1506,6 +1519,17 @@ static int ValidateSceneDesc(const PbrtGpuSceneDesc *desc) {
     uint32_t topNodes = desc->nNodes, topPrims = desc->nPrimitives;
     for (uint32_t k = 0; k < desc->nAnimated; ++k) {
         const PbrtGpuAnimated &a = desc->animated[k];
+        {   // every number the interpolation reads must be one (AnimatedTransform::Interpolate, transform.cpp:437-465)
+            bool finite = std::isfinite(a.startTime) && std::isfinite(a.endTime);
+            for (int i = 0; i < 16; ++i)
+                finite = finite && std::isfinite(a.start.m[i]) && std::isfinite(a.start.mInv[i]) && std::isfinite(a.end.m[i]) && std::isfinite(a.end.mInv[i]);
+            for (int e = 0; e < 2; ++e) {
+                for (int i = 0; i < 3; ++i) finite = finite && std::isfinite(a.T[e][i]);
+                for (int i = 0; i < 4; ++i) finite = finite && std::isfinite(a.R[e][i]);
+                for (int i = 0; i < 16; ++i) finite = finite && std::isfinite(a.S[e][i]);
+            }
+            if (!finite) return Fail(PBRTGPU_EINVAL, "TransformedPrimitive with a non-finite transform or time");
+        }
         if ((uint64_t)a.firstPrimitive + a.nPrimitives > desc->nPrimitives || (uint64_t)a.firstNode + a.nNodes > desc->nNodes ||
             a.nPrimitives == 0 || (a.nNodes == 0 && a.nPrimitives != 1))
             return Fail(PBRTGPU_EINVAL, "TransformedPrimitive range out of bounds");
@@ -1684,6 +1708,58 @@ static int UploadScene(PbrtGpuScene *s, const PbrtGpuSceneDesc *desc) {
         if (desc->lights[i].type == PBRTGPU_LIGHT_INFINITE) s->nInfiniteLights++;
     }
     s->valid = true;
+    return PBRTGPU_OK;
+}
+
+// what a render call checks once it knows the scene: the Sample layout against the scene's lights, recursion depth
+// against the frames a path slot carries
+static int ValidateRenderForScene(const PbrtGpuRenderDesc &rdr, uint32_t nLights, uint32_t nSpecularMaterials) {
+    const PbrtGpuRenderDesc *rd = &rdr;
+    const bool directInteg = rd->integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
+#if PBRT_SPECULAR
+    if (directInteg && nSpecularMaterials && rd->maxDepth > DL_MAX_DEPTH)
+        return Fail(PBRTGPU_EUNSUPPORTED, "DirectLightingIntegrator over specular materials: maxdepth beyond the 8 recursion frames a path slot carries");
+    if (nSpecularMaterials && nLights > 32767) return Fail(PBRTGPU_EUNSUPPORTED, "too many lights");
+#else
+    (void)nSpecularMaterials;
+#endif
+    if (directInteg) {   // the layout must be what DirectLightingIntegrator::RequestSamples builds for this scene's lights
+        const int nl = (int)nLights;
+        const bool all = rd->lightStrategy == PBRTGPU_STRATEGY_ALL;
+        if (rd->lightStrategy != PBRTGPU_STRATEGY_ALL && rd->lightStrategy != PBRTGPU_STRATEGY_ONE)
+            return Fail(PBRTGPU_EINVAL, "bad lightStrategy");
+        if (all ? (rd->n1D != 2 * nl + 2 || rd->n2D != 2 * nl) : (rd->n1D != 5 || rd->n2D != 2))
+            return Fail(PBRTGPU_EINVAL, "Sample layout does not match DirectLightingIntegrator::RequestSamples for this scene (directlighting.cpp:53-78)");
+        for (int i = 0; i < (all ? nl : 0); ++i)
+            if (rd->size1D[2 * i] != rd->size1D[2 * i + 1] || rd->size1D[2 * i] != rd->size2D[2 * i] || rd->size1D[2 * i] != rd->size2D[2 * i + 1])
+                return Fail(PBRTGPU_EINVAL, "a light's four sample arrays must have the same size (light.cpp:64-68, reflection.cpp:502-506)");
+    }
+    return PBRTGPU_OK;
+}
+
+int pbrtgpu_render_validate_scene(const PbrtGpuSceneDesc *desc, const PbrtGpuRenderDesc *rd) {
+    if (!desc || !rd) return Fail(PBRTGPU_EINVAL, "null argument");
+    int rc = ValidateSceneDesc(desc);
+    if (rc != PBRTGPU_OK) return rc;
+    rc = ValidateRenderDesc(*rd);
+    if (rc != PBRTGPU_OK) return rc;
+    uint32_t nSpecular = 0;
+    for (uint32_t i = 0; i < desc->nMaterials; ++i)
+        if (desc->materials[i].type == PBRTGPU_MAT_MIRROR || desc->materials[i].type == PBRTGPU_MAT_GLASS) ++nSpecular;
+    return ValidateRenderForScene(*rd, desc->nLights, nSpecular);
+}
+
+int pbrtgpu_render_validate(const PbrtGpuRenderDesc *rd) {
+    if (!rd) return Fail(PBRTGPU_EINVAL, "null argument");
+    return ValidateRenderDesc(*rd);
+}
+
+int pbrtgpu_film_extent(const PbrtGpuRenderDesc *rd, int32_t extent[4]) {
+    if (!rd || !extent) return Fail(PBRTGPU_EINVAL, "null argument");
+    const int rc = ValidateRenderDesc(*rd);
+    if (rc != PBRTGPU_OK) return rc;
+    const FilmExtent e = ComputeExtent(*rd);
+    extent[0] = e.xPixelStart; extent[1] = e.yPixelStart; extent[2] = e.xPixelCount; extent[3] = e.yPixelCount;
     return PBRTGPU_OK;
 }
 
@@ -2245,21 +2321,9 @@ int pbrtgpu_render_device(PbrtGpuScene *scene, const PbrtGpuRenderDesc *rd, void
     BuildLayout(*rd, &rp.lay, &tables);
     const bool pathLayout = IsPathLayout(*rd);
     const bool directInteg = rd->integrator == PBRTGPU_INTEGRATOR_DIRECTLIGHTING;
-#if PBRT_SPECULAR
-    if (directInteg && scene->nSpecularMaterials && rd->maxDepth > DL_MAX_DEPTH)
-        return Fail(PBRTGPU_EUNSUPPORTED, "DirectLightingIntegrator over specular materials: maxdepth beyond the 8 recursion frames a path slot carries");
-    if (scene->nSpecularMaterials && scene->d.nLights > 32767) return Fail(PBRTGPU_EUNSUPPORTED, "too many lights");
-#endif
-    if (directInteg) {   // the layout must be what DirectLightingIntegrator::RequestSamples builds for this scene's lights
-        const int nl = (int)scene->d.nLights;
-        const bool all = rd->lightStrategy == PBRTGPU_STRATEGY_ALL;
-        if (rd->lightStrategy != PBRTGPU_STRATEGY_ALL && rd->lightStrategy != PBRTGPU_STRATEGY_ONE)
-            return Fail(PBRTGPU_EINVAL, "bad lightStrategy");
-        if (all ? (rd->n1D != 2 * nl + 2 || rd->n2D != 2 * nl) : (rd->n1D != 5 || rd->n2D != 2))
-            return Fail(PBRTGPU_EINVAL, "Sample layout does not match DirectLightingIntegrator::RequestSamples for this scene (directlighting.cpp:53-78)");
-        for (int i = 0; i < (all ? nl : 0); ++i)
-            if (rd->size1D[2 * i] != rd->size1D[2 * i + 1] || rd->size1D[2 * i] != rd->size2D[2 * i] || rd->size1D[2 * i] != rd->size2D[2 * i + 1])
-                return Fail(PBRTGPU_EINVAL, "a light's four sample arrays must have the same size (light.cpp:64-68, reflection.cpp:502-506)");
+    {
+        const int rcs = ValidateRenderForScene(*rd, scene->d.nLights, scene->nSpecularMaterials);
+        if (rcs != PBRTGPU_OK) return rcs;
     }
     const size_t perTask = (size_t)spp * ((size_t)rp.lay.rowStride * 2 + 16 + (directInteg ? 0 : 64) + (pathLayout ? 0 : tables.tgtPerSample)) +
                            SCR_STRIDE * 4 + 2 * MT_N * 4 + 4 + sizeof(TaskRec) + (size_t)std::max(1, spp / 32) * 4;

@@ -164,7 +164,7 @@ def main():
     filt = len(sys.argv) > 3 and "filter" in sys.argv[3]
     so = "/tmp/libdoh_fuzz%s%s%s%s%s.so" % ("_spec" if spec else "", "_pairs" if pairs else "", "_metal" if metal else "", "_inf" if infinite else "", "_filt" if filt else "")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic",
-                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) + (["-DPBRT_PAIR_NODES=1"] if pairs else []) + (["-DPBRT_METAL=1"] if metal else []) + (["-DPBRT_INFINITE=1"] if infinite else []) + (["-DPBRT_FILTER=1"] if filt else []) +
+                    "-I/usr/local/cuda/include"] + (["-DPBRT_SPECULAR=1"] if spec else []) + (["-DPBRT_PAIR_NODES=1"] if pairs else []) + (["-DPBRT_METAL=1"] if metal else []) + (["-DPBRT_INFINITE=1"] if infinite else []) + (["-DPBRT_FILTER=1"] if filt else []) + (["-DPBRT_SAFE_INVERSE=1"] if filt else []) +
                    [os.path.join(REPO, "tests/native/device_on_host.cpp"), "-o", so], check=True)
     doh = C.CDLL(so)
     doh.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]

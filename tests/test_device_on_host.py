@@ -172,7 +172,7 @@ def test_device_state_machine_on_host_variants(staged, doh):
 @pytest.fixture(scope="module")
 def doh_f4(tmp_path_factory):
     """the harness with every gated SURVEY 8(f) rank 4 feature on, as `make variants VARIANT_NAMES=f4` builds the library"""
-    lib = _build(tmp_path_factory, "device_on_host_f4", ["-DPBRT_METAL=1", "-DPBRT_INFINITE=1", "-DPBRT_FILTER=1"])
+    lib = _build(tmp_path_factory, "device_on_host_f4", ["-DPBRT_METAL=1", "-DPBRT_INFINITE=1", "-DPBRT_FILTER=1", "-DPBRT_SAFE_INVERSE=1"])
     lib.doh_render.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc), C.c_void_p]
     return lib
 
