@@ -50,10 +50,17 @@ def gen(rng, path, animated=None):
         L.append("Rotate %g %s" % (rng.uniform(-180, 180), fl(rng.uniform(-1, 1, 3) + 1e-3)))
         light = 'LightSource "infinite" "color L" [%s] "integer nsamples" [%d]' % (fl(rng.uniform(0, .8, 3)), rng.choice([1, 2, 4]))
         if rng.rand() < .6:   # a radiance map: random resolution (mostly not a power of two), RGB or grey, either byte order
-            from helpers import write_env_pfm
-            mapname = os.path.splitext(os.path.basename(path))[0] + "-env.pfm"
-            write_env_pfm(os.path.join(os.path.dirname(path), mapname), int(rng.randint(1, 24)), int(rng.randint(1, 14)),
-                          int(rng.randint(1 << 30)), int(rng.choice([1, 3])), float(rng.choice([-1.0, 1.0, -0.5, 3.0])))
+            from helpers import write_env_pfm, write_tga
+            if rng.rand() < .7:
+                mapname = os.path.splitext(os.path.basename(path))[0] + "-env.pfm"
+                write_env_pfm(os.path.join(os.path.dirname(path), mapname), int(rng.randint(1, 24)), int(rng.randint(1, 14)),
+                              int(rng.randint(1 << 30)), int(rng.choice([1, 3])), float(rng.choice([-1.0, 1.0, -0.5, 3.0])))
+            else:   # a Targa file: grey / BGR(A) / colour-mapped, raw or RLE, any scan direction
+                mapname = os.path.splitext(os.path.basename(path))[0] + "-env.tga"
+                kind = str(rng.choice(["bgr", "mono", "mapped"]))
+                write_tga(os.path.join(os.path.dirname(path), mapname), int(rng.randint(1, 24)), int(rng.randint(1, 14)),
+                          int(rng.randint(1 << 30)), kind, bool(rng.rand() < .5), bool(rng.rand() < .5), bool(rng.rand() < .5),
+                          bool(rng.rand() < .5) and kind != "mono", int(rng.randint(0, 4)))
             light += ' "string mapname" "%s"' % mapname
         L.append(light)
         L.append("AttributeEnd")
@@ -177,12 +184,13 @@ def main():
         ncores = int(rng.choice([1, 2, 64]))
         filtered = "PixelFilter" in open(path).read()
         if filtered: ncores = 1
+        quick = bool(rng.rand() < .2)   # --quick: film / 4, one pixel sample, light samples / 4
         try:
-            hs = pb.HostScene(path, ncores=ncores)
+            hs = pb.HostScene(path, ncores=ncores, quick=quick)
         except pb.PbrtGpuError as e:
             print("seed %d: host front end: %s" % (seed, str(e)[:120])); continue
         try:
-            ref, _ = oa.run_reference(path, ncores, timeout=120)
+            ref, _ = oa.run_reference(path, ncores, timeout=120, extra_args=["--quick"] if quick else [])
         except Exception as e:
             print("seed %d: reference failed: %r" % (seed, e)); continue
         px, _ = oa.render(hs, threads=1)
@@ -191,7 +199,7 @@ def main():
         px2 = hs.new_pixels()
         doh.doh_set_vertex_form(int(rng.choice([3, 17, 4096])) if wave and not filtered else 0)
         doh.doh_render(hs.desc_ptr, C.byref(rd), px2.ctypes.data)
-        own = px["weightSum"] == spp
+        own = px["weightSum"] == rd.samplesPerPixel
         if filtered: own = np.ones_like(own)
         d_ref = int((o.view(np.uint32) != ref.view(np.uint32)).any(axis=2)[own].sum()) if o.shape == ref.shape else -1
         d_dev = int((px2["Lxyz"].view(np.uint32) != px["Lxyz"].view(np.uint32)).any(axis=2)[own].sum())
@@ -199,10 +207,10 @@ def main():
         flag = "" if (d_ref == 0 and d_dev == 0 and w_dev) else "   <<<<<<"
         bad += bool(flag)
         if not flag:   # keep only the scenes worth looking at
-            for f in (path, os.path.splitext(path)[0] + ".pfm", os.path.splitext(path)[0] + "-env.pfm"):
+            for f in (path, os.path.splitext(path)[0] + ".pfm", os.path.splitext(path)[0] + "-env.pfm", os.path.splitext(path)[0] + "-env.tga"):
                 if os.path.exists(f): os.remove(f)
-        print("seed %d: %dx%d spp %d ncores %d integ %d  oracle-vs-reference %d  device-on-host-vs-oracle %d (weights %s)  mean %.4g%s" % (
-            seed, rd.xResolution, rd.yResolution, spp, ncores, rd.integrator, d_ref, d_dev, w_dev, float(ref.mean()), flag), flush=True)
+        print("seed %d: %dx%d spp %d%s ncores %d integ %d  oracle-vs-reference %d  device-on-host-vs-oracle %d (weights %s)  mean %.4g%s" % (
+            seed, rd.xResolution, rd.yResolution, rd.samplesPerPixel, " quick" if quick else "", ncores, rd.integrator, d_ref, d_dev, w_dev, float(ref.mean()), flag), flush=True)
     print("mismatching scenes:", bad)
 
 if __name__ == "__main__":
