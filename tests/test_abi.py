@@ -106,6 +106,14 @@ def test_render_desc_validation_precedes_the_device():
     cases.append((rd, "integrator"))
     rd = _rd(); rd.filterXWidth = 2.0             # wide filters need cross-task splats
     cases.append((rd, "filters wider"))
+    rd = _rd(); rd.cropWindow[:] = [0.5, 0.25, 0, 1]   # low > high
+    cases.append((rd, "crop window"))
+    rd = _rd(); rd.cropWindow[3] = float("nan")
+    cases.append((rd, "crop window"))
+    rd = _rd(); rd.shutterClose = float("inf")   # every ray's time comes from the shutter interval
+    cases.append((rd, "non-finite camera"))
+    rd = _rd(res=65536)
+    cases.append((rd, "2^28 pixels"))
     for rd, needle in cases:
         with pytest.raises(pb.PbrtGpuError) as e:
             pb.ld_samples(rd, 0)
