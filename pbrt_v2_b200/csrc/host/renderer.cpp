@@ -3,6 +3,7 @@
 // pbrtgpu_render() call, and ImageFilm::WriteImage (PFM).
 #include "scene.h"
 #include <unistd.h>
+#include <zlib.h>
 #include <cctype>
 #include <cmath>
 
@@ -93,19 +94,69 @@ static bool WriteTGA(const std::string &name, const std::vector<float> &rgb, int
     return true;
 }
 
+// WriteImage's .png branch (core/imageio.cpp:107-126): 8-bit, gamma 2.2, and -- as the reference stores them -- the blue
+// value in the file's first channel and the red one in its third (stbi_write_png is handed B, G, R bytes as "RGB").  The
+// file itself: signature, IHDR, one IDAT holding the zlib stream of the filter-0 scan lines, IEND; CRCs by zlib.
+static bool WritePNG(const std::string &name, const std::vector<float> &rgb, int w, int h) {
+    auto toByte = [](float v) -> unsigned char {
+        float b = 255.f * powf(v, 1.f / 2.2f);
+        b = b < 0.f ? 0.f : (b > 255.f ? 255.f : b);
+        return (unsigned char)(b == b ? b : 0.f);
+    };
+    std::vector<unsigned char> raw((size_t)h * (1 + 3 * (size_t)w));
+    for (int y = 0; y < h; ++y) {
+        unsigned char *row = &raw[(size_t)y * (1 + 3 * (size_t)w)];
+        row[0] = 0;   // filter type: none
+        for (int x = 0; x < w; ++x) {
+            const float *p = &rgb[3 * ((size_t)y * w + x)];
+            row[1 + 3 * x] = toByte(p[2]); row[2 + 3 * x] = toByte(p[1]); row[3 + 3 * x] = toByte(p[0]);
+        }
+    }
+    uLongf n = compressBound((uLong)raw.size());
+    std::vector<unsigned char> z(n);
+    if (compress(z.data(), &n, raw.data(), (uLong)raw.size()) != Z_OK) return false;
+    FILE *fp = fopen(name.c_str(), "wb");
+    if (!fp) { fprintf(stderr, "Error: Error writing PNG \"%s\"\n", name.c_str()); return false; }
+    auto be32 = [](unsigned char *o, uint32_t v) { o[0] = (unsigned char)(v >> 24); o[1] = (unsigned char)(v >> 16); o[2] = (unsigned char)(v >> 8); o[3] = (unsigned char)v; };
+    auto chunk = [&](const char *type, const unsigned char *data, uint32_t len) {
+        unsigned char head[8];
+        be32(head, len);
+        memcpy(head + 4, type, 4);
+        fwrite(head, 1, 8, fp);
+        if (len) fwrite(data, 1, len, fp);
+        uLong crc = crc32(0L, Z_NULL, 0);
+        crc = crc32(crc, head + 4, 4);
+        if (len) crc = crc32(crc, data, len);
+        unsigned char c[4];
+        be32(c, (uint32_t)crc);
+        fwrite(c, 1, 4, fp);
+    };
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    fwrite(sig, 1, 8, fp);
+    unsigned char ihdr[13];
+    be32(ihdr, (uint32_t)w); be32(ihdr + 4, (uint32_t)h);
+    ihdr[8] = 8; ihdr[9] = 2; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0;   // 8 bits, colour type 2 (RGB), deflate, filter 0, no interlace
+    chunk("IHDR", ihdr, 13);
+    chunk("IDAT", z.data(), (uint32_t)n);
+    chunk("IEND", nullptr, 0);
+    fclose(fp);
+    return true;
+}
+
 bool ImageFilm::WriteImage() const {
-    // ::WriteImage picks the format by the suffix (core/imageio.cpp:85-140); this build has PFM, TGA and EXR (exr.cpp).  A
-    // name this front end cannot honour (.png) is NOT written under that name with other contents: the float image goes to
-    // "<name>.pfm" and a warning says so.
+    // ::WriteImage picks the format by the suffix (core/imageio.cpp:85-140): .exr (exr.cpp), .tga, .pfm, .png.  Any other
+    // name is an error in the reference ("Can't determine image file type"); here the float image still goes to
+    // "<name>.pfm", with a warning.
     std::vector<float> rgb;
     ToRGB(&rgb);
     std::string suffix = filename.size() >= 5 ? filename.substr(filename.size() - 4) : std::string();
     for (char &c : suffix) c = (char)tolower((unsigned char)c);
     if (suffix == ".pfm") return WritePFM(filename, rgb, xPixelCount, yPixelCount);
     if (suffix == ".tga") return WriteTGA(filename, rgb, xPixelCount, yPixelCount);
+    if (suffix == ".png") return WritePNG(filename, rgb, xPixelCount, yPixelCount);
     if (suffix == ".exr") return WriteImageEXR(filename, rgb, xPixelCount, yPixelCount, xResolution, yResolution, xPixelStart, yPixelStart);
     const std::string alt = filename + ".pfm";
-    fprintf(stderr, "Warning: this build writes .pfm, .tga and .exr images; \"%s\" is written as \"%s\" (float RGB, lossless)\n",
+    fprintf(stderr, "Warning: image files are written as .exr, .tga, .pfm or .png; \"%s\" is written as \"%s\" (float RGB, lossless)\n",
             filename.c_str(), alt.c_str());
     return WritePFM(alt, rgb, xPixelCount, yPixelCount);
 }

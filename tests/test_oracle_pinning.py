@@ -271,3 +271,62 @@ def test_synthetic_scene_text_and_direct_routes_match_reference(staged):
     assert np.array_equal(a["Lxyz"].view(np.uint32), b["Lxyz"].view(np.uint32))
     ref, _ = oa.run_reference(path, 1)
     assert np.array_equal(direct.pixels_to_rgb(a).view(np.uint32), ref.view(np.uint32))
+
+
+def _read_png(path):
+    """8-bit RGB PNG -> uint8 [h, w, 3] (all five scan-line filters; what stb_image_write and zlib-based writers produce)"""
+    import struct, zlib
+    d = open(path, "rb").read()
+    assert d[:8] == b"\x89PNG\r\n\x1a\n"
+    p, idat, w, h = 8, b"", 0, 0
+    while p < len(d):
+        n, typ = struct.unpack(">I4s", d[p:p + 8])
+        body = d[p + 8:p + 8 + n]
+        assert zlib.crc32(typ + body) == struct.unpack(">I", d[p + 8 + n:p + 12 + n])[0]
+        if typ == b"IHDR":
+            w, h, depth, ctype = struct.unpack(">IIBB", body[:10])
+            assert (depth, ctype) == (8, 2)
+        elif typ == b"IDAT":
+            idat += body
+        p += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w)
+    out = np.zeros((h, 3 * w), np.int32)
+    for y in range(h):
+        f, line = int(raw[y, 0]), raw[y, 1:].astype(np.int32)
+        up = out[y - 1] if y else np.zeros(3 * w, np.int32)
+        cur = out[y]
+        for i in range(3 * w):
+            a = cur[i - 3] if i >= 3 else 0
+            b, c = up[i], (up[i - 3] if i >= 3 else 0)
+            if f == 0: pred = 0
+            elif f == 1: pred = a
+            elif f == 2: pred = b
+            elif f == 3: pred = (a + b) // 2
+            else:
+                pa, pb_, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                pred = a if pa <= pb_ and pa <= pc else (b if pb_ <= pc else c)
+            cur[i] = (line[i] + pred) & 255
+    return out.reshape(h, w, 3).astype(np.uint8)
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+def test_png_film_output_matches_reference_binary(staged, tmp_path):
+    """ImageFilm::WriteImage to a .png name (core/imageio.cpp:107-126: 8 bits, gamma 2.2, blue in the first channel as the
+    reference stores it): the decoded image of the front end's file = the decoded image of the reference's own"""
+    from pbrt_v2_b200 import scenes
+    path = scenes.variant("bunny", os.path.join(scenes.STAGED, "t-png.pbrt"), 24, 20, 4, filename="t-png.png")
+    ref_png = os.path.join(scenes.STAGED, "t-png.png")
+    if os.path.exists(ref_png):
+        os.remove(ref_png)
+    import subprocess
+    subprocess.run([oa.REF_BIN, "--ncores", "2", "--quiet", os.path.basename(path)], cwd=scenes.STAGED, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    want = _read_png(ref_png)
+    hs = pb.HostScene(path, ncores=2)
+    px, _ = oa.render(hs, threads=2)
+    mine = str(tmp_path / "mine.png")
+    hs.write_image(px, mine)
+    got = _read_png(mine)
+    assert got.shape == want.shape == (20, 24, 3)
+    assert np.array_equal(got, want)
+    assert int(got.max()) > 100 and not np.array_equal(got[..., 0], got[..., 2])
