@@ -90,6 +90,9 @@ static bool WriteTGA(const std::string &name, const std::vector<float> &rgb, int
         }
         fwrite(row.data(), 1, row.size(), fp);
     }
+    // the TGA 2.0 footer tga_write_to_FILE appends (targa.c:25-30, 556-558): no extension area, no developer directory
+    static const char footer[26] = "\0\0\0\0\0\0\0\0TRUEVISION-XFILE.";
+    fwrite(footer, 1, sizeof(footer), fp);
     fclose(fp);
     return true;
 }

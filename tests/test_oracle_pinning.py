@@ -330,3 +330,24 @@ def test_png_film_output_matches_reference_binary(staged, tmp_path):
     assert got.shape == want.shape == (20, 24, 3)
     assert np.array_equal(got, want)
     assert int(got.max()) > 100 and not np.array_equal(got[..., 0], got[..., 2])
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+def test_tga_and_pfm_film_output_are_the_reference_binarys_files(staged, tmp_path):
+    """ImageFilm::WriteImage to a .tga name (WriteImageTGA, core/imageio.cpp:200-225, over targa.c's tga_write_bgr: uncompressed
+    24-bit BGR, gamma 2.2, top-to-bottom rows, the TGA 2.0 footer) and to a .pfm name (WriteImagePFM, :410-455): the files, byte
+    for byte; a crop window gives the cropped image"""
+    import subprocess
+    from pbrt_v2_b200 import scenes
+    for tag, crop, ext in (("full", None, "tga"), ("crop", (0.25, 0.75, 0.1, 0.6), "tga"), ("pfm", (0.25, 0.75, 0.1, 0.6), "pfm")):
+        path = scenes.variant("bunny", os.path.join(scenes.STAGED, "t-tga-%s.pbrt" % tag), 24, 20, 4, filename="t-tga-%s.%s" % (tag, ext), crop=crop)
+        ref_tga = os.path.join(scenes.STAGED, "t-tga-%s.%s" % (tag, ext))
+        if os.path.exists(ref_tga):
+            os.remove(ref_tga)
+        subprocess.run([oa.REF_BIN, "--ncores", "1", "--quiet", os.path.basename(path)], cwd=scenes.STAGED, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        hs = pb.HostScene(path, ncores=1)
+        px, _ = oa.render(hs, threads=1)
+        mine = str(tmp_path / ("mine-%s.%s" % (tag, ext)))
+        hs.write_image(px, mine)
+        assert open(mine, "rb").read() == open(ref_tga, "rb").read(), tag
