@@ -182,6 +182,8 @@ struct GraphicsState {   // core/api.cpp:213-232
     std::string areaLight;
     ParamSet areaLightParams;
     bool reverseOrientation = false;
+    std::map<std::string, int> namedMaterials;   // MakeNamedMaterial (api.cpp:947-961): name -> index into scene->materials
+    std::string currentNamedMaterial;            // NamedMaterial (api.cpp:965-968); Material resets it (:939-944)
 };
 
 struct Api {
@@ -220,6 +222,7 @@ struct Api {
             if (activeBits & (1 << i)) f(curTransform.t[i]);
     }
     int MakeMaterial(const ParamSet &geomParams);
+    int MakeMaterialOfType(const std::string &name, const ParamSet &geomParams, const ParamSet &mp);
     bool DoShape(const std::string &name, const ParamSet &params);
     bool DoLight(const std::string &name, const ParamSet &params);
     bool Finish(LoadedScene *out);
@@ -239,12 +242,18 @@ float TexFloat(const ParamSet &geom, const ParamSet &mat, const std::string &n, 
     return geom.FindOneFloat(n, mat.FindOneFloat(n, def));
 }
 
-int Api::MakeMaterial(const ParamSet &geomParams) {   // core/api.cpp:1062-1077, 317-372
-    const ParamSet &mp = graphicsState.materialParams;
+int Api::MakeMaterial(const ParamSet &geomParams) {   // GraphicsState::CreateMaterial, core/api.cpp:1062-1077
+    if (!graphicsState.currentNamedMaterial.empty()) {
+        auto it = graphicsState.namedMaterials.find(graphicsState.currentNamedMaterial);
+        if (it != graphicsState.namedMaterials.end()) return it->second;
+    }
+    return MakeMaterialOfType(graphicsState.material, geomParams, graphicsState.materialParams);
+}
+
+int Api::MakeMaterialOfType(const std::string &name, const ParamSet &geomParams, const ParamSet &mp) {   // MakeMaterial, api.cpp:317-372
     Material m;
     memset(&m.desc, 0, sizeof(m.desc));
     m.desc.measured = -1;
-    std::string name = graphicsState.material;
     for (const auto &kv : mp.textures) { (void)kv; Fail("texture-valued material parameters are outside the hot-path scope"); return -1; }
     for (const auto &kv : geomParams.textures) { (void)kv; Fail("texture-valued shape parameters are outside the hot-path scope"); return -1; }
     if (geomParams.floats.count("bumpmap") || mp.floats.count("bumpmap")) { Fail("bump maps are out of scope"); return -1; }
@@ -794,6 +803,21 @@ bool ParseStream(Api &api, const std::string &filename, int depth) {
             if (!named(&n, &ps)) return false;
             api.graphicsState.material = n;
             api.graphicsState.materialParams = ps;
+            api.graphicsState.currentNamedMaterial.clear();
+        } else if (d == "MakeNamedMaterial") {   // api.cpp:947-961: the new material's own parameters first, then the current Material's
+            std::string n; ParamSet ps;
+            if (!named(&n, &ps)) return false;
+            const std::string type = ps.FindOneString("type", api.graphicsState.materialParams.FindOneString("type", ""));
+            if (type.empty()) fprintf(stderr, "Error: No parameter string \"type\" found in MakeNamedMaterial\n");
+            else {
+                const int idx = api.MakeMaterialOfType(type, ps, api.graphicsState.materialParams);
+                if (idx < 0) return false;
+                api.graphicsState.namedMaterials[n] = idx;
+            }
+        } else if (d == "NamedMaterial") {   // api.cpp:965-968
+            if (tok.type != Token::STRING) return api.Fail("NamedMaterial: expected a quoted name");
+            api.graphicsState.currentNamedMaterial = tok.text;
+            tok = lx.Next();
         } else if (d == "AreaLightSource") {
             std::string n; ParamSet ps;
             if (!named(&n, &ps)) return false;

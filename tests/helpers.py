@@ -255,6 +255,18 @@ TGA_MAPS = {   # file name -> write_tga arguments after the path
 }
 
 
+# MakeNamedMaterial / NamedMaterial (core/api.cpp:939-968, 1062-1077): a named material made from its own parameters on top of
+# the current Material's; selecting it; Material switching back; the attribute stack restoring the selection
+_NM_DEF = _WB + ('\nMaterial "plastic" "color Ks" [.6 .1 .1]\nMakeNamedMaterial "shiny" "string type" "plastic" "color Kd" [.1 .4 .1] "float roughness" [.05]'
+                 '\nMakeNamedMaterial "chalk" "string type" "matte" "color Kd" [.7 .7 .2]\nMaterial "matte" "color Kd" [.3 .3 .8]\n')
+NAMED_MATERIAL_VARIANTS = [
+    ("path-named-materials", "killeroo-simple", 40, 40, 4, 2, {},
+     [(_WB, _NM_DEF), (_M1, 'NamedMaterial "shiny"'), (_M2, 'AttributeBegin\nNamedMaterial "chalk"\nAttributeEnd\nNamedMaterial "nosuchname"')]),
+    ("direct-named-materials", "killeroo-simple", 40, 40, 4, 2, {"integrator": "directlighting"},
+     [(_WB, _NM_DEF), (_M1, 'NamedMaterial "chalk"'), (_M2, 'NamedMaterial "shiny"\nMaterial "matte"')]),
+]
+
+
 # SURVEY 8(f) rank 4, pixel filters wider than half a pixel (every sample splats into neighbouring tasks' pixels): host front
 # end + oracle, pinned on the reference binary at --ncores 1 (one worker thread runs the tasks in ascending order: the
 # reference's own sums are ordered only there); the device entry points answer PBRTGPU_EUNSUPPORTED
@@ -274,7 +286,7 @@ def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

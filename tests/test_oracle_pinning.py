@@ -170,6 +170,18 @@ def test_oracle_bit_exact_vs_reference_binary_on_variants(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["path-named-materials", "direct-named-materials"])
+def test_named_materials_match_reference_binary(staged, name):
+    """MakeNamedMaterial / NamedMaterial (core/api.cpp:939-968, 1062-1077): own parameters over the current Material's, an
+    unknown name falling back to the current Material, Material resetting the selection, AttributeEnd restoring it"""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 @pytest.mark.parametrize("name", ["direct-infinite", "path-infinite-bunny", "direct-envmap-npot"])
 def test_quick_render_option_matches_reference_binary(staged, name):
     """--quick (PbrtOptions.quickRender): film resolution / 4 (film/image.cpp:244-245), one pixel sample
