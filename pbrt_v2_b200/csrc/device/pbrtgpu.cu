@@ -1533,7 +1533,12 @@ static int ValidateSceneDesc(const PbrtGpuSceneDesc *desc) {
         if ((uint64_t)a.firstPrimitive + a.nPrimitives > desc->nPrimitives || (uint64_t)a.firstNode + a.nNodes > desc->nNodes ||
             a.nPrimitives == 0 || (a.nNodes == 0 && a.nPrimitives != 1))
             return Fail(PBRTGPU_EINVAL, "TransformedPrimitive range out of bounds");
-        for (uint32_t i = 0; i < a.nPrimitives; ++i) nested[a.firstPrimitive + i] = 1;
+        for (uint32_t i = 0; i < a.nPrimitives; ++i) {
+            // a primitive record names the one TransformedPrimitive it lies under (dscene.cuh HitGeometry): instances
+            // that share an aggregate must come with a copy each
+            if (nested[a.firstPrimitive + i]) return Fail(PBRTGPU_EUNSUPPORTED, "TransformedPrimitives with overlapping primitive ranges (a shared instance aggregate)");
+            nested[a.firstPrimitive + i] = 1;
+        }
         for (uint32_t i = 0; i < a.nNodes; ++i) {
             nodeBase[a.firstNode + i] = a.firstNode; nodeEnd[a.firstNode + i] = a.firstNode + a.nNodes;
             primBase[a.firstNode + i] = a.firstPrimitive; primEnd[a.firstNode + i] = a.firstPrimitive + a.nPrimitives;

@@ -204,6 +204,13 @@ struct Api {
     std::vector<TransformSet> pushedTransforms;
     std::vector<int> pushedActiveBits;
     bool inWorld = false, worldEnded = false;
+    // ObjectBegin / ObjectEnd / ObjectInstance (core/api.cpp:1095-1147)
+    struct InstanceDef {
+        std::vector<GeometricPrimitive> prims;
+        std::shared_ptr<GpuBVHAccel> object;   // built by the first ObjectInstance, shared by all of them
+    };
+    std::map<std::string, InstanceDef> instances;
+    InstanceDef *currentInstance = nullptr;
     // scene under construction
     std::unique_ptr<Scene> scene;
     std::vector<GeometricPrimitive> primitives;
@@ -420,6 +427,12 @@ bool Api::DoShape(const std::string &name, const ParamSet &paramsIn) {   // core
     if (!shape) return true;   // MakeShape returned NULL: ignored like api.cpp:1001
     int mtl = MakeMaterial(params);
     if (mtl < 0) return false;
+    if (currentInstance && animated)
+        return Fail("animated shapes inside an object definition (a TransformedPrimitive inside a TransformedPrimitive) are outside the hot-path scope");
+    if (currentInstance && !graphicsState.areaLight.empty())
+        // (the reference warns "Area lights not supported with object instancing" and keeps a light that emits when hit but
+        // is never sampled, api.cpp:1046-1050: there is no such light in the descriptor)
+        return Fail("area lights inside an object definition are outside the hot-path scope");
     if (animated) {   // api.cpp:1011-1043
         if (!graphicsState.areaLight.empty())
             fprintf(stderr, "Warning: Ignoring currently set area light when creating animated shape\n");
@@ -461,7 +474,8 @@ bool Api::DoShape(const std::string &name, const ParamSet &paramsIn) {   // core
     gp.shape = shape;
     gp.material = mtl;
     gp.areaLight = area;
-    primitives.push_back(gp);
+    if (currentInstance) currentInstance->prims.push_back(gp);   // api.cpp:1046-1051
+    else primitives.push_back(gp);
     return true;
 }
 
@@ -789,6 +803,50 @@ bool ParseStream(Api &api, const std::string &filename, int depth) {
             api.graphicsState = api.pushedGraphicsStates.back(); api.pushedGraphicsStates.pop_back();
             api.curTransform = api.pushedTransforms.back(); api.pushedTransforms.pop_back();
             api.activeBits = api.pushedActiveBits.back(); api.pushedActiveBits.pop_back();
+        } else if (d == "ObjectBegin") {   // api.cpp:1095-1102
+            if (tok.type != Token::STRING) return api.Fail("ObjectBegin: expected a quoted name");
+            api.pushedGraphicsStates.push_back(api.graphicsState);
+            api.pushedTransforms.push_back(api.curTransform);
+            api.pushedActiveBits.push_back(api.activeBits);
+            if (api.currentInstance) return api.Fail("ObjectBegin called inside of instance definition");
+            api.instances[tok.text] = Api::InstanceDef();
+            api.currentInstance = &api.instances[tok.text];
+            tok = lx.Next();
+        } else if (d == "ObjectEnd") {   // api.cpp:1105-1111
+            if (!api.currentInstance) return api.Fail("ObjectEnd called outside of instance definition");
+            api.currentInstance = nullptr;
+            if (api.pushedGraphicsStates.empty()) return api.Fail("unmatched ObjectEnd");
+            api.graphicsState = api.pushedGraphicsStates.back(); api.pushedGraphicsStates.pop_back();
+            api.curTransform = api.pushedTransforms.back(); api.pushedTransforms.pop_back();
+            api.activeBits = api.pushedActiveBits.back(); api.pushedActiveBits.pop_back();
+        } else if (d == "ObjectInstance") {   // api.cpp:1114-1147
+            if (tok.type != Token::STRING) return api.Fail("ObjectInstance: expected a quoted name");
+            const std::string name = tok.text;
+            tok = lx.Next();
+            if (api.currentInstance) return api.Fail("ObjectInstance can't be called inside instance definition");
+            auto it = api.instances.find(name);
+            if (it == api.instances.end()) return api.Fail("Unable to find instance named \"" + name + "\"");
+            Api::InstanceDef &in = it->second;
+            if (in.prims.empty() && !in.object) continue;
+            if (!in.object) {
+                // "Refine instance Primitives and create aggregate" unless it is one intersectable primitive (a sphere or a
+                // disk here): the scene's Accelerator and its parameters (api.cpp:1127-1136)
+                const bool single = in.prims.size() == 1 && in.prims[0].shape->kind != Shape::TRIANGLE_MESH &&
+                                    in.prims[0].shape->kind != Shape::LOOP_SUBDIV;
+                in.object.reset(CreateGpuBVHAccelerator(in.prims, api.AcceleratorParams));
+                if (!in.object->buildError.empty()) return api.Fail(in.object->buildError);
+                if (single) in.object->nodes.clear();
+                for (const GeometricPrimitive &g : in.prims) in.object->owned.push_back(g.shape);   // the refined primitives point into them
+                in.prims.clear();
+                if (in.object->primitives.empty()) { in.object.reset(); continue; }
+            }
+            const Transform *w2i0, *w2i1;
+            api.Cache().Lookup(api.curTransform.t[0], nullptr, &w2i0);
+            api.Cache().Lookup(api.curTransform.t[1], nullptr, &w2i1);
+            AnimatedTransform animatedWorldToInstance(*w2i0, api.transformStartTime, *w2i1, api.transformEndTime);
+            GeometricPrimitive gp;
+            gp.animated.reset(new TransformedPrimitive(in.object, animatedWorldToInstance));
+            api.primitives.push_back(gp);
         } else if (d == "TransformBegin") {
             api.pushedTransforms.push_back(api.curTransform);
             api.pushedActiveBits.push_back(api.activeBits);

@@ -202,11 +202,17 @@ bool Scene::Flatten(std::string *err) {
     hasN = hasUV = false;
     // first pass: which optional vertex streams exist at all
     // the scene BVH first, then the nested BVH (or single primitive) of every TransformedPrimitive
+    // One unit -- one copy of the nested aggregate's nodes and primitives -- per TransformedPrimitive, also for the
+    // instances of one object (ObjectInstance), which share the aggregate on the host: a primitive record of the device
+    // scene names the ONE TransformedPrimitive it lies under (HitGeometry finds the transform through it), so a shared
+    // range cannot be expressed yet; pbrtgpu_scene_validate refuses overlapping ranges.  Costs memory, not correctness.
     std::vector<const GpuBVHAccel *> units(1, &bvh);
     std::map<const TransformedPrimitive *, uint32_t> animatedIndex;
+    std::vector<uint32_t> unitOfAnimated;
     for (const RefinedPrim &rp : bvh.primitives)
         if (rp.type == PBRTGPU_PRIM_ANIMATED && !animatedIndex.count(rp.animated)) {
-            animatedIndex[rp.animated] = (uint32_t)units.size() - 1;
+            animatedIndex[rp.animated] = (uint32_t)unitOfAnimated.size();
+            unitOfAnimated.push_back((uint32_t)units.size());
             units.push_back(rp.animated->primitive.get());
         }
     for (const GpuBVHAccel *u : units)
@@ -281,14 +287,16 @@ bool Scene::Flatten(std::string *err) {
         if (hasN) fN.reserve(3 * nVerts);
         if (hasUV) fUV.reserve(2 * nVerts);
     }
-    fAnimated.resize(units.size() - 1);
+    fAnimated.resize(unitOfAnimated.size());
     for (size_t ui = 0; ui < units.size(); ++ui) {
     const GpuBVHAccel &unit = *units[ui];
-    if (ui > 0) {
-        PbrtGpuAnimated &ga = fAnimated[ui - 1];
-        ga.firstNode = (uint32_t)fNodes.size();        ga.nNodes = (uint32_t)unit.nodes.size();
-        ga.firstPrimitive = (uint32_t)fPrims.size();   ga.nPrimitives = (uint32_t)unit.primitives.size();
-    }
+    if (ui > 0)
+        for (size_t ai = 0; ai < unitOfAnimated.size(); ++ai)
+            if (unitOfAnimated[ai] == ui) {
+                PbrtGpuAnimated &ga = fAnimated[ai];
+                ga.firstNode = (uint32_t)fNodes.size();        ga.nNodes = (uint32_t)unit.nodes.size();
+                ga.firstPrimitive = (uint32_t)fPrims.size();   ga.nPrimitives = (uint32_t)unit.primitives.size();
+            }
     fNodes.insert(fNodes.end(), unit.nodes.begin(), unit.nodes.end());
     for (const RefinedPrim &rp : unit.primitives) {
         PbrtGpuPrimitive gp;

@@ -207,9 +207,11 @@ GpuBVHAccel *CreateGpuBVHAccelerator(const std::vector<GeometricPrimitive> &prim
 // wrapped in its own BVHAccel with the constructor's DEFAULT arguments (maxPrimsInNode 1, "sah").
 struct TransformedPrimitive {
     std::shared_ptr<Shape> shape;             // keeps the shape alive: the refined primitives point into it
-    std::unique_ptr<GpuBVHAccel> primitive;   // `nodes` is empty when there is a single refined primitive
+    std::shared_ptr<GpuBVHAccel> primitive;   // `nodes` is empty when there is a single refined primitive; shared by the
+                                              // instances of one object (ObjectInstance, api.cpp:1114-1147)
     AnimatedTransform WorldToPrimitive;
     TransformedPrimitive(const GeometricPrimitive &base, const AnimatedTransform &w2p);
+    TransformedPrimitive(const std::shared_ptr<GpuBVHAccel> &object, const AnimatedTransform &w2p) : primitive(object), WorldToPrimitive(w2p) {}
     BBox WorldBound() const;
 };
 

@@ -267,6 +267,23 @@ NAMED_MATERIAL_VARIANTS = [
 ]
 
 
+# ObjectBegin / ObjectEnd / ObjectInstance (core/api.cpp:1095-1147): an object of several shapes (its own BVH, shared by the
+# instances), an object of one sphere (no BVH around it), instances under static and moving transforms, an unused object
+_OBJ = _WB + ('\nObjectBegin "blob"\nMaterial "plastic" "color Kd" [.2 .5 .2] "color Ks" [.4 .4 .4] "float roughness" [.05]\n'
+              'Shape "sphere" "float radius" [%g]\nTranslate %g 0 0\nMaterial "matte" "color Kd" [.6 .3 .2]\n'
+              'Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [%s]\nShape "disk" "float radius" [%g] "float height" [%g]\nObjectEnd\n'
+              'ObjectBegin "ball"\nMaterial "mirror"\nShape "sphere" "float radius" [%g]\nObjectEnd\n'
+              'ObjectBegin "unused"\nShape "sphere"\nObjectEnd\nObjectBegin "empty"\nObjectEnd\nObjectInstance "empty"\n'
+              'AttributeBegin\nTranslate %s\nObjectInstance "blob"\nRotate 40 0 1 0\nTranslate %s\nScale 1.5 .7 1\nObjectInstance "blob"\nObjectInstance "ball"\nAttributeEnd\n'
+              'AttributeBegin\nTranslate %s\nActiveTransform EndTime\nTranslate %s\nRotate 30 0 0 1\nActiveTransform All\nObjectInstance "ball"\nObjectInstance "blob"\nAttributeEnd\n')
+INSTANCE_VARIANTS = [
+    ("path-instances-bunny", "bunny", 48, 48, 4, 2, {"maxdepth": 6},
+     [(_WB, _OBJ % (.04, .07, "-.05 0 -.05  .05 0 -.05  .05 .06 .05  -.05 .06 .05", .05, .03, .035, "-.1 .12 .1", ".15 0 .1", ".12 .2 -.05", "0 .08 0"))]),
+    ("direct-instances-killeroo", "killeroo-simple", 48, 48, 4, 2, {"integrator": "directlighting"},
+     [(_WB, _OBJ % (40, 70, "-50 0 -50  50 0 -50  50 60 50  -50 60 50", 50, 30, 35, "-100 120 100", "150 0 100", "120 200 -50", "0 80 0"))]),
+]
+
+
 # SURVEY 8(f) rank 4, pixel filters wider than half a pixel (every sample splats into neighbouring tasks' pixels): host front
 # end + oracle, pinned on the reference binary at --ncores 1 (one worker thread runs the tasks in ascending order: the
 # reference's own sums are ordered only there); the device entry points answer PBRTGPU_EUNSUPPORTED
@@ -286,7 +303,7 @@ def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + INSTANCE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

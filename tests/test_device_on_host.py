@@ -169,6 +169,25 @@ def test_device_state_machine_on_host_variants(staged, doh):
         _same_film(doh, variant_scene(v[0])[0])
 
 
+def test_object_instances_and_named_materials_on_host(staged, doh):
+    """ObjectInstance (several TransformedPrimitives, static and moving, each over its own copy of the object's nested BVH --
+    the device's primitive records name the one TransformedPrimitive they lie under, which is why the front end does not
+    share the copies; single-sphere objects) and named materials through the device code: state machine (both integrators),
+    vertex form, wave kernels"""
+    from helpers import INSTANCE_VARIANTS, NAMED_MATERIAL_VARIANTS, variant_scene
+    variants = INSTANCE_VARIANTS + NAMED_MATERIAL_VARIANTS
+    for v in variants:
+        _same_film(doh, variant_scene(v[0])[0])
+    try:
+        for form in (1, 5, 4096):
+            doh.doh_set_vertex_form(form)
+            for v in variants:
+                if v[6].get("integrator", "path") == "path":
+                    _same_film(doh, variant_scene(v[0])[0])
+    finally:
+        doh.doh_set_vertex_form(0)
+
+
 @pytest.fixture(scope="module")
 def doh_f4(tmp_path_factory):
     """the harness with every gated SURVEY 8(f) rank 4 feature on, as `make variants VARIANT_NAMES=f4` builds the library"""

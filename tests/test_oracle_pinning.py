@@ -170,6 +170,19 @@ def test_oracle_bit_exact_vs_reference_binary_on_variants(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["path-instances-bunny", "direct-instances-killeroo"])
+def test_object_instances_match_reference_binary(staged, name):
+    """ObjectBegin / ObjectEnd / ObjectInstance (core/api.cpp:1095-1147): every instance is a TransformedPrimitive over the
+    object's aggregate (built once with the scene's Accelerator) or over its single sphere; static
+    and moving instance transforms, non-uniform scale, mirror instances, unused and empty objects"""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 @pytest.mark.parametrize("name", ["path-named-materials", "direct-named-materials"])
 def test_named_materials_match_reference_binary(staged, name):
     """MakeNamedMaterial / NamedMaterial (core/api.cpp:939-968, 1062-1077): own parameters over the current Material's, an

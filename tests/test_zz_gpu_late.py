@@ -1,0 +1,40 @@
+"""Scenes whose FRONT END landed after the round's last GPU visit: object instances -- several
+TransformedPrimitives with static and moving instance transforms, each over its own copy of the object's nested BVH or
+over a single sphere (the descriptor shape of the animated-shape scenes) -- and named materials (an ordinary descriptor).  The kernels are the GPU-verified ones; these renders
+are their first on hardware, so each runs in its own process and its outcome is reported without deciding the suite:
+xpassed = bit-exact with the oracle on the GPU, xfailed = not."""
+import subprocess
+import sys
+
+import pytest
+
+import pbrt_v2_b200 as pb
+
+pytestmark = pytest.mark.gpu
+
+SNIPPET = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+import numpy as np
+import pbrt_v2_b200 as pb, oracle_api as oa
+from pbrt_v2_b200 import scenes
+from helpers import variant_scene
+scenes.stage()
+hs, _ = variant_scene(%r)
+px_gpu, _ = pb.GpuScene(hs).render()
+px_cpu, _ = oa.render(hs, threads=2)
+assert np.array_equal(px_gpu["weightSum"], px_cpu["weightSum"])
+own = px_cpu["weightSum"] == hs.render_desc().samplesPerPixel
+assert np.array_equal(px_gpu["Lxyz"][own].view(np.uint32), px_cpu["Lxyz"][own].view(np.uint32))
+print("bit-exact on", int(own.sum()), "pixels")
+'''
+
+
+@pytest.mark.xfail(strict=False, reason="first hardware run of a front-end feature written after the last GPU visit")
+@pytest.mark.parametrize("name", ["path-instances-bunny", "direct-instances-killeroo", "path-named-materials", "direct-named-materials"])
+def test_late_front_end_feature_on_the_gpu(staged, name):
+    r = subprocess.run([sys.executable, "-c", SNIPPET % (pb.REPO, pb.REPO, name)], cwd=pb.REPO, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=300)
+    tail = "\n".join(r.stdout.splitlines()[-12:])
+    print("\n[%s]\n%s" % (name, tail))
+    assert r.returncode == 0, tail
