@@ -2,7 +2,7 @@
 """Random in-scope scenes: the unmodified reference binary vs the oracle vs the device code compiled for the host
 (tests/native/device_on_host.cpp).  CPU only.  usage: fuzz_scenes.py [n] [seed0] [flags]
 flags (joined with +): specular, metal (materials; metal builds the harness with -DPBRT_METAL=1), pairs (-DPBRT_PAIR_NODES=1),
-crop, infinite (InfiniteAreaLights, constant or over a random .pfm radiance map; the harness is built with -DPBRT_INFINITE=1), filter (a random
+crop, instances (ObjectBegin / ObjectInstance), infinite (InfiniteAreaLights, constant or over a random .pfm radiance map; the harness is built with -DPBRT_INFINITE=1), filter (a random
 PixelFilter on half of the scenes, harness built with -DPBRT_FILTER=1: such scenes run on one core -- the only order the
 reference defines for them -- through the state machine, and EVERY pixel is compared), wave (PathIntegrator scenes run through the vertex-wavefront KERNELS -- kwave.cuh's k_wshade / k_weval / k_wtrace /
 k_wcompact, launches as loops -- over a pool of 3, 17 or 4096 slots instead of the state machine)"""
@@ -139,6 +139,28 @@ def gen(rng, path, animated=None):
     L.append('Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-4 -1.5 -4  4 -1.5 -4  4 -1.5 4  -4 -1.5 4]')
     if animated is None:
         animated = len(sys.argv) > 3 and "animated" in sys.argv[3]
+    if len(sys.argv) > 3 and "instances" in sys.argv[3] and rng.rand() < .6:
+        # ObjectBegin / ObjectInstance: objects of one to three shapes (one sphere or disk alone gets no aggregate), placed one
+        # to three times each under static or (with "animated") moving transforms; now and then an object nobody instantiates
+        names = []
+        for o in range(rng.randint(1, 3)):
+            L.append('ObjectBegin "obj%d"' % o)
+            for _ in range(rng.randint(1, 4)):
+                if rng.rand() < .5: L += xform()
+                L.append(material())
+                L.append(shape())
+            L.append("ObjectEnd")
+            names.append("obj%d" % o)
+        for _ in range(rng.randint(1, 5)):
+            L.append("AttributeBegin")
+            L += xform()
+            if animated and rng.rand() < .4:
+                L.append("ActiveTransform EndTime")
+                L.append("Translate %s" % fl(rng.uniform(-.5, .5, 3)))
+                if rng.rand() < .5: L.append("Rotate %g %s" % (rng.uniform(-120, 120), fl(rng.uniform(-1, 1, 3) + 1e-3)))
+                L.append("ActiveTransform All")
+            L.append('ObjectInstance "%s"' % names[rng.randint(len(names))])
+            L.append("AttributeEnd")
     for _ in range(rng.randint(2, 7)):
         L.append("AttributeBegin")
         L += xform()
