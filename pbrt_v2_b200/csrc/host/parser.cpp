@@ -182,6 +182,10 @@ struct GraphicsState {   // core/api.cpp:213-232
     std::string areaLight;
     ParamSet areaLightParams;
     bool reverseOrientation = false;
+    // Texture (api.cpp:910-936) for the classes whose value does not depend on the surface point -- "constant", and "scale" /
+    // "mix" of such -- kept as that value: what Texture::Evaluate returns everywhere (textures/{constant,scale,mix}.h)
+    std::map<std::string, float> floatTextures;
+    std::map<std::string, V3> spectrumTextures;
     std::map<std::string, int> namedMaterials;   // MakeNamedMaterial (api.cpp:947-961): name -> index into scene->materials
     std::string currentNamedMaterial;            // NamedMaterial (api.cpp:965-968); Material resets it (:939-944)
 };
@@ -242,10 +246,30 @@ std::string ResolvePath(const std::string &baseDir, const std::string &fn) {   /
 
 // TextureParams lookup order: shape parameters first, then material parameters
 // (core/paramset.cpp:600-640)
+// TextureParams::GetSpectrumTexture / GetFloatTexture (core/paramset.cpp:598-630) evaluated: a named texture if the
+// parameter is given as one ("texture Kd" "name": shape parameters first), else the constant; a name that was never
+// defined is an Error message and then the constant, as in the reference
+static thread_local const GraphicsState *g_texState = nullptr;   // the graphics state the lookups below read (set around MakeMaterialOfType / Texture)
+static std::string FindTexture(const ParamSet &ps, const std::string &n) {
+    auto it = ps.textures.find(n);
+    return it == ps.textures.end() ? std::string() : it->second;
+}
 V3 TexSpectrum(const ParamSet &geom, const ParamSet &mat, const std::string &n, const V3 &def) {
+    std::string name = FindTexture(geom, n);
+    if (name.empty()) name = FindTexture(mat, n);
+    if (!name.empty()) {
+        if (g_texState && g_texState->spectrumTextures.count(name)) return g_texState->spectrumTextures.at(name);
+        fprintf(stderr, "Error: Couldn't find spectrum texture named \"%s\" for parameter \"%s\"\n", name.c_str(), n.c_str());
+    }
     return geom.FindOneSpectrum(n, mat.FindOneSpectrum(n, def));
 }
 float TexFloat(const ParamSet &geom, const ParamSet &mat, const std::string &n, float def) {
+    std::string name = FindTexture(geom, n);
+    if (name.empty()) name = FindTexture(mat, n);
+    if (!name.empty()) {
+        if (g_texState && g_texState->floatTextures.count(name)) return g_texState->floatTextures.at(name);
+        fprintf(stderr, "Error: Couldn't find float texture named \"%s\" for parameter \"%s\"\n", name.c_str(), n.c_str());
+    }
     return geom.FindOneFloat(n, mat.FindOneFloat(n, def));
 }
 
@@ -261,9 +285,11 @@ int Api::MakeMaterialOfType(const std::string &name, const ParamSet &geomParams,
     Material m;
     memset(&m.desc, 0, sizeof(m.desc));
     m.desc.measured = -1;
-    for (const auto &kv : mp.textures) { (void)kv; Fail("texture-valued material parameters are outside the hot-path scope"); return -1; }
-    for (const auto &kv : geomParams.textures) { (void)kv; Fail("texture-valued shape parameters are outside the hot-path scope"); return -1; }
-    if (geomParams.floats.count("bumpmap") || mp.floats.count("bumpmap")) { Fail("bump maps are out of scope"); return -1; }
+    g_texState = &graphicsState;
+    if (geomParams.floats.count("bumpmap") || mp.floats.count("bumpmap") || geomParams.textures.count("bumpmap") || mp.textures.count("bumpmap")) {
+        Fail("bump maps are out of scope");
+        return -1;
+    }
     if (name == "matte") {   // materials/matte.cpp:66-72
         m.desc.type = PBRTGPU_MAT_MATTE;
         V3 kd = TexSpectrum(geomParams, mp, "Kd", V3(0.5f, 0.5f, 0.5f));
@@ -382,6 +408,8 @@ bool Api::DoShape(const std::string &name, const ParamSet &paramsIn) {   // core
         if (!LoadBinaryMesh(ResolvePath(baseDir, binfile), &withMesh, &err)) return Fail(err);
     }
     const ParamSet &params = binfile.empty() ? paramsIn : withMesh;
+    if (params.textures.count("alpha") || params.floats.count("alpha"))   // trianglemesh.cpp:397-406: alpha-tested triangles
+        return Fail("alpha textures on shapes are outside the hot-path scope");
     const bool animated = curTransform.IsAnimated();
     const Transform *o2w, *w2o;
     if (!animated) Cache().Lookup(curTransform.t[0], &o2w, &w2o);
@@ -862,6 +890,40 @@ bool ParseStream(Api &api, const std::string &filename, int depth) {
             api.graphicsState.material = n;
             api.graphicsState.materialParams = ps;
             api.graphicsState.currentNamedMaterial.clear();
+        } else if (d == "Texture") {   // api.cpp:910-936: Texture "name" "float|color|spectrum" "class" parameters
+            std::string texName, texType, texClass;
+            for (std::string *dst : {&texName, &texType, &texClass}) {
+                if (tok.type != Token::STRING) return api.Fail("Texture: expected \"name\" \"type\" \"class\"");
+                *dst = tok.text;
+                tok = lx.Next();
+            }
+            ParamSet ps;
+            if (!ParseParams(lx, tok, &ps, &perr)) return api.Fail("Texture: " + perr);
+            g_texState = &api.graphicsState;
+            const bool isFloat = texType == "float";
+            if (!isFloat && texType != "color" && texType != "spectrum") {
+                fprintf(stderr, "Error: Texture type \"%s\" unknown.\n", texType.c_str());
+            } else if (texClass == "constant") {   // textures/constant.cpp:39-48
+                if (isFloat) api.graphicsState.floatTextures[texName] = ps.FindOneFloat("value", 1.f);
+                else api.graphicsState.spectrumTextures[texName] = ps.FindOneSpectrum("value", V3(1, 1, 1));
+            } else if (texClass == "scale") {      // textures/scale.cpp:39-51, scale.h: tex1 * tex2
+                if (isFloat) api.graphicsState.floatTextures[texName] = TexFloat(ps, ps, "tex1", 1.f) * TexFloat(ps, ps, "tex2", 1.f);
+                else {
+                    const V3 a = TexSpectrum(ps, ps, "tex1", V3(1, 1, 1)), b = TexSpectrum(ps, ps, "tex2", V3(1, 1, 1));
+                    api.graphicsState.spectrumTextures[texName] = V3(a.x * b.x, a.y * b.y, a.z * b.z);
+                }
+            } else if (texClass == "mix") {        // textures/mix.cpp:39-54, mix.h: (1 - amt) * t1 + amt * t2
+                const float amt = TexFloat(ps, ps, "amount", 0.5f);
+                if (isFloat) {
+                    const float t1 = TexFloat(ps, ps, "tex1", 0.f), t2 = TexFloat(ps, ps, "tex2", 1.f);
+                    api.graphicsState.floatTextures[texName] = (1.f - amt) * t1 + amt * t2;
+                } else {
+                    const V3 t1 = TexSpectrum(ps, ps, "tex1", V3(0, 0, 0)), t2 = TexSpectrum(ps, ps, "tex2", V3(1, 1, 1));
+                    api.graphicsState.spectrumTextures[texName] = V3((1.f - amt) * t1.x + amt * t2.x, (1.f - amt) * t1.y + amt * t2.y,
+                                                                     (1.f - amt) * t1.z + amt * t2.z);
+                }
+            } else
+                return api.Fail("texture \"" + texClass + "\" is outside the hot-path scope (constant, scale and mix of constants fold into the material)");
         } else if (d == "MakeNamedMaterial") {   // api.cpp:947-961: the new material's own parameters first, then the current Material's
             std::string n; ParamSet ps;
             if (!named(&n, &ps)) return false;

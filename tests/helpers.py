@@ -267,6 +267,22 @@ NAMED_MATERIAL_VARIANTS = [
 ]
 
 
+# Texture (core/api.cpp:910-936) of the classes that are the same everywhere on a surface: "constant", "scale", "mix" (also of each
+# other); float and colour; a material parameter given as a texture; a name that does not exist (Error + the constant default)
+_TEX = _WB + ('\nTexture "green" "color" "constant" "color value" [.1 .6 .2]\nTexture "half" "float" "constant" "float value" [.5]\n'
+              'Texture "dim" "color" "scale" "texture tex1" "green" "color tex2" [.9 .5 2.]\n'
+              'Texture "blend" "color" "mix" "texture tex1" "dim" "color tex2" [.8 .8 .1] "float amount" [.3]\n'
+              'Texture "rough" "float" "mix" "float tex1" [.02] "float tex2" [.3] "texture amount" "half"\n'
+              'Texture "rougher" "float" "scale" "texture tex1" "rough" "float tex2" [1.5]\n')
+TEXTURE_VARIANTS = [
+    ("path-constant-textures", "killeroo-simple", 40, 40, 4, 2, {},
+     [(_WB, _TEX), (_M1, 'Material "plastic" "texture Kd" "blend" "color Ks" [.5 .5 .5] "texture roughness" "rougher"'),
+      (_M2, 'Material "matte" "texture Kd" "nosuchtexture" "color Kd" [.2 .3 .7]')]),
+    ("direct-constant-textures", "killeroo-simple", 40, 40, 4, 2, {"integrator": "directlighting"},
+     [(_WB, _TEX), (_M1, 'Material "plastic" "texture Kd" "dim" "texture Ks" "green" "texture roughness" "rough"'), (_M2, 'Material "matte" "texture Kd" "blend"')]),
+]
+
+
 # ObjectBegin / ObjectEnd / ObjectInstance (core/api.cpp:1095-1147): an object of several shapes (its own BVH, shared by the
 # instances), an object of one sphere (no BVH around it), instances under static and moving transforms, an unused object
 _OBJ = _WB + ('\nObjectBegin "blob"\nMaterial "plastic" "color Kd" [.2 .5 .2] "color Ks" [.4 .4 .4] "float roughness" [.05]\n'
@@ -303,7 +319,7 @@ def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + INSTANCE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + TEXTURE_VARIANTS + INSTANCE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

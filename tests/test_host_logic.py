@@ -53,7 +53,9 @@ def test_crop_window_extent(staged):
     ('Sampler "random"', "out of scope"),
     ('Material "uber"', "outside the hot-path scope"),
     ('Material "metal" "spectrum eta" "spds/Au.eta.spd"', "not supported by this front end"),
-    ('Texture "t" "float" "constant"', "outside the hot-path scope"),
+    ('Texture "t" "color" "imagemap" "string filename" "x.exr"', "outside the hot-path scope"),   # (constant / scale / mix fold into the material)
+    ('Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0] "float alpha" [0]', "alpha textures"),
+    ('Material "matte" "texture bumpmap" "b"', "bump maps"),
 ])
 def test_out_of_scope_directives_fail_loudly(staged, text, needle):
     src = open(scenes.variant("bunny", os.path.join(scenes.STAGED, "t-err.pbrt"), 8, 8, 1)).read()

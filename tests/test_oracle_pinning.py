@@ -170,6 +170,19 @@ def test_oracle_bit_exact_vs_reference_binary_on_variants(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["path-constant-textures", "direct-constant-textures"])
+def test_constant_textures_match_reference_binary(staged, name):
+    """Texture "constant" / "scale" / "mix" (textures/{constant,scale,mix}.h: values that do not depend on the surface point,
+    folded into the material by the front end) given to Kd, Ks and roughness through "texture" parameters, nested; an undefined
+    texture name (Error, then the parameter's constant, core/paramset.cpp:598-630)"""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 @pytest.mark.parametrize("name", ["path-instances-bunny", "direct-instances-killeroo"])
 def test_object_instances_match_reference_binary(staged, name):
     """ObjectBegin / ObjectEnd / ObjectInstance (core/api.cpp:1095-1147): every instance is a TransformedPrimitive over the

@@ -31,7 +31,8 @@ print("bit-exact on", int(own.sum()), "pixels")
 
 
 @pytest.mark.xfail(strict=False, reason="first hardware run of a front-end feature written after the last GPU visit")
-@pytest.mark.parametrize("name", ["path-instances-bunny", "direct-instances-killeroo", "path-named-materials", "direct-named-materials"])
+@pytest.mark.parametrize("name", ["path-instances-bunny", "direct-instances-killeroo", "path-named-materials", "direct-named-materials",
+                                  "path-constant-textures"])
 def test_late_front_end_feature_on_the_gpu(staged, name):
     r = subprocess.run([sys.executable, "-c", SNIPPET % (pb.REPO, pb.REPO, name)], cwd=pb.REPO, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=300)
