@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <cmath>
 #include <memory>
 #include <thread>
 
@@ -324,6 +325,10 @@ GpuBVHAccel::GpuBVHAccel(const std::vector<GeometricPrimitive> &p, uint32_t mp, 
         o[0] = b.pMin.x; o[1] = b.pMin.y; o[2] = b.pMin.z; o[3] = b.pMax.x; o[4] = b.pMax.y; o[5] = b.pMax.z;
     }
     tb.Stop();
+    // (the reference's SAH bucket index is int(NaN) for a primitive without finite bounds, bvh.cpp:300-306: an
+    // out-of-bounds write there, an error here -- as in pbrtgpu_bvh_build)
+    for (float v : bounds)
+        if (!std::isfinite(v)) { buildError = "a primitive's bounds are not finite (a singular or overflowing transform?)"; return; }
     std::vector<uint32_t> order;
     PrepTimer tbuild("BVH build");
     if (builder == "gpu") {   // the same tree, built on the device (include/pbrtgpu.h: pbrtgpu_bvh_build)

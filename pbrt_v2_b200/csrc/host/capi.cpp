@@ -4,6 +4,8 @@
 // here: rendering goes through include/pbrtgpu.h.
 #include "scene.h"
 
+#include <cmath>
+
 #include <cstdio>
 #include <cstring>
 
@@ -143,6 +145,8 @@ void pbrthost_scene_nodes(PbrtHostScene *h, PbrtGpuBVHNode *out) {
 int pbrthost_bvh_build(const float *bounds, uint32_t n, uint32_t maxPrimsInNode, int splitMethod, PbrtGpuBVHNode *nodes,
                        uint32_t *nNodes, uint32_t *order) {
     if (splitMethod < 0 || splitMethod > 2 || maxPrimsInNode < 1 || maxPrimsInNode > 255) return 1;
+    for (size_t i = 0; i < (size_t)6 * n; ++i)
+        if (!std::isfinite(bounds[i])) return 1;   // (as pbrtgpu_bvh_build: the reference's bucket index is int(NaN) there)
     std::vector<PbrtGpuBVHNode> nv;
     std::vector<uint32_t> ov;
     BuildBVHOnHost(bounds, n, maxPrimsInNode, splitMethod, &nv, &ov);

@@ -152,7 +152,7 @@ def test_config_scene_meshes(staged, emu, base):
     """the BASELINE scenes: the input the scene's own accelerator was built from -> the scene's own node array"""
     pb.keep_build_input(True)
     try:
-        hs = host_scene(base, 32, 32, 4, 32)
+        hs = host_scene(base, 32, 32, 4, 32, tag="-buildinput")   # (its own cache entry: loaded with the build input kept)
     finally:
         pb.keep_build_input(False)
     b = hs.build_input()
