@@ -153,6 +153,10 @@ struct KdBuild {
 
 }  // namespace
 
+// (for the "spectrum" parameter type, parser.cpp)
+bool ReadSpectrumFile(const std::string &filename, std::vector<float> *values) { return ReadFloatFile(filename, values); }
+void SortedSamplesToRGB(const float *lambda, const float *v, int n, float rgb[3]) { SampledToRGB(lambda, v, n, rgb); }
+
 bool LoadIrregIsotropicBRDF(const std::string &filename, MeasuredData *out, std::string *err) {
     std::vector<float> values;
     if (!ReadFloatFile(filename, &values) || values.empty()) {

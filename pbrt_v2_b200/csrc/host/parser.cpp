@@ -689,6 +689,8 @@ bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
     return true;
 }
 
+static thread_local std::string g_paramBaseDir;   // where "spectrum" parameters look for their .spd files: the scene file's directory
+
 bool ParseParams(Lexer &lx, Token &tok, ParamSet *ps, std::string *err) {
     // after the directive's fixed arguments: ("type name" value | [values])*
     while (tok.type == Token::STRING) {
@@ -731,6 +733,48 @@ bool ParseParams(Lexer &lx, Token &tok, ParamSet *ps, std::string *err) {
         else if (type == "vector") triples(ps->vectors[name]);
         else if (type == "normal") triples(ps->normals[name]);
         else if (type == "color" || type == "rgb") triples(ps->spectra[name]);   // RGBSpectrum::FromRGB
+        else if (type == "xyz") {   // ParamSet::AddXYZSpectrum (paramset.cpp:109-118): RGBSpectrum::FromXYZ = XYZToRGB
+            std::vector<V3> xyz;
+            triples(xyz);
+            std::vector<V3> &dst = ps->spectra[name];
+            dst.clear();
+            for (const V3 &c : xyz)
+                dst.push_back(V3(3.240479f * c.x - 1.537150f * c.y - 0.498535f * c.z, -0.969256f * c.x + 1.875991f * c.y + 0.041556f * c.z,
+                                 0.055648f * c.x - 0.204043f * c.y + 1.057311f * c.z));
+        } else if (type == "spectrum") {
+            // ParamSet::AddSampledSpectrum / AddSampledSpectrumFiles (paramset.cpp:138-187): (wavelength, value) pairs, inline or
+            // from .spd files next to the scene, through RGBSpectrum::FromSampled (spectrum.h:428-451; samples sorted first)
+            auto fromPairs = [](const std::vector<float> &vals) {
+                std::vector<std::pair<float, float>> pairs;
+                for (size_t j = 0; j + 1 < vals.size(); j += 2) pairs.push_back(std::make_pair(vals[j], vals[j + 1]));
+                bool sorted = true;
+                for (size_t j = 0; j + 1 < pairs.size(); ++j) sorted = sorted && !(pairs[j].first > pairs[j + 1].first);
+                if (!sorted) std::sort(pairs.begin(), pairs.end());   // SortSpectrumSamples, spectrum.cpp:45-55
+                std::vector<float> wl, v;
+                for (const auto &pr : pairs) { wl.push_back(pr.first); v.push_back(pr.second); }
+                float rgb[3] = {0.f, 0.f, 0.f};
+                if (!wl.empty()) SortedSamplesToRGB(wl.data(), v.data(), (int)wl.size(), rgb);
+                return V3(rgb[0], rgb[1], rgb[2]);
+            };
+            std::vector<V3> &dst = ps->spectra[name];
+            dst.clear();
+            if (!strs.empty()) {
+                for (const std::string &fnIn : strs) {
+                    const std::string fn = ResolvePath(g_paramBaseDir, fnIn);
+                    std::vector<float> vals;
+                    if (!ReadSpectrumFile(fn, &vals)) {
+                        fprintf(stderr, "Warning: Unable to read SPD file \"%s\".  Using black distribution.\n", fn.c_str());
+                        dst.push_back(V3(0, 0, 0));
+                    } else {
+                        if (vals.size() % 2) fprintf(stderr, "Warning: Extra value found in spectrum file \"%s\". Ignoring it.\n", fn.c_str());
+                        dst.push_back(fromPairs(vals));
+                    }
+                }
+            } else {
+                if (nums.size() % 2) { *err = "spectrum \"" + name + "\": wavelength / value pairs expected"; return false; }
+                dst.push_back(fromPairs(nums));
+            }
+        }
         else if (type == "string") ps->strings[name] = strs;
         else if (type == "texture") ps->textures[name] = strs.empty() ? "" : strs[0];
         else { *err = "parameter type \"" + type + "\" is not supported by this front end"; return false; }
@@ -975,6 +1019,7 @@ bool LoadSceneFile(const std::string &filename, const Options &opt, LoadedScene 
     api.scene.reset(new Scene);
     size_t slash = filename.rfind('/');
     api.baseDir = slash == std::string::npos ? "" : filename.substr(0, slash);
+    g_paramBaseDir = api.baseDir;
     if (!ParseStream(api, filename, 0) || !api.error.empty()) {
         out->error = api.error;
         return false;

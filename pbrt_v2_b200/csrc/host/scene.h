@@ -118,6 +118,8 @@ struct MeasuredData {   // materials/measured.cpp:85-135 + core/kdtree.h:101-147
     std::vector<PbrtGpuKdNode> nodes;
     std::vector<PbrtGpuBrdfSample> data;
 };
+bool ReadSpectrumFile(const std::string &filename, std::vector<float> *values);           // ReadFloatFile, core/floatfile.cpp:38-83
+void SortedSamplesToRGB(const float *lambda, const float *v, int n, float rgb[3]);        // RGBSpectrum::FromSampled, sorted samples
 bool LoadIrregIsotropicBRDF(const std::string &filename, MeasuredData *out, std::string *err);
 
 // ------------------------------------------------------------------ Lights --

@@ -23,6 +23,9 @@ _FILES = [
     "geometry/killeroo.pbrt",
     "geometry/bunny.pbrt",
     "brdfs/mystique.brdf",
+    "spds/metals/Au.eta.spd",
+    "spds/metals/Au.k.spd",
+    "spds/cie.stdillum.D6500.spd",
 ]
 
 

@@ -283,6 +283,17 @@ TEXTURE_VARIANTS = [
 ]
 
 
+# "spectrum" parameters (ParamSet::AddSampledSpectrum / AddSampledSpectrumFiles, paramset.cpp:138-187: .spd files and inline
+# wavelength / value pairs -- unsorted ones too -- through RGBSpectrum::FromSampled) and "xyz" parameters
+SPECTRUM_VARIANTS = [
+    ("path-spectrum-params", "killeroo-simple", 40, 40, 4, 2, {},
+     [(_M1, 'Material "metal" "spectrum eta" "spds/metals/Au.eta.spd" "spectrum k" "spds/metals/Au.k.spd" "float roughness" [.05]'),
+      (_M2, 'Material "plastic" "spectrum Kd" [400 .2 500 .6 700 .4 600 .9] "xyz Ks" [.3 .35 .2] "float roughness" [.1]')]),
+    ("direct-spectrum-light", "bunny", 40, 40, 4, 2, {"integrator": "directlighting"},
+     [(_WB, _WB + '\nLightSource "point" "spectrum I" "spds/cie.stdillum.D6500.spd" "color scale" [.05 .05 .05] "point from" [.3 .4 .3]\n')]),
+]
+
+
 # ObjectBegin / ObjectEnd / ObjectInstance (core/api.cpp:1095-1147): an object of several shapes (its own BVH, shared by the
 # instances), an object of one sphere (no BVH around it), instances under static and moving transforms, an unused object
 _OBJ = _WB + ('\nObjectBegin "blob"\nMaterial "plastic" "color Kd" [.2 .5 .2] "color Ks" [.4 .4 .4] "float roughness" [.05]\n'
@@ -319,7 +330,7 @@ def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + TEXTURE_VARIANTS + INSTANCE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + TEXTURE_VARIANTS + SPECTRUM_VARIANTS + INSTANCE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

@@ -170,6 +170,19 @@ def test_oracle_bit_exact_vs_reference_binary_on_variants(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["path-spectrum-params", "direct-spectrum-light"])
+def test_spectrum_parameters_match_reference_binary(staged, name):
+    """"spectrum" parameters from .spd files (gold's measured eta and k for MetalMaterial, the D65 illuminant for a point
+    light) and from inline wavelength / value pairs given out of order, and "xyz" parameters: RGBSpectrum::FromSampled /
+    FromXYZ as the reference's ParamSet applies them (paramset.cpp:109-187, spectrum.h:428-451)"""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 @pytest.mark.parametrize("name", ["path-constant-textures", "direct-constant-textures"])
 def test_constant_textures_match_reference_binary(staged, name):
     """Texture "constant" / "scale" / "mix" (textures/{constant,scale,mix}.h: values that do not depend on the surface point,
