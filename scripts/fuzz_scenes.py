@@ -2,7 +2,7 @@
 """Random in-scope scenes: the unmodified reference binary vs the oracle vs the device code compiled for the host
 (tests/native/device_on_host.cpp).  CPU only.  usage: fuzz_scenes.py [n] [seed0] [flags]
 flags (joined with +): specular, metal (materials; metal builds the harness with -DPBRT_METAL=1), pairs (-DPBRT_PAIR_NODES=1),
-crop, instances (ObjectBegin / ObjectInstance), infinite (InfiniteAreaLights, constant or over a random .pfm radiance map; the harness is built with -DPBRT_INFINITE=1), filter (a random
+crop, params ("xyz" / "spectrum" / constant-texture-valued Kd), instances (ObjectBegin / ObjectInstance), infinite (InfiniteAreaLights, constant or over a random .pfm radiance map; the harness is built with -DPBRT_INFINITE=1), filter (a random
 PixelFilter on half of the scenes, harness built with -DPBRT_FILTER=1: such scenes run on one core -- the only order the
 reference defines for them -- through the state machine, and EVERY pixel is compared), wave (PathIntegrator scenes run through the vertex-wavefront KERNELS -- kwave.cuh's k_wshade / k_weval / k_wtrace /
 k_wcompact, launches as loops -- over a pool of 3, 17 or 4096 slots instead of the state machine)"""
@@ -45,6 +45,10 @@ def gen(rng, path, animated=None):
     if integ == "directlighting" and rng.rand() < .4: s += ' "string strategy" "one"'
     L.append(s)
     L.append("WorldBegin")
+    if len(sys.argv) > 3 and "params" in sys.argv[3]:   # the textures kd() may name: a constant, a scale and a mix of constants
+        L.append('Texture "fuzztex0" "color" "constant" "color value" [%s]' % fl(rng.uniform(0, 1, 3)))
+        L.append('Texture "fuzztex1" "color" "scale" "texture tex1" "fuzztex0" "color tex2" [%s]' % fl(rng.uniform(0, 1.5, 3)))
+        L.append('Texture "fuzztex2" "color" "mix" "texture tex1" "fuzztex1" "color tex2" [%s] "float amount" [%g]' % (fl(rng.uniform(0, 1, 3)), rng.uniform(0, 1)))
     if len(sys.argv) > 3 and "infinite" in sys.argv[3] and rng.rand() < .4:   # constant-radiance InfiniteAreaLight, rotated
         L.append("AttributeBegin")
         L.append("Rotate %g %s" % (rng.uniform(-180, 180), fl(rng.uniform(-1, 1, 3) + 1e-3)))
@@ -75,6 +79,16 @@ def gen(rng, path, animated=None):
         return t
     specular = len(sys.argv) > 3 and "specular" in sys.argv[3]
     metal = len(sys.argv) > 3 and "metal" in sys.argv[3]
+    params = len(sys.argv) > 3 and "params" in sys.argv[3]
+    def kd(hi):   # a diffuse colour in one of the ways a scene file can say it (without the flag: the draws of the earlier campaigns)
+        if not params: return '"color Kd" [%s]' % fl(rng.uniform(0, hi, 3))
+        k = rng.rand()
+        if k < .6: return '"color Kd" [%s]' % fl(rng.uniform(0, hi, 3))
+        if k < .8: return '"xyz Kd" [%s]' % fl(rng.uniform(.1, .8, 3))
+        if k < .9:
+            wl = rng.permutation(np.linspace(380, 780, rng.randint(2, 9)))
+            return '"spectrum Kd" [%s]' % fl(np.stack([wl, rng.uniform(0, 1, len(wl))], 1).ravel())
+        return '"texture Kd" "fuzztex%d"' % rng.randint(3)
     def material():
         if metal and rng.rand() < .3:
             if rng.rand() < .4: return 'Material "metal" "float roughness" [%g]' % rng.choice([.01, .05, .3])
@@ -85,9 +99,9 @@ def gen(rng, path, animated=None):
             return 'Material "glass" "color Kr" [%s] "color Kt" [%s] "float index" [%g]' % (
                 fl(rng.uniform(0, 1, 3)), fl(rng.uniform(0, 1, 3)), rng.choice([1.0, 1.2, 1.5, 2.4]))
         k = rng.rand()
-        if k < .4: return 'Material "matte" "color Kd" [%s]' % fl(rng.uniform(0, 1, 3))
-        if k < .8: return 'Material "plastic" "color Kd" [%s] "color Ks" [%s] "float roughness" [%g]' % (
-            fl(rng.uniform(0, .6, 3)), fl(rng.uniform(0, .6, 3)), rng.choice([.5, .1, .03, 1e-5]))
+        if k < .4: return 'Material "matte" %s' % kd(1)
+        if k < .8: return 'Material "plastic" %s "color Ks" [%s] "float roughness" [%g]' % (
+            kd(.6), fl(rng.uniform(0, .6, 3)), rng.choice([.5, .1, .03, 1e-5]))
         return 'Material "measured" "string filename" "brdfs/mystique.brdf"'
     def shape():
         k = rng.rand()
