@@ -14,7 +14,7 @@ EXTREME = ["0", "-1", "1e30", "-1e30", "nan", "inf", "2147483647", "-2147483648"
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    sys.argv = sys.argv[:1] + ["0", "0", "specular+metal+crop+infinite+filter+animated+instances"]   # what fuzz_scenes.gen reads its flags from
+    sys.argv = sys.argv[:1] + ["0", "0", "specular+metal+crop+infinite+filter+animated+instances+params"]   # what fuzz_scenes.gen reads its flags from
     tmp = tempfile.mkdtemp(prefix="pbrt_san_parser")
     exe = os.path.join(tmp, "san_parser")
     host = os.path.join(REPO, "pbrt_v2_b200", "csrc", "host")
