@@ -14,6 +14,7 @@
 #include "scene.h"
 
 #include <cctype>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -741,6 +742,27 @@ bool ParseParams(Lexer &lx, Token &tok, ParamSet *ps, std::string *err) {
             for (const V3 &c : xyz)
                 dst.push_back(V3(3.240479f * c.x - 1.537150f * c.y - 0.498535f * c.z, -0.969256f * c.x + 1.875991f * c.y + 0.041556f * c.z,
                                  0.055648f * c.x - 0.204043f * c.y + 1.057311f * c.z));
+        } else if (type == "blackbody") {
+            // ParamSet::AddBlackbodySpectrum (paramset.cpp:121-135): (temperature in K, scale) pairs; Blackbody() over the CIE
+            // wavelengths (spectrum.cpp:195-204: Planck's law normalised at 555 nm, in double) -> FromSampled -> times scale
+            if (nums.size() % 2) { *err = "blackbody \"" + name + "\": temperature / scale pairs expected"; return false; }
+            std::vector<V3> &dst = ps->spectra[name];
+            dst.clear();
+            for (size_t j = 0; j + 1 < nums.size(); j += 2) {
+                const float temp = nums[j], scale = nums[j + 1];
+                float wl[471], v[471];
+                for (int i = 0; i < 471; ++i) wl[i] = float(360 + i);   // CIE_lambda
+                if (temp <= 0) {
+                    for (int i = 0; i < 471; ++i) v[i] = 0.f;
+                } else {
+                    const double C2 = 1.4388e7;
+                    double norm = pow(555.0, 5.0) * (exp(C2 / (555.0 * temp)) - 1.);
+                    for (int i = 0; i < 471; ++i) v[i] = float(norm / (pow(double(wl[i]), 5.0) * (exp(C2 / (wl[i] * temp)) - 1.)));
+                }
+                float rgb[3];
+                SortedSamplesToRGB(wl, v, 471, rgb);
+                dst.push_back(V3(rgb[0] * scale, rgb[1] * scale, rgb[2] * scale));
+            }
         } else if (type == "spectrum") {
             // ParamSet::AddSampledSpectrum / AddSampledSpectrumFiles (paramset.cpp:138-187): (wavelength, value) pairs, inline or
             // from .spd files next to the scene, through RGBSpectrum::FromSampled (spectrum.h:428-451; samples sorted first)

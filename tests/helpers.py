@@ -289,6 +289,8 @@ SPECTRUM_VARIANTS = [
     ("path-spectrum-params", "killeroo-simple", 40, 40, 4, 2, {},
      [(_M1, 'Material "metal" "spectrum eta" "spds/metals/Au.eta.spd" "spectrum k" "spds/metals/Au.k.spd" "float roughness" [.05]'),
       (_M2, 'Material "plastic" "spectrum Kd" [400 .2 500 .6 700 .4 600 .9] "xyz Ks" [.3 .35 .2] "float roughness" [.1]')]),
+    ("path-blackbody-light", "bunny", 40, 40, 4, 2, {},
+     [(_WB, _WB + '\nLightSource "point" "blackbody I" [3200 .08] "point from" [.3 .4 .3]\nLightSource "point" "blackbody I" [9000 .03] "point from" [-.3 .4 .2]\n')]),
     ("direct-spectrum-light", "bunny", 40, 40, 4, 2, {"integrator": "directlighting"},
      [(_WB, _WB + '\nLightSource "point" "spectrum I" "spds/cie.stdillum.D6500.spd" "color scale" [.05 .05 .05] "point from" [.3 .4 .3]\n')]),
 ]

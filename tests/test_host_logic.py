@@ -52,7 +52,7 @@ def test_crop_window_extent(staged):
     ('SurfaceIntegrator "whitted"', "outside the scope"),
     ('Sampler "random"', "out of scope"),
     ('Material "uber"', "outside the hot-path scope"),
-    ('Material "metal" "blackbody eta" [5500 1]', "not supported by this front end"),
+    ('Material "metal" "frobnicate eta" [5500 1]', "not supported by this front end"),
     ('Texture "t" "color" "imagemap" "string filename" "x.exr"', "outside the hot-path scope"),   # (constant / scale / mix fold into the material)
     ('Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0] "float alpha" [0]', "alpha textures"),
     ('Material "matte" "texture bumpmap" "b"', "bump maps"),

@@ -170,11 +170,12 @@ def test_oracle_bit_exact_vs_reference_binary_on_variants(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
-@pytest.mark.parametrize("name", ["path-spectrum-params", "direct-spectrum-light"])
+@pytest.mark.parametrize("name", ["path-spectrum-params", "direct-spectrum-light", "path-blackbody-light"])
 def test_spectrum_parameters_match_reference_binary(staged, name):
     """"spectrum" parameters from .spd files (gold's measured eta and k for MetalMaterial, the D65 illuminant for a point
-    light) and from inline wavelength / value pairs given out of order, and "xyz" parameters: RGBSpectrum::FromSampled /
-    FromXYZ as the reference's ParamSet applies them (paramset.cpp:109-187, spectrum.h:428-451)"""
+    light) and from inline wavelength / value pairs given out of order, "xyz" parameters, "blackbody" parameters (Planck's
+    law over the CIE wavelengths, spectrum.cpp:195-204): RGBSpectrum::FromSampled / FromXYZ as the reference's ParamSet applies
+    them (paramset.cpp:109-187, spectrum.h:428-451)"""
     from helpers import variant_scene
     hs, ncores = variant_scene(name)
     px, _ = oa.render(hs, threads=4)
