@@ -422,6 +422,35 @@ bool Api::DoShape(const std::string &name, const ParamSet &paramsIn) {   // core
     std::shared_ptr<Shape> shape;
     if (name == "trianglemesh") {
         shape.reset(CreateTriangleMeshShape(o2w, w2o, ro, params));
+    } else if (name == "heightfield") {
+        // shapes/heightfield.cpp:120-130 + Heightfield::Refine (:69-117): nu x nv heights over the unit square become ONE
+        // triangle mesh (two triangles per cell, uv = xy) -- which is all FullyRefine ever sees of the shape
+        const int nu = params.FindOneInt("nu", -1), nv = params.FindOneInt("nv", -1);
+        const std::vector<float> *Pz = params.FindFloat("Pz");
+        if (nu < 2 || nv < 2 || !Pz || (long long)Pz->size() != (long long)nu * nv || (long long)nu * nv > (1ll << 26))
+            return Fail("heightfield: \"integer nu\", \"integer nv\" (at least 2 each) and nu x nv \"float Pz\" values expected");
+        ParamSet mesh;
+        std::vector<V3> &P = mesh.points["P"];
+        std::vector<float> &uv = mesh.floats["uv"];
+        std::vector<int> &idx = mesh.ints["indices"];
+        P.resize((size_t)nu * nv);
+        uv.resize((size_t)2 * nu * nv);
+        int pos = 0;
+        for (int y = 0; y < nv; ++y)
+            for (int x = 0; x < nu; ++x) {
+                P[pos].x = uv[2 * pos] = (float)x / (float)(nu - 1);
+                P[pos].y = uv[2 * pos + 1] = (float)y / (float)(nv - 1);
+                P[pos].z = (*Pz)[pos];
+                ++pos;
+            }
+        idx.reserve((size_t)6 * (nu - 1) * (nv - 1));
+        auto vert = [nu](int x, int y) { return x + y * nu; };
+        for (int y = 0; y < nv - 1; ++y)
+            for (int x = 0; x < nu - 1; ++x) {
+                idx.push_back(vert(x, y)); idx.push_back(vert(x + 1, y)); idx.push_back(vert(x + 1, y + 1));
+                idx.push_back(vert(x, y)); idx.push_back(vert(x + 1, y + 1)); idx.push_back(vert(x, y + 1));
+            }
+        shape.reset(CreateTriangleMeshShape(o2w, w2o, ro, mesh));
     } else if (name == "sphere") {   // shapes/sphere.cpp:216-224
         float radius = params.FindOneFloat("radius", 1.f);
         float zmin = params.FindOneFloat("zmin", -radius);

@@ -296,6 +296,18 @@ SPECTRUM_VARIANTS = [
 ]
 
 
+# Shape "heightfield" (shapes/heightfield.cpp: refined into one triangle mesh with uv = xy)
+def _heightfield(nu, nv, seed, place):
+    z = np.random.RandomState(seed).uniform(0, .35, nu * nv)
+    return (_WB + '\nAttributeBegin\n%s\nMaterial "plastic" "color Kd" [.3 .5 .7] "color Ks" [.3 .3 .3] "float roughness" [.1]\n'
+            'Shape "heightfield" "integer nu" [%d] "integer nv" [%d] "float Pz" [%s]\nAttributeEnd\n' % (place, nu, nv, " ".join("%.6g" % v for v in z)))
+HEIGHTFIELD_VARIANTS = [
+    ("path-heightfield", "bunny", 40, 40, 4, 2, {}, [(_WB, _heightfield(9, 7, 1, "Translate -.15 .02 -.1\nRotate -90 1 0 0\nScale .3 .3 .3"))]),
+    ("direct-heightfield", "killeroo-simple", 40, 40, 4, 2, {"integrator": "directlighting"},
+     [(_WB, _heightfield(5, 12, 2, "Translate -150 20 -100\nScale 300 300 300"))]),
+]
+
+
 # ObjectBegin / ObjectEnd / ObjectInstance (core/api.cpp:1095-1147): an object of several shapes (its own BVH, shared by the
 # instances), an object of one sphere (no BVH around it), instances under static and moving transforms, an unused object
 _OBJ = _WB + ('\nObjectBegin "blob"\nMaterial "plastic" "color Kd" [.2 .5 .2] "color Ks" [.4 .4 .4] "float roughness" [.05]\n'
@@ -332,7 +344,7 @@ def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + TEXTURE_VARIANTS + SPECTRUM_VARIANTS + INSTANCE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + TEXTURE_VARIANTS + SPECTRUM_VARIANTS + HEIGHTFIELD_VARIANTS + INSTANCE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

@@ -184,6 +184,18 @@ def test_spectrum_parameters_match_reference_binary(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
+@pytest.mark.parametrize("name", ["path-heightfield", "direct-heightfield"])
+def test_heightfield_shape_matches_reference_binary(staged, name):
+    """Shape "heightfield" (shapes/heightfield.cpp:69-130): the nu x nv grid refined into one triangle mesh, two triangles per
+    cell in the reference's winding, uv = xy; under a transform with rotation and non-uniform use of the unit square"""
+    from helpers import variant_scene
+    hs, ncores = variant_scene(name)
+    px, _ = oa.render(hs, threads=4)
+    ref, _ = oa.run_reference(hs.filename, ncores)
+    assert np.array_equal(hs.pixels_to_rgb(px).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
 @pytest.mark.parametrize("name", ["path-constant-textures", "direct-constant-textures"])
 def test_constant_textures_match_reference_binary(staged, name):
     """Texture "constant" / "scale" / "mix" (textures/{constant,scale,mix}.h: values that do not depend on the surface point,
