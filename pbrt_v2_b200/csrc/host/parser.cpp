@@ -411,6 +411,8 @@ bool Api::DoShape(const std::string &name, const ParamSet &paramsIn) {   // core
     const ParamSet &params = binfile.empty() ? paramsIn : withMesh;
     if (params.textures.count("alpha") || params.floats.count("alpha"))   // trianglemesh.cpp:397-406: alpha-tested triangles
         return Fail("alpha textures on shapes are outside the hot-path scope");
+    if (name == "trianglemesh" && params.vectors.count("S"))   // trianglemesh.cpp:392-396: they turn the shading frame (:254-266)
+        return Fail("per-vertex tangents (\"vector S\") on triangle meshes are outside the hot-path scope");
     const bool animated = curTransform.IsAnimated();
     const Transform *o2w, *w2o;
     if (!animated) Cache().Lookup(curTransform.t[0], &o2w, &w2o);

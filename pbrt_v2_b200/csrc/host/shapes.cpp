@@ -22,8 +22,7 @@ TriangleMesh::TriangleMesh(const Transform *o2w, const Transform *w2o, bool ro, 
     for (int i = 0; i < nv; ++i) p[i] = ObjectToWorld->Pt(P[i]);
 }
 
-// shapes/trianglemesh.cpp:371-441 (validation subset; S tangents, alpha textures
-// and discarddegenerateUVs are not used by the config scenes -> rejected/ignored)
+// shapes/trianglemesh.cpp:371-441 ("vector S" tangents and alpha textures are refused by the caller, parser.cpp DoShape)
 TriangleMesh *CreateTriangleMeshShape(const Transform *o2w, const Transform *w2o, bool ro,
                                       const ParamSet &params) {
     const std::vector<int> *vi = params.FindInt("indices");
@@ -35,6 +34,24 @@ TriangleMesh *CreateTriangleMeshShape(const Transform *o2w, const Transform *w2o
     if (uvs && (int)uvs->size() < 2 * npi) uvs = nullptr;
     const std::vector<V3> *N = params.FindNormal("N");
     if (N && (int)N->size() != npi) N = nullptr;
+    if (params.FindOneBool("discarddegenerateUVs", false) && uvs && N) {   // trianglemesh.cpp:402-421
+        // "if there are normals, check for bad uv's that give degenerate mappings; discard them if so"
+        const std::vector<int> &v = *vi;
+        for (size_t i = 0; i + 2 < v.size(); i += 3) {
+            if (v[i] < 0 || v[i + 1] < 0 || v[i + 2] < 0 || v[i] >= npi || v[i + 1] >= npi || v[i + 2] >= npi) break;   // (refused below)
+            const V3 &p0 = (*P)[v[i]], &p1 = (*P)[v[i + 1]], &p2 = (*P)[v[i + 2]];
+            float area = .5f * Length(Cross(p0 - p1, p2 - p1));
+            if (area < 1e-7) continue;
+            const float *u = uvs->data();
+            if ((u[2 * v[i]] == u[2 * v[i + 1]] && u[2 * v[i] + 1] == u[2 * v[i + 1] + 1]) ||
+                (u[2 * v[i + 1]] == u[2 * v[i + 2]] && u[2 * v[i + 1] + 1] == u[2 * v[i + 2] + 1]) ||
+                (u[2 * v[i + 2]] == u[2 * v[i]] && u[2 * v[i + 2] + 1] == u[2 * v[i] + 1])) {
+                fprintf(stderr, "Warning: Degenerate uv coordinates in triangle mesh.  Discarding all uvs.\n");
+                uvs = nullptr;
+                break;
+            }
+        }
+    }
     for (int idx : *vi)
         if (idx < 0 || idx >= npi) {   // (the reference checks the upper bound only, trianglemesh.cpp:386-391, and reads out of bounds below 0)
             fprintf(stderr, "trianglemesh has out of-bounds vertex index %d (%d \"P\" values were given)\n", idx, npi);

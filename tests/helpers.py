@@ -301,6 +301,15 @@ def _heightfield(nu, nv, seed, place):
     z = np.random.RandomState(seed).uniform(0, .35, nu * nv)
     return (_WB + '\nAttributeBegin\n%s\nMaterial "plastic" "color Kd" [.3 .5 .7] "color Ks" [.3 .3 .3] "float roughness" [.1]\n'
             'Shape "heightfield" "integer nu" [%d] "integer nv" [%d] "float Pz" [%s]\nAttributeEnd\n' % (place, nu, nv, " ".join("%.6g" % v for v in z)))
+# "bool discarddegenerateUVs" (trianglemesh.cpp:379, 402-421): with normals present, uvs that coincide on a triangle are dropped
+# for the whole mesh -- which changes dpdu / dpdv, hence the shading frame, hence the image
+_DEGEN = _WB + ('\nAttributeBegin\nTranslate -.12 .05 .1\nScale .25 .25 .25\nMaterial "plastic" "color Kd" [.6 .4 .2] "color Ks" [.4 .4 .4] "float roughness" [.05]\n'
+                'Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [0 0 0 1 0 .2 1 1 0 0 1 .3] "normal N" [0 0 1 .2 0 1 0 .2 1 -.2 0 1]\n'
+                '  "float uv" [0 0 1 0 1 0 0 1] "bool discarddegenerateUVs" ["%s"]\nAttributeEnd\n')
+DEGENERATE_UV_VARIANTS = [
+    ("path-discard-degenerate-uvs", "bunny", 40, 40, 4, 2, {}, [(_WB, _DEGEN % "true")]),
+    ("path-keep-degenerate-uvs", "bunny", 40, 40, 4, 2, {}, [(_WB, _DEGEN % "false")]),
+]
 HEIGHTFIELD_VARIANTS = [
     ("path-heightfield", "bunny", 40, 40, 4, 2, {}, [(_WB, _heightfield(9, 7, 1, "Translate -.15 .02 -.1\nRotate -90 1 0 0\nScale .3 .3 .3"))]),
     ("direct-heightfield", "killeroo-simple", 40, 40, 4, 2, {"integrator": "directlighting"},
@@ -344,7 +353,7 @@ def variant_scene(name):
     """HostScene of one of VARIANTS (thin-lens camera, maxdepth extremes, non-square crop window, shutter interval)."""
     key = ("variant", name)
     if key not in _cache:
-        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + TEXTURE_VARIANTS + SPECTRUM_VARIANTS + HEIGHTFIELD_VARIANTS + INSTANCE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
+        _, base, xres, yres, spp, ncores, kw, edits = [v for v in VARIANTS + EDGE_VARIANTS + SPECULAR_VARIANTS + METAL_VARIANTS + INFINITE_VARIANTS + ENVMAP_VARIANTS + NAMED_MATERIAL_VARIANTS + TEXTURE_VARIANTS + SPECTRUM_VARIANTS + HEIGHTFIELD_VARIANTS + DEGENERATE_UV_VARIANTS + INSTANCE_VARIANTS + FILTER_VARIANTS if v[0] == name][0]
         path = scenes.variant(base, scenes.STAGED + "/variant-%s.pbrt" % name, xres, yres, spp, **kw)
         text = open(path).read()
         for a, b in edits:

@@ -56,6 +56,7 @@ def test_crop_window_extent(staged):
     ('Texture "t" "color" "imagemap" "string filename" "x.exr"', "outside the hot-path scope"),   # (constant / scale / mix fold into the material)
     ('Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0] "float alpha" [0]', "alpha textures"),
     ('Material "matte" "texture bumpmap" "b"', "bump maps"),
+    ('Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0] "vector S" [1 0 0 1 0 0 1 0 0]', "tangents"),
 ])
 def test_out_of_scope_directives_fail_loudly(staged, text, needle):
     src = open(scenes.variant("bunny", os.path.join(scenes.STAGED, "t-err.pbrt"), 8, 8, 1)).read()

@@ -184,10 +184,11 @@ def test_spectrum_parameters_match_reference_binary(staged, name):
 
 
 @pytest.mark.skipif(not oa.have_reference(), reason="oracle/_ref/bin/pbrt not built")
-@pytest.mark.parametrize("name", ["path-heightfield", "direct-heightfield"])
+@pytest.mark.parametrize("name", ["path-heightfield", "direct-heightfield", "path-discard-degenerate-uvs", "path-keep-degenerate-uvs"])
 def test_heightfield_shape_matches_reference_binary(staged, name):
     """Shape "heightfield" (shapes/heightfield.cpp:69-130): the nu x nv grid refined into one triangle mesh, two triangles per
-    cell in the reference's winding, uv = xy; under a transform with rotation and non-uniform use of the unit square"""
+    cell in the reference's winding, uv = xy; under a transform with rotation and non-uniform use of the unit square.  And
+    "bool discarddegenerateUVs" on a triangle mesh with normals (trianglemesh.cpp:402-421): on and off"""
     from helpers import variant_scene
     hs, ncores = variant_scene(name)
     px, _ = oa.render(hs, threads=4)
