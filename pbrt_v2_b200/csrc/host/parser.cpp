@@ -708,6 +708,8 @@ bool Api::Finish(LoadedScene *out) {   // core/api.cpp:1150-1281
         return Fail("too many lights for the sample-array table of the C ABI (PBRTGPU_MAX_SAMPLE_ARRAYS)");
     if (RendererName != "sampler" && RendererName != "gpusampler")
         return Fail("renderer \"" + RendererName + "\" is out of scope (sampler)");
+    if (RendererParams.FindOneBool("visualizeobjectids", false))   // api.cpp:1250, samplerrenderer.cpp:96-110: colours by primitive id
+        return Fail("Renderer \"sampler\" \"bool visualizeobjectids\" is out of scope");
     // --- accelerator (api.cpp:580-594, 1186-1207) ---
     if (AcceleratorName != "bvh" && AcceleratorName != "gpubvh")
         return Fail("accelerator \"" + AcceleratorName + "\" is out of scope (bvh)");
