@@ -58,7 +58,7 @@ int main(int argc, char *argv[]) {
             return 0;
         } else files.push_back(argv[i]);
     }
-    if (files.empty()) { fprintf(stderr, "pbrt_b200: no scene file given\n"); return 1; }
+    if (files.empty()) files.push_back("-");   // "Parse scene from standard input" (main/pbrt.cpp:71-74)
     PbrtGpuComm *comm = nullptr;
     if (world > 1) {
         if (rank < 0 || rank >= world || rendezvous.empty()) { fprintf(stderr, "pbrt_b200: --world needs --rank and --rendezvous\n"); return 1; }

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <functional>
+#include <iostream>
 #include <set>
 #include <sstream>
 
@@ -81,10 +82,13 @@ struct Lexer {
     std::string file;
     int line = 1;
     bool Load(const std::string &fn) {
-        std::ifstream f(fn, std::ios::binary);
-        if (!f) return false;
         std::stringstream ss;
-        ss << f.rdbuf();
+        if (fn == "-") ss << std::cin.rdbuf();   // ParseFile("-"): the scene on standard input (core/parser.cpp:58-60)
+        else {
+            std::ifstream f(fn, std::ios::binary);
+            if (!f) return false;
+            ss << f.rdbuf();
+        }
         buf = ss.str();
         file = fn;
         return true;
