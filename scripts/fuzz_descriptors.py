@@ -67,7 +67,7 @@ def main():
     lib.pbrtgpu_render_validate_scene.argtypes = [C.c_void_p, C.POINTER(pb.RenderDesc)]
     lib.pbrtgpu_film_extent.argtypes = [C.POINTER(pb.RenderDesc), C.c_void_p]
 
-    sys.argv = sys.argv[:1] + ["0", "0", "specular+crop+animated" if only_rd else "specular+metal+crop+infinite+animated"]
+    sys.argv = sys.argv[:1] + ["0", "0", "specular+crop+animated+instances" if only_rd else "specular+metal+crop+infinite+animated+instances+params"]
     rs = np.random.RandomState(seed)
     from pbrt_v2_b200 import scenes
     scenes.stage()
